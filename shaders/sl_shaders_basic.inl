@@ -1,0 +1,93 @@
+/*
+ * Built-in shader pairs, part 1: the draw-test shader and config C1 (Lambert).
+ *
+ * This file is *shader source*, i.e. user input to the pipeline, not part of
+ * it.  It is written once against the reference's shader-facing API
+ * (`math::` = ls::math, SL_VertexParam / SL_FragmentParam field names,
+ * SL_Shader.hpp:41-97) and compiled three times:
+ *   - oracle/ref/slref_shim.cpp : math = ls::math (the real x86 intrinsics)
+ *   - oracle/port/slor_oracle.cpp : math = the oracle's plain-C restatement
+ *   - softlight_b200/csrc/*.cu  : math = sld::math (__device__ mirrors)
+ * The including context defines SL_SHADER_FN and the `math` namespace alias.
+ */
+
+/* ---- "vcolor": the shader of softlight/tests/sl_draw_test.cpp:27-83 ------ */
+struct VColorVertex
+{
+    math::vec4 pos;
+    math::vec4 color;
+};
+
+SL_SHADER_FN math::vec4 vcolor_vs(SL_VertexParam& param)
+{
+    const VColorVertex& vert = *(param.pVbo->template element<const VColorVertex>(param.pVao->offset(0, param.vertId)));
+    param.pVaryings[0] = vert.color;
+    return vert.pos;
+}
+
+SL_SHADER_FN bool vcolor_fs(SL_FragmentParam& fragParam)
+{
+    fragParam.pOutputs[0] = fragParam.pVaryings[0];
+    return true;
+}
+
+/* ---- "lambert": config C1 ------------------------- */
+struct LambertUniforms
+{
+    math::mat4 mvp;
+    math::vec4 lightDir;
+};
+
+struct LambertVertex
+{
+    math::vec4 pos;
+    math::vec4 nrm;
+};
+
+SL_SHADER_FN math::vec4 lambert_vs(SL_VertexParam& param)
+{
+    const LambertUniforms* pUniforms = param.pUniforms->template as<LambertUniforms>();
+    const LambertVertex&   vert      = *(param.pVbo->template element<const LambertVertex>(param.pVao->offset(0, param.vertId)));
+
+    param.pVaryings[0] = vert.nrm;
+    return pUniforms->mvp * vert.pos;
+}
+
+SL_SHADER_FN bool lambert_fs(SL_FragmentParam& fragParam)
+{
+    const LambertUniforms* pUniforms = fragParam.pUniforms->template as<LambertUniforms>();
+    const math::vec4&      n         = fragParam.pVaryings[0];
+    const float            d         = math::max(math::dot(n, pUniforms->lightDir), 0.f);
+
+    fragParam.pOutputs[0] = math::vec4{d, d, d, 1.f};
+    return true;
+}
+
+/* ---- "flat": constant colour from the uniform block; discards odd primitives
+ * never -- used by tests that need a shader with zero varyings. ------------ */
+struct FlatUniforms
+{
+    math::mat4 mvp;
+    math::vec4 color;
+};
+
+SL_SHADER_FN math::vec4 flat_vs(SL_VertexParam& param)
+{
+    const FlatUniforms* pUniforms = param.pUniforms->template as<FlatUniforms>();
+    const math::vec4&   pos       = *(param.pVbo->template element<const math::vec4>(param.pVao->offset(0, param.vertId)));
+    return pUniforms->mvp * pos;
+}
+
+SL_SHADER_FN bool flat_fs(SL_FragmentParam& fragParam)
+{
+    const FlatUniforms* pUniforms = fragParam.pUniforms->template as<FlatUniforms>();
+    fragParam.pOutputs[0] = pUniforms->color;
+    return true;
+}
+
+SL_REGISTER_VERTEX_SHADER("vcolor", vcolor_vs)
+SL_REGISTER_FRAGMENT_SHADER("vcolor", vcolor_fs)
+SL_REGISTER_VERTEX_SHADER("lambert", lambert_vs)
+SL_REGISTER_FRAGMENT_SHADER("lambert", lambert_fs)
+SL_REGISTER_VERTEX_SHADER("flat", flat_vs)
+SL_REGISTER_FRAGMENT_SHADER("flat", flat_fs)

@@ -1,0 +1,289 @@
+"""Synthetic scenes for the BASELINE.json configs.
+
+A scene is pure input data (numpy buffers + pipeline state + a draw list) that
+is replayed, call for call, through any library exporting the C ABI of
+include/slcu.h: the CUDA product, the compiled reference or the CPU
+restatement.  All randomness is a seeded numpy Generator; all matrices are
+column-major float32 like ls::math::mat4.
+"""
+from __future__ import annotations
+
+import struct
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional
+
+import numpy as np
+
+from . import capi as A
+
+
+# ------------------------------------------------------------------ matrices
+def perspective(fovy_deg: float, aspect: float, znear: float, zfar: float) -> np.ndarray:
+    f = 1.0 / np.tan(np.radians(fovy_deg) / 2.0)
+    m = np.zeros((4, 4), dtype=np.float64)  # m[col][row]
+    m[0][0] = f / aspect
+    m[1][1] = f
+    m[2][2] = (zfar + znear) / (znear - zfar)
+    m[2][3] = -1.0
+    m[3][2] = (2.0 * zfar * znear) / (znear - zfar)
+    return m.astype(np.float32)
+
+
+def infinite_perspective(fovy_deg: float, aspect: float, znear: float) -> np.ndarray:
+    """Reversed-Z style infinite projection (z_ndc -> 0 at infinity, 1 at near)."""
+    f = 1.0 / np.tan(np.radians(fovy_deg) / 2.0)
+    m = np.zeros((4, 4), dtype=np.float64)
+    m[0][0] = f / aspect
+    m[1][1] = f
+    m[2][2] = 0.0
+    m[2][3] = -1.0
+    m[3][2] = znear
+    return m.astype(np.float32)
+
+
+def look_at(eye, target, up) -> np.ndarray:
+    eye = np.asarray(eye, dtype=np.float64)
+    target = np.asarray(target, dtype=np.float64)
+    up = np.asarray(up, dtype=np.float64)
+    fwd = target - eye
+    fwd /= np.linalg.norm(fwd)
+    s = np.cross(fwd, up)
+    s /= np.linalg.norm(s)
+    u = np.cross(s, fwd)
+    m = np.identity(4, dtype=np.float64)
+    m[0][0], m[1][0], m[2][0] = s
+    m[0][1], m[1][1], m[2][1] = u
+    m[0][2], m[1][2], m[2][2] = -fwd
+    m[3][0] = -np.dot(s, eye)
+    m[3][1] = -np.dot(u, eye)
+    m[3][2] = np.dot(fwd, eye)
+    return m.astype(np.float32)
+
+
+def matmul_cm(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """Column-major product a*b (both stored m[col][row])."""
+    return (b.astype(np.float64) @ a.astype(np.float64)).astype(np.float32)
+
+
+def translate_scale(t, s) -> np.ndarray:
+    m = np.identity(4, dtype=np.float32)
+    m[0][0] = m[1][1] = m[2][2] = s
+    m[3][0:3] = t
+    return m
+
+
+# ------------------------------------------------------------------ geometry
+def uv_sphere(stacks: int, slices: int, radius: float = 1.0):
+    """(stacks+1)*(slices+1) vertices, stacks*slices*2 triangles (CCW seen from outside)."""
+    v = np.linspace(0.0, np.pi, stacks + 1)
+    u = np.linspace(0.0, 2.0 * np.pi, slices + 1)
+    vv, uu = np.meshgrid(v, u, indexing="ij")
+    x = np.sin(vv) * np.cos(uu)
+    y = np.cos(vv)
+    z = np.sin(vv) * np.sin(uu)
+    nrm = np.stack([x, y, z], axis=-1).reshape(-1, 3)
+    pos = nrm * radius
+    uv = np.stack([uu / (2.0 * np.pi), vv / np.pi], axis=-1).reshape(-1, 2)
+    i, j = np.meshgrid(np.arange(stacks), np.arange(slices), indexing="ij")
+    a = (i * (slices + 1) + j).reshape(-1)
+    b = a + 1
+    c = a + (slices + 1)
+    d = c + 1
+    tris = np.stack([a, b, c, b, d, c], axis=-1).reshape(-1, 3)
+    return pos.astype(np.float32), nrm.astype(np.float32), uv.astype(np.float32), tris.astype(np.uint32)
+
+
+def value_noise_texture(seed: int, w: int, h: int, channels: int) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, 256, size=(h // 8 + 1, w // 8 + 1, channels)).astype(np.float32)
+    ys = np.arange(h) / 8.0
+    xs = np.arange(w) / 8.0
+    y0 = ys.astype(int)
+    x0 = xs.astype(int)
+    fy = (ys - y0)[:, None, None]
+    fx = (xs - x0)[None, :, None]
+    t = (base[y0][:, x0] * (1 - fx) * (1 - fy) + base[y0][:, x0 + 1] * fx * (1 - fy)
+         + base[y0 + 1][:, x0] * (1 - fx) * fy + base[y0 + 1][:, x0 + 1] * fx * fy)
+    t = t + rng.integers(-12, 13, size=t.shape)
+    return np.clip(t, 0, 255).astype(np.uint8)
+
+
+# --------------------------------------------------------------------- scene
+@dataclass
+class Scene:
+    name: str
+    width: int
+    height: int
+    color_type: int
+    depth_type: int
+    clear_color: tuple
+    clear_depth: float
+    setup: Callable  # (ctx) -> state dict
+    frame: Callable  # (ctx, state) -> None   (clear + all draws of one frame)
+    tris_per_frame: int = 0
+    draws_per_frame: int = 1
+    note: str = ""
+    upload_bytes_per_frame: int = 0
+    per_frame_update: Optional[Callable] = None  # (ctx, state, frame_idx) -> bytes uploaded
+
+
+class SceneInstance:
+    """A scene bound to one context (one library)."""
+
+    def __init__(self, scene: Scene, ctx: A.Context):
+        self.scene = scene
+        self.ctx = ctx
+        self.state = scene.setup(ctx)
+
+    def render(self):
+        self.scene.frame(self.ctx, self.state)
+
+    def read_color(self) -> np.ndarray:
+        s = self.scene
+        return self.ctx.texture_read(self.state["color"], s.color_type, s.width, s.height)
+
+    def read_depth(self) -> np.ndarray:
+        s = self.scene
+        return self.ctx.texture_read(self.state["depth"], s.depth_type, s.width, s.height)[..., 0]
+
+
+def _make_targets(ctx: A.Context, scene_w, scene_h, color_type, depth_type):
+    color = ctx.create_texture(color_type, scene_w, scene_h, 1)
+    depth = ctx.create_texture(depth_type, scene_w, scene_h, 1)
+    fbo = ctx.create_framebuffer([color], depth)
+    assert ctx.fbo_valid(fbo) == 0
+    return color, depth, fbo
+
+
+# ---- draw-test triangle (softlight/tests/sl_draw_test.cpp:85-197) -----------
+def draw_test_scene(width=640, height=480, depth_type=A.SL_COLOR_R_FLOAT) -> Scene:
+    tri = np.array([[-0.5, -0.5, 0, 1, 1, 0, 0, 1],
+                    [0.0, 0.5, 0, 1, 0, 1, 0, 1],
+                    [0.5, -0.5, 0, 1, 0, 0, 1, 1]], dtype=np.float32)
+    idx = np.array([0, 2, 1], dtype=np.uint8)
+
+    def setup(ctx):
+        color, depth, fbo = _make_targets(ctx, width, height, A.SL_COLOR_RGBA_8U, depth_type)
+        vbo = ctx.create_vbo(tri)
+        ibo = ctx.create_ibo(idx)
+        vao = ctx.create_vao(vbo, ibo, [(0, 32, A.VERTEX_DIMENSION_4, A.VERTEX_DATA_FLOAT),
+                                        (16, 32, A.VERTEX_DIMENSION_4, A.VERTEX_DATA_FLOAT)])
+        ubo = ctx.create_ubo(b"\0" * 16)
+        sh = ctx.create_shader("vcolor", "vcolor", ubo, vs_varyings=1, fs_varyings=1, cull=A.SL_CULL_BACK_FACE,
+                               blend=A.SL_BLEND_OFF, depth_test=A.SL_DEPTH_TEST_OFF, depth_mask=A.SL_DEPTH_MASK_OFF)
+        assert sh != A.INVALID_ID
+        return dict(color=color, depth=depth, fbo=fbo, shader=sh, mesh=ctx.mesh(vao, 0, 3))
+
+    def frame(ctx, st):
+        ctx.clear_framebuffer(st["fbo"], 0, (1.0, 0.0, 1.0, 1.0), 0.0)
+        ctx.draw(st["mesh"], st["shader"], st["fbo"])
+
+    return Scene("draw_test", width, height, A.SL_COLOR_RGBA_8U, depth_type, (1, 0, 1, 1), 0.0, setup, frame,
+                 tris_per_frame=1)
+
+
+# ---- C1: 100k-triangle UV sphere, Lambert -----------------------------------
+def sphere_scene(width=1024, height=768, stacks=224, slices=224, depth_type=A.SL_COLOR_R_FLOAT,
+                 color_type=A.SL_COLOR_RGBA_8U, depth_test=A.SL_DEPTH_TEST_LESS_THAN, cull=A.SL_CULL_BACK_FACE,
+                 blend=A.SL_BLEND_OFF, eye=(0.0, 0.0, 2.2), name=None, clear_depth=1.0, reps=1) -> Scene:
+    pos, nrm, _, tris = uv_sphere(stacks, slices)
+    verts = np.zeros((pos.shape[0], 8), dtype=np.float32)
+    verts[:, 0:3] = pos
+    verts[:, 3] = 1.0
+    verts[:, 4:7] = nrm
+    mvp = matmul_cm(perspective(60.0, width / height, 0.1, 100.0), look_at(eye, (0, 0, 0), (0, 1, 0)))
+    light = np.array([0.3, 0.5, 1.0, 0.0], dtype=np.float64)
+    light = (light / np.linalg.norm(light)).astype(np.float32)
+    blob = mvp.tobytes() + light.tobytes()
+    idx = tris.reshape(-1)
+
+    def setup(ctx):
+        color, depth, fbo = _make_targets(ctx, width, height, color_type, depth_type)
+        vbo = ctx.create_vbo(verts)
+        ibo = ctx.create_ibo(idx)
+        vao = ctx.create_vao(vbo, ibo, [(0, 32, A.VERTEX_DIMENSION_4, A.VERTEX_DATA_FLOAT),
+                                        (16, 32, A.VERTEX_DIMENSION_4, A.VERTEX_DATA_FLOAT)])
+        ubo = ctx.create_ubo(blob)
+        sh = ctx.create_shader("lambert", "lambert", ubo, vs_varyings=1, fs_varyings=1, cull=cull, blend=blend,
+                               depth_test=depth_test, depth_mask=A.SL_DEPTH_MASK_ON)
+        assert sh != A.INVALID_ID
+        return dict(color=color, depth=depth, fbo=fbo, shader=sh, mesh=ctx.mesh(vao, 0, idx.size))
+
+    def frame(ctx, st):
+        ctx.clear_framebuffer(st["fbo"], 0, (0.0, 0.0, 0.0, 1.0), clear_depth)
+        for _ in range(reps):
+            ctx.draw(st["mesh"], st["shader"], st["fbo"])
+
+    return Scene(name or f"sphere{tris.shape[0] // 1000}k_{width}x{height}", width, height, color_type, depth_type,
+                 (0, 0, 0, 1), clear_depth, setup, frame, tris_per_frame=tris.shape[0] * reps, draws_per_frame=reps)
+
+
+# ---- C2: instanced textured spheres (sl_instancing_test.cpp:80-171, 286-310) -
+def instancing_scene(width=1920, height=1080, grid=(25, 20, 20), stacks=16, slices=32, depth_type=A.SL_COLOR_R_HALF,
+                     name=None) -> Scene:
+    pos, nrm, uv, tris = uv_sphere(stacks, slices)
+    nverts = pos.shape[0]
+    verts = np.zeros((nverts, 8), dtype=np.float32)
+    verts[:, 0:3] = pos
+    verts[:, 3:5] = uv * 4.0  # a few repeats so REPEAT wrapping is exercised
+    verts[:, 5:8] = nrm
+    idx = tris.reshape(-1).astype(np.uint16)
+    gx, gy, gz = grid
+    ninst = gx * gy * gz
+    spacing = 25.0
+    scale = 0.125 * 40.0  # spheres of radius 5 on a 25-unit lattice
+    mats = np.zeros((ninst, 4, 4), dtype=np.float32)
+    n = 0
+    for z in range(gz):
+        for y in range(gy):
+            for x in range(gx):
+                t = (spacing * (x - gx / 2.0 + 0.5), spacing * (y - gy / 2.0 + 0.5), -spacing * (z + 1.5))
+                mats[n] = translate_scale(t, scale)
+                n += 1
+    tex = value_noise_texture(2, 256, 256, 3)
+    proj = infinite_perspective(60.0, width / height, 0.01)
+    cam = (0.0, 0.0, 30.0)
+    view = look_at(cam, (0, 0, -100.0), (0, 1, 0))
+    vp = matmul_cm(proj, view)
+    model = np.identity(4, dtype=np.float32)
+    # InstTexUniforms layout (shaders/sl_shaders_scene.inl): ptr@0, ambient@16, diffuse@32, ptr@48, model@64, vp@128, cam@192
+    blob = bytearray(208)
+    blob[16:32] = np.array([0.2, 0.2, 0.2, 1.0], dtype=np.float32).tobytes()
+    blob[32:48] = np.array([0.8, 0.8, 0.8, 0.0], dtype=np.float32).tobytes()
+    blob[64:128] = model.tobytes()
+    blob[128:192] = vp.tobytes()
+    blob[192:208] = np.array([cam[0], cam[1], cam[2], 1.0], dtype=np.float32).tobytes()
+
+    def setup(ctx):
+        color, depth, fbo = _make_targets(ctx, width, height, A.SL_COLOR_RGBA_8U, depth_type)
+        vbo = ctx.create_vbo(verts)
+        ibo = ctx.create_ibo(idx)
+        vao = ctx.create_vao(vbo, ibo, [(0, 32, A.VERTEX_DIMENSION_3, A.VERTEX_DATA_FLOAT),
+                                        (12, 32, A.VERTEX_DIMENSION_2, A.VERTEX_DATA_FLOAT),
+                                        (20, 32, A.VERTEX_DIMENSION_3, A.VERTEX_DATA_FLOAT)])
+        t = ctx.create_texture(A.SL_COLOR_RGB_8U, 256, 256, 1, tex)
+        inst = ctx.create_vbo(mats)
+        ubo = ctx.create_ubo(bytes(blob))
+        ctx.ubo_bind_texture(ubo, 0, t)
+        ctx.ubo_bind_buffer(ubo, 48, inst, 0)
+        sh = ctx.create_shader("inst_tex", "inst_tex", ubo, vs_varyings=3, fs_varyings=3, cull=A.SL_CULL_BACK_FACE,
+                               blend=A.SL_BLEND_PREMULTIPLED_ALPHA, depth_test=A.SL_DEPTH_TEST_GREATER_EQUAL,
+                               depth_mask=A.SL_DEPTH_MASK_ON)
+        assert sh != A.INVALID_ID
+        return dict(color=color, depth=depth, fbo=fbo, shader=sh, mesh=ctx.mesh(vao, 0, idx.size), ubo=ubo)
+
+    def frame(ctx, st):
+        ctx.clear_framebuffer(st["fbo"], 0, (0.6, 0.6, 0.6, 1.0), 0.0)
+        ctx.draw_instanced(st["mesh"], ninst, st["shader"], st["fbo"])
+
+    return Scene(name or f"instancing{ninst}_{width}x{height}", width, height, A.SL_COLOR_RGBA_8U, depth_type,
+                 (0.6, 0.6, 0.6, 1.0), 0.0, setup, frame, tris_per_frame=tris.shape[0] * ninst, draws_per_frame=1)
+
+
+SCENES: Dict[str, Callable[[], Scene]] = {
+    "draw_test": draw_test_scene,
+    "c1_sphere100k": sphere_scene,
+    "c1_small": lambda: sphere_scene(256, 192, 48, 48, name="sphere4k_256x192"),
+    "c2_instancing10k": instancing_scene,
+    "c2_small": lambda: instancing_scene(320, 240, (5, 4, 3), 8, 16, name="instancing60_320x240"),
+}
