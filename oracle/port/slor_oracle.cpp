@@ -1,0 +1,1080 @@
+/*
+ * slor_oracle.cpp -- TEST INFRASTRUCTURE ONLY.
+ *
+ * CPU restatement ("port") of the SoftLight draw path: a plain, sequential,
+ * scalar C++ re-telling of what the reference's x86/AVX2 source path computes
+ * with num_threads(1), function by function, each citing the reference
+ * file:line it follows.  It exists so that the CUDA product can be checked on
+ * a box where /root/reference is absent, and so that the algorithm is written
+ * down once without SIMD.  It is pinned against the compiled reference itself
+ * (oracle/_ref/libslref_strict.so; tests/test_oracle_vs_ref.py) and against the
+ * committed golden frames (tests/golden/).
+ *
+ * Only tests/, bench.py's cpu_baseline leg and __graft_entry__.smoke() may load
+ * this library.  The product (softlight_b200/libslcu.so) never does.
+ *
+ * Exports the C ABI of include/slcu.h with the prefix slor_.
+ */
+#include <algorithm>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "slor_math.h"
+#include "slor_shader_api.h"
+
+#define SLCU_PREFIX slor_
+#include "slcu.h"
+
+namespace slo
+{
+
+uint32_t g_rcp_table[2048];
+
+/* Measure the rcpss table from the CPU this runs on (the reference executes
+ * the real instruction, so "same box" means "same table"). */
+static void measure_host_rcp_table(uint32_t* t)
+{
+    for (uint32_t i = 0; i < 2048; ++i)
+    {
+        float in = u2f(0x3f800000u | (i << 12));
+        float out;
+        __asm__ volatile("rcpss %1, %0" : "=x"(out) : "x"(in));
+        t[i] = f2u(out);
+    }
+}
+
+/* ---- shader registry ---------------------------------------------------- */
+typedef math::vec4 (*VsFn)(SL_VertexParam&);
+typedef bool (*FsFn)(SL_FragmentParam&);
+static std::map<std::string, VsFn>& vs_registry() { static std::map<std::string, VsFn> r; return r; }
+static std::map<std::string, FsFn>& fs_registry() { static std::map<std::string, FsFn> r; return r; }
+struct VsReg { VsReg(const char* n, VsFn f) { vs_registry()[n] = f; } };
+struct FsReg { FsReg(const char* n, FsFn f) { fs_registry()[n] = f; } };
+
+#define SL_SHADER_FN static inline
+#define SL_CAT2(a, b) a##b
+#define SL_CAT(a, b) SL_CAT2(a, b)
+#define SL_REGISTER_VERTEX_SHADER(name, fn) static VsReg SL_CAT(vsreg_, fn){name, fn};
+#define SL_REGISTER_FRAGMENT_SHADER(name, fn) static FsReg SL_CAT(fsreg_, fn){name, fn};
+
+#include "sl_shaders_basic.inl"
+#include "sl_shaders_scene.inl"
+
+/* ---- objects ------------------------------------------------------------- */
+struct IndexBuffer
+{
+    int type = 0;
+    uint32_t count = 0;
+    unsigned bytesPerId = 0;
+    std::vector<unsigned char> data;
+};
+
+struct Framebuffer
+{
+    unsigned numColors = 0;
+    size_t colors[4] = {(size_t)-1, (size_t)-1, (size_t)-1, (size_t)-1};
+    size_t depth = (size_t)-1;
+};
+
+struct Shader
+{
+    int cullMode, depthTest, depthMask, blend, numVaryings, numOutputs;
+    VsFn vs;
+    FsFn fs;
+    size_t ubo;
+};
+
+struct UboFixup { size_t ubo, offset; int kind; size_t id, byteOffset; };
+
+/* SL_FragmentBin (SL_ShaderUtil.hpp:627-647) */
+struct Bin
+{
+    math::vec4 mScreenCoords[3];
+    math::vec4 mBarycentricCoords[3];
+    math::vec4 mVaryings[12];
+    uint64_t primIndex;
+};
+
+struct TransformedVert
+{
+    math::vec4 vert;
+    math::vec4 varyings[4];
+};
+
+} // namespace slo
+
+using namespace slo;
+
+struct slcu_context
+{
+    std::vector<SL_VertexBuffer> vbos;
+    std::vector<IndexBuffer> ibos;
+    std::vector<SL_VertexArray> vaos;
+    std::vector<SL_UniformBuffer> ubos;
+    std::vector<SL_Texture*> textures;
+    std::vector<Framebuffer> fbos;
+    std::vector<Shader> shaders;
+    std::vector<UboFixup> fixups;
+    int32_t viewport[4] = {0, 0, 65535, 65535}; /* SL_ViewportState defaults */
+    int32_t scissor[4] = {0, 0, 65535, 65535};
+    uint32_t rcpTable[2048];
+    std::string err;
+    slcu_stats stats{};
+
+    /* per-draw state */
+    const Shader* shader = nullptr;
+    SL_Texture* colorBufs[4] = {};
+    SL_Texture* depthBuf = nullptr;
+    std::vector<Bin> bins;
+
+    ~slcu_context()
+    {
+        for (SL_Texture* t : textures) { if (t) { free(t->mTexels); delete t; } }
+    }
+};
+
+namespace slo
+{
+
+/* ===========================================================================
+ * Fragment stage
+ * =========================================================================*/
+
+/* ---- colour placement: assign_pixel<T> (src/SL_Framebuffer.cpp:44-217) ---- */
+static inline unsigned chan_bytes(int type) { static const unsigned b[7] = {1, 2, 4, 8, 2, 4, 8}; return b[type % 7]; }
+
+static void store_color(SL_Texture& t, uint16_t x, uint16_t y, const math::vec4& c)
+{
+    const size_t idx = (size_t)x + (size_t)t.mWidth * y; /* linear, never swizzled */
+    unsigned char* p = t.mTexels + idx * t.mBpt;
+    const int kind = t.mType % 7;
+    const unsigned n = t.mChannels;
+    switch (kind)
+    {
+        case 0: /* 8U: color_cast<uint8_t,float> = (vec4<u8>)(c*255) */
+        {
+            const math::vec4_t<uint8_t> r = (math::vec4_t<uint8_t>)(c * 255.f);
+            for (unsigned i = 0; i < n; ++i) p[i] = r.v[i];
+            break;
+        }
+        case 1: /* 16U: cvtps2dq + packus_epi32 (vec4f_impl.h) */
+        {
+            const math::vec4 s = c * 65535.f;
+            for (unsigned i = 0; i < n; ++i)
+            {
+                const int32_t v = cvt_rn(s.v[i]);
+                const uint16_t u = (uint16_t)(v < 0 ? 0 : (v > 65535 ? 65535 : v));
+                memcpy(p + 2 * i, &u, 2);
+            }
+            break;
+        }
+        case 4: /* HALF: vec4<float> -> vec4<half> is cvtps2ph round-toward-zero */
+        {
+            for (unsigned i = 0; i < n; ++i) { const uint16_t h = float_to_half_rz(c.v[i]); memcpy(p + 2 * i, &h, 2); }
+            break;
+        }
+        case 5: /* FLOAT */
+            memcpy(p, c.v, 4 * n);
+            break;
+        case 6: /* DOUBLE */
+        {
+            for (unsigned i = 0; i < n; ++i) { const double d = (double)c.v[i]; memcpy(p + 8 * i, &d, 8); }
+            break;
+        }
+        default:
+            break; /* 32U/64U colour targets: not covered by the oracle */
+    }
+}
+
+static math::vec4 load_color_as_float(const SL_Texture& t, uint16_t x, uint16_t y)
+{
+    /* assign_alpha_pixel's destination read (src/SL_Framebuffer.cpp:284-312),
+     * including the 3-channel quirk that replicates channel 0 (:308). */
+    const size_t idx = (size_t)x + (size_t)t.mWidth * y;
+    const unsigned char* p = t.mTexels + idx * t.mBpt;
+    const int kind = t.mType % 7;
+    const unsigned n = t.mChannels;
+    float ch[4];
+    float lo, hi, scale;
+    auto rd = [&](unsigned i) -> float {
+        switch (kind)
+        {
+            case 0: return (float)p[i];
+            case 1: { uint16_t u; memcpy(&u, p + 2 * i, 2); return (float)u; }
+            case 4: { uint16_t u; memcpy(&u, p + 2 * i, 2); return half_to_float(u); }
+            case 5: { float f; memcpy(&f, p + 4 * i, 4); return f; }
+            case 6: { double d; memcpy(&d, p + 8 * i, 8); return (float)d; }
+            default: return 0.f;
+        }
+    };
+    switch (kind)
+    {
+        case 0: lo = 0.f; hi = 255.f; scale = 0.00392156862745f; break;
+        case 1: lo = 0.f; hi = 65535.f; scale = 1.f / 65535.f; break;
+        default: lo = 0.f; hi = 1.f; scale = 1.f; break;
+    }
+    switch (n)
+    {
+        case 1: ch[0] = rd(0); ch[1] = lo; ch[2] = lo; ch[3] = hi; break;
+        case 2: ch[0] = rd(0); ch[1] = rd(1); ch[2] = lo; ch[3] = hi; break;
+        case 3: ch[0] = rd(0); ch[1] = rd(0); ch[2] = rd(0); ch[3] = hi; break;
+        default: ch[0] = rd(0); ch[1] = rd(1); ch[2] = rd(2); ch[3] = rd(3); break;
+    }
+    math::vec4 d{ch[0], ch[1], ch[2], ch[3]};
+    if (kind == 0 || kind == 1) d = d * scale;
+    return d;
+}
+
+/* assign_alpha_pixel<T> (src/SL_Framebuffer.cpp:270-368) */
+static void blend_color(SL_Texture& t, uint16_t x, uint16_t y, const math::vec4& rgba, int blendMode)
+{
+    math::vec4 d = load_color_as_float(t, x, y);
+    const math::vec4 srcAlpha{rgba.v[3]};
+    const math::vec4 modulation = math::vec4{1.f} - srcAlpha;
+    if (blendMode == 1) /* SL_BLEND_ALPHA */
+    {
+        const math::vec4 dstMod = modulation * d.v[3];
+        const math::vec4 dstAlpha = dstMod + srcAlpha;
+        const math::vec4 dstRgb = math::fmadd(rgba, srcAlpha, (d * dstMod)) * math::rcp(dstAlpha);
+        d = math::vec4{dstRgb.v[0], dstRgb.v[1], dstRgb.v[2], dstAlpha.v[0]};
+    }
+    else if (blendMode == 2) /* SL_BLEND_PREMULTIPLED_ALPHA */
+    {
+        d = math::fmadd(d, modulation, rgba);
+    }
+    else if (blendMode == 3) /* SL_BLEND_ADDITIVE */
+    {
+        d = math::fmadd(rgba, srcAlpha, d);
+    }
+    else if (blendMode == 4) /* SL_BLEND_SCREEN */
+    {
+        d = (rgba * srcAlpha) + (d * modulation);
+    }
+    d = math::clamp(d, math::vec4{0.f, 0.f, 0.f, 0.f}, math::vec4{1.f, 1.f, 1.f, 1.f});
+    store_color(t, x, y, d);
+}
+
+/* depth texel read (src/SL_TriRasterizer.cpp:40-102) / write (src/SL_FragmentProcessor.cpp:526-529) */
+static inline float load_depth(const SL_Texture& t, size_t idx)
+{
+    switch (t.mBpt)
+    {
+        case 2: { uint16_t h; memcpy(&h, t.mTexels + idx * 2, 2); return half_to_float(h); }
+        case 4: { float f; memcpy(&f, t.mTexels + idx * 4, 4); return f; }
+        default: { double d; memcpy(&d, t.mTexels + idx * 8, 8); return (float)d; }
+    }
+}
+static inline void store_depth(SL_Texture& t, size_t idx, float z)
+{
+    switch (t.mBpt)
+    {
+        case 2: { const uint16_t h = float_to_half_rn(z); memcpy(t.mTexels + idx * 2, &h, 2); break; }
+        case 4: memcpy(t.mTexels + idx * 4, &z, 4); break;
+        default: { const double d = (double)z; memcpy(t.mTexels + idx * 8, &d, 8); break; }
+    }
+}
+
+/* SL_DepthFunc* (SL_ShaderUtil.hpp:240-507): _CMP_xx_OQ, false on NaN */
+static inline bool depth_cmp(int func, float z, float d)
+{
+    switch (func)
+    {
+        case 0: return true;
+        case 1: return z < d;
+        case 2: return z <= d;
+        case 3: return z > d;
+        case 4: return z >= d;
+        case 5: return z == d;
+        case 6: return (z < d) || (z > d); /* NEQ_OQ */
+        default: return false;
+    }
+}
+
+/* SL_ScanlineBounds (SL_ScanlineBounds.hpp:125-347) */
+struct ScanlineBounds
+{
+    float v0y, v1y, v0x, v1x, p20y, p20x, p21xy, p10xy;
+
+    void init(math::vec4 p0, math::vec4 p1, math::vec4 p2)
+    {
+        /* sl_sort_minmax x3 (:60-68,139-141): swap when a.y < b.y (ordered) */
+        if (p0.v[1] < p1.v[1]) std::swap(p0, p1);
+        if (p0.v[1] < p2.v[1]) std::swap(p0, p2);
+        if (p1.v[1] < p2.v[1]) std::swap(p1, p2);
+        /* :164-181 */
+        const math::vec4 p2p0 = p2 - p0;
+        const math::vec4 p2p1 = p2 - p1;
+        const math::vec4 p1p0 = p1 - p0;
+        v0y = p0.v[1];
+        v1y = p1.v[1];
+        v0x = p0.v[0];
+        v1x = p1.v[0];
+        p20y = x86_rcp(p2p0.v[1]);
+        p20x = p2p0.v[0];
+        p21xy = p2p1.v[0] * x86_rcp(p2p1.v[1]);
+        p10xy = p1p0.v[0] * x86_rcp(p1p0.v[1]);
+    }
+
+    /* :326-347 */
+    void step(float yf, int32_t& xMin, int32_t& xMax) const
+    {
+        const float d0 = yf - v0y;
+        const float d1 = yf - v1y;
+        const float alpha = d0 * p20y;
+        const float lo = sfma(p20x, alpha, v0x);
+        const float pdv0 = sfma(p10xy, d0, v0x);
+        const float pdv1 = sfma(p21xy, d1, v1x);
+        const float hi = sign_bit(d1) ? pdv1 : pdv0; /* blendv on the sign bit of d1 */
+        xMin = cvt_rn(smin(lo, hi));
+        xMax = cvt_rn(smax(lo, hi));
+    }
+};
+
+/* One queued fragment (SL_FragCoord, SL_ShaderUtil.hpp:668-689) */
+struct QueuedFrag { math::vec4 bc; uint16_t x, y; float z; };
+
+/* SL_FragmentProcessor::flush_tri_fragments (src/SL_FragmentProcessor.cpp:416-531) for ONE fragment */
+static void shade_fragment(slcu_context* c, const Bin& bin, const QueuedFrag& q)
+{
+    const Shader& sh = *c->shader;
+    /* :438-460 perspective correction */
+    const math::vec4 homogenous{bin.mScreenCoords[0].v[3], bin.mScreenCoords[1].v[3], bin.mScreenCoords[2].v[3], 0.f};
+    math::vec4 bc = q.bc * homogenous;
+    const float d = (bc.v[0] + bc.v[1]) + (bc.v[2] + bc.v[3]);
+    const float persp = x86_rcp(d);
+    bc = bc * persp;
+
+    /* interpolate_tri_varyings, AVX2 branch (:163-193): all four slots */
+    SL_FragmentParam fp;
+    fp.pUniforms = &c->ubos[sh.ubo];
+    for (int s = 0; s < 4; ++s)
+    {
+        for (int k = 0; k < 4; ++k)
+        {
+            float v = bc.v[0] * bin.mVaryings[s + 0].v[k];
+            v = sfma(bc.v[1], bin.mVaryings[s + 4].v[k], v);
+            v = sfma(bc.v[2], bin.mVaryings[s + 8].v[k], v);
+            fp.pVaryings[s].v[k] = v;
+        }
+    }
+    fp.coord.x = q.x;
+    fp.coord.y = q.y;
+    fp.coord.depth = q.z;
+    for (int i = 0; i < 4; ++i) fp.pOutputs[i] = math::vec4{0.f};
+
+    c->stats.fragsShaded++;
+    const bool haveOutputs = sh.fs(fp); /* :501 */
+    if (haveOutputs)
+    {
+        for (int i = sh.numOutputs - 1; i >= 0; --i) /* :507-523 */
+        {
+            if (sh.blend != 0) blend_color(*c->colorBufs[i], fp.coord.x, fp.coord.y, fp.pOutputs[i], sh.blend);
+            else store_color(*c->colorBufs[i], fp.coord.x, fp.coord.y, fp.pOutputs[i]);
+        }
+    }
+    if (sh.depthMask) /* :526-529, regardless of the shader's result */
+    {
+        store_depth(*c->depthBuf, (size_t)fp.coord.x + (size_t)c->depthBuf->mWidth * fp.coord.y, fp.coord.depth);
+    }
+}
+
+/* SL_TriRasterizer::render_triangle_simd (src/SL_TriRasterizer.cpp:413-559), one thread */
+static void render_triangle(slcu_context* c, const Bin& bin)
+{
+    const Shader& sh = *c->shader;
+    SL_Texture& depthBuffer = *c->depthBuf;
+    const math::vec4& p0 = bin.mScreenCoords[0];
+    const math::vec4& p1 = bin.mScreenCoords[1];
+    const math::vec4& p2 = bin.mScreenCoords[2];
+
+    /* :431-433 */
+    const int32_t bboxMinY = cvt_rn(smin(smin(p0.v[1], p1.v[1]), p2.v[1]));
+    const int32_t bboxMaxY = cvt_rn(smax(smax(p0.v[1], p1.v[1]), p2.v[1]));
+    int32_t y = bboxMinY; /* sl_scanline_offset(1, 0, y) == 0 */
+    if (y >= bboxMaxY) return;
+
+    const float depth[4] = {p0.v[2], p1.v[2], p2.v[2], 0.f}; /* :444-445 */
+    ScanlineBounds scanline;
+    scanline.init(p0, p1, p2);
+    const math::vec4 bc0 = bin.mBarycentricCoords[0];
+    const math::vec4 bc1 = bin.mBarycentricCoords[1];
+    const math::vec4 bc2 = bin.mBarycentricCoords[2];
+
+    static thread_local std::vector<QueuedFrag> queue;
+    queue.clear();
+
+    do
+    {
+        int32_t xMin, xMax;
+        const float yf = (float)y;
+        scanline.step(yf, xMin, xMax);
+        if (!(xMin < xMax)) { y += 1; continue; }
+        c->stats.spans++;
+
+        /* :471-481 */
+        math::vec4 bcY;
+        for (int k = 0; k < 4; ++k) bcY.v[k] = sfma(bc1.v[k], yf, bc2.v[k]);
+        int32_t x4[4] = {xMin, xMin + 1, xMin + 2, xMin + 3};
+        math::vec4 bc[4];
+        for (int j = 0; j < 4; ++j)
+        {
+            const float xf = (float)x4[j];
+            for (int k = 0; k < 4; ++k) bc[j].v[k] = (xf * bc0.v[k]) + bcY.v[k];
+        }
+        math::vec4 bcX;
+        for (int k = 0; k < 4; ++k) bcX.v[k] = bc0.v[k] * 4.f;
+        int64_t pd = (int64_t)xMin + (int64_t)depthBuffer.mWidth * y;
+
+        do
+        {
+            /* :484-490 */
+            bool m[4];
+            float z[4];
+            int any = 0;
+            for (int j = 0; j < 4; ++j)
+            {
+                /* _sl_mul_vec4_mat4_ps (:376-393): (w+z) + (y+x) */
+                const float rx = depth[0] * bc[j].v[0];
+                const float ry = depth[1] * bc[j].v[1];
+                const float rz = depth[2] * bc[j].v[2];
+                const float rw = depth[3] * bc[j].v[3];
+                z[j] = (rw + rz) + (ry + rx);
+                const bool xBound = x4[j] < xMax;
+                /* the reference loads 4 texels unconditionally; lanes past xMax are masked off */
+                const float dv = xBound ? load_depth(depthBuffer, (size_t)(pd + j)) : 0.f;
+                m[j] = xBound && depth_cmp(sh.depthTest, z[j], dv);
+                any |= m[j];
+            }
+            if (any)
+            {
+                /* :496-498: in-place compaction of the barycentric registers (kept for the next groups!) */
+                bc[2] = m[2] ? bc[2] : bc[3];
+                bc[1] = m[1] ? bc[1] : bc[2];
+                bc[0] = m[0] ? bc[0] : bc[1];
+                /* :500-526: survivor s gets bc[s] (new) and the coords of its own lane */
+                int s = 0;
+                for (int j = 0; j < 4; ++j)
+                {
+                    if (m[j])
+                    {
+                        QueuedFrag q;
+                        q.bc = bc[s];
+                        q.x = (uint16_t)x4[j];
+                        q.y = (uint16_t)y;
+                        q.z = z[j];
+                        queue.push_back(q);
+                        ++s;
+                    }
+                }
+                /* :529-533: flush when the queue is nearly full.  Fragments of one
+                 * triangle never overlap, so flushing here or at the end is the same. */
+            }
+            for (int j = 0; j < 4; ++j)
+            {
+                for (int k = 0; k < 4; ++k) bc[j].v[k] = bc[j].v[k] + bcX.v[k]; /* :539-542 */
+                x4[j] += 4;
+            }
+            pd += 4;
+        } while (x4[0] < xMax); /* :548 */
+
+        y += 1;
+    } while (y < bboxMaxY);
+
+    for (const QueuedFrag& q : queue) shade_fragment(c, bin, q);
+}
+
+/* SL_VertexProcessor::flush_rasterizer<SL_TriRasterizer> (src/SL_VertexProcessor.cpp:84-181), one thread */
+static void flush_bins(slcu_context* c)
+{
+    std::vector<uint32_t> ids(c->bins.size());
+    for (size_t i = 0; i < ids.size(); ++i) ids[i] = (uint32_t)i;
+    if (c->shader->blend != 0)
+    {
+        /* :110-119 LSD radix sort by primIndex == a stable sort */
+        std::stable_sort(ids.begin(), ids.end(), [&](uint32_t a, uint32_t b) { return c->bins[a].primIndex < c->bins[b].primIndex; });
+    }
+    for (uint32_t id : ids) render_triangle(c, c->bins[id]);
+    c->bins.clear();
+}
+
+/* ===========================================================================
+ * Vertex stage
+ * =========================================================================*/
+
+/* SL_TriProcessor::push_bin (src/SL_TriProcessor.cpp:248-342) */
+static void push_bin(slcu_context* c, uint64_t primIndex, const TransformedVert& a, const TransformedVert& b, const TransformedVert& cc)
+{
+    const math::vec4& p0 = a.vert;
+    const math::vec4& p1 = b.vert;
+    const math::vec4& p2 = cc.vert;
+    const math::vec4 bboxMin = math::min(math::min(p0, p1), p2);
+    const math::vec4 bboxMax = math::max(math::max(p0, p1), p2);
+    const int isPrimHidden = (bboxMax.v[0] - bboxMin.v[0] < 1.f) || (bboxMax.v[1] - bboxMin.v[1] < 1.f);
+    if (isPrimHidden) return;
+
+    /* :271-287 */
+    const float xy0 = p0.v[0] - p1.v[0], xy1 = p0.v[1] - p1.v[1];
+    const float zy0 = p2.v[0] - p1.v[0], zy1 = p2.v[1] - p1.v[1];
+    /* math::cross(vec2 zy, vec2 xy) = zy.x*xy.y - zy.y*xy.x (generic/vec_utils_impl.h) */
+    const float denom = x86_rcp((zy0 * xy1) - (zy1 * xy0));
+    const math::vec4 ptX{p0.v[0], p1.v[0], p2.v[0], 0.f}; /* transpose(mat4{p0,p1,p2,0}).m[0] */
+    const math::vec4 ptY{p0.v[1], p1.v[1], p2.v[1], 0.f};
+    const math::vec4 one{1.f};
+    const math::vec4 ddx = math::cross(ptY, one);
+    const math::vec4 ddy = math::cross(one, ptX);
+    const math::vec4 ddz = math::cross(ptX, ptY);
+
+    if (c->bins.size() >= 1024) flush_bins(c); /* :290-303 SL_SHADER_MAX_BINNED_PRIMS */
+
+    Bin bin;
+    bin.mScreenCoords[0] = p0;
+    bin.mScreenCoords[1] = p1;
+    bin.mScreenCoords[2] = p2;
+    bin.mBarycentricCoords[0] = ddx * denom;
+    bin.mBarycentricCoords[1] = ddy * denom;
+    bin.mBarycentricCoords[2] = ddz * denom;
+    for (int i = 0; i < 12; ++i) bin.mVaryings[i] = math::vec4{0.f};
+    for (int s = 0; s < c->shader->numVaryings; ++s)
+    {
+        bin.mVaryings[s + 0] = a.varyings[s];
+        bin.mVaryings[s + 4] = b.varyings[s];
+        bin.mVaryings[s + 8] = cc.varyings[s];
+    }
+    bin.primIndex = primIndex;
+    c->bins.push_back(bin);
+    c->stats.trisBinned++;
+}
+
+/* sl_perspective_divide (SL_PostVertexTransform.hpp:160-178) */
+static inline void perspective_divide(math::vec4& v)
+{
+    const float wInv = x86_rcp(v.v[3]);
+    v = math::vec4{v.v[0] * wInv, v.v[1] * wInv, v.v[2] * wInv, wInv};
+}
+
+/* sl_ndc_to_screen_coords (SL_PostVertexTransform.hpp:412-449, FMA branch) */
+static inline void ndc_to_screen(math::vec4& p, const math::vec4& dims)
+{
+    const float whx = dims.v[2] * 0.5f; /* wh = (halfDims.z, halfDims.w, 1, 1) */
+    const float why = dims.v[3] * 0.5f;
+    float vx = sfma(1.f + p.v[0], whx, dims.v[0]);
+    float vy = sfma(1.f + p.v[1], why, dims.v[1]);
+    vx = smax(math::floor(vx), 0.f);
+    vy = smax(math::floor(vy), 0.f);
+    p.v[0] = vx;
+    p.v[1] = vy;
+}
+
+/* sl_ndc_clip_status (SL_PostVertexTransform.hpp:590-616) */
+static inline int clip_status(const math::vec4& c0, const math::vec4& c1, const math::vec4& c2)
+{
+    const math::vec4* cs[3] = {&c0, &c1, &c2};
+    bool vis = true, part = false;
+    for (int i = 0; i < 3; ++i)
+    {
+        const float w = cs[i]->v[3];
+        const float nw = u2f(f2u(w) | 0x80000000u);
+        for (int k = 0; k < 4; ++k) vis = vis && (nw <= cs[i]->v[k]) && (w >= cs[i]->v[k]);
+        part = part || (w > 0.f);
+    }
+    return (vis ? 3 : 0) | (part ? 1 : 0);
+}
+
+/* SL_TriProcessor::clip_and_process_tris (src/SL_TriProcessor.cpp:370-519) */
+static void clip_and_process_tris(slcu_context* c, uint64_t primIndex, const math::vec4& viewportDims,
+                                  const TransformedVert& a, const TransformedVert& b, const TransformedVert& cc)
+{
+    const unsigned numVarys = (unsigned)c->shader->numVaryings;
+    unsigned numTotalVerts = 3;
+    math::vec4 tempVerts[9], newVerts[9];
+    math::vec4 tempVarys[9 * 4], newVarys[9 * 4];
+    const math::vec4 clipEdges[6] = {
+        {1.f, 0.f, 0.f, 1.f}, {-1.f, 0.f, 0.f, 1.f}, {0.f, 1.f, 0.f, 1.f},
+        {0.f, -1.f, 0.f, 1.f}, {0.f, 0.f, 1.f, 1.f}, {0.f, 0.f, -1.f, 1.f}};
+
+    newVerts[0] = a.vert;
+    newVerts[1] = b.vert;
+    newVerts[2] = cc.vert;
+    for (unsigned i = 0; i < numVarys; ++i)
+    {
+        newVarys[0 * 4 + i] = a.varyings[i];
+        newVarys[1 * 4 + i] = b.varyings[i];
+        newVarys[2 * 4 + i] = cc.varyings[i];
+    }
+
+    for (const math::vec4& edge : clipEdges)
+    {
+        unsigned numNewVerts = 0;
+        unsigned j = numTotalVerts - 1;
+        math::vec4 p0 = newVerts[numTotalVerts - 1];
+        float t0 = math::dot(p0, edge);
+        int visible0 = !sign_bit(t0);
+        for (unsigned k = 0; k < numTotalVerts; ++k)
+        {
+            const math::vec4& p1 = newVerts[k];
+            const float t1 = math::dot(p1, edge);
+            const int visible1 = !sign_bit(t1);
+            if (visible0 ^ visible1)
+            {
+                const float t = t0 * x86_rcp(t0 - t1);
+                tempVerts[numNewVerts] = math::mix(p0, p1, t);
+                for (unsigned i = 0; i < numVarys; ++i)
+                {
+                    tempVarys[numNewVerts * 4 + i] = math::mix(newVarys[j * 4 + i], newVarys[k * 4 + i], t);
+                }
+                ++numNewVerts;
+            }
+            if (visible1)
+            {
+                tempVerts[numNewVerts] = p1;
+                for (unsigned i = 0; i < numVarys; ++i) tempVarys[numNewVerts * 4 + i] = newVarys[k * 4 + i];
+                ++numNewVerts;
+            }
+            j = k;
+            p0 = p1;
+            t0 = t1;
+            visible0 = visible1;
+        }
+        if (!numNewVerts) return;
+        numTotalVerts = numNewVerts;
+        for (unsigned i = 0; i < numNewVerts; ++i)
+        {
+            newVerts[i] = tempVerts[i];
+            for (unsigned v = 0; v < 4; ++v) newVarys[i * 4 + v] = tempVarys[i * 4 + v];
+        }
+    }
+    if (numTotalVerts < 3) return;
+
+    for (unsigned i = 0; i < numTotalVerts; ++i)
+    {
+        perspective_divide(newVerts[i]);
+        ndc_to_screen(newVerts[i], viewportDims);
+    }
+    /* NB (:482-499): the reference transforms vertices in groups of three, so
+     * for 4,5,7,8 vertices it also transforms stale entries past the end; those
+     * are never read. */
+
+    TransformedVert p0, p1, p2;
+    p0.vert = newVerts[0];
+    for (unsigned i = 0; i < numVarys; ++i) p0.varyings[i] = newVarys[i];
+    for (unsigned i = numTotalVerts - 2; i--;) /* :505-518, reverse fan order */
+    {
+        const unsigned j = i + 1;
+        const unsigned k = i + 2;
+        p1.vert = newVerts[j];
+        p2.vert = newVerts[k];
+        for (unsigned v = 0; v < numVarys; ++v)
+        {
+            p1.varyings[v] = newVarys[j * 4 + v];
+            p2.varyings[v] = newVarys[k * 4 + v];
+        }
+        push_bin(c, primIndex, p0, p1, p2);
+    }
+}
+
+/* face_determinant, SSE4.1 branch (src/SL_TriProcessor.cpp:40-66) */
+static inline float face_determinant(const math::vec4& p0, const math::vec4& p1, const math::vec4& p2)
+{
+    /* col4 = (p0.x, p0.y, p0.w, 0); p1_201 = (p1.w,p1.x,p1.y,.), p2_120 = (p2.y,p2.w,p2.x,.)
+     * p1_120 = (p1.y,p1.w,p1.x,.), p2_201 = (p2.w,p2.x,p2.y,.) */
+    const float col3[3] = {p1.v[3] * p2.v[1], p1.v[0] * p2.v[3], p1.v[1] * p2.v[0]};
+    const float col1[3] = {p1.v[1] * p2.v[3], p1.v[3] * p2.v[0], p1.v[0] * p2.v[1]};
+    const float col4[3] = {p0.v[0], p0.v[1], p0.v[3]};
+    float mul2[3];
+    for (int i = 0; i < 3; ++i) mul2[i] = (col1[i] - col3[i]) * col4[i];
+    /* hi = movehdup(mul2) -> lane0 = mul2[1]; lo = hi + mul2 (ss) = mul2[1]+mul2[0]; w = mul2[2]; w + lo */
+    return mul2[2] + (mul2[1] + mul2[0]);
+}
+
+/* sl_scissor + SL_ViewportState::scissor_matrix / viewport_rect (src/SL_ViewportState.cpp:17-111) */
+static math::mat4 scissor_matrix(const int32_t sc[4], float fboW, float fboH)
+{
+    const math::vec4 fboInv = math::rcp(math::vec4{fboW, fboH, fboW, fboH});
+    const math::vec4 s = math::vec4{(float)sc[0], (float)sc[1], (float)sc[2], (float)sc[3]} * fboInv;
+    float x = s.v[0], y = s.v[1], w = s.v[2], h = s.v[3];
+    if (x < 0.f) { w += x; x = 0.f; }
+    if (y < 0.f) { h += y; y = 0.f; }
+    w = math::min(1.f - x, w);
+    h = math::min(1.f - y, h);
+    const float nm00 = x86_rcp(w);
+    const float nm11 = x86_rcp(h);
+    const float nm30 = nm00 - 1.f;
+    const float nm31 = nm11 - 1.f;
+    const float m30 = sfma(x, (-2.f * nm00), nm30);
+    const float m31 = sfma(y, (-2.f * nm11), nm31);
+    math::mat4 r;
+    r.m[0] = math::vec4{nm00, 0.f, 0.f, 0.f};
+    r.m[1] = math::vec4{0.f, nm11, 0.f, 0.f};
+    r.m[2] = math::vec4{0.f, 0.f, 1.f, 0.f};
+    r.m[3] = math::vec4{m30, m31, 0.f, 1.f};
+    return r;
+}
+
+static inline float min3(float a, float b, float c) { return smin(c, smin(a, b)); } /* scalarf_utils_impl.h:32-38 */
+
+static math::vec4 viewport_rect(const int32_t vp[4], const int32_t sc[4], float fboW, float fboH)
+{
+    const float s0 = (float)sc[0], s1 = (float)sc[1], s2 = (float)sc[2], s3 = (float)sc[3];
+    math::vec4 d{(float)vp[0], (float)vp[1], (float)vp[2], (float)vp[3]};
+    d.v[0] = math::clamp(d.v[0] + s0, 0.f, fboW);
+    d.v[1] = math::clamp(d.v[1] + s1, 0.f, fboH);
+    d.v[2] = min3(d.v[2], (s0 + s2) - d.v[0], fboW - d.v[0]);
+    d.v[3] = min3(d.v[3], (s1 + s3) - d.v[1], fboH - d.v[1]);
+    return d;
+}
+
+/* SL_TriProcessor::process_verts (src/SL_TriProcessor.cpp:527-640), one thread */
+static void process_verts(slcu_context* c, const slcu_mesh& m, size_t instanceId, bool usingIndices,
+                          const math::mat4& scissorMat, const math::vec4& viewportDims)
+{
+    const Shader& sh = *c->shader;
+    const SL_VertexArray& vao = c->vaos[m.vaoId];
+    const IndexBuffer* pIbo = vao.has_index_buffer() ? &c->ibos[vao.mIboId] : nullptr;
+
+    SL_VertexParam params;
+    params.pUniforms = &c->ubos[sh.ubo];
+    params.instanceId = instanceId;
+    params.pVao = &vao;
+    params.pVbo = &c->vbos[vao.mVboId];
+
+    const size_t numElements = m.elementEnd - m.elementBegin;
+    const size_t primOffset = numElements * instanceId;
+    TransformedVert v[3];
+
+    for (size_t i = m.elementBegin; i < m.elementEnd; i += 3)
+    {
+        c->stats.trisSubmitted++;
+        size_t vertId[3];
+        if (usingIndices) /* get_next_vertex3 (:125-234) */
+        {
+            for (int k = 0; k < 3; ++k)
+            {
+                const unsigned char* p = pIbo->data.data() + (i + k) * pIbo->bytesPerId;
+                switch (pIbo->type)
+                {
+                    case 0: vertId[k] = *p; break;
+                    case 1: { uint16_t u; memcpy(&u, p, 2); vertId[k] = u; break; }
+                    default: { uint32_t u; memcpy(&u, p, 4); vertId[k] = u; break; }
+                }
+            }
+        }
+        else
+        {
+            vertId[0] = i; vertId[1] = i + 1; vertId[2] = i + 2;
+        }
+        for (int k = 0; k < 3; ++k) /* :584-594 */
+        {
+            params.vertId = vertId[k];
+            params.pVaryings = v[k].varyings;
+            v[k].vert = sh.vs(params);
+        }
+        if (sh.cullMode != 2) /* :597-612 */
+        {
+            const float det = face_determinant(v[0].vert, v[1].vert, v[2].vert);
+            const bool culled = (sh.cullMode == 1) ^ sign_bit(det);
+            if (culled) continue;
+        }
+        for (int k = 0; k < 3; ++k) v[k].vert = scissorMat * v[k].vert; /* :615-617 */
+
+        const int visStatus = clip_status(v[0].vert, v[1].vert, v[2].vert);
+        if (visStatus == 3)
+        {
+            for (int k = 0; k < 3; ++k) { perspective_divide(v[k].vert); ndc_to_screen(v[k].vert, viewportDims); }
+            push_bin(c, primOffset + i, v[0], v[1], v[2]);
+        }
+        else if (visStatus == 1)
+        {
+            clip_and_process_tris(c, primOffset + i, viewportDims, v[0], v[1], v[2]);
+        }
+    }
+}
+
+static void apply_fixups(slcu_context* c)
+{
+    for (const UboFixup& f : c->fixups)
+    {
+        const void* ptr;
+        if (f.kind == 0) ptr = c->textures[f.id];
+        else ptr = c->vbos[f.id].mBuffer.data() + f.byteOffset;
+        memcpy(c->ubos[f.ubo].mBytes + f.offset, &ptr, sizeof(ptr));
+    }
+}
+
+/* SL_ProcessorPool::run_shader_processors + SL_TriProcessor::execute
+ * (src/SL_ProcessorPool.cpp:280-380, src/SL_TriProcessor.cpp:665-716) */
+static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, size_t numInstances, size_t shaderId, size_t fboId)
+{
+    if (shaderId >= c->shaders.size() || fboId >= c->fbos.size()) return SLCU_ERR_ARG;
+    memcpy(g_rcp_table, c->rcpTable, sizeof(g_rcp_table));
+    apply_fixups(c);
+    const Framebuffer& fbo = c->fbos[fboId];
+    c->shader = &c->shaders[shaderId];
+    for (unsigned i = 0; i < 4; ++i) c->colorBufs[i] = (i < fbo.numColors && fbo.colors[i] != (size_t)-1) ? c->textures[fbo.colors[i]] : nullptr;
+    if (fbo.depth == (size_t)-1) return SLCU_ERR_ARG;
+    c->depthBuf = c->textures[fbo.depth];
+    c->stats.drawCalls++;
+
+    const float fboW = (float)c->depthBuf->mWidth, fboH = (float)c->depthBuf->mHeight;
+    const math::mat4 scissorMat = scissor_matrix(c->scissor, fboW, fboH);
+    const math::vec4 viewportDims = viewport_rect(c->viewport, c->scissor, fboW, fboH);
+
+    if (numInstances == 1)
+    {
+        for (size_t i = 0; i < numMeshes; ++i)
+        {
+            const bool usingIndices = (meshes[i].mode == 0x30) || (meshes[i].mode == 0x70);
+            process_verts(c, meshes[i], 0, usingIndices, scissorMat, viewportDims);
+        }
+    }
+    else
+    {
+        const bool usingIndices = (meshes[0].mode == 0x30) || (meshes[0].mode == 0x70);
+        for (size_t i = 0; i < numInstances; ++i) process_verts(c, meshes[0], i, usingIndices, scissorMat, viewportDims);
+    }
+    if (!c->bins.empty()) flush_bins(c); /* cleanup<SL_TriRasterizer>() */
+    return 0;
+}
+
+/* SL_ClearProcessor::clear_texture (src/SL_ClearProcessor.cpp:23-63): w*h texels (depth dim ignored) */
+static void clear_texture(SL_Texture& t, const void* texel)
+{
+    const size_t n = (size_t)t.mWidth * t.mHeight;
+    for (size_t i = 0; i < n; ++i) memcpy(t.mTexels + i * t.mBpt, texel, t.mBpt);
+}
+
+/* sl_match_color_for_type (src/SL_Color.cpp:135-190): vecN<double> -> typed texel */
+static void match_color(int type, const double rgba[4], unsigned char out[32])
+{
+    const int kind = type % 7;
+    const unsigned n = (unsigned)(type / 7 + 1);
+    for (unsigned i = 0; i < n; ++i)
+    {
+        switch (kind)
+        {
+            case 0: { const uint8_t v = (uint8_t)(rgba[i] * 255.0); out[i] = v; break; }          /* generic (T)(double) truncation */
+            case 1: { const uint16_t v = (uint16_t)(rgba[i] * 65535.0); memcpy(out + 2 * i, &v, 2); break; }
+            case 2: { const uint32_t v = (uint32_t)(rgba[i] * 4294967295.0); memcpy(out + 4 * i, &v, 4); break; }
+            case 3: { const uint64_t v = (uint64_t)(rgba[i] * 18446744073709551615.0); memcpy(out + 8 * i, &v, 8); break; }
+            case 4: { const uint16_t v = float_to_half_rn((float)rgba[i]); memcpy(out + 2 * i, &v, 2); break; }
+            case 5: { const float v = (float)rgba[i]; memcpy(out + 4 * i, &v, 4); break; }
+            default: { memcpy(out + 8 * i, &rgba[i], 8); break; }
+        }
+    }
+}
+
+static bool depth_texel(const SL_Texture& t, double depth, unsigned char out[8])
+{
+    /* SL_Context::clear_depth_buffer (src/SL_Context.cpp:896-925) */
+    switch (t.mBpt)
+    {
+        case 2: { const uint16_t h = float_to_half_rn((float)depth); memcpy(out, &h, 2); return true; }
+        case 4: { const float f = (float)depth; memcpy(out, &f, 4); return true; }
+        case 8: memcpy(out, &depth, 8); return true;
+        default: return false;
+    }
+}
+
+} // namespace slo
+
+/* ===========================================================================
+ * C ABI
+ * =========================================================================*/
+extern "C" {
+
+int slor_context_create(slcu_context** out, int)
+{
+    if (!out) return SLCU_ERR_ARG;
+    slcu_context* c = new slcu_context{};
+    measure_host_rcp_table(c->rcpTable);
+    *out = c;
+    return 0;
+}
+void slor_context_destroy(slcu_context* c) { delete c; }
+unsigned slor_num_threads(slcu_context*, unsigned n) { return n < 1 ? 1 : n; }
+const char* slor_last_error(slcu_context* c) { return c->err.c_str(); }
+const char* slor_impl_name(void) { return "oracle-port(scalar C++ restatement)"; }
+int slor_set_rcp_table(slcu_context* c, const uint32_t* t) { memcpy(c->rcpTable, t, sizeof(c->rcpTable)); return 0; }
+int slor_get_rcp_table(slcu_context* c, uint32_t* t) { memcpy(t, c->rcpTable, sizeof(c->rcpTable)); return 0; }
+
+size_t slor_create_vbo(slcu_context* c) { c->vbos.emplace_back(); return c->vbos.size() - 1; }
+size_t slor_create_ibo(slcu_context* c) { c->ibos.emplace_back(); return c->ibos.size() - 1; }
+size_t slor_create_vao(slcu_context* c) { c->vaos.emplace_back(); return c->vaos.size() - 1; }
+size_t slor_create_ubo(slcu_context* c) { c->ubos.emplace_back(); memset(c->ubos.back().mBytes, 0, 1024); return c->ubos.size() - 1; }
+size_t slor_create_texture(slcu_context* c) { c->textures.push_back(new SL_Texture{}); return c->textures.size() - 1; }
+size_t slor_create_framebuffer(slcu_context* c) { c->fbos.emplace_back(); return c->fbos.size() - 1; }
+
+int slor_vbo_init(slcu_context* c, size_t vbo, size_t n)
+{
+    if (vbo >= c->vbos.size()) return SLCU_ERR_ARG;
+    c->vbos[vbo].mBuffer.assign(n + 64, 0);
+    return 0;
+}
+int slor_vbo_assign(slcu_context* c, size_t vbo, const void* d, size_t off, size_t n)
+{
+    if (vbo >= c->vbos.size() || off + n > c->vbos[vbo].mBuffer.size()) return SLCU_ERR_ARG;
+    memcpy(c->vbos[vbo].mBuffer.data() + off, d, n);
+    return 0;
+}
+int slor_ibo_init(slcu_context* c, size_t ibo, uint32_t n, int type, const void* d)
+{
+    if (ibo >= c->ibos.size() || type < 0 || type > 2) return SLCU_ERR_ARG;
+    IndexBuffer& b = c->ibos[ibo];
+    b.type = type;
+    b.count = n;
+    b.bytesPerId = 1u << type;
+    b.data.assign((size_t)n * b.bytesPerId + 16, 0);
+    if (d) memcpy(b.data.data(), d, (size_t)n * b.bytesPerId);
+    return 0;
+}
+int slor_vao_set_vertex_buffer(slcu_context* c, size_t vao, size_t vbo) { c->vaos[vao].mVboId = vbo; return 0; }
+int slor_vao_set_index_buffer(slcu_context* c, size_t vao, size_t ibo) { c->vaos[vao].mIboId = ibo; return 0; }
+int slor_vao_set_num_bindings(slcu_context* c, size_t vao, int n)
+{
+    if (n >= 8 || n < 0) return -1; /* src/SL_VertexArray.cpp:162-167 */
+    c->vaos[vao].mNumBindings = n;
+    return n;
+}
+int slor_vao_set_binding(slcu_context* c, size_t vao, size_t bind, ptrdiff_t off, ptrdiff_t stride, int dim, int type)
+{
+    if (bind >= 8) return SLCU_ERR_ARG;
+    c->vaos[vao].mBindings[bind] = SL_VertexArray::Binding{dim, type, off, stride};
+    return 0;
+}
+int slor_ubo_assign(slcu_context* c, size_t ubo, const void* d, size_t off, size_t n)
+{
+    if (ubo >= c->ubos.size() || off + n > 1024) return SLCU_ERR_ARG;
+    memcpy(c->ubos[ubo].mBytes + off, d, n);
+    return 0;
+}
+static void set_fixup(slcu_context* c, const UboFixup& f)
+{
+    for (UboFixup& g : c->fixups) { if (g.ubo == f.ubo && g.offset == f.offset) { g = f; return; } }
+    c->fixups.push_back(f);
+}
+int slor_ubo_bind_texture(slcu_context* c, size_t ubo, size_t off, size_t tex) { set_fixup(c, UboFixup{ubo, off, 0, tex, 0}); return 0; }
+int slor_ubo_bind_buffer(slcu_context* c, size_t ubo, size_t off, size_t vbo, size_t bo) { set_fixup(c, UboFixup{ubo, off, 1, vbo, bo}); return 0; }
+
+int slor_texture_init(slcu_context* c, size_t tex, int type, uint16_t w, uint16_t h, uint16_t d)
+{
+    if (tex >= c->textures.size() || type < 0 || type >= 28) return SLCU_ERR_ARG;
+    SL_Texture& t = *c->textures[tex];
+    free(t.mTexels);
+    t.mWidth = w; t.mHeight = h; t.mDepth = d;
+    t.mChannels = (uint8_t)(type / 7 + 1);
+    t.mBpt = (uint8_t)(chan_bytes(type) * t.mChannels);
+    t.mType = type;
+    /* _sl_allocate_texture (src/SL_Texture.cpp:28-54): every dimension padded up by 4-(dim%4) */
+    const size_t pw = w + (4 - (w % 4)), ph = h + (4 - (h % 4)), pd = d + (4 - (d % 4));
+    t.mAllocBytes = pw * ph * pd * t.mBpt + 4 * t.mBpt;
+    t.mTexels = (unsigned char*)calloc(t.mAllocBytes, 1);
+    return t.mTexels ? 0 : -1;
+}
+int slor_texture_set_texels(slcu_context* c, size_t tex, int order, uint16_t x, uint16_t y, uint16_t z, uint16_t w, uint16_t h, uint16_t d, const void* data)
+{
+    if (tex >= c->textures.size()) return SLCU_ERR_ARG;
+    SL_Texture& t = *c->textures[tex];
+    const unsigned char* src = (const unsigned char*)data;
+    for (uint16_t k = 0, z0 = z; k < d; ++k, ++z0)
+        for (uint16_t j = 0, y0 = y; j < h; ++j, ++y0)
+            for (uint16_t i = 0, x0 = x; i < w; ++i, ++x0)
+            {
+                const ptrdiff_t index = i + w * (j + (h * k));
+                /* set_texel<order> (SL_Texture.hpp:388-410): 2-D map when depth <= 1, else the 3-D map */
+                ptrdiff_t dst;
+                if (1 >= t.mDepth) dst = order == 0 ? t.map_coordinate<SL_TexelOrder::ORDERED>(x0, y0) : t.map_coordinate<SL_TexelOrder::SWIZZLED>(x0, y0);
+                else dst = order == 0 ? t.map_coordinate<SL_TexelOrder::ORDERED>(x0, y0, z0) : t.map_coordinate<SL_TexelOrder::SWIZZLED>(x0, y0, z0);
+                memcpy(t.mTexels + dst * t.mBpt, src + index * t.mBpt, t.mBpt);
+            }
+    return 0;
+}
+int slor_texture_read(slcu_context* c, size_t tex, void* out, size_t n)
+{
+    if (tex >= c->textures.size() || n > c->textures[tex]->mAllocBytes) return SLCU_ERR_ARG;
+    memcpy(out, c->textures[tex]->mTexels, n);
+    return 0;
+}
+
+int slor_fbo_reserve_color_buffers(slcu_context* c, size_t fbo, unsigned n)
+{
+    if (n < 1) return -1;
+    if (n > 4) return -2;
+    Framebuffer& f = c->fbos[fbo];
+    f = Framebuffer{};
+    f.numColors = n;
+    return 0;
+}
+int slor_fbo_attach_color_buffer(slcu_context* c, size_t fbo, unsigned i, size_t tex)
+{
+    if (i >= c->fbos[fbo].numColors) return -1;
+    c->fbos[fbo].colors[i] = tex;
+    return 0;
+}
+int slor_fbo_attach_depth_buffer(slcu_context* c, size_t fbo, size_t tex) { c->fbos[fbo].depth = tex; return 0; }
+int slor_fbo_valid(slcu_context* c, size_t fbo)
+{
+    const Framebuffer& f = c->fbos[fbo];
+    if (!f.numColors) return -1;
+    if (f.depth == (size_t)-1) return -6;
+    for (unsigned i = 0; i < f.numColors; ++i) if (f.colors[i] == (size_t)-1) return -3;
+    return 0;
+}
+
+size_t slor_create_shader(slcu_context* c, const slcu_vertex_shader* vs, const slcu_fragment_shader* fs, size_t ubo)
+{
+    /* SL_Context::create_shader validation (src/SL_Context.cpp:488-540) */
+    if (ubo >= c->ubos.size() || vs->numVaryings > 4 || fs->numVaryings > vs->numVaryings || fs->numOutputs > 4 || !fs->numOutputs) return SLCU_INVALID_ID;
+    auto v = vs_registry().find(vs->shader);
+    auto f = fs_registry().find(fs->shader);
+    if (v == vs_registry().end() || f == fs_registry().end()) { c->err = "unknown shader"; return SLCU_INVALID_ID; }
+    Shader s;
+    s.cullMode = vs->cullMode; s.depthTest = fs->depthTest; s.depthMask = fs->depthMask; s.blend = fs->blend;
+    s.numVaryings = fs->numVaryings; s.numOutputs = fs->numOutputs; s.vs = v->second; s.fs = f->second; s.ubo = ubo;
+    c->shaders.push_back(s);
+    return c->shaders.size() - 1;
+}
+
+int slor_viewport(slcu_context* c, int32_t x, int32_t y, uint16_t w, uint16_t h) { c->viewport[0] = x; c->viewport[1] = y; c->viewport[2] = w; c->viewport[3] = h; return 0; }
+int slor_scissor(slcu_context* c, int32_t x, int32_t y, uint16_t w, uint16_t h) { c->scissor[0] = x; c->scissor[1] = y; c->scissor[2] = w; c->scissor[3] = h; return 0; }
+
+int slor_clear_color_buffer(slcu_context* c, size_t fbo, unsigned att, const double rgba[4])
+{
+    SL_Texture& t = *c->textures[c->fbos[fbo].colors[att]];
+    unsigned char texel[32];
+    match_color(t.mType, rgba, texel);
+    clear_texture(t, texel);
+    return 0;
+}
+int slor_clear_depth_buffer(slcu_context* c, size_t fbo, double depth)
+{
+    SL_Texture& t = *c->textures[c->fbos[fbo].depth];
+    unsigned char texel[8];
+    if (depth_texel(t, depth, texel)) clear_texture(t, texel);
+    return 0;
+}
+int slor_clear_framebuffer(slcu_context* c, size_t fbo, unsigned att, const double rgba[4], double depth)
+{
+    SL_Texture& d = *c->textures[c->fbos[fbo].depth];
+    unsigned char dt[8];
+    if (!depth_texel(d, depth, dt)) return 0; /* reference returns before clearing anything */
+    slor_clear_color_buffer(c, fbo, att, rgba);
+    clear_texture(d, dt);
+    return 0;
+}
+
+int slor_draw(slcu_context* c, const slcu_mesh* m, size_t shader, size_t fbo) { return run_draw(c, m, 1, 1, shader, fbo); }
+int slor_draw_multiple(slcu_context* c, const slcu_mesh* m, size_t n, size_t shader, size_t fbo)
+{
+    if (!m || !n) return 0;
+    return run_draw(c, m, n, 1, shader, fbo);
+}
+int slor_draw_instanced(slcu_context* c, const slcu_mesh* m, size_t inst, size_t shader, size_t fbo) { return run_draw(c, m, 1, inst, shader, fbo); }
+
+int slor_blit(slcu_context*, size_t, size_t) { return SLCU_ERR_UNSUPPORTED; }
+int slor_blit_rect(slcu_context*, size_t, size_t, uint16_t, uint16_t, uint16_t, uint16_t, uint16_t, uint16_t, uint16_t, uint16_t) { return SLCU_ERR_UNSUPPORTED; }
+int slor_sync(slcu_context*) { return 0; }
+int slor_reset_stats(slcu_context* c) { if (c) memset(&c->stats, 0, sizeof(c->stats)); return 0; }
+int slor_get_stats(slcu_context* c, slcu_stats* out) { *out = c->stats; return 0; }
+
+} // extern "C"

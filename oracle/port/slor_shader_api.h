@@ -1,0 +1,232 @@
+/*
+ * slor_shader_api.h -- TEST INFRASTRUCTURE ONLY (CPU oracle).
+ *
+ * The shader-facing objects of the reference, restated for the oracle so the
+ * shared shader sources under shaders/ compile against it: SL_UniformBuffer,
+ * SL_VertexBuffer, SL_VertexArray, SL_Texture (+ swizzle maps), the samplers
+ * and color_cast.  Each item cites the reference code it follows.
+ */
+#ifndef SLOR_SHADER_API_H
+#define SLOR_SHADER_API_H
+
+#include <cstddef>
+#include <cstdint>
+#include <cstdlib>
+#include <vector>
+
+#include "slor_math.h"
+
+namespace slo
+{
+
+/* SL_UniformBuffer.hpp:23-125: 1 KiB POD blob */
+struct alignas(16) SL_UniformBuffer
+{
+    unsigned char mBytes[1024];
+    template <typename T> const T* as() const { return reinterpret_cast<const T*>(mBytes); }
+};
+
+/* SL_VertexBuffer.hpp:71-88 */
+struct SL_VertexBuffer
+{
+    std::vector<unsigned char> mBuffer;
+    template <typename T> const T* element(ptrdiff_t offset) const { return reinterpret_cast<const T*>(mBuffer.data() + offset); }
+    const void* data() const { return mBuffer.data(); }
+};
+
+/* SL_VertexArray.hpp:18-37,107-126 */
+struct SL_VertexArray
+{
+    struct Binding { int dimens; int type; ptrdiff_t offset; ptrdiff_t stride; };
+    Binding mBindings[8];
+    int mNumBindings = 0;
+    size_t mVboId = (size_t)-1;
+    size_t mIboId = (size_t)-1;
+    ptrdiff_t offset(size_t bindId, size_t vertId) const { return mBindings[bindId].offset + mBindings[bindId].stride * (ptrdiff_t)vertId; }
+    bool has_index_buffer() const { return mIboId != (size_t)-1; }
+};
+
+enum class SL_TexelOrder { ORDERED, SWIZZLED };
+
+/* SL_Texture.hpp:29-44,189-231 ; SL_Swizzle.hpp:43-88 ; src/SL_Texture.cpp:28-54 */
+struct SL_Texture
+{
+    uint16_t mWidth = 0, mHeight = 0, mDepth = 0;
+    uint8_t mBpt = 0, mChannels = 0;
+    int mType = 0;
+    unsigned char* mTexels = nullptr;
+    size_t mAllocBytes = 0;
+
+    uint16_t width() const { return mWidth; }
+    uint16_t height() const { return mHeight; }
+    uint16_t depth() const { return mDepth; }
+    const void* data() const { return mTexels; }
+
+    template <SL_TexelOrder order> ptrdiff_t map_coordinate(uint_fast32_t x, uint_fast32_t y) const
+    {
+        if (order == SL_TexelOrder::ORDERED) return (ptrdiff_t)(x + (uint_fast32_t)mWidth * y);
+        const uint_fast32_t tileId = (x >> 2) + ((uint_fast32_t)mWidth >> 2) * (y >> 2);
+        const uint_fast32_t innerId = (x & 3u) + ((y & 3u) << 2);
+        return (ptrdiff_t)(innerId + tileId * 16u);
+    }
+    template <SL_TexelOrder order> ptrdiff_t map_coordinate(uint_fast32_t x, uint_fast32_t y, uint_fast32_t z) const
+    {
+        if (order == SL_TexelOrder::ORDERED) return (ptrdiff_t)(x + mWidth * (y + mHeight * z));
+        const uint_fast32_t tileId = (x >> 2) + (((uint_fast32_t)mWidth >> 2) * ((y >> 2) + (((uint_fast32_t)mHeight >> 2) * (z >> 2))));
+        const uint_fast32_t innerId = (x & 3u) + (((y & 3u) << 2) + (4u * ((z & 3u) << 2)));
+        return (ptrdiff_t)(innerId + tileId * 64u);
+    }
+    template <typename color_type, SL_TexelOrder order = SL_TexelOrder::ORDERED>
+    const color_type texel(uint16_t x, uint16_t y) const { return reinterpret_cast<const color_type*>(mTexels)[map_coordinate<order>(x, y)]; }
+    template <typename color_type, SL_TexelOrder order = SL_TexelOrder::ORDERED>
+    const color_type texel(uint16_t x, uint16_t y, uint16_t z) const { return reinterpret_cast<const color_type*>(mTexels)[map_coordinate<order>(x, y, z)]; }
+};
+
+/* SL_Shader.hpp:41-97 */
+struct SL_FragCoordXYZ { uint16_t x, y; float depth; };
+
+struct SL_VertexParam
+{
+    const SL_UniformBuffer* pUniforms;
+    size_t vertId;
+    size_t instanceId;
+    const SL_VertexArray* pVao;
+    const SL_VertexBuffer* pVbo;
+    math::vec4* pVaryings;
+};
+
+struct SL_FragmentParam
+{
+    SL_FragCoordXYZ coord;
+    const SL_UniformBuffer* pUniforms;
+    math::vec4 pVaryings[4];
+    math::vec4 pOutputs[4];
+};
+
+/* ---- color_cast (SL_Color.hpp:480-690) ---- */
+template <typename T> struct color_max;
+template <> struct color_max<uint8_t> { static constexpr float f() { return 255.f; } };
+template <> struct color_max<uint16_t> { static constexpr float f() { return 65535.f; } };
+
+template <typename T, typename U> struct ColorCast;
+/* integer -> float: p * (1/max), u8 uses the literal 0.00392156862745f (:549,:666) */
+template <> struct ColorCast<float, uint8_t>
+{
+    static math::vec4 run(const math::vec4_t<uint8_t>& p) { return math::vec4{(float)p.v[0], (float)p.v[1], (float)p.v[2], (float)p.v[3]} * 0.00392156862745f; }
+    static math::vec3 run(const math::vec3_t<uint8_t>& p) { return math::vec3{(float)p.v[0], (float)p.v[1], (float)p.v[2]} * 0.00392156862745f; }
+    static float run(uint8_t p) { return (float)p * 0.00392156862745f; }
+};
+template <> struct ColorCast<float, uint16_t>
+{
+    static math::vec4 run(const math::vec4_t<uint16_t>& p) { return math::vec4{(float)p.v[0], (float)p.v[1], (float)p.v[2], (float)p.v[3]} * (1.f / 65535.f); }
+};
+template <> struct ColorCast<float, float>
+{
+    static math::vec4 run(const math::vec4& p) { return p; }
+    static math::vec3 run(const math::vec3& p) { return p; }
+    static float run(float p) { return p; }
+};
+/* float -> integer: (vecN<T>)(p * max): vec4 = cvtps2dq + packs, vec3/scalar = C truncation (:506,:623) */
+template <> struct ColorCast<uint8_t, float>
+{
+    static math::vec4_t<uint8_t> run(const math::vec4& p) { return (math::vec4_t<uint8_t>)(p * 255.f); }
+    static math::vec3_t<uint8_t> run(const math::vec3& p)
+    {
+        const math::vec3 s = p * 255.f;
+        return math::vec3_t<uint8_t>{(uint8_t)cvt_tr(s.v[0]), (uint8_t)cvt_tr(s.v[1]), (uint8_t)cvt_tr(s.v[2])};
+    }
+    static uint8_t run(float p) { return (uint8_t)cvt_tr(p * 255.f); }
+};
+template <> struct ColorCast<float, half>
+{
+    static math::vec4 run(const math::vec4_t<half>& p) { return (math::vec4)p; }
+};
+
+template <typename T, typename U, typename V> static inline auto color_cast(const V& p) -> decltype(ColorCast<T, U>::run(p)) { return ColorCast<T, U>::run(p); }
+
+/* ---- wrap modes + samplers (SL_Sampler.hpp:51-372) ---- */
+struct SL_WrapModeClampEdge
+{
+    float operator()(float uvw) const { return math::clamp(uvw, 0.f, 1.f); }
+    static constexpr bool border = false;
+};
+struct SL_WrapModeClampBorder
+{
+    float operator()(float uvw) const { return (uvw >= 0.f && uvw < 1.f) ? uvw : -1.f; }
+    static constexpr bool border = true;
+};
+struct SL_WrapModeRepeat
+{
+    float operator()(float uvw) const { return (uvw < 0.f ? 1.f : 0.f) + math::fmod_1(uvw); }
+    static constexpr bool border = false;
+};
+namespace SL_WrapMode
+{
+typedef SL_WrapModeClampEdge EDGE;
+typedef SL_WrapModeClampBorder BORDER;
+typedef SL_WrapModeRepeat REPEAT;
+}
+
+template <typename C> struct zero_color { static C get() { C c; memset(&c, 0, sizeof(c)); return c; } };
+
+/* (uint16_t)float: cvttss2si, low 16 bits */
+static inline uint16_t f2u16(float f) { return (uint16_t)cvt_tr(f); }
+
+template <typename color_type, class WrapMode, SL_TexelOrder order = SL_TexelOrder::ORDERED>
+inline color_type sl_sample_nearest(const SL_Texture& tex, float x, float y)
+{
+    if (WrapMode::border && (x < 0.f || x >= 1.f || y < 0.f || y >= 1.f)) return zero_color<color_type>::get();
+    const WrapMode wrapMode{};
+    const float wx = wrapMode(x);
+    const float wy = wrapMode(y);
+    /* (uint_fast32_t)(float): cvttss2si 64-bit, then truncated to 32 */
+    const uint32_t xi = (uint32_t)(int64_t)((float)tex.width() * wx);
+    const uint32_t yi = (uint32_t)(int64_t)((float)tex.height() * wy);
+    return reinterpret_cast<const color_type*>(tex.data())[tex.map_coordinate<order>(xi, yi)];
+}
+
+template <typename color_type, class WrapMode, SL_TexelOrder order = SL_TexelOrder::ORDERED>
+inline color_type sl_sample_nearest(const SL_Texture& tex, float x, float y, float z)
+{
+    if (WrapMode::border && (x < 0.f || x >= 1.f || y < 0.f || y >= 1.f || z < 0.f || z >= 1.f)) return zero_color<color_type>::get();
+    const WrapMode wrapMode{};
+    const float wx = wrapMode(x);
+    const float wy = wrapMode(y);
+    const float wz = wrapMode(z);
+    const uint32_t xi = (uint32_t)(int64_t)((float)tex.width() * wx);
+    const uint32_t yi = (uint32_t)(int64_t)((float)tex.height() * wy);
+    const uint32_t zi = (uint32_t)(int64_t)math::round((float)tex.depth() * wz);
+    return reinterpret_cast<const color_type*>(tex.data())[tex.map_coordinate<order>(xi, yi, zi)];
+}
+
+template <typename color_type, class WrapMode, SL_TexelOrder order = SL_TexelOrder::ORDERED>
+inline color_type sl_sample_bilinear(const SL_Texture& tex, float x, float y)
+{
+    typedef typename color_type::value_type T;
+    if (WrapMode::border && (x < 0.f || x >= 1.f || y < 0.f || y >= 1.f)) return zero_color<color_type>::get();
+    const WrapMode wrapMode{};
+    const float xf = wrapMode(x) * (float)tex.width();
+    const float yf = wrapMode(y) * (float)tex.height();
+    const uint16_t xi0 = f2u16(xf);
+    const uint16_t yi0 = f2u16(yf);
+    const uint16_t xi1 = (uint16_t)math::clamp<unsigned>(xi0 + 1u, 0u, tex.width());  /* clamp<uint16_t>(xi0+1u,...): arg narrowed to u16 first */
+    const uint16_t yi1 = (uint16_t)math::clamp<unsigned>(yi0 + 1u, 0u, tex.height());
+    const float dx = xf - (float)xi0;
+    const float dy = yf - (float)yi0;
+    const float omdx = 1.f - dx;
+    const float omdy = 1.f - dy;
+    const auto pixel0 = color_cast<float, T>(tex.texel<color_type, order>(xi0, yi0));
+    const auto pixel1 = color_cast<float, T>(tex.texel<color_type, order>(xi0, yi1));
+    const auto pixel2 = color_cast<float, T>(tex.texel<color_type, order>(xi1, yi0));
+    const auto pixel3 = color_cast<float, T>(tex.texel<color_type, order>(xi1, yi1));
+    const auto weight0 = pixel0 * omdx * omdy;
+    const auto weight1 = pixel1 * omdx * dy;
+    const auto weight2 = pixel2 * dx * omdy;
+    const auto weight3 = pixel3 * dx * dy;
+    const auto ret = math::sum(weight0, weight1, weight2, weight3);
+    return color_cast<T, float>(ret);
+}
+
+} // namespace slo
+
+#endif

@@ -78,3 +78,5 @@ SL_SHADER_FN bool inst_tex_fs(SL_FragmentParam& fragParam)
 
 SL_REGISTER_VERTEX_SHADER("inst_tex", inst_tex_vs)
 SL_REGISTER_FRAGMENT_SHADER("inst_tex", inst_tex_fs)
+
+static_assert(sizeof(InstTexUniforms) == 208, "InstTexUniforms layout must be identical in every back-end");
