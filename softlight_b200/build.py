@@ -1,0 +1,73 @@
+"""Build recipes (called by __graft_entry__.build()).
+
+* build_cuda():   nvcc -> softlight_b200/libslcu.so (sm_100a only, -lineinfo, -fmad=false)
+* build_oracle(): g++  -> oracle/libslor.so (CPU restatement) and, when /root/reference is
+                  present, oracle/_ref/libslref_{strict,fast}.so (the compiled reference).
+Everything is built in-tree so the .so files travel to the GPU box.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "softlight_b200", "csrc")
+LIB = os.path.join(ROOT, "softlight_b200", "libslcu.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-fmad=false",  # nothing is contracted behind our back; FMAs are explicit (__fmaf_rn)
+    "-shared", "-Xcompiler", "-fPIC,-fvisibility=hidden",
+]
+
+
+def _newer(target: str, sources) -> bool:
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources)
+
+
+def cuda_sources():
+    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))]
+    srcs += [os.path.join(ROOT, "shaders", f) for f in sorted(os.listdir(os.path.join(ROOT, "shaders")))]
+    srcs.append(os.path.join(ROOT, "include", "slcu.h"))
+    return srcs
+
+
+def build_cuda(force: bool = False, verbose: bool = False) -> str:
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not force and _newer(LIB, cuda_sources()):
+        return LIB
+    cmd = [nvcc] + NVCC_FLAGS + ["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "shaders"), "-I" + CSRC,
+                                 os.path.join(CSRC, "slcu.cu"), "-o", LIB]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed")
+    if verbose:
+        sys.stderr.write(r.stderr)
+    return LIB
+
+
+def build_oracle() -> None:
+    odir = os.path.join(ROOT, "oracle")
+    r = subprocess.run(["make", "-s", "-C", odir, "port"], capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("oracle port build failed")
+    if os.path.isdir("/root/reference/softlight/src"):
+        r = subprocess.run(["make", "-s", "-j8", "-C", odir, "ref"], capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("oracle/_ref build failed")
+
+
+if __name__ == "__main__":
+    build_cuda(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    build_oracle()
+    print("built", LIB)

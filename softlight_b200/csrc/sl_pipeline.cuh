@@ -1,0 +1,923 @@
+/*
+ * sl_pipeline.cuh -- the draw path as sm_100a kernels.
+ *
+ *   k_vertex<VS>      SL_TriProcessor::process_verts / clip_and_process_tris /
+ *                     push_bin's visibility test (src/SL_TriProcessor.cpp:248-640):
+ *                     one thread per primitive; index fetch, 3x vertex shader,
+ *                     cull, scissor matrix, clip status, Sutherland-Hodgman,
+ *                     perspective divide, viewport; writes *triangle records*
+ *                     (screen coords + varyings) in submission order per block.
+ *   k_span<MODE>      SL_ScanlineBounds::init/step (SL_ScanlineBounds.hpp:137-347)
+ *                     for every (record,row): counts / fills the per-row span
+ *                     lists in exact submission order.  Rows are the bins: a
+ *                     full-width row is the only tile shape for which the
+ *                     reference's left-to-right compaction state machine
+ *                     (SURVEY.md section 0 finding 6) stays tile-local.
+ *   k_raster<FS>      SL_TriRasterizer::render_triangle_simd +
+ *                     SL_FragmentProcessor::flush_tri_fragments + assign_pixel /
+ *                     assign_alpha_pixel (src/SL_TriRasterizer.cpp:413-559,
+ *                     src/SL_FragmentProcessor.cpp:416-531, src/SL_Framebuffer.cpp:
+ *                     44-368): one warp per row walks the row's spans in order;
+ *                     lanes take spans whose x-ranges do not overlap.
+ *
+ * Data layout in HBM:
+ *   record r      : float4[3 + 3*NV]  = p0,p1,p2 (x,y,z,1/w) then varyings [slot][vert]
+ *   span entry    : {u32 record, u16 xMin, u16 xMax}, grouped by row, ordered
+ *   cnt[vb][y]    : u16 spans of vertex-block vb on row y;  off[vb][y] : u32 exclusive prefix over vb
+ */
+#pragma once
+
+#include "sl_shader_api.cuh"
+
+namespace sld
+{
+
+typedef math::vec4 (*VsFn)(SL_VertexParam&);
+typedef bool (*FsFn)(SL_FragmentParam&);
+
+constexpr int SL_VB_THREADS = 256;        /* threads per vertex block                       */
+constexpr int SL_VB_ROUNDS = 4;           /* primitives per thread                          */
+constexpr int SL_VB_PRIMS = SL_VB_THREADS * SL_VB_ROUNDS;
+constexpr int SL_MAX_ROWS = 8192;         /* framebuffer height limit of the row binner     */
+constexpr int SL_SPAN_WIN = 256;          /* rows per mask window in k_span                 */
+
+struct SLSegment { uint32_t base, count; };
+struct SLBlockInfo { SLSegment seg[SL_VB_ROUNDS]; };
+
+struct SLSpanEntry { uint32_t rec; uint16_t xMin, xMax; };
+
+/* device-side counters of one context */
+struct SLCounters
+{
+    unsigned long long recAlloc;     /* triangle records allocated (reset per batch)      */
+    unsigned long long trisBinned;
+    unsigned long long spans;
+    unsigned long long fragsShaded;
+    unsigned int errorFlags;         /* bit0 record overflow, bit1 span x out of range    */
+    unsigned int pad;
+};
+
+struct SLVertexParams
+{
+    SL_UniformBuffer uniforms;
+    SL_VertexArray vao;
+    SL_VertexBuffer vbo;
+    const unsigned char* ibo;
+    int iboType;          /* SL_DataType: 0 u8, 1 u16, 2 u32 */
+    int usingIndices;
+    int cullMode;         /* SL_CullMode */
+    int numVaryings;
+    float scissor[16];    /* column-major scissor matrix (host, SL_ViewportState::scissor_matrix) */
+    float viewport[4];    /* viewport_rect */
+    unsigned long long elementBegin;
+    unsigned long long primsPerInstance;
+    unsigned long long numPrims;      /* primsPerInstance * instances */
+    unsigned int firstBlock;          /* index of this launch's first vertex block in blockInfo */
+    unsigned int recCapacity;
+    float4* records;
+    SLBlockInfo* blockInfo;
+    SLCounters* counters;
+};
+
+/* ------------------------------------------------------------------------
+ * Vertex stage helpers
+ * ----------------------------------------------------------------------*/
+struct SLVert
+{
+    math::vec4 vert;
+    math::vec4 varyings[4];
+};
+
+/* face_determinant, SSE4.1 branch (src/SL_TriProcessor.cpp:40-66) */
+SLD_FN float sl_face_determinant(const math::vec4& p0, const math::vec4& p1, const math::vec4& p2)
+{
+    const float m0 = ((p1.v[1] * p2.v[3]) - (p1.v[3] * p2.v[1])) * p0.v[0];
+    const float m1 = ((p1.v[3] * p2.v[0]) - (p1.v[0] * p2.v[3])) * p0.v[1];
+    const float m2 = ((p1.v[0] * p2.v[1]) - (p1.v[1] * p2.v[0])) * p0.v[3];
+    return m2 + (m1 + m0);
+}
+
+/* sl_ndc_clip_status (SL_PostVertexTransform.hpp:590-616): 3 fully, 1 partially, 0 not visible */
+SLD_FN int sl_clip_status(const math::vec4& c0, const math::vec4& c1, const math::vec4& c2)
+{
+    bool vis = true, part = false;
+    const math::vec4* cs[3] = {&c0, &c1, &c2};
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+    {
+        const float w = cs[i]->v[3];
+        const float nw = __uint_as_float(__float_as_uint(w) | 0x80000000u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) vis = vis && (nw <= cs[i]->v[k]) && (w >= cs[i]->v[k]);
+        part = part || (w > 0.f);
+    }
+    return (vis ? 3 : 0) | (part ? 1 : 0);
+}
+
+/* sl_perspective_divide + sl_ndc_to_screen_coords (SL_PostVertexTransform.hpp:160-178, 412-449) */
+SLD_FN void sl_to_screen(math::vec4& v, const float* dims)
+{
+    const float wInv = sl_rcp(v.v[3]);
+    const float nx = v.v[0] * wInv, ny = v.v[1] * wInv, nz = v.v[2] * wInv;
+    float sx = sl_fma(1.f + nx, dims[2] * 0.5f, dims[0]);
+    float sy = sl_fma(1.f + ny, dims[3] * 0.5f, dims[1]);
+    sx = sl_max(floorf(sx), 0.f);
+    sy = sl_max(floorf(sy), 0.f);
+    v = math::vec4{sx, sy, nz, wInv};
+}
+
+/* push_bin's visibility test (src/SL_TriProcessor.cpp:257-264) */
+SLD_FN bool sl_prim_hidden(const math::vec4& p0, const math::vec4& p1, const math::vec4& p2)
+{
+    const float minX = sl_min(sl_min(p0.v[0], p1.v[0]), p2.v[0]);
+    const float maxX = sl_max(sl_max(p0.v[0], p1.v[0]), p2.v[0]);
+    const float minY = sl_min(sl_min(p0.v[1], p1.v[1]), p2.v[1]);
+    const float maxY = sl_max(sl_max(p0.v[1], p1.v[1]), p2.v[1]);
+    return (maxX - minX < 1.f) || (maxY - minY < 1.f);
+}
+
+SLD_FN void sl_write_record(float4* rec, int numVaryings, const math::vec4& p0, const math::vec4& p1, const math::vec4& p2,
+                            const math::vec4* va, const math::vec4* vb, const math::vec4* vc)
+{
+    rec[0] = *reinterpret_cast<const float4*>(&p0);
+    rec[1] = *reinterpret_cast<const float4*>(&p1);
+    rec[2] = *reinterpret_cast<const float4*>(&p2);
+    for (int s = 0; s < numVaryings; ++s)
+    {
+        rec[3 + 3 * s + 0] = *reinterpret_cast<const float4*>(&va[s]);
+        rec[3 + 3 * s + 1] = *reinterpret_cast<const float4*>(&vb[s]);
+        rec[3 + 3 * s + 2] = *reinterpret_cast<const float4*>(&vc[s]);
+    }
+}
+
+/* SL_TriProcessor::clip_and_process_tris (src/SL_TriProcessor.cpp:370-519).  Rare
+ * path: the polygon lives in local memory.  Returns the number of vertices (0
+ * when nothing is left); verts are already in screen space. */
+struct SLClipPoly
+{
+    math::vec4 verts[9];
+    math::vec4 varys[9 * 4];
+};
+
+__device__ __noinline__ int sl_clip_polygon(SLClipPoly& poly, int numVarys, const float* dims)
+{
+    SLClipPoly tmp;
+    int numTotalVerts = 3;
+    const float edges[6][4] = {{1.f, 0.f, 0.f, 1.f}, {-1.f, 0.f, 0.f, 1.f}, {0.f, 1.f, 0.f, 1.f},
+                               {0.f, -1.f, 0.f, 1.f}, {0.f, 0.f, 1.f, 1.f}, {0.f, 0.f, -1.f, 1.f}};
+    for (int e = 0; e < 6; ++e)
+    {
+        const math::vec4 edge{edges[e][0], edges[e][1], edges[e][2], edges[e][3]};
+        int numNewVerts = 0;
+        int j = numTotalVerts - 1;
+        math::vec4 p0 = poly.verts[numTotalVerts - 1];
+        float t0 = math::dot(p0, edge);
+        int visible0 = !sl_signbit(t0);
+        for (int k = 0; k < numTotalVerts; ++k)
+        {
+            const math::vec4 p1 = poly.verts[k];
+            const float t1 = math::dot(p1, edge);
+            const int visible1 = !sl_signbit(t1);
+            if (visible0 ^ visible1)
+            {
+                const float t = t0 * sl_rcp(t0 - t1);
+                tmp.verts[numNewVerts] = math::mix(p0, p1, t);
+                for (int i = 0; i < numVarys; ++i) tmp.varys[numNewVerts * 4 + i] = math::mix(poly.varys[j * 4 + i], poly.varys[k * 4 + i], t);
+                ++numNewVerts;
+            }
+            if (visible1)
+            {
+                tmp.verts[numNewVerts] = p1;
+                for (int i = 0; i < numVarys; ++i) tmp.varys[numNewVerts * 4 + i] = poly.varys[k * 4 + i];
+                ++numNewVerts;
+            }
+            j = k;
+            p0 = p1;
+            t0 = t1;
+            visible0 = visible1;
+        }
+        if (!numNewVerts) return 0;
+        numTotalVerts = numNewVerts;
+        for (int i = 0; i < numNewVerts; ++i)
+        {
+            poly.verts[i] = tmp.verts[i];
+            for (int v = 0; v < numVarys; ++v) poly.varys[i * 4 + v] = tmp.varys[i * 4 + v];
+        }
+    }
+    if (numTotalVerts < 3) return 0;
+    for (int i = 0; i < numTotalVerts; ++i) sl_to_screen(poly.verts[i], dims);
+    return numTotalVerts;
+}
+
+/* ------------------------------------------------------------------------
+ * k_vertex
+ * ----------------------------------------------------------------------*/
+template <VsFn VS>
+__global__ void __launch_bounds__(SL_VB_THREADS) k_vertex(const __grid_constant__ SLVertexParams P)
+{
+    __shared__ uint32_t sWarpSums[SL_VB_THREADS / 32];
+    __shared__ uint32_t sBase, sGranted;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const unsigned long long blockFirst = (unsigned long long)blockIdx.x * SL_VB_PRIMS;
+    const int NV = P.numVaryings;
+    const int recStride = 3 + 3 * NV;
+
+    SL_VertexParam params;
+    params.pUniforms = &P.uniforms;
+    params.pVao = &P.vao;
+    params.pVbo = &P.vbo;
+
+    const math::mat4& scissorMat = *reinterpret_cast<const math::mat4*>(P.scissor);
+
+    for (int round = 0; round < SL_VB_ROUNDS; ++round)
+    {
+        const unsigned long long g = blockFirst + (unsigned long long)round * SL_VB_THREADS + tid;
+        SLVert v[3];
+        SLClipPoly poly;
+        int n = 0;         /* records this thread emits */
+        int polyVerts = 0; /* > 0: clipped path */
+
+        if (g < P.numPrims)
+        {
+            const unsigned long long instanceId = g / P.primsPerInstance;
+            const unsigned long long i = P.elementBegin + 3ull * (g - instanceId * P.primsPerInstance);
+            unsigned long long vertId[3];
+            if (P.usingIndices) /* get_next_vertex3 (src/SL_TriProcessor.cpp:125-234) */
+            {
+                if (P.iboType == 0) { const uint8_t* p = P.ibo + i; vertId[0] = p[0]; vertId[1] = p[1]; vertId[2] = p[2]; }
+                else if (P.iboType == 1) { const uint16_t* p = reinterpret_cast<const uint16_t*>(P.ibo) + i; vertId[0] = p[0]; vertId[1] = p[1]; vertId[2] = p[2]; }
+                else { const uint32_t* p = reinterpret_cast<const uint32_t*>(P.ibo) + i; vertId[0] = p[0]; vertId[1] = p[1]; vertId[2] = p[2]; }
+            }
+            else { vertId[0] = i; vertId[1] = i + 1; vertId[2] = i + 2; }
+
+            params.instanceId = (size_t)instanceId;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) /* src/SL_TriProcessor.cpp:584-594 */
+            {
+                params.vertId = (size_t)vertId[k];
+                params.pVaryings = v[k].varyings;
+                v[k].vert = VS(params);
+            }
+
+            bool culled = false;
+            if (P.cullMode != 2) /* :597-612 */
+            {
+                const float det = sl_face_determinant(v[0].vert, v[1].vert, v[2].vert);
+                culled = (P.cullMode == 1) ^ sl_signbit(det);
+            }
+            if (!culled)
+            {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) v[k].vert = scissorMat * v[k].vert; /* :615-617 */
+                const int vis = sl_clip_status(v[0].vert, v[1].vert, v[2].vert);
+                if (vis == 3)
+                {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) sl_to_screen(v[k].vert, P.viewport);
+                    n = sl_prim_hidden(v[0].vert, v[1].vert, v[2].vert) ? 0 : 1;
+                }
+                else if (vis == 1)
+                {
+                    for (int k = 0; k < 3; ++k)
+                    {
+                        poly.verts[k] = v[k].vert;
+                        for (int s = 0; s < NV; ++s) poly.varys[k * 4 + s] = v[k].varyings[s];
+                    }
+                    polyVerts = sl_clip_polygon(poly, NV, P.viewport);
+                    for (int f = polyVerts - 2; f-- > 0;)
+                    {
+                        if (!sl_prim_hidden(poly.verts[0], poly.verts[f + 1], poly.verts[f + 2])) ++n;
+                    }
+                }
+            }
+        }
+
+        /* ordered compaction inside the block: exclusive scan of n */
+        uint32_t incl = (uint32_t)n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) sWarpSums[warp] = incl;
+        __syncthreads();
+        uint32_t warpOff = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < SL_VB_THREADS / 32; ++w)
+        {
+            const uint32_t s = sWarpSums[w];
+            if (w < warp) warpOff += s;
+            total += s;
+        }
+        if (tid == 0)
+        {
+            uint32_t base = 0, granted = total;
+            if (total)
+            {
+                base = (uint32_t)atomicAdd(&P.counters->recAlloc, (unsigned long long)total);
+                if ((unsigned long long)base + total > P.recCapacity)
+                {
+                    atomicOr(&P.counters->errorFlags, 1u); /* host re-issues the draw with a larger record buffer */
+                    granted = 0;
+                }
+                else atomicAdd(&P.counters->trisBinned, (unsigned long long)total);
+            }
+            sBase = base;
+            sGranted = granted;
+            P.blockInfo[P.firstBlock + blockIdx.x].seg[round] = SLSegment{base, granted};
+        }
+        __syncthreads();
+        if (n && sGranted)
+        {
+            uint32_t slot = sBase + warpOff + (incl - (uint32_t)n);
+            if (!polyVerts)
+            {
+                sl_write_record(P.records + (size_t)slot * recStride, NV, v[0].vert, v[1].vert, v[2].vert, v[0].varyings, v[1].varyings, v[2].varyings);
+            }
+            else
+            {
+                for (int f = polyVerts - 2; f-- > 0;) /* reverse fan order (:505-518) */
+                {
+                    const int j = f + 1, k = f + 2;
+                    if (sl_prim_hidden(poly.verts[0], poly.verts[j], poly.verts[k])) continue;
+                    sl_write_record(P.records + (size_t)slot * recStride, NV, poly.verts[0], poly.verts[j], poly.verts[k],
+                                    &poly.varys[0], &poly.varys[j * 4], &poly.varys[k * 4]);
+                    ++slot;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+/* ------------------------------------------------------------------------
+ * Span set-up: SL_ScanlineBounds (SL_ScanlineBounds.hpp:125-347)
+ * ----------------------------------------------------------------------*/
+struct SLScanline
+{
+    float v0y, v1y, v0x, v1x, p20y, p20x, p21xy, p10xy;
+
+    SLD_FN void init(float4 p0, float4 p1, float4 p2)
+    {
+        /* sl_sort_minmax x3 (:60-68,139-141): swap when a.y < b.y */
+        float4 t;
+        if (p0.y < p1.y) { t = p0; p0 = p1; p1 = t; }
+        if (p0.y < p2.y) { t = p0; p0 = p2; p2 = t; }
+        if (p1.y < p2.y) { t = p1; p1 = p2; p2 = t; }
+        v0y = p0.y;
+        v1y = p1.y;
+        v0x = p0.x;
+        v1x = p1.x;
+        p20y = sl_rcp(p2.y - p0.y);
+        p20x = p2.x - p0.x;
+        p21xy = (p2.x - p1.x) * sl_rcp(p2.y - p1.y);
+        p10xy = (p1.x - p0.x) * sl_rcp(p1.y - p0.y);
+    }
+
+    SLD_FN void step(float yf, int32_t& xMin, int32_t& xMax) const /* :326-347 */
+    {
+        const float d0 = yf - v0y;
+        const float d1 = yf - v1y;
+        const float alpha = d0 * p20y;
+        const float lo = sl_fma(p20x, alpha, v0x);
+        const float pdv0 = sl_fma(p10xy, d0, v0x);
+        const float pdv1 = sl_fma(p21xy, d1, v1x);
+        const float hi = sl_signbit(d1) ? pdv1 : pdv0;
+        xMin = sl_cvt_rn(sl_min(lo, hi));
+        xMax = sl_cvt_rn(sl_max(lo, hi));
+    }
+};
+
+struct SLSpanParams
+{
+    const float4* records;
+    const SLBlockInfo* blockInfo;
+    unsigned int firstBlock;     /* first vertex block of the batch          */
+    unsigned int numRows;        /* framebuffer height                       */
+    unsigned int rowPitch;       /* padded row count of cnt/off              */
+    int recStride;               /* float4 per record                        */
+    uint16_t* cnt;               /* [numBlocks][rowPitch]                    */
+    const uint32_t* off;         /* [numBlocks][rowPitch] exclusive over vb  */
+    const uint32_t* rowStart;    /* [numRows+1]                              */
+    SLSpanEntry* entries;
+    SLCounters* counters;
+};
+
+/* MODE 0: count spans per (vertex block, row).  MODE 1: fill the row lists. */
+template <int MODE>
+__global__ void __launch_bounds__(256) k_span(const __grid_constant__ SLSpanParams P)
+{
+    __shared__ uint16_t sRowRun[SL_MAX_ROWS];
+    __shared__ uint32_t sMask[SL_SPAN_WIN][8];
+    __shared__ int sMinY, sMaxY;
+
+    const int tid = threadIdx.x;
+    const unsigned int vb = blockIdx.x;
+    const int H = (int)P.numRows;
+    for (int y = tid; y < H; y += 256) sRowRun[y] = 0;
+    __syncthreads();
+
+    const SLBlockInfo info = P.blockInfo[P.firstBlock + vb];
+    for (int seg = 0; seg < SL_VB_ROUNDS; ++seg)
+    {
+        const uint32_t segBase = info.seg[seg].base, segCount = info.seg[seg].count;
+        for (uint32_t sub = 0; sub < segCount; sub += 256)
+        {
+            const bool valid = sub + tid < segCount;
+            const uint32_t rec = segBase + sub + tid;
+            SLScanline sl;
+            int y0 = 0x7fffffff, y1 = -1;
+            if (valid)
+            {
+                const float4* r = P.records + (size_t)rec * P.recStride;
+                const float4 p0 = r[0], p1 = r[1], p2 = r[2];
+                /* src/SL_TriRasterizer.cpp:431-433 */
+                y0 = sl_cvt_rn(sl_min(sl_min(p0.y, p1.y), p2.y));
+                y1 = sl_cvt_rn(sl_max(sl_max(p0.y, p1.y), p2.y));
+                y0 = y0 < 0 ? 0 : y0;
+                y1 = y1 > H ? H : y1;
+                sl.init(p0, p1, p2);
+            }
+            if (tid == 0) { sMinY = 0x7fffffff; sMaxY = -1; }
+            __syncthreads();
+            if (valid && y0 < y1) { atomicMin(&sMinY, y0); atomicMax(&sMaxY, y1); }
+            __syncthreads();
+            const int cy0 = sMinY, cy1 = sMaxY;
+            for (int w0 = cy0; w0 < cy1; w0 += SL_SPAN_WIN)
+            {
+                const int w1 = min(w0 + SL_SPAN_WIN, cy1);
+                for (int i = tid; i < SL_SPAN_WIN * 8; i += 256) (&sMask[0][0])[i] = 0u;
+                __syncthreads();
+                const int ya = max(y0, w0), yb = min(y1, w1);
+                for (int y = ya; y < yb; ++y)
+                {
+                    int32_t xMin, xMax;
+                    sl.step((float)y, xMin, xMax);
+                    if (xMin < xMax) atomicOr(&sMask[y - w0][tid >> 5], 1u << (tid & 31));
+                }
+                __syncthreads();
+                if (MODE == 1)
+                {
+                    for (int y = ya; y < yb; ++y)
+                    {
+                        int32_t xMin, xMax;
+                        sl.step((float)y, xMin, xMax);
+                        if (xMin < xMax)
+                        {
+                            uint32_t rank = 0;
+                            const int wq = tid >> 5;
+                            for (int q = 0; q < wq; ++q) rank += __popc(sMask[y - w0][q]);
+                            rank += __popc(sMask[y - w0][wq] & ((1u << (tid & 31)) - 1u));
+                            const size_t slot = (size_t)P.rowStart[y] + P.off[(size_t)vb * P.rowPitch + y] + sRowRun[y] + rank;
+                            if (xMin < 0 || xMax > 65535) { atomicOr(&P.counters->errorFlags, 2u); xMin = 0; xMax = 0; }
+                            P.entries[slot] = SLSpanEntry{rec, (uint16_t)xMin, (uint16_t)xMax};
+                        }
+                    }
+                    __syncthreads();
+                }
+                for (int yy = w0 + tid; yy < w1; yy += 256)
+                {
+                    uint32_t c = 0;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) c += __popc(sMask[yy - w0][q]);
+                    sRowRun[yy] = (uint16_t)(sRowRun[yy] + c);
+                }
+                __syncthreads();
+            }
+        }
+    }
+    if (MODE == 0)
+    {
+        for (int y = tid; y < (int)P.rowPitch; y += 256) P.cnt[(size_t)vb * P.rowPitch + y] = y < H ? sRowRun[y] : (uint16_t)0;
+    }
+}
+
+/* column scans of cnt over the vertex blocks, two-level */
+constexpr int SL_SCAN_SEGS = 64;
+
+__global__ void k_scan_seg_sums(const uint16_t* cnt, uint32_t* segSums, unsigned numBlocks, unsigned rowPitch, unsigned blocksPerSeg)
+{
+    const unsigned y = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned seg = blockIdx.y;
+    if (y >= rowPitch) return;
+    const unsigned b0 = seg * blocksPerSeg;
+    const unsigned b1 = min(b0 + blocksPerSeg, numBlocks);
+    uint32_t s = 0;
+    for (unsigned b = b0; b < b1; ++b) s += cnt[(size_t)b * rowPitch + y];
+    segSums[(size_t)seg * rowPitch + y] = s;
+}
+
+__global__ void k_scan_rows(uint32_t* segSums, uint32_t* rowTotals, unsigned rowPitch, unsigned numSegs)
+{
+    const unsigned y = blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= rowPitch) return;
+    uint32_t run = 0;
+    for (unsigned s = 0; s < numSegs; ++s)
+    {
+        const uint32_t c = segSums[(size_t)s * rowPitch + y];
+        segSums[(size_t)s * rowPitch + y] = run;
+        run += c;
+    }
+    rowTotals[y] = run;
+}
+
+/* single block: exclusive scan of rowTotals -> rowStart[0..numRows] ; also accumulates the span counter */
+__global__ void __launch_bounds__(1024) k_scan_row_starts(const uint32_t* rowTotals, uint32_t* rowStart, unsigned numRows, SLCounters* counters)
+{
+    __shared__ uint32_t sPart[1024];
+    const int tid = threadIdx.x;
+    const unsigned per = (numRows + 1023u) / 1024u;
+    const unsigned a = tid * per;
+    const unsigned b = min(a + per, numRows);
+    uint32_t s = 0;
+    for (unsigned y = a; y < b; ++y) s += rowTotals[y];
+    sPart[tid] = s;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1)
+    {
+        const uint32_t t = tid >= d ? sPart[tid - d] : 0u;
+        __syncthreads();
+        sPart[tid] += t;
+        __syncthreads();
+    }
+    uint32_t run = sPart[tid] - s;
+    for (unsigned y = a; y < b; ++y)
+    {
+        rowStart[y] = run;
+        run += rowTotals[y];
+    }
+    if (tid == 1023)
+    {
+        rowStart[numRows] = sPart[1023];
+        atomicAdd(&counters->spans, (unsigned long long)sPart[1023]);
+    }
+}
+
+__global__ void k_scan_offsets(const uint16_t* cnt, const uint32_t* segSums, uint32_t* off, unsigned numBlocks, unsigned rowPitch, unsigned blocksPerSeg)
+{
+    const unsigned y = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned seg = blockIdx.y;
+    if (y >= rowPitch) return;
+    const unsigned b0 = seg * blocksPerSeg;
+    const unsigned b1 = min(b0 + blocksPerSeg, numBlocks);
+    uint32_t run = segSums[(size_t)seg * rowPitch + y];
+    for (unsigned b = b0; b < b1; ++b)
+    {
+        off[(size_t)b * rowPitch + y] = run;
+        run += cnt[(size_t)b * rowPitch + y];
+    }
+}
+
+/* ------------------------------------------------------------------------
+ * Fragment stage
+ * ----------------------------------------------------------------------*/
+struct SLRasterParams
+{
+    SL_UniformBuffer uniforms;
+    const float4* records;
+    const SLSpanEntry* entries;
+    const uint32_t* rowStart;
+    int recStride;
+    int numVaryings;
+    int numOutputs;
+    int depthTest;   /* SL_DepthTest */
+    int depthMask;
+    int blend;       /* SL_BlendMode */
+    unsigned int numRows;
+    unsigned int width;       /* depth attachment width (row stride of every attachment, like the reference) */
+    unsigned char* depth;
+    int depthBpt;
+    unsigned char* color[4];
+    int colorType[4];         /* SL_ColorDataType */
+    int colorWidth[4];
+    SLCounters* counters;
+};
+
+/* depth texel read (src/SL_TriRasterizer.cpp:40-102) */
+SLD_FN float sl_load_depth(const unsigned char* base, int bpt, size_t idx)
+{
+    if (bpt == 2) return sl_h2f(reinterpret_cast<const uint16_t*>(base)[idx]);
+    if (bpt == 4) return reinterpret_cast<const float*>(base)[idx];
+    return (float)reinterpret_cast<const double*>(base)[idx];
+}
+/* depth write (src/SL_FragmentProcessor.cpp:526-529) */
+SLD_FN void sl_store_depth(unsigned char* base, int bpt, size_t idx, float z)
+{
+    if (bpt == 2) reinterpret_cast<uint16_t*>(base)[idx] = sl_f2h_rn(z);
+    else if (bpt == 4) reinterpret_cast<float*>(base)[idx] = z;
+    else reinterpret_cast<double*>(base)[idx] = (double)z;
+}
+
+/* SL_DepthFunc* (SL_ShaderUtil.hpp:240-507): ordered, quiet */
+SLD_FN bool sl_depth_cmp(int func, float z, float d)
+{
+    switch (func)
+    {
+        case 0: return true;
+        case 1: return z < d;
+        case 2: return z <= d;
+        case 3: return z > d;
+        case 4: return z >= d;
+        case 5: return z == d;
+        default: return (z < d) || (z > d);
+    }
+}
+
+/* assign_pixel<T> (src/SL_Framebuffer.cpp:44-217) */
+SLD_FN void sl_store_color(unsigned char* base, int type, size_t idx, const math::vec4& c)
+{
+    const int kind = type % 7;
+    const int n = type / 7 + 1;
+    if (kind == 0)
+    {
+        const math::vec4_t<uint8_t> r = math::vec4_to_u8(c * 255.f);
+        if (n == 4) reinterpret_cast<uint32_t*>(base)[idx] = (uint32_t)r.v[0] | ((uint32_t)r.v[1] << 8) | ((uint32_t)r.v[2] << 16) | ((uint32_t)r.v[3] << 24);
+        else { unsigned char* p = base + idx * n; for (int i = 0; i < n; ++i) p[i] = r.v[i]; }
+    }
+    else if (kind == 1)
+    {
+        uint16_t* p = reinterpret_cast<uint16_t*>(base) + idx * n;
+        for (int i = 0; i < n; ++i)
+        {
+            const int32_t v = sl_cvt_rn(c.v[i] * 65535.f);
+            p[i] = (uint16_t)(v < 0 ? 0 : (v > 65535 ? 65535 : v));
+        }
+    }
+    else if (kind == 4)
+    {
+        uint16_t* p = reinterpret_cast<uint16_t*>(base) + idx * n;
+        for (int i = 0; i < n; ++i) p[i] = sl_f2h_rz(c.v[i]); /* vec4<float> -> vec4<half>: cvtps2ph toward zero */
+    }
+    else if (kind == 5)
+    {
+        if (n == 4) reinterpret_cast<float4*>(base)[idx] = make_float4(c.v[0], c.v[1], c.v[2], c.v[3]);
+        else { float* p = reinterpret_cast<float*>(base) + idx * n; for (int i = 0; i < n; ++i) p[i] = c.v[i]; }
+    }
+    else if (kind == 6)
+    {
+        double* p = reinterpret_cast<double*>(base) + idx * n;
+        for (int i = 0; i < n; ++i) p[i] = (double)c.v[i];
+    }
+}
+
+/* destination read of assign_alpha_pixel (src/SL_Framebuffer.cpp:284-312), 3-channel quirk (:308) included */
+SLD_FN math::vec4 sl_load_color(const unsigned char* base, int type, size_t idx)
+{
+    const int kind = type % 7;
+    const int n = type / 7 + 1;
+    float ch[4];
+    float hi = 1.f, scale = 1.f;
+    if (kind == 0)
+    {
+        const unsigned char* p = base + idx * n;
+        for (int i = 0; i < n; ++i) ch[i] = (float)p[i];
+        hi = 255.f;
+        scale = 0.00392156862745f;
+    }
+    else if (kind == 1)
+    {
+        const uint16_t* p = reinterpret_cast<const uint16_t*>(base) + idx * n;
+        for (int i = 0; i < n; ++i) ch[i] = (float)p[i];
+        hi = 65535.f;
+        scale = 1.f / 65535.f;
+    }
+    else if (kind == 4)
+    {
+        const uint16_t* p = reinterpret_cast<const uint16_t*>(base) + idx * n;
+        for (int i = 0; i < n; ++i) ch[i] = sl_h2f(p[i]);
+    }
+    else if (kind == 5)
+    {
+        const float* p = reinterpret_cast<const float*>(base) + idx * n;
+        for (int i = 0; i < n; ++i) ch[i] = p[i];
+    }
+    else
+    {
+        const double* p = reinterpret_cast<const double*>(base) + idx * n;
+        for (int i = 0; i < n; ++i) ch[i] = (float)p[i];
+    }
+    math::vec4 d;
+    if (n == 1) d = math::vec4{ch[0], 0.f, 0.f, hi};
+    else if (n == 2) d = math::vec4{ch[0], ch[1], 0.f, hi};
+    else if (n == 3) d = math::vec4{ch[0], ch[0], ch[0], hi};
+    else d = math::vec4{ch[0], ch[1], ch[2], ch[3]};
+    if (kind <= 1) d = d * scale;
+    return d;
+}
+
+/* assign_alpha_pixel<T> (src/SL_Framebuffer.cpp:270-368) */
+SLD_FN void sl_blend_color(unsigned char* base, int type, size_t idx, const math::vec4& rgba, int blendMode)
+{
+    math::vec4 d = sl_load_color(base, type, idx);
+    const math::vec4 srcAlpha{rgba.v[3]};
+    const math::vec4 modulation = math::vec4{1.f} - srcAlpha;
+    if (blendMode == 1)
+    {
+        const math::vec4 dstMod = modulation * d.v[3];
+        const math::vec4 dstAlpha = dstMod + srcAlpha;
+        const math::vec4 dstRgb = math::fmadd(rgba, srcAlpha, (d * dstMod)) * math::rcp(dstAlpha);
+        d = math::vec4{dstRgb.v[0], dstRgb.v[1], dstRgb.v[2], dstAlpha.v[0]};
+    }
+    else if (blendMode == 2) d = math::fmadd(d, modulation, rgba);
+    else if (blendMode == 3) d = math::fmadd(rgba, srcAlpha, d);
+    else if (blendMode == 4) d = (rgba * srcAlpha) + (d * modulation);
+    d = math::clamp(d, math::vec4{0.f, 0.f, 0.f, 0.f}, math::vec4{1.f, 1.f, 1.f, 1.f});
+    sl_store_color(base, type, idx, d);
+}
+
+struct SLTriSetup
+{
+    math::vec4 bc0, bc1, bc2; /* barycentric plane equations (push_bin, src/SL_TriProcessor.cpp:271-314) */
+    float z0, z1, z2;         /* vertex depths                                                           */
+    float w0, w1, w2;         /* 1/w of the three vertices                                               */
+};
+
+SLD_FN void sl_tri_setup(SLTriSetup& t, const float4 p0, const float4 p1, const float4 p2)
+{
+    const float xy0 = p0.x - p1.x, xy1 = p0.y - p1.y;
+    const float zy0 = p2.x - p1.x, zy1 = p2.y - p1.y;
+    const float denom = sl_rcp((zy0 * xy1) - (zy1 * xy0)); /* math::cross(vec2 zy, vec2 xy), generic */
+    const math::vec4 ptX{p0.x, p1.x, p2.x, 0.f};
+    const math::vec4 ptY{p0.y, p1.y, p2.y, 0.f};
+    const math::vec4 one{1.f};
+    t.bc0 = math::cross(ptY, one) * denom;
+    t.bc1 = math::cross(one, ptX) * denom;
+    t.bc2 = math::cross(ptX, ptY) * denom;
+    t.z0 = p0.z; t.z1 = p1.z; t.z2 = p2.z;
+    t.w0 = p0.w; t.w1 = p1.w; t.w2 = p2.w;
+}
+
+/* SL_FragmentProcessor::flush_tri_fragments for one fragment (src/SL_FragmentProcessor.cpp:416-531) */
+template <FsFn FS>
+SLD_FN void sl_shade_fragment(const SLRasterParams& P, const SLTriSetup& t, const float4* rec, const math::vec4& bcIn, int x, int y, float z)
+{
+    /* :438-460 perspective correction */
+    math::vec4 bc = bcIn * math::vec4{t.w0, t.w1, t.w2, 0.f};
+    const float persp = sl_rcp((bc.v[0] + bc.v[1]) + (bc.v[2] + bc.v[3]));
+    bc = bc * persp;
+
+    SL_FragmentParam fp;
+    fp.pUniforms = &P.uniforms;
+    /* interpolate_tri_varyings, AVX2 branch (:163-193).  The reference interpolates all four slots; slots past
+     * numVaryings hold stale bin data there and are never read by a well-formed shader. */
+    for (int s = 0; s < P.numVaryings; ++s)
+    {
+        const float4 a = rec[3 + 3 * s + 0], b = rec[3 + 3 * s + 1], c = rec[3 + 3 * s + 2];
+        fp.pVaryings[s] = math::vec4{
+            sl_fma(bc.v[2], c.x, sl_fma(bc.v[1], b.x, bc.v[0] * a.x)), sl_fma(bc.v[2], c.y, sl_fma(bc.v[1], b.y, bc.v[0] * a.y)),
+            sl_fma(bc.v[2], c.z, sl_fma(bc.v[1], b.z, bc.v[0] * a.z)), sl_fma(bc.v[2], c.w, sl_fma(bc.v[1], b.w, bc.v[0] * a.w))};
+    }
+    fp.coord.x = (uint16_t)x;
+    fp.coord.y = (uint16_t)y;
+    fp.coord.depth = z;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) fp.pOutputs[i] = math::vec4{0.f};
+
+    const bool haveOutputs = FS(fp); /* :501 */
+    const size_t idx = (size_t)x + (size_t)P.width * (size_t)y;
+    if (haveOutputs)
+    {
+        for (int i = P.numOutputs - 1; i >= 0; --i) /* :507-523 */
+        {
+            const size_t cidx = (size_t)x + (size_t)P.colorWidth[i] * (size_t)y;
+            if (P.blend != 0) sl_blend_color(P.color[i], P.colorType[i], cidx, fp.pOutputs[i], P.blend);
+            else sl_store_color(P.color[i], P.colorType[i], cidx, fp.pOutputs[i]);
+        }
+    }
+    if (P.depthMask) sl_store_depth(P.depth, P.depthBpt, idx, z); /* :526-529 */
+}
+
+/* One (triangle,row) span, walked left to right by ONE lane: the 4-pixel group
+ * loop of render_triangle_simd (src/SL_TriRasterizer.cpp:471-548), including
+ * the in-place compaction of the barycentric registers (:496-498). */
+template <FsFn FS>
+SLD_FN unsigned sl_walk_span(const SLRasterParams& P, const SLSpanEntry e, int y)
+{
+    const float4* rec = P.records + (size_t)e.rec * P.recStride;
+    SLTriSetup t;
+    sl_tri_setup(t, rec[0], rec[1], rec[2]);
+
+    const float yf = (float)y;
+    const int xMin = e.xMin, xMax = e.xMax;
+    const math::vec4 bcY = math::fmadd(t.bc1, math::vec4{yf}, t.bc2); /* :474 */
+    math::vec4 a0 = (t.bc0 * (float)(xMin + 0)) + bcY;                /* :476-481 */
+    math::vec4 a1 = (t.bc0 * (float)(xMin + 1)) + bcY;
+    math::vec4 a2 = (t.bc0 * (float)(xMin + 2)) + bcY;
+    math::vec4 a3 = (t.bc0 * (float)(xMin + 3)) + bcY;
+    const math::vec4 bcX = t.bc0 * 4.f;
+    const size_t rowBase = (size_t)P.width * (size_t)y;
+    unsigned shaded = 0;
+
+    for (int x4 = xMin; x4 < xMax; x4 += 4)
+    {
+        /* _sl_mul_vec4_mat4_ps (:376-393): z = (w*0 + z*z2) + (y*z1 + x*z0) */
+        const float zA = ((a0.v[3] * 0.f) + (a0.v[2] * t.z2)) + ((a0.v[1] * t.z1) + (a0.v[0] * t.z0));
+        const float zB = ((a1.v[3] * 0.f) + (a1.v[2] * t.z2)) + ((a1.v[1] * t.z1) + (a1.v[0] * t.z0));
+        const float zC = ((a2.v[3] * 0.f) + (a2.v[2] * t.z2)) + ((a2.v[1] * t.z1) + (a2.v[0] * t.z0));
+        const float zD = ((a3.v[3] * 0.f) + (a3.v[2] * t.z2)) + ((a3.v[1] * t.z1) + (a3.v[0] * t.z0));
+        const bool inA = x4 + 0 < xMax, inB = x4 + 1 < xMax, inC = x4 + 2 < xMax, inD = x4 + 3 < xMax;
+        const bool mA = inA && sl_depth_cmp(P.depthTest, zA, P.depthTest ? sl_load_depth(P.depth, P.depthBpt, rowBase + x4 + 0) : 0.f);
+        const bool mB = inB && sl_depth_cmp(P.depthTest, zB, P.depthTest ? sl_load_depth(P.depth, P.depthBpt, rowBase + x4 + 1) : 0.f);
+        const bool mC = inC && sl_depth_cmp(P.depthTest, zC, P.depthTest ? sl_load_depth(P.depth, P.depthBpt, rowBase + x4 + 2) : 0.f);
+        const bool mD = inD && sl_depth_cmp(P.depthTest, zD, P.depthTest ? sl_load_depth(P.depth, P.depthBpt, rowBase + x4 + 3) : 0.f);
+        if (mA || mB || mC || mD)
+        {
+            /* :496-498 -- the registers keep these values for the following groups */
+            a2 = mC ? a2 : a3;
+            a1 = mB ? a1 : a2;
+            a0 = mA ? a0 : a1;
+            /* :500-526 -- survivor number s is shaded with register s (new values) and its own x, z */
+            int s = 0;
+            if (mA) { sl_shade_fragment<FS>(P, t, rec, a0, x4 + 0, y, zA); ++s; }
+            if (mB) { sl_shade_fragment<FS>(P, t, rec, s == 0 ? a0 : a1, x4 + 1, y, zB); ++s; }
+            if (mC) { sl_shade_fragment<FS>(P, t, rec, s == 0 ? a0 : (s == 1 ? a1 : a2), x4 + 2, y, zC); ++s; }
+            if (mD) { sl_shade_fragment<FS>(P, t, rec, s == 0 ? a0 : (s == 1 ? a1 : (s == 2 ? a2 : a3)), x4 + 3, y, zD); ++s; }
+            shaded += s;
+        }
+        a0 += bcX; /* :539-542 */
+        a1 += bcX;
+        a2 += bcX;
+        a3 += bcX;
+    }
+    return shaded;
+}
+
+/* One warp per framebuffer row.  The row's spans are taken 32 at a time in
+ * submission order; a lane may run its span as soon as no earlier, still
+ * pending span of the batch overlaps it in x (fragments of disjoint x-ranges
+ * commute; everything else is serialised in order). */
+template <FsFn FS>
+__global__ void __launch_bounds__(128) k_raster(const __grid_constant__ SLRasterParams P)
+{
+    const int lane = threadIdx.x & 31;
+    const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (y >= (int)P.numRows) return;
+    const uint32_t begin = P.rowStart[y], end = P.rowStart[y + 1];
+    unsigned shaded = 0;
+
+    for (uint32_t base = begin; base < end; base += 32)
+    {
+        const bool valid = base + lane < end;
+        SLSpanEntry e = SLSpanEntry{0u, 0, 0};
+        if (valid) e = P.entries[base + lane];
+        uint32_t dep = 0;
+        for (int i = 0; i < 31; ++i)
+        {
+            const int oMin = __shfl_sync(0xffffffffu, (int)e.xMin, i);
+            const int oMax = __shfl_sync(0xffffffffu, (int)e.xMax, i);
+            if (i < lane && oMin < (int)e.xMax && (int)e.xMin < oMax) dep |= 1u << i;
+        }
+        bool done = !valid;
+        uint32_t doneMask = __ballot_sync(0xffffffffu, done);
+        while (doneMask != 0xffffffffu)
+        {
+            if (!done && (dep & ~doneMask) == 0u)
+            {
+                shaded += sl_walk_span<FS>(P, e, y);
+                done = true;
+            }
+            __syncwarp();
+            doneMask = __ballot_sync(0xffffffffu, done);
+        }
+    }
+    for (int d = 16; d > 0; d >>= 1) shaded += __shfl_down_sync(0xffffffffu, shaded, d);
+    if (lane == 0 && shaded) atomicAdd(&P.counters->fragsShaded, (unsigned long long)shaded);
+}
+
+/* ------------------------------------------------------------------------
+ * SL_ClearProcessor::clear_texture (src/SL_ClearProcessor.cpp:23-63): typed fill
+ * ----------------------------------------------------------------------*/
+struct SLClearParams
+{
+    unsigned char* dst;
+    unsigned long long numTexels;
+    int bpt;
+    unsigned char texel[32];
+};
+
+__global__ void k_clear(const __grid_constant__ SLClearParams P)
+{
+    /* 16-byte stores: a 16-byte pattern covers bpt in {1,2,4,8,16}; other sizes go texel by texel */
+    const unsigned long long totalBytes = P.numTexels * (unsigned long long)P.bpt;
+    const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    if (16 % P.bpt == 0)
+    {
+        uint4 pat;
+        unsigned char* pb = reinterpret_cast<unsigned char*>(&pat);
+        for (int i = 0; i < 16; ++i) pb[i] = P.texel[i % P.bpt];
+        const unsigned long long n16 = totalBytes / 16ull;
+        uint4* d16 = reinterpret_cast<uint4*>(P.dst);
+        for (unsigned long long i = tid; i < n16; i += stride) d16[i] = pat;
+        for (unsigned long long i = n16 * 16ull + tid; i < totalBytes; i += stride) P.dst[i] = P.texel[i % P.bpt];
+    }
+    else
+    {
+        for (unsigned long long i = tid; i < totalBytes; i += stride) P.dst[i] = P.texel[i % P.bpt];
+    }
+}
+
+} // namespace sld

@@ -1,0 +1,62 @@
+/*
+ * sl_x86emu.cuh -- device primitives that reproduce the x86 instructions the
+ * reference's source path is written in:
+ *
+ *   rcpss/rcpps  -> sl_rcp():   2048-entry table indexed by the top 11 mantissa
+ *                   bits, exponent handled exactly; the table is measured from
+ *                   the host CPU at context creation (or pinned by a test).
+ *   minps/maxps  -> sl_min()/sl_max(): (a<b)?a:b, second operand on NaN/equal.
+ *   cvtps2dq     -> sl_cvt_rn(): RNE, 0x80000000 when out of range / NaN.
+ *   cvttps2dq    -> sl_cvt_tr().
+ *   fmadd/fmsub  -> __fmaf_rn (the TU is compiled with -fmad=false so that
+ *                   nothing else is contracted).
+ *   cmpps _OQ    -> plain C comparisons (false on NaN).
+ *   cvtps2ph     -> __float2half_rn (scalar depth path) / _rz (vec4 colour path).
+ */
+#pragma once
+
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace sld
+{
+
+/* One table per process: contexts that use a different table re-upload it
+ * before their work is enqueued (slcu.cu: ensure_rcp_table). */
+__device__ uint32_t g_rcp_table[2048];
+
+__device__ __forceinline__ float sl_rcp(float x)
+{
+    const uint32_t xb = __float_as_uint(x);
+    const uint32_t s = xb & 0x80000000u;
+    const uint32_t e = (xb >> 23) & 0xffu;
+    const uint32_t m = xb & 0x7fffffu;
+    if (e == 0xffu) return __uint_as_float(m ? (xb | 0x00400000u) : s);
+    if (e == 0u) return __uint_as_float(s | 0x7f800000u);
+    const uint32_t r = __ldg(&g_rcp_table[m >> 12]);
+    const int re = (int)((r >> 23) & 0xffu) - ((int)e - 127);
+    if (re <= 0) return __uint_as_float(s);
+    return __uint_as_float(s | ((uint32_t)re << 23) | (r & 0x7fffffu));
+}
+
+__device__ __forceinline__ float sl_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ float sl_min(float a, float b) { return (a < b) ? a : b; }
+__device__ __forceinline__ float sl_max(float a, float b) { return (a > b) ? a : b; }
+__device__ __forceinline__ bool sl_signbit(float x) { return (__float_as_uint(x) >> 31) != 0u; }
+
+__device__ __forceinline__ int32_t sl_cvt_rn(float x)
+{
+    if (!(x >= -2147483648.0f && x < 2147483648.0f)) return (int32_t)0x80000000;
+    return __float2int_rn(x);
+}
+__device__ __forceinline__ int32_t sl_cvt_tr(float x)
+{
+    if (!(x >= -2147483648.0f && x < 2147483648.0f)) return (int32_t)0x80000000;
+    return __float2int_rz(x);
+}
+
+__device__ __forceinline__ uint16_t sl_f2h_rn(float f) { return __half_as_ushort(__float2half_rn(f)); }
+__device__ __forceinline__ uint16_t sl_f2h_rz(float f) { return __half_as_ushort(__float2half_rz(f)); }
+__device__ __forceinline__ float sl_h2f(uint16_t h) { return __half2float(__ushort_as_half(h)); }
+
+} // namespace sld

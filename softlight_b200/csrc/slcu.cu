@@ -1,0 +1,867 @@
+/*
+ * slcu.cu -- host side of the C ABI (include/slcu.h): the device mirrors of
+ * SL_Context's resources and the replacements of SL_ProcessorPool::run_*.
+ *
+ * Everything here only manages memory and launches; the arithmetic of the path
+ * runs in the kernels of sl_pipeline.cuh.  The few scalars the reference
+ * computes once per draw on the host (scissor matrix, viewport rectangle,
+ * clear colours; src/SL_ViewportState.cpp:17-111, src/SL_Context.cpp:881-963)
+ * are computed here with the same rcp table the device uses.
+ *
+ * There is no CPU fallback: without a CUDA device context_create fails.
+ */
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "slcu.h"
+#include "sl_pipeline.cuh"
+
+using namespace sld;
+
+/* ===========================================================================
+ * Shader registry: SL_REGISTER_VERTEX_SHADER / SL_REGISTER_FRAGMENT_SHADER
+ * pair a name with a __device__ callable; the kernels are instantiated with it
+ * as a template argument (direct, inlinable calls -- never interpreted).
+ * =========================================================================*/
+typedef cudaError_t (*VertexLauncher)(unsigned grid, cudaStream_t s, const SLVertexParams& p);
+typedef cudaError_t (*RasterLauncher)(unsigned grid, unsigned block, cudaStream_t s, const SLRasterParams& p);
+
+struct VsEntry { const char* name; VertexLauncher launch; };
+struct FsEntry { const char* name; RasterLauncher launch; };
+static std::vector<VsEntry>& vs_registry() { static std::vector<VsEntry> r; return r; }
+static std::vector<FsEntry>& fs_registry() { static std::vector<FsEntry> r; return r; }
+
+template <VsFn VS> static cudaError_t launch_vertex(unsigned grid, cudaStream_t s, const SLVertexParams& p)
+{
+    k_vertex<VS><<<grid, SL_VB_THREADS, 0, s>>>(p);
+    return cudaGetLastError();
+}
+template <FsFn FS> static cudaError_t launch_raster(unsigned grid, unsigned block, cudaStream_t s, const SLRasterParams& p)
+{
+    k_raster<FS><<<grid, block, 0, s>>>(p);
+    return cudaGetLastError();
+}
+struct VsReg { VsReg(const char* n, VertexLauncher l) { vs_registry().push_back(VsEntry{n, l}); } };
+struct FsReg { FsReg(const char* n, RasterLauncher l) { fs_registry().push_back(FsEntry{n, l}); } };
+
+#define SL_SHADER_FN static __device__ __forceinline__
+#define SL_CAT2(a, b) a##b
+#define SL_CAT(a, b) SL_CAT2(a, b)
+#define SL_REGISTER_VERTEX_SHADER(name, fn) static VsReg SL_CAT(vsreg_, fn){name, launch_vertex<fn>};
+#define SL_REGISTER_FRAGMENT_SHADER(name, fn) static FsReg SL_CAT(fsreg_, fn){name, launch_raster<fn>};
+
+namespace sld
+{
+#include "sl_shaders_basic.inl"
+#include "sl_shaders_scene.inl"
+}
+
+/* ===========================================================================
+ * Host copies of the two x86 behaviours the per-draw host scalars need
+ * =========================================================================*/
+static inline uint32_t h_f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float h_u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+static float h_rcp(const uint32_t* table, float x)
+{
+    const uint32_t xb = h_f2u(x);
+    const uint32_t s = xb & 0x80000000u, e = (xb >> 23) & 0xffu, m = xb & 0x7fffffu;
+    if (e == 0xffu) return h_u2f(m ? (xb | 0x00400000u) : s);
+    if (e == 0u) return h_u2f(s | 0x7f800000u);
+    const uint32_t r = table[m >> 12];
+    const int re = (int)((r >> 23) & 0xffu) - ((int)e - 127);
+    if (re <= 0) return h_u2f(s);
+    return h_u2f(s | ((uint32_t)re << 23) | (r & 0x7fffffu));
+}
+static inline float h_min(float a, float b) { return a < b ? a : b; }
+static inline float h_max(float a, float b) { return a > b ? a : b; }
+
+#if defined(__x86_64__)
+static inline float host_rcpss(float x)
+{
+    float out;
+    __asm__ volatile("rcpss %1, %0" : "=x"(out) : "x"(x));
+    return out;
+}
+#endif
+
+/* The reference executes rcpss on the host CPU; to match it on the same box the
+ * table is measured from that CPU, and the "11 mantissa bits in, exponent
+ * exact" structure the device emulation relies on is verified by sampling. */
+static bool measure_host_rcp_table(uint32_t* t, std::string& err)
+{
+#if defined(__x86_64__)
+    for (uint32_t i = 0; i < 2048; ++i) t[i] = h_f2u(host_rcpss(h_u2f(0x3f800000u | (i << 12))));
+    uint64_t s = 0x9E3779B97F4A7C15ull;
+    for (int i = 0; i < 2000000; ++i)
+    {
+        s ^= s >> 12; s ^= s << 25; s ^= s >> 27;
+        const uint32_t xb = (uint32_t)((s * 0x2545F4914F6CDD1Dull) >> 32);
+        const float x = h_u2f(xb);
+        if (h_f2u(host_rcpss(x)) != h_f2u(h_rcp(t, x)))
+        {
+            err = "host rcpss is not an 11-bit table with exact exponent handling; this CPU is not supported yet";
+            return false;
+        }
+    }
+    return true;
+#else
+    (void)t;
+    err = "no x86 host: pin the rcp table with set_rcp_table";
+    return false;
+#endif
+}
+
+/* ===========================================================================
+ * Context
+ * =========================================================================*/
+struct DevBuffer
+{
+    unsigned char* ptr = nullptr;
+    size_t bytes = 0;
+};
+
+struct HostTexture
+{
+    uint16_t w = 0, h = 0, d = 0;
+    uint8_t bpt = 0, channels = 0;
+    int type = 0;
+    unsigned char* dev = nullptr;
+    size_t allocBytes = 0;
+    std::vector<unsigned char> shadow; /* only for textures written with set_texels */
+};
+
+struct HostIbo { int type = 0; uint32_t count = 0; DevBuffer buf; };
+struct HostVao { SL_VertexArray vao; int numBindings = 0; size_t vbo = (size_t)-1, ibo = (size_t)-1; };
+struct HostFbo { unsigned numColors = 0; size_t colors[4] = {(size_t)-1, (size_t)-1, (size_t)-1, (size_t)-1}; size_t depth = (size_t)-1; };
+struct HostShader { int cullMode, depthTest, depthMask, blend, numVaryings, numOutputs; VertexLauncher vs; RasterLauncher fs; size_t ubo; };
+struct UboFixup { size_t ubo, offset; int kind; size_t id, byteOffset; };
+struct HostUbo { unsigned char bytes[1024]; };
+
+struct Scratch
+{
+    DevBuffer buf;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= buf.bytes) return cudaSuccess;
+        if (buf.ptr) cudaFree(buf.ptr);
+        buf.ptr = nullptr;
+        buf.bytes = 0;
+        const size_t want = bytes + bytes / 4 + 4096;
+        cudaError_t e = cudaMalloc(&buf.ptr, want);
+        if (e == cudaSuccess) buf.bytes = want;
+        return e;
+    }
+    void release() { if (buf.ptr) cudaFree(buf.ptr); buf.ptr = nullptr; buf.bytes = 0; }
+};
+
+struct slcu_context
+{
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<DevBuffer> vbos;
+    std::vector<HostIbo> ibos;
+    std::vector<HostVao> vaos;
+    std::vector<HostUbo> ubos;
+    std::vector<HostTexture> textures;
+    std::vector<HostFbo> fbos;
+    std::vector<HostShader> shaders;
+    std::vector<UboFixup> fixups;
+    SL_Texture* devTextures = nullptr; /* device array of texture descriptors (fix-up targets) */
+    size_t devTexturesCap = 0;
+    int32_t viewport[4] = {0, 0, 65535, 65535};
+    int32_t scissor[4] = {0, 0, 65535, 65535};
+    uint32_t rcpTable[2048];
+    bool rcpValid = false;
+    std::string err;
+    slcu_stats stats{};
+    SLCounters* counters = nullptr;     /* device */
+    SLCounters* hostCounters = nullptr; /* pinned */
+    Scratch records, blockInfo, cnt, off, segSums, rowTotals, rowStart, entries;
+};
+
+static const uint32_t* g_activeRcpOwner = nullptr; /* whose table g_rcp_table currently holds */
+static uint32_t g_activeRcpCopy[2048];
+
+#define CK(call)                                                                         \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess) {                                                         \
+            c->err = std::string(#call) + ": " + cudaGetErrorString(e_);                 \
+            return SLCU_ERR_CUDA;                                                        \
+        }                                                                                \
+    } while (0)
+
+static int ensure_rcp_table(slcu_context* c)
+{
+    if (!c->rcpValid) { c->err = "no rcp table"; return SLCU_ERR_ARG; }
+    if (g_activeRcpOwner && memcmp(g_activeRcpCopy, c->rcpTable, sizeof(g_activeRcpCopy)) == 0) return 0;
+    CK(cudaDeviceSynchronize()); /* table switch: rare (tests pinning a table) */
+    CK(cudaMemcpyToSymbol(g_rcp_table, c->rcpTable, sizeof(c->rcpTable)));
+    memcpy(g_activeRcpCopy, c->rcpTable, sizeof(g_activeRcpCopy));
+    g_activeRcpOwner = c->rcpTable;
+    return 0;
+}
+
+static inline unsigned chan_bytes(int type) { static const unsigned b[7] = {1, 2, 4, 8, 2, 4, 8}; return b[type % 7]; }
+
+static int upload_texture_descs(slcu_context* c)
+{
+    const size_t n = c->textures.size();
+    if (n > c->devTexturesCap)
+    {
+        /* descriptors must not move once a draw may be in flight: sync, then grow */
+        CK(cudaStreamSynchronize(c->stream));
+        if (c->devTextures) cudaFree(c->devTextures);
+        c->devTexturesCap = n + 64;
+        CK(cudaMalloc(&c->devTextures, c->devTexturesCap * sizeof(SL_Texture)));
+    }
+    std::vector<SL_Texture> h(n);
+    for (size_t i = 0; i < n; ++i)
+    {
+        const HostTexture& t = c->textures[i];
+        h[i].mWidth = t.w; h[i].mHeight = t.h; h[i].mDepth = t.d; h[i].mBpt = t.bpt; h[i].mChannels = t.channels;
+        h[i].mType = t.type; h[i].mTexels = t.dev;
+    }
+    if (n) CK(cudaMemcpyAsync(c->devTextures, h.data(), n * sizeof(SL_Texture), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream)); /* h goes out of scope */
+    return 0;
+}
+
+/* ===========================================================================
+ * Per-draw host scalars (src/SL_ViewportState.cpp:17-111)
+ * =========================================================================*/
+static void host_scissor_matrix(const slcu_context* c, float fboW, float fboH, float m[16])
+{
+    const uint32_t* T = c->rcpTable;
+    const float inv[4] = {h_rcp(T, fboW), h_rcp(T, fboH), h_rcp(T, fboW), h_rcp(T, fboH)};
+    float x = (float)c->scissor[0] * inv[0], y = (float)c->scissor[1] * inv[1];
+    float w = (float)c->scissor[2] * inv[2], h = (float)c->scissor[3] * inv[3];
+    if (x < 0.f) { w += x; x = 0.f; }
+    if (y < 0.f) { h += y; y = 0.f; }
+    w = h_min(1.f - x, w);
+    h = h_min(1.f - y, h);
+    const float nm00 = h_rcp(T, w), nm11 = h_rcp(T, h);
+    const float nm30 = nm00 - 1.f, nm31 = nm11 - 1.f;
+    const float m30 = fmaf(x, (-2.f * nm00), nm30);
+    const float m31 = fmaf(y, (-2.f * nm11), nm31);
+    const float r[16] = {nm00, 0.f, 0.f, 0.f, 0.f, nm11, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f, m30, m31, 0.f, 1.f};
+    memcpy(m, r, sizeof(r));
+}
+
+static void host_viewport_rect(const slcu_context* c, float fboW, float fboH, float d[4])
+{
+    const float s0 = (float)c->scissor[0], s1 = (float)c->scissor[1], s2 = (float)c->scissor[2], s3 = (float)c->scissor[3];
+    d[0] = (float)c->viewport[0]; d[1] = (float)c->viewport[1]; d[2] = (float)c->viewport[2]; d[3] = (float)c->viewport[3];
+    /* clamp(n,lo,hi) = max(min(n,hi),lo); min(a,b,c) = min(c, min(a,b)) (x86/scalarf_utils_impl.h:32-38,88) */
+    d[0] = h_max(h_min(d[0] + s0, fboW), 0.f);
+    d[1] = h_max(h_min(d[1] + s1, fboH), 0.f);
+    d[2] = h_min(fboW - d[0], h_min(d[2], (s0 + s2) - d[0]));
+    d[3] = h_min(fboH - d[1], h_min(d[3], (s1 + s3) - d[1]));
+}
+
+/* ===========================================================================
+ * run_shader_processors replacement
+ * =========================================================================*/
+static void snapshot_uniforms(slcu_context* c, size_t ubo, SL_UniformBuffer& out)
+{
+    memcpy(out.mBytes, c->ubos[ubo].bytes, 1024);
+    for (const UboFixup& f : c->fixups)
+    {
+        if (f.ubo != ubo) continue;
+        const void* ptr;
+        if (f.kind == 0) ptr = c->devTextures + f.id;
+        else ptr = c->vbos[f.id].ptr + f.byteOffset;
+        memcpy(out.mBytes + f.offset, &ptr, sizeof(ptr));
+    }
+}
+
+static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, size_t numInstances, size_t shaderId, size_t fboId)
+{
+    if (!meshes || !numMeshes) return 0;
+    if (shaderId >= c->shaders.size() || fboId >= c->fbos.size()) { c->err = "bad shader/fbo id"; return SLCU_ERR_ARG; }
+    const HostShader& sh = c->shaders[shaderId];
+    const HostFbo& fbo = c->fbos[fboId];
+    if (fbo.depth == (size_t)-1 || fbo.depth >= c->textures.size()) { c->err = "fbo has no depth attachment"; return SLCU_ERR_ARG; }
+    const HostTexture& depthTex = c->textures[fbo.depth];
+    if (depthTex.h > SL_MAX_ROWS) { c->err = "framebuffer taller than SL_MAX_ROWS"; return SLCU_ERR_UNSUPPORTED; }
+    if (depthTex.bpt != 2 && depthTex.bpt != 4 && depthTex.bpt != 8) { c->err = "depth attachment must be R_HALF/R_FLOAT/R_DOUBLE"; return SLCU_ERR_ARG; }
+    int rc = ensure_rcp_table(c);
+    if (rc) return rc;
+    cudaSetDevice(c->device);
+
+    const float fboW = (float)depthTex.w, fboH = (float)depthTex.h;
+    const unsigned H = depthTex.h;
+    const unsigned rowPitch = (H + 31u) & ~31u;
+    const int NV = sh.numVaryings;
+    const int recStride = 3 + 3 * NV;
+
+    /* ---- vertex stage: one launch per mesh (draw_multiple) or one for all instances ---- */
+    std::vector<unsigned> launchBlocks;
+    unsigned long long totalPrims = 0;
+    const size_t launches = (numInstances == 1) ? numMeshes : 1;
+    for (size_t i = 0; i < launches; ++i)
+    {
+        const unsigned long long prims = (meshes[i].elementEnd - meshes[i].elementBegin + 2) / 3 * (numInstances == 1 ? 1 : numInstances);
+        /* the reference loop is `for (i = begin; i < end; i += 3)` (src/SL_TriProcessor.cpp:574) */
+        launchBlocks.push_back((unsigned)((prims + SL_VB_PRIMS - 1) / SL_VB_PRIMS));
+        totalPrims += prims;
+    }
+    unsigned numBlocks = 0;
+    for (unsigned b : launchBlocks) numBlocks += b;
+    c->stats.drawCalls++;
+    c->stats.trisSubmitted += totalPrims;
+    if (!numBlocks) return 0;
+
+    unsigned long long recCapacity = totalPrims + totalPrims / 8 + 4096;
+    for (int attempt = 0;; ++attempt)
+    {
+        if (recCapacity > 0xfffffff0ull) { c->err = "draw too large for one batch"; return SLCU_ERR_UNSUPPORTED; }
+        CK(c->records.ensure((size_t)recCapacity * recStride * sizeof(float4)));
+        CK(c->blockInfo.ensure((size_t)numBlocks * sizeof(SLBlockInfo)));
+        CK(cudaMemsetAsync(&c->counters->recAlloc, 0, sizeof(unsigned long long), c->stream));
+
+        unsigned firstBlock = 0;
+        for (size_t i = 0; i < launches; ++i)
+        {
+            if (!launchBlocks[i]) continue;
+            const slcu_mesh& m = meshes[i];
+            if (m.vaoId >= c->vaos.size()) { c->err = "bad vao id"; return SLCU_ERR_ARG; }
+            const HostVao& vao = c->vaos[m.vaoId];
+            if (vao.vbo >= c->vbos.size()) { c->err = "vao has no vertex buffer"; return SLCU_ERR_ARG; }
+            SLVertexParams vp;
+            snapshot_uniforms(c, sh.ubo, vp.uniforms);
+            vp.vao = vao.vao;
+            vp.vbo.mBuffer = c->vbos[vao.vbo].ptr;
+            const bool usingIndices = (m.mode == 0x30u) || (m.mode == 0x70u);
+            vp.usingIndices = usingIndices ? 1 : 0;
+            vp.ibo = nullptr;
+            vp.iboType = 2;
+            if (usingIndices)
+            {
+                if (vao.ibo >= c->ibos.size()) { c->err = "indexed draw without index buffer"; return SLCU_ERR_ARG; }
+                vp.ibo = c->ibos[vao.ibo].buf.ptr;
+                vp.iboType = c->ibos[vao.ibo].type;
+            }
+            vp.cullMode = sh.cullMode;
+            vp.numVaryings = NV;
+            host_scissor_matrix(c, fboW, fboH, vp.scissor);
+            host_viewport_rect(c, fboW, fboH, vp.viewport);
+            vp.elementBegin = m.elementBegin;
+            vp.primsPerInstance = (m.elementEnd - m.elementBegin + 2) / 3;
+            vp.numPrims = vp.primsPerInstance * (numInstances == 1 ? 1 : numInstances);
+            vp.firstBlock = firstBlock;
+            vp.recCapacity = (unsigned)recCapacity;
+            vp.records = reinterpret_cast<float4*>(c->records.buf.ptr);
+            vp.blockInfo = reinterpret_cast<SLBlockInfo*>(c->blockInfo.buf.ptr);
+            vp.counters = c->counters;
+            CK(sh.vs(launchBlocks[i], c->stream, vp));
+            c->stats.kernelLaunches++;
+            firstBlock += launchBlocks[i];
+        }
+
+        /* ---- span count + scans ---- */
+        CK(c->cnt.ensure((size_t)numBlocks * rowPitch * sizeof(uint16_t)));
+        CK(c->off.ensure((size_t)numBlocks * rowPitch * sizeof(uint32_t)));
+        const unsigned numSegs = numBlocks < (unsigned)SL_SCAN_SEGS ? numBlocks : (unsigned)SL_SCAN_SEGS;
+        const unsigned blocksPerSeg = (numBlocks + numSegs - 1) / numSegs;
+        const unsigned usedSegs = (numBlocks + blocksPerSeg - 1) / blocksPerSeg;
+        CK(c->segSums.ensure((size_t)usedSegs * rowPitch * sizeof(uint32_t)));
+        CK(c->rowTotals.ensure((size_t)rowPitch * sizeof(uint32_t)));
+        CK(c->rowStart.ensure((size_t)(H + 1) * sizeof(uint32_t)));
+
+        SLSpanParams sp;
+        sp.records = reinterpret_cast<const float4*>(c->records.buf.ptr);
+        sp.blockInfo = reinterpret_cast<const SLBlockInfo*>(c->blockInfo.buf.ptr);
+        sp.firstBlock = 0;
+        sp.numRows = H;
+        sp.rowPitch = rowPitch;
+        sp.recStride = recStride;
+        sp.cnt = reinterpret_cast<uint16_t*>(c->cnt.buf.ptr);
+        sp.off = reinterpret_cast<const uint32_t*>(c->off.buf.ptr);
+        sp.rowStart = reinterpret_cast<const uint32_t*>(c->rowStart.buf.ptr);
+        sp.entries = nullptr;
+        sp.counters = c->counters;
+        k_span<0><<<numBlocks, 256, 0, c->stream>>>(sp);
+        CK(cudaGetLastError());
+        const dim3 sgrid((rowPitch + 127) / 128, usedSegs);
+        k_scan_seg_sums<<<sgrid, 128, 0, c->stream>>>(sp.cnt, reinterpret_cast<uint32_t*>(c->segSums.buf.ptr), numBlocks, rowPitch, blocksPerSeg);
+        CK(cudaGetLastError());
+        k_scan_rows<<<(rowPitch + 127) / 128, 128, 0, c->stream>>>(reinterpret_cast<uint32_t*>(c->segSums.buf.ptr), reinterpret_cast<uint32_t*>(c->rowTotals.buf.ptr), rowPitch, usedSegs);
+        CK(cudaGetLastError());
+        k_scan_row_starts<<<1, 1024, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(c->rowTotals.buf.ptr), reinterpret_cast<uint32_t*>(c->rowStart.buf.ptr), H, c->counters);
+        CK(cudaGetLastError());
+        k_scan_offsets<<<sgrid, 128, 0, c->stream>>>(sp.cnt, reinterpret_cast<const uint32_t*>(c->segSums.buf.ptr), reinterpret_cast<uint32_t*>(c->off.buf.ptr), numBlocks, rowPitch, blocksPerSeg);
+        CK(cudaGetLastError());
+        c->stats.kernelLaunches += 5;
+
+        /* the span lists are sized from the count: one small read-back per draw */
+        uint32_t totalSpans = 0;
+        CK(cudaMemcpyAsync(c->hostCounters, c->counters, sizeof(SLCounters), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(&c->hostCounters[1], reinterpret_cast<uint32_t*>(c->rowStart.buf.ptr) + H, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        memcpy(&totalSpans, &c->hostCounters[1], sizeof(uint32_t));
+        if (c->hostCounters->errorFlags & 1u)
+        {
+            /* more records than reserved (heavy clipping): retry once with the worst case */
+            CK(cudaMemsetAsync(&c->counters->errorFlags, 0, sizeof(unsigned), c->stream));
+            if (attempt == 0) { recCapacity = totalPrims * 7 + 4096; continue; }
+            c->err = "triangle record buffer overflow";
+            return SLCU_ERR_OOM;
+        }
+        if (!totalSpans) return 0;
+
+        CK(c->entries.ensure((size_t)totalSpans * sizeof(SLSpanEntry)));
+        sp.entries = reinterpret_cast<SLSpanEntry*>(c->entries.buf.ptr);
+        k_span<1><<<numBlocks, 256, 0, c->stream>>>(sp);
+        CK(cudaGetLastError());
+        c->stats.kernelLaunches++;
+        break;
+    }
+
+    /* ---- fragment stage ---- */
+    SLRasterParams rp;
+    snapshot_uniforms(c, sh.ubo, rp.uniforms);
+    rp.records = reinterpret_cast<const float4*>(c->records.buf.ptr);
+    rp.entries = reinterpret_cast<const SLSpanEntry*>(c->entries.buf.ptr);
+    rp.rowStart = reinterpret_cast<const uint32_t*>(c->rowStart.buf.ptr);
+    rp.recStride = recStride;
+    rp.numVaryings = NV;
+    rp.numOutputs = sh.numOutputs;
+    rp.depthTest = sh.depthTest;
+    rp.depthMask = sh.depthMask;
+    rp.blend = sh.blend;
+    rp.numRows = H;
+    rp.width = depthTex.w;
+    rp.depth = depthTex.dev;
+    rp.depthBpt = depthTex.bpt;
+    for (int i = 0; i < 4; ++i)
+    {
+        rp.color[i] = nullptr;
+        rp.colorType[i] = 0;
+        rp.colorWidth[i] = 0;
+        if (i < sh.numOutputs)
+        {
+            if ((unsigned)i >= fbo.numColors || fbo.colors[i] >= c->textures.size()) { c->err = "shader writes an unattached colour buffer"; return SLCU_ERR_ARG; }
+            const HostTexture& t = c->textures[fbo.colors[i]];
+            const int kind = t.type % 7;
+            if (kind == 2 || kind == 3) { c->err = "32/64-bit integer colour targets are not implemented"; return SLCU_ERR_UNSUPPORTED; }
+            rp.color[i] = t.dev;
+            rp.colorType[i] = t.type;
+            rp.colorWidth[i] = t.w;
+        }
+    }
+    rp.counters = c->counters;
+    const unsigned warpsPerBlock = 4;
+    CK(sh.fs((H + warpsPerBlock - 1) / warpsPerBlock, warpsPerBlock * 32, c->stream, rp));
+    c->stats.kernelLaunches++;
+    return 0;
+}
+
+/* ===========================================================================
+ * run_clear_processors replacement (src/SL_Context.cpp:881-963)
+ * =========================================================================*/
+static void host_match_color(int type, const double rgba[4], unsigned char out[32])
+{
+    /* sl_match_color_for_type (src/SL_Color.cpp:135-190): color_cast<T,double> = (T)(c * max) element-wise */
+    const int kind = type % 7;
+    const unsigned n = (unsigned)(type / 7 + 1);
+    for (unsigned i = 0; i < n; ++i)
+    {
+        switch (kind)
+        {
+            case 0: { const uint8_t v = (uint8_t)(rgba[i] * 255.0); out[i] = v; break; }
+            case 1: { const uint16_t v = (uint16_t)(rgba[i] * 65535.0); memcpy(out + 2 * i, &v, 2); break; }
+            case 2: { const uint32_t v = (uint32_t)(rgba[i] * 4294967295.0); memcpy(out + 4 * i, &v, 4); break; }
+            case 3: { const uint64_t v = (uint64_t)(rgba[i] * 18446744073709551615.0); memcpy(out + 8 * i, &v, 8); break; }
+            case 4: { const __half hv = __float2half_rn((float)rgba[i]); memcpy(out + 2 * i, &hv, 2); break; }
+            case 5: { const float v = (float)rgba[i]; memcpy(out + 4 * i, &v, 4); break; }
+            default: memcpy(out + 8 * i, &rgba[i], 8); break;
+        }
+    }
+}
+
+static bool host_depth_texel(const HostTexture& t, double depth, unsigned char out[8])
+{
+    switch (t.bpt)
+    {
+        case 2: { const __half hv = __float2half_rn((float)depth); memcpy(out, &hv, 2); return true; }
+        case 4: { const float f = (float)depth; memcpy(out, &f, 4); return true; }
+        case 8: memcpy(out, &depth, 8); return true;
+        default: return false;
+    }
+}
+
+static int clear_texture(slcu_context* c, const HostTexture& t, const unsigned char* texel)
+{
+    SLClearParams p;
+    p.dst = t.dev;
+    p.numTexels = (unsigned long long)t.w * t.h; /* the reference ignores the depth dimension (src/SL_ClearProcessor.cpp:23-63) */
+    p.bpt = t.bpt;
+    memset(p.texel, 0, sizeof(p.texel));
+    memcpy(p.texel, texel, t.bpt);
+    const unsigned long long bytes = p.numTexels * t.bpt;
+    unsigned grid = (unsigned)((bytes / 16 + 255) / 256);
+    if (grid < 1) grid = 1;
+    if (grid > 148 * 16) grid = 148 * 16;
+    k_clear<<<grid, 256, 0, c->stream>>>(p);
+    CK(cudaGetLastError());
+    c->stats.kernelLaunches++;
+    return 0;
+}
+
+/* ===========================================================================
+ * C ABI
+ * =========================================================================*/
+extern "C" {
+
+int slcu_context_create(slcu_context** out, int device)
+{
+    if (!out) return SLCU_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return SLCU_ERR_NO_DEVICE;
+    if (cudaSetDevice(device) != cudaSuccess) return SLCU_ERR_CUDA;
+    slcu_context* c = new slcu_context{};
+    c->device = device;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return SLCU_ERR_CUDA; }
+    if (cudaMalloc(&c->counters, sizeof(SLCounters)) != cudaSuccess) { delete c; return SLCU_ERR_CUDA; }
+    cudaMemset(c->counters, 0, sizeof(SLCounters));
+    if (cudaMallocHost(&c->hostCounters, 2 * sizeof(SLCounters)) != cudaSuccess) { delete c; return SLCU_ERR_CUDA; }
+    c->rcpValid = measure_host_rcp_table(c->rcpTable, c->err);
+    *out = c;
+    return 0;
+}
+
+void slcu_context_destroy(slcu_context* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (DevBuffer& b : c->vbos) if (b.ptr) cudaFree(b.ptr);
+    for (HostIbo& b : c->ibos) if (b.buf.ptr) cudaFree(b.buf.ptr);
+    for (HostTexture& t : c->textures) if (t.dev) cudaFree(t.dev);
+    if (c->devTextures) cudaFree(c->devTextures);
+    if (c->counters) cudaFree(c->counters);
+    if (c->hostCounters) cudaFreeHost(c->hostCounters);
+    Scratch* s[] = {&c->records, &c->blockInfo, &c->cnt, &c->off, &c->segSums, &c->rowTotals, &c->rowStart, &c->entries};
+    for (Scratch* x : s) x->release();
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+unsigned slcu_num_threads(slcu_context*, unsigned n) { return n < 1 ? 1 : n; } /* src/SL_ProcessorPool.cpp:231-274: returns the value set */
+const char* slcu_last_error(slcu_context* c) { return c ? c->err.c_str() : ""; }
+const char* slcu_impl_name(void) { return "softlight-b200 (sm_100a CUDA)"; }
+
+int slcu_set_rcp_table(slcu_context* c, const uint32_t* t)
+{
+    if (!c || !t) return SLCU_ERR_ARG;
+    memcpy(c->rcpTable, t, sizeof(c->rcpTable));
+    c->rcpValid = true;
+    return 0;
+}
+int slcu_get_rcp_table(slcu_context* c, uint32_t* t)
+{
+    if (!c || !t || !c->rcpValid) return SLCU_ERR_ARG;
+    memcpy(t, c->rcpTable, sizeof(c->rcpTable));
+    return 0;
+}
+
+size_t slcu_create_vbo(slcu_context* c) { c->vbos.emplace_back(); return c->vbos.size() - 1; }
+size_t slcu_create_ibo(slcu_context* c) { c->ibos.emplace_back(); return c->ibos.size() - 1; }
+size_t slcu_create_vao(slcu_context* c) { c->vaos.emplace_back(); memset(&c->vaos.back().vao, 0, sizeof(SL_VertexArray)); return c->vaos.size() - 1; }
+size_t slcu_create_ubo(slcu_context* c) { c->ubos.emplace_back(); memset(c->ubos.back().bytes, 0, 1024); return c->ubos.size() - 1; }
+size_t slcu_create_texture(slcu_context* c) { c->textures.emplace_back(); return c->textures.size() - 1; }
+size_t slcu_create_framebuffer(slcu_context* c) { c->fbos.emplace_back(); return c->fbos.size() - 1; }
+
+int slcu_vbo_init(slcu_context* c, size_t vbo, size_t numBytes)
+{
+    if (vbo >= c->vbos.size()) return SLCU_ERR_ARG;
+    cudaSetDevice(c->device);
+    DevBuffer& b = c->vbos[vbo];
+    CK(cudaStreamSynchronize(c->stream));
+    if (b.ptr) cudaFree(b.ptr);
+    b.ptr = nullptr;
+    b.bytes = 0;
+    CK(cudaMalloc(&b.ptr, numBytes + 64));
+    CK(cudaMemsetAsync(b.ptr, 0, numBytes + 64, c->stream));
+    b.bytes = numBytes;
+    return 0;
+}
+
+int slcu_vbo_assign(slcu_context* c, size_t vbo, const void* data, size_t offset, size_t numBytes)
+{
+    if (vbo >= c->vbos.size() || !data || offset + numBytes > c->vbos[vbo].bytes) return SLCU_ERR_ARG;
+    cudaSetDevice(c->device);
+    CK(cudaMemcpyAsync(c->vbos[vbo].ptr + offset, data, numBytes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream)); /* the caller may reuse `data` on return */
+    return 0;
+}
+
+int slcu_ibo_init(slcu_context* c, size_t ibo, uint32_t numElements, int dataType, const void* data)
+{
+    if (ibo >= c->ibos.size() || dataType < 0 || dataType > 2) return SLCU_ERR_ARG;
+    cudaSetDevice(c->device);
+    HostIbo& b = c->ibos[ibo];
+    CK(cudaStreamSynchronize(c->stream));
+    if (b.buf.ptr) cudaFree(b.buf.ptr);
+    const size_t bytes = (size_t)numElements << dataType;
+    CK(cudaMalloc(&b.buf.ptr, bytes + 16)); /* padded like src/SL_IndexBuffer.cpp:138-161 */
+    CK(cudaMemsetAsync(b.buf.ptr, 0, bytes + 16, c->stream));
+    b.buf.bytes = bytes;
+    b.type = dataType;
+    b.count = numElements;
+    if (data)
+    {
+        CK(cudaMemcpyAsync(b.buf.ptr, data, bytes, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+int slcu_vao_set_vertex_buffer(slcu_context* c, size_t vao, size_t vbo) { if (vao >= c->vaos.size()) return SLCU_ERR_ARG; c->vaos[vao].vbo = vbo; return 0; }
+int slcu_vao_set_index_buffer(slcu_context* c, size_t vao, size_t ibo) { if (vao >= c->vaos.size()) return SLCU_ERR_ARG; c->vaos[vao].ibo = ibo; return 0; }
+int slcu_vao_set_num_bindings(slcu_context* c, size_t vao, int n)
+{
+    if (vao >= c->vaos.size() || n < 0 || n >= 8) return -1; /* src/SL_VertexArray.cpp:162-167 */
+    c->vaos[vao].numBindings = n;
+    return n;
+}
+int slcu_vao_set_binding(slcu_context* c, size_t vao, size_t bind, ptrdiff_t offset, ptrdiff_t stride, int dim, int type)
+{
+    if (vao >= c->vaos.size() || bind >= 8) return SLCU_ERR_ARG;
+    c->vaos[vao].vao.mBindings[bind] = SL_VertexArray::Binding{dim, type, offset, stride};
+    return 0;
+}
+
+int slcu_ubo_assign(slcu_context* c, size_t ubo, const void* data, size_t offset, size_t numBytes)
+{
+    if (ubo >= c->ubos.size() || !data || offset + numBytes > 1024) return SLCU_ERR_ARG;
+    memcpy(c->ubos[ubo].bytes + offset, data, numBytes);
+    return 0;
+}
+static void set_fixup(slcu_context* c, const UboFixup& f)
+{
+    for (UboFixup& g : c->fixups) { if (g.ubo == f.ubo && g.offset == f.offset) { g = f; return; } }
+    c->fixups.push_back(f);
+}
+int slcu_ubo_bind_texture(slcu_context* c, size_t ubo, size_t offset, size_t tex)
+{
+    if (ubo >= c->ubos.size() || offset + 8 > 1024 || tex >= c->textures.size()) return SLCU_ERR_ARG;
+    set_fixup(c, UboFixup{ubo, offset, 0, tex, 0});
+    return 0;
+}
+int slcu_ubo_bind_buffer(slcu_context* c, size_t ubo, size_t offset, size_t vbo, size_t byteOffset)
+{
+    if (ubo >= c->ubos.size() || offset + 8 > 1024 || vbo >= c->vbos.size()) return SLCU_ERR_ARG;
+    set_fixup(c, UboFixup{ubo, offset, 1, vbo, byteOffset});
+    return 0;
+}
+
+int slcu_texture_init(slcu_context* c, size_t tex, int type, uint16_t w, uint16_t h, uint16_t d)
+{
+    if (tex >= c->textures.size() || type < 0 || type >= 28) return -1;
+    cudaSetDevice(c->device);
+    HostTexture& t = c->textures[tex];
+    CK(cudaStreamSynchronize(c->stream));
+    if (t.dev) cudaFree(t.dev);
+    t.dev = nullptr;
+    t.shadow.clear();
+    t.w = w; t.h = h; t.d = d; t.type = type;
+    t.channels = (uint8_t)(type / 7 + 1);
+    t.bpt = (uint8_t)(chan_bytes(type) * t.channels);
+    /* _sl_allocate_texture (src/SL_Texture.cpp:28-54): w,h padded up by 4-(dim%4), zero-filled.  The reference also
+     * pads the depth to 4+ slices even for 2-D textures; the device copy keeps only the slices that can be addressed. */
+    const size_t pw = w + (4 - (w % 4)), ph = h + (4 - (h % 4)), pd = (d <= 1) ? 1 : (size_t)d + (4 - (d % 4));
+    t.allocBytes = pw * ph * pd * t.bpt + 4 * t.bpt;
+    CK(cudaMalloc(&t.dev, t.allocBytes));
+    CK(cudaMemsetAsync(t.dev, 0, t.allocBytes, c->stream));
+    return upload_texture_descs(c);
+}
+
+int slcu_texture_set_texels(slcu_context* c, size_t tex, int order, uint16_t x, uint16_t y, uint16_t z, uint16_t w, uint16_t h, uint16_t d, const void* data)
+{
+    if (tex >= c->textures.size() || !data) return SLCU_ERR_ARG;
+    cudaSetDevice(c->device);
+    HostTexture& t = c->textures[tex];
+    if (!t.dev) return SLCU_ERR_ARG;
+    if (t.shadow.empty())
+    {
+        t.shadow.assign(t.allocBytes, 0);
+        CK(cudaMemcpyAsync(t.shadow.data(), t.dev, t.allocBytes, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    /* SL_Texture::set_texels<order> (SL_Texture.hpp:418-444) on the shadow, then one upload */
+    const unsigned char* src = (const unsigned char*)data;
+    const uint32_t W = t.w, Hh = t.h;
+    for (uint32_t k = 0, z0 = z; k < d; ++k, ++z0)
+        for (uint32_t j = 0, y0 = y; j < h; ++j, ++y0)
+            for (uint32_t i = 0, x0 = x; i < w; ++i, ++x0)
+            {
+                const size_t index = i + (size_t)w * (j + ((size_t)h * k));
+                size_t dst;
+                if (order == 0) dst = (t.d <= 1) ? (x0 + (size_t)W * y0) : (x0 + (size_t)W * (y0 + (size_t)Hh * z0));
+                else if (t.d <= 1) dst = ((x0 & 3u) + ((y0 & 3u) << 2)) + (size_t)((x0 >> 2) + (W >> 2) * (y0 >> 2)) * 16u;
+                else dst = ((x0 & 3u) + (((y0 & 3u) << 2) + (4u * ((z0 & 3u) << 2)))) + (size_t)((x0 >> 2) + ((W >> 2) * ((y0 >> 2) + ((Hh >> 2) * (z0 >> 2))))) * 64u;
+                if ((dst + 1) * t.bpt > t.allocBytes) return SLCU_ERR_ARG;
+                memcpy(t.shadow.data() + dst * t.bpt, src + index * t.bpt, t.bpt);
+            }
+    CK(cudaMemcpyAsync(t.dev, t.shadow.data(), t.allocBytes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int slcu_texture_read(slcu_context* c, size_t tex, void* out, size_t numBytes)
+{
+    if (tex >= c->textures.size() || !out || numBytes > c->textures[tex].allocBytes) return SLCU_ERR_ARG;
+    cudaSetDevice(c->device);
+    CK(cudaMemcpyAsync(out, c->textures[tex].dev, numBytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int slcu_fbo_reserve_color_buffers(slcu_context* c, size_t fbo, unsigned n)
+{
+    if (fbo >= c->fbos.size()) return SLCU_ERR_ARG;
+    if (n < 1) return -1; /* src/SL_Framebuffer.cpp:823-848 */
+    if (n > 4) return -2;
+    c->fbos[fbo] = HostFbo{};
+    c->fbos[fbo].numColors = n;
+    return 0;
+}
+int slcu_fbo_attach_color_buffer(slcu_context* c, size_t fbo, unsigned index, size_t tex)
+{
+    if (fbo >= c->fbos.size() || tex >= c->textures.size()) return SLCU_ERR_ARG;
+    if (index >= c->fbos[fbo].numColors) return -1;
+    c->fbos[fbo].colors[index] = tex;
+    return 0;
+}
+int slcu_fbo_attach_depth_buffer(slcu_context* c, size_t fbo, size_t tex)
+{
+    if (fbo >= c->fbos.size() || tex >= c->textures.size()) return SLCU_ERR_ARG;
+    c->fbos[fbo].depth = tex;
+    return 0;
+}
+int slcu_fbo_valid(slcu_context* c, size_t fbo)
+{
+    /* SL_Framebuffer::valid (src/SL_Framebuffer.cpp:930-990) */
+    if (fbo >= c->fbos.size()) return SLCU_ERR_ARG;
+    const HostFbo& f = c->fbos[fbo];
+    if (!f.numColors) return -1;
+    for (unsigned i = 0; i < f.numColors; ++i)
+    {
+        if (f.colors[i] == (size_t)-1 || !c->textures[f.colors[i]].dev) return -3;
+    }
+    if (f.depth == (size_t)-1 || !c->textures[f.depth].dev) return -6;
+    const HostTexture& d = c->textures[f.depth];
+    if (d.type != 4 && d.type != 5 && d.type != 6) return -8;
+    for (unsigned i = 0; i < f.numColors; ++i)
+    {
+        const HostTexture& t = c->textures[f.colors[i]];
+        if (t.w != d.w || t.h != d.h) return -10;
+    }
+    return 0;
+}
+
+size_t slcu_create_shader(slcu_context* c, const slcu_vertex_shader* vs, const slcu_fragment_shader* fs, size_t ubo)
+{
+    /* validation of SL_Context::create_shader (src/SL_Context.cpp:488-540) */
+    if (!vs || !fs || !vs->shader || !fs->shader || ubo >= c->ubos.size()) return SLCU_INVALID_ID;
+    if (vs->numVaryings > 4 || fs->numVaryings > vs->numVaryings || fs->numOutputs > 4 || fs->numOutputs < 1) return SLCU_INVALID_ID;
+    if (vs->cullMode > 2 || fs->blend > 4 || fs->depthTest > 6 || fs->depthMask > 1) return SLCU_INVALID_ID;
+    VertexLauncher vl = nullptr;
+    RasterLauncher fl = nullptr;
+    for (const VsEntry& e : vs_registry()) if (!strcmp(e.name, vs->shader)) vl = e.launch;
+    for (const FsEntry& e : fs_registry()) if (!strcmp(e.name, fs->shader)) fl = e.launch;
+    if (!vl || !fl)
+    {
+        c->err = "shader not registered as a __device__ callable (no CPU fallback)";
+        return SLCU_INVALID_ID;
+    }
+    HostShader s;
+    s.cullMode = vs->cullMode; s.depthTest = fs->depthTest; s.depthMask = fs->depthMask; s.blend = fs->blend;
+    s.numVaryings = fs->numVaryings; s.numOutputs = fs->numOutputs; s.vs = vl; s.fs = fl; s.ubo = ubo;
+    c->shaders.push_back(s);
+    return c->shaders.size() - 1;
+}
+
+int slcu_viewport(slcu_context* c, int32_t x, int32_t y, uint16_t w, uint16_t h) { c->viewport[0] = x; c->viewport[1] = y; c->viewport[2] = w; c->viewport[3] = h; return 0; }
+int slcu_scissor(slcu_context* c, int32_t x, int32_t y, uint16_t w, uint16_t h) { c->scissor[0] = x; c->scissor[1] = y; c->scissor[2] = w; c->scissor[3] = h; return 0; }
+
+int slcu_clear_color_buffer(slcu_context* c, size_t fbo, unsigned att, const double rgba[4])
+{
+    if (fbo >= c->fbos.size() || att >= c->fbos[fbo].numColors || c->fbos[fbo].colors[att] >= c->textures.size()) return SLCU_ERR_ARG;
+    cudaSetDevice(c->device);
+    const HostTexture& t = c->textures[c->fbos[fbo].colors[att]];
+    unsigned char texel[32];
+    host_match_color(t.type, rgba, texel);
+    return clear_texture(c, t, texel);
+}
+int slcu_clear_depth_buffer(slcu_context* c, size_t fbo, double depth)
+{
+    if (fbo >= c->fbos.size() || c->fbos[fbo].depth >= c->textures.size()) return SLCU_ERR_ARG;
+    cudaSetDevice(c->device);
+    const HostTexture& t = c->textures[c->fbos[fbo].depth];
+    unsigned char texel[8];
+    if (!host_depth_texel(t, depth, texel)) return 0; /* silently ignored like src/SL_Context.cpp:904-920 */
+    return clear_texture(c, t, texel);
+}
+int slcu_clear_framebuffer(slcu_context* c, size_t fbo, unsigned att, const double rgba[4], double depth)
+{
+    if (fbo >= c->fbos.size() || c->fbos[fbo].depth >= c->textures.size()) return SLCU_ERR_ARG;
+    const HostTexture& d = c->textures[c->fbos[fbo].depth];
+    unsigned char texel[8];
+    if (!host_depth_texel(d, depth, texel)) return 0; /* src/SL_Context.cpp:944-960 returns before clearing anything */
+    int rc = slcu_clear_color_buffer(c, fbo, att, rgba);
+    if (rc) return rc;
+    return clear_texture(c, d, texel);
+}
+
+int slcu_draw(slcu_context* c, const slcu_mesh* m, size_t shader, size_t fbo) { return run_draw(c, m, 1, 1, shader, fbo); }
+int slcu_draw_multiple(slcu_context* c, const slcu_mesh* m, size_t n, size_t shader, size_t fbo) { return run_draw(c, m, n, 1, shader, fbo); }
+int slcu_draw_instanced(slcu_context* c, const slcu_mesh* m, size_t inst, size_t shader, size_t fbo) { return run_draw(c, m, 1, inst, shader, fbo); }
+
+int slcu_blit(slcu_context* c, size_t, size_t) { c->err = "blit: not implemented yet"; return SLCU_ERR_UNSUPPORTED; }
+int slcu_blit_rect(slcu_context* c, size_t, size_t, uint16_t, uint16_t, uint16_t, uint16_t, uint16_t, uint16_t, uint16_t, uint16_t)
+{
+    c->err = "blit: not implemented yet";
+    return SLCU_ERR_UNSUPPORTED;
+}
+
+int slcu_sync(slcu_context* c)
+{
+    cudaSetDevice(c->device);
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int slcu_reset_stats(slcu_context* c)
+{
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    memset(&c->stats, 0, sizeof(c->stats));
+    CK(cudaMemsetAsync(c->counters, 0, sizeof(SLCounters), c->stream));
+    return 0;
+}
+
+int slcu_get_stats(slcu_context* c, slcu_stats* out)
+{
+    if (!c || !out) return SLCU_ERR_ARG;
+    cudaSetDevice(c->device);
+    CK(cudaMemcpyAsync(c->hostCounters, c->counters, sizeof(SLCounters), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->stats.trisBinned = c->hostCounters->trisBinned;
+    c->stats.spans = c->hostCounters->spans;
+    c->stats.fragsShaded = c->hostCounters->fragsShaded;
+    *out = c->stats;
+    return 0;
+}
+
+} // extern "C"
