@@ -192,9 +192,27 @@ SLCU_EXPORT int SLCU_FN(blit_rect)(slcu_context* ctx, size_t outTexture, size_t 
  * enqueue on one stream; sync() is the join.  texture_read syncs by itself. */
 SLCU_EXPORT int SLCU_FN(sync)(slcu_context* ctx);
 
-/* ours: counters + device timing of the work enqueued between begin/end. */
+/* ours: counters of the work enqueued since reset_stats. */
 SLCU_EXPORT int SLCU_FN(reset_stats)(slcu_context* ctx);
 SLCU_EXPORT int SLCU_FN(get_stats)(slcu_context* ctx, slcu_stats* out);
+
+/* ours: per-kernel device time.  Between profile_begin and profile_end every
+ * kernel launch is bracketed by CUDA events on the context's own stream;
+ * profile_end synchronises and returns the summed milliseconds and launch
+ * counts per kernel class.  Used by bench.py for the roofline of the dominant
+ * kernel; off by default (the events serialise nothing but cost a few us). */
+enum { SLCU_K_CLEAR = 0, SLCU_K_VERTEX, SLCU_K_SPAN_COUNT, SLCU_K_SCAN, SLCU_K_SPAN_FILL, SLCU_K_RASTER, SLCU_K_BLIT, SLCU_K_COMPOSITE, SLCU_K_NUM };
+typedef struct slcu_kernel_times
+{
+    double ms[SLCU_K_NUM];
+    uint64_t launches[SLCU_K_NUM];
+} slcu_kernel_times;
+/* ours: device time of everything enqueued between the two calls, measured
+ * with a CUDA event pair on the context's own stream (timer_end synchronises). */
+SLCU_EXPORT int SLCU_FN(timer_begin)(slcu_context* ctx);
+SLCU_EXPORT int SLCU_FN(timer_end)(slcu_context* ctx, double* ms);
+SLCU_EXPORT int SLCU_FN(profile_begin)(slcu_context* ctx);
+SLCU_EXPORT int SLCU_FN(profile_end)(slcu_context* ctx, slcu_kernel_times* out);
 
 #ifdef __cplusplus
 }

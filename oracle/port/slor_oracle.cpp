@@ -16,6 +16,7 @@
  * Exports the C ABI of include/slcu.h with the prefix slor_.
  */
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <map>
 #include <string>
@@ -1076,5 +1077,12 @@ int slor_blit_rect(slcu_context*, size_t, size_t, uint16_t, uint16_t, uint16_t, 
 int slor_sync(slcu_context*) { return 0; }
 int slor_reset_stats(slcu_context* c) { if (c) memset(&c->stats, 0, sizeof(c->stats)); return 0; }
 int slor_get_stats(slcu_context* c, slcu_stats* out) { *out = c->stats; return 0; }
+
+static double g_t0;
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+int slor_timer_begin(slcu_context*) { g_t0 = now_ms(); return 0; }
+int slor_timer_end(slcu_context*, double* ms) { *ms = now_ms() - g_t0; return 0; }
+int slor_profile_begin(slcu_context*) { return 0; }
+int slor_profile_end(slcu_context*, slcu_kernel_times* out) { memset(out, 0, sizeof(*out)); return 0; }
 
 } // extern "C"

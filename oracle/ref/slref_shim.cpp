@@ -12,6 +12,7 @@
  * with num_threads(1)) and libslref_fast.so (the project's shipped flags,
  * timing baseline).  See SURVEY.md section 8c / appendix B.
  */
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -367,5 +368,12 @@ int slref_get_stats(slcu_context* c, slcu_stats* out)
     *out = c->stats;
     return 0;
 }
+
+static double g_t0;
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+int slref_timer_begin(slcu_context*) { g_t0 = now_ms(); return 0; }
+int slref_timer_end(slcu_context*, double* ms) { *ms = now_ms() - g_t0; return 0; }
+int slref_profile_begin(slcu_context*) { return 0; }
+int slref_profile_end(slcu_context*, slcu_kernel_times* out) { memset(out, 0, sizeof(*out)); return 0; }
 
 } // extern "C"

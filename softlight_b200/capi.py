@@ -85,6 +85,13 @@ class Stats(C.Structure):
                 ("fragsShaded", C.c_uint64), ("kernelLaunches", C.c_uint64), ("drawCalls", C.c_uint64)]
 
 
+KERNEL_CLASSES = ["clear", "vertex", "span_count", "scan", "span_fill", "raster", "blit", "composite"]
+
+
+class KernelTimes(C.Structure):
+    _fields_ = [("ms", C.c_double * 8), ("launches", C.c_uint64 * 8)]
+
+
 # name -> (restype, argtypes) ; ctx pointer is c_void_p
 _P = C.c_void_p
 _SZ = C.c_size_t
@@ -130,6 +137,10 @@ _SIGS = {
     "sync": (C.c_int, [_P]),
     "reset_stats": (C.c_int, [_P]),
     "get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
+    "timer_begin": (C.c_int, [_P]),
+    "timer_end": (C.c_int, [_P, C.POINTER(C.c_double)]),
+    "profile_begin": (C.c_int, [_P]),
+    "profile_end": (C.c_int, [_P, C.POINTER(KernelTimes)]),
 }
 
 EXPORTED_SYMBOLS = sorted(_SIGS)
@@ -340,6 +351,29 @@ class Context:
 
     def reset_stats(self):
         self.f["reset_stats"](self.h)
+
+    def timer_begin(self):
+        self._chk(self.f["timer_begin"](self.h), "timer_begin")
+
+    def timer_end(self) -> float:
+        ms = C.c_double(0.0)
+        self._chk(self.f["timer_end"](self.h, C.byref(ms)), "timer_end")
+        return ms.value
+
+    def vbo_assign_raw(self, vid: int, ptr: int, nbytes: int, offset: int = 0):
+        """Upload from a raw host pointer (e.g. pinned memory) without a numpy copy."""
+        self._chk(self.f["vbo_assign"](self.h, vid, C.c_void_p(ptr), offset, nbytes), "vbo_assign")
+
+    def texture_read_into(self, tid: int, ptr: int, nbytes: int):
+        self._chk(self.f["texture_read"](self.h, tid, C.c_void_p(ptr), nbytes), "texture_read")
+
+    def profile_begin(self):
+        self._chk(self.f["profile_begin"](self.h), "profile_begin")
+
+    def profile_end(self) -> dict:
+        kt = KernelTimes()
+        self._chk(self.f["profile_end"](self.h, C.byref(kt)), "profile_end")
+        return {k: {"ms": kt.ms[i], "launches": int(kt.launches[i])} for i, k in enumerate(KERNEL_CLASSES)}
 
     def get_stats(self) -> dict:
         s = Stats()

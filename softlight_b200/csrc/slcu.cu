@@ -184,6 +184,34 @@ struct slcu_context
     SLCounters* counters = nullptr;     /* device */
     SLCounters* hostCounters = nullptr; /* pinned */
     Scratch records, blockInfo, cnt, off, segSums, rowTotals, rowStart, entries;
+    /* optional per-kernel event timing (profile_begin / profile_end) */
+    cudaEvent_t timerA = nullptr, timerB = nullptr;
+    bool profiling = false;
+    struct ProfEvent { int cls; cudaEvent_t a, b; };
+    std::vector<ProfEvent> profEvents;
+    std::vector<cudaEvent_t> eventPool;
+};
+
+/* RAII bracket of one kernel launch: counts it and, when profiling, records events around it */
+struct KernelScope
+{
+    slcu_context* c;
+    cudaEvent_t b = nullptr;
+    KernelScope(slcu_context* ctx, int cls) : c(ctx)
+    {
+        c->stats.kernelLaunches++;
+        if (!c->profiling) return;
+        cudaEvent_t ev[2];
+        for (int i = 0; i < 2; ++i)
+        {
+            if (!c->eventPool.empty()) { ev[i] = c->eventPool.back(); c->eventPool.pop_back(); }
+            else cudaEventCreate(&ev[i]);
+        }
+        cudaEventRecord(ev[0], c->stream);
+        b = ev[1];
+        c->profEvents.push_back(slcu_context::ProfEvent{cls, ev[0], ev[1]});
+    }
+    ~KernelScope() { if (b) cudaEventRecord(b, c->stream); }
 };
 
 static const uint32_t* g_activeRcpOwner = nullptr; /* whose table g_rcp_table currently holds */
@@ -361,8 +389,7 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
             vp.records = reinterpret_cast<float4*>(c->records.buf.ptr);
             vp.blockInfo = reinterpret_cast<SLBlockInfo*>(c->blockInfo.buf.ptr);
             vp.counters = c->counters;
-            CK(sh.vs(launchBlocks[i], c->stream, vp));
-            c->stats.kernelLaunches++;
+            { KernelScope ks(c, SLCU_K_VERTEX); CK(sh.vs(launchBlocks[i], c->stream, vp)); }
             firstBlock += launchBlocks[i];
         }
 
@@ -388,18 +415,17 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
         sp.rowStart = reinterpret_cast<const uint32_t*>(c->rowStart.buf.ptr);
         sp.entries = nullptr;
         sp.counters = c->counters;
-        k_span<0><<<numBlocks, 256, 0, c->stream>>>(sp);
+        { KernelScope ks(c, SLCU_K_SPAN_COUNT); k_span<0><<<numBlocks, 256, 0, c->stream>>>(sp); }
         CK(cudaGetLastError());
         const dim3 sgrid((rowPitch + 127) / 128, usedSegs);
-        k_scan_seg_sums<<<sgrid, 128, 0, c->stream>>>(sp.cnt, reinterpret_cast<uint32_t*>(c->segSums.buf.ptr), numBlocks, rowPitch, blocksPerSeg);
+        { KernelScope ks(c, SLCU_K_SCAN); k_scan_seg_sums<<<sgrid, 128, 0, c->stream>>>(sp.cnt, reinterpret_cast<uint32_t*>(c->segSums.buf.ptr), numBlocks, rowPitch, blocksPerSeg); }
         CK(cudaGetLastError());
-        k_scan_rows<<<(rowPitch + 127) / 128, 128, 0, c->stream>>>(reinterpret_cast<uint32_t*>(c->segSums.buf.ptr), reinterpret_cast<uint32_t*>(c->rowTotals.buf.ptr), rowPitch, usedSegs);
+        { KernelScope ks(c, SLCU_K_SCAN); k_scan_rows<<<(rowPitch + 127) / 128, 128, 0, c->stream>>>(reinterpret_cast<uint32_t*>(c->segSums.buf.ptr), reinterpret_cast<uint32_t*>(c->rowTotals.buf.ptr), rowPitch, usedSegs); }
         CK(cudaGetLastError());
-        k_scan_row_starts<<<1, 1024, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(c->rowTotals.buf.ptr), reinterpret_cast<uint32_t*>(c->rowStart.buf.ptr), H, c->counters);
+        { KernelScope ks(c, SLCU_K_SCAN); k_scan_row_starts<<<1, 1024, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(c->rowTotals.buf.ptr), reinterpret_cast<uint32_t*>(c->rowStart.buf.ptr), H, c->counters); }
         CK(cudaGetLastError());
-        k_scan_offsets<<<sgrid, 128, 0, c->stream>>>(sp.cnt, reinterpret_cast<const uint32_t*>(c->segSums.buf.ptr), reinterpret_cast<uint32_t*>(c->off.buf.ptr), numBlocks, rowPitch, blocksPerSeg);
+        { KernelScope ks(c, SLCU_K_SCAN); k_scan_offsets<<<sgrid, 128, 0, c->stream>>>(sp.cnt, reinterpret_cast<const uint32_t*>(c->segSums.buf.ptr), reinterpret_cast<uint32_t*>(c->off.buf.ptr), numBlocks, rowPitch, blocksPerSeg); }
         CK(cudaGetLastError());
-        c->stats.kernelLaunches += 5;
 
         /* the span lists are sized from the count: one small read-back per draw */
         uint32_t totalSpans = 0;
@@ -419,9 +445,8 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
 
         CK(c->entries.ensure((size_t)totalSpans * sizeof(SLSpanEntry)));
         sp.entries = reinterpret_cast<SLSpanEntry*>(c->entries.buf.ptr);
-        k_span<1><<<numBlocks, 256, 0, c->stream>>>(sp);
+        { KernelScope ks(c, SLCU_K_SPAN_FILL); k_span<1><<<numBlocks, 256, 0, c->stream>>>(sp); }
         CK(cudaGetLastError());
-        c->stats.kernelLaunches++;
         break;
     }
 
@@ -459,8 +484,7 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
     }
     rp.counters = c->counters;
     const unsigned warpsPerBlock = 4;
-    CK(sh.fs((H + warpsPerBlock - 1) / warpsPerBlock, warpsPerBlock * 32, c->stream, rp));
-    c->stats.kernelLaunches++;
+    { KernelScope ks(c, SLCU_K_RASTER); CK(sh.fs((H + warpsPerBlock - 1) / warpsPerBlock, warpsPerBlock * 32, c->stream, rp)); }
     return 0;
 }
 
@@ -510,9 +534,8 @@ static int clear_texture(slcu_context* c, const HostTexture& t, const unsigned c
     unsigned grid = (unsigned)((bytes / 16 + 255) / 256);
     if (grid < 1) grid = 1;
     if (grid > 148 * 16) grid = 148 * 16;
-    k_clear<<<grid, 256, 0, c->stream>>>(p);
+    { KernelScope ks(c, SLCU_K_CLEAR); k_clear<<<grid, 256, 0, c->stream>>>(p); }
     CK(cudaGetLastError());
-    c->stats.kernelLaunches++;
     return 0;
 }
 
@@ -861,6 +884,58 @@ int slcu_get_stats(slcu_context* c, slcu_stats* out)
     c->stats.spans = c->hostCounters->spans;
     c->stats.fragsShaded = c->hostCounters->fragsShaded;
     *out = c->stats;
+    return 0;
+}
+
+int slcu_timer_begin(slcu_context* c)
+{
+    if (!c) return SLCU_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (!c->timerA) { CK(cudaEventCreate(&c->timerA)); CK(cudaEventCreate(&c->timerB)); }
+    CK(cudaEventRecord(c->timerA, c->stream));
+    return 0;
+}
+
+int slcu_timer_end(slcu_context* c, double* ms)
+{
+    if (!c || !ms || !c->timerA) return SLCU_ERR_ARG;
+    cudaSetDevice(c->device);
+    CK(cudaEventRecord(c->timerB, c->stream));
+    CK(cudaEventSynchronize(c->timerB));
+    float f = 0.f;
+    CK(cudaEventElapsedTime(&f, c->timerA, c->timerB));
+    *ms = (double)f;
+    return 0;
+}
+
+int slcu_profile_begin(slcu_context* c)
+{
+    if (!c) return SLCU_ERR_ARG;
+    cudaSetDevice(c->device);
+    CK(cudaStreamSynchronize(c->stream));
+    for (auto& e : c->profEvents) { c->eventPool.push_back(e.a); c->eventPool.push_back(e.b); }
+    c->profEvents.clear();
+    c->profiling = true;
+    return 0;
+}
+
+int slcu_profile_end(slcu_context* c, slcu_kernel_times* out)
+{
+    if (!c || !out) return SLCU_ERR_ARG;
+    cudaSetDevice(c->device);
+    memset(out, 0, sizeof(*out));
+    c->profiling = false;
+    CK(cudaStreamSynchronize(c->stream));
+    for (auto& e : c->profEvents)
+    {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e.a, e.b));
+        out->ms[e.cls] += ms;
+        out->launches[e.cls]++;
+        c->eventPool.push_back(e.a);
+        c->eventPool.push_back(e.b);
+    }
+    c->profEvents.clear();
     return 0;
 }
 

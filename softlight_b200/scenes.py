@@ -270,7 +270,8 @@ def instancing_scene(width=1920, height=1080, grid=(25, 20, 20), stacks=16, slic
                                blend=A.SL_BLEND_PREMULTIPLED_ALPHA, depth_test=A.SL_DEPTH_TEST_GREATER_EQUAL,
                                depth_mask=A.SL_DEPTH_MASK_ON)
         assert sh != A.INVALID_ID
-        return dict(color=color, depth=depth, fbo=fbo, shader=sh, mesh=ctx.mesh(vao, 0, idx.size), ubo=ubo)
+        return dict(color=color, depth=depth, fbo=fbo, shader=sh, mesh=ctx.mesh(vao, 0, idx.size), ubo=ubo, inst=inst,
+                    per_frame={"inst": mats})
 
     def frame(ctx, st):
         ctx.clear_framebuffer(st["fbo"], 0, (0.6, 0.6, 0.6, 1.0), 0.0)
@@ -278,6 +279,73 @@ def instancing_scene(width=1920, height=1080, grid=(25, 20, 20), stacks=16, slic
 
     return Scene(name or f"instancing{ninst}_{width}x{height}", width, height, A.SL_COLOR_RGBA_8U, depth_type,
                  (0.6, 0.6, 0.6, 1.0), 0.0, setup, frame, tris_per_frame=tris.shape[0] * ninst, draws_per_frame=1)
+
+
+# ---- torture scene: random clip-space triangles (overlap, near-plane clipping, tiny + huge) ----
+def random_tris_scene(seed=1, n=400, width=200, height=150, blend=A.SL_BLEND_OFF, depth_test=A.SL_DEPTH_TEST_LESS_THAN,
+                      depth_mask=A.SL_DEPTH_MASK_ON, depth_type=A.SL_COLOR_R_FLOAT, color_type=A.SL_COLOR_RGBA_8U,
+                      cull=A.SL_CULL_OFF, index_dtype=np.uint16, clip_fraction=0.3, clear_depth=1.0, viewport=None,
+                      scissor=None, split_draws=1, multiple=False, name=None, empty_draw=False) -> Scene:
+    rng = np.random.default_rng(seed)
+    verts = np.zeros((n * 3, 8), dtype=np.float32)
+    centers = rng.uniform(-1.1, 1.1, size=(n, 1, 2))
+    size = np.where(rng.random((n, 1, 1)) < 0.15, 1.2, 0.12) * rng.uniform(0.2, 1.0, size=(n, 1, 1))
+    xy = centers + rng.uniform(-1, 1, size=(n, 3, 2)) * size
+    w = rng.uniform(0.5, 2.0, size=(n, 3))
+    clipped = rng.random(n) < clip_fraction
+    w[clipped, 0] = rng.uniform(-0.5, 0.2, size=int(clipped.sum()))  # one vertex behind / on the near side
+    z = rng.uniform(-0.9, 0.9, size=(n, 3)) * np.abs(w)
+    verts[:, 0:2] = (xy * w[..., None]).reshape(-1, 2)
+    verts[:, 2] = z.reshape(-1)
+    verts[:, 3] = w.reshape(-1)
+    verts[:, 4:7] = rng.uniform(0, 1, size=(n * 3, 3))
+    verts[:, 7] = rng.uniform(0.2, 1.0, size=n * 3) if blend != A.SL_BLEND_OFF else 1.0
+    idx = None
+    if index_dtype is not None:
+        idx = rng.permutation(n * 3).astype(np.int64)
+        # keep triangles intact but reference vertices through a shuffled index buffer
+        order = np.argsort(idx)
+        verts = verts[idx]          # vertex i now lives at position order[i]
+        idx = order.astype(index_dtype)
+        if index_dtype == np.uint8:
+            assert n * 3 <= 256
+    count = n * 3
+
+    def setup(ctx):
+        color, depth, fbo = _make_targets(ctx, width, height, color_type, depth_type)
+        vbo = ctx.create_vbo(verts)
+        ibo = ctx.create_ibo(idx) if idx is not None else None
+        vao = ctx.create_vao(vbo, ibo, [(0, 32, A.VERTEX_DIMENSION_4, A.VERTEX_DATA_FLOAT),
+                                        (16, 32, A.VERTEX_DIMENSION_4, A.VERTEX_DATA_FLOAT)])
+        ubo = ctx.create_ubo(b"\0" * 16)
+        sh = ctx.create_shader("vcolor", "vcolor", ubo, vs_varyings=1, fs_varyings=1, cull=cull, blend=blend,
+                               depth_test=depth_test, depth_mask=depth_mask)
+        assert sh != A.INVALID_ID
+        mode = A.RENDER_MODE_INDEXED_TRIANGLES if idx is not None else A.RENDER_MODE_TRIANGLES
+        per = (n // split_draws) * 3
+        meshes = []
+        for d in range(split_draws):
+            b = d * per
+            e = count if d == split_draws - 1 else b + per
+            if empty_draw:
+                e = b
+            meshes.append(ctx.mesh(vao, b, e, mode))
+        if viewport is not None:
+            ctx.viewport(*viewport)
+        if scissor is not None:
+            ctx.scissor(*scissor)
+        return dict(color=color, depth=depth, fbo=fbo, shader=sh, meshes=meshes)
+
+    def frame(ctx, st):
+        ctx.clear_framebuffer(st["fbo"], 0, (0.1, 0.2, 0.3, 1.0), clear_depth)
+        if multiple:
+            ctx.draw_multiple(st["meshes"], st["shader"], st["fbo"])
+        else:
+            for m in st["meshes"]:
+                ctx.draw(m, st["shader"], st["fbo"])
+
+    return Scene(name or f"random{n}_s{seed}", width, height, color_type, depth_type, (0.1, 0.2, 0.3, 1.0), clear_depth,
+                 setup, frame, tris_per_frame=n, draws_per_frame=split_draws)
 
 
 SCENES: Dict[str, Callable[[], Scene]] = {

@@ -1,0 +1,69 @@
+"""Named parity cases shared by the CPU (oracle pinning) and GPU (CUDA parity) tests."""
+import numpy as np
+
+from softlight_b200 import capi as A
+from softlight_b200 import scenes as S
+
+
+def _variants():
+    v = []
+    for dt in (A.SL_DEPTH_TEST_OFF, A.SL_DEPTH_TEST_LESS_THAN, A.SL_DEPTH_TEST_LESS_EQUAL, A.SL_DEPTH_TEST_GREATER_THAN,
+               A.SL_DEPTH_TEST_GREATER_EQUAL, A.SL_DEPTH_TEST_EQUAL, A.SL_DEPTH_TEST_NOT_EQUAL):
+        v.append((f"depthfunc{dt}", dict(depth_test=dt, clear_depth=0.5)))
+    for b in range(5):
+        v.append((f"blend{b}", dict(blend=b)))
+    for d, n in ((A.SL_COLOR_R_HALF, "half"), (A.SL_COLOR_R_FLOAT, "float"), (A.SL_COLOR_R_DOUBLE, "double")):
+        v.append((f"depth_{n}_premult", dict(depth_type=d, blend=2)))
+    for ct in (A.SL_COLOR_RGBA_8U, A.SL_COLOR_RGBA_16U, A.SL_COLOR_RGBA_HALF, A.SL_COLOR_RGBA_FLOAT, A.SL_COLOR_RGB_8U,
+               A.SL_COLOR_RG_8U, A.SL_COLOR_R_8U, A.SL_COLOR_RGB_FLOAT, A.SL_COLOR_R_FLOAT, A.SL_COLOR_RGBA_DOUBLE):
+        v.append((f"color{ct}", dict(color_type=ct)))
+        v.append((f"color{ct}_alpha", dict(color_type=ct, blend=1)))
+    for c in range(3):
+        v.append((f"cull{c}", dict(cull=c)))
+    for idt, n in ((None, "none"), (np.uint8, "u8"), (np.uint16, "u16"), (np.uint32, "u32")):
+        v.append((f"index_{n}", dict(index_dtype=idt, n=80)))
+    v.append(("viewport", dict(viewport=(20, 10, 120, 90))))
+    v.append(("scissor", dict(scissor=(30, 20, 100, 80))))
+    v.append(("viewport_scissor", dict(viewport=(20, 10, 120, 90), scissor=(30, 20, 100, 80))))
+    v.append(("split3", dict(split_draws=3)))
+    v.append(("multi3", dict(split_draws=3, multiple=True)))
+    v.append(("clip_heavy", dict(n=3000, width=320, height=200, clip_fraction=0.5)))
+    v.append(("nomask_additive", dict(depth_mask=A.SL_DEPTH_MASK_OFF, blend=3)))
+    v.append(("empty", dict(n=30, empty_draw=True)))
+    v.append(("ragged_odd_size", dict(n=300, width=333, height=77)))
+    v.append(("tiny_1x1", dict(n=50, width=1, height=1)))
+    return v
+
+
+CASES = {}
+for _i, (_name, _kw) in enumerate(_variants()):
+    CASES["rand_" + _name] = (lambda i=_i, kw=_kw, name=_name: S.random_tris_scene(seed=100 + i, name="rand_" + name, **kw))
+CASES["draw_test"] = S.SCENES["draw_test"]
+CASES["c1_small"] = S.SCENES["c1_small"]
+CASES["c2_small"] = S.SCENES["c2_small"]
+
+# full-size configs: compared through hashes / live checkers only
+BIG_CASES = {
+    "c1_sphere100k": S.SCENES["c1_sphere100k"],
+    "c2_instancing10k": S.SCENES["c2_instancing10k"],
+}
+
+# cases whose images are committed in full (the rest of CASES is pinned by sha256)
+FULL_IMAGE_CASES = ["draw_test", "c1_small", "c2_small", "rand_blend1", "rand_clip_heavy", "rand_depth_half_premult"]
+
+
+def bits(a: np.ndarray) -> np.ndarray:
+    return a.view({1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[a.dtype.itemsize])
+
+
+def render(impl: str, scene, rcp_table=None, device=0, threads=1):
+    ctx = A.Context(impl, device=device, threads=threads)
+    if rcp_table is not None and not impl.startswith("ref"):
+        ctx.set_rcp_table(rcp_table)
+    ctx.reset_stats()
+    inst = S.SceneInstance(scene, ctx)
+    inst.render()
+    ctx.sync()
+    color, depth, stats = inst.read_color(), inst.read_depth(), ctx.get_stats()
+    ctx.close()
+    return color, depth, stats

@@ -1,0 +1,46 @@
+"""Regenerates tests/golden/* by running the UNMODIFIED reference (oracle/_ref/libslref_strict.so,
+compiled from /root/reference by oracle/Makefile) with num_threads(1) on the synthetic cases of
+tests/cases.py.  Run in the dev container (needs /root/reference):  python tests/golden/make_golden.py
+The rcp table of the generating CPU is stored next to the frames: parity tests pin it, so the
+goldens hold on any host CPU."""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(HERE))
+
+from softlight_b200 import capi as A  # noqa: E402
+import cases  # noqa: E402
+
+
+def main():
+    ctx = A.Context("ref_strict")
+    rcp = ctx.get_rcp_table()
+    frames = {"rcp_table": rcp}
+    hashes = {}
+    allcases = dict(cases.CASES)
+    allcases.update(cases.BIG_CASES)
+    for name, factory in allcases.items():
+        scene = factory()
+        color, depth, stats = cases.render("ref_strict", scene)
+        hashes[name] = {
+            "color_sha256": hashlib.sha256(np.ascontiguousarray(color).tobytes()).hexdigest(),
+            "depth_sha256": hashlib.sha256(np.ascontiguousarray(depth).tobytes()).hexdigest(),
+            "frags": int(stats["fragsShaded"]), "width": scene.width, "height": scene.height,
+        }
+        if name in cases.FULL_IMAGE_CASES:
+            frames[name + ".color"] = color
+            frames[name + ".depth"] = cases.bits(depth)
+        print(name, hashes[name]["frags"], flush=True)
+    np.savez_compressed(os.path.join(HERE, "golden_frames.npz"), **frames)
+    json.dump({"generator": ctx.impl_name(), "cases": hashes}, open(os.path.join(HERE, "golden_hashes.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

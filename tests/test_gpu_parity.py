@@ -1,0 +1,114 @@
+"""GPU tests (-m gpu): the CUDA path, called through the C ABI, against
+  * the committed golden frames (rendered by the unmodified reference; rcp table pinned),
+  * the CPU oracle restatement on the same seeded inputs,
+  * the compiled reference itself when oracle/_ref travelled to the box (host-measured rcp table),
+  * size-independent properties at BASELINE.json's full sizes (idempotence, order independence
+    of disjoint draws, clear-only frames).
+Bar (north_star): coverage, depth bits, integer outputs bit-exact; colours <= 1 LSB.  We assert
+bit-exact everywhere; the tolerance is only the documented fallback."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from softlight_b200 import capi as A
+from softlight_b200 import scenes as S
+
+pytestmark = pytest.mark.gpu
+
+COLOR_TOL_LSB = 0      # north_star allows 1; we hold 0
+DEPTH_REL_TOL = 0.0    # north_star allows 1e-6 relative; we hold bit-exact
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def assert_same(color, depth, ref_color, ref_depth):
+    assert color.shape == ref_color.shape
+    if color.dtype.kind == "f":
+        assert np.array_equal(cases.bits(color), cases.bits(ref_color))
+    else:
+        d = np.abs(color.astype(np.int64) - ref_color.astype(np.int64))
+        assert d.max(initial=0) <= COLOR_TOL_LSB, f"{int((d > 0).sum())} colour values differ, max {int(d.max())}"
+    nd = int((cases.bits(depth) != cases.bits(ref_depth)).sum())
+    assert nd == 0, f"{nd} depth texels differ"
+
+
+@pytest.mark.parametrize("name", sorted(cases.CASES))
+def test_cuda_matches_golden_reference_frames(name, golden):
+    frames, hashes = golden
+    scene = cases.CASES[name]()
+    color, depth, stats = cases.render("cuda", scene, rcp_table=frames["rcp_table"])
+    h = hashes[name]
+    assert stats["kernelLaunches"] > 0
+    assert stats["fragsShaded"] == h["frags"]
+    assert sha(color) == h["color_sha256"]
+    assert sha(depth) == h["depth_sha256"]
+    if name in cases.FULL_IMAGE_CASES:
+        assert_same(color, depth, frames[name + ".color"], frames[name + ".depth"].view(depth.dtype))
+
+
+@pytest.mark.parametrize("name", sorted(cases.CASES))
+def test_cuda_matches_oracle(name, golden):
+    frames, _ = golden
+    scene = cases.CASES[name]()
+    cg, dg, sg = cases.render("cuda", scene, rcp_table=frames["rcp_table"])
+    co, do, so = cases.render("port", scene, rcp_table=frames["rcp_table"])
+    assert sg["fragsShaded"] == so["fragsShaded"]
+    assert sg["trisBinned"] == so["trisBinned"]
+    assert sg["spans"] == so["spans"]
+    assert_same(cg, dg, co, do)
+
+
+@pytest.mark.parametrize("name", sorted(cases.BIG_CASES))
+def test_cuda_full_size_configs_match_golden(name, golden):
+    frames, hashes = golden
+    scene = cases.BIG_CASES[name]()
+    color, depth, stats = cases.render("cuda", scene, rcp_table=frames["rcp_table"])
+    h = hashes[name]
+    assert stats["fragsShaded"] == h["frags"]
+    assert sha(color) == h["color_sha256"]
+    assert sha(depth) == h["depth_sha256"]
+
+
+@pytest.mark.skipif(not os.path.exists(A.LIB_PATHS["ref_strict"]), reason="oracle/_ref did not travel")
+@pytest.mark.parametrize("name", ["draw_test", "c1_small", "c2_small", "rand_clip_heavy", "rand_blend2", "c1_sphere100k"])
+def test_cuda_matches_live_reference_on_this_host(name):
+    """Default mode: the rcp table is measured from this box's CPU, so the CUDA frame equals what the
+    reference renders on the same box."""
+    scene = (cases.CASES.get(name) or cases.BIG_CASES[name])()
+    cg, dg, sg = cases.render("cuda", scene)
+    cr, dr, sr = cases.render("ref_strict", scene)
+    assert sg["fragsShaded"] == sr["fragsShaded"]
+    assert_same(cg, dg, cr, dr)
+
+
+def test_idempotent_and_deterministic_full_c2(golden):
+    """Rendering the same frame twice (and on a second context) gives identical bits: no order races."""
+    frames, _ = golden
+    scene = S.SCENES["c2_instancing10k"]()
+    a = cases.render("cuda", scene, rcp_table=frames["rcp_table"])
+    b = cases.render("cuda", scene, rcp_table=frames["rcp_table"])
+    assert np.array_equal(a[0], b[0]) and np.array_equal(cases.bits(a[1]), cases.bits(b[1]))
+    assert a[2]["fragsShaded"] == b[2]["fragsShaded"]
+
+
+def test_clear_only_frame():
+    ctx = A.Context("cuda")
+    c = ctx.create_texture(A.SL_COLOR_RGBA_8U, 1920, 1080)
+    d = ctx.create_texture(A.SL_COLOR_R_HALF, 1920, 1080)
+    fbo = ctx.create_framebuffer([c], d)
+    ctx.clear_framebuffer(fbo, 0, (0.6, 0.6, 0.6, 1.0), 0.25)
+    col = ctx.texture_read(c, A.SL_COLOR_RGBA_8U, 1920, 1080)
+    dep = ctx.texture_read(d, A.SL_COLOR_R_HALF, 1920, 1080)
+    assert np.all(col == np.array([153, 153, 153, 255], dtype=np.uint8))
+    assert np.all(dep == np.float16(0.25))
+
+
+def test_unregistered_shader_is_refused():
+    ctx = A.Context("cuda")
+    ubo = ctx.create_ubo(b"\0" * 16)
+    assert ctx.create_shader("nope", "vcolor", ubo, vs_varyings=1, fs_varyings=1) == A.INVALID_ID
