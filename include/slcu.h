@@ -98,8 +98,9 @@ typedef struct slcu_stats
 {
     uint64_t trisSubmitted;   /* primitives fed to the vertex stage             */
     uint64_t trisBinned;      /* triangle records that reached the rasteriser   */
-    uint64_t spans;           /* non-empty (triangle,row) spans                  */
-    uint64_t fragsShaded;     /* fragment-shader invocations                    */
+    uint64_t spans;           /* non-empty (triangle,row) spans in rows < height */
+    uint64_t fragsShaded;     /* fragment-shader invocations that land inside
+                                 the width*height texels of the framebuffer    */
     uint64_t kernelLaunches;  /* CUDA kernels launched by this context          */
     uint64_t drawCalls;
 } slcu_stats;

@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -336,6 +337,10 @@ struct ScanlineBounds
 /* One queued fragment (SL_FragCoord, SL_ShaderUtil.hpp:668-689) */
 struct QueuedFrag { math::vec4 bc; uint16_t x, y; float z; };
 
+/* debug aid: SL_FRAG_TRACE=<file> records the (x,y) of every fragment-shader call */
+static std::vector<uint32_t> gFragTrace;
+static const char* gFragTracePath = getenv("SL_FRAG_TRACE");
+
 /* SL_FragmentProcessor::flush_tri_fragments (src/SL_FragmentProcessor.cpp:416-531) for ONE fragment */
 static void shade_fragment(slcu_context* c, const Bin& bin, const QueuedFrag& q)
 {
@@ -365,7 +370,9 @@ static void shade_fragment(slcu_context* c, const Bin& bin, const QueuedFrag& q)
     fp.coord.depth = q.z;
     for (int i = 0; i < 4; ++i) fp.pOutputs[i] = math::vec4{0.f};
 
-    c->stats.fragsShaded++;
+    /* the metric counts fragments that land inside the w*h texels (see oracle/ref/slref_shim.cpp counting_fs) */
+    if ((size_t)q.x + (size_t)c->depthBuf->mWidth * q.y < (size_t)c->depthBuf->mWidth * c->depthBuf->mHeight) c->stats.fragsShaded++;
+    if (gFragTracePath) gFragTrace.push_back((uint32_t)q.x | ((uint32_t)q.y << 16));
     const bool haveOutputs = sh.fs(fp); /* :501 */
     if (haveOutputs)
     {
@@ -412,7 +419,7 @@ static void render_triangle(slcu_context* c, const Bin& bin)
         const float yf = (float)y;
         scanline.step(yf, xMin, xMax);
         if (!(xMin < xMax)) { y += 1; continue; }
-        c->stats.spans++;
+        if (y < (int32_t)depthBuffer.mHeight) c->stats.spans++; /* rows a read-back can see */
 
         /* :471-481 */
         math::vec4 bcY;
@@ -469,8 +476,15 @@ static void render_triangle(slcu_context* c, const Bin& bin)
                         ++s;
                     }
                 }
-                /* :529-533: flush when the queue is nearly full.  Fragments of one
-                 * triangle never overlap, so flushing here or at the end is the same. */
+                /* :529-533: flush when the queue is nearly full (SL_SHADER_MAX_QUEUED_FRAGS - 4).  This is observable:
+                 * a span that runs past the row end wraps onto the start of the next row, which the same triangle's
+                 * next span may cover too; whether that span's depth test sees the wrapped fragments depends on
+                 * whether a flush happened in between. */
+                if (queue.size() > 600 - 4)
+                {
+                    for (const QueuedFrag& q : queue) shade_fragment(c, bin, q);
+                    queue.clear();
+                }
             }
             for (int j = 0; j < 4; ++j)
             {
@@ -841,7 +855,11 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
 /* SL_ClearProcessor::clear_texture (src/SL_ClearProcessor.cpp:23-63): w*h texels (depth dim ignored) */
 static void clear_texture(SL_Texture& t, const void* texel)
 {
-    const size_t n = (size_t)t.mWidth * t.mHeight;
+    /* sl_calc_indexed_parition2<1>(count, 1, 0) (SL_ShaderUtil.hpp:222-231): the single thread's range is
+     * count + (1 - count % 3) clipped to count, i.e. the LAST texel stays untouched when count % 3 == 2 */
+    const size_t count = (size_t)t.mWidth * t.mHeight;
+    const size_t range = count + (1 - (count % 3));
+    const size_t n = range < count ? range : count;
     for (size_t i = 0; i < n; ++i) memcpy(t.mTexels + i * t.mBpt, texel, t.mBpt);
 }
 
@@ -1075,8 +1093,17 @@ int slor_draw_instanced(slcu_context* c, const slcu_mesh* m, size_t inst, size_t
 int slor_blit(slcu_context*, size_t, size_t) { return SLCU_ERR_UNSUPPORTED; }
 int slor_blit_rect(slcu_context*, size_t, size_t, uint16_t, uint16_t, uint16_t, uint16_t, uint16_t, uint16_t, uint16_t, uint16_t) { return SLCU_ERR_UNSUPPORTED; }
 int slor_sync(slcu_context*) { return 0; }
-int slor_reset_stats(slcu_context* c) { if (c) memset(&c->stats, 0, sizeof(c->stats)); return 0; }
-int slor_get_stats(slcu_context* c, slcu_stats* out) { *out = c->stats; return 0; }
+int slor_reset_stats(slcu_context* c) { gFragTrace.clear(); if (c) memset(&c->stats, 0, sizeof(c->stats)); return 0; }
+int slor_get_stats(slcu_context* c, slcu_stats* out)
+{
+    if (gFragTracePath)
+    {
+        FILE* f = fopen(gFragTracePath, "wb");
+        if (f) { fwrite(gFragTrace.data(), 4, gFragTrace.size(), f); fclose(f); }
+    }
+    *out = c->stats;
+    return 0;
+}
 
 static double g_t0;
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }

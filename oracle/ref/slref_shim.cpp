@@ -14,6 +14,7 @@
  */
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -65,10 +66,20 @@ struct FsReg { FsReg(const char* n, FsFn f) { fs_registry()[n] = f; } };
 std::atomic<uint64_t> gFragsShaded{0};
 bool gCountFrags = false;
 
+/* debug aid: SL_FRAG_TRACE=<file> records the (x,y) of every fragment-shader call (1 thread only) */
+std::vector<uint32_t> gFragTrace;
+const char* gFragTracePath = getenv("SL_FRAG_TRACE");
+
+/* Only fragments that land inside the w*h texels of the framebuffer are counted.  The reference addresses pixels as
+ * x + w*y inside an allocation padded to ~4x (src/SL_Texture.cpp:28-54), so clip-generated triangles that end above
+ * the viewport shade fragments nobody can read back; they are not part of the metric. */
+size_t gFboW = 0, gFboH = 0;
+
 template <FsFn fn>
 bool counting_fs(SL_FragmentParam& p)
 {
-    gFragsShaded.fetch_add(1, std::memory_order_relaxed);
+    if ((size_t)p.coord.x + gFboW * (size_t)p.coord.y < gFboW * gFboH) gFragsShaded.fetch_add(1, std::memory_order_relaxed);
+    if (gFragTracePath) gFragTrace.push_back((uint32_t)p.coord.x | ((uint32_t)p.coord.y << 16));
     return fn(p);
 }
 struct FsCountReg { FsCountReg(const char* n, FsFn f) { fs_registry()[std::string("#count#") + n] = f; } };
@@ -311,11 +322,19 @@ int slref_clear_framebuffer(slcu_context* c, size_t fbo, unsigned att, const dou
     return 0;
 }
 
+static void set_fbo_dims(slcu_context* c, size_t fbo)
+{
+    const SL_TextureView& d = c->ctx.framebuffer(fbo).get_depth_buffer();
+    gFboW = d.width;
+    gFboH = d.height;
+}
+
 int slref_draw(slcu_context* c, const slcu_mesh* m, size_t shader, size_t fbo)
 {
     apply_fixups(c);
     c->stats.trisSubmitted += count_prims(m, 1, 1);
     c->stats.drawCalls++;
+    set_fbo_dims(c, fbo);
     c->ctx.draw(to_mesh(*m), shader, fbo);
     return 0;
 }
@@ -327,6 +346,7 @@ int slref_draw_multiple(slcu_context* c, const slcu_mesh* m, size_t n, size_t sh
     for (size_t i = 0; i < n; ++i) meshes.push_back(to_mesh(m[i]));
     c->stats.trisSubmitted += count_prims(m, n, 1);
     c->stats.drawCalls++;
+    set_fbo_dims(c, fbo);
     c->ctx.draw_multiple(meshes.data(), n, shader, fbo);
     return 0;
 }
@@ -336,6 +356,7 @@ int slref_draw_instanced(slcu_context* c, const slcu_mesh* m, size_t inst, size_
     apply_fixups(c);
     c->stats.trisSubmitted += count_prims(m, 1, inst);
     c->stats.drawCalls++;
+    set_fbo_dims(c, fbo);
     c->ctx.draw_instanced(to_mesh(*m), inst, shader, fbo);
     return 0;
 }
@@ -358,6 +379,7 @@ int slref_reset_stats(slcu_context* c)
     if (!c) { gCountFrags = false; return 0; }
     gCountFrags = true;
     gFragsShaded.store(0);
+    gFragTrace.clear();
     memset(&c->stats, 0, sizeof(c->stats));
     return 0;
 }
@@ -365,6 +387,11 @@ int slref_reset_stats(slcu_context* c)
 int slref_get_stats(slcu_context* c, slcu_stats* out)
 {
     c->stats.fragsShaded = gFragsShaded.load();
+    if (gFragTracePath)
+    {
+        FILE* f = fopen(gFragTracePath, "wb");
+        if (f) { fwrite(gFragTrace.data(), 4, gFragTrace.size(), f); fclose(f); }
+    }
     *out = c->stats;
     return 0;
 }

@@ -50,12 +50,26 @@ struct SLSpanEntry { uint32_t rec; uint16_t xMin, xMax; };
 struct SLCounters
 {
     unsigned long long recAlloc;     /* triangle records allocated (reset per batch)      */
+    unsigned long long overflowPairs;/* spans cut at the row end (reset per batch)        */
     unsigned long long trisBinned;
     unsigned long long spans;
     unsigned long long fragsShaded;
-    unsigned int errorFlags;         /* bit0 record overflow, bit1 span x out of range    */
-    unsigned int pad;
+    unsigned int errorFlags;         /* bit0 record overflow, bit1 span x out of range, bit2 span starts left of x=0,
+                                        bit3 overflow of a triangle that was classified as "cannot overflow" */
+    unsigned int rasterTicket;       /* row ticket of k_raster (reset by k_scan_row_starts)                   */
 };
+
+/* A span whose xMax exceeds the framebuffer width keeps going in linear memory:
+ * the reference addresses pixels as x + width*y (src/SL_TriRasterizer.cpp:472,
+ * src/SL_FragmentProcessor.cpp:507-529), so those fragments land at the start of
+ * row y+1 (clip-generated vertices do end up right of the viewport because the
+ * clipper's t comes from rcpps).  Row y+1 is owned by another warp, so such a
+ * span is cut at the row end: the in-row part stays in row y's list, the rest
+ * becomes an "overflow entry" in row y+1's list (same position in submission
+ * order), and the walker state at the cut (lane map of the compaction state
+ * machine + depth outcomes of the straddling group's in-row lanes) is handed
+ * over through a small hash table in global memory. */
+constexpr uint32_t SL_ENTRY_OVERFLOW = 0x80000000u;
 
 struct SLVertexParams
 {
@@ -396,8 +410,9 @@ struct SLSpanParams
     const float4* records;
     const SLBlockInfo* blockInfo;
     unsigned int firstBlock;     /* first vertex block of the batch          */
-    unsigned int numRows;        /* framebuffer height                       */
+    unsigned int numRows;        /* rows incl. the texture's padding rows    */
     unsigned int rowPitch;       /* padded row count of cnt/off              */
+    unsigned int width;          /* framebuffer width (row stride)           */
     int recStride;               /* float4 per record                        */
     uint16_t* cnt;               /* [numBlocks][rowPitch]                    */
     const uint32_t* off;         /* [numBlocks][rowPitch] exclusive over vb  */
@@ -406,17 +421,32 @@ struct SLSpanParams
     SLCounters* counters;
 };
 
-/* MODE 0: count spans per (vertex block, row).  MODE 1: fill the row lists. */
+/* What one (record,row) span contributes to the row lists.  bit0: an entry in
+ * its own row (some pixel left of the row end), bit1: an overflow entry in the
+ * next row (some pixel at or beyond the row end). */
+SLD_FN int sl_classify_span(const SLSpanParams& P, int32_t& xMin, int32_t& xMax)
+{
+    if (!(xMin < xMax)) return 0;
+    const int32_t W = (int32_t)P.width;
+    if (xMin < 0) { atomicOr(&P.counters->errorFlags, 4u); xMin = 0; }      /* would address the previous row: not reproduced */
+    if (xMax > 2 * W) { atomicOr(&P.counters->errorFlags, 2u); xMax = 2 * W; }
+    if (!(xMin < xMax)) return 0;
+    return (xMin < W ? 1 : 0) | (xMax > W ? 2 : 0);
+}
+
+/* MODE 0: count entries per (vertex block, row).  MODE 1: fill the row lists. */
 template <int MODE>
 __global__ void __launch_bounds__(256) k_span(const __grid_constant__ SLSpanParams P)
 {
     __shared__ uint16_t sRowRun[SL_MAX_ROWS];
-    __shared__ uint32_t sMask[SL_SPAN_WIN][8];
+    __shared__ uint32_t sMask[2][SL_SPAN_WIN][8]; /* [0] overflow entries coming from the row below, [1] own spans */
     __shared__ int sMinY, sMaxY;
 
     const int tid = threadIdx.x;
     const unsigned int vb = blockIdx.x;
     const int H = (int)P.numRows;
+    const uint32_t myBit = 1u << (tid & 31);
+    const int wq = tid >> 5;
     for (int y = tid; y < H; y += 256) sRowRun[y] = 0;
     __syncthreads();
 
@@ -429,7 +459,8 @@ __global__ void __launch_bounds__(256) k_span(const __grid_constant__ SLSpanPara
             const bool valid = sub + tid < segCount;
             const uint32_t rec = segBase + sub + tid;
             SLScanline sl;
-            int y0 = 0x7fffffff, y1 = -1;
+            int y0 = 0x7fffffff, y1 = -1, yEnd = -1;
+            bool mayOver = false;
             if (valid)
             {
                 const float4* r = P.records + (size_t)rec * P.recStride;
@@ -440,40 +471,57 @@ __global__ void __launch_bounds__(256) k_span(const __grid_constant__ SLSpanPara
                 y0 = y0 < 0 ? 0 : y0;
                 y1 = y1 > H ? H : y1;
                 sl.init(p0, p1, p2);
+                /* span ends interpolate the vertex x's (rcpps error << 8 px), so only these can pass the row end */
+                mayOver = sl_max(sl_max(p0.x, p1.x), p2.x) + 8.f > (float)P.width;
+                yEnd = (mayOver && y1 < H) ? y1 + 1 : y1;
             }
             if (tid == 0) { sMinY = 0x7fffffff; sMaxY = -1; }
             __syncthreads();
-            if (valid && y0 < y1) { atomicMin(&sMinY, y0); atomicMax(&sMaxY, y1); }
+            if (valid && y0 < y1) { atomicMin(&sMinY, y0); atomicMax(&sMaxY, yEnd); }
             __syncthreads();
             const int cy0 = sMinY, cy1 = sMaxY;
             for (int w0 = cy0; w0 < cy1; w0 += SL_SPAN_WIN)
             {
                 const int w1 = min(w0 + SL_SPAN_WIN, cy1);
-                for (int i = tid; i < SL_SPAN_WIN * 8; i += 256) (&sMask[0][0])[i] = 0u;
+                for (int i = tid; i < 2 * SL_SPAN_WIN * 8; i += 256) (&sMask[0][0][0])[i] = 0u;
                 __syncthreads();
-                const int ya = max(y0, w0), yb = min(y1, w1);
-                for (int y = ya; y < yb; ++y)
-                {
-                    int32_t xMin, xMax;
-                    sl.step((float)y, xMin, xMax);
-                    if (xMin < xMax) atomicOr(&sMask[y - w0][tid >> 5], 1u << (tid & 31));
-                }
-                __syncthreads();
-                if (MODE == 1)
+                const int ya = max(y0, w0), yb = min(yEnd, w1);
+                for (int pass = 0; pass <= MODE; ++pass)
                 {
                     for (int y = ya; y < yb; ++y)
                     {
-                        int32_t xMin, xMax;
-                        sl.step((float)y, xMin, xMax);
-                        if (xMin < xMax)
+                        int32_t xMin, xMax, oMin = 0, oMax = 0;
+                        int own = 0, over = 0;
+                        if (y < y1)
+                        {
+                            sl.step((float)y, xMin, xMax);
+                            const int c = sl_classify_span(P, xMin, xMax);
+                            own = c & 1;
+                            if ((c & 2) && !mayOver) atomicOr(&P.counters->errorFlags, 8u);
+                            if (MODE == 0 && c == 3 && y + 1 < H)
+                            {
+                                atomicAdd(&P.counters->overflowPairs, 1ull);
+                                atomicAdd(&P.counters->spans, ~0ull); /* two entries, one span */
+                            }
+                        }
+                        if (mayOver && y > y0)
+                        {
+                            sl.step((float)(y - 1), oMin, oMax);
+                            over = (sl_classify_span(P, oMin, oMax) >> 1) & 1;
+                        }
+                        if (pass == 0)
+                        {
+                            if (over) atomicOr(&sMask[0][y - w0][wq], myBit);
+                            if (own) atomicOr(&sMask[1][y - w0][wq], myBit);
+                        }
+                        else if (own | over)
                         {
                             uint32_t rank = 0;
-                            const int wq = tid >> 5;
-                            for (int q = 0; q < wq; ++q) rank += __popc(sMask[y - w0][q]);
-                            rank += __popc(sMask[y - w0][wq] & ((1u << (tid & 31)) - 1u));
-                            const size_t slot = (size_t)P.rowStart[y] + P.off[(size_t)vb * P.rowPitch + y] + sRowRun[y] + rank;
-                            if (xMin < 0 || xMax > 65535) { atomicOr(&P.counters->errorFlags, 2u); xMin = 0; xMax = 0; }
-                            P.entries[slot] = SLSpanEntry{rec, (uint16_t)xMin, (uint16_t)xMax};
+                            for (int q = 0; q < wq; ++q) rank += __popc(sMask[0][y - w0][q]) + __popc(sMask[1][y - w0][q]);
+                            rank += __popc(sMask[0][y - w0][wq] & (myBit - 1u)) + __popc(sMask[1][y - w0][wq] & (myBit - 1u));
+                            size_t slot = (size_t)P.rowStart[y] + P.off[(size_t)vb * P.rowPitch + y] + sRowRun[y] + rank;
+                            if (over) P.entries[slot++] = SLSpanEntry{rec | SL_ENTRY_OVERFLOW, (uint16_t)oMin, (uint16_t)oMax};
+                            if (own) P.entries[slot] = SLSpanEntry{rec, (uint16_t)xMin, (uint16_t)xMax};
                         }
                     }
                     __syncthreads();
@@ -482,7 +530,7 @@ __global__ void __launch_bounds__(256) k_span(const __grid_constant__ SLSpanPara
                 {
                     uint32_t c = 0;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) c += __popc(sMask[yy - w0][q]);
+                    for (int q = 0; q < 8; ++q) c += __popc(sMask[0][yy - w0][q]) + __popc(sMask[1][yy - w0][q]);
                     sRowRun[yy] = (uint16_t)(sRowRun[yy] + c);
                 }
                 __syncthreads();
@@ -553,6 +601,7 @@ __global__ void __launch_bounds__(1024) k_scan_row_starts(const uint32_t* rowTot
     {
         rowStart[numRows] = sPart[1023];
         atomicAdd(&counters->spans, (unsigned long long)sPart[1023]);
+        counters->rasterTicket = 0u;
     }
 }
 
@@ -586,8 +635,10 @@ struct SLRasterParams
     int depthTest;   /* SL_DepthTest */
     int depthMask;
     int blend;       /* SL_BlendMode */
-    unsigned int numRows;
+    unsigned int numRows;     /* rows incl. the texture's padding rows */
     unsigned int width;       /* depth attachment width (row stride of every attachment, like the reference) */
+    unsigned long long* handoff; /* hash table of row-end hand-overs (null when the batch has none) */
+    unsigned int handoffMask;
     unsigned char* depth;
     int depthBpt;
     unsigned char* color[4];
@@ -790,18 +841,55 @@ SLD_FN void sl_shade_fragment(const SLRasterParams& P, const SLTriSetup& t, cons
     if (P.depthMask) sl_store_depth(P.depth, P.depthBpt, idx, z); /* :526-529 */
 }
 
+/* Row-end hand-over (see SL_ENTRY_OVERFLOW).  One 64-bit word per cut span:
+ * [63:16] key = rec<<14 | row, [15] valid, [10:8] depth outcomes of the in-row
+ * lanes of the straddling group, [7:0] lane map (2 bits per register). */
+SLD_FN unsigned long long sl_handoff_key(uint32_t rec, int y) { return ((unsigned long long)rec << 14) | (unsigned long long)(y & 0x3fff); }
+SLD_FN uint32_t sl_handoff_hash(unsigned long long key) { return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 40); }
+
+SLD_FN void sl_handoff_publish(const SLRasterParams& P, uint32_t rec, int y, uint32_t payload)
+{
+    const unsigned long long key = sl_handoff_key(rec, y);
+    const unsigned long long word = (key << 16) | 0x8000ull | (unsigned long long)(payload & 0x7ffu);
+    uint32_t i = sl_handoff_hash(key) & P.handoffMask;
+    while (atomicCAS(&P.handoff[i], 0ull, word) != 0ull) i = (i + 1u) & P.handoffMask;
+}
+
+SLD_FN bool sl_handoff_poll(const SLRasterParams& P, uint32_t rec, int y, uint32_t& payload)
+{
+    if (!P.handoff) { atomicOr(&P.counters->errorFlags, 8u); return true; }
+    const unsigned long long key = sl_handoff_key(rec, y);
+    uint32_t i = sl_handoff_hash(key) & P.handoffMask;
+    for (;;)
+    {
+        const unsigned long long w = *reinterpret_cast<volatile unsigned long long*>(&P.handoff[i]);
+        if (w == 0ull) return false;
+        if ((w >> 16) == key) { payload = (uint32_t)(w & 0x7ffu); return true; }
+        i = (i + 1u) & P.handoffMask;
+    }
+}
+
 /* One (triangle,row) span, walked left to right by ONE lane: the 4-pixel group
  * loop of render_triangle_simd (src/SL_TriRasterizer.cpp:471-548), including
- * the in-place compaction of the barycentric registers (:496-498). */
+ * the in-place compaction of the barycentric registers (:496-498).
+ * `yRow` is the row this warp owns.  A plain entry covers the span's pixels
+ * left of the row end; an overflow entry continues the span of row yRow-1 at
+ * the row end with the handed-over state. */
 template <FsFn FS>
-SLD_FN unsigned sl_walk_span(const SLRasterParams& P, const SLSpanEntry e, int y)
+SLD_FN unsigned sl_walk_span(const SLRasterParams& P, const SLSpanEntry e, int yRow, uint32_t handState)
 {
-    const float4* rec = P.records + (size_t)e.rec * P.recStride;
+    const bool isOver = (e.rec & SL_ENTRY_OVERFLOW) != 0u;
+    const uint32_t recId = e.rec & ~SL_ENTRY_OVERFLOW;
+    const int y = isOver ? yRow - 1 : yRow;
+    const int W = (int)P.width;
+    const float4* rec = P.records + (size_t)recId * P.recStride;
     SLTriSetup t;
     sl_tri_setup(t, rec[0], rec[1], rec[2]);
 
     const float yf = (float)y;
     const int xMin = e.xMin, xMax = e.xMax;
+    const bool cut = xMax > W; /* the span passes the row end */
+    const bool publish = cut && !isOver && (yRow + 1 < (int)P.numRows) && P.handoff != nullptr;
     const math::vec4 bcY = math::fmadd(t.bc1, math::vec4{yf}, t.bc2); /* :474 */
     math::vec4 a0 = (t.bc0 * (float)(xMin + 0)) + bcY;                /* :476-481 */
     math::vec4 a1 = (t.bc0 * (float)(xMin + 1)) + bcY;
@@ -810,32 +898,69 @@ SLD_FN unsigned sl_walk_span(const SLRasterParams& P, const SLSpanEntry e, int y
     const math::vec4 bcX = t.bc0 * 4.f;
     const size_t rowBase = (size_t)P.width * (size_t)y;
     unsigned shaded = 0;
+    int s0 = 0, s1 = 1, s2 = 2, s3 = 3; /* lane map: register i holds accumulator chain s_i (only tracked for cut spans) */
+    int x4 = xMin;
+    unsigned handM = 0u;
 
-    for (int x4 = xMin; x4 < xMax; x4 += 4)
+    if (isOver && xMin < W)
     {
+        /* replay the accumulator chains up to the group that contains the row end, then apply the handed-over lane map */
+        for (; x4 + 3 < W; x4 += 4) { a0 += bcX; a1 += bcX; a2 += bcX; a3 += bcX; }
+        const math::vec4 c[4] = {a0, a1, a2, a3};
+        a0 = c[handState & 3u];
+        a1 = c[(handState >> 2) & 3u];
+        a2 = c[(handState >> 4) & 3u];
+        a3 = c[(handState >> 6) & 3u];
+        handM = (handState >> 8) & 7u;
+    }
+
+    for (; x4 < xMax; x4 += 4)
+    {
+        const bool straddle = cut && (x4 + 3 >= W) && (x4 < W); /* lanes on both sides of the row end */
+        if (!isOver && x4 >= W)
+        {
+            /* the row end falls on a group boundary: everything from here on belongs to row yRow+1 */
+            if (publish) sl_handoff_publish(P, recId, y, (uint32_t)s0 | ((uint32_t)s1 << 2) | ((uint32_t)s2 << 4) | ((uint32_t)s3 << 6));
+            break;
+        }
         /* _sl_mul_vec4_mat4_ps (:376-393): z = (w*0 + z*z2) + (y*z1 + x*z0) */
         const float zA = ((a0.v[3] * 0.f) + (a0.v[2] * t.z2)) + ((a0.v[1] * t.z1) + (a0.v[0] * t.z0));
         const float zB = ((a1.v[3] * 0.f) + (a1.v[2] * t.z2)) + ((a1.v[1] * t.z1) + (a1.v[0] * t.z0));
         const float zC = ((a2.v[3] * 0.f) + (a2.v[2] * t.z2)) + ((a2.v[1] * t.z1) + (a2.v[0] * t.z0));
         const float zD = ((a3.v[3] * 0.f) + (a3.v[2] * t.z2)) + ((a3.v[1] * t.z1) + (a3.v[0] * t.z0));
-        const bool inA = x4 + 0 < xMax, inB = x4 + 1 < xMax, inC = x4 + 2 < xMax, inD = x4 + 3 < xMax;
-        const bool mA = inA && sl_depth_cmp(P.depthTest, zA, P.depthTest ? sl_load_depth(P.depth, P.depthBpt, rowBase + x4 + 0) : 0.f);
-        const bool mB = inB && sl_depth_cmp(P.depthTest, zB, P.depthTest ? sl_load_depth(P.depth, P.depthBpt, rowBase + x4 + 1) : 0.f);
-        const bool mC = inC && sl_depth_cmp(P.depthTest, zC, P.depthTest ? sl_load_depth(P.depth, P.depthBpt, rowBase + x4 + 2) : 0.f);
-        const bool mD = inD && sl_depth_cmp(P.depthTest, zD, P.depthTest ? sl_load_depth(P.depth, P.depthBpt, rowBase + x4 + 3) : 0.f);
-        if (mA || mB || mC || mD)
+        /* lanes this entry owns: left of the row end for a plain entry, at or beyond it for an overflow entry */
+        const bool ownA = (x4 + 0 < xMax) && ((x4 + 0 >= W) == isOver);
+        const bool ownB = (x4 + 1 < xMax) && ((x4 + 1 >= W) == isOver);
+        const bool ownC = (x4 + 2 < xMax) && ((x4 + 2 >= W) == isOver);
+        const bool ownD = (x4 + 3 < xMax) && ((x4 + 3 >= W) == isOver);
+        bool mA = ownA && sl_depth_cmp(P.depthTest, zA, P.depthTest ? sl_load_depth(P.depth, P.depthBpt, rowBase + x4 + 0) : 0.f);
+        bool mB = ownB && sl_depth_cmp(P.depthTest, zB, P.depthTest ? sl_load_depth(P.depth, P.depthBpt, rowBase + x4 + 1) : 0.f);
+        bool mC = ownC && sl_depth_cmp(P.depthTest, zC, P.depthTest ? sl_load_depth(P.depth, P.depthBpt, rowBase + x4 + 2) : 0.f);
+        bool mD = ownD && sl_depth_cmp(P.depthTest, zD, P.depthTest ? sl_load_depth(P.depth, P.depthBpt, rowBase + x4 + 3) : 0.f);
+        if (publish && x4 + 3 >= W)
+        {
+            const uint32_t payload = (uint32_t)s0 | ((uint32_t)s1 << 2) | ((uint32_t)s2 << 4) | ((uint32_t)s3 << 6) |
+                                     ((mA ? 1u : 0u) << 8) | ((mB ? 2u : 0u) << 8) | ((mC ? 4u : 0u) << 8);
+            sl_handoff_publish(P, recId, y, payload);
+        }
+        /* outcomes of the lanes the other entry owns: known (handed over) on the overflow side; on the in-row side they
+         * cannot change which register an in-row survivor reads (a survivor's register is resolved at or before its own lane) */
+        bool fA = false, fB = false, fC = false;
+        if (isOver && straddle) { fA = (handM & 1u) != 0u; fB = (handM & 2u) != 0u; fC = (handM & 4u) != 0u; handM = 0u; }
+        const bool tA = mA || fA, tB = mB || fB, tC = mC || fC, tD = mD;
+        if (tA || tB || tC || tD)
         {
             /* :496-498 -- the registers keep these values for the following groups */
-            a2 = mC ? a2 : a3;
-            a1 = mB ? a1 : a2;
-            a0 = mA ? a0 : a1;
+            a2 = tC ? a2 : a3;
+            a1 = tB ? a1 : a2;
+            a0 = tA ? a0 : a1;
+            if (cut) { s2 = tC ? s2 : s3; s1 = tB ? s1 : s2; s0 = tA ? s0 : s1; }
             /* :500-526 -- survivor number s is shaded with register s (new values) and its own x, z */
             int s = 0;
-            if (mA) { sl_shade_fragment<FS>(P, t, rec, a0, x4 + 0, y, zA); ++s; }
-            if (mB) { sl_shade_fragment<FS>(P, t, rec, s == 0 ? a0 : a1, x4 + 1, y, zB); ++s; }
-            if (mC) { sl_shade_fragment<FS>(P, t, rec, s == 0 ? a0 : (s == 1 ? a1 : a2), x4 + 2, y, zC); ++s; }
-            if (mD) { sl_shade_fragment<FS>(P, t, rec, s == 0 ? a0 : (s == 1 ? a1 : (s == 2 ? a2 : a3)), x4 + 3, y, zD); ++s; }
-            shaded += s;
+            if (tA) { if (mA) { sl_shade_fragment<FS>(P, t, rec, a0, x4 + 0, y, zA); ++shaded; } ++s; }
+            if (tB) { if (mB) { sl_shade_fragment<FS>(P, t, rec, s == 0 ? a0 : a1, x4 + 1, y, zB); ++shaded; } ++s; }
+            if (tC) { if (mC) { sl_shade_fragment<FS>(P, t, rec, s == 0 ? a0 : (s == 1 ? a1 : a2), x4 + 2, y, zC); ++shaded; } ++s; }
+            if (tD) { if (mD) { sl_shade_fragment<FS>(P, t, rec, s == 0 ? a0 : (s == 1 ? a1 : (s == 2 ? a2 : a3)), x4 + 3, y, zD); ++shaded; } ++s; }
         }
         a0 += bcX; /* :539-542 */
         a1 += bcX;
@@ -845,16 +970,21 @@ SLD_FN unsigned sl_walk_span(const SLRasterParams& P, const SLSpanEntry e, int y
     return shaded;
 }
 
-/* One warp per framebuffer row.  The row's spans are taken 32 at a time in
- * submission order; a lane may run its span as soon as no earlier, still
- * pending span of the batch overlaps it in x (fragments of disjoint x-ranges
- * commute; everything else is serialised in order). */
+/* One warp per framebuffer row (rows are handed out through a ticket so that a
+ * row can wait for the hand-over of the row below it).  The row's entries are
+ * taken 32 at a time in submission order; a lane may run its entry as soon as
+ * no earlier, still pending entry of the batch overlaps it in x (fragments of
+ * disjoint x-ranges commute; everything else is serialised in order). */
 template <FsFn FS>
 __global__ void __launch_bounds__(128) k_raster(const __grid_constant__ SLRasterParams P)
 {
+    __shared__ unsigned sTicket;
+    if (threadIdx.x == 0) sTicket = atomicAdd(&P.counters->rasterTicket, 1u);
+    __syncthreads();
     const int lane = threadIdx.x & 31;
-    const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int y = (int)(sTicket * (blockDim.x >> 5) + (threadIdx.x >> 5));
     if (y >= (int)P.numRows) return;
+    const int W = (int)P.width;
     const uint32_t begin = P.rowStart[y], end = P.rowStart[y + 1];
     unsigned shaded = 0;
 
@@ -863,21 +993,30 @@ __global__ void __launch_bounds__(128) k_raster(const __grid_constant__ SLRaster
         const bool valid = base + lane < end;
         SLSpanEntry e = SLSpanEntry{0u, 0, 0};
         if (valid) e = P.entries[base + lane];
+        /* pixels of row y this entry touches */
+        const bool isOver = (e.rec & SL_ENTRY_OVERFLOW) != 0u;
+        const int pMin = isOver ? max((int)e.xMin - W, 0) : (int)e.xMin;
+        const int pMax = isOver ? (int)e.xMax - W : min((int)e.xMax, W);
         uint32_t dep = 0;
         for (int i = 0; i < 31; ++i)
         {
-            const int oMin = __shfl_sync(0xffffffffu, (int)e.xMin, i);
-            const int oMax = __shfl_sync(0xffffffffu, (int)e.xMax, i);
-            if (i < lane && oMin < (int)e.xMax && (int)e.xMin < oMax) dep |= 1u << i;
+            const int oMin = __shfl_sync(0xffffffffu, pMin, i);
+            const int oMax = __shfl_sync(0xffffffffu, pMax, i);
+            if (i < lane && oMin < pMax && pMin < oMax) dep |= 1u << i;
         }
+        const bool needsHand = valid && isOver && (int)e.xMin < W;
         bool done = !valid;
         uint32_t doneMask = __ballot_sync(0xffffffffu, done);
         while (doneMask != 0xffffffffu)
         {
             if (!done && (dep & ~doneMask) == 0u)
             {
-                shaded += sl_walk_span<FS>(P, e, y);
-                done = true;
+                uint32_t hand = 0xE4u; /* identity lane map */
+                if (!needsHand || sl_handoff_poll(P, e.rec & ~SL_ENTRY_OVERFLOW, y - 1, hand))
+                {
+                    shaded += sl_walk_span<FS>(P, e, y, hand);
+                    done = true;
+                }
             }
             __syncwarp();
             doneMask = __ballot_sync(0xffffffffu, done);

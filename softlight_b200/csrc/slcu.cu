@@ -183,7 +183,7 @@ struct slcu_context
     slcu_stats stats{};
     SLCounters* counters = nullptr;     /* device */
     SLCounters* hostCounters = nullptr; /* pinned */
-    Scratch records, blockInfo, cnt, off, segSums, rowTotals, rowStart, entries;
+    Scratch records, blockInfo, cnt, off, segSums, rowTotals, rowStart, entries, handoff;
     /* optional per-kernel event timing (profile_begin / profile_end) */
     cudaEvent_t timerA = nullptr, timerB = nullptr;
     bool profiling = false;
@@ -318,14 +318,18 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
     const HostFbo& fbo = c->fbos[fboId];
     if (fbo.depth == (size_t)-1 || fbo.depth >= c->textures.size()) { c->err = "fbo has no depth attachment"; return SLCU_ERR_ARG; }
     const HostTexture& depthTex = c->textures[fbo.depth];
-    if (depthTex.h > SL_MAX_ROWS) { c->err = "framebuffer taller than SL_MAX_ROWS"; return SLCU_ERR_UNSUPPORTED; }
+    /* The reference addresses pixels linearly inside an allocation padded to ~4x the texels (src/SL_Texture.cpp:28-54), so
+     * clip-generated triangles that end above the viewport shade fragments in rows >= h.  Nothing can read those back and
+     * they cannot influence a texel below h*w, so rows >= h are not rasterised (and not counted, see slcu_stats). */
+    const unsigned H = depthTex.h;
+    if (H > (unsigned)SL_MAX_ROWS) { c->err = "framebuffer taller than SL_MAX_ROWS"; return SLCU_ERR_UNSUPPORTED; }
+    if (depthTex.w > 32767) { c->err = "framebuffer wider than 32767"; return SLCU_ERR_UNSUPPORTED; }
     if (depthTex.bpt != 2 && depthTex.bpt != 4 && depthTex.bpt != 8) { c->err = "depth attachment must be R_HALF/R_FLOAT/R_DOUBLE"; return SLCU_ERR_ARG; }
     int rc = ensure_rcp_table(c);
     if (rc) return rc;
     cudaSetDevice(c->device);
 
     const float fboW = (float)depthTex.w, fboH = (float)depthTex.h;
-    const unsigned H = depthTex.h;
     const unsigned rowPitch = (H + 31u) & ~31u;
     const int NV = sh.numVaryings;
     const int recStride = 3 + 3 * NV;
@@ -348,12 +352,13 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
     if (!numBlocks) return 0;
 
     unsigned long long recCapacity = totalPrims + totalPrims / 8 + 4096;
+    unsigned long long numHandoffs = 0;
     for (int attempt = 0;; ++attempt)
     {
         if (recCapacity > 0xfffffff0ull) { c->err = "draw too large for one batch"; return SLCU_ERR_UNSUPPORTED; }
         CK(c->records.ensure((size_t)recCapacity * recStride * sizeof(float4)));
         CK(c->blockInfo.ensure((size_t)numBlocks * sizeof(SLBlockInfo)));
-        CK(cudaMemsetAsync(&c->counters->recAlloc, 0, sizeof(unsigned long long), c->stream));
+        CK(cudaMemsetAsync(&c->counters->recAlloc, 0, 2 * sizeof(unsigned long long), c->stream)); /* recAlloc + overflowPairs */
 
         unsigned firstBlock = 0;
         for (size_t i = 0; i < launches; ++i)
@@ -409,6 +414,7 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
         sp.firstBlock = 0;
         sp.numRows = H;
         sp.rowPitch = rowPitch;
+        sp.width = depthTex.w;
         sp.recStride = recStride;
         sp.cnt = reinterpret_cast<uint16_t*>(c->cnt.buf.ptr);
         sp.off = reinterpret_cast<const uint32_t*>(c->off.buf.ptr);
@@ -442,6 +448,7 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
             return SLCU_ERR_OOM;
         }
         if (!totalSpans) return 0;
+        numHandoffs = c->hostCounters->overflowPairs;
 
         CK(c->entries.ensure((size_t)totalSpans * sizeof(SLSpanEntry)));
         sp.entries = reinterpret_cast<SLSpanEntry*>(c->entries.buf.ptr);
@@ -466,6 +473,17 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
     rp.width = depthTex.w;
     rp.depth = depthTex.dev;
     rp.depthBpt = depthTex.bpt;
+    rp.handoff = nullptr;
+    rp.handoffMask = 0;
+    if (numHandoffs)
+    {
+        size_t cap = 64;
+        while (cap < 2 * numHandoffs) cap <<= 1;
+        CK(c->handoff.ensure(cap * sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(c->handoff.buf.ptr, 0, cap * sizeof(unsigned long long), c->stream));
+        rp.handoff = reinterpret_cast<unsigned long long*>(c->handoff.buf.ptr);
+        rp.handoffMask = (unsigned)(cap - 1);
+    }
     for (int i = 0; i < 4; ++i)
     {
         rp.color[i] = nullptr;
@@ -526,7 +544,11 @@ static int clear_texture(slcu_context* c, const HostTexture& t, const unsigned c
 {
     SLClearParams p;
     p.dst = t.dev;
-    p.numTexels = (unsigned long long)t.w * t.h; /* the reference ignores the depth dimension (src/SL_ClearProcessor.cpp:23-63) */
+    /* The reference ignores the depth dimension, and its one-thread slice is count + (1 - count % 3) clipped to count
+     * (sl_calc_indexed_parition2<1>, SL_ShaderUtil.hpp:222-231; src/SL_ClearProcessor.cpp:23-33): the last texel is left
+     * untouched when count % 3 == 2.  Parity is against the 1-thread reference, so the same texels are written here. */
+    p.numTexels = (unsigned long long)t.w * t.h;
+    if (p.numTexels % 3ull == 2ull) p.numTexels -= 1ull;
     p.bpt = t.bpt;
     memset(p.texel, 0, sizeof(p.texel));
     memcpy(p.texel, texel, t.bpt);
@@ -573,7 +595,7 @@ void slcu_context_destroy(slcu_context* c)
     if (c->devTextures) cudaFree(c->devTextures);
     if (c->counters) cudaFree(c->counters);
     if (c->hostCounters) cudaFreeHost(c->hostCounters);
-    Scratch* s[] = {&c->records, &c->blockInfo, &c->cnt, &c->off, &c->segSums, &c->rowTotals, &c->rowStart, &c->entries};
+    Scratch* s[] = {&c->records, &c->blockInfo, &c->cnt, &c->off, &c->segSums, &c->rowTotals, &c->rowStart, &c->entries, &c->handoff};
     for (Scratch* x : s) x->release();
     cudaStreamDestroy(c->stream);
     delete c;
@@ -883,6 +905,14 @@ int slcu_get_stats(slcu_context* c, slcu_stats* out)
     c->stats.trisBinned = c->hostCounters->trisBinned;
     c->stats.spans = c->hostCounters->spans;
     c->stats.fragsShaded = c->hostCounters->fragsShaded;
+    if (c->hostCounters->errorFlags & ~1u)
+    {
+        /* inputs whose reference behaviour is not reproduced bit for bit */
+        char buf[160];
+        snprintf(buf, sizeof(buf), "device flags 0x%x: bit1 span longer than two rows, bit2 span starts left of x=0, bit3 unexpected row overflow",
+                 c->hostCounters->errorFlags);
+        c->err = buf;
+    }
     *out = c->stats;
     return 0;
 }

@@ -32,6 +32,11 @@ def _variants():
     v.append(("empty", dict(n=30, empty_draw=True)))
     v.append(("ragged_odd_size", dict(n=300, width=333, height=77)))
     v.append(("tiny_1x1", dict(n=50, width=1, height=1)))
+    # clip-generated triangles that end right of / above the viewport: fragments wrap into the next row / the padding rows
+    v.append(("overflow_wide", dict(n=900, width=640, height=48, clip_fraction=0.8)))
+    v.append(("overflow_blend", dict(n=700, width=257, height=131, clip_fraction=0.9, blend=1)))
+    v.append(("overflow_half_ge", dict(n=700, width=512, height=64, clip_fraction=0.9, depth_type=A.SL_COLOR_R_HALF,
+                                       depth_test=A.SL_DEPTH_TEST_GREATER_EQUAL, clear_depth=-1.0)))
     return v
 
 
