@@ -201,8 +201,18 @@ def run_cuda(args, rank, world, local_rank, dist):
     scene = S.SCENES[args.config]()
     ctx = A.Context("cuda", device=local_rank)
     inst = S.SceneInstance(scene, ctx)
+    sf, final = None, []
     if world > 1:
-        raise SystemExit("multi-GPU sort-first path not wired into bench.py yet")
+        # sort-first: this rank rasterises its interleaved row strips; composite = stores into rank 0's texture over NVLink
+        from softlight_b200.sortfirst import SortFirst
+
+        sf = SortFirst(ctx, dist, rank, world, strip_rows=args.strip_rows)
+        final = [sf.make_target(scene.color_type, scene.width, scene.height) for _ in range(2)]  # double-buffered
+
+    def render_frame(i):
+        inst.render()
+        if sf is not None:
+            sf.composite(inst.state["color"], final[i % 2])
 
     # L2 flush buffer (written between timed frames, outside the timed region)
     import ctypes as C
@@ -218,9 +228,9 @@ def run_cuda(args, rank, world, local_rank, dist):
         if dist is not None:
             dist.barrier()
 
-    for _ in range(max(args.warmup, 3)):
-        inst.render()
-    ctx.sync()
+    for i in range(max(args.warmup, 3)):
+        render_frame(i)
+    barrier()
 
     # ---- device-timed steps ------------------------------------------------------------
     sampler = ClockSampler(local_rank)
@@ -228,30 +238,35 @@ def run_cuda(args, rank, world, local_rank, dist):
     barrier()
     sampler.start()
     step_ms = []
-    for _ in range(args.steps):
+    for i in range(args.steps):
         flush_l2()
         ctx.timer_begin()
-        inst.render()
+        render_frame(i)
         step_ms.append(ctx.timer_end())
     barrier()
     clocks = sampler.stop()
     st = ctx.get_stats()
-    total_ms = float(sum(step_ms))
+    frags_total = st["fragsShaded"]
     if dist is not None:
+        # a frame is complete when the slowest rank's rows have landed: per-step MAX over ranks, then the sum
         import torch
-        t = torch.tensor([total_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+        t = torch.tensor(step_ms, dtype=torch.float64, device=f"cuda:{local_rank}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+        step_ms = [float(v) for v in t.tolist()]
+        f = torch.tensor([frags_total], dtype=torch.int64, device=f"cuda:{local_rank}")
+        dist.all_reduce(f, op=dist.ReduceOp.SUM)
+        frags_total = int(f.item())
+    total_ms = float(sum(step_ms))
     ms = total_ms / args.steps
-    frags = st["fragsShaded"] // args.steps
+    frags = frags_total // args.steps
     launches = st["kernelLaunches"] - args.steps  # minus the L2-flush clears
     value = scene.tris_per_frame / (ms * 1e-3) / 1e6
 
     # ---- per-kernel times for the roofline (separate pass; events around every launch) ----
     prof_frames = max(3, min(args.steps, 10))
     ctx.profile_begin()
-    for _ in range(prof_frames):
-        inst.render()
+    for i in range(prof_frames):
+        render_frame(i)
     kt = ctx.profile_end()
     alg = algorithmic_bytes(args.config, scene, frags)
     peak, peak_src = measured_peaks()
@@ -289,13 +304,23 @@ def run_cuda(args, rank, world, local_rank, dist):
         t0 = time.perf_counter()
         for key, (pin, _) in staged.items():
             ctx.vbo_assign_raw(inst.state[key], pin.ctypes.data, pin.nbytes)
-        inst.render()
-        ctx.texture_read_into(inst.state["color"], out_pin.ctypes.data, cbytes)
+        render_frame(i)
+        if sf is not None:
+            sf.frame_barrier()
+            if rank == 0:
+                ctx.texture_read_into(final[i % 2], out_pin.ctypes.data, cbytes)
+        else:
+            ctx.texture_read_into(inst.state["color"], out_pin.ctypes.data, cbytes)
         dt = (time.perf_counter() - t0) * 1e3
         if i >= 2:
             e2e_ms.append(dt)
+    if dist is not None:
+        import torch
+        t = torch.tensor(e2e_ms, dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = [float(v) for v in t.tolist()]
     e2e_ms_avg = float(np.mean(e2e_ms))
-    e2e = {"value": scene.tris_per_frame / (e2e_ms_avg * 1e-3) / 1e6, "unit": METRIC, "h2d_bytes_per_step": int(h2d + 1024),
+    e2e = {"value": scene.tris_per_frame / (e2e_ms_avg * 1e-3) / 1e6, "unit": METRIC, "h2d_bytes_per_step": int((h2d + 1024) * world),
            "d2h_bytes_per_step": int(cbytes), "ms_per_step": e2e_ms_avg, "checksum": int(out_pin[::4097].astype(np.uint64).sum())}
 
     line = {
@@ -303,7 +328,8 @@ def run_cuda(args, rank, world, local_rank, dist):
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.config}: {scene.name}, {scene.tris_per_frame} tris/frame, {scene.draws_per_frame} draw(s), "
                                f"{scene.width}x{scene.height}", "l2": "flushed between timed frames (256 MiB clear, untimed)",
-                   "parallelism": f"sort-first x{world}"},
+                   "parallelism": f"sort-first x{world}" + (f", {args.strip_rows}-row strips interleaved over ranks, geometry replicated, "
+                                                              "composite = peer stores into rank 0 over NVLink" if world > 1 else "")},
         "gfrags_per_s": frags / (ms * 1e-3) / 1e9, "fps": 1e3 / ms, "frags_per_frame": int(frags),
         "tris_binned_per_frame": int(st["trisBinned"] // args.steps), "spans_per_frame": int(st["spans"] // args.steps),
         "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline,
@@ -321,6 +347,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--config", default=DEFAULT_CONFIG)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strip-rows", type=int, default=8, help="rows per ownership strip of the sort-first partition")
     args = ap.parse_args()
 
     rank = env_int("RANK", 0)

@@ -189,6 +189,19 @@ SLCU_EXPORT int SLCU_FN(blit_rect)(slcu_context* ctx, size_t outTexture, size_t 
                                    uint16_t srcX0, uint16_t srcY0, uint16_t srcX1, uint16_t srcY1,
                                    uint16_t dstX0, uint16_t dstY0, uint16_t dstX1, uint16_t dstY1);
 
+/* ---- sort-first multi-GPU: ours (the reference is one process; its analogue is the per-thread scan-line interleave of
+ * SL_ScanlineBounds.hpp:31-50 / src/SL_TriRasterizer.cpp:436-438).  One process and one context per GPU.
+ * set_partition: this context rasterises only rows y with (y / stripRows) % world == rank (geometry and uniforms are
+ *   replicated by issuing the same calls on every rank).
+ * texture_ipc_export/import: a 64-byte CUDA IPC handle of a texture's texels, to be carried to the peer ranks by any
+ *   transport, and mapped there.
+ * composite: stores the rows this rank owns of its srcTexture into rank `root`'s dstTexture (a peer mapping over
+ *   NVLink when root != rank).  The caller synchronises the ranks (sync + barrier) before the root reads. */
+SLCU_EXPORT int SLCU_FN(set_partition)(slcu_context* ctx, unsigned rank, unsigned world, unsigned stripRows);
+SLCU_EXPORT int SLCU_FN(texture_ipc_export)(slcu_context* ctx, size_t texture, void* handle64);
+SLCU_EXPORT int SLCU_FN(texture_ipc_import)(slcu_context* ctx, size_t texture, unsigned peerRank, const void* handle64);
+SLCU_EXPORT int SLCU_FN(composite)(slcu_context* ctx, size_t srcTexture, size_t dstTexture, unsigned root);
+
 /* The reference's draw/clear/blit return after all workers joined.  Ours
  * enqueue on one stream; sync() is the join.  texture_read syncs by itself. */
 SLCU_EXPORT int SLCU_FN(sync)(slcu_context* ctx);

@@ -143,7 +143,15 @@ _SIGS = {
     "profile_end": (C.c_int, [_P, C.POINTER(KernelTimes)]),
 }
 
-EXPORTED_SYMBOLS = sorted(_SIGS)
+# product-only entry points (sort-first multi-GPU); the two checker libraries are single-process
+_SIGS_PRODUCT = {
+    "set_partition": (C.c_int, [_P, C.c_uint, C.c_uint, C.c_uint]),
+    "texture_ipc_export": (C.c_int, [_P, _SZ, _P]),
+    "texture_ipc_import": (C.c_int, [_P, _SZ, C.c_uint, _P]),
+    "composite": (C.c_int, [_P, _SZ, _SZ, C.c_uint]),
+}
+
+EXPORTED_SYMBOLS = sorted(list(_SIGS) + list(_SIGS_PRODUCT))
 
 _LIBS = {}
 
@@ -162,7 +170,10 @@ def load_library(impl: str):
     lib = C.CDLL(path, mode=C.RTLD_LOCAL)
     pre = PREFIX[impl]
     fns = {}
-    for name, (res, args) in _SIGS.items():
+    sigs = dict(_SIGS)
+    if impl == "cuda":
+        sigs.update(_SIGS_PRODUCT)
+    for name, (res, args) in sigs.items():
         fn = getattr(lib, pre + name)
         fn.restype = res
         fn.argtypes = args
@@ -348,6 +359,22 @@ class Context:
 
     def sync(self):
         self._chk(self.f["sync"](self.h), "sync")
+
+    # -- sort-first multi-GPU (product only) ---------------------------------
+    def set_partition(self, rank: int, world: int, strip_rows: int = 8):
+        self._chk(self.f["set_partition"](self.h, rank, world, strip_rows), "set_partition")
+
+    def texture_ipc_export(self, tid: int) -> bytes:
+        buf = (C.c_ubyte * 64)()
+        self._chk(self.f["texture_ipc_export"](self.h, tid, buf), "texture_ipc_export")
+        return bytes(buf)
+
+    def texture_ipc_import(self, tid: int, peer_rank: int, handle: bytes):
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        self._chk(self.f["texture_ipc_import"](self.h, tid, peer_rank, buf), "texture_ipc_import")
+
+    def composite(self, src_tex: int, dst_tex: int, root: int = 0):
+        self._chk(self.f["composite"](self.h, src_tex, dst_tex, root), "composite")
 
     def reset_stats(self):
         self.f["reset_stats"](self.h)

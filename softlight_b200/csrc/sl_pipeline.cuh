@@ -419,6 +419,9 @@ struct SLSpanParams
     const uint32_t* rowStart;    /* [numRows+1]                              */
     SLSpanEntry* entries;
     SLCounters* counters;
+    /* sort-first partition (null when this context owns every row) */
+    uint8_t* rowFlags;           /* MODE 0 out: 1 = some span of the row below runs over into this row */
+    const uint8_t* rowNeeded;    /* MODE 1 in : rows this rank rasterises (owned + the rows their hand-overs come from) */
 };
 
 /* What one (record,row) span contributes to the row lists.  bit0: an entry in
@@ -502,6 +505,7 @@ __global__ void __launch_bounds__(256) k_span(const __grid_constant__ SLSpanPara
                             {
                                 atomicAdd(&P.counters->overflowPairs, 1ull);
                                 atomicAdd(&P.counters->spans, ~0ull); /* two entries, one span */
+                                if (P.rowFlags) P.rowFlags[y + 1] = 1;
                             }
                         }
                         if (mayOver && y > y0)
@@ -514,7 +518,7 @@ __global__ void __launch_bounds__(256) k_span(const __grid_constant__ SLSpanPara
                             if (over) atomicOr(&sMask[0][y - w0][wq], myBit);
                             if (own) atomicOr(&sMask[1][y - w0][wq], myBit);
                         }
-                        else if (own | over)
+                        else if ((own | over) && (!P.rowNeeded || P.rowNeeded[y]))
                         {
                             uint32_t rank = 0;
                             for (int q = 0; q < wq; ++q) rank += __popc(sMask[0][y - w0][q]) + __popc(sMask[1][y - w0][q]);
@@ -546,11 +550,27 @@ __global__ void __launch_bounds__(256) k_span(const __grid_constant__ SLSpanPara
 /* column scans of cnt over the vertex blocks, two-level */
 constexpr int SL_SCAN_SEGS = 64;
 
-__global__ void k_scan_seg_sums(const uint16_t* cnt, uint32_t* segSums, unsigned numBlocks, unsigned rowPitch, unsigned blocksPerSeg)
+/* Sort-first partition: a rank rasterises the rows it owns plus, transitively, every row whose spans run over into a row
+ * it rasterises (that row's walker state is needed for the hand-over; it is recomputed locally instead of exchanged). */
+__global__ void k_row_closure(const uint8_t* rowFlags, uint8_t* rowNeeded, unsigned numRows, unsigned rank, unsigned world, unsigned stripRows)
+{
+    const unsigned y = blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= numRows) return;
+    bool needed = false;
+    for (unsigned k = y;; ++k)
+    {
+        if ((k / stripRows) % world == rank) { needed = true; break; }
+        if (k + 1 >= numRows || !rowFlags[k + 1]) break;
+    }
+    rowNeeded[y] = needed ? 1 : 0;
+}
+
+__global__ void k_scan_seg_sums(const uint16_t* cnt, uint32_t* segSums, unsigned numBlocks, unsigned rowPitch, unsigned blocksPerSeg, const uint8_t* rowNeeded, unsigned numRows)
 {
     const unsigned y = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned seg = blockIdx.y;
     if (y >= rowPitch) return;
+    if (rowNeeded && (y >= numRows || !rowNeeded[y])) { segSums[(size_t)seg * rowPitch + y] = 0; return; }
     const unsigned b0 = seg * blocksPerSeg;
     const unsigned b1 = min(b0 + blocksPerSeg, numBlocks);
     uint32_t s = 0;
@@ -605,11 +625,12 @@ __global__ void __launch_bounds__(1024) k_scan_row_starts(const uint32_t* rowTot
     }
 }
 
-__global__ void k_scan_offsets(const uint16_t* cnt, const uint32_t* segSums, uint32_t* off, unsigned numBlocks, unsigned rowPitch, unsigned blocksPerSeg)
+__global__ void k_scan_offsets(const uint16_t* cnt, const uint32_t* segSums, uint32_t* off, unsigned numBlocks, unsigned rowPitch, unsigned blocksPerSeg, const uint8_t* rowNeeded, unsigned numRows)
 {
     const unsigned y = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned seg = blockIdx.y;
     if (y >= rowPitch) return;
+    if (rowNeeded && (y >= numRows || !rowNeeded[y])) return;
     const unsigned b0 = seg * blocksPerSeg;
     const unsigned b1 = min(b0 + blocksPerSeg, numBlocks);
     uint32_t run = segSums[(size_t)seg * rowPitch + y];
@@ -639,6 +660,7 @@ struct SLRasterParams
     unsigned int width;       /* depth attachment width (row stride of every attachment, like the reference) */
     unsigned long long* handoff; /* hash table of row-end hand-overs (null when the batch has none) */
     unsigned int handoffMask;
+    const uint8_t* rowNeeded;    /* sort-first partition: rows this rank rasterises (null = all) */
     unsigned char* depth;
     int depthBpt;
     unsigned char* color[4];
@@ -984,6 +1006,7 @@ __global__ void __launch_bounds__(128) k_raster(const __grid_constant__ SLRaster
     const int lane = threadIdx.x & 31;
     const int y = (int)(sTicket * (blockDim.x >> 5) + (threadIdx.x >> 5));
     if (y >= (int)P.numRows) return;
+    if (P.rowNeeded && !P.rowNeeded[y]) return;
     const int W = (int)P.width;
     const uint32_t begin = P.rowStart[y], end = P.rowStart[y + 1];
     unsigned shaded = 0;
@@ -1056,6 +1079,42 @@ __global__ void k_clear(const __grid_constant__ SLClearParams P)
     else
     {
         for (unsigned long long i = tid; i < totalBytes; i += stride) P.dst[i] = P.texel[i % P.bpt];
+    }
+}
+
+/* ------------------------------------------------------------------------
+ * Sort-first composite: every rank stores the rows it owns into the root's
+ * copy of the attachment (a peer mapping over NVLink, or local memory on the
+ * root itself).  Ownership is exclusive per row, so this is a pure gather.
+ * ----------------------------------------------------------------------*/
+struct SLCompositeParams
+{
+    const unsigned char* src;
+    unsigned char* dst;
+    unsigned long long rowBytes;
+    unsigned int numRows, rank, world, stripRows;
+};
+
+__global__ void __launch_bounds__(256) k_composite(const __grid_constant__ SLCompositeParams P)
+{
+    const bool vec = (P.rowBytes % 16ull == 0ull) && ((reinterpret_cast<uintptr_t>(P.src) | reinterpret_cast<uintptr_t>(P.dst)) % 16u == 0u);
+    for (unsigned y = blockIdx.y; y < P.numRows; y += gridDim.y)
+    {
+        if ((y / P.stripRows) % P.world != P.rank) continue;
+        const unsigned char* s = P.src + (unsigned long long)y * P.rowBytes;
+        unsigned char* d = P.dst + (unsigned long long)y * P.rowBytes;
+        const unsigned long long t0 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+        const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+        if (vec)
+        {
+            const uint4* s4 = reinterpret_cast<const uint4*>(s);
+            uint4* d4 = reinterpret_cast<uint4*>(d);
+            for (unsigned long long i = t0; i < P.rowBytes / 16ull; i += stride) d4[i] = s4[i];
+        }
+        else
+        {
+            for (unsigned long long i = t0; i < P.rowBytes; i += stride) d[i] = s[i];
+        }
     }
 }
 

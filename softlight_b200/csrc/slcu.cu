@@ -183,7 +183,11 @@ struct slcu_context
     slcu_stats stats{};
     SLCounters* counters = nullptr;     /* device */
     SLCounters* hostCounters = nullptr; /* pinned */
-    Scratch records, blockInfo, cnt, off, segSums, rowTotals, rowStart, entries, handoff;
+    Scratch records, blockInfo, cnt, off, segSums, rowTotals, rowStart, entries, handoff, rowFlags, rowNeeded;
+    /* sort-first partition (slcu_set_partition) */
+    unsigned partRank = 0, partWorld = 1, partStripRows = 8;
+    struct PeerMap { size_t tex; unsigned rank; void* ptr; };
+    std::vector<PeerMap> peerMaps;
     /* optional per-kernel event timing (profile_begin / profile_end) */
     cudaEvent_t timerA = nullptr, timerB = nullptr;
     bool profiling = false;
@@ -353,6 +357,7 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
 
     unsigned long long recCapacity = totalPrims + totalPrims / 8 + 4096;
     unsigned long long numHandoffs = 0;
+    const uint8_t* rowNeeded = nullptr;
     for (int attempt = 0;; ++attempt)
     {
         if (recCapacity > 0xfffffff0ull) { c->err = "draw too large for one batch"; return SLCU_ERR_UNSUPPORTED; }
@@ -421,16 +426,33 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
         sp.rowStart = reinterpret_cast<const uint32_t*>(c->rowStart.buf.ptr);
         sp.entries = nullptr;
         sp.counters = c->counters;
+        sp.rowFlags = nullptr;
+        sp.rowNeeded = nullptr;
+        const bool partitioned = c->partWorld > 1;
+        if (partitioned)
+        {
+            CK(c->rowFlags.ensure(H + 1));
+            CK(c->rowNeeded.ensure(H + 1));
+            CK(cudaMemsetAsync(c->rowFlags.buf.ptr, 0, H + 1, c->stream));
+            sp.rowFlags = c->rowFlags.buf.ptr;
+        }
         { KernelScope ks(c, SLCU_K_SPAN_COUNT); k_span<0><<<numBlocks, 256, 0, c->stream>>>(sp); }
         CK(cudaGetLastError());
+        if (partitioned)
+        {
+            KernelScope ks(c, SLCU_K_SCAN);
+            k_row_closure<<<(H + 255) / 256, 256, 0, c->stream>>>(c->rowFlags.buf.ptr, c->rowNeeded.buf.ptr, H, c->partRank, c->partWorld, c->partStripRows);
+            rowNeeded = c->rowNeeded.buf.ptr;
+            sp.rowNeeded = rowNeeded;
+        }
         const dim3 sgrid((rowPitch + 127) / 128, usedSegs);
-        { KernelScope ks(c, SLCU_K_SCAN); k_scan_seg_sums<<<sgrid, 128, 0, c->stream>>>(sp.cnt, reinterpret_cast<uint32_t*>(c->segSums.buf.ptr), numBlocks, rowPitch, blocksPerSeg); }
+        { KernelScope ks(c, SLCU_K_SCAN); k_scan_seg_sums<<<sgrid, 128, 0, c->stream>>>(sp.cnt, reinterpret_cast<uint32_t*>(c->segSums.buf.ptr), numBlocks, rowPitch, blocksPerSeg, rowNeeded, H); }
         CK(cudaGetLastError());
         { KernelScope ks(c, SLCU_K_SCAN); k_scan_rows<<<(rowPitch + 127) / 128, 128, 0, c->stream>>>(reinterpret_cast<uint32_t*>(c->segSums.buf.ptr), reinterpret_cast<uint32_t*>(c->rowTotals.buf.ptr), rowPitch, usedSegs); }
         CK(cudaGetLastError());
         { KernelScope ks(c, SLCU_K_SCAN); k_scan_row_starts<<<1, 1024, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(c->rowTotals.buf.ptr), reinterpret_cast<uint32_t*>(c->rowStart.buf.ptr), H, c->counters); }
         CK(cudaGetLastError());
-        { KernelScope ks(c, SLCU_K_SCAN); k_scan_offsets<<<sgrid, 128, 0, c->stream>>>(sp.cnt, reinterpret_cast<const uint32_t*>(c->segSums.buf.ptr), reinterpret_cast<uint32_t*>(c->off.buf.ptr), numBlocks, rowPitch, blocksPerSeg); }
+        { KernelScope ks(c, SLCU_K_SCAN); k_scan_offsets<<<sgrid, 128, 0, c->stream>>>(sp.cnt, reinterpret_cast<const uint32_t*>(c->segSums.buf.ptr), reinterpret_cast<uint32_t*>(c->off.buf.ptr), numBlocks, rowPitch, blocksPerSeg, rowNeeded, H); }
         CK(cudaGetLastError());
 
         /* the span lists are sized from the count: one small read-back per draw */
@@ -475,6 +497,7 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
     rp.depthBpt = depthTex.bpt;
     rp.handoff = nullptr;
     rp.handoffMask = 0;
+    rp.rowNeeded = rowNeeded;
     if (numHandoffs)
     {
         size_t cap = 64;
@@ -595,7 +618,8 @@ void slcu_context_destroy(slcu_context* c)
     if (c->devTextures) cudaFree(c->devTextures);
     if (c->counters) cudaFree(c->counters);
     if (c->hostCounters) cudaFreeHost(c->hostCounters);
-    Scratch* s[] = {&c->records, &c->blockInfo, &c->cnt, &c->off, &c->segSums, &c->rowTotals, &c->rowStart, &c->entries, &c->handoff};
+    for (auto& pm : c->peerMaps) if (pm.ptr) cudaIpcCloseMemHandle(pm.ptr);
+    Scratch* s[] = {&c->records, &c->blockInfo, &c->cnt, &c->off, &c->segSums, &c->rowTotals, &c->rowStart, &c->entries, &c->handoff, &c->rowFlags, &c->rowNeeded};
     for (Scratch* x : s) x->release();
     cudaStreamDestroy(c->stream);
     delete c;
@@ -878,6 +902,73 @@ int slcu_blit_rect(slcu_context* c, size_t, size_t, uint16_t, uint16_t, uint16_t
 {
     c->err = "blit: not implemented yet";
     return SLCU_ERR_UNSUPPORTED;
+}
+
+/* ---- sort-first multi-GPU ---- */
+int slcu_set_partition(slcu_context* c, unsigned rank, unsigned world, unsigned stripRows)
+{
+    if (!c || world < 1 || rank >= world || stripRows < 1) return SLCU_ERR_ARG;
+    c->partRank = rank;
+    c->partWorld = world;
+    c->partStripRows = stripRows;
+    return 0;
+}
+
+int slcu_texture_ipc_export(slcu_context* c, size_t tex, void* handle64)
+{
+    if (!c || tex >= c->textures.size() || !handle64 || !c->textures[tex].dev) return SLCU_ERR_ARG;
+    cudaSetDevice(c->device);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the ABI");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, c->textures[tex].dev));
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+
+int slcu_texture_ipc_import(slcu_context* c, size_t tex, unsigned peerRank, const void* handle64)
+{
+    if (!c || tex >= c->textures.size() || !handle64) return SLCU_ERR_ARG;
+    cudaSetDevice(c->device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* ptr = nullptr;
+    CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    for (auto& pm : c->peerMaps)
+    {
+        if (pm.tex == tex && pm.rank == peerRank) { cudaIpcCloseMemHandle(pm.ptr); pm.ptr = ptr; return 0; }
+    }
+    c->peerMaps.push_back(slcu_context::PeerMap{tex, peerRank, ptr});
+    return 0;
+}
+
+int slcu_composite(slcu_context* c, size_t srcTex, size_t dstTex, unsigned root)
+{
+    if (!c || srcTex >= c->textures.size() || dstTex >= c->textures.size()) return SLCU_ERR_ARG;
+    cudaSetDevice(c->device);
+    const HostTexture& s = c->textures[srcTex];
+    const HostTexture& d = c->textures[dstTex];
+    if (s.w != d.w || s.h != d.h || s.bpt != d.bpt) { c->err = "composite: source and destination differ in size or format"; return SLCU_ERR_ARG; }
+    SLCompositeParams p;
+    p.src = s.dev;
+    p.dst = nullptr;
+    if (root == c->partRank) p.dst = d.dev;
+    else
+    {
+        for (const auto& pm : c->peerMaps) if (pm.tex == dstTex && pm.rank == root) p.dst = (unsigned char*)pm.ptr;
+    }
+    if (!p.dst) { c->err = "composite: the root's texture was not imported (slcu_texture_ipc_import)"; return SLCU_ERR_ARG; }
+    p.rowBytes = (unsigned long long)s.w * s.bpt;
+    p.numRows = s.h;
+    p.rank = c->partRank;
+    p.world = c->partWorld;
+    p.stripRows = c->partStripRows;
+    unsigned gx = (unsigned)((p.rowBytes / 16 + 255) / 256);
+    if (gx < 1) gx = 1;
+    if (gx > 8) gx = 8;
+    unsigned gy = s.h < 148u * 4u ? s.h : 148u * 4u;
+    { KernelScope ks(c, SLCU_K_COMPOSITE); k_composite<<<dim3(gx, gy), 256, 0, c->stream>>>(p); }
+    CK(cudaGetLastError());
+    return 0;
 }
 
 int slcu_sync(slcu_context* c)

@@ -112,3 +112,37 @@ def test_unregistered_shader_is_refused():
     ctx = A.Context("cuda")
     ubo = ctx.create_ubo(b"\0" * 16)
     assert ctx.create_shader("nope", "vcolor", ubo, vs_varyings=1, fs_varyings=1) == A.INVALID_ID
+
+
+@pytest.mark.parametrize("name,world,strip", [("c1_small", 2, 8), ("rand_clip_heavy", 2, 1), ("rand_overflow_wide", 3, 2),
+                                               ("rand_overflow_blend", 4, 1), ("c2_small", 8, 8), ("rand_overflow_half_ge", 2, 1)])
+def test_sort_first_partition_is_bit_identical(name, world, strip, golden):
+    """Every rank's context (all on this GPU) rasterises only its row strips (+ the rows its hand-overs come from);
+    the composite of the owned rows equals the unpartitioned frame bit for bit, spans that wrap across an ownership
+    boundary included."""
+    from softlight_b200 import sortfirst as SF
+
+    frames, hashes = golden
+    scene = cases.CASES[name]()
+    ctxs, insts, finals_c, finals_d = [], [], [], []
+    for r in range(world):
+        ctx = A.Context("cuda")
+        ctx.set_rcp_table(frames["rcp_table"])
+        ctx.set_partition(r, world, strip)
+        inst = S.SceneInstance(scene, ctx)
+        inst.render()
+        # local composite path (root == rank): owned rows -> a zero-initialised texture
+        fc = ctx.create_texture(scene.color_type, scene.width, scene.height)
+        fd = ctx.create_texture(scene.depth_type, scene.width, scene.height)
+        ctx.composite(inst.state["color"], fc, r)
+        ctx.composite(inst.state["depth"], fd, r)
+        ctx.sync()
+        finals_c.append(ctx.texture_read(fc, scene.color_type, scene.width, scene.height))
+        finals_d.append(ctx.texture_read(fd, scene.depth_type, scene.width, scene.height)[..., 0])
+        mine = SF.owned_rows(scene.height, r, world, strip)
+        assert not finals_c[-1][~mine].any(), "composite wrote a row this rank does not own"
+        ctxs.append(ctx)
+    color = SF.merge_owned_rows(finals_c, strip)
+    depth = SF.merge_owned_rows(finals_d, strip)
+    assert sha(color) == hashes[name]["color_sha256"]
+    assert sha(depth) == hashes[name]["depth_sha256"]
