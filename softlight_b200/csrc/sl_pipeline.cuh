@@ -50,7 +50,7 @@ struct SLSpanEntry { uint32_t rec; uint16_t xMin, xMax; };
 struct SLCounters
 {
     unsigned long long recAlloc;     /* triangle records allocated (reset per batch)      */
-    unsigned long long overflowPairs;/* spans cut at the row end (reset per batch)        */
+    unsigned long long handoffs;     /* span cuts (segment boundaries + row ends) that need a state hand-over (reset per batch) */
     unsigned long long trisBinned;
     unsigned long long spans;
     unsigned long long fragsShaded;
@@ -413,6 +413,9 @@ struct SLSpanParams
     unsigned int numRows;        /* rows incl. the texture's padding rows    */
     unsigned int rowPitch;       /* padded row count of cnt/off              */
     unsigned int width;          /* framebuffer width (row stride)           */
+    unsigned int segWidth;       /* x-segment width of the rasteriser        */
+    unsigned int numSegs;        /* segments per row                         */
+    int chained;                 /* depth test on: cut spans need hand-overs */
     int recStride;               /* float4 per record                        */
     uint16_t* cnt;               /* [numBlocks][rowPitch]                    */
     const uint32_t* off;         /* [numBlocks][rowPitch] exclusive over vb  */
@@ -435,6 +438,23 @@ SLD_FN int sl_classify_span(const SLSpanParams& P, int32_t& xMin, int32_t& xMax)
     if (xMax > 2 * W) { atomicOr(&P.counters->errorFlags, 2u); xMax = 2 * W; }
     if (!(xMin < xMax)) return 0;
     return (xMin < W ? 1 : 0) | (xMax > W ? 2 : 0);
+}
+
+/* Number of cuts of a (clamped) span of row y that need a hand-over: segment boundaries b*segWidth (b = 1..numSegs-1)
+ * and the row end W strictly inside (xMin, xMax), and the same boundaries shifted by W for the part that wraps into row
+ * y+1 (only when that row exists). */
+SLD_FN unsigned sl_count_cuts(const SLSpanParams& P, int32_t xMin, int32_t xMax, bool nextRowExists)
+{
+    const int32_t W = (int32_t)P.width, TW = (int32_t)P.segWidth, NS = (int32_t)P.numSegs;
+    unsigned n = 0;
+    for (int32_t b = xMin / TW + 1; b < NS && b * TW < xMax; ++b) ++n;
+    if (xMax > W && nextRowExists)
+    {
+        if (xMin < W) ++n;
+        const int32_t oMin = xMin > W ? xMin - W : 0;
+        for (int32_t b = oMin / TW + 1; b < NS && b * TW < xMax - W; ++b) { if (b * TW > xMin - W) ++n; }
+    }
+    return n;
 }
 
 /* MODE 0: count entries per (vertex block, row).  MODE 1: fill the row lists. */
@@ -464,6 +484,7 @@ __global__ void __launch_bounds__(256) k_span(const __grid_constant__ SLSpanPara
             SLScanline sl;
             int y0 = 0x7fffffff, y1 = -1, yEnd = -1;
             bool mayOver = false;
+            unsigned myCuts = 0;
             if (valid)
             {
                 const float4* r = P.records + (size_t)rec * P.recStride;
@@ -501,11 +522,14 @@ __global__ void __launch_bounds__(256) k_span(const __grid_constant__ SLSpanPara
                             const int c = sl_classify_span(P, xMin, xMax);
                             own = c & 1;
                             if ((c & 2) && !mayOver) atomicOr(&P.counters->errorFlags, 8u);
-                            if (MODE == 0 && c == 3 && y + 1 < H)
+                            if (MODE == 0 && c)
                             {
-                                atomicAdd(&P.counters->overflowPairs, 1ull);
-                                atomicAdd(&P.counters->spans, ~0ull); /* two entries, one span */
-                                if (P.rowFlags) P.rowFlags[y + 1] = 1;
+                                if (P.chained) myCuts += sl_count_cuts(P, xMin, xMax, y + 1 < H);
+                                if (c == 3 && y + 1 < H)
+                                {
+                                    atomicAdd(&P.counters->spans, ~0ull); /* two entries, one span */
+                                    if (P.rowFlags) P.rowFlags[y + 1] = 1;
+                                }
                             }
                         }
                         if (mayOver && y > y0)
@@ -538,6 +562,11 @@ __global__ void __launch_bounds__(256) k_span(const __grid_constant__ SLSpanPara
                     sRowRun[yy] = (uint16_t)(sRowRun[yy] + c);
                 }
                 __syncthreads();
+            }
+            if (MODE == 0)
+            {
+                for (int d = 16; d > 0; d >>= 1) myCuts += __shfl_down_sync(0xffffffffu, myCuts, d);
+                if ((tid & 31) == 0 && myCuts) atomicAdd(&P.counters->handoffs, (unsigned long long)myCuts);
             }
         }
     }
@@ -658,14 +687,17 @@ struct SLRasterParams
     int blend;       /* SL_BlendMode */
     unsigned int numRows;     /* rows incl. the texture's padding rows */
     unsigned int width;       /* depth attachment width (row stride of every attachment, like the reference) */
-    unsigned long long* handoff; /* hash table of row-end hand-overs (null when the batch has none) */
+    unsigned long long* handoff; /* hash table of hand-overs (null when the batch has none) */
     unsigned int handoffMask;
+    unsigned int segWidth;       /* x-segment width */
+    unsigned int numSegs;        /* segments per row (<= 32) */
+    unsigned int tileBytes;      /* shared memory per warp for its segment's depth + colour texels (0: work in global memory) */
     const uint8_t* rowNeeded;    /* sort-first partition: rows this rank rasterises (null = all) */
     unsigned char* depth;
     int depthBpt;
     unsigned char* color[4];
     int colorType[4];         /* SL_ColorDataType */
-    int colorWidth[4];
+    int colorBpt[4];          /* bytes per texel */
     SLCounters* counters;
 };
 
@@ -699,8 +731,9 @@ SLD_FN bool sl_depth_cmp(int func, float z, float d)
     }
 }
 
-/* assign_pixel<T> (src/SL_Framebuffer.cpp:44-217) */
-SLD_FN void sl_store_color(unsigned char* base, int type, size_t idx, const math::vec4& c)
+/* assign_pixel<T> (src/SL_Framebuffer.cpp:44-217), every format.  Kept out of line: the two formats the configs use
+ * have inline fast paths below, and the rasteriser's instruction footprint matters (profiles/). */
+__device__ __noinline__ void sl_store_color_generic(unsigned char* base, int type, size_t idx, const math::vec4& c)
 {
     const int kind = type % 7;
     const int n = type / 7 + 1;
@@ -736,8 +769,20 @@ SLD_FN void sl_store_color(unsigned char* base, int type, size_t idx, const math
     }
 }
 
+SLD_FN void sl_store_color(unsigned char* base, int type, size_t idx, const math::vec4& c)
+{
+    if (type == 21) /* SL_COLOR_RGBA_8U */
+    {
+        const math::vec4_t<uint8_t> r = math::vec4_to_u8(c * 255.f);
+        reinterpret_cast<uint32_t*>(base)[idx] = (uint32_t)r.v[0] | ((uint32_t)r.v[1] << 8) | ((uint32_t)r.v[2] << 16) | ((uint32_t)r.v[3] << 24);
+    }
+    else if (type == 26) /* SL_COLOR_RGBA_FLOAT */
+        reinterpret_cast<float4*>(base)[idx] = make_float4(c.v[0], c.v[1], c.v[2], c.v[3]);
+    else sl_store_color_generic(base, type, idx, c);
+}
+
 /* destination read of assign_alpha_pixel (src/SL_Framebuffer.cpp:284-312), 3-channel quirk (:308) included */
-SLD_FN math::vec4 sl_load_color(const unsigned char* base, int type, size_t idx)
+__device__ __noinline__ math::vec4 sl_load_color_generic(const unsigned char* base, int type, size_t idx)
 {
     const int kind = type % 7;
     const int n = type / 7 + 1;
@@ -779,6 +824,21 @@ SLD_FN math::vec4 sl_load_color(const unsigned char* base, int type, size_t idx)
     else d = math::vec4{ch[0], ch[1], ch[2], ch[3]};
     if (kind <= 1) d = d * scale;
     return d;
+}
+
+SLD_FN math::vec4 sl_load_color(const unsigned char* base, int type, size_t idx)
+{
+    if (type == 21) /* SL_COLOR_RGBA_8U: color_cast<float,uint8_t> = (float)c * 0.00392156862745f */
+    {
+        const uint32_t u = reinterpret_cast<const uint32_t*>(base)[idx];
+        return math::vec4{(float)(u & 0xffu), (float)((u >> 8) & 0xffu), (float)((u >> 16) & 0xffu), (float)(u >> 24)} * 0.00392156862745f;
+    }
+    if (type == 26) /* SL_COLOR_RGBA_FLOAT */
+    {
+        const float4 f = reinterpret_cast<const float4*>(base)[idx];
+        return math::vec4{f.x, f.y, f.z, f.w};
+    }
+    return sl_load_color_generic(base, type, idx);
 }
 
 /* assign_alpha_pixel<T> (src/SL_Framebuffer.cpp:270-368) */
@@ -823,9 +883,19 @@ SLD_FN void sl_tri_setup(SLTriSetup& t, const float4 p0, const float4 p1, const 
     t.w0 = p0.w; t.w1 = p1.w; t.w2 = p2.w;
 }
 
+/* Where a warp's pixels live while it works on them: the depth and colour texels of its (row, x-segment) staged into
+ * shared memory (origin = linear index x + width*y of the segment's first pixel), or the attachments themselves
+ * (origin 0) when a segment does not fit the shared-memory budget. */
+struct SLTile
+{
+    unsigned char* depth;
+    unsigned char* color[4];
+    long long origin;
+};
+
 /* SL_FragmentProcessor::flush_tri_fragments for one fragment (src/SL_FragmentProcessor.cpp:416-531) */
 template <FsFn FS>
-SLD_FN void sl_shade_fragment(const SLRasterParams& P, const SLTriSetup& t, const float4* rec, const math::vec4& bcIn, int x, int y, float z)
+SLD_FN void sl_shade_fragment(const SLRasterParams& P, const SLTile& T, const SLTriSetup& t, const float4* rec, const math::vec4& bcIn, int x, int y, float z)
 {
     /* :438-460 perspective correction */
     math::vec4 bc = bcIn * math::vec4{t.w0, t.w1, t.w2, 0.f};
@@ -850,200 +920,504 @@ SLD_FN void sl_shade_fragment(const SLRasterParams& P, const SLTriSetup& t, cons
     for (int i = 0; i < 4; ++i) fp.pOutputs[i] = math::vec4{0.f};
 
     const bool haveOutputs = FS(fp); /* :501 */
-    const size_t idx = (size_t)x + (size_t)P.width * (size_t)y;
+    /* every attachment is addressed as x + width*y with the depth attachment's width (the reference uses each colour
+     * view's own width; SL_Framebuffer::valid requires them to be equal, and run_draw refuses anything else) */
+    const size_t idx = (size_t)((long long)x + (long long)P.width * (long long)y - T.origin);
     if (haveOutputs)
     {
         for (int i = P.numOutputs - 1; i >= 0; --i) /* :507-523 */
         {
-            const size_t cidx = (size_t)x + (size_t)P.colorWidth[i] * (size_t)y;
-            if (P.blend != 0) sl_blend_color(P.color[i], P.colorType[i], cidx, fp.pOutputs[i], P.blend);
-            else sl_store_color(P.color[i], P.colorType[i], cidx, fp.pOutputs[i]);
+            if (P.blend != 0) sl_blend_color(T.color[i], P.colorType[i], idx, fp.pOutputs[i], P.blend);
+            else sl_store_color(T.color[i], P.colorType[i], idx, fp.pOutputs[i]);
         }
     }
-    if (P.depthMask) sl_store_depth(P.depth, P.depthBpt, idx, z); /* :526-529 */
+    if (P.depthMask) sl_store_depth(T.depth, P.depthBpt, idx, z); /* :526-529 */
 }
 
-/* Row-end hand-over (see SL_ENTRY_OVERFLOW).  One 64-bit word per cut span:
- * [63:16] key = rec<<14 | row, [15] valid, [10:8] depth outcomes of the in-row
- * lanes of the straddling group, [7:0] lane map (2 bits per register). */
-SLD_FN unsigned long long sl_handoff_key(uint32_t rec, int y) { return ((unsigned long long)rec << 14) | (unsigned long long)(y & 0x3fff); }
-SLD_FN uint32_t sl_handoff_hash(unsigned long long key) { return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 40); }
-
-SLD_FN void sl_handoff_publish(const SLRasterParams& P, uint32_t rec, int y, uint32_t payload)
+/* Hand-over of the walker state at a cut (see SL_ENTRY_OVERFLOW).  A row is rasterised by numSegs warps, one per
+ * x-segment; a span that crosses a segment boundary (or the row end) is walked piece by piece, and the piece on the
+ * right needs the state the piece on the left ends with.  One 64-bit word per cut in a hash table:
+ * [63:12] key = record<<20 | source row<<7 | boundary index, [11] valid, [10:8] depth outcomes of the straddling
+ * group's lanes left of the cut, [7:0] lane map (2 bits per register).  Boundary b of a span of row y: x = b*segWidth
+ * for b < numSegs, x = W for b = numSegs (row end), x = W + (b-numSegs)*segWidth beyond (the part that wrapped into
+ * row y+1).  A consumer only ever waits for a warp with a smaller ticket (left segment of its row, or the row below),
+ * and tickets are taken in launch order, so the wait cannot deadlock. */
+SLD_FN unsigned long long sl_handoff_key(uint32_t rec, int y, int boundary)
 {
-    const unsigned long long key = sl_handoff_key(rec, y);
-    const unsigned long long word = (key << 16) | 0x8000ull | (unsigned long long)(payload & 0x7ffu);
+    return ((unsigned long long)rec << 20) | ((unsigned long long)(y & 0x1fff) << 7) | (unsigned long long)(boundary & 0x7f);
+}
+SLD_FN uint32_t sl_handoff_hash(unsigned long long key) { return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 36); }
+
+SLD_FN void sl_handoff_publish(const SLRasterParams& P, uint32_t rec, int y, int boundary, uint32_t payload)
+{
+    if (!P.handoff) { atomicOr(&P.counters->errorFlags, 16u); return; } /* the count pass and the walkers disagree */
+    const unsigned long long key = sl_handoff_key(rec, y, boundary);
+    const unsigned long long word = (key << 12) | 0x800ull | (unsigned long long)(payload & 0x7ffu);
     uint32_t i = sl_handoff_hash(key) & P.handoffMask;
     while (atomicCAS(&P.handoff[i], 0ull, word) != 0ull) i = (i + 1u) & P.handoffMask;
 }
 
-SLD_FN bool sl_handoff_poll(const SLRasterParams& P, uint32_t rec, int y, uint32_t& payload)
+SLD_FN bool sl_handoff_poll(const SLRasterParams& P, uint32_t rec, int y, int boundary, uint32_t& payload)
 {
     if (!P.handoff) { atomicOr(&P.counters->errorFlags, 8u); return true; }
-    const unsigned long long key = sl_handoff_key(rec, y);
+    const unsigned long long key = sl_handoff_key(rec, y, boundary);
     uint32_t i = sl_handoff_hash(key) & P.handoffMask;
     for (;;)
     {
         const unsigned long long w = *reinterpret_cast<volatile unsigned long long*>(&P.handoff[i]);
         if (w == 0ull) return false;
-        if ((w >> 16) == key) { payload = (uint32_t)(w & 0x7ffu); return true; }
+        if ((w >> 12) == key) { payload = (uint32_t)(w & 0x7ffu); return true; }
         i = (i + 1u) & P.handoffMask;
     }
 }
 
-/* One (triangle,row) span, walked left to right by ONE lane: the 4-pixel group
- * loop of render_triangle_simd (src/SL_TriRasterizer.cpp:471-548), including
- * the in-place compaction of the barycentric registers (:496-498).
- * `yRow` is the row this warp owns.  A plain entry covers the span's pixels
- * left of the row end; an overflow entry continues the span of row yRow-1 at
- * the row end with the handed-over state. */
-template <FsFn FS>
-SLD_FN unsigned sl_walk_span(const SLRasterParams& P, const SLSpanEntry e, int yRow, uint32_t handState)
+constexpr uint32_t SL_STATE_IDENTITY = 0xE4u; /* lane map (0,1,2,3) */
+
+/* the compaction of src/SL_TriRasterizer.cpp:496-498 on the lane map: t = outcomes of the four lanes (bit i = lane i) */
+SLD_FN uint32_t sl_state_step(uint32_t st, uint32_t t)
 {
-    const bool isOver = (e.rec & SL_ENTRY_OVERFLOW) != 0u;
-    const uint32_t recId = e.rec & ~SL_ENTRY_OVERFLOW;
-    const int y = isOver ? yRow - 1 : yRow;
-    const int W = (int)P.width;
+    if (!t) return st;
+    const uint32_t s3 = (st >> 6) & 3u;
+    const uint32_t s2 = (t & 4u) ? ((st >> 4) & 3u) : s3;
+    const uint32_t s1 = (t & 2u) ? ((st >> 2) & 3u) : s2;
+    const uint32_t s0 = (t & 1u) ? (st & 3u) : s1;
+    return s0 | (s1 << 2) | (s2 << 4) | (s3 << 6);
+}
+
+/* One piece [p0,p1) of the span [xMin,xMax) of source row y, walked left to right by ONE lane: the 4-pixel group loop
+ * of render_triangle_simd (src/SL_TriRasterizer.cpp:471-548), including the in-place compaction of the barycentric
+ * registers (:496-498).  Pixels are addressed linearly from the source row, exactly like the reference, so a piece
+ * that lies beyond the row end needs no coordinate change.  `hand`: state at p0 (lane map + outcomes of the lanes of
+ * the straddling group left of p0) when the piece does not start the span. */
+template <FsFn FS>
+SLD_FN unsigned sl_walk_piece(const SLRasterParams& P, const SLTile& T, uint32_t recId, int y, int xMin, int xMax, int p0, int p1, uint32_t hand,
+                              bool publish, int outBoundary)
+{
     const float4* rec = P.records + (size_t)recId * P.recStride;
     SLTriSetup t;
     sl_tri_setup(t, rec[0], rec[1], rec[2]);
 
     const float yf = (float)y;
-    const int xMin = e.xMin, xMax = e.xMax;
-    const bool cut = xMax > W; /* the span passes the row end */
-    const bool publish = cut && !isOver && (yRow + 1 < (int)P.numRows) && P.handoff != nullptr;
     const math::vec4 bcY = math::fmadd(t.bc1, math::vec4{yf}, t.bc2); /* :474 */
     math::vec4 a0 = (t.bc0 * (float)(xMin + 0)) + bcY;                /* :476-481 */
     math::vec4 a1 = (t.bc0 * (float)(xMin + 1)) + bcY;
     math::vec4 a2 = (t.bc0 * (float)(xMin + 2)) + bcY;
     math::vec4 a3 = (t.bc0 * (float)(xMin + 3)) + bcY;
     const math::vec4 bcX = t.bc0 * 4.f;
-    const size_t rowBase = (size_t)P.width * (size_t)y;
+    const long long rowBase = (long long)P.width * (long long)y - T.origin;
     unsigned shaded = 0;
-    int s0 = 0, s1 = 1, s2 = 2, s3 = 3; /* lane map: register i holds accumulator chain s_i (only tracked for cut spans) */
+    uint32_t st = SL_STATE_IDENTITY; /* lane map: register i holds accumulator chain (st >> 2i) & 3 */
+    uint32_t fM = 0u;                /* outcomes of the first group's lanes that another piece owns */
     int x4 = xMin;
-    unsigned handM = 0u;
+    bool published = false;
 
-    if (isOver && xMin < W)
+    if (xMin < p0)
     {
-        /* replay the accumulator chains up to the group that contains the row end, then apply the handed-over lane map */
-        for (; x4 + 3 < W; x4 += 4) { a0 += bcX; a1 += bcX; a2 += bcX; a3 += bcX; }
-        const math::vec4 c[4] = {a0, a1, a2, a3};
-        a0 = c[handState & 3u];
-        a1 = c[(handState >> 2) & 3u];
-        a2 = c[(handState >> 4) & 3u];
-        a3 = c[(handState >> 6) & 3u];
-        handM = (handState >> 8) & 7u;
+        /* replay the accumulator chains up to the group that contains p0, then apply the handed-over lane map */
+        for (; x4 + 3 < p0; x4 += 4) { a0 += bcX; a1 += bcX; a2 += bcX; a3 += bcX; }
+        st = hand & 0xffu;
+        if (st != SL_STATE_IDENTITY)
+        {
+            const math::vec4 c[4] = {a0, a1, a2, a3};
+            a0 = c[st & 3u];
+            a1 = c[(st >> 2) & 3u];
+            a2 = c[(st >> 4) & 3u];
+            a3 = c[(st >> 6) & 3u];
+        }
+        fM = (hand >> 8) & 7u;
     }
 
-    for (; x4 < xMax; x4 += 4)
+    for (; x4 < p1; x4 += 4)
     {
-        const bool straddle = cut && (x4 + 3 >= W) && (x4 < W); /* lanes on both sides of the row end */
-        if (!isOver && x4 >= W)
-        {
-            /* the row end falls on a group boundary: everything from here on belongs to row yRow+1 */
-            if (publish) sl_handoff_publish(P, recId, y, (uint32_t)s0 | ((uint32_t)s1 << 2) | ((uint32_t)s2 << 4) | ((uint32_t)s3 << 6));
-            break;
-        }
         /* _sl_mul_vec4_mat4_ps (:376-393): z = (w*0 + z*z2) + (y*z1 + x*z0) */
         const float zA = ((a0.v[3] * 0.f) + (a0.v[2] * t.z2)) + ((a0.v[1] * t.z1) + (a0.v[0] * t.z0));
         const float zB = ((a1.v[3] * 0.f) + (a1.v[2] * t.z2)) + ((a1.v[1] * t.z1) + (a1.v[0] * t.z0));
         const float zC = ((a2.v[3] * 0.f) + (a2.v[2] * t.z2)) + ((a2.v[1] * t.z1) + (a2.v[0] * t.z0));
         const float zD = ((a3.v[3] * 0.f) + (a3.v[2] * t.z2)) + ((a3.v[1] * t.z1) + (a3.v[0] * t.z0));
-        /* lanes this entry owns: left of the row end for a plain entry, at or beyond it for an overflow entry */
-        const bool ownA = (x4 + 0 < xMax) && ((x4 + 0 >= W) == isOver);
-        const bool ownB = (x4 + 1 < xMax) && ((x4 + 1 >= W) == isOver);
-        const bool ownC = (x4 + 2 < xMax) && ((x4 + 2 >= W) == isOver);
-        const bool ownD = (x4 + 3 < xMax) && ((x4 + 3 >= W) == isOver);
-        bool mA = ownA && sl_depth_cmp(P.depthTest, zA, P.depthTest ? sl_load_depth(P.depth, P.depthBpt, rowBase + x4 + 0) : 0.f);
-        bool mB = ownB && sl_depth_cmp(P.depthTest, zB, P.depthTest ? sl_load_depth(P.depth, P.depthBpt, rowBase + x4 + 1) : 0.f);
-        bool mC = ownC && sl_depth_cmp(P.depthTest, zC, P.depthTest ? sl_load_depth(P.depth, P.depthBpt, rowBase + x4 + 2) : 0.f);
-        bool mD = ownD && sl_depth_cmp(P.depthTest, zD, P.depthTest ? sl_load_depth(P.depth, P.depthBpt, rowBase + x4 + 3) : 0.f);
-        if (publish && x4 + 3 >= W)
+        const bool ownA = (x4 + 0 >= p0) && (x4 + 0 < p1);
+        const bool ownB = (x4 + 1 >= p0) && (x4 + 1 < p1);
+        const bool ownC = (x4 + 2 >= p0) && (x4 + 2 < p1);
+        const bool ownD = (x4 + 3 >= p0) && (x4 + 3 < p1);
+        const bool mA = ownA && sl_depth_cmp(P.depthTest, zA, P.depthTest ? sl_load_depth(T.depth, P.depthBpt, (size_t)(rowBase + x4 + 0)) : 0.f);
+        const bool mB = ownB && sl_depth_cmp(P.depthTest, zB, P.depthTest ? sl_load_depth(T.depth, P.depthBpt, (size_t)(rowBase + x4 + 1)) : 0.f);
+        const bool mC = ownC && sl_depth_cmp(P.depthTest, zC, P.depthTest ? sl_load_depth(T.depth, P.depthBpt, (size_t)(rowBase + x4 + 2)) : 0.f);
+        const bool mD = ownD && sl_depth_cmp(P.depthTest, zD, P.depthTest ? sl_load_depth(T.depth, P.depthBpt, (size_t)(rowBase + x4 + 3)) : 0.f);
+        /* outcomes of the lanes left of p0 are known (handed over); lanes at or beyond p1 are unknown, but they cannot
+         * change which register a survivor of this piece reads (that is resolved at or before the survivor's own lane) */
+        const bool tA = mA || (fM & 1u), tB = mB || (fM & 2u), tC = mC || (fM & 4u), tD = mD;
+        const uint32_t tBits = (tA ? 1u : 0u) | (tB ? 2u : 0u) | (tC ? 4u : 0u) | (tD ? 8u : 0u);
+        fM = 0u;
+        if (publish && x4 + 3 >= p1)
         {
-            const uint32_t payload = (uint32_t)s0 | ((uint32_t)s1 << 2) | ((uint32_t)s2 << 4) | ((uint32_t)s3 << 6) |
-                                     ((mA ? 1u : 0u) << 8) | ((mB ? 2u : 0u) << 8) | ((mC ? 4u : 0u) << 8);
-            sl_handoff_publish(P, recId, y, payload);
+            /* the cut lies inside this group: state before the group + outcomes of its lanes left of the cut */
+            const uint32_t below = (1u << (p1 - x4)) - 1u;
+            sl_handoff_publish(P, recId, y, outBoundary, st | ((tBits & below & 7u) << 8));
+            published = true;
         }
-        /* outcomes of the lanes the other entry owns: known (handed over) on the overflow side; on the in-row side they
-         * cannot change which register an in-row survivor reads (a survivor's register is resolved at or before its own lane) */
-        bool fA = false, fB = false, fC = false;
-        if (isOver && straddle) { fA = (handM & 1u) != 0u; fB = (handM & 2u) != 0u; fC = (handM & 4u) != 0u; handM = 0u; }
-        const bool tA = mA || fA, tB = mB || fB, tC = mC || fC, tD = mD;
-        if (tA || tB || tC || tD)
+        if (tBits)
         {
             /* :496-498 -- the registers keep these values for the following groups */
             a2 = tC ? a2 : a3;
             a1 = tB ? a1 : a2;
             a0 = tA ? a0 : a1;
-            if (cut) { s2 = tC ? s2 : s3; s1 = tB ? s1 : s2; s0 = tA ? s0 : s1; }
-            /* :500-526 -- survivor number s is shaded with register s (new values) and its own x, z */
-            int s = 0;
-            if (tA) { if (mA) { sl_shade_fragment<FS>(P, t, rec, a0, x4 + 0, y, zA); ++shaded; } ++s; }
-            if (tB) { if (mB) { sl_shade_fragment<FS>(P, t, rec, s == 0 ? a0 : a1, x4 + 1, y, zB); ++shaded; } ++s; }
-            if (tC) { if (mC) { sl_shade_fragment<FS>(P, t, rec, s == 0 ? a0 : (s == 1 ? a1 : a2), x4 + 2, y, zC); ++shaded; } ++s; }
-            if (tD) { if (mD) { sl_shade_fragment<FS>(P, t, rec, s == 0 ? a0 : (s == 1 ? a1 : (s == 2 ? a2 : a3)), x4 + 3, y, zD); ++shaded; } ++s; }
+            st = sl_state_step(st, tBits);
+            /* :500-526 -- survivor number s is shaded with register s (new values) and its own x, z.  One call site,
+             * not four: the shading code is the bulk of the kernel and must stay small enough for the instruction cache */
+            const uint32_t mBits = (mA ? 1u : 0u) | (mB ? 2u : 0u) | (mC ? 4u : 0u) | (mD ? 8u : 0u);
+            int sIdx = 0;
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j)
+            {
+                if (!((tBits >> j) & 1u)) continue;
+                if ((mBits >> j) & 1u)
+                {
+                    const math::vec4 bc = sIdx == 0 ? a0 : (sIdx == 1 ? a1 : (sIdx == 2 ? a2 : a3));
+                    const float z = j == 0 ? zA : (j == 1 ? zB : (j == 2 ? zC : zD));
+                    sl_shade_fragment<FS>(P, T, t, rec, bc, x4 + j, y, z);
+                    ++shaded;
+                }
+                ++sIdx;
+            }
         }
         a0 += bcX; /* :539-542 */
         a1 += bcX;
         a2 += bcX;
         a3 += bcX;
     }
+    if (publish && !published) sl_handoff_publish(P, recId, y, outBoundary, st); /* the cut falls on a group boundary */
     return shaded;
 }
 
-/* One warp per framebuffer row (rows are handed out through a ticket so that a
- * row can wait for the hand-over of the row below it).  The row's entries are
- * taken 32 at a time in submission order; a lane may run its entry as soon as
- * no earlier, still pending entry of the batch overlaps it in x (fragments of
- * disjoint x-ranges commute; everything else is serialised in order). */
+/* The same piece walked by the WHOLE warp: lane l takes group g0 + 32c + l of chunk c.  The lane map only ever
+ * degrades (14 reachable states, (3,3,3,3) absorbing), so a span sees at most a handful of state changes; between two
+ * changes the groups are independent given the state.  Each chunk is therefore resolved by iterating "evaluate all
+ * pending groups under the current state; everything up to and including the first group that changes it is final".
+ * The hand-over for the next piece is published as soon as the piece's last group is resolved, before any shading. */
 template <FsFn FS>
-__global__ void __launch_bounds__(128) k_raster(const __grid_constant__ SLRasterParams P)
+SLD_FN unsigned sl_walk_piece_warp(const SLRasterParams& P, const SLTile& T, uint32_t recId, int y, int xMin, int xMax, int p0, int p1, uint32_t hand,
+                                   bool publish, int outBoundary)
 {
-    __shared__ unsigned sTicket;
-    if (threadIdx.x == 0) sTicket = atomicAdd(&P.counters->rasterTicket, 1u);
-    __syncthreads();
     const int lane = threadIdx.x & 31;
-    const int y = (int)(sTicket * (blockDim.x >> 5) + (threadIdx.x >> 5));
+    const float4* rec = P.records + (size_t)recId * P.recStride;
+    SLTriSetup t;
+    sl_tri_setup(t, rec[0], rec[1], rec[2]);
+
+    const float yf = (float)y;
+    const math::vec4 bcY = math::fmadd(t.bc1, math::vec4{yf}, t.bc2);
+    math::vec4 a0 = (t.bc0 * (float)(xMin + 0)) + bcY;
+    math::vec4 a1 = (t.bc0 * (float)(xMin + 1)) + bcY;
+    math::vec4 a2 = (t.bc0 * (float)(xMin + 2)) + bcY;
+    math::vec4 a3 = (t.bc0 * (float)(xMin + 3)) + bcY;
+    const math::vec4 bcX = t.bc0 * 4.f;
+    const long long rowBase = (long long)P.width * (long long)y - T.origin;
+    unsigned shaded = 0;
+
+    const int g0 = (p0 - xMin) >> 2;       /* first group with a pixel of the piece */
+    const int gLast = (p1 - 1 - xMin) >> 2; /* last one                               */
+    const int gPub = (p1 - xMin) >> 2;      /* group that contains the cut p1         */
+    uint32_t st = (xMin < p0) ? (hand & 0xffu) : SL_STATE_IDENTITY; /* warp-uniform */
+    const uint32_t handM = (xMin < p0) ? ((hand >> 8) & 7u) : 0u;
+
+    /* accumulator chains of this lane's first group: g0 + lane additions, one rounding each (:539-542) */
+    for (int i = 0; i < g0; ++i) { a0 += bcX; a1 += bcX; a2 += bcX; a3 += bcX; }
+    for (int i = 0; i < 31; ++i)
+    {
+        if (i < lane) { a0 += bcX; a1 += bcX; a2 += bcX; a3 += bcX; }
+    }
+
+    for (int gc = g0; gc <= gLast; gc += 32)
+    {
+        const int g = gc + lane;
+        const int x4 = xMin + 4 * g;
+        const bool active = g <= gLast;
+        /* depth of the four clean chains at this group; register i of the reference holds chain (st >> 2i) & 3 */
+        const float zc0 = ((a0.v[3] * 0.f) + (a0.v[2] * t.z2)) + ((a0.v[1] * t.z1) + (a0.v[0] * t.z0));
+        const float zc1 = ((a1.v[3] * 0.f) + (a1.v[2] * t.z2)) + ((a1.v[1] * t.z1) + (a1.v[0] * t.z0));
+        const float zc2 = ((a2.v[3] * 0.f) + (a2.v[2] * t.z2)) + ((a2.v[1] * t.z1) + (a2.v[0] * t.z0));
+        const float zc3 = ((a3.v[3] * 0.f) + (a3.v[2] * t.z2)) + ((a3.v[1] * t.z1) + (a3.v[0] * t.z0));
+        bool own[4];
+        float d[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+        {
+            own[j] = active && (x4 + j >= p0) && (x4 + j < p1);
+            d[j] = (own[j] && P.depthTest) ? sl_load_depth(T.depth, P.depthBpt, (size_t)(rowBase + x4 + j)) : 0.f;
+        }
+        const uint32_t fM = (g == g0) ? handM : 0u;
+
+        uint32_t stIn = st, mBits = 0u, tBits = 0u;
+        bool pending = active;
+        for (;;)
+        {
+            uint32_t m = 0u;
+            if (pending)
+            {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                {
+                    const uint32_t sj = (st >> (2 * j)) & 3u;
+                    const float z = sj == 0u ? zc0 : (sj == 1u ? zc1 : (sj == 2u ? zc2 : zc3));
+                    if (own[j] && sl_depth_cmp(P.depthTest, z, d[j])) m |= 1u << j;
+                }
+            }
+            const uint32_t tt = m | fM;
+            const uint32_t stOut = sl_state_step(st, tt);
+            const uint32_t pend = __ballot_sync(0xffffffffu, pending);
+            if (!pend) break;
+            const uint32_t chg = __ballot_sync(0xffffffffu, pending && stOut != st);
+            const int f = chg ? (__ffs(chg) - 1) : 32;
+            if (pending && lane <= f) { stIn = st; mBits = m; tBits = tt; pending = false; }
+            if (f == 32) break;
+            st = __shfl_sync(0xffffffffu, stOut, f);
+        }
+        /* state after this chunk = state after its last active group */
+        {
+            const int lastLane = min(31, gLast - gc);
+            const uint32_t mine = sl_state_step(stIn, tBits);
+            st = __shfl_sync(0xffffffffu, mine, lastLane);
+            if (publish && gLast - gc < 32 && lane == lastLane)
+            {
+                if (gPub == gLast)
+                {
+                    const uint32_t below = (1u << (p1 - x4)) - 1u;
+                    sl_handoff_publish(P, recId, y, outBoundary, stIn | ((tBits & below & 7u) << 8));
+                }
+                else sl_handoff_publish(P, recId, y, outBoundary, mine);
+            }
+        }
+        /* shade: survivor number s reads register s after the compaction = the chain of the first passing lane >= s */
+        if (mBits)
+        {
+            int s = 0;
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j)
+            {
+                if (!((tBits >> j) & 1u)) continue;
+                if ((mBits >> j) & 1u)
+                {
+                    const uint32_t ge = tBits & ~((1u << s) - 1u);
+                    const int pLane = __ffs(ge) - 1;
+                    const uint32_t sj = (stIn >> (2 * pLane)) & 3u;
+                    const math::vec4 bc = sj == 0u ? a0 : (sj == 1u ? a1 : (sj == 2u ? a2 : a3));
+                    const uint32_t zj = (stIn >> (2 * j)) & 3u;
+                    const float z = zj == 0u ? zc0 : (zj == 1u ? zc1 : (zj == 2u ? zc2 : zc3));
+                    sl_shade_fragment<FS>(P, T, t, rec, bc, x4 + j, y, z);
+                    ++shaded;
+                }
+                ++s;
+            }
+        }
+        /* advance every lane by one chunk */
+        if (gc + 32 <= gLast)
+        {
+            for (int i = 0; i < 32; ++i) { a0 += bcX; a1 += bcX; a2 += bcX; a3 += bcX; }
+        }
+    }
+    return shaded;
+}
+
+constexpr int SL_LONG_GROUPS = 6; /* pieces of at least this many 4-pixel groups are walked by the whole warp */
+constexpr int SL_RASTER_WARPS = 4;
+
+SLD_FN unsigned sl_align16(unsigned n) { return (n + 15u) & ~15u; }
+
+/* warp-wide copy between a segment of an attachment and its shared-memory tile (16-byte accesses when both sides allow) */
+SLD_FN void sl_copy_warp(unsigned char* dst, const unsigned char* src, unsigned bytes, int lane)
+{
+    const uintptr_t both = reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src);
+    if ((both & 15u) == 0u)
+    {
+        const unsigned n16 = bytes >> 4;
+        for (unsigned i = lane; i < n16; i += 32) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+        for (unsigned i = (n16 << 4) + lane; i < bytes; i += 32) dst[i] = src[i];
+    }
+    else if ((both & 3u) == 0u)
+    {
+        const unsigned n4 = bytes >> 2;
+        for (unsigned i = lane; i < n4; i += 32) reinterpret_cast<uint32_t*>(dst)[i] = reinterpret_cast<const uint32_t*>(src)[i];
+        for (unsigned i = (n4 << 2) + lane; i < bytes; i += 32) dst[i] = src[i];
+    }
+    else
+    {
+        for (unsigned i = lane; i < bytes; i += 32) dst[i] = src[i];
+    }
+}
+
+/* One warp per (row, x-segment); work is handed out through a ticket in row-major order.  The warp stages the depth
+ * and colour texels of its segment into shared memory once, streams the row's ordered entry list, keeps the pieces
+ * that fall into its segment (compacted into a 32-deep queue so that the lanes of a batch are busy), and writes the
+ * segment back at the end.  Short pieces run one per lane as soon as no earlier, still pending piece of the batch
+ * overlaps them in x (fragments of disjoint x-ranges commute; everything else is serialised in submission order);
+ * long pieces are walked by the whole warp. */
+template <FsFn FS>
+__global__ void __launch_bounds__(SL_RASTER_WARPS * 32) k_raster(const __grid_constant__ SLRasterParams P)
+{
+    extern __shared__ __align__(16) unsigned char sDyn[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned ticket = 0;
+    if (lane == 0) ticket = atomicAdd(&P.counters->rasterTicket, 1u);
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    const int NS = (int)P.numSegs;
+    const int y = (int)(ticket / (unsigned)NS), seg = (int)(ticket % (unsigned)NS);
     if (y >= (int)P.numRows) return;
     if (P.rowNeeded && !P.rowNeeded[y]) return;
     const int W = (int)P.width;
+    const int sx0 = seg * (int)P.segWidth;
+    const int sx1 = (seg == NS - 1) ? W : sx0 + (int)P.segWidth;
+    const bool chained = P.depthTest != 0;
     const uint32_t begin = P.rowStart[y], end = P.rowStart[y + 1];
+    if (begin == end) return;
     unsigned shaded = 0;
 
-    for (uint32_t base = begin; base < end; base += 32)
+    SLSpanEntry* queue = reinterpret_cast<SLSpanEntry*>(sDyn) + warp * 32;
+    unsigned char* tileMem = sDyn + SL_RASTER_WARPS * 32 * sizeof(SLSpanEntry) + (size_t)warp * P.tileBytes;
+    const unsigned segPixels = (unsigned)(sx1 - sx0);
+    const long long segOrigin = (long long)W * y + sx0;
+    SLTile T;
+    bool staged = false;
+    if (P.tileBytes)
     {
-        const bool valid = base + lane < end;
+        unsigned off = 0;
+        T.depth = tileMem;
+        off += sl_align16(P.segWidth * (unsigned)P.depthBpt);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+        {
+            T.color[i] = tileMem + off;
+            if (i < P.numOutputs) off += sl_align16(P.segWidth * (unsigned)P.colorBpt[i]);
+        }
+        T.origin = segOrigin;
+    }
+    else
+    {
+        T.depth = P.depth;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) T.color[i] = P.color[i];
+        T.origin = 0;
+    }
+
+    uint32_t base = begin;
+    while (base < end)
+    {
+        /* ---- collect up to 32 pieces of this segment, in list order (four 32-entry batches in flight) ---- */
+        int qn = 0;
+        bool full = false;
+        while (base < end && !full)
+        {
+            SLSpanEntry c[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+            {
+                const uint32_t idx = base + 32u * k + lane;
+                c[k] = SLSpanEntry{0u, 0, 0};
+                if (idx < end) c[k] = P.entries[idx];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+            {
+                if (full || base >= end) continue;
+                const int cb = (c[k].rec & SL_ENTRY_OVERFLOW) ? W : 0;
+                const bool cHas = max((int)c[k].xMin, cb + sx0) < min((int)c[k].xMax, cb + sx1); /* empty entries: 0 < 0 */
+                const uint32_t hm = __ballot_sync(0xffffffffu, cHas);
+                const int cnt = __popc(hm);
+                if (qn + cnt > 32) { full = true; continue; } /* process what is queued, then come back to this batch */
+                if (cHas)
+                {
+                    queue[qn + __popc(hm & ((1u << lane) - 1u))] = c[k];
+                    /* the walker's first access: pull the triangle record towards the SM now */
+                    const float4* r = P.records + (size_t)(c[k].rec & ~SL_ENTRY_OVERFLOW) * P.recStride;
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(r));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(r + 8));
+                }
+                qn += cnt;
+                base += 32;
+            }
+        }
+        __syncwarp();
+        if (!qn) continue;
+        if (P.tileBytes && !staged)
+        {
+            /* stage the segment in: one coalesced read per attachment */
+            sl_copy_warp(T.depth, P.depth + (size_t)segOrigin * P.depthBpt, segPixels * (unsigned)P.depthBpt, lane);
+            for (int i = 0; i < P.numOutputs; ++i)
+                sl_copy_warp(T.color[i], P.color[i] + (size_t)segOrigin * P.colorBpt[i], segPixels * (unsigned)P.colorBpt[i], lane);
+            staged = true;
+            __syncwarp();
+        }
+        const bool valid = lane < qn;
         SLSpanEntry e = SLSpanEntry{0u, 0, 0};
-        if (valid) e = P.entries[base + lane];
-        /* pixels of row y this entry touches */
+        if (valid) e = queue[lane];
+        __syncwarp();
         const bool isOver = (e.rec & SL_ENTRY_OVERFLOW) != 0u;
-        const int pMin = isOver ? max((int)e.xMin - W, 0) : (int)e.xMin;
-        const int pMax = isOver ? (int)e.xMax - W : min((int)e.xMax, W);
+        const uint32_t recId = e.rec & ~SL_ENTRY_OVERFLOW;
+        const int xBase = isOver ? W : 0; /* the entry's x coordinates are those of its source row */
+        const int ySrc = isOver ? y - 1 : y;
+        const int xMin = e.xMin, xMax = e.xMax;
+        const int p0 = max(xMin, xBase + sx0), p1 = min(xMax, xBase + sx1);
+        const bool has = valid && p0 < p1;
+        const int lMin = has ? p0 - xBase : 0, lMax = has ? p1 - xBase : 0; /* pixels of this row the piece touches */
         uint32_t dep = 0;
         for (int i = 0; i < 31; ++i)
         {
-            const int oMin = __shfl_sync(0xffffffffu, pMin, i);
-            const int oMax = __shfl_sync(0xffffffffu, pMax, i);
-            if (i < lane && oMin < pMax && pMin < oMax) dep |= 1u << i;
+            const int oMin = __shfl_sync(0xffffffffu, lMin, i);
+            const int oMax = __shfl_sync(0xffffffffu, lMax, i);
+            if (i < lane && oMin < lMax && lMin < oMax) dep |= 1u << i;
         }
-        const bool needsHand = valid && isOver && (int)e.xMin < W;
-        bool done = !valid;
-        uint32_t doneMask = __ballot_sync(0xffffffffu, done);
-        while (doneMask != 0xffffffffu)
+        const bool startsMid = has && xMin < p0;
+        const bool needsIn = startsMid && chained;
+        const bool publish = has && chained && xMax > p1 && (seg < NS - 1 || (!isOver && y + 1 < (int)P.numRows));
+        const int bIn = (isOver ? NS : 0) + seg;
+        const int groups = has ? (((p1 - 1 - xMin) >> 2) - ((p0 - xMin) >> 2) + 1) : 0;
+        const bool isLong = groups >= SL_LONG_GROUPS;
+        bool done = !has;
+        for (;;)
         {
-            if (!done && (dep & ~doneMask) == 0u)
+            const uint32_t pendMask = ~__ballot_sync(0xffffffffu, done);
+            if (!pendMask) break;
+            const bool ready = !done && (dep & pendMask) == 0u;
+            uint32_t hand = SL_STATE_IDENTITY;
+            bool go = ready;
+            if (ready && startsMid)
             {
-                uint32_t hand = 0xE4u; /* identity lane map */
-                if (!needsHand || sl_handoff_poll(P, e.rec & ~SL_ENTRY_OVERFLOW, y - 1, hand))
+                if (needsIn) go = sl_handoff_poll(P, recId, ySrc, bIn, hand);
+                else
                 {
-                    shaded += sl_walk_span<FS>(P, e, y, hand);
-                    done = true;
+                    /* depth test off: every lane left of the cut passed and the lane map is still the identity */
+                    const int x4 = xMin + (((p0 - xMin) >> 2) << 2);
+                    hand = SL_STATE_IDENTITY | ((((1u << (p0 - x4)) - 1u) & 7u) << 8);
                 }
             }
+            const int first = __ffs(pendMask) - 1;
+            const bool firstLong = __shfl_sync(0xffffffffu, isLong ? 1 : 0, first) != 0;
+            const bool firstGo = __shfl_sync(0xffffffffu, go ? 1 : 0, first) != 0;
+            if (firstLong && firstGo)
+            {
+                const uint32_t bRec = __shfl_sync(0xffffffffu, recId, first);
+                const int bY = __shfl_sync(0xffffffffu, ySrc, first);
+                const int bXMin = __shfl_sync(0xffffffffu, xMin, first), bXMax = __shfl_sync(0xffffffffu, xMax, first);
+                const int bP0 = __shfl_sync(0xffffffffu, p0, first), bP1 = __shfl_sync(0xffffffffu, p1, first);
+                const uint32_t bHand = __shfl_sync(0xffffffffu, hand, first);
+                const bool bPub = __shfl_sync(0xffffffffu, publish ? 1 : 0, first) != 0;
+                const int bOut = __shfl_sync(0xffffffffu, bIn + 1, first);
+                shaded += sl_walk_piece_warp<FS>(P, T, bRec, bY, bXMin, bXMax, bP0, bP1, bHand, bPub, bOut);
+                if (lane == first) done = true;
+            }
+            else if (go && !isLong)
+            {
+                shaded += sl_walk_piece<FS>(P, T, recId, ySrc, xMin, xMax, p0, p1, hand, publish, bIn + 1);
+                done = true;
+            }
             __syncwarp();
-            doneMask = __ballot_sync(0xffffffffu, done);
         }
+    }
+    const bool dirty = __any_sync(0xffffffffu, shaded != 0u);
+    if (staged && dirty)
+    {
+        /* write the segment back: one coalesced store per attachment that can have changed */
+        __syncwarp();
+        if (P.depthMask) sl_copy_warp(P.depth + (size_t)segOrigin * P.depthBpt, T.depth, segPixels * (unsigned)P.depthBpt, lane);
+        for (int i = 0; i < P.numOutputs; ++i)
+            sl_copy_warp(P.color[i] + (size_t)segOrigin * P.colorBpt[i], T.color[i], segPixels * (unsigned)P.colorBpt[i], lane);
     }
     for (int d = 16; d > 0; d >>= 1) shaded += __shfl_down_sync(0xffffffffu, shaded, d);
     if (lane == 0 && shaded) atomicAdd(&P.counters->fragsShaded, (unsigned long long)shaded);

@@ -30,7 +30,7 @@ using namespace sld;
  * as a template argument (direct, inlinable calls -- never interpreted).
  * =========================================================================*/
 typedef cudaError_t (*VertexLauncher)(unsigned grid, cudaStream_t s, const SLVertexParams& p);
-typedef cudaError_t (*RasterLauncher)(unsigned grid, unsigned block, cudaStream_t s, const SLRasterParams& p);
+typedef cudaError_t (*RasterLauncher)(unsigned grid, unsigned block, unsigned smemBytes, cudaStream_t s, const SLRasterParams& p);
 
 struct VsEntry { const char* name; VertexLauncher launch; };
 struct FsEntry { const char* name; RasterLauncher launch; };
@@ -42,9 +42,9 @@ template <VsFn VS> static cudaError_t launch_vertex(unsigned grid, cudaStream_t 
     k_vertex<VS><<<grid, SL_VB_THREADS, 0, s>>>(p);
     return cudaGetLastError();
 }
-template <FsFn FS> static cudaError_t launch_raster(unsigned grid, unsigned block, cudaStream_t s, const SLRasterParams& p)
+template <FsFn FS> static cudaError_t launch_raster(unsigned grid, unsigned block, unsigned smemBytes, cudaStream_t s, const SLRasterParams& p)
 {
-    k_raster<FS><<<grid, block, 0, s>>>(p);
+    k_raster<FS><<<grid, block, smemBytes, s>>>(p);
     return cudaGetLastError();
 }
 struct VsReg { VsReg(const char* n, VertexLauncher l) { vs_registry().push_back(VsEntry{n, l}); } };
@@ -335,6 +335,12 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
 
     const float fboW = (float)depthTex.w, fboH = (float)depthTex.h;
     const unsigned rowPitch = (H + 31u) & ~31u;
+    /* x-segments of the rasteriser: one warp per (row, segment), about 128 pixels each, at most 32 per row */
+    unsigned rasterSegs = (depthTex.w + 127u) / 128u;
+    if (rasterSegs < 1u) rasterSegs = 1u;
+    if (rasterSegs > 32u) rasterSegs = 32u;
+    const unsigned segWidth = (depthTex.w + rasterSegs - 1u) / rasterSegs;
+    rasterSegs = (depthTex.w + segWidth - 1u) / segWidth;
     const int NV = sh.numVaryings;
     const int recStride = 3 + 3 * NV;
 
@@ -363,7 +369,7 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
         if (recCapacity > 0xfffffff0ull) { c->err = "draw too large for one batch"; return SLCU_ERR_UNSUPPORTED; }
         CK(c->records.ensure((size_t)recCapacity * recStride * sizeof(float4)));
         CK(c->blockInfo.ensure((size_t)numBlocks * sizeof(SLBlockInfo)));
-        CK(cudaMemsetAsync(&c->counters->recAlloc, 0, 2 * sizeof(unsigned long long), c->stream)); /* recAlloc + overflowPairs */
+        CK(cudaMemsetAsync(&c->counters->recAlloc, 0, 2 * sizeof(unsigned long long), c->stream)); /* recAlloc + handoffs */
 
         unsigned firstBlock = 0;
         for (size_t i = 0; i < launches; ++i)
@@ -420,6 +426,9 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
         sp.numRows = H;
         sp.rowPitch = rowPitch;
         sp.width = depthTex.w;
+        sp.segWidth = segWidth;
+        sp.numSegs = rasterSegs;
+        sp.chained = sh.depthTest != 0 ? 1 : 0;
         sp.recStride = recStride;
         sp.cnt = reinterpret_cast<uint16_t*>(c->cnt.buf.ptr);
         sp.off = reinterpret_cast<const uint32_t*>(c->off.buf.ptr);
@@ -470,7 +479,10 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
             return SLCU_ERR_OOM;
         }
         if (!totalSpans) return 0;
-        numHandoffs = c->hostCounters->overflowPairs;
+        numHandoffs = c->hostCounters->handoffs;
+        if (getenv("SLCU_DEBUG"))
+            fprintf(stderr, "[slcu] draw: prims=%llu records=%llu entries=%u handoffs=%llu segs=%ux%u flags=0x%x\n", totalPrims,
+                    (unsigned long long)c->hostCounters->recAlloc, totalSpans, numHandoffs, rasterSegs, segWidth, c->hostCounters->errorFlags);
 
         CK(c->entries.ensure((size_t)totalSpans * sizeof(SLSpanEntry)));
         sp.entries = reinterpret_cast<SLSpanEntry*>(c->entries.buf.ptr);
@@ -498,6 +510,8 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
     rp.handoff = nullptr;
     rp.handoffMask = 0;
     rp.rowNeeded = rowNeeded;
+    rp.segWidth = segWidth;
+    rp.numSegs = rasterSegs;
     if (numHandoffs)
     {
         size_t cap = 64;
@@ -507,11 +521,12 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
         rp.handoff = reinterpret_cast<unsigned long long*>(c->handoff.buf.ptr);
         rp.handoffMask = (unsigned)(cap - 1);
     }
+    unsigned tileBytes = (segWidth * depthTex.bpt + 15u) & ~15u;
     for (int i = 0; i < 4; ++i)
     {
         rp.color[i] = nullptr;
         rp.colorType[i] = 0;
-        rp.colorWidth[i] = 0;
+        rp.colorBpt[i] = 0;
         if (i < sh.numOutputs)
         {
             if ((unsigned)i >= fbo.numColors || fbo.colors[i] >= c->textures.size()) { c->err = "shader writes an unattached colour buffer"; return SLCU_ERR_ARG; }
@@ -519,13 +534,20 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
             const int kind = t.type % 7;
             if (kind == 2 || kind == 3) { c->err = "32/64-bit integer colour targets are not implemented"; return SLCU_ERR_UNSUPPORTED; }
             rp.color[i] = t.dev;
+            if (t.w != depthTex.w || t.h != depthTex.h) { c->err = "colour and depth attachments differ in size (SL_Framebuffer::valid -10)"; return SLCU_ERR_ARG; }
             rp.colorType[i] = t.type;
-            rp.colorWidth[i] = t.w;
+            rp.colorBpt[i] = t.bpt;
+            tileBytes += (segWidth * t.bpt + 15u) & ~15u;
         }
     }
     rp.counters = c->counters;
-    const unsigned warpsPerBlock = 4;
-    { KernelScope ks(c, SLCU_K_RASTER); CK(sh.fs((H + warpsPerBlock - 1) / warpsPerBlock, warpsPerBlock * 32, c->stream, rp)); }
+    const unsigned warpsPerBlock = SL_RASTER_WARPS;
+    const unsigned long long numWarps = (unsigned long long)H * rasterSegs;
+    /* each warp keeps its segment's depth + colour texels in shared memory; segments too fat for that work in place */
+    const unsigned queueBytes = warpsPerBlock * 32u * (unsigned)sizeof(SLSpanEntry);
+    if (tileBytes > 10u * 1024u) tileBytes = 0;
+    rp.tileBytes = tileBytes;
+    { KernelScope ks(c, SLCU_K_RASTER); CK(sh.fs((unsigned)((numWarps + warpsPerBlock - 1) / warpsPerBlock), warpsPerBlock * 32, queueBytes + warpsPerBlock * tileBytes, c->stream, rp)); }
     return 0;
 }
 
