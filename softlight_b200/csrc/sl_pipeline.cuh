@@ -21,7 +21,9 @@
  *                     lanes take spans whose x-ranges do not overlap.
  *
  * Data layout in HBM:
- *   record r      : float4[3 + 3*NV]  = p0,p1,p2 (x,y,z,1/w) then varyings [slot][vert]
+ *   record r      : float4[3 + 3*NV]  = p0,p1,p2 (x,y,z,1/w) then varyings [slot][vert].  (A plane-major layout was
+ *                   measured too: it makes the vertex stage's writes and the span stage's reads coalesced, but the
+ *                   rasteriser's per-piece gathers then touch twice the sectors and the frame got slower.)
  *   span entry    : {u32 record, u16 xMin, u16 xMax}, grouped by row, ordered
  *   cnt[vb][y]    : u16 spans of vertex-block vb on row y;  off[vb][y] : u32 exclusive prefix over vb
  */
@@ -87,7 +89,10 @@ struct SLVertexParams
     unsigned long long primsPerInstance;
     unsigned long long numPrims;      /* primsPerInstance * instances */
     unsigned int firstBlock;          /* index of this launch's first vertex block in blockInfo */
-    unsigned int recCapacity;
+    unsigned int cacheBytes;          /* dynamic shared memory of the post-transform cache (0: off) */
+    unsigned int recCapacity;         /* record slots per plane: fixed per-block regions + overflow area */
+    unsigned int recOverflowBase;     /* first slot of the overflow area                                */
+    unsigned int recOverflowCapacity; /* its size                                                       */
     float4* records;
     SLBlockInfo* blockInfo;
     SLCounters* counters;
@@ -156,11 +161,15 @@ SLD_FN void sl_write_record(float4* rec, int numVaryings, const math::vec4& p0, 
     rec[0] = *reinterpret_cast<const float4*>(&p0);
     rec[1] = *reinterpret_cast<const float4*>(&p1);
     rec[2] = *reinterpret_cast<const float4*>(&p2);
-    for (int s = 0; s < numVaryings; ++s)
+#pragma unroll
+    for (int s = 0; s < 4; ++s) /* static indices: the shader outputs stay in registers */
     {
-        rec[3 + 3 * s + 0] = *reinterpret_cast<const float4*>(&va[s]);
-        rec[3 + 3 * s + 1] = *reinterpret_cast<const float4*>(&vb[s]);
-        rec[3 + 3 * s + 2] = *reinterpret_cast<const float4*>(&vc[s]);
+        if (s < numVaryings)
+        {
+            rec[3 + 3 * s + 0] = *reinterpret_cast<const float4*>(&va[s]);
+            rec[3 + 3 * s + 1] = *reinterpret_cast<const float4*>(&vb[s]);
+            rec[3 + 3 * s + 2] = *reinterpret_cast<const float4*>(&vc[s]);
+        }
     }
 }
 
@@ -223,14 +232,57 @@ __device__ __noinline__ int sl_clip_polygon(SLClipPoly& poly, int numVarys, cons
     return numTotalVerts;
 }
 
+/* Exact shortcut for the clipper above.  Sutherland-Hodgman visits the planes in a fixed order; as long as every
+ * vertex was on the visible side of the planes visited so far, the polygon is still the input triangle.  If at that
+ * point all three vertices are on the invisible side of the next plane, the clipper would end with zero vertices
+ * (src/SL_TriProcessor.cpp:455-459) -- same dot products, same sign tests, no interpolation involved.  The reference
+ * sends every triangle that is outside the frustum but in front of the eye through the clipper (status "partially
+ * visible" = any w > 0, SL_PostVertexTransform.hpp:598-616); most of them end here. */
+SLD_FN bool sl_clip_rejects(const math::vec4& p0, const math::vec4& p1, const math::vec4& p2)
+{
+    const float edges[6][4] = {{1.f, 0.f, 0.f, 1.f}, {-1.f, 0.f, 0.f, 1.f}, {0.f, 1.f, 0.f, 1.f},
+                               {0.f, -1.f, 0.f, 1.f}, {0.f, 0.f, 1.f, 1.f}, {0.f, 0.f, -1.f, 1.f}};
+#pragma unroll
+    for (int e = 0; e < 6; ++e)
+    {
+        const math::vec4 edge{edges[e][0], edges[e][1], edges[e][2], edges[e][3]};
+        const int vis = (sl_signbit(math::dot(p0, edge)) ? 0 : 1) + (sl_signbit(math::dot(p1, edge)) ? 0 : 1) + (sl_signbit(math::dot(p2, edge)) ? 0 : 1);
+        if (vis == 0) return true;
+        if (vis != 3) return false;
+    }
+    return false;
+}
+
 /* ------------------------------------------------------------------------
  * k_vertex
  * ----------------------------------------------------------------------*/
-template <VsFn VS>
+constexpr int SL_VCACHE_VERTS = 1024; /* post-transform vertex cache of one vertex block (shared memory) */
+
+/* get_next_vertex3 (src/SL_TriProcessor.cpp:125-234) */
+SLD_FN void sl_fetch_vertex_ids(const SLVertexParams& P, unsigned long long i, unsigned long long vertId[3])
+{
+    if (P.usingIndices)
+    {
+        if (P.iboType == 0) { const uint8_t* p = P.ibo + i; vertId[0] = p[0]; vertId[1] = p[1]; vertId[2] = p[2]; }
+        else if (P.iboType == 1) { const uint16_t* p = reinterpret_cast<const uint16_t*>(P.ibo) + i; vertId[0] = p[0]; vertId[1] = p[1]; vertId[2] = p[2]; }
+        else { const uint32_t* p = reinterpret_cast<const uint32_t*>(P.ibo) + i; vertId[0] = p[0]; vertId[1] = p[1]; vertId[2] = p[2]; }
+    }
+    else { vertId[0] = i; vertId[1] = i + 1; vertId[2] = i + 2; }
+}
+
+/* The reference runs the vertex shader three times per triangle with no post-transform cache
+ * (src/SL_TriProcessor.cpp:584-594; SL_VertexCache is compiled out, SL_Config.hpp:10-12).  A vertex shader is a pure
+ * function of (uniforms, vertId, instanceId), so shading each vertex a block of 1024 primitives references ONCE gives
+ * the same bits: when the block's primitives belong to one instance of an indexed mesh and their indices span at most
+ * SL_VCACHE_VERTS vertices, the block shades that index range into shared memory first and assembles its triangles
+ * from there; otherwise every primitive shades its own three vertices like the reference. */
+template <VsFn VS, bool CACHE>
 __global__ void __launch_bounds__(SL_VB_THREADS) k_vertex(const __grid_constant__ SLVertexParams P)
 {
-    __shared__ uint32_t sWarpSums[SL_VB_THREADS / 32];
+    extern __shared__ __align__(16) unsigned char sVCache[]; /* float4 [1 + NV][SL_VCACHE_VERTS] when P.cacheBytes != 0 */
+    __shared__ uint32_t sWarpSums[SL_VB_ROUNDS][SL_VB_THREADS / 32];
     __shared__ uint32_t sBase, sGranted;
+    __shared__ unsigned long long sIdMin, sIdMax;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -245,6 +297,61 @@ __global__ void __launch_bounds__(SL_VB_THREADS) k_vertex(const __grid_constant_
 
     const math::mat4& scissorMat = *reinterpret_cast<const math::mat4*>(P.scissor);
 
+    /* ---- post-transform cache ---- */
+    bool cached = false;
+    unsigned long long cacheBase = 0;
+    float4* cache = reinterpret_cast<float4*>(sVCache);
+    if (CACHE && P.cacheBytes && P.usingIndices && blockFirst < P.numPrims)
+    {
+        const unsigned long long blockLast = min(blockFirst + (unsigned long long)SL_VB_PRIMS, P.numPrims) - 1ull;
+        const unsigned long long instFirst = blockFirst / P.primsPerInstance;
+        if (instFirst == blockLast / P.primsPerInstance) /* one instance: block-uniform */
+        {
+            if (tid == 0) { sIdMin = ~0ull; sIdMax = 0ull; }
+            __syncthreads();
+            unsigned long long lo = ~0ull, hi = 0ull;
+            for (int round = 0; round < SL_VB_ROUNDS; ++round)
+            {
+                const unsigned long long g = blockFirst + (unsigned long long)round * SL_VB_THREADS + tid;
+                if (g <= blockLast)
+                {
+                    unsigned long long id[3];
+                    sl_fetch_vertex_ids(P, P.elementBegin + 3ull * (g - instFirst * P.primsPerInstance), id);
+                    lo = min(lo, min(id[0], min(id[1], id[2])));
+                    hi = max(hi, max(id[0], max(id[1], id[2])));
+                }
+            }
+            for (int d = 16; d > 0; d >>= 1)
+            {
+                lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+                hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+            }
+            if (lane == 0) { atomicMin(&sIdMin, lo); atomicMax(&sIdMax, hi); }
+            __syncthreads();
+            cacheBase = sIdMin;
+            const unsigned long long range = sIdMax - sIdMin + 1ull;
+            if (range <= (unsigned long long)SL_VCACHE_VERTS)
+            {
+                cached = true;
+                params.instanceId = (size_t)instFirst;
+                for (unsigned v = tid; v < (unsigned)range; v += SL_VB_THREADS)
+                {
+                    math::vec4 vary[4];
+                    params.vertId = (size_t)(cacheBase + v);
+                    params.pVaryings = vary;
+                    const math::vec4 pos = VS(params);
+                    cache[v] = make_float4(pos.v[0], pos.v[1], pos.v[2], pos.v[3]);
+#pragma unroll
+                    for (int s = 0; s < 4; ++s)
+                    {
+                        if (s < NV) cache[(1 + s) * SL_VCACHE_VERTS + v] = make_float4(vary[s].v[0], vary[s].v[1], vary[s].v[2], vary[s].v[3]);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+
     for (int round = 0; round < SL_VB_ROUNDS; ++round)
     {
         const unsigned long long g = blockFirst + (unsigned long long)round * SL_VB_THREADS + tid;
@@ -258,21 +365,37 @@ __global__ void __launch_bounds__(SL_VB_THREADS) k_vertex(const __grid_constant_
             const unsigned long long instanceId = g / P.primsPerInstance;
             const unsigned long long i = P.elementBegin + 3ull * (g - instanceId * P.primsPerInstance);
             unsigned long long vertId[3];
-            if (P.usingIndices) /* get_next_vertex3 (src/SL_TriProcessor.cpp:125-234) */
-            {
-                if (P.iboType == 0) { const uint8_t* p = P.ibo + i; vertId[0] = p[0]; vertId[1] = p[1]; vertId[2] = p[2]; }
-                else if (P.iboType == 1) { const uint16_t* p = reinterpret_cast<const uint16_t*>(P.ibo) + i; vertId[0] = p[0]; vertId[1] = p[1]; vertId[2] = p[2]; }
-                else { const uint32_t* p = reinterpret_cast<const uint32_t*>(P.ibo) + i; vertId[0] = p[0]; vertId[1] = p[1]; vertId[2] = p[2]; }
-            }
-            else { vertId[0] = i; vertId[1] = i + 1; vertId[2] = i + 2; }
+            sl_fetch_vertex_ids(P, i, vertId);
 
-            params.instanceId = (size_t)instanceId;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) /* src/SL_TriProcessor.cpp:584-594 */
+            if (CACHE && cached)
             {
-                params.vertId = (size_t)vertId[k];
-                params.pVaryings = v[k].varyings;
-                v[k].vert = VS(params);
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                {
+                    const unsigned c = (unsigned)(vertId[k] - cacheBase);
+                    const float4 pos = cache[c];
+                    v[k].vert = math::vec4{pos.x, pos.y, pos.z, pos.w};
+#pragma unroll
+                    for (int s = 0; s < 4; ++s)
+                    {
+                        if (s < NV)
+                        {
+                            const float4 f = cache[(1 + s) * SL_VCACHE_VERTS + c];
+                            v[k].varyings[s] = math::vec4{f.x, f.y, f.z, f.w};
+                        }
+                    }
+                }
+            }
+            else
+            {
+                params.instanceId = (size_t)instanceId;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) /* src/SL_TriProcessor.cpp:584-594 */
+                {
+                    params.vertId = (size_t)vertId[k];
+                    params.pVaryings = v[k].varyings;
+                    v[k].vert = VS(params);
+                }
             }
 
             bool culled = false;
@@ -292,12 +415,14 @@ __global__ void __launch_bounds__(SL_VB_THREADS) k_vertex(const __grid_constant_
                     for (int k = 0; k < 3; ++k) sl_to_screen(v[k].vert, P.viewport);
                     n = sl_prim_hidden(v[0].vert, v[1].vert, v[2].vert) ? 0 : 1;
                 }
-                else if (vis == 1)
+                else if (vis == 1 && !sl_clip_rejects(v[0].vert, v[1].vert, v[2].vert))
                 {
+#pragma unroll
                     for (int k = 0; k < 3; ++k)
                     {
                         poly.verts[k] = v[k].vert;
-                        for (int s = 0; s < NV; ++s) poly.varys[k * 4 + s] = v[k].varyings[s];
+#pragma unroll
+                        for (int s = 0; s < 4; ++s) { if (s < NV) poly.varys[k * 4 + s] = v[k].varyings[s]; }
                     }
                     polyVerts = sl_clip_polygon(poly, NV, P.viewport);
                     for (int f = polyVerts - 2; f-- > 0;)
@@ -316,37 +441,46 @@ __global__ void __launch_bounds__(SL_VB_THREADS) k_vertex(const __grid_constant_
             const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += t;
         }
-        if (lane == 31) sWarpSums[warp] = incl;
+        if (lane == 31) sWarpSums[round][warp] = incl;
         __syncthreads();
         uint32_t warpOff = 0, total = 0;
 #pragma unroll
         for (int w = 0; w < SL_VB_THREADS / 32; ++w)
         {
-            const uint32_t s = sWarpSums[w];
+            const uint32_t s = sWarpSums[round][w];
             if (w < warp) warpOff += s;
             total += s;
         }
+        /* Every (block, round) owns SL_VB_THREADS record slots at a fixed place, enough unless clipping fanned primitives
+         * out; only then does the round take its slots from the shared overflow area (one atomic).  No atomics, no
+         * second barrier and no allocation-order dependence in the common case. */
+        uint32_t base = (P.firstBlock + blockIdx.x) * (uint32_t)SL_VB_PRIMS + (uint32_t)round * SL_VB_THREADS;
+        uint32_t granted = total;
+        if (total > (uint32_t)SL_VB_THREADS) /* block-uniform */
+        {
+            if (tid == 0)
+            {
+                const unsigned long long o = atomicAdd(&P.counters->recAlloc, (unsigned long long)total);
+                if (o + total > (unsigned long long)P.recOverflowCapacity)
+                {
+                    atomicOr(&P.counters->errorFlags, 1u); /* host re-issues the draw with a larger overflow area */
+                    sBase = 0u;
+                    sGranted = 0u;
+                }
+                else { sBase = P.recOverflowBase + (uint32_t)o; sGranted = total; }
+            }
+            __syncthreads();
+            base = sBase;
+            granted = sGranted;
+        }
         if (tid == 0)
         {
-            uint32_t base = 0, granted = total;
-            if (total)
-            {
-                base = (uint32_t)atomicAdd(&P.counters->recAlloc, (unsigned long long)total);
-                if ((unsigned long long)base + total > P.recCapacity)
-                {
-                    atomicOr(&P.counters->errorFlags, 1u); /* host re-issues the draw with a larger record buffer */
-                    granted = 0;
-                }
-                else atomicAdd(&P.counters->trisBinned, (unsigned long long)total);
-            }
-            sBase = base;
-            sGranted = granted;
+            if (granted) atomicAdd(&P.counters->trisBinned, (unsigned long long)granted);
             P.blockInfo[P.firstBlock + blockIdx.x].seg[round] = SLSegment{base, granted};
         }
-        __syncthreads();
-        if (n && sGranted)
+        if (n && granted)
         {
-            uint32_t slot = sBase + warpOff + (incl - (uint32_t)n);
+            uint32_t slot = base + warpOff + (incl - (uint32_t)n);
             if (!polyVerts)
             {
                 sl_write_record(P.records + (size_t)slot * recStride, NV, v[0].vert, v[1].vert, v[2].vert, v[0].varyings, v[1].varyings, v[2].varyings);
@@ -363,7 +497,6 @@ __global__ void __launch_bounds__(SL_VB_THREADS) k_vertex(const __grid_constant_
                 }
             }
         }
-        __syncthreads();
     }
 }
 

@@ -29,7 +29,8 @@ using namespace sld;
  * pair a name with a __device__ callable; the kernels are instantiated with it
  * as a template argument (direct, inlinable calls -- never interpreted).
  * =========================================================================*/
-typedef cudaError_t (*VertexLauncher)(unsigned grid, cudaStream_t s, const SLVertexParams& p);
+typedef cudaError_t (*VertexLauncher)(unsigned grid, cudaStream_t s, const SLVertexParams& p, bool cache);
+static const unsigned kVertexCacheMaxBytes = 5u * SL_VCACHE_VERTS * (unsigned)sizeof(float4); /* position + 4 varyings */
 typedef cudaError_t (*RasterLauncher)(unsigned grid, unsigned block, unsigned smemBytes, cudaStream_t s, const SLRasterParams& p);
 
 struct VsEntry { const char* name; VertexLauncher launch; };
@@ -37,9 +38,21 @@ struct FsEntry { const char* name; RasterLauncher launch; };
 static std::vector<VsEntry>& vs_registry() { static std::vector<VsEntry> r; return r; }
 static std::vector<FsEntry>& fs_registry() { static std::vector<FsEntry> r; return r; }
 
-template <VsFn VS> static cudaError_t launch_vertex(unsigned grid, cudaStream_t s, const SLVertexParams& p)
+template <VsFn VS> static cudaError_t launch_vertex(unsigned grid, cudaStream_t s, const SLVertexParams& p, bool cache)
 {
-    k_vertex<VS><<<grid, SL_VB_THREADS, 0, s>>>(p);
+    if (!cache)
+    {
+        k_vertex<VS, false><<<grid, SL_VB_THREADS, 0, s>>>(p);
+        return cudaGetLastError();
+    }
+    static bool attrSet = false; /* one opt-in per instantiation: the cache may exceed the 48 KB default */
+    if (!attrSet)
+    {
+        cudaError_t e = cudaFuncSetAttribute(k_vertex<VS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVertexCacheMaxBytes);
+        if (e != cudaSuccess) return e;
+        attrSet = true;
+    }
+    k_vertex<VS, true><<<grid, SL_VB_THREADS, p.cacheBytes, s>>>(p);
     return cudaGetLastError();
 }
 template <FsFn FS> static cudaError_t launch_raster(unsigned grid, unsigned block, unsigned smemBytes, cudaStream_t s, const SLRasterParams& p)
@@ -361,7 +374,11 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
     c->stats.trisSubmitted += totalPrims;
     if (!numBlocks) return 0;
 
-    unsigned long long recCapacity = totalPrims + totalPrims / 8 + 4096;
+    /* record slots: SL_VB_THREADS per (block, round) at fixed places + an overflow area for rounds that clipping fans out */
+    const unsigned long long recFixed = (unsigned long long)numBlocks * SL_VB_PRIMS;
+    unsigned long long recOverflow = totalPrims / 8 + 4096;
+    unsigned long long recCapacity = recFixed + recOverflow;
+    static const bool useVertexCache = getenv("SLCU_VERTEX_CACHE") != nullptr && atoi(getenv("SLCU_VERTEX_CACHE")) != 0;
     unsigned long long numHandoffs = 0;
     const uint8_t* rowNeeded = nullptr;
     for (int attempt = 0;; ++attempt)
@@ -401,11 +418,15 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
             vp.primsPerInstance = (m.elementEnd - m.elementBegin + 2) / 3;
             vp.numPrims = vp.primsPerInstance * (numInstances == 1 ? 1 : numInstances);
             vp.firstBlock = firstBlock;
+            const bool cache = useVertexCache && usingIndices;
+            vp.cacheBytes = cache ? (unsigned)((1 + NV) * SL_VCACHE_VERTS * sizeof(float4)) : 0u;
             vp.recCapacity = (unsigned)recCapacity;
+            vp.recOverflowBase = (unsigned)recFixed;
+            vp.recOverflowCapacity = (unsigned)recOverflow;
             vp.records = reinterpret_cast<float4*>(c->records.buf.ptr);
             vp.blockInfo = reinterpret_cast<SLBlockInfo*>(c->blockInfo.buf.ptr);
             vp.counters = c->counters;
-            { KernelScope ks(c, SLCU_K_VERTEX); CK(sh.vs(launchBlocks[i], c->stream, vp)); }
+            { KernelScope ks(c, SLCU_K_VERTEX); CK(sh.vs(launchBlocks[i], c->stream, vp, cache)); }
             firstBlock += launchBlocks[i];
         }
 
@@ -474,7 +495,7 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
         {
             /* more records than reserved (heavy clipping): retry once with the worst case */
             CK(cudaMemsetAsync(&c->counters->errorFlags, 0, sizeof(unsigned), c->stream));
-            if (attempt == 0) { recCapacity = totalPrims * 7 + 4096; continue; }
+            if (attempt == 0) { recOverflow = totalPrims * 7 + 4096; recCapacity = recFixed + recOverflow; continue; }
             c->err = "triangle record buffer overflow";
             return SLCU_ERR_OOM;
         }
