@@ -1090,8 +1090,57 @@ int slor_draw_multiple(slcu_context* c, const slcu_mesh* m, size_t n, size_t sha
 }
 int slor_draw_instanced(slcu_context* c, const slcu_mesh* m, size_t inst, size_t shader, size_t fbo) { return run_draw(c, m, 1, inst, shader, fbo); }
 
-int slor_blit(slcu_context*, size_t, size_t) { return SLCU_ERR_UNSUPPORTED; }
-int slor_blit_rect(slcu_context*, size_t, size_t, uint16_t, uint16_t, uint16_t, uint16_t, uint16_t, uint16_t, uint16_t, uint16_t) { return SLCU_ERR_UNSUPPORTED; }
+/* SL_BlitProcessor::blit_nearest (src/SL_BlitProcessor.cpp:620-667), one thread; conversions: same type, RGBA_FLOAT ->
+ * RGBA_8U ((vec4<u8>)(p*255.f), :400-415), RGBA_8U -> RGBA_FLOAT (SL_Color.hpp:665-669) */
+int slor_blit_rect(slcu_context* c, size_t outTex, size_t inTex, uint16_t sx0, uint16_t sy0, uint16_t sx1, uint16_t sy1,
+                   uint16_t dx0, uint16_t dy0, uint16_t dx1, uint16_t dy1)
+{
+    if (outTex >= c->textures.size() || inTex >= c->textures.size()) return SLCU_ERR_ARG;
+    const SL_Texture& s = *c->textures[inTex];
+    SL_Texture& d = *c->textures[outTex];
+    int mode;
+    if (s.mType == d.mType) mode = 0;
+    else if (s.mType == 26 && d.mType == 21) mode = 1;
+    else if (s.mType == 21 && d.mType == 26) mode = 2;
+    else return SLCU_ERR_UNSUPPORTED;
+    if (sx1 < sx0 || sy1 < sy0 || dx1 <= dx0 || dy1 <= dy0) return 0;
+    const uint64_t inW = (uint64_t)sx1 - sx0, inH = (uint64_t)sy1 - sy0, outW = (uint64_t)dx1 - dx0;
+    const uint64_t totalOutW = d.mWidth, totalOutH = d.mHeight;
+    const uint64_t x0 = dx0, x1 = std::min<uint64_t>(totalOutW, x0 + outW);
+    const uint64_t foutW = ((inW << 16) / totalOutW) + 1u, foutH = ((inH << 16) / totalOutH) + 1u;
+    for (uint64_t y = dy0; y < dy1 && y < totalOutH; ++y)
+    {
+        const uint64_t yf = (y * foutH) >> 16;
+        const uint64_t srcY = (uint64_t)sy1 - ((uint64_t)sy0 + yf) - 1u;
+        for (uint64_t x = x0; x < x1; ++x)
+        {
+            const uint64_t srcX = (x * foutW) >> 16;
+            if (srcX >= s.mWidth || srcY >= s.mHeight) continue;
+            const size_t si = (size_t)(srcX + (uint64_t)s.mWidth * srcY), di = (size_t)(x + totalOutW * y);
+            if (mode == 1)
+            {
+                math::vec4 f;
+                memcpy(f.v, s.mTexels + si * 16, 16);
+                const math::vec4_t<uint8_t> r = (math::vec4_t<uint8_t>)(f * 255.f);
+                memcpy(d.mTexels + di * 4, r.v, 4);
+            }
+            else if (mode == 2)
+            {
+                const unsigned char* p = s.mTexels + si * 4;
+                const math::vec4 f = math::vec4{(float)p[0], (float)p[1], (float)p[2], (float)p[3]} * 0.00392156862745f;
+                memcpy(d.mTexels + di * 16, f.v, 16);
+            }
+            else memcpy(d.mTexels + di * d.mBpt, s.mTexels + si * s.mBpt, d.mBpt);
+        }
+    }
+    return 0;
+}
+int slor_blit(slcu_context* c, size_t outTex, size_t inTex)
+{
+    if (outTex >= c->textures.size() || inTex >= c->textures.size()) return SLCU_ERR_ARG;
+    return slor_blit_rect(c, outTex, inTex, 0, 0, c->textures[inTex]->mWidth, c->textures[inTex]->mHeight, 0, 0,
+                          c->textures[outTex]->mWidth, c->textures[outTex]->mHeight);
+}
 int slor_sync(slcu_context*) { return 0; }
 int slor_reset_stats(slcu_context* c) { gFragTrace.clear(); if (c) memset(&c->stats, 0, sizeof(c->stats)); return 0; }
 int slor_get_stats(slcu_context* c, slcu_stats* out)

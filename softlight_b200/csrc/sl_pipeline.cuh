@@ -1590,6 +1590,61 @@ __global__ void k_clear(const __grid_constant__ SLClearParams P)
 }
 
 /* ------------------------------------------------------------------------
+ * SL_BlitProcessor::blit_nearest (src/SL_BlitProcessor.cpp:620-667): nearest
+ * neighbour, 16.16 fixed point, vertically flipped, format converting.  One
+ * thread per destination texel.  Conversions (color_cast, SL_Color.hpp:560-700):
+ *   mode 0  same type: texel copy
+ *   mode 1  RGBA_FLOAT -> RGBA_8U: (vec4<u8>)(p * 255.f) = cvtps2dq + saturating packs (:400-415, x86/vec4f_impl.h:299-309)
+ *   mode 2  RGBA_8U -> RGBA_FLOAT: (vec4)p * 0.00392156862745f (SL_Color.hpp:665-669)
+ * ----------------------------------------------------------------------*/
+struct SLBlitParams
+{
+    const unsigned char* src;
+    unsigned char* dst;
+    unsigned int srcW, srcH, dstW, dstH;
+    unsigned int srcX0, srcY0, srcX1, srcY1, dstX0, dstY0, dstX1, dstY1;
+    int mode, bpt;
+};
+
+__global__ void __launch_bounds__(256) k_blit(const __grid_constant__ SLBlitParams P)
+{
+    const unsigned long long inW = (unsigned long long)P.srcX1 - P.srcX0, inH = (unsigned long long)P.srcY1 - P.srcY0;
+    const unsigned long long outW = (unsigned long long)P.dstX1 - P.dstX0;
+    const unsigned long long x0 = P.dstX0;
+    const unsigned long long x1 = min((unsigned long long)P.dstW, x0 + outW);
+    const unsigned long long foutW = ((inW << 16) / P.dstW) + 1ull; /* relative to the WHOLE destination, like the reference */
+    const unsigned long long foutH = ((inH << 16) / P.dstH) + 1ull;
+    const unsigned long long x = x0 + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= x1) return;
+    for (unsigned long long y = (unsigned long long)P.dstY0 + blockIdx.y; y < P.dstY1 && y < P.dstH; y += gridDim.y)
+    {
+        const unsigned long long yf = (y * foutH) >> 16;
+        const unsigned long long srcY = (unsigned long long)P.srcY1 - ((unsigned long long)P.srcY0 + yf) - 1ull;
+        const unsigned long long srcX = (x * foutW) >> 16;
+        if (srcX >= P.srcW || srcY >= P.srcH) continue; /* the reference would read outside the source here */
+        const size_t si = (size_t)(srcX + (unsigned long long)P.srcW * srcY), di = (size_t)(x + (unsigned long long)P.dstW * y);
+        if (P.mode == 1)
+        {
+            const float4 f = reinterpret_cast<const float4*>(P.src)[si];
+            const math::vec4_t<uint8_t> r = math::vec4_to_u8(math::vec4{f.x, f.y, f.z, f.w} * 255.f);
+            reinterpret_cast<uint32_t*>(P.dst)[di] = (uint32_t)r.v[0] | ((uint32_t)r.v[1] << 8) | ((uint32_t)r.v[2] << 16) | ((uint32_t)r.v[3] << 24);
+        }
+        else if (P.mode == 2)
+        {
+            const uint32_t u = reinterpret_cast<const uint32_t*>(P.src)[si];
+            const math::vec4 c = math::vec4{(float)(u & 0xffu), (float)((u >> 8) & 0xffu), (float)((u >> 16) & 0xffu), (float)(u >> 24)} * 0.00392156862745f;
+            reinterpret_cast<float4*>(P.dst)[di] = make_float4(c.v[0], c.v[1], c.v[2], c.v[3]);
+        }
+        else if (P.bpt == 4) reinterpret_cast<uint32_t*>(P.dst)[di] = reinterpret_cast<const uint32_t*>(P.src)[si];
+        else if (P.bpt == 16) reinterpret_cast<uint4*>(P.dst)[di] = reinterpret_cast<const uint4*>(P.src)[si];
+        else
+        {
+            for (int b = 0; b < P.bpt; ++b) P.dst[di * P.bpt + b] = P.src[si * P.bpt + b];
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------
  * Sort-first composite: every rank stores the rows it owns into the root's
  * copy of the attachment (a peer mapping over NVLink, or local memory on the
  * root itself).  Ownership is exclusive per row, so this is a pure gather.

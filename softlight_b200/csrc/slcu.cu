@@ -940,11 +940,40 @@ int slcu_draw(slcu_context* c, const slcu_mesh* m, size_t shader, size_t fbo) { 
 int slcu_draw_multiple(slcu_context* c, const slcu_mesh* m, size_t n, size_t shader, size_t fbo) { return run_draw(c, m, n, 1, shader, fbo); }
 int slcu_draw_instanced(slcu_context* c, const slcu_mesh* m, size_t inst, size_t shader, size_t fbo) { return run_draw(c, m, 1, inst, shader, fbo); }
 
-int slcu_blit(slcu_context* c, size_t, size_t) { c->err = "blit: not implemented yet"; return SLCU_ERR_UNSUPPORTED; }
-int slcu_blit_rect(slcu_context* c, size_t, size_t, uint16_t, uint16_t, uint16_t, uint16_t, uint16_t, uint16_t, uint16_t, uint16_t)
+/* run_blit_processors replacement (src/SL_ProcessorPool.cpp:400-445) */
+int slcu_blit_rect(slcu_context* c, size_t outTex, size_t inTex, uint16_t sx0, uint16_t sy0, uint16_t sx1, uint16_t sy1,
+                   uint16_t dx0, uint16_t dy0, uint16_t dx1, uint16_t dy1)
 {
-    c->err = "blit: not implemented yet";
-    return SLCU_ERR_UNSUPPORTED;
+    if (!c || outTex >= c->textures.size() || inTex >= c->textures.size()) return SLCU_ERR_ARG;
+    cudaSetDevice(c->device);
+    const HostTexture& s = c->textures[inTex];
+    const HostTexture& d = c->textures[outTex];
+    if (!s.dev || !d.dev || !d.w || !d.h) return SLCU_ERR_ARG;
+    SLBlitParams p;
+    if (s.type == d.type) p.mode = 0;
+    else if (s.type == 26 && d.type == 21) p.mode = 1; /* RGBA_FLOAT -> RGBA_8U */
+    else if (s.type == 21 && d.type == 26) p.mode = 2; /* RGBA_8U -> RGBA_FLOAT */
+    else { c->err = "blit: this format conversion is not implemented (same type, RGBA_FLOAT<->RGBA_8U are)"; return SLCU_ERR_UNSUPPORTED; }
+    if (sx1 < sx0 || sy1 < sy0 || dx1 <= dx0 || dy1 <= dy0) return 0;
+    p.src = s.dev; p.dst = d.dev;
+    p.srcW = s.w; p.srcH = s.h; p.dstW = d.w; p.dstH = d.h;
+    p.srcX0 = sx0; p.srcY0 = sy0; p.srcX1 = sx1; p.srcY1 = sy1;
+    p.dstX0 = dx0; p.dstY0 = dy0; p.dstX1 = dx1; p.dstY1 = dy1;
+    p.bpt = d.bpt;
+    const unsigned outW = (unsigned)dx1 - dx0, outH = (unsigned)dy1 - dy0;
+    const dim3 grid((outW + 255u) / 256u, outH < 148u * 8u ? outH : 148u * 8u);
+    { KernelScope ks(c, SLCU_K_BLIT); k_blit<<<grid, 256, 0, c->stream>>>(p); }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int slcu_blit(slcu_context* c, size_t outTex, size_t inTex)
+{
+    /* SL_Context::blit(out, in) (src/SL_Context.cpp:747-766): whole source onto whole destination */
+    if (!c || outTex >= c->textures.size() || inTex >= c->textures.size()) return SLCU_ERR_ARG;
+    const HostTexture& s = c->textures[inTex];
+    const HostTexture& d = c->textures[outTex];
+    return slcu_blit_rect(c, outTex, inTex, 0, 0, s.w, s.h, 0, 0, d.w, d.h);
 }
 
 /* ---- sort-first multi-GPU ---- */

@@ -34,6 +34,11 @@ def golden():
     return frames, hashes
 
 
+@pytest.fixture(scope="session")
+def golden_blits():
+    return json.load(open(os.path.join(HERE, "golden", "golden_hashes.json")))["blits"]
+
+
 def have_cuda() -> bool:
     try:
         import torch

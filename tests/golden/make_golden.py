@@ -17,6 +17,7 @@ sys.path.insert(0, os.path.dirname(HERE))
 
 from softlight_b200 import capi as A  # noqa: E402
 import cases  # noqa: E402
+import blit_cases  # noqa: E402
 
 
 def main():
@@ -38,8 +39,13 @@ def main():
             frames[name + ".color"] = color
             frames[name + ".depth"] = cases.bits(depth)
         print(name, hashes[name]["frags"], flush=True)
+    blits = {}
+    for name in blit_cases.BLIT_CASES:
+        out = blit_cases.run_blit("ref_strict", name)
+        blits[name] = hashlib.sha256(np.ascontiguousarray(out).tobytes()).hexdigest()
+        print("blit", name, blits[name][:12], flush=True)
     np.savez_compressed(os.path.join(HERE, "golden_frames.npz"), **frames)
-    json.dump({"generator": ctx.impl_name(), "cases": hashes}, open(os.path.join(HERE, "golden_hashes.json"), "w"), indent=1)
+    json.dump({"generator": ctx.impl_name(), "cases": hashes, "blits": blits}, open(os.path.join(HERE, "golden_hashes.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":
