@@ -118,7 +118,9 @@ def algorithmic_bytes(scene_name: str, scene: S.Scene, frags: int) -> dict:
         # per shaded fragment: depth read+write, RGBA8 read+write (blend), 4 bilinear taps of RGB8 (reuse = 0: upper figure)
         out["raster"] = frags * (2 * dbpt + 2 * cbpt + 4 * 3)
     elif scene_name.startswith("c1"):
-        out["vertex"] = scene.tris_per_frame * 3 * 4 + 50625 * 32
+        # u32 indices + every vertex once (32 B) ; per shaded fragment: depth read + write, RGBA8 write
+        nverts = (int(round((scene.tris_per_frame / 2) ** 0.5)) + 1) ** 2
+        out["vertex"] = scene.tris_per_frame * 3 * 4 + nverts * 32
         out["raster"] = frags * (2 * dbpt + cbpt)
     else:
         out["vertex"] = 0

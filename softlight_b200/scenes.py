@@ -354,4 +354,7 @@ SCENES: Dict[str, Callable[[], Scene]] = {
     "c1_small": lambda: sphere_scene(256, 192, 48, 48, name="sphere4k_256x192"),
     "c2_instancing10k": instancing_scene,
     "c2_small": lambda: instancing_scene(320, 240, (5, 4, 3), 8, 16, name="instancing60_320x240"),
+    # the survey's 4K anchors: the C1 sphere at 3840x2160 with 100k and 1M triangles
+    "c1_sphere100k_4k": lambda: sphere_scene(3840, 2160, 224, 224, name="sphere100k_3840x2160"),
+    "c1_sphere1m_4k": lambda: sphere_scene(3840, 2160, 708, 708, name="sphere1m_3840x2160"),
 }

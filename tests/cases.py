@@ -51,6 +51,8 @@ CASES["c2_small"] = S.SCENES["c2_small"]
 BIG_CASES = {
     "c1_sphere100k": S.SCENES["c1_sphere100k"],
     "c2_instancing10k": S.SCENES["c2_instancing10k"],
+    "c1_sphere100k_4k": S.SCENES["c1_sphere100k_4k"],
+    "c1_sphere1m_4k": S.SCENES["c1_sphere1m_4k"],
 }
 
 # cases whose images are committed in full (the rest of CASES is pinned by sha256)
