@@ -117,6 +117,12 @@ def algorithmic_bytes(scene_name: str, scene: S.Scene, frags: int) -> dict:
         out["vertex"] = 3072 * 2 + 561 * 32 + (scene.tris_per_frame // 1024) * 64
         # per shaded fragment: depth read+write, RGBA8 read+write (blend), 4 bilinear taps of RGB8 (reuse = 0: upper figure)
         out["raster"] = frags * (2 * dbpt + 2 * cbpt + 4 * 3)
+    elif scene_name.startswith("c3"):
+        # per draw: u32 indices + the room's 24-byte vertices + the 1 KiB uniform block; per shaded fragment: depth read +
+        # write, RGBA8 write, 4 bilinear taps of RGBA8 (reuse = 0: upper figure)
+        tris_per_draw = scene.tris_per_frame // scene.draws_per_frame
+        out["vertex"] = scene.draws_per_frame * (tris_per_draw * 3 * 4 + (tris_per_draw // 2 + 2 * 6 * 27) * 24 + 1024)
+        out["raster"] = frags * (2 * dbpt + cbpt + 4 * 4)
     elif scene_name.startswith("c1"):
         # u32 indices + every vertex once (32 B) ; per shaded fragment: depth read + write, RGBA8 write
         nverts = (int(round((scene.tris_per_frame / 2) ** 0.5)) + 1) ** 2

@@ -103,6 +103,24 @@ struct SL_FragmentParam
     math::vec4 pOutputs[4];
 };
 
+
+/* constants.h:13-21 (double literals, like the reference: expressions that mix them with floats evaluate in double) */
+#ifndef LS_PI
+#define LS_PI 3.14159265358979323846
+#define LS_PI_INVERSE 0.31830988618379067153
+#define LS_EPSILON 1.0e-9
+#endif
+
+/* SL_PackedVertex.hpp:20-100,185-188: three sign-extended 10-bit fields * (1/511); the w field is always 0 */
+static inline math::vec4 sl_unpack_vec4_10_10_10_2I(int32_t norm)
+{
+    const int32_t v = norm & 0x3FFFFFFF;
+    const int32_t x = (int32_t)((uint32_t)v << 22) >> 22;
+    const int32_t y = (int32_t)((uint32_t)v << 12) >> 22;
+    const int32_t z = (int32_t)((uint32_t)v << 2) >> 22;
+    return math::vec4{(float)x * (1.f / 511.f), (float)y * (1.f / 511.f), (float)z * (1.f / 511.f), 0.f * (1.f / 511.f)};
+}
+
 /* ---- color_cast (SL_Color.hpp:480-690) ---- */
 template <typename T> struct color_max;
 template <> struct color_max<uint8_t> { static constexpr float f() { return 255.f; } };

@@ -28,6 +28,8 @@ LIB_PATHS = {
     "ref_fast": os.path.join(ROOT, "oracle", "_ref", "libslref_fast.so"),
     "port": os.path.join(ROOT, "oracle", "libslor.so"),
 }
+if os.environ.get("SLCU_LIB"):  # development aid: A/B a differently compiled product library
+    LIB_PATHS["cuda"] = os.path.abspath(os.environ["SLCU_LIB"])
 PREFIX = {"cuda": "slcu_", "ref_strict": "slref_", "ref_fast": "slref_", "port": "slor_"}
 
 INVALID_ID = C.c_size_t(-1).value

@@ -242,5 +242,32 @@ template <typename T> SLD_FN vec2_t<T> vec2_cast(const vec3_t<T>& v) { return ve
 /* variadic sum (generic/scalar_utils_impl.h:1009-1023): right fold */
 template <typename T> SLD_FN T sum(const T& a, const T& b, const T& c, const T& d) { return a + (b + (c + d)); }
 
+/* -------------------- log / exp / pow: the "fast approximate" forms that are live in the reference (LS_MATH_HIGH_PREC
+ * is never defined; -mfma selects the fmadd branches).  Scalar (x86/scalarf_utils_impl.h:305-326,334-358,389-423,550-590)
+ * and vec4 (x86/vecf_utils_impl.h:382-549) versions are lane-wise identical. */
+SLD_FN float log2(float n)
+{
+    const uint32_t vxi = __float_as_uint(n);
+    const float mxf = __uint_as_float((vxi & 0x007FFFFFu) | 0x3f000000u);
+    const float a = sl_rcp(0.3520887068f + mxf);
+    const float b = sl_fma(1.1920928955078125e-7f, (float)(int32_t)vxi, -124.22551499f);
+    const float c = sl_fma(-1.498030302f, mxf, b);
+    return sl_fma(-1.72587999f, a, c);
+}
+SLD_FN float log(float n) { return 0.69314718056f * log2(n); }
+SLD_FN float exp2(float x)
+{
+    const float clipp = sl_max(x, -126.f);
+    const float clipp2 = clipp + 126.94269504f;
+    return __uint_as_float((uint32_t)sl_cvt_rn((float)(1 << 23) * clipp2));
+}
+SLD_FN float exp(float x) { return exp2(x * 1.4426950408889634f); }
+SLD_FN float pow(float x, float y) { return exp(log(x) * y); }
+SLD_FN vec4 log2(const vec4& n) { return vec4{log2(n.v[0]), log2(n.v[1]), log2(n.v[2]), log2(n.v[3])}; }
+SLD_FN vec4 log(const vec4& n) { return vec4{log(n.v[0]), log(n.v[1]), log(n.v[2]), log(n.v[3])}; }
+SLD_FN vec4 exp2(const vec4& x) { return vec4{exp2(x.v[0]), exp2(x.v[1]), exp2(x.v[2]), exp2(x.v[3])}; }
+SLD_FN vec4 exp(const vec4& x) { return vec4{exp(x.v[0]), exp(x.v[1]), exp(x.v[2]), exp(x.v[3])}; }
+SLD_FN vec4 pow(const vec4& x, const vec4& y) { return exp(log(x) * y); }
+
 } // namespace math
 } // namespace sld

@@ -1351,6 +1351,9 @@ SLD_FN unsigned sl_walk_piece_warp(const SLRasterParams& P, const SLTile& T, uin
 
 constexpr int SL_LONG_GROUPS = 6; /* pieces of at least this many 4-pixel groups are walked by the whole warp */
 constexpr int SL_RASTER_WARPS = 4;
+#ifndef SL_RASTER_MIN_BLOCKS
+#define SL_RASTER_MIN_BLOCKS 4
+#endif
 
 SLD_FN unsigned sl_align16(unsigned n) { return (n + 15u) & ~15u; }
 
@@ -1383,7 +1386,7 @@ SLD_FN void sl_copy_warp(unsigned char* dst, const unsigned char* src, unsigned 
  * overlaps them in x (fragments of disjoint x-ranges commute; everything else is serialised in submission order);
  * long pieces are walked by the whole warp. */
 template <FsFn FS>
-__global__ void __launch_bounds__(SL_RASTER_WARPS * 32) k_raster(const __grid_constant__ SLRasterParams P)
+__global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_raster(const __grid_constant__ SLRasterParams P)
 {
     extern __shared__ __align__(16) unsigned char sDyn[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

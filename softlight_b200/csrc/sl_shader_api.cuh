@@ -97,6 +97,24 @@ struct SL_FragmentParam
     math::vec4 pOutputs[4];
 };
 
+
+/* constants.h:13-21 (double literals, like the reference: expressions that mix them with floats evaluate in double) */
+#ifndef LS_PI
+#define LS_PI 3.14159265358979323846
+#define LS_PI_INVERSE 0.31830988618379067153
+#define LS_EPSILON 1.0e-9
+#endif
+
+/* SL_PackedVertex.hpp:20-100,185-188: three sign-extended 10-bit fields * (1/511); the w field is always 0 */
+SLD_FN math::vec4 sl_unpack_vec4_10_10_10_2I(int32_t norm)
+{
+    const int32_t v = norm & 0x3FFFFFFF;
+    const int32_t x = (int32_t)((uint32_t)v << 22) >> 22;
+    const int32_t y = (int32_t)((uint32_t)v << 12) >> 22;
+    const int32_t z = (int32_t)((uint32_t)v << 2) >> 22;
+    return math::vec4{(float)x * (1.f / 511.f), (float)y * (1.f / 511.f), (float)z * (1.f / 511.f), 0.f * (1.f / 511.f)};
+}
+
 /* ------------------------------------------------------------ color_cast */
 template <typename T, typename U> struct ColorCast;
 template <> struct ColorCast<float, uint8_t> /* SL_Color.hpp:549,666: (float)p * 0.00392156862745f */

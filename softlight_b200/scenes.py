@@ -281,6 +281,110 @@ def instancing_scene(width=1920, height=1080, grid=(25, 20, 20), stacks=16, slic
                  (0.6, 0.6, 0.6, 1.0), 0.0, setup, frame, tris_per_frame=tris.shape[0] * ninst, draws_per_frame=1)
 
 
+# ---- C3: indoor scene, 16x16 inward-facing tessellated rooms, one textured PBR draw per room --------------------
+def _room_mesh(quads: int, half: float):
+    """Inward-facing box: 6 faces x quads^2 x 2 triangles, CCW seen from inside; vertex = (vec3 pos, vec2 uv, packed normal)."""
+    verts, tris = [], []
+    axes = [((1, 0, 0), (0, 1, 0), (0, 0, 1)), ((0, 1, 0), (0, 0, 1), (1, 0, 0)), ((0, 0, 1), (1, 0, 0), (0, 1, 0))]
+    g = np.linspace(-1.0, 1.0, quads + 1)
+    for n_ax, u_ax, v_ax in axes:
+        for sign in (1.0, -1.0):
+            n = np.array(n_ax, dtype=np.float64) * sign          # inward normal of the wall at -sign*half
+            u = np.array(u_ax, dtype=np.float64)
+            v = np.array(v_ax, dtype=np.float64) * sign          # keeps u x v = n
+            base = len(verts) and sum(len(x) for x in verts)
+            aa, bb = np.meshgrid(g, g, indexing="ij")
+            p = (-n[None, None, :] + aa[..., None] * u + bb[..., None] * v) * half
+            uv = np.stack([(aa + 1.0) * 1.5, (bb + 1.0) * 1.5], axis=-1)   # three repeats per wall
+            packed = ((int(n[0] * 511) & 0x3FF) | ((int(n[1] * 511) & 0x3FF) << 10) | ((int(n[2] * 511) & 0x3FF) << 20))
+            rec = np.zeros((quads + 1, quads + 1), dtype=[("pos", "<f4", 3), ("uv", "<f4", 2), ("nrm", "<i4")])
+            rec["pos"], rec["uv"], rec["nrm"] = p, uv, np.int32(packed)
+            verts.append(rec.reshape(-1))
+            i, j = np.meshgrid(np.arange(quads), np.arange(quads), indexing="ij")
+            a = (base + i * (quads + 1) + j).reshape(-1)
+            b = a + (quads + 1)
+            c = a + 1
+            d = b + 1
+            tris.append(np.stack([a, b, c, b, d, c], axis=-1).reshape(-1, 3))
+    return np.concatenate(verts), np.concatenate(tris).astype(np.uint32)
+
+
+def _room_texture(i: int, size: int) -> np.ndarray:
+    """Cheap, distinct, deterministic RGBA8 texture per room: one value-noise base, rolled and tinted by the room index."""
+    base = _room_texture.cache.get(size)
+    if base is None:
+        base = value_noise_texture(3, size, size, 4)
+        _room_texture.cache[size] = base
+    t = np.roll(base, (37 * i % size, 91 * i % size), axis=(0, 1)).astype(np.int32)
+    tint = np.array([(53 * i) % 97, (29 * i) % 89, (71 * i) % 83, 0], dtype=np.int32)
+    t = np.clip(t + tint - 40, 0, 255).astype(np.uint8)
+    t[..., 3] = 255
+    return t
+
+
+_room_texture.cache = {}
+
+
+def indoor_scene(width=3840, height=2160, rooms=(16, 16), quads=26, tex_size=512, depth_type=A.SL_COLOR_R_HALF, name=None) -> Scene:
+    half = 10.0
+    verts, tris = _room_mesh(quads, half)
+    idx = tris.reshape(-1)
+    rx, rz = rooms
+    nrooms = rx * rz
+    spacing = 2.2 * half
+    proj = infinite_perspective(60.0, width / height, 0.01)
+    # just outside the grid, looking down the rows: the near wall of every room is back-facing (culled), so each room shows
+    # its floor, ceiling, side walls and far wall, and the rooms of a row hide one another (early-Z rejects, overdraw)
+    cam = np.array([-(rx / 2.0) * spacing - 1.2 * half, 0.25 * half, 0.15 * half])
+    target = cam + np.array([1.0, -0.03, 0.22])
+    view = look_at(cam, target, (0, 1, 0))
+    vp = matmul_cm(proj, view)
+    centers = [np.array([(x - rx / 2.0 + 0.5) * spacing, 0.0, (z - rz / 2.0) * spacing]) for z in range(rz) for x in range(rx)]
+    light_pos = np.array([cam[0] + 1.5 * half, cam[1] + 0.4 * half, cam[2] + 0.2 * half, 1.0], dtype=np.float32)
+
+    def blob_for(i):
+        model = translate_scale(centers[i].astype(np.float32), 1.0)
+        mvp = matmul_cm(vp, model)
+        # MeshUniforms: ptr@0, camPos@16, light{pos@32, ambient@48, diffuse@64}, point@80, model@96, mvp@160
+        b = bytearray(224)
+        b[16:32] = np.array([cam[0], cam[1], cam[2], 1.0], dtype=np.float32).tobytes()
+        b[32:48] = light_pos.tobytes()
+        b[48:64] = np.array([0.25, 0.25, 0.25, 1.0], dtype=np.float32).tobytes()
+        b[64:80] = np.array([0.09, 0.085, 0.08, 1.0], dtype=np.float32).tobytes()
+        b[80:96] = np.array([1.0, 0.09, 0.032, 0.0], dtype=np.float32).tobytes()
+        b[96:160] = model.tobytes()
+        b[160:224] = mvp.tobytes()
+        return bytes(b)
+
+    blobs = [blob_for(i) for i in range(nrooms)]
+
+    def setup(ctx):
+        color, depth, fbo = _make_targets(ctx, width, height, A.SL_COLOR_RGBA_8U, depth_type)
+        vbo = ctx.create_vbo(verts)
+        ibo = ctx.create_ibo(idx)
+        vao = ctx.create_vao(vbo, ibo, [(0, 24, A.VERTEX_DIMENSION_3, A.VERTEX_DATA_FLOAT), (12, 24, A.VERTEX_DIMENSION_2, A.VERTEX_DATA_FLOAT),
+                                        (20, 24, A.VERTEX_DIMENSION_1, A.VERTEX_DATA_INT)])
+        texs = [ctx.create_texture(A.SL_COLOR_RGBA_8U, tex_size, tex_size, 1, _room_texture(i, tex_size), order=A.TEXEL_SWIZZLED)
+                for i in range(nrooms)]
+        ubo = ctx.create_ubo(blobs[0])
+        ctx.ubo_bind_texture(ubo, 0, texs[0])
+        sh = ctx.create_shader("mesh_pbr", "mesh_pbr", ubo, vs_varyings=3, fs_varyings=3, cull=A.SL_CULL_BACK_FACE, blend=A.SL_BLEND_OFF,
+                               depth_test=A.SL_DEPTH_TEST_GREATER_EQUAL, depth_mask=A.SL_DEPTH_MASK_ON)
+        assert sh != A.INVALID_ID
+        return dict(color=color, depth=depth, fbo=fbo, shader=sh, mesh=ctx.mesh(vao, 0, idx.size), ubo=ubo, texs=texs)
+
+    def frame(ctx, st):
+        ctx.clear_framebuffer(st["fbo"], 0, (0.0, 0.0, 0.0, 1.0), 0.0)
+        for i in range(nrooms):  # the demo's pattern: per-mesh uniforms, then draw (sl_large_scene_test.cpp:700-730)
+            ctx.ubo_assign(st["ubo"], blobs[i])
+            ctx.ubo_bind_texture(st["ubo"], 0, st["texs"][i])
+            ctx.draw(st["mesh"], st["shader"], st["fbo"])
+
+    return Scene(name or f"indoor{nrooms}x{tris.shape[0]}_{width}x{height}", width, height, A.SL_COLOR_RGBA_8U, depth_type,
+                 (0, 0, 0, 1), 0.0, setup, frame, tris_per_frame=tris.shape[0] * nrooms, draws_per_frame=nrooms,
+                 upload_bytes_per_frame=1024 * nrooms)
+
+
 # ---- torture scene: random clip-space triangles (overlap, near-plane clipping, tiny + huge) ----
 def random_tris_scene(seed=1, n=400, width=200, height=150, blend=A.SL_BLEND_OFF, depth_test=A.SL_DEPTH_TEST_LESS_THAN,
                       depth_mask=A.SL_DEPTH_MASK_ON, depth_type=A.SL_COLOR_R_FLOAT, color_type=A.SL_COLOR_RGBA_8U,
@@ -355,6 +459,8 @@ SCENES: Dict[str, Callable[[], Scene]] = {
     "c2_instancing10k": instancing_scene,
     "c2_small": lambda: instancing_scene(320, 240, (5, 4, 3), 8, 16, name="instancing60_320x240"),
     # the survey's 4K anchors: the C1 sphere at 3840x2160 with 100k and 1M triangles
+    "c3_indoor2m": indoor_scene,
+    "c3_small": lambda: indoor_scene(480, 270, (4, 4), 6, 64, name="indoor16x432_480x270"),
     "c1_sphere100k_4k": lambda: sphere_scene(3840, 2160, 224, 224, name="sphere100k_3840x2160"),
     "c1_sphere1m_4k": lambda: sphere_scene(3840, 2160, 708, 708, name="sphere1m_3840x2160"),
 }
