@@ -103,6 +103,8 @@ typedef struct slcu_stats
                                  the width*height texels of the framebuffer    */
     uint64_t kernelLaunches;  /* CUDA kernels launched by this context          */
     uint64_t drawCalls;
+    uint64_t batches;         /* pipeline passes the draw calls were executed in (CUDA: consecutive draws with one
+                                 shader + framebuffer share a pass; CPU checkers: == drawCalls)                 */
 } slcu_stats;
 
 /* ---- context: SL_Context ctor/dtor, num_threads (SL_Context.cpp:1135-1148) */

@@ -229,6 +229,20 @@ inline vec4_t<half>::operator vec4_t<float>() const
     return vec4_t<float>{half_to_float(v[0].bits), half_to_float(v[1].bits), half_to_float(v[2].bits), half_to_float(v[3].bits)};
 }
 
+/* vec4<uint32_t> -> vec4<float> (vec4f_impl.h:236-245): cvtdq2ps has no unsigned form, so the reference converts v>>1
+ * and v&1 separately: (float)(v>>1) * 2 + (float)(v&1), two roundings for values >= 2^24 */
+template <> template <>
+inline vec4_t<uint32_t>::operator vec4_t<float>() const
+{
+    vec4_t<float> r;
+    for (int i = 0; i < 4; ++i)
+    {
+        const float hi = (float)(int32_t)(v[i] >> 1), lo = (float)(int32_t)(v[i] & 1u);
+        r.v[i] = (hi + hi) + lo;
+    }
+    return r;
+}
+
 typedef vec2_t<float> vec2;
 typedef vec3_t<float> vec3;
 typedef vec4_t<float> vec4;
@@ -237,6 +251,13 @@ typedef vec4_t<float> vec4;
 template <typename T> struct mat4_t
 {
     vec4_t<T> m[4];
+    mat4_t() = default;
+    /* generic/mat4_impl.h: mat4_t(n) = n on the diagonal */
+    explicit constexpr mat4_t(T n) : m{vec4_t<T>{n, T(0), T(0), T(0)}, vec4_t<T>{T(0), n, T(0), T(0)}, vec4_t<T>{T(0), T(0), n, T(0)}, vec4_t<T>{T(0), T(0), T(0), n}} {}
+    constexpr mat4_t(const vec4_t<T>& a, const vec4_t<T>& b, const vec4_t<T>& c, const vec4_t<T>& d) : m{a, b, c, d} {}
+    /* generic/mat4_impl.h:205-213,474-482: column-wise, element-wise */
+    mat4_t operator+(const mat4_t& n) const { return mat4_t{m[0] + n.m[0], m[1] + n.m[1], m[2] + n.m[2], m[3] + n.m[3]}; }
+    mat4_t operator*(T n) const { return mat4_t{m[0] * n, m[1] * n, m[2] * n, m[3] * n}; }
     const vec4_t<T>& operator[](int i) const { return m[i]; }
     vec4_t<T>& operator[](int i) { return m[i]; }
     /* x86/mat4f_impl.h:123-146 (FMA branch): v1 = fma(m1,y, m0*x); v3 = fma(m3,w, m2*z); v1+v3 */
@@ -286,6 +307,8 @@ static inline float fmadd(float x, float m, float a) { return sfma(x, m, a); } /
 static inline int sign_mask(float x) { return sign_bit(x) ? 1 : 0; }          /* :250 */
 static inline float sqrt(float x) { return __builtin_sqrtf(x); }
 static inline float abs(float x) { return u2f(f2u(x) & 0x7fffffffu); }
+static inline float min(float a, float b, float c) { return smin(c, smin(a, b)); } /* :32-38 */
+static inline float max(float a, float b, float c) { return smax(c, smax(a, b)); } /* :64-70 */
 template <typename T> static inline T clamp(T n, T lo, T hi) { return n < lo ? lo : (n > hi ? hi : n); } /* generic ints */
 template <typename T> static inline T min(T a, T b) { return a < b ? a : b; }
 template <typename T> static inline T max(T a, T b) { return a > b ? a : b; }
@@ -358,8 +381,25 @@ template <typename T> static inline vec3_t<T> vec3_cast(const vec2_t<T>& v, cons
 template <typename T> static inline vec2_t<T> vec2_cast(const vec4_t<T>& v) { return vec2_t<T>{v.v[0], v.v[1]}; }
 template <typename T> static inline vec2_t<T> vec2_cast(const vec3_t<T>& v) { return vec2_t<T>{v.v[0], v.v[1]}; }
 
+/* generic vec2 min/max (generic/vec_utils_impl.h:120-147): math::min<num_t>/max<num_t> with an explicit template
+ * argument = the generic (a < b) ? a : b / (a > b) ? a : b */
+template <typename T> static inline vec2_t<T> min(const vec2_t<T>& a, const vec2_t<T>& b) { return vec2_t<T>{a.v[0] < b.v[0] ? a.v[0] : b.v[0], a.v[1] < b.v[1] ? a.v[1] : b.v[1]}; }
+template <typename T> static inline vec2_t<T> max(const vec2_t<T>& a, const vec2_t<T>& b) { return vec2_t<T>{a.v[0] > b.v[0] ? a.v[0] : b.v[0], a.v[1] > b.v[1] ? a.v[1] : b.v[1]}; }
+
+/* math::scale(mat4, vec3) (generic/mat_utils_impl.h:433-440): only the diagonal is multiplied */
+template <typename T> static inline mat4_t<T> scale(const mat4_t<T>& m, const vec3_t<T>& s)
+{
+    mat4_t<T> r = m;
+    r.m[0].v[0] = m.m[0].v[0] * s.v[0];
+    r.m[1].v[1] = m.m[1].v[1] * s.v[1];
+    r.m[2].v[2] = m.m[2].v[2] * s.v[2];
+    return r;
+}
+
 /* variadic sum (generic/scalar_utils_impl.h:1009-1023): right fold */
-template <typename T> static inline T sum(const T& a, const T& b, const T& c, const T& d) { return a + (b + (c + d)); }
+template <typename T> static inline T sum_fold(const T& a) { return a; }
+template <typename T, typename... R> static inline T sum_fold(const T& a, const R&... rest) { return a + sum_fold(rest...); }
+template <typename T, typename... R> static inline T sum(const T& a, const T& b, const R&... rest) { return a + sum_fold(b, rest...); }
 
 /* -------------------- log / exp / pow: the "fast approximate" forms that are live in the reference (LS_MATH_HIGH_PREC
  * is never defined; -mfma selects the fmadd branches).  Scalar (x86/scalarf_utils_impl.h:305-326,334-358,389-423,550-590)

@@ -63,6 +63,7 @@ struct FsReg { FsReg(const char* n, FsFn f) { fs_registry()[n] = f; } };
 
 #include "sl_shaders_basic.inl"
 #include "sl_shaders_scene.inl"
+#include "sl_shaders_anim_volume.inl"
 
 /* ---- objects ------------------------------------------------------------- */
 struct IndexBuffer
@@ -1150,6 +1151,7 @@ int slor_get_stats(slcu_context* c, slcu_stats* out)
         FILE* f = fopen(gFragTracePath, "wb");
         if (f) { fwrite(gFragTrace.data(), 4, gFragTrace.size(), f); fclose(f); }
     }
+    c->stats.batches = c->stats.drawCalls; /* every draw call is executed on its own */
     *out = c->stats;
     return 0;
 }

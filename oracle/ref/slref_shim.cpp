@@ -95,6 +95,7 @@ struct FsCountReg { FsCountReg(const char* n, FsFn f) { fs_registry()[std::strin
 
 #include "sl_shaders_basic.inl"
 #include "sl_shaders_scene.inl"
+#include "sl_shaders_anim_volume.inl"
 
 /* --------------------------------------------------------------------------
  * Context wrapper
@@ -392,6 +393,7 @@ int slref_get_stats(slcu_context* c, slcu_stats* out)
         FILE* f = fopen(gFragTracePath, "wb");
         if (f) { fwrite(gFragTrace.data(), 4, gFragTrace.size(), f); fclose(f); }
     }
+    c->stats.batches = c->stats.drawCalls; /* every draw call is executed on its own */
     *out = c->stats;
     return 0;
 }

@@ -84,7 +84,7 @@ class FragmentShader(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("trisSubmitted", C.c_uint64), ("trisBinned", C.c_uint64), ("spans", C.c_uint64),
-                ("fragsShaded", C.c_uint64), ("kernelLaunches", C.c_uint64), ("drawCalls", C.c_uint64)]
+                ("fragsShaded", C.c_uint64), ("kernelLaunches", C.c_uint64), ("drawCalls", C.c_uint64), ("batches", C.c_uint64)]
 
 
 KERNEL_CLASSES = ["clear", "vertex", "span_count", "scan", "span_fill", "raster", "blit", "composite"]

@@ -73,22 +73,34 @@ struct SLCounters
  * over through a small hash table in global memory. */
 constexpr uint32_t SL_ENTRY_OVERFLOW = 0x80000000u;
 
-struct SLVertexParams
+/* One submitted draw of a batch (one mesh of draw / draw_multiple, or one draw_instanced): everything that may differ
+ * between the draws of a batch.  The table lives in HBM; a batch holds consecutive draws that share the shader object
+ * and the framebuffer (SL_Shader state and attachments are batch constants).  Uniforms are snapshotted at submission,
+ * exactly what the reference's synchronous draw would have read. */
+struct alignas(16) SLDrawDesc
 {
     SL_UniformBuffer uniforms;
+    alignas(16) float scissor[16]; /* column-major scissor matrix (host, SL_ViewportState::scissor_matrix); read as a mat4 */
+    alignas(16) float viewport[4]; /* viewport_rect */
     SL_VertexArray vao;
     SL_VertexBuffer vbo;
     const unsigned char* ibo;
     int iboType;          /* SL_DataType: 0 u8, 1 u16, 2 u32 */
     int usingIndices;
-    int cullMode;         /* SL_CullMode */
-    int numVaryings;
-    float scissor[16];    /* column-major scissor matrix (host, SL_ViewportState::scissor_matrix) */
-    float viewport[4];    /* viewport_rect */
     unsigned long long elementBegin;
     unsigned long long primsPerInstance;
     unsigned long long numPrims;      /* primsPerInstance * instances */
-    unsigned int firstBlock;          /* index of this launch's first vertex block in blockInfo */
+    unsigned int firstBlock;          /* index of this draw's first vertex block in the batch */
+    unsigned int pad_;
+};
+
+struct SLVertexParams
+{
+    const SLDrawDesc* draws;          /* draw table of the batch (HBM)                                  */
+    const uint32_t* blockDraw;        /* vertex block -> index into draws                               */
+    uint16_t* recDraw;                /* record slot -> index into draws (read by the rasteriser)       */
+    int cullMode;                     /* SL_CullMode */
+    int numVaryings;
     unsigned int cacheBytes;          /* dynamic shared memory of the post-transform cache (0: off) */
     unsigned int recCapacity;         /* record slots per plane: fixed per-block regions + overflow area */
     unsigned int recOverflowBase;     /* first slot of the overflow area                                */
@@ -259,7 +271,7 @@ SLD_FN bool sl_clip_rejects(const math::vec4& p0, const math::vec4& p1, const ma
 constexpr int SL_VCACHE_VERTS = 1024; /* post-transform vertex cache of one vertex block (shared memory) */
 
 /* get_next_vertex3 (src/SL_TriProcessor.cpp:125-234) */
-SLD_FN void sl_fetch_vertex_ids(const SLVertexParams& P, unsigned long long i, unsigned long long vertId[3])
+SLD_FN void sl_fetch_vertex_ids(const SLDrawDesc& P, unsigned long long i, unsigned long long vertId[3])
 {
     if (P.usingIndices)
     {
@@ -286,26 +298,29 @@ __global__ void __launch_bounds__(SL_VB_THREADS) k_vertex(const __grid_constant_
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const unsigned long long blockFirst = (unsigned long long)blockIdx.x * SL_VB_PRIMS;
+    const uint32_t drawIdx = P.blockDraw[blockIdx.x];
+    const SLDrawDesc& D = P.draws[drawIdx];
+    const unsigned long long blockFirst = (unsigned long long)(blockIdx.x - D.firstBlock) * SL_VB_PRIMS;
     const int NV = P.numVaryings;
     const int recStride = 3 + 3 * NV;
 
     SL_VertexParam params;
-    params.pUniforms = &P.uniforms;
-    params.pVao = &P.vao;
-    params.pVbo = &P.vbo;
+    params.pUniforms = &D.uniforms;
+    params.pVao = &D.vao;
+    params.pVbo = &D.vbo;
 
-    const math::mat4& scissorMat = *reinterpret_cast<const math::mat4*>(P.scissor);
+    const math::mat4 scissorMat = *reinterpret_cast<const math::mat4*>(D.scissor);
+    const float viewport[4] = {D.viewport[0], D.viewport[1], D.viewport[2], D.viewport[3]};
 
     /* ---- post-transform cache ---- */
     bool cached = false;
     unsigned long long cacheBase = 0;
     float4* cache = reinterpret_cast<float4*>(sVCache);
-    if (CACHE && P.cacheBytes && P.usingIndices && blockFirst < P.numPrims)
+    if (CACHE && P.cacheBytes && D.usingIndices && blockFirst < D.numPrims)
     {
-        const unsigned long long blockLast = min(blockFirst + (unsigned long long)SL_VB_PRIMS, P.numPrims) - 1ull;
-        const unsigned long long instFirst = blockFirst / P.primsPerInstance;
-        if (instFirst == blockLast / P.primsPerInstance) /* one instance: block-uniform */
+        const unsigned long long blockLast = min(blockFirst + (unsigned long long)SL_VB_PRIMS, D.numPrims) - 1ull;
+        const unsigned long long instFirst = blockFirst / D.primsPerInstance;
+        if (instFirst == blockLast / D.primsPerInstance) /* one instance: block-uniform */
         {
             if (tid == 0) { sIdMin = ~0ull; sIdMax = 0ull; }
             __syncthreads();
@@ -316,7 +331,7 @@ __global__ void __launch_bounds__(SL_VB_THREADS) k_vertex(const __grid_constant_
                 if (g <= blockLast)
                 {
                     unsigned long long id[3];
-                    sl_fetch_vertex_ids(P, P.elementBegin + 3ull * (g - instFirst * P.primsPerInstance), id);
+                    sl_fetch_vertex_ids(D, D.elementBegin + 3ull * (g - instFirst * D.primsPerInstance), id);
                     lo = min(lo, min(id[0], min(id[1], id[2])));
                     hi = max(hi, max(id[0], max(id[1], id[2])));
                 }
@@ -360,12 +375,12 @@ __global__ void __launch_bounds__(SL_VB_THREADS) k_vertex(const __grid_constant_
         int n = 0;         /* records this thread emits */
         int polyVerts = 0; /* > 0: clipped path */
 
-        if (g < P.numPrims)
+        if (g < D.numPrims)
         {
-            const unsigned long long instanceId = g / P.primsPerInstance;
-            const unsigned long long i = P.elementBegin + 3ull * (g - instanceId * P.primsPerInstance);
+            const unsigned long long instanceId = g / D.primsPerInstance;
+            const unsigned long long i = D.elementBegin + 3ull * (g - instanceId * D.primsPerInstance);
             unsigned long long vertId[3];
-            sl_fetch_vertex_ids(P, i, vertId);
+            sl_fetch_vertex_ids(D, i, vertId);
 
             if (CACHE && cached)
             {
@@ -412,7 +427,7 @@ __global__ void __launch_bounds__(SL_VB_THREADS) k_vertex(const __grid_constant_
                 if (vis == 3)
                 {
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) sl_to_screen(v[k].vert, P.viewport);
+                    for (int k = 0; k < 3; ++k) sl_to_screen(v[k].vert, viewport);
                     n = sl_prim_hidden(v[0].vert, v[1].vert, v[2].vert) ? 0 : 1;
                 }
                 else if (vis == 1 && !sl_clip_rejects(v[0].vert, v[1].vert, v[2].vert))
@@ -424,7 +439,7 @@ __global__ void __launch_bounds__(SL_VB_THREADS) k_vertex(const __grid_constant_
 #pragma unroll
                         for (int s = 0; s < 4; ++s) { if (s < NV) poly.varys[k * 4 + s] = v[k].varyings[s]; }
                     }
-                    polyVerts = sl_clip_polygon(poly, NV, P.viewport);
+                    polyVerts = sl_clip_polygon(poly, NV, viewport);
                     for (int f = polyVerts - 2; f-- > 0;)
                     {
                         if (!sl_prim_hidden(poly.verts[0], poly.verts[f + 1], poly.verts[f + 2])) ++n;
@@ -454,7 +469,7 @@ __global__ void __launch_bounds__(SL_VB_THREADS) k_vertex(const __grid_constant_
         /* Every (block, round) owns SL_VB_THREADS record slots at a fixed place, enough unless clipping fanned primitives
          * out; only then does the round take its slots from the shared overflow area (one atomic).  No atomics, no
          * second barrier and no allocation-order dependence in the common case. */
-        uint32_t base = (P.firstBlock + blockIdx.x) * (uint32_t)SL_VB_PRIMS + (uint32_t)round * SL_VB_THREADS;
+        uint32_t base = blockIdx.x * (uint32_t)SL_VB_PRIMS + (uint32_t)round * SL_VB_THREADS;
         uint32_t granted = total;
         if (total > (uint32_t)SL_VB_THREADS) /* block-uniform */
         {
@@ -476,13 +491,14 @@ __global__ void __launch_bounds__(SL_VB_THREADS) k_vertex(const __grid_constant_
         if (tid == 0)
         {
             if (granted) atomicAdd(&P.counters->trisBinned, (unsigned long long)granted);
-            P.blockInfo[P.firstBlock + blockIdx.x].seg[round] = SLSegment{base, granted};
+            P.blockInfo[blockIdx.x].seg[round] = SLSegment{base, granted};
         }
         if (n && granted)
         {
             uint32_t slot = base + warpOff + (incl - (uint32_t)n);
             if (!polyVerts)
             {
+                P.recDraw[slot] = (uint16_t)drawIdx;
                 sl_write_record(P.records + (size_t)slot * recStride, NV, v[0].vert, v[1].vert, v[2].vert, v[0].varyings, v[1].varyings, v[2].varyings);
             }
             else
@@ -491,6 +507,7 @@ __global__ void __launch_bounds__(SL_VB_THREADS) k_vertex(const __grid_constant_
                 {
                     const int j = f + 1, k = f + 2;
                     if (sl_prim_hidden(poly.verts[0], poly.verts[j], poly.verts[k])) continue;
+                    P.recDraw[slot] = (uint16_t)drawIdx;
                     sl_write_record(P.records + (size_t)slot * recStride, NV, poly.verts[0], poly.verts[j], poly.verts[k],
                                     &poly.varys[0], &poly.varys[j * 4], &poly.varys[k * 4]);
                     ++slot;
@@ -808,7 +825,8 @@ __global__ void k_scan_offsets(const uint16_t* cnt, const uint32_t* segSums, uin
  * ----------------------------------------------------------------------*/
 struct SLRasterParams
 {
-    SL_UniformBuffer uniforms;
+    const SLDrawDesc* draws;     /* draw table of the batch: the fragment shader's uniforms are draws[recDraw[record]].uniforms */
+    const uint16_t* recDraw;
     const float4* records;
     const SLSpanEntry* entries;
     const uint32_t* rowStart;
@@ -1028,7 +1046,7 @@ struct SLTile
 
 /* SL_FragmentProcessor::flush_tri_fragments for one fragment (src/SL_FragmentProcessor.cpp:416-531) */
 template <FsFn FS>
-SLD_FN void sl_shade_fragment(const SLRasterParams& P, const SLTile& T, const SLTriSetup& t, const float4* rec, const math::vec4& bcIn, int x, int y, float z)
+SLD_FN void sl_shade_fragment(const SLRasterParams& P, const SLTile& T, const SLTriSetup& t, uint32_t recId, const float4* rec, const math::vec4& bcIn, int x, int y, float z)
 {
     /* :438-460 perspective correction */
     math::vec4 bc = bcIn * math::vec4{t.w0, t.w1, t.w2, 0.f};
@@ -1036,7 +1054,7 @@ SLD_FN void sl_shade_fragment(const SLRasterParams& P, const SLTile& T, const SL
     bc = bc * persp;
 
     SL_FragmentParam fp;
-    fp.pUniforms = &P.uniforms;
+    fp.pUniforms = &P.draws[P.recDraw[recId]].uniforms;
     /* interpolate_tri_varyings, AVX2 branch (:163-193).  The reference interpolates all four slots; slots past
      * numVaryings hold stale bin data there and are never read by a well-formed shader. */
     for (int s = 0; s < P.numVaryings; ++s)
@@ -1206,7 +1224,7 @@ SLD_FN unsigned sl_walk_piece(const SLRasterParams& P, const SLTile& T, uint32_t
                 {
                     const math::vec4 bc = sIdx == 0 ? a0 : (sIdx == 1 ? a1 : (sIdx == 2 ? a2 : a3));
                     const float z = j == 0 ? zA : (j == 1 ? zB : (j == 2 ? zC : zD));
-                    sl_shade_fragment<FS>(P, T, t, rec, bc, x4 + j, y, z);
+                    sl_shade_fragment<FS>(P, T, t, recId, rec, bc, x4 + j, y, z);
                     ++shaded;
                 }
                 ++sIdx;
@@ -1334,7 +1352,7 @@ SLD_FN unsigned sl_walk_piece_warp(const SLRasterParams& P, const SLTile& T, uin
                     const math::vec4 bc = sj == 0u ? a0 : (sj == 1u ? a1 : (sj == 2u ? a2 : a3));
                     const uint32_t zj = (stIn >> (2 * j)) & 3u;
                     const float z = zj == 0u ? zc0 : (zj == 1u ? zc1 : (zj == 2u ? zc2 : zc3));
-                    sl_shade_fragment<FS>(P, T, t, rec, bc, x4 + j, y, z);
+                    sl_shade_fragment<FS>(P, T, t, recId, rec, bc, x4 + j, y, z);
                     ++shaded;
                 }
                 ++s;

@@ -174,6 +174,16 @@ struct Scratch
     void release() { if (buf.ptr) cudaFree(buf.ptr); buf.ptr = nullptr; buf.bytes = 0; }
 };
 
+struct Batch
+{
+    size_t shaderId = 0, fboId = 0;
+    std::vector<SLDrawDesc> descs;
+    std::vector<uint32_t> blockDraw;
+    unsigned numBlocks = 0;
+    unsigned long long totalPrims = 0;
+    void clear() { descs.clear(); blockDraw.clear(); numBlocks = 0; totalPrims = 0; }
+};
+
 struct slcu_context
 {
     int device = 0;
@@ -196,7 +206,9 @@ struct slcu_context
     slcu_stats stats{};
     SLCounters* counters = nullptr;     /* device */
     SLCounters* hostCounters = nullptr; /* pinned */
-    Scratch records, blockInfo, cnt, off, segSums, rowTotals, rowStart, entries, handoff, rowFlags, rowNeeded;
+    Scratch records, blockInfo, cnt, off, segSums, rowTotals, rowStart, entries, handoff, rowFlags, rowNeeded, drawTable, blockDraw, recDraw;
+    Batch batch;            /* submitted, not yet executed draws */
+    bool syncDraws = false; /* SLCU_SYNC_DRAWS=1: execute every draw call on its own (debug / parity mode) */
     /* sort-first partition (slcu_set_partition) */
     unsigned partRank = 0, partWorld = 1, partStripRows = 8;
     struct PeerMap { size_t tex; unsigned rank; void* ptr; };
@@ -234,6 +246,12 @@ struct KernelScope
 static const uint32_t* g_activeRcpOwner = nullptr; /* whose table g_rcp_table currently holds */
 static uint32_t g_activeRcpCopy[2048];
 
+/* execute the pending draw batch before anything that reads or changes what it uses */
+#define SLCU_FLUSH()                                                                     \
+    do {                                                                                 \
+        if (c && !c->batch.descs.empty()) { const int frc_ = flush_draws(c); if (frc_) return frc_; } \
+    } while (0)
+
 #define CK(call)                                                                         \
     do {                                                                                 \
         cudaError_t e_ = (call);                                                         \
@@ -242,6 +260,8 @@ static uint32_t g_activeRcpCopy[2048];
             return SLCU_ERR_CUDA;                                                        \
         }                                                                                \
     } while (0)
+
+static int flush_draws(slcu_context* c);
 
 static int ensure_rcp_table(slcu_context* c)
 {
@@ -327,6 +347,17 @@ static void snapshot_uniforms(slcu_context* c, size_t ubo, SL_UniformBuffer& out
     }
 }
 
+/* Draws are not executed one by one.  Consecutive draws that use the same shader object and framebuffer are collected
+ * into a batch (their uniforms, viewport and scissor are snapshotted at submission, like the reference's synchronous draw
+ * would have read them) and the whole batch goes through the pipeline at once when anything else needs the result: a draw
+ * with another shader or framebuffer, a clear, a blit, a read-back, an upload into a resource, slcu_sync.  Primitive order
+ * across the draws of a batch is submission order, so the frame is bit-identical to draw-by-draw execution; what changes
+ * is that a 256-draw frame fills the GPU with 8 launches instead of 2,000 under-filled ones. */
+static const unsigned kMaxBatchBlocks = 24576; /* 24 M primitives */
+static const size_t kMaxBatchDraws = 65535;    /* recDraw is 16 bits */
+
+static int flush_draws(slcu_context* c);
+
 static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, size_t numInstances, size_t shaderId, size_t fboId)
 {
     if (!meshes || !numMeshes) return 0;
@@ -342,11 +373,94 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
     if (H > (unsigned)SL_MAX_ROWS) { c->err = "framebuffer taller than SL_MAX_ROWS"; return SLCU_ERR_UNSUPPORTED; }
     if (depthTex.w > 32767) { c->err = "framebuffer wider than 32767"; return SLCU_ERR_UNSUPPORTED; }
     if (depthTex.bpt != 2 && depthTex.bpt != 4 && depthTex.bpt != 8) { c->err = "depth attachment must be R_HALF/R_FLOAT/R_DOUBLE"; return SLCU_ERR_ARG; }
+    for (int i = 0; i < sh.numOutputs; ++i)
+    {
+        if ((unsigned)i >= fbo.numColors || fbo.colors[i] >= c->textures.size()) { c->err = "shader writes an unattached colour buffer"; return SLCU_ERR_ARG; }
+        const HostTexture& t = c->textures[fbo.colors[i]];
+        const int kind = t.type % 7;
+        if (kind == 2 || kind == 3) { c->err = "32/64-bit integer colour targets are not implemented"; return SLCU_ERR_UNSUPPORTED; }
+        if (t.w != depthTex.w || t.h != depthTex.h) { c->err = "colour and depth attachments differ in size (SL_Framebuffer::valid -10)"; return SLCU_ERR_ARG; }
+    }
+    const float fboW = (float)depthTex.w, fboH = (float)depthTex.h;
+
+    /* one table entry per mesh (draw / draw_multiple) or one for all instances (draw_instanced) */
+    const size_t launches = (numInstances == 1) ? numMeshes : 1;
+    for (size_t i = 0; i < launches; ++i)
+    {
+        const slcu_mesh& m = meshes[i];
+        if (m.vaoId >= c->vaos.size()) { c->err = "bad vao id"; return SLCU_ERR_ARG; }
+        const HostVao& vao = c->vaos[m.vaoId];
+        if (vao.vbo >= c->vbos.size()) { c->err = "vao has no vertex buffer"; return SLCU_ERR_ARG; }
+        const bool usingIndices = (m.mode == 0x30u) || (m.mode == 0x70u);
+        if (usingIndices && vao.ibo >= c->ibos.size()) { c->err = "indexed draw without index buffer"; return SLCU_ERR_ARG; }
+    }
+    c->stats.drawCalls++;
+    for (size_t i = 0; i < launches; ++i)
+    {
+        const slcu_mesh& m = meshes[i];
+        /* the reference loop is `for (i = begin; i < end; i += 3)` (src/SL_TriProcessor.cpp:574) */
+        const unsigned long long primsPerInstance = (m.elementEnd - m.elementBegin + 2) / 3;
+        const unsigned long long prims = primsPerInstance * (numInstances == 1 ? 1 : numInstances);
+        const unsigned long long blocks64 = (prims + SL_VB_PRIMS - 1) / SL_VB_PRIMS;
+        c->stats.trisSubmitted += prims;
+        if (!blocks64) continue;
+        if (blocks64 > 0x3fffffull) { c->err = "draw too large for one batch"; return SLCU_ERR_UNSUPPORTED; }
+        const unsigned blocks = (unsigned)blocks64;
+        Batch& B = c->batch;
+        if (!B.descs.empty() && (B.shaderId != shaderId || B.fboId != fboId || B.numBlocks + blocks > kMaxBatchBlocks || B.descs.size() >= kMaxBatchDraws))
+        {
+            const int rc = flush_draws(c);
+            if (rc) return rc;
+        }
+        B.shaderId = shaderId;
+        B.fboId = fboId;
+        const HostVao& vao = c->vaos[m.vaoId];
+        const bool usingIndices = (m.mode == 0x30u) || (m.mode == 0x70u);
+        B.descs.emplace_back();
+        SLDrawDesc& d = B.descs.back();
+        snapshot_uniforms(c, sh.ubo, d.uniforms);
+        d.vao = vao.vao;
+        d.vbo.mBuffer = c->vbos[vao.vbo].ptr;
+        d.usingIndices = usingIndices ? 1 : 0;
+        d.ibo = usingIndices ? c->ibos[vao.ibo].buf.ptr : nullptr;
+        d.iboType = usingIndices ? c->ibos[vao.ibo].type : 2;
+        host_scissor_matrix(c, fboW, fboH, d.scissor);
+        host_viewport_rect(c, fboW, fboH, d.viewport);
+        d.elementBegin = m.elementBegin;
+        d.primsPerInstance = primsPerInstance;
+        d.numPrims = prims;
+        d.firstBlock = B.numBlocks;
+        d.pad_ = 0;
+        B.blockDraw.insert(B.blockDraw.end(), blocks, (uint32_t)(B.descs.size() - 1));
+        B.numBlocks += blocks;
+        B.totalPrims += prims;
+    }
+    if (c->syncDraws) return flush_draws(c);
+    return 0;
+}
+
+static int flush_draws_impl(slcu_context* c);
+static int flush_draws(slcu_context* c)
+{
+    if (c->batch.descs.empty()) return 0;
+    const int rc = flush_draws_impl(c);
+    c->batch.clear();
+    return rc;
+}
+
+static int flush_draws_impl(slcu_context* c)
+{
+    Batch& B = c->batch;
+    const size_t shaderId = B.shaderId, fboId = B.fboId;
+    const HostShader& sh = c->shaders[shaderId];
+    const HostFbo& fbo = c->fbos[fboId];
+    const HostTexture& depthTex = c->textures[fbo.depth];
+    const unsigned H = depthTex.h;
     int rc = ensure_rcp_table(c);
     if (rc) return rc;
     cudaSetDevice(c->device);
+    c->stats.batches++;
 
-    const float fboW = (float)depthTex.w, fboH = (float)depthTex.h;
     const unsigned rowPitch = (H + 31u) & ~31u;
     /* x-segments of the rasteriser: one warp per (row, segment), about 128 pixels each, at most 32 per row */
     unsigned rasterSegs = (depthTex.w + 127u) / 128u;
@@ -356,23 +470,14 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
     rasterSegs = (depthTex.w + segWidth - 1u) / segWidth;
     const int NV = sh.numVaryings;
     const int recStride = 3 + 3 * NV;
+    const unsigned numBlocks = B.numBlocks;
+    const unsigned long long totalPrims = B.totalPrims;
 
-    /* ---- vertex stage: one launch per mesh (draw_multiple) or one for all instances ---- */
-    std::vector<unsigned> launchBlocks;
-    unsigned long long totalPrims = 0;
-    const size_t launches = (numInstances == 1) ? numMeshes : 1;
-    for (size_t i = 0; i < launches; ++i)
-    {
-        const unsigned long long prims = (meshes[i].elementEnd - meshes[i].elementBegin + 2) / 3 * (numInstances == 1 ? 1 : numInstances);
-        /* the reference loop is `for (i = begin; i < end; i += 3)` (src/SL_TriProcessor.cpp:574) */
-        launchBlocks.push_back((unsigned)((prims + SL_VB_PRIMS - 1) / SL_VB_PRIMS));
-        totalPrims += prims;
-    }
-    unsigned numBlocks = 0;
-    for (unsigned b : launchBlocks) numBlocks += b;
-    c->stats.drawCalls++;
-    c->stats.trisSubmitted += totalPrims;
-    if (!numBlocks) return 0;
+    /* the draw table and the block -> draw map of the batch */
+    CK(c->drawTable.ensure(B.descs.size() * sizeof(SLDrawDesc)));
+    CK(c->blockDraw.ensure((size_t)numBlocks * sizeof(uint32_t)));
+    CK(cudaMemcpyAsync(c->drawTable.buf.ptr, B.descs.data(), B.descs.size() * sizeof(SLDrawDesc), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->blockDraw.buf.ptr, B.blockDraw.data(), (size_t)numBlocks * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
 
     /* record slots: SL_VB_THREADS per (block, round) at fixed places + an overflow area for rounds that clipping fans out */
     const unsigned long long recFixed = (unsigned long long)numBlocks * SL_VB_PRIMS;
@@ -383,42 +488,21 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
     const uint8_t* rowNeeded = nullptr;
     for (int attempt = 0;; ++attempt)
     {
-        if (recCapacity > 0xfffffff0ull) { c->err = "draw too large for one batch"; return SLCU_ERR_UNSUPPORTED; }
+        if (recCapacity > 0x7ffffff0ull) { c->err = "batch too large"; return SLCU_ERR_UNSUPPORTED; }
         CK(c->records.ensure((size_t)recCapacity * recStride * sizeof(float4)));
+        CK(c->recDraw.ensure((size_t)recCapacity * sizeof(uint16_t)));
         CK(c->blockInfo.ensure((size_t)numBlocks * sizeof(SLBlockInfo)));
         CK(cudaMemsetAsync(&c->counters->recAlloc, 0, 2 * sizeof(unsigned long long), c->stream)); /* recAlloc + handoffs */
 
-        unsigned firstBlock = 0;
-        for (size_t i = 0; i < launches; ++i)
         {
-            if (!launchBlocks[i]) continue;
-            const slcu_mesh& m = meshes[i];
-            if (m.vaoId >= c->vaos.size()) { c->err = "bad vao id"; return SLCU_ERR_ARG; }
-            const HostVao& vao = c->vaos[m.vaoId];
-            if (vao.vbo >= c->vbos.size()) { c->err = "vao has no vertex buffer"; return SLCU_ERR_ARG; }
             SLVertexParams vp;
-            snapshot_uniforms(c, sh.ubo, vp.uniforms);
-            vp.vao = vao.vao;
-            vp.vbo.mBuffer = c->vbos[vao.vbo].ptr;
-            const bool usingIndices = (m.mode == 0x30u) || (m.mode == 0x70u);
-            vp.usingIndices = usingIndices ? 1 : 0;
-            vp.ibo = nullptr;
-            vp.iboType = 2;
-            if (usingIndices)
-            {
-                if (vao.ibo >= c->ibos.size()) { c->err = "indexed draw without index buffer"; return SLCU_ERR_ARG; }
-                vp.ibo = c->ibos[vao.ibo].buf.ptr;
-                vp.iboType = c->ibos[vao.ibo].type;
-            }
+            vp.draws = reinterpret_cast<const SLDrawDesc*>(c->drawTable.buf.ptr);
+            vp.blockDraw = reinterpret_cast<const uint32_t*>(c->blockDraw.buf.ptr);
+            vp.recDraw = reinterpret_cast<uint16_t*>(c->recDraw.buf.ptr);
             vp.cullMode = sh.cullMode;
             vp.numVaryings = NV;
-            host_scissor_matrix(c, fboW, fboH, vp.scissor);
-            host_viewport_rect(c, fboW, fboH, vp.viewport);
-            vp.elementBegin = m.elementBegin;
-            vp.primsPerInstance = (m.elementEnd - m.elementBegin + 2) / 3;
-            vp.numPrims = vp.primsPerInstance * (numInstances == 1 ? 1 : numInstances);
-            vp.firstBlock = firstBlock;
-            const bool cache = useVertexCache && usingIndices;
+            bool cache = useVertexCache;
+            for (const SLDrawDesc& d : B.descs) cache = cache && d.usingIndices;
             vp.cacheBytes = cache ? (unsigned)((1 + NV) * SL_VCACHE_VERTS * sizeof(float4)) : 0u;
             vp.recCapacity = (unsigned)recCapacity;
             vp.recOverflowBase = (unsigned)recFixed;
@@ -426,8 +510,7 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
             vp.records = reinterpret_cast<float4*>(c->records.buf.ptr);
             vp.blockInfo = reinterpret_cast<SLBlockInfo*>(c->blockInfo.buf.ptr);
             vp.counters = c->counters;
-            { KernelScope ks(c, SLCU_K_VERTEX); CK(sh.vs(launchBlocks[i], c->stream, vp, cache)); }
-            firstBlock += launchBlocks[i];
+            { KernelScope ks(c, SLCU_K_VERTEX); CK(sh.vs(numBlocks, c->stream, vp, cache)); }
         }
 
         /* ---- span count + scans ---- */
@@ -485,7 +568,7 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
         { KernelScope ks(c, SLCU_K_SCAN); k_scan_offsets<<<sgrid, 128, 0, c->stream>>>(sp.cnt, reinterpret_cast<const uint32_t*>(c->segSums.buf.ptr), reinterpret_cast<uint32_t*>(c->off.buf.ptr), numBlocks, rowPitch, blocksPerSeg, rowNeeded, H); }
         CK(cudaGetLastError());
 
-        /* the span lists are sized from the count: one small read-back per draw */
+        /* the span lists are sized from the count: one small read-back per batch */
         uint32_t totalSpans = 0;
         CK(cudaMemcpyAsync(c->hostCounters, c->counters, sizeof(SLCounters), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaMemcpyAsync(&c->hostCounters[1], reinterpret_cast<uint32_t*>(c->rowStart.buf.ptr) + H, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -502,7 +585,7 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
         if (!totalSpans) return 0;
         numHandoffs = c->hostCounters->handoffs;
         if (getenv("SLCU_DEBUG"))
-            fprintf(stderr, "[slcu] draw: prims=%llu records=%llu entries=%u handoffs=%llu segs=%ux%u flags=0x%x\n", totalPrims,
+            fprintf(stderr, "[slcu] batch: draws=%zu prims=%llu records=%llu entries=%u handoffs=%llu segs=%ux%u flags=0x%x\n", B.descs.size(), totalPrims,
                     (unsigned long long)c->hostCounters->recAlloc, totalSpans, numHandoffs, rasterSegs, segWidth, c->hostCounters->errorFlags);
 
         CK(c->entries.ensure((size_t)totalSpans * sizeof(SLSpanEntry)));
@@ -514,7 +597,8 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
 
     /* ---- fragment stage ---- */
     SLRasterParams rp;
-    snapshot_uniforms(c, sh.ubo, rp.uniforms);
+    rp.draws = reinterpret_cast<const SLDrawDesc*>(c->drawTable.buf.ptr);
+    rp.recDraw = reinterpret_cast<const uint16_t*>(c->recDraw.buf.ptr);
     rp.records = reinterpret_cast<const float4*>(c->records.buf.ptr);
     rp.entries = reinterpret_cast<const SLSpanEntry*>(c->entries.buf.ptr);
     rp.rowStart = reinterpret_cast<const uint32_t*>(c->rowStart.buf.ptr);
@@ -550,12 +634,8 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
         rp.colorBpt[i] = 0;
         if (i < sh.numOutputs)
         {
-            if ((unsigned)i >= fbo.numColors || fbo.colors[i] >= c->textures.size()) { c->err = "shader writes an unattached colour buffer"; return SLCU_ERR_ARG; }
             const HostTexture& t = c->textures[fbo.colors[i]];
-            const int kind = t.type % 7;
-            if (kind == 2 || kind == 3) { c->err = "32/64-bit integer colour targets are not implemented"; return SLCU_ERR_UNSUPPORTED; }
             rp.color[i] = t.dev;
-            if (t.w != depthTex.w || t.h != depthTex.h) { c->err = "colour and depth attachments differ in size (SL_Framebuffer::valid -10)"; return SLCU_ERR_ARG; }
             rp.colorType[i] = t.type;
             rp.colorBpt[i] = t.bpt;
             tileBytes += (segWidth * t.bpt + 15u) & ~15u;
@@ -646,6 +726,7 @@ int slcu_context_create(slcu_context** out, int device)
     cudaMemset(c->counters, 0, sizeof(SLCounters));
     if (cudaMallocHost(&c->hostCounters, 2 * sizeof(SLCounters)) != cudaSuccess) { delete c; return SLCU_ERR_CUDA; }
     c->rcpValid = measure_host_rcp_table(c->rcpTable, c->err);
+    c->syncDraws = getenv("SLCU_SYNC_DRAWS") != nullptr && atoi(getenv("SLCU_SYNC_DRAWS")) != 0;
     *out = c;
     return 0;
 }
@@ -654,6 +735,7 @@ void slcu_context_destroy(slcu_context* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
+    if (!c->batch.descs.empty()) flush_draws(c);
     cudaStreamSynchronize(c->stream);
     for (DevBuffer& b : c->vbos) if (b.ptr) cudaFree(b.ptr);
     for (HostIbo& b : c->ibos) if (b.buf.ptr) cudaFree(b.buf.ptr);
@@ -662,7 +744,7 @@ void slcu_context_destroy(slcu_context* c)
     if (c->counters) cudaFree(c->counters);
     if (c->hostCounters) cudaFreeHost(c->hostCounters);
     for (auto& pm : c->peerMaps) if (pm.ptr) cudaIpcCloseMemHandle(pm.ptr);
-    Scratch* s[] = {&c->records, &c->blockInfo, &c->cnt, &c->off, &c->segSums, &c->rowTotals, &c->rowStart, &c->entries, &c->handoff, &c->rowFlags, &c->rowNeeded};
+    Scratch* s[] = {&c->records, &c->blockInfo, &c->cnt, &c->off, &c->segSums, &c->rowTotals, &c->rowStart, &c->entries, &c->handoff, &c->rowFlags, &c->rowNeeded, &c->drawTable, &c->blockDraw, &c->recDraw};
     for (Scratch* x : s) x->release();
     cudaStreamDestroy(c->stream);
     delete c;
@@ -674,6 +756,7 @@ const char* slcu_impl_name(void) { return "softlight-b200 (sm_100a CUDA)"; }
 
 int slcu_set_rcp_table(slcu_context* c, const uint32_t* t)
 {
+    SLCU_FLUSH();
     if (!c || !t) return SLCU_ERR_ARG;
     memcpy(c->rcpTable, t, sizeof(c->rcpTable));
     c->rcpValid = true;
@@ -695,6 +778,7 @@ size_t slcu_create_framebuffer(slcu_context* c) { c->fbos.emplace_back(); return
 
 int slcu_vbo_init(slcu_context* c, size_t vbo, size_t numBytes)
 {
+    SLCU_FLUSH();
     if (vbo >= c->vbos.size()) return SLCU_ERR_ARG;
     cudaSetDevice(c->device);
     DevBuffer& b = c->vbos[vbo];
@@ -710,6 +794,7 @@ int slcu_vbo_init(slcu_context* c, size_t vbo, size_t numBytes)
 
 int slcu_vbo_assign(slcu_context* c, size_t vbo, const void* data, size_t offset, size_t numBytes)
 {
+    SLCU_FLUSH();
     if (vbo >= c->vbos.size() || !data || offset + numBytes > c->vbos[vbo].bytes) return SLCU_ERR_ARG;
     cudaSetDevice(c->device);
     CK(cudaMemcpyAsync(c->vbos[vbo].ptr + offset, data, numBytes, cudaMemcpyHostToDevice, c->stream));
@@ -719,6 +804,7 @@ int slcu_vbo_assign(slcu_context* c, size_t vbo, const void* data, size_t offset
 
 int slcu_ibo_init(slcu_context* c, size_t ibo, uint32_t numElements, int dataType, const void* data)
 {
+    SLCU_FLUSH();
     if (ibo >= c->ibos.size() || dataType < 0 || dataType > 2) return SLCU_ERR_ARG;
     cudaSetDevice(c->device);
     HostIbo& b = c->ibos[ibo];
@@ -779,6 +865,7 @@ int slcu_ubo_bind_buffer(slcu_context* c, size_t ubo, size_t offset, size_t vbo,
 
 int slcu_texture_init(slcu_context* c, size_t tex, int type, uint16_t w, uint16_t h, uint16_t d)
 {
+    SLCU_FLUSH();
     if (tex >= c->textures.size() || type < 0 || type >= 28) return -1;
     cudaSetDevice(c->device);
     HostTexture& t = c->textures[tex];
@@ -800,6 +887,7 @@ int slcu_texture_init(slcu_context* c, size_t tex, int type, uint16_t w, uint16_
 
 int slcu_texture_set_texels(slcu_context* c, size_t tex, int order, uint16_t x, uint16_t y, uint16_t z, uint16_t w, uint16_t h, uint16_t d, const void* data)
 {
+    SLCU_FLUSH();
     if (tex >= c->textures.size() || !data) return SLCU_ERR_ARG;
     cudaSetDevice(c->device);
     HostTexture& t = c->textures[tex];
@@ -832,6 +920,7 @@ int slcu_texture_set_texels(slcu_context* c, size_t tex, int order, uint16_t x, 
 
 int slcu_texture_read(slcu_context* c, size_t tex, void* out, size_t numBytes)
 {
+    SLCU_FLUSH();
     if (tex >= c->textures.size() || !out || numBytes > c->textures[tex].allocBytes) return SLCU_ERR_ARG;
     cudaSetDevice(c->device);
     CK(cudaMemcpyAsync(out, c->textures[tex].dev, numBytes, cudaMemcpyDeviceToHost, c->stream));
@@ -841,6 +930,7 @@ int slcu_texture_read(slcu_context* c, size_t tex, void* out, size_t numBytes)
 
 int slcu_fbo_reserve_color_buffers(slcu_context* c, size_t fbo, unsigned n)
 {
+    SLCU_FLUSH();
     if (fbo >= c->fbos.size()) return SLCU_ERR_ARG;
     if (n < 1) return -1; /* src/SL_Framebuffer.cpp:823-848 */
     if (n > 4) return -2;
@@ -850,6 +940,7 @@ int slcu_fbo_reserve_color_buffers(slcu_context* c, size_t fbo, unsigned n)
 }
 int slcu_fbo_attach_color_buffer(slcu_context* c, size_t fbo, unsigned index, size_t tex)
 {
+    SLCU_FLUSH();
     if (fbo >= c->fbos.size() || tex >= c->textures.size()) return SLCU_ERR_ARG;
     if (index >= c->fbos[fbo].numColors) return -1;
     c->fbos[fbo].colors[index] = tex;
@@ -857,6 +948,7 @@ int slcu_fbo_attach_color_buffer(slcu_context* c, size_t fbo, unsigned index, si
 }
 int slcu_fbo_attach_depth_buffer(slcu_context* c, size_t fbo, size_t tex)
 {
+    SLCU_FLUSH();
     if (fbo >= c->fbos.size() || tex >= c->textures.size()) return SLCU_ERR_ARG;
     c->fbos[fbo].depth = tex;
     return 0;
@@ -909,6 +1001,7 @@ int slcu_scissor(slcu_context* c, int32_t x, int32_t y, uint16_t w, uint16_t h) 
 
 int slcu_clear_color_buffer(slcu_context* c, size_t fbo, unsigned att, const double rgba[4])
 {
+    SLCU_FLUSH();
     if (fbo >= c->fbos.size() || att >= c->fbos[fbo].numColors || c->fbos[fbo].colors[att] >= c->textures.size()) return SLCU_ERR_ARG;
     cudaSetDevice(c->device);
     const HostTexture& t = c->textures[c->fbos[fbo].colors[att]];
@@ -918,6 +1011,7 @@ int slcu_clear_color_buffer(slcu_context* c, size_t fbo, unsigned att, const dou
 }
 int slcu_clear_depth_buffer(slcu_context* c, size_t fbo, double depth)
 {
+    SLCU_FLUSH();
     if (fbo >= c->fbos.size() || c->fbos[fbo].depth >= c->textures.size()) return SLCU_ERR_ARG;
     cudaSetDevice(c->device);
     const HostTexture& t = c->textures[c->fbos[fbo].depth];
@@ -927,6 +1021,7 @@ int slcu_clear_depth_buffer(slcu_context* c, size_t fbo, double depth)
 }
 int slcu_clear_framebuffer(slcu_context* c, size_t fbo, unsigned att, const double rgba[4], double depth)
 {
+    SLCU_FLUSH();
     if (fbo >= c->fbos.size() || c->fbos[fbo].depth >= c->textures.size()) return SLCU_ERR_ARG;
     const HostTexture& d = c->textures[c->fbos[fbo].depth];
     unsigned char texel[8];
@@ -944,6 +1039,7 @@ int slcu_draw_instanced(slcu_context* c, const slcu_mesh* m, size_t inst, size_t
 int slcu_blit_rect(slcu_context* c, size_t outTex, size_t inTex, uint16_t sx0, uint16_t sy0, uint16_t sx1, uint16_t sy1,
                    uint16_t dx0, uint16_t dy0, uint16_t dx1, uint16_t dy1)
 {
+    SLCU_FLUSH();
     if (!c || outTex >= c->textures.size() || inTex >= c->textures.size()) return SLCU_ERR_ARG;
     cudaSetDevice(c->device);
     const HostTexture& s = c->textures[inTex];
@@ -979,6 +1075,7 @@ int slcu_blit(slcu_context* c, size_t outTex, size_t inTex)
 /* ---- sort-first multi-GPU ---- */
 int slcu_set_partition(slcu_context* c, unsigned rank, unsigned world, unsigned stripRows)
 {
+    SLCU_FLUSH();
     if (!c || world < 1 || rank >= world || stripRows < 1) return SLCU_ERR_ARG;
     c->partRank = rank;
     c->partWorld = world;
@@ -988,6 +1085,7 @@ int slcu_set_partition(slcu_context* c, unsigned rank, unsigned world, unsigned 
 
 int slcu_texture_ipc_export(slcu_context* c, size_t tex, void* handle64)
 {
+    SLCU_FLUSH();
     if (!c || tex >= c->textures.size() || !handle64 || !c->textures[tex].dev) return SLCU_ERR_ARG;
     cudaSetDevice(c->device);
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the ABI");
@@ -999,6 +1097,7 @@ int slcu_texture_ipc_export(slcu_context* c, size_t tex, void* handle64)
 
 int slcu_texture_ipc_import(slcu_context* c, size_t tex, unsigned peerRank, const void* handle64)
 {
+    SLCU_FLUSH();
     if (!c || tex >= c->textures.size() || !handle64) return SLCU_ERR_ARG;
     cudaSetDevice(c->device);
     cudaIpcMemHandle_t h;
@@ -1015,6 +1114,7 @@ int slcu_texture_ipc_import(slcu_context* c, size_t tex, unsigned peerRank, cons
 
 int slcu_composite(slcu_context* c, size_t srcTex, size_t dstTex, unsigned root)
 {
+    SLCU_FLUSH();
     if (!c || srcTex >= c->textures.size() || dstTex >= c->textures.size()) return SLCU_ERR_ARG;
     cudaSetDevice(c->device);
     const HostTexture& s = c->textures[srcTex];
@@ -1045,6 +1145,7 @@ int slcu_composite(slcu_context* c, size_t srcTex, size_t dstTex, unsigned root)
 
 int slcu_sync(slcu_context* c)
 {
+    SLCU_FLUSH();
     cudaSetDevice(c->device);
     CK(cudaStreamSynchronize(c->stream));
     return 0;
@@ -1052,6 +1153,7 @@ int slcu_sync(slcu_context* c)
 
 int slcu_reset_stats(slcu_context* c)
 {
+    SLCU_FLUSH();
     if (!c) return 0;
     cudaSetDevice(c->device);
     memset(&c->stats, 0, sizeof(c->stats));
@@ -1061,6 +1163,7 @@ int slcu_reset_stats(slcu_context* c)
 
 int slcu_get_stats(slcu_context* c, slcu_stats* out)
 {
+    SLCU_FLUSH();
     if (!c || !out) return SLCU_ERR_ARG;
     cudaSetDevice(c->device);
     CK(cudaMemcpyAsync(c->hostCounters, c->counters, sizeof(SLCounters), cudaMemcpyDeviceToHost, c->stream));
@@ -1082,6 +1185,7 @@ int slcu_get_stats(slcu_context* c, slcu_stats* out)
 
 int slcu_timer_begin(slcu_context* c)
 {
+    SLCU_FLUSH();
     if (!c) return SLCU_ERR_ARG;
     cudaSetDevice(c->device);
     if (!c->timerA) { CK(cudaEventCreate(&c->timerA)); CK(cudaEventCreate(&c->timerB)); }
@@ -1091,6 +1195,7 @@ int slcu_timer_begin(slcu_context* c)
 
 int slcu_timer_end(slcu_context* c, double* ms)
 {
+    SLCU_FLUSH();
     if (!c || !ms || !c->timerA) return SLCU_ERR_ARG;
     cudaSetDevice(c->device);
     CK(cudaEventRecord(c->timerB, c->stream));
@@ -1103,6 +1208,7 @@ int slcu_timer_end(slcu_context* c, double* ms)
 
 int slcu_profile_begin(slcu_context* c)
 {
+    SLCU_FLUSH();
     if (!c) return SLCU_ERR_ARG;
     cudaSetDevice(c->device);
     CK(cudaStreamSynchronize(c->stream));
@@ -1114,6 +1220,7 @@ int slcu_profile_begin(slcu_context* c)
 
 int slcu_profile_end(slcu_context* c, slcu_kernel_times* out)
 {
+    SLCU_FLUSH();
     if (!c || !out) return SLCU_ERR_ARG;
     cudaSetDevice(c->device);
     memset(out, 0, sizeof(*out));

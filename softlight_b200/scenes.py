@@ -452,6 +452,216 @@ def random_tris_scene(seed=1, n=400, width=200, height=150, blend=A.SL_BLEND_OFF
                  setup, frame, tris_per_frame=n, draws_per_frame=split_draws)
 
 
+# ---- C4: skinned characters (sl_animation_test.cpp:199-280): 64-bone capsule chains, alpha blending -------------------
+def _pack_normal(n: np.ndarray) -> np.ndarray:
+    """10-10-10-2 signed packing read back by sl_unpack_vec4_10_10_10_2I (SL_PackedVertex.hpp:20-100)."""
+    q = np.clip(np.rint(n * 511.0), -511, 511).astype(np.int32)
+    return ((q[..., 0] & 0x3FF) | ((q[..., 1] & 0x3FF) << 10) | ((q[..., 2] & 0x3FF) << 20)).astype(np.int32)
+
+
+def _capsule_chain(bones: int, around: int, radius: float, height: float):
+    """A tube of `bones` segments along +Y, `around` quads per ring; every ring follows its own bone and its neighbours.
+    Vertex = Tuple<vec3 pos, vec2h uv, int32 packed normal, vec4<u16> bone ids, vec4h bone weights> (36 bytes)."""
+    rings = bones + 1
+    k = np.arange(rings)
+    a = np.arange(around + 1) * (2.0 * np.pi / around)
+    taper = np.sin(np.clip((k + 0.5) / rings, 0, 1) * np.pi) ** 0.35          # rounded ends
+    rr = (radius * taper)[:, None]
+    pos = np.stack([rr * np.cos(a)[None, :], np.broadcast_to((k * (height / bones))[:, None], (rings, around + 1)),
+                    rr * np.sin(a)[None, :]], axis=-1)
+    nrm = np.stack([np.broadcast_to(np.cos(a)[None, :], (rings, around + 1)), np.zeros((rings, around + 1)),
+                    np.broadcast_to(np.sin(a)[None, :], (rings, around + 1))], axis=-1)
+    uv = np.stack([np.broadcast_to((np.arange(around + 1) / around * 4.0)[None, :], (rings, around + 1)),
+                   np.broadcast_to((k / bones * 6.0)[:, None], (rings, around + 1))], axis=-1)
+    ids = np.stack([np.clip(k, 0, bones - 1), np.clip(k - 1, 0, bones - 1), np.clip(k + 1, 0, bones - 1), np.clip(k - 2, 0, bones - 1)], axis=-1)
+    wts = np.array([0.5, 0.25, 0.1875, 0.0625])                               # exact in half precision, sum 1
+    rec = np.zeros((rings, around + 1), dtype=[("pos", "<f4", 3), ("uv", "<f2", 2), ("nrm", "<i4"), ("ids", "<u2", 4), ("wts", "<f2", 4)])
+    rec["pos"], rec["uv"], rec["nrm"] = pos, uv, _pack_normal(nrm)
+    rec["ids"] = ids[:, None, :]
+    rec["wts"] = wts[None, None, :]
+    assert rec.dtype.itemsize == 36
+    i, j = np.meshgrid(np.arange(bones), np.arange(around), indexing="ij")
+    v00 = (i * (around + 1) + j).reshape(-1)
+    v01 = v00 + 1
+    v10 = v00 + (around + 1)
+    v11 = v10 + 1
+    tris = np.stack([v00, v10, v01, v01, v10, v11], axis=-1).reshape(-1, 3)   # CCW seen from outside
+    return rec.reshape(-1), tris.astype(np.uint32)
+
+
+def _rot_z(angle: float) -> np.ndarray:
+    c, s_ = np.cos(angle), np.sin(angle)
+    m = np.identity(4)
+    m[0, 0], m[0, 1], m[1, 0], m[1, 1] = c, -s_, s_, c
+    return m
+
+
+def _bone_chain(bones: int, seg: float, phase: float, amp: float) -> np.ndarray:
+    """Column-major mat4 per bone: a chain that sways; bone b rotates everything above joint b a little further."""
+    out = np.zeros((bones, 4, 4), dtype=np.float32)
+    cur = np.identity(4)
+    for b in range(bones):
+        ang = amp * np.sin(phase + 0.21 * b)
+        joint = np.identity(4); joint[1, 3] = b * seg
+        back = np.identity(4); back[1, 3] = -b * seg
+        cur = cur @ joint @ _rot_z(ang) @ back
+        out[b] = cur.T.astype(np.float32)   # stored column-major
+    return out
+
+
+def skinned_scene(width=1920, height=1080, grid=(10, 10), bones=64, around=160, tex_size=256, depth_type=A.SL_COLOR_R_HALF, name=None) -> Scene:
+    char_h, radius = 7.0, 0.9
+    verts, tris = _capsule_chain(bones, around, radius, char_h)
+    idx = tris.reshape(-1)
+    gx, gz = grid
+    nchars = gx * gz
+    spacing = 2.6
+    all_bones = np.concatenate([_bone_chain(bones, char_h / bones, 0.37 * i, 0.035 + 0.004 * (i % 5)) for i in range(nchars)])
+    tex = value_noise_texture(4, tex_size, tex_size, 4)
+    tex[..., 3] = 96 + (tex[..., 0] // 2)            # translucent: alpha 96..223 -> SL_BLEND_ALPHA does real work
+    proj = infinite_perspective(60.0, width / height, 0.01)
+    cam = (0.0, 6.0, 0.5 * gz * spacing + 9.0)
+    view = look_at(cam, (0.0, 3.0, 0.0), (0, 1, 0))
+    vp = matmul_cm(proj, view)
+
+    def blob_for(i):
+        x, z = i % gx, i // gx
+        model = translate_scale(((x - gx / 2.0 + 0.5) * spacing, 0.0, (z - gz / 2.0 + 0.5) * spacing), 1.0)
+        # AnimUniforms: pTexture@0, pBones@8, model@16, vp@80, camPos@144
+        b = bytearray(160)
+        b[16:80] = model.tobytes()
+        b[80:144] = vp.tobytes()
+        b[144:160] = np.array([cam[0], cam[1], cam[2], 1.0], dtype=np.float32).tobytes()
+        return bytes(b)
+
+    blobs = [blob_for(i) for i in range(nchars)]
+
+    def setup(ctx):
+        color, depth, fbo = _make_targets(ctx, width, height, A.SL_COLOR_RGBA_8U, depth_type)
+        vbo = ctx.create_vbo(verts)
+        ibo = ctx.create_ibo(idx)
+        vao = ctx.create_vao(vbo, ibo, [(0, 36, A.VERTEX_DIMENSION_3, A.VERTEX_DATA_FLOAT), (12, 36, A.VERTEX_DIMENSION_2, A.VERTEX_DATA_SHORT),
+                                        (16, 36, A.VERTEX_DIMENSION_1, A.VERTEX_DATA_INT), (20, 36, A.VERTEX_DIMENSION_4, A.VERTEX_DATA_SHORT),
+                                        (28, 36, A.VERTEX_DIMENSION_4, A.VERTEX_DATA_SHORT)])
+        t = ctx.create_texture(A.SL_COLOR_RGBA_8U, tex_size, tex_size, 1, tex)
+        bone_vbo = ctx.create_vbo(all_bones)
+        ubo = ctx.create_ubo(blobs[0])
+        ctx.ubo_bind_texture(ubo, 0, t)
+        ctx.ubo_bind_buffer(ubo, 8, bone_vbo, 0)
+        sh = ctx.create_shader("skin_tex", "skin_tex", ubo, vs_varyings=3, fs_varyings=3, cull=A.SL_CULL_BACK_FACE, blend=A.SL_BLEND_ALPHA,
+                               depth_test=A.SL_DEPTH_TEST_GREATER_EQUAL, depth_mask=A.SL_DEPTH_MASK_ON)
+        assert sh != A.INVALID_ID
+        return dict(color=color, depth=depth, fbo=fbo, shader=sh, mesh=ctx.mesh(vao, 0, idx.size), ubo=ubo, tex=t, bones=bone_vbo,
+                    per_frame={"bones": all_bones})
+
+    def frame(ctx, st):
+        ctx.clear_framebuffer(st["fbo"], 0, (0.2, 0.2, 0.25, 1.0), 0.0)
+        for i in range(nchars):   # the demo's pattern: per-mesh uniforms (model matrix, bone palette), then draw
+            ctx.ubo_assign(st["ubo"], blobs[i])
+            ctx.ubo_bind_texture(st["ubo"], 0, st["tex"])
+            ctx.ubo_bind_buffer(st["ubo"], 8, st["bones"], i * bones * 64)
+            ctx.draw(st["mesh"], st["shader"], st["fbo"])
+
+    return Scene(name or f"skinned{nchars}x{tris.shape[0]}_{width}x{height}", width, height, A.SL_COLOR_RGBA_8U, depth_type,
+                 (0.2, 0.2, 0.25, 1.0), 0.0, setup, frame, tris_per_frame=tris.shape[0] * nchars, draws_per_frame=nchars,
+                 upload_bytes_per_frame=all_bones.nbytes + 1024 * nchars)
+
+
+# ---- C5: volume ray march (sl_volume_rendering_test.cpp:72-254, 298-520) ---------------------------------------------
+def synthetic_volume(n: int, seed: int = 5) -> np.ndarray:
+    """R8 n^3 volume: six Gaussian blobs + low-frequency value noise, empty (0) outside a sphere -- the ray marcher gets
+    empty-space rejection, early saturation and long marches, like a CT head."""
+    rng = np.random.default_rng(seed)
+    g = (np.arange(n, dtype=np.float32) + 0.5) / n * 2.0 - 1.0
+    z, y, x = np.meshgrid(g, g, g, indexing="ij")
+    vol = np.zeros((n, n, n), dtype=np.float32)
+    for _ in range(6):
+        c = rng.uniform(-0.45, 0.45, size=3)
+        sg = rng.uniform(0.18, 0.38)
+        amp = rng.uniform(0.45, 1.0)
+        vol += amp * np.exp(-((x - c[0]) ** 2 + (y - c[1]) ** 2 + (z - c[2]) ** 2) / (2.0 * sg * sg))
+    m = max(n // 16, 2)
+    coarse = rng.random((m + 1, m + 1, m + 1)).astype(np.float32)
+    t = (np.arange(n) + 0.5) / n * m
+    i0 = np.minimum(t.astype(int), m - 1)
+    f = (t - i0).astype(np.float32)
+
+    def lerp_axis(a, axis):
+        lo = np.take(a, i0, axis=axis)
+        hi = np.take(a, i0 + 1, axis=axis)
+        shape = [1, 1, 1]
+        shape[axis] = n
+        w = f.reshape(shape)
+        return lo * (1 - w) + hi * w
+
+    noise = lerp_axis(lerp_axis(lerp_axis(coarse, 0), 1), 2)
+    vol = vol * (0.75 + 0.5 * noise)
+    vol[(x * x + y * y + z * z) > 0.92] = 0.0
+    return np.clip(vol * 200.0, 0, 255).astype(np.uint8)
+
+
+def _unit_cube() -> np.ndarray:
+    """36 vec3 vertices, 12 triangles, CCW seen from outside, non-indexed."""
+    out = []
+    for axis in range(3):
+        for sign in (1.0, -1.0):
+            u, v = (axis + 1) % 3, (axis + 2) % 3
+            def P(a, b):
+                p = [0.0, 0.0, 0.0]
+                p[axis], p[u], p[v] = sign, a, b
+                return p
+            quad = [P(-1, -1), P(1, -1), P(1, 1), P(-1, 1)]
+            if sign < 0:
+                quad = quad[::-1]
+            out += [quad[0], quad[1], quad[2], quad[2], quad[3], quad[0]]
+    return np.array(out, dtype=np.float32)
+
+
+def volume_scene(width=7680, height=4320, vol_size=256, depth_type=A.SL_COLOR_R_HALF, name=None) -> Scene:
+    verts = _unit_cube()
+    vol = synthetic_volume(vol_size)
+    # transfer functions of the demo (sl_volume_rendering_test.cpp:405-520): 16-wide bands; the last entry of each band stays 0
+    opacity = np.zeros(256, dtype=np.float32)
+    for b, o in enumerate([0.0, 0.1, 0.1, 0.25, 0.5, 0.2] + [0.05] * 10):
+        opacity[16 * b:16 * b + 15] = o
+    colors = np.zeros((256, 3), dtype=np.float32)
+    band_rgb = [(0, 0, 0), (0.2, 0.2, 0.5), (0.4, 0.3, 0.1), (1.0, 0.3, 0.3), (1.0, 1.0, 1.0), (0.6, 0.6, 0.6)] + [(1.0, 1.0, 1.0)] * 10
+    for b, c in enumerate(band_rgb):
+        colors[16 * b:16 * b + 15] = c
+    proj = perspective(60.0, width / height, 0.1, 100.0)
+    cam = np.array([1.35, 1.0, 1.9])
+    view = look_at(cam, (0, 0, 0), (0, 1, 0))
+    vp = matmul_cm(proj, view)
+    # VolumeUniforms: pCubeMap@0, pOpacityMap@8, pColorMap@16, spacing@32, camPos@48, mvp@64
+    blob = bytearray(128)
+    blob[32:48] = np.array([1.0, 1.0, 1.0, 1.0], dtype=np.float32).tobytes()
+    blob[48:64] = np.array([cam[0], cam[1], cam[2], 0.0], dtype=np.float32).tobytes()
+    blob[64:128] = vp.tobytes()
+
+    def setup(ctx):
+        color, depth, fbo = _make_targets(ctx, width, height, A.SL_COLOR_RGBA_FLOAT, depth_type)
+        vbo = ctx.create_vbo(verts)
+        vao = ctx.create_vao(vbo, None, [(0, 12, A.VERTEX_DIMENSION_3, A.VERTEX_DATA_FLOAT)])
+        tv = ctx.create_texture(A.SL_COLOR_R_8U, vol_size, vol_size, vol_size, vol)
+        to = ctx.create_texture(A.SL_COLOR_R_FLOAT, 256, 1, 1, opacity)
+        tc = ctx.create_texture(A.SL_COLOR_RGB_FLOAT, 256, 1, 1, colors)
+        ubo = ctx.create_ubo(bytes(blob))
+        ctx.ubo_bind_texture(ubo, 0, tv)
+        ctx.ubo_bind_texture(ubo, 8, to)
+        ctx.ubo_bind_texture(ubo, 16, tc)
+        sh = ctx.create_shader("volume", "volume", ubo, vs_varyings=2, fs_varyings=2, cull=A.SL_CULL_BACK_FACE,
+                               blend=A.SL_BLEND_PREMULTIPLED_ALPHA, depth_test=A.SL_DEPTH_TEST_OFF, depth_mask=A.SL_DEPTH_MASK_OFF)
+        assert sh != A.INVALID_ID
+        return dict(color=color, depth=depth, fbo=fbo, shader=sh, mesh=ctx.mesh(vao, 0, 36, A.RENDER_MODE_TRIANGLES), ubo=ubo)
+
+    def frame(ctx, st):
+        ctx.clear_framebuffer(st["fbo"], 0, (0.0, 0.0, 0.0, 0.0), 0.0)
+        ctx.draw(st["mesh"], st["shader"], st["fbo"])
+
+    return Scene(name or f"volume{vol_size}_{width}x{height}", width, height, A.SL_COLOR_RGBA_FLOAT, depth_type, (0, 0, 0, 0), 0.0,
+                 setup, frame, tris_per_frame=12, draws_per_frame=1)
+
+
 SCENES: Dict[str, Callable[[], Scene]] = {
     "draw_test": draw_test_scene,
     "c1_sphere100k": sphere_scene,
@@ -461,6 +671,11 @@ SCENES: Dict[str, Callable[[], Scene]] = {
     # the survey's 4K anchors: the C1 sphere at 3840x2160 with 100k and 1M triangles
     "c3_indoor2m": indoor_scene,
     "c3_small": lambda: indoor_scene(480, 270, (4, 4), 6, 64, name="indoor16x432_480x270"),
+    "c4_skinned100": skinned_scene,
+    "c4_small": lambda: skinned_scene(480, 270, (3, 2), 64, 24, 64, name="skinned6x3072_480x270"),
+    "c5_volume8k": volume_scene,
+    "c5_volume4k": lambda: volume_scene(3840, 2160, 256, name="volume256_3840x2160"),
+    "c5_small": lambda: volume_scene(160, 90, 32, name="volume32_160x90"),
     "c1_sphere100k_4k": lambda: sphere_scene(3840, 2160, 224, 224, name="sphere100k_3840x2160"),
     "c1_sphere1m_4k": lambda: sphere_scene(3840, 2160, 708, 708, name="sphere1m_3840x2160"),
 }

@@ -96,6 +96,58 @@ def test_idempotent_and_deterministic_full_c2(golden):
     assert a[2]["fragsShaded"] == b[2]["fragsShaded"]
 
 
+@pytest.mark.parametrize("name", ["c3_small", "rand_split3", "rand_multi3", "rand_overflow_blend", "c2_small"])
+def test_batched_draws_equal_draw_by_draw(name, golden, monkeypatch):
+    """Consecutive draws with one shader + framebuffer are executed as ONE pipeline pass; with
+    SLCU_SYNC_DRAWS=1 every draw call is its own pass, like the reference.  Both give the same bits, and the batched
+    context really did batch."""
+    frames, hashes = golden
+    scene = cases.CASES[name]()
+    cb, db, sb = cases.render("cuda", scene, rcp_table=frames["rcp_table"])
+    monkeypatch.setenv("SLCU_SYNC_DRAWS", "1")
+    cs, ds, ss = cases.render("cuda", scene, rcp_table=frames["rcp_table"])
+    assert ss["batches"] == ss["drawCalls"] or scene.draws_per_frame == 1
+    assert sb["batches"] <= ss["batches"]
+    if name == "c3_small":
+        assert sb["batches"] == 1 and sb["drawCalls"] == 16
+    assert sb["fragsShaded"] == ss["fragsShaded"] == hashes[name]["frags"]
+    assert sha(cb) == sha(cs) == hashes[name]["color_sha256"]
+    assert sha(db) == sha(ds) == hashes[name]["depth_sha256"]
+
+
+def test_uniform_updates_between_batched_draws_are_snapshotted():
+    """ubo_assign between two draws of a batch must not leak into the first draw (the reference's draw is synchronous)."""
+    ctx = A.Context("cuda")
+    c = ctx.create_texture(A.SL_COLOR_RGBA_8U, 64, 64)
+    d = ctx.create_texture(A.SL_COLOR_R_FLOAT, 64, 64)
+    fbo = ctx.create_framebuffer([c], d)
+    tri = np.array([[-1, -1, 0, 1], [1, -1, 0, 1], [0, 1, 0, 1]], dtype=np.float32)
+    left = tri.copy(); left[:, 0] = left[:, 0] * 0.5 - 0.5
+    right = tri.copy(); right[:, 0] = right[:, 0] * 0.5 + 0.5
+    verts = np.zeros((6, 8), dtype=np.float32)
+    verts[:3, :4], verts[3:, :4] = left, right
+    vbo = ctx.create_vbo(verts)
+    vao = ctx.create_vao(vbo, None, [(0, 32, A.VERTEX_DIMENSION_4, A.VERTEX_DATA_FLOAT), (16, 32, A.VERTEX_DIMENSION_4, A.VERTEX_DATA_FLOAT)])
+    ident = np.identity(4, dtype=np.float32)
+
+    def blob(col):
+        return ident.tobytes() + np.array(col, dtype=np.float32).tobytes()
+
+    ubo = ctx.create_ubo(blob((1, 0, 0, 1)))
+    sh = ctx.create_shader("flat", "flat", ubo, vs_varyings=0, fs_varyings=0, cull=A.SL_CULL_OFF, blend=A.SL_BLEND_OFF,
+                           depth_test=A.SL_DEPTH_TEST_OFF, depth_mask=A.SL_DEPTH_MASK_OFF)
+    assert sh != A.INVALID_ID
+    ctx.clear_framebuffer(fbo, 0, (0, 0, 0, 1), 1.0)
+    ctx.draw(ctx.mesh(vao, 0, 3, A.RENDER_MODE_TRIANGLES), sh, fbo)
+    ctx.ubo_assign(ubo, blob((0, 0, 1, 1)))
+    ctx.draw(ctx.mesh(vao, 3, 6, A.RENDER_MODE_TRIANGLES), sh, fbo)
+    img = ctx.texture_read(c, A.SL_COLOR_RGBA_8U, 64, 64)
+    st = ctx.get_stats()
+    assert st["batches"] == 1 and st["drawCalls"] == 2
+    assert tuple(img[20, 16]) == (255, 0, 0, 255)
+    assert tuple(img[20, 48]) == (0, 0, 255, 255)
+
+
 def test_clear_only_frame():
     ctx = A.Context("cuda")
     c = ctx.create_texture(A.SL_COLOR_RGBA_8U, 1920, 1080)

@@ -28,5 +28,6 @@ for r in rows:
 tot_s = sum(x[3] for x in recs) or 1; tot_i = sum(x[4] for x in recs) or 1
 print(f"total samples {tot_s:.0f}  total warp-instructions {tot_i:.0f}")
 print(f"{'file:line':28s} {'samp%':>6s} {'inst%':>6s} {'no_inst':>7s} {'long_sb':>7s} {'wait':>6s} {'short':>6s} {'branch':>6s}  source")
-for x in sorted(recs, key=lambda x: -x[3])[:top]:
+key = 4 if (len(sys.argv) > 3 and sys.argv[3] == "inst") else 3
+for x in sorted(recs, key=lambda x: -x[key])[:top]:
     print(f"{x[0][:20]+':'+str(x[1]):28s} {x[3]/tot_s*100:6.2f} {x[4]/tot_i*100:6.2f} {x[5]:7.0f} {x[6]:7.0f} {x[7]:6.0f} {x[8]:6.0f} {x[9]:6.0f}  {x[2]}")
