@@ -128,6 +128,18 @@ def algorithmic_bytes(scene_name: str, scene: S.Scene, frags: int) -> dict:
         nverts = (int(round((scene.tris_per_frame / 2) ** 0.5)) + 1) ** 2
         out["vertex"] = scene.tris_per_frame * 3 * 4 + nverts * 32
         out["raster"] = frags * (2 * dbpt + cbpt)
+    elif scene_name.startswith("c4"):
+        # per draw: u32 indices + the character's 36-byte vertices + 64 bone matrices + the uniform block; per shaded fragment:
+        # depth read + write, RGBA8 read + write (SL_BLEND_ALPHA), 4 bilinear taps of RGBA8 (reuse = 0: upper figure)
+        tris_per_draw = scene.tris_per_frame // scene.draws_per_frame
+        out["vertex"] = scene.draws_per_frame * (tris_per_draw * 3 * 4 + (tris_per_draw // 2 + 160) * 36 + 64 * 64 + 1024)
+        out["raster"] = frags * (2 * dbpt + 2 * cbpt + 4 * 4)
+    elif scene_name.startswith("c5"):
+        # 36 non-indexed 12-byte vertices; per fragment that reaches the blend: RGBA_FLOAT read + write (premultiplied alpha), no
+        # depth traffic (test and mask off).  The ray march's volume taps (<= 32 nearest + 256 x 8 + 3 x 8 per lit step, R8) hit
+        # a 16.8 MB L2-resident volume: the shader is issue-bound, the HBM figure is the framebuffer traffic only
+        out["vertex"] = 36 * 12 + 1024
+        out["raster"] = frags * (2 * cbpt)
     else:
         out["vertex"] = 0
         out["raster"] = frags * (2 * dbpt + cbpt)

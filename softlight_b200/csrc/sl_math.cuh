@@ -102,6 +102,21 @@ template <typename T> struct alignas(vec4_align<T>::value) vec4_t
     template <typename U> SLD_FN explicit operator vec4_t<U>() const { return vec4_t<U>{(U)v[0], (U)v[1], (U)v[2], (U)v[3]}; }
 };
 
+/* vec4<uint32_t> -> vec4<float> (x86/vec4f_impl.h:236-245): cvtdq2ps has no unsigned form, so the reference converts
+ * v>>1 and v&1 separately: (float)(v>>1) * 2 + (float)(v&1) */
+template <> template <>
+SLD_FN vec4_t<uint32_t>::operator vec4_t<float>() const
+{
+    vec4_t<float> r;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+    {
+        const float hi = (float)(int32_t)(v[i] >> 1), lo = (float)(int32_t)(v[i] & 1u);
+        r.v[i] = (hi + hi) + lo;
+    }
+    return r;
+}
+
 typedef vec2_t<float> vec2;
 typedef vec3_t<float> vec3;
 typedef vec4_t<float> vec4;
@@ -124,6 +139,13 @@ SLD_FN vec4_t<uint8_t> vec4_to_u8(const vec4& f)
 template <typename T> struct alignas(16) mat4_t
 {
     vec4_t<T> m[4]; /* columns */
+    mat4_t() = default;
+    /* generic/mat4_impl.h: mat4_t(n) = n on the diagonal */
+    SLD_FN explicit constexpr mat4_t(T n) : m{vec4_t<T>{n, T(0), T(0), T(0)}, vec4_t<T>{T(0), n, T(0), T(0)}, vec4_t<T>{T(0), T(0), n, T(0)}, vec4_t<T>{T(0), T(0), T(0), n}} {}
+    SLD_FN constexpr mat4_t(const vec4_t<T>& a, const vec4_t<T>& b, const vec4_t<T>& c, const vec4_t<T>& d) : m{a, b, c, d} {}
+    /* generic/mat4_impl.h:205-213,474-482: column-wise, element-wise */
+    SLD_FN mat4_t operator+(const mat4_t& n) const { return mat4_t{m[0] + n.m[0], m[1] + n.m[1], m[2] + n.m[2], m[3] + n.m[3]}; }
+    SLD_FN mat4_t operator*(T n) const { return mat4_t{m[0] * n, m[1] * n, m[2] * n, m[3] * n}; }
     SLD_FN const vec4_t<T>& operator[](int i) const { return m[i]; }
     SLD_FN vec4_t<T>& operator[](int i) { return m[i]; }
     /* x86/mat4f_impl.h:123-146, FMA branch: (m0*x (+)fma m1*y) + (m2*z (+)fma m3*w) */
@@ -174,6 +196,8 @@ SLD_FN float fmadd(float x, float m, float a) { return sl_fma(x, m, a); }       
 SLD_FN int sign_mask(float x) { return sl_signbit(x) ? 1 : 0; }                       /* :250 */
 SLD_FN float sqrt(float x) { return sqrtf(x); }
 SLD_FN float abs(float x) { return __uint_as_float(__float_as_uint(x) & 0x7fffffffu); }
+SLD_FN float min(float a, float b, float c) { return sl_min(c, sl_min(a, b)); }         /* :32-38 */
+SLD_FN float max(float a, float b, float c) { return sl_max(c, sl_max(a, b)); }         /* :64-70 */
 template <typename T> SLD_FN T clamp(T n, T lo, T hi) { return n < lo ? lo : (n > hi ? hi : n); }
 template <typename T> SLD_FN T min(T a, T b) { return a < b ? a : b; }
 template <typename T> SLD_FN T max(T a, T b) { return a > b ? a : b; }
@@ -239,8 +263,24 @@ template <typename T> SLD_FN vec3_t<T> vec3_cast(const vec2_t<T>& v, const T& s)
 template <typename T> SLD_FN vec2_t<T> vec2_cast(const vec4_t<T>& v) { return vec2_t<T>{v.v[0], v.v[1]}; }
 template <typename T> SLD_FN vec2_t<T> vec2_cast(const vec3_t<T>& v) { return vec2_t<T>{v.v[0], v.v[1]}; }
 
+/* generic vec2 min/max (generic/vec_utils_impl.h:120-147): (a < b) ? a : b / (a > b) ? a : b per element */
+template <typename T> SLD_FN vec2_t<T> min(const vec2_t<T>& a, const vec2_t<T>& b) { return vec2_t<T>{a.v[0] < b.v[0] ? a.v[0] : b.v[0], a.v[1] < b.v[1] ? a.v[1] : b.v[1]}; }
+template <typename T> SLD_FN vec2_t<T> max(const vec2_t<T>& a, const vec2_t<T>& b) { return vec2_t<T>{a.v[0] > b.v[0] ? a.v[0] : b.v[0], a.v[1] > b.v[1] ? a.v[1] : b.v[1]}; }
+
+/* math::scale(mat4, vec3) (generic/mat_utils_impl.h:433-440): only the diagonal is multiplied */
+template <typename T> SLD_FN mat4_t<T> scale(const mat4_t<T>& m, const vec3_t<T>& s)
+{
+    mat4_t<T> r = m;
+    r.m[0].v[0] = m.m[0].v[0] * s.v[0];
+    r.m[1].v[1] = m.m[1].v[1] * s.v[1];
+    r.m[2].v[2] = m.m[2].v[2] * s.v[2];
+    return r;
+}
+
 /* variadic sum (generic/scalar_utils_impl.h:1009-1023): right fold */
-template <typename T> SLD_FN T sum(const T& a, const T& b, const T& c, const T& d) { return a + (b + (c + d)); }
+template <typename T> SLD_FN T sum_fold(const T& a) { return a; }
+template <typename T, typename... R> SLD_FN T sum_fold(const T& a, const R&... rest) { return a + sum_fold(rest...); }
+template <typename T, typename... R> SLD_FN T sum(const T& a, const T& b, const R&... rest) { return a + sum_fold(b, rest...); }
 
 /* -------------------- log / exp / pow: the "fast approximate" forms that are live in the reference (LS_MATH_HIGH_PREC
  * is never defined; -mfma selects the fmadd branches).  Scalar (x86/scalarf_utils_impl.h:305-326,334-358,389-423,550-590)

@@ -55,7 +55,10 @@ struct SL_Texture
     SLD_FN uint16_t width() const { return mWidth; }
     SLD_FN uint16_t height() const { return mHeight; }
     SLD_FN uint16_t depth() const { return mDepth; }
+    SLD_FN uint32_t channels() const { return (uint32_t)mChannels; } /* SL_Texture.hpp:349-352 */
     SLD_FN const void* data() const { return mTexels; }
+    /* raw texel by linear index (SL_Texture.hpp:451-455) */
+    template <typename color_type> SLD_FN const color_type texel(ptrdiff_t index) const { return reinterpret_cast<const color_type*>(mTexels)[index]; }
 
     template <SL_TexelOrder order> SLD_FN ptrdiff_t map_coordinate(uint32_t x, uint32_t y) const
     {
@@ -115,6 +118,22 @@ SLD_FN math::vec4 sl_unpack_vec4_10_10_10_2I(int32_t norm)
     return math::vec4{(float)x * (1.f / 511.f), (float)y * (1.f / 511.f), (float)z * (1.f / 511.f), 0.f * (1.f / 511.f)};
 }
 
+/* SL_ColorRType (SL_Color.hpp:184-241): one channel with element-wise operators */
+template <typename T> struct alignas(sizeof(T)) SL_ColorRType
+{
+    typedef T value_type;
+    T r;
+    SL_ColorRType() = default;
+    SLD_FN explicit constexpr SL_ColorRType(T n) : r{n} {}
+    SLD_FN constexpr SL_ColorRType operator+(const SL_ColorRType& n) const { return SL_ColorRType{(T)(r + n.r)}; }
+    SLD_FN constexpr SL_ColorRType operator-(const SL_ColorRType& n) const { return SL_ColorRType{(T)(r - n.r)}; }
+    SLD_FN constexpr SL_ColorRType operator*(const SL_ColorRType& n) const { return SL_ColorRType{(T)(r * n.r)}; }
+    SLD_FN constexpr SL_ColorRType operator*(const T n) const { return SL_ColorRType{(T)(r * n)}; }
+};
+typedef SL_ColorRType<uint8_t> SL_ColorR8;
+typedef SL_ColorRType<float> SL_ColorRf;
+typedef math::vec3_t<float> SL_ColorRGBf; /* SL_Color.hpp:466,477 */
+
 /* ------------------------------------------------------------ color_cast */
 template <typename T, typename U> struct ColorCast;
 template <> struct ColorCast<float, uint8_t> /* SL_Color.hpp:549,666: (float)p * 0.00392156862745f */
@@ -122,6 +141,7 @@ template <> struct ColorCast<float, uint8_t> /* SL_Color.hpp:549,666: (float)p *
     static SLD_FN math::vec4 run(const math::vec4_t<uint8_t>& p) { return math::vec4{(float)p.v[0], (float)p.v[1], (float)p.v[2], (float)p.v[3]} * 0.00392156862745f; }
     static SLD_FN math::vec3 run(const math::vec3_t<uint8_t>& p) { return math::vec3{(float)p.v[0], (float)p.v[1], (float)p.v[2]} * 0.00392156862745f; }
     static SLD_FN float run(uint8_t p) { return (float)p * 0.00392156862745f; }
+    static SLD_FN SL_ColorRType<float> run(const SL_ColorRType<uint8_t>& p) { return SL_ColorRType<float>{(float)p.r * 0.00392156862745f}; } /* :314-318 */
 };
 template <> struct ColorCast<float, uint16_t>
 {
@@ -142,6 +162,8 @@ template <> struct ColorCast<uint8_t, float> /* :506,:623: (vecN<u8>)(p*255): ve
         return math::vec3_t<uint8_t>{(uint8_t)sl_cvt_tr(s.v[0]), (uint8_t)sl_cvt_tr(s.v[1]), (uint8_t)sl_cvt_tr(s.v[2])};
     }
     static SLD_FN uint8_t run(float p) { return (uint8_t)sl_cvt_tr(p * 255.f); }
+    /* :270-275: (SL_ColorRType<T>)(p.r * max) = explicit ctor from float = C truncation */
+    static SLD_FN SL_ColorRType<uint8_t> run(const SL_ColorRType<float>& p) { return SL_ColorRType<uint8_t>{(uint8_t)sl_cvt_tr(p.r * 255.f)}; }
 };
 template <typename T, typename U, typename V> SLD_FN auto color_cast(const V& p) -> decltype(ColorCast<T, U>::run(p)) { return ColorCast<T, U>::run(p); }
 
@@ -230,6 +252,56 @@ SLD_FN color_type sl_sample_bilinear(const SL_Texture& tex, float x, float y)
     const auto weight2 = pixel2 * dx * omdy;
     const auto weight3 = pixel3 * dx * dy;
     const auto ret = math::sum(weight0, weight1, weight2, weight3);
+    return color_cast<T, float>(ret);
+}
+
+/* SL_Sampler.hpp:315-372: "trilinear" = 8 taps at (x-1|x, y-1|y, z-1|z) weighted by the fractions of x, y, z; the
+ * implicit float -> uint16_t conversions of si/ti/ri are cvttss2si */
+template <typename color_type, class WrapMode, SL_TexelOrder order = SL_TexelOrder::ORDERED>
+SLD_FN color_type sl_sample_trilinear(const SL_Texture& tex, float x, float y, float z)
+{
+    typedef typename color_type::value_type T;
+    if (WrapMode::border && (x < 0.f || x >= 1.f || y < 0.f || y >= 1.f || z < 0.f || z >= 1.f)) return sl_zero_color<color_type>();
+    const WrapMode wrapMode{};
+
+    x = wrapMode(x) * (float)tex.width();
+    const uint16_t xi = sl_f2u16(x);
+    const uint16_t si = sl_f2u16(math::max(x - 1.f, 0.f));
+
+    y = wrapMode(y) * (float)tex.height();
+    const uint16_t yi = sl_f2u16(y);
+    const uint16_t ti = sl_f2u16(math::max(y - 1.f, 0.f));
+
+    z = wrapMode(z) * (float)tex.depth();
+    const uint16_t zi = sl_f2u16(z);
+    const uint16_t ri = sl_f2u16(math::max(z - 1.f, 0.f));
+
+    const auto c000 = color_cast<float, T>(tex.texel<color_type, order>(si, ti, ri));
+    const auto c100 = color_cast<float, T>(tex.texel<color_type, order>(xi, ti, ri));
+    const auto c010 = color_cast<float, T>(tex.texel<color_type, order>(si, yi, ri));
+    const auto c001 = color_cast<float, T>(tex.texel<color_type, order>(si, ti, zi));
+    const auto c101 = color_cast<float, T>(tex.texel<color_type, order>(xi, ti, zi));
+    const auto c011 = color_cast<float, T>(tex.texel<color_type, order>(si, yi, zi));
+    const auto c110 = color_cast<float, T>(tex.texel<color_type, order>(xi, yi, ri));
+    const auto c111 = color_cast<float, T>(tex.texel<color_type, order>(xi, yi, zi));
+
+    const float xf = x - math::floor(x);
+    const float yf = y - math::floor(y);
+    const float zf = z - math::floor(z);
+    const float xd = 1.f - xf;
+    const float yd = 1.f - yf;
+    const float zd = 1.f - zf;
+
+    const auto weight000 = c000 * xd * yd * zd;
+    const auto weight100 = c100 * xf * yd * zd;
+    const auto weight010 = c010 * xd * yf * zd;
+    const auto weight001 = c001 * xd * yd * zf;
+    const auto weight101 = c101 * xf * yd * zf;
+    const auto weight011 = c011 * xd * yf * zf;
+    const auto weight110 = c110 * xf * yf * zd;
+    const auto weight111 = c111 * xf * yf * zf;
+
+    const auto ret = math::sum(weight000, weight100, weight010, weight001, weight101, weight011, weight110, weight111);
     return color_cast<T, float>(ret);
 }
 

@@ -73,6 +73,7 @@ namespace sld
 {
 #include "sl_shaders_basic.inl"
 #include "sl_shaders_scene.inl"
+#include "sl_shaders_anim_volume.inl"
 }
 
 /* ===========================================================================

@@ -47,18 +47,23 @@ CASES["draw_test"] = S.SCENES["draw_test"]
 CASES["c1_small"] = S.SCENES["c1_small"]
 CASES["c2_small"] = S.SCENES["c2_small"]
 CASES["c3_small"] = S.SCENES["c3_small"]
+CASES["c4_small"] = S.SCENES["c4_small"]
+CASES["c5_small"] = S.SCENES["c5_small"]
 
 # full-size configs: compared through hashes / live checkers only
 BIG_CASES = {
     "c1_sphere100k": S.SCENES["c1_sphere100k"],
     "c2_instancing10k": S.SCENES["c2_instancing10k"],
     "c3_indoor2m": S.SCENES["c3_indoor2m"],
+    "c4_skinned100": S.SCENES["c4_skinned100"],
+    "c5_volume4k": S.SCENES["c5_volume4k"],
+    "c5_volume8k": S.SCENES["c5_volume8k"],
     "c1_sphere100k_4k": S.SCENES["c1_sphere100k_4k"],
     "c1_sphere1m_4k": S.SCENES["c1_sphere1m_4k"],
 }
 
 # cases whose images are committed in full (the rest of CASES is pinned by sha256)
-FULL_IMAGE_CASES = ["draw_test", "c1_small", "c2_small", "c3_small", "rand_blend1", "rand_clip_heavy", "rand_depth_half_premult"]
+FULL_IMAGE_CASES = ["draw_test", "c1_small", "c2_small", "c3_small", "c4_small", "c5_small", "rand_blend1", "rand_clip_heavy", "rand_depth_half_premult"]
 
 
 def bits(a: np.ndarray) -> np.ndarray:
