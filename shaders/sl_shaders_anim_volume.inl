@@ -261,4 +261,71 @@ SL_SHADER_FN bool volume_fs(SL_FragmentParam& fragParam)
 SL_REGISTER_VERTEX_SHADER("volume", volume_vs)
 SL_REGISTER_FRAGMENT_SHADER("volume", volume_fs)
 
+/* Diagnostic variants of "volume" (parity bisection on the GPU box, tools/gpu_compare.py): same vertex shader, the
+ * fragment shader writes intermediate values of volume_fs instead of the composited colour. */
+SL_SHADER_FN bool volume_dbg0_fs(SL_FragmentParam& fragParam)
+{
+    fragParam.pOutputs[0] = fragParam.pVaryings[0] + fragParam.pVaryings[1];
+    return true;
+}
+
+SL_SHADER_FN bool volume_dbg1_fs(SL_FragmentParam& fragParam)
+{
+    const VolumeUniforms* pUniforms = fragParam.pUniforms->template as<VolumeUniforms>();
+    const math::vec4&     spacing   = pUniforms->spacing;
+    const math::vec4&&    scaling   = math::rcp(spacing);
+    const math::vec4&&    pos       = fragParam.pVaryings[0] * scaling;
+    const math::vec4&&    rayDir    = math::normalize(fragParam.pVaryings[1]);
+    float                 nearPos   = 0.f;
+    float                 farPos    = 0.f;
+    volume_intersect_ray_box(pos, rayDir, spacing, nearPos, farPos);
+    fragParam.pOutputs[0] = math::vec4{nearPos, farPos, rayDir[0] + rayDir[1], rayDir[2]};
+    return true;
+}
+
+SL_SHADER_FN bool volume_dbg2_fs(SL_FragmentParam& fragParam)
+{
+    constexpr unsigned numSteps = 256;
+    constexpr float step = 1.f / (float)numSteps;
+    const VolumeUniforms* pUniforms = fragParam.pUniforms->template as<VolumeUniforms>();
+    const math::vec4&     spacing   = pUniforms->spacing;
+    const math::vec4&&    scaling   = math::rcp(spacing);
+    const SL_Texture&     volumeTex = *pUniforms->pCubeMap;
+    const SL_Texture&     alphaTex  = *pUniforms->pOpacityMap;
+    const math::vec4&&    pos       = fragParam.pVaryings[0] * scaling;
+    const math::vec4&&    rayDir    = math::normalize(fragParam.pVaryings[1]);
+    float                 nearPos;
+    float                 farPos;
+    if (!volume_intersect_ray_box(pos, rayDir, spacing, nearPos, farPos))
+    {
+        return false;
+    }
+    const math::vec4&& rayFar    = (pos + rayDir * farPos + 1.f) * 0.5f;
+    const math::vec4&& rayNear   = (pos + rayDir * nearPos + 1.f) * 0.5f;
+    const math::vec4&& ray       = rayFar - rayNear;
+    const math::vec4&& rayStep   = ray * step;
+    math::vec4         rayPos    = rayFar;
+    float sumI = 0.f, sumA = 0.f, sumL = 0.f, sumN = 0.f;
+    for (unsigned i = 0; i < numSteps; ++i)
+    {
+        const unsigned intensity = sl_sample_trilinear<SL_ColorR8, SL_WrapMode::EDGE>(volumeTex, rayPos[0], rayPos[1], rayPos[2]).r;
+        sumI += (float)(int)intensity;
+        if (intensity > 16)
+        {
+            const float srcAlpha = alphaTex.template texel<float>(intensity) * step * 100.f;
+            sumA += srcAlpha;
+            const math::vec4&& norm = volume_calc_normal<numSteps>(volumeTex, rayPos);
+            sumN += (norm[0] + norm[1]) + norm[2];
+            sumL += 2.f * math::clamp(math::dot(norm, math::vec4{1.f, 0.f, 1.f, 0.f}), 0.f, 1.f);
+        }
+        rayPos -= rayStep;
+    }
+    fragParam.pOutputs[0] = math::vec4{sumI, sumA, sumN, sumL};
+    return true;
+}
+
+SL_REGISTER_FRAGMENT_SHADER("volume_dbg0", volume_dbg0_fs)
+SL_REGISTER_FRAGMENT_SHADER("volume_dbg1", volume_dbg1_fs)
+SL_REGISTER_FRAGMENT_SHADER("volume_dbg2", volume_dbg2_fs)
+
 static_assert(sizeof(VolumeUniforms) == 128, "VolumeUniforms layout must be identical in every back-end");

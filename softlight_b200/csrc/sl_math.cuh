@@ -266,6 +266,8 @@ template <typename T> SLD_FN vec2_t<T> vec2_cast(const vec3_t<T>& v) { return ve
 /* generic vec2 min/max (generic/vec_utils_impl.h:120-147): (a < b) ? a : b / (a > b) ? a : b per element */
 template <typename T> SLD_FN vec2_t<T> min(const vec2_t<T>& a, const vec2_t<T>& b) { return vec2_t<T>{a.v[0] < b.v[0] ? a.v[0] : b.v[0], a.v[1] < b.v[1] ? a.v[1] : b.v[1]}; }
 template <typename T> SLD_FN vec2_t<T> max(const vec2_t<T>& a, const vec2_t<T>& b) { return vec2_t<T>{a.v[0] > b.v[0] ? a.v[0] : b.v[0], a.v[1] > b.v[1] ? a.v[1] : b.v[1]}; }
+SLD_FN vec2_t<float> min(const vec2_t<float>& a, const vec2_t<float>& b) { return vec2_t<float>{sl_min(a.v[0], b.v[0]), sl_min(a.v[1], b.v[1])}; } /* same selection, not foldable into .SAT */
+SLD_FN vec2_t<float> max(const vec2_t<float>& a, const vec2_t<float>& b) { return vec2_t<float>{sl_max(a.v[0], b.v[0]), sl_max(a.v[1], b.v[1])}; }
 
 /* math::scale(mat4, vec3) (generic/mat_utils_impl.h:433-440): only the diagonal is multiplied */
 template <typename T> SLD_FN mat4_t<T> scale(const mat4_t<T>& m, const vec3_t<T>& s)

@@ -1044,45 +1044,170 @@ struct SLTile
     long long origin;
 };
 
-/* SL_FragmentProcessor::flush_tri_fragments for one fragment (src/SL_FragmentProcessor.cpp:416-531) */
-template <FsFn FS>
-SLD_FN void sl_shade_fragment(const SLRasterParams& P, const SLTile& T, const SLTriSetup& t, uint32_t recId, const float4* rec, const math::vec4& bcIn, int x, int y, float z)
+/* ------------------------------------------------------------------------
+ * The rasteriser works in two phases inside one warp.
+ *
+ *   Phase A ("resolve"): the span walkers below run the 4-pixel group loop of render_triangle_simd
+ *   (src/SL_TriRasterizer.cpp:471-548): depth of the four lanes, depth test against the tile, the in-place compaction
+ *   of the barycentric registers (:496-498), the depth write (src/SL_FragmentProcessor.cpp:526-529 -- the value is the
+ *   rasteriser's z and does not depend on the shader).  Every surviving fragment is pushed to the warp's fragment
+ *   queue in shared memory: {barycentrics the reference would hand to the shader, z, x, y, record}.
+ *
+ *   Phase B ("shade"): whenever 32 fragments are queued the whole warp shades them, one fragment per lane
+ *   (flush_tri_fragments, src/SL_FragmentProcessor.cpp:416-531): perspective correction, varyings, the fragment
+ *   shader, colour write / blend.  The queue is first-in first-out and fragments of one pixel are pushed in submission
+ *   order, so colour writes to a pixel happen in submission order; fragments of one batch that hit the same pixel are
+ *   ordered by lane.
+ *
+ * The fragment shader is instantiated once per kernel (sl_shade_batch is not inlined) and always runs with converged
+ * lanes; the walkers never contain shading code.
+ * ----------------------------------------------------------------------*/
+constexpr int SL_FQ_CAP = 160;                               /* < 32 left over + at most 4 x 32 pushed per step */
+constexpr unsigned SL_FQ_BYTES = SL_FQ_CAP * (16u + 4u + 4u + 4u);
+constexpr unsigned SL_PIECEQ_BYTES = 32u * (unsigned)sizeof(SLSpanEntry);
+
+struct SLFragQueue
 {
-    /* :438-460 perspective correction */
-    math::vec4 bc = bcIn * math::vec4{t.w0, t.w1, t.w2, 0.f};
-    const float persp = sl_rcp((bc.v[0] + bc.v[1]) + (bc.v[2] + bc.v[3]));
-    bc = bc * persp;
+    float4* bc;    /* barycentrics (register s of the reference after the compaction) */
+    float* z;
+    uint32_t* xy;  /* x | y << 16: coordinates relative to the span's source row (x >= width for fragments that wrapped) */
+    uint32_t* rec;
+    int count;     /* warp-uniform */
 
-    SL_FragmentParam fp;
-    fp.pUniforms = &P.draws[P.recDraw[recId]].uniforms;
-    /* interpolate_tri_varyings, AVX2 branch (:163-193).  The reference interpolates all four slots; slots past
-     * numVaryings hold stale bin data there and are never read by a well-formed shader. */
-    for (int s = 0; s < P.numVaryings; ++s)
+    SLD_FN void bind(unsigned char* mem)
     {
-        const float4 a = rec[3 + 3 * s + 0], b = rec[3 + 3 * s + 1], c = rec[3 + 3 * s + 2];
-        fp.pVaryings[s] = math::vec4{
-            sl_fma(bc.v[2], c.x, sl_fma(bc.v[1], b.x, bc.v[0] * a.x)), sl_fma(bc.v[2], c.y, sl_fma(bc.v[1], b.y, bc.v[0] * a.y)),
-            sl_fma(bc.v[2], c.z, sl_fma(bc.v[1], b.z, bc.v[0] * a.z)), sl_fma(bc.v[2], c.w, sl_fma(bc.v[1], b.w, bc.v[0] * a.w))};
+        bc = reinterpret_cast<float4*>(mem);
+        z = reinterpret_cast<float*>(mem + SL_FQ_CAP * 16u);
+        xy = reinterpret_cast<uint32_t*>(mem + SL_FQ_CAP * 20u);
+        rec = reinterpret_cast<uint32_t*>(mem + SL_FQ_CAP * 24u);
     }
-    fp.coord.x = (uint16_t)x;
-    fp.coord.y = (uint16_t)y;
-    fp.coord.depth = z;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) fp.pOutputs[i] = math::vec4{0.f};
+};
 
-    const bool haveOutputs = FS(fp); /* :501 */
-    /* every attachment is addressed as x + width*y with the depth attachment's width (the reference uses each colour
-     * view's own width; SL_Framebuffer::valid requires them to be equal, and run_draw refuses anything else) */
-    const size_t idx = (size_t)((long long)x + (long long)P.width * (long long)y - T.origin);
-    if (haveOutputs)
+/* Phase B for fragments [first, first + n) of the queue, n <= 32 */
+template <FsFn FS>
+__device__ __noinline__ void sl_shade_batch(const SLRasterParams& P, const SLTile& T, unsigned char* queueMem, int first, int n)
+{
+    const int lane = threadIdx.x & 31;
+    SLFragQueue Q;
+    Q.bind(queueMem);
+    SL_FragmentParam fp;
+    bool haveOutputs = false;
+    uint32_t key = 0xffffff00u + (uint32_t)lane; /* idle lanes: a key no pixel has */
+    if (lane < n)
     {
-        for (int i = P.numOutputs - 1; i >= 0; --i) /* :507-523 */
+        const int e = first + lane;
+        const float4 b4 = Q.bc[e];
+        const float z = Q.z[e];
+        const uint32_t xy = Q.xy[e];
+        const uint32_t recId = Q.rec[e];
+        const int x = (int)(xy & 0xffffu), y = (int)(xy >> 16);
+        const float4* rec = P.records + (size_t)recId * P.recStride;
+        /* :438-460 perspective correction */
+        math::vec4 bc = math::vec4{b4.x, b4.y, b4.z, b4.w} * math::vec4{rec[0].w, rec[1].w, rec[2].w, 0.f};
+        const float persp = sl_rcp((bc.v[0] + bc.v[1]) + (bc.v[2] + bc.v[3]));
+        bc = bc * persp;
+
+        fp.pUniforms = &P.draws[P.recDraw[recId]].uniforms;
+        /* interpolate_tri_varyings, AVX2 branch (:163-193).  The reference interpolates all four slots; slots past
+         * numVaryings hold stale bin data there and are never read by a well-formed shader. */
+        for (int s = 0; s < P.numVaryings; ++s)
         {
-            if (P.blend != 0) sl_blend_color(T.color[i], P.colorType[i], idx, fp.pOutputs[i], P.blend);
-            else sl_store_color(T.color[i], P.colorType[i], idx, fp.pOutputs[i]);
+            const float4 a = rec[3 + 3 * s + 0], b = rec[3 + 3 * s + 1], c = rec[3 + 3 * s + 2];
+            fp.pVaryings[s] = math::vec4{
+                sl_fma(bc.v[2], c.x, sl_fma(bc.v[1], b.x, bc.v[0] * a.x)), sl_fma(bc.v[2], c.y, sl_fma(bc.v[1], b.y, bc.v[0] * a.y)),
+                sl_fma(bc.v[2], c.z, sl_fma(bc.v[1], b.z, bc.v[0] * a.z)), sl_fma(bc.v[2], c.w, sl_fma(bc.v[1], b.w, bc.v[0] * a.w))};
+        }
+        fp.coord.x = (uint16_t)x;
+        fp.coord.y = (uint16_t)y;
+        fp.coord.depth = z;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) fp.pOutputs[i] = math::vec4{0.f};
+
+        haveOutputs = FS(fp); /* :501 */
+        /* every attachment is addressed as x + width*y with the depth attachment's width (the reference uses each
+         * colour view's own width; SL_Framebuffer::valid requires them to be equal, and run_draw refuses anything else) */
+        key = (uint32_t)((long long)x + (long long)P.width * (long long)y - T.origin);
+    }
+    /* :507-523, in submission order per pixel */
+    const uint32_t peers = __match_any_sync(0xffffffffu, key);
+    if (P.blend == 0)
+    {
+        /* plain stores: the last fragment of a pixel that has outputs wins */
+        const uint32_t hv = __ballot_sync(0xffffffffu, haveOutputs) & peers;
+        if (haveOutputs && (hv >> lane) == 1u)
+        {
+            for (int i = P.numOutputs - 1; i >= 0; --i) sl_store_color(T.color[i], P.colorType[i], (size_t)key, fp.pOutputs[i]);
         }
     }
-    if (P.depthMask) sl_store_depth(T.depth, P.depthBpt, idx, z); /* :526-529 */
+    else
+    {
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        const int maxRank = (int)__reduce_max_sync(0xffffffffu, (unsigned)rank);
+        for (int r = 0; r <= maxRank; ++r)
+        {
+            if (rank == r && haveOutputs)
+            {
+                for (int i = P.numOutputs - 1; i >= 0; --i) sl_blend_color(T.color[i], P.colorType[i], (size_t)key, fp.pOutputs[i], P.blend);
+            }
+            __syncwarp();
+        }
+    }
+}
+
+/* push the survivors of one 4-pixel group per lane (warp-collective; mBits == 0 for idle lanes) */
+SLD_FN void sl_push_frags(SLFragQueue& Q, int lane, uint32_t mBits, const math::vec4 (&bcJ)[4], const float (&zJ)[4], int x4, int y, uint32_t recId)
+{
+    if (!__any_sync(0xffffffffu, mBits != 0u)) return;
+    const uint32_t below = (1u << lane) - 1u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+    {
+        const bool has = ((mBits >> j) & 1u) != 0u;
+        const uint32_t b = __ballot_sync(0xffffffffu, has);
+        if (has)
+        {
+            const int e = Q.count + __popc(b & below);
+            Q.bc[e] = make_float4(bcJ[j].v[0], bcJ[j].v[1], bcJ[j].v[2], bcJ[j].v[3]);
+            Q.z[e] = zJ[j];
+            Q.xy[e] = (uint32_t)(x4 + j) | ((uint32_t)y << 16);
+            Q.rec[e] = recId;
+        }
+        Q.count += __popc(b);
+    }
+}
+
+/* shade every full batch of the queue (and the rest too when `all`); what is left moves to the front */
+template <FsFn FS>
+SLD_FN void sl_flush(const SLRasterParams& P, const SLTile& T, SLFragQueue& Q, int lane, bool all)
+{
+    if (Q.count < 32 && !(all && Q.count > 0)) return;
+    const SLTile Tc = T; /* the callee gets a copy: T itself stays in registers */
+    unsigned char* mem = reinterpret_cast<unsigned char*>(Q.bc);
+    __syncwarp();
+    int first = 0;
+    while (Q.count - first >= 32)
+    {
+        sl_shade_batch<FS>(P, Tc, mem, first, 32);
+        first += 32;
+    }
+    int r = Q.count - first;
+    if (all && r > 0)
+    {
+        sl_shade_batch<FS>(P, Tc, mem, first, r);
+        r = 0;
+    }
+    if (r > 0) /* first >= 32 > r: source and destination do not overlap */
+    {
+        if (lane < r)
+        {
+            Q.bc[lane] = Q.bc[first + lane];
+            Q.z[lane] = Q.z[first + lane];
+            Q.xy[lane] = Q.xy[first + lane];
+            Q.rec[lane] = Q.rec[first + lane];
+        }
+    }
+    Q.count = r;
+    __syncwarp();
 }
 
 /* Hand-over of the walker state at a cut (see SL_ENTRY_OVERFLOW).  A row is rasterised by numSegs warps, one per
@@ -1092,7 +1217,8 @@ SLD_FN void sl_shade_fragment(const SLRasterParams& P, const SLTile& T, const SL
  * group's lanes left of the cut, [7:0] lane map (2 bits per register).  Boundary b of a span of row y: x = b*segWidth
  * for b < numSegs, x = W for b = numSegs (row end), x = W + (b-numSegs)*segWidth beyond (the part that wrapped into
  * row y+1).  A consumer only ever waits for a warp with a smaller ticket (left segment of its row, or the row below),
- * and tickets are taken in launch order, so the wait cannot deadlock. */
+ * and tickets are taken in launch order, so the wait cannot deadlock.  Hand-overs are published in phase A, i.e.
+ * without waiting for any shading. */
 SLD_FN unsigned long long sl_handoff_key(uint32_t rec, int y, int boundary)
 {
     return ((unsigned long long)rec << 20) | ((unsigned long long)(y & 0x1fff) << 7) | (unsigned long long)(boundary & 0x7f);
@@ -1135,118 +1261,136 @@ SLD_FN uint32_t sl_state_step(uint32_t st, uint32_t t)
     return s0 | (s1 << 2) | (s2 << 4) | (s3 << 6);
 }
 
-/* One piece [p0,p1) of the span [xMin,xMax) of source row y, walked left to right by ONE lane: the 4-pixel group loop
- * of render_triangle_simd (src/SL_TriRasterizer.cpp:471-548), including the in-place compaction of the barycentric
- * registers (:496-498).  Pixels are addressed linearly from the source row, exactly like the reference, so a piece
- * that lies beyond the row end needs no coordinate change.  `hand`: state at p0 (lane map + outcomes of the lanes of
- * the straddling group left of p0) when the piece does not start the span. */
-template <FsFn FS>
-SLD_FN unsigned sl_walk_piece(const SLRasterParams& P, const SLTile& T, uint32_t recId, int y, int xMin, int xMax, int p0, int p1, uint32_t hand,
-                              bool publish, int outBoundary)
+SLD_FN math::vec4 sl_pick4(uint32_t s, const math::vec4& a0, const math::vec4& a1, const math::vec4& a2, const math::vec4& a3)
+{
+    return s == 0u ? a0 : (s == 1u ? a1 : (s == 2u ? a2 : a3));
+}
+
+/* One piece [p0,p1) of the span [xMin,xMax) of source row y, walked left to right by ONE lane, one 4-pixel group per
+ * call of sl_walk_group (all lanes of the warp step their pieces in lock step so that the survivors can be pushed with
+ * warp-wide ballots).  Pixels are addressed linearly from the source row, exactly like the reference, so a piece that
+ * lies beyond the row end needs no coordinate change.  `hand`: state at p0 (lane map + outcomes of the lanes of the
+ * straddling group left of p0) when the piece does not start the span. */
+struct SLWalk
+{
+    math::vec4 a0, a1, a2, a3, bcX; /* the four barycentric registers (:476-481) and their per-group increment */
+    float z0, z1, z2;
+    uint32_t recId, st, fM;
+    int y, x4, p0, p1, rowBase, outBoundary;
+    bool publish, published;
+};
+
+SLD_FN void sl_walk_begin(SLWalk& w, const SLRasterParams& P, const SLTile& T, uint32_t recId, int y, int xMin, int p0, int p1, uint32_t hand,
+                          bool publish, int outBoundary)
 {
     const float4* rec = P.records + (size_t)recId * P.recStride;
     SLTriSetup t;
     sl_tri_setup(t, rec[0], rec[1], rec[2]);
-
     const float yf = (float)y;
     const math::vec4 bcY = math::fmadd(t.bc1, math::vec4{yf}, t.bc2); /* :474 */
-    math::vec4 a0 = (t.bc0 * (float)(xMin + 0)) + bcY;                /* :476-481 */
-    math::vec4 a1 = (t.bc0 * (float)(xMin + 1)) + bcY;
-    math::vec4 a2 = (t.bc0 * (float)(xMin + 2)) + bcY;
-    math::vec4 a3 = (t.bc0 * (float)(xMin + 3)) + bcY;
-    const math::vec4 bcX = t.bc0 * 4.f;
-    const long long rowBase = (long long)P.width * (long long)y - T.origin;
-    unsigned shaded = 0;
-    uint32_t st = SL_STATE_IDENTITY; /* lane map: register i holds accumulator chain (st >> 2i) & 3 */
-    uint32_t fM = 0u;                /* outcomes of the first group's lanes that another piece owns */
+    w.a0 = (t.bc0 * (float)(xMin + 0)) + bcY;                         /* :476-481 */
+    w.a1 = (t.bc0 * (float)(xMin + 1)) + bcY;
+    w.a2 = (t.bc0 * (float)(xMin + 2)) + bcY;
+    w.a3 = (t.bc0 * (float)(xMin + 3)) + bcY;
+    w.bcX = t.bc0 * 4.f;
+    w.z0 = t.z0; w.z1 = t.z1; w.z2 = t.z2;
+    w.recId = recId;
+    w.y = y;
+    w.p0 = p0;
+    w.p1 = p1;
+    w.rowBase = (int)((long long)P.width * (long long)y - T.origin);
+    w.outBoundary = outBoundary;
+    w.publish = publish;
+    w.published = false;
+    w.st = SL_STATE_IDENTITY; /* lane map: register i holds accumulator chain (st >> 2i) & 3 */
+    w.fM = 0u;                /* outcomes of the first group's lanes that another piece owns */
     int x4 = xMin;
-    bool published = false;
-
     if (xMin < p0)
     {
         /* replay the accumulator chains up to the group that contains p0, then apply the handed-over lane map */
-        for (; x4 + 3 < p0; x4 += 4) { a0 += bcX; a1 += bcX; a2 += bcX; a3 += bcX; }
-        st = hand & 0xffu;
-        if (st != SL_STATE_IDENTITY)
+        for (; x4 + 3 < p0; x4 += 4) { w.a0 += w.bcX; w.a1 += w.bcX; w.a2 += w.bcX; w.a3 += w.bcX; }
+        w.st = hand & 0xffu;
+        if (w.st != SL_STATE_IDENTITY)
         {
-            const math::vec4 c[4] = {a0, a1, a2, a3};
-            a0 = c[st & 3u];
-            a1 = c[(st >> 2) & 3u];
-            a2 = c[(st >> 4) & 3u];
-            a3 = c[(st >> 6) & 3u];
+            const math::vec4 c0 = w.a0, c1 = w.a1, c2 = w.a2, c3 = w.a3;
+            w.a0 = sl_pick4(w.st & 3u, c0, c1, c2, c3);
+            w.a1 = sl_pick4((w.st >> 2) & 3u, c0, c1, c2, c3);
+            w.a2 = sl_pick4((w.st >> 4) & 3u, c0, c1, c2, c3);
+            w.a3 = sl_pick4((w.st >> 6) & 3u, c0, c1, c2, c3);
         }
-        fM = (hand >> 8) & 7u;
+        w.fM = (hand >> 8) & 7u;
     }
+    w.x4 = x4;
+}
 
-    for (; x4 < p1; x4 += 4)
+/* one group: returns the mask of this piece's surviving lanes; bcJ/zJ[j] = what the reference shades lane j with */
+SLD_FN uint32_t sl_walk_group(SLWalk& w, const SLRasterParams& P, const SLTile& T, math::vec4 (&bcJ)[4], float (&zJ)[4])
+{
+    const int x4 = w.x4, p0 = w.p0, p1 = w.p1;
+    /* _sl_mul_vec4_mat4_ps (:376-393): z = (w*0 + z*z2) + (y*z1 + x*z0) */
+    zJ[0] = ((w.a0.v[3] * 0.f) + (w.a0.v[2] * w.z2)) + ((w.a0.v[1] * w.z1) + (w.a0.v[0] * w.z0));
+    zJ[1] = ((w.a1.v[3] * 0.f) + (w.a1.v[2] * w.z2)) + ((w.a1.v[1] * w.z1) + (w.a1.v[0] * w.z0));
+    zJ[2] = ((w.a2.v[3] * 0.f) + (w.a2.v[2] * w.z2)) + ((w.a2.v[1] * w.z1) + (w.a2.v[0] * w.z0));
+    zJ[3] = ((w.a3.v[3] * 0.f) + (w.a3.v[2] * w.z2)) + ((w.a3.v[1] * w.z1) + (w.a3.v[0] * w.z0));
+    uint32_t mBits = 0u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
     {
-        /* _sl_mul_vec4_mat4_ps (:376-393): z = (w*0 + z*z2) + (y*z1 + x*z0) */
-        const float zA = ((a0.v[3] * 0.f) + (a0.v[2] * t.z2)) + ((a0.v[1] * t.z1) + (a0.v[0] * t.z0));
-        const float zB = ((a1.v[3] * 0.f) + (a1.v[2] * t.z2)) + ((a1.v[1] * t.z1) + (a1.v[0] * t.z0));
-        const float zC = ((a2.v[3] * 0.f) + (a2.v[2] * t.z2)) + ((a2.v[1] * t.z1) + (a2.v[0] * t.z0));
-        const float zD = ((a3.v[3] * 0.f) + (a3.v[2] * t.z2)) + ((a3.v[1] * t.z1) + (a3.v[0] * t.z0));
-        const bool ownA = (x4 + 0 >= p0) && (x4 + 0 < p1);
-        const bool ownB = (x4 + 1 >= p0) && (x4 + 1 < p1);
-        const bool ownC = (x4 + 2 >= p0) && (x4 + 2 < p1);
-        const bool ownD = (x4 + 3 >= p0) && (x4 + 3 < p1);
-        const bool mA = ownA && sl_depth_cmp(P.depthTest, zA, P.depthTest ? sl_load_depth(T.depth, P.depthBpt, (size_t)(rowBase + x4 + 0)) : 0.f);
-        const bool mB = ownB && sl_depth_cmp(P.depthTest, zB, P.depthTest ? sl_load_depth(T.depth, P.depthBpt, (size_t)(rowBase + x4 + 1)) : 0.f);
-        const bool mC = ownC && sl_depth_cmp(P.depthTest, zC, P.depthTest ? sl_load_depth(T.depth, P.depthBpt, (size_t)(rowBase + x4 + 2)) : 0.f);
-        const bool mD = ownD && sl_depth_cmp(P.depthTest, zD, P.depthTest ? sl_load_depth(T.depth, P.depthBpt, (size_t)(rowBase + x4 + 3)) : 0.f);
-        /* outcomes of the lanes left of p0 are known (handed over); lanes at or beyond p1 are unknown, but they cannot
-         * change which register a survivor of this piece reads (that is resolved at or before the survivor's own lane) */
-        const bool tA = mA || (fM & 1u), tB = mB || (fM & 2u), tC = mC || (fM & 4u), tD = mD;
-        const uint32_t tBits = (tA ? 1u : 0u) | (tB ? 2u : 0u) | (tC ? 4u : 0u) | (tD ? 8u : 0u);
-        fM = 0u;
-        if (publish && x4 + 3 >= p1)
+        const bool own = (x4 + j >= p0) && (x4 + j < p1);
+        if (own && sl_depth_cmp(P.depthTest, zJ[j], P.depthTest ? sl_load_depth(T.depth, P.depthBpt, (size_t)(w.rowBase + x4 + j)) : 0.f)) mBits |= 1u << j;
+    }
+    /* outcomes of the lanes left of p0 are known (handed over); lanes at or beyond p1 are unknown, but they cannot
+     * change which register a survivor of this piece reads (that is resolved at or before the survivor's own lane) */
+    const uint32_t tBits = mBits | w.fM;
+    w.fM = 0u;
+    if (w.publish && x4 + 3 >= p1)
+    {
+        /* the cut lies inside this group: state before the group + outcomes of its lanes left of the cut */
+        const uint32_t below = (1u << (p1 - x4)) - 1u;
+        sl_handoff_publish(P, w.recId, w.y, w.outBoundary, w.st | ((tBits & below & 7u) << 8));
+        w.published = true;
+    }
+    if (tBits)
+    {
+        /* :496-498 -- the registers keep these values for the following groups */
+        w.a2 = (tBits & 4u) ? w.a2 : w.a3;
+        w.a1 = (tBits & 2u) ? w.a1 : w.a2;
+        w.a0 = (tBits & 1u) ? w.a0 : w.a1;
+        w.st = sl_state_step(w.st, tBits);
+        /* :500-526 -- survivor number s is shaded with register s (new values) and its own x, z */
+        bcJ[0] = w.a0;
+        bcJ[1] = (tBits & 1u) ? w.a1 : w.a0;
+        bcJ[2] = sl_pick4((uint32_t)__popc(tBits & 3u), w.a0, w.a1, w.a2, w.a3);
+        bcJ[3] = sl_pick4((uint32_t)__popc(tBits & 7u), w.a0, w.a1, w.a2, w.a3);
+        if (P.depthMask) /* src/SL_FragmentProcessor.cpp:526-529 */
         {
-            /* the cut lies inside this group: state before the group + outcomes of its lanes left of the cut */
-            const uint32_t below = (1u << (p1 - x4)) - 1u;
-            sl_handoff_publish(P, recId, y, outBoundary, st | ((tBits & below & 7u) << 8));
-            published = true;
-        }
-        if (tBits)
-        {
-            /* :496-498 -- the registers keep these values for the following groups */
-            a2 = tC ? a2 : a3;
-            a1 = tB ? a1 : a2;
-            a0 = tA ? a0 : a1;
-            st = sl_state_step(st, tBits);
-            /* :500-526 -- survivor number s is shaded with register s (new values) and its own x, z.  One call site,
-             * not four: the shading code is the bulk of the kernel and must stay small enough for the instruction cache */
-            const uint32_t mBits = (mA ? 1u : 0u) | (mB ? 2u : 0u) | (mC ? 4u : 0u) | (mD ? 8u : 0u);
-            int sIdx = 0;
-#pragma unroll 1
+#pragma unroll
             for (int j = 0; j < 4; ++j)
             {
-                if (!((tBits >> j) & 1u)) continue;
-                if ((mBits >> j) & 1u)
-                {
-                    const math::vec4 bc = sIdx == 0 ? a0 : (sIdx == 1 ? a1 : (sIdx == 2 ? a2 : a3));
-                    const float z = j == 0 ? zA : (j == 1 ? zB : (j == 2 ? zC : zD));
-                    sl_shade_fragment<FS>(P, T, t, recId, rec, bc, x4 + j, y, z);
-                    ++shaded;
-                }
-                ++sIdx;
+                if ((mBits >> j) & 1u) sl_store_depth(T.depth, P.depthBpt, (size_t)(w.rowBase + x4 + j), zJ[j]);
             }
         }
-        a0 += bcX; /* :539-542 */
-        a1 += bcX;
-        a2 += bcX;
-        a3 += bcX;
     }
-    if (publish && !published) sl_handoff_publish(P, recId, y, outBoundary, st); /* the cut falls on a group boundary */
-    return shaded;
+    return mBits;
+}
+
+SLD_FN void sl_walk_advance(SLWalk& w)
+{
+    w.a0 += w.bcX; /* :539-542 */
+    w.a1 += w.bcX;
+    w.a2 += w.bcX;
+    w.a3 += w.bcX;
+    w.x4 += 4;
 }
 
 /* The same piece walked by the WHOLE warp: lane l takes group g0 + 32c + l of chunk c.  The lane map only ever
  * degrades (14 reachable states, (3,3,3,3) absorbing), so a span sees at most a handful of state changes; between two
  * changes the groups are independent given the state.  Each chunk is therefore resolved by iterating "evaluate all
  * pending groups under the current state; everything up to and including the first group that changes it is final".
- * The hand-over for the next piece is published as soon as the piece's last group is resolved, before any shading. */
+ * The hand-over for the next piece is published as soon as the piece's last group is resolved. */
 template <FsFn FS>
-SLD_FN unsigned sl_walk_piece_warp(const SLRasterParams& P, const SLTile& T, uint32_t recId, int y, int xMin, int xMax, int p0, int p1, uint32_t hand,
-                                   bool publish, int outBoundary)
+SLD_FN unsigned sl_walk_piece_warp(const SLRasterParams& P, const SLTile& T, SLFragQueue& Q, uint32_t recId, int y, int xMin, int xMax, int p0, int p1,
+                                   uint32_t hand, bool publish, int outBoundary)
 {
     const int lane = threadIdx.x & 31;
     const float4* rec = P.records + (size_t)recId * P.recStride;
@@ -1260,10 +1404,10 @@ SLD_FN unsigned sl_walk_piece_warp(const SLRasterParams& P, const SLTile& T, uin
     math::vec4 a2 = (t.bc0 * (float)(xMin + 2)) + bcY;
     math::vec4 a3 = (t.bc0 * (float)(xMin + 3)) + bcY;
     const math::vec4 bcX = t.bc0 * 4.f;
-    const long long rowBase = (long long)P.width * (long long)y - T.origin;
+    const int rowBase = (int)((long long)P.width * (long long)y - T.origin);
     unsigned shaded = 0;
 
-    const int g0 = (p0 - xMin) >> 2;       /* first group with a pixel of the piece */
+    const int g0 = (p0 - xMin) >> 2;        /* first group with a pixel of the piece */
     const int gLast = (p1 - 1 - xMin) >> 2; /* last one                               */
     const int gPub = (p1 - xMin) >> 2;      /* group that contains the cut p1         */
     uint32_t st = (xMin < p0) ? (hand & 0xffu) : SL_STATE_IDENTITY; /* warp-uniform */
@@ -1336,28 +1480,26 @@ SLD_FN unsigned sl_walk_piece_warp(const SLRasterParams& P, const SLTile& T, uin
                 else sl_handoff_publish(P, recId, y, outBoundary, mine);
             }
         }
-        /* shade: survivor number s reads register s after the compaction = the chain of the first passing lane >= s */
+        /* survivors: number s reads register s after the compaction = the chain of the first passing lane >= s */
+        math::vec4 bcJ[4];
+        float zJ[4];
         if (mBits)
         {
-            int s = 0;
-#pragma unroll 1
+#pragma unroll
             for (int j = 0; j < 4; ++j)
             {
-                if (!((tBits >> j) & 1u)) continue;
-                if ((mBits >> j) & 1u)
-                {
-                    const uint32_t ge = tBits & ~((1u << s) - 1u);
-                    const int pLane = __ffs(ge) - 1;
-                    const uint32_t sj = (stIn >> (2 * pLane)) & 3u;
-                    const math::vec4 bc = sj == 0u ? a0 : (sj == 1u ? a1 : (sj == 2u ? a2 : a3));
-                    const uint32_t zj = (stIn >> (2 * j)) & 3u;
-                    const float z = zj == 0u ? zc0 : (zj == 1u ? zc1 : (zj == 2u ? zc2 : zc3));
-                    sl_shade_fragment<FS>(P, T, t, recId, rec, bc, x4 + j, y, z);
-                    ++shaded;
-                }
-                ++s;
+                const uint32_t s = (uint32_t)__popc(tBits & ((1u << j) - 1u));
+                const uint32_t ge = tBits & ~((1u << s) - 1u);
+                const int pLane = __ffs(ge) - 1;
+                bcJ[j] = sl_pick4((stIn >> (2 * (pLane & 3))) & 3u, a0, a1, a2, a3);
+                const uint32_t zj = (stIn >> (2 * j)) & 3u;
+                zJ[j] = zj == 0u ? zc0 : (zj == 1u ? zc1 : (zj == 2u ? zc2 : zc3));
+                if (P.depthMask && ((mBits >> j) & 1u)) sl_store_depth(T.depth, P.depthBpt, (size_t)(rowBase + x4 + j), zJ[j]);
             }
+            shaded += (unsigned)__popc(mBits);
         }
+        sl_push_frags(Q, lane, mBits, bcJ, zJ, x4, y, recId);
+        sl_flush<FS>(P, T, Q, lane, false);
         /* advance every lane by one chunk */
         if (gc + 32 <= gLast)
         {
@@ -1399,10 +1541,11 @@ SLD_FN void sl_copy_warp(unsigned char* dst, const unsigned char* src, unsigned 
 
 /* One warp per (row, x-segment); work is handed out through a ticket in row-major order.  The warp stages the depth
  * and colour texels of its segment into shared memory once, streams the row's ordered entry list, keeps the pieces
- * that fall into its segment (compacted into a 32-deep queue so that the lanes of a batch are busy), and writes the
- * segment back at the end.  Short pieces run one per lane as soon as no earlier, still pending piece of the batch
- * overlaps them in x (fragments of disjoint x-ranges commute; everything else is serialised in submission order);
- * long pieces are walked by the whole warp. */
+ * that fall into its segment (compacted into a 32-deep queue so that the lanes of a batch are busy), resolves them
+ * (phase A) and shades the queued fragments 32 at a time (phase B), and writes the segment back at the end.  Short
+ * pieces run one per lane as soon as no earlier, still pending piece of the batch overlaps them in x (fragments of
+ * disjoint x-ranges commute; everything else is serialised in submission order); long pieces are walked by the whole
+ * warp. */
 template <FsFn FS>
 __global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_raster(const __grid_constant__ SLRasterParams P)
 {
@@ -1423,8 +1566,12 @@ __global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_
     if (begin == end) return;
     unsigned shaded = 0;
 
-    SLSpanEntry* queue = reinterpret_cast<SLSpanEntry*>(sDyn) + warp * 32;
-    unsigned char* tileMem = sDyn + SL_RASTER_WARPS * 32 * sizeof(SLSpanEntry) + (size_t)warp * P.tileBytes;
+    unsigned char* warpMem = sDyn + (size_t)warp * (SL_PIECEQ_BYTES + SL_FQ_BYTES + P.tileBytes);
+    SLSpanEntry* queue = reinterpret_cast<SLSpanEntry*>(warpMem);
+    SLFragQueue Q;
+    Q.bind(warpMem + SL_PIECEQ_BYTES);
+    Q.count = 0;
+    unsigned char* tileMem = warpMem + SL_PIECEQ_BYTES + SL_FQ_BYTES;
     const unsigned segPixels = (unsigned)(sx1 - sx0);
     const long long segOrigin = (long long)W * y + sx0;
     SLTile T;
@@ -1553,17 +1700,48 @@ __global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_
                 const uint32_t bHand = __shfl_sync(0xffffffffu, hand, first);
                 const bool bPub = __shfl_sync(0xffffffffu, publish ? 1 : 0, first) != 0;
                 const int bOut = __shfl_sync(0xffffffffu, bIn + 1, first);
-                shaded += sl_walk_piece_warp<FS>(P, T, bRec, bY, bXMin, bXMax, bP0, bP1, bHand, bPub, bOut);
+                shaded += sl_walk_piece_warp<FS>(P, T, Q, bRec, bY, bXMin, bXMax, bP0, bP1, bHand, bPub, bOut);
                 if (lane == first) done = true;
             }
-            else if (go && !isLong)
+            else
             {
-                shaded += sl_walk_piece<FS>(P, T, recId, ySrc, xMin, xMax, p0, p1, hand, publish, bIn + 1);
-                done = true;
+                const bool mine = go && !isLong;
+                if (__any_sync(0xffffffffu, mine))
+                {
+                    /* every ready short piece is walked by its lane, all lanes in lock step, one group per step */
+                    SLWalk w;
+                    w.x4 = 0;
+                    w.p1 = 0;
+                    w.y = 0;
+                    w.recId = 0u;
+                    if (mine) sl_walk_begin(w, P, T, recId, ySrc, xMin, p0, p1, hand, publish, bIn + 1);
+                    for (;;)
+                    {
+                        const bool act = mine && w.x4 < w.p1;
+                        if (!__any_sync(0xffffffffu, act)) break;
+                        math::vec4 bcJ[4];
+                        float zJ[4];
+                        uint32_t mBits = 0u;
+                        if (act)
+                        {
+                            mBits = sl_walk_group(w, P, T, bcJ, zJ);
+                            shaded += (unsigned)__popc(mBits);
+                        }
+                        sl_push_frags(Q, lane, mBits, bcJ, zJ, w.x4, w.y, w.recId);
+                        if (act) sl_walk_advance(w);
+                        sl_flush<FS>(P, T, Q, lane, false);
+                    }
+                    if (mine)
+                    {
+                        if (w.publish && !w.published) sl_handoff_publish(P, recId, ySrc, bIn + 1, w.st); /* the cut falls on a group boundary */
+                        done = true;
+                    }
+                }
             }
             __syncwarp();
         }
     }
+    sl_flush<FS>(P, T, Q, lane, true);
     const bool dirty = __any_sync(0xffffffffu, shaded != 0u);
     if (staged && dirty)
     {

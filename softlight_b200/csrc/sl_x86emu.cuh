@@ -5,7 +5,7 @@
  *   rcpss/rcpps  -> sl_rcp():   2048-entry table indexed by the top 11 mantissa
  *                   bits, exponent handled exactly; the table is measured from
  *                   the host CPU at context creation (or pinned by a test).
- *   minps/maxps  -> sl_min()/sl_max(): (a<b)?a:b, second operand on NaN/equal.
+ *   minps/maxps  -> sl_min()/sl_max(): (a<b)?a:b, second operand on NaN/equal (FSETP + FSEL, never FMNMX/.SAT).
  *   cvtps2dq     -> sl_cvt_rn(): RNE, 0x80000000 when out of range / NaN.
  *   cvttps2dq    -> sl_cvt_tr().
  *   fmadd/fmsub  -> __fmaf_rn (the TU is compiled with -fmad=false so that
@@ -40,8 +40,22 @@ __device__ __forceinline__ float sl_rcp(float x)
 }
 
 __device__ __forceinline__ float sl_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
-__device__ __forceinline__ float sl_min(float a, float b) { return (a < b) ? a : b; }
-__device__ __forceinline__ float sl_max(float a, float b) { return (a > b) ? a : b; }
+/* minss/maxss: (a < b) ? a : b -- the SECOND operand when either is NaN or both are equal.  Written with the compare
+ * result materialised as an integer: for the plain C form (and for setp/selp pairs) ptxas folds max(min(x, 1), 0) into
+ * a .SAT modifier, which turns NaN into 0 where the x86 sequence gives 1 (seen on config C5: clamp() of the lighting
+ * term of a zero-length normal).  This form compiles to FSETP + FSEL and is never folded. */
+__device__ __forceinline__ float sl_min(float a, float b)
+{
+    unsigned c;
+    asm("{.reg .pred p; setp.lt.f32 p, %1, %2; selp.u32 %0, 1, 0, p;}" : "=r"(c) : "f"(a), "f"(b));
+    return c ? a : b;
+}
+__device__ __forceinline__ float sl_max(float a, float b)
+{
+    unsigned c;
+    asm("{.reg .pred p; setp.gt.f32 p, %1, %2; selp.u32 %0, 1, 0, p;}" : "=r"(c) : "f"(a), "f"(b));
+    return c ? a : b;
+}
 __device__ __forceinline__ bool sl_signbit(float x) { return (__float_as_uint(x) >> 31) != 0u; }
 
 __device__ __forceinline__ int32_t sl_cvt_rn(float x)

@@ -31,6 +31,8 @@ using namespace sld;
  * =========================================================================*/
 typedef cudaError_t (*VertexLauncher)(unsigned grid, cudaStream_t s, const SLVertexParams& p, bool cache);
 static const unsigned kVertexCacheMaxBytes = 5u * SL_VCACHE_VERTS * (unsigned)sizeof(float4); /* position + 4 varyings */
+static const unsigned kRasterTileMaxBytes = 10u * 1024u; /* per warp; fatter segments work in place */
+static const unsigned kRasterMaxSmemBytes = SL_RASTER_WARPS * (SL_PIECEQ_BYTES + SL_FQ_BYTES + kRasterTileMaxBytes);
 typedef cudaError_t (*RasterLauncher)(unsigned grid, unsigned block, unsigned smemBytes, cudaStream_t s, const SLRasterParams& p);
 
 struct VsEntry { const char* name; VertexLauncher launch; };
@@ -57,6 +59,13 @@ template <VsFn VS> static cudaError_t launch_vertex(unsigned grid, cudaStream_t 
 }
 template <FsFn FS> static cudaError_t launch_raster(unsigned grid, unsigned block, unsigned smemBytes, cudaStream_t s, const SLRasterParams& p)
 {
+    static bool attrSet = false; /* one opt-in per instantiation: fragment queues + tiles may exceed the 48 KB default */
+    if (!attrSet)
+    {
+        cudaError_t e = cudaFuncSetAttribute(k_raster<FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRasterMaxSmemBytes);
+        if (e != cudaSuccess) return e;
+        attrSet = true;
+    }
     k_raster<FS><<<grid, block, smemBytes, s>>>(p);
     return cudaGetLastError();
 }
@@ -646,10 +655,10 @@ static int flush_draws_impl(slcu_context* c)
     const unsigned warpsPerBlock = SL_RASTER_WARPS;
     const unsigned long long numWarps = (unsigned long long)H * rasterSegs;
     /* each warp keeps its segment's depth + colour texels in shared memory; segments too fat for that work in place */
-    const unsigned queueBytes = warpsPerBlock * 32u * (unsigned)sizeof(SLSpanEntry);
-    if (tileBytes > 10u * 1024u) tileBytes = 0;
+    if (tileBytes > kRasterTileMaxBytes) tileBytes = 0;
     rp.tileBytes = tileBytes;
-    { KernelScope ks(c, SLCU_K_RASTER); CK(sh.fs((unsigned)((numWarps + warpsPerBlock - 1) / warpsPerBlock), warpsPerBlock * 32, queueBytes + warpsPerBlock * tileBytes, c->stream, rp)); }
+    const unsigned smemBytes = warpsPerBlock * (SL_PIECEQ_BYTES + SL_FQ_BYTES + tileBytes); /* piece queue + fragment queue + tile, per warp */
+    { KernelScope ks(c, SLCU_K_RASTER); CK(sh.fs((unsigned)((numWarps + warpsPerBlock - 1) / warpsPerBlock), warpsPerBlock * 32, smemBytes, c->stream, rp)); }
     return 0;
 }
 

@@ -617,7 +617,7 @@ def _unit_cube() -> np.ndarray:
     return np.array(out, dtype=np.float32)
 
 
-def volume_scene(width=7680, height=4320, vol_size=256, depth_type=A.SL_COLOR_R_HALF, name=None) -> Scene:
+def volume_scene(width=7680, height=4320, vol_size=256, depth_type=A.SL_COLOR_R_HALF, name=None, blend=A.SL_BLEND_PREMULTIPLED_ALPHA, fs="volume") -> Scene:
     verts = _unit_cube()
     vol = synthetic_volume(vol_size)
     # transfer functions of the demo (sl_volume_rendering_test.cpp:405-520): 16-wide bands; the last entry of each band stays 0
@@ -649,8 +649,8 @@ def volume_scene(width=7680, height=4320, vol_size=256, depth_type=A.SL_COLOR_R_
         ctx.ubo_bind_texture(ubo, 0, tv)
         ctx.ubo_bind_texture(ubo, 8, to)
         ctx.ubo_bind_texture(ubo, 16, tc)
-        sh = ctx.create_shader("volume", "volume", ubo, vs_varyings=2, fs_varyings=2, cull=A.SL_CULL_BACK_FACE,
-                               blend=A.SL_BLEND_PREMULTIPLED_ALPHA, depth_test=A.SL_DEPTH_TEST_OFF, depth_mask=A.SL_DEPTH_MASK_OFF)
+        sh = ctx.create_shader("volume", fs, ubo, vs_varyings=2, fs_varyings=2, cull=A.SL_CULL_BACK_FACE,
+                               blend=blend, depth_test=A.SL_DEPTH_TEST_OFF, depth_mask=A.SL_DEPTH_MASK_OFF)
         assert sh != A.INVALID_ID
         return dict(color=color, depth=depth, fbo=fbo, shader=sh, mesh=ctx.mesh(vao, 0, 36, A.RENDER_MODE_TRIANGLES), ubo=ubo)
 
@@ -675,6 +675,10 @@ SCENES: Dict[str, Callable[[], Scene]] = {
     "c4_small": lambda: skinned_scene(480, 270, (3, 2), 64, 24, 64, name="skinned6x3072_480x270"),
     "c5_volume8k": volume_scene,
     "c5_volume4k": lambda: volume_scene(3840, 2160, 256, name="volume256_3840x2160"),
+    "c5_volume4k_noblend": lambda: volume_scene(3840, 2160, 256, name="volume256_3840x2160_noblend", blend=A.SL_BLEND_OFF),
+    "c5_dbg0": lambda: volume_scene(3840, 2160, 256, name="volume_dbg0", blend=A.SL_BLEND_OFF, fs="volume_dbg0"),
+    "c5_dbg1": lambda: volume_scene(3840, 2160, 256, name="volume_dbg1", blend=A.SL_BLEND_OFF, fs="volume_dbg1"),
+    "c5_dbg2": lambda: volume_scene(3840, 2160, 256, name="volume_dbg2", blend=A.SL_BLEND_OFF, fs="volume_dbg2"),
     "c5_small": lambda: volume_scene(160, 90, 32, name="volume32_160x90"),
     "c1_sphere100k_4k": lambda: sphere_scene(3840, 2160, 224, 224, name="sphere100k_3840x2160"),
     "c1_sphere1m_4k": lambda: sphere_scene(3840, 2160, 708, 708, name="sphere1m_3840x2160"),

@@ -29,13 +29,17 @@ def main():
         others = ["port"] + (["ref_strict"] if os.path.exists(A.LIB_PATHS["ref_strict"]) else [])
         for o in others:
             co, do, so, to, _ = run(o, sc, rcp)
-            dc = np.abs(cg.astype(np.int64) - co.astype(np.int64))
+            if cg.dtype.kind == "f":
+                dc = (bits(cg) != bits(co)).astype(np.int64)
+            else:
+                dc = np.abs(cg.astype(np.int64) - co.astype(np.int64))
             ncol = int((dc.max(axis=-1) > 0).sum()); ndep = int((bits(dg) != bits(do)).sum())
             print(f"{n}: cuda vs {o}: colour px diff={ncol} (max {int(dc.max())}) depth diff={ndep} | frags {sg['fragsShaded']/3:.0f} vs {so['fragsShaded']} | spans {sg['spans']/3:.0f} vs {so['spans']} | binned {sg['trisBinned']/3:.0f} vs {so['trisBinned']} | t {tg*1e3:.2f} ms vs {to*1e3:.1f} ms", flush=True)
             if ncol or ndep:
                 ok = False
                 ys, xs = np.nonzero(dc.max(axis=-1) > 0)
-                for y, x in list(zip(ys, xs))[:5]:
+                print("   colour diff bbox x", xs.min(), xs.max(), "y", ys.min(), ys.max())
+                for y, x in list(zip(ys, xs))[:12]:
                     print("   colour", x, y, cg[y, x], co[y, x])
                 ys, xs = np.nonzero(bits(dg) != bits(do))
                 for y, x in list(zip(ys, xs))[:5]:

@@ -1,0 +1,14 @@
+# round-1 (e): two-phase rasteriser (resolve -> fragment queue -> converged shading): parity + bench; C5 numerics bisection
+mkdir -p gpurun_out
+(time timeout 1500 python -m pytest tests -m gpu -q) > gpurun_out/pytest_gpu.log 2>&1
+tail -8 gpurun_out/pytest_gpu.log
+for c in c2_instancing10k c3_indoor2m c1_sphere100k c4_skinned100 c5_volume4k; do
+  timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --config $c > gpurun_out/bench_$c.json 2> gpurun_out/bench_$c.err
+  python -c "
+import json,sys
+d=json.load(open('gpurun_out/bench_$c.json'))
+print('$c', round(d['ms_per_step'],3),'ms', round(d['gfrags_per_s'],3),'Gfrag/s', {k:round(v,3) for k,v in d['roofline']['kernel_ms_per_frame'].items()})
+" || tail -3 gpurun_out/bench_$c.err
+done
+timeout 900 python tools/gpu_compare.py c5_dbg0 c5_dbg1 c5_dbg2 > gpurun_out/cmp_c5dbg.log 2>&1
+grep -v "^   colour" gpurun_out/cmp_c5dbg.log | cut -c1-200
