@@ -107,7 +107,9 @@ def measured_peaks():
 
 
 def algorithmic_bytes(scene_name: str, scene: S.Scene, frags: int) -> dict:
-    """bytes the frame must move, per kernel class."""
+    """bytes the frame must move, per kernel class.  The fragment stage is two
+    kernels: "raster" = k_resolve (depth traffic), "shade" = k_shade (colour + texture traffic); the fragment lists that
+    travel between them are this design's own intermediate and are NOT counted as algorithmic bytes."""
     cbpt = A.bytes_per_texel(scene.color_type)
     dbpt = A.bytes_per_texel(scene.depth_type)
     px = scene.width * scene.height
@@ -116,33 +118,39 @@ def algorithmic_bytes(scene_name: str, scene: S.Scene, frags: int) -> dict:
         # one 16x32 sphere reused by every instance: u16 indices, 32 B vertices, one mat4 per instance
         out["vertex"] = 3072 * 2 + 561 * 32 + (scene.tris_per_frame // 1024) * 64
         # per shaded fragment: depth read+write, RGBA8 read+write (blend), 4 bilinear taps of RGB8 (reuse = 0: upper figure)
-        out["raster"] = frags * (2 * dbpt + 2 * cbpt + 4 * 3)
+        out["raster"] = frags * (2 * dbpt)
+        out["shade"] = frags * (2 * cbpt + 4 * 3)
     elif scene_name.startswith("c3"):
         # per draw: u32 indices + the room's 24-byte vertices + the 1 KiB uniform block; per shaded fragment: depth read +
         # write, RGBA8 write, 4 bilinear taps of RGBA8 (reuse = 0: upper figure)
         tris_per_draw = scene.tris_per_frame // scene.draws_per_frame
         out["vertex"] = scene.draws_per_frame * (tris_per_draw * 3 * 4 + (tris_per_draw // 2 + 2 * 6 * 27) * 24 + 1024)
-        out["raster"] = frags * (2 * dbpt + cbpt + 4 * 4)
+        out["raster"] = frags * (2 * dbpt)
+        out["shade"] = frags * (cbpt + 4 * 4)
     elif scene_name.startswith("c1"):
         # u32 indices + every vertex once (32 B) ; per shaded fragment: depth read + write, RGBA8 write
         nverts = (int(round((scene.tris_per_frame / 2) ** 0.5)) + 1) ** 2
         out["vertex"] = scene.tris_per_frame * 3 * 4 + nverts * 32
-        out["raster"] = frags * (2 * dbpt + cbpt)
+        out["raster"] = frags * (2 * dbpt)
+        out["shade"] = frags * cbpt
     elif scene_name.startswith("c4"):
         # per draw: u32 indices + the character's 36-byte vertices + 64 bone matrices + the uniform block; per shaded fragment:
         # depth read + write, RGBA8 read + write (SL_BLEND_ALPHA), 4 bilinear taps of RGBA8 (reuse = 0: upper figure)
         tris_per_draw = scene.tris_per_frame // scene.draws_per_frame
         out["vertex"] = scene.draws_per_frame * (tris_per_draw * 3 * 4 + (tris_per_draw // 2 + 160) * 36 + 64 * 64 + 1024)
-        out["raster"] = frags * (2 * dbpt + 2 * cbpt + 4 * 4)
+        out["raster"] = frags * (2 * dbpt)
+        out["shade"] = frags * (2 * cbpt + 4 * 4)
     elif scene_name.startswith("c5"):
         # 36 non-indexed 12-byte vertices; per fragment that reaches the blend: RGBA_FLOAT read + write (premultiplied alpha), no
         # depth traffic (test and mask off).  The ray march's volume taps (<= 32 nearest + 256 x 8 + 3 x 8 per lit step, R8) hit
         # a 16.8 MB L2-resident volume: the shader is issue-bound, the HBM figure is the framebuffer traffic only
         out["vertex"] = 36 * 12 + 1024
-        out["raster"] = frags * (2 * cbpt)
+        out["raster"] = 0
+        out["shade"] = frags * (2 * cbpt)
     else:
         out["vertex"] = 0
-        out["raster"] = frags * (2 * dbpt + cbpt)
+        out["raster"] = frags * (2 * dbpt)
+        out["shade"] = frags * cbpt
     out["frame"] = sum(out.values())
     return out
 
@@ -299,7 +307,7 @@ def run_cuda(args, rank, world, local_rank, dist):
     kernel_ms_per_frame = {k: v["ms"] / prof_frames for k, v in classes.items()}
     frame_kernel_ms = sum(kernel_ms_per_frame.values())
     roofline = {
-        "bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "bound": "hbm", "kernel": {"raster": "k_resolve", "shade": "k_shade"}.get(dom, "k_" + dom), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
         "kernel_ms_per_launch": dom_ms, "kernel_share_of_frame": kernel_ms_per_frame[dom] / frame_kernel_ms,
         "frame_algorithmic_bytes": alg["frame"], "frame_achieved_gbs": alg["frame"] / (ms * 1e-3) / 1e9,

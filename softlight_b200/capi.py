@@ -87,11 +87,11 @@ class Stats(C.Structure):
                 ("fragsShaded", C.c_uint64), ("kernelLaunches", C.c_uint64), ("drawCalls", C.c_uint64), ("batches", C.c_uint64)]
 
 
-KERNEL_CLASSES = ["clear", "vertex", "span_count", "scan", "span_fill", "raster", "blit", "composite"]
+KERNEL_CLASSES = ["clear", "vertex", "span_count", "scan", "span_fill", "raster", "blit", "composite", "shade"]
 
 
 class KernelTimes(C.Structure):
-    _fields_ = [("ms", C.c_double * 8), ("launches", C.c_uint64 * 8)]
+    _fields_ = [("ms", C.c_double * len(KERNEL_CLASSES)), ("launches", C.c_uint64 * len(KERNEL_CLASSES))]
 
 
 # name -> (restype, argtypes) ; ctx pointer is c_void_p

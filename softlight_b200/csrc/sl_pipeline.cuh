@@ -13,12 +13,15 @@
  *                     full-width row is the only tile shape for which the
  *                     reference's left-to-right compaction state machine
  *                     (SURVEY.md section 0 finding 6) stays tile-local.
- *   k_raster<FS>      SL_TriRasterizer::render_triangle_simd +
- *                     SL_FragmentProcessor::flush_tri_fragments + assign_pixel /
- *                     assign_alpha_pixel (src/SL_TriRasterizer.cpp:413-559,
- *                     src/SL_FragmentProcessor.cpp:416-531, src/SL_Framebuffer.cpp:
- *                     44-368): one warp per row walks the row's spans in order;
- *                     lanes take spans whose x-ranges do not overlap.
+ *   k_resolve         SL_TriRasterizer::render_triangle_simd (src/SL_TriRasterizer.cpp:
+ *                     413-559) + the depth write of flush_tri_fragments: one warp
+ *                     per (row, x-segment) walks the row's spans in order, lanes
+ *                     take spans whose x-ranges do not overlap; output = ordered
+ *                     fragment lists in HBM.
+ *   k_shade<FS>       SL_FragmentProcessor::flush_tri_fragments + assign_pixel /
+ *                     assign_alpha_pixel (src/SL_FragmentProcessor.cpp:416-531,
+ *                     src/SL_Framebuffer.cpp:44-368): one warp per fragment list,
+ *                     32 fragments per step, converged shader calls.
  *
  * Data layout in HBM:
  *   record r      : float4[3 + 3*NV]  = p0,p1,p2 (x,y,z,1/w) then varyings [slot][vert].  (A plane-major layout was
@@ -53,12 +56,15 @@ struct SLCounters
 {
     unsigned long long recAlloc;     /* triangle records allocated (reset per batch)      */
     unsigned long long handoffs;     /* span cuts (segment boundaries + row ends) that need a state hand-over (reset per batch) */
+    unsigned long long pixelsCovered; /* sum of span lengths = upper bound of the batch's fragments (reset per batch) */
     unsigned long long trisBinned;
     unsigned long long spans;
     unsigned long long fragsShaded;
     unsigned int errorFlags;         /* bit0 record overflow, bit1 span x out of range, bit2 span starts left of x=0,
                                         bit3 overflow of a triangle that was classified as "cannot overflow" */
-    unsigned int rasterTicket;       /* row ticket of k_raster (reset by k_scan_row_starts)                   */
+    unsigned int rasterTicket;       /* (row, segment) ticket of k_resolve (reset by k_scan_row_starts)       */
+    unsigned int chunkAlloc;         /* fragment chunks handed out by k_resolve (reset by k_scan_row_starts)  */
+    unsigned int pad_;
 };
 
 /* A span whose xMax exceeds the framebuffer width keeps going in linear memory:
@@ -635,6 +641,7 @@ __global__ void __launch_bounds__(256) k_span(const __grid_constant__ SLSpanPara
             int y0 = 0x7fffffff, y1 = -1, yEnd = -1;
             bool mayOver = false;
             unsigned myCuts = 0;
+            unsigned long long myPix = 0;
             if (valid)
             {
                 const float4* r = P.records + (size_t)rec * P.recStride;
@@ -674,6 +681,7 @@ __global__ void __launch_bounds__(256) k_span(const __grid_constant__ SLSpanPara
                             if ((c & 2) && !mayOver) atomicOr(&P.counters->errorFlags, 8u);
                             if (MODE == 0 && c)
                             {
+                                myPix += (unsigned long long)(xMax - xMin);
                                 if (P.chained) myCuts += sl_count_cuts(P, xMin, xMax, y + 1 < H);
                                 if (c == 3 && y + 1 < H)
                                 {
@@ -717,6 +725,8 @@ __global__ void __launch_bounds__(256) k_span(const __grid_constant__ SLSpanPara
             {
                 for (int d = 16; d > 0; d >>= 1) myCuts += __shfl_down_sync(0xffffffffu, myCuts, d);
                 if ((tid & 31) == 0 && myCuts) atomicAdd(&P.counters->handoffs, (unsigned long long)myCuts);
+                for (int d = 16; d > 0; d >>= 1) myPix += __shfl_down_sync(0xffffffffu, myPix, d);
+                if ((tid & 31) == 0 && myPix) atomicAdd(&P.counters->pixelsCovered, myPix);
             }
         }
     }
@@ -801,6 +811,7 @@ __global__ void __launch_bounds__(1024) k_scan_row_starts(const uint32_t* rowTot
         rowStart[numRows] = sPart[1023];
         atomicAdd(&counters->spans, (unsigned long long)sPart[1023]);
         counters->rasterTicket = 0u;
+        counters->chunkAlloc = 0u;
     }
 }
 
@@ -823,33 +834,58 @@ __global__ void k_scan_offsets(const uint16_t* cnt, const uint32_t* segSums, uin
 /* ------------------------------------------------------------------------
  * Fragment stage
  * ----------------------------------------------------------------------*/
+/* Fragment lists (k_resolve -> k_shade).  One list per (row, x-segment) = per resolving warp, in submission order per
+ * pixel; a list is a chain of chunks of 32 fragments, structure of arrays inside the chunk so that both sides move
+ * whole 128/512-byte lines:  chunk c = [float4 bc[32]] [float z[32]] [u32 x|y<<16 [32]] [u32 record[32]]. */
+constexpr unsigned SL_CHUNK_FRAGS = 32u;
+constexpr unsigned SL_CHUNK_BYTES = SL_CHUNK_FRAGS * (16u + 4u + 4u + 4u);
+constexpr uint32_t SL_NO_CHUNK = 0xffffffffu;
+
+struct SLFragLists
+{
+    unsigned char* pool;      /* chunkCapacity * SL_CHUNK_BYTES                          */
+    uint32_t* chunkNext;      /* [chunkCapacity]                                         */
+    uint32_t* listHead;       /* [numRows * numSegs] first chunk of the list             */
+    uint32_t* listCount;      /* [numRows * numSegs] fragments in the list (zeroed per batch) */
+    unsigned int chunkCapacity;
+};
+
 struct SLRasterParams
 {
-    const SLDrawDesc* draws;     /* draw table of the batch: the fragment shader's uniforms are draws[recDraw[record]].uniforms */
-    const uint16_t* recDraw;
     const float4* records;
     const SLSpanEntry* entries;
     const uint32_t* rowStart;
     int recStride;
-    int numVaryings;
-    int numOutputs;
     int depthTest;   /* SL_DepthTest */
     int depthMask;
-    int blend;       /* SL_BlendMode */
     unsigned int numRows;     /* rows incl. the texture's padding rows */
     unsigned int width;       /* depth attachment width (row stride of every attachment, like the reference) */
     unsigned long long* handoff; /* hash table of hand-overs (null when the batch has none) */
     unsigned int handoffMask;
     unsigned int segWidth;       /* x-segment width */
     unsigned int numSegs;        /* segments per row (<= 32) */
-    unsigned int tileBytes;      /* shared memory per warp for its segment's depth + colour texels (0: work in global memory) */
+    unsigned int tileBytes;      /* shared memory per warp for its segment's depth texels (0: work in global memory) */
     const uint8_t* rowNeeded;    /* sort-first partition: rows this rank rasterises (null = all) */
     unsigned char* depth;
     int depthBpt;
+    SLFragLists lists;
+    SLCounters* counters;
+};
+
+struct SLShadeParams
+{
+    const SLDrawDesc* draws;     /* draw table of the batch: the fragment shader's uniforms are draws[recDraw[record]].uniforms */
+    const uint16_t* recDraw;
+    const float4* records;
+    int recStride;
+    int numVaryings;
+    int numOutputs;
+    int blend;                /* SL_BlendMode */
+    unsigned int width;
+    unsigned int numLists;
     unsigned char* color[4];
     int colorType[4];         /* SL_ColorDataType */
-    int colorBpt[4];          /* bytes per texel */
-    SLCounters* counters;
+    SLFragLists lists;
 };
 
 /* depth texel read (src/SL_TriRasterizer.cpp:40-102) */
@@ -1034,33 +1070,32 @@ SLD_FN void sl_tri_setup(SLTriSetup& t, const float4 p0, const float4 p1, const 
     t.w0 = p0.w; t.w1 = p1.w; t.w2 = p2.w;
 }
 
-/* Where a warp's pixels live while it works on them: the depth and colour texels of its (row, x-segment) staged into
- * shared memory (origin = linear index x + width*y of the segment's first pixel), or the attachments themselves
+/* Where a resolving warp's depth texels live while it works on them: the depth texels of its (row, x-segment) staged
+ * into shared memory (origin = linear index x + width*y of the segment's first pixel), or the attachment itself
  * (origin 0) when a segment does not fit the shared-memory budget. */
 struct SLTile
 {
     unsigned char* depth;
-    unsigned char* color[4];
     long long origin;
 };
 
 /* ------------------------------------------------------------------------
- * The rasteriser works in two phases inside one warp.
+ * The fragment stage is two kernels.
  *
- *   Phase A ("resolve"): the span walkers below run the 4-pixel group loop of render_triangle_simd
+ *   k_resolve (one for every shader): the span walkers below run the 4-pixel group loop of render_triangle_simd
  *   (src/SL_TriRasterizer.cpp:471-548): depth of the four lanes, depth test against the tile, the in-place compaction
  *   of the barycentric registers (:496-498), the depth write (src/SL_FragmentProcessor.cpp:526-529 -- the value is the
- *   rasteriser's z and does not depend on the shader).  Every surviving fragment is pushed to the warp's fragment
- *   queue in shared memory: {barycentrics the reference would hand to the shader, z, x, y, record}.
+ *   rasteriser's z and does not depend on the shader).  Every surviving fragment goes to the warp's fragment queue in
+ *   shared memory and from there, 32 at a time, to the (row, segment)'s fragment list in HBM: {barycentrics the
+ *   reference would hand to the shader, z, x, y, record}.  All ordering constraints of the path (submission order per
+ *   pixel, the left-to-right compaction state of a span, hand-overs between segments and rows) are settled here, by a
+ *   kernel that is small, needs few registers and never waits for shading.
  *
- *   Phase B ("shade"): whenever 32 fragments are queued the whole warp shades them, one fragment per lane
- *   (flush_tri_fragments, src/SL_FragmentProcessor.cpp:416-531): perspective correction, varyings, the fragment
- *   shader, colour write / blend.  The queue is first-in first-out and fragments of one pixel are pushed in submission
- *   order, so colour writes to a pixel happen in submission order; fragments of one batch that hit the same pixel are
- *   ordered by lane.
- *
- * The fragment shader is instantiated once per kernel (sl_shade_batch is not inlined) and always runs with converged
- * lanes; the walkers never contain shading code.
+ *   k_shade<FS>: one warp per fragment list, 32 fragments per step, one per lane (flush_tri_fragments,
+ *   src/SL_FragmentProcessor.cpp:416-531): perspective correction, varyings, the fragment shader, colour write /
+ *   blend.  Lists are in submission order per pixel and a list is walked front to back, so colour writes to a pixel
+ *   happen in submission order; fragments of one step that hit the same pixel are ordered by lane.  Lists never share
+ *   a pixel, so list order is free.  The shader always runs with converged lanes.
  * ----------------------------------------------------------------------*/
 constexpr int SL_FQ_CAP = 160;                               /* < 32 left over + at most 4 x 32 pushed per step */
 constexpr unsigned SL_FQ_BYTES = SL_FQ_CAP * (16u + 4u + 4u + 4u);
@@ -1073,6 +1108,8 @@ struct SLFragQueue
     uint32_t* xy;  /* x | y << 16: coordinates relative to the span's source row (x >= width for fragments that wrapped) */
     uint32_t* rec;
     int count;     /* warp-uniform */
+    /* the list this warp appends to */
+    uint32_t list, tail, total;
 
     SLD_FN void bind(unsigned char* mem)
     {
@@ -1082,77 +1119,6 @@ struct SLFragQueue
         rec = reinterpret_cast<uint32_t*>(mem + SL_FQ_CAP * 24u);
     }
 };
-
-/* Phase B for fragments [first, first + n) of the queue, n <= 32 */
-template <FsFn FS>
-__device__ __noinline__ void sl_shade_batch(const SLRasterParams& P, const SLTile& T, unsigned char* queueMem, int first, int n)
-{
-    const int lane = threadIdx.x & 31;
-    SLFragQueue Q;
-    Q.bind(queueMem);
-    SL_FragmentParam fp;
-    bool haveOutputs = false;
-    uint32_t key = 0xffffff00u + (uint32_t)lane; /* idle lanes: a key no pixel has */
-    if (lane < n)
-    {
-        const int e = first + lane;
-        const float4 b4 = Q.bc[e];
-        const float z = Q.z[e];
-        const uint32_t xy = Q.xy[e];
-        const uint32_t recId = Q.rec[e];
-        const int x = (int)(xy & 0xffffu), y = (int)(xy >> 16);
-        const float4* rec = P.records + (size_t)recId * P.recStride;
-        /* :438-460 perspective correction */
-        math::vec4 bc = math::vec4{b4.x, b4.y, b4.z, b4.w} * math::vec4{rec[0].w, rec[1].w, rec[2].w, 0.f};
-        const float persp = sl_rcp((bc.v[0] + bc.v[1]) + (bc.v[2] + bc.v[3]));
-        bc = bc * persp;
-
-        fp.pUniforms = &P.draws[P.recDraw[recId]].uniforms;
-        /* interpolate_tri_varyings, AVX2 branch (:163-193).  The reference interpolates all four slots; slots past
-         * numVaryings hold stale bin data there and are never read by a well-formed shader. */
-        for (int s = 0; s < P.numVaryings; ++s)
-        {
-            const float4 a = rec[3 + 3 * s + 0], b = rec[3 + 3 * s + 1], c = rec[3 + 3 * s + 2];
-            fp.pVaryings[s] = math::vec4{
-                sl_fma(bc.v[2], c.x, sl_fma(bc.v[1], b.x, bc.v[0] * a.x)), sl_fma(bc.v[2], c.y, sl_fma(bc.v[1], b.y, bc.v[0] * a.y)),
-                sl_fma(bc.v[2], c.z, sl_fma(bc.v[1], b.z, bc.v[0] * a.z)), sl_fma(bc.v[2], c.w, sl_fma(bc.v[1], b.w, bc.v[0] * a.w))};
-        }
-        fp.coord.x = (uint16_t)x;
-        fp.coord.y = (uint16_t)y;
-        fp.coord.depth = z;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) fp.pOutputs[i] = math::vec4{0.f};
-
-        haveOutputs = FS(fp); /* :501 */
-        /* every attachment is addressed as x + width*y with the depth attachment's width (the reference uses each
-         * colour view's own width; SL_Framebuffer::valid requires them to be equal, and run_draw refuses anything else) */
-        key = (uint32_t)((long long)x + (long long)P.width * (long long)y - T.origin);
-    }
-    /* :507-523, in submission order per pixel */
-    const uint32_t peers = __match_any_sync(0xffffffffu, key);
-    if (P.blend == 0)
-    {
-        /* plain stores: the last fragment of a pixel that has outputs wins */
-        const uint32_t hv = __ballot_sync(0xffffffffu, haveOutputs) & peers;
-        if (haveOutputs && (hv >> lane) == 1u)
-        {
-            for (int i = P.numOutputs - 1; i >= 0; --i) sl_store_color(T.color[i], P.colorType[i], (size_t)key, fp.pOutputs[i]);
-        }
-    }
-    else
-    {
-        const int rank = __popc(peers & ((1u << lane) - 1u));
-        const int maxRank = (int)__reduce_max_sync(0xffffffffu, (unsigned)rank);
-        for (int r = 0; r <= maxRank; ++r)
-        {
-            if (rank == r && haveOutputs)
-            {
-                for (int i = P.numOutputs - 1; i >= 0; --i) sl_blend_color(T.color[i], P.colorType[i], (size_t)key, fp.pOutputs[i], P.blend);
-            }
-            __syncwarp();
-        }
-    }
-}
 
 /* push the survivors of one 4-pixel group per lane (warp-collective; mBits == 0 for idle lanes) */
 SLD_FN void sl_push_frags(SLFragQueue& Q, int lane, uint32_t mBits, const math::vec4 (&bcJ)[4], const float (&zJ)[4], int x4, int y, uint32_t recId)
@@ -1176,26 +1142,41 @@ SLD_FN void sl_push_frags(SLFragQueue& Q, int lane, uint32_t mBits, const math::
     }
 }
 
-/* shade every full batch of the queue (and the rest too when `all`); what is left moves to the front */
-template <FsFn FS>
-SLD_FN void sl_flush(const SLRasterParams& P, const SLTile& T, SLFragQueue& Q, int lane, bool all)
+/* append every full batch of the queue (and the rest too when `all`) to the warp's fragment list; what is left moves
+ * to the front */
+SLD_FN void sl_flush(const SLRasterParams& P, SLFragQueue& Q, int lane, bool all)
 {
     if (Q.count < 32 && !(all && Q.count > 0)) return;
-    const SLTile Tc = T; /* the callee gets a copy: T itself stays in registers */
-    unsigned char* mem = reinterpret_cast<unsigned char*>(Q.bc);
     __syncwarp();
     int first = 0;
-    while (Q.count - first >= 32)
+    while (Q.count - first >= 32 || (all && Q.count - first > 0))
     {
-        sl_shade_batch<FS>(P, Tc, mem, first, 32);
-        first += 32;
+        const int n = min(32, Q.count - first);
+        uint32_t chunk = 0u;
+        if (lane == 0)
+        {
+            chunk = atomicAdd(&P.counters->chunkAlloc, 1u);
+            if (chunk >= P.lists.chunkCapacity) { atomicOr(&P.counters->errorFlags, 32u); chunk = SL_NO_CHUNK; }
+            else if (Q.tail == SL_NO_CHUNK) P.lists.listHead[Q.list] = chunk;
+            else P.lists.chunkNext[Q.tail] = chunk;
+        }
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        if (chunk != SL_NO_CHUNK)
+        {
+            unsigned char* c = P.lists.pool + (size_t)chunk * SL_CHUNK_BYTES;
+            if (lane < n)
+            {
+                reinterpret_cast<float4*>(c)[lane] = Q.bc[first + lane];
+                reinterpret_cast<float*>(c + 512)[lane] = Q.z[first + lane];
+                reinterpret_cast<uint32_t*>(c + 640)[lane] = Q.xy[first + lane];
+                reinterpret_cast<uint32_t*>(c + 768)[lane] = Q.rec[first + lane];
+            }
+            Q.tail = chunk;
+            Q.total += (uint32_t)n;
+        }
+        first += n;
     }
-    int r = Q.count - first;
-    if (all && r > 0)
-    {
-        sl_shade_batch<FS>(P, Tc, mem, first, r);
-        r = 0;
-    }
+    const int r = Q.count - first;
     if (r > 0) /* first >= 32 > r: source and destination do not overlap */
     {
         if (lane < r)
@@ -1388,7 +1369,6 @@ SLD_FN void sl_walk_advance(SLWalk& w)
  * changes the groups are independent given the state.  Each chunk is therefore resolved by iterating "evaluate all
  * pending groups under the current state; everything up to and including the first group that changes it is final".
  * The hand-over for the next piece is published as soon as the piece's last group is resolved. */
-template <FsFn FS>
 SLD_FN unsigned sl_walk_piece_warp(const SLRasterParams& P, const SLTile& T, SLFragQueue& Q, uint32_t recId, int y, int xMin, int xMax, int p0, int p1,
                                    uint32_t hand, bool publish, int outBoundary)
 {
@@ -1499,7 +1479,7 @@ SLD_FN unsigned sl_walk_piece_warp(const SLRasterParams& P, const SLTile& T, SLF
             shaded += (unsigned)__popc(mBits);
         }
         sl_push_frags(Q, lane, mBits, bcJ, zJ, x4, y, recId);
-        sl_flush<FS>(P, T, Q, lane, false);
+        sl_flush(P, Q, lane, false);
         /* advance every lane by one chunk */
         if (gc + 32 <= gLast)
         {
@@ -1512,7 +1492,7 @@ SLD_FN unsigned sl_walk_piece_warp(const SLRasterParams& P, const SLTile& T, SLF
 constexpr int SL_LONG_GROUPS = 6; /* pieces of at least this many 4-pixel groups are walked by the whole warp */
 constexpr int SL_RASTER_WARPS = 4;
 #ifndef SL_RASTER_MIN_BLOCKS
-#define SL_RASTER_MIN_BLOCKS 4
+#define SL_RASTER_MIN_BLOCKS 6
 #endif
 
 SLD_FN unsigned sl_align16(unsigned n) { return (n + 15u) & ~15u; }
@@ -1540,14 +1520,12 @@ SLD_FN void sl_copy_warp(unsigned char* dst, const unsigned char* src, unsigned 
 }
 
 /* One warp per (row, x-segment); work is handed out through a ticket in row-major order.  The warp stages the depth
- * and colour texels of its segment into shared memory once, streams the row's ordered entry list, keeps the pieces
- * that fall into its segment (compacted into a 32-deep queue so that the lanes of a batch are busy), resolves them
- * (phase A) and shades the queued fragments 32 at a time (phase B), and writes the segment back at the end.  Short
- * pieces run one per lane as soon as no earlier, still pending piece of the batch overlaps them in x (fragments of
- * disjoint x-ranges commute; everything else is serialised in submission order); long pieces are walked by the whole
- * warp. */
-template <FsFn FS>
-__global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_raster(const __grid_constant__ SLRasterParams P)
+ * texels of its segment into shared memory once, streams the row's ordered entry list, keeps the pieces that fall into
+ * its segment (compacted into a 32-deep queue so that the lanes of a batch are busy), resolves them and appends the
+ * surviving fragments to its fragment list, and writes the depth segment back at the end.  Short pieces run one per
+ * lane as soon as no earlier, still pending piece of the batch overlaps them in x (fragments of disjoint x-ranges
+ * commute; everything else is serialised in submission order); long pieces are walked by the whole warp. */
+__global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_resolve(const __grid_constant__ SLRasterParams P)
 {
     extern __shared__ __align__(16) unsigned char sDyn[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1571,29 +1549,23 @@ __global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_
     SLFragQueue Q;
     Q.bind(warpMem + SL_PIECEQ_BYTES);
     Q.count = 0;
+    Q.list = ticket;
+    Q.tail = SL_NO_CHUNK;
+    Q.total = 0u;
     unsigned char* tileMem = warpMem + SL_PIECEQ_BYTES + SL_FQ_BYTES;
     const unsigned segPixels = (unsigned)(sx1 - sx0);
     const long long segOrigin = (long long)W * y + sx0;
+    const bool useDepth = P.depthTest != 0 || P.depthMask != 0;
     SLTile T;
     bool staged = false;
-    if (P.tileBytes)
+    if (P.tileBytes && useDepth)
     {
-        unsigned off = 0;
         T.depth = tileMem;
-        off += sl_align16(P.segWidth * (unsigned)P.depthBpt);
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-        {
-            T.color[i] = tileMem + off;
-            if (i < P.numOutputs) off += sl_align16(P.segWidth * (unsigned)P.colorBpt[i]);
-        }
         T.origin = segOrigin;
     }
     else
     {
         T.depth = P.depth;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) T.color[i] = P.color[i];
         T.origin = 0;
     }
 
@@ -1628,7 +1600,6 @@ __global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_
                     /* the walker's first access: pull the triangle record towards the SM now */
                     const float4* r = P.records + (size_t)(c[k].rec & ~SL_ENTRY_OVERFLOW) * P.recStride;
                     asm volatile("prefetch.global.L1 [%0];" ::"l"(r));
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(r + 8));
                 }
                 qn += cnt;
                 base += 32;
@@ -1636,12 +1607,10 @@ __global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_
         }
         __syncwarp();
         if (!qn) continue;
-        if (P.tileBytes && !staged)
+        if (P.tileBytes && useDepth && !staged)
         {
-            /* stage the segment in: one coalesced read per attachment */
+            /* stage the depth segment in: one coalesced read */
             sl_copy_warp(T.depth, P.depth + (size_t)segOrigin * P.depthBpt, segPixels * (unsigned)P.depthBpt, lane);
-            for (int i = 0; i < P.numOutputs; ++i)
-                sl_copy_warp(T.color[i], P.color[i] + (size_t)segOrigin * P.colorBpt[i], segPixels * (unsigned)P.colorBpt[i], lane);
             staged = true;
             __syncwarp();
         }
@@ -1671,6 +1640,7 @@ __global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_
         const int groups = has ? (((p1 - 1 - xMin) >> 2) - ((p0 - xMin) >> 2) + 1) : 0;
         const bool isLong = groups >= SL_LONG_GROUPS;
         bool done = !has;
+        unsigned idle = 0;
         for (;;)
         {
             const uint32_t pendMask = ~__ballot_sync(0xffffffffu, done);
@@ -1691,6 +1661,7 @@ __global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_
             const int first = __ffs(pendMask) - 1;
             const bool firstLong = __shfl_sync(0xffffffffu, isLong ? 1 : 0, first) != 0;
             const bool firstGo = __shfl_sync(0xffffffffu, go ? 1 : 0, first) != 0;
+            bool progress = false;
             if (firstLong && firstGo)
             {
                 const uint32_t bRec = __shfl_sync(0xffffffffu, recId, first);
@@ -1700,8 +1671,9 @@ __global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_
                 const uint32_t bHand = __shfl_sync(0xffffffffu, hand, first);
                 const bool bPub = __shfl_sync(0xffffffffu, publish ? 1 : 0, first) != 0;
                 const int bOut = __shfl_sync(0xffffffffu, bIn + 1, first);
-                shaded += sl_walk_piece_warp<FS>(P, T, Q, bRec, bY, bXMin, bXMax, bP0, bP1, bHand, bPub, bOut);
+                shaded += sl_walk_piece_warp(P, T, Q, bRec, bY, bXMin, bXMax, bP0, bP1, bHand, bPub, bOut);
                 if (lane == first) done = true;
+                progress = true;
             }
             else
             {
@@ -1729,30 +1701,124 @@ __global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_
                         }
                         sl_push_frags(Q, lane, mBits, bcJ, zJ, w.x4, w.y, w.recId);
                         if (act) sl_walk_advance(w);
-                        sl_flush<FS>(P, T, Q, lane, false);
+                        sl_flush(P, Q, lane, false);
                     }
                     if (mine)
                     {
                         if (w.publish && !w.published) sl_handoff_publish(P, recId, ySrc, bIn + 1, w.st); /* the cut falls on a group boundary */
                         done = true;
                     }
+                    progress = true;
                 }
             }
+            /* nothing could run: every ready piece waits for a hand-over from the segment on its left (or the row
+             * below).  Back off so that the polling does not take issue slots from the warps that produce them. */
+            if (!progress) { idle = min(idle + 1u, 8u); __nanosleep(32u << idle); }
+            else idle = 0;
             __syncwarp();
         }
     }
-    sl_flush<FS>(P, T, Q, lane, true);
+    sl_flush(P, Q, lane, true);
+    if (lane == 0 && Q.total) P.lists.listCount[Q.list] = Q.total;
     const bool dirty = __any_sync(0xffffffffu, shaded != 0u);
-    if (staged && dirty)
+    if (staged && dirty && P.depthMask)
     {
-        /* write the segment back: one coalesced store per attachment that can have changed */
+        /* write the depth segment back: one coalesced store */
         __syncwarp();
-        if (P.depthMask) sl_copy_warp(P.depth + (size_t)segOrigin * P.depthBpt, T.depth, segPixels * (unsigned)P.depthBpt, lane);
-        for (int i = 0; i < P.numOutputs; ++i)
-            sl_copy_warp(P.color[i] + (size_t)segOrigin * P.colorBpt[i], T.color[i], segPixels * (unsigned)P.colorBpt[i], lane);
+        sl_copy_warp(P.depth + (size_t)segOrigin * P.depthBpt, T.depth, segPixels * (unsigned)P.depthBpt, lane);
     }
     for (int d = 16; d > 0; d >>= 1) shaded += __shfl_down_sync(0xffffffffu, shaded, d);
     if (lane == 0 && shaded) atomicAdd(&P.counters->fragsShaded, (unsigned long long)shaded);
+}
+
+/* ------------------------------------------------------------------------
+ * k_shade<FS>: SL_FragmentProcessor::flush_tri_fragments (src/SL_FragmentProcessor.cpp:416-531) + assign_pixel /
+ * assign_alpha_pixel (src/SL_Framebuffer.cpp:44-368) over the fragment lists.  One warp per list.
+ * ----------------------------------------------------------------------*/
+constexpr int SL_SHADE_WARPS = 4;
+#ifndef SL_SHADE_MIN_BLOCKS
+#define SL_SHADE_MIN_BLOCKS 4
+#endif
+
+template <FsFn FS>
+__global__ void __launch_bounds__(SL_SHADE_WARPS * 32, SL_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ SLShadeParams P)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned list = blockIdx.x * SL_SHADE_WARPS + (threadIdx.x >> 5);
+    if (list >= P.numLists) return;
+    int remaining = (int)P.lists.listCount[list];
+    if (remaining <= 0) return;
+    uint32_t chunk = P.lists.listHead[list];
+    for (; remaining > 0; remaining -= 32)
+    {
+        const int n = min(remaining, 32);
+        const unsigned char* c = P.lists.pool + (size_t)chunk * SL_CHUNK_BYTES;
+        if (remaining > 32) chunk = P.lists.chunkNext[chunk];
+        SL_FragmentParam fp;
+        bool haveOutputs = false;
+        uint32_t key = 0xffffff00u + (uint32_t)lane; /* idle lanes: a key no pixel has */
+        if (lane < n)
+        {
+            const float4 b4 = reinterpret_cast<const float4*>(c)[lane];
+            const float z = reinterpret_cast<const float*>(c + 512)[lane];
+            const uint32_t xy = reinterpret_cast<const uint32_t*>(c + 640)[lane];
+            const uint32_t recId = reinterpret_cast<const uint32_t*>(c + 768)[lane];
+            const int x = (int)(xy & 0xffffu), y = (int)(xy >> 16);
+            const float4* rec = P.records + (size_t)recId * P.recStride;
+            /* :438-460 perspective correction */
+            math::vec4 bc = math::vec4{b4.x, b4.y, b4.z, b4.w} * math::vec4{rec[0].w, rec[1].w, rec[2].w, 0.f};
+            const float persp = sl_rcp((bc.v[0] + bc.v[1]) + (bc.v[2] + bc.v[3]));
+            bc = bc * persp;
+
+            fp.pUniforms = &P.draws[P.recDraw[recId]].uniforms;
+            /* interpolate_tri_varyings, AVX2 branch (:163-193).  The reference interpolates all four slots; slots past
+             * numVaryings hold stale bin data there and are never read by a well-formed shader. */
+            for (int s = 0; s < P.numVaryings; ++s)
+            {
+                const float4 a = rec[3 + 3 * s + 0], b = rec[3 + 3 * s + 1], cc = rec[3 + 3 * s + 2];
+                fp.pVaryings[s] = math::vec4{
+                    sl_fma(bc.v[2], cc.x, sl_fma(bc.v[1], b.x, bc.v[0] * a.x)), sl_fma(bc.v[2], cc.y, sl_fma(bc.v[1], b.y, bc.v[0] * a.y)),
+                    sl_fma(bc.v[2], cc.z, sl_fma(bc.v[1], b.z, bc.v[0] * a.z)), sl_fma(bc.v[2], cc.w, sl_fma(bc.v[1], b.w, bc.v[0] * a.w))};
+            }
+            fp.coord.x = (uint16_t)x;
+            fp.coord.y = (uint16_t)y;
+            fp.coord.depth = z;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) fp.pOutputs[i] = math::vec4{0.f};
+
+            haveOutputs = FS(fp); /* :501 */
+            /* every attachment is addressed as x + width*y with the depth attachment's width (the reference uses each
+             * colour view's own width; SL_Framebuffer::valid requires them to be equal, and run_draw refuses anything
+             * else); x, y are relative to the span's source row, so fragments that ran past the row end land at the
+             * start of the next row exactly like in the reference */
+            key = (uint32_t)x + P.width * (uint32_t)y;
+        }
+        /* :507-523, in submission order per pixel */
+        const uint32_t peers = __match_any_sync(0xffffffffu, key);
+        if (P.blend == 0)
+        {
+            /* plain stores: the last fragment of a pixel that has outputs wins */
+            const uint32_t hv = __ballot_sync(0xffffffffu, haveOutputs) & peers;
+            if (haveOutputs && (hv >> lane) == 1u)
+            {
+                for (int i = P.numOutputs - 1; i >= 0; --i) sl_store_color(P.color[i], P.colorType[i], (size_t)key, fp.pOutputs[i]);
+            }
+        }
+        else
+        {
+            const int rank = __popc(peers & ((1u << lane) - 1u));
+            const int maxRank = (int)__reduce_max_sync(0xffffffffu, (unsigned)rank);
+            for (int r = 0; r <= maxRank; ++r)
+            {
+                if (rank == r && haveOutputs)
+                {
+                    for (int i = P.numOutputs - 1; i >= 0; --i) sl_blend_color(P.color[i], P.colorType[i], (size_t)key, fp.pOutputs[i], P.blend);
+                }
+                __syncwarp();
+            }
+        }
+        __syncwarp(); /* the next step's loads of a pixel come after this step's stores to it */
+    }
 }
 
 /* ------------------------------------------------------------------------

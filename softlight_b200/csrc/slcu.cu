@@ -31,9 +31,7 @@ using namespace sld;
  * =========================================================================*/
 typedef cudaError_t (*VertexLauncher)(unsigned grid, cudaStream_t s, const SLVertexParams& p, bool cache);
 static const unsigned kVertexCacheMaxBytes = 5u * SL_VCACHE_VERTS * (unsigned)sizeof(float4); /* position + 4 varyings */
-static const unsigned kRasterTileMaxBytes = 10u * 1024u; /* per warp; fatter segments work in place */
-static const unsigned kRasterMaxSmemBytes = SL_RASTER_WARPS * (SL_PIECEQ_BYTES + SL_FQ_BYTES + kRasterTileMaxBytes);
-typedef cudaError_t (*RasterLauncher)(unsigned grid, unsigned block, unsigned smemBytes, cudaStream_t s, const SLRasterParams& p);
+typedef cudaError_t (*RasterLauncher)(unsigned grid, cudaStream_t s, const SLShadeParams& p);
 
 struct VsEntry { const char* name; VertexLauncher launch; };
 struct FsEntry { const char* name; RasterLauncher launch; };
@@ -57,16 +55,9 @@ template <VsFn VS> static cudaError_t launch_vertex(unsigned grid, cudaStream_t 
     k_vertex<VS, true><<<grid, SL_VB_THREADS, p.cacheBytes, s>>>(p);
     return cudaGetLastError();
 }
-template <FsFn FS> static cudaError_t launch_raster(unsigned grid, unsigned block, unsigned smemBytes, cudaStream_t s, const SLRasterParams& p)
+template <FsFn FS> static cudaError_t launch_raster(unsigned grid, cudaStream_t s, const SLShadeParams& p)
 {
-    static bool attrSet = false; /* one opt-in per instantiation: fragment queues + tiles may exceed the 48 KB default */
-    if (!attrSet)
-    {
-        cudaError_t e = cudaFuncSetAttribute(k_raster<FS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRasterMaxSmemBytes);
-        if (e != cudaSuccess) return e;
-        attrSet = true;
-    }
-    k_raster<FS><<<grid, block, smemBytes, s>>>(p);
+    k_shade<FS><<<grid, SL_SHADE_WARPS * 32, 0, s>>>(p);
     return cudaGetLastError();
 }
 struct VsReg { VsReg(const char* n, VertexLauncher l) { vs_registry().push_back(VsEntry{n, l}); } };
@@ -217,6 +208,7 @@ struct slcu_context
     SLCounters* counters = nullptr;     /* device */
     SLCounters* hostCounters = nullptr; /* pinned */
     Scratch records, blockInfo, cnt, off, segSums, rowTotals, rowStart, entries, handoff, rowFlags, rowNeeded, drawTable, blockDraw, recDraw;
+    Scratch fragPool, chunkNext, listInfo; /* fragment lists, k_resolve -> k_shade */
     Batch batch;            /* submitted, not yet executed draws */
     bool syncDraws = false; /* SLCU_SYNC_DRAWS=1: execute every draw call on its own (debug / parity mode) */
     /* sort-first partition (slcu_set_partition) */
@@ -502,7 +494,7 @@ static int flush_draws_impl(slcu_context* c)
         CK(c->records.ensure((size_t)recCapacity * recStride * sizeof(float4)));
         CK(c->recDraw.ensure((size_t)recCapacity * sizeof(uint16_t)));
         CK(c->blockInfo.ensure((size_t)numBlocks * sizeof(SLBlockInfo)));
-        CK(cudaMemsetAsync(&c->counters->recAlloc, 0, 2 * sizeof(unsigned long long), c->stream)); /* recAlloc + handoffs */
+        CK(cudaMemsetAsync(&c->counters->recAlloc, 0, 3 * sizeof(unsigned long long), c->stream)); /* recAlloc + handoffs + pixelsCovered */
 
         {
             SLVertexParams vp;
@@ -605,19 +597,34 @@ static int flush_draws_impl(slcu_context* c)
         break;
     }
 
-    /* ---- fragment stage ---- */
+    /* ---- fragment stage: k_resolve (depth, coverage, order) -> fragment lists -> k_shade<FS> ---- */
+    const unsigned long long numLists = (unsigned long long)H * rasterSegs;
+    /* every fragment is a pixel of a span, and a list ends with at most one partial chunk */
+    const unsigned long long pixelsCovered = c->hostCounters->pixelsCovered;
+    const unsigned long long chunkCap = pixelsCovered / SL_CHUNK_FRAGS + numLists + 64ull;
+    if (chunkCap > 0xfffffff0ull || chunkCap * SL_CHUNK_BYTES > (96ull << 30))
+    {
+        c->err = "fragment list pool too large";
+        return SLCU_ERR_OOM;
+    }
+    CK(c->fragPool.ensure((size_t)chunkCap * SL_CHUNK_BYTES));
+    CK(c->chunkNext.ensure((size_t)chunkCap * sizeof(uint32_t)));
+    CK(c->listInfo.ensure((size_t)numLists * 2 * sizeof(uint32_t)));
+    CK(cudaMemsetAsync(c->listInfo.buf.ptr, 0, (size_t)numLists * 2 * sizeof(uint32_t), c->stream));
+    SLFragLists lists;
+    lists.pool = c->fragPool.buf.ptr;
+    lists.chunkNext = reinterpret_cast<uint32_t*>(c->chunkNext.buf.ptr);
+    lists.listHead = reinterpret_cast<uint32_t*>(c->listInfo.buf.ptr);
+    lists.listCount = lists.listHead + numLists;
+    lists.chunkCapacity = (unsigned)chunkCap;
+
     SLRasterParams rp;
-    rp.draws = reinterpret_cast<const SLDrawDesc*>(c->drawTable.buf.ptr);
-    rp.recDraw = reinterpret_cast<const uint16_t*>(c->recDraw.buf.ptr);
     rp.records = reinterpret_cast<const float4*>(c->records.buf.ptr);
     rp.entries = reinterpret_cast<const SLSpanEntry*>(c->entries.buf.ptr);
     rp.rowStart = reinterpret_cast<const uint32_t*>(c->rowStart.buf.ptr);
     rp.recStride = recStride;
-    rp.numVaryings = NV;
-    rp.numOutputs = sh.numOutputs;
     rp.depthTest = sh.depthTest;
     rp.depthMask = sh.depthMask;
-    rp.blend = sh.blend;
     rp.numRows = H;
     rp.width = depthTex.w;
     rp.depth = depthTex.dev;
@@ -627,6 +634,7 @@ static int flush_draws_impl(slcu_context* c)
     rp.rowNeeded = rowNeeded;
     rp.segWidth = segWidth;
     rp.numSegs = rasterSegs;
+    rp.lists = lists;
     if (numHandoffs)
     {
         size_t cap = 64;
@@ -636,29 +644,47 @@ static int flush_draws_impl(slcu_context* c)
         rp.handoff = reinterpret_cast<unsigned long long*>(c->handoff.buf.ptr);
         rp.handoffMask = (unsigned)(cap - 1);
     }
-    unsigned tileBytes = (segWidth * depthTex.bpt + 15u) & ~15u;
+    /* each resolving warp keeps its segment's depth texels in shared memory (at most 32 x ... pixels x 8 bytes) */
+    rp.tileBytes = (segWidth * depthTex.bpt + 15u) & ~15u;
+    rp.counters = c->counters;
+    const unsigned warpsPerBlock = SL_RASTER_WARPS;
+    const unsigned smemBytes = warpsPerBlock * (SL_PIECEQ_BYTES + SL_FQ_BYTES + rp.tileBytes); /* piece queue + fragment queue + tile, per warp */
+    {
+        static bool attrSet = false;
+        if (!attrSet)
+        {
+            CK(cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            attrSet = true;
+        }
+        if (smemBytes > 96u * 1024u) { c->err = "framebuffer too wide for the resolve tile"; return SLCU_ERR_ARG; }
+        KernelScope ks(c, SLCU_K_RASTER);
+        k_resolve<<<(unsigned)((numLists + warpsPerBlock - 1) / warpsPerBlock), warpsPerBlock * 32, smemBytes, c->stream>>>(rp);
+        CK(cudaGetLastError());
+    }
+
+    SLShadeParams shp;
+    shp.draws = reinterpret_cast<const SLDrawDesc*>(c->drawTable.buf.ptr);
+    shp.recDraw = reinterpret_cast<const uint16_t*>(c->recDraw.buf.ptr);
+    shp.records = reinterpret_cast<const float4*>(c->records.buf.ptr);
+    shp.recStride = recStride;
+    shp.numVaryings = NV;
+    shp.numOutputs = sh.numOutputs;
+    shp.blend = sh.blend;
+    shp.width = depthTex.w;
+    shp.numLists = (unsigned)numLists;
+    shp.lists = lists;
     for (int i = 0; i < 4; ++i)
     {
-        rp.color[i] = nullptr;
-        rp.colorType[i] = 0;
-        rp.colorBpt[i] = 0;
+        shp.color[i] = nullptr;
+        shp.colorType[i] = 0;
         if (i < sh.numOutputs)
         {
             const HostTexture& t = c->textures[fbo.colors[i]];
-            rp.color[i] = t.dev;
-            rp.colorType[i] = t.type;
-            rp.colorBpt[i] = t.bpt;
-            tileBytes += (segWidth * t.bpt + 15u) & ~15u;
+            shp.color[i] = t.dev;
+            shp.colorType[i] = t.type;
         }
     }
-    rp.counters = c->counters;
-    const unsigned warpsPerBlock = SL_RASTER_WARPS;
-    const unsigned long long numWarps = (unsigned long long)H * rasterSegs;
-    /* each warp keeps its segment's depth + colour texels in shared memory; segments too fat for that work in place */
-    if (tileBytes > kRasterTileMaxBytes) tileBytes = 0;
-    rp.tileBytes = tileBytes;
-    const unsigned smemBytes = warpsPerBlock * (SL_PIECEQ_BYTES + SL_FQ_BYTES + tileBytes); /* piece queue + fragment queue + tile, per warp */
-    { KernelScope ks(c, SLCU_K_RASTER); CK(sh.fs((unsigned)((numWarps + warpsPerBlock - 1) / warpsPerBlock), warpsPerBlock * 32, smemBytes, c->stream, rp)); }
+    { KernelScope ks(c, SLCU_K_SHADE); CK(sh.fs((unsigned)((numLists + SL_SHADE_WARPS - 1) / SL_SHADE_WARPS), c->stream, shp)); }
     return 0;
 }
 
@@ -754,7 +780,7 @@ void slcu_context_destroy(slcu_context* c)
     if (c->counters) cudaFree(c->counters);
     if (c->hostCounters) cudaFreeHost(c->hostCounters);
     for (auto& pm : c->peerMaps) if (pm.ptr) cudaIpcCloseMemHandle(pm.ptr);
-    Scratch* s[] = {&c->records, &c->blockInfo, &c->cnt, &c->off, &c->segSums, &c->rowTotals, &c->rowStart, &c->entries, &c->handoff, &c->rowFlags, &c->rowNeeded, &c->drawTable, &c->blockDraw, &c->recDraw};
+    Scratch* s[] = {&c->records, &c->blockInfo, &c->cnt, &c->off, &c->segSums, &c->rowTotals, &c->rowStart, &c->entries, &c->handoff, &c->rowFlags, &c->rowNeeded, &c->drawTable, &c->blockDraw, &c->recDraw, &c->fragPool, &c->chunkNext, &c->listInfo};
     for (Scratch* x : s) x->release();
     cudaStreamDestroy(c->stream);
     delete c;
