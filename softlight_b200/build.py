@@ -43,6 +43,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
         return LIB
     cmd = [nvcc] + NVCC_FLAGS + ["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "shaders"), "-I" + CSRC,
                                  os.path.join(CSRC, "slcu.cu"), "-o", LIB]
+    cmd[1:1] = os.environ.get("SLCU_NVCC_EXTRA", "").split()  # tuning experiments only (e.g. -DSL_RASTER_MIN_BLOCKS=4)
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

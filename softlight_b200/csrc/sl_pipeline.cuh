@@ -861,6 +861,7 @@ struct SLRasterParams
     unsigned int numRows;     /* rows incl. the texture's padding rows */
     unsigned int width;       /* depth attachment width (row stride of every attachment, like the reference) */
     unsigned long long* handoff; /* hash table of hand-overs (null when the batch has none) */
+    float4* handoffRegs;         /* [slots][4]: the four barycentric registers at the cut    */
     unsigned int handoffMask;
     unsigned int segWidth;       /* x-segment width */
     unsigned int numSegs;        /* segments per row (<= 32) */
@@ -1120,26 +1121,32 @@ struct SLFragQueue
     }
 };
 
-/* push the survivors of one 4-pixel group per lane (warp-collective; mBits == 0 for idle lanes) */
+/* push the survivors of one 4-pixel group per lane, in lane order (warp-collective; mBits == 0 for idle lanes) */
 SLD_FN void sl_push_frags(SLFragQueue& Q, int lane, uint32_t mBits, const math::vec4 (&bcJ)[4], const float (&zJ)[4], int x4, int y, uint32_t recId)
 {
     if (!__any_sync(0xffffffffu, mBits != 0u)) return;
-    const uint32_t below = (1u << lane) - 1u;
+    const int n = __popc(mBits);
+    int incl = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    int e = Q.count + incl - n;
 #pragma unroll
     for (int j = 0; j < 4; ++j)
     {
-        const bool has = ((mBits >> j) & 1u) != 0u;
-        const uint32_t b = __ballot_sync(0xffffffffu, has);
-        if (has)
+        if ((mBits >> j) & 1u)
         {
-            const int e = Q.count + __popc(b & below);
             Q.bc[e] = make_float4(bcJ[j].v[0], bcJ[j].v[1], bcJ[j].v[2], bcJ[j].v[3]);
             Q.z[e] = zJ[j];
             Q.xy[e] = (uint32_t)(x4 + j) | ((uint32_t)y << 16);
             Q.rec[e] = recId;
+            ++e;
         }
-        Q.count += __popc(b);
     }
+    Q.count += __shfl_sync(0xffffffffu, incl, 31);
 }
 
 /* append every full batch of the queue (and the rest too when `all`) to the warp's fragment list; what is left moves
@@ -1191,31 +1198,47 @@ SLD_FN void sl_flush(const SLRasterParams& P, SLFragQueue& Q, int lane, bool all
     __syncwarp();
 }
 
-/* Hand-over of the walker state at a cut (see SL_ENTRY_OVERFLOW).  A row is rasterised by numSegs warps, one per
+/* Hand-over of the walker state at a cut (see SL_ENTRY_OVERFLOW).  A row is resolved by numSegs warps, one per
  * x-segment; a span that crosses a segment boundary (or the row end) is walked piece by piece, and the piece on the
- * right needs the state the piece on the left ends with.  One 64-bit word per cut in a hash table:
- * [63:12] key = record<<20 | source row<<7 | boundary index, [11] valid, [10:8] depth outcomes of the straddling
- * group's lanes left of the cut, [7:0] lane map (2 bits per register).  Boundary b of a span of row y: x = b*segWidth
- * for b < numSegs, x = W for b = numSegs (row end), x = W + (b-numSegs)*segWidth beyond (the part that wrapped into
- * row y+1).  A consumer only ever waits for a warp with a smaller ticket (left segment of its row, or the row below),
- * and tickets are taken in launch order, so the wait cannot deadlock.  Hand-overs are published in phase A, i.e.
- * without waiting for any shading. */
+ * right continues from the state the piece on the left ends with: the four barycentric registers as the reference
+ * holds them at the start of the group that contains the cut (accumulated rounding and in-place compaction included,
+ * so the right piece neither replays the accumulator chains nor needs the lane map) and the depth outcomes of that
+ * group's lanes left of the cut.  Hash table in HBM, one slot per cut: a 64-bit word
+ * [63:12] key = record<<20 | source row<<7 | boundary index, [11] claimed, [3] ready, [2:0] outcomes, and 4 x float4
+ * registers.  Boundary b of a span of row y: x = b*segWidth for b < numSegs, x = W for b = numSegs (row end),
+ * x = W + (b-numSegs)*segWidth beyond (the part that wrapped into row y+1).  A consumer only ever waits for a warp with
+ * a smaller ticket (left segment of its row, or the row below), and tickets are taken in launch order, so the wait
+ * cannot deadlock. */
+struct SLHand
+{
+    math::vec4 r[4];   /* registers at the start of the group that contains the cut */
+    uint32_t fM;       /* outcomes of that group's lanes left of the cut            */
+};
+
 SLD_FN unsigned long long sl_handoff_key(uint32_t rec, int y, int boundary)
 {
     return ((unsigned long long)rec << 20) | ((unsigned long long)(y & 0x1fff) << 7) | (unsigned long long)(boundary & 0x7f);
 }
 SLD_FN uint32_t sl_handoff_hash(unsigned long long key) { return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 36); }
 
-SLD_FN void sl_handoff_publish(const SLRasterParams& P, uint32_t rec, int y, int boundary, uint32_t payload)
+SLD_FN void sl_handoff_publish(const SLRasterParams& P, uint32_t rec, int y, int boundary, uint32_t outcomes, const math::vec4& r0, const math::vec4& r1,
+                               const math::vec4& r2, const math::vec4& r3)
 {
     if (!P.handoff) { atomicOr(&P.counters->errorFlags, 16u); return; } /* the count pass and the walkers disagree */
     const unsigned long long key = sl_handoff_key(rec, y, boundary);
-    const unsigned long long word = (key << 12) | 0x800ull | (unsigned long long)(payload & 0x7ffu);
+    const unsigned long long word = (key << 12) | 0x800ull | (unsigned long long)(outcomes & 7u);
     uint32_t i = sl_handoff_hash(key) & P.handoffMask;
     while (atomicCAS(&P.handoff[i], 0ull, word) != 0ull) i = (i + 1u) & P.handoffMask;
+    float4* dst = P.handoffRegs + (size_t)i * 4;
+    __stcg(dst + 0, make_float4(r0.v[0], r0.v[1], r0.v[2], r0.v[3]));
+    __stcg(dst + 1, make_float4(r1.v[0], r1.v[1], r1.v[2], r1.v[3]));
+    __stcg(dst + 2, make_float4(r2.v[0], r2.v[1], r2.v[2], r2.v[3]));
+    __stcg(dst + 3, make_float4(r3.v[0], r3.v[1], r3.v[2], r3.v[3]));
+    __threadfence();
+    atomicOr(&P.handoff[i], 0x8ull);
 }
 
-SLD_FN bool sl_handoff_poll(const SLRasterParams& P, uint32_t rec, int y, int boundary, uint32_t& payload)
+SLD_FN bool sl_handoff_poll(const SLRasterParams& P, uint32_t rec, int y, int boundary, SLHand& hand)
 {
     if (!P.handoff) { atomicOr(&P.counters->errorFlags, 8u); return true; }
     const unsigned long long key = sl_handoff_key(rec, y, boundary);
@@ -1224,7 +1247,20 @@ SLD_FN bool sl_handoff_poll(const SLRasterParams& P, uint32_t rec, int y, int bo
     {
         const unsigned long long w = *reinterpret_cast<volatile unsigned long long*>(&P.handoff[i]);
         if (w == 0ull) return false;
-        if ((w >> 12) == key) { payload = (uint32_t)(w & 0x7ffu); return true; }
+        if ((w >> 12) == key)
+        {
+            if (!(w & 0x8ull)) return false; /* claimed, registers not yet visible */
+            __threadfence();
+            const float4* src = P.handoffRegs + (size_t)i * 4;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+            {
+                const float4 f = __ldcg(src + k);
+                hand.r[k] = math::vec4{f.x, f.y, f.z, f.w};
+            }
+            hand.fM = (uint32_t)(w & 7ull);
+            return true;
+        }
         i = (i + 1u) & P.handoffMask;
     }
 }
@@ -1247,253 +1283,11 @@ SLD_FN math::vec4 sl_pick4(uint32_t s, const math::vec4& a0, const math::vec4& a
     return s == 0u ? a0 : (s == 1u ? a1 : (s == 2u ? a2 : a3));
 }
 
-/* One piece [p0,p1) of the span [xMin,xMax) of source row y, walked left to right by ONE lane, one 4-pixel group per
- * call of sl_walk_group (all lanes of the warp step their pieces in lock step so that the survivors can be pushed with
- * warp-wide ballots).  Pixels are addressed linearly from the source row, exactly like the reference, so a piece that
- * lies beyond the row end needs no coordinate change.  `hand`: state at p0 (lane map + outcomes of the lanes of the
- * straddling group left of p0) when the piece does not start the span. */
-struct SLWalk
-{
-    math::vec4 a0, a1, a2, a3, bcX; /* the four barycentric registers (:476-481) and their per-group increment */
-    float z0, z1, z2;
-    uint32_t recId, st, fM;
-    int y, x4, p0, p1, rowBase, outBoundary;
-    bool publish, published;
-};
-
-SLD_FN void sl_walk_begin(SLWalk& w, const SLRasterParams& P, const SLTile& T, uint32_t recId, int y, int xMin, int p0, int p1, uint32_t hand,
-                          bool publish, int outBoundary)
-{
-    const float4* rec = P.records + (size_t)recId * P.recStride;
-    SLTriSetup t;
-    sl_tri_setup(t, rec[0], rec[1], rec[2]);
-    const float yf = (float)y;
-    const math::vec4 bcY = math::fmadd(t.bc1, math::vec4{yf}, t.bc2); /* :474 */
-    w.a0 = (t.bc0 * (float)(xMin + 0)) + bcY;                         /* :476-481 */
-    w.a1 = (t.bc0 * (float)(xMin + 1)) + bcY;
-    w.a2 = (t.bc0 * (float)(xMin + 2)) + bcY;
-    w.a3 = (t.bc0 * (float)(xMin + 3)) + bcY;
-    w.bcX = t.bc0 * 4.f;
-    w.z0 = t.z0; w.z1 = t.z1; w.z2 = t.z2;
-    w.recId = recId;
-    w.y = y;
-    w.p0 = p0;
-    w.p1 = p1;
-    w.rowBase = (int)((long long)P.width * (long long)y - T.origin);
-    w.outBoundary = outBoundary;
-    w.publish = publish;
-    w.published = false;
-    w.st = SL_STATE_IDENTITY; /* lane map: register i holds accumulator chain (st >> 2i) & 3 */
-    w.fM = 0u;                /* outcomes of the first group's lanes that another piece owns */
-    int x4 = xMin;
-    if (xMin < p0)
-    {
-        /* replay the accumulator chains up to the group that contains p0, then apply the handed-over lane map */
-        for (; x4 + 3 < p0; x4 += 4) { w.a0 += w.bcX; w.a1 += w.bcX; w.a2 += w.bcX; w.a3 += w.bcX; }
-        w.st = hand & 0xffu;
-        if (w.st != SL_STATE_IDENTITY)
-        {
-            const math::vec4 c0 = w.a0, c1 = w.a1, c2 = w.a2, c3 = w.a3;
-            w.a0 = sl_pick4(w.st & 3u, c0, c1, c2, c3);
-            w.a1 = sl_pick4((w.st >> 2) & 3u, c0, c1, c2, c3);
-            w.a2 = sl_pick4((w.st >> 4) & 3u, c0, c1, c2, c3);
-            w.a3 = sl_pick4((w.st >> 6) & 3u, c0, c1, c2, c3);
-        }
-        w.fM = (hand >> 8) & 7u;
-    }
-    w.x4 = x4;
-}
-
-/* one group: returns the mask of this piece's surviving lanes; bcJ/zJ[j] = what the reference shades lane j with */
-SLD_FN uint32_t sl_walk_group(SLWalk& w, const SLRasterParams& P, const SLTile& T, math::vec4 (&bcJ)[4], float (&zJ)[4])
-{
-    const int x4 = w.x4, p0 = w.p0, p1 = w.p1;
-    /* _sl_mul_vec4_mat4_ps (:376-393): z = (w*0 + z*z2) + (y*z1 + x*z0) */
-    zJ[0] = ((w.a0.v[3] * 0.f) + (w.a0.v[2] * w.z2)) + ((w.a0.v[1] * w.z1) + (w.a0.v[0] * w.z0));
-    zJ[1] = ((w.a1.v[3] * 0.f) + (w.a1.v[2] * w.z2)) + ((w.a1.v[1] * w.z1) + (w.a1.v[0] * w.z0));
-    zJ[2] = ((w.a2.v[3] * 0.f) + (w.a2.v[2] * w.z2)) + ((w.a2.v[1] * w.z1) + (w.a2.v[0] * w.z0));
-    zJ[3] = ((w.a3.v[3] * 0.f) + (w.a3.v[2] * w.z2)) + ((w.a3.v[1] * w.z1) + (w.a3.v[0] * w.z0));
-    uint32_t mBits = 0u;
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-    {
-        const bool own = (x4 + j >= p0) && (x4 + j < p1);
-        if (own && sl_depth_cmp(P.depthTest, zJ[j], P.depthTest ? sl_load_depth(T.depth, P.depthBpt, (size_t)(w.rowBase + x4 + j)) : 0.f)) mBits |= 1u << j;
-    }
-    /* outcomes of the lanes left of p0 are known (handed over); lanes at or beyond p1 are unknown, but they cannot
-     * change which register a survivor of this piece reads (that is resolved at or before the survivor's own lane) */
-    const uint32_t tBits = mBits | w.fM;
-    w.fM = 0u;
-    if (w.publish && x4 + 3 >= p1)
-    {
-        /* the cut lies inside this group: state before the group + outcomes of its lanes left of the cut */
-        const uint32_t below = (1u << (p1 - x4)) - 1u;
-        sl_handoff_publish(P, w.recId, w.y, w.outBoundary, w.st | ((tBits & below & 7u) << 8));
-        w.published = true;
-    }
-    if (tBits)
-    {
-        /* :496-498 -- the registers keep these values for the following groups */
-        w.a2 = (tBits & 4u) ? w.a2 : w.a3;
-        w.a1 = (tBits & 2u) ? w.a1 : w.a2;
-        w.a0 = (tBits & 1u) ? w.a0 : w.a1;
-        w.st = sl_state_step(w.st, tBits);
-        /* :500-526 -- survivor number s is shaded with register s (new values) and its own x, z */
-        bcJ[0] = w.a0;
-        bcJ[1] = (tBits & 1u) ? w.a1 : w.a0;
-        bcJ[2] = sl_pick4((uint32_t)__popc(tBits & 3u), w.a0, w.a1, w.a2, w.a3);
-        bcJ[3] = sl_pick4((uint32_t)__popc(tBits & 7u), w.a0, w.a1, w.a2, w.a3);
-        if (P.depthMask) /* src/SL_FragmentProcessor.cpp:526-529 */
-        {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-            {
-                if ((mBits >> j) & 1u) sl_store_depth(T.depth, P.depthBpt, (size_t)(w.rowBase + x4 + j), zJ[j]);
-            }
-        }
-    }
-    return mBits;
-}
-
-SLD_FN void sl_walk_advance(SLWalk& w)
-{
-    w.a0 += w.bcX; /* :539-542 */
-    w.a1 += w.bcX;
-    w.a2 += w.bcX;
-    w.a3 += w.bcX;
-    w.x4 += 4;
-}
-
-/* The same piece walked by the WHOLE warp: lane l takes group g0 + 32c + l of chunk c.  The lane map only ever
- * degrades (14 reachable states, (3,3,3,3) absorbing), so a span sees at most a handful of state changes; between two
- * changes the groups are independent given the state.  Each chunk is therefore resolved by iterating "evaluate all
- * pending groups under the current state; everything up to and including the first group that changes it is final".
- * The hand-over for the next piece is published as soon as the piece's last group is resolved. */
-SLD_FN unsigned sl_walk_piece_warp(const SLRasterParams& P, const SLTile& T, SLFragQueue& Q, uint32_t recId, int y, int xMin, int xMax, int p0, int p1,
-                                   uint32_t hand, bool publish, int outBoundary)
-{
-    const int lane = threadIdx.x & 31;
-    const float4* rec = P.records + (size_t)recId * P.recStride;
-    SLTriSetup t;
-    sl_tri_setup(t, rec[0], rec[1], rec[2]);
-
-    const float yf = (float)y;
-    const math::vec4 bcY = math::fmadd(t.bc1, math::vec4{yf}, t.bc2);
-    math::vec4 a0 = (t.bc0 * (float)(xMin + 0)) + bcY;
-    math::vec4 a1 = (t.bc0 * (float)(xMin + 1)) + bcY;
-    math::vec4 a2 = (t.bc0 * (float)(xMin + 2)) + bcY;
-    math::vec4 a3 = (t.bc0 * (float)(xMin + 3)) + bcY;
-    const math::vec4 bcX = t.bc0 * 4.f;
-    const int rowBase = (int)((long long)P.width * (long long)y - T.origin);
-    unsigned shaded = 0;
-
-    const int g0 = (p0 - xMin) >> 2;        /* first group with a pixel of the piece */
-    const int gLast = (p1 - 1 - xMin) >> 2; /* last one                               */
-    const int gPub = (p1 - xMin) >> 2;      /* group that contains the cut p1         */
-    uint32_t st = (xMin < p0) ? (hand & 0xffu) : SL_STATE_IDENTITY; /* warp-uniform */
-    const uint32_t handM = (xMin < p0) ? ((hand >> 8) & 7u) : 0u;
-
-    /* accumulator chains of this lane's first group: g0 + lane additions, one rounding each (:539-542) */
-    for (int i = 0; i < g0; ++i) { a0 += bcX; a1 += bcX; a2 += bcX; a3 += bcX; }
-    for (int i = 0; i < 31; ++i)
-    {
-        if (i < lane) { a0 += bcX; a1 += bcX; a2 += bcX; a3 += bcX; }
-    }
-
-    for (int gc = g0; gc <= gLast; gc += 32)
-    {
-        const int g = gc + lane;
-        const int x4 = xMin + 4 * g;
-        const bool active = g <= gLast;
-        /* depth of the four clean chains at this group; register i of the reference holds chain (st >> 2i) & 3 */
-        const float zc0 = ((a0.v[3] * 0.f) + (a0.v[2] * t.z2)) + ((a0.v[1] * t.z1) + (a0.v[0] * t.z0));
-        const float zc1 = ((a1.v[3] * 0.f) + (a1.v[2] * t.z2)) + ((a1.v[1] * t.z1) + (a1.v[0] * t.z0));
-        const float zc2 = ((a2.v[3] * 0.f) + (a2.v[2] * t.z2)) + ((a2.v[1] * t.z1) + (a2.v[0] * t.z0));
-        const float zc3 = ((a3.v[3] * 0.f) + (a3.v[2] * t.z2)) + ((a3.v[1] * t.z1) + (a3.v[0] * t.z0));
-        bool own[4];
-        float d[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-        {
-            own[j] = active && (x4 + j >= p0) && (x4 + j < p1);
-            d[j] = (own[j] && P.depthTest) ? sl_load_depth(T.depth, P.depthBpt, (size_t)(rowBase + x4 + j)) : 0.f;
-        }
-        const uint32_t fM = (g == g0) ? handM : 0u;
-
-        uint32_t stIn = st, mBits = 0u, tBits = 0u;
-        bool pending = active;
-        for (;;)
-        {
-            uint32_t m = 0u;
-            if (pending)
-            {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                {
-                    const uint32_t sj = (st >> (2 * j)) & 3u;
-                    const float z = sj == 0u ? zc0 : (sj == 1u ? zc1 : (sj == 2u ? zc2 : zc3));
-                    if (own[j] && sl_depth_cmp(P.depthTest, z, d[j])) m |= 1u << j;
-                }
-            }
-            const uint32_t tt = m | fM;
-            const uint32_t stOut = sl_state_step(st, tt);
-            const uint32_t pend = __ballot_sync(0xffffffffu, pending);
-            if (!pend) break;
-            const uint32_t chg = __ballot_sync(0xffffffffu, pending && stOut != st);
-            const int f = chg ? (__ffs(chg) - 1) : 32;
-            if (pending && lane <= f) { stIn = st; mBits = m; tBits = tt; pending = false; }
-            if (f == 32) break;
-            st = __shfl_sync(0xffffffffu, stOut, f);
-        }
-        /* state after this chunk = state after its last active group */
-        {
-            const int lastLane = min(31, gLast - gc);
-            const uint32_t mine = sl_state_step(stIn, tBits);
-            st = __shfl_sync(0xffffffffu, mine, lastLane);
-            if (publish && gLast - gc < 32 && lane == lastLane)
-            {
-                if (gPub == gLast)
-                {
-                    const uint32_t below = (1u << (p1 - x4)) - 1u;
-                    sl_handoff_publish(P, recId, y, outBoundary, stIn | ((tBits & below & 7u) << 8));
-                }
-                else sl_handoff_publish(P, recId, y, outBoundary, mine);
-            }
-        }
-        /* survivors: number s reads register s after the compaction = the chain of the first passing lane >= s */
-        math::vec4 bcJ[4];
-        float zJ[4];
-        if (mBits)
-        {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-            {
-                const uint32_t s = (uint32_t)__popc(tBits & ((1u << j) - 1u));
-                const uint32_t ge = tBits & ~((1u << s) - 1u);
-                const int pLane = __ffs(ge) - 1;
-                bcJ[j] = sl_pick4((stIn >> (2 * (pLane & 3))) & 3u, a0, a1, a2, a3);
-                const uint32_t zj = (stIn >> (2 * j)) & 3u;
-                zJ[j] = zj == 0u ? zc0 : (zj == 1u ? zc1 : (zj == 2u ? zc2 : zc3));
-                if (P.depthMask && ((mBits >> j) & 1u)) sl_store_depth(T.depth, P.depthBpt, (size_t)(rowBase + x4 + j), zJ[j]);
-            }
-            shaded += (unsigned)__popc(mBits);
-        }
-        sl_push_frags(Q, lane, mBits, bcJ, zJ, x4, y, recId);
-        sl_flush(P, Q, lane, false);
-        /* advance every lane by one chunk */
-        if (gc + 32 <= gLast)
-        {
-            for (int i = 0; i < 32; ++i) { a0 += bcX; a1 += bcX; a2 += bcX; a3 += bcX; }
-        }
-    }
-    return shaded;
-}
-
-constexpr int SL_LONG_GROUPS = 6; /* pieces of at least this many 4-pixel groups are walked by the whole warp */
 constexpr int SL_RASTER_WARPS = 4;
 #ifndef SL_RASTER_MIN_BLOCKS
-#define SL_RASTER_MIN_BLOCKS 6
+#define SL_RASTER_MIN_BLOCKS 4
 #endif
+constexpr unsigned SL_PIECEREG_BYTES = 32u * 4u * (unsigned)sizeof(float4); /* per warp: the registers a piece continues from */
 
 SLD_FN unsigned sl_align16(unsigned n) { return (n + 15u) & ~15u; }
 
@@ -1519,16 +1313,32 @@ SLD_FN void sl_copy_warp(unsigned char* dst, const unsigned char* src, unsigned 
     }
 }
 
-/* One warp per (row, x-segment); work is handed out through a ticket in row-major order.  The warp stages the depth
- * texels of its segment into shared memory once, streams the row's ordered entry list, keeps the pieces that fall into
- * its segment (compacted into a 32-deep queue so that the lanes of a batch are busy), resolves them and appends the
- * surviving fragments to its fragment list, and writes the depth segment back at the end.  Short pieces run one per
- * lane as soon as no earlier, still pending piece of the batch overlaps them in x (fragments of disjoint x-ranges
- * commute; everything else is serialised in submission order); long pieces are walked by the whole warp. */
+/* k_resolve: one warp per (row, x-segment); work is handed out through a ticket in row-major order.  The warp stages
+ * the depth texels of its segment into shared memory once, streams the row's ordered entry list and keeps the pieces
+ * (spans clipped to the segment) that fall into its segment, 32 at a time.
+ *
+ * The pieces are resolved in *windows of 32 four-pixel groups*: lane l of a window works on one group of the 4-pixel
+ * loop of render_triangle_simd (src/SL_TriRasterizer.cpp:471-548), groups of consecutive pieces packed side by side in
+ * submission order (a long piece simply fills several windows).  Every lane sets up its triangle, brings the four
+ * barycentric registers to its group (one rounded addition per group, :539-542) and then the window is settled in
+ * waves that honour the two orders the reference defines:
+ *   - pixel order: a lane may test and write depth only when no earlier lane of another piece that touches one of its
+ *     pixels is still pending;
+ *   - register order: the in-place compaction (:496-498) makes the registers of a group depend on the depth outcomes
+ *     of the groups to its left.  What happened so far is a lane map (which initial register each register now holds;
+ *     14 reachable states, (3,3,3,3) absorbing).  Lanes evaluate under the lane map of their piece's last settled
+ *     group; a wave settles, per piece, the leading run of lanes up to and including the first one that changes it.
+ * The earliest pending lane always settles, so a window needs at most as many waves as its longest dependency chain,
+ * and a wave is a few dozen instructions.  Survivors go to the fragment queue in lane order = submission order.
+ *
+ * A piece that does not start its span continues from the registers handed over by the piece on its left (SLHand);
+ * with the depth test off nothing ever waits: such a piece replays the accumulator chain from the span start instead
+ * (every lane left of the cut passed, the registers were never compacted). */
 __global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_resolve(const __grid_constant__ SLRasterParams P)
 {
     extern __shared__ __align__(16) unsigned char sDyn[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t ltMask = (1u << lane) - 1u;
     unsigned ticket = 0;
     if (lane == 0) ticket = atomicAdd(&P.counters->rasterTicket, 1u);
     ticket = __shfl_sync(0xffffffffu, ticket, 0);
@@ -1544,7 +1354,7 @@ __global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_
     if (begin == end) return;
     unsigned shaded = 0;
 
-    unsigned char* warpMem = sDyn + (size_t)warp * (SL_PIECEQ_BYTES + SL_FQ_BYTES + P.tileBytes);
+    unsigned char* warpMem = sDyn + (size_t)warp * (SL_PIECEQ_BYTES + SL_FQ_BYTES + SL_PIECEREG_BYTES + P.tileBytes);
     SLSpanEntry* queue = reinterpret_cast<SLSpanEntry*>(warpMem);
     SLFragQueue Q;
     Q.bind(warpMem + SL_PIECEQ_BYTES);
@@ -1552,7 +1362,8 @@ __global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_
     Q.list = ticket;
     Q.tail = SL_NO_CHUNK;
     Q.total = 0u;
-    unsigned char* tileMem = warpMem + SL_PIECEQ_BYTES + SL_FQ_BYTES;
+    float4* pieceRegs = reinterpret_cast<float4*>(warpMem + SL_PIECEQ_BYTES + SL_FQ_BYTES);
+    unsigned char* tileMem = warpMem + SL_PIECEQ_BYTES + SL_FQ_BYTES + SL_PIECEREG_BYTES;
     const unsigned segPixels = (unsigned)(sx1 - sx0);
     const long long segOrigin = (long long)W * y + sx0;
     const bool useDepth = P.depthTest != 0 || P.depthMask != 0;
@@ -1596,8 +1407,8 @@ __global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_
                 if (qn + cnt > 32) { full = true; continue; } /* process what is queued, then come back to this batch */
                 if (cHas)
                 {
-                    queue[qn + __popc(hm & ((1u << lane) - 1u))] = c[k];
-                    /* the walker's first access: pull the triangle record towards the SM now */
+                    queue[qn + __popc(hm & ltMask)] = c[k];
+                    /* the first access of the window that holds the piece: pull the triangle record towards the SM now */
                     const float4* r = P.records + (size_t)(c[k].rec & ~SL_ENTRY_OVERFLOW) * P.recStride;
                     asm volatile("prefetch.global.L1 [%0];" ::"l"(r));
                 }
@@ -1614,9 +1425,10 @@ __global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_
             staged = true;
             __syncwarp();
         }
-        const bool valid = lane < qn;
+
+        /* ---- lane i keeps the book for piece i of the queue ---- */
         SLSpanEntry e = SLSpanEntry{0u, 0, 0};
-        if (valid) e = queue[lane];
+        if (lane < qn) e = queue[lane];
         __syncwarp();
         const bool isOver = (e.rec & SL_ENTRY_OVERFLOW) != 0u;
         const uint32_t recId = e.rec & ~SL_ENTRY_OVERFLOW;
@@ -1624,97 +1436,263 @@ __global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_
         const int ySrc = isOver ? y - 1 : y;
         const int xMin = e.xMin, xMax = e.xMax;
         const int p0 = max(xMin, xBase + sx0), p1 = min(xMax, xBase + sx1);
-        const bool has = valid && p0 < p1;
-        const int lMin = has ? p0 - xBase : 0, lMax = has ? p1 - xBase : 0; /* pixels of this row the piece touches */
-        uint32_t dep = 0;
-        for (int i = 0; i < 31; ++i)
-        {
-            const int oMin = __shfl_sync(0xffffffffu, lMin, i);
-            const int oMax = __shfl_sync(0xffffffffu, lMax, i);
-            if (i < lane && oMin < lMax && lMin < oMax) dep |= 1u << i;
-        }
-        const bool startsMid = has && xMin < p0;
-        const bool needsIn = startsMid && chained;
+        const bool has = lane < qn && p0 < p1;
+        const bool needsIn = has && xMin < p0 && chained;
         const bool publish = has && chained && xMax > p1 && (seg < NS - 1 || (!isOver && y + 1 < (int)P.numRows));
         const int bIn = (isOver ? NS : 0) + seg;
-        const int groups = has ? (((p1 - 1 - xMin) >> 2) - ((p0 - xMin) >> 2) + 1) : 0;
-        const bool isLong = groups >= SL_LONG_GROUPS;
-        bool done = !has;
+        int gNext = has ? ((p0 - xMin) >> 2) : 0;               /* next group of the piece to resolve            */
+        const int gEnd = has ? (((p1 - 1 - xMin) >> 2) + 1) : 0; /* one past its last group                       */
+        bool started = false;                                   /* pieceRegs[lane] holds the registers at gBase  */
+        int gBase = 0;
+        uint32_t pfM = 0u;
         unsigned idle = 0;
+
         for (;;)
         {
-            const uint32_t pendMask = ~__ballot_sync(0xffffffffu, done);
-            if (!pendMask) break;
-            const bool ready = !done && (dep & pendMask) == 0u;
-            uint32_t hand = SL_STATE_IDENTITY;
-            bool go = ready;
-            if (ready && startsMid)
+            const int cnt = gEnd - gNext;
+            const uint32_t nz = __ballot_sync(0xffffffffu, cnt > 0);
+            if (!nz) break;
+            /* pieces that continue a span of the segment on the left (or of the row below) need its hand-over first */
+            bool ready = true;
+            if (cnt > 0 && needsIn && !started)
             {
-                if (needsIn) go = sl_handoff_poll(P, recId, ySrc, bIn, hand);
-                else
+                SLHand h;
+                ready = sl_handoff_poll(P, recId, ySrc, bIn, h);
+                if (ready)
                 {
-                    /* depth test off: every lane left of the cut passed and the lane map is still the identity */
-                    const int x4 = xMin + (((p0 - xMin) >> 2) << 2);
-                    hand = SL_STATE_IDENTITY | ((((1u << (p0 - x4)) - 1u) & 7u) << 8);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) pieceRegs[lane * 4 + k] = make_float4(h.r[k].v[0], h.r[k].v[1], h.r[k].v[2], h.r[k].v[3]);
+                    pfM = h.fM;
+                    gBase = gNext;
+                    started = true;
                 }
             }
-            const int first = __ffs(pendMask) - 1;
-            const bool firstLong = __shfl_sync(0xffffffffu, isLong ? 1 : 0, first) != 0;
-            const bool firstGo = __shfl_sync(0xffffffffu, go ? 1 : 0, first) != 0;
-            bool progress = false;
-            if (firstLong && firstGo)
+            int incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1)
             {
-                const uint32_t bRec = __shfl_sync(0xffffffffu, recId, first);
-                const int bY = __shfl_sync(0xffffffffu, ySrc, first);
-                const int bXMin = __shfl_sync(0xffffffffu, xMin, first), bXMax = __shfl_sync(0xffffffffu, xMax, first);
-                const int bP0 = __shfl_sync(0xffffffffu, p0, first), bP1 = __shfl_sync(0xffffffffu, p1, first);
-                const uint32_t bHand = __shfl_sync(0xffffffffu, hand, first);
-                const bool bPub = __shfl_sync(0xffffffffu, publish ? 1 : 0, first) != 0;
-                const int bOut = __shfl_sync(0xffffffffu, bIn + 1, first);
-                shaded += sl_walk_piece_warp(P, T, Q, bRec, bY, bXMin, bXMax, bP0, bP1, bHand, bPub, bOut);
-                if (lane == first) done = true;
-                progress = true;
+                const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            const int start = incl - cnt; /* lane of the window this piece's next group would get */
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            const uint32_t notReady = __ballot_sync(0xffffffffu, cnt > 0 && !ready);
+            int limit = min(32, total);
+            if (notReady) limit = min(limit, __shfl_sync(0xffffffffu, start, __ffs(notReady) - 1));
+            if (limit == 0)
+            {
+                /* the first unresolved piece waits for its hand-over: back off so that the polling does not take issue
+                 * slots from the warps that produce it */
+                idle = min(idle + 1u, 4u);
+                __nanosleep(20u << idle);
+                continue;
+            }
+            idle = 0;
+            __syncwarp();
+
+            /* ---- this lane as a worker: group `lane` of the window ---- */
+            const uint32_t heads = __reduce_or_sync(0xffffffffu, (cnt > 0 && start < limit) ? (1u << start) : 0u);
+            const bool act = lane < limit;
+            const int ord = __popc(heads & (0xffffffffu >> (31 - lane))) - 1;
+            const int pi = act ? (int)__fns(nz, 0u, ord + 1) : 0; /* the lane that keeps this group's piece */
+            const uint32_t wRec = __shfl_sync(0xffffffffu, recId, pi);
+            const int wY = __shfl_sync(0xffffffffu, ySrc, pi);
+            const int wXMin = __shfl_sync(0xffffffffu, xMin, pi);
+            const int wP0 = __shfl_sync(0xffffffffu, p0, pi);
+            const int wP1 = __shfl_sync(0xffffffffu, p1, pi);
+            const int wXBase = __shfl_sync(0xffffffffu, xBase, pi);
+            const int wStart = __shfl_sync(0xffffffffu, start, pi);
+            const int wGNext = __shfl_sync(0xffffffffu, gNext, pi);
+            const int wGEnd = __shfl_sync(0xffffffffu, gEnd, pi);
+            const int wGBase = __shfl_sync(0xffffffffu, gBase, pi);
+            const uint32_t wFM = __shfl_sync(0xffffffffu, pfM, pi);
+            const uint32_t wFlags = __shfl_sync(0xffffffffu, (started ? 1u : 0u) | (publish ? 2u : 0u), pi);
+            const int wOut = __shfl_sync(0xffffffffu, bIn + 1, pi);
+            const bool wStarted = (wFlags & 1u) != 0u, wPublish = (wFlags & 2u) != 0u;
+            const int g = wGNext + (lane - wStart);
+            const int x4 = wXMin + 4 * g;
+
+            const float4* rec = P.records + (size_t)wRec * P.recStride;
+            SLTriSetup t;
+            sl_tri_setup(t, rec[0], rec[1], rec[2]);
+            const math::vec4 bcX = t.bc0 * 4.f;
+            math::vec4 a0, a1, a2, a3;
+            int nAdd;
+            uint32_t fM = 0u; /* outcomes of this group's lanes that another piece owns (left of the cut) */
+            if (wStarted)
+            {
+                const float4 r0 = pieceRegs[pi * 4 + 0], r1 = pieceRegs[pi * 4 + 1], r2 = pieceRegs[pi * 4 + 2], r3 = pieceRegs[pi * 4 + 3];
+                a0 = math::vec4{r0.x, r0.y, r0.z, r0.w};
+                a1 = math::vec4{r1.x, r1.y, r1.z, r1.w};
+                a2 = math::vec4{r2.x, r2.y, r2.z, r2.w};
+                a3 = math::vec4{r3.x, r3.y, r3.z, r3.w};
+                nAdd = g - wGBase;
+                if (g == wGBase) fM = wFM;
             }
             else
             {
-                const bool mine = go && !isLong;
-                if (__any_sync(0xffffffffu, mine))
+                const float yf = (float)wY;
+                const math::vec4 bcY = math::fmadd(t.bc1, math::vec4{yf}, t.bc2); /* :474 */
+                a0 = (t.bc0 * (float)(wXMin + 0)) + bcY;                          /* :476-481 */
+                a1 = (t.bc0 * (float)(wXMin + 1)) + bcY;
+                a2 = (t.bc0 * (float)(wXMin + 2)) + bcY;
+                a3 = (t.bc0 * (float)(wXMin + 3)) + bcY;
+                nAdd = g;
+                /* depth test off and the piece starts inside its span: the lanes left of the cut passed */
+                if (wXMin < wP0 && g == ((wP0 - wXMin) >> 2)) fM = ((1u << (wP0 - x4)) - 1u) & 7u;
+            }
+            if (!act) nAdd = 0;
+            for (int i = 0; i < nAdd; ++i) { a0 += bcX; a1 += bcX; a2 += bcX; a3 += bcX; } /* :539-542, one rounding per group */
+
+            /* depth of the four registers' initial contents at this group (_sl_mul_vec4_mat4_ps, :376-393) */
+            const float zc0 = ((a0.v[3] * 0.f) + (a0.v[2] * t.z2)) + ((a0.v[1] * t.z1) + (a0.v[0] * t.z0));
+            const float zc1 = ((a1.v[3] * 0.f) + (a1.v[2] * t.z2)) + ((a1.v[1] * t.z1) + (a1.v[0] * t.z0));
+            const float zc2 = ((a2.v[3] * 0.f) + (a2.v[2] * t.z2)) + ((a2.v[1] * t.z1) + (a2.v[0] * t.z0));
+            const float zc3 = ((a3.v[3] * 0.f) + (a3.v[2] * t.z2)) + ((a3.v[1] * t.z1) + (a3.v[0] * t.z0));
+            const int rowBase = (int)((long long)W * (long long)wY - T.origin);
+            uint32_t ownBits = 0u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+            {
+                if (act && x4 + j >= wP0 && x4 + j < wP1) ownBits |= 1u << j;
+            }
+            /* pixels of THIS row the group touches, and the earlier lanes of other pieces that touch them too */
+            const int ra = act ? max(x4, wP0) - wXBase : 0, rb = act ? min(x4 + 4, wP1) - wXBase : 0;
+            uint32_t ov = 0u;
+            if (useDepth)
+            {
+                for (int i = 0; i < 31; ++i)
                 {
-                    /* every ready short piece is walked by its lane, all lanes in lock step, one group per step */
-                    SLWalk w;
-                    w.x4 = 0;
-                    w.p1 = 0;
-                    w.y = 0;
-                    w.recId = 0u;
-                    if (mine) sl_walk_begin(w, P, T, recId, ySrc, xMin, p0, p1, hand, publish, bIn + 1);
-                    for (;;)
-                    {
-                        const bool act = mine && w.x4 < w.p1;
-                        if (!__any_sync(0xffffffffu, act)) break;
-                        math::vec4 bcJ[4];
-                        float zJ[4];
-                        uint32_t mBits = 0u;
-                        if (act)
-                        {
-                            mBits = sl_walk_group(w, P, T, bcJ, zJ);
-                            shaded += (unsigned)__popc(mBits);
-                        }
-                        sl_push_frags(Q, lane, mBits, bcJ, zJ, w.x4, w.y, w.recId);
-                        if (act) sl_walk_advance(w);
-                        sl_flush(P, Q, lane, false);
-                    }
-                    if (mine)
-                    {
-                        if (w.publish && !w.published) sl_handoff_publish(P, recId, ySrc, bIn + 1, w.st); /* the cut falls on a group boundary */
-                        done = true;
-                    }
-                    progress = true;
+                    const int oa = __shfl_sync(0xffffffffu, ra, i);
+                    const int ob = __shfl_sync(0xffffffffu, rb, i);
+                    const int op = __shfl_sync(0xffffffffu, pi, i);
+                    if (i < lane && op != pi && oa < rb && ra < ob) ov |= 1u << i;
                 }
             }
-            /* nothing could run: every ready piece waits for a hand-over from the segment on its left (or the row
-             * below).  Back off so that the polling does not take issue slots from the warps that produce them. */
-            if (!progress) { idle = min(idle + 1u, 8u); __nanosleep(32u << idle); }
-            else idle = 0;
+            const uint32_t before = ltMask & ~((1u << wStart) - 1u); /* earlier lanes of my piece in this window */
+
+            /* ---- waves ---- */
+            bool pending = act;
+            uint32_t stCur = SL_STATE_IDENTITY; /* lane map after my piece's last settled group (relative to a0..a3) */
+            uint32_t stIn = SL_STATE_IDENTITY, mBits = 0u, tBits = 0u;
+            for (;;)
+            {
+                const uint32_t PEND = __ballot_sync(0xffffffffu, pending);
+                if (!PEND) break;
+                const bool dSafe = pending && (ov & PEND) == 0u;
+                uint32_t m = 0u;
+                if (dSafe)
+                {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                    {
+                        if ((ownBits >> j) & 1u)
+                        {
+                            const uint32_t sj = (stCur >> (2 * j)) & 3u;
+                            const float z = sj == 0u ? zc0 : (sj == 1u ? zc1 : (sj == 2u ? zc2 : zc3));
+                            const float d = P.depthTest ? sl_load_depth(T.depth, P.depthBpt, (size_t)(rowBase + x4 + j)) : 0.f;
+                            if (sl_depth_cmp(P.depthTest, z, d)) m |= 1u << j;
+                        }
+                    }
+                }
+                const uint32_t tt = m | fM;
+                const uint32_t stOut = sl_state_step(stCur, tt);
+                const uint32_t D = __ballot_sync(0xffffffffu, dSafe);
+                const uint32_t CH = __ballot_sync(0xffffffffu, dSafe && stOut != stCur);
+                const bool commit = dSafe && (((~D) | CH) & PEND & before) == 0u;
+                if (commit)
+                {
+                    stIn = stCur;
+                    mBits = m;
+                    tBits = tt;
+                    pending = false;
+                    if (P.depthMask && m) /* src/SL_FragmentProcessor.cpp:526-529 */
+                    {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                        {
+                            if ((m >> j) & 1u)
+                            {
+                                const uint32_t sj = (stCur >> (2 * j)) & 3u;
+                                const float z = sj == 0u ? zc0 : (sj == 1u ? zc1 : (sj == 2u ? zc2 : zc3));
+                                sl_store_depth(T.depth, P.depthBpt, (size_t)(rowBase + x4 + j), z);
+                            }
+                        }
+                    }
+                }
+                /* the still pending lanes of a piece go on under the lane map its last settled lane left behind */
+                const uint32_t C = __ballot_sync(0xffffffffu, commit);
+                const uint32_t cand = C & before;
+                const int src = cand ? (31 - __clz(cand)) : lane;
+                const uint32_t sNew = __shfl_sync(0xffffffffu, stOut, src);
+                if (pending && cand) stCur = sNew;
+                __syncwarp(); /* depth stores of this wave before the loads of the next */
+            }
+
+            /* ---- the piece's last group: hand over to the piece on the right; a piece cut by the window end: carry on ---- */
+            const uint32_t stAfter = sl_state_step(stIn, tBits);
+            if (act && g == wGEnd - 1)
+            {
+                if (wPublish)
+                {
+                    if (((wP1 - wXMin) >> 2) == g)
+                    {
+                        /* the cut lies inside this group: the registers before its compaction + outcomes left of the cut */
+                        const uint32_t below = (1u << (wP1 - x4)) - 1u;
+                        sl_handoff_publish(P, wRec, wY, wOut, tBits & below & 7u, sl_pick4(stIn & 3u, a0, a1, a2, a3), sl_pick4((stIn >> 2) & 3u, a0, a1, a2, a3),
+                                           sl_pick4((stIn >> 4) & 3u, a0, a1, a2, a3), sl_pick4((stIn >> 6) & 3u, a0, a1, a2, a3));
+                    }
+                    else
+                    {
+                        /* the cut falls on the group boundary: the registers after the compaction, advanced to the next group */
+                        sl_handoff_publish(P, wRec, wY, wOut, 0u, sl_pick4(stAfter & 3u, a0, a1, a2, a3) + bcX, sl_pick4((stAfter >> 2) & 3u, a0, a1, a2, a3) + bcX,
+                                           sl_pick4((stAfter >> 4) & 3u, a0, a1, a2, a3) + bcX, sl_pick4((stAfter >> 6) & 3u, a0, a1, a2, a3) + bcX);
+                    }
+                }
+            }
+            else if (act && lane == limit - 1)
+            {
+                const math::vec4 c0 = sl_pick4(stAfter & 3u, a0, a1, a2, a3) + bcX, c1 = sl_pick4((stAfter >> 2) & 3u, a0, a1, a2, a3) + bcX;
+                const math::vec4 c2 = sl_pick4((stAfter >> 4) & 3u, a0, a1, a2, a3) + bcX, c3 = sl_pick4((stAfter >> 6) & 3u, a0, a1, a2, a3) + bcX;
+                pieceRegs[pi * 4 + 0] = make_float4(c0.v[0], c0.v[1], c0.v[2], c0.v[3]);
+                pieceRegs[pi * 4 + 1] = make_float4(c1.v[0], c1.v[1], c1.v[2], c1.v[3]);
+                pieceRegs[pi * 4 + 2] = make_float4(c2.v[0], c2.v[1], c2.v[2], c2.v[3]);
+                pieceRegs[pi * 4 + 3] = make_float4(c3.v[0], c3.v[1], c3.v[2], c3.v[3]);
+            }
+
+            /* ---- survivors, in lane order: number s is shaded with register s after the compaction = the initial
+             * register of the first passing lane >= s (:500-526), and with its own x and z ---- */
+            math::vec4 bcJ[4];
+            float zJ[4];
+            if (mBits)
+            {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                {
+                    const uint32_t sIdx = (uint32_t)__popc(tBits & ((1u << j) - 1u));
+                    const uint32_t ge = tBits & ~((1u << sIdx) - 1u);
+                    const int pLane = __ffs(ge) - 1;
+                    bcJ[j] = sl_pick4((stIn >> (2 * (pLane & 3))) & 3u, a0, a1, a2, a3);
+                    const uint32_t zj = (stIn >> (2 * j)) & 3u;
+                    zJ[j] = zj == 0u ? zc0 : (zj == 1u ? zc1 : (zj == 2u ? zc2 : zc3));
+                }
+                shaded += (unsigned)__popc(mBits);
+            }
+            sl_push_frags(Q, lane, mBits, bcJ, zJ, x4, wY, wRec);
+            sl_flush(P, Q, lane, false);
+
+            /* ---- book-keeping of the pieces ---- */
+            const int consumed = min(cnt, max(0, limit - start));
+            if (consumed > 0)
+            {
+                gNext += consumed;
+                if (gNext < gEnd)
+                {
+                    started = true; /* pieceRegs[lane] was written by the worker of the last consumed group */
+                    gBase = gNext;
+                    pfM = 0u;
+                }
+            }
             __syncwarp();
         }
     }

@@ -209,6 +209,7 @@ struct slcu_context
     SLCounters* hostCounters = nullptr; /* pinned */
     Scratch records, blockInfo, cnt, off, segSums, rowTotals, rowStart, entries, handoff, rowFlags, rowNeeded, drawTable, blockDraw, recDraw;
     Scratch fragPool, chunkNext, listInfo; /* fragment lists, k_resolve -> k_shade */
+    Scratch handoffRegs;
     Batch batch;            /* submitted, not yet executed draws */
     bool syncDraws = false; /* SLCU_SYNC_DRAWS=1: execute every draw call on its own (debug / parity mode) */
     /* sort-first partition (slcu_set_partition) */
@@ -465,7 +466,9 @@ static int flush_draws_impl(slcu_context* c)
 
     const unsigned rowPitch = (H + 31u) & ~31u;
     /* x-segments of the rasteriser: one warp per (row, segment), about 128 pixels each, at most 32 per row */
-    unsigned rasterSegs = (depthTex.w + 127u) / 128u;
+    unsigned segTarget = 128u;
+    if (const char* e = getenv("SLCU_SEG_WIDTH")) { const int v = atoi(e); if (v >= 16) segTarget = (unsigned)v; }
+    unsigned rasterSegs = (depthTex.w + segTarget - 1u) / segTarget;
     if (rasterSegs < 1u) rasterSegs = 1u;
     if (rasterSegs > 32u) rasterSegs = 32u;
     const unsigned segWidth = (depthTex.w + rasterSegs - 1u) / rasterSegs;
@@ -587,8 +590,9 @@ static int flush_draws_impl(slcu_context* c)
         if (!totalSpans) return 0;
         numHandoffs = c->hostCounters->handoffs;
         if (getenv("SLCU_DEBUG"))
-            fprintf(stderr, "[slcu] batch: draws=%zu prims=%llu records=%llu entries=%u handoffs=%llu segs=%ux%u flags=0x%x\n", B.descs.size(), totalPrims,
-                    (unsigned long long)c->hostCounters->recAlloc, totalSpans, numHandoffs, rasterSegs, segWidth, c->hostCounters->errorFlags);
+            fprintf(stderr, "[slcu] batch: draws=%zu prims=%llu records=%llu entries=%u handoffs=%llu segs=%ux%u pixels=%llu flags=0x%x\n", B.descs.size(), totalPrims,
+                    (unsigned long long)c->hostCounters->recAlloc, totalSpans, numHandoffs, rasterSegs, segWidth, (unsigned long long)c->hostCounters->pixelsCovered,
+                    c->hostCounters->errorFlags);
 
         CK(c->entries.ensure((size_t)totalSpans * sizeof(SLSpanEntry)));
         sp.entries = reinterpret_cast<SLSpanEntry*>(c->entries.buf.ptr);
@@ -630,6 +634,7 @@ static int flush_draws_impl(slcu_context* c)
     rp.depth = depthTex.dev;
     rp.depthBpt = depthTex.bpt;
     rp.handoff = nullptr;
+    rp.handoffRegs = nullptr;
     rp.handoffMask = 0;
     rp.rowNeeded = rowNeeded;
     rp.segWidth = segWidth;
@@ -641,14 +646,16 @@ static int flush_draws_impl(slcu_context* c)
         while (cap < 2 * numHandoffs) cap <<= 1;
         CK(c->handoff.ensure(cap * sizeof(unsigned long long)));
         CK(cudaMemsetAsync(c->handoff.buf.ptr, 0, cap * sizeof(unsigned long long), c->stream));
+        CK(c->handoffRegs.ensure(cap * 4 * sizeof(float4)));
         rp.handoff = reinterpret_cast<unsigned long long*>(c->handoff.buf.ptr);
+        rp.handoffRegs = reinterpret_cast<float4*>(c->handoffRegs.buf.ptr);
         rp.handoffMask = (unsigned)(cap - 1);
     }
     /* each resolving warp keeps its segment's depth texels in shared memory (at most 32 x ... pixels x 8 bytes) */
     rp.tileBytes = (segWidth * depthTex.bpt + 15u) & ~15u;
     rp.counters = c->counters;
     const unsigned warpsPerBlock = SL_RASTER_WARPS;
-    const unsigned smemBytes = warpsPerBlock * (SL_PIECEQ_BYTES + SL_FQ_BYTES + rp.tileBytes); /* piece queue + fragment queue + tile, per warp */
+    const unsigned smemBytes = warpsPerBlock * (SL_PIECEQ_BYTES + SL_FQ_BYTES + SL_PIECEREG_BYTES + rp.tileBytes); /* piece queue + fragment queue + piece registers + tile, per warp */
     {
         static bool attrSet = false;
         if (!attrSet)
@@ -780,7 +787,7 @@ void slcu_context_destroy(slcu_context* c)
     if (c->counters) cudaFree(c->counters);
     if (c->hostCounters) cudaFreeHost(c->hostCounters);
     for (auto& pm : c->peerMaps) if (pm.ptr) cudaIpcCloseMemHandle(pm.ptr);
-    Scratch* s[] = {&c->records, &c->blockInfo, &c->cnt, &c->off, &c->segSums, &c->rowTotals, &c->rowStart, &c->entries, &c->handoff, &c->rowFlags, &c->rowNeeded, &c->drawTable, &c->blockDraw, &c->recDraw, &c->fragPool, &c->chunkNext, &c->listInfo};
+    Scratch* s[] = {&c->records, &c->blockInfo, &c->cnt, &c->off, &c->segSums, &c->rowTotals, &c->rowStart, &c->entries, &c->handoff, &c->rowFlags, &c->rowNeeded, &c->drawTable, &c->blockDraw, &c->recDraw, &c->fragPool, &c->chunkNext, &c->listInfo, &c->handoffRegs};
     for (Scratch* x : s) x->release();
     cudaStreamDestroy(c->stream);
     delete c;
