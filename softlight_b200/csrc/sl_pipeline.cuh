@@ -865,6 +865,7 @@ struct SLRasterParams
     unsigned int handoffMask;
     unsigned int segWidth;       /* x-segment width */
     unsigned int numSegs;        /* segments per row (<= 32) */
+    unsigned int numSubLists;    /* fragment lists per segment: one per 2^SL_SHADE_SHIFT pixels */
     unsigned int tileBytes;      /* shared memory per warp for its segment's depth texels (0: work in global memory) */
     const uint8_t* rowNeeded;    /* sort-first partition: rows this rank rasterises (null = all) */
     unsigned char* depth;
@@ -1098,104 +1099,90 @@ struct SLTile
  *   happen in submission order; fragments of one step that hit the same pixel are ordered by lane.  Lists never share
  *   a pixel, so list order is free.  The shader always runs with converged lanes.
  * ----------------------------------------------------------------------*/
-constexpr int SL_FQ_CAP = 160;                               /* < 32 left over + at most 4 x 32 pushed per step */
-constexpr unsigned SL_FQ_BYTES = SL_FQ_CAP * (16u + 4u + 4u + 4u);
 constexpr unsigned SL_PIECEQ_BYTES = 32u * (unsigned)sizeof(SLSpanEntry);
+constexpr int SL_MAX_SUBLISTS = 8;      /* fragment lists per resolving warp: one per SL_SHADE_WIDTH pixels of its segment */
+constexpr int SL_SHADE_SHIFT = 7;       /* log2(SL_SHADE_WIDTH)                                                          */
+constexpr unsigned SL_SUBLIST_BYTES = SL_MAX_SUBLISTS * 3u * 4u + 32u; /* per warp: tail chunk, fill, total of every sub-list */
 
-struct SLFragQueue
+/* Append the survivors of a window to the warp's fragment lists, straight into the chunks in HBM.  Lists are ordered by
+ * (lane, pixel) = submission order per pixel; a group's pixels may fall into two neighbouring sub-lists.  Per sub-list:
+ * an exclusive scan of the lanes' counts gives every fragment its position behind the list's tail; the chunks that
+ * position range needs beyond the tail chunk are taken with ONE atomic and linked by the first lanes. */
+struct SLListState
 {
-    float4* bc;    /* barycentrics (register s of the reference after the compaction) */
-    float* z;
-    uint32_t* xy;  /* x | y << 16: coordinates relative to the span's source row (x >= width for fragments that wrapped) */
-    uint32_t* rec;
-    int count;     /* warp-uniform */
-    /* the list this warp appends to */
-    uint32_t list, tail, total;
-
-    SLD_FN void bind(unsigned char* mem)
-    {
-        bc = reinterpret_cast<float4*>(mem);
-        z = reinterpret_cast<float*>(mem + SL_FQ_CAP * 16u);
-        xy = reinterpret_cast<uint32_t*>(mem + SL_FQ_CAP * 20u);
-        rec = reinterpret_cast<uint32_t*>(mem + SL_FQ_CAP * 24u);
-    }
+    uint32_t* tail;   /* [nsub] current chunk of the sub-list (SL_NO_CHUNK: none yet)  */
+    uint32_t* fill;   /* [nsub] fragments in it, 1..32 (32 when there is no chunk)      */
+    uint32_t* total;  /* [nsub] fragments of the sub-list so far                        */
+    uint32_t firstList;
+    int nsub;
 };
 
-/* push the survivors of one 4-pixel group per lane, in lane order (warp-collective; mBits == 0 for idle lanes) */
-SLD_FN void sl_push_frags(SLFragQueue& Q, int lane, uint32_t mBits, const math::vec4 (&bcJ)[4], const float (&zJ)[4], int x4, int y, uint32_t recId)
+SLD_FN void sl_push_frags(const SLRasterParams& P, const SLListState& L, int lane, uint32_t mBits, const math::vec4 (&bcJ)[4], const float (&zJ)[4], int x4,
+                          int relX, int y, uint32_t recId)
 {
     if (!__any_sync(0xffffffffu, mBits != 0u)) return;
-    const int n = __popc(mBits);
-    int incl = n;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1)
+    /* sub-list of every pixel of the group (relX = x of the group's first pixel relative to the segment start) */
+    const int sFirst = relX >> SL_SHADE_SHIFT, sLast = (relX + 3) >> SL_SHADE_SHIFT;
+    const int jSplit = sLast != sFirst ? (((sFirst + 1) << SL_SHADE_SHIFT) - relX) : 4; /* pixels j >= jSplit belong to sLast */
+    const uint32_t loBits = mBits & ((1u << jSplit) - 1u), hiBits = mBits & ~((1u << jSplit) - 1u);
+    const int sMin = __reduce_min_sync(0xffffffffu, mBits ? (loBits ? sFirst : sLast) : 0x7fffffff);
+    const int sMax = __reduce_max_sync(0xffffffffu, mBits ? (hiBits ? sLast : sFirst) : -1);
+    for (int sub = sMin; sub <= sMax; ++sub)
     {
-        const int t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += t;
-    }
-    int e = Q.count + incl - n;
+        const uint32_t bits = (sub == sFirst ? loBits : 0u) | (sub == sLast ? hiBits : 0u);
+        const int n = __popc(bits);
+        int incl = n;
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-    {
-        if ((mBits >> j) & 1u)
+        for (int d = 1; d < 32; d <<= 1)
         {
-            Q.bc[e] = make_float4(bcJ[j].v[0], bcJ[j].v[1], bcJ[j].v[2], bcJ[j].v[3]);
-            Q.z[e] = zJ[j];
-            Q.xy[e] = (uint32_t)(x4 + j) | ((uint32_t)y << 16);
-            Q.rec[e] = recId;
-            ++e;
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
         }
-    }
-    Q.count += __shfl_sync(0xffffffffu, incl, 31);
-}
-
-/* append every full batch of the queue (and the rest too when `all`) to the warp's fragment list; what is left moves
- * to the front */
-SLD_FN void sl_flush(const SLRasterParams& P, SLFragQueue& Q, int lane, bool all)
-{
-    if (Q.count < 32 && !(all && Q.count > 0)) return;
-    __syncwarp();
-    int first = 0;
-    while (Q.count - first >= 32 || (all && Q.count - first > 0))
-    {
-        const int n = min(32, Q.count - first);
-        uint32_t chunk = 0u;
+        const int T = __shfl_sync(0xffffffffu, incl, 31);
+        if (!T) continue;
+        const uint32_t tail = L.tail[sub], fill = L.fill[sub];
+        const uint32_t need = (fill + (uint32_t)T - 1u) >> 5; /* chunks beyond the tail chunk */
+        uint32_t baseChunk = 0u;
+        if (need)
+        {
+            if (lane == 0)
+            {
+                baseChunk = atomicAdd(&P.counters->chunkAlloc, need);
+                if (baseChunk + need > P.lists.chunkCapacity) { atomicOr(&P.counters->errorFlags, 32u); baseChunk = SL_NO_CHUNK; }
+            }
+            baseChunk = __shfl_sync(0xffffffffu, baseChunk, 0);
+            if (baseChunk == SL_NO_CHUNK) continue; /* pool exhausted: flagged, fragments dropped */
+            if ((uint32_t)lane < need)
+            {
+                const uint32_t prev = lane == 0 ? tail : baseChunk + (uint32_t)lane - 1u;
+                if (prev == SL_NO_CHUNK) P.lists.listHead[L.firstList + sub] = baseChunk;
+                else P.lists.chunkNext[prev] = baseChunk + (uint32_t)lane;
+            }
+        }
+        uint32_t q = fill + (uint32_t)(incl - n);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+        {
+            if ((bits >> j) & 1u)
+            {
+                const uint32_t ci = q >> 5, slot = q & 31u;
+                unsigned char* c = P.lists.pool + (size_t)(ci ? baseChunk + ci - 1u : tail) * SL_CHUNK_BYTES;
+                reinterpret_cast<float4*>(c)[slot] = make_float4(bcJ[j].v[0], bcJ[j].v[1], bcJ[j].v[2], bcJ[j].v[3]);
+                reinterpret_cast<float*>(c + 512)[slot] = zJ[j];
+                reinterpret_cast<uint32_t*>(c + 640)[slot] = (uint32_t)(x4 + j) | ((uint32_t)y << 16);
+                reinterpret_cast<uint32_t*>(c + 768)[slot] = recId;
+                ++q;
+            }
+        }
+        __syncwarp();
         if (lane == 0)
         {
-            chunk = atomicAdd(&P.counters->chunkAlloc, 1u);
-            if (chunk >= P.lists.chunkCapacity) { atomicOr(&P.counters->errorFlags, 32u); chunk = SL_NO_CHUNK; }
-            else if (Q.tail == SL_NO_CHUNK) P.lists.listHead[Q.list] = chunk;
-            else P.lists.chunkNext[Q.tail] = chunk;
+            L.fill[sub] = ((fill + (uint32_t)T - 1u) & 31u) + 1u;
+            if (need) L.tail[sub] = baseChunk + need - 1u;
+            L.total[sub] += (uint32_t)T;
         }
-        chunk = __shfl_sync(0xffffffffu, chunk, 0);
-        if (chunk != SL_NO_CHUNK)
-        {
-            unsigned char* c = P.lists.pool + (size_t)chunk * SL_CHUNK_BYTES;
-            if (lane < n)
-            {
-                reinterpret_cast<float4*>(c)[lane] = Q.bc[first + lane];
-                reinterpret_cast<float*>(c + 512)[lane] = Q.z[first + lane];
-                reinterpret_cast<uint32_t*>(c + 640)[lane] = Q.xy[first + lane];
-                reinterpret_cast<uint32_t*>(c + 768)[lane] = Q.rec[first + lane];
-            }
-            Q.tail = chunk;
-            Q.total += (uint32_t)n;
-        }
-        first += n;
+        __syncwarp();
     }
-    const int r = Q.count - first;
-    if (r > 0) /* first >= 32 > r: source and destination do not overlap */
-    {
-        if (lane < r)
-        {
-            Q.bc[lane] = Q.bc[first + lane];
-            Q.z[lane] = Q.z[first + lane];
-            Q.xy[lane] = Q.xy[first + lane];
-            Q.rec[lane] = Q.rec[first + lane];
-        }
-    }
-    Q.count = r;
-    __syncwarp();
 }
 
 /* Hand-over of the walker state at a cut (see SL_ENTRY_OVERFLOW).  A row is resolved by numSegs warps, one per
@@ -1288,6 +1275,7 @@ constexpr int SL_RASTER_WARPS = 4;
 #define SL_RASTER_MIN_BLOCKS 4
 #endif
 constexpr unsigned SL_PIECEREG_BYTES = 32u * 4u * (unsigned)sizeof(float4); /* per warp: the registers a piece continues from */
+constexpr unsigned SL_WINSCRATCH_BYTES = 32u * 4u + 32u * 16u; /* head -> piece, piece book (+ 4 bytes per pixel of the segment: toucher masks) */
 
 SLD_FN unsigned sl_align16(unsigned n) { return (n + 15u) & ~15u; }
 
@@ -1353,20 +1341,34 @@ __global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_
     const uint32_t begin = P.rowStart[y], end = P.rowStart[y + 1];
     if (begin == end) return;
     unsigned shaded = 0;
-
-    unsigned char* warpMem = sDyn + (size_t)warp * (SL_PIECEQ_BYTES + SL_FQ_BYTES + SL_PIECEREG_BYTES + P.tileBytes);
-    SLSpanEntry* queue = reinterpret_cast<SLSpanEntry*>(warpMem);
-    SLFragQueue Q;
-    Q.bind(warpMem + SL_PIECEQ_BYTES);
-    Q.count = 0;
-    Q.list = ticket;
-    Q.tail = SL_NO_CHUNK;
-    Q.total = 0u;
-    float4* pieceRegs = reinterpret_cast<float4*>(warpMem + SL_PIECEQ_BYTES + SL_FQ_BYTES);
-    unsigned char* tileMem = warpMem + SL_PIECEQ_BYTES + SL_FQ_BYTES + SL_PIECEREG_BYTES;
-    const unsigned segPixels = (unsigned)(sx1 - sx0);
-    const long long segOrigin = (long long)W * y + sx0;
     const bool useDepth = P.depthTest != 0 || P.depthMask != 0;
+
+    const unsigned pixMaskBytes = sl_align16(4u * P.segWidth);
+    unsigned char* warpMem = sDyn + (size_t)warp * (SL_PIECEQ_BYTES + SL_SUBLIST_BYTES + SL_PIECEREG_BYTES + SL_WINSCRATCH_BYTES + pixMaskBytes + P.tileBytes);
+    SLSpanEntry* queue = reinterpret_cast<SLSpanEntry*>(warpMem);
+    SLListState L;
+    L.tail = reinterpret_cast<uint32_t*>(warpMem + SL_PIECEQ_BYTES);
+    L.fill = L.tail + SL_MAX_SUBLISTS;
+    L.total = L.fill + SL_MAX_SUBLISTS;
+    L.nsub = (int)P.numSubLists;
+    L.firstList = ticket * P.numSubLists;
+    if (lane < SL_MAX_SUBLISTS)
+    {
+        L.tail[lane] = SL_NO_CHUNK;
+        L.fill[lane] = 32u;
+        L.total[lane] = 0u;
+    }
+    float4* pieceRegs = reinterpret_cast<float4*>(warpMem + SL_PIECEQ_BYTES + SL_SUBLIST_BYTES);
+    uint32_t* slotPiece = reinterpret_cast<uint32_t*>(warpMem + SL_PIECEQ_BYTES + SL_SUBLIST_BYTES + SL_PIECEREG_BYTES);
+    int4* pieceBook = reinterpret_cast<int4*>(slotPiece + 32);
+    uint32_t* pixMask = reinterpret_cast<uint32_t*>(pieceBook + 32); /* [segWidth] lanes of the current window that touch the pixel */
+    unsigned char* tileMem = warpMem + SL_PIECEQ_BYTES + SL_SUBLIST_BYTES + SL_PIECEREG_BYTES + SL_WINSCRATCH_BYTES + pixMaskBytes;
+    const unsigned segPixels = (unsigned)(sx1 - sx0);
+    if (useDepth)
+    {
+        for (unsigned i = lane; i < P.segWidth; i += 32) pixMask[i] = 0u;
+    }
+    const long long segOrigin = (long long)W * y + sx0;
     SLTile T;
     bool staged = false;
     if (P.tileBytes && useDepth)
@@ -1491,26 +1493,40 @@ __global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_
             __syncwarp();
 
             /* ---- this lane as a worker: group `lane` of the window ---- */
-            const uint32_t heads = __reduce_or_sync(0xffffffffu, (cnt > 0 && start < limit) ? (1u << start) : 0u);
+            const bool headHere = cnt > 0 && start < limit;
+            const uint32_t heads = __ballot_sync(0xffffffffu, headHere); /* piece lanes whose piece has groups in the window */
+            if (headHere)
+            {
+                slotPiece[start] = (uint32_t)lane;
+                pieceBook[lane] = make_int4(start, gNext, gBase, (int)(pfM | (started ? 8u : 0u) | (publish ? 16u : 0u)));
+            }
+            __syncwarp();
             const bool act = lane < limit;
-            const int ord = __popc(heads & (0xffffffffu >> (31 - lane))) - 1;
-            const int pi = act ? (int)__fns(nz, 0u, ord + 1) : 0; /* the lane that keeps this group's piece */
-            const uint32_t wRec = __shfl_sync(0xffffffffu, recId, pi);
-            const int wY = __shfl_sync(0xffffffffu, ySrc, pi);
-            const int wXMin = __shfl_sync(0xffffffffu, xMin, pi);
-            const int wP0 = __shfl_sync(0xffffffffu, p0, pi);
-            const int wP1 = __shfl_sync(0xffffffffu, p1, pi);
-            const int wXBase = __shfl_sync(0xffffffffu, xBase, pi);
-            const int wStart = __shfl_sync(0xffffffffu, start, pi);
-            const int wGNext = __shfl_sync(0xffffffffu, gNext, pi);
-            const int wGEnd = __shfl_sync(0xffffffffu, gEnd, pi);
-            const int wGBase = __shfl_sync(0xffffffffu, gBase, pi);
-            const uint32_t wFM = __shfl_sync(0xffffffffu, pfM, pi);
-            const uint32_t wFlags = __shfl_sync(0xffffffffu, (started ? 1u : 0u) | (publish ? 2u : 0u), pi);
-            const int wOut = __shfl_sync(0xffffffffu, bIn + 1, pi);
-            const bool wStarted = (wFlags & 1u) != 0u, wPublish = (wFlags & 2u) != 0u;
+            /* the piece of this group: the last piece that starts at or before this lane */
+            uint32_t startBits = 0u;
+            {
+                /* bit k set when some piece of the window starts at lane k */
+                const uint32_t mine = headHere ? (1u << start) : 0u;
+                startBits = __reduce_or_sync(0xffffffffu, mine);
+            }
+            const int headLane = 31 - __clz((int)(startBits & (0xffffffffu >> (31 - lane))));
+            const int pi = act ? (int)slotPiece[headLane] : 0; /* the lane that keeps this group's piece */
+            const SLSpanEntry we = queue[pi];
+            const int4 wb = pieceBook[pi];
+            const bool wOver = (we.rec & SL_ENTRY_OVERFLOW) != 0u;
+            const uint32_t wRec = we.rec & ~SL_ENTRY_OVERFLOW;
+            const int wXBase = wOver ? W : 0;
+            const int wY = wOver ? y - 1 : y;
+            const int wXMin = we.xMin;
+            const int wP0 = max(wXMin, wXBase + sx0), wP1 = min((int)we.xMax, wXBase + sx1);
+            const int wStart = wb.x, wGNext = wb.y, wGBase = wb.z;
+            const uint32_t wFM = (uint32_t)wb.w & 7u;
+            const bool wStarted = ((uint32_t)wb.w & 8u) != 0u, wPublish = ((uint32_t)wb.w & 16u) != 0u;
+            const int wGEnd = ((wP1 - 1 - wXMin) >> 2) + 1;
+            const int wOut = (wOver ? NS : 0) + seg + 1;
             const int g = wGNext + (lane - wStart);
             const int x4 = wXMin + 4 * g;
+            (void)heads;
 
             const float4* rec = P.records + (size_t)wRec * P.recStride;
             SLTriSetup t;
@@ -1556,20 +1572,32 @@ __global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_
             {
                 if (act && x4 + j >= wP0 && x4 + j < wP1) ownBits |= 1u << j;
             }
-            /* pixels of THIS row the group touches, and the earlier lanes of other pieces that touch them too */
-            const int ra = act ? max(x4, wP0) - wXBase : 0, rb = act ? min(x4 + 4, wP1) - wXBase : 0;
+            /* the earlier lanes of other pieces that touch one of this group's pixels: every lane adds itself to the
+             * toucher mask of its pixels, reads them back, and clears them again for the next window */
+            const uint32_t before = ltMask & ~((1u << wStart) - 1u); /* earlier lanes of my piece in this window */
             uint32_t ov = 0u;
             if (useDepth)
             {
-                for (int i = 0; i < 31; ++i)
+                const int px = x4 - wXBase - sx0; /* segment-relative x of the group's first pixel */
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
                 {
-                    const int oa = __shfl_sync(0xffffffffu, ra, i);
-                    const int ob = __shfl_sync(0xffffffffu, rb, i);
-                    const int op = __shfl_sync(0xffffffffu, pi, i);
-                    if (i < lane && op != pi && oa < rb && ra < ob) ov |= 1u << i;
+                    if ((ownBits >> j) & 1u) atomicOr(&pixMask[px + j], 1u << lane);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                {
+                    if ((ownBits >> j) & 1u) ov |= pixMask[px + j];
+                }
+                ov &= ltMask & ~before;
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                {
+                    if ((ownBits >> j) & 1u) pixMask[px + j] = 0u;
                 }
             }
-            const uint32_t before = ltMask & ~((1u << wStart) - 1u); /* earlier lanes of my piece in this window */
 
             /* ---- waves ---- */
             bool pending = act;
@@ -1678,8 +1706,7 @@ __global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_
                 }
                 shaded += (unsigned)__popc(mBits);
             }
-            sl_push_frags(Q, lane, mBits, bcJ, zJ, x4, wY, wRec);
-            sl_flush(P, Q, lane, false);
+            sl_push_frags(P, L, lane, mBits, bcJ, zJ, x4, x4 - wXBase - sx0, wY, wRec);
 
             /* ---- book-keeping of the pieces ---- */
             const int consumed = min(cnt, max(0, limit - start));
@@ -1696,8 +1723,8 @@ __global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_
             __syncwarp();
         }
     }
-    sl_flush(P, Q, lane, true);
-    if (lane == 0 && Q.total) P.lists.listCount[Q.list] = Q.total;
+    __syncwarp();
+    if (lane < L.nsub && L.total[lane]) P.lists.listCount[L.firstList + lane] = L.total[lane];
     const bool dirty = __any_sync(0xffffffffu, shaded != 0u);
     if (staged && dirty && P.depthMask)
     {

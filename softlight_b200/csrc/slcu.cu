@@ -466,7 +466,7 @@ static int flush_draws_impl(slcu_context* c)
 
     const unsigned rowPitch = (H + 31u) & ~31u;
     /* x-segments of the rasteriser: one warp per (row, segment), about 128 pixels each, at most 32 per row */
-    unsigned segTarget = 128u;
+    unsigned segTarget = 512u;
     if (const char* e = getenv("SLCU_SEG_WIDTH")) { const int v = atoi(e); if (v >= 16) segTarget = (unsigned)v; }
     unsigned rasterSegs = (depthTex.w + segTarget - 1u) / segTarget;
     if (rasterSegs < 1u) rasterSegs = 1u;
@@ -602,7 +602,9 @@ static int flush_draws_impl(slcu_context* c)
     }
 
     /* ---- fragment stage: k_resolve (depth, coverage, order) -> fragment lists -> k_shade<FS> ---- */
-    const unsigned long long numLists = (unsigned long long)H * rasterSegs;
+    unsigned numSubLists = (segWidth + (1u << SL_SHADE_SHIFT) - 1u) >> SL_SHADE_SHIFT;
+    if (numSubLists > (unsigned)SL_MAX_SUBLISTS) { c->err = "segment too wide for the sub-list table"; return SLCU_ERR_ARG; }
+    const unsigned long long numLists = (unsigned long long)H * rasterSegs * numSubLists;
     /* every fragment is a pixel of a span, and a list ends with at most one partial chunk */
     const unsigned long long pixelsCovered = c->hostCounters->pixelsCovered;
     const unsigned long long chunkCap = pixelsCovered / SL_CHUNK_FRAGS + numLists + 64ull;
@@ -639,6 +641,7 @@ static int flush_draws_impl(slcu_context* c)
     rp.rowNeeded = rowNeeded;
     rp.segWidth = segWidth;
     rp.numSegs = rasterSegs;
+    rp.numSubLists = numSubLists;
     rp.lists = lists;
     if (numHandoffs)
     {
@@ -655,7 +658,7 @@ static int flush_draws_impl(slcu_context* c)
     rp.tileBytes = (segWidth * depthTex.bpt + 15u) & ~15u;
     rp.counters = c->counters;
     const unsigned warpsPerBlock = SL_RASTER_WARPS;
-    const unsigned smemBytes = warpsPerBlock * (SL_PIECEQ_BYTES + SL_FQ_BYTES + SL_PIECEREG_BYTES + rp.tileBytes); /* piece queue + fragment queue + piece registers + tile, per warp */
+    const unsigned smemBytes = warpsPerBlock * (SL_PIECEQ_BYTES + SL_SUBLIST_BYTES + SL_PIECEREG_BYTES + SL_WINSCRATCH_BYTES + ((4u * segWidth + 15u) & ~15u) + rp.tileBytes); /* piece queue, fragment queue, piece registers, window scratch, tile: per warp */
     {
         static bool attrSet = false;
         if (!attrSet)
@@ -665,7 +668,8 @@ static int flush_draws_impl(slcu_context* c)
         }
         if (smemBytes > 96u * 1024u) { c->err = "framebuffer too wide for the resolve tile"; return SLCU_ERR_ARG; }
         KernelScope ks(c, SLCU_K_RASTER);
-        k_resolve<<<(unsigned)((numLists + warpsPerBlock - 1) / warpsPerBlock), warpsPerBlock * 32, smemBytes, c->stream>>>(rp);
+        const unsigned long long numWarps = (unsigned long long)H * rasterSegs;
+        k_resolve<<<(unsigned)((numWarps + warpsPerBlock - 1) / warpsPerBlock), warpsPerBlock * 32, smemBytes, c->stream>>>(rp);
         CK(cudaGetLastError());
     }
 
