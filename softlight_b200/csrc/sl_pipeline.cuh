@@ -613,72 +613,124 @@ SLD_FN unsigned sl_count_cuts(const SLSpanParams& P, int32_t xMin, int32_t xMax,
     return n;
 }
 
-/* MODE 0: count entries per (vertex block, row).  MODE 1: fill the row lists. */
+/* MODE 0: count entries per (vertex block, row).  MODE 1: fill the row lists.
+ *
+ * One CTA per vertex block; its records are taken 256 at a time (one per thread: bounding rows + SL_ScanlineBounds
+ * set-up, kept in shared memory).  The (record, row) pairs of such a batch are then flattened and dealt out evenly to
+ * the 256 threads, row window by row window, so that a triangle that covers a thousand rows costs the block as much
+ * as a thousand one-row triangles.  Order inside the batch comes from a bit mask per (row, kind): bit i = record i
+ * of the batch has an entry in that row; an entry's place in its row list is the number of set bits below its own. */
 template <int MODE>
 __global__ void __launch_bounds__(256) k_span(const __grid_constant__ SLSpanParams P)
 {
     __shared__ uint16_t sRowRun[SL_MAX_ROWS];
     __shared__ uint32_t sMask[2][SL_SPAN_WIN][8]; /* [0] overflow entries coming from the row below, [1] own spans */
+    __shared__ SLScanline sSl[256];
+    __shared__ int sY0[256], sY1[256], sYEnd[256];
+    __shared__ uint32_t sPairOff[257];
+    __shared__ uint32_t sWarpTot[8];
     __shared__ int sMinY, sMaxY;
 
     const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
     const unsigned int vb = blockIdx.x;
     const int H = (int)P.numRows;
-    const uint32_t myBit = 1u << (tid & 31);
-    const int wq = tid >> 5;
     for (int y = tid; y < H; y += 256) sRowRun[y] = 0;
     __syncthreads();
 
+    unsigned myCuts = 0;
+    unsigned long long myPix = 0;
     const SLBlockInfo info = P.blockInfo[P.firstBlock + vb];
     for (int seg = 0; seg < SL_VB_ROUNDS; ++seg)
     {
         const uint32_t segBase = info.seg[seg].base, segCount = info.seg[seg].count;
         for (uint32_t sub = 0; sub < segCount; sub += 256)
         {
+            /* ---- one record per thread: rows it can have entries in, scan-line set-up ---- */
             const bool valid = sub + tid < segCount;
-            const uint32_t rec = segBase + sub + tid;
-            SLScanline sl;
-            int y0 = 0x7fffffff, y1 = -1, yEnd = -1;
+            int y0 = 0, y1 = 0, yEnd = 0; /* yEnd < 0 below marks "can run over the row end" in sYEnd's sign-free copy */
             bool mayOver = false;
-            unsigned myCuts = 0;
-            unsigned long long myPix = 0;
             if (valid)
             {
-                const float4* r = P.records + (size_t)rec * P.recStride;
+                const float4* r = P.records + (size_t)(segBase + sub + tid) * P.recStride;
                 const float4 p0 = r[0], p1 = r[1], p2 = r[2];
                 /* src/SL_TriRasterizer.cpp:431-433 */
                 y0 = sl_cvt_rn(sl_min(sl_min(p0.y, p1.y), p2.y));
                 y1 = sl_cvt_rn(sl_max(sl_max(p0.y, p1.y), p2.y));
                 y0 = y0 < 0 ? 0 : y0;
                 y1 = y1 > H ? H : y1;
+                SLScanline sl;
                 sl.init(p0, p1, p2);
+                sSl[tid] = sl;
                 /* span ends interpolate the vertex x's (rcpps error << 8 px), so only these can pass the row end */
                 mayOver = sl_max(sl_max(p0.x, p1.x), p2.x) + 8.f > (float)P.width;
                 yEnd = (mayOver && y1 < H) ? y1 + 1 : y1;
+                if (!(y0 < y1)) { y0 = 0; y1 = 0; yEnd = 0; }
             }
+            sY0[tid] = y0;
+            sY1[tid] = mayOver ? -y1 - 1 : y1; /* sign bit: the record can run over the row end */
+            sYEnd[tid] = yEnd;
             if (tid == 0) { sMinY = 0x7fffffff; sMaxY = -1; }
             __syncthreads();
-            if (valid && y0 < y1) { atomicMin(&sMinY, y0); atomicMax(&sMaxY, yEnd); }
+            if (y0 < yEnd) { atomicMin(&sMinY, y0); atomicMax(&sMaxY, yEnd); }
             __syncthreads();
             const int cy0 = sMinY, cy1 = sMaxY;
             for (int w0 = cy0; w0 < cy1; w0 += SL_SPAN_WIN)
             {
                 const int w1 = min(w0 + SL_SPAN_WIN, cy1);
                 for (int i = tid; i < 2 * SL_SPAN_WIN * 8; i += 256) (&sMask[0][0][0])[i] = 0u;
+                /* ---- flatten the (record, row) pairs of this window: exclusive scan of the per-record row counts ---- */
+                const int na = max(0, min(yEnd, w1) - max(y0, w0));
+                uint32_t incl = (uint32_t)na;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1)
+                {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                if (lane == 31) sWarpTot[warp] = incl;
                 __syncthreads();
-                const int ya = max(y0, w0), yb = min(yEnd, w1);
+                uint32_t warpOff = 0, total = 0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w)
+                {
+                    const uint32_t t = sWarpTot[w];
+                    if (w < warp) warpOff += t;
+                    total += t;
+                }
+                sPairOff[tid] = warpOff + incl - (uint32_t)na;
+                if (tid == 0) sPairOff[256] = total;
+                __syncthreads();
+
                 for (int pass = 0; pass <= MODE; ++pass)
                 {
-                    for (int y = ya; y < yb; ++y)
+                    for (uint32_t p = tid; p < total; p += 256)
                     {
-                        int32_t xMin, xMax, oMin = 0, oMax = 0;
-                        int own = 0, over = 0;
-                        if (y < y1)
+                        /* the record of pair p: last i with sPairOff[i] <= p */
+                        int lo = 0, hi = 255;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
                         {
-                            sl.step((float)y, xMin, xMax);
+                            const int mid = (lo + hi + 1) >> 1;
+                            if (sPairOff[mid] <= p) lo = mid; else hi = mid - 1;
+                        }
+                        const int i = lo;
+                        const int ry0 = sY0[i];
+                        const int ry1raw = sY1[i];
+                        const bool rOver = ry1raw < 0;
+                        const int ry1 = rOver ? -ry1raw - 1 : ry1raw;
+                        const int y = max(ry0, w0) + (int)(p - sPairOff[i]);
+                        const uint32_t rec = segBase + sub + (uint32_t)i;
+                        const uint32_t bit = 1u << (i & 31);
+                        const int q = i >> 5;
+                        int32_t xMin = 0, xMax = 0, oMin = 0, oMax = 0;
+                        int own = 0, over = 0;
+                        if (y < ry1)
+                        {
+                            sSl[i].step((float)y, xMin, xMax);
                             const int c = sl_classify_span(P, xMin, xMax);
                             own = c & 1;
-                            if ((c & 2) && !mayOver) atomicOr(&P.counters->errorFlags, 8u);
+                            if ((c & 2) && !rOver) atomicOr(&P.counters->errorFlags, 8u);
                             if (MODE == 0 && c)
                             {
                                 myPix += (unsigned long long)(xMax - xMin);
@@ -690,21 +742,21 @@ __global__ void __launch_bounds__(256) k_span(const __grid_constant__ SLSpanPara
                                 }
                             }
                         }
-                        if (mayOver && y > y0)
+                        if (rOver && y > ry0)
                         {
-                            sl.step((float)(y - 1), oMin, oMax);
+                            sSl[i].step((float)(y - 1), oMin, oMax);
                             over = (sl_classify_span(P, oMin, oMax) >> 1) & 1;
                         }
                         if (pass == 0)
                         {
-                            if (over) atomicOr(&sMask[0][y - w0][wq], myBit);
-                            if (own) atomicOr(&sMask[1][y - w0][wq], myBit);
+                            if (over) atomicOr(&sMask[0][y - w0][q], bit);
+                            if (own) atomicOr(&sMask[1][y - w0][q], bit);
                         }
                         else if ((own | over) && (!P.rowNeeded || P.rowNeeded[y]))
                         {
                             uint32_t rank = 0;
-                            for (int q = 0; q < wq; ++q) rank += __popc(sMask[0][y - w0][q]) + __popc(sMask[1][y - w0][q]);
-                            rank += __popc(sMask[0][y - w0][wq] & (myBit - 1u)) + __popc(sMask[1][y - w0][wq] & (myBit - 1u));
+                            for (int k = 0; k < q; ++k) rank += __popc(sMask[0][y - w0][k]) + __popc(sMask[1][y - w0][k]);
+                            rank += __popc(sMask[0][y - w0][q] & (bit - 1u)) + __popc(sMask[1][y - w0][q] & (bit - 1u));
                             size_t slot = (size_t)P.rowStart[y] + P.off[(size_t)vb * P.rowPitch + y] + sRowRun[y] + rank;
                             if (over) P.entries[slot++] = SLSpanEntry{rec | SL_ENTRY_OVERFLOW, (uint16_t)oMin, (uint16_t)oMax};
                             if (own) P.entries[slot] = SLSpanEntry{rec, (uint16_t)xMin, (uint16_t)xMax};
@@ -716,22 +768,19 @@ __global__ void __launch_bounds__(256) k_span(const __grid_constant__ SLSpanPara
                 {
                     uint32_t c = 0;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) c += __popc(sMask[0][yy - w0][q]) + __popc(sMask[1][yy - w0][q]);
+                    for (int k = 0; k < 8; ++k) c += __popc(sMask[0][yy - w0][k]) + __popc(sMask[1][yy - w0][k]);
                     sRowRun[yy] = (uint16_t)(sRowRun[yy] + c);
                 }
                 __syncthreads();
-            }
-            if (MODE == 0)
-            {
-                for (int d = 16; d > 0; d >>= 1) myCuts += __shfl_down_sync(0xffffffffu, myCuts, d);
-                if ((tid & 31) == 0 && myCuts) atomicAdd(&P.counters->handoffs, (unsigned long long)myCuts);
-                for (int d = 16; d > 0; d >>= 1) myPix += __shfl_down_sync(0xffffffffu, myPix, d);
-                if ((tid & 31) == 0 && myPix) atomicAdd(&P.counters->pixelsCovered, myPix);
             }
         }
     }
     if (MODE == 0)
     {
+        for (int d = 16; d > 0; d >>= 1) myCuts += __shfl_down_sync(0xffffffffu, myCuts, d);
+        if (lane == 0 && myCuts) atomicAdd(&P.counters->handoffs, (unsigned long long)myCuts);
+        for (int d = 16; d > 0; d >>= 1) myPix += __shfl_down_sync(0xffffffffu, myPix, d);
+        if (lane == 0 && myPix) atomicAdd(&P.counters->pixelsCovered, myPix);
         for (int y = tid; y < (int)P.rowPitch; y += 256) P.cnt[(size_t)vb * P.rowPitch + y] = y < H ? sRowRun[y] : (uint16_t)0;
     }
 }
