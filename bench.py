@@ -155,6 +155,29 @@ def algorithmic_bytes(scene_name: str, scene: S.Scene, frags: int) -> dict:
     return out
 
 
+def ncu_traffic(dom: str, config: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the newest committed `ncu --set full` summary
+    (profiles/rNN?_k_<kernel>_<cfg>.txt, written by tools/ncu_summary.py), per launch; None when there is no capture."""
+    kern = {"raster": "resolve", "shade": "shade", "vertex": "vertex", "span_count": "span", "span_fill": "span"}.get(dom)
+    cfg = config.split("_")[0]
+    if kern is None:
+        return None, None
+    pdir = os.path.join(ROOT, "profiles")
+    try:
+        cands = sorted(f for f in os.listdir(pdir) if f.endswith(f"_k_{kern}_{cfg}.txt"))
+    except OSError:
+        return None, None
+    if not cands:
+        return None, None
+    total = 0.0
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for ln in open(os.path.join(pdir, cands[-1])):
+        f = ln.split()
+        if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            total += float(f[1]) * unit.get(f[2], 1.0)
+    return (total or None), "profiles/" + cands[-1]
+
+
 def pinned_array(shape, dtype):
     """Host staging in pinned memory when torch+CUDA are present (plumbing only)."""
     try:
@@ -306,9 +329,10 @@ def run_cuda(args, rank, world, local_rank, dist):
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     kernel_ms_per_frame = {k: v["ms"] / prof_frames for k, v in classes.items()}
     frame_kernel_ms = sum(kernel_ms_per_frame.values())
+    traffic, traffic_src = ncu_traffic(dom, args.config)
     roofline = {
         "bound": "hbm", "kernel": {"raster": "k_resolve", "shade": "k_shade"}.get(dom, "k_" + dom), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
+        "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
         "kernel_ms_per_launch": dom_ms, "kernel_share_of_frame": kernel_ms_per_frame[dom] / frame_kernel_ms,
         "frame_algorithmic_bytes": alg["frame"], "frame_achieved_gbs": alg["frame"] / (ms * 1e-3) / 1e9,
         "frame_frac": alg["frame"] / (ms * 1e-3) / 1e9 / peak, "kernel_ms_per_frame": kernel_ms_per_frame,
