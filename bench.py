@@ -406,10 +406,22 @@ def main():
     world = env_int("WORLD_SIZE", 1)
     local_rank = env_int("LOCAL_RANK", 0)
 
+    # stdout carries exactly ONE line (the JSON): anything native libraries print meanwhile (NCCL's version banner, ...)
+    # goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
+
     if args.impl == "reference":
         line = run_reference(args, rank, world)
         if line is not None:
-            print(json.dumps(line), flush=True)
+            emit(line)
         return 0
 
     dist = None
@@ -422,7 +434,7 @@ def main():
         dist = dist_mod
     line = run_cuda(args, rank, world, local_rank, dist)
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0

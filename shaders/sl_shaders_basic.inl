@@ -85,8 +85,22 @@ SL_SHADER_FN bool flat_fs(SL_FragmentParam& fragParam)
     return true;
 }
 
+/* four render targets, like softlight/tests/sl_mrt_test.cpp:105-123 (clamped colour / position / uv / normal): here four
+ * clamped functions of the interpolated colour and of the fragment coordinate */
+SL_SHADER_FN bool vcolor_mrt_fs(SL_FragmentParam& fragParam)
+{
+    const math::vec4& c = fragParam.pVaryings[0];
+    const math::vec4 coord{(float)(fragParam.coord.x & 255) * (1.f / 255.f), (float)(fragParam.coord.y & 255) * (1.f / 255.f), fragParam.coord.depth, 1.f};
+    fragParam.pOutputs[0] = math::clamp(c, math::vec4{0.f}, math::vec4{1.f});
+    fragParam.pOutputs[1] = math::clamp(c * c, math::vec4{0.f}, math::vec4{1.f});
+    fragParam.pOutputs[2] = math::clamp(coord, math::vec4{0.f}, math::vec4{1.f});
+    fragParam.pOutputs[3] = math::clamp(math::vec4{1.f} - c, math::vec4{0.f}, math::vec4{1.f});
+    return true;
+}
+
 SL_REGISTER_VERTEX_SHADER("vcolor", vcolor_vs)
 SL_REGISTER_FRAGMENT_SHADER("vcolor", vcolor_fs)
+SL_REGISTER_FRAGMENT_SHADER("vcolor_mrt", vcolor_mrt_fs)
 SL_REGISTER_VERTEX_SHADER("lambert", lambert_vs)
 SL_REGISTER_FRAGMENT_SHADER("lambert", lambert_fs)
 SL_REGISTER_VERTEX_SHADER("flat", flat_vs)

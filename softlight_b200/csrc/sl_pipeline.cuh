@@ -65,6 +65,9 @@ struct SLCounters
     unsigned int rasterTicket;       /* (row, segment) ticket of k_resolve (reset by k_scan_row_starts)       */
     unsigned int chunkAlloc;         /* fragment chunks handed out by k_resolve (reset by k_scan_row_starts)  */
     unsigned int pad_;
+    /* k_resolve diagnostics (SLCU_DEBUG=1): windows, their groups and waves, polls that found nothing, per-warp clocks */
+    unsigned long long resolveWindows, resolveWaves, resolveIdle, resolveGroups;
+    unsigned long long resolveCycles, resolveMaxCycles, resolveMaxWindows, resolveWarps;
 };
 
 /* A span whose xMax exceeds the framebuffer width keeps going in linear memory:
@@ -108,6 +111,7 @@ struct SLVertexParams
     int cullMode;                     /* SL_CullMode */
     int numVaryings;
     unsigned int cacheBytes;          /* dynamic shared memory of the post-transform cache (0: off) */
+    unsigned int cacheVerts;          /* vertices the cache holds (<= SL_VCACHE_VERTS, multiple of 32)  */
     unsigned int recCapacity;         /* record slots per plane: fixed per-block regions + overflow area */
     unsigned int recOverflowBase;     /* first slot of the overflow area                                */
     unsigned int recOverflowCapacity; /* its size                                                       */
@@ -297,7 +301,7 @@ SLD_FN void sl_fetch_vertex_ids(const SLDrawDesc& P, unsigned long long i, unsig
 template <VsFn VS, bool CACHE>
 __global__ void __launch_bounds__(SL_VB_THREADS) k_vertex(const __grid_constant__ SLVertexParams P)
 {
-    extern __shared__ __align__(16) unsigned char sVCache[]; /* float4 [1 + NV][SL_VCACHE_VERTS] when P.cacheBytes != 0 */
+    extern __shared__ __align__(16) unsigned char sVCache[]; /* float4 [2 + NV][cacheVerts] (clip position, screen position, varyings) + u8 flags [cacheVerts] */
     __shared__ uint32_t sWarpSums[SL_VB_ROUNDS][SL_VB_THREADS / 32];
     __shared__ uint32_t sBase, sGranted;
     __shared__ unsigned long long sIdMin, sIdMax;
@@ -322,6 +326,8 @@ __global__ void __launch_bounds__(SL_VB_THREADS) k_vertex(const __grid_constant_
     bool cached = false;
     unsigned long long cacheBase = 0;
     float4* cache = reinterpret_cast<float4*>(sVCache);
+    const unsigned CV = P.cacheVerts;
+    uint8_t* cacheFlags = sVCache + (size_t)(2 + NV) * CV * sizeof(float4);
     if (CACHE && P.cacheBytes && D.usingIndices && blockFirst < D.numPrims)
     {
         const unsigned long long blockLast = min(blockFirst + (unsigned long long)SL_VB_PRIMS, D.numPrims) - 1ull;
@@ -351,7 +357,7 @@ __global__ void __launch_bounds__(SL_VB_THREADS) k_vertex(const __grid_constant_
             __syncthreads();
             cacheBase = sIdMin;
             const unsigned long long range = sIdMax - sIdMin + 1ull;
-            if (range <= (unsigned long long)SL_VCACHE_VERTS)
+            if (range <= (unsigned long long)CV)
             {
                 cached = true;
                 params.instanceId = (size_t)instFirst;
@@ -362,10 +368,22 @@ __global__ void __launch_bounds__(SL_VB_THREADS) k_vertex(const __grid_constant_
                     params.pVaryings = vary;
                     const math::vec4 pos = VS(params);
                     cache[v] = make_float4(pos.v[0], pos.v[1], pos.v[2], pos.v[3]);
+                    /* everything after the vertex shader that is a function of the vertex alone: scissor transform
+                     * (:615-617), its share of sl_ndc_clip_status, perspective divide + viewport (valid when the
+                     * triangle turns out fully visible) */
+                    math::vec4 sc = scissorMat * pos;
+                    const float w = sc.v[3];
+                    const float nw = __uint_as_float(__float_as_uint(w) | 0x80000000u);
+                    bool vis = true;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) vis = vis && (nw <= sc.v[k]) && (w >= sc.v[k]);
+                    cacheFlags[v] = (uint8_t)((vis ? 1u : 0u) | ((w > 0.f) ? 2u : 0u));
+                    sl_to_screen(sc, viewport);
+                    cache[CV + v] = make_float4(sc.v[0], sc.v[1], sc.v[2], sc.v[3]);
 #pragma unroll
                     for (int s = 0; s < 4; ++s)
                     {
-                        if (s < NV) cache[(1 + s) * SL_VCACHE_VERTS + v] = make_float4(vary[s].v[0], vary[s].v[1], vary[s].v[2], vary[s].v[3]);
+                        if (s < NV) cache[(2 + s) * CV + v] = make_float4(vary[s].v[0], vary[s].v[1], vary[s].v[2], vary[s].v[3]);
                     }
                 }
             }
@@ -380,6 +398,8 @@ __global__ void __launch_bounds__(SL_VB_THREADS) k_vertex(const __grid_constant_
         SLClipPoly poly;
         int n = 0;         /* records this thread emits */
         int polyVerts = 0; /* > 0: clipped path */
+        unsigned ci[3] = {0u, 0u, 0u}; /* cache slots of the three vertices */
+        bool fromCache = false;        /* the record is assembled from the cache at write time */
 
         if (g < D.numPrims)
         {
@@ -390,19 +410,56 @@ __global__ void __launch_bounds__(SL_VB_THREADS) k_vertex(const __grid_constant_
 
             if (CACHE && cached)
             {
+                ci[0] = (unsigned)(vertId[0] - cacheBase);
+                ci[1] = (unsigned)(vertId[1] - cacheBase);
+                ci[2] = (unsigned)(vertId[2] - cacheBase);
+                math::vec4 cp[3];
 #pragma unroll
                 for (int k = 0; k < 3; ++k)
                 {
-                    const unsigned c = (unsigned)(vertId[k] - cacheBase);
-                    const float4 pos = cache[c];
-                    v[k].vert = math::vec4{pos.x, pos.y, pos.z, pos.w};
-#pragma unroll
-                    for (int s = 0; s < 4; ++s)
+                    const float4 pos = cache[ci[k]];
+                    cp[k] = math::vec4{pos.x, pos.y, pos.z, pos.w};
+                }
+                bool culled = false;
+                if (P.cullMode != 2) /* :597-612 */
+                {
+                    const float det = sl_face_determinant(cp[0], cp[1], cp[2]);
+                    culled = (P.cullMode == 1) ^ sl_signbit(det);
+                }
+                if (!culled)
+                {
+                    const unsigned f0 = cacheFlags[ci[0]], f1 = cacheFlags[ci[1]], f2 = cacheFlags[ci[2]];
+                    if (f0 & f1 & f2 & 1u) /* fully visible */
                     {
-                        if (s < NV)
+                        const float4 s0 = cache[CV + ci[0]], s1 = cache[CV + ci[1]], s2 = cache[CV + ci[2]];
+                        fromCache = true;
+                        n = sl_prim_hidden(math::vec4{s0.x, s0.y, s0.z, s0.w}, math::vec4{s1.x, s1.y, s1.z, s1.w}, math::vec4{s2.x, s2.y, s2.z, s2.w}) ? 0 : 1;
+                    }
+                    else if ((f0 | f1 | f2) & 2u) /* partially visible: the clipper works on the scissored clip-space vertices */
+                    {
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) v[k].vert = scissorMat * cp[k];
+                        if (!sl_clip_rejects(v[0].vert, v[1].vert, v[2].vert))
                         {
-                            const float4 f = cache[(1 + s) * SL_VCACHE_VERTS + c];
-                            v[k].varyings[s] = math::vec4{f.x, f.y, f.z, f.w};
+#pragma unroll
+                            for (int k = 0; k < 3; ++k)
+                            {
+                                poly.verts[k] = v[k].vert;
+#pragma unroll
+                                for (int s = 0; s < 4; ++s)
+                                {
+                                    if (s < NV)
+                                    {
+                                        const float4 f = cache[(2 + s) * CV + ci[k]];
+                                        poly.varys[k * 4 + s] = math::vec4{f.x, f.y, f.z, f.w};
+                                    }
+                                }
+                            }
+                            polyVerts = sl_clip_polygon(poly, NV, viewport);
+                            for (int f = polyVerts - 2; f-- > 0;)
+                            {
+                                if (!sl_prim_hidden(poly.verts[0], poly.verts[f + 1], poly.verts[f + 2])) ++n;
+                            }
                         }
                     }
                 }
@@ -417,38 +474,38 @@ __global__ void __launch_bounds__(SL_VB_THREADS) k_vertex(const __grid_constant_
                     params.pVaryings = v[k].varyings;
                     v[k].vert = VS(params);
                 }
-            }
 
-            bool culled = false;
-            if (P.cullMode != 2) /* :597-612 */
-            {
-                const float det = sl_face_determinant(v[0].vert, v[1].vert, v[2].vert);
-                culled = (P.cullMode == 1) ^ sl_signbit(det);
-            }
-            if (!culled)
-            {
-#pragma unroll
-                for (int k = 0; k < 3; ++k) v[k].vert = scissorMat * v[k].vert; /* :615-617 */
-                const int vis = sl_clip_status(v[0].vert, v[1].vert, v[2].vert);
-                if (vis == 3)
+                bool culled = false;
+                if (P.cullMode != 2) /* :597-612 */
                 {
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) sl_to_screen(v[k].vert, viewport);
-                    n = sl_prim_hidden(v[0].vert, v[1].vert, v[2].vert) ? 0 : 1;
+                    const float det = sl_face_determinant(v[0].vert, v[1].vert, v[2].vert);
+                    culled = (P.cullMode == 1) ^ sl_signbit(det);
                 }
-                else if (vis == 1 && !sl_clip_rejects(v[0].vert, v[1].vert, v[2].vert))
+                if (!culled)
                 {
 #pragma unroll
-                    for (int k = 0; k < 3; ++k)
+                    for (int k = 0; k < 3; ++k) v[k].vert = scissorMat * v[k].vert; /* :615-617 */
+                    const int vis = sl_clip_status(v[0].vert, v[1].vert, v[2].vert);
+                    if (vis == 3)
                     {
-                        poly.verts[k] = v[k].vert;
 #pragma unroll
-                        for (int s = 0; s < 4; ++s) { if (s < NV) poly.varys[k * 4 + s] = v[k].varyings[s]; }
+                        for (int k = 0; k < 3; ++k) sl_to_screen(v[k].vert, viewport);
+                        n = sl_prim_hidden(v[0].vert, v[1].vert, v[2].vert) ? 0 : 1;
                     }
-                    polyVerts = sl_clip_polygon(poly, NV, viewport);
-                    for (int f = polyVerts - 2; f-- > 0;)
+                    else if (vis == 1 && !sl_clip_rejects(v[0].vert, v[1].vert, v[2].vert))
                     {
-                        if (!sl_prim_hidden(poly.verts[0], poly.verts[f + 1], poly.verts[f + 2])) ++n;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k)
+                        {
+                            poly.verts[k] = v[k].vert;
+#pragma unroll
+                            for (int s = 0; s < 4; ++s) { if (s < NV) poly.varys[k * 4 + s] = v[k].varyings[s]; }
+                        }
+                        polyVerts = sl_clip_polygon(poly, NV, viewport);
+                        for (int f = polyVerts - 2; f-- > 0;)
+                        {
+                            if (!sl_prim_hidden(poly.verts[0], poly.verts[f + 1], poly.verts[f + 2])) ++n;
+                        }
                     }
                 }
             }
@@ -499,10 +556,31 @@ __global__ void __launch_bounds__(SL_VB_THREADS) k_vertex(const __grid_constant_
             if (granted) atomicAdd(&P.counters->trisBinned, (unsigned long long)granted);
             P.blockInfo[blockIdx.x].seg[round] = SLSegment{base, granted};
         }
-        if (n && granted)
+        /* (Staging a warp's records in shared memory and storing them as one contiguous stream was measured: slower on
+         * every config -- the kernel is bound by its barriers and index/vertex fetch latency, not by the record stores.) */
+        const bool emit = n != 0 && granted != 0;
+        if (emit)
         {
             uint32_t slot = base + warpOff + (incl - (uint32_t)n);
-            if (!polyVerts)
+            if (CACHE && fromCache)
+            {
+                P.recDraw[slot] = (uint16_t)drawIdx;
+                float4* rec = P.records + (size_t)slot * recStride;
+                rec[0] = cache[CV + ci[0]];
+                rec[1] = cache[CV + ci[1]];
+                rec[2] = cache[CV + ci[2]];
+#pragma unroll
+                for (int s = 0; s < 4; ++s)
+                {
+                    if (s < NV)
+                    {
+                        rec[3 + 3 * s + 0] = cache[(2 + s) * CV + ci[0]];
+                        rec[3 + 3 * s + 1] = cache[(2 + s) * CV + ci[1]];
+                        rec[3 + 3 * s + 2] = cache[(2 + s) * CV + ci[2]];
+                    }
+                }
+            }
+            else if (!polyVerts)
             {
                 P.recDraw[slot] = (uint16_t)drawIdx;
                 sl_write_record(P.records + (size_t)slot * recStride, NV, v[0].vert, v[1].vert, v[2].vert, v[0].varyings, v[1].varyings, v[2].varyings);
@@ -627,6 +705,7 @@ __global__ void __launch_bounds__(256) k_span(const __grid_constant__ SLSpanPara
     __shared__ uint32_t sMask[2][SL_SPAN_WIN][8]; /* [0] overflow entries coming from the row below, [1] own spans */
     __shared__ SLScanline sSl[256];
     __shared__ int sY0[256], sY1[256], sYEnd[256];
+    __shared__ uint32_t sRec[256];
     __shared__ uint32_t sPairOff[257];
     __shared__ uint32_t sWarpTot[8];
     __shared__ int sMinY, sMaxY;
@@ -641,18 +720,33 @@ __global__ void __launch_bounds__(256) k_span(const __grid_constant__ SLSpanPara
     unsigned myCuts = 0;
     unsigned long long myPix = 0;
     const SLBlockInfo info = P.blockInfo[P.firstBlock + vb];
-    for (int seg = 0; seg < SL_VB_ROUNDS; ++seg)
+    /* the block's records live in SL_VB_ROUNDS regions (one per round of k_vertex); they are taken as ONE stream in
+     * round order = submission order, 256 at a time */
+    uint32_t segStart[SL_VB_ROUNDS + 1];
+    segStart[0] = 0u;
+#pragma unroll
+    for (int k = 0; k < SL_VB_ROUNDS; ++k) segStart[k + 1] = segStart[k] + info.seg[k].count;
+    const uint32_t numRecs = segStart[SL_VB_ROUNDS];
     {
-        const uint32_t segBase = info.seg[seg].base, segCount = info.seg[seg].count;
-        for (uint32_t sub = 0; sub < segCount; sub += 256)
+        for (uint32_t sub = 0; sub < numRecs; sub += 256)
         {
             /* ---- one record per thread: rows it can have entries in, scan-line set-up ---- */
-            const bool valid = sub + tid < segCount;
-            int y0 = 0, y1 = 0, yEnd = 0; /* yEnd < 0 below marks "can run over the row end" in sYEnd's sign-free copy */
+            const bool valid = sub + tid < numRecs;
+            uint32_t myRec = 0u;
+            if (valid)
+            {
+                const uint32_t v = sub + tid;
+                int k = 0;
+#pragma unroll
+                for (int q = 1; q < SL_VB_ROUNDS; ++q) k += (v >= segStart[q]) ? 1 : 0;
+                myRec = info.seg[k].base + (v - segStart[k]);
+            }
+            sRec[tid] = myRec;
+            int y0 = 0, y1 = 0, yEnd = 0;
             bool mayOver = false;
             if (valid)
             {
-                const float4* r = P.records + (size_t)(segBase + sub + tid) * P.recStride;
+                const float4* r = P.records + (size_t)myRec * P.recStride;
                 const float4 p0 = r[0], p1 = r[1], p2 = r[2];
                 /* src/SL_TriRasterizer.cpp:431-433 */
                 y0 = sl_cvt_rn(sl_min(sl_min(p0.y, p1.y), p2.y));
@@ -720,7 +814,7 @@ __global__ void __launch_bounds__(256) k_span(const __grid_constant__ SLSpanPara
                         const bool rOver = ry1raw < 0;
                         const int ry1 = rOver ? -ry1raw - 1 : ry1raw;
                         const int y = max(ry0, w0) + (int)(p - sPairOff[i]);
-                        const uint32_t rec = segBase + sub + (uint32_t)i;
+                        const uint32_t rec = sRec[i];
                         const uint32_t bit = 1u << (i & 31);
                         const int q = i >> 5;
                         int32_t xMin = 0, xMax = 0, oMin = 0, oMax = 0;
@@ -921,6 +1015,7 @@ struct SLRasterParams
     int depthBpt;
     SLFragLists lists;
     SLCounters* counters;
+    int diagnostics;             /* SLCU_DEBUG: count windows / waves / idle polls / clocks */
 };
 
 struct SLShadeParams
@@ -1390,6 +1485,8 @@ __global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_
     const uint32_t begin = P.rowStart[y], end = P.rowStart[y + 1];
     if (begin == end) return;
     unsigned shaded = 0;
+    unsigned dbgWindows = 0, dbgWaves = 0, dbgIdle = 0, dbgGroups = 0;
+    const long long dbgT0 = P.diagnostics ? clock64() : 0ll;
     const bool useDepth = P.depthTest != 0 || P.depthMask != 0;
 
     const unsigned pixMaskBytes = sl_align16(4u * P.segWidth);
@@ -1536,9 +1633,12 @@ __global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_
                  * slots from the warps that produce it */
                 idle = min(idle + 1u, 4u);
                 __nanosleep(20u << idle);
+                ++dbgIdle;
                 continue;
             }
             idle = 0;
+            ++dbgWindows;
+            dbgGroups += (unsigned)limit;
             __syncwarp();
 
             /* ---- this lane as a worker: group `lane` of the window ---- */
@@ -1656,6 +1756,7 @@ __global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_
             {
                 const uint32_t PEND = __ballot_sync(0xffffffffu, pending);
                 if (!PEND) break;
+                ++dbgWaves;
                 const bool dSafe = pending && (ov & PEND) == 0u;
                 uint32_t m = 0u;
                 if (dSafe)
@@ -1783,6 +1884,18 @@ __global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_
     }
     for (int d = 16; d > 0; d >>= 1) shaded += __shfl_down_sync(0xffffffffu, shaded, d);
     if (lane == 0 && shaded) atomicAdd(&P.counters->fragsShaded, (unsigned long long)shaded);
+    if (lane == 0 && P.diagnostics)
+    {
+        const unsigned long long cyc = (unsigned long long)(clock64() - dbgT0);
+        atomicAdd(&P.counters->resolveWindows, (unsigned long long)dbgWindows);
+        atomicAdd(&P.counters->resolveWaves, (unsigned long long)dbgWaves);
+        atomicAdd(&P.counters->resolveIdle, (unsigned long long)dbgIdle);
+        atomicAdd(&P.counters->resolveGroups, (unsigned long long)dbgGroups);
+        atomicAdd(&P.counters->resolveCycles, cyc);
+        atomicMax(&P.counters->resolveMaxCycles, cyc);
+        atomicMax(&P.counters->resolveMaxWindows, (unsigned long long)dbgWindows);
+        atomicAdd(&P.counters->resolveWarps, 1ull);
+    }
 }
 
 /* ------------------------------------------------------------------------

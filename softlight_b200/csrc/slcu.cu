@@ -30,7 +30,7 @@ using namespace sld;
  * as a template argument (direct, inlinable calls -- never interpreted).
  * =========================================================================*/
 typedef cudaError_t (*VertexLauncher)(unsigned grid, cudaStream_t s, const SLVertexParams& p, bool cache);
-static const unsigned kVertexCacheMaxBytes = 5u * SL_VCACHE_VERTS * (unsigned)sizeof(float4); /* position + 4 varyings */
+static const unsigned kVertexCacheMaxBytes = 6u * SL_VCACHE_VERTS * (unsigned)sizeof(float4) + SL_VCACHE_VERTS; /* clip + screen position, 4 varyings, flags */
 typedef cudaError_t (*RasterLauncher)(unsigned grid, cudaStream_t s, const SLShadeParams& p);
 
 struct VsEntry { const char* name; VertexLauncher launch; };
@@ -182,7 +182,8 @@ struct Batch
     std::vector<uint32_t> blockDraw;
     unsigned numBlocks = 0;
     unsigned long long totalPrims = 0;
-    void clear() { descs.clear(); blockDraw.clear(); numBlocks = 0; totalPrims = 0; }
+    unsigned long long maxVerts = 0; /* vertices of the largest vertex buffer of the batch (binding 0) */
+    void clear() { descs.clear(); blockDraw.clear(); numBlocks = 0; totalPrims = 0; maxVerts = 0; }
 };
 
 struct slcu_context
@@ -434,6 +435,11 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
         d.numPrims = prims;
         d.firstBlock = B.numBlocks;
         d.pad_ = 0;
+        {
+            const ptrdiff_t stride = vao.vao.mBindings[0].stride;
+            const unsigned long long nv = stride > 0 ? (unsigned long long)(c->vbos[vao.vbo].bytes / (size_t)stride) : ~0ull;
+            if (nv > B.maxVerts) B.maxVerts = nv;
+        }
         B.blockDraw.insert(B.blockDraw.end(), blocks, (uint32_t)(B.descs.size() - 1));
         B.numBlocks += blocks;
         B.totalPrims += prims;
@@ -488,7 +494,7 @@ static int flush_draws_impl(slcu_context* c)
     const unsigned long long recFixed = (unsigned long long)numBlocks * SL_VB_PRIMS;
     unsigned long long recOverflow = totalPrims / 8 + 4096;
     unsigned long long recCapacity = recFixed + recOverflow;
-    static const bool useVertexCache = getenv("SLCU_VERTEX_CACHE") != nullptr && atoi(getenv("SLCU_VERTEX_CACHE")) != 0;
+    static const bool useVertexCache = getenv("SLCU_VERTEX_CACHE") != nullptr && atoi(getenv("SLCU_VERTEX_CACHE")) != 0; /* opt-in: measured slower on C3, +3 % on C2 */
     unsigned long long numHandoffs = 0;
     const uint8_t* rowNeeded = nullptr;
     for (int attempt = 0;; ++attempt)
@@ -508,7 +514,13 @@ static int flush_draws_impl(slcu_context* c)
             vp.numVaryings = NV;
             bool cache = useVertexCache;
             for (const SLDrawDesc& d : B.descs) cache = cache && d.usingIndices;
-            vp.cacheBytes = cache ? (unsigned)((1 + NV) * SL_VCACHE_VERTS * sizeof(float4)) : 0u;
+            /* the cache holds the vertices a block of 1024 primitives can reference: at most SL_VCACHE_VERTS, and no more
+             * than the vertex buffer has (small instanced meshes: more blocks per SM) */
+            unsigned long long cv = B.maxVerts < (unsigned long long)SL_VCACHE_VERTS ? B.maxVerts : (unsigned long long)SL_VCACHE_VERTS;
+            cv = (cv + 31ull) & ~31ull;
+            if (cv < 32ull) cv = 32ull;
+            vp.cacheVerts = (unsigned)cv;
+            vp.cacheBytes = cache ? (unsigned)((2 + NV) * cv * sizeof(float4) + cv) : 0u;
             vp.recCapacity = (unsigned)recCapacity;
             vp.recOverflowBase = (unsigned)recFixed;
             vp.recOverflowCapacity = (unsigned)recOverflow;
@@ -657,6 +669,7 @@ static int flush_draws_impl(slcu_context* c)
     /* each resolving warp keeps its segment's depth texels in shared memory (at most 32 x ... pixels x 8 bytes) */
     rp.tileBytes = (segWidth * depthTex.bpt + 15u) & ~15u;
     rp.counters = c->counters;
+    rp.diagnostics = getenv("SLCU_DEBUG") ? 1 : 0;
     const unsigned warpsPerBlock = SL_RASTER_WARPS;
     const unsigned smemBytes = warpsPerBlock * (SL_PIECEQ_BYTES + SL_SUBLIST_BYTES + SL_PIECEREG_BYTES + SL_WINSCRATCH_BYTES + ((4u * segWidth + 15u) & ~15u) + rp.tileBytes); /* piece queue, fragment queue, piece registers, window scratch, tile: per warp */
     {
@@ -1218,6 +1231,12 @@ int slcu_get_stats(slcu_context* c, slcu_stats* out)
     c->stats.trisBinned = c->hostCounters->trisBinned;
     c->stats.spans = c->hostCounters->spans;
     c->stats.fragsShaded = c->hostCounters->fragsShaded;
+    if (getenv("SLCU_DEBUG"))
+        fprintf(stderr, "[slcu] resolve: windows=%llu groups=%llu waves=%llu idle polls=%llu | warps=%llu clocks sum=%llu max=%llu maxWindows=%llu\n",
+                (unsigned long long)c->hostCounters->resolveWindows, (unsigned long long)c->hostCounters->resolveGroups,
+                (unsigned long long)c->hostCounters->resolveWaves, (unsigned long long)c->hostCounters->resolveIdle,
+                (unsigned long long)c->hostCounters->resolveWarps, (unsigned long long)c->hostCounters->resolveCycles,
+                (unsigned long long)c->hostCounters->resolveMaxCycles, (unsigned long long)c->hostCounters->resolveMaxWindows);
     if (c->hostCounters->errorFlags & ~1u)
     {
         /* inputs whose reference behaviour is not reproduced bit for bit */

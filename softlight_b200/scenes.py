@@ -146,6 +146,14 @@ class SceneInstance:
         s = self.scene
         return self.ctx.texture_read(self.state["depth"], s.depth_type, s.width, s.height)[..., 0]
 
+    def read_colors(self):
+        """Every colour attachment (render targets 1.. exist for MRT scenes only)."""
+        s = self.scene
+        out = [self.read_color()]
+        for tex, t in zip(self.state.get("extra", []), self.state.get("extra_types", [])):
+            out.append(self.ctx.texture_read(tex, t, s.width, s.height))
+        return out
+
 
 def _make_targets(ctx: A.Context, scene_w, scene_h, color_type, depth_type):
     color = ctx.create_texture(color_type, scene_w, scene_h, 1)
@@ -389,7 +397,9 @@ def indoor_scene(width=3840, height=2160, rooms=(16, 16), quads=26, tex_size=512
 def random_tris_scene(seed=1, n=400, width=200, height=150, blend=A.SL_BLEND_OFF, depth_test=A.SL_DEPTH_TEST_LESS_THAN,
                       depth_mask=A.SL_DEPTH_MASK_ON, depth_type=A.SL_COLOR_R_FLOAT, color_type=A.SL_COLOR_RGBA_8U,
                       cull=A.SL_CULL_OFF, index_dtype=np.uint16, clip_fraction=0.3, clear_depth=1.0, viewport=None,
-                      scissor=None, split_draws=1, multiple=False, name=None, empty_draw=False) -> Scene:
+                      scissor=None, split_draws=1, multiple=False, name=None, empty_draw=False, mrt_types=None) -> Scene:
+    """mrt_types: colour types of render targets 1..3 (sl_mrt_test.cpp:150-200 attaches four); the "vcolor_mrt" fragment shader
+    then writes four outputs and SceneInstance.read_colors() returns all attachments."""
     rng = np.random.default_rng(seed)
     verts = np.zeros((n * 3, 8), dtype=np.float32)
     centers = rng.uniform(-1.1, 1.1, size=(n, 1, 2))
@@ -417,13 +427,18 @@ def random_tris_scene(seed=1, n=400, width=200, height=150, blend=A.SL_BLEND_OFF
 
     def setup(ctx):
         color, depth, fbo = _make_targets(ctx, width, height, color_type, depth_type)
+        extra = []
+        if mrt_types:
+            extra = [ctx.create_texture(t, width, height, 1) for t in mrt_types]
+            fbo = ctx.create_framebuffer([color] + extra, depth)
+            assert ctx.fbo_valid(fbo) == 0
         vbo = ctx.create_vbo(verts)
         ibo = ctx.create_ibo(idx) if idx is not None else None
         vao = ctx.create_vao(vbo, ibo, [(0, 32, A.VERTEX_DIMENSION_4, A.VERTEX_DATA_FLOAT),
                                         (16, 32, A.VERTEX_DIMENSION_4, A.VERTEX_DATA_FLOAT)])
         ubo = ctx.create_ubo(b"\0" * 16)
-        sh = ctx.create_shader("vcolor", "vcolor", ubo, vs_varyings=1, fs_varyings=1, cull=cull, blend=blend,
-                               depth_test=depth_test, depth_mask=depth_mask)
+        sh = ctx.create_shader("vcolor", "vcolor_mrt" if mrt_types else "vcolor", ubo, vs_varyings=1, fs_varyings=1, cull=cull, blend=blend,
+                               depth_test=depth_test, depth_mask=depth_mask, outputs=1 + len(extra))
         assert sh != A.INVALID_ID
         mode = A.RENDER_MODE_INDEXED_TRIANGLES if idx is not None else A.RENDER_MODE_TRIANGLES
         per = (n // split_draws) * 3
@@ -438,10 +453,12 @@ def random_tris_scene(seed=1, n=400, width=200, height=150, blend=A.SL_BLEND_OFF
             ctx.viewport(*viewport)
         if scissor is not None:
             ctx.scissor(*scissor)
-        return dict(color=color, depth=depth, fbo=fbo, shader=sh, meshes=meshes)
+        return dict(color=color, depth=depth, fbo=fbo, shader=sh, meshes=meshes, extra=extra, extra_types=list(mrt_types or []))
 
     def frame(ctx, st):
         ctx.clear_framebuffer(st["fbo"], 0, (0.1, 0.2, 0.3, 1.0), clear_depth)
+        for i in range(len(st["extra"])):
+            ctx.clear_color_buffer(st["fbo"], 1 + i, (0.05 * (i + 1), 0.5, 0.25, 1.0))
         if multiple:
             ctx.draw_multiple(st["meshes"], st["shader"], st["fbo"])
         else:

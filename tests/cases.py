@@ -40,6 +40,33 @@ def _variants():
     return v
 
 
+# multiple render targets (sl_mrt_test.cpp attaches RGB8, RGB8, RG8, RGB8 + half depth): compared attachment by attachment
+MRT_CASES = {
+    "mrt_rgb8x3_rg8_half": dict(n=500, width=211, height=160, color_type=A.SL_COLOR_RGB_8U,
+                                mrt_types=[A.SL_COLOR_RGB_8U, A.SL_COLOR_RG_8U, A.SL_COLOR_RGB_8U], depth_type=A.SL_COLOR_R_HALF),
+    "mrt_mixed_alpha": dict(n=400, width=200, height=150, color_type=A.SL_COLOR_RGBA_8U, blend=1,
+                            mrt_types=[A.SL_COLOR_RGBA_FLOAT, A.SL_COLOR_RGBA_16U, A.SL_COLOR_RGBA_HALF]),
+    "mrt_two_noblend_4seg": dict(n=1500, width=1100, height=64, color_type=A.SL_COLOR_RGBA_8U, mrt_types=[A.SL_COLOR_R_FLOAT]),
+}
+
+
+def mrt_scene(name):
+    return S.random_tris_scene(seed=700 + sorted(MRT_CASES).index(name), name=name, **MRT_CASES[name])
+
+
+def render_mrt(impl: str, scene, rcp_table=None):
+    ctx = A.Context(impl)
+    if rcp_table is not None and not impl.startswith("ref"):
+        ctx.set_rcp_table(rcp_table)
+    ctx.reset_stats()
+    inst = S.SceneInstance(scene, ctx)
+    inst.render()
+    ctx.sync()
+    colors, depth, stats = inst.read_colors(), inst.read_depth(), ctx.get_stats()
+    ctx.close()
+    return colors, depth, stats
+
+
 CASES = {}
 for _i, (_name, _kw) in enumerate(_variants()):
     CASES["rand_" + _name] = (lambda i=_i, kw=_kw, name=_name: S.random_tris_scene(seed=100 + i, name="rand_" + name, **kw))

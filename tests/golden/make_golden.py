@@ -39,13 +39,19 @@ def main():
             frames[name + ".color"] = color
             frames[name + ".depth"] = cases.bits(depth)
         print(name, hashes[name]["frags"], flush=True)
+    mrt = {}
+    for name in sorted(cases.MRT_CASES):
+        colors, depth, stats = cases.render_mrt("ref_strict", cases.mrt_scene(name))
+        mrt[name] = {"colors_sha256": [hashlib.sha256(np.ascontiguousarray(c).tobytes()).hexdigest() for c in colors],
+                     "depth_sha256": hashlib.sha256(np.ascontiguousarray(depth).tobytes()).hexdigest(), "frags": int(stats["fragsShaded"])}
+        print("mrt", name, mrt[name]["frags"], flush=True)
     blits = {}
     for name in blit_cases.BLIT_CASES:
         out = blit_cases.run_blit("ref_strict", name)
         blits[name] = hashlib.sha256(np.ascontiguousarray(out).tobytes()).hexdigest()
         print("blit", name, blits[name][:12], flush=True)
     np.savez_compressed(os.path.join(HERE, "golden_frames.npz"), **frames)
-    json.dump({"generator": ctx.impl_name(), "cases": hashes, "blits": blits}, open(os.path.join(HERE, "golden_hashes.json"), "w"), indent=1)
+    json.dump({"generator": ctx.impl_name(), "cases": hashes, "blits": blits, "mrt": mrt}, open(os.path.join(HERE, "golden_hashes.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":

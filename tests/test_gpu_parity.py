@@ -63,6 +63,23 @@ def test_cuda_matches_oracle(name, golden):
     assert_same(cg, dg, co, do)
 
 
+@pytest.mark.parametrize("name", sorted(cases.MRT_CASES))
+def test_cuda_mrt_matches_golden_and_oracle(name, golden):
+    """Multiple render targets: every attachment bit-exact against the golden hashes (unmodified reference) and the oracle."""
+    import json
+    frames, _ = golden
+    want = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_hashes.json")))["mrt"][name]
+    scene = cases.mrt_scene(name)
+    cg, dg, sg = cases.render_mrt("cuda", scene, rcp_table=frames["rcp_table"])
+    co, do, so = cases.render_mrt("port", scene, rcp_table=frames["rcp_table"])
+    assert sg["fragsShaded"] == so["fragsShaded"] == want["frags"]
+    assert len(cg) == len(co) == len(want["colors_sha256"])
+    for a, b, h in zip(cg, co, want["colors_sha256"]):
+        assert np.array_equal(cases.bits(a) if a.dtype.kind == "f" else a, cases.bits(b) if b.dtype.kind == "f" else b)
+        assert sha(a) == h
+    assert sha(dg) == want["depth_sha256"]
+
+
 @pytest.mark.parametrize("name", sorted(cases.BIG_CASES))
 def test_cuda_full_size_configs_match_golden(name, golden):
     frames, hashes = golden

@@ -89,3 +89,15 @@ def test_half_conversion_restatement():
         ctx.clear_depth_buffer(fbo, float(v))
         got = ctx.texture_read(tex_d, A.SL_COLOR_R_HALF, 1, 1)[0, 0, 0]
         assert got.view(np.uint16) == w.view(np.uint16) or (np.isnan(got) and np.isnan(w)), (v, got, w)
+
+
+@pytest.mark.parametrize("name", sorted(cases.MRT_CASES))
+def test_port_mrt_matches_golden(name, golden):
+    """Multiple render targets: every attachment of the oracle equals the unmodified reference's."""
+    import json
+    frames, _ = golden
+    want = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_hashes.json")))["mrt"][name]
+    colors, depth, stats = cases.render_mrt("port", cases.mrt_scene(name), rcp_table=frames["rcp_table"])
+    assert stats["fragsShaded"] == want["frags"]
+    assert [sha(c) for c in colors] == want["colors_sha256"]
+    assert sha(depth) == want["depth_sha256"]
