@@ -47,7 +47,8 @@ constexpr int SL_MAX_ROWS = 8192;         /* framebuffer height limit of the row
 constexpr int SL_SPAN_WIN = 256;          /* rows per mask window in k_span                 */
 
 struct SLSegment { uint32_t base, count; };
-struct SLBlockInfo { SLSegment seg[SL_VB_ROUNDS]; };
+constexpr int SL_VB_SEGS = SL_VB_ROUNDS * (SL_VB_THREADS / 32); /* one record segment per (round, warp) of a vertex block */
+struct SLBlockInfo { SLSegment seg[SL_VB_SEGS]; };
 
 struct SLSpanEntry { uint32_t rec; uint16_t xMin, xMax; };
 
@@ -298,12 +299,14 @@ SLD_FN void sl_fetch_vertex_ids(const SLDrawDesc& P, unsigned long long i, unsig
  * the same bits: when the block's primitives belong to one instance of an indexed mesh and their indices span at most
  * SL_VCACHE_VERTS vertices, the block shades that index range into shared memory first and assembles its triangles
  * from there; otherwise every primitive shades its own three vertices like the reference. */
+#ifndef SL_VERTEX_MIN_BLOCKS
+#define SL_VERTEX_MIN_BLOCKS 1
+#endif
 template <VsFn VS, bool CACHE>
-__global__ void __launch_bounds__(SL_VB_THREADS) k_vertex(const __grid_constant__ SLVertexParams P)
+__global__ void __launch_bounds__(SL_VB_THREADS, SL_VERTEX_MIN_BLOCKS) k_vertex(const __grid_constant__ SLVertexParams P)
 {
     extern __shared__ __align__(16) unsigned char sVCache[]; /* float4 [2 + NV][cacheVerts] (clip position, screen position, varyings) + u8 flags [cacheVerts] */
-    __shared__ uint32_t sWarpSums[SL_VB_ROUNDS][SL_VB_THREADS / 32];
-    __shared__ uint32_t sBase, sGranted;
+    uint32_t binned = 0u; /* lane 0: records of this warp */
     __shared__ unsigned long long sIdMin, sIdMax;
 
     const int tid = threadIdx.x;
@@ -519,42 +522,34 @@ __global__ void __launch_bounds__(SL_VB_THREADS) k_vertex(const __grid_constant_
             const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += t;
         }
-        if (lane == 31) sWarpSums[round][warp] = incl;
-        __syncthreads();
-        uint32_t warpOff = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < SL_VB_THREADS / 32; ++w)
-        {
-            const uint32_t s = sWarpSums[round][w];
-            if (w < warp) warpOff += s;
-            total += s;
-        }
-        /* Every (block, round) owns SL_VB_THREADS record slots at a fixed place, enough unless clipping fanned primitives
-         * out; only then does the round take its slots from the shared overflow area (one atomic).  No atomics, no
-         * second barrier and no allocation-order dependence in the common case. */
-        uint32_t base = blockIdx.x * (uint32_t)SL_VB_PRIMS + (uint32_t)round * SL_VB_THREADS;
+        /* Every (block, round, warp) owns 32 record slots at a fixed place, enough unless clipping fanned primitives
+         * out; only then does the warp take its slots from the shared overflow area (one atomic).  No barrier, no
+         * atomics and no allocation-order dependence in the common case: the warps of a block never wait for each
+         * other (the block-wide scan this replaces made the barrier the kernel's top stall). */
+        const uint32_t warpOff = 0u;
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t base = blockIdx.x * (uint32_t)SL_VB_PRIMS + (uint32_t)round * SL_VB_THREADS + (uint32_t)warp * 32u;
         uint32_t granted = total;
-        if (total > (uint32_t)SL_VB_THREADS) /* block-uniform */
+        if (total > 32u) /* warp-uniform */
         {
-            if (tid == 0)
+            if (lane == 0)
             {
                 const unsigned long long o = atomicAdd(&P.counters->recAlloc, (unsigned long long)total);
                 if (o + total > (unsigned long long)P.recOverflowCapacity)
                 {
                     atomicOr(&P.counters->errorFlags, 1u); /* host re-issues the draw with a larger overflow area */
-                    sBase = 0u;
-                    sGranted = 0u;
+                    base = 0u;
+                    granted = 0u;
                 }
-                else { sBase = P.recOverflowBase + (uint32_t)o; sGranted = total; }
+                else base = P.recOverflowBase + (uint32_t)o;
             }
-            __syncthreads();
-            base = sBase;
-            granted = sGranted;
+            base = __shfl_sync(0xffffffffu, base, 0);
+            granted = __shfl_sync(0xffffffffu, granted, 0);
         }
-        if (tid == 0)
+        if (lane == 0)
         {
-            if (granted) atomicAdd(&P.counters->trisBinned, (unsigned long long)granted);
-            P.blockInfo[blockIdx.x].seg[round] = SLSegment{base, granted};
+            binned += granted;
+            P.blockInfo[blockIdx.x].seg[round * (SL_VB_THREADS / 32) + warp] = SLSegment{base, granted};
         }
         /* (Staging a warp's records in shared memory and storing them as one contiguous stream was measured: slower on
          * every config -- the kernel is bound by its barriers and index/vertex fetch latency, not by the record stores.) */
@@ -599,6 +594,7 @@ __global__ void __launch_bounds__(SL_VB_THREADS) k_vertex(const __grid_constant_
             }
         }
     }
+    if (lane == 0 && binned) atomicAdd(&P.counters->trisBinned, (unsigned long long)binned);
 }
 
 /* ------------------------------------------------------------------------
@@ -706,6 +702,7 @@ __global__ void __launch_bounds__(256) k_span(const __grid_constant__ SLSpanPara
     __shared__ SLScanline sSl[256];
     __shared__ int sY0[256], sY1[256], sYEnd[256];
     __shared__ uint32_t sRec[256];
+    __shared__ uint32_t sSegStart[SL_VB_SEGS + 1], sSegBase[SL_VB_SEGS];
     __shared__ uint32_t sPairOff[257];
     __shared__ uint32_t sWarpTot[8];
     __shared__ int sMinY, sMaxY;
@@ -719,14 +716,27 @@ __global__ void __launch_bounds__(256) k_span(const __grid_constant__ SLSpanPara
 
     unsigned myCuts = 0;
     unsigned long long myPix = 0;
-    const SLBlockInfo info = P.blockInfo[P.firstBlock + vb];
-    /* the block's records live in SL_VB_ROUNDS regions (one per round of k_vertex); they are taken as ONE stream in
-     * round order = submission order, 256 at a time */
-    uint32_t segStart[SL_VB_ROUNDS + 1];
-    segStart[0] = 0u;
+    /* the block's records live in SL_VB_SEGS regions (one per round and warp of k_vertex); they are taken as ONE stream
+     * in (round, warp) order = submission order, 256 at a time */
+    static_assert(SL_VB_SEGS == 32, "the segment scan below is one warp wide");
+    if (tid < 32)
+    {
+        /* exclusive scan of the segment counts */
+        const SLSegment sg = P.blockInfo[P.firstBlock + vb].seg[tid];
+        const uint32_t cnt = sg.count;
+        uint32_t inc = cnt;
 #pragma unroll
-    for (int k = 0; k < SL_VB_ROUNDS; ++k) segStart[k + 1] = segStart[k] + info.seg[k].count;
-    const uint32_t numRecs = segStart[SL_VB_ROUNDS];
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (tid >= d) inc += t;
+        }
+        sSegStart[tid] = inc - cnt;
+        sSegBase[tid] = sg.base;
+        if (tid == 31) sSegStart[32] = inc;
+    }
+    __syncthreads();
+    const uint32_t numRecs = sSegStart[32];
     {
         for (uint32_t sub = 0; sub < numRecs; sub += 256)
         {
@@ -736,10 +746,13 @@ __global__ void __launch_bounds__(256) k_span(const __grid_constant__ SLSpanPara
             if (valid)
             {
                 const uint32_t v = sub + tid;
-                int k = 0;
+                int k = 0; /* last segment that starts at or before v */
 #pragma unroll
-                for (int q = 1; q < SL_VB_ROUNDS; ++q) k += (v >= segStart[q]) ? 1 : 0;
-                myRec = info.seg[k].base + (v - segStart[k]);
+                for (int step = 16; step > 0; step >>= 1)
+                {
+                    if (sSegStart[k + step] <= v) k += step;
+                }
+                myRec = sSegBase[k] + (v - sSegStart[k]);
             }
             sRec[tid] = myRec;
             int y0 = 0, y1 = 0, yEnd = 0;
