@@ -58,6 +58,7 @@ struct SLCounters
     unsigned long long recAlloc;     /* triangle records allocated (reset per batch)      */
     unsigned long long handoffs;     /* span cuts (segment boundaries + row ends) that need a state hand-over (reset per batch) */
     unsigned long long pixelsCovered; /* sum of span lengths = upper bound of the batch's fragments (reset per batch) */
+    unsigned long long rowEndCuts;    /* spans that run past the row end into an existing row (reset per batch)       */
     unsigned long long trisBinned;
     unsigned long long spans;
     unsigned long long fragsShaded;
@@ -300,7 +301,7 @@ SLD_FN void sl_fetch_vertex_ids(const SLDrawDesc& P, unsigned long long i, unsig
  * SL_VCACHE_VERTS vertices, the block shades that index range into shared memory first and assembles its triangles
  * from there; otherwise every primitive shades its own three vertices like the reference. */
 #ifndef SL_VERTEX_MIN_BLOCKS
-#define SL_VERTEX_MIN_BLOCKS 1
+#define SL_VERTEX_MIN_BLOCKS 2 /* (256, 1) lets ptxas take > 128 registers: one block per SM, measured 35 % slower */
 #endif
 template <VsFn VS, bool CACHE>
 __global__ void __launch_bounds__(SL_VB_THREADS, SL_VERTEX_MIN_BLOCKS) k_vertex(const __grid_constant__ SLVertexParams P)
@@ -845,6 +846,7 @@ __global__ void __launch_bounds__(256) k_span(const __grid_constant__ SLSpanPara
                                 if (c == 3 && y + 1 < H)
                                 {
                                     atomicAdd(&P.counters->spans, ~0ull); /* two entries, one span */
+                                    atomicAdd(&P.counters->rowEndCuts, 1ull);
                                     if (P.rowFlags) P.rowFlags[y + 1] = 1;
                                 }
                             }
@@ -1024,6 +1026,7 @@ struct SLRasterParams
     unsigned int numSubLists;    /* fragment lists per segment: one per 2^SL_SHADE_SHIFT pixels */
     unsigned int tileBytes;      /* shared memory per warp for its segment's depth texels (0: work in global memory) */
     const uint8_t* rowNeeded;    /* sort-first partition: rows this rank rasterises (null = all) */
+    const uint32_t* ticketOrder; /* ticket -> row << 6 | segment (null: row-major)               */
     unsigned char* depth;
     int depthBpt;
     SLFragLists lists;
@@ -1488,8 +1491,18 @@ __global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_
     if (lane == 0) ticket = atomicAdd(&P.counters->rasterTicket, 1u);
     ticket = __shfl_sync(0xffffffffu, ticket, 0);
     const int NS = (int)P.numSegs;
-    const int y = (int)(ticket / (unsigned)NS), seg = (int)(ticket % (unsigned)NS);
-    if (y >= (int)P.numRows) return;
+    if (ticket >= P.numRows * P.numSegs) return;
+    /* Work order.  Row-major by default.  When no span of the batch runs past a row end, the only hand-overs are from
+     * a segment to its right neighbour, and the host hands out a skewed order (row y of segment s together with row
+     * y + s*D of segment 0, D*numSegs >= the number of resident warps): a piece's left neighbour then took its
+     * ticket a whole machine-load earlier and its hand-over is normally there before it is asked for. */
+    int y = (int)(ticket / (unsigned)NS), seg = (int)(ticket % (unsigned)NS);
+    if (P.ticketOrder)
+    {
+        const uint32_t o = P.ticketOrder[ticket];
+        y = (int)(o >> 6);
+        seg = (int)(o & 63u);
+    }
     if (P.rowNeeded && !P.rowNeeded[y]) return;
     const int W = (int)P.width;
     const int sx0 = seg * (int)P.segWidth;
@@ -1510,7 +1523,7 @@ __global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_
     L.fill = L.tail + SL_MAX_SUBLISTS;
     L.total = L.fill + SL_MAX_SUBLISTS;
     L.nsub = (int)P.numSubLists;
-    L.firstList = ticket * P.numSubLists;
+    L.firstList = (uint32_t)(y * NS + seg) * P.numSubLists;
     if (lane < SL_MAX_SUBLISTS)
     {
         L.tail[lane] = SL_NO_CHUNK;
@@ -1917,7 +1930,7 @@ __global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_
  * ----------------------------------------------------------------------*/
 constexpr int SL_SHADE_WARPS = 4;
 #ifndef SL_SHADE_MIN_BLOCKS
-#define SL_SHADE_MIN_BLOCKS 4
+#define SL_SHADE_MIN_BLOCKS 8 /* 64 registers: measured best on every config (C3 shade 0.63 -> 0.54 ms) */
 #endif
 
 template <FsFn FS>

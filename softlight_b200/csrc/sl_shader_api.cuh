@@ -276,14 +276,36 @@ SLD_FN color_type sl_sample_trilinear(const SL_Texture& tex, float x, float y, f
     const uint16_t zi = sl_f2u16(z);
     const uint16_t ri = sl_f2u16(math::max(z - 1.f, 0.f));
 
-    const auto c000 = color_cast<float, T>(tex.texel<color_type, order>(si, ti, ri));
-    const auto c100 = color_cast<float, T>(tex.texel<color_type, order>(xi, ti, ri));
-    const auto c010 = color_cast<float, T>(tex.texel<color_type, order>(si, yi, ri));
-    const auto c001 = color_cast<float, T>(tex.texel<color_type, order>(si, ti, zi));
-    const auto c101 = color_cast<float, T>(tex.texel<color_type, order>(xi, ti, zi));
-    const auto c011 = color_cast<float, T>(tex.texel<color_type, order>(si, yi, zi));
-    const auto c110 = color_cast<float, T>(tex.texel<color_type, order>(xi, yi, ri));
-    const auto c111 = color_cast<float, T>(tex.texel<color_type, order>(xi, yi, zi));
+    /* the eight taps.  Texel addresses are integer arithmetic (SL_Texture::map_coordinate, SL_Texture.hpp:189-231), so
+     * they may be formed any way that gives the same index: the texture's shape and base pointer are read once and
+     * the (y, z) row bases are shared by the two x taps (ORDERED layout). */
+    const color_type* texels = reinterpret_cast<const color_type*>(tex.data());
+    ptrdiff_t i000, i100, i010, i001, i101, i011, i110, i111;
+    if (order == SL_TexelOrder::ORDERED)
+    {
+        const uint32_t W = tex.width(), H = tex.height();
+        const uint32_t rowTR = W * ((uint32_t)ti + H * (uint32_t)ri), rowYR = W * ((uint32_t)yi + H * (uint32_t)ri);
+        const uint32_t rowTZ = W * ((uint32_t)ti + H * (uint32_t)zi), rowYZ = W * ((uint32_t)yi + H * (uint32_t)zi);
+        i000 = (ptrdiff_t)((uint32_t)si + rowTR); i100 = (ptrdiff_t)((uint32_t)xi + rowTR);
+        i010 = (ptrdiff_t)((uint32_t)si + rowYR); i110 = (ptrdiff_t)((uint32_t)xi + rowYR);
+        i001 = (ptrdiff_t)((uint32_t)si + rowTZ); i101 = (ptrdiff_t)((uint32_t)xi + rowTZ);
+        i011 = (ptrdiff_t)((uint32_t)si + rowYZ); i111 = (ptrdiff_t)((uint32_t)xi + rowYZ);
+    }
+    else
+    {
+        i000 = tex.map_coordinate<order>(si, ti, ri); i100 = tex.map_coordinate<order>(xi, ti, ri);
+        i010 = tex.map_coordinate<order>(si, yi, ri); i110 = tex.map_coordinate<order>(xi, yi, ri);
+        i001 = tex.map_coordinate<order>(si, ti, zi); i101 = tex.map_coordinate<order>(xi, ti, zi);
+        i011 = tex.map_coordinate<order>(si, yi, zi); i111 = tex.map_coordinate<order>(xi, yi, zi);
+    }
+    const auto c000 = color_cast<float, T>(texels[i000]);
+    const auto c100 = color_cast<float, T>(texels[i100]);
+    const auto c010 = color_cast<float, T>(texels[i010]);
+    const auto c001 = color_cast<float, T>(texels[i001]);
+    const auto c101 = color_cast<float, T>(texels[i101]);
+    const auto c011 = color_cast<float, T>(texels[i011]);
+    const auto c110 = color_cast<float, T>(texels[i110]);
+    const auto c111 = color_cast<float, T>(texels[i111]);
 
     const float xf = x - math::floor(x);
     const float yf = y - math::floor(y);

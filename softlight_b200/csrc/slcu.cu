@@ -211,6 +211,8 @@ struct slcu_context
     Scratch records, blockInfo, cnt, off, segSums, rowTotals, rowStart, entries, handoff, rowFlags, rowNeeded, drawTable, blockDraw, recDraw;
     Scratch fragPool, chunkNext, listInfo; /* fragment lists, k_resolve -> k_shade */
     Scratch handoffRegs;
+    Scratch ticketOrder; /* skewed work order of k_resolve, cached per (rows, segments, skew) */
+    unsigned orderRows = 0, orderSegs = 0, orderSkew = 0;
     Batch batch;            /* submitted, not yet executed draws */
     bool syncDraws = false; /* SLCU_SYNC_DRAWS=1: execute every draw call on its own (debug / parity mode) */
     /* sort-first partition (slcu_set_partition) */
@@ -503,7 +505,7 @@ static int flush_draws_impl(slcu_context* c)
         CK(c->records.ensure((size_t)recCapacity * recStride * sizeof(float4)));
         CK(c->recDraw.ensure((size_t)recCapacity * sizeof(uint16_t)));
         CK(c->blockInfo.ensure((size_t)numBlocks * sizeof(SLBlockInfo)));
-        CK(cudaMemsetAsync(&c->counters->recAlloc, 0, 3 * sizeof(unsigned long long), c->stream)); /* recAlloc + handoffs + pixelsCovered */
+        CK(cudaMemsetAsync(&c->counters->recAlloc, 0, 4 * sizeof(unsigned long long), c->stream)); /* recAlloc + handoffs + pixelsCovered + rowEndCuts */
 
         {
             SLVertexParams vp;
@@ -669,6 +671,40 @@ static int flush_draws_impl(slcu_context* c)
     /* each resolving warp keeps its segment's depth texels in shared memory (at most 32 x ... pixels x 8 bytes) */
     rp.tileBytes = (segWidth * depthTex.bpt + 15u) & ~15u;
     rp.counters = c->counters;
+    rp.ticketOrder = nullptr;
+    {
+        /* skewed work order (see k_resolve): only when every hand-over goes from a segment to its right neighbour */
+        static const int skewEnv = getenv("SLCU_TICKET_SKEW") ? atoi(getenv("SLCU_TICKET_SKEW")) : -1;
+        int numSMs = 148;
+        cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, c->device);
+        const unsigned resident = (unsigned)numSMs * 4u * SL_RASTER_WARPS; /* warps of k_resolve that fit the machine */
+        const unsigned skew = skewEnv >= 0 ? (unsigned)skewEnv : (resident + rasterSegs - 1) / rasterSegs + 32u;
+        if (sh.depthTest != 0 && rasterSegs > 1 && rasterSegs <= 64 && skew > 0 && numHandoffs && c->hostCounters->rowEndCuts == 0 && !rowNeeded)
+        {
+            if (c->orderRows != H || c->orderSegs != rasterSegs || c->orderSkew != skew)
+            {
+                std::vector<uint32_t> order;
+                order.reserve((size_t)H * rasterSegs);
+                /* pairs (y, s) sorted by key y + s*skew, then by s: walk the keys */
+                const unsigned long long maxKey = (unsigned long long)H - 1ull + (unsigned long long)(rasterSegs - 1) * skew;
+                for (unsigned long long key = 0; key <= maxKey; ++key)
+                {
+                    for (unsigned s2 = 0; s2 < rasterSegs; ++s2)
+                    {
+                        const unsigned long long off = (unsigned long long)s2 * skew;
+                        if (key < off) break;
+                        const unsigned long long yy = key - off;
+                        if (yy < H) order.push_back((uint32_t)(yy << 6) | s2);
+                    }
+                }
+                CK(c->ticketOrder.ensure(order.size() * sizeof(uint32_t)));
+                CK(cudaMemcpyAsync(c->ticketOrder.buf.ptr, order.data(), order.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+                CK(cudaStreamSynchronize(c->stream)); /* `order` is a temporary */
+                c->orderRows = H; c->orderSegs = rasterSegs; c->orderSkew = skew;
+            }
+            rp.ticketOrder = reinterpret_cast<const uint32_t*>(c->ticketOrder.buf.ptr);
+        }
+    }
     rp.diagnostics = getenv("SLCU_DEBUG") ? 1 : 0;
     const unsigned warpsPerBlock = SL_RASTER_WARPS;
     const unsigned smemBytes = warpsPerBlock * (SL_PIECEQ_BYTES + SL_SUBLIST_BYTES + SL_PIECEREG_BYTES + SL_WINSCRATCH_BYTES + ((4u * segWidth + 15u) & ~15u) + rp.tileBytes); /* piece queue, fragment queue, piece registers, window scratch, tile: per warp */
@@ -804,7 +840,7 @@ void slcu_context_destroy(slcu_context* c)
     if (c->counters) cudaFree(c->counters);
     if (c->hostCounters) cudaFreeHost(c->hostCounters);
     for (auto& pm : c->peerMaps) if (pm.ptr) cudaIpcCloseMemHandle(pm.ptr);
-    Scratch* s[] = {&c->records, &c->blockInfo, &c->cnt, &c->off, &c->segSums, &c->rowTotals, &c->rowStart, &c->entries, &c->handoff, &c->rowFlags, &c->rowNeeded, &c->drawTable, &c->blockDraw, &c->recDraw, &c->fragPool, &c->chunkNext, &c->listInfo, &c->handoffRegs};
+    Scratch* s[] = {&c->records, &c->blockInfo, &c->cnt, &c->off, &c->segSums, &c->rowTotals, &c->rowStart, &c->entries, &c->handoff, &c->rowFlags, &c->rowNeeded, &c->drawTable, &c->blockDraw, &c->recDraw, &c->fragPool, &c->chunkNext, &c->listInfo, &c->handoffRegs, &c->ticketOrder};
     for (Scratch* x : s) x->release();
     cudaStreamDestroy(c->stream);
     delete c;
