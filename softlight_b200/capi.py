@@ -277,8 +277,12 @@ class Context:
         return uid
 
     def ubo_assign(self, uid: int, blob, offset: int = 0):
-        buf = np.frombuffer(bytes(blob), dtype=np.uint8).copy()
-        self._chk(self.f["ubo_assign"](self.h, uid, _ptr(buf), offset, buf.nbytes), "ubo_assign")
+        # per-draw call of the multi-draw configs: keep the Python side thin (bytes go straight through ctypes)
+        if not isinstance(blob, bytes):
+            blob = bytes(blob)
+        rc = self.f["ubo_assign"](self.h, uid, blob, offset, len(blob))
+        if rc < 0:
+            self._chk(rc, "ubo_assign")
 
     def ubo_bind_texture(self, uid: int, offset: int, tex: int):
         self._chk(self.f["ubo_bind_texture"](self.h, uid, offset, tex), "ubo_bind_texture")

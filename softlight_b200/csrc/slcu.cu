@@ -678,8 +678,10 @@ static int flush_draws_impl(slcu_context* c)
         int numSMs = 148;
         cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, c->device);
         const unsigned resident = (unsigned)numSMs * 4u * SL_RASTER_WARPS; /* warps of k_resolve that fit the machine */
-        const unsigned skew = skewEnv >= 0 ? (unsigned)skewEnv : (resident + rasterSegs - 1) / rasterSegs + 32u;
-        if (sh.depthTest != 0 && rasterSegs > 1 && rasterSegs <= 64 && skew > 0 && numHandoffs && c->hostCounters->rowEndCuts == 0 && !rowNeeded)
+        /* sort-first partition: only 1/world of the rows does any work on this rank, so the skew is world times longer */
+        const unsigned world = c->partWorld > 1 ? c->partWorld : 1u;
+        const unsigned skew = skewEnv >= 0 ? (unsigned)skewEnv : (resident * world + rasterSegs - 1) / rasterSegs + 32u;
+        if (sh.depthTest != 0 && rasterSegs > 1 && rasterSegs <= 64 && skew > 0 && numHandoffs && c->hostCounters->rowEndCuts == 0)
         {
             if (c->orderRows != H || c->orderSegs != rasterSegs || c->orderSkew != skew)
             {
