@@ -285,7 +285,9 @@ class Context:
             self._chk(rc, "ubo_assign")
 
     def ubo_bind_texture(self, uid: int, offset: int, tex: int):
-        self._chk(self.f["ubo_bind_texture"](self.h, uid, offset, tex), "ubo_bind_texture")
+        rc = self.f["ubo_bind_texture"](self.h, uid, offset, tex)
+        if rc < 0:
+            self._chk(rc, "ubo_bind_texture")
 
     def ubo_bind_buffer(self, uid: int, offset: int, vbo: int, byte_offset: int = 0):
         self._chk(self.f["ubo_bind_buffer"](self.h, uid, offset, vbo, byte_offset), "ubo_bind_buffer")
@@ -348,7 +350,9 @@ class Context:
         return Mesh(vao, begin, end, mode, material)
 
     def draw(self, mesh: Mesh, shader: int, fbo: int):
-        self._chk(self.f["draw"](self.h, C.byref(mesh), shader, fbo), "draw")
+        rc = self.f["draw"](self.h, C.byref(mesh), shader, fbo)
+        if rc < 0:
+            self._chk(rc, "draw")
 
     def draw_multiple(self, meshes, shader: int, fbo: int):
         arr = (Mesh * len(meshes))(*meshes)

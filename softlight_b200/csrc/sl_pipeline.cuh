@@ -920,8 +920,18 @@ __global__ void k_scan_seg_sums(const uint16_t* cnt, uint32_t* segSums, unsigned
     if (rowNeeded && (y >= numRows || !rowNeeded[y])) { segSums[(size_t)seg * rowPitch + y] = 0; return; }
     const unsigned b0 = seg * blocksPerSeg;
     const unsigned b1 = min(b0 + blocksPerSeg, numBlocks);
+    /* independent loads, eight in flight (the loop is latency-bound otherwise) */
     uint32_t s = 0;
-    for (unsigned b = b0; b < b1; ++b) s += cnt[(size_t)b * rowPitch + y];
+    unsigned b = b0;
+    for (; b + 8 <= b1; b += 8)
+    {
+        uint32_t v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = cnt[(size_t)(b + k) * rowPitch + y];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += v[k];
+    }
+    for (; b < b1; ++b) s += cnt[(size_t)b * rowPitch + y];
     segSums[(size_t)seg * rowPitch + y] = s;
 }
 
@@ -982,7 +992,20 @@ __global__ void k_scan_offsets(const uint16_t* cnt, const uint32_t* segSums, uin
     const unsigned b0 = seg * blocksPerSeg;
     const unsigned b1 = min(b0 + blocksPerSeg, numBlocks);
     uint32_t run = segSums[(size_t)seg * rowPitch + y];
-    for (unsigned b = b0; b < b1; ++b)
+    unsigned b = b0;
+    for (; b + 8 <= b1; b += 8)
+    {
+        uint32_t v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = cnt[(size_t)(b + k) * rowPitch + y];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+        {
+            off[(size_t)(b + k) * rowPitch + y] = run;
+            run += v[k];
+        }
+    }
+    for (; b < b1; ++b)
     {
         off[(size_t)b * rowPitch + y] = run;
         run += cnt[(size_t)b * rowPitch + y];
