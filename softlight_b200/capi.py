@@ -290,7 +290,9 @@ class Context:
             self._chk(rc, "ubo_bind_texture")
 
     def ubo_bind_buffer(self, uid: int, offset: int, vbo: int, byte_offset: int = 0):
-        self._chk(self.f["ubo_bind_buffer"](self.h, uid, offset, vbo, byte_offset), "ubo_bind_buffer")
+        rc = self.f["ubo_bind_buffer"](self.h, uid, offset, vbo, byte_offset)
+        if rc < 0:
+            self._chk(rc, "ubo_bind_buffer")
 
     def create_texture(self, color_type: int, w: int, h: int, d: int = 1, texels: Optional[np.ndarray] = None,
                        order: int = TEXEL_ORDERED) -> int:

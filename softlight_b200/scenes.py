@@ -383,10 +383,12 @@ def indoor_scene(width=3840, height=2160, rooms=(16, 16), quads=26, tex_size=512
 
     def frame(ctx, st):
         ctx.clear_framebuffer(st["fbo"], 0, (0.0, 0.0, 0.0, 1.0), 0.0)
+        ubo, texs, mesh, sh, fbo = st["ubo"], st["texs"], st["mesh"], st["shader"], st["fbo"]
+        assign, bind, draw = ctx.ubo_assign, ctx.ubo_bind_texture, ctx.draw
         for i in range(nrooms):  # the demo's pattern: per-mesh uniforms, then draw (sl_large_scene_test.cpp:700-730)
-            ctx.ubo_assign(st["ubo"], blobs[i])
-            ctx.ubo_bind_texture(st["ubo"], 0, st["texs"][i])
-            ctx.draw(st["mesh"], st["shader"], st["fbo"])
+            assign(ubo, blobs[i])
+            bind(ubo, 0, texs[i])
+            draw(mesh, sh, fbo)
 
     return Scene(name or f"indoor{nrooms}x{tris.shape[0]}_{width}x{height}", width, height, A.SL_COLOR_RGBA_8U, depth_type,
                  (0, 0, 0, 1), 0.0, setup, frame, tris_per_frame=tris.shape[0] * nrooms, draws_per_frame=nrooms,
@@ -573,11 +575,13 @@ def skinned_scene(width=1920, height=1080, grid=(10, 10), bones=64, around=160, 
 
     def frame(ctx, st):
         ctx.clear_framebuffer(st["fbo"], 0, (0.2, 0.2, 0.25, 1.0), 0.0)
+        ubo, tex, bonebuf, mesh, sh, fbo = st["ubo"], st["tex"], st["bones"], st["mesh"], st["shader"], st["fbo"]
+        assign, bind, bindbuf, draw = ctx.ubo_assign, ctx.ubo_bind_texture, ctx.ubo_bind_buffer, ctx.draw
         for i in range(nchars):   # the demo's pattern: per-mesh uniforms (model matrix, bone palette), then draw
-            ctx.ubo_assign(st["ubo"], blobs[i])
-            ctx.ubo_bind_texture(st["ubo"], 0, st["tex"])
-            ctx.ubo_bind_buffer(st["ubo"], 8, st["bones"], i * bones * 64)
-            ctx.draw(st["mesh"], st["shader"], st["fbo"])
+            assign(ubo, blobs[i])
+            bind(ubo, 0, tex)
+            bindbuf(ubo, 8, bonebuf, i * bones * 64)
+            draw(mesh, sh, fbo)
 
     return Scene(name or f"skinned{nchars}x{tris.shape[0]}_{width}x{height}", width, height, A.SL_COLOR_RGBA_8U, depth_type,
                  (0.2, 0.2, 0.25, 1.0), 0.0, setup, frame, tris_per_frame=tris.shape[0] * nchars, draws_per_frame=nchars,
