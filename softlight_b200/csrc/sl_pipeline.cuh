@@ -66,7 +66,7 @@ struct SLCounters
                                         bit3 overflow of a triangle that was classified as "cannot overflow" */
     unsigned int rasterTicket;       /* (row, segment) ticket of k_resolve (reset by k_scan_row_starts)       */
     unsigned int chunkAlloc;         /* fragment chunks handed out by k_resolve (reset by k_scan_row_starts)  */
-    unsigned int pad_;
+    unsigned int shadeTicket;        /* list ticket of k_shade (reset by k_scan_row_starts)                   */
     /* k_resolve diagnostics (SLCU_DEBUG=1): windows, their groups and waves, polls that found nothing, per-warp clocks */
     unsigned long long resolveWindows, resolveWaves, resolveIdle, resolveGroups;
     unsigned long long resolveCycles, resolveMaxCycles, resolveMaxWindows, resolveWarps;
@@ -828,6 +828,7 @@ __global__ void __launch_bounds__(256) k_span(const __grid_constant__ SLSpanPara
                         const bool rOver = ry1raw < 0;
                         const int ry1 = rOver ? -ry1raw - 1 : ry1raw;
                         const int y = max(ry0, w0) + (int)(p - sPairOff[i]);
+                        if (MODE == 1 && P.rowNeeded && !P.rowNeeded[y]) continue; /* sort-first: another rank's row */
                         const uint32_t rec = sRec[i];
                         const uint32_t bit = 1u << (i & 31);
                         const int q = i >> 5;
@@ -980,6 +981,7 @@ __global__ void __launch_bounds__(1024) k_scan_row_starts(const uint32_t* rowTot
         atomicAdd(&counters->spans, (unsigned long long)sPart[1023]);
         counters->rasterTicket = 0u;
         counters->chunkAlloc = 0u;
+        counters->shadeTicket = 0u;
     }
 }
 
@@ -1071,6 +1073,7 @@ struct SLShadeParams
     unsigned char* color[4];
     int colorType[4];         /* SL_ColorDataType */
     SLFragLists lists;
+    unsigned int* shadeTicket; /* list ticket of k_shade (zeroed per batch) */
 };
 
 /* depth texel read (src/SL_TriRasterizer.cpp:40-102) */
@@ -1510,6 +1513,10 @@ __global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_
     extern __shared__ __align__(16) unsigned char sDyn[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t ltMask = (1u << lane) - 1u;
+    unsigned dbgWindows = 0, dbgWaves = 0, dbgIdle = 0, dbgGroups = 0;
+    /* One ticket per warp.  (Persistent warps that loop over tickets were measured: slower on C2/C3/C4 -- more
+     * co-resident working warps do not raise this kernel's throughput -- so the simple form stays.) */
+    {
     unsigned ticket = 0;
     if (lane == 0) ticket = atomicAdd(&P.counters->rasterTicket, 1u);
     ticket = __shfl_sync(0xffffffffu, ticket, 0);
@@ -1534,7 +1541,7 @@ __global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_
     const uint32_t begin = P.rowStart[y], end = P.rowStart[y + 1];
     if (begin == end) return;
     unsigned shaded = 0;
-    unsigned dbgWindows = 0, dbgWaves = 0, dbgIdle = 0, dbgGroups = 0;
+    dbgWindows = 0; dbgWaves = 0; dbgIdle = 0; dbgGroups = 0;
     const long long dbgT0 = P.diagnostics ? clock64() : 0ll;
     const bool useDepth = P.depthTest != 0 || P.depthMask != 0;
 
@@ -1945,6 +1952,7 @@ __global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_
         atomicMax(&P.counters->resolveMaxWindows, (unsigned long long)dbgWindows);
         atomicAdd(&P.counters->resolveWarps, 1ull);
     }
+    }
 }
 
 /* ------------------------------------------------------------------------
@@ -1960,10 +1968,15 @@ template <FsFn FS>
 __global__ void __launch_bounds__(SL_SHADE_WARPS * 32, SL_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ SLShadeParams P)
 {
     const int lane = threadIdx.x & 31;
-    const unsigned list = blockIdx.x * SL_SHADE_WARPS + (threadIdx.x >> 5);
-    if (list >= P.numLists) return;
+    /* persistent warps: lists are handed out through a ticket (a block would otherwise live as long as its longest list) */
+    for (;;)
+    {
+    unsigned list = 0;
+    if (lane == 0) list = atomicAdd(P.shadeTicket, 1u);
+    list = __shfl_sync(0xffffffffu, list, 0);
+    if (list >= P.numLists) break;
     int remaining = (int)P.lists.listCount[list];
-    if (remaining <= 0) return;
+    if (remaining <= 0) continue;
     uint32_t chunk = P.lists.listHead[list];
     for (; remaining > 0; remaining -= 32)
     {
@@ -2035,6 +2048,7 @@ __global__ void __launch_bounds__(SL_SHADE_WARPS * 32, SL_SHADE_MIN_BLOCKS) k_sh
         }
         __syncwarp(); /* the next step's loads of a pixel come after this step's stores to it */
     }
+    } /* next list */
 }
 
 /* ------------------------------------------------------------------------

@@ -746,7 +746,16 @@ static int flush_draws_impl(slcu_context* c)
             shp.colorType[i] = t.type;
         }
     }
-    { KernelScope ks(c, SLCU_K_SHADE); CK(sh.fs((unsigned)((numLists + SL_SHADE_WARPS - 1) / SL_SHADE_WARPS), c->stream, shp)); }
+    shp.shadeTicket = &c->counters->shadeTicket;
+    {
+        int numSMs = 148;
+        cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, c->device);
+        unsigned long long grid = (unsigned long long)numSMs * SL_SHADE_MIN_BLOCKS; /* persistent warps */
+        const unsigned long long needBlocks = (numLists + SL_SHADE_WARPS - 1) / SL_SHADE_WARPS;
+        if (grid > needBlocks) grid = needBlocks;
+        KernelScope ks(c, SLCU_K_SHADE);
+        CK(sh.fs((unsigned)grid, c->stream, shp));
+    }
     return 0;
 }
 
