@@ -1270,16 +1270,16 @@ struct SLTile
 /* ------------------------------------------------------------------------
  * The fragment stage is two kernels.
  *
- *   k_resolve (one for every shader): the span walkers below run the 4-pixel group loop of render_triangle_simd
+ *   k_resolve (one for every shader) runs the 4-pixel group loop of render_triangle_simd
  *   (src/SL_TriRasterizer.cpp:471-548): depth of the four lanes, depth test against the tile, the in-place compaction
  *   of the barycentric registers (:496-498), the depth write (src/SL_FragmentProcessor.cpp:526-529 -- the value is the
- *   rasteriser's z and does not depend on the shader).  Every surviving fragment goes to the warp's fragment queue in
- *   shared memory and from there, 32 at a time, to the (row, segment)'s fragment list in HBM: {barycentrics the
+ *   rasteriser's z and does not depend on the shader).  Every surviving fragment goes straight into the chunks of the
+ *   fragment list of its (row, 128-pixel column) in HBM: {barycentrics the
  *   reference would hand to the shader, z, x, y, record}.  All ordering constraints of the path (submission order per
  *   pixel, the left-to-right compaction state of a span, hand-overs between segments and rows) are settled here, by a
- *   kernel that is small, needs few registers and never waits for shading.
+ *   kernel that is shared by all shaders and never waits for shading.
  *
- *   k_shade<FS>: one warp per fragment list, 32 fragments per step, one per lane (flush_tri_fragments,
+ *   k_shade<FS>: persistent warps take fragment lists through a ticket; 32 fragments per step, one per lane (flush_tri_fragments,
  *   src/SL_FragmentProcessor.cpp:416-531): perspective correction, varyings, the fragment shader, colour write /
  *   blend.  Lists are in submission order per pixel and a list is walked front to back, so colour writes to a pixel
  *   happen in submission order; fragments of one step that hit the same pixel are ordered by lane.  Lists never share
@@ -1397,7 +1397,7 @@ SLD_FN uint32_t sl_handoff_hash(unsigned long long key) { return (uint32_t)((key
 SLD_FN void sl_handoff_publish(const SLRasterParams& P, uint32_t rec, int y, int boundary, uint32_t outcomes, const math::vec4& r0, const math::vec4& r1,
                                const math::vec4& r2, const math::vec4& r3)
 {
-    if (!P.handoff) { atomicOr(&P.counters->errorFlags, 16u); return; } /* the count pass and the walkers disagree */
+    if (!P.handoff) { atomicOr(&P.counters->errorFlags, 16u); return; } /* the count pass and the resolve pass disagree */
     const unsigned long long key = sl_handoff_key(rec, y, boundary);
     const unsigned long long word = (key << 12) | 0x800ull | (unsigned long long)(outcomes & 7u);
     uint32_t i = sl_handoff_hash(key) & P.handoffMask;
@@ -1503,7 +1503,7 @@ SLD_FN void sl_copy_warp(unsigned char* dst, const unsigned char* src, unsigned 
  *     14 reachable states, (3,3,3,3) absorbing).  Lanes evaluate under the lane map of their piece's last settled
  *     group; a wave settles, per piece, the leading run of lanes up to and including the first one that changes it.
  * The earliest pending lane always settles, so a window needs at most as many waves as its longest dependency chain,
- * and a wave is a few dozen instructions.  Survivors go to the fragment queue in lane order = submission order.
+ * and a wave is a few dozen instructions.  Survivors are appended to the fragment lists in lane order = submission order.
  *
  * A piece that does not start its span continues from the registers handed over by the piece on its left (SLHand);
  * with the depth test off nothing ever waits: such a piece replays the accumulator chain from the span start instead

@@ -709,7 +709,7 @@ static int flush_draws_impl(slcu_context* c)
     }
     rp.diagnostics = getenv("SLCU_DEBUG") ? 1 : 0;
     const unsigned warpsPerBlock = SL_RASTER_WARPS;
-    const unsigned smemBytes = warpsPerBlock * (SL_PIECEQ_BYTES + SL_SUBLIST_BYTES + SL_PIECEREG_BYTES + SL_WINSCRATCH_BYTES + ((4u * segWidth + 15u) & ~15u) + rp.tileBytes); /* piece queue, fragment queue, piece registers, window scratch, tile: per warp */
+    const unsigned smemBytes = warpsPerBlock * (SL_PIECEQ_BYTES + SL_SUBLIST_BYTES + SL_PIECEREG_BYTES + SL_WINSCRATCH_BYTES + ((4u * segWidth + 15u) & ~15u) + rp.tileBytes); /* piece queue, sub-list state, piece registers, window scratch, toucher masks, depth tile: per warp */
     {
         static bool attrSet = false;
         if (!attrSet)
