@@ -844,6 +844,9 @@ __global__ void __launch_bounds__(256) k_span(const __grid_constant__ SLSpanPara
                             {
                                 myPix += (unsigned long long)(xMax - xMin);
                                 if (P.chained) myCuts += sl_count_cuts(P, xMin, xMax, y + 1 < H);
+                                /* the span statistic counts spans, the row lists hold entries: a span of the last row that
+                                 * lies entirely beyond the row end has no entry at all (its pixels are outside the image) */
+                                if (c == 2 && y + 1 >= H) atomicAdd(&P.counters->spans, 1ull);
                                 if (c == 3 && y + 1 < H)
                                 {
                                     atomicAdd(&P.counters->spans, ~0ull); /* two entries, one span */

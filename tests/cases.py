@@ -37,6 +37,12 @@ def _variants():
     v.append(("overflow_blend", dict(n=700, width=257, height=131, clip_fraction=0.9, blend=1)))
     v.append(("overflow_half_ge", dict(n=700, width=512, height=64, clip_fraction=0.9, depth_type=A.SL_COLOR_R_HALF,
                                        depth_test=A.SL_DEPTH_TEST_GREATER_EQUAL, clear_depth=-1.0)))
+    # the remaining colour formats the path supports (every 8/16-bit unorm, half, float and double layout; 32/64-bit
+    # integer targets are refused): appended last so that the seeds of the cases above do not move
+    for ct in (A.SL_COLOR_R_16U, A.SL_COLOR_R_HALF, A.SL_COLOR_R_DOUBLE, A.SL_COLOR_RG_16U, A.SL_COLOR_RG_HALF, A.SL_COLOR_RG_FLOAT,
+               A.SL_COLOR_RG_DOUBLE, A.SL_COLOR_RGB_16U, A.SL_COLOR_RGB_HALF, A.SL_COLOR_RGB_DOUBLE):
+        v.append((f"color{ct}", dict(color_type=ct)))
+        v.append((f"color{ct}_premult", dict(color_type=ct, blend=2)))
     return v
 
 
