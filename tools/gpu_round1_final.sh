@@ -1,4 +1,4 @@
-# round-1 (final): evidence run for the resolve/shade pipeline: parity log, bench of every config (with the CPU reference beside it),
+# round-1 (final, r01g): evidence run for the resolve/shade pipeline: parity log, bench of every config (with the CPU reference beside it),
 # reference arm, ncu launch lists and full captures of the top kernels
 mkdir -p gpurun_out
 nvidia-smi -L > gpurun_out/box.txt; lscpu | grep -E 'Model name|^CPU\(s\)|Thread|Socket' >> gpurun_out/box.txt
