@@ -12,6 +12,6 @@ print('$1', '$c', round(d['ms_per_step'],3),'ms', {k:round(v,3) for k,v in d['ro
 " || tail -3 gpurun_out/b.err
   done
 }
-CONFIGS="c2_instancing10k c3_indoor2m c1_sphere100k c4_skinned100 c1_sphere1m_4k c5_volume4k"
+CONFIGS="c2_instancing10k c3_indoor2m c1_sphere100k c4_skinned100"
 run head
 
