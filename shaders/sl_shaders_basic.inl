@@ -98,8 +98,48 @@ SL_SHADER_FN bool vcolor_mrt_fs(SL_FragmentParam& fragParam)
     return true;
 }
 
+/* ---- "sampler_matrix": parity of SL_Sampler.hpp / SL_Texture.hpp addressing beyond what the configs use: every filter
+ * (nearest, bilinear, trilinear) x wrap mode (REPEAT, EDGE, BORDER) x texel order (ORDERED, SWIZZLED) over 8-bit RGBA / RGB /
+ * R textures in 2-D and 3-D; uniforms select the combination, the interpolated colour carries (u, v, w) beyond [0, 1). ---- */
+struct SamplerMatrixUniforms
+{
+    const SL_Texture* pRgba2dOrdered;
+    const SL_Texture* pRgba2dSwizzled;
+    const SL_Texture* pRgb2dOrdered;
+    const SL_Texture* pR3dOrdered;
+    const SL_Texture* pR3dSwizzled;
+    const SL_Texture* pRgba3dOrdered;
+    int               mode;
+    int               pad;
+};
+
+SL_SHADER_FN bool sampler_matrix_fs(SL_FragmentParam& fragParam)
+{
+    const SamplerMatrixUniforms* pUniforms = fragParam.pUniforms->template as<SamplerMatrixUniforms>();
+    const float u = fragParam.pVaryings[0][0], v = fragParam.pVaryings[0][1], w = fragParam.pVaryings[0][2];
+    math::vec4 out{0.f, 0.f, 0.f, 1.f};
+    switch (pUniforms->mode)
+    {
+        case 0: out = color_cast<float, uint8_t>(sl_sample_nearest<math::vec4_t<uint8_t>, SL_WrapMode::REPEAT, SL_TexelOrder::ORDERED>(*pUniforms->pRgba2dOrdered, u, v)); break;
+        case 1: out = color_cast<float, uint8_t>(sl_sample_nearest<math::vec4_t<uint8_t>, SL_WrapMode::EDGE, SL_TexelOrder::SWIZZLED>(*pUniforms->pRgba2dSwizzled, u, v)); break;
+        case 2: out = math::vec4_cast(color_cast<float, uint8_t>(sl_sample_nearest<math::vec3_t<uint8_t>, SL_WrapMode::BORDER, SL_TexelOrder::ORDERED>(*pUniforms->pRgb2dOrdered, u, v)), 1.f); break;
+        case 3: out = color_cast<float, uint8_t>(sl_sample_bilinear<math::vec4_t<uint8_t>, SL_WrapMode::REPEAT, SL_TexelOrder::SWIZZLED>(*pUniforms->pRgba2dSwizzled, u, v)); break;
+        case 4: out = math::vec4_cast(color_cast<float, uint8_t>(sl_sample_bilinear<math::vec3_t<uint8_t>, SL_WrapMode::EDGE, SL_TexelOrder::ORDERED>(*pUniforms->pRgb2dOrdered, u, v)), 1.f); break;
+        case 5: out = color_cast<float, uint8_t>(sl_sample_bilinear<math::vec4_t<uint8_t>, SL_WrapMode::BORDER, SL_TexelOrder::ORDERED>(*pUniforms->pRgba2dOrdered, u, v)); break;
+        case 6: out = math::vec4{color_cast<float, uint8_t>(sl_sample_nearest<SL_ColorR8, SL_WrapMode::REPEAT, SL_TexelOrder::ORDERED>(*pUniforms->pR3dOrdered, u, v, w)).r, 0.f, 0.f, 1.f}; break;
+        case 7: out = math::vec4{color_cast<float, uint8_t>(sl_sample_nearest<SL_ColorR8, SL_WrapMode::BORDER, SL_TexelOrder::SWIZZLED>(*pUniforms->pR3dSwizzled, u, v, w)).r, 0.f, 0.f, 1.f}; break;
+        case 8: out = math::vec4{color_cast<float, uint8_t>(sl_sample_trilinear<SL_ColorR8, SL_WrapMode::REPEAT, SL_TexelOrder::ORDERED>(*pUniforms->pR3dOrdered, u, v, w)).r, 0.f, 0.f, 1.f}; break;
+        case 9: out = math::vec4{color_cast<float, uint8_t>(sl_sample_trilinear<SL_ColorR8, SL_WrapMode::EDGE, SL_TexelOrder::SWIZZLED>(*pUniforms->pR3dSwizzled, u, v, w)).r, 0.f, 0.f, 1.f}; break;
+        case 10: out = color_cast<float, uint8_t>(sl_sample_trilinear<math::vec4_t<uint8_t>, SL_WrapMode::BORDER, SL_TexelOrder::ORDERED>(*pUniforms->pRgba3dOrdered, u, v, w)); break;
+        default: out = color_cast<float, uint8_t>(sl_sample_bilinear<math::vec4_t<uint8_t>, SL_WrapMode::EDGE, SL_TexelOrder::SWIZZLED>(*pUniforms->pRgba2dSwizzled, u, v)); break;
+    }
+    fragParam.pOutputs[0] = out;
+    return true;
+}
+
 SL_REGISTER_VERTEX_SHADER("vcolor", vcolor_vs)
 SL_REGISTER_FRAGMENT_SHADER("vcolor", vcolor_fs)
+SL_REGISTER_FRAGMENT_SHADER("sampler_matrix", sampler_matrix_fs)
 SL_REGISTER_FRAGMENT_SHADER("vcolor_mrt", vcolor_mrt_fs)
 SL_REGISTER_VERTEX_SHADER("lambert", lambert_vs)
 SL_REGISTER_FRAGMENT_SHADER("lambert", lambert_fs)

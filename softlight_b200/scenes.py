@@ -683,7 +683,60 @@ def volume_scene(width=7680, height=4320, vol_size=256, depth_type=A.SL_COLOR_R_
                  setup, frame, tris_per_frame=12, draws_per_frame=1)
 
 
+# ---- sampler matrix: every filter x wrap mode x texel order the shader API offers, one viewport tile per combination ----
+def sampler_matrix_scene(tile_w=64, tile_h=48, name=None) -> Scene:
+    cols, rows, modes = 4, 3, 12
+    width, height = cols * tile_w, rows * tile_h
+    rng = np.random.default_rng(4242)
+    # a quad over the whole viewport; the "colour" attribute carries (u, v, w): beyond [0, 1) on every side
+    def vert(x, y):
+        u = -0.6 + 2.3 * (x + 1) / 2
+        v = -0.4 + 1.9 * (y + 1) / 2
+        return [x, y, 0.0, 1.0, u, v, 0.35 * u + 0.4 * v + 0.1, 1.0]
+    quad = np.array([vert(-1, -1), vert(1, -1), vert(1, 1), vert(-1, -1), vert(1, 1), vert(-1, 1)], dtype=np.float32)
+    rgba2d = rng.integers(0, 256, size=(12, 20, 4), dtype=np.uint8)
+    rgb2d = rng.integers(0, 256, size=(13, 19, 3), dtype=np.uint8)
+    r3d = rng.integers(0, 256, size=(8, 8, 12, 1), dtype=np.uint8)
+    rgba3d = rng.integers(0, 256, size=(4, 8, 8, 4), dtype=np.uint8)
+
+    def blob(mode):
+        b = bytearray(64)
+        b[48:52] = np.array([mode], dtype=np.int32).tobytes()
+        return bytes(b)
+
+    def setup(ctx):
+        color, depth, fbo = _make_targets(ctx, width, height, A.SL_COLOR_RGBA_FLOAT, A.SL_COLOR_R_FLOAT)
+        vbo = ctx.create_vbo(quad)
+        vao = ctx.create_vao(vbo, None, [(0, 32, A.VERTEX_DIMENSION_4, A.VERTEX_DATA_FLOAT), (16, 32, A.VERTEX_DIMENSION_4, A.VERTEX_DATA_FLOAT)])
+        texs = [ctx.create_texture(A.SL_COLOR_RGBA_8U, 20, 12, 1, rgba2d, A.TEXEL_ORDERED),
+                ctx.create_texture(A.SL_COLOR_RGBA_8U, 20, 12, 1, rgba2d, A.TEXEL_SWIZZLED),
+                ctx.create_texture(A.SL_COLOR_RGB_8U, 19, 13, 1, rgb2d, A.TEXEL_ORDERED),
+                ctx.create_texture(A.SL_COLOR_R_8U, 12, 8, 8, r3d, A.TEXEL_ORDERED),
+                ctx.create_texture(A.SL_COLOR_R_8U, 12, 8, 8, r3d, A.TEXEL_SWIZZLED),
+                ctx.create_texture(A.SL_COLOR_RGBA_8U, 8, 8, 4, rgba3d, A.TEXEL_ORDERED)]
+        ubo = ctx.create_ubo(blob(0))
+        for i, t in enumerate(texs):
+            ctx.ubo_bind_texture(ubo, 8 * i, t)
+        sh = ctx.create_shader("vcolor", "sampler_matrix", ubo, vs_varyings=1, fs_varyings=1, cull=A.SL_CULL_OFF, blend=A.SL_BLEND_OFF,
+                               depth_test=A.SL_DEPTH_TEST_OFF, depth_mask=A.SL_DEPTH_MASK_OFF)
+        assert sh != A.INVALID_ID
+        return dict(color=color, depth=depth, fbo=fbo, shader=sh, ubo=ubo, mesh=ctx.mesh(vao, 0, 6, A.RENDER_MODE_TRIANGLES))
+
+    def frame(ctx, st):
+        ctx.viewport(0, 0, width, height)
+        ctx.clear_framebuffer(st["fbo"], 0, (0.0, 0.0, 0.0, 0.0), 0.0)
+        for mode in range(modes):
+            ctx.viewport((mode % cols) * tile_w, (mode // cols) * tile_h, tile_w, tile_h)
+            ctx.ubo_assign(st["ubo"], blob(mode))
+            ctx.draw(st["mesh"], st["shader"], st["fbo"])
+        ctx.viewport(0, 0, 65535, 65535)
+
+    return Scene(name or f"sampler_matrix_{width}x{height}", width, height, A.SL_COLOR_RGBA_FLOAT, A.SL_COLOR_R_FLOAT, (0, 0, 0, 0), 0.0,
+                 setup, frame, tris_per_frame=2 * modes, draws_per_frame=modes)
+
+
 SCENES: Dict[str, Callable[[], Scene]] = {
+    "sampler_matrix": sampler_matrix_scene,
     "draw_test": draw_test_scene,
     "c1_sphere100k": sphere_scene,
     "c1_small": lambda: sphere_scene(256, 192, 48, 48, name="sphere4k_256x192"),

@@ -82,6 +82,7 @@ CASES["c2_small"] = S.SCENES["c2_small"]
 CASES["c3_small"] = S.SCENES["c3_small"]
 CASES["c4_small"] = S.SCENES["c4_small"]
 CASES["c5_small"] = S.SCENES["c5_small"]
+CASES["sampler_matrix"] = S.SCENES["sampler_matrix"]
 
 # full-size configs: compared through hashes / live checkers only
 BIG_CASES = {
@@ -96,7 +97,7 @@ BIG_CASES = {
 }
 
 # cases whose images are committed in full (the rest of CASES is pinned by sha256)
-FULL_IMAGE_CASES = ["draw_test", "c1_small", "c2_small", "c3_small", "c4_small", "c5_small", "rand_blend1", "rand_clip_heavy", "rand_depth_half_premult"]
+FULL_IMAGE_CASES = ["draw_test", "c1_small", "c2_small", "c3_small", "c4_small", "c5_small", "sampler_matrix", "rand_blend1", "rand_clip_heavy", "rand_depth_half_premult"]
 
 
 def bits(a: np.ndarray) -> np.ndarray:
