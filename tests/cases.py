@@ -43,6 +43,10 @@ def _variants():
                A.SL_COLOR_RG_DOUBLE, A.SL_COLOR_RGB_16U, A.SL_COLOR_RGB_HALF, A.SL_COLOR_RGB_DOUBLE):
         v.append((f"color{ct}", dict(color_type=ct)))
         v.append((f"color{ct}_premult", dict(color_type=ct, blend=2)))
+    # extreme framebuffer shape: the row binner's height limit (SL_MAX_ROWS = 8192).  (A 16000-pixel-wide stress case is NOT
+    # here: with clip-generated spans thousands of pixels long, the reference enters the behaviours DESIGN.md section 2 lists
+    # as not reproduced -- its oracle restatement already differs there; widths up to 7680 (config C5) are pinned.)
+    v.append(("tall_8192", dict(n=600, width=48, height=8192, clip_fraction=0.4)))
     return v
 
 
