@@ -807,6 +807,76 @@ static void process_verts(slcu_context* c, const slcu_mesh& m, size_t instanceId
     }
 }
 
+/* SL_PointProcessor::process_verts + SL_PointRasterizer::render_point (src/SL_PointProcessor.cpp:70-113,
+ * src/SL_PointRasterizer.cpp:27-101), one thread: every element is one vertex; a vertex inside the clip volume
+ * (sl_ndc_clip_status, one-vertex form, SL_PostVertexTransform.hpp:536-553) becomes one fragment at its screen
+ * position: depth test against the buffer, varyings = the vertex's own, shader, colour write / blend, depth write. */
+static void process_points(slcu_context* c, const slcu_mesh& m, size_t instanceId, bool usingIndices, const math::mat4& scissorMat,
+                           const math::vec4& viewportDims)
+{
+    const Shader& sh = *c->shader;
+    const SL_VertexArray& vao = c->vaos[m.vaoId];
+    const IndexBuffer* pIbo = vao.has_index_buffer() ? &c->ibos[vao.mIboId] : nullptr;
+    SL_Texture& depthBuffer = *c->depthBuf;
+
+    SL_VertexParam params;
+    params.pUniforms = &c->ubos[sh.ubo];
+    params.instanceId = instanceId;
+    params.pVao = &vao;
+    params.pVbo = &c->vbos[vao.mVboId];
+
+    c->stats.trisSubmitted += (m.elementEnd - m.elementBegin) / 3; /* the harness counts elements / 3 for every mode */
+    for (size_t i = m.elementBegin; i < m.elementEnd; ++i)
+    {
+        size_t vertId = i;
+        if (usingIndices)
+        {
+            const unsigned char* p = pIbo->data.data() + i * pIbo->bytesPerId;
+            switch (pIbo->type)
+            {
+                case 0: vertId = *p; break;
+                case 1: { uint16_t u; memcpy(&u, p, 2); vertId = u; break; }
+                default: { uint32_t u; memcpy(&u, p, 4); vertId = u; break; }
+            }
+        }
+        TransformedVert tv;
+        params.vertId = vertId;
+        params.pVaryings = tv.varyings;
+        tv.vert = scissorMat * sh.vs(params);
+
+        const float w0p = tv.vert.v[3];
+        const float w0n = -w0p;
+        bool visible = w0p > 0.f;
+        for (int k = 0; k < 4; ++k) visible = visible && (tv.vert.v[k] <= w0p) && (tv.vert.v[k] >= w0n);
+        if (!visible) continue;
+        perspective_divide(tv.vert);
+        ndc_to_screen(tv.vert, viewportDims);
+        c->stats.trisBinned++;
+
+        SL_FragmentParam fp;
+        fp.pUniforms = &c->ubos[sh.ubo];
+        fp.coord.x = (uint16_t)cvt_tr(tv.vert.v[0]);
+        fp.coord.y = (uint16_t)cvt_tr(tv.vert.v[1]);
+        fp.coord.depth = tv.vert.v[2];
+        const size_t idx = (size_t)fp.coord.x + (size_t)depthBuffer.mWidth * fp.coord.y;
+        const float d = load_depth(depthBuffer, idx);
+        if (!depth_cmp(sh.depthTest, fp.coord.depth, d)) continue;
+        for (int s2 = 0; s2 < sh.numVaryings; ++s2) fp.pVaryings[s2] = tv.varyings[s2];
+        for (int k = 0; k < 4; ++k) fp.pOutputs[k] = math::vec4{0.f};
+        if (idx < (size_t)depthBuffer.mWidth * depthBuffer.mHeight) c->stats.fragsShaded++;
+        const bool haveOutputs = sh.fs(fp);
+        if (haveOutputs)
+        {
+            for (int k = sh.numOutputs - 1; k >= 0; --k)
+            {
+                if (sh.blend != 0) blend_color(*c->colorBufs[k], fp.coord.x, fp.coord.y, fp.pOutputs[k], sh.blend);
+                else store_color(*c->colorBufs[k], fp.coord.x, fp.coord.y, fp.pOutputs[k]);
+            }
+        }
+        if (sh.depthMask) store_depth(depthBuffer, idx, fp.coord.depth);
+    }
+}
+
 static void apply_fixups(slcu_context* c)
 {
     for (const UboFixup& f : c->fixups)
@@ -836,6 +906,19 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
     const math::mat4 scissorMat = scissor_matrix(c->scissor, fboW, fboH);
     const math::vec4 viewportDims = viewport_rect(c->viewport, c->scissor, fboW, fboH);
 
+    const bool points = (meshes[0].mode == 0x01) || (meshes[0].mode == 0x03); /* RENDER_MODE_POINTS / INDEXED_POINTS -> SL_PointProcessor */
+    if (points)
+    {
+        if (numInstances == 1)
+        {
+            for (size_t i = 0; i < numMeshes; ++i) process_points(c, meshes[i], 0, meshes[i].mode == 0x03, scissorMat, viewportDims);
+        }
+        else
+        {
+            for (size_t i = 0; i < numInstances; ++i) process_points(c, meshes[0], i, meshes[0].mode == 0x03, scissorMat, viewportDims);
+        }
+        return 0;
+    }
     if (numInstances == 1)
     {
         for (size_t i = 0; i < numMeshes; ++i)

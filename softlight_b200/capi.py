@@ -57,8 +57,14 @@ def texel_dtype(color_type: int):
 VERTEX_DATA_BYTE, VERTEX_DATA_SHORT, VERTEX_DATA_INT, VERTEX_DATA_LONG, VERTEX_DATA_FLOAT, VERTEX_DATA_DOUBLE = range(6)
 VERTEX_DIMENSION_1, VERTEX_DIMENSION_2, VERTEX_DIMENSION_3, VERTEX_DIMENSION_4 = range(4)
 # SL_RenderMode (SL_Mesh.hpp)
+RENDER_MODE_POINTS = 0x01
+RENDER_MODE_INDEXED_POINTS = 0x03
+RENDER_MODE_LINES = 0x04
+RENDER_MODE_INDEXED_LINES = 0x0C
 RENDER_MODE_TRIANGLES = 0x10
 RENDER_MODE_INDEXED_TRIANGLES = 0x30
+RENDER_MODE_TRI_WIRE = 0x50
+RENDER_MODE_INDEXED_TRI_WIRE = 0x70
 # SL_PipelineState.hpp:15-64
 SL_CULL_BACK_FACE, SL_CULL_FRONT_FACE, SL_CULL_OFF = range(3)
 (SL_DEPTH_TEST_OFF, SL_DEPTH_TEST_LESS_THAN, SL_DEPTH_TEST_LESS_EQUAL, SL_DEPTH_TEST_GREATER_THAN,

@@ -21,6 +21,8 @@
 
 #include "slcu.h"
 #include "sl_pipeline.cuh"
+#include "sl_points.cuh"
+#include <cub/device/device_radix_sort.cuh>
 
 using namespace sld;
 
@@ -33,8 +35,11 @@ typedef cudaError_t (*VertexLauncher)(unsigned grid, cudaStream_t s, const SLVer
 static const unsigned kVertexCacheMaxBytes = 6u * SL_VCACHE_VERTS * (unsigned)sizeof(float4) + SL_VCACHE_VERTS; /* clip + screen position, 4 varyings, flags */
 typedef cudaError_t (*RasterLauncher)(unsigned grid, cudaStream_t s, const SLShadeParams& p);
 
-struct VsEntry { const char* name; VertexLauncher launch; };
-struct FsEntry { const char* name; RasterLauncher launch; };
+typedef cudaError_t (*PointVertexLauncher)(unsigned grid, cudaStream_t s, const SLPointParams& p);
+typedef cudaError_t (*PointShadeLauncher)(unsigned grid, cudaStream_t s, const SLPointShadeParams& p);
+
+struct VsEntry { const char* name; VertexLauncher launch; PointVertexLauncher launchPoints; };
+struct FsEntry { const char* name; RasterLauncher launch; PointShadeLauncher launchPoints; };
 static std::vector<VsEntry>& vs_registry() { static std::vector<VsEntry> r; return r; }
 static std::vector<FsEntry>& fs_registry() { static std::vector<FsEntry> r; return r; }
 
@@ -60,14 +65,24 @@ template <FsFn FS> static cudaError_t launch_raster(unsigned grid, cudaStream_t 
     k_shade<FS><<<grid, SL_SHADE_WARPS * 32, 0, s>>>(p);
     return cudaGetLastError();
 }
-struct VsReg { VsReg(const char* n, VertexLauncher l) { vs_registry().push_back(VsEntry{n, l}); } };
-struct FsReg { FsReg(const char* n, RasterLauncher l) { fs_registry().push_back(FsEntry{n, l}); } };
+template <VsFn VS> static cudaError_t launch_point_vertex(unsigned grid, cudaStream_t s, const SLPointParams& p)
+{
+    k_point_vertex<VS><<<grid, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+template <FsFn FS> static cudaError_t launch_point_shade(unsigned grid, cudaStream_t s, const SLPointShadeParams& p)
+{
+    k_point_shade<FS><<<grid, 128, 0, s>>>(p);
+    return cudaGetLastError();
+}
+struct VsReg { VsReg(const char* n, VertexLauncher l, PointVertexLauncher pl) { vs_registry().push_back(VsEntry{n, l, pl}); } };
+struct FsReg { FsReg(const char* n, RasterLauncher l, PointShadeLauncher pl) { fs_registry().push_back(FsEntry{n, l, pl}); } };
 
 #define SL_SHADER_FN static __device__ __forceinline__
 #define SL_CAT2(a, b) a##b
 #define SL_CAT(a, b) SL_CAT2(a, b)
-#define SL_REGISTER_VERTEX_SHADER(name, fn) static VsReg SL_CAT(vsreg_, fn){name, launch_vertex<fn>};
-#define SL_REGISTER_FRAGMENT_SHADER(name, fn) static FsReg SL_CAT(fsreg_, fn){name, launch_raster<fn>};
+#define SL_REGISTER_VERTEX_SHADER(name, fn) static VsReg SL_CAT(vsreg_, fn){name, launch_vertex<fn>, launch_point_vertex<fn>};
+#define SL_REGISTER_FRAGMENT_SHADER(name, fn) static FsReg SL_CAT(fsreg_, fn){name, launch_raster<fn>, launch_point_shade<fn>};
 
 namespace sld
 {
@@ -154,7 +169,7 @@ struct HostTexture
 struct HostIbo { int type = 0; uint32_t count = 0; DevBuffer buf; };
 struct HostVao { SL_VertexArray vao; int numBindings = 0; size_t vbo = (size_t)-1, ibo = (size_t)-1; };
 struct HostFbo { unsigned numColors = 0; size_t colors[4] = {(size_t)-1, (size_t)-1, (size_t)-1, (size_t)-1}; size_t depth = (size_t)-1; };
-struct HostShader { int cullMode, depthTest, depthMask, blend, numVaryings, numOutputs; VertexLauncher vs; RasterLauncher fs; size_t ubo; };
+struct HostShader { int cullMode, depthTest, depthMask, blend, numVaryings, numOutputs; VertexLauncher vs; RasterLauncher fs; PointVertexLauncher pointVs; PointShadeLauncher pointFs; size_t ubo; };
 struct UboFixup { size_t ubo, offset; int kind; size_t id, byteOffset; };
 struct HostUbo { unsigned char bytes[1024]; };
 
@@ -211,6 +226,7 @@ struct slcu_context
     Scratch records, blockInfo, cnt, off, segSums, rowTotals, rowStart, entries, handoff, rowFlags, rowNeeded, drawTable, blockDraw, recDraw;
     Scratch fragPool, chunkNext, listInfo; /* fragment lists, k_resolve -> k_shade */
     Scratch handoffRegs;
+    Scratch pointKeys, pointRecs, pointSortTemp; /* point primitives: sort keys (double buffer), records, radix-sort scratch */
     Scratch ticketOrder; /* skewed work order of k_resolve, cached per (rows, segments, skew) */
     unsigned orderRows = 0, orderSegs = 0, orderSkew = 0;
     Batch batch;            /* submitted, not yet executed draws */
@@ -363,11 +379,21 @@ static const unsigned kMaxBatchBlocks = 24576; /* 24 M primitives */
 static const size_t kMaxBatchDraws = 65535;    /* recDraw is 16 bits */
 
 static int flush_draws(slcu_context* c);
+static int run_points(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, size_t numInstances, size_t shaderId, size_t fboId);
 
 static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, size_t numInstances, size_t shaderId, size_t fboId)
 {
     if (!meshes || !numMeshes) return 0;
     if (shaderId >= c->shaders.size() || fboId >= c->fbos.size()) { c->err = "bad shader/fbo id"; return SLCU_ERR_ARG; }
+    /* the processor is chosen from the first mesh's mode (src/SL_ProcessorPool.cpp:286-293, 339-346) */
+    switch (meshes[0].mode)
+    {
+        case 0x10u: case 0x30u: break;                                                                /* triangles */
+        case 0x01u: case 0x03u: return run_points(c, meshes, numMeshes, numInstances, shaderId, fboId); /* points */
+        case 0x04u: case 0x0cu: c->err = "RENDER_MODE_LINES / INDEXED_LINES are not implemented (no CPU fallback)"; return SLCU_ERR_UNSUPPORTED;
+        case 0x50u: case 0x70u: c->err = "RENDER_MODE_TRI_WIRE / INDEXED_TRI_WIRE are not implemented (no CPU fallback)"; return SLCU_ERR_UNSUPPORTED;
+        default: c->err = "unknown render mode"; return SLCU_ERR_ARG;
+    }
     const HostShader& sh = c->shaders[shaderId];
     const HostFbo& fbo = c->fbos[fboId];
     if (fbo.depth == (size_t)-1 || fbo.depth >= c->textures.size()) { c->err = "fbo has no depth attachment"; return SLCU_ERR_ARG; }
@@ -447,6 +473,117 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
         B.totalPrims += prims;
     }
     if (c->syncDraws) return flush_draws(c);
+    return 0;
+}
+
+/* SL_PointProcessor + SL_PointRasterizer (src/SL_PointProcessor.cpp, src/SL_PointRasterizer.cpp): executed at submission,
+ * after the triangle batch that precedes it; one (vertex, sort, shade) pass per mesh / per instanced draw. */
+static int run_points(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, size_t numInstances, size_t shaderId, size_t fboId)
+{
+    int rc = flush_draws(c);
+    if (rc) return rc;
+    const HostShader& sh = c->shaders[shaderId];
+    const HostFbo& fbo = c->fbos[fboId];
+    if (fbo.depth == (size_t)-1 || fbo.depth >= c->textures.size()) { c->err = "fbo has no depth attachment"; return SLCU_ERR_ARG; }
+    const HostTexture& depthTex = c->textures[fbo.depth];
+    if (depthTex.w > 32767 || depthTex.h > 65535) { c->err = "framebuffer too large"; return SLCU_ERR_UNSUPPORTED; }
+    if (depthTex.bpt != 2 && depthTex.bpt != 4 && depthTex.bpt != 8) { c->err = "depth attachment must be R_HALF/R_FLOAT/R_DOUBLE"; return SLCU_ERR_ARG; }
+    for (int i = 0; i < sh.numOutputs; ++i)
+    {
+        if ((unsigned)i >= fbo.numColors || fbo.colors[i] >= c->textures.size()) { c->err = "shader writes an unattached colour buffer"; return SLCU_ERR_ARG; }
+        const HostTexture& t = c->textures[fbo.colors[i]];
+        const int kind = t.type % 7;
+        if (kind == 2 || kind == 3) { c->err = "32/64-bit integer colour targets are not implemented"; return SLCU_ERR_UNSUPPORTED; }
+        if (t.w != depthTex.w || t.h != depthTex.h) { c->err = "colour and depth attachments differ in size (SL_Framebuffer::valid -10)"; return SLCU_ERR_ARG; }
+    }
+    const size_t launches = (numInstances == 1) ? numMeshes : 1;
+    for (size_t i = 0; i < launches; ++i)
+    {
+        const slcu_mesh& m = meshes[i];
+        if (m.vaoId >= c->vaos.size()) { c->err = "bad vao id"; return SLCU_ERR_ARG; }
+        const HostVao& vao = c->vaos[m.vaoId];
+        if (vao.vbo >= c->vbos.size()) { c->err = "vao has no vertex buffer"; return SLCU_ERR_ARG; }
+        if (m.mode == 0x03u && vao.ibo >= c->ibos.size()) { c->err = "indexed draw without index buffer"; return SLCU_ERR_ARG; }
+    }
+    rc = ensure_rcp_table(c);
+    if (rc) return rc;
+    cudaSetDevice(c->device);
+    c->stats.drawCalls++;
+    const float fboW = (float)depthTex.w, fboH = (float)depthTex.h;
+    const int NV = sh.numVaryings;
+    unsigned pixBits = 1;
+    while ((1ull << pixBits) <= (unsigned long long)depthTex.w * depthTex.h) ++pixBits; /* 2^pixBits - 1 >= w*h: the invisible key sorts last */
+    for (size_t i = 0; i < launches; ++i)
+    {
+        const slcu_mesh& m = meshes[i];
+        const unsigned long long per = m.elementEnd > m.elementBegin ? (unsigned long long)(m.elementEnd - m.elementBegin) : 0ull;
+        const unsigned long long numPoints = per * (numInstances == 1 ? 1 : numInstances);
+        c->stats.trisSubmitted += (per / 3) * (numInstances == 1 ? 1 : numInstances);
+        if (!numPoints) continue;
+        if (numPoints > 0x7ffffff0ull) { c->err = "draw too large for one pass"; return SLCU_ERR_UNSUPPORTED; }
+        const HostVao& vao = c->vaos[m.vaoId];
+        const bool usingIndices = m.mode == 0x03u; /* per mesh (src/SL_PointProcessor.cpp:86) */
+        SLDrawDesc d;
+        memset(&d, 0, sizeof(d));
+        snapshot_uniforms(c, sh.ubo, d.uniforms);
+        d.vao = vao.vao;
+        d.vbo.mBuffer = c->vbos[vao.vbo].ptr;
+        d.usingIndices = usingIndices ? 1 : 0;
+        d.ibo = usingIndices ? c->ibos[vao.ibo].buf.ptr : nullptr;
+        d.iboType = usingIndices ? c->ibos[vao.ibo].type : 2;
+        host_scissor_matrix(c, fboW, fboH, d.scissor);
+        host_viewport_rect(c, fboW, fboH, d.viewport);
+        d.elementBegin = m.elementBegin;
+        d.primsPerInstance = per;
+        d.numPrims = numPoints;
+        CK(c->drawTable.ensure(sizeof(SLDrawDesc)));
+        CK(cudaMemcpyAsync(c->drawTable.buf.ptr, &d, sizeof(SLDrawDesc), cudaMemcpyHostToDevice, c->stream)); /* pageable source: staged before the call returns */
+        CK(c->pointKeys.ensure((size_t)numPoints * 2 * sizeof(unsigned long long)));
+        CK(c->pointRecs.ensure((size_t)numPoints * (1 + NV) * sizeof(float4)));
+        unsigned long long* keysA = reinterpret_cast<unsigned long long*>(c->pointKeys.buf.ptr);
+        cub::DoubleBuffer<unsigned long long> keys(keysA, keysA + numPoints);
+        size_t tempBytes = 0;
+        CK(cub::DeviceRadixSort::SortKeys(nullptr, tempBytes, keys, (int)numPoints, 32, 32 + (int)pixBits, c->stream));
+        CK(c->pointSortTemp.ensure(tempBytes));
+
+        SLPointParams vp;
+        vp.draw = reinterpret_cast<const SLDrawDesc*>(c->drawTable.buf.ptr);
+        vp.numPoints = numPoints;
+        vp.elementsPerInstance = per;
+        vp.numVaryings = NV;
+        vp.width = depthTex.w;
+        vp.height = depthTex.h;
+        vp.rank = c->partRank;
+        vp.world = c->partWorld;
+        vp.stripRows = c->partStripRows;
+        vp.keys = keysA;
+        vp.points = reinterpret_cast<float4*>(c->pointRecs.buf.ptr);
+        vp.counters = c->counters;
+        { KernelScope ks(c, SLCU_K_VERTEX); CK(sh.pointVs((unsigned)((numPoints + 255ull) / 256ull), c->stream, vp)); }
+        /* stable LSD sort on the pixel bits only: inside a pixel the keys stay in submission order */
+        { KernelScope ks(c, SLCU_K_SCAN); CK(cub::DeviceRadixSort::SortKeys(c->pointSortTemp.buf.ptr, tempBytes, keys, (int)numPoints, 32, 32 + (int)pixBits, c->stream)); }
+
+        SLPointShadeParams sp;
+        sp.draw = vp.draw;
+        sp.keys = keys.Current();
+        sp.points = vp.points;
+        sp.numPoints = numPoints;
+        sp.numVaryings = NV;
+        sp.numOutputs = sh.numOutputs;
+        sp.blend = sh.blend;
+        sp.depthTest = sh.depthTest;
+        sp.depthMask = sh.depthMask;
+        sp.depth = depthTex.dev;
+        sp.depthBpt = depthTex.bpt;
+        for (int k = 0; k < 4; ++k)
+        {
+            sp.color[k] = nullptr;
+            sp.colorType[k] = 0;
+            if (k < sh.numOutputs) { const HostTexture& t = c->textures[fbo.colors[k]]; sp.color[k] = t.dev; sp.colorType[k] = t.type; }
+        }
+        sp.counters = c->counters;
+        { KernelScope ks(c, SLCU_K_SHADE); CK(sh.pointFs((unsigned)((numPoints + 127ull) / 128ull), c->stream, sp)); }
+    }
     return 0;
 }
 
@@ -851,7 +988,7 @@ void slcu_context_destroy(slcu_context* c)
     if (c->counters) cudaFree(c->counters);
     if (c->hostCounters) cudaFreeHost(c->hostCounters);
     for (auto& pm : c->peerMaps) if (pm.ptr) cudaIpcCloseMemHandle(pm.ptr);
-    Scratch* s[] = {&c->records, &c->blockInfo, &c->cnt, &c->off, &c->segSums, &c->rowTotals, &c->rowStart, &c->entries, &c->handoff, &c->rowFlags, &c->rowNeeded, &c->drawTable, &c->blockDraw, &c->recDraw, &c->fragPool, &c->chunkNext, &c->listInfo, &c->handoffRegs, &c->ticketOrder};
+    Scratch* s[] = {&c->records, &c->blockInfo, &c->cnt, &c->off, &c->segSums, &c->rowTotals, &c->rowStart, &c->entries, &c->handoff, &c->rowFlags, &c->rowNeeded, &c->drawTable, &c->blockDraw, &c->recDraw, &c->fragPool, &c->chunkNext, &c->listInfo, &c->handoffRegs, &c->ticketOrder, &c->pointKeys, &c->pointRecs, &c->pointSortTemp};
     for (Scratch* x : s) x->release();
     cudaStreamDestroy(c->stream);
     delete c;
@@ -1089,8 +1226,10 @@ size_t slcu_create_shader(slcu_context* c, const slcu_vertex_shader* vs, const s
     if (vs->cullMode > 2 || fs->blend > 4 || fs->depthTest > 6 || fs->depthMask > 1) return SLCU_INVALID_ID;
     VertexLauncher vl = nullptr;
     RasterLauncher fl = nullptr;
-    for (const VsEntry& e : vs_registry()) if (!strcmp(e.name, vs->shader)) vl = e.launch;
-    for (const FsEntry& e : fs_registry()) if (!strcmp(e.name, fs->shader)) fl = e.launch;
+    PointVertexLauncher pvl = nullptr;
+    PointShadeLauncher pfl = nullptr;
+    for (const VsEntry& e : vs_registry()) if (!strcmp(e.name, vs->shader)) { vl = e.launch; pvl = e.launchPoints; }
+    for (const FsEntry& e : fs_registry()) if (!strcmp(e.name, fs->shader)) { fl = e.launch; pfl = e.launchPoints; }
     if (!vl || !fl)
     {
         c->err = "shader not registered as a __device__ callable (no CPU fallback)";
@@ -1098,7 +1237,7 @@ size_t slcu_create_shader(slcu_context* c, const slcu_vertex_shader* vs, const s
     }
     HostShader s;
     s.cullMode = vs->cullMode; s.depthTest = fs->depthTest; s.depthMask = fs->depthMask; s.blend = fs->blend;
-    s.numVaryings = fs->numVaryings; s.numOutputs = fs->numOutputs; s.vs = vl; s.fs = fl; s.ubo = ubo;
+    s.numVaryings = fs->numVaryings; s.numOutputs = fs->numOutputs; s.vs = vl; s.fs = fl; s.pointVs = pvl; s.pointFs = pfl; s.ubo = ubo;
     c->shaders.push_back(s);
     return c->shaders.size() - 1;
 }

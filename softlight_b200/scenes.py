@@ -399,8 +399,11 @@ def indoor_scene(width=3840, height=2160, rooms=(16, 16), quads=26, tex_size=512
 def random_tris_scene(seed=1, n=400, width=200, height=150, blend=A.SL_BLEND_OFF, depth_test=A.SL_DEPTH_TEST_LESS_THAN,
                       depth_mask=A.SL_DEPTH_MASK_ON, depth_type=A.SL_COLOR_R_FLOAT, color_type=A.SL_COLOR_RGBA_8U,
                       cull=A.SL_CULL_OFF, index_dtype=np.uint16, clip_fraction=0.3, clear_depth=1.0, viewport=None,
-                      scissor=None, split_draws=1, multiple=False, name=None, empty_draw=False, mrt_types=None) -> Scene:
-    """mrt_types: colour types of render targets 1..3 (sl_mrt_test.cpp:150-200 attaches four); the "vcolor_mrt" fragment shader
+                      scissor=None, split_draws=1, multiple=False, name=None, empty_draw=False, mrt_types=None, points=False, instances=1) -> Scene:
+    """points: the same vertices drawn as RENDER_MODE_POINTS / INDEXED_POINTS (one fragment per visible vertex,
+    SL_PointProcessor / SL_PointRasterizer); instances > 1 issues draw_instanced (the vertex shader ignores the id, so every
+    instance lands on the same pixels: a pure ordering test).
+    mrt_types: colour types of render targets 1..3 (sl_mrt_test.cpp:150-200 attaches four); the "vcolor_mrt" fragment shader
     then writes four outputs and SceneInstance.read_colors() returns all attachments."""
     rng = np.random.default_rng(seed)
     verts = np.zeros((n * 3, 8), dtype=np.float32)
@@ -416,6 +419,15 @@ def random_tris_scene(seed=1, n=400, width=200, height=150, blend=A.SL_BLEND_OFF
     verts[:, 3] = w.reshape(-1)
     verts[:, 4:7] = rng.uniform(0, 1, size=(n * 3, 3))
     verts[:, 7] = rng.uniform(0.2, 1.0, size=n * 3) if blend != A.SL_BLEND_OFF else 1.0
+    if points:
+        # vertices exactly on the clip planes: ndc 1.0 maps to x == width (the texel wraps into the next row) or y == height
+        # (the reference's allocation padding), ndc -1.0 to column / row 0
+        edge = rng.random(n * 3) < 0.15
+        side = rng.integers(0, 4, size=n * 3)
+        verts[edge & (side == 0), 0] = verts[edge & (side == 0), 3]
+        verts[edge & (side == 1), 0] = -verts[edge & (side == 1), 3]
+        verts[edge & (side == 2), 1] = verts[edge & (side == 2), 3]
+        verts[edge & (side == 3), 1] = -verts[edge & (side == 3), 3]
     idx = None
     if index_dtype is not None:
         idx = rng.permutation(n * 3).astype(np.int64)
@@ -443,6 +455,8 @@ def random_tris_scene(seed=1, n=400, width=200, height=150, blend=A.SL_BLEND_OFF
                                depth_test=depth_test, depth_mask=depth_mask, outputs=1 + len(extra))
         assert sh != A.INVALID_ID
         mode = A.RENDER_MODE_INDEXED_TRIANGLES if idx is not None else A.RENDER_MODE_TRIANGLES
+        if points:
+            mode = A.RENDER_MODE_INDEXED_POINTS if idx is not None else A.RENDER_MODE_POINTS
         per = (n // split_draws) * 3
         meshes = []
         for d in range(split_draws):
@@ -463,6 +477,9 @@ def random_tris_scene(seed=1, n=400, width=200, height=150, blend=A.SL_BLEND_OFF
             ctx.clear_color_buffer(st["fbo"], 1 + i, (0.05 * (i + 1), 0.5, 0.25, 1.0))
         if multiple:
             ctx.draw_multiple(st["meshes"], st["shader"], st["fbo"])
+        elif instances > 1:
+            for m in st["meshes"]:
+                ctx.draw_instanced(m, instances, st["shader"], st["fbo"])
         else:
             for m in st["meshes"]:
                 ctx.draw(m, st["shader"], st["fbo"])

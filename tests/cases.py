@@ -80,6 +80,26 @@ def render_mrt(impl: str, scene, rcp_table=None):
 CASES = {}
 for _i, (_name, _kw) in enumerate(_variants()):
     CASES["rand_" + _name] = (lambda i=_i, kw=_kw, name=_name: S.random_tris_scene(seed=100 + i, name="rand_" + name, **kw))
+
+# RENDER_MODE_POINTS / INDEXED_POINTS (SL_PointProcessor + SL_PointRasterizer): many points per pixel, so the per-pixel
+# submission order decides every depth test and blend
+POINT_CASES = {
+    "points_dense": dict(n=4000, width=64, height=48),
+    "points_alpha_nodepth": dict(n=4000, width=64, height=48, blend=1, depth_test=A.SL_DEPTH_TEST_OFF, depth_mask=A.SL_DEPTH_MASK_OFF),
+    "points_premult_half_le": dict(n=3000, width=100, height=50, blend=2, depth_type=A.SL_COLOR_R_HALF, depth_test=A.SL_DEPTH_TEST_LESS_EQUAL),
+    "points_noindex_split3": dict(n=3000, width=200, height=150, index_dtype=None, split_draws=3),
+    "points_multi4_u32": dict(n=3000, width=100, height=50, multiple=True, split_draws=4, index_dtype=np.uint32),
+    "points_instanced3_additive": dict(n=1000, width=100, height=50, instances=3, blend=3),
+    "points_viewport_scissor": dict(n=3000, width=100, height=50, viewport=(10, 5, 80, 40), scissor=(20, 10, 50, 30)),
+    "points_rgbf_double_ge": dict(n=2000, width=77, height=33, color_type=A.SL_COLOR_RGB_FLOAT, depth_type=A.SL_COLOR_R_DOUBLE,
+                                  depth_test=A.SL_DEPTH_TEST_GREATER_EQUAL, clear_depth=-1.0),
+    "points_sparse_1080p": dict(n=20000, width=1920, height=1080),
+    "points_one_pixel": dict(n=700, width=1, height=1, blend=1, depth_test=A.SL_DEPTH_TEST_OFF, depth_mask=A.SL_DEPTH_MASK_OFF),
+    # (no empty point draw here: the unmodified reference dies with SIGFPE on one -- a modulo by the element count in its
+    # partitioning -- so there is nothing to pin; the CUDA path treats it as a no-op, tests/test_gpu_parity.py)
+}
+for _i, _name in enumerate(POINT_CASES):
+    CASES[_name] = (lambda i=_i, name=_name: S.random_tris_scene(seed=900 + i, name=name, points=True, **POINT_CASES[name]))
 CASES["draw_test"] = S.SCENES["draw_test"]
 CASES["c1_small"] = S.SCENES["c1_small"]
 CASES["c2_small"] = S.SCENES["c2_small"]
@@ -101,7 +121,7 @@ BIG_CASES = {
 }
 
 # cases whose images are committed in full (the rest of CASES is pinned by sha256)
-FULL_IMAGE_CASES = ["draw_test", "c1_small", "c2_small", "c3_small", "c4_small", "c5_small", "sampler_matrix", "rand_blend1", "rand_clip_heavy", "rand_depth_half_premult"]
+FULL_IMAGE_CASES = ["draw_test", "c1_small", "c2_small", "c3_small", "c4_small", "c5_small", "sampler_matrix", "rand_blend1", "rand_clip_heavy", "rand_depth_half_premult", "points_dense"]
 
 
 def bits(a: np.ndarray) -> np.ndarray:

@@ -21,12 +21,36 @@ import blit_cases  # noqa: E402
 
 
 def main():
+    """`--only a,b,c` regenerates just those draw cases and merges them into the committed files."""
+    only = None
+    if "--only" in sys.argv:
+        only = set(sys.argv[sys.argv.index("--only") + 1].split(","))
     ctx = A.Context("ref_strict")
     rcp = ctx.get_rcp_table()
     frames = {"rcp_table": rcp}
     hashes = {}
     allcases = dict(cases.CASES)
     allcases.update(cases.BIG_CASES)
+    if only is not None:
+        old = json.load(open(os.path.join(HERE, "golden_hashes.json")))
+        oldFrames = dict(np.load(os.path.join(HERE, "golden_frames.npz")))
+        assert np.array_equal(oldFrames["rcp_table"], rcp), "the committed goldens were generated with another rcp table"
+        assert only <= set(allcases), only - set(allcases)
+        for name in sorted(only):
+            scene = allcases[name]()
+            color, depth, stats = cases.render("ref_strict", scene)
+            old["cases"][name] = {
+                "color_sha256": hashlib.sha256(np.ascontiguousarray(color).tobytes()).hexdigest(),
+                "depth_sha256": hashlib.sha256(np.ascontiguousarray(depth).tobytes()).hexdigest(),
+                "frags": int(stats["fragsShaded"]), "width": scene.width, "height": scene.height,
+            }
+            if name in cases.FULL_IMAGE_CASES:
+                oldFrames[name + ".color"] = color
+                oldFrames[name + ".depth"] = cases.bits(depth)
+            print(name, old["cases"][name]["frags"], flush=True)
+        np.savez_compressed(os.path.join(HERE, "golden_frames.npz"), **oldFrames)
+        json.dump(old, open(os.path.join(HERE, "golden_hashes.json"), "w"), indent=1)
+        return
     for name, factory in allcases.items():
         scene = factory()
         color, depth, stats = cases.render("ref_strict", scene)

@@ -183,8 +183,53 @@ def test_unregistered_shader_is_refused():
     assert ctx.create_shader("nope", "vcolor", ubo, vs_varyings=1, fs_varyings=1) == A.INVALID_ID
 
 
+def test_empty_point_draw_is_a_noop():
+    """The unmodified reference dies with SIGFPE on a point draw without elements, so there is no golden; here it leaves the
+    cleared frame untouched."""
+    scene = S.random_tris_scene(seed=5, n=30, points=True, empty_draw=True)
+    color, depth, stats = cases.render("cuda", scene)
+    assert stats["fragsShaded"] == 0
+    assert np.all(color == color[0, 0]) and np.all(depth == 1.0)
+
+
+@pytest.mark.parametrize("mode", [A.RENDER_MODE_LINES, A.RENDER_MODE_INDEXED_LINES, A.RENDER_MODE_TRI_WIRE, A.RENDER_MODE_INDEXED_TRI_WIRE, 0x1234])
+def test_unimplemented_render_modes_are_refused_loudly(mode):
+    ctx = A.Context("cuda")
+    st = S.SceneInstance(S.random_tris_scene(seed=2, n=10), ctx)
+    m = st.state["meshes"][0]
+    with pytest.raises(A.SlError):
+        ctx.draw(ctx.mesh(m.vaoId, m.elementBegin, m.elementEnd, mode), st.state["shader"], st.state["fbo"])
+
+
+def test_points_between_triangle_draws_keep_submission_order(golden):
+    """triangles, points, triangles on one framebuffer: the point pass executes between the two triangle batches, exactly
+    like the oracle's draw-by-draw execution."""
+    frames, _ = golden
+
+    def run(impl):
+        ctx = A.Context(impl)
+        ctx.set_rcp_table(frames["rcp_table"])
+        tri = S.SceneInstance(S.random_tris_scene(seed=31, n=300, blend=1), ctx)
+        st = tri.state
+        ctx.clear_framebuffer(st["fbo"], 0, (0.1, 0.2, 0.3, 1.0), 1.0)
+        m = st["meshes"][0]
+        third = (m.elementEnd - m.elementBegin) // 9 * 3
+        ctx.draw(ctx.mesh(m.vaoId, 0, third, A.RENDER_MODE_INDEXED_TRIANGLES), st["shader"], st["fbo"])
+        ctx.draw(ctx.mesh(m.vaoId, 0, m.elementEnd, A.RENDER_MODE_INDEXED_POINTS), st["shader"], st["fbo"])
+        ctx.draw(ctx.mesh(m.vaoId, third, m.elementEnd, A.RENDER_MODE_INDEXED_TRIANGLES), st["shader"], st["fbo"])
+        c = ctx.texture_read(st["color"], A.SL_COLOR_RGBA_8U, 200, 150)
+        d = ctx.texture_read(st["depth"], A.SL_COLOR_R_FLOAT, 200, 150)
+        n = ctx.get_stats()["fragsShaded"]
+        ctx.close()
+        return c, d, n
+
+    a, b = run("cuda"), run("port")
+    assert np.array_equal(a[0], b[0]) and np.array_equal(cases.bits(a[1]), cases.bits(b[1])) and a[2] == b[2]
+
+
 @pytest.mark.parametrize("name,world,strip", [("c1_small", 2, 8), ("rand_clip_heavy", 2, 1), ("rand_overflow_wide", 3, 2),
-                                               ("rand_overflow_blend", 4, 1), ("c2_small", 8, 8), ("rand_overflow_half_ge", 2, 1)])
+                                               ("rand_overflow_blend", 4, 1), ("c2_small", 8, 8), ("rand_overflow_half_ge", 2, 1),
+                                               ("points_dense", 2, 1), ("points_sparse_1080p", 4, 8)])
 def test_sort_first_partition_is_bit_identical(name, world, strip, golden):
     """Every rank's context (all on this GPU) rasterises only its row strips (+ the rows its hand-overs come from);
     the composite of the owned rows equals the unpartitioned frame bit for bit, spans that wrap across an ownership
