@@ -64,7 +64,7 @@ typedef struct slcu_mesh
     uint64_t vaoId;
     uint64_t elementBegin;
     uint64_t elementEnd;
-    uint32_t mode;       /* SL_RenderMode */
+    uint32_t mode;       /* SL_RenderMode: 0x10/0x30 triangles, 0x50/0x70 wireframe triangles, 0x01/0x03 points; 0x04/0x0C (lines) -> SLCU_ERR_UNSUPPORTED */
     uint32_t materialId;
 } slcu_mesh;
 

@@ -128,6 +128,7 @@ struct slcu_context
 
     /* per-draw state */
     const Shader* shader = nullptr;
+    bool wire = false; /* RENDER_MODE_TRI_WIRE / INDEXED_TRI_WIRE: the rasteriser draws edges only */
     SL_Texture* colorBufs[4] = {};
     SL_Texture* depthBuf = nullptr;
     std::vector<Bin> bins;
@@ -501,6 +502,78 @@ static void render_triangle(slcu_context* c, const Bin& bin)
     for (const QueuedFrag& q : queue) shade_fragment(c, bin, q);
 }
 
+static inline int32_t wire_edge_width(int32_t a, int32_t b)
+{
+    const int32_t d = (int32_t)((uint32_t)a - (uint32_t)b);
+    const int32_t ad = d < 0 ? (int32_t)(0u - (uint32_t)d) : d;
+    return ad > 1 ? ad : 1;
+}
+
+/* SL_TriRasterizer::render_wireframe (src/SL_TriRasterizer.cpp:116-202), one thread: per scan line only the pixels
+ * next to the two edges -- d0 pixels from xMin (the distance the left bound moved since the previous line, at least 1)
+ * and the last d1 pixels before xMax -- scalar barycentrics (fmadd), depth = dot(depth, bc). */
+static void render_wireframe(slcu_context* c, const Bin& bin)
+{
+    const Shader& sh = *c->shader;
+    SL_Texture& depthBuffer = *c->depthBuf;
+    const math::vec4& p0 = bin.mScreenCoords[0];
+    const math::vec4& p1 = bin.mScreenCoords[1];
+    const math::vec4& p2 = bin.mScreenCoords[2];
+    const int32_t bboxMinY = cvt_tr(smin(p2.v[1], smin(p0.v[1], p1.v[1]))); /* :136-137, C casts */
+    const int32_t bboxMaxY = cvt_tr(smax(p2.v[1], smax(p0.v[1], p1.v[1])));
+    ScanlineBounds scanline;
+    scanline.init(p0, p1, p2);
+    const math::vec4 bc0 = bin.mBarycentricCoords[0];
+    const math::vec4 bc1 = bin.mBarycentricCoords[1];
+    const math::vec4 bc2 = bin.mBarycentricCoords[2];
+    const math::vec4 depth{p0.v[2], p1.v[2], p2.v[2], 0.f};
+
+    static thread_local std::vector<QueuedFrag> queue;
+    queue.clear();
+    for (int32_t y = bboxMinY; y < bboxMaxY; ++y)
+    {
+        const float yf = (float)y;
+        math::vec4 bcY;
+        for (int k = 0; k < 4; ++k) bcY.v[k] = sfma(bc1.v[k], k < 3 ? yf : 0.f, bc2.v[k]); /* :149 */
+        int32_t xMinMax0[2], xMinMax1[2];
+        scanline.step(yf, xMinMax0[0], xMinMax0[1]);
+        scanline.step(yf - 1.f, xMinMax1[0], xMinMax1[1]);
+        /* :157-158 max(abs(a - b), 1) in wrapping 32-bit arithmetic: on the line above the top vertex the bounds are the x86
+         * "integer indefinite" 0x80000000 (cvtss2si of NaN/inf), a - b and abs() wrap back to INT_MIN and the max picks 1 */
+        const int32_t d0 = wire_edge_width(xMinMax0[0], xMinMax1[0]);
+        const int32_t d1 = wire_edge_width(xMinMax0[1], xMinMax1[1]);
+        const int64_t rowBase = (int64_t)depthBuffer.mWidth * y;
+        bool counted = false;
+        for (int32_t ix = 0, x = xMinMax0[0]; (uint32_t)x < (uint32_t)xMinMax0[1]; ++ix, ++x)
+        {
+            if (ix == d0) /* :165-169 skip to the start of the right edge */
+            {
+                x = std::max(xMinMax0[0], (int32_t)((uint32_t)xMinMax0[1] - (uint32_t)d1 - 1u));
+                continue;
+            }
+            if (!counted && y < (int32_t)depthBuffer.mHeight) { c->stats.spans++; counted = true; }
+            const float xf = (float)x;
+            math::vec4 bc;
+            for (int k = 0; k < 4; ++k) bc.v[k] = sfma(bc0.v[k], k < 3 ? xf : 0.f, bcY.v[k]); /* :173 */
+            const float z = math::dot(depth, bc);
+            const float d = load_depth(depthBuffer, (size_t)(rowBase + x));
+            if (!depth_cmp(sh.depthTest, z, d)) continue;
+            QueuedFrag q;
+            q.bc = bc;
+            q.x = (uint16_t)x;
+            q.y = (uint16_t)y;
+            q.z = z;
+            queue.push_back(q);
+            if (queue.size() == 600) /* :188-192 SL_SHADER_MAX_QUEUED_FRAGS */
+            {
+                for (const QueuedFrag& f : queue) shade_fragment(c, bin, f);
+                queue.clear();
+            }
+        }
+    }
+    for (const QueuedFrag& f : queue) shade_fragment(c, bin, f);
+}
+
 /* SL_VertexProcessor::flush_rasterizer<SL_TriRasterizer> (src/SL_VertexProcessor.cpp:84-181), one thread */
 static void flush_bins(slcu_context* c)
 {
@@ -511,7 +584,7 @@ static void flush_bins(slcu_context* c)
         /* :110-119 LSD radix sort by primIndex == a stable sort */
         std::stable_sort(ids.begin(), ids.end(), [&](uint32_t a, uint32_t b) { return c->bins[a].primIndex < c->bins[b].primIndex; });
     }
-    for (uint32_t id : ids) render_triangle(c, c->bins[id]);
+    for (uint32_t id : ids) { if (c->wire) render_wireframe(c, c->bins[id]); else render_triangle(c, c->bins[id]); } /* SL_TriRasterizer::dispatch_bins :970-1005 */
     c->bins.clear();
 }
 
@@ -906,6 +979,7 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
     const math::mat4 scissorMat = scissor_matrix(c->scissor, fboW, fboH);
     const math::vec4 viewportDims = viewport_rect(c->viewport, c->scissor, fboW, fboH);
 
+    c->wire = (meshes[0].mode == 0x50) || (meshes[0].mode == 0x70); /* mRenderMode = meshes->mode (src/SL_ProcessorPool.cpp:301,354) */
     const bool points = (meshes[0].mode == 0x01) || (meshes[0].mode == 0x03); /* RENDER_MODE_POINTS / INDEXED_POINTS -> SL_PointProcessor */
     if (points)
     {

@@ -1,0 +1,356 @@
+/* Wireframe triangles: RENDER_MODE_TRI_WIRE / RENDER_MODE_INDEXED_TRI_WIRE.
+ *
+ * The vertex stage is the triangle path's (k_vertex: same SL_TriProcessor); only the rasteriser differs:
+ * SL_TriRasterizer::render_wireframe (src/SL_TriRasterizer.cpp:116-202) visits, per scan line, d0 pixels from xMin and
+ * the last d1 pixels before xMax (d = how far that bound moved since the previous line, at least 1), with scalar
+ * barycentrics.  Edge fragments are sparse, so instead of the span / resolve machinery of filled triangles they are
+ * handled like points (sl_points.cuh):
+ *
+ *   k_wire<EMIT=0>     counts the fragments candidates of every triangle record (sizes the buffers)
+ *   k_wire<EMIT=1>     writes one (key, payload) per candidate: key = linear pixel << 31 | submission ordinal of the
+ *                      record << 3 | visit order of that record on that pixel
+ *   (radix sort of the keys)
+ *   k_wire_shade<FS>   the thread that holds the first key of a pixel walks that pixel's candidates in submission
+ *                      order: depth test, SL_FragmentProcessor::flush_tri_fragments shading, colour / depth writes.
+ *
+ * The reference tests a candidate when it is queued and writes depth when the queue is flushed (600 fragments, or at
+ * the end of the triangle), and render_wireframe does revisit pixels (the jump to the right edge can land left of where
+ * the left edge stopped; a run that crosses the row end wraps onto pixels of the next line).  All candidates of ONE
+ * record on a pixel are therefore tested against the depth the pixel had before that record -- unless a queue flush fell
+ * between two visits: a visit sees the depth written by an earlier visit of the same record iff that one was flushed
+ * first, i.e. iff its flush epoch (passed fragments of the record before it / 600) is smaller.  Epochs depend on the depth
+ * outcomes and the outcomes on the epochs; both are independent of the fragment shader (depth is written whatever the
+ * shader returns), so for batches with records of 600+ candidates the host iterates k_wire_depth (per-pixel depth
+ * simulation -> pass flags) and k_wire_epoch (per-record prefix of the pass flags -> epochs) to the fixed point before
+ * k_wire_shade runs with the final epochs.  Candidates that are not stored (allocation padding beyond width*height, rows
+ * of another rank under the sort-first partition) are not counted in the epochs. */
+#pragma once
+
+#include "sl_pipeline.cuh"
+
+namespace sld
+{
+
+constexpr int SL_WIRE_ORD_BITS = 28; /* (vertex block * 32 + segment) << 8 | index in the segment */
+constexpr int SL_WIRE_SUB_BITS = 3;
+constexpr int SL_WIRE_LOW_BITS = SL_WIRE_ORD_BITS + SL_WIRE_SUB_BITS;
+
+struct SLWireParams
+{
+    const float4* records;
+    const SLBlockInfo* blockInfo;
+    unsigned int numBlocks;
+    int recStride;
+    unsigned int width, height;
+    unsigned int rank, world, stripRows;  /* sort-first partition */
+    unsigned long long capacity;          /* EMIT: fragment slots */
+    unsigned long long* keys;
+    uint32_t* slots;                      /* sort values: payload slot of the key */
+    float4* fragBc;
+    float* fragZ;
+    uint32_t* fragXY;
+    uint32_t* fragRec;
+    uint32_t* recBase;                    /* EMIT out: [record] first slot of the record's candidates (visit order)     */
+    uint32_t* recCount;                   /* EMIT out: [record] candidates stored                                         */
+    SLCounters* counters;                 /* pixelsCovered: candidates (COUNT) / slot allocator (EMIT); rowEndCuts: records with 600+ candidates (COUNT) */
+};
+
+constexpr unsigned SL_WIRE_QUEUE = 600u; /* SL_SHADER_MAX_QUEUED_FRAGS */
+
+/* max(abs(a - b), 1) in wrapping 32-bit arithmetic (src/SL_TriRasterizer.cpp:157-158): on the line above the top vertex
+ * the bounds are 0x80000000 (cvtss2si of NaN / inf); a - b and abs() wrap back to INT_MIN and the max picks 1 */
+SLD_FN int32_t sl_wire_edge_width(int32_t a, int32_t b)
+{
+    const int32_t d = (int32_t)((uint32_t)a - (uint32_t)b);
+    const int32_t ad = d < 0 ? (int32_t)(0u - (uint32_t)d) : d;
+    return ad > 1 ? ad : 1;
+}
+
+/* the visit loop of one scan line (:162-169); f(x, run) is called for every visited x, run = 0 before the jump */
+template <typename F>
+SLD_FN void sl_wire_row(int32_t x0, int32_t x1, int32_t d0, int32_t d1, int32_t xLimit, F f)
+{
+    int run = 0;
+    for (int32_t ix = 0, x = x0; (uint32_t)x < (uint32_t)x1 && x < xLimit; ++ix, ++x)
+    {
+        if (ix == d0)
+        {
+            const int32_t j = (int32_t)((uint32_t)x1 - (uint32_t)d1 - 1u);
+            x = x0 > j ? x0 : j;
+            run = 1;
+            continue;
+        }
+        f(x, run);
+    }
+}
+
+template <int EMIT>
+__global__ void __launch_bounds__(128) k_wire(const __grid_constant__ SLWireParams P)
+{
+    /* one thread per (vertex block, segment, index): segments are the (round, warp) record regions of k_vertex, taken in
+     * submission order exactly like k_span does */
+    const unsigned long long t = (unsigned long long)blockIdx.x * 128ull + threadIdx.x;
+    const unsigned vb = (unsigned)(t >> 13), seg = (unsigned)(t >> 8) & 31u, idx = (unsigned)t & 255u;
+    unsigned long long n = 0;
+    unsigned rowsHit = 0;
+    bool active = false;
+    uint32_t recId = 0;
+    if (vb < P.numBlocks)
+    {
+        const SLSegment sg = P.blockInfo[vb].seg[seg];
+        if (sg.count > 256u && idx == 0u) atomicOr(&P.counters->errorFlags, 16u);
+        if (idx < sg.count) { active = true; recId = sg.base + idx; }
+    }
+    if (!active) return;
+
+    const float4* r = P.records + (size_t)recId * P.recStride;
+    const float4 p0 = r[0], p1 = r[1], p2 = r[2];
+    const int32_t W = (int32_t)P.width, H = (int32_t)P.height;
+    int32_t yBegin = sl_cvt_tr(sl_min(p2.y, sl_min(p0.y, p1.y))); /* :136-137 */
+    int32_t yEnd = sl_cvt_tr(sl_max(p2.y, sl_max(p0.y, p1.y)));
+    if (yBegin < 0) yBegin = 0;
+    if (yEnd > H) yEnd = H; /* rows >= H only reach the allocation padding */
+    SLScanline sl;
+    sl.init(p0, p1, p2);
+    const int32_t xLimit = 4 * W; /* further right than three wraps: flagged, not drawn */
+    const unsigned long long numPix = (unsigned long long)P.width * P.height;
+    const uint32_t ordinal = ((vb * 32u + seg) << 8) | idx;
+
+    auto owned = [&](unsigned long long pix) -> bool {
+        if (pix >= numPix) return false;
+        if (P.world <= 1u) return true;
+        const unsigned row = (unsigned)(pix / P.width);
+        return (row / P.stripRows) % P.world == P.rank;
+    };
+
+    for (int32_t y = yBegin; y < yEnd; ++y)
+    {
+        const float yf = (float)y;
+        int32_t x0, x1, q0, q1;
+        sl.step(yf, x0, x1);
+        sl.step(yf - 1.f, q0, q1);
+        const int32_t d0 = sl_wire_edge_width(x0, q0), d1 = sl_wire_edge_width(x1, q1);
+        bool hit = false;
+        sl_wire_row(x0, x1, d0, d1, xLimit, [&](int32_t x, int) {
+            hit = true;
+            if (owned((unsigned long long)x + (unsigned long long)P.width * (unsigned)y)) ++n;
+        });
+        if ((uint32_t)x0 < (uint32_t)x1 && x1 > xLimit) atomicOr(&P.counters->errorFlags, 2u);
+        rowsHit += hit ? 1u : 0u;
+    }
+    if (!EMIT)
+    {
+        if (n) atomicAdd(&P.counters->pixelsCovered, n);
+        if (n >= SL_WIRE_QUEUE) atomicAdd(&P.counters->rowEndCuts, 1ull);
+        return;
+    }
+    if (rowsHit) atomicAdd(&P.counters->spans, (unsigned long long)rowsHit); /* the statistic: (record, line) pairs with a visit */
+    P.recCount[recId] = (uint32_t)n;
+    if (!n) return;
+    unsigned long long slot = atomicAdd(&P.counters->pixelsCovered, n);
+    if (slot + n > P.capacity) { atomicOr(&P.counters->errorFlags, 32u); P.recCount[recId] = 0u; return; }
+    P.recBase[recId] = (uint32_t)slot;
+
+    SLTriSetup ts;
+    sl_tri_setup(ts, p0, p1, p2);
+    const math::vec4 depth{p0.z, p1.z, p2.z, 0.f};
+    for (int32_t y = yBegin; y < yEnd; ++y)
+    {
+        const float yf = (float)y;
+        const math::vec4 yv{yf, yf, yf, 0.f};
+        math::vec4 bcY;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) bcY.v[k] = sl_fma(ts.bc1.v[k], yv.v[k], ts.bc2.v[k]); /* :149 */
+        int32_t x0, x1, q0, q1;
+        sl.step(yf, x0, x1);
+        sl.step(yf - 1.f, q0, q1);
+        const int32_t d0 = sl_wire_edge_width(x0, q0), d1 = sl_wire_edge_width(x1, q1);
+        sl_wire_row(x0, x1, d0, d1, xLimit, [&](int32_t x, int run) {
+            const unsigned long long pix = (unsigned long long)x + (unsigned long long)P.width * (unsigned)y;
+            if (!owned(pix)) return;
+            const float xf = (float)x;
+            const math::vec4 xv{xf, xf, xf, 0.f};
+            math::vec4 bc;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) bc.v[k] = sl_fma(ts.bc0.v[k], xv.v[k], bcY.v[k]); /* :173 */
+            const float z = math::dot(depth, bc);
+            /* visit order of this record on this pixel: the line the visit came from (a wrapped run belongs to an earlier
+             * line than the pixel's own), then the run */
+            const unsigned wraps = (unsigned)(x / W); /* 0..3 */
+            const unsigned sub = ((3u - wraps) << 1) | (unsigned)run;
+            P.keys[slot] = (pix << SL_WIRE_LOW_BITS) | ((unsigned long long)ordinal << SL_WIRE_SUB_BITS) | sub;
+            P.slots[slot] = (uint32_t)slot;
+            P.fragBc[slot] = make_float4(bc.v[0], bc.v[1], bc.v[2], bc.v[3]);
+            P.fragZ[slot] = z;
+            P.fragXY[slot] = ((uint32_t)x & 0xffffu) | (((uint32_t)y & 0xffffu) << 16);
+            P.fragRec[slot] = recId;
+            ++slot;
+        });
+    }
+}
+
+struct SLWireShadeParams
+{
+    const SLDrawDesc* draws;
+    const uint16_t* recDraw;
+    const float4* records;
+    int recStride;
+    const unsigned long long* keys;   /* sorted */
+    const uint32_t* slots;            /* sorted along with the keys */
+    const float4* fragBc;
+    const float* fragZ;
+    const uint32_t* fragXY;
+    const uint32_t* fragRec;
+    const uint16_t* fragEpoch;        /* flush epoch of every candidate (null: all 0) */
+    uint8_t* fragPass;                /* k_wire_depth out: depth outcome of every candidate */
+    unsigned long long numFrags;
+    int numVaryings;
+    int numOutputs;
+    int blend;
+    int depthTest;
+    int depthMask;
+    unsigned char* depth;
+    int depthBpt;
+    unsigned char* color[4];
+    int colorType[4];
+    SLCounters* counters;
+};
+
+/* The walk both kernels share: the thread that holds the first key of a pixel takes that pixel's candidates in order,
+ * record by record; f(slot, z) is called for every candidate that passes its depth test and must perform the depth write
+ * itself if it wants one (k_wire_depth only tracks the value). */
+template <bool SHADE, typename F>
+SLD_FN void sl_wire_walk_pixel(const SLWireShadeParams& P, unsigned long long t, F f)
+{
+    const unsigned long long pix = P.keys[t] >> SL_WIRE_LOW_BITS;
+    if (t != 0ull && (P.keys[t - 1ull] >> SL_WIRE_LOW_BITS) == pix) return;
+    float dCur = sl_load_depth(P.depth, P.depthBpt, (size_t)pix);
+    unsigned long long j = t;
+    bool more = true;
+    while (more)
+    {
+        const uint32_t ord = (uint32_t)(P.keys[j] >> SL_WIRE_SUB_BITS) & ((1u << SL_WIRE_ORD_BITS) - 1u);
+        const float dPre = dCur;
+        float zs[8];
+        uint32_t eps[8];
+        int gs = 0;
+        for (;;)
+        {
+            const uint32_t s = P.slots[j];
+            const float z = P.fragZ[s];
+            const uint32_t ep = P.fragEpoch ? (uint32_t)P.fragEpoch[s] : 0u;
+            /* what this visit sees: the depth before the record, or the last earlier visit that passed and was flushed */
+            float dSeen = dPre;
+            if (P.depthMask)
+            {
+                for (int i = 0; i < gs; ++i) { if (eps[i] < ep) dSeen = zs[i]; }
+            }
+            const bool pass = sl_depth_cmp(P.depthTest, z, dSeen);
+            if (!SHADE) P.fragPass[s] = pass ? 1 : 0;
+            if (pass)
+            {
+                f(s, z, pix);
+                const float stored = P.depthBpt == 2 ? sl_h2f(sl_f2h_rn(z)) : z; /* what a later read of the texel returns */
+                if (P.depthMask) dCur = stored;
+                if (gs < 8) { zs[gs] = stored; eps[gs] = ep; ++gs; }
+            }
+            if (++j >= P.numFrags) { more = false; break; }
+            const unsigned long long k = P.keys[j];
+            if ((k >> SL_WIRE_LOW_BITS) != pix) { more = false; break; }
+            if (((uint32_t)(k >> SL_WIRE_SUB_BITS) & ((1u << SL_WIRE_ORD_BITS) - 1u)) != ord) break;
+        }
+    }
+}
+
+/* depth-only simulation of the batch with the current epochs: pass flag per candidate; the attachment is not written */
+__global__ void __launch_bounds__(128) k_wire_depth(const __grid_constant__ SLWireShadeParams P)
+{
+    const unsigned long long t = (unsigned long long)blockIdx.x * 128ull + threadIdx.x;
+    if (t < P.numFrags) sl_wire_walk_pixel<false>(P, t, [](uint32_t, float, unsigned long long) {});
+}
+
+struct SLWireEpochParams
+{
+    const SLBlockInfo* blockInfo;
+    unsigned int numBlocks;
+    const uint32_t* recBase;
+    const uint32_t* recCount;
+    const uint8_t* fragPass;
+    uint16_t* fragEpoch;
+    unsigned int* changed;
+};
+
+/* flush epoch of every candidate of the records with 600+ candidates: passed candidates before it / 600 */
+__global__ void __launch_bounds__(128) k_wire_epoch(const __grid_constant__ SLWireEpochParams P)
+{
+    const unsigned long long t = (unsigned long long)blockIdx.x * 128ull + threadIdx.x;
+    const unsigned vb = (unsigned)(t >> 13), seg = (unsigned)(t >> 8) & 31u, idx = (unsigned)t & 255u;
+    if (vb >= P.numBlocks) return;
+    const SLSegment sg = P.blockInfo[vb].seg[seg];
+    if (idx >= sg.count) return;
+    const uint32_t recId = sg.base + idx;
+    const uint32_t n = P.recCount[recId];
+    if (n < SL_WIRE_QUEUE) return;
+    const uint32_t base = P.recBase[recId];
+    uint32_t passed = 0u;
+    bool ch = false;
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        const uint32_t e = passed / SL_WIRE_QUEUE;
+        const uint16_t ep = (uint16_t)(e > 0xffffu ? 0xffffu : e);
+        if (P.fragEpoch[base + i] != ep) { P.fragEpoch[base + i] = ep; ch = true; }
+        passed += P.fragPass[base + i];
+    }
+    if (ch) atomicAdd(P.changed, 1u);
+}
+
+template <FsFn FS>
+__global__ void __launch_bounds__(128) k_wire_shade(const __grid_constant__ SLWireShadeParams P)
+{
+    const unsigned long long t = (unsigned long long)blockIdx.x * 128ull + threadIdx.x;
+    unsigned shaded = 0u;
+    if (t < P.numFrags)
+    {
+        sl_wire_walk_pixel<true>(P, t, [&](uint32_t s, float z, unsigned long long pix) {
+            const float4 b4 = P.fragBc[s];
+            const uint32_t xy = P.fragXY[s];
+            const uint32_t recId = P.fragRec[s];
+            const float4* rec = P.records + (size_t)recId * P.recStride;
+            SL_FragmentParam fp;
+            /* flush_tri_fragments (src/SL_FragmentProcessor.cpp:438-529), as in k_shade */
+            math::vec4 bc = math::vec4{b4.x, b4.y, b4.z, b4.w} * math::vec4{rec[0].w, rec[1].w, rec[2].w, 0.f};
+            const float persp = sl_rcp((bc.v[0] + bc.v[1]) + (bc.v[2] + bc.v[3]));
+            bc = bc * persp;
+            fp.pUniforms = &P.draws[P.recDraw[recId]].uniforms;
+            for (int v = 0; v < P.numVaryings; ++v)
+            {
+                const float4 a = rec[3 + 3 * v + 0], b = rec[3 + 3 * v + 1], cc = rec[3 + 3 * v + 2];
+                fp.pVaryings[v] = math::vec4{
+                    sl_fma(bc.v[2], cc.x, sl_fma(bc.v[1], b.x, bc.v[0] * a.x)), sl_fma(bc.v[2], cc.y, sl_fma(bc.v[1], b.y, bc.v[0] * a.y)),
+                    sl_fma(bc.v[2], cc.z, sl_fma(bc.v[1], b.z, bc.v[0] * a.z)), sl_fma(bc.v[2], cc.w, sl_fma(bc.v[1], b.w, bc.v[0] * a.w))};
+            }
+            fp.coord.x = (uint16_t)(xy & 0xffffu);
+            fp.coord.y = (uint16_t)(xy >> 16);
+            fp.coord.depth = z;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) fp.pOutputs[i] = math::vec4{0.f};
+            ++shaded;
+            if (FS(fp))
+            {
+                if (P.blend == 0)
+                {
+                    for (int i = P.numOutputs - 1; i >= 0; --i) sl_store_color(P.color[i], P.colorType[i], (size_t)pix, fp.pOutputs[i]);
+                }
+                else
+                {
+                    for (int i = P.numOutputs - 1; i >= 0; --i) sl_blend_color(P.color[i], P.colorType[i], (size_t)pix, fp.pOutputs[i], P.blend);
+                }
+            }
+            if (P.depthMask) sl_store_depth(P.depth, P.depthBpt, (size_t)pix, z);
+        });
+    }
+    for (int o = 16; o > 0; o >>= 1) shaded += __shfl_xor_sync(0xffffffffu, shaded, o);
+    if ((threadIdx.x & 31) == 0 && shaded) atomicAdd(&P.counters->fragsShaded, (unsigned long long)shaded);
+}
+
+} // namespace sld

@@ -22,6 +22,7 @@
 #include "slcu.h"
 #include "sl_pipeline.cuh"
 #include "sl_points.cuh"
+#include "sl_wire.cuh"
 #include <cub/device/device_radix_sort.cuh>
 
 using namespace sld;
@@ -37,9 +38,10 @@ typedef cudaError_t (*RasterLauncher)(unsigned grid, cudaStream_t s, const SLSha
 
 typedef cudaError_t (*PointVertexLauncher)(unsigned grid, cudaStream_t s, const SLPointParams& p);
 typedef cudaError_t (*PointShadeLauncher)(unsigned grid, cudaStream_t s, const SLPointShadeParams& p);
+typedef cudaError_t (*WireShadeLauncher)(unsigned grid, cudaStream_t s, const SLWireShadeParams& p);
 
 struct VsEntry { const char* name; VertexLauncher launch; PointVertexLauncher launchPoints; };
-struct FsEntry { const char* name; RasterLauncher launch; PointShadeLauncher launchPoints; };
+struct FsEntry { const char* name; RasterLauncher launch; PointShadeLauncher launchPoints; WireShadeLauncher launchWire; };
 static std::vector<VsEntry>& vs_registry() { static std::vector<VsEntry> r; return r; }
 static std::vector<FsEntry>& fs_registry() { static std::vector<FsEntry> r; return r; }
 
@@ -75,14 +77,19 @@ template <FsFn FS> static cudaError_t launch_point_shade(unsigned grid, cudaStre
     k_point_shade<FS><<<grid, 128, 0, s>>>(p);
     return cudaGetLastError();
 }
+template <FsFn FS> static cudaError_t launch_wire_shade(unsigned grid, cudaStream_t s, const SLWireShadeParams& p)
+{
+    k_wire_shade<FS><<<grid, 128, 0, s>>>(p);
+    return cudaGetLastError();
+}
 struct VsReg { VsReg(const char* n, VertexLauncher l, PointVertexLauncher pl) { vs_registry().push_back(VsEntry{n, l, pl}); } };
-struct FsReg { FsReg(const char* n, RasterLauncher l, PointShadeLauncher pl) { fs_registry().push_back(FsEntry{n, l, pl}); } };
+struct FsReg { FsReg(const char* n, RasterLauncher l, PointShadeLauncher pl, WireShadeLauncher wl) { fs_registry().push_back(FsEntry{n, l, pl, wl}); } };
 
 #define SL_SHADER_FN static __device__ __forceinline__
 #define SL_CAT2(a, b) a##b
 #define SL_CAT(a, b) SL_CAT2(a, b)
 #define SL_REGISTER_VERTEX_SHADER(name, fn) static VsReg SL_CAT(vsreg_, fn){name, launch_vertex<fn>, launch_point_vertex<fn>};
-#define SL_REGISTER_FRAGMENT_SHADER(name, fn) static FsReg SL_CAT(fsreg_, fn){name, launch_raster<fn>, launch_point_shade<fn>};
+#define SL_REGISTER_FRAGMENT_SHADER(name, fn) static FsReg SL_CAT(fsreg_, fn){name, launch_raster<fn>, launch_point_shade<fn>, launch_wire_shade<fn>};
 
 namespace sld
 {
@@ -169,7 +176,7 @@ struct HostTexture
 struct HostIbo { int type = 0; uint32_t count = 0; DevBuffer buf; };
 struct HostVao { SL_VertexArray vao; int numBindings = 0; size_t vbo = (size_t)-1, ibo = (size_t)-1; };
 struct HostFbo { unsigned numColors = 0; size_t colors[4] = {(size_t)-1, (size_t)-1, (size_t)-1, (size_t)-1}; size_t depth = (size_t)-1; };
-struct HostShader { int cullMode, depthTest, depthMask, blend, numVaryings, numOutputs; VertexLauncher vs; RasterLauncher fs; PointVertexLauncher pointVs; PointShadeLauncher pointFs; size_t ubo; };
+struct HostShader { int cullMode, depthTest, depthMask, blend, numVaryings, numOutputs; VertexLauncher vs; RasterLauncher fs; PointVertexLauncher pointVs; PointShadeLauncher pointFs; WireShadeLauncher wireFs; size_t ubo; };
 struct UboFixup { size_t ubo, offset; int kind; size_t id, byteOffset; };
 struct HostUbo { unsigned char bytes[1024]; };
 
@@ -198,7 +205,8 @@ struct Batch
     unsigned numBlocks = 0;
     unsigned long long totalPrims = 0;
     unsigned long long maxVerts = 0; /* vertices of the largest vertex buffer of the batch (binding 0) */
-    void clear() { descs.clear(); blockDraw.clear(); numBlocks = 0; totalPrims = 0; maxVerts = 0; }
+    bool wire = false;               /* RENDER_MODE_TRI_WIRE / INDEXED_TRI_WIRE: edges only (sl_wire.cuh) */
+    void clear() { descs.clear(); blockDraw.clear(); numBlocks = 0; totalPrims = 0; maxVerts = 0; wire = false; }
 };
 
 struct slcu_context
@@ -226,6 +234,7 @@ struct slcu_context
     Scratch records, blockInfo, cnt, off, segSums, rowTotals, rowStart, entries, handoff, rowFlags, rowNeeded, drawTable, blockDraw, recDraw;
     Scratch fragPool, chunkNext, listInfo; /* fragment lists, k_resolve -> k_shade */
     Scratch handoffRegs;
+    Scratch wireSlots, wireRecInfo; /* wireframe: sort values (double buffer); first slot + candidate count per record */
     Scratch pointKeys, pointRecs, pointSortTemp; /* point primitives: sort keys (double buffer), records, radix-sort scratch */
     Scratch ticketOrder; /* skewed work order of k_resolve, cached per (rows, segments, skew) */
     unsigned orderRows = 0, orderSegs = 0, orderSkew = 0;
@@ -389,9 +398,9 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
     switch (meshes[0].mode)
     {
         case 0x10u: case 0x30u: break;                                                                /* triangles */
+        case 0x50u: case 0x70u: break;                                                                /* wireframe triangles */
         case 0x01u: case 0x03u: return run_points(c, meshes, numMeshes, numInstances, shaderId, fboId); /* points */
         case 0x04u: case 0x0cu: c->err = "RENDER_MODE_LINES / INDEXED_LINES are not implemented (no CPU fallback)"; return SLCU_ERR_UNSUPPORTED;
-        case 0x50u: case 0x70u: c->err = "RENDER_MODE_TRI_WIRE / INDEXED_TRI_WIRE are not implemented (no CPU fallback)"; return SLCU_ERR_UNSUPPORTED;
         default: c->err = "unknown render mode"; return SLCU_ERR_ARG;
     }
     const HostShader& sh = c->shaders[shaderId];
@@ -414,6 +423,7 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
         if (t.w != depthTex.w || t.h != depthTex.h) { c->err = "colour and depth attachments differ in size (SL_Framebuffer::valid -10)"; return SLCU_ERR_ARG; }
     }
     const float fboW = (float)depthTex.w, fboH = (float)depthTex.h;
+    const bool wire = (meshes[0].mode == 0x50u) || (meshes[0].mode == 0x70u); /* mRenderMode = meshes->mode (src/SL_ProcessorPool.cpp:301,354) */
 
     /* one table entry per mesh (draw / draw_multiple) or one for all instances (draw_instanced) */
     const size_t launches = (numInstances == 1) ? numMeshes : 1;
@@ -439,13 +449,14 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
         if (blocks64 > 0x3fffffull) { c->err = "draw too large for one batch"; return SLCU_ERR_UNSUPPORTED; }
         const unsigned blocks = (unsigned)blocks64;
         Batch& B = c->batch;
-        if (!B.descs.empty() && (B.shaderId != shaderId || B.fboId != fboId || B.numBlocks + blocks > kMaxBatchBlocks || B.descs.size() >= kMaxBatchDraws))
+        if (!B.descs.empty() && (B.shaderId != shaderId || B.fboId != fboId || B.wire != wire || B.numBlocks + blocks > kMaxBatchBlocks || B.descs.size() >= kMaxBatchDraws))
         {
             const int rc = flush_draws(c);
             if (rc) return rc;
         }
         B.shaderId = shaderId;
         B.fboId = fboId;
+        B.wire = wire;
         const HostVao& vao = c->vaos[m.vaoId];
         const bool usingIndices = (m.mode == 0x30u) || (m.mode == 0x70u);
         B.descs.emplace_back();
@@ -667,6 +678,128 @@ static int flush_draws_impl(slcu_context* c)
             vp.blockInfo = reinterpret_cast<SLBlockInfo*>(c->blockInfo.buf.ptr);
             vp.counters = c->counters;
             { KernelScope ks(c, SLCU_K_VERTEX); CK(sh.vs(numBlocks, c->stream, vp, cache)); }
+        }
+
+        if (B.wire)
+        {
+            /* ---- wireframe: edge fragments are counted, emitted with an order key, sorted and shaded (sl_wire.cuh) ---- */
+            SLWireParams wp;
+            memset(&wp, 0, sizeof(wp));
+            wp.records = reinterpret_cast<const float4*>(c->records.buf.ptr);
+            wp.blockInfo = reinterpret_cast<const SLBlockInfo*>(c->blockInfo.buf.ptr);
+            wp.numBlocks = numBlocks;
+            wp.recStride = recStride;
+            wp.width = depthTex.w;
+            wp.height = H;
+            wp.rank = c->partRank;
+            wp.world = c->partWorld;
+            wp.stripRows = c->partStripRows;
+            wp.counters = c->counters;
+            const unsigned wireGrid = numBlocks * (SL_VB_SEGS * 256u / 128u);
+            { KernelScope ks(c, SLCU_K_SPAN_COUNT); k_wire<0><<<wireGrid, 128, 0, c->stream>>>(wp); }
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(c->hostCounters, c->counters, sizeof(SLCounters), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            if (c->hostCounters->errorFlags & 1u)
+            {
+                CK(cudaMemsetAsync(&c->counters->errorFlags, 0, sizeof(unsigned), c->stream));
+                if (attempt == 0) { recOverflow = totalPrims * 7 + 4096; recCapacity = recFixed + recOverflow; continue; }
+                c->err = "triangle record buffer overflow";
+                return SLCU_ERR_OOM;
+            }
+            const unsigned long long numFrags = c->hostCounters->pixelsCovered;
+            if (!numFrags) return 0;
+            if (numFrags > 0x7ffffff0ull) { c->err = "too many wireframe fragments for one batch"; return SLCU_ERR_UNSUPPORTED; }
+            CK(c->pointKeys.ensure((size_t)numFrags * 2 * sizeof(unsigned long long)));
+            CK(c->wireSlots.ensure((size_t)numFrags * 2 * sizeof(uint32_t)));
+            const unsigned long long bigRecords = c->hostCounters->rowEndCuts; /* records with 600+ candidates: their queue flushes are observable */
+            CK(c->pointRecs.ensure((size_t)numFrags * (sizeof(float4) + 3 * sizeof(uint32_t) + sizeof(uint16_t) + 2)));
+            CK(c->wireRecInfo.ensure((size_t)recCapacity * 2 * sizeof(uint32_t)));
+            unsigned long long* keysA = reinterpret_cast<unsigned long long*>(c->pointKeys.buf.ptr);
+            uint32_t* slotsA = reinterpret_cast<uint32_t*>(c->wireSlots.buf.ptr);
+            wp.capacity = numFrags;
+            wp.keys = keysA;
+            wp.slots = slotsA;
+            wp.fragBc = reinterpret_cast<float4*>(c->pointRecs.buf.ptr);
+            wp.fragZ = reinterpret_cast<float*>(wp.fragBc + numFrags);
+            wp.fragXY = reinterpret_cast<uint32_t*>(wp.fragZ + numFrags);
+            wp.fragRec = wp.fragXY + numFrags;
+            uint16_t* fragEpoch = reinterpret_cast<uint16_t*>(wp.fragRec + numFrags);
+            uint8_t* fragPass = reinterpret_cast<uint8_t*>(fragEpoch + numFrags);
+            wp.recBase = reinterpret_cast<uint32_t*>(c->wireRecInfo.buf.ptr);
+            wp.recCount = wp.recBase + recCapacity;
+            CK(cudaMemsetAsync(&c->counters->pixelsCovered, 0, sizeof(unsigned long long), c->stream)); /* now the slot allocator */
+            { KernelScope ks(c, SLCU_K_SPAN_FILL); k_wire<1><<<wireGrid, 128, 0, c->stream>>>(wp); }
+            CK(cudaGetLastError());
+
+            unsigned pixBits = 1;
+            while ((1ull << pixBits) < (unsigned long long)depthTex.w * H) ++pixBits;
+            cub::DoubleBuffer<unsigned long long> keys(keysA, keysA + numFrags);
+            cub::DoubleBuffer<uint32_t> slots(slotsA, slotsA + numFrags);
+            size_t tempBytes = 0;
+            CK(cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, keys, slots, (int)numFrags, 0, SL_WIRE_LOW_BITS + (int)pixBits, c->stream));
+            CK(c->pointSortTemp.ensure(tempBytes));
+            { KernelScope ks(c, SLCU_K_SCAN); CK(cub::DeviceRadixSort::SortPairs(c->pointSortTemp.buf.ptr, tempBytes, keys, slots, (int)numFrags, 0, SL_WIRE_LOW_BITS + (int)pixBits, c->stream)); }
+
+            SLWireShadeParams ws;
+            ws.draws = reinterpret_cast<const SLDrawDesc*>(c->drawTable.buf.ptr);
+            ws.recDraw = reinterpret_cast<const uint16_t*>(c->recDraw.buf.ptr);
+            ws.records = wp.records;
+            ws.recStride = recStride;
+            ws.keys = keys.Current();
+            ws.slots = slots.Current();
+            ws.fragBc = wp.fragBc;
+            ws.fragZ = wp.fragZ;
+            ws.fragXY = wp.fragXY;
+            ws.fragRec = wp.fragRec;
+            ws.fragEpoch = nullptr;
+            ws.fragPass = fragPass;
+            ws.numFrags = numFrags;
+            ws.numVaryings = NV;
+            ws.numOutputs = sh.numOutputs;
+            ws.blend = sh.blend;
+            ws.depthTest = sh.depthTest;
+            ws.depthMask = sh.depthMask;
+            ws.depth = depthTex.dev;
+            ws.depthBpt = depthTex.bpt;
+            for (int k = 0; k < 4; ++k)
+            {
+                ws.color[k] = nullptr;
+                ws.colorType[k] = 0;
+                if (k < sh.numOutputs) { const HostTexture& t = c->textures[fbo.colors[k]]; ws.color[k] = t.dev; ws.colorType[k] = t.type; }
+            }
+            ws.counters = c->counters;
+            const unsigned shadeGrid = (unsigned)((numFrags + 127ull) / 128ull);
+            if (bigRecords && sh.depthTest != 0 && sh.depthMask)
+            {
+                /* flush epochs of the big records: iterate depth outcomes <-> epochs to the fixed point (sl_wire.cuh) */
+                ws.fragEpoch = fragEpoch;
+                CK(cudaMemsetAsync(fragEpoch, 0, (size_t)numFrags * sizeof(uint16_t), c->stream));
+                SLWireEpochParams ep;
+                ep.blockInfo = wp.blockInfo;
+                ep.numBlocks = numBlocks;
+                ep.recBase = wp.recBase;
+                ep.recCount = wp.recCount;
+                ep.fragPass = fragPass;
+                ep.fragEpoch = fragEpoch;
+                ep.changed = &c->counters->rasterTicket; /* a free per-batch word */
+                bool settled = false;
+                for (int it = 0; it < 16 && !settled; ++it)
+                {
+                    CK(cudaMemsetAsync(ep.changed, 0, sizeof(unsigned), c->stream));
+                    { KernelScope ks(c, SLCU_K_RASTER); k_wire_depth<<<shadeGrid, 128, 0, c->stream>>>(ws); }
+                    { KernelScope ks(c, SLCU_K_SCAN); k_wire_epoch<<<wireGrid, 128, 0, c->stream>>>(ep); }
+                    CK(cudaGetLastError());
+                    unsigned changed = 0;
+                    CK(cudaMemcpyAsync(&c->hostCounters[1], ep.changed, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+                    CK(cudaStreamSynchronize(c->stream));
+                    memcpy(&changed, &c->hostCounters[1], sizeof(unsigned));
+                    settled = changed == 0;
+                }
+                if (!settled) { CK(cudaMemsetAsync(ep.changed, 0, sizeof(unsigned), c->stream)); c->err = "wireframe flush epochs did not settle"; return SLCU_ERR_UNSUPPORTED; }
+            }
+            { KernelScope ks(c, SLCU_K_SHADE); CK(sh.wireFs(shadeGrid, c->stream, ws)); }
+            return 0;
         }
 
         /* ---- span count + scans ---- */
@@ -988,7 +1121,7 @@ void slcu_context_destroy(slcu_context* c)
     if (c->counters) cudaFree(c->counters);
     if (c->hostCounters) cudaFreeHost(c->hostCounters);
     for (auto& pm : c->peerMaps) if (pm.ptr) cudaIpcCloseMemHandle(pm.ptr);
-    Scratch* s[] = {&c->records, &c->blockInfo, &c->cnt, &c->off, &c->segSums, &c->rowTotals, &c->rowStart, &c->entries, &c->handoff, &c->rowFlags, &c->rowNeeded, &c->drawTable, &c->blockDraw, &c->recDraw, &c->fragPool, &c->chunkNext, &c->listInfo, &c->handoffRegs, &c->ticketOrder, &c->pointKeys, &c->pointRecs, &c->pointSortTemp};
+    Scratch* s[] = {&c->records, &c->blockInfo, &c->cnt, &c->off, &c->segSums, &c->rowTotals, &c->rowStart, &c->entries, &c->handoff, &c->rowFlags, &c->rowNeeded, &c->drawTable, &c->blockDraw, &c->recDraw, &c->fragPool, &c->chunkNext, &c->listInfo, &c->handoffRegs, &c->ticketOrder, &c->pointKeys, &c->pointRecs, &c->pointSortTemp, &c->wireSlots, &c->wireRecInfo};
     for (Scratch* x : s) x->release();
     cudaStreamDestroy(c->stream);
     delete c;
@@ -1228,8 +1361,9 @@ size_t slcu_create_shader(slcu_context* c, const slcu_vertex_shader* vs, const s
     RasterLauncher fl = nullptr;
     PointVertexLauncher pvl = nullptr;
     PointShadeLauncher pfl = nullptr;
+    WireShadeLauncher wfl = nullptr;
     for (const VsEntry& e : vs_registry()) if (!strcmp(e.name, vs->shader)) { vl = e.launch; pvl = e.launchPoints; }
-    for (const FsEntry& e : fs_registry()) if (!strcmp(e.name, fs->shader)) { fl = e.launch; pfl = e.launchPoints; }
+    for (const FsEntry& e : fs_registry()) if (!strcmp(e.name, fs->shader)) { fl = e.launch; pfl = e.launchPoints; wfl = e.launchWire; }
     if (!vl || !fl)
     {
         c->err = "shader not registered as a __device__ callable (no CPU fallback)";
@@ -1237,7 +1371,7 @@ size_t slcu_create_shader(slcu_context* c, const slcu_vertex_shader* vs, const s
     }
     HostShader s;
     s.cullMode = vs->cullMode; s.depthTest = fs->depthTest; s.depthMask = fs->depthMask; s.blend = fs->blend;
-    s.numVaryings = fs->numVaryings; s.numOutputs = fs->numOutputs; s.vs = vl; s.fs = fl; s.pointVs = pvl; s.pointFs = pfl; s.ubo = ubo;
+    s.numVaryings = fs->numVaryings; s.numOutputs = fs->numOutputs; s.vs = vl; s.fs = fl; s.pointVs = pvl; s.pointFs = pfl; s.wireFs = wfl; s.ubo = ubo;
     c->shaders.push_back(s);
     return c->shaders.size() - 1;
 }

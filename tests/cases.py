@@ -100,6 +100,28 @@ POINT_CASES = {
 }
 for _i, _name in enumerate(POINT_CASES):
     CASES[_name] = (lambda i=_i, name=_name: S.random_tris_scene(seed=900 + i, name=name, points=True, **POINT_CASES[name]))
+
+# RENDER_MODE_TRI_WIRE / INDEXED_TRI_WIRE (SL_TriRasterizer::render_wireframe): the triangle scenes, edges only.  Blending
+# makes the rasteriser's pixel revisits visible (a revisited pixel is blended twice), the overflow cases wrap edge runs
+# across the row end.
+WIRE_CASES = {
+    "wire_basic": dict(n=400),
+    "wire_alpha": dict(n=400, blend=1),
+    "wire_noindex_split3_additive": dict(n=300, index_dtype=None, split_draws=3, blend=3, depth_mask=A.SL_DEPTH_MASK_OFF),
+    "wire_multi3_u32": dict(n=300, index_dtype=np.uint32, split_draws=3, multiple=True),
+    "wire_clip_heavy": dict(n=3000, width=320, height=200, clip_fraction=0.5),
+    "wire_overflow_wide": dict(n=900, width=640, height=48, clip_fraction=0.8),
+    "wire_overflow_premult": dict(n=700, width=257, height=131, clip_fraction=0.9, blend=2),
+    "wire_overflow_half_ge": dict(n=700, width=512, height=64, clip_fraction=0.9, depth_type=A.SL_COLOR_R_HALF,
+                                  depth_test=A.SL_DEPTH_TEST_GREATER_EQUAL, clear_depth=-1.0),
+    "wire_nodepth_rgbf": dict(n=500, depth_test=A.SL_DEPTH_TEST_OFF, color_type=A.SL_COLOR_RGB_FLOAT, cull=1),
+    "wire_viewport_scissor": dict(n=400, viewport=(20, 10, 120, 90), scissor=(30, 20, 100, 80)),
+    "wire_1080p": dict(n=200, width=1920, height=1080, clip_fraction=0.2),
+    "wire_tiny_1x1": dict(n=50, width=1, height=1),
+    "wire_empty": dict(n=30, empty_draw=True),
+}
+for _i, _name in enumerate(WIRE_CASES):
+    CASES[_name] = (lambda i=_i, name=_name: S.random_tris_scene(seed=950 + i, name=name, wire=True, **WIRE_CASES[name]))
 CASES["draw_test"] = S.SCENES["draw_test"]
 CASES["c1_small"] = S.SCENES["c1_small"]
 CASES["c2_small"] = S.SCENES["c2_small"]
@@ -121,7 +143,7 @@ BIG_CASES = {
 }
 
 # cases whose images are committed in full (the rest of CASES is pinned by sha256)
-FULL_IMAGE_CASES = ["draw_test", "c1_small", "c2_small", "c3_small", "c4_small", "c5_small", "sampler_matrix", "rand_blend1", "rand_clip_heavy", "rand_depth_half_premult", "points_dense"]
+FULL_IMAGE_CASES = ["draw_test", "c1_small", "c2_small", "c3_small", "c4_small", "c5_small", "sampler_matrix", "rand_blend1", "rand_clip_heavy", "rand_depth_half_premult", "points_dense", "wire_alpha"]
 
 
 def bits(a: np.ndarray) -> np.ndarray:

@@ -192,7 +192,7 @@ def test_empty_point_draw_is_a_noop():
     assert np.all(color == color[0, 0]) and np.all(depth == 1.0)
 
 
-@pytest.mark.parametrize("mode", [A.RENDER_MODE_LINES, A.RENDER_MODE_INDEXED_LINES, A.RENDER_MODE_TRI_WIRE, A.RENDER_MODE_INDEXED_TRI_WIRE, 0x1234])
+@pytest.mark.parametrize("mode", [A.RENDER_MODE_LINES, A.RENDER_MODE_INDEXED_LINES, 0x1234])
 def test_unimplemented_render_modes_are_refused_loudly(mode):
     ctx = A.Context("cuda")
     st = S.SceneInstance(S.random_tris_scene(seed=2, n=10), ctx)
@@ -229,7 +229,8 @@ def test_points_between_triangle_draws_keep_submission_order(golden):
 
 @pytest.mark.parametrize("name,world,strip", [("c1_small", 2, 8), ("rand_clip_heavy", 2, 1), ("rand_overflow_wide", 3, 2),
                                                ("rand_overflow_blend", 4, 1), ("c2_small", 8, 8), ("rand_overflow_half_ge", 2, 1),
-                                               ("points_dense", 2, 1), ("points_sparse_1080p", 4, 8)])
+                                               ("points_dense", 2, 1), ("points_sparse_1080p", 4, 8),
+                                               ("wire_alpha", 2, 1), ("wire_overflow_premult", 3, 2), ("wire_overflow_half_ge", 2, 1)])
 def test_sort_first_partition_is_bit_identical(name, world, strip, golden):
     """Every rank's context (all on this GPU) rasterises only its row strips (+ the rows its hand-overs come from);
     the composite of the owned rows equals the unpartitioned frame bit for bit, spans that wrap across an ownership
