@@ -6,7 +6,7 @@
  * barycentrics.  Edge fragments are sparse, so instead of the span / resolve machinery of filled triangles they are
  * handled like points (sl_points.cuh):
  *
- *   k_wire<EMIT=0>     counts the fragments candidates of every triangle record (sizes the buffers)
+ *   k_wire<EMIT=0>     counts the fragment candidates of every triangle record (sizes the buffers)
  *   k_wire<EMIT=1>     writes one (key, payload) per candidate: key = linear pixel << 31 | submission ordinal of the
  *                      record << 3 | visit order of that record on that pixel
  *   (radix sort of the keys)
@@ -84,24 +84,22 @@ SLD_FN void sl_wire_row(int32_t x0, int32_t x1, int32_t d0, int32_t d1, int32_t 
     }
 }
 
+/* One WARP per (vertex block, segment, index): segments are the (round, warp) record regions of k_vertex, taken in
+ * submission order exactly like k_span does; the lanes take the record's scan lines 32 at a time, and a warp scan of the
+ * per-line counts keeps the record's candidates contiguous and in visit order (line by line). */
+constexpr unsigned SL_WIRE_BLOCKS_PER_VB = SL_VB_SEGS * 256u / 4u; /* 128 threads = 4 warps = 4 record slots */
+
 template <int EMIT>
 __global__ void __launch_bounds__(128) k_wire(const __grid_constant__ SLWireParams P)
 {
-    /* one thread per (vertex block, segment, index): segments are the (round, warp) record regions of k_vertex, taken in
-     * submission order exactly like k_span does */
-    const unsigned long long t = (unsigned long long)blockIdx.x * 128ull + threadIdx.x;
-    const unsigned vb = (unsigned)(t >> 13), seg = (unsigned)(t >> 8) & 31u, idx = (unsigned)t & 255u;
-    unsigned long long n = 0;
-    unsigned rowsHit = 0;
-    bool active = false;
-    uint32_t recId = 0;
-    if (vb < P.numBlocks)
-    {
-        const SLSegment sg = P.blockInfo[vb].seg[seg];
-        if (sg.count > 256u && idx == 0u) atomicOr(&P.counters->errorFlags, 16u);
-        if (idx < sg.count) { active = true; recId = sg.base + idx; }
-    }
-    if (!active) return;
+    const unsigned long long w = ((unsigned long long)blockIdx.x * 128ull + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const unsigned vb = (unsigned)(w >> 13), seg = (unsigned)(w >> 8) & 31u, idx = (unsigned)w & 255u;
+    if (vb >= P.numBlocks) return; /* warp-uniform exits */
+    const SLSegment sg = P.blockInfo[vb].seg[seg];
+    if (sg.count > 256u && idx == 0u && lane == 0) atomicOr(&P.counters->errorFlags, 16u);
+    if (idx >= sg.count) return;
+    const uint32_t recId = sg.base + idx;
 
     const float4* r = P.records + (size_t)recId * P.recStride;
     const float4 p0 = r[0], p1 = r[1], p2 = r[2];
@@ -122,49 +120,86 @@ __global__ void __launch_bounds__(128) k_wire(const __grid_constant__ SLWirePara
         const unsigned row = (unsigned)(pix / P.width);
         return (row / P.stripRows) % P.world == P.rank;
     };
-
-    for (int32_t y = yBegin; y < yEnd; ++y)
-    {
+    /* candidates of line y that this context stores; hit = the line has a visit at all */
+    auto count_row = [&](int32_t y, int32_t& x0, int32_t& x1, int32_t& d0, int32_t& d1, bool& hit) -> unsigned {
         const float yf = (float)y;
-        int32_t x0, x1, q0, q1;
+        int32_t q0, q1;
         sl.step(yf, x0, x1);
         sl.step(yf - 1.f, q0, q1);
-        const int32_t d0 = sl_wire_edge_width(x0, q0), d1 = sl_wire_edge_width(x1, q1);
-        bool hit = false;
+        d0 = sl_wire_edge_width(x0, q0);
+        d1 = sl_wire_edge_width(x1, q1);
+        unsigned c = 0;
+        bool h = false;
         sl_wire_row(x0, x1, d0, d1, xLimit, [&](int32_t x, int) {
-            hit = true;
-            if (owned((unsigned long long)x + (unsigned long long)P.width * (unsigned)y)) ++n;
+            h = true;
+            if (owned((unsigned long long)x + (unsigned long long)P.width * (unsigned)y)) ++c;
         });
         if ((uint32_t)x0 < (uint32_t)x1 && x1 > xLimit) atomicOr(&P.counters->errorFlags, 2u);
+        hit = h;
+        return c;
+    };
+
+    unsigned n = 0, rowsHit = 0;
+    for (int32_t y = yBegin + lane; y < yEnd; y += 32)
+    {
+        int32_t x0, x1, d0, d1;
+        bool hit;
+        n += count_row(y, x0, x1, d0, d1, hit);
         rowsHit += hit ? 1u : 0u;
     }
+    n = __reduce_add_sync(0xffffffffu, n);
     if (!EMIT)
     {
-        if (n) atomicAdd(&P.counters->pixelsCovered, n);
-        if (n >= SL_WIRE_QUEUE) atomicAdd(&P.counters->rowEndCuts, 1ull);
+        if (lane == 0)
+        {
+            if (n) atomicAdd(&P.counters->pixelsCovered, (unsigned long long)n);
+            if (n >= SL_WIRE_QUEUE) atomicAdd(&P.counters->rowEndCuts, 1ull);
+        }
         return;
     }
-    if (rowsHit) atomicAdd(&P.counters->spans, (unsigned long long)rowsHit); /* the statistic: (record, line) pairs with a visit */
-    P.recCount[recId] = (uint32_t)n;
-    if (!n) return;
-    unsigned long long slot = atomicAdd(&P.counters->pixelsCovered, n);
-    if (slot + n > P.capacity) { atomicOr(&P.counters->errorFlags, 32u); P.recCount[recId] = 0u; return; }
-    P.recBase[recId] = (uint32_t)slot;
+    rowsHit = __reduce_add_sync(0xffffffffu, rowsHit);
+    unsigned long long base = 0;
+    if (lane == 0)
+    {
+        if (rowsHit) atomicAdd(&P.counters->spans, (unsigned long long)rowsHit); /* the statistic: (record, line) pairs with a visit */
+        if (n) base = atomicAdd(&P.counters->pixelsCovered, (unsigned long long)n);
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    const bool fits = base + n <= P.capacity;
+    if (lane == 0)
+    {
+        P.recCount[recId] = fits ? n : 0u;
+        P.recBase[recId] = (uint32_t)base;
+        if (!fits) atomicOr(&P.counters->errorFlags, 32u);
+    }
+    if (!n || !fits) return;
 
     SLTriSetup ts;
     sl_tri_setup(ts, p0, p1, p2);
     const math::vec4 depth{p0.z, p1.z, p2.z, 0.f};
-    for (int32_t y = yBegin; y < yEnd; ++y)
+    unsigned long long running = base;
+    for (int32_t yBase = yBegin; yBase < yEnd; yBase += 32)
     {
+        const int32_t y = yBase + lane;
+        int32_t x0 = 0, x1 = 0, d0 = 1, d1 = 1;
+        bool hit = false;
+        unsigned c = 0;
+        if (y < yEnd) c = count_row(y, x0, x1, d0, d1, hit);
+        unsigned inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            const unsigned t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        unsigned long long slot = running + (inc - c);
+        running += __shfl_sync(0xffffffffu, inc, 31);
+        if (!c) continue;
         const float yf = (float)y;
         const math::vec4 yv{yf, yf, yf, 0.f};
         math::vec4 bcY;
 #pragma unroll
         for (int k = 0; k < 4; ++k) bcY.v[k] = sl_fma(ts.bc1.v[k], yv.v[k], ts.bc2.v[k]); /* :149 */
-        int32_t x0, x1, q0, q1;
-        sl.step(yf, x0, x1);
-        sl.step(yf - 1.f, q0, q1);
-        const int32_t d0 = sl_wire_edge_width(x0, q0), d1 = sl_wire_edge_width(x1, q1);
         sl_wire_row(x0, x1, d0, d1, xLimit, [&](int32_t x, int run) {
             const unsigned long long pix = (unsigned long long)x + (unsigned long long)P.width * (unsigned)y;
             if (!owned(pix)) return;
@@ -280,11 +315,13 @@ struct SLWireEpochParams
     unsigned int* changed;
 };
 
-/* flush epoch of every candidate of the records with 600+ candidates: passed candidates before it / 600 */
+/* flush epoch of every candidate of the records with 600+ candidates: passed candidates before it / 600.  One warp per
+ * record slot (the indexing of k_wire), 32 candidates per step. */
 __global__ void __launch_bounds__(128) k_wire_epoch(const __grid_constant__ SLWireEpochParams P)
 {
-    const unsigned long long t = (unsigned long long)blockIdx.x * 128ull + threadIdx.x;
-    const unsigned vb = (unsigned)(t >> 13), seg = (unsigned)(t >> 8) & 31u, idx = (unsigned)t & 255u;
+    const unsigned long long w = ((unsigned long long)blockIdx.x * 128ull + threadIdx.x) >> 5;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned vb = (unsigned)(w >> 13), seg = (unsigned)(w >> 8) & 31u, idx = (unsigned)w & 255u;
     if (vb >= P.numBlocks) return;
     const SLSegment sg = P.blockInfo[vb].seg[seg];
     if (idx >= sg.count) return;
@@ -292,16 +329,19 @@ __global__ void __launch_bounds__(128) k_wire_epoch(const __grid_constant__ SLWi
     const uint32_t n = P.recCount[recId];
     if (n < SL_WIRE_QUEUE) return;
     const uint32_t base = P.recBase[recId];
-    uint32_t passed = 0u;
+    uint32_t passedBefore = 0u;
     bool ch = false;
-    for (uint32_t i = 0; i < n; ++i)
+    for (uint32_t i0 = 0; i0 < n; i0 += 32u)
     {
-        const uint32_t e = passed / SL_WIRE_QUEUE;
+        const uint32_t i = i0 + lane;
+        const bool p = i < n && P.fragPass[base + i] != 0;
+        const uint32_t b = __ballot_sync(0xffffffffu, p);
+        const uint32_t e = (passedBefore + __popc(b & ((1u << lane) - 1u))) / SL_WIRE_QUEUE;
         const uint16_t ep = (uint16_t)(e > 0xffffu ? 0xffffu : e);
-        if (P.fragEpoch[base + i] != ep) { P.fragEpoch[base + i] = ep; ch = true; }
-        passed += P.fragPass[base + i];
+        if (i < n && P.fragEpoch[base + i] != ep) { P.fragEpoch[base + i] = ep; ch = true; }
+        passedBefore += __popc(b);
     }
-    if (ch) atomicAdd(P.changed, 1u);
+    if (__any_sync(0xffffffffu, ch) && lane == 0u) atomicAdd(P.changed, 1u);
 }
 
 template <FsFn FS>

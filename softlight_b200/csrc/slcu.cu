@@ -695,7 +695,7 @@ static int flush_draws_impl(slcu_context* c)
             wp.world = c->partWorld;
             wp.stripRows = c->partStripRows;
             wp.counters = c->counters;
-            const unsigned wireGrid = numBlocks * (SL_VB_SEGS * 256u / 128u);
+            const unsigned wireGrid = numBlocks * SL_WIRE_BLOCKS_PER_VB; /* one warp per record slot */
             { KernelScope ks(c, SLCU_K_SPAN_COUNT); k_wire<0><<<wireGrid, 128, 0, c->stream>>>(wp); }
             CK(cudaGetLastError());
             CK(cudaMemcpyAsync(c->hostCounters, c->counters, sizeof(SLCounters), cudaMemcpyDeviceToHost, c->stream));

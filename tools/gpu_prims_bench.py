@@ -1,0 +1,49 @@
+"""Throughput of the point and wireframe paths on one GPU, with the compiled reference (when oracle/_ref travelled) timed
+beside it on the host: python tools/gpu_prims_bench.py > gpurun_out/prims_bench.txt"""
+import os, sys, time, json
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+from softlight_b200 import capi as A, scenes as S
+
+CONFIGS = {
+    "points_4m_1080p": dict(n=1333334, width=1920, height=1080, points=True, index_dtype=np.uint32),
+    "points_4m_1080p_alpha": dict(n=1333334, width=1920, height=1080, points=True, index_dtype=np.uint32, blend=1,
+                                  depth_test=A.SL_DEPTH_TEST_OFF, depth_mask=A.SL_DEPTH_MASK_OFF),
+    "wire_200k_1080p": dict(n=200000, width=1920, height=1080, wire=True, index_dtype=np.uint32, clip_fraction=0.05),
+    "wire_2k_large_1080p": dict(n=2000, width=1920, height=1080, wire=True, index_dtype=np.uint32, clip_fraction=0.2),
+}
+
+
+def time_impl(impl, scene, frames, threads=None):
+    ctx = A.Context(impl)
+    if threads:
+        ctx.num_threads(threads)
+    inst = S.SceneInstance(scene, ctx)
+    inst.render(); ctx.sync()
+    ctx.reset_stats()
+    t0 = time.perf_counter()
+    for _ in range(frames):
+        inst.render()
+    ctx.sync()
+    dt = (time.perf_counter() - t0) / frames
+    st = ctx.get_stats()
+    prof = None
+    if impl == "cuda":
+        ctx.profile_begin()
+        inst.render()
+        prof = {k: round(v["ms"], 3) for k, v in ctx.profile_end().items() if v["launches"]}
+    ctx.close()
+    return dt, st["fragsShaded"] // frames, prof
+
+
+for name, kw in CONFIGS.items():
+    scene = S.random_tris_scene(seed=77, name=name, **kw)
+    elems = kw["n"] * (3 if kw.get("points") else 1)
+    dt, frags, prof = time_impl("cuda", scene, 10)
+    out = {"config": name, "elements": elems, "frags_per_frame": int(frags), "cuda_ms": round(dt * 1e3, 3), "cuda_Melem_s": round(elems / dt / 1e6, 1), "kernel_ms": prof}
+    if os.path.exists(A.LIB_PATHS["ref_fast"]):
+        cores = os.cpu_count() or 1
+        rdt, rfrags, _ = time_impl("ref_fast", scene, 1, threads=cores)
+        out.update({"ref_ms": round(rdt * 1e3, 1), "ref_threads": cores, "speedup": round(rdt / dt, 1)})
+    print(json.dumps(out), flush=True)
