@@ -7,11 +7,12 @@
  * handled like points (sl_points.cuh):
  *
  *   k_wire<EMIT=0>     counts the fragment candidates of every triangle record (sizes the buffers)
- *   k_wire<EMIT=1>     writes one (key, payload) per candidate: key = linear pixel << 31 | submission ordinal of the
- *                      record << 3 | visit order of that record on that pixel
+ *   k_wire<EMIT=1>     writes one (key, payload) per candidate: key = linear pixel << lowBits | submission ordinal of
+ *                      the record << 3 | visit order of that record on that pixel; sort value = depth | payload slot
  *   (radix sort of the keys)
- *   k_wire_shade<FS>   the thread that holds the first key of a pixel walks that pixel's candidates in submission
- *                      order: depth test, SL_FragmentProcessor::flush_tri_fragments shading, colour / depth writes.
+ *   k_wire_leaders     compacts the positions where a pixel's candidates start
+ *   k_wire_shade<FS>   one thread per pixel walks that pixel's candidates in submission order: depth test,
+ *                      SL_FragmentProcessor::flush_tri_fragments shading, colour / depth writes.
  *
  * The reference tests a candidate when it is queued and writes depth when the queue is flushed (600 fragments, or at
  * the end of the triangle), and render_wireframe does revisit pixels (the jump to the right edge can land left of where
@@ -31,9 +32,9 @@
 namespace sld
 {
 
-constexpr int SL_WIRE_ORD_BITS = 28; /* (vertex block * 32 + segment) << 8 | index in the segment */
 constexpr int SL_WIRE_SUB_BITS = 3;
-constexpr int SL_WIRE_LOW_BITS = SL_WIRE_ORD_BITS + SL_WIRE_SUB_BITS;
+/* key = pixel << lowBits | ordinal << 3 | visit order, ordinal = (vertex block * 32 + segment) << 8 | index in the segment;
+ * lowBits = 3 + the bits the batch's ordinals need (13 + bits(numBlocks - 1)): fewer radix passes for small batches */
 
 struct SLWireParams
 {
@@ -44,10 +45,10 @@ struct SLWireParams
     unsigned int width, height;
     unsigned int rank, world, stripRows;  /* sort-first partition */
     unsigned long long capacity;          /* EMIT: fragment slots */
+    int lowBits;
     unsigned long long* keys;
-    uint32_t* slots;                      /* sort values: payload slot of the key */
+    unsigned long long* vals;             /* sort values: depth bits << 32 | payload slot of the key */
     float4* fragBc;
-    float* fragZ;
     uint32_t* fragXY;
     uint32_t* fragRec;
     uint32_t* recBase;                    /* EMIT out: [record] first slot of the record's candidates (visit order)     */
@@ -213,10 +214,9 @@ __global__ void __launch_bounds__(128) k_wire(const __grid_constant__ SLWirePara
              * line than the pixel's own), then the run */
             const unsigned wraps = (unsigned)(x / W); /* 0..3 */
             const unsigned sub = ((3u - wraps) << 1) | (unsigned)run;
-            P.keys[slot] = (pix << SL_WIRE_LOW_BITS) | ((unsigned long long)ordinal << SL_WIRE_SUB_BITS) | sub;
-            P.slots[slot] = (uint32_t)slot;
+            P.keys[slot] = (pix << P.lowBits) | ((unsigned long long)ordinal << SL_WIRE_SUB_BITS) | sub;
+            P.vals[slot] = ((unsigned long long)__float_as_uint(z) << 32) | (unsigned long long)(uint32_t)slot;
             P.fragBc[slot] = make_float4(bc.v[0], bc.v[1], bc.v[2], bc.v[3]);
-            P.fragZ[slot] = z;
             P.fragXY[slot] = ((uint32_t)x & 0xffffu) | (((uint32_t)y & 0xffffu) << 16);
             P.fragRec[slot] = recId;
             ++slot;
@@ -230,12 +230,14 @@ struct SLWireShadeParams
     const uint16_t* recDraw;
     const float4* records;
     int recStride;
+    int lowBits;
     const unsigned long long* keys;   /* sorted */
-    const uint32_t* slots;            /* sorted along with the keys */
+    const unsigned long long* vals;   /* sorted along with the keys: depth bits << 32 | slot */
     const float4* fragBc;
-    const float* fragZ;
     const uint32_t* fragXY;
     const uint32_t* fragRec;
+    uint32_t* leaders;                /* k_wire_leaders out: positions in the sorted order where a pixel's candidates start */
+    unsigned int* numLeaders;
     const uint16_t* fragEpoch;        /* flush epoch of every candidate (null: all 0) */
     uint8_t* fragPass;                /* k_wire_depth out: depth outcome of every candidate */
     unsigned long long numFrags;
@@ -257,22 +259,23 @@ struct SLWireShadeParams
 template <bool SHADE, typename F>
 SLD_FN void sl_wire_walk_pixel(const SLWireShadeParams& P, unsigned long long t, F f)
 {
-    const unsigned long long pix = P.keys[t] >> SL_WIRE_LOW_BITS;
-    if (t != 0ull && (P.keys[t - 1ull] >> SL_WIRE_LOW_BITS) == pix) return;
+    const unsigned long long pix = P.keys[t] >> P.lowBits;
     float dCur = sl_load_depth(P.depth, P.depthBpt, (size_t)pix);
     unsigned long long j = t;
     bool more = true;
     while (more)
     {
-        const uint32_t ord = (uint32_t)(P.keys[j] >> SL_WIRE_SUB_BITS) & ((1u << SL_WIRE_ORD_BITS) - 1u);
+        const unsigned long long ordMask = (1ull << (P.lowBits - SL_WIRE_SUB_BITS)) - 1ull;
+        const unsigned long long ord = (P.keys[j] >> SL_WIRE_SUB_BITS) & ordMask;
         const float dPre = dCur;
         float zs[8];
         uint32_t eps[8];
         int gs = 0;
         for (;;)
         {
-            const uint32_t s = P.slots[j];
-            const float z = P.fragZ[s];
+            const unsigned long long v = P.vals[j];
+            const uint32_t s = (uint32_t)v;
+            const float z = __uint_as_float((uint32_t)(v >> 32));
             const uint32_t ep = P.fragEpoch ? (uint32_t)P.fragEpoch[s] : 0u;
             /* what this visit sees: the depth before the record, or the last earlier visit that passed and was flushed */
             float dSeen = dPre;
@@ -291,17 +294,34 @@ SLD_FN void sl_wire_walk_pixel(const SLWireShadeParams& P, unsigned long long t,
             }
             if (++j >= P.numFrags) { more = false; break; }
             const unsigned long long k = P.keys[j];
-            if ((k >> SL_WIRE_LOW_BITS) != pix) { more = false; break; }
-            if (((uint32_t)(k >> SL_WIRE_SUB_BITS) & ((1u << SL_WIRE_ORD_BITS) - 1u)) != ord) break;
+            if ((k >> P.lowBits) != pix) { more = false; break; }
+            if (((k >> SL_WIRE_SUB_BITS) & ordMask) != ord) break;
         }
     }
+}
+
+/* The pixels of the batch: positions in the sorted order whose predecessor belongs to another pixel, compacted so that
+ * the walking kernels run one pixel per lane (walking from every candidate and letting the non-first ones exit left 1.5
+ * of 32 lanes busy: profiles/r01h_k_wire_depth.txt).  One atomic per warp keeps the list close to sorted. */
+__global__ void __launch_bounds__(256) k_wire_leaders(const __grid_constant__ SLWireShadeParams P)
+{
+    const unsigned long long t = (unsigned long long)blockIdx.x * 256ull + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    bool leader = false;
+    if (t < P.numFrags) leader = t == 0ull || (P.keys[t - 1ull] >> P.lowBits) != (P.keys[t] >> P.lowBits);
+    const unsigned b = __ballot_sync(0xffffffffu, leader);
+    if (!b) return;
+    unsigned base = 0u;
+    if (lane == (unsigned)(__ffs(b) - 1)) base = atomicAdd(P.numLeaders, (unsigned)__popc(b));
+    base = __shfl_sync(0xffffffffu, base, __ffs(b) - 1);
+    if (leader) P.leaders[base + __popc(b & ((1u << lane) - 1u))] = (uint32_t)t;
 }
 
 /* depth-only simulation of the batch with the current epochs: pass flag per candidate; the attachment is not written */
 __global__ void __launch_bounds__(128) k_wire_depth(const __grid_constant__ SLWireShadeParams P)
 {
-    const unsigned long long t = (unsigned long long)blockIdx.x * 128ull + threadIdx.x;
-    if (t < P.numFrags) sl_wire_walk_pixel<false>(P, t, [](uint32_t, float, unsigned long long) {});
+    const unsigned long long i = (unsigned long long)blockIdx.x * 128ull + threadIdx.x;
+    if (i < (unsigned long long)*P.numLeaders) sl_wire_walk_pixel<false>(P, P.leaders[i], [](uint32_t, float, unsigned long long) {});
 }
 
 struct SLWireEpochParams
@@ -347,11 +367,11 @@ __global__ void __launch_bounds__(128) k_wire_epoch(const __grid_constant__ SLWi
 template <FsFn FS>
 __global__ void __launch_bounds__(128) k_wire_shade(const __grid_constant__ SLWireShadeParams P)
 {
-    const unsigned long long t = (unsigned long long)blockIdx.x * 128ull + threadIdx.x;
+    const unsigned long long li = (unsigned long long)blockIdx.x * 128ull + threadIdx.x;
     unsigned shaded = 0u;
-    if (t < P.numFrags)
+    if (li < (unsigned long long)*P.numLeaders)
     {
-        sl_wire_walk_pixel<true>(P, t, [&](uint32_t s, float z, unsigned long long pix) {
+        sl_wire_walk_pixel<true>(P, P.leaders[li], [&](uint32_t s, float z, unsigned long long pix) {
             const float4 b4 = P.fragBc[s];
             const uint32_t xy = P.fragXY[s];
             const uint32_t recId = P.fragRec[s];

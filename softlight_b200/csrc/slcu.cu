@@ -234,6 +234,7 @@ struct slcu_context
     Scratch records, blockInfo, cnt, off, segSums, rowTotals, rowStart, entries, handoff, rowFlags, rowNeeded, drawTable, blockDraw, recDraw;
     Scratch fragPool, chunkNext, listInfo; /* fragment lists, k_resolve -> k_shade */
     Scratch handoffRegs;
+    Scratch wireLeaders;
     Scratch wireSlots, wireRecInfo; /* wireframe: sort values (double buffer); first slot + candidate count per record */
     Scratch pointKeys, pointRecs, pointSortTemp; /* point primitives: sort keys (double buffer), records, radix-sort scratch */
     Scratch ticketOrder; /* skewed work order of k_resolve, cached per (rows, segments, skew) */
@@ -711,18 +712,20 @@ static int flush_draws_impl(slcu_context* c)
             if (!numFrags) return 0;
             if (numFrags > 0x7ffffff0ull) { c->err = "too many wireframe fragments for one batch"; return SLCU_ERR_UNSUPPORTED; }
             CK(c->pointKeys.ensure((size_t)numFrags * 2 * sizeof(unsigned long long)));
-            CK(c->wireSlots.ensure((size_t)numFrags * 2 * sizeof(uint32_t)));
+            CK(c->wireSlots.ensure((size_t)numFrags * 2 * sizeof(unsigned long long)));
             const unsigned long long bigRecords = c->hostCounters->rowEndCuts; /* records with 600+ candidates: their queue flushes are observable */
             CK(c->pointRecs.ensure((size_t)numFrags * (sizeof(float4) + 3 * sizeof(uint32_t) + sizeof(uint16_t) + 2)));
             CK(c->wireRecInfo.ensure((size_t)recCapacity * 2 * sizeof(uint32_t)));
             unsigned long long* keysA = reinterpret_cast<unsigned long long*>(c->pointKeys.buf.ptr);
-            uint32_t* slotsA = reinterpret_cast<uint32_t*>(c->wireSlots.buf.ptr);
+            unsigned long long* valsA = reinterpret_cast<unsigned long long*>(c->wireSlots.buf.ptr);
+            int ordBits = 13; /* segment (5) + index (8) + the bits of the vertex block */
+            while ((1u << (ordBits - 13)) < numBlocks) ++ordBits;
+            wp.lowBits = ordBits + SL_WIRE_SUB_BITS;
             wp.capacity = numFrags;
             wp.keys = keysA;
-            wp.slots = slotsA;
+            wp.vals = valsA;
             wp.fragBc = reinterpret_cast<float4*>(c->pointRecs.buf.ptr);
-            wp.fragZ = reinterpret_cast<float*>(wp.fragBc + numFrags);
-            wp.fragXY = reinterpret_cast<uint32_t*>(wp.fragZ + numFrags);
+            wp.fragXY = reinterpret_cast<uint32_t*>(wp.fragBc + numFrags);
             wp.fragRec = wp.fragXY + numFrags;
             uint16_t* fragEpoch = reinterpret_cast<uint16_t*>(wp.fragRec + numFrags);
             uint8_t* fragPass = reinterpret_cast<uint8_t*>(fragEpoch + numFrags);
@@ -735,25 +738,28 @@ static int flush_draws_impl(slcu_context* c)
             unsigned pixBits = 1;
             while ((1ull << pixBits) < (unsigned long long)depthTex.w * H) ++pixBits;
             cub::DoubleBuffer<unsigned long long> keys(keysA, keysA + numFrags);
-            cub::DoubleBuffer<uint32_t> slots(slotsA, slotsA + numFrags);
+            cub::DoubleBuffer<unsigned long long> slots(valsA, valsA + numFrags);
             size_t tempBytes = 0;
-            CK(cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, keys, slots, (int)numFrags, 0, SL_WIRE_LOW_BITS + (int)pixBits, c->stream));
+            CK(cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, keys, slots, (int)numFrags, 0, wp.lowBits + (int)pixBits, c->stream));
             CK(c->pointSortTemp.ensure(tempBytes));
-            { KernelScope ks(c, SLCU_K_SCAN); CK(cub::DeviceRadixSort::SortPairs(c->pointSortTemp.buf.ptr, tempBytes, keys, slots, (int)numFrags, 0, SL_WIRE_LOW_BITS + (int)pixBits, c->stream)); }
+            { KernelScope ks(c, SLCU_K_SCAN); CK(cub::DeviceRadixSort::SortPairs(c->pointSortTemp.buf.ptr, tempBytes, keys, slots, (int)numFrags, 0, wp.lowBits + (int)pixBits, c->stream)); }
 
             SLWireShadeParams ws;
             ws.draws = reinterpret_cast<const SLDrawDesc*>(c->drawTable.buf.ptr);
             ws.recDraw = reinterpret_cast<const uint16_t*>(c->recDraw.buf.ptr);
             ws.records = wp.records;
             ws.recStride = recStride;
+            ws.lowBits = wp.lowBits;
             ws.keys = keys.Current();
-            ws.slots = slots.Current();
+            ws.vals = slots.Current();
             ws.fragBc = wp.fragBc;
-            ws.fragZ = wp.fragZ;
             ws.fragXY = wp.fragXY;
             ws.fragRec = wp.fragRec;
             ws.fragEpoch = nullptr;
             ws.fragPass = fragPass;
+            CK(c->wireLeaders.ensure((size_t)numFrags * sizeof(uint32_t)));
+            ws.leaders = reinterpret_cast<uint32_t*>(c->wireLeaders.buf.ptr);
+            ws.numLeaders = &c->counters->chunkAlloc; /* a free per-batch word */
             ws.numFrags = numFrags;
             ws.numVaryings = NV;
             ws.numOutputs = sh.numOutputs;
@@ -769,7 +775,12 @@ static int flush_draws_impl(slcu_context* c)
                 if (k < sh.numOutputs) { const HostTexture& t = c->textures[fbo.colors[k]]; ws.color[k] = t.dev; ws.colorType[k] = t.type; }
             }
             ws.counters = c->counters;
-            const unsigned shadeGrid = (unsigned)((numFrags + 127ull) / 128ull);
+            CK(cudaMemsetAsync(ws.numLeaders, 0, sizeof(unsigned), c->stream));
+            { KernelScope ks(c, SLCU_K_SCAN); k_wire_leaders<<<(unsigned)((numFrags + 255ull) / 256ull), 256, 0, c->stream>>>(ws); }
+            CK(cudaGetLastError());
+            /* pixels touched <= min(candidates, texels): the walkers exit past the leader count */
+            const unsigned long long maxLeaders = numFrags < (unsigned long long)depthTex.w * H ? numFrags : (unsigned long long)depthTex.w * H;
+            const unsigned shadeGrid = (unsigned)((maxLeaders + 127ull) / 128ull);
             if (bigRecords && sh.depthTest != 0 && sh.depthMask)
             {
                 /* flush epochs of the big records: iterate depth outcomes <-> epochs to the fixed point (sl_wire.cuh) */
@@ -1121,7 +1132,7 @@ void slcu_context_destroy(slcu_context* c)
     if (c->counters) cudaFree(c->counters);
     if (c->hostCounters) cudaFreeHost(c->hostCounters);
     for (auto& pm : c->peerMaps) if (pm.ptr) cudaIpcCloseMemHandle(pm.ptr);
-    Scratch* s[] = {&c->records, &c->blockInfo, &c->cnt, &c->off, &c->segSums, &c->rowTotals, &c->rowStart, &c->entries, &c->handoff, &c->rowFlags, &c->rowNeeded, &c->drawTable, &c->blockDraw, &c->recDraw, &c->fragPool, &c->chunkNext, &c->listInfo, &c->handoffRegs, &c->ticketOrder, &c->pointKeys, &c->pointRecs, &c->pointSortTemp, &c->wireSlots, &c->wireRecInfo};
+    Scratch* s[] = {&c->records, &c->blockInfo, &c->cnt, &c->off, &c->segSums, &c->rowTotals, &c->rowStart, &c->entries, &c->handoff, &c->rowFlags, &c->rowNeeded, &c->drawTable, &c->blockDraw, &c->recDraw, &c->fragPool, &c->chunkNext, &c->listInfo, &c->handoffRegs, &c->ticketOrder, &c->pointKeys, &c->pointRecs, &c->pointSortTemp, &c->wireSlots, &c->wireRecInfo, &c->wireLeaders};
     for (Scratch* x : s) x->release();
     cudaStreamDestroy(c->stream);
     delete c;

@@ -37,12 +37,17 @@ def time_impl(impl, scene, frames, threads=None):
     return dt, st["fragsShaded"] // frames, prof
 
 
+NO_REF = "--no-ref" in sys.argv
+ONLY = sys.argv[sys.argv.index("--only") + 1].split(",") if "--only" in sys.argv else None
+FRAMES = int(os.environ.get("SLCU_PRIMS_FRAMES", "10"))
 for name, kw in CONFIGS.items():
+    if ONLY and name not in ONLY:
+        continue
     scene = S.random_tris_scene(seed=77, name=name, **kw)
     elems = kw["n"] * (3 if kw.get("points") else 1)
-    dt, frags, prof = time_impl("cuda", scene, 10)
+    dt, frags, prof = time_impl("cuda", scene, FRAMES)
     out = {"config": name, "elements": elems, "frags_per_frame": int(frags), "cuda_ms": round(dt * 1e3, 3), "cuda_Melem_s": round(elems / dt / 1e6, 1), "kernel_ms": prof}
-    if os.path.exists(A.LIB_PATHS["ref_fast"]):
+    if not NO_REF and os.path.exists(A.LIB_PATHS["ref_fast"]):
         cores = os.cpu_count() or 1
         rdt, rfrags, _ = time_impl("ref_fast", scene, 1, threads=cores)
         out.update({"ref_ms": round(rdt * 1e3, 1), "ref_threads": cores, "speedup": round(rdt / dt, 1)})
