@@ -10,7 +10,7 @@
  *   k_wire<EMIT=1>     writes one (key, payload) per candidate: key = linear pixel << lowBits | submission ordinal of
  *                      the record << 3 | visit order of that record on that pixel; sort value = depth | payload slot
  *   (radix sort of the keys)
- *   k_wire_leaders     compacts the positions where a pixel's candidates start
+ *   k_pixel_leaders    (sl_points.cuh) compacts the positions where a pixel's candidates start
  *   k_wire_shade<FS>   one thread per pixel walks that pixel's candidates in submission order: depth test,
  *                      SL_FragmentProcessor::flush_tri_fragments shading, colour / depth writes.
  *
@@ -28,6 +28,7 @@
 #pragma once
 
 #include "sl_pipeline.cuh"
+#include "sl_points.cuh" /* k_pixel_leaders */
 
 namespace sld
 {
@@ -236,7 +237,7 @@ struct SLWireShadeParams
     const float4* fragBc;
     const uint32_t* fragXY;
     const uint32_t* fragRec;
-    uint32_t* leaders;                /* k_wire_leaders out: positions in the sorted order where a pixel's candidates start */
+    uint32_t* leaders;                /* k_pixel_leaders out: positions in the sorted order where a pixel's candidates start */
     unsigned int* numLeaders;
     const uint16_t* fragEpoch;        /* flush epoch of every candidate (null: all 0) */
     uint8_t* fragPass;                /* k_wire_depth out: depth outcome of every candidate */
@@ -298,23 +299,6 @@ SLD_FN void sl_wire_walk_pixel(const SLWireShadeParams& P, unsigned long long t,
             if (((k >> SL_WIRE_SUB_BITS) & ordMask) != ord) break;
         }
     }
-}
-
-/* The pixels of the batch: positions in the sorted order whose predecessor belongs to another pixel, compacted so that
- * the walking kernels run one pixel per lane (walking from every candidate and letting the non-first ones exit left 1.5
- * of 32 lanes busy: profiles/r01h_k_wire_depth.txt).  One atomic per warp keeps the list close to sorted. */
-__global__ void __launch_bounds__(256) k_wire_leaders(const __grid_constant__ SLWireShadeParams P)
-{
-    const unsigned long long t = (unsigned long long)blockIdx.x * 256ull + threadIdx.x;
-    const unsigned lane = threadIdx.x & 31u;
-    bool leader = false;
-    if (t < P.numFrags) leader = t == 0ull || (P.keys[t - 1ull] >> P.lowBits) != (P.keys[t] >> P.lowBits);
-    const unsigned b = __ballot_sync(0xffffffffu, leader);
-    if (!b) return;
-    unsigned base = 0u;
-    if (lane == (unsigned)(__ffs(b) - 1)) base = atomicAdd(P.numLeaders, (unsigned)__popc(b));
-    base = __shfl_sync(0xffffffffu, base, __ffs(b) - 1);
-    if (leader) P.leaders[base + __popc(b & ((1u << lane) - 1u))] = (uint32_t)t;
 }
 
 /* depth-only simulation of the batch with the current epochs: pass flag per candidate; the attachment is not written */

@@ -234,7 +234,7 @@ struct slcu_context
     Scratch records, blockInfo, cnt, off, segSums, rowTotals, rowStart, entries, handoff, rowFlags, rowNeeded, drawTable, blockDraw, recDraw;
     Scratch fragPool, chunkNext, listInfo; /* fragment lists, k_resolve -> k_shade */
     Scratch handoffRegs;
-    Scratch wireLeaders;
+    Scratch wireLeaders; /* wireframe: positions where a pixel's sorted candidates start */
     Scratch wireSlots, wireRecInfo; /* wireframe: sort values (double buffer); first slot + candidate count per record */
     Scratch pointKeys, pointRecs, pointSortTemp; /* point primitives: sort keys (double buffer), records, radix-sort scratch */
     Scratch ticketOrder; /* skewed work order of k_resolve, cached per (rows, segments, skew) */
@@ -776,7 +776,16 @@ static int flush_draws_impl(slcu_context* c)
             }
             ws.counters = c->counters;
             CK(cudaMemsetAsync(ws.numLeaders, 0, sizeof(unsigned), c->stream));
-            { KernelScope ks(c, SLCU_K_SCAN); k_wire_leaders<<<(unsigned)((numFrags + 255ull) / 256ull), 256, 0, c->stream>>>(ws); }
+            {
+                SLLeaderParams lp;
+                lp.keys = ws.keys;
+                lp.n = numFrags;
+                lp.shift = ws.lowBits;
+                lp.leaders = ws.leaders;
+                lp.numLeaders = ws.numLeaders;
+                KernelScope ks(c, SLCU_K_SCAN);
+                k_pixel_leaders<<<(unsigned)((numFrags + 255ull) / 256ull), 256, 0, c->stream>>>(lp);
+            }
             CK(cudaGetLastError());
             /* pixels touched <= min(candidates, texels): the walkers exit past the leader count */
             const unsigned long long maxLeaders = numFrags < (unsigned long long)depthTex.w * H ? numFrags : (unsigned long long)depthTex.w * H;
