@@ -119,6 +119,7 @@ WIRE_CASES = {
     "wire_1080p": dict(n=200, width=1920, height=1080, clip_fraction=0.2),
     "wire_tiny_1x1": dict(n=50, width=1, height=1),
     "wire_empty": dict(n=30, empty_draw=True),
+    "wire_instanced3_alpha": dict(n=200, instances=3, blend=1, depth_test=A.SL_DEPTH_TEST_LESS_EQUAL),
 }
 for _i, _name in enumerate(WIRE_CASES):
     CASES[_name] = (lambda i=_i, name=_name: S.random_tris_scene(seed=950 + i, name=name, wire=True, **WIRE_CASES[name]))
