@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256) k_point_vertex(const __grid_constant__ SL
 
 /* The pixels of a sorted key array: positions whose predecessor belongs to another pixel, compacted so that the walking
  * kernels run one pixel per lane (walking from every key and letting the non-first ones exit left 1.5 of 32 lanes busy
- * on the wireframe path: profiles/r01h_k_wire_depth.txt).  One atomic per warp keeps the list close to sorted. */
+ * on the wireframe path: profiles/r01h_k_wire_depth_before_compaction.txt).  One atomic per block keeps the list close to sorted. */
 struct SLLeaderParams
 {
     const unsigned long long* keys;
@@ -117,16 +117,24 @@ struct SLLeaderParams
 
 __global__ void __launch_bounds__(256) k_pixel_leaders(const __grid_constant__ SLLeaderParams P)
 {
+    __shared__ unsigned sWarp[8];
+    __shared__ unsigned sBase;
     const unsigned long long t = (unsigned long long)blockIdx.x * 256ull + threadIdx.x;
-    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     bool leader = false;
     if (t < P.n) leader = t == 0ull || (P.keys[t - 1ull] >> P.shift) != (P.keys[t] >> P.shift);
     const unsigned b = __ballot_sync(0xffffffffu, leader);
-    if (!b) return;
-    unsigned base = 0u;
-    if (lane == (unsigned)(__ffs(b) - 1)) base = atomicAdd(P.numLeaders, (unsigned)__popc(b));
-    base = __shfl_sync(0xffffffffu, base, __ffs(b) - 1);
-    if (leader) P.leaders[base + __popc(b & ((1u << lane) - 1u))] = (uint32_t)t;
+    if (lane == 0u) sWarp[warp] = (unsigned)__popc(b);
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        /* one atomic per block (one per warp was 0.7 ms of serialised atomics for 8.6 M keys) */
+        unsigned tot = 0u;
+        for (int w = 0; w < 8; ++w) { const unsigned c = sWarp[w]; sWarp[w] = tot; tot += c; }
+        sBase = tot ? atomicAdd(P.numLeaders, tot) : 0u;
+    }
+    __syncthreads();
+    if (leader) P.leaders[sBase + sWarp[warp] + __popc(b & ((1u << lane) - 1u))] = (uint32_t)t;
 }
 
 struct SLPointShadeParams
