@@ -71,8 +71,8 @@ typedef struct slcu_mesh
 /* SL_VertexShader / SL_FragmentShader (SL_Shader.hpp:58-63, 88-97).  The
  * reference stores a raw C function pointer; the device cannot call it, so the
  * `shader` member is the registry name of the __device__ callable that was
- * registered for that function (SL_REGISTER_VERTEX_SHADER / _FRAGMENT_SHADER in
- * softlight_b200/csrc/shader_registry.cuh).  An unknown name makes
+ * registered for that function (SL_REGISTER_VERTEX_SHADER / _FRAGMENT_SHADER,
+ * softlight_b200/csrc/slcu.cu).  An unknown name makes
  * create_shader return SLCU_INVALID_ID, like the reference's validation
  * failures (softlight/src/SL_Context.cpp:488-540). */
 typedef struct slcu_vertex_shader
@@ -116,7 +116,7 @@ SLCU_EXPORT const char* SLCU_FN(impl_name)(void);
 
 /* rcpss/rcpps table.  2048 entries: the 11 low-zero-padded
  * 12-bit result mantissas (bits 22..11 of the result, as result_bits >> 11 of
- * the [1,2) input binade... see softlight_b200/csrc/x86emu.cuh).  By default
+ * the [1,2) input binade... see softlight_b200/csrc/sl_x86emu.cuh).  By default
  * the table is measured from the host CPU at context_create so results match
  * the reference running on the same box; tests pin it to the committed one. */
 SLCU_EXPORT int SLCU_FN(set_rcp_table)(slcu_context* ctx, const uint32_t* table2048);

@@ -7,7 +7,7 @@
  * file:line it follows.  It exists so that the CUDA product can be checked on
  * a box where /root/reference is absent, and so that the algorithm is written
  * down once without SIMD.  It is pinned against the compiled reference itself
- * (oracle/_ref/libslref_strict.so; tests/test_oracle_vs_ref.py) and against the
+ * (oracle/_ref/libslref_strict.so; tests/test_oracle_cpu.py) and against the
  * committed golden frames (tests/golden/).
  *
  * Only tests/, bench.py's cpu_baseline leg and __graft_entry__.smoke() may load
@@ -74,11 +74,15 @@ struct IndexBuffer
     std::vector<unsigned char> data;
 };
 
+/* the SL_TextureView snapshot SL_Framebuffer keeps per attachment (src/SL_Framebuffer.cpp:855-920) */
+struct FboView { bool texels = false; uint16_t w = 0, h = 0, d = 0; int type = 0; };
 struct Framebuffer
 {
     unsigned numColors = 0;
     size_t colors[4] = {(size_t)-1, (size_t)-1, (size_t)-1, (size_t)-1};
     size_t depth = (size_t)-1;
+    FboView colorViews[4];
+    FboView depthView;
 };
 
 struct Shader
@@ -1182,19 +1186,40 @@ int slor_fbo_reserve_color_buffers(slcu_context* c, size_t fbo, unsigned n)
     f.numColors = n;
     return 0;
 }
+static FboView make_view(const SL_Texture& t) { return FboView{t.mTexels != nullptr, t.mWidth, t.mHeight, t.mDepth, t.mType}; }
 int slor_fbo_attach_color_buffer(slcu_context* c, size_t fbo, unsigned i, size_t tex)
 {
     if (i >= c->fbos[fbo].numColors) return -1;
     c->fbos[fbo].colors[i] = tex;
+    c->fbos[fbo].colorViews[i] = make_view(*c->textures[tex]);
     return 0;
 }
-int slor_fbo_attach_depth_buffer(slcu_context* c, size_t fbo, size_t tex) { c->fbos[fbo].depth = tex; return 0; }
+int slor_fbo_attach_depth_buffer(slcu_context* c, size_t fbo, size_t tex)
+{
+    c->fbos[fbo].depth = tex;
+    c->fbos[fbo].depthView = make_view(*c->textures[tex]);
+    return 0;
+}
+/* SL_Framebuffer::valid (src/SL_Framebuffer.cpp:928-990): same checks, same order, same codes */
 int slor_fbo_valid(slcu_context* c, size_t fbo)
 {
     const Framebuffer& f = c->fbos[fbo];
     if (!f.numColors) return -1;
-    if (f.depth == (size_t)-1) return -6;
-    for (unsigned i = 0; i < f.numColors; ++i) if (f.colors[i] == (size_t)-1) return -3;
+    const FboView& c0 = f.colorViews[0];
+    for (unsigned i = 0; i < f.numColors; ++i)
+    {
+        const FboView& v = f.colorViews[i];
+        if (!v.texels) return -2;
+        if (v.w != c0.w) return -3;
+        if (v.h != c0.h) return -4;
+        if (v.d != c0.d) return -5;
+    }
+    const FboView& d = f.depthView;
+    if (!d.texels) return -6;
+    if (d.w != c0.w) return -7;
+    if (d.h != c0.h) return -8;
+    if (d.d > 1) return -9;
+    if (d.type != 4 && d.type != 5 && d.type != 6) return -10;
     return 0;
 }
 

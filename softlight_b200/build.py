@@ -37,12 +37,13 @@ def cuda_sources():
     return srcs
 
 
-def build_cuda(force: bool = False, verbose: bool = False) -> str:
+def build_cuda(force: bool = False, verbose: bool = False, out: str = LIB) -> str:
+    """`out` other than LIB: an A/B variant (SLCU_NVCC_EXTRA flags), selected at run time with SLCU_LIB=<path>."""
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    if not force and _newer(LIB, cuda_sources()):
-        return LIB
+    if not force and _newer(out, cuda_sources()):
+        return out
     cmd = [nvcc] + NVCC_FLAGS + ["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "shaders"), "-I" + CSRC,
-                                 os.path.join(CSRC, "slcu.cu"), "-o", LIB]
+                                 os.path.join(CSRC, "slcu.cu"), "-o", out]
     cmd[1:1] = os.environ.get("SLCU_NVCC_EXTRA", "").split()  # tuning experiments only (e.g. -DSL_RASTER_MIN_BLOCKS=4)
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
@@ -52,7 +53,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed")
     if verbose:
         sys.stderr.write(r.stderr)
-    return LIB
+    return out
 
 
 def build_oracle() -> None:
@@ -69,6 +70,11 @@ def build_oracle() -> None:
 
 
 if __name__ == "__main__":
-    build_cuda(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    _out = LIB
+    for _a in sys.argv[1:]:
+        if _a.startswith("--out="):
+            _out = os.path.abspath(_a[6:])
+            os.makedirs(os.path.dirname(_out), exist_ok=True)
+    build_cuda(force="--force" in sys.argv, verbose="-v" in sys.argv, out=_out)
     build_oracle()
-    print("built", LIB)
+    print("built", _out)

@@ -1459,7 +1459,10 @@ SLD_FN math::vec4 sl_pick4(uint32_t s, const math::vec4& a0, const math::vec4& a
     return s == 0u ? a0 : (s == 1u ? a1 : (s == 2u ? a2 : a3));
 }
 
-constexpr int SL_RASTER_WARPS = 4;
+#ifndef SL_RASTER_WARPS_N
+#define SL_RASTER_WARPS_N 4
+#endif
+constexpr int SL_RASTER_WARPS = SL_RASTER_WARPS_N;
 #ifndef SL_RASTER_MIN_BLOCKS
 #define SL_RASTER_MIN_BLOCKS 4
 #endif

@@ -1,0 +1,517 @@
+/*
+ * sl_resolve2.cuh -- k_resolve2: the depth / coverage / order stage with ONE LANE PER SPAN PIECE.
+ *
+ * Same contract as k_resolve (sl_pipeline.cuh): SL_TriRasterizer::render_triangle_simd (src/SL_TriRasterizer.cpp:413-559)
+ * + the depth write of flush_tri_fragments (src/SL_FragmentProcessor.cpp:526-529); input = the ordered per-row span
+ * lists, output = ordered fragment lists in HBM, hand-overs between x-segments and rows through the same table.
+ *
+ * k_resolve spreads the 4-pixel groups of consecutive pieces over the lanes of a window and settles the window in waves;
+ * every lane pays the whole book-keeping for one group.  For scenes made of short spans (a few groups per span: every
+ * triangle-dense config) that overhead is ~13x the arithmetic.  Here a lane owns a piece (a span clipped to the
+ * warp's x-segment) and walks its groups left to right exactly like the reference's loop does: the barycentric
+ * registers are advanced by real additions (:539-542) and compacted in place (:496-498), so there is no lane map, no
+ * replay and no per-group set-up.  What remains to be coordinated between lanes is the submission order per pixel:
+ *
+ *   - pieces are handed to free lanes in list order; every lane knows which lanes hold EARLIER pieces (a bit mask kept
+ *     up to date at hand-out time);
+ *   - a piece marks all its pixels in a per-pixel lane mask in shared memory when it starts and clears a pixel's mark
+ *     when it has resolved it; a lane may work on its next SL_R2_GROUPS groups only when no earlier lane still has a mark
+ *     on one of those pixels.  The earliest unfinished piece never waits, lanes that run in the same round touch disjoint
+ *     pixels, and a later piece follows an earlier one as closely as one round behind.
+ *
+ * The depth texels of the segment live in shared memory for the whole ticket: staged in with one bulk copy
+ * (cp.async.bulk + mbarrier, the TMA engine's 1-D path) and written back with one bulk store.
+ * Fragments go straight into the HBM chunks of their (row, 128-pixel column) list: positions come from shared-memory
+ * atomics, chunks are reserved once per round for the pixels about to be resolved.
+ */
+#pragma once
+
+#include "sl_pipeline.cuh"
+
+namespace sld
+{
+
+#ifndef SL_R2_GROUPS
+#define SL_R2_GROUPS 2 /* groups a lane resolves per round */
+#endif
+#ifndef SL_R2_WARPS_N
+#define SL_R2_WARPS_N 4
+#endif
+#ifndef SL_R2_MIN_BLOCKS
+#define SL_R2_MIN_BLOCKS 4
+#endif
+constexpr int SL_R2_WARPS = SL_R2_WARPS_N;
+constexpr int SL_R2_RING = 64;       /* pieces waiting for a lane (per warp) */
+constexpr int SL_R2_CHUNK_RING = 32; /* newest chunk ids remembered per sub-list */
+constexpr unsigned SL_R2_RCP_BYTES = 2048u * 4u; /* per block: the rcp table */
+constexpr unsigned SL_R2_RING_BYTES = SL_R2_RING * (unsigned)sizeof(SLSpanEntry);
+constexpr unsigned SL_R2_SUB_BYTES = SL_MAX_SUBLISTS * 4u * 4u + SL_MAX_SUBLISTS * SL_R2_CHUNK_RING * 4u; /* count, chunks, want, last chunk + id ring */
+constexpr unsigned SL_R2_FIXED_BYTES = SL_R2_RING_BYTES + SL_R2_SUB_BYTES + 16u; /* + the tile's mbarrier */
+
+__host__ __device__ inline unsigned sl_r2_warp_bytes(unsigned segWidth, unsigned tileBytes) { return SL_R2_FIXED_BYTES + ((4u * segWidth + 15u) & ~15u) + tileBytes; }
+
+/* ---- 1-D bulk copies through the TMA engine (cp.async.bulk) ---- */
+SLD_FN uint32_t sl_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+SLD_FN void sl_mbar_init(void* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sl_smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+SLD_FN void sl_bulk_load(void* dstSmem, const void* srcGlobal, unsigned bytes, void* bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sl_smem_addr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sl_smem_addr(dstSmem)), "l"(srcGlobal), "r"(bytes),
+                 "r"(sl_smem_addr(bar))
+                 : "memory");
+}
+SLD_FN void sl_mbar_wait(void* bar, unsigned phase)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(sl_smem_addr(bar)),
+        "r"(phase)
+        : "memory");
+}
+SLD_FN void sl_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+SLD_FN void sl_bulk_store(void* dstGlobal, const void* srcSmem, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dstGlobal), "r"(sl_smem_addr(srcSmem)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+SLD_FN void sl_bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+/* depth of one barycentric register (_sl_mul_vec4_mat4_ps, src/SL_TriRasterizer.cpp:376-393) */
+SLD_FN float sl_zdot(const math::vec4& a, float z0, float z1, float z2) { return ((a.v[3] * 0.f) + (a.v[2] * z2)) + ((a.v[1] * z1) + (a.v[0] * z0)); }
+
+__global__ void __launch_bounds__(SL_R2_WARPS * 32, SL_R2_MIN_BLOCKS) k_resolve2(const __grid_constant__ SLRasterParams P)
+{
+    extern __shared__ __align__(16) unsigned char sDyn[];
+    uint32_t* sRcp = reinterpret_cast<uint32_t*>(sDyn);
+    for (unsigned i = threadIdx.x; i < 2048u; i += blockDim.x) sRcp[i] = g_rcp_table[i];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t ltMask = (1u << lane) - 1u, myBit = 1u << lane;
+    const int W = (int)P.width, NS = (int)P.numSegs;
+    const bool chained = P.depthTest != 0;
+    const bool useDepth = P.depthTest != 0 || P.depthMask != 0;
+    const int nsub = (int)P.numSubLists;
+
+    unsigned char* warpMem = sDyn + SL_R2_RCP_BYTES + (size_t)warp * sl_r2_warp_bytes(P.segWidth, P.tileBytes);
+    SLSpanEntry* ring = reinterpret_cast<SLSpanEntry*>(warpMem);
+    uint32_t* subCount = reinterpret_cast<uint32_t*>(warpMem + SL_R2_RING_BYTES); /* fragments in the sub-list so far  */
+    uint32_t* subChunks = subCount + SL_MAX_SUBLISTS;                              /* chunks it owns                    */
+    uint32_t* subWant = subChunks + SL_MAX_SUBLISTS;                               /* pixels about to be resolved       */
+    uint32_t* subLast = subWant + SL_MAX_SUBLISTS;                                 /* its newest chunk                  */
+    uint32_t* chunkRing = subLast + SL_MAX_SUBLISTS;                               /* [sub][SL_R2_CHUNK_RING] chunk ids */
+    unsigned long long* tileBar = reinterpret_cast<unsigned long long*>(warpMem + SL_R2_RING_BYTES + SL_R2_SUB_BYTES);
+    uint32_t* pixMask = reinterpret_cast<uint32_t*>(warpMem + SL_R2_FIXED_BYTES); /* [segWidth] lanes whose piece still has to resolve the pixel */
+    unsigned char* tile = warpMem + SL_R2_FIXED_BYTES + ((4u * P.segWidth + 15u) & ~15u);
+    if (lane == 0) sl_mbar_init(tileBar, 1u);
+    unsigned tilePhase = 0u;
+    __syncthreads();
+
+    unsigned long long dbgRounds = 0, dbgIdle = 0, dbgGroups = 0;
+    const long long dbgT0 = P.diagnostics ? clock64() : 0ll;
+    unsigned shaded = 0;
+    const unsigned numTickets = P.numRows * P.numSegs;
+
+    /* persistent warps: (row, segment) tickets in launch order; a consumer of a hand-over only ever waits for a smaller
+     * ticket, which a running warp holds */
+    for (;;)
+    {
+        unsigned ticket = 0;
+        if (lane == 0) ticket = atomicAdd(&P.counters->rasterTicket, 1u);
+        ticket = __shfl_sync(0xffffffffu, ticket, 0);
+        if (ticket >= numTickets) break;
+        int y = (int)(ticket / (unsigned)NS), seg = (int)(ticket % (unsigned)NS);
+        if (P.ticketOrder)
+        {
+            const uint32_t o = P.ticketOrder[ticket];
+            y = (int)(o >> 6);
+            seg = (int)(o & 63u);
+        }
+        if (P.rowNeeded && !P.rowNeeded[y]) continue;
+        const uint32_t begin = P.rowStart[y], end = P.rowStart[y + 1];
+        if (begin == end) continue;
+        const int sx0 = seg * (int)P.segWidth;
+        const int sx1 = (seg == NS - 1) ? W : sx0 + (int)P.segWidth;
+        const unsigned segPixels = (unsigned)(sx1 - sx0);
+        const long long segOrigin = (long long)W * y + sx0;
+        const uint32_t firstList = (uint32_t)(y * NS + seg) * P.numSubLists;
+        const unsigned tileLoadBytes = segPixels * (unsigned)P.depthBpt;
+        unsigned char* tileSrc = P.depth + (size_t)segOrigin * P.depthBpt;
+        const bool bulkOk = (tileLoadBytes & 15u) == 0u && (reinterpret_cast<uintptr_t>(tileSrc) & 15u) == 0u;
+
+        if (lane < SL_MAX_SUBLISTS)
+        {
+            subCount[lane] = 0u;
+            subChunks[lane] = 0u;
+            subWant[lane] = 0u;
+            subLast[lane] = SL_NO_CHUNK;
+        }
+        bool staged = false, tileReady = false, dirty = false;
+
+        /* lane state: the piece this lane walks */
+        bool busy = false, ready = false, publish = false;
+        uint32_t earlier = 0u, recId = 0u, fM = 0u;
+        int xMin = 0, p0 = 0, p1 = 0, g = 0, gEnd = 0, xBase = 0, ySrc = 0, bOut = 0;
+        math::vec4 a0{0.f}, a1{0.f}, a2{0.f}, a3{0.f}, bcX{0.f};
+        float z0 = 0.f, z1 = 0.f, z2 = 0.f;
+
+        uint32_t base = begin;
+        unsigned ringHead = 0u, ringCount = 0u, idle = 0u;
+        for (;;)
+        {
+            const uint32_t busyMask = __ballot_sync(0xffffffffu, busy);
+            /* ---- keep the ring of waiting pieces filled: the row's entries that reach into this segment, in list order ---- */
+            while (ringCount <= (unsigned)(SL_R2_RING - 32) && base < end)
+            {
+                const uint32_t idx = base + (uint32_t)lane;
+                SLSpanEntry c = SLSpanEntry{0u, 0, 0};
+                if (idx < end) c = P.entries[idx];
+                const int cb = (c.rec & SL_ENTRY_OVERFLOW) ? W : 0;
+                const bool cHas = max((int)c.xMin, cb + sx0) < min((int)c.xMax, cb + sx1); /* empty entries: 0 < 0 */
+                const uint32_t hm = __ballot_sync(0xffffffffu, cHas);
+                if (cHas)
+                {
+                    ring[(ringHead + ringCount + (unsigned)__popc(hm & ltMask)) & (SL_R2_RING - 1)] = c;
+                    const float4* r = P.records + (size_t)(c.rec & ~SL_ENTRY_OVERFLOW) * P.recStride;
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(r));
+                }
+                ringCount += (unsigned)__popc(hm);
+                base += 32u;
+            }
+            if (!busyMask && !ringCount) break;
+            __syncwarp();
+
+            /* ---- hand the waiting pieces to the free lanes, in order ---- */
+            const unsigned myk = (unsigned)__popc(~busyMask & ltMask);
+            const bool take = !busy && myk < ringCount;
+            const uint32_t newMask = __ballot_sync(0xffffffffu, take);
+            if (newMask)
+            {
+                if (useDepth && !staged)
+                {
+                    /* the first piece of this segment: bring its depth texels in (one bulk copy, overlapped with the set-up) */
+                    staged = true;
+                    if (bulkOk)
+                    {
+                        if (lane == 0)
+                        {
+                            sl_fence_async_smem();
+                            sl_bulk_load(tile, tileSrc, tileLoadBytes, tileBar);
+                        }
+                    }
+                    else
+                    {
+                        sl_copy_warp(tile, tileSrc, tileLoadBytes, lane);
+                        tileReady = true;
+                    }
+                    for (unsigned i = lane; i < segPixels; i += 32) pixMask[i] = 0u;
+                    __syncwarp();
+                }
+                if (take)
+                {
+                    const SLSpanEntry e = ring[(ringHead + myk) & (SL_R2_RING - 1)];
+                    const bool isOver = (e.rec & SL_ENTRY_OVERFLOW) != 0u;
+                    recId = e.rec & ~SL_ENTRY_OVERFLOW;
+                    xBase = isOver ? W : 0; /* the entry's x coordinates are those of its source row */
+                    ySrc = isOver ? y - 1 : y;
+                    xMin = e.xMin;
+                    const int xMax = e.xMax;
+                    p0 = max(xMin, xBase + sx0);
+                    p1 = min(xMax, xBase + sx1);
+                    const bool needsIn = xMin < p0 && chained;
+                    publish = chained && xMax > p1 && (seg < NS - 1 || (!isOver && y + 1 < (int)P.numRows));
+                    bOut = (isOver ? NS : 0) + seg + 1;
+                    g = (p0 - xMin) >> 2;
+                    gEnd = ((p1 - 1 - xMin) >> 2) + 1;
+                    busy = true;
+                    earlier = busyMask | (newMask & ltMask);
+
+                    /* triangle set-up (push_bin, src/SL_TriProcessor.cpp:271-314), once per piece */
+                    const float4* rec = P.records + (size_t)recId * P.recStride;
+                    const float4 q0 = rec[0], q1 = rec[1], q2 = rec[2];
+                    const float xy0 = q0.x - q1.x, xy1 = q0.y - q1.y;
+                    const float zy0 = q2.x - q1.x, zy1 = q2.y - q1.y;
+                    const float denom = sl_rcp_tab(sRcp, (zy0 * xy1) - (zy1 * xy0));
+                    const math::vec4 ptX{q0.x, q1.x, q2.x, 0.f};
+                    const math::vec4 ptY{q0.y, q1.y, q2.y, 0.f};
+                    const math::vec4 one{1.f};
+                    const math::vec4 bc0 = math::cross(ptY, one) * denom;
+                    z0 = q0.z; z1 = q1.z; z2 = q2.z;
+                    bcX = bc0 * 4.f;
+                    fM = 0u;
+                    if (!needsIn)
+                    {
+                        const math::vec4 bc1 = math::cross(one, ptX) * denom;
+                        const math::vec4 bc2 = math::cross(ptX, ptY) * denom;
+                        const math::vec4 bcY = math::fmadd(bc1, math::vec4{(float)ySrc}, bc2); /* src/SL_TriRasterizer.cpp:474 */
+                        a0 = (bc0 * (float)(xMin + 0)) + bcY;                                  /* :476-481 */
+                        a1 = (bc0 * (float)(xMin + 1)) + bcY;
+                        a2 = (bc0 * (float)(xMin + 2)) + bcY;
+                        a3 = (bc0 * (float)(xMin + 3)) + bcY;
+                        /* depth test off and the piece starts inside its span: the lanes left of the cut passed and the
+                         * registers were never compacted -- replay the additions from the span start (:539-542) */
+                        for (int i = 0; i < g; ++i) { a0 += bcX; a1 += bcX; a2 += bcX; a3 += bcX; }
+                        if (xMin < p0) fM = ((1u << (p0 - (xMin + 4 * g))) - 1u) & 7u;
+                        ready = true;
+                    }
+                    else ready = false; /* continues a span of the segment on the left (or of the row below): needs its hand-over */
+                    if (useDepth)
+                    {
+                        const int m0 = p0 - xBase - sx0, m1 = p1 - xBase - sx0;
+                        for (int px = m0; px < m1; ++px) atomicOr(&pixMask[px], myBit);
+                    }
+                }
+                else earlier &= ~newMask; /* those lanes now hold later pieces */
+                const unsigned nTaken = (unsigned)__popc(newMask);
+                ringHead += nTaken;
+                ringCount -= nTaken;
+                __syncwarp();
+            }
+
+            /* ---- which lanes may resolve their next groups ---- */
+            bool go = false;
+            int cx = 0, ce = 0;
+            if (busy)
+            {
+                if (!ready)
+                {
+                    SLHand h;
+                    if (sl_handoff_poll(P, recId, ySrc, bOut - 1, h))
+                    {
+                        a0 = h.r[0]; a1 = h.r[1]; a2 = h.r[2]; a3 = h.r[3];
+                        fM = h.fM;
+                        ready = true;
+                    }
+                }
+                if (ready)
+                {
+                    cx = max(p0, xMin + 4 * g) - xBase - sx0;
+                    ce = min(p1, xMin + 4 * (g + SL_R2_GROUPS)) - xBase - sx0;
+                    uint32_t ov = 0u;
+                    if (useDepth)
+                    {
+                        for (int px = cx; px < ce; ++px) ov |= pixMask[px];
+                    }
+                    go = (ov & earlier) == 0u;
+                }
+            }
+            const uint32_t goMask = __ballot_sync(0xffffffffu, go);
+            if (!goMask)
+            {
+                /* everything that could run waits for a hand-over: back off so that the polling does not take issue slots
+                 * from the warps that produce it */
+                idle = min(idle + 1u, 4u);
+                __nanosleep(20u << idle);
+                ++dbgIdle;
+                continue;
+            }
+            idle = 0u;
+            ++dbgRounds;
+            if (go)
+            {
+                const int sA = cx >> SL_SHADE_SHIFT, sB = (ce - 1) >> SL_SHADE_SHIFT;
+                if (sA == sB) atomicAdd(&subWant[sA], (uint32_t)(ce - cx));
+                else
+                {
+                    const int split = sB << SL_SHADE_SHIFT;
+                    atomicAdd(&subWant[sA], (uint32_t)(split - cx));
+                    atomicAdd(&subWant[sB], (uint32_t)(ce - split));
+                }
+            }
+            __syncwarp();
+            /* ---- chunks for the pixels of this round: lane s looks after sub-list s ---- */
+            if (lane < nsub)
+            {
+                const uint32_t want = subWant[lane];
+                if (want)
+                {
+                    subWant[lane] = 0u;
+                    const uint32_t have = subChunks[lane];
+                    const uint32_t needTotal = (subCount[lane] + want + 31u) >> 5;
+                    if (needTotal > have)
+                    {
+                        const uint32_t need = needTotal - have;
+                        uint32_t b = atomicAdd(&P.counters->chunkAlloc, need);
+                        if (b + need > P.lists.chunkCapacity)
+                        {
+                            atomicOr(&P.counters->errorFlags, 32u); /* pool exhausted: flagged, fragments dropped */
+                            for (uint32_t i = 0; i < need; ++i) chunkRing[lane * SL_R2_CHUNK_RING + ((have + i) & (SL_R2_CHUNK_RING - 1))] = SL_NO_CHUNK;
+                        }
+                        else
+                        {
+                            const uint32_t prev = subLast[lane];
+                            if (prev == SL_NO_CHUNK) P.lists.listHead[firstList + lane] = b;
+                            else P.lists.chunkNext[prev] = b;
+                            for (uint32_t i = 0; i < need; ++i)
+                            {
+                                chunkRing[lane * SL_R2_CHUNK_RING + ((have + i) & (SL_R2_CHUNK_RING - 1))] = b + i;
+                                if (i + 1u < need) P.lists.chunkNext[b + i] = b + i + 1u;
+                            }
+                            subLast[lane] = b + need - 1u;
+                        }
+                        subChunks[lane] = needTotal;
+                    }
+                }
+            }
+            if (staged && !tileReady)
+            {
+                sl_mbar_wait(tileBar, tilePhase);
+                tilePhase ^= 1u;
+                tileReady = true;
+            }
+            __syncwarp();
+
+            /* ---- resolve: up to SL_R2_GROUPS groups per lane, the reference's loop body (src/SL_TriRasterizer.cpp:483-548) ---- */
+            const int nIt = (int)__reduce_max_sync(0xffffffffu, go ? (unsigned)min(SL_R2_GROUPS, gEnd - g) : 0u);
+            for (int it = 0; it < nIt; ++it)
+            {
+                if (go && g < gEnd)
+                {
+                    ++dbgGroups;
+                    const int x4 = xMin + 4 * g;
+                    const int rel = x4 - xBase - sx0; /* segment-relative x of the group's first pixel */
+                    const bool last = g == gEnd - 1;
+                    const float zc0 = sl_zdot(a0, z0, z1, z2), zc1 = sl_zdot(a1, z0, z1, z2), zc2 = sl_zdot(a2, z0, z1, z2), zc3 = sl_zdot(a3, z0, z1, z2);
+                    const float zc[4] = {zc0, zc1, zc2, zc3};
+                    uint32_t own = 0u, m = 0u;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                    {
+                        if (x4 + j >= p0 && x4 + j < p1)
+                        {
+                            own |= 1u << j;
+                            const float d = P.depthTest ? sl_load_depth(tile, P.depthBpt, (size_t)(rel + j)) : 0.f;
+                            if (sl_depth_cmp(P.depthTest, zc[j], d)) m |= 1u << j;
+                        }
+                    }
+                    const uint32_t tt = m | fM;
+                    fM = 0u;
+                    const bool cutInside = last && publish && ((p1 - xMin) >> 2) == g;
+                    if (cutInside)
+                    {
+                        /* the cut lies inside this group: the registers before its compaction + the outcomes left of the cut */
+                        const uint32_t below = (1u << (p1 - x4)) - 1u;
+                        sl_handoff_publish(P, recId, ySrc, bOut, tt & below & 7u, a0, a1, a2, a3);
+                    }
+                    if (tt)
+                    {
+                        /* in-place compaction (:496-498) */
+                        const math::vec4 n2 = (tt & 4u) ? a2 : a3;
+                        const math::vec4 n1 = (tt & 2u) ? a1 : n2;
+                        const math::vec4 n0 = (tt & 1u) ? a0 : n1;
+                        if (m)
+                        {
+                            shaded += (unsigned)__popc(m);
+                            /* positions in the fragment lists: a group's pixels fall into at most two sub-lists */
+                            const int sFirst = rel >> SL_SHADE_SHIFT, sLast = (rel + 3) >> SL_SHADE_SHIFT;
+                            const int jSplit = sLast != sFirst ? (((sFirst + 1) << SL_SHADE_SHIFT) - rel) : 4;
+                            const uint32_t loBits = m & ((1u << jSplit) - 1u), hiBits = m & ~((1u << jSplit) - 1u);
+                            uint32_t posLo = 0u, posHi = 0u;
+                            if (loBits) posLo = atomicAdd(&subCount[sFirst], (uint32_t)__popc(loBits));
+                            if (hiBits) posHi = atomicAdd(&subCount[sLast], (uint32_t)__popc(hiBits));
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                            {
+                                if ((m >> j) & 1u)
+                                {
+                                    /* survivor number s of the group is shaded with register s after the compaction (:500-526),
+                                     * and with its own x and z */
+                                    const uint32_t sIdx = (uint32_t)__popc(tt & ((1u << j) - 1u));
+                                    const math::vec4 bc = sIdx == 0u ? n0 : (sIdx == 1u ? n1 : (sIdx == 2u ? n2 : a3));
+                                    if (P.depthMask) sl_store_depth(tile, P.depthBpt, (size_t)(rel + j), zc[j]); /* src/SL_FragmentProcessor.cpp:526-529 */
+                                    const bool lo = j < jSplit;
+                                    const uint32_t pos = lo ? posLo++ : posHi++;
+                                    const int sub = lo ? sFirst : sLast;
+                                    const uint32_t chunk = chunkRing[sub * SL_R2_CHUNK_RING + ((pos >> 5) & (SL_R2_CHUNK_RING - 1))];
+                                    if (chunk != SL_NO_CHUNK)
+                                    {
+                                        unsigned char* c = P.lists.pool + (size_t)chunk * SL_CHUNK_BYTES;
+                                        const uint32_t slot = pos & 31u;
+                                        reinterpret_cast<float4*>(c)[slot] = make_float4(bc.v[0], bc.v[1], bc.v[2], bc.v[3]);
+                                        reinterpret_cast<float*>(c + 512)[slot] = zc[j];
+                                        reinterpret_cast<uint32_t*>(c + 640)[slot] = (uint32_t)(x4 + j) | ((uint32_t)ySrc << 16);
+                                        reinterpret_cast<uint32_t*>(c + 768)[slot] = recId;
+                                    }
+                                }
+                            }
+                        }
+                        a0 = n0; a1 = n1; a2 = n2;
+                    }
+                    if (useDepth)
+                    {
+                        /* these pixels are resolved: later pieces may have them (lanes of one round touch disjoint pixels) */
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                        {
+                            if ((own >> j) & 1u) pixMask[rel + j] &= ~myBit;
+                        }
+                    }
+                    a0 += bcX; a1 += bcX; a2 += bcX; a3 += bcX; /* :539-542, one rounding per group */
+                    if (last)
+                    {
+                        /* the cut falls on the group boundary: the registers after the compaction, advanced to the next group */
+                        if (publish && !cutInside) sl_handoff_publish(P, recId, ySrc, bOut, 0u, a0, a1, a2, a3);
+                        busy = false;
+                    }
+                    ++g;
+                }
+            }
+            __syncwarp();
+        }
+
+        /* ---- end of the ticket ---- */
+        dirty = __any_sync(0xffffffffu, shaded != 0u) && P.depthMask != 0;
+        __syncwarp();
+        if (lane < nsub && subCount[lane]) P.lists.listCount[firstList + lane] = subCount[lane];
+        if (staged)
+        {
+            if (dirty)
+            {
+                /* write the depth segment back: one bulk store */
+                if (bulkOk)
+                {
+                    sl_fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0)
+                    {
+                        sl_bulk_store(tileSrc, tile, tileLoadBytes);
+                        sl_bulk_store_wait_read();
+                    }
+                }
+                else sl_copy_warp(tileSrc, tile, tileLoadBytes, lane);
+            }
+            __syncwarp();
+        }
+        for (int d = 16; d > 0; d >>= 1) shaded += __shfl_down_sync(0xffffffffu, shaded, d);
+        if (lane == 0 && shaded) atomicAdd(&P.counters->fragsShaded, (unsigned long long)shaded);
+        shaded = 0u;
+    }
+
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); /* the last depth store has landed */
+
+    if (P.diagnostics)
+    {
+        for (int d = 16; d > 0; d >>= 1) dbgGroups += __shfl_down_sync(0xffffffffu, dbgGroups, d);
+        if (lane == 0)
+        {
+            const unsigned long long cyc = (unsigned long long)(clock64() - dbgT0);
+            atomicAdd(&P.counters->resolveWindows, dbgRounds);
+            atomicAdd(&P.counters->resolveIdle, dbgIdle);
+            atomicAdd(&P.counters->resolveGroups, dbgGroups);
+            atomicAdd(&P.counters->resolveCycles, cyc);
+            atomicMax(&P.counters->resolveMaxCycles, cyc);
+            atomicAdd(&P.counters->resolveWarps, 1ull);
+        }
+    }
+}
+
+} // namespace sld

@@ -39,6 +39,21 @@ __device__ __forceinline__ float sl_rcp(float x)
     return __uint_as_float(s | ((uint32_t)re << 23) | (r & 0x7fffffu));
 }
 
+/* the same with the table at a caller-supplied address (a copy staged in shared memory) */
+__device__ __forceinline__ float sl_rcp_tab(const uint32_t* __restrict__ table, float x)
+{
+    const uint32_t xb = __float_as_uint(x);
+    const uint32_t s = xb & 0x80000000u;
+    const uint32_t e = (xb >> 23) & 0xffu;
+    const uint32_t m = xb & 0x7fffffu;
+    if (e == 0xffu) return __uint_as_float(m ? (xb | 0x00400000u) : s);
+    if (e == 0u) return __uint_as_float(s | 0x7f800000u);
+    const uint32_t r = table[m >> 12];
+    const int re = (int)((r >> 23) & 0xffu) - ((int)e - 127);
+    if (re <= 0) return __uint_as_float(s);
+    return __uint_as_float(s | ((uint32_t)re << 23) | (r & 0x7fffffu));
+}
+
 __device__ __forceinline__ float sl_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 /* minss/maxss: (a < b) ? a : b -- the SECOND operand when either is NaN or both are equal.  Written with the compare
  * result materialised as an integer: for the plain C form (and for setp/selp pairs) ptxas folds max(min(x, 1), 0) into

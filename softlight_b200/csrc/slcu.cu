@@ -21,6 +21,7 @@
 
 #include "slcu.h"
 #include "sl_pipeline.cuh"
+#include "sl_resolve2.cuh"
 #include "sl_points.cuh"
 #include "sl_wire.cuh"
 #include <cub/device/device_radix_sort.cuh>
@@ -175,7 +176,10 @@ struct HostTexture
 
 struct HostIbo { int type = 0; uint32_t count = 0; DevBuffer buf; };
 struct HostVao { SL_VertexArray vao; int numBindings = 0; size_t vbo = (size_t)-1, ibo = (size_t)-1; };
-struct HostFbo { unsigned numColors = 0; size_t colors[4] = {(size_t)-1, (size_t)-1, (size_t)-1, (size_t)-1}; size_t depth = (size_t)-1; };
+/* SL_TextureView as SL_Framebuffer keeps it: a snapshot taken when the attachment is made (src/SL_Framebuffer.cpp:855-920);
+ * valid() judges these snapshots, the draw path addresses the texture itself */
+struct FboView { bool texels = false; uint16_t w = 0, h = 0, d = 0; int type = 0; };
+struct HostFbo { unsigned numColors = 0; size_t colors[4] = {(size_t)-1, (size_t)-1, (size_t)-1, (size_t)-1}; size_t depth = (size_t)-1; FboView colorViews[4]; FboView depthView; };
 struct HostShader { int cullMode, depthTest, depthMask, blend, numVaryings, numOutputs; VertexLauncher vs; RasterLauncher fs; PointVertexLauncher pointVs; PointShadeLauncher pointFs; WireShadeLauncher wireFs; size_t ubo; };
 struct UboFixup { size_t ubo, offset; int kind; size_t id, byteOffset; };
 struct HostUbo { unsigned char bytes[1024]; };
@@ -421,7 +425,7 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
         const HostTexture& t = c->textures[fbo.colors[i]];
         const int kind = t.type % 7;
         if (kind == 2 || kind == 3) { c->err = "32/64-bit integer colour targets are not implemented"; return SLCU_ERR_UNSUPPORTED; }
-        if (t.w != depthTex.w || t.h != depthTex.h) { c->err = "colour and depth attachments differ in size (SL_Framebuffer::valid -10)"; return SLCU_ERR_ARG; }
+        if (t.w != depthTex.w || t.h != depthTex.h) { c->err = "colour and depth attachments differ in size (SL_Framebuffer::valid -7 / -8)"; return SLCU_ERR_ARG; }
     }
     const float fboW = (float)depthTex.w, fboH = (float)depthTex.h;
     const bool wire = (meshes[0].mode == 0x50u) || (meshes[0].mode == 0x70u); /* mRenderMode = meshes->mode (src/SL_ProcessorPool.cpp:301,354) */
@@ -506,7 +510,7 @@ static int run_points(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes
         const HostTexture& t = c->textures[fbo.colors[i]];
         const int kind = t.type % 7;
         if (kind == 2 || kind == 3) { c->err = "32/64-bit integer colour targets are not implemented"; return SLCU_ERR_UNSUPPORTED; }
-        if (t.w != depthTex.w || t.h != depthTex.h) { c->err = "colour and depth attachments differ in size (SL_Framebuffer::valid -10)"; return SLCU_ERR_ARG; }
+        if (t.w != depthTex.w || t.h != depthTex.h) { c->err = "colour and depth attachments differ in size (SL_Framebuffer::valid -7 / -8)"; return SLCU_ERR_ARG; }
     }
     const size_t launches = (numInstances == 1) ? numMeshes : 1;
     for (size_t i = 0; i < launches; ++i)
@@ -647,6 +651,7 @@ static int flush_draws_impl(slcu_context* c)
     unsigned long long recCapacity = recFixed + recOverflow;
     static const bool useVertexCache = getenv("SLCU_VERTEX_CACHE") != nullptr && atoi(getenv("SLCU_VERTEX_CACHE")) != 0; /* opt-in: measured slower on C3, +3 % on C2 */
     unsigned long long numHandoffs = 0;
+    unsigned long long totalSpansHost = 0;
     const uint8_t* rowNeeded = nullptr;
     for (int attempt = 0;; ++attempt)
     {
@@ -892,6 +897,7 @@ static int flush_draws_impl(slcu_context* c)
             return SLCU_ERR_OOM;
         }
         if (!totalSpans) return 0;
+        totalSpansHost = totalSpans;
         numHandoffs = c->hostCounters->handoffs;
         if (getenv("SLCU_DEBUG"))
             fprintf(stderr, "[slcu] batch: draws=%zu prims=%llu records=%llu entries=%u handoffs=%llu segs=%ux%u pixels=%llu flags=0x%x\n", B.descs.size(), totalPrims,
@@ -967,7 +973,7 @@ static int flush_draws_impl(slcu_context* c)
         static const int skewEnv = getenv("SLCU_TICKET_SKEW") ? atoi(getenv("SLCU_TICKET_SKEW")) : -1;
         int numSMs = 148;
         cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, c->device);
-        const unsigned resident = (unsigned)numSMs * 4u * SL_RASTER_WARPS; /* warps of k_resolve that fit the machine */
+        const unsigned resident = (unsigned)numSMs * (unsigned)SL_RASTER_MIN_BLOCKS * SL_RASTER_WARPS; /* warps of k_resolve that fit the machine */
         /* sort-first partition: only 1/world of the rows does any work on this rank, so the skew is world times longer */
         const unsigned world = c->partWorld > 1 ? c->partWorld : 1u;
         const unsigned skew = skewEnv >= 0 ? (unsigned)skewEnv : (resident * world + rasterSegs - 1) / rasterSegs + 32u;
@@ -998,6 +1004,34 @@ static int flush_draws_impl(slcu_context* c)
         }
     }
     rp.diagnostics = getenv("SLCU_DEBUG") ? 1 : 0;
+    /* Two implementations of the stage (same inputs, same outputs): k_resolve2 walks every span piece with one lane
+     * (sl_resolve2.cuh: short spans, i.e. every triangle-dense scene), k_resolve spreads the groups of a piece over the
+     * lanes of a window (long spans).  SLCU_RESOLVE=1|2 forces one of them. */
+    static const int resolveEnv = getenv("SLCU_RESOLVE") ? atoi(getenv("SLCU_RESOLVE")) : 0;
+    const unsigned long long avgSpan = totalSpansHost ? pixelsCovered / totalSpansHost : 0ull;
+    const bool useResolve2 = resolveEnv == 2 || (resolveEnv != 1 && avgSpan < 48ull);
+    if (useResolve2)
+    {
+        const unsigned smemBytes = SL_R2_RCP_BYTES + SL_R2_WARPS * sl_r2_warp_bytes(segWidth, rp.tileBytes);
+        static bool attrSet2 = false;
+        if (!attrSet2)
+        {
+            CK(cudaFuncSetAttribute(k_resolve2, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            attrSet2 = true;
+        }
+        if (smemBytes > 160u * 1024u) { c->err = "framebuffer too wide for the resolve tile"; return SLCU_ERR_ARG; }
+        int numSMs = 148;
+        cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, c->device);
+        const unsigned long long numWarps = (unsigned long long)H * rasterSegs;
+        unsigned long long grid = (unsigned long long)numSMs * SL_R2_MIN_BLOCKS; /* persistent warps */
+        const unsigned long long needBlocks = (numWarps + SL_R2_WARPS - 1) / SL_R2_WARPS;
+        if (grid > needBlocks) grid = needBlocks;
+        KernelScope ks(c, SLCU_K_RASTER);
+        k_resolve2<<<(unsigned)grid, SL_R2_WARPS * 32, smemBytes, c->stream>>>(rp);
+        CK(cudaGetLastError());
+    }
+    else
+    {
     const unsigned warpsPerBlock = SL_RASTER_WARPS;
     const unsigned smemBytes = warpsPerBlock * (SL_PIECEQ_BYTES + SL_SUBLIST_BYTES + SL_PIECEREG_BYTES + SL_WINSCRATCH_BYTES + ((4u * segWidth + 15u) & ~15u) + rp.tileBytes); /* piece queue, sub-list state, piece registers, window scratch, toucher masks, depth tile: per warp */
     {
@@ -1012,6 +1046,7 @@ static int flush_draws_impl(slcu_context* c)
         const unsigned long long numWarps = (unsigned long long)H * rasterSegs;
         k_resolve<<<(unsigned)((numWarps + warpsPerBlock - 1) / warpsPerBlock), warpsPerBlock * 32, smemBytes, c->stream>>>(rp);
         CK(cudaGetLastError());
+    }
     }
 
     SLShadeParams shp;
@@ -1341,6 +1376,8 @@ int slcu_fbo_attach_color_buffer(slcu_context* c, size_t fbo, unsigned index, si
     if (fbo >= c->fbos.size() || tex >= c->textures.size()) return SLCU_ERR_ARG;
     if (index >= c->fbos[fbo].numColors) return -1;
     c->fbos[fbo].colors[index] = tex;
+    const HostTexture& t = c->textures[tex];
+    c->fbos[fbo].colorViews[index] = FboView{t.dev != nullptr, t.w, t.h, t.d, t.type};
     return 0;
 }
 int slcu_fbo_attach_depth_buffer(slcu_context* c, size_t fbo, size_t tex)
@@ -1348,27 +1385,37 @@ int slcu_fbo_attach_depth_buffer(slcu_context* c, size_t fbo, size_t tex)
     SLCU_FLUSH();
     if (fbo >= c->fbos.size() || tex >= c->textures.size()) return SLCU_ERR_ARG;
     c->fbos[fbo].depth = tex;
+    const HostTexture& t = c->textures[tex];
+    c->fbos[fbo].depthView = FboView{t.dev != nullptr, t.w, t.h, t.d, t.type};
     return 0;
 }
+/* SL_Framebuffer::valid (src/SL_Framebuffer.cpp:928-990): same checks, same order, same codes.  An attachment that was
+ * never made (or whose texture was never initialised) is the reference's reset view: no texels, zero dimensions. */
+static int fbo_valid_code(const HostFbo& f)
+{
+    if (!f.numColors) return -1;
+    const FboView& c0 = f.colorViews[0];
+    for (unsigned i = 0; i < f.numColors; ++i)
+    {
+        const FboView& v = f.colorViews[i];
+        if (!v.texels) return -2;
+        if (v.w != c0.w) return -3;
+        if (v.h != c0.h) return -4;
+        if (v.d != c0.d) return -5;
+    }
+    const FboView& d = f.depthView;
+    if (!d.texels) return -6;
+    if (d.w != c0.w) return -7;
+    if (d.h != c0.h) return -8;
+    if (d.d > 1) return -9;
+    if (d.type != 4 && d.type != 5 && d.type != 6) return -10; /* SL_COLOR_R_HALF / R_FLOAT / R_DOUBLE */
+    return 0;
+}
+
 int slcu_fbo_valid(slcu_context* c, size_t fbo)
 {
-    /* SL_Framebuffer::valid (src/SL_Framebuffer.cpp:930-990) */
-    if (fbo >= c->fbos.size()) return SLCU_ERR_ARG;
-    const HostFbo& f = c->fbos[fbo];
-    if (!f.numColors) return -1;
-    for (unsigned i = 0; i < f.numColors; ++i)
-    {
-        if (f.colors[i] == (size_t)-1 || !c->textures[f.colors[i]].dev) return -3;
-    }
-    if (f.depth == (size_t)-1 || !c->textures[f.depth].dev) return -6;
-    const HostTexture& d = c->textures[f.depth];
-    if (d.type != 4 && d.type != 5 && d.type != 6) return -8;
-    for (unsigned i = 0; i < f.numColors; ++i)
-    {
-        const HostTexture& t = c->textures[f.colors[i]];
-        if (t.w != d.w || t.h != d.h) return -10;
-    }
-    return 0;
+    if (!c || fbo >= c->fbos.size()) return SLCU_ERR_ARG;
+    return fbo_valid_code(c->fbos[fbo]);
 }
 
 size_t slcu_create_shader(slcu_context* c, const slcu_vertex_shader* vs, const slcu_fragment_shader* fs, size_t ubo)
