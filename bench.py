@@ -4,15 +4,18 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl cuda|reference] [--config NAME]
 
 A "step" is one frame of the workload: clear_framebuffer + every draw of the frame
-(+ the sort-first composite when N > 1).  At N=1 the workload is BASELINE.json
-configs[1] (10k instanced meshes, 1920x1080), SURVEY.md section 8d "C2".
+(+ the sort-first composite when N > 1).  The workload is the configuration BASELINE.json's
+metric is quoted on ("... shaded at 4K"): configs[2], the 2M-triangle indoor scene with 256 textured
+draws at 3840x2160 (SURVEY.md section 8d "C3"), at every N.
 
 One JSON line is printed by rank 0:
   value     Mtris/s, whole job, inputs resident in HBM, device time (CUDA events on the library's stream)
   e2e       same metric through the C ABI with host buffers: per-frame H2D of the frame's inputs from pinned
             memory and D2H of the colour attachment inside the timed region (host wall clock)
-  roofline  the dominant kernel's algorithmic bytes / its event-measured duration vs MEASURED_PEAKS.json hbm_gbs
+  roofline  the dominant kernel against BOTH bounds of SURVEY.md section 8d: algorithmic bytes / event-measured
+            duration vs MEASURED_PEAKS.json hbm_gbs, and warp instructions / duration vs 148 SMs x 4 issue slots x f_SM
   cpu_baseline  the compiled reference (oracle/_ref/libslref_fast.so, shipped flags, all host threads) on the same frame
+  other_configs (N=1)  device ms + e2e ms of the other BASELINE configs (C1, C2, C4, C5-8K), C5-8K with its CPU baseline
 --impl reference times only that CPU path (the driver computes the ratio itself).
 """
 from __future__ import annotations
@@ -34,7 +37,8 @@ from softlight_b200 import capi as A  # noqa: E402
 from softlight_b200 import scenes as S  # noqa: E402
 
 METRIC = "Mtris/s"
-DEFAULT_CONFIG = "c2_instancing10k"
+DEFAULT_CONFIG = "c3_indoor2m"
+OTHER_CONFIGS = ["c1_sphere100k", "c2_instancing10k", "c4_skinned100", "c5_volume8k"]
 
 
 # ----------------------------------------------------------------------------- helpers
@@ -155,27 +159,37 @@ def algorithmic_bytes(scene_name: str, scene: S.Scene, frags: int) -> dict:
     return out
 
 
-def ncu_traffic(dom: str, config: str):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the newest committed `ncu --set full` summary
-    (profiles/rNN?_k_<kernel>_<cfg>.txt, written by tools/ncu_summary.py), per launch; None when there is no capture."""
-    kern = {"raster": "resolve", "shade": "shade", "vertex": "vertex", "span_count": "span", "span_fill": "span"}.get(dom)
-    cfg = config.split("_")[0]
-    if kern is None:
-        return None, None
-    pdir = os.path.join(ROOT, "profiles")
+def kernel_source_sha() -> str:
+    """Hash of everything that is compiled into libslcu.so: ncu figures are only quoted for the sources they were captured on."""
+    import hashlib
+
+    from softlight_b200 import build as B
+
+    h = hashlib.sha256()
+    for f in B.cuda_sources():
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
+def ncu_counters(dom: str, config: str):
+    """Per-launch ncu counters of the dominant kernel (dram bytes, warp instructions) from profiles/ncu_counters.json, written
+    by tools/ncu_counters.py from an `ncu --set full` capture of this same command.  Entries are stamped with the hash of the
+    kernel sources they were measured on and ignored when the sources have changed since."""
+    kern = {"raster": "k_resolve", "shade": "k_shade", "vertex": "k_vertex", "span_count": "k_span<0>", "span_fill": "k_span<1>"}.get(dom)
+    path = os.path.join(ROOT, "profiles", "ncu_counters.json")
+    if kern is None or not os.path.exists(path):
+        return None
     try:
-        cands = sorted(f for f in os.listdir(pdir) if f.endswith(f"_k_{kern}_{cfg}.txt"))
-    except OSError:
-        return None, None
-    if not cands:
-        return None, None
-    total = 0.0
-    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    for ln in open(os.path.join(pdir, cands[-1])):
-        f = ln.split()
-        if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-            total += float(f[1]) * unit.get(f[2], 1.0)
-    return (total or None), "profiles/" + cands[-1]
+        db = json.load(open(path))
+    except Exception:
+        return None
+    if db.get("source_sha") != kernel_source_sha():
+        return None
+    ent = db.get("configs", {}).get(config, {})
+    for name, v in ent.items():
+        if name.startswith(kern):
+            return dict(v, kernel=name, source="profiles/ncu_counters.json@" + db["source_sha"])
+    return None
 
 
 def pinned_array(shape, dtype):
@@ -192,17 +206,32 @@ def pinned_array(shape, dtype):
 
 
 # ----------------------------------------------------------------------------- arms
+def workload_config(config: str, scene: S.Scene) -> dict:
+    """The `config` object of the JSON line: identical in both arms."""
+    return {"workload": f"{config}: {scene.name}, {scene.tris_per_frame} tris/frame, {scene.draws_per_frame} draw(s), "
+                        f"{scene.width}x{scene.height}"}
+
+
+def cpu_context():
+    cores = os.cpu_count() or 1
+    if os.path.exists(A.LIB_PATHS["ref_fast"]):
+        impl, kind, threads = "ref_fast", "reference", cores
+    else:
+        impl, kind, threads = "port", "port", 1
+    A.load_library(impl)["reset_stats"](None)  # frag counting off
+    return A.Context(impl, threads=threads), kind, threads
+
+
+CPU_BUILD_NOTE = ("the unmodified reference compiled by oracle/Makefile with g++ -O2 and the project's shipped flags "
+                  "(-mavx2 -mfma -ffast-math; its README names clang as the fastest compiler, which this image does not have)")
+
+
 def run_reference(args, rank, world):
     """The reference's own CPU implementation on this box's host cores (shipped flags, all threads)."""
     if rank != 0:
         return None
     scene = S.SCENES[args.config]()
-    cores = os.cpu_count() or 1
-    kind = "reference" if os.path.exists(A.LIB_PATHS["ref_fast"]) else "port"
-    impl = "ref_fast" if kind == "reference" else "port"
-    threads = cores if kind == "reference" else 1
-    A.load_library(impl)["reset_stats"](None)  # frag counting off
-    ctx = A.Context(impl, threads=threads)
+    ctx, kind, threads = cpu_context()
     inst = S.SceneInstance(scene, ctx)
     for _ in range(args.warmup):
         inst.render()
@@ -215,113 +244,176 @@ def run_reference(args, rank, world):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.config}: {scene.name}, {scene.tris_per_frame} tris/frame, {scene.draws_per_frame} draw(s), "
-                               f"{scene.width}x{scene.height}", "l2": "n/a (CPU)"},
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args.config, scene),
         "cpu_baseline": {"value": value, "unit": METRIC, "cores": threads, "kind": kind,
-                         "sample": f"{args.steps} full frames of {args.config} ({ctx.impl_name()})"},
+                         "sample": f"{args.steps} full frames of {args.config} ({ctx.impl_name()})", "build": CPU_BUILD_NOTE},
         "e2e": {"value": value, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "fps": 1e3 / ms,
     }
     return line
 
 
-def cpu_baseline_leg(config: str, budget_s: float = 12.0) -> dict:
+def cpu_baseline_leg(config: str, budget_s: float = 12.0, max_frames: int = 50) -> dict:
     scene = S.SCENES[config]()
-    cores = os.cpu_count() or 1
-    if os.path.exists(A.LIB_PATHS["ref_fast"]):
-        impl, kind, threads = "ref_fast", "reference", cores
-    else:
-        impl, kind, threads = "port", "port", 1
-    A.load_library(impl)["reset_stats"](None)
-    ctx = A.Context(impl, threads=threads)
+    ctx, kind, threads = cpu_context()
     inst = S.SceneInstance(scene, ctx)
     inst.render()
     n, t0 = 0, time.perf_counter()
     while True:
         inst.render()
         n += 1
-        if time.perf_counter() - t0 > budget_s or n >= 50:
+        if time.perf_counter() - t0 > budget_s or n >= max_frames:
             break
     ms = (time.perf_counter() - t0) * 1e3 / n
     return {"value": scene.tris_per_frame / (ms * 1e-3) / 1e6, "unit": METRIC, "cores": threads, "kind": kind,
-            "ms_per_frame": ms, "sample": f"{n} full frames of {config} after 1 warm-up ({ctx.impl_name()}, {threads} threads)"}
+            "ms_per_frame": ms, "sample": f"{n} full frames of {config} after 1 warm-up ({ctx.impl_name()}, {threads} threads)",
+            "build": CPU_BUILD_NOTE}
 
 
-def run_cuda(args, rank, world, local_rank, dist):
-    scene = S.SCENES[args.config]()
-    ctx = A.Context("cuda", device=local_rank)
-    inst = S.SceneInstance(scene, ctx)
-    sf, final = None, []
-    if world > 1:
-        # sort-first: this rank rasterises its interleaved row strips; composite = stores into rank 0's texture over NVLink
-        from softlight_b200.sortfirst import SortFirst
+class Harness:
+    """One scene on one context (+ the sort-first plumbing when world > 1) with the timing loops of the contract."""
 
-        sf = SortFirst(ctx, dist, rank, world, strip_rows=args.strip_rows)
-        final = [sf.make_target(scene.color_type, scene.width, scene.height) for _ in range(2)]  # double-buffered
+    def __init__(self, config, rank, world, local_rank, dist, strip_rows):
+        self.config, self.rank, self.world, self.local_rank, self.dist = config, rank, world, local_rank, dist
+        self.scene = S.SCENES[config]()
+        self.ctx = A.Context("cuda", device=local_rank)
+        self.inst = S.SceneInstance(self.scene, self.ctx)
+        self.sf, self.final = None, []
+        if world > 1:
+            # sort-first: this rank rasterises its interleaved row strips; composite = stores into rank 0's texture over NVLink
+            from softlight_b200.sortfirst import SortFirst
 
-    def render_frame(i):
-        inst.render()
-        if sf is not None:
-            sf.composite(inst.state["color"], final[i % 2])
+            self.sf = SortFirst(self.ctx, dist, rank, world, strip_rows=strip_rows)
+            self.final = [self.sf.make_target(self.scene.color_type, self.scene.width, self.scene.height) for _ in range(2)]
+        # L2 flush buffer (written between timed frames, outside the timed region)
+        ctx = self.ctx
+        self.flush_tex = ctx.create_texture(A.SL_COLOR_RGBA_32U, 4096, 4096, 1)  # 256 MiB > 126 MB L2
+        self.flush_fbo = ctx.create_framebuffer([self.flush_tex], ctx.create_texture(A.SL_COLOR_R_FLOAT, 4, 4, 1))
+        self._torch_flush = None
 
-    # L2 flush buffer (written between timed frames, outside the timed region)
-    import ctypes as C
-    flush_tex = ctx.create_texture(A.SL_COLOR_RGBA_32U, 4096, 4096, 1)  # 256 MiB > 126 MB L2
-    flush_fbo_depth = ctx.create_texture(A.SL_COLOR_R_FLOAT, 4, 4, 1)
-    flush_fbo = ctx.create_framebuffer([flush_tex], flush_fbo_depth)
+    def render_frame(self, i):
+        self.inst.render()
+        if self.sf is not None:
+            self.sf.composite(self.inst.state["color"], self.final[i % 2])
 
-    def flush_l2():
-        ctx.clear_color_buffer(flush_fbo, 0, (0.0, 0.0, 0.0, 0.0))
+    def flush_l2(self):
+        self.ctx.clear_color_buffer(self.flush_fbo, 0, (0.0, 0.0, 0.0, 0.0))
 
-    def barrier():
-        ctx.sync()
-        if dist is not None:
-            dist.barrier()
+    def flush_l2_outside_library(self):
+        """L2 flush that does not show up in the library's per-kernel timers (used by the per-kernel pass): a 256 MiB fill on
+        torch's stream, bracketed by synchronisation."""
+        try:
+            import torch
 
-    for i in range(max(args.warmup, 3)):
-        render_frame(i)
-    barrier()
+            if self._torch_flush is None:
+                self._torch_flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{self.local_rank}")
+            self.ctx.sync()
+            self._torch_flush.zero_()
+            torch.cuda.synchronize(self.local_rank)
+            return True
+        except Exception:
+            return False
 
-    # ---- device-timed steps ------------------------------------------------------------
-    sampler = ClockSampler(local_rank)
-    ctx.reset_stats()
-    barrier()
-    sampler.start()
-    step_ms = []
-    for i in range(args.steps):
-        flush_l2()
-        ctx.timer_begin()
-        render_frame(i)
-        step_ms.append(ctx.timer_end())
-    barrier()
-    clocks = sampler.stop()
-    st = ctx.get_stats()
-    frags_total = st["fragsShaded"]
-    if dist is not None:
-        # a frame is complete when the slowest rank's rows have landed: per-step MAX over ranks, then the sum
+    def barrier(self):
+        self.ctx.sync()
+        if self.dist is not None:
+            self.dist.barrier()
+
+    def max_over_ranks(self, values):
+        if self.dist is None:
+            return list(values)
         import torch
-        t = torch.tensor(step_ms, dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        step_ms = [float(v) for v in t.tolist()]
-        f = torch.tensor([frags_total], dtype=torch.int64, device=f"cuda:{local_rank}")
-        dist.all_reduce(f, op=dist.ReduceOp.SUM)
-        frags_total = int(f.item())
-    total_ms = float(sum(step_ms))
-    ms = total_ms / args.steps
-    frags = frags_total // args.steps
-    launches = st["kernelLaunches"] - args.steps  # minus the L2-flush clears
-    value = scene.tris_per_frame / (ms * 1e-3) / 1e6
 
-    # ---- per-kernel times for the roofline (separate pass; events around every launch) ----
-    prof_frames = max(3, min(args.steps, 10))
-    ctx.profile_begin()
-    for i in range(prof_frames):
-        render_frame(i)
-    kt = ctx.profile_end()
-    alg = algorithmic_bytes(args.config, scene, frags)
+        t = torch.tensor(list(values), dtype=torch.float64, device=f"cuda:{self.local_rank}")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+
+    def sum_over_ranks(self, value: int) -> int:
+        if self.dist is None:
+            return int(value)
+        import torch
+
+        t = torch.tensor([value], dtype=torch.int64, device=f"cuda:{self.local_rank}")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return int(t.item())
+
+    def device_timed(self, steps, warmup):
+        """K frames, each bracketed by CUDA events on the library's stream, L2 flushed before each; max over ranks per frame."""
+        for i in range(max(warmup, 3)):
+            self.render_frame(i)
+        self.barrier()
+        sampler = ClockSampler(self.local_rank)
+        self.ctx.reset_stats()
+        self.barrier()
+        sampler.start()
+        step_ms = []
+        for i in range(steps):
+            self.flush_l2()
+            self.ctx.timer_begin()
+            self.render_frame(i)
+            step_ms.append(self.ctx.timer_end())
+        self.barrier()
+        clocks = sampler.stop()
+        st = self.ctx.get_stats()
+        step_ms = self.max_over_ranks(step_ms)  # a frame is complete when the slowest rank's rows have landed
+        frags = self.sum_over_ranks(st["fragsShaded"]) // steps
+        return {"ms": float(sum(step_ms)) / steps, "frags": frags, "stats": st, "clocks": clocks,
+                "launches": int(st["kernelLaunches"] - steps)}  # minus the L2-flush clears
+
+    def per_kernel(self, frames):
+        """Event-bracketed launches (slcu_profile_*), L2 flushed before every frame like the timed loop."""
+        self.ctx.profile_begin()
+        flushed = True
+        for i in range(frames):
+            flushed = self.flush_l2_outside_library() and flushed
+            self.render_frame(i)
+        kt = self.ctx.profile_end()
+        classes = {k: v for k, v in kt.items() if v["launches"]}
+        return classes, flushed
+
+    def end_to_end(self, steps):
+        """Host buffers: per-frame H2D of the frame's inputs from pinned memory, the frame, D2H of the colour attachment."""
+        scene, ctx, inst = self.scene, self.ctx, self.inst
+        per_frame = inst.state.get("per_frame", {})
+        staged, h2d = {}, 0
+        for key, arr in per_frame.items():
+            pin, keep = pinned_array(arr.shape, arr.dtype)
+            pin[...] = arr
+            staged[key] = (pin, keep)
+            h2d += arr.nbytes
+        cbytes = scene.width * scene.height * A.bytes_per_texel(scene.color_type)
+        out_pin, out_keep = pinned_array((cbytes,), np.uint8)
+        e2e_ms = []
+        for i in range(steps + 2):
+            self.flush_l2()
+            ctx.sync()
+            t0 = time.perf_counter()
+            for key, (pin, _) in staged.items():
+                ctx.vbo_assign_raw(inst.state[key], pin.ctypes.data, pin.nbytes)
+            self.render_frame(i)
+            if self.sf is not None:
+                self.sf.frame_barrier()
+                if self.rank == 0:
+                    ctx.texture_read_into(self.final[i % 2], out_pin.ctypes.data, cbytes)
+            else:
+                ctx.texture_read_into(inst.state["color"], out_pin.ctypes.data, cbytes)
+            dt = (time.perf_counter() - t0) * 1e3
+            if i >= 2:
+                e2e_ms.append(dt)
+        e2e_ms = self.max_over_ranks(e2e_ms)
+        ms = float(np.mean(e2e_ms))
+        return {"value": scene.tris_per_frame / (ms * 1e-3) / 1e6, "unit": METRIC,
+                "h2d_bytes_per_step": int((h2d + scene.upload_bytes_per_frame) * self.world), "d2h_bytes_per_step": int(cbytes), "ms_per_step": ms,
+                "checksum": int(out_pin[::4097].astype(np.uint64).sum())}
+
+    def close(self):
+        self.ctx.close()
+
+
+def rooflines(config, scene, frags, frame_ms, classes, prof_frames, clocks):
+    """The dominant kernel against both bounds of SURVEY.md section 8d."""
+    alg = algorithmic_bytes(config, scene, frags)
     peak, peak_src = measured_peaks()
-    classes = {k: v for k, v in kt.items() if v["launches"]}
     dom = max(classes, key=lambda k: classes[k]["ms"])
     dom_ms = classes[dom]["ms"] / classes[dom]["launches"]
     launches_per_frame = classes[dom]["launches"] / prof_frames
@@ -329,65 +421,88 @@ def run_cuda(args, rank, world, local_rank, dist):
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     kernel_ms_per_frame = {k: v["ms"] / prof_frames for k, v in classes.items()}
     frame_kernel_ms = sum(kernel_ms_per_frame.values())
-    traffic, traffic_src = ncu_traffic(dom, args.config)
-    roofline = {
-        "bound": "hbm", "kernel": {"raster": "k_resolve", "shade": "k_shade"}.get(dom, "k_" + dom), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
-        "kernel_ms_per_launch": dom_ms, "kernel_share_of_frame": kernel_ms_per_frame[dom] / frame_kernel_ms,
-        "frame_algorithmic_bytes": alg["frame"], "frame_achieved_gbs": alg["frame"] / (ms * 1e-3) / 1e9,
-        "frame_frac": alg["frame"] / (ms * 1e-3) / 1e9 / peak, "kernel_ms_per_frame": kernel_ms_per_frame,
+    ncu = ncu_counters(dom, config)
+    kname = (ncu or {}).get("kernel") or {"raster": "k_resolve", "shade": "k_shade"}.get(dom, "k_" + dom)
+    hbm = {
+        "bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": (ncu["dram_bytes_read"] + ncu["dram_bytes_write"]) if ncu else None, "traffic_source": ncu["source"] if ncu else None,
+        "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms_per_launch": dom_ms,
+        "kernel_share_of_frame": kernel_ms_per_frame[dom] / frame_kernel_ms, "frame_algorithmic_bytes": alg["frame"],
+        "frame_achieved_gbs": alg["frame"] / (frame_ms * 1e-3) / 1e9, "frame_frac": alg["frame"] / (frame_ms * 1e-3) / 1e9 / peak,
+        "kernel_ms_per_frame": kernel_ms_per_frame,
     }
+    # bound 2: instruction issue.  148 SMs x 4 schedulers x f_SM warp instructions per second; f_SM = the SM clock
+    # sampled under load in this run.  The kernel's warp-instruction count per launch comes from the ncu capture of the same
+    # sources (profiles/ncu_counters.json); its duration is measured live.
+    f_sm = (clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0) * 1e6
+    issue_peak = 148 * 4 * f_sm / 1e9
+    issue = {"bound": "issue", "kernel": kname, "peak": issue_peak, "unit": "Gwarp-inst/s", "achieved": None, "frac": None,
+             "sm_mhz": f_sm / 1e6, "frags_per_launch": frags / max(launches_per_frame, 1)}
+    if ncu and dom_ms > 0:
+        issue["warp_instructions_per_launch"] = ncu["inst_executed"]
+        issue["achieved"] = ncu["inst_executed"] / (dom_ms * 1e-3) / 1e9
+        issue["frac"] = issue["achieved"] / issue_peak
+        issue["counter_source"] = ncu["source"]
+        if frags:
+            per_frag = ncu["inst_executed"] * launches_per_frame / frags
+            issue["warp_instructions_per_fragment"] = per_frag
+            issue["fragment_rate_ceiling_gfrag_s"] = issue_peak / per_frag
+            issue["fragment_rate_achieved_gfrag_s"] = frags / launches_per_frame / (dom_ms * 1e-3) / 1e9
+    hbm["issue"] = issue
+    return hbm
 
-    # ---- end to end: host buffers, H2D of the frame inputs, D2H of the colour attachment ------
-    per_frame = inst.state.get("per_frame", {})
-    staged = {}
-    h2d = 0
-    for key, arr in per_frame.items():
-        pin, keep = pinned_array(arr.shape, arr.dtype)
-        pin[...] = arr
-        staged[key] = (pin, keep)
-        h2d += arr.nbytes
-    cbytes = scene.width * scene.height * A.bytes_per_texel(scene.color_type)
-    out_pin, out_keep = pinned_array((cbytes,), np.uint8)
-    e2e_ms = []
-    for i in range(args.steps + 2):
-        flush_l2()
-        ctx.sync()
-        t0 = time.perf_counter()
-        for key, (pin, _) in staged.items():
-            ctx.vbo_assign_raw(inst.state[key], pin.ctypes.data, pin.nbytes)
-        render_frame(i)
-        if sf is not None:
-            sf.frame_barrier()
-            if rank == 0:
-                ctx.texture_read_into(final[i % 2], out_pin.ctypes.data, cbytes)
-        else:
-            ctx.texture_read_into(inst.state["color"], out_pin.ctypes.data, cbytes)
-        dt = (time.perf_counter() - t0) * 1e3
-        if i >= 2:
-            e2e_ms.append(dt)
-    if dist is not None:
-        import torch
-        t = torch.tensor(e2e_ms, dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = [float(v) for v in t.tolist()]
-    e2e_ms_avg = float(np.mean(e2e_ms))
-    e2e = {"value": scene.tris_per_frame / (e2e_ms_avg * 1e-3) / 1e6, "unit": METRIC, "h2d_bytes_per_step": int((h2d + 1024) * world),
-           "d2h_bytes_per_step": int(cbytes), "ms_per_step": e2e_ms_avg, "checksum": int(out_pin[::4097].astype(np.uint64).sum())}
 
+def other_config_leg(config, local_rank, with_cpu):
+    """Device ms + e2e ms of another BASELINE config in the same run (N = 1)."""
+    h = Harness(config, 0, 1, local_rank, None, 8)
+    steps = 3 if config.startswith("c5") else 8
+    d = h.device_timed(steps, 3)
+    e = h.end_to_end(3 if config.startswith("c5") else 5)
+    classes, _ = h.per_kernel(3)
+    out = {"workload": workload_config(config, h.scene)["workload"], "ms_per_step": d["ms"], "fps": 1e3 / d["ms"],
+           "mtris_per_s": h.scene.tris_per_frame / (d["ms"] * 1e-3) / 1e6, "gfrags_per_s": d["frags"] / (d["ms"] * 1e-3) / 1e9,
+           "frags_per_frame": d["frags"], "e2e_ms_per_step": e["ms_per_step"], "h2d_bytes_per_step": e["h2d_bytes_per_step"],
+           "d2h_bytes_per_step": e["d2h_bytes_per_step"], "steps": steps,
+           "kernel_ms_per_frame": {k: v["ms"] / 3 for k, v in classes.items()}}
+    h.close()
+    if with_cpu:
+        out["cpu_baseline"] = cpu_baseline_leg(config, budget_s=8.0, max_frames=3)
+    return out
+
+
+def run_cuda(args, rank, world, local_rank, dist):
+    h = Harness(args.config, rank, world, local_rank, dist, args.strip_rows)
+    scene = h.scene
+    d = h.device_timed(args.steps, args.warmup)
+    ms, frags, st = d["ms"], d["frags"], d["stats"]
+    value = scene.tris_per_frame / (ms * 1e-3) / 1e6
+    prof_frames = max(3, min(args.steps, 10))
+    classes, flushed = h.per_kernel(prof_frames)
+    roofline = rooflines(args.config, scene, frags, ms, classes, prof_frames, d["clocks"])
+    roofline["per_kernel_pass"] = "L2 flushed before every frame (256 MiB fill outside the library's timers)" if flushed else "L2 not flushed (torch unavailable)"
+    e2e = h.end_to_end(args.steps)
     line = {
         "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.config}: {scene.name}, {scene.tris_per_frame} tris/frame, {scene.draws_per_frame} draw(s), "
-                               f"{scene.width}x{scene.height}", "l2": "flushed between timed frames (256 MiB clear, untimed)",
-                   "parallelism": f"sort-first x{world}" + (f", {args.strip_rows}-row strips interleaved over ranks, geometry replicated, "
-                                                              "composite = peer stores into rank 0 over NVLink" if world > 1 else "")},
+        "config": workload_config(args.config, scene),
+        "l2": "flushed between timed frames (256 MiB clear, untimed)",
+        "parallelism": f"sort-first x{world}" + (f", {args.strip_rows}-row strips interleaved over ranks, geometry replicated, "
+                                                 "composite = peer stores into rank 0 over NVLink" if world > 1 else ""),
         "gfrags_per_s": frags / (ms * 1e-3) / 1e9, "fps": 1e3 / ms, "frags_per_frame": int(frags),
         "tris_binned_per_frame": int(st["trisBinned"] // args.steps), "spans_per_frame": int(st["spans"] // args.steps),
-        "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline,
+        "gpu_launches": d["launches"], "clocks": d["clocks"], "e2e": e2e, "roofline": roofline,
     }
+    h.close()
     if rank == 0 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_leg(args.config)
+    if rank == 0 and world == 1 and not args.no_other_configs and args.config == DEFAULT_CONFIG:
+        others = {}
+        for cfg in OTHER_CONFIGS:
+            try:
+                others[cfg] = other_config_leg(cfg, local_rank, with_cpu=cfg.startswith("c5") and not args.no_cpu_baseline)
+            except Exception as ex:  # a failing extra must not take the headline down
+                others[cfg] = {"error": repr(ex)}
+        line["other_configs"] = others
     return line
 
 
@@ -399,6 +514,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--config", default=DEFAULT_CONFIG)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the extra per-config measurements of the default run")
     ap.add_argument("--strip-rows", type=int, default=8, help="rows per ownership strip of the sort-first partition")
     args = ap.parse_args()
 

@@ -1179,10 +1179,12 @@ int slor_texture_read(slcu_context* c, size_t tex, void* out, size_t n)
 
 int slor_fbo_reserve_color_buffers(slcu_context* c, size_t fbo, unsigned n)
 {
+    /* src/SL_Framebuffer.cpp:823-848: same count = no-op (checked first), the colour views are reset, the depth view stays */
+    Framebuffer& f = c->fbos[fbo];
+    if (n == f.numColors) return 0;
     if (n < 1) return -1;
     if (n > 4) return -2;
-    Framebuffer& f = c->fbos[fbo];
-    f = Framebuffer{};
+    for (int i = 0; i < 4; ++i) { f.colors[i] = (size_t)-1; f.colorViews[i] = FboView{}; }
     f.numColors = n;
     return 0;
 }

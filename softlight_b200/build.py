@@ -56,6 +56,21 @@ def build_cuda(force: bool = False, verbose: bool = False, out: str = LIB) -> st
     return out
 
 
+HARNESS_LIB = os.path.join(ROOT, "softlight_b200", "libslharness.so")
+
+
+def build_harness() -> str:
+    """The measurement harness' call replayer (plain C): softlight_b200/harness/slharness.c -> libslharness.so."""
+    src = os.path.join(ROOT, "softlight_b200", "harness", "slharness.c")
+    if _newer(HARNESS_LIB, [src]):
+        return HARNESS_LIB
+    r = subprocess.run(["gcc", "-O2", "-shared", "-fPIC", src, "-o", HARNESS_LIB], capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("harness build failed")
+    return HARNESS_LIB
+
+
 def build_oracle() -> None:
     odir = os.path.join(ROOT, "oracle")
     r = subprocess.run(["make", "-s", "-C", odir, "port"], capture_output=True, text=True)
@@ -76,5 +91,6 @@ if __name__ == "__main__":
             _out = os.path.abspath(_a[6:])
             os.makedirs(os.path.dirname(_out), exist_ok=True)
     build_cuda(force="--force" in sys.argv, verbose="-v" in sys.argv, out=_out)
+    build_harness()
     build_oracle()
     print("built", _out)

@@ -194,6 +194,76 @@ def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+class _Cmd(C.Structure):
+    _fields_ = [("op", C.c_int32), ("pad_", C.c_int32), ("a", C.c_uint64), ("b", C.c_uint64), ("c", C.c_uint64), ("d", C.c_uint64),
+                ("p", C.c_void_p)]
+
+
+class _Api(C.Structure):
+    _fields_ = [("ubo_assign", C.c_void_p), ("ubo_bind_texture", C.c_void_p), ("ubo_bind_buffer", C.c_void_p), ("draw", C.c_void_p),
+                ("draw_instanced", C.c_void_p)]
+
+
+_HARNESS = None
+
+
+def _harness():
+    """softlight_b200/libslharness.so: replays a recorded list of per-draw calls from C (measurement harness, see slharness.c)."""
+    global _HARNESS
+    if _HARNESS is None:
+        path = os.path.join(ROOT, "softlight_b200", "libslharness.so")
+        if not os.path.exists(path):
+            from softlight_b200 import build as B
+
+            B.build_harness()
+        lib = C.CDLL(path)
+        lib.slh_replay.restype = C.c_size_t
+        lib.slh_replay.argtypes = [C.POINTER(_Api), C.c_void_p, C.POINTER(_Cmd), C.c_size_t, C.POINTER(C.c_int)]
+        _HARNESS = lib
+    return _HARNESS
+
+
+class CommandList:
+    """The per-draw calls of one frame (uniform updates, pointer bindings, draws), recorded once and replayed from C so that a
+    measured frame contains what a C/C++ host would execute, not the Python interpreter.  Same call order, same arguments."""
+
+    def __init__(self, ctx: "Context"):
+        self.ctx = ctx
+        self.cmds = []
+        self.keep = []
+        self.array = None
+        self.api = _Api(*[C.cast(ctx.f[n], C.c_void_p).value for n in ("ubo_assign", "ubo_bind_texture", "ubo_bind_buffer", "draw", "draw_instanced")])
+
+    def ubo_assign(self, uid, blob, offset=0):
+        buf = C.create_string_buffer(bytes(blob), len(blob))
+        self.keep.append(buf)
+        self.cmds.append(_Cmd(0, 0, uid, offset, len(blob), 0, C.cast(buf, C.c_void_p).value))
+
+    def ubo_bind_texture(self, uid, offset, tex):
+        self.cmds.append(_Cmd(1, 0, uid, offset, tex, 0, None))
+
+    def ubo_bind_buffer(self, uid, offset, vbo, byte_offset=0):
+        self.cmds.append(_Cmd(2, 0, uid, offset, vbo, byte_offset, None))
+
+    def draw(self, mesh, shader, fbo):
+        m = Mesh(mesh.vaoId, mesh.elementBegin, mesh.elementEnd, mesh.mode, mesh.materialId)
+        self.keep.append(m)
+        self.cmds.append(_Cmd(3, 0, shader, fbo, 0, 0, C.addressof(m)))
+
+    def draw_instanced(self, mesh, instances, shader, fbo):
+        m = Mesh(mesh.vaoId, mesh.elementBegin, mesh.elementEnd, mesh.mode, mesh.materialId)
+        self.keep.append(m)
+        self.cmds.append(_Cmd(4, 0, instances, shader, fbo, 0, C.addressof(m)))
+
+    def replay(self):
+        if self.array is None or len(self.array) != len(self.cmds):
+            self.array = (_Cmd * len(self.cmds))(*self.cmds)
+        rc = C.c_int(0)
+        bad = _harness().slh_replay(C.byref(self.api), self.ctx.h, self.array, len(self.cmds), C.byref(rc))
+        if bad:
+            self.ctx._chk(rc.value, f"replayed call #{bad - 1} (op {self.cmds[bad - 1].op})")
+
+
 class Context:
     """Thin object wrapper over one slcu_context (an SL_Context stand-in)."""
 

@@ -55,22 +55,44 @@ struct SLSpanEntry { uint32_t rec; uint16_t xMin, xMax; };
 /* device-side counters of one context */
 struct SLCounters
 {
-    unsigned long long recAlloc;     /* triangle records allocated (reset per batch)      */
-    unsigned long long handoffs;     /* span cuts (segment boundaries + row ends) that need a state hand-over (reset per batch) */
-    unsigned long long pixelsCovered; /* sum of span lengths = upper bound of the batch's fragments (reset per batch) */
-    unsigned long long rowEndCuts;    /* spans that run past the row end into an existing row (reset per batch)       */
-    unsigned long long trisBinned;
-    unsigned long long spans;
-    unsigned long long fragsShaded;
-    unsigned int errorFlags;         /* bit0 record overflow, bit1 span x out of range, bit2 span starts left of x=0,
-                                        bit3 overflow of a triangle that was classified as "cannot overflow" */
-    unsigned int rasterTicket;       /* (row, segment) ticket of k_resolve (reset by k_scan_row_starts)       */
-    unsigned int chunkAlloc;         /* fragment chunks handed out by k_resolve (reset by k_scan_row_starts)  */
-    unsigned int shadeTicket;        /* list ticket of k_shade (reset by k_scan_row_starts)                   */
+    /* ---- of the running batch: zeroed by one memset when the batch is enqueued (SL_COUNTERS_BATCH_BYTES) ---- */
+    unsigned long long recAlloc;      /* triangle records taken from the overflow area                                  */
+    unsigned long long handoffs;      /* span cuts (segment boundaries + row ends) that need a state hand-over          */
+    unsigned long long pixelsCovered; /* sum of span lengths = upper bound of the batch's fragments                     */
+    unsigned long long rowEndCuts;    /* spans that run past the row end into an existing row                           */
+    unsigned long long trisBinned, spans, fragsShaded; /* statistics of the batch; k_commit adds them to the totals     */
+    unsigned int abortBatch;          /* SL_ABORT_*: the batch does not fit the buffers it was given.  Set before anything
+                                         visible is written; k_span<1>, k_resolve*, k_shade then return at once and the host
+                                         runs the batch again with larger buffers (slcu.cu: verify_inflight)            */
+    unsigned int rasterTicket;        /* (row, segment) ticket of k_resolve (reset by k_scan_row_starts)                */
+    unsigned int chunkAlloc;          /* fragment chunks handed out by k_resolve (reset by k_scan_row_starts)           */
+    unsigned int shadeTicket;         /* list ticket of k_shade (reset by k_scan_row_starts)                            */
+    unsigned int totalEntries;        /* entries of the row lists (= rowStart[numRows]), for the host's sizing           */
+    unsigned int batchPad_;
+    /* ---- since reset_stats ---- */
+    unsigned long long totalTrisBinned, totalSpans, totalFragsShaded;
+    unsigned int errorFlags;          /* SL_ERR_*: sticky until the host reports them                                   */
+    unsigned int pad_;
     /* k_resolve diagnostics (SLCU_DEBUG=1): windows, their groups and waves, polls that found nothing, per-warp clocks */
     unsigned long long resolveWindows, resolveWaves, resolveIdle, resolveGroups;
     unsigned long long resolveCycles, resolveMaxCycles, resolveMaxWindows, resolveWarps;
 };
+#define SL_COUNTERS_BATCH_BYTES offsetof(SLCounters, totalTrisBinned)
+
+/* abortBatch bits */
+constexpr unsigned SL_ABORT_RECORDS = 1u;  /* more triangle records than the overflow area holds (clipping fan-out)      */
+constexpr unsigned SL_ABORT_ENTRIES = 2u;  /* more span entries than the row lists hold                                  */
+constexpr unsigned SL_ABORT_CHUNKS = 4u;   /* the fragment pool could run out                                            */
+constexpr unsigned SL_ABORT_HANDOFFS = 8u; /* more hand-overs than the table holds                                       */
+/* errorFlags bits: one per condition */
+constexpr unsigned SL_ERR_SPAN_TWO_ROWS = 0x2u;     /* a span longer than two rows: not reproduced                        */
+constexpr unsigned SL_ERR_SPAN_NEGATIVE_X = 0x4u;   /* a span that starts left of x = 0: not reproduced                   */
+constexpr unsigned SL_ERR_UNEXPECTED_OVERFLOW = 0x8u; /* row overflow of a triangle classified as "cannot overflow"       */
+constexpr unsigned SL_ERR_HANDOFF_PUBLISH = 0x10u;  /* a cut the count pass did not see (no hand-over table)              */
+constexpr unsigned SL_ERR_POOL = 0x20u;             /* fragment chunk pool exhausted: fragments dropped                   */
+constexpr unsigned SL_ERR_HANDOFF_POLL = 0x40u;     /* a piece waits for a hand-over but there is no table                */
+constexpr unsigned SL_ERR_WIRE_SEGMENT = 0x80u;     /* wireframe: a record segment with more than 256 records             */
+constexpr unsigned SL_ERR_WIRE_SLOTS = 0x100u;      /* wireframe: candidate slots exhausted                               */
 
 /* A span whose xMax exceeds the framebuffer width keeps going in linear memory:
  * the reference addresses pixels as x + width*y (src/SL_TriRasterizer.cpp:472,
@@ -538,7 +560,7 @@ __global__ void __launch_bounds__(SL_VB_THREADS, SL_VERTEX_MIN_BLOCKS) k_vertex(
                 const unsigned long long o = atomicAdd(&P.counters->recAlloc, (unsigned long long)total);
                 if (o + total > (unsigned long long)P.recOverflowCapacity)
                 {
-                    atomicOr(&P.counters->errorFlags, 1u); /* host re-issues the draw with a larger overflow area */
+                    atomicOr(&P.counters->abortBatch, SL_ABORT_RECORDS); /* the host runs the batch again with a larger overflow area */
                     base = 0u;
                     granted = 0u;
                 }
@@ -665,8 +687,8 @@ SLD_FN int sl_classify_span(const SLSpanParams& P, int32_t& xMin, int32_t& xMax)
 {
     if (!(xMin < xMax)) return 0;
     const int32_t W = (int32_t)P.width;
-    if (xMin < 0) { atomicOr(&P.counters->errorFlags, 4u); xMin = 0; }      /* would address the previous row: not reproduced */
-    if (xMax > 2 * W) { atomicOr(&P.counters->errorFlags, 2u); xMax = 2 * W; }
+    if (xMin < 0) { atomicOr(&P.counters->errorFlags, SL_ERR_SPAN_NEGATIVE_X); xMin = 0; }      /* would address the previous row: not reproduced */
+    if (xMax > 2 * W) { atomicOr(&P.counters->errorFlags, SL_ERR_SPAN_TWO_ROWS); xMax = 2 * W; }
     if (!(xMin < xMax)) return 0;
     return (xMin < W ? 1 : 0) | (xMax > W ? 2 : 0);
 }
@@ -712,6 +734,7 @@ __global__ void __launch_bounds__(256) k_span(const __grid_constant__ SLSpanPara
     const int lane = tid & 31, warp = tid >> 5;
     const unsigned int vb = blockIdx.x;
     const int H = (int)P.numRows;
+    if (MODE == 1 && P.counters->abortBatch) return; /* the lists would not fit: the batch is run again */
     for (int y = tid; y < H; y += 256) sRowRun[y] = 0;
     __syncthreads();
 
@@ -839,7 +862,7 @@ __global__ void __launch_bounds__(256) k_span(const __grid_constant__ SLSpanPara
                             sSl[i].step((float)y, xMin, xMax);
                             const int c = sl_classify_span(P, xMin, xMax);
                             own = c & 1;
-                            if ((c & 2) && !rOver) atomicOr(&P.counters->errorFlags, 8u);
+                            if ((c & 2) && !rOver) atomicOr(&P.counters->errorFlags, SL_ERR_UNEXPECTED_OVERFLOW);
                             if (MODE == 0 && c)
                             {
                                 myPix += (unsigned long long)(xMax - xMin);
@@ -953,8 +976,20 @@ __global__ void k_scan_rows(uint32_t* segSums, uint32_t* rowTotals, unsigned row
     rowTotals[y] = run;
 }
 
-/* single block: exclusive scan of rowTotals -> rowStart[0..numRows] ; also accumulates the span counter */
-__global__ void __launch_bounds__(1024) k_scan_row_starts(const uint32_t* rowTotals, uint32_t* rowStart, unsigned numRows, SLCounters* counters)
+/* what the batch was given; k_scan_row_starts compares it with what the count pass found */
+struct SLBatchCaps
+{
+    unsigned long long entries;      /* span entries the row lists hold          */
+    unsigned long long chunks;       /* chunks of the fragment pool              */
+    unsigned long long handoffSlots; /* slots of the hand-over table             */
+    unsigned long long numLists;     /* fragment lists (one partial chunk each)  */
+    unsigned long long chunkSlack;   /* chunks the resolving warps may hold back */
+    int chained;
+};
+
+/* single block: exclusive scan of rowTotals -> rowStart[0..numRows]; also accumulates the span counter and decides
+ * whether the batch fits its buffers */
+__global__ void __launch_bounds__(1024) k_scan_row_starts(const uint32_t* rowTotals, uint32_t* rowStart, unsigned numRows, SLCounters* counters, const SLBatchCaps caps)
 {
     __shared__ uint32_t sPart[1024];
     const int tid = threadIdx.x;
@@ -980,12 +1015,29 @@ __global__ void __launch_bounds__(1024) k_scan_row_starts(const uint32_t* rowTot
     }
     if (tid == 1023)
     {
-        rowStart[numRows] = sPart[1023];
-        atomicAdd(&counters->spans, (unsigned long long)sPart[1023]);
+        const uint32_t total = sPart[1023];
+        rowStart[numRows] = total;
+        atomicAdd(&counters->spans, (unsigned long long)total);
+        counters->totalEntries = total;
         counters->rasterTicket = 0u;
         counters->chunkAlloc = 0u;
         counters->shadeTicket = 0u;
+        unsigned abortBits = 0u;
+        if ((unsigned long long)total > caps.entries) abortBits |= SL_ABORT_ENTRIES;
+        /* every fragment is a pixel of a span, and a list ends with at most one partial chunk */
+        if (counters->pixelsCovered / 32ull + caps.numLists + caps.chunkSlack > caps.chunks) abortBits |= SL_ABORT_CHUNKS;
+        if (caps.chained && 2ull * counters->handoffs > caps.handoffSlots) abortBits |= SL_ABORT_HANDOFFS;
+        if (abortBits) atomicOr(&counters->abortBatch, abortBits);
     }
+}
+
+/* end of a batch: its statistics join the totals unless it has to be run again */
+__global__ void k_commit(SLCounters* counters)
+{
+    if (counters->abortBatch) return;
+    counters->totalTrisBinned += counters->trisBinned;
+    counters->totalSpans += counters->spans;
+    counters->totalFragsShaded += counters->fragsShaded;
 }
 
 __global__ void k_scan_offsets(const uint16_t* cnt, const uint32_t* segSums, uint32_t* off, unsigned numBlocks, unsigned rowPitch, unsigned blocksPerSeg, const uint8_t* rowNeeded, unsigned numRows)
@@ -1077,6 +1129,7 @@ struct SLShadeParams
     int colorType[4];         /* SL_ColorDataType */
     SLFragLists lists;
     unsigned int* shadeTicket; /* list ticket of k_shade (zeroed per batch) */
+    const unsigned int* abortBatch; /* SLCounters::abortBatch */
 };
 
 /* depth texel read (src/SL_TriRasterizer.cpp:40-102) */
@@ -1337,7 +1390,7 @@ SLD_FN void sl_push_frags(const SLRasterParams& P, const SLListState& L, int lan
             if (lane == 0)
             {
                 baseChunk = atomicAdd(&P.counters->chunkAlloc, need);
-                if (baseChunk + need > P.lists.chunkCapacity) { atomicOr(&P.counters->errorFlags, 32u); baseChunk = SL_NO_CHUNK; }
+                if (baseChunk + need > P.lists.chunkCapacity) { atomicOr(&P.counters->errorFlags, SL_ERR_POOL); baseChunk = SL_NO_CHUNK; }
             }
             baseChunk = __shfl_sync(0xffffffffu, baseChunk, 0);
             if (baseChunk == SL_NO_CHUNK) continue; /* pool exhausted: flagged, fragments dropped */
@@ -1400,7 +1453,7 @@ SLD_FN uint32_t sl_handoff_hash(unsigned long long key) { return (uint32_t)((key
 SLD_FN void sl_handoff_publish(const SLRasterParams& P, uint32_t rec, int y, int boundary, uint32_t outcomes, const math::vec4& r0, const math::vec4& r1,
                                const math::vec4& r2, const math::vec4& r3)
 {
-    if (!P.handoff) { atomicOr(&P.counters->errorFlags, 16u); return; } /* the count pass and the resolve pass disagree */
+    if (!P.handoff) { atomicOr(&P.counters->errorFlags, SL_ERR_HANDOFF_PUBLISH); return; } /* the count pass and the resolve pass disagree */
     const unsigned long long key = sl_handoff_key(rec, y, boundary);
     const unsigned long long word = (key << 12) | 0x800ull | (unsigned long long)(outcomes & 7u);
     uint32_t i = sl_handoff_hash(key) & P.handoffMask;
@@ -1416,7 +1469,7 @@ SLD_FN void sl_handoff_publish(const SLRasterParams& P, uint32_t rec, int y, int
 
 SLD_FN bool sl_handoff_poll(const SLRasterParams& P, uint32_t rec, int y, int boundary, SLHand& hand)
 {
-    if (!P.handoff) { atomicOr(&P.counters->errorFlags, 8u); return true; }
+    if (!P.handoff) { atomicOr(&P.counters->errorFlags, SL_ERR_HANDOFF_POLL); return true; }
     const unsigned long long key = sl_handoff_key(rec, y, boundary);
     uint32_t i = sl_handoff_hash(key) & P.handoffMask;
     for (;;)
@@ -1523,6 +1576,7 @@ __global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_
     /* One ticket per warp.  (Persistent warps that loop over tickets were measured: slower on C2/C3/C4 -- more
      * co-resident working warps do not raise this kernel's throughput -- so the simple form stays.) */
     {
+    if (P.counters->abortBatch) return; /* the batch did not fit: it is run again, nothing visible may be written */
     unsigned ticket = 0;
     if (lane == 0) ticket = atomicAdd(&P.counters->rasterTicket, 1u);
     ticket = __shfl_sync(0xffffffffu, ticket, 0);
@@ -1533,7 +1587,7 @@ __global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_
      * y + s*D of segment 0, D*numSegs >= the number of resident warps): a piece's left neighbour then took its
      * ticket a whole machine-load earlier and its hand-over is normally there before it is asked for. */
     int y = (int)(ticket / (unsigned)NS), seg = (int)(ticket % (unsigned)NS);
-    if (P.ticketOrder)
+    if (P.ticketOrder && P.counters->rowEndCuts == 0ull) /* the skew assumes that hand-overs only go to the right neighbour */
     {
         const uint32_t o = P.ticketOrder[ticket];
         y = (int)(o >> 6);
@@ -1974,6 +2028,7 @@ template <FsFn FS>
 __global__ void __launch_bounds__(SL_SHADE_WARPS * 32, SL_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ SLShadeParams P)
 {
     const int lane = threadIdx.x & 31;
+    if (P.abortBatch && *P.abortBatch) return; /* the batch did not fit: it is run again, nothing visible may be written */
     /* persistent warps: lists are handed out through a ticket (a block would otherwise live as long as its longest list) */
     for (;;)
     {

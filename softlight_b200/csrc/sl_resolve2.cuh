@@ -41,12 +41,15 @@ namespace sld
 #define SL_R2_MIN_BLOCKS 4
 #endif
 constexpr int SL_R2_WARPS = SL_R2_WARPS_N;
-constexpr int SL_R2_RING = 64;       /* pieces waiting for a lane (per warp) */
+constexpr int SL_R2_RING = 256;      /* pieces waiting for a lane (per warp) */
+constexpr int SL_R2_FIFO = 64;       /* free chunk ids held by the warp */
+constexpr unsigned SL_R2_FIFO_BLOCK = 16u; /* chunks taken from the global pool at a time */
 constexpr int SL_R2_CHUNK_RING = 32; /* newest chunk ids remembered per sub-list */
 constexpr unsigned SL_R2_RCP_BYTES = 2048u * 4u; /* per block: the rcp table */
 constexpr unsigned SL_R2_RING_BYTES = SL_R2_RING * (unsigned)sizeof(SLSpanEntry);
 constexpr unsigned SL_R2_SUB_BYTES = SL_MAX_SUBLISTS * 4u * 4u + SL_MAX_SUBLISTS * SL_R2_CHUNK_RING * 4u; /* count, chunks, want, last chunk + id ring */
-constexpr unsigned SL_R2_FIXED_BYTES = SL_R2_RING_BYTES + SL_R2_SUB_BYTES + 16u; /* + the tile's mbarrier */
+constexpr unsigned SL_R2_FIFO_BYTES = SL_R2_FIFO * 4u;
+constexpr unsigned SL_R2_FIXED_BYTES = SL_R2_RING_BYTES + SL_R2_SUB_BYTES + SL_R2_FIFO_BYTES + 16u; /* + the tile's mbarrier */
 
 __host__ __device__ inline unsigned sl_r2_warp_bytes(unsigned segWidth, unsigned tileBytes) { return SL_R2_FIXED_BYTES + ((4u * segWidth + 15u) & ~15u) + tileBytes; }
 
@@ -89,6 +92,40 @@ SLD_FN void sl_bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.r
 /* depth of one barycentric register (_sl_mul_vec4_mat4_ps, src/SL_TriRasterizer.cpp:376-393) */
 SLD_FN float sl_zdot(const math::vec4& a, float z0, float z1, float z2) { return ((a.v[3] * 0.f) + (a.v[2] * z2)) + ((a.v[1] * z1) + (a.v[0] * z0)); }
 
+/* depth texel of the staged segment, typed at compile time (src/SL_TriRasterizer.cpp:40-102, src/SL_FragmentProcessor.cpp:526-529) */
+template <int BPT> SLD_FN float sl_tile_load(const unsigned char* tile, int idx)
+{
+    if (BPT == 2) return sl_h2f(reinterpret_cast<const uint16_t*>(tile)[idx]);
+    if (BPT == 4) return reinterpret_cast<const float*>(tile)[idx];
+    return (float)reinterpret_cast<const double*>(tile)[idx];
+}
+template <int BPT> SLD_FN void sl_tile_store(unsigned char* tile, int idx, float z)
+{
+    if (BPT == 2) reinterpret_cast<uint16_t*>(tile)[idx] = sl_f2h_rn(z);
+    else if (BPT == 4) reinterpret_cast<float*>(tile)[idx] = z;
+    else reinterpret_cast<double*>(tile)[idx] = (double)z;
+}
+/* SL_DepthFunc* (SL_ShaderUtil.hpp:240-507) as a truth table over (z < d, z > d, z == d): ordered, quiet -- all three false
+ * on NaN, which only OFF lets pass.  Bit index = lt | gt << 1 | eq << 2. */
+SLD_FN uint32_t sl_depth_table(int func)
+{
+    return func == 0 ? 0xffu : func == 1 ? 0x02u : func == 2 ? 0x12u : func == 3 ? 0x04u : func == 4 ? 0x14u : func == 5 ? 0x10u : 0x06u;
+}
+SLD_FN bool sl_depth_pass(uint32_t table, float z, float d)
+{
+    const uint32_t idx = (z < d ? 1u : 0u) | (z > d ? 2u : 0u) | (z == d ? 4u : 0u);
+    return ((table >> idx) & 1u) != 0u;
+}
+
+/* first probe of a hand-over slot, issued early in the round (acquire: the registers are read after the flag) */
+SLD_FN unsigned long long sl_ld_acquire_u64(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <int BPT>
 __global__ void __launch_bounds__(SL_R2_WARPS * 32, SL_R2_MIN_BLOCKS) k_resolve2(const __grid_constant__ SLRasterParams P)
 {
     extern __shared__ __align__(16) unsigned char sDyn[];
@@ -109,17 +146,26 @@ __global__ void __launch_bounds__(SL_R2_WARPS * 32, SL_R2_MIN_BLOCKS) k_resolve2
     uint32_t* subWant = subChunks + SL_MAX_SUBLISTS;                               /* pixels about to be resolved       */
     uint32_t* subLast = subWant + SL_MAX_SUBLISTS;                                 /* its newest chunk                  */
     uint32_t* chunkRing = subLast + SL_MAX_SUBLISTS;                               /* [sub][SL_R2_CHUNK_RING] chunk ids */
-    unsigned long long* tileBar = reinterpret_cast<unsigned long long*>(warpMem + SL_R2_RING_BYTES + SL_R2_SUB_BYTES);
+    uint32_t* chunkFifo = chunkRing + SL_MAX_SUBLISTS * SL_R2_CHUNK_RING;          /* free chunk ids of this warp       */
+    unsigned long long* tileBar = reinterpret_cast<unsigned long long*>(warpMem + SL_R2_RING_BYTES + SL_R2_SUB_BYTES + SL_R2_FIFO_BYTES);
     uint32_t* pixMask = reinterpret_cast<uint32_t*>(warpMem + SL_R2_FIXED_BYTES); /* [segWidth] lanes whose piece still has to resolve the pixel */
     unsigned char* tile = warpMem + SL_R2_FIXED_BYTES + ((4u * P.segWidth + 15u) & ~15u);
     if (lane == 0) sl_mbar_init(tileBar, 1u);
     unsigned tilePhase = 0u;
     __syncthreads();
+    if (P.counters->abortBatch) return; /* the batch did not fit: it is run again, nothing visible may be written */
+    const bool skewed = P.ticketOrder && P.counters->rowEndCuts == 0ull; /* the skew assumes that hand-overs only go to the right neighbour */
 
     unsigned long long dbgRounds = 0, dbgIdle = 0, dbgGroups = 0;
     const long long dbgT0 = P.diagnostics ? clock64() : 0ll;
     unsigned shaded = 0;
     const unsigned numTickets = P.numRows * P.numSegs;
+    const uint32_t depthTable = sl_depth_table(P.depthTest);
+    /* free chunks of this warp: a FIFO of ids in shared memory, topped up SL_R2_FIFO_BLOCK at a time; the top-up's atomic
+     * is issued a round before its result is needed (lane 0 keeps it in flight) and what is left over goes to the next ticket */
+    unsigned fifoHead = 0u, fifoCount = 0u;
+    uint32_t pendingBase = 0u; /* lane 0 */
+    bool pendingValid = false; /* warp-uniform */
 
     /* persistent warps: (row, segment) tickets in launch order; a consumer of a hand-over only ever waits for a smaller
      * ticket, which a running warp holds */
@@ -130,7 +176,7 @@ __global__ void __launch_bounds__(SL_R2_WARPS * 32, SL_R2_MIN_BLOCKS) k_resolve2
         ticket = __shfl_sync(0xffffffffu, ticket, 0);
         if (ticket >= numTickets) break;
         int y = (int)(ticket / (unsigned)NS), seg = (int)(ticket % (unsigned)NS);
-        if (P.ticketOrder)
+        if (skewed)
         {
             const uint32_t o = P.ticketOrder[ticket];
             y = (int)(o >> 6);
@@ -144,8 +190,8 @@ __global__ void __launch_bounds__(SL_R2_WARPS * 32, SL_R2_MIN_BLOCKS) k_resolve2
         const unsigned segPixels = (unsigned)(sx1 - sx0);
         const long long segOrigin = (long long)W * y + sx0;
         const uint32_t firstList = (uint32_t)(y * NS + seg) * P.numSubLists;
-        const unsigned tileLoadBytes = segPixels * (unsigned)P.depthBpt;
-        unsigned char* tileSrc = P.depth + (size_t)segOrigin * P.depthBpt;
+        const unsigned tileLoadBytes = segPixels * (unsigned)BPT;
+        unsigned char* tileSrc = P.depth + (size_t)segOrigin * BPT;
         const bool bulkOk = (tileLoadBytes & 15u) == 0u && (reinterpret_cast<uintptr_t>(tileSrc) & 15u) == 0u;
 
         if (lane < SL_MAX_SUBLISTS)
@@ -164,28 +210,58 @@ __global__ void __launch_bounds__(SL_R2_WARPS * 32, SL_R2_MIN_BLOCKS) k_resolve2
         math::vec4 a0{0.f}, a1{0.f}, a2{0.f}, a3{0.f}, bcX{0.f};
         float z0 = 0.f, z1 = 0.f, z2 = 0.f;
 
+        /* the row's entry list is read 128 entries ahead: four loads per lane in flight while the warp works */
         uint32_t base = begin;
+        SLSpanEntry pre[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+        {
+            const uint32_t idx = base + 32u * k + (uint32_t)lane;
+            pre[k] = SLSpanEntry{0u, 0, 0};
+            if (idx < end) pre[k] = P.entries[idx];
+        }
         unsigned ringHead = 0u, ringCount = 0u, idle = 0u;
         for (;;)
         {
             const uint32_t busyMask = __ballot_sync(0xffffffffu, busy);
-            /* ---- keep the ring of waiting pieces filled: the row's entries that reach into this segment, in list order ---- */
-            while (ringCount <= (unsigned)(SL_R2_RING - 32) && base < end)
+            /* hand-over slots are probed early: the load travels while the warp fills its ring and sets pieces up */
+            unsigned long long pollW = 0ull;
+            uint32_t pollI = 0u;
+            if (busy && !ready)
             {
-                const uint32_t idx = base + (uint32_t)lane;
-                SLSpanEntry c = SLSpanEntry{0u, 0, 0};
-                if (idx < end) c = P.entries[idx];
-                const int cb = (c.rec & SL_ENTRY_OVERFLOW) ? W : 0;
-                const bool cHas = max((int)c.xMin, cb + sx0) < min((int)c.xMax, cb + sx1); /* empty entries: 0 < 0 */
-                const uint32_t hm = __ballot_sync(0xffffffffu, cHas);
-                if (cHas)
+                if (!P.handoff) { atomicOr(&P.counters->errorFlags, SL_ERR_HANDOFF_POLL); pollW = ~0ull; }
+                else
                 {
-                    ring[(ringHead + ringCount + (unsigned)__popc(hm & ltMask)) & (SL_R2_RING - 1)] = c;
-                    const float4* r = P.records + (size_t)(c.rec & ~SL_ENTRY_OVERFLOW) * P.recStride;
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(r));
+                    pollI = sl_handoff_hash(sl_handoff_key(recId, ySrc, bOut - 1)) & P.handoffMask;
+                    pollW = sl_ld_acquire_u64(&P.handoff[pollI]);
                 }
-                ringCount += (unsigned)__popc(hm);
-                base += 32u;
+            }
+            /* ---- keep the ring of waiting pieces filled: the row's entries that reach into this segment, in list order ---- */
+            while (ringCount <= (unsigned)(SL_R2_RING - 128) && base < end)
+            {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                {
+                    const SLSpanEntry c = pre[k];
+                    const int cb = (c.rec & SL_ENTRY_OVERFLOW) ? W : 0;
+                    const bool cHas = max((int)c.xMin, cb + sx0) < min((int)c.xMax, cb + sx1); /* empty entries: 0 < 0 */
+                    const uint32_t hm = __ballot_sync(0xffffffffu, cHas);
+                    if (cHas)
+                    {
+                        ring[(ringHead + ringCount + (unsigned)__popc(hm & ltMask)) & (SL_R2_RING - 1)] = c;
+                        const float4* r = P.records + (size_t)(c.rec & ~SL_ENTRY_OVERFLOW) * P.recStride;
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(r));
+                    }
+                    ringCount += (unsigned)__popc(hm);
+                }
+                base += 128u;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                {
+                    const uint32_t idx = base + 32u * k + (uint32_t)lane;
+                    pre[k] = SLSpanEntry{0u, 0, 0};
+                    if (idx < end) pre[k] = P.entries[idx];
+                }
             }
             if (!busyMask && !ringCount) break;
             __syncwarp();
@@ -284,11 +360,27 @@ __global__ void __launch_bounds__(SL_R2_WARPS * 32, SL_R2_MIN_BLOCKS) k_resolve2
             {
                 if (!ready)
                 {
-                    SLHand h;
-                    if (sl_handoff_poll(P, recId, ySrc, bOut - 1, h))
+                    /* the slot probed at the top of the round; on a key mismatch keep probing (open addressing) */
+                    const unsigned long long key = sl_handoff_key(recId, ySrc, bOut - 1);
+                    bool found = pollW == ~0ull;
+                    while (!found && pollW != 0ull)
                     {
-                        a0 = h.r[0]; a1 = h.r[1]; a2 = h.r[2]; a3 = h.r[3];
-                        fM = h.fM;
+                        if ((pollW >> 12) == key) { found = (pollW & 0x8ull) != 0ull; break; }
+                        pollI = (pollI + 1u) & P.handoffMask;
+                        pollW = sl_ld_acquire_u64(&P.handoff[pollI]);
+                    }
+                    if (found)
+                    {
+                        if (pollW != ~0ull)
+                        {
+                            const float4* src = P.handoffRegs + (size_t)pollI * 4;
+                            const float4 f0 = __ldcg(src + 0), f1 = __ldcg(src + 1), f2 = __ldcg(src + 2), f3 = __ldcg(src + 3);
+                            a0 = math::vec4{f0.x, f0.y, f0.z, f0.w};
+                            a1 = math::vec4{f1.x, f1.y, f1.z, f1.w};
+                            a2 = math::vec4{f2.x, f2.y, f2.z, f2.w};
+                            a3 = math::vec4{f3.x, f3.y, f3.z, f3.w};
+                            fM = (uint32_t)(pollW & 7ull);
+                        }
                         ready = true;
                     }
                 }
@@ -328,39 +420,80 @@ __global__ void __launch_bounds__(SL_R2_WARPS * 32, SL_R2_MIN_BLOCKS) k_resolve2
                 }
             }
             __syncwarp();
-            /* ---- chunks for the pixels of this round: lane s looks after sub-list s ---- */
+            /* ---- chunks for the pixels of this round: lane s looks after sub-list s, ids come from the warp's FIFO ---- */
+            if (pendingValid)
+            {
+                /* the top-up asked for a round ago has landed */
+                const uint32_t b = __shfl_sync(0xffffffffu, pendingBase, 0);
+                if (lane < (int)SL_R2_FIFO_BLOCK) chunkFifo[(fifoHead + fifoCount + (unsigned)lane) & (SL_R2_FIFO - 1)] = b == SL_NO_CHUNK ? SL_NO_CHUNK : b + (uint32_t)lane;
+                fifoCount += SL_R2_FIFO_BLOCK;
+                pendingValid = false;
+            }
+            uint32_t need = 0u, have = 0u;
             if (lane < nsub)
             {
                 const uint32_t want = subWant[lane];
                 if (want)
                 {
                     subWant[lane] = 0u;
-                    const uint32_t have = subChunks[lane];
+                    have = subChunks[lane];
                     const uint32_t needTotal = (subCount[lane] + want + 31u) >> 5;
-                    if (needTotal > have)
-                    {
-                        const uint32_t need = needTotal - have;
-                        uint32_t b = atomicAdd(&P.counters->chunkAlloc, need);
-                        if (b + need > P.lists.chunkCapacity)
-                        {
-                            atomicOr(&P.counters->errorFlags, 32u); /* pool exhausted: flagged, fragments dropped */
-                            for (uint32_t i = 0; i < need; ++i) chunkRing[lane * SL_R2_CHUNK_RING + ((have + i) & (SL_R2_CHUNK_RING - 1))] = SL_NO_CHUNK;
-                        }
-                        else
-                        {
-                            const uint32_t prev = subLast[lane];
-                            if (prev == SL_NO_CHUNK) P.lists.listHead[firstList + lane] = b;
-                            else P.lists.chunkNext[prev] = b;
-                            for (uint32_t i = 0; i < need; ++i)
-                            {
-                                chunkRing[lane * SL_R2_CHUNK_RING + ((have + i) & (SL_R2_CHUNK_RING - 1))] = b + i;
-                                if (i + 1u < need) P.lists.chunkNext[b + i] = b + i + 1u;
-                            }
-                            subLast[lane] = b + need - 1u;
-                        }
-                        subChunks[lane] = needTotal;
-                    }
+                    if (needTotal > have) need = needTotal - have;
                 }
+            }
+            uint32_t incl = need;
+#pragma unroll
+            for (int d = 1; d < SL_MAX_SUBLISTS; d <<= 1)
+            {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            const uint32_t totalNeed = __shfl_sync(0xffffffffu, incl, SL_MAX_SUBLISTS - 1);
+            if (totalNeed)
+            {
+                while (fifoCount < totalNeed)
+                {
+                    /* more than the FIFO holds (the first rounds of a warp, bursts): take a block now */
+                    uint32_t b = 0u;
+                    if (lane == 0)
+                    {
+                        b = atomicAdd(&P.counters->chunkAlloc, SL_R2_FIFO_BLOCK);
+                        if (b + SL_R2_FIFO_BLOCK > P.lists.chunkCapacity) { atomicOr(&P.counters->errorFlags, SL_ERR_POOL); b = SL_NO_CHUNK; } /* pool exhausted: flagged, fragments dropped */
+                    }
+                    b = __shfl_sync(0xffffffffu, b, 0);
+                    if (lane < (int)SL_R2_FIFO_BLOCK) chunkFifo[(fifoHead + fifoCount + (unsigned)lane) & (SL_R2_FIFO - 1)] = b == SL_NO_CHUNK ? SL_NO_CHUNK : b + (uint32_t)lane;
+                    fifoCount += SL_R2_FIFO_BLOCK;
+                }
+                __syncwarp();
+                if (need)
+                {
+                    uint32_t prev = subLast[lane];
+                    const unsigned first = fifoHead + (incl - need);
+                    for (uint32_t i = 0; i < need; ++i)
+                    {
+                        const uint32_t id = chunkFifo[(first + i) & (SL_R2_FIFO - 1)];
+                        chunkRing[lane * SL_R2_CHUNK_RING + ((have + i) & (SL_R2_CHUNK_RING - 1))] = id;
+                        if (id != SL_NO_CHUNK)
+                        {
+                            if (prev == SL_NO_CHUNK) P.lists.listHead[firstList + lane] = id;
+                            else P.lists.chunkNext[prev] = id;
+                            prev = id;
+                        }
+                    }
+                    subLast[lane] = prev;
+                    subChunks[lane] = have + need;
+                }
+                fifoHead += totalNeed;
+                fifoCount -= totalNeed;
+            }
+            if (fifoCount < SL_R2_FIFO_BLOCK * 2u && !pendingValid)
+            {
+                if (lane == 0)
+                {
+                    pendingBase = atomicAdd(&P.counters->chunkAlloc, SL_R2_FIFO_BLOCK);
+                    if (pendingBase + SL_R2_FIFO_BLOCK > P.lists.chunkCapacity) { atomicOr(&P.counters->errorFlags, SL_ERR_POOL); pendingBase = SL_NO_CHUNK; }
+                }
+                pendingValid = true;
             }
             if (staged && !tileReady)
             {
@@ -389,8 +522,8 @@ __global__ void __launch_bounds__(SL_R2_WARPS * 32, SL_R2_MIN_BLOCKS) k_resolve2
                         if (x4 + j >= p0 && x4 + j < p1)
                         {
                             own |= 1u << j;
-                            const float d = P.depthTest ? sl_load_depth(tile, P.depthBpt, (size_t)(rel + j)) : 0.f;
-                            if (sl_depth_cmp(P.depthTest, zc[j], d)) m |= 1u << j;
+                            const float d = P.depthTest ? sl_tile_load<BPT>(tile, rel + j) : 0.f;
+                            if (sl_depth_pass(depthTable, zc[j], d)) m |= 1u << j;
                         }
                     }
                     const uint32_t tt = m | fM;
@@ -427,7 +560,7 @@ __global__ void __launch_bounds__(SL_R2_WARPS * 32, SL_R2_MIN_BLOCKS) k_resolve2
                                      * and with its own x and z */
                                     const uint32_t sIdx = (uint32_t)__popc(tt & ((1u << j) - 1u));
                                     const math::vec4 bc = sIdx == 0u ? n0 : (sIdx == 1u ? n1 : (sIdx == 2u ? n2 : a3));
-                                    if (P.depthMask) sl_store_depth(tile, P.depthBpt, (size_t)(rel + j), zc[j]); /* src/SL_FragmentProcessor.cpp:526-529 */
+                                    if (P.depthMask) sl_tile_store<BPT>(tile, rel + j, zc[j]); /* src/SL_FragmentProcessor.cpp:526-529 */
                                     const bool lo = j < jSplit;
                                     const uint32_t pos = lo ? posLo++ : posHi++;
                                     const int sub = lo ? sFirst : sLast;

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(128) k_wire(const __grid_constant__ SLWirePara
     const unsigned vb = (unsigned)(w >> 13), seg = (unsigned)(w >> 8) & 31u, idx = (unsigned)w & 255u;
     if (vb >= P.numBlocks) return; /* warp-uniform exits */
     const SLSegment sg = P.blockInfo[vb].seg[seg];
-    if (sg.count > 256u && idx == 0u && lane == 0) atomicOr(&P.counters->errorFlags, 16u);
+    if (sg.count > 256u && idx == 0u && lane == 0) atomicOr(&P.counters->errorFlags, SL_ERR_WIRE_SEGMENT);
     if (idx >= sg.count) return;
     const uint32_t recId = sg.base + idx;
 
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(128) k_wire(const __grid_constant__ SLWirePara
             h = true;
             if (owned((unsigned long long)x + (unsigned long long)P.width * (unsigned)y)) ++c;
         });
-        if ((uint32_t)x0 < (uint32_t)x1 && x1 > xLimit) atomicOr(&P.counters->errorFlags, 2u);
+        if ((uint32_t)x0 < (uint32_t)x1 && x1 > xLimit) atomicOr(&P.counters->errorFlags, SL_ERR_SPAN_TWO_ROWS);
         hit = h;
         return c;
     };
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(128) k_wire(const __grid_constant__ SLWirePara
     {
         P.recCount[recId] = fits ? n : 0u;
         P.recBase[recId] = (uint32_t)base;
-        if (!fits) atomicOr(&P.counters->errorFlags, 32u);
+        if (!fits) atomicOr(&P.counters->errorFlags, SL_ERR_WIRE_SLOTS);
     }
     if (!n || !fits) return;
 

@@ -53,12 +53,14 @@ template <VsFn VS> static cudaError_t launch_vertex(unsigned grid, cudaStream_t 
         k_vertex<VS, false><<<grid, SL_VB_THREADS, 0, s>>>(p);
         return cudaGetLastError();
     }
-    static bool attrSet = false; /* one opt-in per instantiation: the cache may exceed the 48 KB default */
-    if (!attrSet)
+    static bool attrSet[64] = {}; /* one opt-in per instantiation and device: the cache may exceed the 48 KB default */
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attrSet[dev & 63])
     {
         cudaError_t e = cudaFuncSetAttribute(k_vertex<VS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVertexCacheMaxBytes);
         if (e != cudaSuccess) return e;
-        attrSet = true;
+        attrSet[dev & 63] = true;
     }
     k_vertex<VS, true><<<grid, SL_VB_THREADS, p.cacheBytes, s>>>(p);
     return cudaGetLastError();
@@ -244,6 +246,11 @@ struct slcu_context
     Scratch ticketOrder; /* skewed work order of k_resolve, cached per (rows, segments, skew) */
     unsigned orderRows = 0, orderSegs = 0, orderSkew = 0;
     Batch batch;            /* submitted, not yet executed draws */
+    /* A batch is enqueued with the buffer sizes its predecessors needed and checked at its end (run_batch): no host round
+     * trip in the middle of a frame.  When the device found the buffers too small it has skipped every kernel that writes
+     * something visible, and the batch is run again with sizes taken from its own counters. */
+    cudaEvent_t batchDone = nullptr;
+    struct Caps { unsigned long long recOverflow = 0, entries = 0, chunks = 0, handoffSlots = 0, avgSpan = 0; } caps;
     bool syncDraws = false; /* SLCU_SYNC_DRAWS=1: execute every draw call on its own (debug / parity mode) */
     /* sort-first partition (slcu_set_partition) */
     unsigned partRank = 0, partWorld = 1, partStripRows = 8;
@@ -279,8 +286,9 @@ struct KernelScope
     ~KernelScope() { if (b) cudaEventRecord(b, c->stream); }
 };
 
-static const uint32_t* g_activeRcpOwner = nullptr; /* whose table g_rcp_table currently holds */
-static uint32_t g_activeRcpCopy[2048];
+/* what g_rcp_table holds on each device (function attributes and __device__ symbols are per device) */
+static bool g_activeRcpValid[64];
+static uint32_t g_activeRcpCopy[64][2048];
 
 /* execute the pending draw batch before anything that reads or changes what it uses */
 #define SLCU_FLUSH()                                                                     \
@@ -298,15 +306,16 @@ static uint32_t g_activeRcpCopy[2048];
     } while (0)
 
 static int flush_draws(slcu_context* c);
-
 static int ensure_rcp_table(slcu_context* c)
 {
     if (!c->rcpValid) { c->err = "no rcp table"; return SLCU_ERR_ARG; }
-    if (g_activeRcpOwner && memcmp(g_activeRcpCopy, c->rcpTable, sizeof(g_activeRcpCopy)) == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    const int d = c->device & 63;
+    if (g_activeRcpValid[d] && memcmp(g_activeRcpCopy[d], c->rcpTable, sizeof(c->rcpTable)) == 0) return 0;
     CK(cudaDeviceSynchronize()); /* table switch: rare (tests pinning a table) */
     CK(cudaMemcpyToSymbol(g_rcp_table, c->rcpTable, sizeof(c->rcpTable)));
-    memcpy(g_activeRcpCopy, c->rcpTable, sizeof(g_activeRcpCopy));
-    g_activeRcpOwner = c->rcpTable;
+    memcpy(g_activeRcpCopy[d], c->rcpTable, sizeof(c->rcpTable));
+    g_activeRcpValid[d] = true;
     return 0;
 }
 
@@ -525,6 +534,7 @@ static int run_points(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes
     if (rc) return rc;
     cudaSetDevice(c->device);
     c->stats.drawCalls++;
+    CK(cudaMemsetAsync(c->counters, 0, SL_COUNTERS_BATCH_BYTES, c->stream)); /* the per-batch part; k_commit adds it to the totals */
     const float fboW = (float)depthTex.w, fboH = (float)depthTex.h;
     const int NV = sh.numVaryings;
     unsigned pixBits = 1;
@@ -600,21 +610,66 @@ static int run_points(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes
         sp.counters = c->counters;
         { KernelScope ks(c, SLCU_K_SHADE); CK(sh.pointFs((unsigned)((numPoints + 127ull) / 128ull), c->stream, sp)); }
     }
+    k_commit<<<1, 1, 0, c->stream>>>(c->counters);
+    CK(cudaGetLastError());
     return 0;
 }
 
-static int flush_draws_impl(slcu_context* c);
+static int enqueue_batch(slcu_context* c, Batch& B, bool& verify);
+
+/* The counters of the batch that just ran are in hostCounters[0].  Returns true when the device refused it (abortBatch):
+ * the sizes it needs are then known exactly and become the new minimum for every later batch. */
+static bool batch_was_refused(slcu_context* c)
+{
+    const SLCounters& h = c->hostCounters[0];
+    if (h.totalEntries) c->caps.avgSpan = h.pixelsCovered / h.totalEntries;
+    if (getenv("SLCU_DEBUG"))
+        fprintf(stderr, "[slcu] batch: records(overflow area)=%llu entries=%u handoffs=%llu pixels=%llu rowEndCuts=%llu abort=0x%x flags=0x%x\n",
+                (unsigned long long)h.recAlloc, h.totalEntries, (unsigned long long)h.handoffs, (unsigned long long)h.pixelsCovered,
+                (unsigned long long)h.rowEndCuts, h.abortBatch, h.errorFlags);
+    if (!h.abortBatch) return false;
+    auto grow = [](unsigned long long& cap, unsigned long long need) { const unsigned long long want = need + need / 4 + 4096; if (want > cap) cap = want; };
+    grow(c->caps.recOverflow, h.recAlloc);
+    grow(c->caps.entries, h.totalEntries);
+    grow(c->caps.chunks, h.pixelsCovered / SL_CHUNK_FRAGS);
+    grow(c->caps.handoffSlots, 2ull * h.handoffs);
+    return true;
+}
+
+/* Run one batch.  Its kernels are enqueued back to back with the buffer sizes earlier batches needed -- no host round trip
+ * in the middle -- and its counters come back with one async copy behind the last kernel.  The host waits for that copy
+ * (the end of the batch, where the caller's own join is in the usual clear / draw ... / read frame) and, when the device
+ * refused the batch, runs it again with the sizes its own counters ask for.  Everything that depends on the batch
+ * (another shader's draws, clears, blits, read-backs) is enqueued after this returns. */
+static int run_batch(slcu_context* c, Batch& B)
+{
+    for (int attempt = 0; attempt < 6; ++attempt)
+    {
+        bool verify = false;
+        const int rc = enqueue_batch(c, B, verify);
+        if (rc) return rc;
+        if (!verify) return 0; /* executed with its own host round trips (wireframe) or empty */
+        CK(cudaMemcpyAsync(c->hostCounters, c->counters, sizeof(SLCounters), cudaMemcpyDeviceToHost, c->stream));
+        if (!c->batchDone) CK(cudaEventCreateWithFlags(&c->batchDone, cudaEventDisableTiming));
+        CK(cudaEventRecord(c->batchDone, c->stream));
+        CK(cudaEventSynchronize(c->batchDone));
+        if (!batch_was_refused(c)) return 0;
+    }
+    c->err = "batch does not fit its buffers after repeated growth";
+    return SLCU_ERR_OOM;
+}
+
 static int flush_draws(slcu_context* c)
 {
     if (c->batch.descs.empty()) return 0;
-    const int rc = flush_draws_impl(c);
+    const int rc = run_batch(c, c->batch);
     c->batch.clear();
     return rc;
 }
 
-static int flush_draws_impl(slcu_context* c)
+static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
 {
-    Batch& B = c->batch;
+    verify = false;
     const size_t shaderId = B.shaderId, fboId = B.fboId;
     const HostShader& sh = c->shaders[shaderId];
     const HostFbo& fbo = c->fbos[fboId];
@@ -648,18 +703,21 @@ static int flush_draws_impl(slcu_context* c)
     /* record slots: SL_VB_THREADS per (block, round) at fixed places + an overflow area for rounds that clipping fans out */
     const unsigned long long recFixed = (unsigned long long)numBlocks * SL_VB_PRIMS;
     unsigned long long recOverflow = totalPrims / 8 + 4096;
+    if (c->caps.recOverflow > recOverflow) recOverflow = c->caps.recOverflow;
     unsigned long long recCapacity = recFixed + recOverflow;
     static const bool useVertexCache = getenv("SLCU_VERTEX_CACHE") != nullptr && atoi(getenv("SLCU_VERTEX_CACHE")) != 0; /* opt-in: measured slower on C3, +3 % on C2 */
-    unsigned long long numHandoffs = 0;
-    unsigned long long totalSpansHost = 0;
     const uint8_t* rowNeeded = nullptr;
+    unsigned numSubLists = (segWidth + (1u << SL_SHADE_SHIFT) - 1u) >> SL_SHADE_SHIFT;
+    if (numSubLists > (unsigned)SL_MAX_SUBLISTS) { c->err = "segment too wide for the sub-list table"; return SLCU_ERR_ARG; }
+    const unsigned long long numLists = (unsigned long long)H * rasterSegs * numSubLists;
+    unsigned long long chunkCap = 0, handoffSlots = 0;
     for (int attempt = 0;; ++attempt)
     {
         if (recCapacity > 0x7ffffff0ull) { c->err = "batch too large"; return SLCU_ERR_UNSUPPORTED; }
         CK(c->records.ensure((size_t)recCapacity * recStride * sizeof(float4)));
         CK(c->recDraw.ensure((size_t)recCapacity * sizeof(uint16_t)));
         CK(c->blockInfo.ensure((size_t)numBlocks * sizeof(SLBlockInfo)));
-        CK(cudaMemsetAsync(&c->counters->recAlloc, 0, 4 * sizeof(unsigned long long), c->stream)); /* recAlloc + handoffs + pixelsCovered + rowEndCuts */
+        CK(cudaMemsetAsync(c->counters, 0, SL_COUNTERS_BATCH_BYTES, c->stream)); /* the per-batch part */
 
         {
             SLVertexParams vp;
@@ -706,15 +764,14 @@ static int flush_draws_impl(slcu_context* c)
             CK(cudaGetLastError());
             CK(cudaMemcpyAsync(c->hostCounters, c->counters, sizeof(SLCounters), cudaMemcpyDeviceToHost, c->stream));
             CK(cudaStreamSynchronize(c->stream));
-            if (c->hostCounters->errorFlags & 1u)
+            if (c->hostCounters->abortBatch & SL_ABORT_RECORDS)
             {
-                CK(cudaMemsetAsync(&c->counters->errorFlags, 0, sizeof(unsigned), c->stream));
-                if (attempt == 0) { recOverflow = totalPrims * 7 + 4096; recCapacity = recFixed + recOverflow; continue; }
+                if (attempt == 0) { recOverflow = totalPrims * 7 + 4096; recCapacity = recFixed + recOverflow; c->caps.recOverflow = recOverflow; continue; }
                 c->err = "triangle record buffer overflow";
                 return SLCU_ERR_OOM;
             }
             const unsigned long long numFrags = c->hostCounters->pixelsCovered;
-            if (!numFrags) return 0;
+            if (!numFrags) { k_commit<<<1, 1, 0, c->stream>>>(c->counters); return 0; }
             if (numFrags > 0x7ffffff0ull) { c->err = "too many wireframe fragments for one batch"; return SLCU_ERR_UNSUPPORTED; }
             CK(c->pointKeys.ensure((size_t)numFrags * 2 * sizeof(unsigned long long)));
             CK(c->wireSlots.ensure((size_t)numFrags * 2 * sizeof(unsigned long long)));
@@ -824,6 +881,8 @@ static int flush_draws_impl(slcu_context* c)
                 if (!settled) { CK(cudaMemsetAsync(ep.changed, 0, sizeof(unsigned), c->stream)); c->err = "wireframe flush epochs did not settle"; return SLCU_ERR_UNSUPPORTED; }
             }
             { KernelScope ks(c, SLCU_K_SHADE); CK(sh.wireFs(shadeGrid, c->stream, ws)); }
+            k_commit<<<1, 1, 0, c->stream>>>(c->counters);
+            CK(cudaGetLastError());
             return 0;
         }
 
@@ -877,34 +936,39 @@ static int flush_draws_impl(slcu_context* c)
         CK(cudaGetLastError());
         { KernelScope ks(c, SLCU_K_SCAN); k_scan_rows<<<(rowPitch + 127) / 128, 128, 0, c->stream>>>(reinterpret_cast<uint32_t*>(c->segSums.buf.ptr), reinterpret_cast<uint32_t*>(c->rowTotals.buf.ptr), rowPitch, usedSegs); }
         CK(cudaGetLastError());
-        { KernelScope ks(c, SLCU_K_SCAN); k_scan_row_starts<<<1, 1024, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(c->rowTotals.buf.ptr), reinterpret_cast<uint32_t*>(c->rowStart.buf.ptr), H, c->counters); }
+        /* what this batch gets: the sizes its predecessors needed (first batch: a guess; the device refuses the batch when
+         * it does not fit and the host then knows the exact figures) */
+        unsigned long long capEntries = c->caps.entries ? c->caps.entries : totalPrims / 2 + 65536ull;
+        CK(c->entries.ensure((size_t)capEntries * sizeof(SLSpanEntry)));
+        capEntries = c->entries.buf.bytes / sizeof(SLSpanEntry);
+        if (capEntries > 0xfffffff0ull) capEntries = 0xfffffff0ull;
+        const unsigned long long chunkSlack = 64ull + 160ull * SL_R2_MIN_BLOCKS * SL_R2_WARPS * (SL_R2_FIFO_BLOCK * 3ull); /* what the resolving warps hold in their FIFOs */
+        chunkCap = (c->caps.chunks ? c->caps.chunks : (unsigned long long)depthTex.w * H / 8ull) + numLists + chunkSlack;
+        if (chunkCap > 0xfffffff0ull || chunkCap * SL_CHUNK_BYTES > (96ull << 30)) { c->err = "fragment list pool too large"; return SLCU_ERR_OOM; }
+        CK(c->fragPool.ensure((size_t)chunkCap * SL_CHUNK_BYTES));
+        chunkCap = c->fragPool.buf.bytes / SL_CHUNK_BYTES;
+        if (chunkCap > 0xfffffff0ull) chunkCap = 0xfffffff0ull;
+        CK(c->chunkNext.ensure((size_t)chunkCap * sizeof(uint32_t)));
+        if (sh.depthTest != 0)
+        {
+            handoffSlots = 4096;
+            while (handoffSlots < c->caps.handoffSlots) handoffSlots <<= 1;
+            CK(c->handoff.ensure((size_t)handoffSlots * sizeof(unsigned long long)));
+            CK(c->handoffRegs.ensure((size_t)handoffSlots * 4 * sizeof(float4)));
+            CK(cudaMemsetAsync(c->handoff.buf.ptr, 0, (size_t)handoffSlots * sizeof(unsigned long long), c->stream));
+        }
+        SLBatchCaps caps;
+        caps.entries = capEntries;
+        caps.chunks = chunkCap;
+        caps.handoffSlots = handoffSlots;
+        caps.numLists = numLists;
+        caps.chunkSlack = chunkSlack;
+        caps.chained = sh.depthTest != 0 ? 1 : 0;
+        { KernelScope ks(c, SLCU_K_SCAN); k_scan_row_starts<<<1, 1024, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(c->rowTotals.buf.ptr), reinterpret_cast<uint32_t*>(c->rowStart.buf.ptr), H, c->counters, caps); }
         CK(cudaGetLastError());
         { KernelScope ks(c, SLCU_K_SCAN); k_scan_offsets<<<sgrid, 128, 0, c->stream>>>(sp.cnt, reinterpret_cast<const uint32_t*>(c->segSums.buf.ptr), reinterpret_cast<uint32_t*>(c->off.buf.ptr), numBlocks, rowPitch, blocksPerSeg, rowNeeded, H); }
         CK(cudaGetLastError());
 
-        /* the span lists are sized from the count: one small read-back per batch */
-        uint32_t totalSpans = 0;
-        CK(cudaMemcpyAsync(c->hostCounters, c->counters, sizeof(SLCounters), cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaMemcpyAsync(&c->hostCounters[1], reinterpret_cast<uint32_t*>(c->rowStart.buf.ptr) + H, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
-        memcpy(&totalSpans, &c->hostCounters[1], sizeof(uint32_t));
-        if (c->hostCounters->errorFlags & 1u)
-        {
-            /* more records than reserved (heavy clipping): retry once with the worst case */
-            CK(cudaMemsetAsync(&c->counters->errorFlags, 0, sizeof(unsigned), c->stream));
-            if (attempt == 0) { recOverflow = totalPrims * 7 + 4096; recCapacity = recFixed + recOverflow; continue; }
-            c->err = "triangle record buffer overflow";
-            return SLCU_ERR_OOM;
-        }
-        if (!totalSpans) return 0;
-        totalSpansHost = totalSpans;
-        numHandoffs = c->hostCounters->handoffs;
-        if (getenv("SLCU_DEBUG"))
-            fprintf(stderr, "[slcu] batch: draws=%zu prims=%llu records=%llu entries=%u handoffs=%llu segs=%ux%u pixels=%llu flags=0x%x\n", B.descs.size(), totalPrims,
-                    (unsigned long long)c->hostCounters->recAlloc, totalSpans, numHandoffs, rasterSegs, segWidth, (unsigned long long)c->hostCounters->pixelsCovered,
-                    c->hostCounters->errorFlags);
-
-        CK(c->entries.ensure((size_t)totalSpans * sizeof(SLSpanEntry)));
         sp.entries = reinterpret_cast<SLSpanEntry*>(c->entries.buf.ptr);
         { KernelScope ks(c, SLCU_K_SPAN_FILL); k_span<1><<<numBlocks, 256, 0, c->stream>>>(sp); }
         CK(cudaGetLastError());
@@ -912,19 +976,6 @@ static int flush_draws_impl(slcu_context* c)
     }
 
     /* ---- fragment stage: k_resolve (depth, coverage, order) -> fragment lists -> k_shade<FS> ---- */
-    unsigned numSubLists = (segWidth + (1u << SL_SHADE_SHIFT) - 1u) >> SL_SHADE_SHIFT;
-    if (numSubLists > (unsigned)SL_MAX_SUBLISTS) { c->err = "segment too wide for the sub-list table"; return SLCU_ERR_ARG; }
-    const unsigned long long numLists = (unsigned long long)H * rasterSegs * numSubLists;
-    /* every fragment is a pixel of a span, and a list ends with at most one partial chunk */
-    const unsigned long long pixelsCovered = c->hostCounters->pixelsCovered;
-    const unsigned long long chunkCap = pixelsCovered / SL_CHUNK_FRAGS + numLists + 64ull;
-    if (chunkCap > 0xfffffff0ull || chunkCap * SL_CHUNK_BYTES > (96ull << 30))
-    {
-        c->err = "fragment list pool too large";
-        return SLCU_ERR_OOM;
-    }
-    CK(c->fragPool.ensure((size_t)chunkCap * SL_CHUNK_BYTES));
-    CK(c->chunkNext.ensure((size_t)chunkCap * sizeof(uint32_t)));
     CK(c->listInfo.ensure((size_t)numLists * 2 * sizeof(uint32_t)));
     CK(cudaMemsetAsync(c->listInfo.buf.ptr, 0, (size_t)numLists * 2 * sizeof(uint32_t), c->stream));
     SLFragLists lists;
@@ -953,16 +1004,11 @@ static int flush_draws_impl(slcu_context* c)
     rp.numSegs = rasterSegs;
     rp.numSubLists = numSubLists;
     rp.lists = lists;
-    if (numHandoffs)
+    if (handoffSlots)
     {
-        size_t cap = 64;
-        while (cap < 2 * numHandoffs) cap <<= 1;
-        CK(c->handoff.ensure(cap * sizeof(unsigned long long)));
-        CK(cudaMemsetAsync(c->handoff.buf.ptr, 0, cap * sizeof(unsigned long long), c->stream));
-        CK(c->handoffRegs.ensure(cap * 4 * sizeof(float4)));
         rp.handoff = reinterpret_cast<unsigned long long*>(c->handoff.buf.ptr);
         rp.handoffRegs = reinterpret_cast<float4*>(c->handoffRegs.buf.ptr);
-        rp.handoffMask = (unsigned)(cap - 1);
+        rp.handoffMask = (unsigned)(handoffSlots - 1);
     }
     /* each resolving warp keeps its segment's depth texels in shared memory (at most 32 x ... pixels x 8 bytes) */
     rp.tileBytes = (segWidth * depthTex.bpt + 15u) & ~15u;
@@ -977,7 +1023,7 @@ static int flush_draws_impl(slcu_context* c)
         /* sort-first partition: only 1/world of the rows does any work on this rank, so the skew is world times longer */
         const unsigned world = c->partWorld > 1 ? c->partWorld : 1u;
         const unsigned skew = skewEnv >= 0 ? (unsigned)skewEnv : (resident * world + rasterSegs - 1) / rasterSegs + 32u;
-        if (sh.depthTest != 0 && rasterSegs > 1 && rasterSegs <= 64 && skew > 0 && numHandoffs && c->hostCounters->rowEndCuts == 0)
+        if (sh.depthTest != 0 && rasterSegs > 1 && rasterSegs <= 64 && skew > 0) /* used by the kernel only when no span runs past a row end */
         {
             if (c->orderRows != H || c->orderSegs != rasterSegs || c->orderSkew != skew)
             {
@@ -1008,16 +1054,17 @@ static int flush_draws_impl(slcu_context* c)
      * (sl_resolve2.cuh: short spans, i.e. every triangle-dense scene), k_resolve spreads the groups of a piece over the
      * lanes of a window (long spans).  SLCU_RESOLVE=1|2 forces one of them. */
     static const int resolveEnv = getenv("SLCU_RESOLVE") ? atoi(getenv("SLCU_RESOLVE")) : 0;
-    const unsigned long long avgSpan = totalSpansHost ? pixelsCovered / totalSpansHost : 0ull;
-    const bool useResolve2 = resolveEnv == 2 || (resolveEnv != 1 && avgSpan < 48ull);
+    const bool useResolve2 = resolveEnv == 2 || (resolveEnv != 1 && c->caps.avgSpan < 48ull); /* average span of the last verified batch */
     if (useResolve2)
     {
         const unsigned smemBytes = SL_R2_RCP_BYTES + SL_R2_WARPS * sl_r2_warp_bytes(segWidth, rp.tileBytes);
-        static bool attrSet2 = false;
-        if (!attrSet2)
+        static bool attrSet2[64] = {};
+        if (!attrSet2[c->device & 63])
         {
-            CK(cudaFuncSetAttribute(k_resolve2, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            attrSet2 = true;
+            CK(cudaFuncSetAttribute(k_resolve2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            CK(cudaFuncSetAttribute(k_resolve2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            CK(cudaFuncSetAttribute(k_resolve2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            attrSet2[c->device & 63] = true;
         }
         if (smemBytes > 160u * 1024u) { c->err = "framebuffer too wide for the resolve tile"; return SLCU_ERR_ARG; }
         int numSMs = 148;
@@ -1027,7 +1074,9 @@ static int flush_draws_impl(slcu_context* c)
         const unsigned long long needBlocks = (numWarps + SL_R2_WARPS - 1) / SL_R2_WARPS;
         if (grid > needBlocks) grid = needBlocks;
         KernelScope ks(c, SLCU_K_RASTER);
-        k_resolve2<<<(unsigned)grid, SL_R2_WARPS * 32, smemBytes, c->stream>>>(rp);
+        if (depthTex.bpt == 2) k_resolve2<2><<<(unsigned)grid, SL_R2_WARPS * 32, smemBytes, c->stream>>>(rp);
+        else if (depthTex.bpt == 4) k_resolve2<4><<<(unsigned)grid, SL_R2_WARPS * 32, smemBytes, c->stream>>>(rp);
+        else k_resolve2<8><<<(unsigned)grid, SL_R2_WARPS * 32, smemBytes, c->stream>>>(rp);
         CK(cudaGetLastError());
     }
     else
@@ -1035,11 +1084,11 @@ static int flush_draws_impl(slcu_context* c)
     const unsigned warpsPerBlock = SL_RASTER_WARPS;
     const unsigned smemBytes = warpsPerBlock * (SL_PIECEQ_BYTES + SL_SUBLIST_BYTES + SL_PIECEREG_BYTES + SL_WINSCRATCH_BYTES + ((4u * segWidth + 15u) & ~15u) + rp.tileBytes); /* piece queue, sub-list state, piece registers, window scratch, toucher masks, depth tile: per warp */
     {
-        static bool attrSet = false;
-        if (!attrSet)
+        static bool attrSet[64] = {};
+        if (!attrSet[c->device & 63])
         {
             CK(cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            attrSet = true;
+            attrSet[c->device & 63] = true;
         }
         if (smemBytes > 96u * 1024u) { c->err = "framebuffer too wide for the resolve tile"; return SLCU_ERR_ARG; }
         KernelScope ks(c, SLCU_K_RASTER);
@@ -1072,6 +1121,7 @@ static int flush_draws_impl(slcu_context* c)
         }
     }
     shp.shadeTicket = &c->counters->shadeTicket;
+    shp.abortBatch = &c->counters->abortBatch;
     {
         int numSMs = 148;
         cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, c->device);
@@ -1081,6 +1131,9 @@ static int flush_draws_impl(slcu_context* c)
         KernelScope ks(c, SLCU_K_SHADE);
         CK(sh.fs((unsigned)grid, c->stream, shp));
     }
+    k_commit<<<1, 1, 0, c->stream>>>(c->counters);
+    CK(cudaGetLastError());
+    verify = true;
     return 0;
 }
 
@@ -1139,6 +1192,26 @@ static int clear_texture(slcu_context* c, const HostTexture& t, const unsigned c
     return 0;
 }
 
+/* Device error flags (SL_ERR_*) seen by a read-back of the counters: turned into a return code and a decoded message,
+ * then cleared on the device so that each occurrence is reported once. */
+static int report_device_flags(slcu_context* c, unsigned flags)
+{
+    if (!flags) return 0;
+    std::string m = "device flags:";
+    if (flags & SL_ERR_SPAN_TWO_ROWS) m += " [span longer than two rows: reference behaviour not reproduced]";
+    if (flags & SL_ERR_SPAN_NEGATIVE_X) m += " [span starts left of x=0: reference behaviour not reproduced]";
+    if (flags & SL_ERR_UNEXPECTED_OVERFLOW) m += " [row overflow of a triangle that cannot overflow]";
+    if (flags & SL_ERR_HANDOFF_PUBLISH) m += " [hand-over published without a table]";
+    if (flags & SL_ERR_HANDOFF_POLL) m += " [hand-over awaited without a table]";
+    if (flags & SL_ERR_POOL) m += " [fragment pool exhausted: fragments dropped]";
+    if (flags & SL_ERR_WIRE_SEGMENT) m += " [wireframe: record segment over 256]";
+    if (flags & SL_ERR_WIRE_SLOTS) m += " [wireframe: candidate slots exhausted]";
+    c->err = m;
+    cudaMemsetAsync(&c->counters->errorFlags, 0, sizeof(unsigned), c->stream);
+    if (flags & (SL_ERR_POOL | SL_ERR_WIRE_SLOTS)) return SLCU_ERR_OOM;
+    return SLCU_ERR_UNSUPPORTED;
+}
+
 /* ===========================================================================
  * C ABI
  * =========================================================================*/
@@ -1154,9 +1227,9 @@ int slcu_context_create(slcu_context** out, int device)
     slcu_context* c = new slcu_context{};
     c->device = device;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return SLCU_ERR_CUDA; }
-    if (cudaMalloc(&c->counters, sizeof(SLCounters)) != cudaSuccess) { delete c; return SLCU_ERR_CUDA; }
+    if (cudaMalloc(&c->counters, sizeof(SLCounters)) != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; return SLCU_ERR_CUDA; }
     cudaMemset(c->counters, 0, sizeof(SLCounters));
-    if (cudaMallocHost(&c->hostCounters, 2 * sizeof(SLCounters)) != cudaSuccess) { delete c; return SLCU_ERR_CUDA; }
+    if (cudaMallocHost(&c->hostCounters, 2 * sizeof(SLCounters)) != cudaSuccess) { cudaFree(c->counters); cudaStreamDestroy(c->stream); delete c; return SLCU_ERR_CUDA; }
     c->rcpValid = measure_host_rcp_table(c->rcpTable, c->err);
     c->syncDraws = getenv("SLCU_SYNC_DRAWS") != nullptr && atoi(getenv("SLCU_SYNC_DRAWS")) != 0;
     *out = c;
@@ -1167,8 +1240,13 @@ void slcu_context_destroy(slcu_context* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    if (!c->batch.descs.empty()) flush_draws(c);
+    flush_draws(c);
     cudaStreamSynchronize(c->stream);
+    if (c->batchDone) cudaEventDestroy(c->batchDone);
+    if (c->timerA) cudaEventDestroy(c->timerA);
+    if (c->timerB) cudaEventDestroy(c->timerB);
+    for (auto& e : c->profEvents) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    for (cudaEvent_t e : c->eventPool) cudaEventDestroy(e);
     for (DevBuffer& b : c->vbos) if (b.ptr) cudaFree(b.ptr);
     for (HostIbo& b : c->ibos) if (b.buf.ptr) cudaFree(b.buf.ptr);
     for (HostTexture& t : c->textures) if (t.dev) cudaFree(t.dev);
@@ -1364,10 +1442,13 @@ int slcu_fbo_reserve_color_buffers(slcu_context* c, size_t fbo, unsigned n)
 {
     SLCU_FLUSH();
     if (fbo >= c->fbos.size()) return SLCU_ERR_ARG;
-    if (n < 1) return -1; /* src/SL_Framebuffer.cpp:823-848 */
+    /* src/SL_Framebuffer.cpp:823-848: same count = no-op (checked first), the colour views are reset, the depth view stays */
+    HostFbo& f = c->fbos[fbo];
+    if (n == f.numColors) return 0;
+    if (n < 1) return -1;
     if (n > 4) return -2;
-    c->fbos[fbo] = HostFbo{};
-    c->fbos[fbo].numColors = n;
+    for (int i = 0; i < 4; ++i) { f.colors[i] = (size_t)-1; f.colorViews[i] = FboView{}; }
+    f.numColors = n;
     return 0;
 }
 int slcu_fbo_attach_color_buffer(slcu_context* c, size_t fbo, unsigned index, size_t tex)
@@ -1594,8 +1675,10 @@ int slcu_sync(slcu_context* c)
 {
     SLCU_FLUSH();
     cudaSetDevice(c->device);
+    /* the join of the reference's workers; also where frames that could not be rendered like the reference are reported */
+    CK(cudaMemcpyAsync(&c->hostCounters[1].errorFlags, &c->counters->errorFlags, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    return 0;
+    return report_device_flags(c, c->hostCounters[1].errorFlags);
 }
 
 int slcu_reset_stats(slcu_context* c)
@@ -1615,25 +1698,17 @@ int slcu_get_stats(slcu_context* c, slcu_stats* out)
     cudaSetDevice(c->device);
     CK(cudaMemcpyAsync(c->hostCounters, c->counters, sizeof(SLCounters), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    c->stats.trisBinned = c->hostCounters->trisBinned;
-    c->stats.spans = c->hostCounters->spans;
-    c->stats.fragsShaded = c->hostCounters->fragsShaded;
+    c->stats.trisBinned = c->hostCounters->totalTrisBinned;
+    c->stats.spans = c->hostCounters->totalSpans;
+    c->stats.fragsShaded = c->hostCounters->totalFragsShaded;
     if (getenv("SLCU_DEBUG"))
         fprintf(stderr, "[slcu] resolve: windows=%llu groups=%llu waves=%llu idle polls=%llu | warps=%llu clocks sum=%llu max=%llu maxWindows=%llu\n",
                 (unsigned long long)c->hostCounters->resolveWindows, (unsigned long long)c->hostCounters->resolveGroups,
                 (unsigned long long)c->hostCounters->resolveWaves, (unsigned long long)c->hostCounters->resolveIdle,
                 (unsigned long long)c->hostCounters->resolveWarps, (unsigned long long)c->hostCounters->resolveCycles,
                 (unsigned long long)c->hostCounters->resolveMaxCycles, (unsigned long long)c->hostCounters->resolveMaxWindows);
-    if (c->hostCounters->errorFlags & ~1u)
-    {
-        /* inputs whose reference behaviour is not reproduced bit for bit */
-        char buf[160];
-        snprintf(buf, sizeof(buf), "device flags 0x%x: bit1 span longer than two rows, bit2 span starts left of x=0, bit3 unexpected row overflow",
-                 c->hostCounters->errorFlags);
-        c->err = buf;
-    }
     *out = c->stats;
-    return 0;
+    return report_device_flags(c, c->hostCounters->errorFlags);
 }
 
 int slcu_timer_begin(slcu_context* c)
@@ -1648,7 +1723,7 @@ int slcu_timer_begin(slcu_context* c)
 
 int slcu_timer_end(slcu_context* c, double* ms)
 {
-    SLCU_FLUSH();
+    SLCU_FLUSH(); /* a batch that has to be run again is part of the timed region */
     if (!c || !ms || !c->timerA) return SLCU_ERR_ARG;
     cudaSetDevice(c->device);
     CK(cudaEventRecord(c->timerB, c->stream));

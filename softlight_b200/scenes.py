@@ -383,12 +383,16 @@ def indoor_scene(width=3840, height=2160, rooms=(16, 16), quads=26, tex_size=512
 
     def frame(ctx, st):
         ctx.clear_framebuffer(st["fbo"], 0, (0.0, 0.0, 0.0, 1.0), 0.0)
-        ubo, texs, mesh, sh, fbo = st["ubo"], st["texs"], st["mesh"], st["shader"], st["fbo"]
-        assign, bind, draw = ctx.ubo_assign, ctx.ubo_bind_texture, ctx.draw
-        for i in range(nrooms):  # the demo's pattern: per-mesh uniforms, then draw (sl_large_scene_test.cpp:700-730)
-            assign(ubo, blobs[i])
-            bind(ubo, 0, texs[i])
-            draw(mesh, sh, fbo)
+        if "calls" not in st:
+            # the demo's pattern: per-mesh uniforms, then draw (sl_large_scene_test.cpp:700-730); recorded once, replayed from C
+            ubo, texs, mesh, sh, fbo = st["ubo"], st["texs"], st["mesh"], st["shader"], st["fbo"]
+            calls = A.CommandList(ctx)
+            for i in range(nrooms):
+                calls.ubo_assign(ubo, blobs[i])
+                calls.ubo_bind_texture(ubo, 0, texs[i])
+                calls.draw(mesh, sh, fbo)
+            st["calls"] = calls
+        st["calls"].replay()
 
     return Scene(name or f"indoor{nrooms}x{tris.shape[0]}_{width}x{height}", width, height, A.SL_COLOR_RGBA_8U, depth_type,
                  (0, 0, 0, 1), 0.0, setup, frame, tris_per_frame=tris.shape[0] * nrooms, draws_per_frame=nrooms,
@@ -594,13 +598,17 @@ def skinned_scene(width=1920, height=1080, grid=(10, 10), bones=64, around=160, 
 
     def frame(ctx, st):
         ctx.clear_framebuffer(st["fbo"], 0, (0.2, 0.2, 0.25, 1.0), 0.0)
-        ubo, tex, bonebuf, mesh, sh, fbo = st["ubo"], st["tex"], st["bones"], st["mesh"], st["shader"], st["fbo"]
-        assign, bind, bindbuf, draw = ctx.ubo_assign, ctx.ubo_bind_texture, ctx.ubo_bind_buffer, ctx.draw
-        for i in range(nchars):   # the demo's pattern: per-mesh uniforms (model matrix, bone palette), then draw
-            assign(ubo, blobs[i])
-            bind(ubo, 0, tex)
-            bindbuf(ubo, 8, bonebuf, i * bones * 64)
-            draw(mesh, sh, fbo)
+        if "calls" not in st:
+            # the demo's pattern: per-mesh uniforms (model matrix, bone palette), then draw; recorded once, replayed from C
+            ubo, tex, bonebuf, mesh, sh, fbo = st["ubo"], st["tex"], st["bones"], st["mesh"], st["shader"], st["fbo"]
+            calls = A.CommandList(ctx)
+            for i in range(nchars):
+                calls.ubo_assign(ubo, blobs[i])
+                calls.ubo_bind_texture(ubo, 0, tex)
+                calls.ubo_bind_buffer(ubo, 8, bonebuf, i * bones * 64)
+                calls.draw(mesh, sh, fbo)
+            st["calls"] = calls
+        st["calls"].replay()
 
     return Scene(name or f"skinned{nchars}x{tris.shape[0]}_{width}x{height}", width, height, A.SL_COLOR_RGBA_8U, depth_type,
                  (0.2, 0.2, 0.25, 1.0), 0.0, setup, frame, tris_per_frame=tris.shape[0] * nchars, draws_per_frame=nchars,

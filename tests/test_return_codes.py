@@ -54,9 +54,10 @@ def drive(impl: str):
         return fb
 
     fb = f["create_framebuffer"](h)
-    out.append(("reserve(0)", f["fbo_reserve_color_buffers"](h, fb, 0)))
+    out.append(("reserve(0) on a fresh fbo", f["fbo_reserve_color_buffers"](h, fb, 0)))  # same count: no-op, 0
     out.append(("reserve(5)", f["fbo_reserve_color_buffers"](h, fb, 5)))
     out.append(("reserve(2)", f["fbo_reserve_color_buffers"](h, fb, 2)))
+    out.append(("reserve(0)", f["fbo_reserve_color_buffers"](h, fb, 0)))
     out.append(("attach(index 2 of 2)", f["fbo_attach_color_buffer"](h, fb, 2, c8)))
     out.append(("attach(index 4 of 2)", f["fbo_attach_color_buffer"](h, fb, 4, c8)))
 
@@ -81,8 +82,13 @@ def drive(impl: str):
     fbo_case("depth_width_and_type", 1, [(0, c16x8)], dbad)       # -7
     # reserve resets every view
     fb2 = fbo_case("reset_by_reserve", 1, [(0, c8)], df)
-    out.append(("reset_by_reserve:reserve-again", f["fbo_reserve_color_buffers"](h, fb2, 1)))
-    out.append(("reset_by_reserve:valid-after", f["fbo_valid"](h, fb2)))
+    out.append(("reset_by_reserve:reserve-same", f["fbo_reserve_color_buffers"](h, fb2, 1)))
+    out.append(("reset_by_reserve:valid-after-same", f["fbo_valid"](h, fb2)))       # same count: nothing is reset
+    out.append(("reset_by_reserve:reserve-2", f["fbo_reserve_color_buffers"](h, fb2, 2)))
+    out.append(("reset_by_reserve:valid-after-2", f["fbo_valid"](h, fb2)))          # colour views gone: -2
+    out.append(("reset_by_reserve:attach0", f["fbo_attach_color_buffer"](h, fb2, 0, c8)))
+    out.append(("reset_by_reserve:attach1", f["fbo_attach_color_buffer"](h, fb2, 1, c8b)))
+    out.append(("reset_by_reserve:valid-depth-kept", f["fbo_valid"](h, fb2)))       # the depth view survived the reserve: 0
 
     vao = f["create_vao"](h)
     for n in (0, 1, 7, 8, 9):
@@ -121,7 +127,8 @@ def test_oracle_codes_follow_the_reference_table():
         "colour_depth_differs:valid": -5, "no_depth:valid": -6, "depth_without_texels:valid": -6,
         "depth_width_differs:valid": -7, "depth_height_differs:valid": -8, "depth_is_3d:valid": -9,
         "depth_type_rgba8:valid": -10, "depth_type_r16u:valid": -10, "depth_width_and_type:valid": -7,
-        "reset_by_reserve:valid": 0, "reset_by_reserve:valid-after": -2,
+        "reset_by_reserve:valid": 0, "reset_by_reserve:valid-after-same": 0, "reset_by_reserve:valid-after-2": -2,
+        "reset_by_reserve:valid-depth-kept": 0, "reserve(0) on a fresh fbo": 0,
         "reserve(0)": -1, "reserve(5)": -2, "reserve(2)": 0, "attach(index 2 of 2)": -1, "attach(index 4 of 2)": -1,
         "set_num_bindings(7)": 7, "set_num_bindings(8)": -1, "set_num_bindings(9)": -1,
         "shader_ok": 0, "shader_fs_more_varyings": -1, "shader_vs_5_varyings": -1, "shader_fs_5_varyings": -1,

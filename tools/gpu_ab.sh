@@ -6,7 +6,7 @@ CONFIGS="$1"; shift
 for v in "$@"; do
   lib=build/$v.so; [ "$v" = base ] && lib=softlight_b200/libslcu.so
   for c in $CONFIGS; do
-    SLCU_LIB=$lib timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --config $c > gpurun_out/ab.json 2> gpurun_out/ab.err
+    SLCU_LIB=$lib timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-other-configs --config $c > gpurun_out/ab.json 2> gpurun_out/ab.err
     python - "$v" "$c" <<'PY' || tail -3 gpurun_out/ab.err
 import json, sys
 d = json.loads(open('gpurun_out/ab.json').read().splitlines()[-1])
