@@ -339,8 +339,13 @@ class Harness:
 
     def device_timed(self, steps, warmup):
         """K frames, each bracketed by CUDA events on the library's stream, L2 flushed before each; max over ranks per frame."""
-        for i in range(max(warmup, 3)):
+        # W untimed frames, and at least 0.4 s of them: the SM clock of an idle GPU takes that long to come up
+        t0, i = time.perf_counter(), 0
+        while i < max(warmup, 3) or (time.perf_counter() - t0 < 0.4 and i < 2000):
             self.render_frame(i)
+            i += 1
+            if i % 8 == 0:
+                self.ctx.sync()
         self.barrier()
         sampler = ClockSampler(self.local_rank)
         self.ctx.reset_stats()
@@ -422,7 +427,7 @@ def rooflines(config, scene, frags, frame_ms, classes, prof_frames, clocks):
     kernel_ms_per_frame = {k: v["ms"] / prof_frames for k, v in classes.items()}
     frame_kernel_ms = sum(kernel_ms_per_frame.values())
     ncu = ncu_counters(dom, config)
-    kname = (ncu or {}).get("kernel") or {"raster": "k_resolve", "shade": "k_shade"}.get(dom, "k_" + dom)
+    kname = (ncu or {}).get("kernel") or {"raster": "k_resolve2 (k_resolve for long-span batches)", "shade": "k_shade"}.get(dom, "k_" + dom)
     hbm = {
         "bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": (ncu["dram_bytes_read"] + ncu["dram_bytes_write"]) if ncu else None, "traffic_source": ncu["source"] if ncu else None,

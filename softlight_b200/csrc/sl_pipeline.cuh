@@ -48,7 +48,10 @@ constexpr int SL_SPAN_WIN = 256;          /* rows per mask window in k_span     
 
 struct SLSegment { uint32_t base, count; };
 constexpr int SL_VB_SEGS = SL_VB_ROUNDS * (SL_VB_THREADS / 32); /* one record segment per (round, warp) of a vertex block */
-struct SLBlockInfo { SLSegment seg[SL_VB_SEGS]; };
+/* negYMin / yMax: the rows the block's records can have span entries in (complement of the minimum so that a zeroed
+ * struct means "none" and both are kept with atomicMax); k_span_items cuts every block into 256-row work items with it */
+struct SLBlockInfo { SLSegment seg[SL_VB_SEGS]; uint32_t negYMin, yMax; };
+constexpr int SL_SPAN_BAND_SHIFT = 8; /* log2(SL_SPAN_WIN): rows per work item of k_span */
 
 struct SLSpanEntry { uint32_t rec; uint16_t xMin, xMax; };
 
@@ -68,7 +71,8 @@ struct SLCounters
     unsigned int chunkAlloc;          /* fragment chunks handed out by k_resolve (reset by k_scan_row_starts)           */
     unsigned int shadeTicket;         /* list ticket of k_shade (reset by k_scan_row_starts)                            */
     unsigned int totalEntries;        /* entries of the row lists (= rowStart[numRows]), for the host's sizing           */
-    unsigned int batchPad_;
+    unsigned int spanTicket[2];       /* item tickets of k_span<0> / k_span<1>                                          */
+    unsigned int spanItems;           /* work items of k_span (k_span_items)                                            */
     /* ---- since reset_stats ---- */
     unsigned long long totalTrisBinned, totalSpans, totalFragsShaded;
     unsigned int errorFlags;          /* SL_ERR_*: sticky until the host reports them                                   */
@@ -84,6 +88,7 @@ constexpr unsigned SL_ABORT_RECORDS = 1u;  /* more triangle records than the ove
 constexpr unsigned SL_ABORT_ENTRIES = 2u;  /* more span entries than the row lists hold                                  */
 constexpr unsigned SL_ABORT_CHUNKS = 4u;   /* the fragment pool could run out                                            */
 constexpr unsigned SL_ABORT_HANDOFFS = 8u; /* more hand-overs than the table holds                                       */
+constexpr unsigned SL_ABORT_PARTITION = 16u; /* sort-first fast path: a span runs past the row end into another rank's row */
 /* errorFlags bits: one per condition */
 constexpr unsigned SL_ERR_SPAN_TWO_ROWS = 0x2u;     /* a span longer than two rows: not reproduced                        */
 constexpr unsigned SL_ERR_SPAN_NEGATIVE_X = 0x4u;   /* a span that starts left of x = 0: not reproduced                   */
@@ -574,6 +579,42 @@ __global__ void __launch_bounds__(SL_VB_THREADS, SL_VERTEX_MIN_BLOCKS) k_vertex(
             binned += granted;
             P.blockInfo[blockIdx.x].seg[round * (SL_VB_THREADS / 32) + warp] = SLSegment{base, granted};
         }
+        if (granted) /* warp-uniform */
+        {
+            /* rows the records of this warp touch (conservative: vertex rows, one more for spans that run past the row end) */
+            float fy0 = 3.0e38f, fy1 = -1.f;
+            if (n)
+            {
+                if (CACHE && fromCache)
+                {
+                    const float a = cache[CV + ci[0]].y, b = cache[CV + ci[1]].y, cc = cache[CV + ci[2]].y;
+                    fy0 = fminf(a, fminf(b, cc));
+                    fy1 = fmaxf(a, fmaxf(b, cc));
+                }
+                else if (!polyVerts)
+                {
+                    fy0 = fminf(v[0].vert.v[1], fminf(v[1].vert.v[1], v[2].vert.v[1]));
+                    fy1 = fmaxf(v[0].vert.v[1], fmaxf(v[1].vert.v[1], v[2].vert.v[1]));
+                }
+                else
+                {
+                    for (int k = 0; k < polyVerts; ++k) { fy0 = fminf(fy0, poly.verts[k].v[1]); fy1 = fmaxf(fy1, poly.verts[k].v[1]); }
+                }
+            }
+            for (int d = 16; d > 0; d >>= 1)
+            {
+                fy0 = fminf(fy0, __shfl_xor_sync(0xffffffffu, fy0, d));
+                fy1 = fmaxf(fy1, __shfl_xor_sync(0xffffffffu, fy1, d));
+            }
+            if (lane == 0 && fy1 >= 0.f)
+            {
+                /* screen y is a non-negative integer stored as a float (sl_to_screen); NaN rows produce no spans */
+                const uint32_t r0 = fy0 < 65535.f ? (uint32_t)fy0 : 65535u;
+                const uint32_t r1 = fy1 < 65535.f ? (uint32_t)fy1 + 2u : 65535u;
+                atomicMax(&P.blockInfo[blockIdx.x].negYMin, ~r0);
+                atomicMax(&P.blockInfo[blockIdx.x].yMax, r1);
+            }
+        }
         /* (Staging a warp's records in shared memory and storing them as one contiguous stream was measured: slower on
          * every config -- the kernel is bound by its barriers and index/vertex fetch latency, not by the record stores.) */
         const bool emit = n != 0 && granted != 0;
@@ -678,6 +719,13 @@ struct SLSpanParams
     /* sort-first partition (null when this context owns every row) */
     uint8_t* rowFlags;           /* MODE 0 out: 1 = some span of the row below runs over into this row */
     const uint8_t* rowNeeded;    /* MODE 1 in : rows this rank rasterises (owned + the rows their hand-overs come from) */
+    const uint32_t* items;       /* work items: vertex block | row band << 16 (k_span_items)               */
+    const uint32_t* numItems;
+    unsigned int* ticket;        /* item ticket of this pass (zeroed per batch)                              */
+    int partFast;                /* sort-first fast path: rowNeeded = the rows this rank owns, and both passes leave every
+                                    other row alone.  Valid as long as no span runs past the row end into a row of another
+                                    rank; k_span<0> looks for exactly that and refuses the batch (SL_ABORT_PARTITION), the
+                                    host then runs it again with every row counted and the rows closed over (k_row_closure) */
 };
 
 /* What one (record,row) span contributes to the row lists.  bit0: an entry in
@@ -710,17 +758,62 @@ SLD_FN unsigned sl_count_cuts(const SLSpanParams& P, int32_t xMin, int32_t xMax,
     return n;
 }
 
+/* Work items of k_span: one per (vertex block, band of SL_SPAN_WIN rows the block's records touch).  A block of large
+ * triangles covers a thousand rows and would keep one CTA busy long after the rest of the grid has drained; cut into bands
+ * it is shared by several.  Bands of one block are independent: an entry's place in its row list depends on the block's
+ * earlier records in that ROW only. */
+__global__ void __launch_bounds__(1024) k_span_items(const SLBlockInfo* blockInfo, unsigned numBlocks, unsigned numRows, uint32_t* items, uint32_t* numItems)
+{
+    __shared__ uint32_t sPart[1024];
+    __shared__ uint32_t sBase;
+    const int tid = threadIdx.x;
+    if (tid == 0) sBase = 0u;
+    __syncthreads();
+    for (unsigned b0 = 0; b0 < numBlocks; b0 += 1024u)
+    {
+        const unsigned vb = b0 + (unsigned)tid;
+        uint32_t first = 0u, n = 0u;
+        if (vb < numBlocks)
+        {
+            const uint32_t y0 = ~blockInfo[vb].negYMin;
+            uint32_t y1 = blockInfo[vb].yMax;
+            if (y1 > numRows) y1 = numRows;
+            if (y0 < y1)
+            {
+                first = y0 >> SL_SPAN_BAND_SHIFT;
+                n = ((y1 - 1u) >> SL_SPAN_BAND_SHIFT) - first + 1u;
+            }
+        }
+        sPart[tid] = n;
+        __syncthreads();
+        for (int d = 1; d < 1024; d <<= 1)
+        {
+            const uint32_t t = tid >= d ? sPart[tid - d] : 0u;
+            __syncthreads();
+            sPart[tid] += t;
+            __syncthreads();
+        }
+        const uint32_t off = sBase + sPart[tid] - n;
+        for (uint32_t k = 0; k < n; ++k) items[off + k] = vb | ((first + k) << 16);
+        __syncthreads();
+        if (tid == 1023) sBase += sPart[1023];
+        __syncthreads();
+    }
+    if (tid == 0) *numItems = sBase;
+}
+
 /* MODE 0: count entries per (vertex block, row).  MODE 1: fill the row lists.
  *
- * One CTA per vertex block; its records are taken 256 at a time (one per thread: bounding rows + SL_ScanlineBounds
- * set-up, kept in shared memory).  The (record, row) pairs of such a batch are then flattened and dealt out evenly to
- * the 256 threads, row window by row window, so that a triangle that covers a thousand rows costs the block as much
- * as a thousand one-row triangles.  Order inside the batch comes from a bit mask per (row, kind): bit i = record i
- * of the batch has an entry in that row; an entry's place in its row list is the number of set bits below its own. */
+ * Persistent CTAs take (vertex block, row band) items through a ticket.  The block's records are taken 256 at a time (one
+ * per thread: bounding rows + SL_ScanlineBounds set-up, kept in shared memory).  The (record, row) pairs of such a batch
+ * that fall into the band are then flattened and dealt out evenly to the 256 threads, so that a triangle that covers the
+ * whole band costs the CTA as much as 256 one-row triangles.  Order inside the batch comes from a bit mask per (row, kind):
+ * bit i = record i of the batch has an entry in that row; an entry's place in its row list is the number of set bits
+ * below its own. */
 template <int MODE>
 __global__ void __launch_bounds__(256) k_span(const __grid_constant__ SLSpanParams P)
 {
-    __shared__ uint16_t sRowRun[SL_MAX_ROWS];
+    __shared__ uint16_t sRowRun[SL_SPAN_WIN];
     __shared__ uint32_t sMask[2][SL_SPAN_WIN][8]; /* [0] overflow entries coming from the row below, [1] own spans */
     __shared__ SLScanline sSl[256];
     __shared__ int sY0[256], sY1[256], sYEnd[256];
@@ -728,40 +821,51 @@ __global__ void __launch_bounds__(256) k_span(const __grid_constant__ SLSpanPara
     __shared__ uint32_t sSegStart[SL_VB_SEGS + 1], sSegBase[SL_VB_SEGS];
     __shared__ uint32_t sPairOff[257];
     __shared__ uint32_t sWarpTot[8];
-    __shared__ int sMinY, sMaxY;
+    __shared__ uint32_t sItem;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const unsigned int vb = blockIdx.x;
     const int H = (int)P.numRows;
     if (MODE == 1 && P.counters->abortBatch) return; /* the lists would not fit: the batch is run again */
-    for (int y = tid; y < H; y += 256) sRowRun[y] = 0;
-    __syncthreads();
+    const uint32_t numItems = *P.numItems;
 
     unsigned myCuts = 0;
     unsigned long long myPix = 0;
-    /* the block's records live in SL_VB_SEGS regions (one per round and warp of k_vertex); they are taken as ONE stream
-     * in (round, warp) order = submission order, 256 at a time */
-    static_assert(SL_VB_SEGS == 32, "the segment scan below is one warp wide");
-    if (tid < 32)
+    for (;;)
     {
-        /* exclusive scan of the segment counts */
-        const SLSegment sg = P.blockInfo[P.firstBlock + vb].seg[tid];
-        const uint32_t cnt = sg.count;
-        uint32_t inc = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1)
+        __syncthreads(); /* the previous item's shared state is no longer read */
+        if (tid == 0) sItem = atomicAdd(P.ticket, 1u);
+        __syncthreads();
+        const uint32_t item = sItem;
+        if (item >= numItems) break;
+        const uint32_t packed = P.items[item];
+        const unsigned int vb = packed & 0xffffu;
+        const int band0 = (int)(packed >> 16) << SL_SPAN_BAND_SHIFT;
+        const int band1 = min(band0 + SL_SPAN_WIN, H);
+        sRowRun[tid] = 0;
+
+        /* the block's records live in SL_VB_SEGS regions (one per round and warp of k_vertex); they are taken as ONE stream
+         * in (round, warp) order = submission order, 256 at a time */
+        static_assert(SL_VB_SEGS == 32, "the segment scan below is one warp wide");
+        static_assert(SL_SPAN_WIN == 256, "one row of the band per thread");
+        if (tid < 32)
         {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
-            if (tid >= d) inc += t;
+            /* exclusive scan of the segment counts */
+            const SLSegment sg = P.blockInfo[P.firstBlock + vb].seg[tid];
+            const uint32_t cnt = sg.count;
+            uint32_t inc = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1)
+            {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+                if (tid >= d) inc += t;
+            }
+            sSegStart[tid] = inc - cnt;
+            sSegBase[tid] = sg.base;
+            if (tid == 31) sSegStart[32] = inc;
         }
-        sSegStart[tid] = inc - cnt;
-        sSegBase[tid] = sg.base;
-        if (tid == 31) sSegStart[32] = inc;
-    }
-    __syncthreads();
-    const uint32_t numRecs = sSegStart[32];
-    {
+        __syncthreads();
+        const uint32_t numRecs = sSegStart[32];
         for (uint32_t sub = 0; sub < numRecs; sub += 256)
         {
             /* ---- one record per thread: rows it can have entries in, scan-line set-up ---- */
@@ -778,7 +882,6 @@ __global__ void __launch_bounds__(256) k_span(const __grid_constant__ SLSpanPara
                 }
                 myRec = sSegBase[k] + (v - sSegStart[k]);
             }
-            sRec[tid] = myRec;
             int y0 = 0, y1 = 0, yEnd = 0;
             bool mayOver = false;
             if (valid)
@@ -790,126 +893,145 @@ __global__ void __launch_bounds__(256) k_span(const __grid_constant__ SLSpanPara
                 y1 = sl_cvt_rn(sl_max(sl_max(p0.y, p1.y), p2.y));
                 y0 = y0 < 0 ? 0 : y0;
                 y1 = y1 > H ? H : y1;
-                SLScanline sl;
-                sl.init(p0, p1, p2);
-                sSl[tid] = sl;
                 /* span ends interpolate the vertex x's (rcpps error << 8 px), so only these can pass the row end */
                 mayOver = sl_max(sl_max(p0.x, p1.x), p2.x) + 8.f > (float)P.width;
                 yEnd = (mayOver && y1 < H) ? y1 + 1 : y1;
                 if (!(y0 < y1)) { y0 = 0; y1 = 0; yEnd = 0; }
+                if (max(y0, band0) < min(yEnd, band1)) /* only records that reach into the band need the set-up */
+                {
+                    SLScanline sl;
+                    sl.init(p0, p1, p2);
+                    sSl[tid] = sl;
+                }
             }
+            __syncthreads(); /* the previous batch's tables are no longer read */
+            sRec[tid] = myRec;
             sY0[tid] = y0;
             sY1[tid] = mayOver ? -y1 - 1 : y1; /* sign bit: the record can run over the row end */
             sYEnd[tid] = yEnd;
-            if (tid == 0) { sMinY = 0x7fffffff; sMaxY = -1; }
-            __syncthreads();
-            if (y0 < yEnd) { atomicMin(&sMinY, y0); atomicMax(&sMaxY, yEnd); }
-            __syncthreads();
-            const int cy0 = sMinY, cy1 = sMaxY;
-            for (int w0 = cy0; w0 < cy1; w0 += SL_SPAN_WIN)
+            const int w0 = band0, w1 = band1;
+            for (int i = tid; i < 2 * SL_SPAN_WIN * 8; i += 256) (&sMask[0][0][0])[i] = 0u;
+            /* ---- flatten the (record, row) pairs of the band: exclusive scan of the per-record row counts ---- */
+            const int na = max(0, min(yEnd, w1) - max(y0, w0));
+            uint32_t incl = (uint32_t)na;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1)
             {
-                const int w1 = min(w0 + SL_SPAN_WIN, cy1);
-                for (int i = tid; i < 2 * SL_SPAN_WIN * 8; i += 256) (&sMask[0][0][0])[i] = 0u;
-                /* ---- flatten the (record, row) pairs of this window: exclusive scan of the per-record row counts ---- */
-                const int na = max(0, min(yEnd, w1) - max(y0, w0));
-                uint32_t incl = (uint32_t)na;
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            if (lane == 31) sWarpTot[warp] = incl;
+            __syncthreads();
+            uint32_t warpOff = 0, total = 0;
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1)
-                {
-                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += t;
-                }
-                if (lane == 31) sWarpTot[warp] = incl;
-                __syncthreads();
-                uint32_t warpOff = 0, total = 0;
-#pragma unroll
-                for (int w = 0; w < 8; ++w)
-                {
-                    const uint32_t t = sWarpTot[w];
-                    if (w < warp) warpOff += t;
-                    total += t;
-                }
-                sPairOff[tid] = warpOff + incl - (uint32_t)na;
-                if (tid == 0) sPairOff[256] = total;
-                __syncthreads();
+            for (int w = 0; w < 8; ++w)
+            {
+                const uint32_t t = sWarpTot[w];
+                if (w < warp) warpOff += t;
+                total += t;
+            }
+            sPairOff[tid] = warpOff + incl - (uint32_t)na;
+            if (tid == 0) sPairOff[256] = total;
+            __syncthreads();
+            if (!total) continue; /* block-uniform */
 
-                for (int pass = 0; pass <= MODE; ++pass)
+            for (int pass = 0; pass <= MODE; ++pass)
+            {
+                for (uint32_t p = tid; p < total; p += 256)
                 {
-                    for (uint32_t p = tid; p < total; p += 256)
-                    {
-                        /* the record of pair p: last i with sPairOff[i] <= p */
-                        int lo = 0, hi = 255;
+                    /* the record of pair p: last i with sPairOff[i] <= p */
+                    int lo = 0, hi = 255;
 #pragma unroll
-                        for (int k = 0; k < 8; ++k)
+                    for (int k = 0; k < 8; ++k)
+                    {
+                        const int mid = (lo + hi + 1) >> 1;
+                        if (sPairOff[mid] <= p) lo = mid; else hi = mid - 1;
+                    }
+                    const int i = lo;
+                    const int ry0 = sY0[i];
+                    const int ry1raw = sY1[i];
+                    const bool rOver = ry1raw < 0;
+                    const int ry1 = rOver ? -ry1raw - 1 : ry1raw;
+                    const int y = max(ry0, w0) + (int)(p - sPairOff[i]);
+                    if (MODE == 1 && P.rowNeeded && !P.rowNeeded[y]) continue; /* sort-first: another rank's row */
+                    if (MODE == 0 && P.partFast)
+                    {
+                        /* another rank's row: only a span that could run over into one of MY rows matters here */
+                        const bool mine = P.rowNeeded[y] != 0;
+                        const bool nextMine = y + 1 < H && P.rowNeeded[y + 1] != 0;
+                        if (!mine)
                         {
-                            const int mid = (lo + hi + 1) >> 1;
-                            if (sPairOff[mid] <= p) lo = mid; else hi = mid - 1;
+                            if (!(rOver && nextMine && y < ry1)) continue;
+                            int32_t tMin = 0, tMax = 0;
+                            sSl[i].step((float)y, tMin, tMax);
+                            if (sl_classify_span(P, tMin, tMax) & 2) atomicOr(&P.counters->abortBatch, SL_ABORT_PARTITION);
+                            continue;
                         }
-                        const int i = lo;
-                        const int ry0 = sY0[i];
-                        const int ry1raw = sY1[i];
-                        const bool rOver = ry1raw < 0;
-                        const int ry1 = rOver ? -ry1raw - 1 : ry1raw;
-                        const int y = max(ry0, w0) + (int)(p - sPairOff[i]);
-                        if (MODE == 1 && P.rowNeeded && !P.rowNeeded[y]) continue; /* sort-first: another rank's row */
-                        const uint32_t rec = sRec[i];
-                        const uint32_t bit = 1u << (i & 31);
-                        const int q = i >> 5;
-                        int32_t xMin = 0, xMax = 0, oMin = 0, oMax = 0;
-                        int own = 0, over = 0;
-                        if (y < ry1)
+                        if (rOver && y < ry1 && y + 1 < H && !nextMine)
                         {
-                            sSl[i].step((float)y, xMin, xMax);
-                            const int c = sl_classify_span(P, xMin, xMax);
-                            own = c & 1;
-                            if ((c & 2) && !rOver) atomicOr(&P.counters->errorFlags, SL_ERR_UNEXPECTED_OVERFLOW);
-                            if (MODE == 0 && c)
-                            {
-                                myPix += (unsigned long long)(xMax - xMin);
-                                if (P.chained) myCuts += sl_count_cuts(P, xMin, xMax, y + 1 < H);
-                                /* the span statistic counts spans, the row lists hold entries: a span of the last row that
-                                 * lies entirely beyond the row end has no entry at all (its pixels are outside the image) */
-                                if (c == 2 && y + 1 >= H) atomicAdd(&P.counters->spans, 1ull);
-                                if (c == 3 && y + 1 < H)
-                                {
-                                    atomicAdd(&P.counters->spans, ~0ull); /* two entries, one span */
-                                    atomicAdd(&P.counters->rowEndCuts, 1ull);
-                                    if (P.rowFlags) P.rowFlags[y + 1] = 1;
-                                }
-                            }
-                        }
-                        if (rOver && y > ry0)
-                        {
-                            sSl[i].step((float)(y - 1), oMin, oMax);
-                            over = (sl_classify_span(P, oMin, oMax) >> 1) & 1;
-                        }
-                        if (pass == 0)
-                        {
-                            if (over) atomicOr(&sMask[0][y - w0][q], bit);
-                            if (own) atomicOr(&sMask[1][y - w0][q], bit);
-                        }
-                        else if ((own | over) && (!P.rowNeeded || P.rowNeeded[y]))
-                        {
-                            uint32_t rank = 0;
-                            for (int k = 0; k < q; ++k) rank += __popc(sMask[0][y - w0][k]) + __popc(sMask[1][y - w0][k]);
-                            rank += __popc(sMask[0][y - w0][q] & (bit - 1u)) + __popc(sMask[1][y - w0][q] & (bit - 1u));
-                            size_t slot = (size_t)P.rowStart[y] + P.off[(size_t)vb * P.rowPitch + y] + sRowRun[y] + rank;
-                            if (over) P.entries[slot++] = SLSpanEntry{rec | SL_ENTRY_OVERFLOW, (uint16_t)oMin, (uint16_t)oMax};
-                            if (own) P.entries[slot] = SLSpanEntry{rec, (uint16_t)xMin, (uint16_t)xMax};
+                            int32_t tMin = 0, tMax = 0;
+                            sSl[i].step((float)y, tMin, tMax);
+                            if (sl_classify_span(P, tMin, tMax) & 2) atomicOr(&P.counters->abortBatch, SL_ABORT_PARTITION);
                         }
                     }
-                    __syncthreads();
-                }
-                for (int yy = w0 + tid; yy < w1; yy += 256)
-                {
-                    uint32_t c = 0;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) c += __popc(sMask[0][yy - w0][k]) + __popc(sMask[1][yy - w0][k]);
-                    sRowRun[yy] = (uint16_t)(sRowRun[yy] + c);
+                    const uint32_t rec = sRec[i];
+                    const uint32_t bit = 1u << (i & 31);
+                    const int q = i >> 5;
+                    int32_t xMin = 0, xMax = 0, oMin = 0, oMax = 0;
+                    int own = 0, over = 0;
+                    if (y < ry1)
+                    {
+                        sSl[i].step((float)y, xMin, xMax);
+                        const int c = sl_classify_span(P, xMin, xMax);
+                        own = c & 1;
+                        if ((c & 2) && !rOver) atomicOr(&P.counters->errorFlags, SL_ERR_UNEXPECTED_OVERFLOW);
+                        if (MODE == 0 && c)
+                        {
+                            myPix += (unsigned long long)(xMax - xMin);
+                            if (P.chained) myCuts += sl_count_cuts(P, xMin, xMax, y + 1 < H);
+                            /* the span statistic counts spans, the row lists hold entries: a span of the last row that
+                             * lies entirely beyond the row end has no entry at all (its pixels are outside the image) */
+                            if (c == 2 && y + 1 >= H) atomicAdd(&P.counters->spans, 1ull);
+                            if (c == 3 && y + 1 < H)
+                            {
+                                atomicAdd(&P.counters->spans, ~0ull); /* two entries, one span */
+                                atomicAdd(&P.counters->rowEndCuts, 1ull);
+                                if (P.rowFlags) P.rowFlags[y + 1] = 1;
+                            }
+                        }
+                    }
+                    if (rOver && y > ry0)
+                    {
+                        sSl[i].step((float)(y - 1), oMin, oMax);
+                        over = (sl_classify_span(P, oMin, oMax) >> 1) & 1;
+                    }
+                    if (pass == 0)
+                    {
+                        if (over) atomicOr(&sMask[0][y - w0][q], bit);
+                        if (own) atomicOr(&sMask[1][y - w0][q], bit);
+                    }
+                    else if ((own | over) && (!P.rowNeeded || P.rowNeeded[y]))
+                    {
+                        uint32_t rank = 0;
+                        for (int k = 0; k < q; ++k) rank += __popc(sMask[0][y - w0][k]) + __popc(sMask[1][y - w0][k]);
+                        rank += __popc(sMask[0][y - w0][q] & (bit - 1u)) + __popc(sMask[1][y - w0][q] & (bit - 1u));
+                        size_t slot = (size_t)P.rowStart[y] + P.off[(size_t)vb * P.rowPitch + y] + sRowRun[y - w0] + rank;
+                        if (over) P.entries[slot++] = SLSpanEntry{rec | SL_ENTRY_OVERFLOW, (uint16_t)oMin, (uint16_t)oMax};
+                        if (own) P.entries[slot] = SLSpanEntry{rec, (uint16_t)xMin, (uint16_t)xMax};
+                    }
                 }
                 __syncthreads();
             }
+            if (w0 + tid < w1)
+            {
+                uint32_t c = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) c += __popc(sMask[0][tid][k]) + __popc(sMask[1][tid][k]);
+                sRowRun[tid] = (uint16_t)(sRowRun[tid] + c);
+            }
         }
+        __syncthreads();
+        if (MODE == 0 && band0 + tid < band1) P.cnt[(size_t)vb * P.rowPitch + band0 + tid] = sRowRun[tid]; /* the other rows stay zero (memset per batch) */
     }
     if (MODE == 0)
     {
@@ -917,7 +1039,6 @@ __global__ void __launch_bounds__(256) k_span(const __grid_constant__ SLSpanPara
         if (lane == 0 && myCuts) atomicAdd(&P.counters->handoffs, (unsigned long long)myCuts);
         for (int d = 16; d > 0; d >>= 1) myPix += __shfl_down_sync(0xffffffffu, myPix, d);
         if (lane == 0 && myPix) atomicAdd(&P.counters->pixelsCovered, myPix);
-        for (int y = tid; y < (int)P.rowPitch; y += 256) P.cnt[(size_t)vb * P.rowPitch + y] = y < H ? sRowRun[y] : (uint16_t)0;
     }
 }
 

@@ -212,7 +212,8 @@ struct Batch
     unsigned long long totalPrims = 0;
     unsigned long long maxVerts = 0; /* vertices of the largest vertex buffer of the batch (binding 0) */
     bool wire = false;               /* RENDER_MODE_TRI_WIRE / INDEXED_TRI_WIRE: edges only (sl_wire.cuh) */
-    void clear() { descs.clear(); blockDraw.clear(); numBlocks = 0; totalPrims = 0; maxVerts = 0; wire = false; }
+    bool partFull = false;           /* sort-first: the fast path was refused, count every row (enqueue_batch) */
+    void clear() { descs.clear(); blockDraw.clear(); numBlocks = 0; totalPrims = 0; maxVerts = 0; wire = false; partFull = false; }
 };
 
 struct slcu_context
@@ -243,6 +244,7 @@ struct slcu_context
     Scratch wireLeaders; /* wireframe: positions where a pixel's sorted candidates start */
     Scratch wireSlots, wireRecInfo; /* wireframe: sort values (double buffer); first slot + candidate count per record */
     Scratch pointKeys, pointRecs, pointSortTemp; /* point primitives: sort keys (double buffer), records, radix-sort scratch */
+    Scratch spanItems;   /* (vertex block, row band) work items of k_span */
     Scratch ticketOrder; /* skewed work order of k_resolve, cached per (rows, segments, skew) */
     unsigned orderRows = 0, orderSegs = 0, orderSkew = 0;
     Batch batch;            /* submitted, not yet executed draws */
@@ -250,6 +252,7 @@ struct slcu_context
      * trip in the middle of a frame.  When the device found the buffers too small it has skipped every kernel that writes
      * something visible, and the batch is run again with sizes taken from its own counters. */
     cudaEvent_t batchDone = nullptr;
+    bool refusedPartition = false; /* the last refusal was the sort-first fast path's (a span crosses into another rank's row) */
     struct Caps { unsigned long long recOverflow = 0, entries = 0, chunks = 0, handoffSlots = 0, avgSpan = 0; } caps;
     bool syncDraws = false; /* SLCU_SYNC_DRAWS=1: execute every draw call on its own (debug / parity mode) */
     /* sort-first partition (slcu_set_partition) */
@@ -628,6 +631,7 @@ static bool batch_was_refused(slcu_context* c)
                 (unsigned long long)h.recAlloc, h.totalEntries, (unsigned long long)h.handoffs, (unsigned long long)h.pixelsCovered,
                 (unsigned long long)h.rowEndCuts, h.abortBatch, h.errorFlags);
     if (!h.abortBatch) return false;
+    if (h.abortBatch & SL_ABORT_PARTITION) c->refusedPartition = true;
     auto grow = [](unsigned long long& cap, unsigned long long need) { const unsigned long long want = need + need / 4 + 4096; if (want > cap) cap = want; };
     grow(c->caps.recOverflow, h.recAlloc);
     grow(c->caps.entries, h.totalEntries);
@@ -654,6 +658,7 @@ static int run_batch(slcu_context* c, Batch& B)
         CK(cudaEventRecord(c->batchDone, c->stream));
         CK(cudaEventSynchronize(c->batchDone));
         if (!batch_was_refused(c)) return 0;
+        if (c->refusedPartition) { B.partFull = true; c->refusedPartition = false; }
     }
     c->err = "batch does not fit its buffers after repeated growth";
     return SLCU_ERR_OOM;
@@ -717,6 +722,7 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
         CK(c->records.ensure((size_t)recCapacity * recStride * sizeof(float4)));
         CK(c->recDraw.ensure((size_t)recCapacity * sizeof(uint16_t)));
         CK(c->blockInfo.ensure((size_t)numBlocks * sizeof(SLBlockInfo)));
+        CK(cudaMemsetAsync(c->blockInfo.buf.ptr, 0, (size_t)numBlocks * sizeof(SLBlockInfo), c->stream)); /* row ranges start empty */
         CK(cudaMemsetAsync(c->counters, 0, SL_COUNTERS_BATCH_BYTES, c->stream)); /* the per-batch part */
 
         {
@@ -914,17 +920,42 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
         sp.counters = c->counters;
         sp.rowFlags = nullptr;
         sp.rowNeeded = nullptr;
+        sp.partFast = 0;
         const bool partitioned = c->partWorld > 1;
+        const bool partFast = partitioned && !B.partFull;
         if (partitioned)
         {
             CK(c->rowFlags.ensure(H + 1));
             CK(c->rowNeeded.ensure(H + 1));
             CK(cudaMemsetAsync(c->rowFlags.buf.ptr, 0, H + 1, c->stream));
             sp.rowFlags = c->rowFlags.buf.ptr;
+            if (partFast)
+            {
+                /* fast path: the rows this rank owns and nothing else, in the count pass already (see SLSpanParams::partFast) */
+                KernelScope ks(c, SLCU_K_SCAN);
+                k_row_closure<<<(H + 255) / 256, 256, 0, c->stream>>>(c->rowFlags.buf.ptr, c->rowNeeded.buf.ptr, H, c->partRank, c->partWorld, c->partStripRows);
+                rowNeeded = c->rowNeeded.buf.ptr;
+                sp.rowNeeded = rowNeeded;
+                sp.rowFlags = nullptr;
+                sp.partFast = 1;
+            }
         }
-        { KernelScope ks(c, SLCU_K_SPAN_COUNT); k_span<0><<<numBlocks, 256, 0, c->stream>>>(sp); }
+        /* work items of the span stage: (vertex block, 256-row band) pairs, taken through a ticket by persistent CTAs */
+        const unsigned numBands = (H + SL_SPAN_WIN - 1) / SL_SPAN_WIN;
+        CK(c->spanItems.ensure((size_t)numBlocks * numBands * sizeof(uint32_t)));
+        CK(cudaMemsetAsync(c->cnt.buf.ptr, 0, (size_t)numBlocks * rowPitch * sizeof(uint16_t), c->stream)); /* k_span<0> writes the rows of its items only */
+        sp.items = reinterpret_cast<const uint32_t*>(c->spanItems.buf.ptr);
+        sp.numItems = &c->counters->spanItems;
+        { KernelScope ks(c, SLCU_K_SCAN); k_span_items<<<1, 1024, 0, c->stream>>>(sp.blockInfo, numBlocks, H, reinterpret_cast<uint32_t*>(c->spanItems.buf.ptr), &c->counters->spanItems); }
         CK(cudaGetLastError());
-        if (partitioned)
+        int spanSMs = 148;
+        cudaDeviceGetAttribute(&spanSMs, cudaDevAttrMultiProcessorCount, c->device);
+        unsigned spanGrid = (unsigned)spanSMs * 6u;
+        if (spanGrid > numBlocks * numBands) spanGrid = numBlocks * numBands;
+        sp.ticket = &c->counters->spanTicket[0];
+        { KernelScope ks(c, SLCU_K_SPAN_COUNT); k_span<0><<<spanGrid, 256, 0, c->stream>>>(sp); }
+        CK(cudaGetLastError());
+        if (partitioned && !partFast)
         {
             KernelScope ks(c, SLCU_K_SCAN);
             k_row_closure<<<(H + 255) / 256, 256, 0, c->stream>>>(c->rowFlags.buf.ptr, c->rowNeeded.buf.ptr, H, c->partRank, c->partWorld, c->partStripRows);
@@ -970,7 +1001,8 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
         CK(cudaGetLastError());
 
         sp.entries = reinterpret_cast<SLSpanEntry*>(c->entries.buf.ptr);
-        { KernelScope ks(c, SLCU_K_SPAN_FILL); k_span<1><<<numBlocks, 256, 0, c->stream>>>(sp); }
+        sp.ticket = &c->counters->spanTicket[1];
+        { KernelScope ks(c, SLCU_K_SPAN_FILL); k_span<1><<<spanGrid, 256, 0, c->stream>>>(sp); }
         CK(cudaGetLastError());
         break;
     }
@@ -1254,7 +1286,7 @@ void slcu_context_destroy(slcu_context* c)
     if (c->counters) cudaFree(c->counters);
     if (c->hostCounters) cudaFreeHost(c->hostCounters);
     for (auto& pm : c->peerMaps) if (pm.ptr) cudaIpcCloseMemHandle(pm.ptr);
-    Scratch* s[] = {&c->records, &c->blockInfo, &c->cnt, &c->off, &c->segSums, &c->rowTotals, &c->rowStart, &c->entries, &c->handoff, &c->rowFlags, &c->rowNeeded, &c->drawTable, &c->blockDraw, &c->recDraw, &c->fragPool, &c->chunkNext, &c->listInfo, &c->handoffRegs, &c->ticketOrder, &c->pointKeys, &c->pointRecs, &c->pointSortTemp, &c->wireSlots, &c->wireRecInfo, &c->wireLeaders};
+    Scratch* s[] = {&c->records, &c->blockInfo, &c->cnt, &c->off, &c->segSums, &c->rowTotals, &c->rowStart, &c->entries, &c->handoff, &c->rowFlags, &c->rowNeeded, &c->drawTable, &c->blockDraw, &c->recDraw, &c->fragPool, &c->chunkNext, &c->listInfo, &c->handoffRegs, &c->ticketOrder, &c->spanItems, &c->pointKeys, &c->pointRecs, &c->pointSortTemp, &c->wireSlots, &c->wireRecInfo, &c->wireLeaders};
     for (Scratch* x : s) x->release();
     cudaStreamDestroy(c->stream);
     delete c;
