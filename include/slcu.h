@@ -130,6 +130,21 @@ SLCU_EXPORT size_t SLCU_FN(create_ubo)(slcu_context* ctx);
 SLCU_EXPORT size_t SLCU_FN(create_texture)(slcu_context* ctx);
 SLCU_EXPORT size_t SLCU_FN(create_framebuffer)(slcu_context* ctx);
 
+/* SL_Context::destroy_* (softlight/src/SL_Context.cpp:192-195, 243-247, 295-298, 346-349, 397-400, 448-451, 612-615): the
+ * object is erased from its vector, so every later id of that kind moves down by one -- exactly the reference's
+ * behaviour, which callers written against it already account for.  What the reference holds by POINTER keeps pointing
+ * at the same object here too: framebuffer attachments and declared uniform pointers (ubo_bind_*) follow a texture /
+ * vertex buffer whose id moved, and lose it when it is the one destroyed.  What the reference holds by INDEX (a vertex
+ * array's buffer ids, a shader's uniform block) is left alone, like there.  Returns 0, or SLCU_ERR_ARG for an id that
+ * does not exist (undefined behaviour in the reference). */
+SLCU_EXPORT int SLCU_FN(destroy_vbo)(slcu_context* ctx, size_t id);
+SLCU_EXPORT int SLCU_FN(destroy_ibo)(slcu_context* ctx, size_t id);
+SLCU_EXPORT int SLCU_FN(destroy_vao)(slcu_context* ctx, size_t id);
+SLCU_EXPORT int SLCU_FN(destroy_ubo)(slcu_context* ctx, size_t id);
+SLCU_EXPORT int SLCU_FN(destroy_texture)(slcu_context* ctx, size_t id);
+SLCU_EXPORT int SLCU_FN(destroy_framebuffer)(slcu_context* ctx, size_t id);
+SLCU_EXPORT int SLCU_FN(destroy_shader)(slcu_context* ctx, size_t id);
+
 /* SL_VertexBuffer::init / assign (SL_VertexBuffer.hpp:45-49, src/SL_VertexBuffer.cpp) */
 SLCU_EXPORT int SLCU_FN(vbo_init)(slcu_context* ctx, size_t vbo, size_t numBytes);
 SLCU_EXPORT int SLCU_FN(vbo_assign)(slcu_context* ctx, size_t vbo, const void* data, size_t offset, size_t numBytes);

@@ -109,7 +109,9 @@ class SL_Resource
 class SL_VertexBuffer : public SL_Resource
 {
     std::vector<unsigned char> mShadow;
+    std::vector<unsigned char> mSent; /* what the device holds, kept once a writable pointer has left the object */
     bool mDirty = false;
+    bool mHandedOut = false;
     friend class SL_Context;
 
   public:
@@ -121,9 +123,9 @@ class SL_VertexBuffer : public SL_Resource
         return slcu_vbo_init(mDev, mId, numBytes);
     }
     size_t num_bytes() const noexcept { return mShadow.size(); }
-    void* data() noexcept { mDirty = true; return mShadow.data(); } /* written in place by the user, uploaded at the next draw */
+    void* data() noexcept { mDirty = true; mHandedOut = true; return mShadow.data(); } /* written in place by the user, uploaded at the next draw */
     const void* data() const noexcept { return mShadow.data(); }
-    template <typename T> T* element(ptrdiff_t offset) noexcept { mDirty = true; return reinterpret_cast<T*>(mShadow.data() + offset); }
+    template <typename T> T* element(ptrdiff_t offset) noexcept { mDirty = true; mHandedOut = true; return reinterpret_cast<T*>(mShadow.data() + offset); }
     void assign(const void* pInputData, ptrdiff_t offset, size_t numBytes) noexcept
     {
         std::memcpy(mShadow.data() + offset, pInputData, numBytes);
@@ -281,13 +283,23 @@ class SL_Context
     /* what the user wrote into host-visible objects since the last entry into the pipeline */
     void upload_dirty() noexcept
     {
+        /* The reference hands out live pointers, and its own programs cache them and keep writing through them between
+         * draws (sl_instancing_test.cpp:236, 251-274).  Uniform blocks (1 KiB, snapshotted at submission anyway) are
+         * therefore sent with every draw; a vertex buffer whose non-const pointer was ever handed out is compared with
+         * what was last sent and re-sent when it differs. */
         for (SL_VertexBuffer* b : mVbos)
         {
-            if (b && b->mDirty && !b->mShadow.empty()) { slcu_vbo_assign(mDev, b->mId, b->mShadow.data(), 0, b->mShadow.size()); b->mDirty = false; }
+            if (!b || b->mShadow.empty()) continue;
+            if (b->mDirty || (b->mHandedOut && (b->mSent.size() != b->mShadow.size() || std::memcmp(b->mSent.data(), b->mShadow.data(), b->mShadow.size()) != 0)))
+            {
+                slcu_vbo_assign(mDev, b->mId, b->mShadow.data(), 0, b->mShadow.size());
+                if (b->mHandedOut) b->mSent = b->mShadow;
+                b->mDirty = false;
+            }
         }
         for (SL_UniformBuffer* u : mUbos)
         {
-            if (u && u->mDirty) { slcu_ubo_assign(mDev, u->mId, u->mBytes, 0, sizeof(u->mBytes)); u->mDirty = false; }
+            if (u) slcu_ubo_assign(mDev, u->mId, u->mBytes, 0, sizeof(u->mBytes));
         }
     }
 
@@ -321,6 +333,23 @@ class SL_Context
     size_t create_ubo() noexcept { return mDev ? add(mUbos, slcu_create_ubo(mDev)) : SLCU_INVALID_ID; }
     size_t create_texture() noexcept { return mDev ? add(mTextures, slcu_create_texture(mDev)) : SLCU_INVALID_ID; }
     size_t create_framebuffer() noexcept { return mDev ? add(mFbos, slcu_create_framebuffer(mDev)) : SLCU_INVALID_ID; }
+
+    /* destroy_* (src/SL_Context.cpp:192-195, 243-247, 295-298, 346-349, 397-400, 448-451, 612-615): the object is erased,
+     * every later index of that kind moves down by one */
+    template <typename T> void erase(std::vector<T*>& v, size_t index) noexcept
+    {
+        if (index >= v.size()) return;
+        delete v[index];
+        v.erase(v.begin() + (ptrdiff_t)index);
+        for (size_t i = index; i < v.size(); ++i) { if (v[i]) v[i]->mId = i; }
+    }
+    void destroy_vbo(size_t index) noexcept { if (mDev && slcu_destroy_vbo(mDev, index) == 0) erase(mVbos, index); }
+    void destroy_ibo(size_t index) noexcept { if (mDev && slcu_destroy_ibo(mDev, index) == 0) erase(mIbos, index); }
+    void destroy_vao(size_t index) noexcept { if (mDev && slcu_destroy_vao(mDev, index) == 0) erase(mVaos, index); }
+    void destroy_ubo(size_t index) noexcept { if (mDev && slcu_destroy_ubo(mDev, index) == 0) erase(mUbos, index); }
+    void destroy_texture(size_t index) noexcept { if (mDev && slcu_destroy_texture(mDev, index) == 0) erase(mTextures, index); }
+    void destroy_framebuffer(size_t index) noexcept { if (mDev && slcu_destroy_framebuffer(mDev, index) == 0) erase(mFbos, index); }
+    void destroy_shader(size_t index) noexcept { if (mDev) slcu_destroy_shader(mDev, index); }
 
     SL_VertexBuffer& vbo(size_t i) noexcept { return *mVbos[i]; }
     SL_IndexBuffer& ibo(size_t i) noexcept { return *mIbos[i]; }

@@ -1086,6 +1086,66 @@ size_t slor_create_ubo(slcu_context* c) { c->ubos.emplace_back(); memset(c->ubos
 size_t slor_create_texture(slcu_context* c) { c->textures.push_back(new SL_Texture{}); return c->textures.size() - 1; }
 size_t slor_create_framebuffer(slcu_context* c) { c->fbos.emplace_back(); return c->fbos.size() - 1; }
 
+/* SL_Context::destroy_* (src/SL_Context.cpp:192-195, 243-247, 295-298, 346-349, 397-400, 448-451, 612-615): vector erase.
+ * Framebuffer attachments and the pointers declared with ubo_bind_* are pointers in the reference and keep following
+ * their object; ids held by vertex arrays and shaders are indices there and are left alone. */
+static void remap_fixups(slcu_context* c, int kind, size_t gone)
+{
+    for (size_t i = 0; i < c->fixups.size();)
+    {
+        UboFixup& f = c->fixups[i];
+        if (f.kind == kind && f.id == gone) { c->fixups.erase(c->fixups.begin() + i); continue; }
+        if (f.kind == kind && f.id > gone) --f.id;
+        ++i;
+    }
+}
+int slor_destroy_vbo(slcu_context* c, size_t id)
+{
+    if (id >= c->vbos.size()) return SLCU_ERR_ARG;
+    c->vbos.erase(c->vbos.begin() + id);
+    remap_fixups(c, 1, id);
+    return 0;
+}
+int slor_destroy_ibo(slcu_context* c, size_t id) { if (id >= c->ibos.size()) return SLCU_ERR_ARG; c->ibos.erase(c->ibos.begin() + id); return 0; }
+int slor_destroy_vao(slcu_context* c, size_t id) { if (id >= c->vaos.size()) return SLCU_ERR_ARG; c->vaos.erase(c->vaos.begin() + id); return 0; }
+int slor_destroy_ubo(slcu_context* c, size_t id)
+{
+    if (id >= c->ubos.size()) return SLCU_ERR_ARG;
+    c->ubos.erase(c->ubos.begin() + id);
+    for (size_t i = 0; i < c->fixups.size();)
+    {
+        UboFixup& f = c->fixups[i];
+        if (f.ubo == id) { c->fixups.erase(c->fixups.begin() + i); continue; }
+        if (f.ubo > id) --f.ubo;
+        ++i;
+    }
+    return 0;
+}
+int slor_destroy_texture(slcu_context* c, size_t id)
+{
+    if (id >= c->textures.size()) return SLCU_ERR_ARG;
+    if (c->textures[id]) { free(c->textures[id]->mTexels); delete c->textures[id]; }
+    c->textures.erase(c->textures.begin() + id);
+    remap_fixups(c, 0, id);
+    for (Framebuffer& f : c->fbos)
+    {
+        for (int i = 0; i < 4; ++i)
+        {
+            if (f.colors[i] == (size_t)-1) continue;
+            if (f.colors[i] == id) { f.colors[i] = (size_t)-1; f.colorViews[i] = FboView{}; }
+            else if (f.colors[i] > id) --f.colors[i];
+        }
+        if (f.depth != (size_t)-1)
+        {
+            if (f.depth == id) { f.depth = (size_t)-1; f.depthView = FboView{}; }
+            else if (f.depth > id) --f.depth;
+        }
+    }
+    return 0;
+}
+int slor_destroy_framebuffer(slcu_context* c, size_t id) { if (id >= c->fbos.size()) return SLCU_ERR_ARG; c->fbos.erase(c->fbos.begin() + id); return 0; }
+int slor_destroy_shader(slcu_context* c, size_t id) { if (id >= c->shaders.size()) return SLCU_ERR_ARG; c->shaders.erase(c->shaders.begin() + id); return 0; }
+
 int slor_vbo_init(slcu_context* c, size_t vbo, size_t n)
 {
     if (vbo >= c->vbos.size()) return SLCU_ERR_ARG;

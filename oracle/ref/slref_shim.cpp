@@ -204,6 +204,37 @@ size_t slref_create_ubo(slcu_context* c) { return c->ctx.create_ubo(); }
 size_t slref_create_texture(slcu_context* c) { return c->ctx.create_texture(); }
 size_t slref_create_framebuffer(slcu_context* c) { return c->ctx.create_framebuffer(); }
 
+/* SL_Context::destroy_* of the unmodified reference.  A host program keeps real pointers in its uniform blocks; this shim
+ * re-derives them from ids at every draw, so the ids of its own book-keeping follow the erase like the pointers would. */
+static void remap_fixups(slcu_context* c, int kind, size_t gone)
+{
+    for (size_t i = 0; i < c->fixups.size();)
+    {
+        UboFixup& f = c->fixups[i];
+        if (f.kind == kind && f.id == gone) { c->fixups.erase(c->fixups.begin() + i); continue; }
+        if (f.kind == kind && f.id > gone) --f.id;
+        ++i;
+    }
+}
+int slref_destroy_vbo(slcu_context* c, size_t id) { c->ctx.destroy_vbo(id); remap_fixups(c, 1, id); return 0; }
+int slref_destroy_ibo(slcu_context* c, size_t id) { c->ctx.destroy_ibo(id); return 0; }
+int slref_destroy_vao(slcu_context* c, size_t id) { c->ctx.destroy_vao(id); return 0; }
+int slref_destroy_ubo(slcu_context* c, size_t id)
+{
+    c->ctx.destroy_ubo(id);
+    for (size_t i = 0; i < c->fixups.size();)
+    {
+        UboFixup& f = c->fixups[i];
+        if (f.ubo == id) { c->fixups.erase(c->fixups.begin() + i); continue; }
+        if (f.ubo > id) --f.ubo;
+        ++i;
+    }
+    return 0;
+}
+int slref_destroy_texture(slcu_context* c, size_t id) { c->ctx.destroy_texture(id); remap_fixups(c, 0, id); return 0; }
+int slref_destroy_framebuffer(slcu_context* c, size_t id) { c->ctx.destroy_framebuffer(id); return 0; }
+int slref_destroy_shader(slcu_context* c, size_t id) { c->ctx.destroy_shader(id); return 0; }
+
 int slref_vbo_init(slcu_context* c, size_t vbo, size_t n) { return c->ctx.vbo(vbo).init(n); }
 
 int slref_vbo_assign(slcu_context* c, size_t vbo, const void* d, size_t off, size_t n)

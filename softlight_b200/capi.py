@@ -114,6 +114,9 @@ _SIGS = {
     "get_rcp_table": (C.c_int, [_P, _P]),
     "create_vbo": (_SZ, [_P]), "create_ibo": (_SZ, [_P]), "create_vao": (_SZ, [_P]),
     "create_ubo": (_SZ, [_P]), "create_texture": (_SZ, [_P]), "create_framebuffer": (_SZ, [_P]),
+    "destroy_vbo": (C.c_int, [_P, _SZ]), "destroy_ibo": (C.c_int, [_P, _SZ]), "destroy_vao": (C.c_int, [_P, _SZ]),
+    "destroy_ubo": (C.c_int, [_P, _SZ]), "destroy_texture": (C.c_int, [_P, _SZ]), "destroy_framebuffer": (C.c_int, [_P, _SZ]),
+    "destroy_shader": (C.c_int, [_P, _SZ]),
     "vbo_init": (C.c_int, [_P, _SZ, _SZ]),
     "vbo_assign": (C.c_int, [_P, _SZ, _P, _SZ, _SZ]),
     "ibo_init": (C.c_int, [_P, _SZ, C.c_uint32, C.c_int, _P]),
@@ -393,6 +396,10 @@ class Context:
             self._chk(self.f["fbo_attach_color_buffer"](self.h, fid, i, t), "attach_color_buffer")
         self._chk(self.f["fbo_attach_depth_buffer"](self.h, fid, depth_tex), "attach_depth_buffer")
         return fid
+
+    def destroy(self, kind: str, oid: int) -> int:
+        """SL_Context::destroy_<kind>: later ids of that kind move down by one."""
+        return self.f["destroy_" + kind](self.h, oid)
 
     def fbo_valid(self, fid: int) -> int:
         return self.f["fbo_valid"](self.h, fid)

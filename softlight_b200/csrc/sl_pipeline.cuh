@@ -722,6 +722,7 @@ struct SLSpanParams
     const uint32_t* items;       /* work items: vertex block | row band << 16 (k_span_items)               */
     const uint32_t* numItems;
     unsigned int* ticket;        /* item ticket of this pass (zeroed per batch)                              */
+    int partRank, partWorld, partStrip; /* sort-first partition: row y belongs to rank (y / partStrip) % partWorld */
     int partFast;                /* sort-first fast path: rowNeeded = the rows this rank owns, and both passes leave every
                                     other row alone.  Valid as long as no span runs past the row end into a row of another
                                     rank; k_span<0> looks for exactly that and refuses the batch (SL_ABORT_PARTITION), the
@@ -756,6 +757,19 @@ SLD_FN unsigned sl_count_cuts(const SLSpanParams& P, int32_t xMin, int32_t xMax,
         for (int32_t b = oMin / TW + 1; b < NS && b * TW < xMax - W; ++b) { if (b * TW > xMin - W) ++n; }
     }
     return n;
+}
+
+/* Sort-first partition, interleaved strips: the number of rows below n that `rank` owns, and the k-th owned row at or above a */
+SLD_FN int sl_owned_below(int n, int strip, int world, int rank)
+{
+    const int period = strip * world;
+    const int q = n / period, r = n - q * period;
+    return q * strip + min(max(r - rank * strip, 0), strip);
+}
+SLD_FN int sl_owned_kth(int a, int k, int strip, int world, int rank)
+{
+    const int j = sl_owned_below(a, strip, world, rank) + k;
+    return (j / strip) * (strip * world) + rank * strip + (j % strip);
 }
 
 /* Work items of k_span: one per (vertex block, band of SL_SPAN_WIN rows the block's records touch).  A block of large
@@ -912,7 +926,10 @@ __global__ void __launch_bounds__(256) k_span(const __grid_constant__ SLSpanPara
             const int w0 = band0, w1 = band1;
             for (int i = tid; i < 2 * SL_SPAN_WIN * 8; i += 256) (&sMask[0][0][0])[i] = 0u;
             /* ---- flatten the (record, row) pairs of the band: exclusive scan of the per-record row counts ---- */
-            const int na = max(0, min(yEnd, w1) - max(y0, w0));
+            /* sort-first fast path: a record that cannot run past the row end contributes its rows of THIS rank only */
+            const bool ownedOnly = P.partFast && !mayOver;
+            const int ra = max(y0, w0), rb = min(yEnd, w1);
+            const int na = ra < rb ? (ownedOnly ? sl_owned_below(rb, P.partStrip, P.partWorld, P.partRank) - sl_owned_below(ra, P.partStrip, P.partWorld, P.partRank) : rb - ra) : 0;
             uint32_t incl = (uint32_t)na;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1)
@@ -952,7 +969,8 @@ __global__ void __launch_bounds__(256) k_span(const __grid_constant__ SLSpanPara
                     const int ry1raw = sY1[i];
                     const bool rOver = ry1raw < 0;
                     const int ry1 = rOver ? -ry1raw - 1 : ry1raw;
-                    const int y = max(ry0, w0) + (int)(p - sPairOff[i]);
+                    const int y = (P.partFast && !rOver) ? sl_owned_kth(max(ry0, w0), (int)(p - sPairOff[i]), P.partStrip, P.partWorld, P.partRank)
+                                                         : max(ry0, w0) + (int)(p - sPairOff[i]);
                     if (MODE == 1 && P.rowNeeded && !P.rowNeeded[y]) continue; /* sort-first: another rank's row */
                     if (MODE == 0 && P.partFast)
                     {
@@ -1152,6 +1170,60 @@ __global__ void __launch_bounds__(1024) k_scan_row_starts(const uint32_t* rowTot
     }
 }
 
+/* Heaviest rows first: rowPerm[i] = the row with the i-th most span entries (64 weight classes, rows of a class in
+ * ascending order).  The resolving warps take their (row, segment) tickets in this order, so the long rows are under way
+ * while there is still plenty of short work to fill the machine with, instead of being the tail of the kernel. */
+__global__ void __launch_bounds__(1024) k_row_order(const uint32_t* rowStart, unsigned numRows, uint32_t* rowPerm)
+{
+    __shared__ uint32_t sMax;
+    __shared__ uint32_t sBin[64];
+    __shared__ uint32_t sBase[64];
+    const int tid = threadIdx.x;
+    if (tid == 0) sMax = 1u;
+    if (tid < 64) sBin[tid] = 0u;
+    __syncthreads();
+    uint32_t m = 0u;
+    for (unsigned y = tid; y < numRows; y += 1024u) m = max(m, rowStart[y + 1] - rowStart[y]);
+    for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if ((tid & 31) == 0) atomicMax(&sMax, m);
+    __syncthreads();
+    const uint32_t top = sMax;
+    /* class 0 = heaviest; rows are visited in ascending order by every thread and ranked inside their class by row index */
+    for (unsigned y = tid; y < numRows; y += 1024u)
+    {
+        const uint32_t n = rowStart[y + 1] - rowStart[y];
+        const uint32_t cls = 63u - (uint32_t)(((unsigned long long)n * 63ull) / top);
+        atomicAdd(&sBin[cls], 1u);
+    }
+    __syncthreads();
+    if (tid == 0)
+    {
+        uint32_t run = 0u;
+        for (int k = 0; k < 64; ++k) { sBase[k] = run; run += sBin[k]; }
+    }
+    __syncthreads();
+    /* deterministic placement: one warp per class walks the rows in order */
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int cls = warp; cls < 64; cls += 32)
+    {
+        if (!sBin[cls]) continue;
+        uint32_t pos = sBase[cls];
+        for (unsigned y0 = 0; y0 < numRows; y0 += 32u)
+        {
+            const unsigned y = y0 + (unsigned)lane;
+            bool in = false;
+            if (y < numRows)
+            {
+                const uint32_t n = rowStart[y + 1] - rowStart[y];
+                in = (63u - (uint32_t)(((unsigned long long)n * 63ull) / top)) == (uint32_t)cls;
+            }
+            const uint32_t mask = __ballot_sync(0xffffffffu, in);
+            if (in) rowPerm[pos + (uint32_t)__popc(mask & ((1u << lane) - 1u))] = y;
+            pos += (uint32_t)__popc(mask);
+        }
+    }
+}
+
 /* end of a batch: its statistics join the totals unless it has to be run again */
 __global__ void k_commit(SLCounters* counters)
 {
@@ -1228,6 +1300,7 @@ struct SLRasterParams
     unsigned int tileBytes;      /* shared memory per warp for its segment's depth texels (0: work in global memory) */
     const uint8_t* rowNeeded;    /* sort-first partition: rows this rank rasterises (null = all) */
     const uint32_t* ticketOrder; /* ticket -> row << 6 | segment (null: row-major)               */
+    const uint32_t* rowPerm;     /* with ticketOrder: its rows are ranks, rowPerm[rank] = the row (heaviest first; k_row_order) */
     unsigned char* depth;
     int depthBpt;
     SLFragLists lists;

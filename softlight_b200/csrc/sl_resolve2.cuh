@@ -181,10 +181,13 @@ __global__ void __launch_bounds__(SL_R2_WARPS * 32, SL_R2_MIN_BLOCKS) k_resolve2
             const uint32_t o = P.ticketOrder[ticket];
             y = (int)(o >> 6);
             seg = (int)(o & 63u);
+            if (P.rowPerm) y = (int)P.rowPerm[y]; /* rows are independent here: the heaviest go first */
         }
         if (P.rowNeeded && !P.rowNeeded[y]) continue;
         const uint32_t begin = P.rowStart[y], end = P.rowStart[y + 1];
         if (begin == end) continue;
+        const long long dbgTicket0 = P.diagnostics ? clock64() : 0ll;
+        unsigned dbgPieces = 0u;
         const int sx0 = seg * (int)P.segWidth;
         const int sx1 = (seg == NS - 1) ? W : sx0 + (int)P.segWidth;
         const unsigned segPixels = (unsigned)(sx1 - sx0);
@@ -348,6 +351,7 @@ __global__ void __launch_bounds__(SL_R2_WARPS * 32, SL_R2_MIN_BLOCKS) k_resolve2
                 }
                 else earlier &= ~newMask; /* those lanes now hold later pieces */
                 const unsigned nTaken = (unsigned)__popc(newMask);
+                dbgPieces += nTaken;
                 ringHead += nTaken;
                 ringCount -= nTaken;
                 __syncwarp();
@@ -627,6 +631,12 @@ __global__ void __launch_bounds__(SL_R2_WARPS * 32, SL_R2_MIN_BLOCKS) k_resolve2
         for (int d = 16; d > 0; d >>= 1) shaded += __shfl_down_sync(0xffffffffu, shaded, d);
         if (lane == 0 && shaded) atomicAdd(&P.counters->fragsShaded, (unsigned long long)shaded);
         shaded = 0u;
+        if (P.diagnostics && lane == 0)
+        {
+            /* the longest ticket: clocks << 32 | pieces << 18 | row << 5 | segment */
+            const unsigned long long cyc = (unsigned long long)(clock64() - dbgTicket0);
+            atomicMax(&P.counters->resolveMaxWindows, (cyc << 32) | ((unsigned long long)min(dbgPieces, 16383u) << 18) | ((unsigned long long)y << 5) | (unsigned long long)seg);
+        }
     }
 
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); /* the last depth store has landed */

@@ -245,6 +245,7 @@ struct slcu_context
     Scratch wireSlots, wireRecInfo; /* wireframe: sort values (double buffer); first slot + candidate count per record */
     Scratch pointKeys, pointRecs, pointSortTemp; /* point primitives: sort keys (double buffer), records, radix-sort scratch */
     Scratch spanItems;   /* (vertex block, row band) work items of k_span */
+    Scratch rowPerm;     /* rows by weight, heaviest first (k_row_order) */
     Scratch ticketOrder; /* skewed work order of k_resolve, cached per (rows, segments, skew) */
     unsigned orderRows = 0, orderSegs = 0, orderSkew = 0;
     Batch batch;            /* submitted, not yet executed draws */
@@ -921,6 +922,9 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
         sp.rowFlags = nullptr;
         sp.rowNeeded = nullptr;
         sp.partFast = 0;
+        sp.partRank = (int)c->partRank;
+        sp.partWorld = (int)c->partWorld;
+        sp.partStrip = (int)c->partStripRows;
         const bool partitioned = c->partWorld > 1;
         const bool partFast = partitioned && !B.partFull;
         if (partitioned)
@@ -1046,6 +1050,7 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
     rp.tileBytes = (segWidth * depthTex.bpt + 15u) & ~15u;
     rp.counters = c->counters;
     rp.ticketOrder = nullptr;
+    rp.rowPerm = nullptr;
     {
         /* skewed work order (see k_resolve): only when every hand-over goes from a segment to its right neighbour */
         static const int skewEnv = getenv("SLCU_TICKET_SKEW") ? atoi(getenv("SLCU_TICKET_SKEW")) : -1;
@@ -1079,6 +1084,14 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
                 c->orderRows = H; c->orderSegs = rasterSegs; c->orderSkew = skew;
             }
             rp.ticketOrder = reinterpret_cast<const uint32_t*>(c->ticketOrder.buf.ptr);
+            static const bool heavyFirst = getenv("SLCU_HEAVY_FIRST") && atoi(getenv("SLCU_HEAVY_FIRST")) != 0; /* opt-in: measured +2 % on k_resolve2, less than k_row_order costs */
+            if (heavyFirst)
+            {
+                CK(c->rowPerm.ensure((size_t)H * sizeof(uint32_t)));
+                KernelScope ks(c, SLCU_K_SCAN);
+                k_row_order<<<1, 1024, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(c->rowStart.buf.ptr), H, reinterpret_cast<uint32_t*>(c->rowPerm.buf.ptr));
+                rp.rowPerm = reinterpret_cast<const uint32_t*>(c->rowPerm.buf.ptr);
+            }
         }
     }
     rp.diagnostics = getenv("SLCU_DEBUG") ? 1 : 0;
@@ -1286,7 +1299,7 @@ void slcu_context_destroy(slcu_context* c)
     if (c->counters) cudaFree(c->counters);
     if (c->hostCounters) cudaFreeHost(c->hostCounters);
     for (auto& pm : c->peerMaps) if (pm.ptr) cudaIpcCloseMemHandle(pm.ptr);
-    Scratch* s[] = {&c->records, &c->blockInfo, &c->cnt, &c->off, &c->segSums, &c->rowTotals, &c->rowStart, &c->entries, &c->handoff, &c->rowFlags, &c->rowNeeded, &c->drawTable, &c->blockDraw, &c->recDraw, &c->fragPool, &c->chunkNext, &c->listInfo, &c->handoffRegs, &c->ticketOrder, &c->spanItems, &c->pointKeys, &c->pointRecs, &c->pointSortTemp, &c->wireSlots, &c->wireRecInfo, &c->wireLeaders};
+    Scratch* s[] = {&c->records, &c->blockInfo, &c->cnt, &c->off, &c->segSums, &c->rowTotals, &c->rowStart, &c->entries, &c->handoff, &c->rowFlags, &c->rowNeeded, &c->drawTable, &c->blockDraw, &c->recDraw, &c->fragPool, &c->chunkNext, &c->listInfo, &c->handoffRegs, &c->ticketOrder, &c->spanItems, &c->rowPerm, &c->pointKeys, &c->pointRecs, &c->pointSortTemp, &c->wireSlots, &c->wireRecInfo, &c->wireLeaders};
     for (Scratch* x : s) x->release();
     cudaStreamDestroy(c->stream);
     delete c;
@@ -1317,6 +1330,111 @@ size_t slcu_create_vao(slcu_context* c) { c->vaos.emplace_back(); memset(&c->vao
 size_t slcu_create_ubo(slcu_context* c) { c->ubos.emplace_back(); memset(c->ubos.back().bytes, 0, 1024); return c->ubos.size() - 1; }
 size_t slcu_create_texture(slcu_context* c) { c->textures.emplace_back(); return c->textures.size() - 1; }
 size_t slcu_create_framebuffer(slcu_context* c) { c->fbos.emplace_back(); return c->fbos.size() - 1; }
+
+/* ---- SL_Context::destroy_* : vector erase, later ids shift (see include/slcu.h) ---- */
+static void remap_fixups(slcu_context* c, int kind, size_t gone)
+{
+    for (size_t i = 0; i < c->fixups.size();)
+    {
+        UboFixup& f = c->fixups[i];
+        if (f.kind == kind && f.id == gone) { c->fixups.erase(c->fixups.begin() + i); continue; }
+        if (f.kind == kind && f.id > gone) --f.id;
+        ++i;
+    }
+}
+static void remap_fixups_ubo(slcu_context* c, size_t gone)
+{
+    /* fix-ups are declared per uniform block (an index, like the block itself) */
+    for (size_t i = 0; i < c->fixups.size();)
+    {
+        UboFixup& f = c->fixups[i];
+        if (f.ubo == gone) { c->fixups.erase(c->fixups.begin() + i); continue; }
+        if (f.ubo > gone) --f.ubo;
+        ++i;
+    }
+}
+int slcu_destroy_vbo(slcu_context* c, size_t id)
+{
+    SLCU_FLUSH();
+    if (!c || id >= c->vbos.size()) return SLCU_ERR_ARG;
+    cudaSetDevice(c->device);
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->vbos[id].ptr) cudaFree(c->vbos[id].ptr);
+    c->vbos.erase(c->vbos.begin() + id);
+    remap_fixups(c, 1, id);
+    return 0;
+}
+int slcu_destroy_ibo(slcu_context* c, size_t id)
+{
+    SLCU_FLUSH();
+    if (!c || id >= c->ibos.size()) return SLCU_ERR_ARG;
+    cudaSetDevice(c->device);
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->ibos[id].buf.ptr) cudaFree(c->ibos[id].buf.ptr);
+    c->ibos.erase(c->ibos.begin() + id);
+    return 0;
+}
+int slcu_destroy_vao(slcu_context* c, size_t id)
+{
+    SLCU_FLUSH();
+    if (!c || id >= c->vaos.size()) return SLCU_ERR_ARG;
+    c->vaos.erase(c->vaos.begin() + id);
+    return 0;
+}
+int slcu_destroy_ubo(slcu_context* c, size_t id)
+{
+    SLCU_FLUSH();
+    if (!c || id >= c->ubos.size()) return SLCU_ERR_ARG;
+    c->ubos.erase(c->ubos.begin() + id);
+    remap_fixups_ubo(c, id);
+    return 0;
+}
+int slcu_destroy_texture(slcu_context* c, size_t id)
+{
+    SLCU_FLUSH();
+    if (!c || id >= c->textures.size()) return SLCU_ERR_ARG;
+    cudaSetDevice(c->device);
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->textures[id].dev) cudaFree(c->textures[id].dev);
+    c->textures.erase(c->textures.begin() + id);
+    remap_fixups(c, 0, id);
+    for (HostFbo& f : c->fbos)
+    {
+        for (int i = 0; i < 4; ++i)
+        {
+            if (f.colors[i] == (size_t)-1) continue;
+            if (f.colors[i] == id) { f.colors[i] = (size_t)-1; f.colorViews[i] = FboView{}; }
+            else if (f.colors[i] > id) --f.colors[i];
+        }
+        if (f.depth != (size_t)-1)
+        {
+            if (f.depth == id) { f.depth = (size_t)-1; f.depthView = FboView{}; }
+            else if (f.depth > id) --f.depth;
+        }
+    }
+    for (size_t i = 0; i < c->peerMaps.size();)
+    {
+        auto& pm = c->peerMaps[i];
+        if (pm.tex == id) { if (pm.ptr) cudaIpcCloseMemHandle(pm.ptr); c->peerMaps.erase(c->peerMaps.begin() + i); continue; }
+        if (pm.tex > id) --pm.tex;
+        ++i;
+    }
+    return upload_texture_descs(c); /* the device-side descriptor array is indexed by id */
+}
+int slcu_destroy_framebuffer(slcu_context* c, size_t id)
+{
+    SLCU_FLUSH();
+    if (!c || id >= c->fbos.size()) return SLCU_ERR_ARG;
+    c->fbos.erase(c->fbos.begin() + id);
+    return 0;
+}
+int slcu_destroy_shader(slcu_context* c, size_t id)
+{
+    SLCU_FLUSH();
+    if (!c || id >= c->shaders.size()) return SLCU_ERR_ARG;
+    c->shaders.erase(c->shaders.begin() + id);
+    return 0;
+}
 
 int slcu_vbo_init(slcu_context* c, size_t vbo, size_t numBytes)
 {
@@ -1739,6 +1857,11 @@ int slcu_get_stats(slcu_context* c, slcu_stats* out)
                 (unsigned long long)c->hostCounters->resolveWaves, (unsigned long long)c->hostCounters->resolveIdle,
                 (unsigned long long)c->hostCounters->resolveWarps, (unsigned long long)c->hostCounters->resolveCycles,
                 (unsigned long long)c->hostCounters->resolveMaxCycles, (unsigned long long)c->hostCounters->resolveMaxWindows);
+    if (getenv("SLCU_DEBUG") && (c->hostCounters->resolveMaxWindows >> 32))
+    {
+        const unsigned long long w = c->hostCounters->resolveMaxWindows; /* k_resolve2: its longest ticket */
+        fprintf(stderr, "[slcu] resolve2 longest ticket: %llu clocks, %llu pieces, row %llu segment %llu\n", w >> 32, (w >> 18) & 16383ull, (w >> 5) & 8191ull, w & 31ull);
+    }
     *out = c->stats;
     return report_device_flags(c, c->hostCounters->errorFlags);
 }

@@ -24,7 +24,7 @@ def main():
     frames = np.load(os.path.join(ROOT, "tests", "golden", "golden_frames.npz"))
     hashes = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_hashes.json")))["cases"]
     bad = 0
-    for name, strip in (("c1_small", 8), ("c2_small", 8), ("rand_clip_heavy", 1), ("rand_overflow_wide", 2), ("c1_sphere100k", 8), ("c2_instancing10k", 8),
+    for name, strip in (("c1_small", 8), ("c2_small", 8), ("rand_clip_heavy", 1), ("rand_overflow_wide", 2), ("c1_sphere100k", 8), ("c2_instancing10k", 8), ("c3_indoor2m", 8), ("c4_skinned100", 8),
                         ("points_dense", 1), ("points_sparse_1080p", 8), ("wire_alpha", 1), ("wire_overflow_premult", 2), ("wire_1080p", 8)):
         scene = (cases.CASES.get(name) or cases.BIG_CASES[name])()
         ctx = A.Context("cuda", device=local)
