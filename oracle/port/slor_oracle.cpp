@@ -1335,19 +1335,193 @@ int slor_draw_multiple(slcu_context* c, const slcu_mesh* m, size_t n, size_t sha
 }
 int slor_draw_instanced(slcu_context* c, const slcu_mesh* m, size_t inst, size_t shader, size_t fbo) { return run_draw(c, m, 1, inst, shader, fbo); }
 
-/* SL_BlitProcessor::blit_nearest (src/SL_BlitProcessor.cpp:620-667), one thread; conversions: same type, RGBA_FLOAT ->
- * RGBA_8U ((vec4<u8>)(p*255.f), :400-415), RGBA_8U -> RGBA_FLOAT (SL_Color.hpp:665-669) */
+/* ---- SL_BlitProcessor's texel conversions (src/SL_BlitProcessor.cpp:20-426 + color_cast, SL_Color.hpp:236-700) ----------
+ * A blit functor builds a colour of the DESTINATION's channel count in the SOURCE's component type (missing channels are
+ * the type's minimum, alpha its maximum; R lands in the LAST colour channel of RGB/RGBA, RG in the middle of RGBA --
+ * :196-204, 304-326), converts it with color_cast and stores it.  "to R" functors convert the whole source colour and keep
+ * component 0, so their conversion runs on the source's channel count.  Conversions of 4-component colours go through
+ * vec4_t's SSE cast operators where one exists (x86/vec4f_impl.h:190-355: float -> u8/u16/u32 = cvtps2dq + saturating packs,
+ * float -> half = cvtps2ph toward zero, u32 -> float = the halves trick); everything else is the element-wise C cast. */
+namespace slo
+{
+struct TexelValue /* one component, in its own type */
+{
+    uint64_t u; /* kinds 0..3 */
+    uint16_t h; /* kind 4: half bits */
+    float f;    /* kind 5 */
+    double d;   /* kind 6 */
+};
+static const uint64_t kIntMax[4] = {0xffull, 0xffffull, 0xffffffffull, 0xffffffffffffffffull};
+
+static inline TexelValue load_component(const unsigned char* p, int kind)
+{
+    TexelValue t{};
+    switch (kind)
+    {
+        case 0: t.u = *p; break;
+        case 1: { uint16_t v; memcpy(&v, p, 2); t.u = v; break; }
+        case 2: { uint32_t v; memcpy(&v, p, 4); t.u = v; break; }
+        case 3: memcpy(&t.u, p, 8); break;
+        case 4: memcpy(&t.h, p, 2); break;
+        case 5: memcpy(&t.f, p, 4); break;
+        default: memcpy(&t.d, p, 8); break;
+    }
+    return t;
+}
+static inline TexelValue limit_component(int kind, bool maxValue)
+{
+    TexelValue t{};
+    if (!maxValue) return t; /* min(): 0 for every type (SL_ColorLimits, SL_Color.hpp:90-175) */
+    if (kind <= 3) t.u = kIntMax[kind];
+    else if (kind == 4) t.h = 0x3c00u;
+    else if (kind == 5) t.f = 1.f;
+    else t.d = 1.0;
+    return t;
+}
+/* (T)x for an integer T, as the x86 code does it: cvttss2si / cvttsd2si (the 64-bit form for 32- and 64-bit unsigned
+ * targets), then the low bits */
+static inline uint64_t trunc_to_int(double x, bool isFloat, int kind)
+{
+    if (kind <= 1)
+    {
+        const bool in = isFloat ? ((float)x >= -2147483648.0f && (float)x < 2147483648.0f) : (x > -2147483649.0 && x < 2147483648.0);
+        const int32_t v = in ? (int32_t)x : INT32_MIN;
+        return (uint64_t)(uint32_t)v & kIntMax[kind];
+    }
+    if (kind == 2)
+    {
+        const bool in = x >= -9223372036854775808.0 && x < 9223372036854775808.0;
+        const int64_t v = in ? (int64_t)x : INT64_MIN;
+        return (uint64_t)v & 0xffffffffull;
+    }
+    /* uint64_t: gcc's sequence (compare with 2^63, subtract, convert, flip the top bit) */
+    if (x >= 9223372036854775808.0)
+    {
+        const double y = x - 9223372036854775808.0;
+        const bool in = y < 9223372036854775808.0;
+        return (uint64_t)(in ? (int64_t)y : INT64_MIN) ^ 0x8000000000000000ull;
+    }
+    const bool in = x >= -9223372036854775808.0;
+    return (uint64_t)(in ? (int64_t)x : INT64_MIN);
+}
+static inline float u32_to_float_halves(uint32_t v) /* vec4_t<uint32_t> -> vec4_t<float> (vec4f_impl.h:236-245) */
+{
+    const float hi = (float)(int32_t)(v >> 1), lo = (float)(int32_t)(v & 1u);
+    return (hi + hi) + lo;
+}
+static inline float int_to_float(uint64_t v, int kind, bool simd4)
+{
+    if (kind == 2 && simd4) return u32_to_float_halves((uint32_t)v);
+    if (kind == 3) return (float)v;
+    return (float)(uint32_t)v;
+}
+static inline uint64_t float_to_int(float x, int kind, bool simd4)
+{
+    if (simd4 && kind <= 2)
+    {
+        const int32_t r = cvt_rn(x); /* cvtps2dq */
+        if (kind == 0) { const int32_t s = r < -32768 ? -32768 : (r > 32767 ? 32767 : r); return (uint64_t)(s < 0 ? 0 : (s > 255 ? 255 : s)); } /* packs_epi32, packus_epi16 */
+        if (kind == 1) return (uint64_t)(r < 0 ? 0 : (r > 65535 ? 65535 : r));                                                                /* packus_epi32 */
+        return (uint64_t)(uint32_t)r;
+    }
+    return trunc_to_int((double)x, true, kind);
+}
+
+static inline TexelValue convert_component(const TexelValue& in, int ik, int ok, int width)
+{
+    const bool simd4 = width == 4;
+    TexelValue o{};
+    if (ik <= 3 && ok <= 3) /* integer -> integer (SL_Color.hpp:236-246) */
+    {
+        const uint64_t tMax = kIntMax[ok], uMax = kIntMax[ik];
+        if (width == 2)
+        {
+            /* the two-component overload scales by max(T) itself instead of by the ratio of the two maxima (:373-380):
+             * widening multiplies by max(T) and wraps, narrowing (and same-type!) divides by max(T) */
+            if (tMax > uMax) o.u = ((in.u & tMax) * tMax) & tMax;
+            else o.u = (in.u / tMax) & tMax;
+            return o;
+        }
+        if (tMax > uMax) o.u = ((in.u & tMax) * (tMax / (uMax & tMax))) & tMax;
+        else o.u = (in.u / (uMax / (tMax & uMax))) & tMax;
+        return o;
+    }
+    if (ok <= 3) /* float kinds -> integer (:250-266): p * (U)max(T), then the cast */
+    {
+        if (ik == 6) { o.u = trunc_to_int(in.d * (double)kIntMax[ok], false, ok); return o; }
+        const float x = (ik == 4 ? half_to_float(in.h) : in.f) * (float)kIntMax[ok];
+        o.u = float_to_int(x, ok, simd4);
+        return o;
+    }
+    if (ik <= 3) /* integer -> float kinds (:270-300) */
+    {
+        if (ok == 6) { o.d = (double)in.u * (1.0 / (double)kIntMax[ik]); return o; }
+        const float scale = (ik == 0 && ok == 5) ? 0.00392156862745f : (1.f / (float)kIntMax[ik]);
+        const float f = int_to_float(in.u, ik, simd4) * scale;
+        if (ok == 5) o.f = f;
+        else o.h = simd4 ? float_to_half_rz(f) : float_to_half_rn(f);
+        return o;
+    }
+    /* float kinds -> float kinds (:304-310): plain casts; half only talks to float */
+    if (ik == ok) return in;
+    if (ik == 4)
+    {
+        const float f = half_to_float(in.h);
+        if (ok == 5) o.f = f; else o.d = (double)f;
+        return o;
+    }
+    if (ik == 5)
+    {
+        if (ok == 6) o.d = (double)in.f;
+        else o.h = simd4 ? float_to_half_rz(in.f) : float_to_half_rn(in.f);
+        return o;
+    }
+    if (ok == 5) o.f = (float)in.d;
+    else o.h = float_to_half_rn((float)in.d); /* vec4_t<double> has no SSE cast: (half)(float)(double) */
+    return o;
+}
+static inline void store_component(unsigned char* p, int kind, const TexelValue& t)
+{
+    switch (kind)
+    {
+        case 0: *p = (unsigned char)t.u; break;
+        case 1: { const uint16_t v = (uint16_t)t.u; memcpy(p, &v, 2); break; }
+        case 2: { const uint32_t v = (uint32_t)t.u; memcpy(p, &v, 4); break; }
+        case 3: memcpy(p, &t.u, 8); break;
+        case 4: memcpy(p, &t.h, 2); break;
+        case 5: memcpy(p, &t.f, 4); break;
+        default: memcpy(p, &t.d, 8); break;
+    }
+}
+/* which source component (or limit) feeds destination component j: 0..3 = source component, -1 = min, -2 = max */
+static inline int blit_channel_source(int srcN, int dstN, int j)
+{
+    if (dstN <= srcN) return j;                                 /* leading components (vec2_cast / vec3_cast, [0]) */
+    if (srcN == 1) return dstN == 2 ? (j == 0 ? 0 : -1) : (j == 2 ? 0 : (j == 3 ? -2 : -1)); /* R -> RG (r, min); -> RGB (min, min, r); -> RGBA (min, min, r, max) */
+    if (srcN == 2) return dstN == 3 ? (j < 2 ? j : -1) : (j == 0 ? -1 : (j == 3 ? -2 : j - 1)); /* RG -> RGB (r, g, min); -> RGBA (min, r, g, max) */
+    return j < 3 ? j : -2;                                      /* RGB -> RGBA (r, g, b, max) */
+}
+static void blit_texel(const unsigned char* src, int srcType, unsigned char* dst, int dstType)
+{
+    static const int kBytes[7] = {1, 2, 4, 8, 2, 4, 8};
+    const int ik = srcType % 7, srcN = srcType / 7 + 1, ok = dstType % 7, dstN = dstType / 7 + 1;
+    const int width = dstN == 1 ? srcN : dstN; /* the channel count color_cast runs on */
+    for (int j = 0; j < dstN; ++j)
+    {
+        const int from = blit_channel_source(srcN, dstN, j);
+        const TexelValue in = from >= 0 ? load_component(src + from * kBytes[ik], ik) : limit_component(ik, from == -2);
+        store_component(dst + j * kBytes[ok], ok, convert_component(in, ik, ok, width));
+    }
+}
+} // namespace slo
+
+/* SL_BlitProcessor::blit_nearest (src/SL_BlitProcessor.cpp:620-667), one thread */
 int slor_blit_rect(slcu_context* c, size_t outTex, size_t inTex, uint16_t sx0, uint16_t sy0, uint16_t sx1, uint16_t sy1,
                    uint16_t dx0, uint16_t dy0, uint16_t dx1, uint16_t dy1)
 {
     if (outTex >= c->textures.size() || inTex >= c->textures.size()) return SLCU_ERR_ARG;
     const SL_Texture& s = *c->textures[inTex];
     SL_Texture& d = *c->textures[outTex];
-    int mode;
-    if (s.mType == d.mType) mode = 0;
-    else if (s.mType == 26 && d.mType == 21) mode = 1;
-    else if (s.mType == 21 && d.mType == 26) mode = 2;
-    else return SLCU_ERR_UNSUPPORTED;
     if (sx1 < sx0 || sy1 < sy0 || dx1 <= dx0 || dy1 <= dy0) return 0;
     const uint64_t inW = (uint64_t)sx1 - sx0, inH = (uint64_t)sy1 - sy0, outW = (uint64_t)dx1 - dx0;
     const uint64_t totalOutW = d.mWidth, totalOutH = d.mHeight;
@@ -1362,20 +1536,9 @@ int slor_blit_rect(slcu_context* c, size_t outTex, size_t inTex, uint16_t sx0, u
             const uint64_t srcX = (x * foutW) >> 16;
             if (srcX >= s.mWidth || srcY >= s.mHeight) continue;
             const size_t si = (size_t)(srcX + (uint64_t)s.mWidth * srcY), di = (size_t)(x + totalOutW * y);
-            if (mode == 1)
-            {
-                math::vec4 f;
-                memcpy(f.v, s.mTexels + si * 16, 16);
-                const math::vec4_t<uint8_t> r = (math::vec4_t<uint8_t>)(f * 255.f);
-                memcpy(d.mTexels + di * 4, r.v, 4);
-            }
-            else if (mode == 2)
-            {
-                const unsigned char* p = s.mTexels + si * 4;
-                const math::vec4 f = math::vec4{(float)p[0], (float)p[1], (float)p[2], (float)p[3]} * 0.00392156862745f;
-                memcpy(d.mTexels + di * 16, f.v, 16);
-            }
-            else memcpy(d.mTexels + di * d.mBpt, s.mTexels + si * s.mBpt, d.mBpt);
+            const bool rgIntQuirk = s.mType == d.mType && s.mType / 7 == 1 && s.mType % 7 <= 3; /* RG integer -> same type: p / max(T), see convert_component */
+            if (s.mType == d.mType && !rgIntQuirk) memcpy(d.mTexels + di * d.mBpt, s.mTexels + si * s.mBpt, d.mBpt);
+            else slo::blit_texel(s.mTexels + si * s.mBpt, s.mType, d.mTexels + di * d.mBpt, d.mType);
         }
     }
     return 0;

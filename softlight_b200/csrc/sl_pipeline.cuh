@@ -778,42 +778,49 @@ SLD_FN int sl_owned_kth(int a, int k, int strip, int world, int rank)
  * earlier records in that ROW only. */
 __global__ void __launch_bounds__(1024) k_span_items(const SLBlockInfo* blockInfo, unsigned numBlocks, unsigned numRows, uint32_t* items, uint32_t* numItems)
 {
-    __shared__ uint32_t sPart[1024];
-    __shared__ uint32_t sBase;
-    const int tid = threadIdx.x;
-    if (tid == 0) sBase = 0u;
-    __syncthreads();
-    for (unsigned b0 = 0; b0 < numBlocks; b0 += 1024u)
+    __shared__ uint32_t sWarp[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned per = (numBlocks + 1023u) / 1024u;
+    const unsigned a = (unsigned)tid * per, b = min(a + per, numBlocks);
+    auto bands = [&](unsigned vb, uint32_t& first) -> uint32_t {
+        const uint32_t y0 = ~blockInfo[vb].negYMin;
+        uint32_t y1 = blockInfo[vb].yMax;
+        if (y1 > numRows) y1 = numRows;
+        if (!(y0 < y1)) { first = 0u; return 0u; }
+        first = y0 >> SL_SPAN_BAND_SHIFT;
+        return ((y1 - 1u) >> SL_SPAN_BAND_SHIFT) - first + 1u;
+    };
+    uint32_t mine = 0u, first = 0u;
+    for (unsigned vb = a; vb < b; ++vb) mine += bands(vb, first);
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
     {
-        const unsigned vb = b0 + (unsigned)tid;
-        uint32_t first = 0u, n = 0u;
-        if (vb < numBlocks)
-        {
-            const uint32_t y0 = ~blockInfo[vb].negYMin;
-            uint32_t y1 = blockInfo[vb].yMax;
-            if (y1 > numRows) y1 = numRows;
-            if (y0 < y1)
-            {
-                first = y0 >> SL_SPAN_BAND_SHIFT;
-                n = ((y1 - 1u) >> SL_SPAN_BAND_SHIFT) - first + 1u;
-            }
-        }
-        sPart[tid] = n;
-        __syncthreads();
-        for (int d = 1; d < 1024; d <<= 1)
-        {
-            const uint32_t t = tid >= d ? sPart[tid - d] : 0u;
-            __syncthreads();
-            sPart[tid] += t;
-            __syncthreads();
-        }
-        const uint32_t off = sBase + sPart[tid] - n;
-        for (uint32_t k = 0; k < n; ++k) items[off + k] = vb | ((first + k) << 16);
-        __syncthreads();
-        if (tid == 1023) sBase += sPart[1023];
-        __syncthreads();
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
     }
-    if (tid == 0) *numItems = sBase;
+    if (lane == 31) sWarp[warp] = incl;
+    __syncthreads();
+    if (warp == 0)
+    {
+        uint32_t w = sWarp[lane], wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += t;
+        }
+        sWarp[lane] = wi - w;
+        if (lane == 31) *numItems = wi;
+    }
+    __syncthreads();
+    uint32_t off = sWarp[warp] + incl - mine;
+    for (unsigned vb = a; vb < b; ++vb)
+    {
+        const uint32_t n = bands(vb, first);
+        for (uint32_t k = 0; k < n; ++k) items[off + k] = vb | ((first + k) << 16);
+        off += n;
+    }
 }
 
 /* MODE 0: count entries per (vertex block, row).  MODE 1: fill the row lists.
@@ -1170,57 +1177,48 @@ __global__ void __launch_bounds__(1024) k_scan_row_starts(const uint32_t* rowTot
     }
 }
 
-/* Heaviest rows first: rowPerm[i] = the row with the i-th most span entries (64 weight classes, rows of a class in
- * ascending order).  The resolving warps take their (row, segment) tickets in this order, so the long rows are under way
- * while there is still plenty of short work to fill the machine with, instead of being the tail of the kernel. */
+/* Heavy rows first: rowPerm lists the rows with more than twice the average number of span entries (in ascending row
+ * order), then all the others.  k_resolve2 is as long as its longest (row, segment) ticket -- a row near the horizon of a
+ * deep scene holds a few thousand overlapping pieces that can only be settled layer after layer -- so those tickets have
+ * to be under way from the start instead of being handed out whenever their row number comes up. */
 __global__ void __launch_bounds__(1024) k_row_order(const uint32_t* rowStart, unsigned numRows, uint32_t* rowPerm)
 {
-    __shared__ uint32_t sMax;
-    __shared__ uint32_t sBin[64];
-    __shared__ uint32_t sBase[64];
-    const int tid = threadIdx.x;
-    if (tid == 0) sMax = 1u;
-    if (tid < 64) sBin[tid] = 0u;
-    __syncthreads();
-    uint32_t m = 0u;
-    for (unsigned y = tid; y < numRows; y += 1024u) m = max(m, rowStart[y + 1] - rowStart[y]);
-    for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
-    if ((tid & 31) == 0) atomicMax(&sMax, m);
-    __syncthreads();
-    const uint32_t top = sMax;
-    /* class 0 = heaviest; rows are visited in ascending order by every thread and ranked inside their class by row index */
-    for (unsigned y = tid; y < numRows; y += 1024u)
+    __shared__ uint32_t sWarp[32];
+    __shared__ uint32_t sTotal;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t limit = 2u * (rowStart[numRows] / (numRows ? numRows : 1u)) + 1u;
+    const unsigned per = (numRows + 1023u) / 1024u;
+    const unsigned a = (unsigned)tid * per, b = min(a + per, numRows);
+    uint32_t heavy = 0u;
+    for (unsigned y = a; y < b; ++y) heavy += (rowStart[y + 1] - rowStart[y]) > limit ? 1u : 0u;
+    uint32_t incl = heavy;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
     {
-        const uint32_t n = rowStart[y + 1] - rowStart[y];
-        const uint32_t cls = 63u - (uint32_t)(((unsigned long long)n * 63ull) / top);
-        atomicAdd(&sBin[cls], 1u);
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
     }
+    if (lane == 31) sWarp[warp] = incl;
     __syncthreads();
-    if (tid == 0)
+    if (warp == 0)
     {
-        uint32_t run = 0u;
-        for (int k = 0; k < 64; ++k) { sBase[k] = run; run += sBin[k]; }
-    }
-    __syncthreads();
-    /* deterministic placement: one warp per class walks the rows in order */
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int cls = warp; cls < 64; cls += 32)
-    {
-        if (!sBin[cls]) continue;
-        uint32_t pos = sBase[cls];
-        for (unsigned y0 = 0; y0 < numRows; y0 += 32u)
+        uint32_t w = sWarp[lane], wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
         {
-            const unsigned y = y0 + (unsigned)lane;
-            bool in = false;
-            if (y < numRows)
-            {
-                const uint32_t n = rowStart[y + 1] - rowStart[y];
-                in = (63u - (uint32_t)(((unsigned long long)n * 63ull) / top)) == (uint32_t)cls;
-            }
-            const uint32_t mask = __ballot_sync(0xffffffffu, in);
-            if (in) rowPerm[pos + (uint32_t)__popc(mask & ((1u << lane) - 1u))] = y;
-            pos += (uint32_t)__popc(mask);
+            const uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += t;
         }
+        sWarp[lane] = wi - w;
+        if (lane == 31) sTotal = wi;
+    }
+    __syncthreads();
+    uint32_t hPos = sWarp[warp] + incl - heavy; /* heavy rows before this thread's chunk */
+    const uint32_t numHeavy = sTotal;
+    for (unsigned y = a; y < b; ++y)
+    {
+        if ((rowStart[y + 1] - rowStart[y]) > limit) rowPerm[hPos++] = y;
+        else rowPerm[numHeavy + (y - hPos)] = y; /* light rows keep their order behind the heavy ones */
     }
 }
 
@@ -2342,10 +2340,17 @@ __global__ void k_clear(const __grid_constant__ SLClearParams P)
 /* ------------------------------------------------------------------------
  * SL_BlitProcessor::blit_nearest (src/SL_BlitProcessor.cpp:620-667): nearest
  * neighbour, 16.16 fixed point, vertically flipped, format converting.  One
- * thread per destination texel.  Conversions (color_cast, SL_Color.hpp:560-700):
- *   mode 0  same type: texel copy
- *   mode 1  RGBA_FLOAT -> RGBA_8U: (vec4<u8>)(p * 255.f) = cvtps2dq + saturating packs (:400-415, x86/vec4f_impl.h:299-309)
- *   mode 2  RGBA_8U -> RGBA_FLOAT: (vec4)p * 0.00392156862745f (SL_Color.hpp:665-669)
+ * thread per destination texel.
+ *
+ * Conversions (src/SL_BlitProcessor.cpp:20-426 + color_cast, SL_Color.hpp:236-700) between the twenty 8/16-bit unorm,
+ * half, float and double layouts.  A blit functor builds a colour of the DESTINATION's channel count in the SOURCE's
+ * component type (missing channels are the type's minimum, alpha its maximum; R lands in the LAST colour channel of
+ * RGB/RGBA, RG in the middle of RGBA), converts it with color_cast and stores it; "to R" functors convert the whole source
+ * colour and keep component 0.  Four-component conversions go through vec4_t's SSE cast operators where one exists
+ * (x86/vec4f_impl.h:190-355: float -> u8/u16 = cvtps2dq + saturating packs, float -> half = cvtps2ph toward zero), the
+ * others are element-wise C casts (cvttss2si / cvttsd2si and the low bits; scalar half conversions round to nearest).
+ * The two-component integer overload scales by max(T) instead of by the ratio of the maxima (SL_Color.hpp:373-380) --
+ * reproduced, including for equal types.
  * ----------------------------------------------------------------------*/
 struct SLBlitParams
 {
@@ -2353,8 +2358,113 @@ struct SLBlitParams
     unsigned char* dst;
     unsigned int srcW, srcH, dstW, dstH;
     unsigned int srcX0, srcY0, srcX1, srcY1, dstX0, dstY0, dstX1, dstY1;
-    int mode, bpt;
+    int mode, bpt;         /* mode 0: texel copy (bpt bytes), 1: RGBA_FLOAT -> RGBA_8U, 2: RGBA_8U -> RGBA_FLOAT, 3: general */
+    int srcType, dstType;  /* SL_ColorDataType */
 };
+
+struct SLTexelValue /* one component in its own type: kind 0 u8, 1 u16, 4 half, 5 float, 6 double */
+{
+    uint32_t u;
+    float f;
+    double d;
+};
+
+SLD_FN SLTexelValue sl_blit_load(const unsigned char* p, int kind)
+{
+    SLTexelValue t{0u, 0.f, 0.0};
+    if (kind == 0) t.u = *p;
+    else if (kind == 1 || kind == 4) t.u = *reinterpret_cast<const uint16_t*>(p);
+    else if (kind == 5) t.f = *reinterpret_cast<const float*>(p);
+    else t.d = *reinterpret_cast<const double*>(p);
+    return t;
+}
+SLD_FN void sl_blit_store(unsigned char* p, int kind, const SLTexelValue& t)
+{
+    if (kind == 0) *p = (unsigned char)t.u;
+    else if (kind == 1 || kind == 4) *reinterpret_cast<uint16_t*>(p) = (uint16_t)t.u;
+    else if (kind == 5) *reinterpret_cast<float*>(p) = t.f;
+    else *reinterpret_cast<double*>(p) = t.d;
+}
+/* (uint8_t) / (uint16_t) of a float or double the way the x86 code does it: cvttss2si / cvttsd2si, then the low bits */
+SLD_FN uint32_t sl_blit_trunc_f(float x, uint32_t mask) { return (uint32_t)sl_cvt_tr(x) & mask; }
+SLD_FN uint32_t sl_blit_trunc_d(double x, uint32_t mask)
+{
+    const int32_t v = (x > -2147483649.0 && x < 2147483648.0) ? __double2int_rz(x) : (int32_t)0x80000000;
+    return (uint32_t)v & mask;
+}
+SLD_FN SLTexelValue sl_blit_convert(const SLTexelValue& in, int ik, int ok, int width)
+{
+    const bool simd4 = width == 4;
+    SLTexelValue o{0u, 0.f, 0.0};
+    const uint32_t tMax = ok == 0 ? 0xffu : 0xffffu, uMax = ik == 0 ? 0xffu : 0xffffu;
+    if (ik <= 1 && ok <= 1) /* integer -> integer */
+    {
+        if (width == 2) o.u = tMax > uMax ? ((in.u * tMax) & tMax) : ((in.u / tMax) & tMax);
+        else o.u = tMax > uMax ? ((in.u * (tMax / uMax)) & tMax) : ((in.u / (uMax / tMax)) & tMax);
+        return o;
+    }
+    if (ok <= 1) /* half / float / double -> integer: p * (U)max(T), then the cast */
+    {
+        if (ik == 6) { o.u = sl_blit_trunc_d(in.d * (double)tMax, tMax); return o; }
+        const float x = (ik == 4 ? sl_h2f((uint16_t)in.u) : in.f) * (float)tMax;
+        if (simd4)
+        {
+            const int32_t r = sl_cvt_rn(x); /* cvtps2dq */
+            if (ok == 0) { const int32_t q = r < -32768 ? -32768 : (r > 32767 ? 32767 : r); o.u = (uint32_t)(q < 0 ? 0 : (q > 255 ? 255 : q)); } /* packs_epi32, packus_epi16 */
+            else o.u = (uint32_t)(r < 0 ? 0 : (r > 65535 ? 65535 : r));                                                                          /* packus_epi32 */
+        }
+        else o.u = sl_blit_trunc_f(x, tMax);
+        return o;
+    }
+    if (ik <= 1) /* integer -> half / float / double */
+    {
+        if (ok == 6) { o.d = (double)in.u * (ik == 0 ? (1.0 / 255.0) : (1.0 / 65535.0)); return o; }
+        const float scale = ik == 0 ? (ok == 5 ? 0.00392156862745f : (1.f / 255.f)) : (1.f / 65535.f);
+        const float f = (float)in.u * scale;
+        if (ok == 5) o.f = f;
+        else o.u = simd4 ? sl_f2h_rz(f) : sl_f2h_rn(f);
+        return o;
+    }
+    /* float kinds -> float kinds: plain casts; half only talks to float */
+    if (ik == ok) return in;
+    if (ik == 4)
+    {
+        const float f = sl_h2f((uint16_t)in.u);
+        if (ok == 5) o.f = f; else o.d = (double)f;
+        return o;
+    }
+    if (ik == 5)
+    {
+        if (ok == 6) o.d = (double)in.f;
+        else o.u = simd4 ? sl_f2h_rz(in.f) : sl_f2h_rn(in.f);
+        return o;
+    }
+    if (ok == 5) o.f = __double2float_rn(in.d);
+    else o.u = sl_f2h_rn(__double2float_rn(in.d)); /* vec4_t<double> has no SSE cast: (half)(float)(double) */
+    return o;
+}
+/* which source component (or limit) feeds destination component j: 0..3 = source component, -1 = min, -2 = max */
+SLD_FN int sl_blit_channel_source(int srcN, int dstN, int j)
+{
+    if (dstN <= srcN) return j;
+    if (srcN == 1) return dstN == 2 ? (j == 0 ? 0 : -1) : (j == 2 ? 0 : (j == 3 ? -2 : -1));
+    if (srcN == 2) return dstN == 3 ? (j < 2 ? j : -1) : (j == 0 ? -1 : (j == 3 ? -2 : j - 1));
+    return j < 3 ? j : -2;
+}
+SLD_FN void sl_blit_texel(const unsigned char* src, int srcType, unsigned char* dst, int dstType)
+{
+    const int ik = srcType % 7, srcN = srcType / 7 + 1, ok = dstType % 7, dstN = dstType / 7 + 1;
+    const int ib = ik == 0 ? 1 : (ik == 5 ? 4 : (ik == 6 ? 8 : 2)), ob = ok == 0 ? 1 : (ok == 5 ? 4 : (ok == 6 ? 8 : 2));
+    const int width = dstN == 1 ? srcN : dstN; /* the channel count color_cast runs on */
+    for (int j = 0; j < dstN; ++j)
+    {
+        const int from = sl_blit_channel_source(srcN, dstN, j);
+        SLTexelValue in{0u, 0.f, 0.0};
+        if (from >= 0) in = sl_blit_load(src + from * ib, ik);
+        else if (from == -2) { if (ik <= 1) in.u = ik == 0 ? 0xffu : 0xffffu; else if (ik == 4) in.u = 0x3c00u; else if (ik == 5) in.f = 1.f; else in.d = 1.0; }
+        sl_blit_store(dst + j * ob, ok, sl_blit_convert(in, ik, ok, width));
+    }
+}
 
 __global__ void __launch_bounds__(256) k_blit(const __grid_constant__ SLBlitParams P)
 {
@@ -2366,6 +2476,7 @@ __global__ void __launch_bounds__(256) k_blit(const __grid_constant__ SLBlitPara
     const unsigned long long foutH = ((inH << 16) / P.dstH) + 1ull;
     const unsigned long long x = x0 + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= x1) return;
+    const int srcBpt = (P.srcType / 7 + 1) * (P.srcType % 7 == 0 ? 1 : (P.srcType % 7 == 5 ? 4 : (P.srcType % 7 == 6 ? 8 : 2)));
     for (unsigned long long y = (unsigned long long)P.dstY0 + blockIdx.y; y < P.dstY1 && y < P.dstH; y += gridDim.y)
     {
         const unsigned long long yf = (y * foutH) >> 16;
@@ -2385,6 +2496,7 @@ __global__ void __launch_bounds__(256) k_blit(const __grid_constant__ SLBlitPara
             const math::vec4 c = math::vec4{(float)(u & 0xffu), (float)((u >> 8) & 0xffu), (float)((u >> 16) & 0xffu), (float)(u >> 24)} * 0.00392156862745f;
             reinterpret_cast<float4*>(P.dst)[di] = make_float4(c.v[0], c.v[1], c.v[2], c.v[3]);
         }
+        else if (P.mode == 3) sl_blit_texel(P.src + si * srcBpt, P.srcType, P.dst + di * P.bpt, P.dstType);
         else if (P.bpt == 4) reinterpret_cast<uint32_t*>(P.dst)[di] = reinterpret_cast<const uint32_t*>(P.src)[si];
         else if (P.bpt == 16) reinterpret_cast<uint4*>(P.dst)[di] = reinterpret_cast<const uint4*>(P.src)[si];
         else

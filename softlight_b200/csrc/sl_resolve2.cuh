@@ -34,6 +34,9 @@ namespace sld
 #ifndef SL_R2_GROUPS
 #define SL_R2_GROUPS 2 /* groups a lane resolves per round */
 #endif
+#ifndef SL_R2_KEEP_LANES
+#define SL_R2_KEEP_LANES 20 /* with at least this many lanes holding a piece, a round skips the hand-out */
+#endif
 #ifndef SL_R2_WARPS_N
 #define SL_R2_WARPS_N 4
 #endif
@@ -125,7 +128,19 @@ SLD_FN unsigned long long sl_ld_acquire_u64(const unsigned long long* p)
     return v;
 }
 
-template <int BPT>
+/* SL_DepthFunc* (SL_ShaderUtil.hpp:240-507) chosen at compile time: ordered, quiet -- false on NaN, which only OFF lets pass */
+template <int FUNC> SLD_FN bool sl_depth_func(float z, float d)
+{
+    if (FUNC == 0) return true;
+    if (FUNC == 1) return z < d;
+    if (FUNC == 2) return z <= d;
+    if (FUNC == 3) return z > d;
+    if (FUNC == 4) return z >= d;
+    if (FUNC == 5) return z == d;
+    return (z < d) || (z > d);
+}
+
+template <int BPT, int FUNC>
 __global__ void __launch_bounds__(SL_R2_WARPS * 32, SL_R2_MIN_BLOCKS) k_resolve2(const __grid_constant__ SLRasterParams P)
 {
     extern __shared__ __align__(16) unsigned char sDyn[];
@@ -135,8 +150,8 @@ __global__ void __launch_bounds__(SL_R2_WARPS * 32, SL_R2_MIN_BLOCKS) k_resolve2
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t ltMask = (1u << lane) - 1u, myBit = 1u << lane;
     const int W = (int)P.width, NS = (int)P.numSegs;
-    const bool chained = P.depthTest != 0;
-    const bool useDepth = P.depthTest != 0 || P.depthMask != 0;
+    constexpr bool chained = FUNC != 0;
+    const bool useDepth = FUNC != 0 || P.depthMask != 0;
     const int nsub = (int)P.numSubLists;
 
     unsigned char* warpMem = sDyn + SL_R2_RCP_BYTES + (size_t)warp * sl_r2_warp_bytes(P.segWidth, P.tileBytes);
@@ -160,7 +175,6 @@ __global__ void __launch_bounds__(SL_R2_WARPS * 32, SL_R2_MIN_BLOCKS) k_resolve2
     const long long dbgT0 = P.diagnostics ? clock64() : 0ll;
     unsigned shaded = 0;
     const unsigned numTickets = P.numRows * P.numSegs;
-    const uint32_t depthTable = sl_depth_table(P.depthTest);
     /* free chunks of this warp: a FIFO of ids in shared memory, topped up SL_R2_FIFO_BLOCK at a time; the top-up's atomic
      * is issued a round before its result is needed (lane 0 keeps it in flight) and what is left over goes to the next ticket */
     unsigned fifoHead = 0u, fifoCount = 0u;
@@ -188,6 +202,7 @@ __global__ void __launch_bounds__(SL_R2_WARPS * 32, SL_R2_MIN_BLOCKS) k_resolve2
         if (begin == end) continue;
         const long long dbgTicket0 = P.diagnostics ? clock64() : 0ll;
         unsigned dbgPieces = 0u;
+        const unsigned long long dbgRounds0 = dbgRounds;
         const int sx0 = seg * (int)P.segWidth;
         const int sx1 = (seg == NS - 1) ? W : sx0 + (int)P.segWidth;
         const unsigned segPixels = (unsigned)(sx1 - sx0);
@@ -224,13 +239,17 @@ __global__ void __launch_bounds__(SL_R2_WARPS * 32, SL_R2_MIN_BLOCKS) k_resolve2
             if (idx < end) pre[k] = P.entries[idx];
         }
         unsigned ringHead = 0u, ringCount = 0u, idle = 0u;
+        /* A round is: top (probe hand-overs, fill the ring, hand pieces to free lanes) + settle (check, reserve chunks,
+         * resolve).  While most lanes still hold a piece the top is skipped: the pieces on board are settled layer after
+         * layer, and what the longest tickets spend per layer is what the kernel takes. */
+        bool skipTop = false;
         for (;;)
         {
             const uint32_t busyMask = __ballot_sync(0xffffffffu, busy);
             /* hand-over slots are probed early: the load travels while the warp fills its ring and sets pieces up */
             unsigned long long pollW = 0ull;
             uint32_t pollI = 0u;
-            if (busy && !ready)
+            if (!skipTop && busy && !ready)
             {
                 if (!P.handoff) { atomicOr(&P.counters->errorFlags, SL_ERR_HANDOFF_POLL); pollW = ~0ull; }
                 else
@@ -240,7 +259,7 @@ __global__ void __launch_bounds__(SL_R2_WARPS * 32, SL_R2_MIN_BLOCKS) k_resolve2
                 }
             }
             /* ---- keep the ring of waiting pieces filled: the row's entries that reach into this segment, in list order ---- */
-            while (ringCount <= (unsigned)(SL_R2_RING - 128) && base < end)
+            while (!skipTop && ringCount <= (unsigned)(SL_R2_RING - 128) && base < end)
             {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
@@ -271,7 +290,7 @@ __global__ void __launch_bounds__(SL_R2_WARPS * 32, SL_R2_MIN_BLOCKS) k_resolve2
 
             /* ---- hand the waiting pieces to the free lanes, in order ---- */
             const unsigned myk = (unsigned)__popc(~busyMask & ltMask);
-            const bool take = !busy && myk < ringCount;
+            const bool take = !skipTop && !busy && myk < ringCount;
             const uint32_t newMask = __ballot_sync(0xffffffffu, take);
             if (newMask)
             {
@@ -357,8 +376,15 @@ __global__ void __launch_bounds__(SL_R2_WARPS * 32, SL_R2_MIN_BLOCKS) k_resolve2
                 __syncwarp();
             }
 
+            if (staged && !tileReady)
+            {
+                sl_mbar_wait(tileBar, tilePhase);
+                tilePhase ^= 1u;
+                tileReady = true;
+            }
             /* ---- which lanes may resolve their next groups ---- */
             bool go = false;
+            bool finishedEarly = false;
             int cx = 0, ce = 0;
             if (busy)
             {
@@ -395,12 +421,65 @@ __global__ void __launch_bounds__(SL_R2_WARPS * 32, SL_R2_MIN_BLOCKS) k_resolve2
                     uint32_t ov = 0u;
                     if (useDepth)
                     {
-                        for (int px = cx; px < ce; ++px) ov |= pixMask[px];
+#pragma unroll
+                        for (int k = 0; k < 4 * SL_R2_GROUPS; ++k)
+                        {
+                            if (cx + k < ce) ov |= pixMask[cx + k];
+                        }
                     }
                     go = (ov & earlier) == 0u;
+                    /* Early rejection.  With a monotone depth function (LESS .. GREATER_EQUAL) the texel a pixel is tested against
+                     * only ever moves in the direction that makes the test harder, so a pixel that fails against the depth of NOW
+                     * fails against the depth the reference would see once the earlier pieces are settled.  A group whose
+                     * pixels all fail changes nothing -- no depth write, no fragment, no compaction (:492-495) -- so a piece that
+                     * still waits for earlier pieces may walk over such groups at once: the hidden layers of a deep scene drain
+                     * without taking their turn in the per-pixel order.  (Not for a group that carries handed-over outcomes or
+                     * has to publish its state.) */
+                    if (!go && FUNC >= 1 && FUNC <= 4)
+                    {
+                        bool advanced = false;
+                        while (g < gEnd && fM == 0u && !(publish && g == gEnd - 1))
+                        {
+                            const int x4 = xMin + 4 * g;
+                            const int rel = x4 - xBase - sx0;
+                            const int oLo = max(p0 - x4, 0), oHi = min(p1 - x4, 4);
+                            const float zq[4] = {sl_zdot(a0, z0, z1, z2), sl_zdot(a1, z0, z1, z2), sl_zdot(a2, z0, z1, z2), sl_zdot(a3, z0, z1, z2)};
+                            bool anyPass = false;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                            {
+                                if (j >= oLo && j < oHi && sl_depth_func<FUNC>(zq[j], sl_tile_load<BPT>(tile, rel + j))) anyPass = true;
+                            }
+                            if (anyPass) break;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                            {
+                                if (j >= oLo && j < oHi) atomicAnd(&pixMask[rel + j], ~myBit); /* other waiting lanes may clear theirs at the same time */
+                            }
+                            a0 += bcX; a1 += bcX; a2 += bcX; a3 += bcX; /* :539-542 */
+                            ++g;
+                            ++dbgGroups;
+                            advanced = true;
+                        }
+                        if (g == gEnd) { busy = false; finishedEarly = true; }
+                        else if (advanced)
+                        {
+                            cx = max(p0, xMin + 4 * g) - xBase - sx0;
+                            ce = min(p1, xMin + 4 * (g + SL_R2_GROUPS)) - xBase - sx0;
+                            ov = 0u;
+#pragma unroll
+                            for (int k = 0; k < 4 * SL_R2_GROUPS; ++k)
+                            {
+                                if (cx + k < ce) ov |= pixMask[cx + k];
+                            }
+                            go = (ov & earlier) == 0u;
+                        }
+                    }
                 }
             }
             const uint32_t goMask = __ballot_sync(0xffffffffu, go);
+            if (!goMask) skipTop = false; /* nothing on board can move: probe the hand-overs, take new pieces */
+            if (!goMask && __any_sync(0xffffffffu, finishedEarly)) continue; /* lanes became free: hand out the next pieces */
             if (!goMask)
             {
                 /* everything that could run waits for a hand-over: back off so that the polling does not take issue slots
@@ -499,12 +578,6 @@ __global__ void __launch_bounds__(SL_R2_WARPS * 32, SL_R2_MIN_BLOCKS) k_resolve2
                 }
                 pendingValid = true;
             }
-            if (staged && !tileReady)
-            {
-                sl_mbar_wait(tileBar, tilePhase);
-                tilePhase ^= 1u;
-                tileReady = true;
-            }
             __syncwarp();
 
             /* ---- resolve: up to SL_R2_GROUPS groups per lane, the reference's loop body (src/SL_TriRasterizer.cpp:483-548) ---- */
@@ -519,15 +592,17 @@ __global__ void __launch_bounds__(SL_R2_WARPS * 32, SL_R2_MIN_BLOCKS) k_resolve2
                     const bool last = g == gEnd - 1;
                     const float zc0 = sl_zdot(a0, z0, z1, z2), zc1 = sl_zdot(a1, z0, z1, z2), zc2 = sl_zdot(a2, z0, z1, z2), zc3 = sl_zdot(a3, z0, z1, z2);
                     const float zc[4] = {zc0, zc1, zc2, zc3};
-                    uint32_t own = 0u, m = 0u;
+                    /* the pixels of the group that belong to this piece: [max(p0 - x4, 0), min(p1 - x4, 4)) */
+                    const int oLo = max(p0 - x4, 0), oHi = min(p1 - x4, 4);
+                    const uint32_t own = ((1u << oHi) - 1u) & ~((1u << oLo) - 1u);
+                    uint32_t m = 0u;
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                     {
-                        if (x4 + j >= p0 && x4 + j < p1)
+                        if ((own >> j) & 1u)
                         {
-                            own |= 1u << j;
-                            const float d = P.depthTest ? sl_tile_load<BPT>(tile, rel + j) : 0.f;
-                            if (sl_depth_pass(depthTable, zc[j], d)) m |= 1u << j;
+                            const float d = FUNC != 0 ? sl_tile_load<BPT>(tile, rel + j) : 0.f;
+                            if (sl_depth_func<FUNC>(zc[j], d)) m |= 1u << j;
                         }
                     }
                     const uint32_t tt = m | fM;
@@ -555,28 +630,35 @@ __global__ void __launch_bounds__(SL_R2_WARPS * 32, SL_R2_MIN_BLOCKS) k_resolve2
                             uint32_t posLo = 0u, posHi = 0u;
                             if (loBits) posLo = atomicAdd(&subCount[sFirst], (uint32_t)__popc(loBits));
                             if (hiBits) posHi = atomicAdd(&subCount[sLast], (uint32_t)__popc(hiBits));
+                            /* survivor number s of the group (the s-th passing lane, handed-over ones included) is shaded with
+                             * register s after the compaction (:500-526) and with its own x and z; register s is known at
+                             * compile time when the survivors are visited by number */
+                            uint32_t rest = tt;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)
+                            for (int sIdx = 0; sIdx < 4; ++sIdx)
                             {
-                                if ((m >> j) & 1u)
+                                if (rest)
                                 {
-                                    /* survivor number s of the group is shaded with register s after the compaction (:500-526),
-                                     * and with its own x and z */
-                                    const uint32_t sIdx = (uint32_t)__popc(tt & ((1u << j) - 1u));
-                                    const math::vec4 bc = sIdx == 0u ? n0 : (sIdx == 1u ? n1 : (sIdx == 2u ? n2 : a3));
-                                    if (P.depthMask) sl_tile_store<BPT>(tile, rel + j, zc[j]); /* src/SL_FragmentProcessor.cpp:526-529 */
-                                    const bool lo = j < jSplit;
-                                    const uint32_t pos = lo ? posLo++ : posHi++;
-                                    const int sub = lo ? sFirst : sLast;
-                                    const uint32_t chunk = chunkRing[sub * SL_R2_CHUNK_RING + ((pos >> 5) & (SL_R2_CHUNK_RING - 1))];
-                                    if (chunk != SL_NO_CHUNK)
+                                    const int j = __ffs((int)rest) - 1;
+                                    rest &= rest - 1u;
+                                    if ((m >> j) & 1u)
                                     {
-                                        unsigned char* c = P.lists.pool + (size_t)chunk * SL_CHUNK_BYTES;
-                                        const uint32_t slot = pos & 31u;
-                                        reinterpret_cast<float4*>(c)[slot] = make_float4(bc.v[0], bc.v[1], bc.v[2], bc.v[3]);
-                                        reinterpret_cast<float*>(c + 512)[slot] = zc[j];
-                                        reinterpret_cast<uint32_t*>(c + 640)[slot] = (uint32_t)(x4 + j) | ((uint32_t)ySrc << 16);
-                                        reinterpret_cast<uint32_t*>(c + 768)[slot] = recId;
+                                        const math::vec4& bc = sIdx == 0 ? n0 : (sIdx == 1 ? n1 : (sIdx == 2 ? n2 : a3));
+                                        const float zj = j == 0 ? zc0 : (j == 1 ? zc1 : (j == 2 ? zc2 : zc3));
+                                        if (P.depthMask) sl_tile_store<BPT>(tile, rel + j, zj); /* src/SL_FragmentProcessor.cpp:526-529 */
+                                        const bool lo = j < jSplit;
+                                        const uint32_t pos = lo ? posLo++ : posHi++;
+                                        const int sub = lo ? sFirst : sLast;
+                                        const uint32_t chunk = chunkRing[sub * SL_R2_CHUNK_RING + ((pos >> 5) & (SL_R2_CHUNK_RING - 1))];
+                                        if (chunk != SL_NO_CHUNK)
+                                        {
+                                            unsigned char* c = P.lists.pool + (size_t)chunk * SL_CHUNK_BYTES;
+                                            const uint32_t slot = pos & 31u;
+                                            reinterpret_cast<float4*>(c)[slot] = make_float4(bc.v[0], bc.v[1], bc.v[2], bc.v[3]);
+                                            reinterpret_cast<float*>(c + 512)[slot] = zj;
+                                            reinterpret_cast<uint32_t*>(c + 640)[slot] = (uint32_t)(x4 + j) | ((uint32_t)ySrc << 16);
+                                            reinterpret_cast<uint32_t*>(c + 768)[slot] = recId;
+                                        }
                                     }
                                 }
                             }
@@ -603,6 +685,11 @@ __global__ void __launch_bounds__(SL_R2_WARPS * 32, SL_R2_MIN_BLOCKS) k_resolve2
                 }
             }
             __syncwarp();
+            /* enough pieces still on board (or nothing left to hand out): settle another layer before the next top */
+            {
+                const uint32_t stillBusy = __ballot_sync(0xffffffffu, busy);
+                skipTop = stillBusy != 0u && (__popc(stillBusy) >= SL_R2_KEEP_LANES || (ringCount == 0u && base >= end));
+            }
         }
 
         /* ---- end of the ticket ---- */
@@ -633,9 +720,9 @@ __global__ void __launch_bounds__(SL_R2_WARPS * 32, SL_R2_MIN_BLOCKS) k_resolve2
         shaded = 0u;
         if (P.diagnostics && lane == 0)
         {
-            /* the longest ticket: clocks << 32 | pieces << 18 | row << 5 | segment */
+            /* the longest ticket: clocks << 32 | pieces << 18 | rounds */
             const unsigned long long cyc = (unsigned long long)(clock64() - dbgTicket0);
-            atomicMax(&P.counters->resolveMaxWindows, (cyc << 32) | ((unsigned long long)min(dbgPieces, 16383u) << 18) | ((unsigned long long)y << 5) | (unsigned long long)seg);
+            atomicMax(&P.counters->resolveMaxWindows, (cyc << 32) | ((unsigned long long)min(dbgPieces, 16383u) << 18) | min(dbgRounds - dbgRounds0, 262143ull));
         }
     }
 

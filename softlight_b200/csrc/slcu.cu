@@ -1084,7 +1084,7 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
                 c->orderRows = H; c->orderSegs = rasterSegs; c->orderSkew = skew;
             }
             rp.ticketOrder = reinterpret_cast<const uint32_t*>(c->ticketOrder.buf.ptr);
-            static const bool heavyFirst = getenv("SLCU_HEAVY_FIRST") && atoi(getenv("SLCU_HEAVY_FIRST")) != 0; /* opt-in: measured +2 % on k_resolve2, less than k_row_order costs */
+            static const bool heavyFirst = !(getenv("SLCU_HEAVY_FIRST") && atoi(getenv("SLCU_HEAVY_FIRST")) == 0);
             if (heavyFirst)
             {
                 CK(c->rowPerm.ensure((size_t)H * sizeof(uint32_t)));
@@ -1103,13 +1103,19 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
     if (useResolve2)
     {
         const unsigned smemBytes = SL_R2_RCP_BYTES + SL_R2_WARPS * sl_r2_warp_bytes(segWidth, rp.tileBytes);
-        static bool attrSet2[64] = {};
-        if (!attrSet2[c->device & 63])
+        /* one instantiation per depth texel size and depth function */
+        typedef void (*ResolveKernel)(const SLRasterParams);
+        static const ResolveKernel resolveKernels[3][7] = {
+            {k_resolve2<2, 0>, k_resolve2<2, 1>, k_resolve2<2, 2>, k_resolve2<2, 3>, k_resolve2<2, 4>, k_resolve2<2, 5>, k_resolve2<2, 6>},
+            {k_resolve2<4, 0>, k_resolve2<4, 1>, k_resolve2<4, 2>, k_resolve2<4, 3>, k_resolve2<4, 4>, k_resolve2<4, 5>, k_resolve2<4, 6>},
+            {k_resolve2<8, 0>, k_resolve2<8, 1>, k_resolve2<8, 2>, k_resolve2<8, 3>, k_resolve2<8, 4>, k_resolve2<8, 5>, k_resolve2<8, 6>}};
+        const ResolveKernel kernel = resolveKernels[depthTex.bpt == 2 ? 0 : (depthTex.bpt == 4 ? 1 : 2)][sh.depthTest];
+        static bool attrSet2[64][3][7] = {};
+        bool& attrDone = attrSet2[c->device & 63][depthTex.bpt == 2 ? 0 : (depthTex.bpt == 4 ? 1 : 2)][sh.depthTest];
+        if (!attrDone)
         {
-            CK(cudaFuncSetAttribute(k_resolve2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            CK(cudaFuncSetAttribute(k_resolve2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            CK(cudaFuncSetAttribute(k_resolve2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            attrSet2[c->device & 63] = true;
+            CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            attrDone = true;
         }
         if (smemBytes > 160u * 1024u) { c->err = "framebuffer too wide for the resolve tile"; return SLCU_ERR_ARG; }
         int numSMs = 148;
@@ -1119,9 +1125,7 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
         const unsigned long long needBlocks = (numWarps + SL_R2_WARPS - 1) / SL_R2_WARPS;
         if (grid > needBlocks) grid = needBlocks;
         KernelScope ks(c, SLCU_K_RASTER);
-        if (depthTex.bpt == 2) k_resolve2<2><<<(unsigned)grid, SL_R2_WARPS * 32, smemBytes, c->stream>>>(rp);
-        else if (depthTex.bpt == 4) k_resolve2<4><<<(unsigned)grid, SL_R2_WARPS * 32, smemBytes, c->stream>>>(rp);
-        else k_resolve2<8><<<(unsigned)grid, SL_R2_WARPS * 32, smemBytes, c->stream>>>(rp);
+        kernel<<<(unsigned)grid, SL_R2_WARPS * 32, smemBytes, c->stream>>>(rp);
         CK(cudaGetLastError());
     }
     else
@@ -1724,10 +1728,15 @@ int slcu_blit_rect(slcu_context* c, size_t outTex, size_t inTex, uint16_t sx0, u
     const HostTexture& d = c->textures[outTex];
     if (!s.dev || !d.dev || !d.w || !d.h) return SLCU_ERR_ARG;
     SLBlitParams p;
-    if (s.type == d.type) p.mode = 0;
+    const int sk = s.type % 7, dk = d.type % 7;
+    const bool rgIntSame = s.type == d.type && s.type / 7 == 1 && sk <= 1; /* RG integer -> same type is p / max(T) in the reference (SL_Color.hpp:373-380) */
+    if (s.type == d.type && !rgIntSame) p.mode = 0;
     else if (s.type == 26 && d.type == 21) p.mode = 1; /* RGBA_FLOAT -> RGBA_8U */
     else if (s.type == 21 && d.type == 26) p.mode = 2; /* RGBA_8U -> RGBA_FLOAT */
-    else { c->err = "blit: this format conversion is not implemented (same type, RGBA_FLOAT<->RGBA_8U are)"; return SLCU_ERR_UNSUPPORTED; }
+    else if (sk == 2 || sk == 3 || dk == 2 || dk == 3) { c->err = "blit: conversions from or to 32/64-bit integer layouts are not implemented"; return SLCU_ERR_UNSUPPORTED; }
+    else p.mode = 3; /* the general conversion between the twenty 8/16-bit unorm, half, float and double layouts */
+    p.srcType = s.type;
+    p.dstType = d.type;
     if (sx1 < sx0 || sy1 < sy0 || dx1 <= dx0 || dy1 <= dy0) return 0;
     p.src = s.dev; p.dst = d.dev;
     p.srcW = s.w; p.srcH = s.h; p.dstW = d.w; p.dstH = d.h;
@@ -1860,7 +1869,7 @@ int slcu_get_stats(slcu_context* c, slcu_stats* out)
     if (getenv("SLCU_DEBUG") && (c->hostCounters->resolveMaxWindows >> 32))
     {
         const unsigned long long w = c->hostCounters->resolveMaxWindows; /* k_resolve2: its longest ticket */
-        fprintf(stderr, "[slcu] resolve2 longest ticket: %llu clocks, %llu pieces, row %llu segment %llu\n", w >> 32, (w >> 18) & 16383ull, (w >> 5) & 8191ull, w & 31ull);
+        fprintf(stderr, "[slcu] resolve2 longest ticket: %llu clocks, %llu pieces, %llu rounds\n", w >> 32, (w >> 18) & 16383ull, w & 262143ull);
     }
     *out = c->stats;
     return report_device_flags(c, c->hostCounters->errorFlags);

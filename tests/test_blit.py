@@ -39,12 +39,13 @@ def test_blit_flips_vertically_known_answer():
     assert out[:, 0, 0].tolist() == [3, 2, 1, 0]
 
 
-def test_unsupported_conversion_is_refused_not_faked():
+def test_cross_layout_conversion_is_converted():
+    """RGB8 -> RGBA16 was refused in round 1; the conversion matrix (tests/test_blit_matrix.py) now covers it."""
     ctx = A.Context("port")
-    src = ctx.create_texture(A.SL_COLOR_RGB_8U, 4, 4, 1)
-    dst = ctx.create_texture(A.SL_COLOR_RGBA_16U, 4, 4, 1)
-    with pytest.raises(A.SlError):
-        ctx.blit(dst, src)
+    src = ctx.create_texture(A.SL_COLOR_RGB_8U, 1, 1, 1, np.array([[[255, 0, 128]]], dtype=np.uint8))
+    dst = ctx.create_texture(A.SL_COLOR_RGBA_16U, 1, 1, 1)
+    ctx.blit(dst, src)
+    assert ctx.texture_read(dst, A.SL_COLOR_RGBA_16U, 1, 1).reshape(-1).tolist() == [65535, 0, 128 * 257, 65535]
 
 
 @pytest.mark.gpu
