@@ -180,6 +180,16 @@ SLCU_EXPORT int SLCU_FN(fbo_attach_color_buffer)(slcu_context* ctx, size_t fbo, 
 SLCU_EXPORT int SLCU_FN(fbo_attach_depth_buffer)(slcu_context* ctx, size_t fbo, size_t texture);
 SLCU_EXPORT int SLCU_FN(fbo_valid)(slcu_context* ctx, size_t fbo);
 
+/* Run-time shader registration (ours; stands where the reference takes a host function pointer, SL_Shader.hpp:63, 97).
+ * `source` is CUDA C++ in the dialect of shaders/(*).inl: SL_SHADER_FN functions over the device mirrors of ls::math and
+ * the SL_* shader API, and SL_REGISTER_VERTEX_SHADER("name", fn) / SL_REGISTER_FRAGMENT_SHADER("name", fn) lines.
+ * NVRTC instantiates the pipeline's kernel templates for every registered function against the headers the library was
+ * built from; the names can then be used in create_shader (a run-time name shadows a built-in one).
+ * register_shader_source returns the number of shaders registered or a negative error (compiler log in last_error);
+ * shader_source_check only compiles (no device needed) and copies the log out. */
+SLCU_EXPORT int SLCU_FN(register_shader_source)(slcu_context* ctx, const char* source);
+SLCU_EXPORT int SLCU_FN(shader_source_check)(const char* source, char* log, size_t logBytes);
+
 /* SL_Context::create_shader (src/SL_Context.cpp:488-605) */
 SLCU_EXPORT size_t SLCU_FN(create_shader)(slcu_context* ctx, const slcu_vertex_shader* vs, const slcu_fragment_shader* fs, size_t ubo);
 

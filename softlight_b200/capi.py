@@ -160,6 +160,8 @@ _SIGS_PRODUCT = {
     "texture_ipc_export": (C.c_int, [_P, _SZ, _P]),
     "texture_ipc_import": (C.c_int, [_P, _SZ, C.c_uint, _P]),
     "composite": (C.c_int, [_P, _SZ, _SZ, C.c_uint]),
+    "register_shader_source": (C.c_int, [_P, C.c_char_p]),
+    "shader_source_check": (C.c_int, [C.c_char_p, C.c_char_p, _SZ]),
 }
 
 EXPORTED_SYMBOLS = sorted(list(_SIGS) + list(_SIGS_PRODUCT))
@@ -396,6 +398,10 @@ class Context:
             self._chk(self.f["fbo_attach_color_buffer"](self.h, fid, i, t), "attach_color_buffer")
         self._chk(self.f["fbo_attach_depth_buffer"](self.h, fid, depth_tex), "attach_depth_buffer")
         return fid
+
+    def register_shader_source(self, source: str) -> int:
+        """Compile (NVRTC) and register the shaders of a source text at run time; returns how many it registered."""
+        return self._chk(self.f["register_shader_source"](self.h, source.encode()), "register_shader_source")
 
     def destroy(self, kind: str, oid: int) -> int:
         """SL_Context::destroy_<kind>: later ids of that kind move down by one."""

@@ -45,6 +45,7 @@ constexpr int SL_VB_ROUNDS = 4;           /* primitives per thread              
 constexpr int SL_VB_PRIMS = SL_VB_THREADS * SL_VB_ROUNDS;
 constexpr int SL_MAX_ROWS = 8192;         /* framebuffer height limit of the row binner     */
 constexpr int SL_SPAN_WIN = 256;          /* rows per mask window in k_span                 */
+constexpr int SL_SHADE_SHIFT_C = 7;       /* log2 of the pixels per fragment list (= SL_SHADE_SHIFT, declared with the lists) */
 
 struct SLSegment { uint32_t base, count; };
 constexpr int SL_VB_SEGS = SL_VB_ROUNDS * (SL_VB_THREADS / 32); /* one record segment per (round, warp) of a vertex block */
@@ -747,14 +748,33 @@ SLD_FN int sl_classify_span(const SLSpanParams& P, int32_t& xMin, int32_t& xMax)
  * y+1 (only when that row exists). */
 SLD_FN unsigned sl_count_cuts(const SLSpanParams& P, int32_t xMin, int32_t xMax, bool nextRowExists)
 {
+    /* an upper bound: k_resolve2 may cut a heavy row every 2^SL_SHADE_SHIFT pixels inside a segment (its fine segments), so
+     * those boundaries are counted for every row */
     const int32_t W = (int32_t)P.width, TW = (int32_t)P.segWidth, NS = (int32_t)P.numSegs;
     unsigned n = 0;
-    for (int32_t b = xMin / TW + 1; b < NS && b * TW < xMax; ++b) ++n;
-    if (xMax > W && nextRowExists)
+    for (int32_t part = 0; part < 2; ++part)
     {
-        if (xMin < W) ++n;
-        const int32_t oMin = xMin > W ? xMin - W : 0;
-        for (int32_t b = oMin / TW + 1; b < NS && b * TW < xMax - W; ++b) { if (b * TW > xMin - W) ++n; }
+        /* part 0: the span inside its own row; part 1: what wrapped into row y+1 (shifted by W) */
+        int32_t a = xMin, b = xMax;
+        if (part == 0) b = min(b, W);
+        else
+        {
+            if (!(xMax > W && nextRowExists)) break;
+            if (xMin < W) ++n; /* the row end itself */
+            a = max(xMin - W, 0);
+            b = xMax - W;
+        }
+        if (!(a < b)) continue;
+        for (int32_t sIdx = a / TW; sIdx < NS && sIdx * TW < b; ++sIdx)
+        {
+            const int32_t s0 = sIdx * TW;
+            if (s0 > a && s0 < b && !(part == 1 && s0 <= xMin - W)) ++n; /* the segment boundary */
+            /* fine boundaries strictly inside (a, b) and inside this segment */
+            const int32_t s1 = (sIdx == NS - 1) ? 0x7fffffff : s0 + TW;
+            const int32_t lo = max(a, s0), hi = min(b, s1);
+            const int32_t kFirst = ((lo - s0) >> SL_SHADE_SHIFT_C) + 1, kLast = (hi - 1 - s0) >> SL_SHADE_SHIFT_C;
+            if (kLast >= kFirst) n += (unsigned)(kLast - kFirst + 1);
+        }
     }
     return n;
 }
@@ -1299,6 +1319,7 @@ struct SLRasterParams
     const uint8_t* rowNeeded;    /* sort-first partition: rows this rank rasterises (null = all) */
     const uint32_t* ticketOrder; /* ticket -> row << 6 | segment (null: row-major)               */
     const uint32_t* rowPerm;     /* with ticketOrder: its rows are ranks, rowPerm[rank] = the row (heaviest first; k_row_order) */
+    unsigned int fineRows;       /* k_resolve2: rows with more than fineRows x the average number of entries get fine segments (0: never) */
     unsigned char* depth;
     int depthBpt;
     SLFragLists lists;
@@ -1535,7 +1556,7 @@ struct SLTile
  * ----------------------------------------------------------------------*/
 constexpr unsigned SL_PIECEQ_BYTES = 32u * (unsigned)sizeof(SLSpanEntry);
 constexpr int SL_MAX_SUBLISTS = 8;      /* fragment lists per resolving warp: one per SL_SHADE_WIDTH pixels of its segment */
-constexpr int SL_SHADE_SHIFT = 7;       /* log2(SL_SHADE_WIDTH)                                                          */
+constexpr int SL_SHADE_SHIFT = SL_SHADE_SHIFT_C; /* log2(SL_SHADE_WIDTH)                                                  */
 constexpr unsigned SL_SUBLIST_BYTES = SL_MAX_SUBLISTS * 3u * 4u + 32u; /* per warp: tail chunk, fill, total of every sub-list */
 
 /* Append the survivors of a window to the warp's fragment lists, straight into the chunks in HBM.  Lists are ordered by

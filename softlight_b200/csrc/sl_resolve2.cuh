@@ -174,7 +174,16 @@ __global__ void __launch_bounds__(SL_R2_WARPS * 32, SL_R2_MIN_BLOCKS) k_resolve2
     unsigned long long dbgRounds = 0, dbgIdle = 0, dbgGroups = 0;
     const long long dbgT0 = P.diagnostics ? clock64() : 0ll;
     unsigned shaded = 0;
-    const unsigned numTickets = P.numRows * P.numSegs;
+    /* Fine segments.  The kernel lasts as long as its longest (row, segment) ticket, and in a deep scene that is a row near
+     * the horizon: thousands of overlapping pieces in one segment, settled layer after layer by ONE warp.  Such rows (more
+     * than P.fineRows times the average number of entries) are cut along the boundaries of their fragment lists instead: every
+     * 2^SL_SHADE_SHIFT pixels get a warp of their own, with hand-overs at the finer boundaries.  Every ticket is therefore
+     * handed out numSubLists times; in the other rows the first does the whole segment and the rest return at once.  Only
+     * in the skewed order (no span runs past a row end: all hand-overs stay inside a row, so one row = one numbering). */
+    const bool fineCapable = skewed && nsub > 1 && NS * nsub <= 64 && P.fineRows != 0u;
+    const unsigned fineF = fineCapable ? (unsigned)nsub : 1u;
+    const unsigned numTickets = P.numRows * P.numSegs * fineF;
+    const uint32_t heavyLimit = P.fineRows * (P.rowStart[P.numRows] / (P.numRows ? P.numRows : 1u)) + 1u;
     /* free chunks of this warp: a FIFO of ids in shared memory, topped up SL_R2_FIFO_BLOCK at a time; the top-up's atomic
      * is issued a round before its result is needed (lane 0 keeps it in flight) and what is left over goes to the next ticket */
     unsigned fifoHead = 0u, fifoCount = 0u;
@@ -189,6 +198,8 @@ __global__ void __launch_bounds__(SL_R2_WARPS * 32, SL_R2_MIN_BLOCKS) k_resolve2
         if (lane == 0) ticket = atomicAdd(&P.counters->rasterTicket, 1u);
         ticket = __shfl_sync(0xffffffffu, ticket, 0);
         if (ticket >= numTickets) break;
+        const unsigned fineK = ticket % fineF;
+        ticket /= fineF;
         int y = (int)(ticket / (unsigned)NS), seg = (int)(ticket % (unsigned)NS);
         if (skewed)
         {
@@ -203,11 +214,26 @@ __global__ void __launch_bounds__(SL_R2_WARPS * 32, SL_R2_MIN_BLOCKS) k_resolve2
         const long long dbgTicket0 = P.diagnostics ? clock64() : 0ll;
         unsigned dbgPieces = 0u;
         const unsigned long long dbgRounds0 = dbgRounds;
-        const int sx0 = seg * (int)P.segWidth;
-        const int sx1 = (seg == NS - 1) ? W : sx0 + (int)P.segWidth;
+        int sx0 = seg * (int)P.segWidth;
+        int sx1 = (seg == NS - 1) ? W : sx0 + (int)P.segWidth;
+        uint32_t firstList = (uint32_t)(y * NS + seg) * P.numSubLists;
+        int segIdx = seg, segCount = NS; /* this warp's place among the row's segments (hand-over boundaries are numbered by it) */
+        if (fineCapable)
+        {
+            const bool heavy = (end - begin) > heavyLimit;
+            if (!heavy && fineK != 0u) continue;
+            if (heavy)
+            {
+                sx0 += (int)(fineK << SL_SHADE_SHIFT);
+                if (sx0 >= sx1) continue;
+                sx1 = min(sx0 + (1 << SL_SHADE_SHIFT), sx1);
+                firstList += fineK; /* exactly the pixels of one fragment list */
+                segIdx = seg * (int)fineF + (int)fineK;
+                segCount = NS * (int)fineF;
+            }
+        }
         const unsigned segPixels = (unsigned)(sx1 - sx0);
         const long long segOrigin = (long long)W * y + sx0;
-        const uint32_t firstList = (uint32_t)(y * NS + seg) * P.numSubLists;
         const unsigned tileLoadBytes = segPixels * (unsigned)BPT;
         unsigned char* tileSrc = P.depth + (size_t)segOrigin * BPT;
         const bool bulkOk = (tileLoadBytes & 15u) == 0u && (reinterpret_cast<uintptr_t>(tileSrc) & 15u) == 0u;
@@ -326,8 +352,8 @@ __global__ void __launch_bounds__(SL_R2_WARPS * 32, SL_R2_MIN_BLOCKS) k_resolve2
                     p0 = max(xMin, xBase + sx0);
                     p1 = min(xMax, xBase + sx1);
                     const bool needsIn = xMin < p0 && chained;
-                    publish = chained && xMax > p1 && (seg < NS - 1 || (!isOver && y + 1 < (int)P.numRows));
-                    bOut = (isOver ? NS : 0) + seg + 1;
+                    publish = chained && xMax > p1 && (segIdx < segCount - 1 || (!isOver && y + 1 < (int)P.numRows));
+                    bOut = (isOver ? segCount : 0) + segIdx + 1;
                     g = (p0 - xMin) >> 2;
                     gEnd = ((p1 - 1 - xMin) >> 2) + 1;
                     busy = true;

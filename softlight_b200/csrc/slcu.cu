@@ -11,6 +11,7 @@
  * There is no CPU fallback: without a CUDA device context_create fails.
  */
 #include <cuda_runtime.h>
+#include <nvrtc.h>
 
 #include <cmath>
 #include <cstdio>
@@ -182,7 +183,14 @@ struct HostVao { SL_VertexArray vao; int numBindings = 0; size_t vbo = (size_t)-
  * valid() judges these snapshots, the draw path addresses the texture itself */
 struct FboView { bool texels = false; uint16_t w = 0, h = 0, d = 0; int type = 0; };
 struct HostFbo { unsigned numColors = 0; size_t colors[4] = {(size_t)-1, (size_t)-1, (size_t)-1, (size_t)-1}; size_t depth = (size_t)-1; FboView colorViews[4]; FboView depthView; };
-struct HostShader { int cullMode, depthTest, depthMask, blend, numVaryings, numOutputs; VertexLauncher vs; RasterLauncher fs; PointVertexLauncher pointVs; PointShadeLauncher pointFs; WireShadeLauncher wireFs; size_t ubo; };
+/* kernels of a shader that was registered at run time (slcu_register_shader_source): the same templates, instantiated by
+ * NVRTC for the user's __device__ callable and loaded with cudaLibraryLoadData */
+struct RtVertexKernels { cudaKernel_t vertex[2] = {nullptr, nullptr}; cudaKernel_t pointVertex = nullptr; };
+struct RtFragmentKernels { cudaKernel_t shade = nullptr, pointShade = nullptr, wireShade = nullptr; };
+struct HostShader { int cullMode, depthTest, depthMask, blend, numVaryings, numOutputs; VertexLauncher vs; RasterLauncher fs; PointVertexLauncher pointVs; PointShadeLauncher pointFs; WireShadeLauncher wireFs; size_t ubo; RtVertexKernels rtV; RtFragmentKernels rtF; };
+struct RtModule { cudaLibrary_t lib = nullptr; void* rcpTable = nullptr; };
+struct RtVsEntry { std::string name; RtVertexKernels k; };
+struct RtFsEntry { std::string name; RtFragmentKernels k; };
 struct UboFixup { size_t ubo, offset; int kind; size_t id, byteOffset; };
 struct HostUbo { unsigned char bytes[1024]; };
 
@@ -228,6 +236,9 @@ struct slcu_context
     std::vector<HostFbo> fbos;
     std::vector<HostShader> shaders;
     std::vector<UboFixup> fixups;
+    std::vector<RtModule> rtModules; /* shader sources compiled at run time */
+    std::vector<RtVsEntry> rtVs;
+    std::vector<RtFsEntry> rtFs;
     SL_Texture* devTextures = nullptr; /* device array of texture descriptors (fix-up targets) */
     size_t devTexturesCap = 0;
     int32_t viewport[4] = {0, 0, 65535, 65535};
@@ -320,6 +331,7 @@ static int ensure_rcp_table(slcu_context* c)
     CK(cudaMemcpyToSymbol(g_rcp_table, c->rcpTable, sizeof(c->rcpTable)));
     memcpy(g_activeRcpCopy[d], c->rcpTable, sizeof(c->rcpTable));
     g_activeRcpValid[d] = true;
+    for (const RtModule& m : c->rtModules) CK(cudaMemcpy(m.rcpTable, c->rcpTable, sizeof(c->rcpTable), cudaMemcpyHostToDevice)); /* every module has its own g_rcp_table */
     return 0;
 }
 
@@ -394,6 +406,38 @@ static void snapshot_uniforms(slcu_context* c, size_t ubo, SL_UniformBuffer& out
         else ptr = c->vbos[f.id].ptr + f.byteOffset;
         memcpy(out.mBytes + f.offset, &ptr, sizeof(ptr));
     }
+}
+
+/* one launch of a pipeline kernel: the build-time instantiation, or the run-time one of a registered source */
+template <typename Params> static cudaError_t launch_rt(cudaKernel_t k, unsigned grid, unsigned block, size_t smem, cudaStream_t s, const Params& p)
+{
+    void* args[] = {const_cast<Params*>(&p)};
+    return cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3(grid), dim3(block), args, smem, s);
+}
+static cudaError_t launch_vertex_stage(const HostShader& sh, unsigned grid, cudaStream_t s, const SLVertexParams& p, bool cache)
+{
+    if (sh.rtV.vertex[0]) return launch_rt(sh.rtV.vertex[cache ? 1 : 0], grid, SL_VB_THREADS, cache ? p.cacheBytes : 0, s, p);
+    return sh.vs(grid, s, p, cache);
+}
+static cudaError_t launch_shade_stage(const HostShader& sh, unsigned grid, cudaStream_t s, const SLShadeParams& p)
+{
+    if (sh.rtF.shade) return launch_rt(sh.rtF.shade, grid, SL_SHADE_WARPS * 32, 0, s, p);
+    return sh.fs(grid, s, p);
+}
+static cudaError_t launch_point_vertex_stage(const HostShader& sh, unsigned grid, cudaStream_t s, const SLPointParams& p)
+{
+    if (sh.rtV.pointVertex) return launch_rt(sh.rtV.pointVertex, grid, 256, 0, s, p);
+    return sh.pointVs(grid, s, p);
+}
+static cudaError_t launch_point_shade_stage(const HostShader& sh, unsigned grid, cudaStream_t s, const SLPointShadeParams& p)
+{
+    if (sh.rtF.pointShade) return launch_rt(sh.rtF.pointShade, grid, 128, 0, s, p);
+    return sh.pointFs(grid, s, p);
+}
+static cudaError_t launch_wire_shade_stage(const HostShader& sh, unsigned grid, cudaStream_t s, const SLWireShadeParams& p)
+{
+    if (sh.rtF.wireShade) return launch_rt(sh.rtF.wireShade, grid, 128, 0, s, p);
+    return sh.wireFs(grid, s, p);
 }
 
 /* Draws are not executed one by one.  Consecutive draws that use the same shader object and framebuffer are collected
@@ -589,7 +633,7 @@ static int run_points(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes
         vp.keys = keysA;
         vp.points = reinterpret_cast<float4*>(c->pointRecs.buf.ptr);
         vp.counters = c->counters;
-        { KernelScope ks(c, SLCU_K_VERTEX); CK(sh.pointVs((unsigned)((numPoints + 255ull) / 256ull), c->stream, vp)); }
+        { KernelScope ks(c, SLCU_K_VERTEX); CK(launch_point_vertex_stage(sh, (unsigned)((numPoints + 255ull) / 256ull), c->stream, vp)); }
         /* stable LSD sort on the pixel bits only: inside a pixel the keys stay in submission order */
         { KernelScope ks(c, SLCU_K_SCAN); CK(cub::DeviceRadixSort::SortKeys(c->pointSortTemp.buf.ptr, tempBytes, keys, (int)numPoints, 32, 32 + (int)pixBits, c->stream)); }
 
@@ -612,7 +656,7 @@ static int run_points(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes
             if (k < sh.numOutputs) { const HostTexture& t = c->textures[fbo.colors[k]]; sp.color[k] = t.dev; sp.colorType[k] = t.type; }
         }
         sp.counters = c->counters;
-        { KernelScope ks(c, SLCU_K_SHADE); CK(sh.pointFs((unsigned)((numPoints + 127ull) / 128ull), c->stream, sp)); }
+        { KernelScope ks(c, SLCU_K_SHADE); CK(launch_point_shade_stage(sh, (unsigned)((numPoints + 127ull) / 128ull), c->stream, sp)); }
     }
     k_commit<<<1, 1, 0, c->stream>>>(c->counters);
     CK(cudaGetLastError());
@@ -748,7 +792,7 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
             vp.records = reinterpret_cast<float4*>(c->records.buf.ptr);
             vp.blockInfo = reinterpret_cast<SLBlockInfo*>(c->blockInfo.buf.ptr);
             vp.counters = c->counters;
-            { KernelScope ks(c, SLCU_K_VERTEX); CK(sh.vs(numBlocks, c->stream, vp, cache)); }
+            { KernelScope ks(c, SLCU_K_VERTEX); CK(launch_vertex_stage(sh, numBlocks, c->stream, vp, cache)); }
         }
 
         if (B.wire)
@@ -887,7 +931,7 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
                 }
                 if (!settled) { CK(cudaMemsetAsync(ep.changed, 0, sizeof(unsigned), c->stream)); c->err = "wireframe flush epochs did not settle"; return SLCU_ERR_UNSUPPORTED; }
             }
-            { KernelScope ks(c, SLCU_K_SHADE); CK(sh.wireFs(shadeGrid, c->stream, ws)); }
+            { KernelScope ks(c, SLCU_K_SHADE); CK(launch_wire_shade_stage(sh, shadeGrid, c->stream, ws)); }
             k_commit<<<1, 1, 0, c->stream>>>(c->counters);
             CK(cudaGetLastError());
             return 0;
@@ -1052,6 +1096,10 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
     rp.ticketOrder = nullptr;
     rp.rowPerm = nullptr;
     {
+        static const int fineEnv = getenv("SLCU_FINE_ROWS") ? atoi(getenv("SLCU_FINE_ROWS")) : 4;
+        rp.fineRows = fineEnv > 0 ? (unsigned)fineEnv : 0u;
+    }
+    {
         /* skewed work order (see k_resolve): only when every hand-over goes from a segment to its right neighbour */
         static const int skewEnv = getenv("SLCU_TICKET_SKEW") ? atoi(getenv("SLCU_TICKET_SKEW")) : -1;
         int numSMs = 148;
@@ -1178,7 +1226,7 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
         const unsigned long long needBlocks = (numLists + SL_SHADE_WARPS - 1) / SL_SHADE_WARPS;
         if (grid > needBlocks) grid = needBlocks;
         KernelScope ks(c, SLCU_K_SHADE);
-        CK(sh.fs((unsigned)grid, c->stream, shp));
+        CK(launch_shade_stage(sh, (unsigned)grid, c->stream, shp));
     }
     k_commit<<<1, 1, 0, c->stream>>>(c->counters);
     CK(cudaGetLastError());
@@ -1291,6 +1339,7 @@ void slcu_context_destroy(slcu_context* c)
     cudaSetDevice(c->device);
     flush_draws(c);
     cudaStreamSynchronize(c->stream);
+    for (RtModule& m : c->rtModules) if (m.lib) cudaLibraryUnload(m.lib);
     if (c->batchDone) cudaEventDestroy(c->batchDone);
     if (c->timerA) cudaEventDestroy(c->timerA);
     if (c->timerB) cudaEventDestroy(c->timerB);
@@ -1653,6 +1702,172 @@ int slcu_fbo_valid(slcu_context* c, size_t fbo)
     return fbo_valid_code(c->fbos[fbo]);
 }
 
+/* ---- run-time shader registration -----------------------------------------------------------------------------------
+ * The reference accepts any host function pointer as a shader (SL_Shader.hpp:63, 97).  A GPU cannot call into host code,
+ * so the counterpart is SOURCE: the body of the user's vertex / fragment function written against the device mirrors of
+ * ls::math and the SL_* shader API (the dialect of shaders/(*).inl), plus SL_REGISTER_VERTEX_SHADER("name", fn) /
+ * SL_REGISTER_FRAGMENT_SHADER("name", fn) lines.  NVRTC instantiates the pipeline's kernel templates for each registered
+ * function -- direct, inlinable calls, never interpreted -- against the very headers this library was built from (embedded
+ * at build time), and the result is loaded into the context's device.  No rebuild of libslcu.so. */
+static const struct { const char* name; const char* text; } kEmbeddedHeaders[] = {
+#include "_embedded_headers.inc"
+};
+
+struct ParsedRegistration { bool vertex; std::string name, fn; };
+static std::vector<ParsedRegistration> parse_registrations(const std::string& src)
+{
+    std::vector<ParsedRegistration> out;
+    for (int kind = 0; kind < 2; ++kind)
+    {
+        const std::string macro = kind == 0 ? "SL_REGISTER_VERTEX_SHADER" : "SL_REGISTER_FRAGMENT_SHADER";
+        size_t pos = 0;
+        while ((pos = src.find(macro, pos)) != std::string::npos)
+        {
+            pos += macro.size();
+            const size_t open = src.find('(', pos);
+            const size_t q0 = src.find('"', pos);
+            if (open == std::string::npos || q0 == std::string::npos) break;
+            const size_t q1 = src.find('"', q0 + 1);
+            const size_t comma = src.find(',', q1);
+            const size_t close = src.find(')', comma);
+            if (q1 == std::string::npos || comma == std::string::npos || close == std::string::npos) break;
+            std::string fn = src.substr(comma + 1, close - comma - 1);
+            fn.erase(0, fn.find_first_not_of(" \t\r\n"));
+            fn.erase(fn.find_last_not_of(" \t\r\n") + 1);
+            out.push_back(ParsedRegistration{kind == 0, src.substr(q0 + 1, q1 - q0 - 1), fn});
+            pos = close;
+        }
+    }
+    return out;
+}
+
+struct CompiledShaders
+{
+    std::vector<char> cubin;
+    std::vector<ParsedRegistration> regs;
+    std::vector<std::string> lowered; /* per registration: 3 kernel names (vertex: k_vertex<,false>, k_vertex<,true>, k_point_vertex; fragment: k_shade, k_point_shade, k_wire_shade) */
+    std::string rcpName;
+};
+
+static int compile_shader_source(const char* source, CompiledShaders& out, std::string& log)
+{
+    if (!source) { log = "no source"; return SLCU_ERR_ARG; }
+    out.regs = parse_registrations(source);
+    if (out.regs.empty()) { log = "the source registers no shader (SL_REGISTER_VERTEX_SHADER / SL_REGISTER_FRAGMENT_SHADER)"; return SLCU_ERR_ARG; }
+    std::string tu = "#include \"sl_pipeline.cuh\"\n#include \"sl_points.cuh\"\n#include \"sl_wire.cuh\"\n"
+                     "#define SL_SHADER_FN static __device__ __forceinline__\n"
+                     "#define SL_REGISTER_VERTEX_SHADER(name, fn)\n#define SL_REGISTER_FRAGMENT_SHADER(name, fn)\n"
+                     "namespace sld {\n#line 1 \"user_shader\"\n";
+    tu += source;
+    tu += "\n}\n";
+    /* the pipeline's headers, and just enough of the C headers they name (NVRTC has no host headers) */
+    std::vector<const char*> names, texts;
+    for (const auto& h : kEmbeddedHeaders) { names.push_back(h.name); texts.push_back(h.text); }
+    names.push_back("stdint.h");
+    texts.push_back("#pragma once\ntypedef signed char int8_t; typedef unsigned char uint8_t; typedef short int16_t; typedef unsigned short uint16_t; typedef int int32_t; "
+                    "typedef unsigned int uint32_t; typedef long long int64_t; typedef unsigned long long uint64_t; typedef unsigned long uintptr_t; typedef long intptr_t;\n");
+    names.push_back("stddef.h");
+    texts.push_back("#pragma once\ntypedef unsigned long size_t; typedef long ptrdiff_t;\n#ifndef offsetof\n#define offsetof(t, m) __builtin_offsetof(t, m)\n#endif\n");
+    names.push_back("string.h");
+    texts.push_back("#pragma once\n");
+    nvrtcProgram prog = nullptr;
+    if (nvrtcCreateProgram(&prog, tu.c_str(), "slcu_runtime_shaders.cu", (int)names.size(), texts.data(), names.data()) != NVRTC_SUCCESS) { log = "nvrtcCreateProgram failed"; return SLCU_ERR_CUDA; }
+    std::vector<std::string> exprs;
+    for (const ParsedRegistration& r : out.regs)
+    {
+        if (r.vertex)
+        {
+            exprs.push_back("&sld::k_vertex<sld::" + r.fn + ", false>");
+            exprs.push_back("&sld::k_vertex<sld::" + r.fn + ", true>");
+            exprs.push_back("&sld::k_point_vertex<sld::" + r.fn + ">");
+        }
+        else
+        {
+            exprs.push_back("&sld::k_shade<sld::" + r.fn + ">");
+            exprs.push_back("&sld::k_point_shade<sld::" + r.fn + ">");
+            exprs.push_back("&sld::k_wire_shade<sld::" + r.fn + ">");
+        }
+    }
+    exprs.push_back("&sld::g_rcp_table");
+    for (const std::string& e : exprs) nvrtcAddNameExpression(prog, e.c_str());
+    const char* cudaHome = getenv("CUDA_HOME") ? getenv("CUDA_HOME") : "/usr/local/cuda";
+    const std::string inc = std::string("-I") + cudaHome + "/include";
+    /* the flags libslcu.so itself is built with: nothing is contracted behind the arithmetic's back (softlight_b200/build.py) */
+    const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-fmad=false", "-lineinfo", "-diag-suppress=177", "-diag-suppress=9", inc.c_str()};
+    const nvrtcResult rc = nvrtcCompileProgram(prog, (int)(sizeof(opts) / sizeof(opts[0])), opts);
+    size_t logSize = 0;
+    nvrtcGetProgramLogSize(prog, &logSize);
+    log.assign(logSize, '\0');
+    if (logSize) nvrtcGetProgramLog(prog, &log[0]);
+    if (rc != NVRTC_SUCCESS) { nvrtcDestroyProgram(&prog); return SLCU_ERR_ARG; }
+    for (size_t i = 0; i < exprs.size(); ++i)
+    {
+        const char* low = nullptr;
+        if (nvrtcGetLoweredName(prog, exprs[i].c_str(), &low) != NVRTC_SUCCESS || !low) { log = "no lowered name for " + exprs[i]; nvrtcDestroyProgram(&prog); return SLCU_ERR_CUDA; }
+        if (i + 1 == exprs.size()) out.rcpName = low; else out.lowered.push_back(low);
+    }
+    size_t bytes = 0;
+    nvrtcGetCUBINSize(prog, &bytes);
+    out.cubin.resize(bytes);
+    nvrtcGetCUBIN(prog, out.cubin.data());
+    nvrtcDestroyProgram(&prog);
+    return 0;
+}
+
+/* compile only (no device needed): 0 when the source would be accepted, the compiler's log in `log` either way */
+int slcu_shader_source_check(const char* source, char* logOut, size_t logBytes)
+{
+    CompiledShaders cs;
+    std::string log;
+    const int rc = compile_shader_source(source, cs, log);
+    if (logOut && logBytes) { strncpy(logOut, log.c_str(), logBytes - 1); logOut[logBytes - 1] = '\0'; }
+    return rc ? rc : (int)cs.regs.size();
+}
+
+/* compile, load, register: returns the number of shaders the source registered, or a negative error (log in last_error) */
+int slcu_register_shader_source(slcu_context* c, const char* source)
+{
+    SLCU_FLUSH();
+    if (!c) return SLCU_ERR_ARG;
+    CompiledShaders cs;
+    std::string log;
+    int rc = compile_shader_source(source, cs, log);
+    if (rc) { c->err = "shader source rejected: " + log; return rc; }
+    cudaSetDevice(c->device);
+    RtModule m;
+    CK(cudaLibraryLoadData(&m.lib, cs.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+    size_t rcpBytes = 0;
+    CK(cudaLibraryGetGlobal(&m.rcpTable, &rcpBytes, m.lib, cs.rcpName.c_str()));
+    if (rcpBytes != sizeof(c->rcpTable)) { c->err = "run-time module: unexpected rcp table size"; return SLCU_ERR_CUDA; }
+    if (c->rcpValid) CK(cudaMemcpy(m.rcpTable, c->rcpTable, sizeof(c->rcpTable), cudaMemcpyHostToDevice));
+    for (size_t i = 0; i < cs.regs.size(); ++i)
+    {
+        cudaKernel_t k[3] = {nullptr, nullptr, nullptr};
+        for (int j = 0; j < 3; ++j) CK(cudaLibraryGetKernel(&k[j], m.lib, cs.lowered[3 * i + j].c_str()));
+        if (cs.regs[i].vertex)
+        {
+            CK(cudaFuncSetAttribute(reinterpret_cast<const void*>(k[1]), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVertexCacheMaxBytes));
+            RtVsEntry e;
+            e.name = cs.regs[i].name;
+            e.k.vertex[0] = k[0]; e.k.vertex[1] = k[1]; e.k.pointVertex = k[2];
+            bool replaced = false;
+            for (RtVsEntry& old : c->rtVs) if (old.name == e.name) { old = e; replaced = true; }
+            if (!replaced) c->rtVs.push_back(e);
+        }
+        else
+        {
+            RtFsEntry e;
+            e.name = cs.regs[i].name;
+            e.k.shade = k[0]; e.k.pointShade = k[1]; e.k.wireShade = k[2];
+            bool replaced = false;
+            for (RtFsEntry& old : c->rtFs) if (old.name == e.name) { old = e; replaced = true; }
+            if (!replaced) c->rtFs.push_back(e);
+        }
+    }
+    c->rtModules.push_back(m);
+    return (int)cs.regs.size();
+}
+
 size_t slcu_create_shader(slcu_context* c, const slcu_vertex_shader* vs, const slcu_fragment_shader* fs, size_t ubo)
 {
     /* validation of SL_Context::create_shader (src/SL_Context.cpp:488-540) */
@@ -1666,14 +1881,18 @@ size_t slcu_create_shader(slcu_context* c, const slcu_vertex_shader* vs, const s
     WireShadeLauncher wfl = nullptr;
     for (const VsEntry& e : vs_registry()) if (!strcmp(e.name, vs->shader)) { vl = e.launch; pvl = e.launchPoints; }
     for (const FsEntry& e : fs_registry()) if (!strcmp(e.name, fs->shader)) { fl = e.launch; pfl = e.launchPoints; wfl = e.launchWire; }
-    if (!vl || !fl)
+    RtVertexKernels rtV;
+    RtFragmentKernels rtF;
+    for (const RtVsEntry& e : c->rtVs) if (e.name == vs->shader) rtV = e.k; /* a run-time registration shadows a built-in of the same name */
+    for (const RtFsEntry& e : c->rtFs) if (e.name == fs->shader) rtF = e.k;
+    if ((!vl && !rtV.vertex[0]) || (!fl && !rtF.shade))
     {
         c->err = "shader not registered as a __device__ callable (no CPU fallback)";
         return SLCU_INVALID_ID;
     }
     HostShader s;
     s.cullMode = vs->cullMode; s.depthTest = fs->depthTest; s.depthMask = fs->depthMask; s.blend = fs->blend;
-    s.numVaryings = fs->numVaryings; s.numOutputs = fs->numOutputs; s.vs = vl; s.fs = fl; s.pointVs = pvl; s.pointFs = pfl; s.wireFs = wfl; s.ubo = ubo;
+    s.numVaryings = fs->numVaryings; s.numOutputs = fs->numOutputs; s.vs = vl; s.fs = fl; s.pointVs = pvl; s.pointFs = pfl; s.wireFs = wfl; s.ubo = ubo; s.rtV = rtV; s.rtF = rtF;
     c->shaders.push_back(s);
     return c->shaders.size() - 1;
 }
