@@ -1197,16 +1197,16 @@ __global__ void __launch_bounds__(1024) k_scan_row_starts(const uint32_t* rowTot
     }
 }
 
-/* Heavy rows first: rowPerm lists the rows with more than twice the average number of span entries (in ascending row
+/* Heavy rows first: rowPerm lists the rows with more than heavyFactor times the average number of span entries (in ascending row
  * order), then all the others.  k_resolve2 is as long as its longest (row, segment) ticket -- a row near the horizon of a
  * deep scene holds a few thousand overlapping pieces that can only be settled layer after layer -- so those tickets have
  * to be under way from the start instead of being handed out whenever their row number comes up. */
-__global__ void __launch_bounds__(1024) k_row_order(const uint32_t* rowStart, unsigned numRows, uint32_t* rowPerm)
+__global__ void __launch_bounds__(1024) k_row_order(const uint32_t* rowStart, unsigned numRows, uint32_t* rowPerm, unsigned heavyFactor)
 {
     __shared__ uint32_t sWarp[32];
     __shared__ uint32_t sTotal;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t limit = 2u * (rowStart[numRows] / (numRows ? numRows : 1u)) + 1u;
+    const uint32_t limit = heavyFactor * (rowStart[numRows] / (numRows ? numRows : 1u)) + 1u;
     const unsigned per = (numRows + 1023u) / 1024u;
     const unsigned a = (unsigned)tid * per, b = min(a + per, numRows);
     uint32_t heavy = 0u;
@@ -1240,6 +1240,7 @@ __global__ void __launch_bounds__(1024) k_row_order(const uint32_t* rowStart, un
         if ((rowStart[y + 1] - rowStart[y]) > limit) rowPerm[hPos++] = y;
         else rowPerm[numHeavy + (y - hPos)] = y; /* light rows keep their order behind the heavy ones */
     }
+    if (tid == 0) rowPerm[numRows] = numHeavy; /* k_resolve2 gives these rows fine segments */
 }
 
 /* end of a batch: its statistics join the totals unless it has to be run again */

@@ -175,15 +175,15 @@ __global__ void __launch_bounds__(SL_R2_WARPS * 32, SL_R2_MIN_BLOCKS) k_resolve2
     const long long dbgT0 = P.diagnostics ? clock64() : 0ll;
     unsigned shaded = 0;
     /* Fine segments.  The kernel lasts as long as its longest (row, segment) ticket, and in a deep scene that is a row near
-     * the horizon: thousands of overlapping pieces in one segment, settled layer after layer by ONE warp.  Such rows (more
-     * than P.fineRows times the average number of entries) are cut along the boundaries of their fragment lists instead: every
-     * 2^SL_SHADE_SHIFT pixels get a warp of their own, with hand-overs at the finer boundaries.  Every ticket is therefore
-     * handed out numSubLists times; in the other rows the first does the whole segment and the rest return at once.  Only
-     * in the skewed order (no span runs past a row end: all hand-overs stay inside a row, so one row = one numbering). */
-    const bool fineCapable = skewed && nsub > 1 && NS * nsub <= 64 && P.fineRows != 0u;
-    const unsigned fineF = fineCapable ? (unsigned)nsub : 1u;
-    const unsigned numTickets = P.numRows * P.numSegs * fineF;
-    const uint32_t heavyLimit = P.fineRows * (P.rowStart[P.numRows] / (P.numRows ? P.numRows : 1u)) + 1u;
+     * the horizon: thousands of overlapping pieces in one segment, settled layer after layer by ONE warp.  The rows
+     * k_row_order found heavy (more than P.fineRows times the average number of entries; they lead rowPerm) are cut along
+     * the boundaries of their fragment lists instead: every 2^SL_SHADE_SHIFT pixels get a warp of their own, with
+     * hand-overs at the finer boundaries.  Their tickets come first, row by row; the tickets of the other rows follow in
+     * the skewed order.  Only when no span runs past a row end: all hand-overs stay inside a row, one row = one numbering. */
+    const unsigned fineF = (unsigned)nsub;
+    const unsigned numHeavy = (skewed && P.rowPerm && nsub > 1 && NS * nsub <= 64 && P.fineRows != 0u) ? P.rowPerm[P.numRows] : 0u;
+    const unsigned fineTickets = numHeavy * (unsigned)NS * fineF;
+    const unsigned numTickets = fineTickets + P.numRows * P.numSegs;
     /* free chunks of this warp: a FIFO of ids in shared memory, topped up SL_R2_FIFO_BLOCK at a time; the top-up's atomic
      * is issued a round before its result is needed (lane 0 keeps it in flight) and what is left over goes to the next ticket */
     unsigned fifoHead = 0u, fifoCount = 0u;
@@ -198,15 +198,34 @@ __global__ void __launch_bounds__(SL_R2_WARPS * 32, SL_R2_MIN_BLOCKS) k_resolve2
         if (lane == 0) ticket = atomicAdd(&P.counters->rasterTicket, 1u);
         ticket = __shfl_sync(0xffffffffu, ticket, 0);
         if (ticket >= numTickets) break;
-        const unsigned fineK = ticket % fineF;
-        ticket /= fineF;
-        int y = (int)(ticket / (unsigned)NS), seg = (int)(ticket % (unsigned)NS);
-        if (skewed)
+        unsigned fineK = 0u;
+        bool fine = false;
+        int y, seg;
+        if (ticket < fineTickets)
         {
-            const uint32_t o = P.ticketOrder[ticket];
-            y = (int)(o >> 6);
-            seg = (int)(o & 63u);
-            if (P.rowPerm) y = (int)P.rowPerm[y]; /* rows are independent here: the heaviest go first */
+            const unsigned perRow = (unsigned)NS * fineF;
+            const unsigned fs = ticket % perRow;
+            y = (int)P.rowPerm[ticket / perRow];
+            seg = (int)(fs / fineF);
+            fineK = fs % fineF;
+            fine = true;
+        }
+        else
+        {
+            ticket -= fineTickets;
+            y = (int)(ticket / (unsigned)NS);
+            seg = (int)(ticket % (unsigned)NS);
+            if (skewed)
+            {
+                const uint32_t o = P.ticketOrder[ticket];
+                y = (int)(o >> 6);
+                seg = (int)(o & 63u);
+                if (P.rowPerm)
+                {
+                    if ((unsigned)y < numHeavy) continue; /* a heavy row: done by the fine tickets */
+                    y = (int)P.rowPerm[y];                /* rows are independent here: the heaviest go first */
+                }
+            }
         }
         if (P.rowNeeded && !P.rowNeeded[y]) continue;
         const uint32_t begin = P.rowStart[y], end = P.rowStart[y + 1];
@@ -218,19 +237,14 @@ __global__ void __launch_bounds__(SL_R2_WARPS * 32, SL_R2_MIN_BLOCKS) k_resolve2
         int sx1 = (seg == NS - 1) ? W : sx0 + (int)P.segWidth;
         uint32_t firstList = (uint32_t)(y * NS + seg) * P.numSubLists;
         int segIdx = seg, segCount = NS; /* this warp's place among the row's segments (hand-over boundaries are numbered by it) */
-        if (fineCapable)
+        if (fine)
         {
-            const bool heavy = (end - begin) > heavyLimit;
-            if (!heavy && fineK != 0u) continue;
-            if (heavy)
-            {
-                sx0 += (int)(fineK << SL_SHADE_SHIFT);
-                if (sx0 >= sx1) continue;
-                sx1 = min(sx0 + (1 << SL_SHADE_SHIFT), sx1);
-                firstList += fineK; /* exactly the pixels of one fragment list */
-                segIdx = seg * (int)fineF + (int)fineK;
-                segCount = NS * (int)fineF;
-            }
+            sx0 += (int)(fineK << SL_SHADE_SHIFT);
+            if (sx0 >= sx1) continue;
+            sx1 = min(sx0 + (1 << SL_SHADE_SHIFT), sx1);
+            firstList += fineK; /* exactly the pixels of one fragment list */
+            segIdx = seg * (int)fineF + (int)fineK;
+            segCount = NS * (int)fineF;
         }
         const unsigned segPixels = (unsigned)(sx1 - sx0);
         const long long segOrigin = (long long)W * y + sx0;

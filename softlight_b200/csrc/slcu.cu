@@ -1096,8 +1096,11 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
     rp.ticketOrder = nullptr;
     rp.rowPerm = nullptr;
     {
-        static const int fineEnv = getenv("SLCU_FINE_ROWS") ? atoi(getenv("SLCU_FINE_ROWS")) : 4;
-        rp.fineRows = fineEnv > 0 ? (unsigned)fineEnv : 0u;
+        /* fine segments shorten the longest ticket and multiply the per-layer overhead of the rows they cut: a loss on one
+         * GPU (k_resolve2 is throughput-bound there: C3 0.84 -> 1.04 ms), a gain under the sort-first partition, where a
+         * rank's few rows leave the kernel as long as its longest ticket (profiles/r02n_*, r02o_*) */
+        static const int fineEnv = getenv("SLCU_FINE_ROWS") ? atoi(getenv("SLCU_FINE_ROWS")) : -1;
+        rp.fineRows = fineEnv >= 0 ? (unsigned)fineEnv : (c->partWorld > 1 ? 3u : 0u);
     }
     {
         /* skewed work order (see k_resolve): only when every hand-over goes from a segment to its right neighbour */
@@ -1135,9 +1138,9 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
             static const bool heavyFirst = !(getenv("SLCU_HEAVY_FIRST") && atoi(getenv("SLCU_HEAVY_FIRST")) == 0);
             if (heavyFirst)
             {
-                CK(c->rowPerm.ensure((size_t)H * sizeof(uint32_t)));
+                CK(c->rowPerm.ensure((size_t)(H + 1) * sizeof(uint32_t)));
                 KernelScope ks(c, SLCU_K_SCAN);
-                k_row_order<<<1, 1024, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(c->rowStart.buf.ptr), H, reinterpret_cast<uint32_t*>(c->rowPerm.buf.ptr));
+                k_row_order<<<1, 1024, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(c->rowStart.buf.ptr), H, reinterpret_cast<uint32_t*>(c->rowPerm.buf.ptr), rp.fineRows ? rp.fineRows : 2u);
                 rp.rowPerm = reinterpret_cast<const uint32_t*>(c->rowPerm.buf.ptr);
             }
         }
