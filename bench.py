@@ -192,19 +192,6 @@ def ncu_counters(dom: str, config: str):
     return None
 
 
-def pinned_array(shape, dtype):
-    """Host staging in pinned memory when torch+CUDA are present (plumbing only)."""
-    try:
-        import torch
-
-        t = torch.empty(int(np.prod(shape)) * np.dtype(dtype).itemsize, dtype=torch.uint8, pin_memory=True)
-        arr = t.numpy().view(dtype).reshape(shape)
-        arr._keep = t if False else None
-        return arr, t
-    except Exception:
-        return np.zeros(shape, dtype=dtype), None
-
-
 # ----------------------------------------------------------------------------- arms
 def workload_config(config: str, scene: S.Scene) -> dict:
     """The `config` object of the JSON line: identical in both arms."""
@@ -284,6 +271,9 @@ class Harness:
             from softlight_b200.sortfirst import SortFirst
 
             self.sf = SortFirst(self.ctx, dist, rank, world, strip_rows=strip_rows)
+            if os.environ.get("SLCU_GEOM_SHARE", "1") != "0":
+                # the ranks split the vertex stage and route the triangle records (two arenas, fixed record slots, <= 4 varyings)
+                self.sf.share_geometry(int(self.scene.tris_per_frame * 1.3) * 242 + (64 << 20))
             self.final = [self.sf.make_target(self.scene.color_type, self.scene.width, self.scene.height) for _ in range(2)]
         # L2 flush buffer (written between timed frames, outside the timed region)
         ctx = self.ctx
@@ -381,13 +371,14 @@ class Harness:
         scene, ctx, inst = self.scene, self.ctx, self.inst
         per_frame = inst.state.get("per_frame", {})
         staged, h2d = {}, 0
+        # host buffers are page-locked (slcu_host_alloc): pageable ones go through the driver's bounce buffer at a third of the link rate
         for key, arr in per_frame.items():
-            pin, keep = pinned_array(arr.shape, arr.dtype)
+            pin = ctx.host_array(arr.shape, arr.dtype)
             pin[...] = arr
-            staged[key] = (pin, keep)
+            staged[key] = (pin, None)
             h2d += arr.nbytes
         cbytes = scene.width * scene.height * A.bytes_per_texel(scene.color_type)
-        out_pin, out_keep = pinned_array((cbytes,), np.uint8)
+        out_pin = ctx.host_array((cbytes,), np.uint8)
         e2e_ms = []
         for i in range(steps + 2):
             self.flush_l2()
@@ -409,7 +400,7 @@ class Harness:
         ms = float(np.mean(e2e_ms))
         return {"value": scene.tris_per_frame / (ms * 1e-3) / 1e6, "unit": METRIC,
                 "h2d_bytes_per_step": int((h2d + scene.upload_bytes_per_frame) * self.world), "d2h_bytes_per_step": int(cbytes), "ms_per_step": ms,
-                "checksum": int(out_pin[::4097].astype(np.uint64).sum())}
+                "host_buffers": "page-locked (slcu_host_alloc)", "checksum": int(out_pin[::4097].astype(np.uint64).sum())}
 
     def close(self):
         self.ctx.close()
@@ -491,8 +482,10 @@ def run_cuda(args, rank, world, local_rank, dist):
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.config, scene),
         "l2": "flushed between timed frames (256 MiB clear, untimed)",
-        "parallelism": f"sort-first x{world}" + (f", {args.strip_rows}-row strips interleaved over ranks, geometry replicated, "
-                                                 "composite = peer stores into rank 0 over NVLink" if world > 1 else ""),
+        "parallelism": f"sort-first x{world}" + (f", {args.strip_rows}-row strips interleaved over ranks, "
+                                                 + ("vertex stage split by vertex block, records routed to the owners of their rows by peer stores, "
+                                                    if os.environ.get("SLCU_GEOM_SHARE", "1") != "0" else "geometry replicated, ")
+                                                 + "composite = peer stores into rank 0 over NVLink" if world > 1 else ""),
         "gfrags_per_s": frags / (ms * 1e-3) / 1e9, "fps": 1e3 / ms, "frags_per_frame": int(frags),
         "tris_binned_per_frame": int(st["trisBinned"] // args.steps), "spans_per_frame": int(st["spans"] // args.steps),
         "gpu_launches": d["launches"], "clocks": d["clocks"], "e2e": e2e, "roofline": roofline,

@@ -174,6 +174,12 @@ SLCU_EXPORT int SLCU_FN(texture_init)(slcu_context* ctx, size_t tex, int colorTy
 SLCU_EXPORT int SLCU_FN(texture_set_texels)(slcu_context* ctx, size_t tex, int texelOrder, uint16_t x, uint16_t y, uint16_t z, uint16_t w, uint16_t h, uint16_t d, const void* data);
 SLCU_EXPORT int SLCU_FN(texture_read)(slcu_context* ctx, size_t tex, void* out, size_t numBytes);
 
+/* ours: page-locked host memory.  The reference's textures and window back buffers are plain host allocations
+ * (src/SL_Texture.cpp:276-294, SL_WindowBuffer); a host that wants texture_read / vbo_assign to run at the link rate hands
+ * the library buffers from here instead (any host pointer is accepted everywhere; pageable ones are just slower). */
+SLCU_EXPORT int SLCU_FN(host_alloc)(slcu_context* ctx, void** out, size_t numBytes);
+SLCU_EXPORT int SLCU_FN(host_free)(slcu_context* ctx, void* ptr);
+
 /* SL_Framebuffer (src/SL_Framebuffer.cpp:823-990) */
 SLCU_EXPORT int SLCU_FN(fbo_reserve_color_buffers)(slcu_context* ctx, size_t fbo, unsigned n);
 SLCU_EXPORT int SLCU_FN(fbo_attach_color_buffer)(slcu_context* ctx, size_t fbo, unsigned index, size_t texture);
@@ -228,6 +234,19 @@ SLCU_EXPORT int SLCU_FN(set_partition)(slcu_context* ctx, unsigned rank, unsigne
 SLCU_EXPORT int SLCU_FN(texture_ipc_export)(slcu_context* ctx, size_t texture, void* handle64);
 SLCU_EXPORT int SLCU_FN(texture_ipc_import)(slcu_context* ctx, size_t texture, unsigned peerRank, const void* handle64);
 SLCU_EXPORT int SLCU_FN(composite)(slcu_context* ctx, size_t srcTexture, size_t dstTexture, unsigned root);
+
+/* Shared vertex stage (ours; SURVEY.md section 8e "shard K1 by primitive range").  Without it every rank runs the vertex
+ * stage on all primitives.  With it rank r shades vertex blocks r, r + world, ... and stores each triangle record straight
+ * into the arenas of the ranks whose rows the triangle touches (peer stores over NVLink; a device-side rendezvous, no host
+ * round trip).  Every rank creates an arena of the same size after set_partition, exports its handle, and imports the
+ * handles of all the others; from then on every triangle batch that fits the arena is shared (the decision is identical
+ * on all ranks because they issue identical calls).  A batch needs about numPrimitives * (3 + 3 * varyings) * 16 * 1.15 bytes.
+ * address / attach replace export / import for contexts that live in one process. */
+SLCU_EXPORT int SLCU_FN(geometry_share_create)(slcu_context* ctx, size_t arenaBytes);
+SLCU_EXPORT int SLCU_FN(geometry_share_export)(slcu_context* ctx, void* handle64);
+SLCU_EXPORT int SLCU_FN(geometry_share_import)(slcu_context* ctx, unsigned peerRank, const void* handle64);
+SLCU_EXPORT int SLCU_FN(geometry_share_address)(slcu_context* ctx, void** address);
+SLCU_EXPORT int SLCU_FN(geometry_share_attach)(slcu_context* ctx, unsigned peerRank, void* address);
 
 /* The reference's draw/clear/blit return after all workers joined.  Ours
  * enqueue on one stream; sync() is the join.  texture_read syncs by itself. */

@@ -162,6 +162,13 @@ _SIGS_PRODUCT = {
     "composite": (C.c_int, [_P, _SZ, _SZ, C.c_uint]),
     "register_shader_source": (C.c_int, [_P, C.c_char_p]),
     "shader_source_check": (C.c_int, [C.c_char_p, C.c_char_p, _SZ]),
+    "geometry_share_create": (C.c_int, [_P, _SZ]),
+    "geometry_share_export": (C.c_int, [_P, _P]),
+    "geometry_share_import": (C.c_int, [_P, C.c_uint, _P]),
+    "geometry_share_address": (C.c_int, [_P, C.POINTER(_P)]),
+    "geometry_share_attach": (C.c_int, [_P, C.c_uint, _P]),
+    "host_alloc": (C.c_int, [_P, C.POINTER(_P), _SZ]),
+    "host_free": (C.c_int, [_P, _P]),
 }
 
 EXPORTED_SYMBOLS = sorted(list(_SIGS) + list(_SIGS_PRODUCT))
@@ -281,11 +288,15 @@ class Context:
             raise SlError(f"{impl}: context_create failed with {rc} (no CPU fallback exists)")
         self.h = h
         self._keep = []
+        self._host_allocs = []
         if threads != 1:
             self.num_threads(threads)
 
     def close(self):
         if self.h:
+            for p in self._host_allocs:
+                self.f["host_free"](self.h, C.c_void_p(p))
+            self._host_allocs = []
             self.f["context_destroy"](self.h)
             self.h = None
 
@@ -474,6 +485,26 @@ class Context:
         buf = (C.c_ubyte * 64).from_buffer_copy(handle)
         self._chk(self.f["texture_ipc_import"](self.h, tid, peer_rank, buf), "texture_ipc_import")
 
+    def geometry_share_create(self, arena_bytes: int):
+        self._chk(self.f["geometry_share_create"](self.h, arena_bytes), "geometry_share_create")
+
+    def geometry_share_export(self) -> bytes:
+        buf = (C.c_ubyte * 64)()
+        self._chk(self.f["geometry_share_export"](self.h, buf), "geometry_share_export")
+        return bytes(buf)
+
+    def geometry_share_import(self, peer_rank: int, handle: bytes):
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        self._chk(self.f["geometry_share_import"](self.h, peer_rank, buf), "geometry_share_import")
+
+    def geometry_share_address(self) -> int:
+        p = C.c_void_p()
+        self._chk(self.f["geometry_share_address"](self.h, C.byref(p)), "geometry_share_address")
+        return p.value
+
+    def geometry_share_attach(self, peer_rank: int, address: int):
+        self._chk(self.f["geometry_share_attach"](self.h, peer_rank, C.c_void_p(address)), "geometry_share_attach")
+
     def composite(self, src_tex: int, dst_tex: int, root: int = 0):
         self._chk(self.f["composite"](self.h, src_tex, dst_tex, root), "composite")
 
@@ -491,6 +522,15 @@ class Context:
     def vbo_assign_raw(self, vid: int, ptr: int, nbytes: int, offset: int = 0):
         """Upload from a raw host pointer (e.g. pinned memory) without a numpy copy."""
         self._chk(self.f["vbo_assign"](self.h, vid, C.c_void_p(ptr), offset, nbytes), "vbo_assign")
+
+    def host_array(self, shape, dtype) -> np.ndarray:
+        """A numpy view of page-locked host memory from slcu_host_alloc (freed with the context; product library only)."""
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        self._chk(self.f["host_alloc"](self.h, C.byref(p), nbytes), "host_alloc")
+        self._host_allocs.append(p.value)
+        buf = (C.c_ubyte * max(nbytes, 1)).from_address(p.value)
+        return np.frombuffer(buf, dtype=np.uint8, count=nbytes).view(dtype).reshape(shape)
 
     def texture_read_into(self, tid: int, ptr: int, nbytes: int):
         self._chk(self.f["texture_read"](self.h, tid, C.c_void_p(ptr), nbytes), "texture_read")

@@ -47,11 +47,13 @@ constexpr int SL_MAX_ROWS = 8192;         /* framebuffer height limit of the row
 constexpr int SL_SPAN_WIN = 256;          /* rows per mask window in k_span                 */
 constexpr int SL_SHADE_SHIFT_C = 7;       /* log2 of the pixels per fragment list (= SL_SHADE_SHIFT, declared with the lists) */
 
-struct SLSegment { uint32_t base, count; };
+/* rows: first | one-past-last << 16 of the rows the segment's records can have span entries in (0xffff = none).  Every segment
+ * is written exactly once per batch by the warp that owns it -- empty ones too -- so the table needs no clearing and can be
+ * filled by several ranks at once (k_vertex) */
+struct SLSegment { uint32_t base, count, rows; };
 constexpr int SL_VB_SEGS = SL_VB_ROUNDS * (SL_VB_THREADS / 32); /* one record segment per (round, warp) of a vertex block */
-/* negYMin / yMax: the rows the block's records can have span entries in (complement of the minimum so that a zeroed
- * struct means "none" and both are kept with atomicMax); k_span_items cuts every block into 256-row work items with it */
-struct SLBlockInfo { SLSegment seg[SL_VB_SEGS]; uint32_t negYMin, yMax; };
+struct SLBlockInfo { SLSegment seg[SL_VB_SEGS]; };
+constexpr int SL_MAX_RANKS = 8;       /* ranks that can share the vertex stage (one NVSwitch domain) */
 constexpr int SL_SPAN_BAND_SHIFT = 8; /* log2(SL_SPAN_WIN): rows per work item of k_span */
 
 struct SLSpanEntry { uint32_t rec; uint16_t xMin, xMax; };
@@ -90,6 +92,7 @@ constexpr unsigned SL_ABORT_ENTRIES = 2u;  /* more span entries than the row lis
 constexpr unsigned SL_ABORT_CHUNKS = 4u;   /* the fragment pool could run out                                            */
 constexpr unsigned SL_ABORT_HANDOFFS = 8u; /* more hand-overs than the table holds                                       */
 constexpr unsigned SL_ABORT_PARTITION = 16u; /* sort-first fast path: a span runs past the row end into another rank's row */
+constexpr unsigned SL_ABORT_GEOMETRY = 32u;  /* shared vertex stage: some rank's record area overflowed; every rank runs the batch again on its own */
 /* errorFlags bits: one per condition */
 constexpr unsigned SL_ERR_SPAN_TWO_ROWS = 0x2u;     /* a span longer than two rows: not reproduced                        */
 constexpr unsigned SL_ERR_SPAN_NEGATIVE_X = 0x4u;   /* a span that starts left of x = 0: not reproduced                   */
@@ -99,6 +102,7 @@ constexpr unsigned SL_ERR_POOL = 0x20u;             /* fragment chunk pool exhau
 constexpr unsigned SL_ERR_HANDOFF_POLL = 0x40u;     /* a piece waits for a hand-over but there is no table                */
 constexpr unsigned SL_ERR_WIRE_SEGMENT = 0x80u;     /* wireframe: a record segment with more than 256 records             */
 constexpr unsigned SL_ERR_WIRE_SLOTS = 0x100u;      /* wireframe: candidate slots exhausted                               */
+constexpr unsigned SL_ERR_GEOM_TIMEOUT = 0x200u;    /* shared vertex stage: a rank never signalled its blocks             */
 
 /* A span whose xMax exceeds the framebuffer width keeps going in linear memory:
  * the reference addresses pixels as x + width*y (src/SL_TriRasterizer.cpp:472,
@@ -130,24 +134,31 @@ struct alignas(16) SLDrawDesc
     unsigned long long primsPerInstance;
     unsigned long long numPrims;      /* primsPerInstance * instances */
     unsigned int firstBlock;          /* index of this draw's first vertex block in the batch */
-    unsigned int pad_;
+    unsigned int blocksPerInstance;   /* vertex blocks never straddle instances: ceil(primsPerInstance / SL_VB_PRIMS) */
+};
+
+/* where the vertex stage's output goes: this context's buffers, or -- when ranks share the stage -- rank t's arena */
+struct SLGeomOut
+{
+    float4* records;
+    uint16_t* recDraw;                /* record slot -> index into draws (read by the rasteriser); SL_REC_ABSENT: not routed here */
+    SLBlockInfo* blockInfo;
 };
 
 struct SLVertexParams
 {
     const SLDrawDesc* draws;          /* draw table of the batch (HBM)                                  */
     const uint32_t* blockDraw;        /* vertex block -> index into draws                               */
-    uint16_t* recDraw;                /* record slot -> index into draws (read by the rasteriser)       */
     int cullMode;                     /* SL_CullMode */
     int numVaryings;
     unsigned int cacheBytes;          /* dynamic shared memory of the post-transform cache (0: off) */
     unsigned int cacheVerts;          /* vertices the cache holds (<= SL_VCACHE_VERTS, multiple of 32)  */
-    unsigned int recCapacity;         /* record slots per plane: fixed per-block regions + overflow area */
-    unsigned int recOverflowBase;     /* first slot of the overflow area                                */
+    unsigned int recOverflowBase;     /* first slot of this rank's overflow area                        */
     unsigned int recOverflowCapacity; /* its size                                                       */
-    float4* records;
-    SLBlockInfo* blockInfo;
     SLCounters* counters;
+    int shardRank, shardWorld;        /* ranks sharing the stage: this one runs blocks rank, rank + world, ... (world 1: all) */
+    int partStrip;                    /* rows per ownership strip of the sort-first partition           */
+    SLGeomOut out[SL_MAX_RANKS];      /* [0] when shardWorld == 1, else indexed by rank                 */
 };
 
 /* ------------------------------------------------------------------------
@@ -234,15 +245,23 @@ struct SLClipPoly
     math::vec4 varys[9 * 4];
 };
 
-__device__ __noinline__ int sl_clip_polygon(SLClipPoly& poly, int numVarys, const float* dims)
+/* bufs[0] holds the triangle; the polygon alternates between the two buffers, one clip plane at a time, and `which` says
+ * where it ended up.  A plane that has every vertex on its visible side leaves the polygon as it is (the reference copies
+ * it vertex by vertex: same values). */
+__device__ __noinline__ int sl_clip_polygon(SLClipPoly* bufs, int numVarys, const float* dims, int& which)
 {
-    SLClipPoly tmp;
+    int src = 0;
     int numTotalVerts = 3;
     const float edges[6][4] = {{1.f, 0.f, 0.f, 1.f}, {-1.f, 0.f, 0.f, 1.f}, {0.f, 1.f, 0.f, 1.f},
                                {0.f, -1.f, 0.f, 1.f}, {0.f, 0.f, 1.f, 1.f}, {0.f, 0.f, -1.f, 1.f}};
     for (int e = 0; e < 6; ++e)
     {
         const math::vec4 edge{edges[e][0], edges[e][1], edges[e][2], edges[e][3]};
+        const SLClipPoly& poly = bufs[src];
+        SLClipPoly& tmp = bufs[src ^ 1];
+        bool allVisible = true;
+        for (int k = 0; k < numTotalVerts; ++k) allVisible = allVisible && !sl_signbit(math::dot(poly.verts[k], edge));
+        if (allVisible) continue;
         int numNewVerts = 0;
         int j = numTotalVerts - 1;
         math::vec4 p0 = poly.verts[numTotalVerts - 1];
@@ -273,14 +292,11 @@ __device__ __noinline__ int sl_clip_polygon(SLClipPoly& poly, int numVarys, cons
         }
         if (!numNewVerts) return 0;
         numTotalVerts = numNewVerts;
-        for (int i = 0; i < numNewVerts; ++i)
-        {
-            poly.verts[i] = tmp.verts[i];
-            for (int v = 0; v < numVarys; ++v) poly.varys[i * 4 + v] = tmp.varys[i * 4 + v];
-        }
+        src ^= 1;
     }
+    which = src;
     if (numTotalVerts < 3) return 0;
-    for (int i = 0; i < numTotalVerts; ++i) sl_to_screen(poly.verts[i], dims);
+    for (int i = 0; i < numTotalVerts; ++i) sl_to_screen(bufs[src].verts[i], dims);
     return numTotalVerts;
 }
 
@@ -322,27 +338,66 @@ SLD_FN void sl_fetch_vertex_ids(const SLDrawDesc& P, unsigned long long i, unsig
     else { vertId[0] = i; vertId[1] = i + 1; vertId[2] = i + 2; }
 }
 
+/* Ranks whose rows a record can have span entries in (sort-first partition, interleaved strips): the rows of its
+ * vertices and one more, for a span that runs past the row end (k_span: y0 .. yEnd).  Screen y is a non-negative
+ * integer stored as a float (sl_to_screen); anything else (NaN, huge) goes to every rank. */
+SLD_FN uint32_t sl_rank_mask(float ya, float yb, float yc, int strip, int world)
+{
+    const uint32_t all = (1u << world) - 1u;
+    const float lo = fminf(ya, fminf(yb, yc)), hi = fmaxf(ya, fmaxf(yb, yc));
+    if (!(ya == ya) || !(yb == yb) || !(yc == yc) || !(hi < 65000.f)) return all;
+    const int sa = (int)lo / strip, sb = ((int)hi + 1) / strip;
+    if (sb - sa + 1 >= world) return all;
+    uint32_t m = 0u;
+    for (int s = sa; s <= sb; ++s) m |= 1u << (s % world);
+    return m;
+}
+
 /* The reference runs the vertex shader three times per triangle with no post-transform cache
  * (src/SL_TriProcessor.cpp:584-594; SL_VertexCache is compiled out, SL_Config.hpp:10-12).  A vertex shader is a pure
- * function of (uniforms, vertId, instanceId), so shading each vertex a block of 1024 primitives references ONCE gives
- * the same bits: when the block's primitives belong to one instance of an indexed mesh and their indices span at most
- * SL_VCACHE_VERTS vertices, the block shades that index range into shared memory first and assembles its triangles
- * from there; otherwise every primitive shades its own three vertices like the reference. */
+ * function of (uniforms, vertId, instanceId), so shading each vertex ONCE per (instance, vertex block) gives the same bits.
+ *
+ * A vertex block is 1024 consecutive primitives of ONE instance of one draw (the last block of an instance is short), 256
+ * threads, four rounds of one primitive per thread.  Two instantiations:
+ *   CACHE = false  every primitive shades its own three vertices, like the reference.
+ *   CACHE = true   for batches whose index buffers address at most SL_VCACHE_VERTS vertices (small instanced meshes: C2's
+ *                  sphere is 561 vertices for 1024 triangles).  The block stages its indices in shared memory, shades every
+ *                  vertex they use once -- together with everything after the shader that is a function of the vertex
+ *                  alone: scissor transform, clip-status terms, perspective divide, viewport -- and assembles its triangles
+ *                  from shared memory.  No per-primitive shader state lives in registers, so twice the blocks fit an SM.
+ *
+ * Records go to fixed places: every (block, round, warp) owns 32 record slots, enough unless clipping fanned primitives
+ * out; only then does the warp take its slots from the overflow area (one atomic).  No barrier, no allocation-order
+ * dependence, and slot order = submission order.
+ *
+ * Ranks that share the vertex stage (slcu_geometry_share_*): rank r runs blocks r, r + world, ... and stores each record
+ * into the arenas of the ranks whose rows it touches (peer stores over NVLink), the 2-byte recDraw word -- 0xffff = "not
+ * for you" -- and the segment table into every rank's.  Slots are the same everywhere, so nothing has to be merged. */
 #ifndef SL_VERTEX_MIN_BLOCKS
 #define SL_VERTEX_MIN_BLOCKS 2 /* (256, 1) lets ptxas take > 128 registers: one block per SM, measured 35 % slower */
 #endif
+#ifndef SL_VERTEX_CACHED_MIN_BLOCKS
+#define SL_VERTEX_CACHED_MIN_BLOCKS 3
+#endif
+constexpr uint16_t SL_REC_ABSENT = 0xffffu; /* recDraw: the record was not routed to this rank */
+
 template <VsFn VS, bool CACHE>
-__global__ void __launch_bounds__(SL_VB_THREADS, SL_VERTEX_MIN_BLOCKS) k_vertex(const __grid_constant__ SLVertexParams P)
+__global__ void __launch_bounds__(SL_VB_THREADS, CACHE ? SL_VERTEX_CACHED_MIN_BLOCKS : SL_VERTEX_MIN_BLOCKS) k_vertex(const __grid_constant__ SLVertexParams P)
 {
-    extern __shared__ __align__(16) unsigned char sVCache[]; /* float4 [2 + NV][cacheVerts] (clip position, screen position, varyings) + u8 flags [cacheVerts] */
+    /* CACHE: u16 indices [3 * SL_VB_PRIMS] | float4 [2 + NV][cacheVerts] (clip position, screen position, varyings) | u32 used bits | u8 flags */
+    extern __shared__ __align__(16) unsigned char sVCache[];
     uint32_t binned = 0u; /* lane 0: records of this warp */
-    __shared__ unsigned long long sIdMin, sIdMax;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const uint32_t drawIdx = P.blockDraw[blockIdx.x];
+    const int world = P.shardWorld;
+    const unsigned vb = world > 1 ? blockIdx.x * (unsigned)world + (unsigned)P.shardRank : blockIdx.x;
+    const uint32_t drawIdx = P.blockDraw[vb];
     const SLDrawDesc& D = P.draws[drawIdx];
-    const unsigned long long blockFirst = (unsigned long long)(blockIdx.x - D.firstBlock) * SL_VB_PRIMS;
+    const unsigned lb = vb - D.firstBlock;
+    const unsigned instanceId = lb / D.blocksPerInstance;
+    const unsigned primBase = (lb - instanceId * D.blocksPerInstance) * (unsigned)SL_VB_PRIMS; /* first primitive of the block inside its instance */
+    const unsigned primsPerInstance = (unsigned)D.primsPerInstance;
     const int NV = P.numVaryings;
     const int recStride = 3 + 3 * NV;
 
@@ -350,313 +405,399 @@ __global__ void __launch_bounds__(SL_VB_THREADS, SL_VERTEX_MIN_BLOCKS) k_vertex(
     params.pUniforms = &D.uniforms;
     params.pVao = &D.vao;
     params.pVbo = &D.vbo;
+    params.instanceId = (size_t)instanceId;
 
     const math::mat4 scissorMat = *reinterpret_cast<const math::mat4*>(D.scissor);
     const float viewport[4] = {D.viewport[0], D.viewport[1], D.viewport[2], D.viewport[3]};
 
     /* ---- post-transform cache ---- */
-    bool cached = false;
-    unsigned long long cacheBase = 0;
-    float4* cache = reinterpret_cast<float4*>(sVCache);
     const unsigned CV = P.cacheVerts;
-    uint8_t* cacheFlags = sVCache + (size_t)(2 + NV) * CV * sizeof(float4);
-    if (CACHE && P.cacheBytes && D.usingIndices && blockFirst < D.numPrims)
+    uint16_t* sIdx = reinterpret_cast<uint16_t*>(sVCache);
+    float4* cache = reinterpret_cast<float4*>(sVCache + 3 * SL_VB_PRIMS * sizeof(uint16_t));
+    uint32_t* sUsed = reinterpret_cast<uint32_t*>(cache + (size_t)(2 + NV) * CV);
+    uint8_t* cacheFlags = reinterpret_cast<uint8_t*>(sUsed + CV / 32u);
+    if constexpr (CACHE)
     {
-        const unsigned long long blockLast = min(blockFirst + (unsigned long long)SL_VB_PRIMS, D.numPrims) - 1ull;
-        const unsigned long long instFirst = blockFirst / D.primsPerInstance;
-        if (instFirst == blockLast / D.primsPerInstance) /* one instance: block-uniform */
-        {
-            if (tid == 0) { sIdMin = ~0ull; sIdMax = 0ull; }
-            __syncthreads();
-            unsigned long long lo = ~0ull, hi = 0ull;
-            for (int round = 0; round < SL_VB_ROUNDS; ++round)
-            {
-                const unsigned long long g = blockFirst + (unsigned long long)round * SL_VB_THREADS + tid;
-                if (g <= blockLast)
-                {
-                    unsigned long long id[3];
-                    sl_fetch_vertex_ids(D, D.elementBegin + 3ull * (g - instFirst * D.primsPerInstance), id);
-                    lo = min(lo, min(id[0], min(id[1], id[2])));
-                    hi = max(hi, max(id[0], max(id[1], id[2])));
-                }
-            }
-            for (int d = 16; d > 0; d >>= 1)
-            {
-                lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
-                hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
-            }
-            if (lane == 0) { atomicMin(&sIdMin, lo); atomicMax(&sIdMax, hi); }
-            __syncthreads();
-            cacheBase = sIdMin;
-            const unsigned long long range = sIdMax - sIdMin + 1ull;
-            if (range <= (unsigned long long)CV)
-            {
-                cached = true;
-                params.instanceId = (size_t)instFirst;
-                for (unsigned v = tid; v < (unsigned)range; v += SL_VB_THREADS)
-                {
-                    math::vec4 vary[4];
-                    params.vertId = (size_t)(cacheBase + v);
-                    params.pVaryings = vary;
-                    const math::vec4 pos = VS(params);
-                    cache[v] = make_float4(pos.v[0], pos.v[1], pos.v[2], pos.v[3]);
-                    /* everything after the vertex shader that is a function of the vertex alone: scissor transform
-                     * (:615-617), its share of sl_ndc_clip_status, perspective divide + viewport (valid when the
-                     * triangle turns out fully visible) */
-                    math::vec4 sc = scissorMat * pos;
-                    const float w = sc.v[3];
-                    const float nw = __uint_as_float(__float_as_uint(w) | 0x80000000u);
-                    bool vis = true;
+        for (unsigned w = tid; w < CV / 32u; w += SL_VB_THREADS) sUsed[w] = 0u;
+        __syncthreads();
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) vis = vis && (nw <= sc.v[k]) && (w >= sc.v[k]);
-                    cacheFlags[v] = (uint8_t)((vis ? 1u : 0u) | ((w > 0.f) ? 2u : 0u));
-                    sl_to_screen(sc, viewport);
-                    cache[CV + v] = make_float4(sc.v[0], sc.v[1], sc.v[2], sc.v[3]);
-#pragma unroll
-                    for (int s = 0; s < 4; ++s)
-                    {
-                        if (s < NV) cache[(2 + s) * CV + v] = make_float4(vary[s].v[0], vary[s].v[1], vary[s].v[2], vary[s].v[3]);
-                    }
-                }
-            }
-            __syncthreads();
-        }
-    }
-
-    for (int round = 0; round < SL_VB_ROUNDS; ++round)
-    {
-        const unsigned long long g = blockFirst + (unsigned long long)round * SL_VB_THREADS + tid;
-        SLVert v[3];
-        SLClipPoly poly;
-        int n = 0;         /* records this thread emits */
-        int polyVerts = 0; /* > 0: clipped path */
-        unsigned ci[3] = {0u, 0u, 0u}; /* cache slots of the three vertices */
-        bool fromCache = false;        /* the record is assembled from the cache at write time */
-
-        if (g < D.numPrims)
+        for (int round = 0; round < SL_VB_ROUNDS; ++round)
         {
-            const unsigned long long instanceId = g / D.primsPerInstance;
-            const unsigned long long i = D.elementBegin + 3ull * (g - instanceId * D.primsPerInstance);
-            unsigned long long vertId[3];
-            sl_fetch_vertex_ids(D, i, vertId);
-
-            if (CACHE && cached)
+            const unsigned p = (unsigned)round * SL_VB_THREADS + (unsigned)tid;
+            if (primBase + p < primsPerInstance)
             {
-                ci[0] = (unsigned)(vertId[0] - cacheBase);
-                ci[1] = (unsigned)(vertId[1] - cacheBase);
-                ci[2] = (unsigned)(vertId[2] - cacheBase);
-                math::vec4 cp[3];
+                unsigned long long id[3];
+                sl_fetch_vertex_ids(D, D.elementBegin + 3ull * (primBase + p), id);
 #pragma unroll
                 for (int k = 0; k < 3; ++k)
                 {
-                    const float4 pos = cache[ci[k]];
-                    cp[k] = math::vec4{pos.x, pos.y, pos.z, pos.w};
+                    const unsigned v = min((unsigned)id[k], CV - 1u); /* the host checked the index buffer: never clamps */
+                    sIdx[3u * p + k] = (uint16_t)v;
+                    atomicOr(&sUsed[v >> 5], 1u << (v & 31u));
                 }
-                bool culled = false;
-                if (P.cullMode != 2) /* :597-612 */
-                {
-                    const float det = sl_face_determinant(cp[0], cp[1], cp[2]);
-                    culled = (P.cullMode == 1) ^ sl_signbit(det);
-                }
-                if (!culled)
-                {
-                    const unsigned f0 = cacheFlags[ci[0]], f1 = cacheFlags[ci[1]], f2 = cacheFlags[ci[2]];
-                    if (f0 & f1 & f2 & 1u) /* fully visible */
-                    {
-                        const float4 s0 = cache[CV + ci[0]], s1 = cache[CV + ci[1]], s2 = cache[CV + ci[2]];
-                        fromCache = true;
-                        n = sl_prim_hidden(math::vec4{s0.x, s0.y, s0.z, s0.w}, math::vec4{s1.x, s1.y, s1.z, s1.w}, math::vec4{s2.x, s2.y, s2.z, s2.w}) ? 0 : 1;
-                    }
-                    else if ((f0 | f1 | f2) & 2u) /* partially visible: the clipper works on the scissored clip-space vertices */
-                    {
+            }
+        }
+        __syncthreads();
+        for (unsigned v = tid; v < CV; v += SL_VB_THREADS)
+        {
+            if (!((sUsed[v >> 5] >> (v & 31u)) & 1u)) continue;
+            math::vec4 vary[4];
+            params.vertId = (size_t)v;
+            params.pVaryings = vary;
+            const math::vec4 pos = VS(params);
+            cache[v] = make_float4(pos.v[0], pos.v[1], pos.v[2], pos.v[3]);
+            /* everything after the vertex shader that is a function of the vertex alone: scissor transform (:615-617),
+             * its share of sl_ndc_clip_status, perspective divide + viewport (valid when the triangle turns out fully
+             * visible) */
+            math::vec4 sc = scissorMat * pos;
+            const float w = sc.v[3];
+            const float nw = __uint_as_float(__float_as_uint(w) | 0x80000000u);
+            bool vis = true;
 #pragma unroll
-                        for (int k = 0; k < 3; ++k) v[k].vert = scissorMat * cp[k];
-                        if (!sl_clip_rejects(v[0].vert, v[1].vert, v[2].vert))
+            for (int k = 0; k < 4; ++k) vis = vis && (nw <= sc.v[k]) && (w >= sc.v[k]);
+            cacheFlags[v] = (uint8_t)((vis ? 1u : 0u) | ((w > 0.f) ? 2u : 0u));
+            sl_to_screen(sc, viewport);
+            cache[CV + v] = make_float4(sc.v[0], sc.v[1], sc.v[2], sc.v[3]);
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+            {
+                if (s < NV) cache[(2 + s) * CV + v] = make_float4(vary[s].v[0], vary[s].v[1], vary[s].v[2], vary[s].v[3]);
+            }
+        }
+        __syncthreads();
+    }
+
+    /* Four passes over the block's primitives, the last three only when some primitive needs the clipper:
+     *   0  the rounds: classify every primitive (culled / hidden / one record / needs the clipper).  A (round, warp) without
+     *      clipper candidates writes its records at once; one with candidates is deferred as a whole and the candidates go
+     *      into a queue.
+     *   1  the queue, one candidate per thread: clip and COUNT the triangles of the fan (and the rows they touch).
+     *   2  the deferred (round, warp)s: now every count is known; slots are assigned, the unclipped primitives' records
+     *      written, the candidates told where theirs go.
+     *   3  the queue again: clip and WRITE.
+     * The clipper is a long serial routine over a polygon in local memory.  Run where it is met, it keeps one lane of a
+     * warp busy and 31 waiting (profiles/r02q_k_vertex_c2.txt: a third of the kernel's issue slots on C2, where a few per
+     * cent of the triangles cross the frustum); run from the queue every lane of the warp clips.  The candidates' vertices
+     * are shaded again from their primitive id in passes 1-3 -- they are few. */
+    __shared__ uint8_t sN[SL_VB_PRIMS];       /* queue candidates: triangles of the clipped fan                          */
+    __shared__ uint32_t sSlot[SL_VB_PRIMS];   /* queue candidates: pass 1 -> rows (first | last + 1 << 16), pass 2 -> first slot (~0: none) */
+    __shared__ uint16_t sClipQ[SL_VB_PRIMS];
+    __shared__ uint8_t sDefer[SL_VB_SEGS];
+    __shared__ unsigned sClipCount;
+    if (tid == 0) sClipCount = 0u;
+    if (tid < SL_VB_SEGS) sDefer[tid] = 0;
+    __syncthreads();
+
+    unsigned clipCount = 0u;
+    for (int pass = 0; pass < 4; ++pass)
+    {
+        const bool queuePass = (pass & 1) != 0;
+        const unsigned iters = queuePass ? (clipCount + SL_VB_THREADS - 1u) / SL_VB_THREADS : (unsigned)SL_VB_ROUNDS;
+        for (unsigned it = 0; it < iters; ++it)
+        {
+            if (pass == 2 && !sDefer[it * (SL_VB_THREADS / 32) + warp]) continue; /* warp-uniform */
+            unsigned p;
+            bool active;
+            if (queuePass)
+            {
+                const unsigned q = it * SL_VB_THREADS + (unsigned)tid;
+                active = q < clipCount;
+                p = active ? sClipQ[q] : 0u;
+            }
+            else
+            {
+                p = it * SL_VB_THREADS + (unsigned)tid;
+                active = primBase + p < primsPerInstance;
+            }
+            SLVert v[3];
+            SLClipPoly poly[2];
+            int n = 0;             /* records this thread emits */
+            int polyVerts = 0;     /* > 0: clipped path, polygon in poly[which] */
+            int which = 0;
+            bool needClip = false; /* partially visible and not rejected by the first plane it misses: the clipper decides */
+            unsigned ci[3] = {0u, 0u, 0u}; /* cache slots of the three vertices */
+
+            if (active)
+            {
+                if constexpr (CACHE)
+                {
+                    ci[0] = sIdx[3u * p + 0];
+                    ci[1] = sIdx[3u * p + 1];
+                    ci[2] = sIdx[3u * p + 2];
+                    math::vec4 cp[3];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                    {
+                        const float4 pos = cache[ci[k]];
+                        cp[k] = math::vec4{pos.x, pos.y, pos.z, pos.w};
+                    }
+                    bool culled = false;
+                    if (P.cullMode != 2) /* :597-612 */
+                    {
+                        const float det = sl_face_determinant(cp[0], cp[1], cp[2]);
+                        culled = (P.cullMode == 1) ^ sl_signbit(det);
+                    }
+                    if (!culled)
+                    {
+                        const unsigned f0 = cacheFlags[ci[0]], f1 = cacheFlags[ci[1]], f2 = cacheFlags[ci[2]];
+                        if (f0 & f1 & f2 & 1u) /* fully visible */
+                        {
+                            const float4 s0 = cache[CV + ci[0]], s1 = cache[CV + ci[1]], s2 = cache[CV + ci[2]];
+                            n = sl_prim_hidden(math::vec4{s0.x, s0.y, s0.z, s0.w}, math::vec4{s1.x, s1.y, s1.z, s1.w}, math::vec4{s2.x, s2.y, s2.z, s2.w}) ? 0 : 1;
+                        }
+                        else if ((f0 | f1 | f2) & 2u) /* partially visible: the clipper works on the scissored clip-space vertices */
                         {
 #pragma unroll
-                            for (int k = 0; k < 3; ++k)
+                            for (int k = 0; k < 3; ++k) cp[k] = scissorMat * cp[k];
+                            needClip = !sl_clip_rejects(cp[0], cp[1], cp[2]);
+                            if (needClip && queuePass)
                             {
-                                poly.verts[k] = v[k].vert;
 #pragma unroll
-                                for (int s = 0; s < 4; ++s)
+                                for (int k = 0; k < 3; ++k)
                                 {
-                                    if (s < NV)
+                                    poly[0].verts[k] = cp[k];
+#pragma unroll
+                                    for (int s = 0; s < 4; ++s)
                                     {
-                                        const float4 f = cache[(2 + s) * CV + ci[k]];
-                                        poly.varys[k * 4 + s] = math::vec4{f.x, f.y, f.z, f.w};
+                                        if (s < NV)
+                                        {
+                                            const float4 f = cache[(2 + s) * CV + ci[k]];
+                                            poly[0].varys[k * 4 + s] = math::vec4{f.x, f.y, f.z, f.w};
+                                        }
                                     }
                                 }
                             }
-                            polyVerts = sl_clip_polygon(poly, NV, viewport);
-                            for (int f = polyVerts - 2; f-- > 0;)
+                        }
+                    }
+                }
+                else
+                {
+                    unsigned long long vertId[3];
+                    sl_fetch_vertex_ids(D, D.elementBegin + 3ull * (primBase + p), vertId);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) /* src/SL_TriProcessor.cpp:584-594 */
+                    {
+                        params.vertId = (size_t)vertId[k];
+                        params.pVaryings = v[k].varyings;
+                        v[k].vert = VS(params);
+                    }
+
+                    bool culled = false;
+                    if (P.cullMode != 2) /* :597-612 */
+                    {
+                        const float det = sl_face_determinant(v[0].vert, v[1].vert, v[2].vert);
+                        culled = (P.cullMode == 1) ^ sl_signbit(det);
+                    }
+                    if (!culled)
+                    {
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) v[k].vert = scissorMat * v[k].vert; /* :615-617 */
+                        const int vis = sl_clip_status(v[0].vert, v[1].vert, v[2].vert);
+                        if (vis == 3)
+                        {
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) sl_to_screen(v[k].vert, viewport);
+                            n = sl_prim_hidden(v[0].vert, v[1].vert, v[2].vert) ? 0 : 1;
+                        }
+                        else if (vis == 1)
+                        {
+                            needClip = !sl_clip_rejects(v[0].vert, v[1].vert, v[2].vert);
+                            if (needClip && queuePass)
                             {
-                                if (!sl_prim_hidden(poly.verts[0], poly.verts[f + 1], poly.verts[f + 2])) ++n;
+#pragma unroll
+                                for (int k = 0; k < 3; ++k)
+                                {
+                                    poly[0].verts[k] = v[k].vert;
+#pragma unroll
+                                    for (int s = 0; s < 4; ++s) { if (s < NV) poly[0].varys[k * 4 + s] = v[k].varyings[s]; }
+                                }
                             }
                         }
                     }
                 }
             }
-            else
-            {
-                params.instanceId = (size_t)instanceId;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) /* src/SL_TriProcessor.cpp:584-594 */
-                {
-                    params.vertId = (size_t)vertId[k];
-                    params.pVaryings = v[k].varyings;
-                    v[k].vert = VS(params);
-                }
 
-                bool culled = false;
-                if (P.cullMode != 2) /* :597-612 */
+            if (queuePass)
+            {
+                /* every active lane is a candidate (it was one in pass 0: same inputs, same arithmetic) */
+                if (needClip)
                 {
-                    const float det = sl_face_determinant(v[0].vert, v[1].vert, v[2].vert);
-                    culled = (P.cullMode == 1) ^ sl_signbit(det);
-                }
-                if (!culled)
-                {
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) v[k].vert = scissorMat * v[k].vert; /* :615-617 */
-                    const int vis = sl_clip_status(v[0].vert, v[1].vert, v[2].vert);
-                    if (vis == 3)
+                    polyVerts = sl_clip_polygon(poly, NV, viewport, which);
+                    const SLClipPoly& pg = poly[which];
+                    if (pass == 1)
                     {
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) sl_to_screen(v[k].vert, viewport);
-                        n = sl_prim_hidden(v[0].vert, v[1].vert, v[2].vert) ? 0 : 1;
-                    }
-                    else if (vis == 1 && !sl_clip_rejects(v[0].vert, v[1].vert, v[2].vert))
-                    {
-#pragma unroll
-                        for (int k = 0; k < 3; ++k)
-                        {
-                            poly.verts[k] = v[k].vert;
-#pragma unroll
-                            for (int s = 0; s < 4; ++s) { if (s < NV) poly.varys[k * 4 + s] = v[k].varyings[s]; }
-                        }
-                        polyVerts = sl_clip_polygon(poly, NV, viewport);
+                        float fy0 = 3.0e38f, fy1 = -1.f;
                         for (int f = polyVerts - 2; f-- > 0;)
                         {
-                            if (!sl_prim_hidden(poly.verts[0], poly.verts[f + 1], poly.verts[f + 2])) ++n;
+                            if (!sl_prim_hidden(pg.verts[0], pg.verts[f + 1], pg.verts[f + 2])) ++n;
+                        }
+                        for (int k = 0; k < polyVerts; ++k) { fy0 = fminf(fy0, pg.verts[k].v[1]); fy1 = fmaxf(fy1, pg.verts[k].v[1]); }
+                        uint32_t rows = 0xffffu;
+                        if (n && fy1 >= 0.f)
+                        {
+                            const uint32_t r0 = fy0 < 65535.f ? (uint32_t)fy0 : 65535u;
+                            const uint32_t r1 = fy1 < 65533.f ? (uint32_t)fy1 + 2u : 65535u;
+                            rows = r0 | (r1 << 16);
+                        }
+                        sN[p] = (uint8_t)n;
+                        sSlot[p] = rows;
+                    }
+                    else
+                    {
+                        uint32_t slot = sSlot[p];
+                        if (slot != 0xffffffffu)
+                        {
+                            for (int f = polyVerts - 2; f-- > 0;) /* reverse fan order (:505-518) */
+                            {
+                                const int j = f + 1, k = f + 2;
+                                if (sl_prim_hidden(pg.verts[0], pg.verts[j], pg.verts[k])) continue;
+                                const uint32_t mask = world > 1 ? sl_rank_mask(pg.verts[0].v[1], pg.verts[j].v[1], pg.verts[k].v[1], P.partStrip, world) : 1u;
+                                for (int t = 0; t < (world > 1 ? world : 1); ++t)
+                                {
+                                    const bool to = (mask >> t) & 1u;
+                                    P.out[t].recDraw[slot] = to ? (uint16_t)drawIdx : SL_REC_ABSENT;
+                                    if (to)
+                                        sl_write_record(P.out[t].records + (size_t)slot * recStride, NV, pg.verts[0], pg.verts[j], pg.verts[k],
+                                                        &pg.varys[0], &pg.varys[j * 4], &pg.varys[k * 4]);
+                                }
+                                ++slot;
+                            }
                         }
                     }
                 }
+                else if (active && pass == 1) { sN[p] = 0; sSlot[p] = 0xffffu; } /* cannot happen: pass 0 queued it on the same arithmetic */
+                continue;
             }
-        }
 
-        /* ordered compaction inside the block: exclusive scan of n */
-        uint32_t incl = (uint32_t)n;
+            if (pass == 0)
+            {
+                if (__any_sync(0xffffffffu, needClip)) /* the whole (round, warp) waits for its candidates' counts */
+                {
+                    if (needClip) sClipQ[atomicAdd(&sClipCount, 1u)] = (uint16_t)p;
+                    if (lane == 0) sDefer[it * (SL_VB_THREADS / 32) + warp] = 1;
+                    continue;
+                }
+            }
+            else if (needClip) n = sN[p];
+
+            /* ordered compaction inside the warp: exclusive scan of n (one ballot unless clipping fanned a primitive out) */
+            uint32_t incl, total;
+            if (!__any_sync(0xffffffffu, n > 1))
+            {
+                const uint32_t m = __ballot_sync(0xffffffffu, n != 0);
+                incl = (uint32_t)__popc(m & (0xffffffffu >> (31 - lane)));
+                total = (uint32_t)__popc(m);
+            }
+            else
+            {
+                incl = (uint32_t)n;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1)
-        {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
-        }
-        /* Every (block, round, warp) owns 32 record slots at a fixed place, enough unless clipping fanned primitives
-         * out; only then does the warp take its slots from the shared overflow area (one atomic).  No barrier, no
-         * atomics and no allocation-order dependence in the common case: the warps of a block never wait for each
-         * other (the block-wide scan this replaces made the barrier the kernel's top stall). */
-        const uint32_t warpOff = 0u;
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        uint32_t base = blockIdx.x * (uint32_t)SL_VB_PRIMS + (uint32_t)round * SL_VB_THREADS + (uint32_t)warp * 32u;
-        uint32_t granted = total;
-        if (total > 32u) /* warp-uniform */
-        {
+                for (int d = 1; d < 32; d <<= 1)
+                {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                total = __shfl_sync(0xffffffffu, incl, 31);
+            }
+            uint32_t base = vb * (uint32_t)SL_VB_PRIMS + it * SL_VB_THREADS + (uint32_t)warp * 32u;
+            uint32_t granted = total;
+            if (total > 32u) /* warp-uniform */
+            {
+                if (lane == 0)
+                {
+                    const unsigned long long o = atomicAdd(&P.counters->recAlloc, (unsigned long long)total);
+                    if (o + total > (unsigned long long)P.recOverflowCapacity)
+                    {
+                        atomicOr(&P.counters->abortBatch, SL_ABORT_RECORDS); /* the host runs the batch again with a larger overflow area */
+                        base = 0u;
+                        granted = 0u;
+                    }
+                    else base = P.recOverflowBase + (uint32_t)o;
+                }
+                base = __shfl_sync(0xffffffffu, base, 0);
+                granted = __shfl_sync(0xffffffffu, granted, 0);
+            }
+            /* rows the records of this warp touch (conservative: vertex rows, one more for spans that run past the row end) */
+            uint32_t r0 = 65535u, r1 = 0u;
+            if (n && granted)
+            {
+                if (needClip) { const uint32_t rows = sSlot[p]; r0 = rows & 0xffffu; r1 = rows >> 16; }
+                else
+                {
+                    float a, b, cc;
+                    if constexpr (CACHE) { a = cache[CV + ci[0]].y; b = cache[CV + ci[1]].y; cc = cache[CV + ci[2]].y; }
+                    else { a = v[0].vert.v[1]; b = v[1].vert.v[1]; cc = v[2].vert.v[1]; }
+                    const float fy0 = fminf(a, fminf(b, cc)), fy1 = fmaxf(a, fmaxf(b, cc));
+                    /* screen y is a non-negative integer stored as a float (sl_to_screen); NaN rows produce no spans */
+                    if (fy1 >= 0.f)
+                    {
+                        r0 = fy0 < 65535.f ? (uint32_t)fy0 : 65535u;
+                        r1 = fy1 < 65533.f ? (uint32_t)fy1 + 2u : 65535u;
+                    }
+                }
+            }
+            if (granted) /* warp-uniform */
+            {
+                r0 = __reduce_min_sync(0xffffffffu, r0);
+                r1 = __reduce_max_sync(0xffffffffu, r1);
+            }
             if (lane == 0)
             {
-                const unsigned long long o = atomicAdd(&P.counters->recAlloc, (unsigned long long)total);
-                if (o + total > (unsigned long long)P.recOverflowCapacity)
-                {
-                    atomicOr(&P.counters->abortBatch, SL_ABORT_RECORDS); /* the host runs the batch again with a larger overflow area */
-                    base = 0u;
-                    granted = 0u;
-                }
-                else base = P.recOverflowBase + (uint32_t)o;
+                binned += granted;
+                const SLSegment sg{base, granted, r0 | (r1 << 16)};
+                const int s = (int)it * (SL_VB_THREADS / 32) + warp;
+                if (world > 1) { for (int t = 0; t < world; ++t) P.out[t].blockInfo[vb].seg[s] = sg; }
+                else P.out[0].blockInfo[vb].seg[s] = sg;
             }
-            base = __shfl_sync(0xffffffffu, base, 0);
-            granted = __shfl_sync(0xffffffffu, granted, 0);
-        }
-        if (lane == 0)
-        {
-            binned += granted;
-            P.blockInfo[blockIdx.x].seg[round * (SL_VB_THREADS / 32) + warp] = SLSegment{base, granted};
-        }
-        if (granted) /* warp-uniform */
-        {
-            /* rows the records of this warp touch (conservative: vertex rows, one more for spans that run past the row end) */
-            float fy0 = 3.0e38f, fy1 = -1.f;
-            if (n)
+            if (needClip) sSlot[p] = (n != 0 && granted != 0) ? base + (incl - (uint32_t)n) : 0xffffffffu; /* written in pass 3 */
+            /* (Staging a warp's records in shared memory and storing them as one contiguous stream was measured: slower on
+             * every config -- the kernel is bound by its index/vertex fetch latency, not by the record stores.) */
+            else if (n != 0 && granted != 0)
             {
-                if (CACHE && fromCache)
+                const uint32_t slot = base + (incl - (uint32_t)n);
+                const int numOut = world > 1 ? world : 1;
+                if constexpr (CACHE)
                 {
-                    const float a = cache[CV + ci[0]].y, b = cache[CV + ci[1]].y, cc = cache[CV + ci[2]].y;
-                    fy0 = fminf(a, fminf(b, cc));
-                    fy1 = fmaxf(a, fmaxf(b, cc));
-                }
-                else if (!polyVerts)
-                {
-                    fy0 = fminf(v[0].vert.v[1], fminf(v[1].vert.v[1], v[2].vert.v[1]));
-                    fy1 = fmaxf(v[0].vert.v[1], fmaxf(v[1].vert.v[1], v[2].vert.v[1]));
+                    const float4 s0 = cache[CV + ci[0]], s1 = cache[CV + ci[1]], s2 = cache[CV + ci[2]];
+                    const uint32_t mask = world > 1 ? sl_rank_mask(s0.y, s1.y, s2.y, P.partStrip, world) : 1u;
+                    for (int t = 0; t < numOut; ++t)
+                    {
+                        const bool to = (mask >> t) & 1u;
+                        P.out[t].recDraw[slot] = to ? (uint16_t)drawIdx : SL_REC_ABSENT;
+                        if (!to) continue;
+                        float4* rec = P.out[t].records + (size_t)slot * recStride;
+                        rec[0] = s0;
+                        rec[1] = s1;
+                        rec[2] = s2;
+#pragma unroll
+                        for (int s = 0; s < 4; ++s)
+                        {
+                            if (s < NV)
+                            {
+                                rec[3 + 3 * s + 0] = cache[(2 + s) * CV + ci[0]];
+                                rec[3 + 3 * s + 1] = cache[(2 + s) * CV + ci[1]];
+                                rec[3 + 3 * s + 2] = cache[(2 + s) * CV + ci[2]];
+                            }
+                        }
+                    }
                 }
                 else
                 {
-                    for (int k = 0; k < polyVerts; ++k) { fy0 = fminf(fy0, poly.verts[k].v[1]); fy1 = fmaxf(fy1, poly.verts[k].v[1]); }
-                }
-            }
-            for (int d = 16; d > 0; d >>= 1)
-            {
-                fy0 = fminf(fy0, __shfl_xor_sync(0xffffffffu, fy0, d));
-                fy1 = fmaxf(fy1, __shfl_xor_sync(0xffffffffu, fy1, d));
-            }
-            if (lane == 0 && fy1 >= 0.f)
-            {
-                /* screen y is a non-negative integer stored as a float (sl_to_screen); NaN rows produce no spans */
-                const uint32_t r0 = fy0 < 65535.f ? (uint32_t)fy0 : 65535u;
-                const uint32_t r1 = fy1 < 65535.f ? (uint32_t)fy1 + 2u : 65535u;
-                atomicMax(&P.blockInfo[blockIdx.x].negYMin, ~r0);
-                atomicMax(&P.blockInfo[blockIdx.x].yMax, r1);
-            }
-        }
-        /* (Staging a warp's records in shared memory and storing them as one contiguous stream was measured: slower on
-         * every config -- the kernel is bound by its barriers and index/vertex fetch latency, not by the record stores.) */
-        const bool emit = n != 0 && granted != 0;
-        if (emit)
-        {
-            uint32_t slot = base + warpOff + (incl - (uint32_t)n);
-            if (CACHE && fromCache)
-            {
-                P.recDraw[slot] = (uint16_t)drawIdx;
-                float4* rec = P.records + (size_t)slot * recStride;
-                rec[0] = cache[CV + ci[0]];
-                rec[1] = cache[CV + ci[1]];
-                rec[2] = cache[CV + ci[2]];
-#pragma unroll
-                for (int s = 0; s < 4; ++s)
-                {
-                    if (s < NV)
+                    const uint32_t mask = world > 1 ? sl_rank_mask(v[0].vert.v[1], v[1].vert.v[1], v[2].vert.v[1], P.partStrip, world) : 1u;
+                    for (int t = 0; t < numOut; ++t)
                     {
-                        rec[3 + 3 * s + 0] = cache[(2 + s) * CV + ci[0]];
-                        rec[3 + 3 * s + 1] = cache[(2 + s) * CV + ci[1]];
-                        rec[3 + 3 * s + 2] = cache[(2 + s) * CV + ci[2]];
+                        const bool to = (mask >> t) & 1u;
+                        P.out[t].recDraw[slot] = to ? (uint16_t)drawIdx : SL_REC_ABSENT;
+                        if (to) sl_write_record(P.out[t].records + (size_t)slot * recStride, NV, v[0].vert, v[1].vert, v[2].vert, v[0].varyings, v[1].varyings, v[2].varyings);
                     }
                 }
             }
-            else if (!polyVerts)
-            {
-                P.recDraw[slot] = (uint16_t)drawIdx;
-                sl_write_record(P.records + (size_t)slot * recStride, NV, v[0].vert, v[1].vert, v[2].vert, v[0].varyings, v[1].varyings, v[2].varyings);
-            }
-            else
-            {
-                for (int f = polyVerts - 2; f-- > 0;) /* reverse fan order (:505-518) */
-                {
-                    const int j = f + 1, k = f + 2;
-                    if (sl_prim_hidden(poly.verts[0], poly.verts[j], poly.verts[k])) continue;
-                    P.recDraw[slot] = (uint16_t)drawIdx;
-                    sl_write_record(P.records + (size_t)slot * recStride, NV, poly.verts[0], poly.verts[j], poly.verts[k],
-                                    &poly.varys[0], &poly.varys[j * 4], &poly.varys[k * 4]);
-                    ++slot;
-                }
-            }
+        }
+        __syncthreads(); /* pass 0 -> 1: the queue is complete; 1 -> 2: the counts; 2 -> 3: the slots */
+        if (pass == 0)
+        {
+            clipCount = sClipCount;
+            if (!clipCount) break; /* block-uniform */
         }
     }
     if (lane == 0 && binned) atomicAdd(&P.counters->trisBinned, (unsigned long long)binned);
@@ -703,6 +844,7 @@ struct SLScanline
 struct SLSpanParams
 {
     const float4* records;
+    const uint16_t* recPresent;  /* shared vertex stage: recDraw, SL_REC_ABSENT = the record was not routed to this rank (null: all present) */
     const SLBlockInfo* blockInfo;
     unsigned int firstBlock;     /* first vertex block of the batch          */
     unsigned int numRows;        /* rows incl. the texture's padding rows    */
@@ -792,19 +934,34 @@ SLD_FN int sl_owned_kth(int a, int k, int strip, int world, int rank)
     return (j / strip) * (strip * world) + rank * strip + (j % strip);
 }
 
+/* Rows a vertex block's records can have span entries in: the union of its segments' (one warp per block). */
+__global__ void __launch_bounds__(256) k_block_rows(const SLBlockInfo* blockInfo, unsigned numBlocks, uint32_t* blockRows)
+{
+    const unsigned vb = blockIdx.x * 8u + (threadIdx.x >> 5);
+    if (vb >= numBlocks) return;
+    const uint32_t rows = blockInfo[vb].seg[threadIdx.x & 31].rows;
+    uint32_t lo = rows & 0xffffu, hi = rows >> 16;
+    for (int d = 16; d > 0; d >>= 1)
+    {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+    }
+    if ((threadIdx.x & 31) == 0) blockRows[vb] = lo | (hi << 16);
+}
+
 /* Work items of k_span: one per (vertex block, band of SL_SPAN_WIN rows the block's records touch).  A block of large
  * triangles covers a thousand rows and would keep one CTA busy long after the rest of the grid has drained; cut into bands
  * it is shared by several.  Bands of one block are independent: an entry's place in its row list depends on the block's
  * earlier records in that ROW only. */
-__global__ void __launch_bounds__(1024) k_span_items(const SLBlockInfo* blockInfo, unsigned numBlocks, unsigned numRows, uint32_t* items, uint32_t* numItems)
+__global__ void __launch_bounds__(1024) k_span_items(const uint32_t* blockRows, unsigned numBlocks, unsigned numRows, uint32_t* items, uint32_t* numItems)
 {
     __shared__ uint32_t sWarp[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned per = (numBlocks + 1023u) / 1024u;
     const unsigned a = (unsigned)tid * per, b = min(a + per, numBlocks);
     auto bands = [&](unsigned vb, uint32_t& first) -> uint32_t {
-        const uint32_t y0 = ~blockInfo[vb].negYMin;
-        uint32_t y1 = blockInfo[vb].yMax;
+        const uint32_t y0 = blockRows[vb] & 0xffffu;
+        uint32_t y1 = blockRows[vb] >> 16;
         if (y1 > numRows) y1 = numRows;
         if (!(y0 < y1)) { first = 0u; return 0u; }
         first = y0 >> SL_SPAN_BAND_SHIFT;
@@ -925,7 +1082,7 @@ __global__ void __launch_bounds__(256) k_span(const __grid_constant__ SLSpanPara
             }
             int y0 = 0, y1 = 0, yEnd = 0;
             bool mayOver = false;
-            if (valid)
+            if (valid && !(P.recPresent && P.recPresent[myRec] == SL_REC_ABSENT)) /* an absent record has no entry in any of this rank's rows */
             {
                 const float4* r = P.records + (size_t)myRec * P.recStride;
                 const float4 p0 = r[0], p1 = r[1], p2 = r[2];
@@ -1241,6 +1398,54 @@ __global__ void __launch_bounds__(1024) k_row_order(const uint32_t* rowStart, un
         else rowPerm[numHeavy + (y - hPos)] = y; /* light rows keep their order behind the heavy ones */
     }
     if (tid == 0) rowPerm[numRows] = numHeavy; /* k_resolve2 gives these rows fine segments */
+}
+
+/* Shared vertex stage: the rendezvous between k_vertex and everything that reads the records.  One thread per rank:
+ * thread t tells rank t that this rank's blocks of batch `epoch` have landed in its arena (k_vertex's peer stores
+ * completed with that kernel; the release store orders the count word before it), then waits for rank t's word to show
+ * up here.  Words alternate with the epoch's parity: a rank can be one batch ahead of another, never two (it cannot
+ * pass the next rendezvous without the slower rank's word).  Bit 31 of a word: that rank's record area overflowed.
+ * The record counts of the other ranks' blocks join this rank's statistic.  `words`: [2][SL_MAX_RANKS] epoch words, then
+ * [2][SL_MAX_RANKS] 64-bit counts, at the head of every rank's shared allocation. */
+struct SLGeomSync
+{
+    unsigned char* head[SL_MAX_RANKS]; /* rank t's shared allocation (peer mapping) */
+    int rank, world;
+    uint32_t epoch;                    /* 1, 2, ...: < 2^31 */
+    SLCounters* counters;
+    long long timeoutClocks;
+};
+constexpr size_t SL_GEOM_HEAD_BYTES = 256;
+__global__ void k_geom_barrier(const __grid_constant__ SLGeomSync P)
+{
+    const int t = (int)threadIdx.x;
+    if (t >= P.world) return;
+    const unsigned par = P.epoch & 1u;
+    uint32_t* theirWords = reinterpret_cast<uint32_t*>(P.head[t]);
+    unsigned long long* theirCounts = reinterpret_cast<unsigned long long*>(P.head[t] + 2 * SL_MAX_RANKS * sizeof(uint32_t));
+    const uint32_t* myWords = reinterpret_cast<const uint32_t*>(P.head[P.rank]);
+    const unsigned long long* myCounts = reinterpret_cast<const unsigned long long*>(P.head[P.rank] + 2 * SL_MAX_RANKS * sizeof(uint32_t));
+    const uint32_t word = P.epoch | ((P.counters->abortBatch & SL_ABORT_RECORDS) ? 0x80000000u : 0u);
+    theirCounts[par * SL_MAX_RANKS + P.rank] = P.counters->trisBinned;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirWords + par * SL_MAX_RANKS + P.rank), "r"(word) : "memory");
+    const uint32_t* src = myWords + par * SL_MAX_RANKS + t;
+    const long long t0 = clock64();
+    uint32_t got = 0u;
+    for (;;)
+    {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(got) : "l"(src) : "memory");
+        if ((got & 0x7fffffffu) == P.epoch) break;
+        if (clock64() - t0 > P.timeoutClocks)
+        {
+            atomicOr(&P.counters->errorFlags, SL_ERR_GEOM_TIMEOUT);
+            atomicOr(&P.counters->abortBatch, SL_ABORT_GEOMETRY);
+            return;
+        }
+        __nanosleep(200);
+    }
+    if (got & 0x80000000u) atomicOr(&P.counters->abortBatch, SL_ABORT_GEOMETRY);
+    if (t != P.rank) atomicAdd(&P.counters->trisBinned, myCounts[par * SL_MAX_RANKS + t]);
 }
 
 /* end of a batch: its statistics join the totals unless it has to be run again */

@@ -35,7 +35,7 @@ using namespace sld;
  * as a template argument (direct, inlinable calls -- never interpreted).
  * =========================================================================*/
 typedef cudaError_t (*VertexLauncher)(unsigned grid, cudaStream_t s, const SLVertexParams& p, bool cache);
-static const unsigned kVertexCacheMaxBytes = 6u * SL_VCACHE_VERTS * (unsigned)sizeof(float4) + SL_VCACHE_VERTS; /* clip + screen position, 4 varyings, flags */
+static const unsigned kVertexCacheMaxBytes = 3u * SL_VB_PRIMS * (unsigned)sizeof(uint16_t) + 6u * SL_VCACHE_VERTS * (unsigned)sizeof(float4) + SL_VCACHE_VERTS / 8u + SL_VCACHE_VERTS; /* indices, clip + screen position, 4 varyings, used bits, flags */
 typedef cudaError_t (*RasterLauncher)(unsigned grid, cudaStream_t s, const SLShadeParams& p);
 
 typedef cudaError_t (*PointVertexLauncher)(unsigned grid, cudaStream_t s, const SLPointParams& p);
@@ -177,7 +177,7 @@ struct HostTexture
     std::vector<unsigned char> shadow; /* only for textures written with set_texels */
 };
 
-struct HostIbo { int type = 0; uint32_t count = 0; DevBuffer buf; };
+struct HostIbo { int type = 0; uint32_t count = 0; unsigned long long maxIndex = 0; /* largest index in the buffer (host scan at init): decides the post-transform cache */ DevBuffer buf; };
 struct HostVao { SL_VertexArray vao; int numBindings = 0; size_t vbo = (size_t)-1, ibo = (size_t)-1; };
 /* SL_TextureView as SL_Framebuffer keeps it: a snapshot taken when the attachment is made (src/SL_Framebuffer.cpp:855-920);
  * valid() judges these snapshots, the draw path addresses the texture itself */
@@ -194,21 +194,26 @@ struct RtFsEntry { std::string name; RtFragmentKernels k; };
 struct UboFixup { size_t ubo, offset; int kind; size_t id, byteOffset; };
 struct HostUbo { unsigned char bytes[1024]; };
 
+/* A grow-only device buffer of the pipeline.  Stream-ordered allocation on the context's stream: growing one in the middle
+ * of a frame neither waits for the device to drain nor stalls other contexts on the same GPU (cudaFree does both -- with
+ * several contexts sharing the vertex stage that is a deadlock: one waits on the device for a peer whose host sits in cudaFree). */
 struct Scratch
 {
     DevBuffer buf;
+    cudaStream_t stream = nullptr;
     cudaError_t ensure(size_t bytes)
     {
         if (bytes <= buf.bytes) return cudaSuccess;
-        if (buf.ptr) cudaFree(buf.ptr);
+        if (buf.ptr) cudaFreeAsync(buf.ptr, stream);
         buf.ptr = nullptr;
         buf.bytes = 0;
         const size_t want = bytes + bytes / 4 + 4096;
-        cudaError_t e = cudaMalloc(&buf.ptr, want);
-        if (e == cudaSuccess) buf.bytes = want;
+        void* p = nullptr;
+        cudaError_t e = cudaMallocAsync(&p, want, stream);
+        if (e == cudaSuccess) { buf.ptr = (unsigned char*)p; buf.bytes = want; }
         return e;
     }
-    void release() { if (buf.ptr) cudaFree(buf.ptr); buf.ptr = nullptr; buf.bytes = 0; }
+    void release() { if (buf.ptr) cudaFreeAsync(buf.ptr, stream); buf.ptr = nullptr; buf.bytes = 0; }
 };
 
 struct Batch
@@ -221,7 +226,9 @@ struct Batch
     unsigned long long maxVerts = 0; /* vertices of the largest vertex buffer of the batch (binding 0) */
     bool wire = false;               /* RENDER_MODE_TRI_WIRE / INDEXED_TRI_WIRE: edges only (sl_wire.cuh) */
     bool partFull = false;           /* sort-first: the fast path was refused, count every row (enqueue_batch) */
-    void clear() { descs.clear(); blockDraw.clear(); numBlocks = 0; totalPrims = 0; maxVerts = 0; wire = false; partFull = false; }
+    unsigned long long maxIndex = 0; /* largest vertex index any draw of the batch can fetch (~0: a draw without index buffer) */
+    bool geomLocal = false;          /* shared vertex stage: this attempt runs every block here (after a refusal) */
+    void clear() { descs.clear(); blockDraw.clear(); numBlocks = 0; totalPrims = 0; maxVerts = 0; wire = false; partFull = false; maxIndex = 0; geomLocal = false; }
 };
 
 struct slcu_context
@@ -256,6 +263,7 @@ struct slcu_context
     Scratch wireSlots, wireRecInfo; /* wireframe: sort values (double buffer); first slot + candidate count per record */
     Scratch pointKeys, pointRecs, pointSortTemp; /* point primitives: sort keys (double buffer), records, radix-sort scratch */
     Scratch spanItems;   /* (vertex block, row band) work items of k_span */
+    Scratch blockRows;   /* rows each vertex block's records touch (k_block_rows) */
     Scratch rowPerm;     /* rows by weight, heaviest first (k_row_order) */
     Scratch ticketOrder; /* skewed work order of k_resolve, cached per (rows, segments, skew) */
     unsigned orderRows = 0, orderSegs = 0, orderSkew = 0;
@@ -271,6 +279,22 @@ struct slcu_context
     unsigned partRank = 0, partWorld = 1, partStripRows = 8;
     struct PeerMap { size_t tex; unsigned rank; void* ptr; };
     std::vector<PeerMap> peerMaps;
+    /* shared vertex stage (slcu_geometry_share_*): one allocation per rank = head (rendezvous words) + two arenas that
+     * alternate from batch to batch; peer[t] = rank t's allocation as mapped here (own pointer for t == rank) */
+    struct GeomShare
+    {
+        unsigned char* base = nullptr;
+        size_t arenaBytes = 0;
+        unsigned char* peer[SL_MAX_RANKS] = {};
+        bool ipcMapped[SL_MAX_RANKS] = {};
+        uint32_t epoch = 0;
+        bool ready(unsigned world) const
+        {
+            if (!base || world < 2 || world > (unsigned)SL_MAX_RANKS) return false;
+            for (unsigned t = 0; t < world; ++t) if (!peer[t]) return false;
+            return true;
+        }
+    } geom;
     /* optional per-kernel event timing (profile_begin / profile_end) */
     cudaEvent_t timerA = nullptr, timerB = nullptr;
     bool profiling = false;
@@ -321,6 +345,20 @@ static uint32_t g_activeRcpCopy[64][2048];
     } while (0)
 
 static int flush_draws(slcu_context* c);
+static void geom_release(slcu_context* c)
+{
+    for (int t = 0; t < SL_MAX_RANKS; ++t)
+    {
+        if (c->geom.peer[t] && c->geom.ipcMapped[t]) cudaIpcCloseMemHandle(c->geom.peer[t]);
+        c->geom.peer[t] = nullptr;
+        c->geom.ipcMapped[t] = false;
+    }
+    if (c->geom.base) cudaFree(c->geom.base);
+    c->geom.base = nullptr;
+    c->geom.arenaBytes = 0;
+    c->geom.epoch = 0;
+}
+
 static int ensure_rcp_table(slcu_context* c)
 {
     if (!c->rcpValid) { c->err = "no rcp table"; return SLCU_ERR_ARG; }
@@ -505,7 +543,9 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
         /* the reference loop is `for (i = begin; i < end; i += 3)` (src/SL_TriProcessor.cpp:574) */
         const unsigned long long primsPerInstance = (m.elementEnd - m.elementBegin + 2) / 3;
         const unsigned long long prims = primsPerInstance * (numInstances == 1 ? 1 : numInstances);
-        const unsigned long long blocks64 = (prims + SL_VB_PRIMS - 1) / SL_VB_PRIMS;
+        /* a vertex block holds primitives of one instance only (k_vertex) */
+        const unsigned long long blocksPerInstance = (primsPerInstance + SL_VB_PRIMS - 1) / SL_VB_PRIMS;
+        const unsigned long long blocks64 = blocksPerInstance * (numInstances == 1 ? 1 : numInstances);
         c->stats.trisSubmitted += prims;
         if (!blocks64) continue;
         if (blocks64 > 0x3fffffull) { c->err = "draw too large for one batch"; return SLCU_ERR_UNSUPPORTED; }
@@ -535,7 +575,11 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
         d.primsPerInstance = primsPerInstance;
         d.numPrims = prims;
         d.firstBlock = B.numBlocks;
-        d.pad_ = 0;
+        d.blocksPerInstance = (unsigned)blocksPerInstance;
+        {
+            const unsigned long long mi = usingIndices ? c->ibos[vao.ibo].maxIndex : ~0ull;
+            if (mi > B.maxIndex) B.maxIndex = mi;
+        }
         {
             const ptrdiff_t stride = vao.vao.mBindings[0].stride;
             const unsigned long long nv = stride > 0 ? (unsigned long long)(c->vbos[vao.vbo].bytes / (size_t)stride) : ~0ull;
@@ -704,6 +748,7 @@ static int run_batch(slcu_context* c, Batch& B)
         CK(cudaEventSynchronize(c->batchDone));
         if (!batch_was_refused(c)) return 0;
         if (c->refusedPartition) { B.partFull = true; c->refusedPartition = false; }
+        B.geomLocal = true; /* shared vertex stage: the other ranks have moved on; this one repeats the batch by itself */
     }
     c->err = "batch does not fit its buffers after repeated growth";
     return SLCU_ERR_OOM;
@@ -755,44 +800,108 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
     unsigned long long recOverflow = totalPrims / 8 + 4096;
     if (c->caps.recOverflow > recOverflow) recOverflow = c->caps.recOverflow;
     unsigned long long recCapacity = recFixed + recOverflow;
-    static const bool useVertexCache = getenv("SLCU_VERTEX_CACHE") != nullptr && atoi(getenv("SLCU_VERTEX_CACHE")) != 0; /* opt-in: measured slower on C3, +3 % on C2 */
+    /* post-transform cache: batches whose index buffers address few enough vertices for one block's shared memory (small
+     * instanced meshes).  SLCU_VERTEX_CACHE=0 turns it off. */
+    static const bool allowVertexCache = !(getenv("SLCU_VERTEX_CACHE") && atoi(getenv("SLCU_VERTEX_CACHE")) == 0);
     const uint8_t* rowNeeded = nullptr;
     unsigned numSubLists = (segWidth + (1u << SL_SHADE_SHIFT) - 1u) >> SL_SHADE_SHIFT;
     if (numSubLists > (unsigned)SL_MAX_SUBLISTS) { c->err = "segment too wide for the sub-list table"; return SLCU_ERR_ARG; }
     const unsigned long long numLists = (unsigned long long)H * rasterSegs * numSubLists;
     unsigned long long chunkCap = 0, handoffSlots = 0;
+    /* Shared vertex stage (k_vertex): every rank runs 1/world of the blocks and routes the records.  The decision is the same
+     * on every rank (same calls, same arena size): the first attempt of a triangle batch that fits the arena.  A refusal
+     * of any kind makes the rank run the batch again by itself, all blocks, into its own buffers. */
+    static const bool allowGeomShare = !(getenv("SLCU_GEOM_SHARE") && atoi(getenv("SLCU_GEOM_SHARE")) == 0);
+    const unsigned world = c->partWorld;
+    bool sharded = false;
+    size_t arenaRecDraw = 0, arenaBlockInfo = 0;
+    if (allowGeomShare && !B.wire && c->geom.ready(world))
+    {
+        const unsigned long long slice = (totalPrims / 8 + 4096) / world + 1024;
+        const unsigned long long cap = recFixed + slice * world;
+        auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+        arenaRecDraw = up((size_t)cap * recStride * sizeof(float4));
+        arenaBlockInfo = arenaRecDraw + up((size_t)cap * sizeof(uint16_t));
+        const size_t need = arenaBlockInfo + up((size_t)numBlocks * sizeof(SLBlockInfo));
+        if (cap <= 0x7ffffff0ull && need <= c->geom.arenaBytes)
+        {
+            if (!B.geomLocal)
+            {
+                sharded = true;
+                recOverflow = slice;
+                recCapacity = cap;
+            }
+        }
+    }
+    float4* recordsPtr = nullptr;
+    uint16_t* recDrawPtr = nullptr;
+    SLBlockInfo* blockInfoPtr = nullptr;
     for (int attempt = 0;; ++attempt)
     {
         if (recCapacity > 0x7ffffff0ull) { c->err = "batch too large"; return SLCU_ERR_UNSUPPORTED; }
-        CK(c->records.ensure((size_t)recCapacity * recStride * sizeof(float4)));
-        CK(c->recDraw.ensure((size_t)recCapacity * sizeof(uint16_t)));
-        CK(c->blockInfo.ensure((size_t)numBlocks * sizeof(SLBlockInfo)));
-        CK(cudaMemsetAsync(c->blockInfo.buf.ptr, 0, (size_t)numBlocks * sizeof(SLBlockInfo), c->stream)); /* row ranges start empty */
         CK(cudaMemsetAsync(c->counters, 0, SL_COUNTERS_BATCH_BYTES, c->stream)); /* the per-batch part */
-
         {
             SLVertexParams vp;
+            memset(&vp, 0, sizeof(vp));
             vp.draws = reinterpret_cast<const SLDrawDesc*>(c->drawTable.buf.ptr);
             vp.blockDraw = reinterpret_cast<const uint32_t*>(c->blockDraw.buf.ptr);
-            vp.recDraw = reinterpret_cast<uint16_t*>(c->recDraw.buf.ptr);
             vp.cullMode = sh.cullMode;
             vp.numVaryings = NV;
-            bool cache = useVertexCache;
-            for (const SLDrawDesc& d : B.descs) cache = cache && d.usingIndices;
-            /* the cache holds the vertices a block of 1024 primitives can reference: at most SL_VCACHE_VERTS, and no more
-             * than the vertex buffer has (small instanced meshes: more blocks per SM) */
-            unsigned long long cv = B.maxVerts < (unsigned long long)SL_VCACHE_VERTS ? B.maxVerts : (unsigned long long)SL_VCACHE_VERTS;
-            cv = (cv + 31ull) & ~31ull;
-            if (cv < 32ull) cv = 32ull;
+            /* the cache holds every vertex the batch's index buffers can name */
+            const bool cache = allowVertexCache && B.maxIndex < (unsigned long long)SL_VCACHE_VERTS;
+            unsigned long long cv = cache ? ((B.maxIndex + 32ull) & ~31ull) : 32ull;
             vp.cacheVerts = (unsigned)cv;
-            vp.cacheBytes = cache ? (unsigned)((2 + NV) * cv * sizeof(float4) + cv) : 0u;
-            vp.recCapacity = (unsigned)recCapacity;
-            vp.recOverflowBase = (unsigned)recFixed;
+            vp.cacheBytes = cache ? (unsigned)(3u * SL_VB_PRIMS * sizeof(uint16_t) + (2 + NV) * cv * sizeof(float4) + cv / 8 + cv) : 0u;
             vp.recOverflowCapacity = (unsigned)recOverflow;
-            vp.records = reinterpret_cast<float4*>(c->records.buf.ptr);
-            vp.blockInfo = reinterpret_cast<SLBlockInfo*>(c->blockInfo.buf.ptr);
             vp.counters = c->counters;
-            { KernelScope ks(c, SLCU_K_VERTEX); CK(launch_vertex_stage(sh, numBlocks, c->stream, vp, cache)); }
+            vp.partStrip = (int)c->partStripRows;
+            unsigned grid = numBlocks;
+            if (sharded)
+            {
+                const uint32_t epoch = ++c->geom.epoch;
+                const size_t arenaOff = SL_GEOM_HEAD_BYTES + (size_t)(epoch & 1u) * c->geom.arenaBytes;
+                vp.shardRank = (int)c->partRank;
+                vp.shardWorld = (int)world;
+                vp.recOverflowBase = (unsigned)(recFixed + (unsigned long long)c->partRank * recOverflow);
+                for (unsigned t = 0; t < world; ++t)
+                {
+                    unsigned char* a = c->geom.peer[t] + arenaOff;
+                    vp.out[t].records = reinterpret_cast<float4*>(a);
+                    vp.out[t].recDraw = reinterpret_cast<uint16_t*>(a + arenaRecDraw);
+                    vp.out[t].blockInfo = reinterpret_cast<SLBlockInfo*>(a + arenaBlockInfo);
+                }
+                recordsPtr = vp.out[c->partRank].records;
+                recDrawPtr = vp.out[c->partRank].recDraw;
+                blockInfoPtr = vp.out[c->partRank].blockInfo;
+                grid = numBlocks > c->partRank ? (numBlocks - c->partRank + world - 1) / world : 0u;
+                if (grid) { KernelScope ks(c, SLCU_K_VERTEX); CK(launch_vertex_stage(sh, grid, c->stream, vp, cache)); }
+                SLGeomSync gs;
+                memset(&gs, 0, sizeof(gs));
+                for (unsigned t = 0; t < world; ++t) gs.head[t] = c->geom.peer[t];
+                gs.rank = (int)c->partRank;
+                gs.world = (int)world;
+                gs.epoch = epoch;
+                gs.counters = c->counters;
+                gs.timeoutClocks = 20000000000ll; /* ~10 s: a rank that never arrives is an error, not a hang */
+                { KernelScope ks(c, SLCU_K_VERTEX); k_geom_barrier<<<1, 32, 0, c->stream>>>(gs); }
+                CK(cudaGetLastError());
+            }
+            else
+            {
+                CK(c->records.ensure((size_t)recCapacity * recStride * sizeof(float4)));
+                CK(c->recDraw.ensure((size_t)recCapacity * sizeof(uint16_t)));
+                CK(c->blockInfo.ensure((size_t)numBlocks * sizeof(SLBlockInfo)));
+                recordsPtr = reinterpret_cast<float4*>(c->records.buf.ptr);
+                recDrawPtr = reinterpret_cast<uint16_t*>(c->recDraw.buf.ptr);
+                blockInfoPtr = reinterpret_cast<SLBlockInfo*>(c->blockInfo.buf.ptr);
+                vp.shardRank = 0;
+                vp.shardWorld = 1;
+                vp.recOverflowBase = (unsigned)recFixed;
+                vp.out[0].records = recordsPtr;
+                vp.out[0].recDraw = recDrawPtr;
+                vp.out[0].blockInfo = blockInfoPtr;
+                { KernelScope ks(c, SLCU_K_VERTEX); CK(launch_vertex_stage(sh, grid, c->stream, vp, cache)); }
+            }
         }
 
         if (B.wire)
@@ -800,8 +909,8 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
             /* ---- wireframe: edge fragments are counted, emitted with an order key, sorted and shaded (sl_wire.cuh) ---- */
             SLWireParams wp;
             memset(&wp, 0, sizeof(wp));
-            wp.records = reinterpret_cast<const float4*>(c->records.buf.ptr);
-            wp.blockInfo = reinterpret_cast<const SLBlockInfo*>(c->blockInfo.buf.ptr);
+            wp.records = recordsPtr;
+            wp.blockInfo = blockInfoPtr;
             wp.numBlocks = numBlocks;
             wp.recStride = recStride;
             wp.width = depthTex.w;
@@ -859,7 +968,7 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
 
             SLWireShadeParams ws;
             ws.draws = reinterpret_cast<const SLDrawDesc*>(c->drawTable.buf.ptr);
-            ws.recDraw = reinterpret_cast<const uint16_t*>(c->recDraw.buf.ptr);
+            ws.recDraw = recDrawPtr;
             ws.records = wp.records;
             ws.recStride = recStride;
             ws.lowBits = wp.lowBits;
@@ -948,8 +1057,9 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
         CK(c->rowStart.ensure((size_t)(H + 1) * sizeof(uint32_t)));
 
         SLSpanParams sp;
-        sp.records = reinterpret_cast<const float4*>(c->records.buf.ptr);
-        sp.blockInfo = reinterpret_cast<const SLBlockInfo*>(c->blockInfo.buf.ptr);
+        sp.records = recordsPtr;
+        sp.recPresent = sharded ? recDrawPtr : nullptr;
+        sp.blockInfo = blockInfoPtr;
         sp.firstBlock = 0;
         sp.numRows = H;
         sp.rowPitch = rowPitch;
@@ -994,7 +1104,9 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
         CK(cudaMemsetAsync(c->cnt.buf.ptr, 0, (size_t)numBlocks * rowPitch * sizeof(uint16_t), c->stream)); /* k_span<0> writes the rows of its items only */
         sp.items = reinterpret_cast<const uint32_t*>(c->spanItems.buf.ptr);
         sp.numItems = &c->counters->spanItems;
-        { KernelScope ks(c, SLCU_K_SCAN); k_span_items<<<1, 1024, 0, c->stream>>>(sp.blockInfo, numBlocks, H, reinterpret_cast<uint32_t*>(c->spanItems.buf.ptr), &c->counters->spanItems); }
+        CK(c->blockRows.ensure((size_t)numBlocks * sizeof(uint32_t)));
+        { KernelScope ks(c, SLCU_K_SCAN); k_block_rows<<<(numBlocks + 7u) / 8u, 256, 0, c->stream>>>(sp.blockInfo, numBlocks, reinterpret_cast<uint32_t*>(c->blockRows.buf.ptr)); }
+        { KernelScope ks(c, SLCU_K_SCAN); k_span_items<<<1, 1024, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(c->blockRows.buf.ptr), numBlocks, H, reinterpret_cast<uint32_t*>(c->spanItems.buf.ptr), &c->counters->spanItems); }
         CK(cudaGetLastError());
         int spanSMs = 148;
         cudaDeviceGetAttribute(&spanSMs, cudaDevAttrMultiProcessorCount, c->device);
@@ -1066,7 +1178,7 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
     lists.chunkCapacity = (unsigned)chunkCap;
 
     SLRasterParams rp;
-    rp.records = reinterpret_cast<const float4*>(c->records.buf.ptr);
+    rp.records = recordsPtr;
     rp.entries = reinterpret_cast<const SLSpanEntry*>(c->entries.buf.ptr);
     rp.rowStart = reinterpret_cast<const uint32_t*>(c->rowStart.buf.ptr);
     rp.recStride = recStride;
@@ -1200,8 +1312,8 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
 
     SLShadeParams shp;
     shp.draws = reinterpret_cast<const SLDrawDesc*>(c->drawTable.buf.ptr);
-    shp.recDraw = reinterpret_cast<const uint16_t*>(c->recDraw.buf.ptr);
-    shp.records = reinterpret_cast<const float4*>(c->records.buf.ptr);
+    shp.recDraw = recDrawPtr;
+    shp.records = recordsPtr;
     shp.recStride = recStride;
     shp.numVaryings = NV;
     shp.numOutputs = sh.numOutputs;
@@ -1294,6 +1406,13 @@ static int clear_texture(slcu_context* c, const HostTexture& t, const unsigned c
 
 /* Device error flags (SL_ERR_*) seen by a read-back of the counters: turned into a return code and a decoded message,
  * then cleared on the device so that each occurrence is reported once. */
+static std::vector<Scratch*> all_scratch(slcu_context* c)
+{
+    return {&c->records, &c->blockInfo, &c->cnt, &c->off, &c->segSums, &c->rowTotals, &c->rowStart, &c->entries, &c->handoff, &c->rowFlags, &c->rowNeeded,
+            &c->drawTable, &c->blockDraw, &c->recDraw, &c->fragPool, &c->chunkNext, &c->listInfo, &c->handoffRegs, &c->ticketOrder, &c->spanItems,
+            &c->blockRows, &c->rowPerm, &c->pointKeys, &c->pointRecs, &c->pointSortTemp, &c->wireSlots, &c->wireRecInfo, &c->wireLeaders};
+}
+
 static int report_device_flags(slcu_context* c, unsigned flags)
 {
     if (!flags) return 0;
@@ -1306,6 +1425,7 @@ static int report_device_flags(slcu_context* c, unsigned flags)
     if (flags & SL_ERR_POOL) m += " [fragment pool exhausted: fragments dropped]";
     if (flags & SL_ERR_WIRE_SEGMENT) m += " [wireframe: record segment over 256]";
     if (flags & SL_ERR_WIRE_SLOTS) m += " [wireframe: candidate slots exhausted]";
+    if (flags & SL_ERR_GEOM_TIMEOUT) m += " [shared vertex stage: a rank never delivered its vertex blocks]";
     c->err = m;
     cudaMemsetAsync(&c->counters->errorFlags, 0, sizeof(unsigned), c->stream);
     if (flags & (SL_ERR_POOL | SL_ERR_WIRE_SLOTS)) return SLCU_ERR_OOM;
@@ -1330,6 +1450,7 @@ int slcu_context_create(slcu_context** out, int device)
     if (cudaMalloc(&c->counters, sizeof(SLCounters)) != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; return SLCU_ERR_CUDA; }
     cudaMemset(c->counters, 0, sizeof(SLCounters));
     if (cudaMallocHost(&c->hostCounters, 2 * sizeof(SLCounters)) != cudaSuccess) { cudaFree(c->counters); cudaStreamDestroy(c->stream); delete c; return SLCU_ERR_CUDA; }
+    for (Scratch* x : all_scratch(c)) x->stream = c->stream;
     c->rcpValid = measure_host_rcp_table(c->rcpTable, c->err);
     c->syncDraws = getenv("SLCU_SYNC_DRAWS") != nullptr && atoi(getenv("SLCU_SYNC_DRAWS")) != 0;
     *out = c;
@@ -1355,8 +1476,9 @@ void slcu_context_destroy(slcu_context* c)
     if (c->counters) cudaFree(c->counters);
     if (c->hostCounters) cudaFreeHost(c->hostCounters);
     for (auto& pm : c->peerMaps) if (pm.ptr) cudaIpcCloseMemHandle(pm.ptr);
-    Scratch* s[] = {&c->records, &c->blockInfo, &c->cnt, &c->off, &c->segSums, &c->rowTotals, &c->rowStart, &c->entries, &c->handoff, &c->rowFlags, &c->rowNeeded, &c->drawTable, &c->blockDraw, &c->recDraw, &c->fragPool, &c->chunkNext, &c->listInfo, &c->handoffRegs, &c->ticketOrder, &c->spanItems, &c->rowPerm, &c->pointKeys, &c->pointRecs, &c->pointSortTemp, &c->wireSlots, &c->wireRecInfo, &c->wireLeaders};
-    for (Scratch* x : s) x->release();
+    geom_release(c);
+    for (Scratch* x : all_scratch(c)) x->release();
+    cudaStreamSynchronize(c->stream);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -1532,9 +1654,15 @@ int slcu_ibo_init(slcu_context* c, size_t ibo, uint32_t numElements, int dataTyp
     b.buf.bytes = bytes;
     b.type = dataType;
     b.count = numElements;
+    b.maxIndex = 0;
     if (data)
     {
         CK(cudaMemcpyAsync(b.buf.ptr, data, bytes, cudaMemcpyHostToDevice, c->stream));
+        for (uint32_t i = 0; i < numElements; ++i)
+        {
+            const unsigned long long v = dataType == 0 ? ((const uint8_t*)data)[i] : (dataType == 1 ? ((const uint16_t*)data)[i] : ((const uint32_t*)data)[i]);
+            if (v > b.maxIndex) b.maxIndex = v;
+        }
         CK(cudaStreamSynchronize(c->stream));
     }
     return 0;
@@ -1641,6 +1769,27 @@ int slcu_texture_read(slcu_context* c, size_t tex, void* out, size_t numBytes)
     cudaSetDevice(c->device);
     CK(cudaMemcpyAsync(out, c->textures[tex].dev, numBytes, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+/* page-locked host memory for read-back / present targets and per-frame inputs: the copy engine reaches the link rate
+ * (~56 GB/s on this box) only from / into pinned pages; pageable memory goes through the driver's bounce buffer (~19 GB/s) */
+int slcu_host_alloc(slcu_context* c, void** out, size_t numBytes)
+{
+    if (!c || !out) return SLCU_ERR_ARG;
+    *out = nullptr;
+    cudaSetDevice(c->device);
+    CK(cudaHostAlloc(out, numBytes ? numBytes : 1, cudaHostAllocPortable));
+    return 0;
+}
+int slcu_host_free(slcu_context* c, void* p)
+{
+    if (!c) return SLCU_ERR_ARG;
+    if (!p) return 0;
+    SLCU_FLUSH();
+    cudaSetDevice(c->device);
+    CK(cudaStreamSynchronize(c->stream)); /* a read-back into it may be in flight */
+    CK(cudaFreeHost(p));
     return 0;
 }
 
@@ -1986,6 +2135,12 @@ int slcu_set_partition(slcu_context* c, unsigned rank, unsigned world, unsigned 
 {
     SLCU_FLUSH();
     if (!c || world < 1 || rank >= world || stripRows < 1) return SLCU_ERR_ARG;
+    if (c->geom.base && (rank != c->partRank || world != c->partWorld || stripRows != c->partStripRows))
+    {
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+        geom_release(c); /* the shared vertex stage was set up for another partition */
+    }
     c->partRank = rank;
     c->partWorld = world;
     c->partStripRows = stripRows;
@@ -2049,6 +2204,83 @@ int slcu_composite(slcu_context* c, size_t srcTex, size_t dstTex, unsigned root)
     unsigned gy = s.h < 148u * 4u ? s.h : 148u * 4u;
     { KernelScope ks(c, SLCU_K_COMPOSITE); k_composite<<<dim3(gx, gy), 256, 0, c->stream>>>(p); }
     CK(cudaGetLastError());
+    return 0;
+}
+
+/* ---- shared vertex stage ------------------------------------------------------------------------------------------ */
+int slcu_geometry_share_create(slcu_context* c, size_t arenaBytes)
+{
+    SLCU_FLUSH();
+    if (!c) return SLCU_ERR_ARG;
+    if (c->partWorld < 2 || c->partWorld > (unsigned)SL_MAX_RANKS) { c->err = "geometry_share_create: set_partition with 2..8 ranks first"; return SLCU_ERR_ARG; }
+    cudaSetDevice(c->device);
+    CK(cudaStreamSynchronize(c->stream));
+    geom_release(c);
+    arenaBytes = (arenaBytes + 255) & ~(size_t)255;
+    if (!arenaBytes) return SLCU_ERR_ARG;
+    void* p = nullptr;
+    if (cudaMalloc(&p, SL_GEOM_HEAD_BYTES + 2 * arenaBytes) != cudaSuccess) { cudaGetLastError(); c->err = "geometry_share_create: out of device memory"; return SLCU_ERR_OOM; }
+    c->geom.base = (unsigned char*)p;
+    c->geom.arenaBytes = arenaBytes;
+    c->geom.peer[c->partRank] = c->geom.base;
+    CK(cudaMemset(c->geom.base, 0, SL_GEOM_HEAD_BYTES));
+    return 0;
+}
+
+int slcu_geometry_share_export(slcu_context* c, void* handle64)
+{
+    if (!c || !handle64 || !c->geom.base) return SLCU_ERR_ARG;
+    cudaSetDevice(c->device);
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, c->geom.base));
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+
+int slcu_geometry_share_import(slcu_context* c, unsigned peerRank, const void* handle64)
+{
+    SLCU_FLUSH();
+    if (!c || !handle64 || !c->geom.base || peerRank >= c->partWorld || peerRank == c->partRank) return SLCU_ERR_ARG;
+    cudaSetDevice(c->device);
+    CK(cudaStreamSynchronize(c->stream));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* ptr = nullptr;
+    CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    if (c->geom.peer[peerRank] && c->geom.ipcMapped[peerRank]) cudaIpcCloseMemHandle(c->geom.peer[peerRank]);
+    c->geom.peer[peerRank] = (unsigned char*)ptr;
+    c->geom.ipcMapped[peerRank] = true;
+    return 0;
+}
+
+/* peers inside one process (several contexts driven by threads of one host program): the allocation's device address */
+int slcu_geometry_share_address(slcu_context* c, void** out)
+{
+    if (!c || !out || !c->geom.base) return SLCU_ERR_ARG;
+    *out = c->geom.base;
+    return 0;
+}
+int slcu_geometry_share_attach(slcu_context* c, unsigned peerRank, void* address)
+{
+    SLCU_FLUSH();
+    if (!c || !address || !c->geom.base || peerRank >= c->partWorld || peerRank == c->partRank) return SLCU_ERR_ARG;
+    cudaSetDevice(c->device);
+    CK(cudaStreamSynchronize(c->stream));
+    cudaPointerAttributes at;
+    CK(cudaPointerGetAttributes(&at, address));
+    if (at.type != cudaMemoryTypeDevice) { c->err = "geometry_share_attach: not a device address"; return SLCU_ERR_ARG; }
+    if (at.device != c->device)
+    {
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, c->device, at.device));
+        if (!can) { c->err = "geometry_share_attach: no peer access between the two devices"; return SLCU_ERR_UNSUPPORTED; }
+        const cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { c->err = cudaGetErrorString(e); return SLCU_ERR_CUDA; }
+        cudaGetLastError();
+    }
+    if (c->geom.peer[peerRank] && c->geom.ipcMapped[peerRank]) cudaIpcCloseMemHandle(c->geom.peer[peerRank]);
+    c->geom.peer[peerRank] = (unsigned char*)address;
+    c->geom.ipcMapped[peerRank] = false;
     return 0;
 }
 

@@ -45,6 +45,17 @@ class SortFirst:
             self.ctx.texture_ipc_import(tex, self.root, box[0])
         return tex
 
+    def share_geometry(self, arena_bytes: int):
+        """The ranks split the vertex stage and route triangle records to the owners of the rows they touch
+        (slcu_geometry_share_*): every rank creates an arena, the handles travel once through torch.distributed."""
+        self.ctx.geometry_share_create(arena_bytes)
+        handles = [None] * self.world
+        self.dist.all_gather_object(handles, self.ctx.geometry_share_export(), group=self.group)
+        for r, h in enumerate(handles):
+            if r != self.rank:
+                self.ctx.geometry_share_import(r, h)
+        self.dist.barrier(group=self.group)
+
     def composite(self, src_tex: int, dst_tex: int):
         self.ctx.composite(src_tex, dst_tex, self.root)
 

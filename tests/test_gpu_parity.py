@@ -261,3 +261,70 @@ def test_sort_first_partition_is_bit_identical(name, world, strip, golden):
     depth = SF.merge_owned_rows(finals_d, strip)
     assert sha(color) == hashes[name]["color_sha256"]
     assert sha(depth) == hashes[name]["depth_sha256"]
+
+
+@pytest.mark.parametrize("name,world,strip", [("c1_small", 2, 8), ("c2_small", 4, 8), ("rand_clip_heavy", 2, 1), ("rand_overflow_wide", 3, 2),
+                                               ("rand_overflow_blend", 4, 1), ("rand_multi3", 2, 4), ("rand_split3", 3, 8),
+                                               ("rand_index_u8", 2, 2), ("rand_depthfunc3", 4, 1), ("c4_small", 2, 8)])
+def test_shared_vertex_stage_is_bit_identical(name, world, strip, golden):
+    """The ranks split the vertex stage (slcu_geometry_share_*): each shades every world-th vertex block and stores the
+    records into the arenas of the ranks whose rows they touch; the device-side rendezvous replaces the host.  All ranks
+    are contexts on this one GPU, one host thread each (a rank waits on the device for its peers' blocks), their arenas
+    attached by address.  The composite of the owned rows equals the unpartitioned frame bit for bit, and every rank
+    reports the whole frame's record count."""
+    import threading
+
+    from softlight_b200 import sortfirst as SF
+
+    if name not in cases.CASES:
+        pytest.skip("case not defined")
+    frames, hashes = golden
+    scene = cases.CASES[name]()
+    ctxs = []
+    for r in range(world):
+        ctx = A.Context("cuda")
+        ctx.set_rcp_table(frames["rcp_table"])
+        ctx.set_partition(r, world, strip)
+        ctx.geometry_share_create(96 << 20)
+        ctxs.append(ctx)
+    for r in range(world):
+        for t in range(world):
+            if t != r:
+                ctxs[r].geometry_share_attach(t, ctxs[t].geometry_share_address())
+    finals_c, finals_d, stats, errors = [None] * world, [None] * world, [None] * world, []
+    ready = threading.Barrier(world)
+
+    def run(r):
+        try:
+            ctx = ctxs[r]
+            inst = S.SceneInstance(scene, ctx)
+            ctx.sync()
+            ready.wait(timeout=60)  # every rank's resources exist before any rank waits on the device for its peers
+            for _ in range(2):  # the second frame runs with the sizes the first one learned: no refusal, no local re-run
+                ctx.reset_stats()
+                inst.render()
+                ctx.sync()
+            stats[r] = ctx.get_stats()
+            fc = ctx.create_texture(scene.color_type, scene.width, scene.height)
+            fd = ctx.create_texture(scene.depth_type, scene.width, scene.height)
+            ctx.composite(inst.state["color"], fc, r)
+            ctx.composite(inst.state["depth"], fd, r)
+            ctx.sync()
+            finals_c[r] = ctx.texture_read(fc, scene.color_type, scene.width, scene.height)
+            finals_d[r] = ctx.texture_read(fd, scene.depth_type, scene.width, scene.height)[..., 0]
+        except Exception as ex:  # noqa: BLE001
+            errors.append((r, repr(ex)))
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+    assert not errors, errors
+    assert all(f is not None for f in finals_c), "a rank did not finish"
+    color = SF.merge_owned_rows(finals_c, strip)
+    depth = SF.merge_owned_rows(finals_d, strip)
+    assert sha(color) == hashes[name]["color_sha256"]
+    assert sha(depth) == hashes[name]["depth_sha256"]
+    binned = {st["trisBinned"] for st in stats}
+    assert len(binned) == 1, f"ranks disagree on the frame's record count: {binned}"
