@@ -273,7 +273,7 @@ class Harness:
             self.sf = SortFirst(self.ctx, dist, rank, world, strip_rows=strip_rows)
             if os.environ.get("SLCU_GEOM_SHARE", "1") != "0":
                 # the ranks split the vertex stage and route the triangle records (two arenas, fixed record slots, <= 4 varyings)
-                self.sf.share_geometry(int(self.scene.tris_per_frame * 1.3) * 242 + (64 << 20))
+                self.sf.share_geometry(int(self.scene.tris_per_frame * 1.3) * 246 + (64 << 20))
             self.final = [self.sf.make_target(self.scene.color_type, self.scene.width, self.scene.height) for _ in range(2)]
         # L2 flush buffer (written between timed frames, outside the timed region)
         ctx = self.ctx
@@ -330,12 +330,16 @@ class Harness:
     def device_timed(self, steps, warmup):
         """K frames, each bracketed by CUDA events on the library's stream, L2 flushed before each; max over ranks per frame."""
         # W untimed frames, and at least 0.4 s of them: the SM clock of an idle GPU takes that long to come up
+        # (with the shared vertex stage a frame is a collective: every rank renders the same number of them, so the ranks
+        # agree on going on after every eighth frame)
         t0, i = time.perf_counter(), 0
-        while i < max(warmup, 3) or (time.perf_counter() - t0 < 0.4 and i < 2000):
+        while True:
             self.render_frame(i)
             i += 1
-            if i % 8 == 0:
+            if i % 8 == 0 or i == max(warmup, 3):
                 self.ctx.sync()
+                if i >= max(warmup, 3) and (self.max_over_ranks([time.perf_counter() - t0])[0] >= 0.4 or i >= 2000):
+                    break
         self.barrier()
         sampler = ClockSampler(self.local_rank)
         self.ctx.reset_stats()
@@ -344,6 +348,8 @@ class Harness:
         step_ms = []
         for i in range(steps):
             self.flush_l2()
+            if self.dist is not None:
+                self.barrier()  # untimed: the ranks start the frame together (they meet on the device inside it when the vertex stage is shared)
             self.ctx.timer_begin()
             self.render_frame(i)
             step_ms.append(self.ctx.timer_end())
@@ -361,6 +367,8 @@ class Harness:
         flushed = True
         for i in range(frames):
             flushed = self.flush_l2_outside_library() and flushed
+            if self.dist is not None:
+                self.barrier()
             self.render_frame(i)
         kt = self.ctx.profile_end()
         classes = {k: v for k, v in kt.items() if v["launches"]}

@@ -261,7 +261,8 @@ SLCU_EXPORT int SLCU_FN(get_stats)(slcu_context* ctx, slcu_stats* out);
  * profile_end synchronises and returns the summed milliseconds and launch
  * counts per kernel class.  Used by bench.py for the roofline of the dominant
  * kernel; off by default (the events serialise nothing but cost a few us). */
-enum { SLCU_K_CLEAR = 0, SLCU_K_VERTEX, SLCU_K_SPAN_COUNT, SLCU_K_SCAN, SLCU_K_SPAN_FILL, SLCU_K_RASTER, SLCU_K_BLIT, SLCU_K_COMPOSITE, SLCU_K_SHADE, SLCU_K_NUM };
+enum { SLCU_K_CLEAR = 0, SLCU_K_VERTEX, SLCU_K_SPAN_COUNT, SLCU_K_SCAN, SLCU_K_SPAN_FILL, SLCU_K_RASTER, SLCU_K_BLIT, SLCU_K_COMPOSITE, SLCU_K_SHADE,
+       SLCU_K_ROUTE /* shared vertex stage: records to their ranks */, SLCU_K_RENDEZVOUS /* ... and the wait for the other ranks' */, SLCU_K_NUM };
 typedef struct slcu_kernel_times
 {
     double ms[SLCU_K_NUM];

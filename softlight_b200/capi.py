@@ -93,7 +93,7 @@ class Stats(C.Structure):
                 ("fragsShaded", C.c_uint64), ("kernelLaunches", C.c_uint64), ("drawCalls", C.c_uint64), ("batches", C.c_uint64)]
 
 
-KERNEL_CLASSES = ["clear", "vertex", "span_count", "scan", "span_fill", "raster", "blit", "composite", "shade"]
+KERNEL_CLASSES = ["clear", "vertex", "span_count", "scan", "span_fill", "raster", "blit", "composite", "shade", "route", "rendezvous"]
 
 
 class KernelTimes(C.Structure):

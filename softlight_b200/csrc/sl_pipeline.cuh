@@ -158,7 +158,8 @@ struct SLVertexParams
     SLCounters* counters;
     int shardRank, shardWorld;        /* ranks sharing the stage: this one runs blocks rank, rank + world, ... (world 1: all) */
     int partStrip;                    /* rows per ownership strip of the sort-first partition           */
-    SLGeomOut out[SL_MAX_RANKS];      /* [0] when shardWorld == 1, else indexed by rank                 */
+    SLGeomOut out;                    /* this rank's buffers (its arena when the stage is shared)       */
+    uint8_t* recMask;                 /* shared stage: record slot -> ranks whose rows the record touches (k_geom_route sends it there) */
 };
 
 /* ------------------------------------------------------------------------
@@ -370,9 +371,10 @@ SLD_FN uint32_t sl_rank_mask(float ya, float yb, float yc, int strip, int world)
  * out; only then does the warp take its slots from the overflow area (one atomic).  No barrier, no allocation-order
  * dependence, and slot order = submission order.
  *
- * Ranks that share the vertex stage (slcu_geometry_share_*): rank r runs blocks r, r + world, ... and stores each record
- * into the arenas of the ranks whose rows it touches (peer stores over NVLink), the 2-byte recDraw word -- 0xffff = "not
- * for you" -- and the segment table into every rank's.  Slots are the same everywhere, so nothing has to be merged. */
+ * Ranks that share the vertex stage (slcu_geometry_share_*): rank r runs blocks r, r + world, ... into its own arena and
+ * notes for every record which ranks' rows it touches; k_geom_route then copies each record into the arenas of those ranks
+ * (peer stores over NVLink, whole records per warp instruction), the 2-byte recDraw word -- 0xffff = "not for you" -- and
+ * the segment table into every rank's.  Slots are the same everywhere, so nothing has to be merged. */
 #ifndef SL_VERTEX_MIN_BLOCKS
 #define SL_VERTEX_MIN_BLOCKS 2 /* (256, 1) lets ptxas take > 128 registers: one block per SM, measured 35 % slower */
 #endif
@@ -651,15 +653,16 @@ __global__ void __launch_bounds__(SL_VB_THREADS, CACHE ? SL_VERTEX_CACHED_MIN_BL
                             {
                                 const int j = f + 1, k = f + 2;
                                 if (sl_prim_hidden(pg.verts[0], pg.verts[j], pg.verts[k])) continue;
-                                const uint32_t mask = world > 1 ? sl_rank_mask(pg.verts[0].v[1], pg.verts[j].v[1], pg.verts[k].v[1], P.partStrip, world) : 1u;
-                                for (int t = 0; t < (world > 1 ? world : 1); ++t)
+                                uint16_t tag = (uint16_t)drawIdx;
+                                if (world > 1)
                                 {
-                                    const bool to = (mask >> t) & 1u;
-                                    P.out[t].recDraw[slot] = to ? (uint16_t)drawIdx : SL_REC_ABSENT;
-                                    if (to)
-                                        sl_write_record(P.out[t].records + (size_t)slot * recStride, NV, pg.verts[0], pg.verts[j], pg.verts[k],
-                                                        &pg.varys[0], &pg.varys[j * 4], &pg.varys[k * 4]);
+                                    const uint32_t mask = sl_rank_mask(pg.verts[0].v[1], pg.verts[j].v[1], pg.verts[k].v[1], P.partStrip, world);
+                                    P.recMask[slot] = (uint8_t)mask;
+                                    if (!((mask >> P.shardRank) & 1u)) tag = SL_REC_ABSENT;
                                 }
+                                P.out.recDraw[slot] = tag;
+                                sl_write_record(P.out.records + (size_t)slot * recStride, NV, pg.verts[0], pg.verts[j], pg.verts[k],
+                                                &pg.varys[0], &pg.varys[j * 4], &pg.varys[k * 4]);
                                 ++slot;
                             }
                         }
@@ -746,8 +749,7 @@ __global__ void __launch_bounds__(SL_VB_THREADS, CACHE ? SL_VERTEX_CACHED_MIN_BL
                 binned += granted;
                 const SLSegment sg{base, granted, r0 | (r1 << 16)};
                 const int s = (int)it * (SL_VB_THREADS / 32) + warp;
-                if (world > 1) { for (int t = 0; t < world; ++t) P.out[t].blockInfo[vb].seg[s] = sg; }
-                else P.out[0].blockInfo[vb].seg[s] = sg;
+                P.out.blockInfo[vb].seg[s] = sg;
             }
             if (needClip) sSlot[p] = (n != 0 && granted != 0) ? base + (incl - (uint32_t)n) : 0xffffffffu; /* written in pass 3 */
             /* (Staging a warp's records in shared memory and storing them as one contiguous stream was measured: slower on
@@ -755,42 +757,42 @@ __global__ void __launch_bounds__(SL_VB_THREADS, CACHE ? SL_VERTEX_CACHED_MIN_BL
             else if (n != 0 && granted != 0)
             {
                 const uint32_t slot = base + (incl - (uint32_t)n);
-                const int numOut = world > 1 ? world : 1;
+                uint16_t tag = (uint16_t)drawIdx;
+                float4* rec = P.out.records + (size_t)slot * recStride;
                 if constexpr (CACHE)
                 {
                     const float4 s0 = cache[CV + ci[0]], s1 = cache[CV + ci[1]], s2 = cache[CV + ci[2]];
-                    const uint32_t mask = world > 1 ? sl_rank_mask(s0.y, s1.y, s2.y, P.partStrip, world) : 1u;
-                    for (int t = 0; t < numOut; ++t)
+                    if (world > 1)
                     {
-                        const bool to = (mask >> t) & 1u;
-                        P.out[t].recDraw[slot] = to ? (uint16_t)drawIdx : SL_REC_ABSENT;
-                        if (!to) continue;
-                        float4* rec = P.out[t].records + (size_t)slot * recStride;
-                        rec[0] = s0;
-                        rec[1] = s1;
-                        rec[2] = s2;
+                        const uint32_t mask = sl_rank_mask(s0.y, s1.y, s2.y, P.partStrip, world);
+                        P.recMask[slot] = (uint8_t)mask;
+                        if (!((mask >> P.shardRank) & 1u)) tag = SL_REC_ABSENT;
+                    }
+                    rec[0] = s0;
+                    rec[1] = s1;
+                    rec[2] = s2;
 #pragma unroll
-                        for (int s = 0; s < 4; ++s)
+                    for (int s = 0; s < 4; ++s)
+                    {
+                        if (s < NV)
                         {
-                            if (s < NV)
-                            {
-                                rec[3 + 3 * s + 0] = cache[(2 + s) * CV + ci[0]];
-                                rec[3 + 3 * s + 1] = cache[(2 + s) * CV + ci[1]];
-                                rec[3 + 3 * s + 2] = cache[(2 + s) * CV + ci[2]];
-                            }
+                            rec[3 + 3 * s + 0] = cache[(2 + s) * CV + ci[0]];
+                            rec[3 + 3 * s + 1] = cache[(2 + s) * CV + ci[1]];
+                            rec[3 + 3 * s + 2] = cache[(2 + s) * CV + ci[2]];
                         }
                     }
                 }
                 else
                 {
-                    const uint32_t mask = world > 1 ? sl_rank_mask(v[0].vert.v[1], v[1].vert.v[1], v[2].vert.v[1], P.partStrip, world) : 1u;
-                    for (int t = 0; t < numOut; ++t)
+                    if (world > 1)
                     {
-                        const bool to = (mask >> t) & 1u;
-                        P.out[t].recDraw[slot] = to ? (uint16_t)drawIdx : SL_REC_ABSENT;
-                        if (to) sl_write_record(P.out[t].records + (size_t)slot * recStride, NV, v[0].vert, v[1].vert, v[2].vert, v[0].varyings, v[1].varyings, v[2].varyings);
+                        const uint32_t mask = sl_rank_mask(v[0].vert.v[1], v[1].vert.v[1], v[2].vert.v[1], P.partStrip, world);
+                        P.recMask[slot] = (uint8_t)mask;
+                        if (!((mask >> P.shardRank) & 1u)) tag = SL_REC_ABSENT;
                     }
+                    sl_write_record(rec, NV, v[0].vert, v[1].vert, v[2].vert, v[0].varyings, v[1].varyings, v[2].varyings);
                 }
+                P.out.recDraw[slot] = tag;
             }
         }
         __syncthreads(); /* pass 0 -> 1: the queue is complete; 1 -> 2: the counts; 2 -> 3: the slots */
@@ -1398,6 +1400,66 @@ __global__ void __launch_bounds__(1024) k_row_order(const uint32_t* rowStart, un
         else rowPerm[numHeavy + (y - hPos)] = y; /* light rows keep their order behind the heavy ones */
     }
     if (tid == 0) rowPerm[numRows] = numHeavy; /* k_resolve2 gives these rows fine segments */
+}
+
+/* Shared vertex stage: what this rank's blocks produced goes to the other ranks.  One CTA per block of this rank, one warp
+ * per record segment: the segment descriptor to every rank, every record to the ranks of its mask, the recDraw word to all
+ * of them (SL_REC_ABSENT where the record does not go).  A warp instruction carries whole records -- lanes of one record
+ * write consecutive float4 -- so the peer stores leave the SM as full 32-byte sectors; k_vertex's own per-thread stores
+ * (one float4 of 32 different records per instruction) would cross NVLink as 16-byte packets. */
+struct SLGeomRoute
+{
+    const uint32_t* blockDraw;
+    SLGeomOut out[SL_MAX_RANKS];       /* every rank's arena (peer mappings); [rank] = the source */
+    const uint8_t* recMask;
+    int rank, world, recStride;
+};
+__global__ void __launch_bounds__(32 * SL_VB_SEGS) k_geom_route(const __grid_constant__ SLGeomRoute P)
+{
+    const unsigned vb = blockIdx.x * (unsigned)P.world + (unsigned)P.rank;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint16_t drawIdx = (uint16_t)P.blockDraw[vb];
+    const int stride = P.recStride;
+    const int perIter = 32 / stride;          /* records per warp instruction (stride <= 15) */
+    const int sub = lane / stride, f = lane - sub * stride;
+    const float4* src = P.out[P.rank].records;
+    {
+        const int s = warp; /* one warp per segment: 32 independent load chains per block */
+        const SLSegment sg = P.out[P.rank].blockInfo[vb].seg[s];
+        if (lane < P.world && lane != P.rank) P.out[lane].blockInfo[vb].seg[s] = sg;
+        for (uint32_t r0 = 0; r0 < sg.count; r0 += 32u)
+        {
+            /* the recDraw words of up to 32 records: one lane each */
+            const uint32_t r = r0 + (uint32_t)lane;
+            const uint32_t mask = r < sg.count ? P.recMask[sg.base + r] : 0u;
+            if (r < sg.count)
+            {
+                for (int t = 0; t < P.world; ++t)
+                {
+                    if (t != P.rank) P.out[t].recDraw[sg.base + r] = ((mask >> t) & 1u) ? drawIdx : SL_REC_ABSENT;
+                }
+            }
+            const uint32_t n = min(32u, sg.count - r0);
+            for (uint32_t q = 0; q < n; q += (uint32_t)perIter)
+            {
+                const uint32_t mine = q + (uint32_t)sub;
+                const uint32_t m = __shfl_sync(0xffffffffu, mask, (int)(mine & 31u));
+                if (sub < perIter && mine < n)
+                {
+                    const size_t at = (size_t)(sg.base + r0 + mine) * stride + f;
+                    const uint32_t others = m & ~(1u << P.rank);
+                    if (others)
+                    {
+                        const float4 val = src[at];
+                        for (int t = 0; t < P.world; ++t)
+                        {
+                            if ((others >> t) & 1u) P.out[t].records[at] = val;
+                        }
+                    }
+                }
+            }
+        }
+    }
 }
 
 /* Shared vertex stage: the rendezvous between k_vertex and everything that reads the records.  One thread per rank:

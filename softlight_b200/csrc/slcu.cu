@@ -814,7 +814,7 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
     static const bool allowGeomShare = !(getenv("SLCU_GEOM_SHARE") && atoi(getenv("SLCU_GEOM_SHARE")) == 0);
     const unsigned world = c->partWorld;
     bool sharded = false;
-    size_t arenaRecDraw = 0, arenaBlockInfo = 0;
+    size_t arenaRecDraw = 0, arenaBlockInfo = 0, arenaRecMask = 0;
     if (allowGeomShare && !B.wire && c->geom.ready(world))
     {
         const unsigned long long slice = (totalPrims / 8 + 4096) / world + 1024;
@@ -822,7 +822,8 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
         auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
         arenaRecDraw = up((size_t)cap * recStride * sizeof(float4));
         arenaBlockInfo = arenaRecDraw + up((size_t)cap * sizeof(uint16_t));
-        const size_t need = arenaBlockInfo + up((size_t)numBlocks * sizeof(SLBlockInfo));
+        arenaRecMask = arenaBlockInfo + up((size_t)numBlocks * sizeof(SLBlockInfo));
+        const size_t need = arenaRecMask + up((size_t)cap);
         if (cap <= 0x7ffffff0ull && need <= c->geom.arenaBytes)
         {
             if (!B.geomLocal)
@@ -863,18 +864,33 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
                 vp.shardRank = (int)c->partRank;
                 vp.shardWorld = (int)world;
                 vp.recOverflowBase = (unsigned)(recFixed + (unsigned long long)c->partRank * recOverflow);
+                SLGeomRoute gr;
+                memset(&gr, 0, sizeof(gr));
                 for (unsigned t = 0; t < world; ++t)
                 {
                     unsigned char* a = c->geom.peer[t] + arenaOff;
-                    vp.out[t].records = reinterpret_cast<float4*>(a);
-                    vp.out[t].recDraw = reinterpret_cast<uint16_t*>(a + arenaRecDraw);
-                    vp.out[t].blockInfo = reinterpret_cast<SLBlockInfo*>(a + arenaBlockInfo);
+                    gr.out[t].records = reinterpret_cast<float4*>(a);
+                    gr.out[t].recDraw = reinterpret_cast<uint16_t*>(a + arenaRecDraw);
+                    gr.out[t].blockInfo = reinterpret_cast<SLBlockInfo*>(a + arenaBlockInfo);
                 }
-                recordsPtr = vp.out[c->partRank].records;
-                recDrawPtr = vp.out[c->partRank].recDraw;
-                blockInfoPtr = vp.out[c->partRank].blockInfo;
+                vp.out = gr.out[c->partRank];
+                vp.recMask = c->geom.peer[c->partRank] + arenaOff + arenaRecMask;
+                recordsPtr = vp.out.records;
+                recDrawPtr = vp.out.recDraw;
+                blockInfoPtr = vp.out.blockInfo;
                 grid = numBlocks > c->partRank ? (numBlocks - c->partRank + world - 1) / world : 0u;
-                if (grid) { KernelScope ks(c, SLCU_K_VERTEX); CK(launch_vertex_stage(sh, grid, c->stream, vp, cache)); }
+                if (grid)
+                {
+                    { KernelScope ks(c, SLCU_K_VERTEX); CK(launch_vertex_stage(sh, grid, c->stream, vp, cache)); }
+                    gr.blockDraw = vp.blockDraw;
+                    gr.recMask = vp.recMask;
+                    gr.rank = (int)c->partRank;
+                    gr.world = (int)world;
+                    gr.recStride = recStride;
+                    KernelScope ks(c, SLCU_K_ROUTE);
+                    k_geom_route<<<grid, 32 * SL_VB_SEGS, 0, c->stream>>>(gr);
+                    CK(cudaGetLastError());
+                }
                 SLGeomSync gs;
                 memset(&gs, 0, sizeof(gs));
                 for (unsigned t = 0; t < world; ++t) gs.head[t] = c->geom.peer[t];
@@ -883,7 +899,7 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
                 gs.epoch = epoch;
                 gs.counters = c->counters;
                 gs.timeoutClocks = 20000000000ll; /* ~10 s: a rank that never arrives is an error, not a hang */
-                { KernelScope ks(c, SLCU_K_VERTEX); k_geom_barrier<<<1, 32, 0, c->stream>>>(gs); }
+                { KernelScope ks(c, SLCU_K_RENDEZVOUS); k_geom_barrier<<<1, 32, 0, c->stream>>>(gs); }
                 CK(cudaGetLastError());
             }
             else
@@ -897,9 +913,10 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
                 vp.shardRank = 0;
                 vp.shardWorld = 1;
                 vp.recOverflowBase = (unsigned)recFixed;
-                vp.out[0].records = recordsPtr;
-                vp.out[0].recDraw = recDrawPtr;
-                vp.out[0].blockInfo = blockInfoPtr;
+                vp.out.records = recordsPtr;
+                vp.out.recDraw = recDrawPtr;
+                vp.out.blockInfo = blockInfoPtr;
+                vp.recMask = nullptr;
                 { KernelScope ks(c, SLCU_K_VERTEX); CK(launch_vertex_stage(sh, grid, c->stream, vp, cache)); }
             }
         }

@@ -30,6 +30,8 @@ def main():
         ctx = A.Context("cuda", device=local)
         ctx.set_rcp_table(frames["rcp_table"])
         sf = SortFirst(ctx, dist, rank, world, strip_rows=strip)
+        if os.environ.get("SLCU_GEOM_SHARE", "1") != "0":  # the ranks split the vertex stage and route the records
+            sf.share_geometry(int(scene.tris_per_frame * 1.3) * 246 + (64 << 20))
         inst = S.SceneInstance(scene, ctx)
         fc = sf.make_target(scene.color_type, scene.width, scene.height)
         fd = sf.make_target(scene.depth_type, scene.width, scene.height)
@@ -42,7 +44,7 @@ def main():
             color = ctx.texture_read(fc, scene.color_type, scene.width, scene.height)
             depth = ctx.texture_read(fd, scene.depth_type, scene.width, scene.height)[..., 0]
             ok = sha(color) == hashes[name]["color_sha256"] and sha(depth) == hashes[name]["depth_sha256"]
-            print(f"{'ok ' if ok else 'BAD'} {name} world={world} strip={strip}", flush=True)
+            print(f"{'ok ' if ok else 'BAD'} {name} world={world} strip={strip} binned={ctx.get_stats()['trisBinned']}", flush=True)
             bad += 0 if ok else 1
         dist.barrier()
         ctx.close()
