@@ -64,7 +64,7 @@ typedef struct slcu_mesh
     uint64_t vaoId;
     uint64_t elementBegin;
     uint64_t elementEnd;
-    uint32_t mode;       /* SL_RenderMode: 0x10/0x30 triangles, 0x50/0x70 wireframe triangles, 0x01/0x03 points; 0x04/0x0C (lines) -> SLCU_ERR_UNSUPPORTED */
+    uint32_t mode;       /* SL_RenderMode: 0x10/0x30 triangles, 0x50/0x70 wireframe triangles, 0x01/0x03 points, 0x04/0x0C lines */
     uint32_t materialId;
 } slcu_mesh;
 
@@ -121,6 +121,12 @@ SLCU_EXPORT const char* SLCU_FN(impl_name)(void);
  * the reference running on the same box; tests pin it to the committed one. */
 SLCU_EXPORT int SLCU_FN(set_rcp_table)(slcu_context* ctx, const uint32_t* table2048);
 SLCU_EXPORT int SLCU_FN(get_rcp_table)(slcu_context* ctx, uint32_t* table2048);
+/* rsqrtss table (line primitives: math::inversesqrt is rsqrtss plus one Newton step, light_math
+ * x86/scalarf_utils_impl.h:183-197).  4096 entries: the instruction's results for the inputs
+ * 2^p * (1 + i / 2048), p = 0, 1 -- exponent parity and the top 11 mantissa bits decide the result,
+ * the exponent is handled exactly.  Measured from the host CPU at context_create like the rcp table. */
+SLCU_EXPORT int SLCU_FN(set_rsqrt_table)(slcu_context* ctx, const uint32_t* table4096);
+SLCU_EXPORT int SLCU_FN(get_rsqrt_table)(slcu_context* ctx, uint32_t* table4096);
 
 /* ---- resources: SL_Context::create_* (SL_Context.cpp:160-460) */
 SLCU_EXPORT size_t SLCU_FN(create_vbo)(slcu_context* ctx);

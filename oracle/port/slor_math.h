@@ -44,6 +44,23 @@ static inline float x86_rcp(float x)
     return u2f(s | ((uint32_t)re << 23) | (r & 0x7fffffu));
 }
 
+/* rsqrtss: a table over (exponent parity, top 11 mantissa bits) with exact exponent handling, measured from the host CPU
+ * like the rcp table (entries: results for inputs in [1, 2) and [2, 4)) */
+extern uint32_t g_rsqrt_table[4096];
+static inline float x86_rsqrt(float x)
+{
+    const uint32_t xb = f2u(x);
+    const uint32_t e = (xb >> 23) & 0xffu;
+    const uint32_t m = xb & 0x7fffffu;
+    if (e == 0xffu) return m ? u2f(xb | 0x00400000u) : ((xb >> 31) ? u2f(0xffc00000u) : 0.f); /* NaN quieted, -inf -> NaN, +inf -> 0 */
+    if (e == 0u) return u2f((xb & 0x80000000u) | 0x7f800000u);                                   /* zero and denormals: signed infinity */
+    if (xb >> 31) return u2f(0xffc00000u);
+    const int p = ((int)e - 127) & 1;
+    const uint32_t r = g_rsqrt_table[(uint32_t)p * 2048u + (m >> 12)];
+    const int re = (int)((r >> 23) & 0xffu) - ((int)e - (127 + p)) / 2;
+    return u2f(((uint32_t)re << 23) | (r & 0x7fffffu));
+}
+
 static inline float sfma(float a, float b, float c) { return __builtin_fmaf(a, b, c); }
 static inline float smin(float a, float b) { return (a < b) ? a : b; }   /* minss/minps */
 static inline float smax(float a, float b) { return (a > b) ? a : b; }   /* maxss/maxps */
@@ -304,6 +321,14 @@ static inline float round(float n) { return __builtin_nearbyintf(n); }        /*
 static inline float fmod_1(float n) { return n - (float)cvt_tr(n); }          /* :170 */
 static inline float rcp(float x) { return x86_rcp(x); }                       /* :220 */
 static inline float fmadd(float x, float m, float a) { return sfma(x, m, a); } /* :599 */
+static inline float inversesqrt(float x)                                      /* :183-197: rsqrtss + one Newton step, FMA branch */
+{
+    const float rsqr = x86_rsqrt(x);
+    const float sqrr = x * rsqr;
+    const float subr = sfma(-sqrr, rsqr, 3.f);
+    const float hlfr = 0.5f * rsqr;
+    return subr * hlfr;
+}
 static inline int sign_mask(float x) { return sign_bit(x) ? 1 : 0; }          /* :250 */
 static inline float sqrt(float x) { return __builtin_sqrtf(x); }
 static inline float abs(float x) { return u2f(f2u(x) & 0x7fffffffu); }

@@ -33,6 +33,22 @@ namespace slo
 {
 
 uint32_t g_rcp_table[2048];
+uint32_t g_rsqrt_table[4096];
+
+/* rsqrtss on this CPU: entries for inputs in [1, 2) and [2, 4), indexed by the top 11 mantissa bits */
+static void measure_host_rsqrt_table(uint32_t* t)
+{
+    for (uint32_t p = 0; p < 2; ++p)
+    {
+        for (uint32_t i = 0; i < 2048; ++i)
+        {
+            float in = u2f(((127u + p) << 23) | (i << 12));
+            float out;
+            __asm__ volatile("rsqrtss %1, %0" : "=x"(out) : "x"(in));
+            t[p * 2048u + i] = f2u(out);
+        }
+    }
+}
 
 /* Measure the rcpss table from the CPU this runs on (the reference executes
  * the real instruction, so "same box" means "same table"). */
@@ -127,6 +143,7 @@ struct slcu_context
     int32_t viewport[4] = {0, 0, 65535, 65535}; /* SL_ViewportState defaults */
     int32_t scissor[4] = {0, 0, 65535, 65535};
     uint32_t rcpTable[2048];
+    uint32_t rsqrtTable[4096];
     std::string err;
     slcu_stats stats{};
 
@@ -954,6 +971,224 @@ static void process_points(slcu_context* c, const slcu_mesh& m, size_t instanceI
     }
 }
 
+/* ---- lines: SL_LineProcessor + SL_LineRasterizer ---------------------------------------------------------------------- */
+
+/* sl_draw_line_bresenham (SL_Geometry.hpp:314-366): sl_lowp_t is int16_t (SL_Setup.hpp:12), arithmetic in int, results
+ * truncated to 16 bits at every assignment; the callback takes uint16_t coordinates. */
+template <typename Callback>
+static void draw_line_bresenham(int16_t x1, int16_t y1, int16_t x2, int16_t y2, Callback&& cb)
+{
+    const bool steep = std::abs((int)x1 - (int)x2) < std::abs((int)y1 - (int)y2);
+    if (steep) { std::swap(x1, y1); std::swap(x2, y2); }
+    if (x1 > x2) { std::swap(x1, x2); std::swap(y1, y2); }
+    const int16_t dx = (int16_t)(x2 - x1);
+    const int16_t dy = (int16_t)(y2 - y1);
+    const int16_t dErr = (int16_t)(std::abs((int)dy) * 2);
+    const int16_t yErr = (y2 > y1) ? 1 : -1;
+    int16_t currentErr = 0;
+    int16_t y = y1;
+    for (int16_t x = x1; x <= x2; ++x)
+    {
+        if (steep) cb((uint16_t)y, (uint16_t)x); else cb((uint16_t)x, (uint16_t)y);
+        currentErr = (int16_t)(currentErr + dErr);
+        if (currentErr > dx)
+        {
+            y = (int16_t)(y + yErr);
+            currentErr = (int16_t)(currentErr - 2 * dx);
+        }
+        if (x == 32767) break; /* ++x would overflow (undefined in the reference; lines never get here) */
+    }
+}
+
+/* SL_LineRasterizer::render_line (src/SL_LineRasterizer.cpp:28-87) + flush_line_fragments
+ * (src/SL_FragmentProcessor.cpp:346-403), one thread.  The depth test reads the buffer while up to 600 of the line's own
+ * fragments are still queued; the queue is restated because a line that touches column `width` and column 0 of the next
+ * row visits one texel twice (linear addressing). */
+static void render_line(slcu_context* c, const TransformedVert& a, const TransformedVert& b)
+{
+    const Shader& sh = *c->shader;
+    SL_Texture& depthBuffer = *c->depthBuf;
+    const float z0 = a.vert.v[2], z1 = b.vert.v[2];
+    const float sc0x = a.vert.v[0], sc0y = a.vert.v[1], sc1x = b.vert.v[0], sc1y = b.vert.v[1];
+    const float ddx = sc1x - sc0x, ddy = sc1y - sc0y;
+    const float dist = math::inversesqrt(ddx * ddx + ddy * ddy); /* length_squared(vec2): sum(v * v), generic */
+
+    struct Queued { float interp; uint16_t x, y; float depth; };
+    std::vector<Queued> queue;
+    auto flush = [&]()
+    {
+        for (const Queued& q : queue)
+        {
+            SL_FragmentParam fp;
+            fp.pUniforms = &c->ubos[sh.ubo];
+            /* interpolate_line_varyings (src/SL_FragmentProcessor.cpp:27-52, AVX2 branch): all four slots, fmadd(v1 - v0, p, v0) */
+            for (int s2 = 0; s2 < 4; ++s2)
+            {
+                for (int k = 0; k < 4; ++k) fp.pVaryings[s2].v[k] = sfma(b.varyings[s2].v[k] - a.varyings[s2].v[k], q.interp, a.varyings[s2].v[k]);
+            }
+            fp.coord.x = q.x;
+            fp.coord.y = q.y;
+            fp.coord.depth = q.depth;
+            for (int k = 0; k < 4; ++k) fp.pOutputs[k] = math::vec4{0.f};
+            const size_t idx = (size_t)q.x + (size_t)depthBuffer.mWidth * q.y;
+            if (idx < (size_t)depthBuffer.mWidth * depthBuffer.mHeight) c->stats.fragsShaded++;
+            if (sh.fs(fp))
+            {
+                for (int k = sh.numOutputs - 1; k >= 0; --k)
+                {
+                    if (sh.blend != 0) blend_color(*c->colorBufs[k], q.x, q.y, fp.pOutputs[k], sh.blend);
+                    else store_color(*c->colorBufs[k], q.x, q.y, fp.pOutputs[k]);
+                }
+            }
+            if (sh.depthMask) store_depth(depthBuffer, idx, q.depth);
+        }
+        queue.clear();
+    };
+    draw_line_bresenham((int16_t)(uint16_t)cvt_tr(sc0x), (int16_t)(uint16_t)cvt_tr(sc0y), (int16_t)(uint16_t)cvt_tr(sc1x), (int16_t)(uint16_t)cvt_tr(sc1y),
+                        [&](uint16_t x, uint16_t y)
+                        {
+                            const math::vec4 d{(float)x - sc0x, (float)y - sc0y, 0.f - 0.f, 0.f - 0.f};
+                            const float currLen = math::length(d);
+                            const float interp = currLen * dist;
+                            const float z = z0 + ((z1 - z0) * interp); /* math::mix, scalar (generic/scalar_utils_impl.h:52) */
+                            const size_t idx = (size_t)x + (size_t)depthBuffer.mWidth * y;
+                            const float dd = load_depth(depthBuffer, idx);
+                            if (!depth_cmp(sh.depthTest, z, dd)) return;
+                            queue.push_back(Queued{interp, x, y, z});
+                            if (queue.size() == 600) flush(); /* SL_SHADER_MAX_QUEUED_FRAGS */
+                        });
+    if (!queue.empty()) flush();
+}
+
+/* SL_LineProcessor::clip_and_process_lines (src/SL_LineProcessor.cpp:68-177): Liang-Barsky against
+ * (viewportDims[0], [1]) .. ([2], [3]) -- the rectangle's width and height are used as its far corner, like the source */
+static void clip_and_process_lines(slcu_context* c, const math::vec4& viewportDims, const TransformedVert& a, const TransformedVert& b)
+{
+    const int numVarys = c->shader->numVaryings;
+    const float dx = b.vert.v[0] - a.vert.v[0];
+    const float dy = b.vert.v[1] - a.vert.v[1];
+    const float xMin = viewportDims.v[0], yMin = viewportDims.v[1], xMax = viewportDims.v[2], yMax = viewportDims.v[3];
+    const double eps = 1.0e-9; /* LS_EPSILON is a double literal: the comparisons are done in double */
+    if ((double)math::abs(dx) < eps && (double)math::abs(dy) < eps)
+    {
+        if (a.vert.v[0] >= xMin && a.vert.v[0] <= xMax && a.vert.v[1] >= yMin && a.vert.v[1] <= yMax)
+        {
+            c->stats.trisBinned++;
+            render_line(c, a, b);
+            return;
+        }
+    }
+    auto clip_segment = [eps](float num, float denom, float& tE, float& tL) -> bool
+    {
+        if ((double)math::abs(denom) < eps) return num < 0.f;
+        const float t = num / denom;
+        if (denom > 0.f)
+        {
+            if (t > tL) return false;
+            if (t > tE) tE = t;
+        }
+        else
+        {
+            if (t < tE) return false;
+            if (t < tL) tL = t;
+        }
+        return true;
+    };
+    TransformedVert p0 = a, p1 = b;
+    float& x1 = p0.vert.v[0];
+    float& y1 = p0.vert.v[1];
+    float& x2 = p1.vert.v[0];
+    float& y2 = p1.vert.v[1];
+    const float ex = p0.vert.v[0] - p1.vert.v[0], ey = p0.vert.v[1] - p1.vert.v[1];
+    const float dist = math::inversesqrt(ex * ex + ey * ey);
+    float tE = 0.f, tL = 1.f;
+    if (clip_segment(xMin - x1, dx, tE, tL) && clip_segment(x1 - xMax, -dx, tE, tL) && clip_segment(yMin - y1, dy, tE, tL) && clip_segment(y1 - yMax, -dy, tE, tL))
+    {
+        if (tL < 1.f)
+        {
+            x2 = x1 + tL * dx;
+            y2 = y1 + tL * dy;
+        }
+        if (tE > 0.f)
+        {
+            x1 += tE * dx;
+            y1 += tE * dy;
+        }
+        const math::vec4 d0{p0.vert.v[0] - a.vert.v[0], p0.vert.v[1] - a.vert.v[1], p0.vert.v[2] - a.vert.v[2], p0.vert.v[3] - a.vert.v[3]};
+        const math::vec4 d1{p1.vert.v[0] - b.vert.v[0], p1.vert.v[1] - b.vert.v[1], p1.vert.v[2] - b.vert.v[2], p1.vert.v[3] - b.vert.v[3]};
+        const float len0 = math::length(d0);
+        const float len1 = math::length(d1);
+        const float interp0 = len0 * dist;
+        const float interp1 = len1 * dist;
+        p0.vert.v[2] = a.vert.v[2] + ((b.vert.v[2] - a.vert.v[2]) * interp0);
+        p0.vert.v[3] = a.vert.v[3] + ((b.vert.v[3] - a.vert.v[3]) * interp0);
+        p1.vert.v[2] = b.vert.v[2] + ((a.vert.v[2] - b.vert.v[2]) * interp1);
+        p1.vert.v[3] = b.vert.v[3] + ((a.vert.v[3] - b.vert.v[3]) * interp1);
+        for (int i = 0; i < numVarys; ++i)
+        {
+            p0.varyings[i] = math::mix(a.varyings[i], b.varyings[i], interp0);
+            p1.varyings[i] = math::mix(b.varyings[i], a.varyings[i], interp1);
+        }
+        c->stats.trisBinned++;
+        render_line(c, p0, p1);
+    }
+}
+
+/* SL_LineProcessor::process_verts (src/SL_LineProcessor.cpp:188-279), one thread, no vertex cache: elements are taken two
+ * at a time; a segment with a vertex behind the eye (w < 0) is dropped, the others are tested with the two-vertex
+ * sl_ndc_clip_status (SL_PostVertexTransform.hpp:560-583), divided, mapped to the screen and drawn or clipped. */
+static void process_lines(slcu_context* c, const slcu_mesh& m, size_t instanceId, bool usingIndices, const math::mat4& scissorMat,
+                          const math::vec4& viewportDims)
+{
+    const Shader& sh = *c->shader;
+    const SL_VertexArray& vao = c->vaos[m.vaoId];
+    const IndexBuffer* pIbo = vao.has_index_buffer() ? &c->ibos[vao.mIboId] : nullptr;
+    SL_VertexParam params;
+    params.pUniforms = &c->ubos[sh.ubo];
+    params.instanceId = instanceId;
+    params.pVao = &vao;
+    params.pVbo = &c->vbos[vao.mVboId];
+    auto fetch = [&](size_t i) -> size_t
+    {
+        if (!usingIndices) return i;
+        const unsigned char* p = pIbo->data.data() + i * pIbo->bytesPerId;
+        switch (pIbo->type)
+        {
+            case 0: return *p;
+            case 1: { uint16_t u; memcpy(&u, p, 2); return u; }
+            default: { uint32_t u; memcpy(&u, p, 4); return u; }
+        }
+    };
+    c->stats.trisSubmitted += (m.elementEnd - m.elementBegin) / 3; /* the harness counts elements / 3 for every mode */
+    for (size_t i = m.elementBegin; i < m.elementEnd; i += 2)
+    {
+        TransformedVert v0, v1;
+        for (int k = 0; k < 4; ++k) { v0.varyings[k] = math::vec4{0.f}; v1.varyings[k] = math::vec4{0.f}; }
+        params.vertId = fetch(i);
+        params.pVaryings = v0.varyings;
+        v0.vert = scissorMat * sh.vs(params);
+        params.vertId = fetch(i + 1);
+        params.pVaryings = v1.varyings;
+        v1.vert = scissorMat * sh.vs(params);
+        if (v0.vert.v[3] < 0.f || v1.vert.v[3] < 0.f) continue;
+        const float w0p = v0.vert.v[3], w1p = v1.vert.v[3];
+        bool vis = true;
+        for (int k = 0; k < 4; ++k) vis = vis && (v0.vert.v[k] <= w0p) && (v1.vert.v[k] <= w1p) && (v0.vert.v[k] >= -w0p) && (v1.vert.v[k] >= -w1p);
+        const bool part = (w0p > 0.f) || (w1p > 0.f);
+        if (!vis && !part) continue;
+        perspective_divide(v0.vert);
+        perspective_divide(v1.vert);
+        ndc_to_screen(v0.vert, viewportDims);
+        ndc_to_screen(v1.vert, viewportDims);
+        if (vis)
+        {
+            c->stats.trisBinned++;
+            render_line(c, v0, v1);
+        }
+        else clip_and_process_lines(c, viewportDims, v0, v1);
+    }
+}
+
 static void apply_fixups(slcu_context* c)
 {
     for (const UboFixup& f : c->fixups)
@@ -971,6 +1206,7 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
 {
     if (shaderId >= c->shaders.size() || fboId >= c->fbos.size()) return SLCU_ERR_ARG;
     memcpy(g_rcp_table, c->rcpTable, sizeof(g_rcp_table));
+    memcpy(g_rsqrt_table, c->rsqrtTable, sizeof(g_rsqrt_table));
     apply_fixups(c);
     const Framebuffer& fbo = c->fbos[fboId];
     c->shader = &c->shaders[shaderId];
@@ -985,6 +1221,19 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
 
     c->wire = (meshes[0].mode == 0x50) || (meshes[0].mode == 0x70); /* mRenderMode = meshes->mode (src/SL_ProcessorPool.cpp:301,354) */
     const bool points = (meshes[0].mode == 0x01) || (meshes[0].mode == 0x03); /* RENDER_MODE_POINTS / INDEXED_POINTS -> SL_PointProcessor */
+    const bool lines = (meshes[0].mode == 0x04) || (meshes[0].mode == 0x0c); /* RENDER_MODE_LINES / INDEXED_LINES -> SL_LineProcessor */
+    if (lines)
+    {
+        if (numInstances == 1)
+        {
+            for (size_t i = 0; i < numMeshes; ++i) process_lines(c, meshes[i], 0, meshes[i].mode == 0x0c, scissorMat, viewportDims);
+        }
+        else
+        {
+            for (size_t i = 0; i < numInstances; ++i) process_lines(c, meshes[0], i, meshes[0].mode == 0x0c, scissorMat, viewportDims);
+        }
+        return 0;
+    }
     if (points)
     {
         if (numInstances == 1)
@@ -1069,6 +1318,7 @@ int slor_context_create(slcu_context** out, int)
     if (!out) return SLCU_ERR_ARG;
     slcu_context* c = new slcu_context{};
     measure_host_rcp_table(c->rcpTable);
+    measure_host_rsqrt_table(c->rsqrtTable);
     *out = c;
     return 0;
 }
@@ -1078,6 +1328,8 @@ const char* slor_last_error(slcu_context* c) { return c->err.c_str(); }
 const char* slor_impl_name(void) { return "oracle-port(scalar C++ restatement)"; }
 int slor_set_rcp_table(slcu_context* c, const uint32_t* t) { memcpy(c->rcpTable, t, sizeof(c->rcpTable)); return 0; }
 int slor_get_rcp_table(slcu_context* c, uint32_t* t) { memcpy(t, c->rcpTable, sizeof(c->rcpTable)); return 0; }
+int slor_set_rsqrt_table(slcu_context* c, const uint32_t* t) { memcpy(c->rsqrtTable, t, sizeof(c->rsqrtTable)); return 0; }
+int slor_get_rsqrt_table(slcu_context* c, uint32_t* t) { memcpy(t, c->rsqrtTable, sizeof(c->rsqrtTable)); return 0; }
 
 size_t slor_create_vbo(slcu_context* c) { c->vbos.emplace_back(); return c->vbos.size() - 1; }
 size_t slor_create_ibo(slcu_context* c) { c->ibos.emplace_back(); return c->ibos.size() - 1; }

@@ -41,6 +41,7 @@
 #include "softlight/SL_ImgFile.hpp"
 
 #define SLCU_PREFIX slref_
+#include <immintrin.h>
 #include "slcu.h"
 
 /* The only undefined symbol of the hot-path source subset. */
@@ -193,6 +194,24 @@ int slref_get_rcp_table(slcu_context*, uint32_t* t)
         in.u = 0x3f800000u | (i << 12);
         o.f = math::rcp(in.f);
         t[i] = o.u;
+    }
+    return 0;
+}
+
+int slref_set_rsqrt_table(slcu_context*, const uint32_t*) { return SLCU_ERR_UNSUPPORTED; /* hardware rsqrtss */ }
+
+/* the instruction math::inversesqrt is built on (light_math x86/scalarf_utils_impl.h:183-197), inputs in [1, 2) and [2, 4) */
+int slref_get_rsqrt_table(slcu_context*, uint32_t* t)
+{
+    for (uint32_t p = 0; p < 2; ++p)
+    {
+        for (uint32_t i = 0; i < 2048; ++i)
+        {
+            union { uint32_t u; float f; } in, o;
+            in.u = ((127u + p) << 23) | (i << 12);
+            o.f = _mm_cvtss_f32(_mm_rsqrt_ss(_mm_set_ss(in.f)));
+            t[p * 2048u + i] = o.u;
+        }
     }
     return 0;
 }

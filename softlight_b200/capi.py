@@ -112,6 +112,8 @@ _SIGS = {
     "impl_name": (C.c_char_p, []),
     "set_rcp_table": (C.c_int, [_P, _P]),
     "get_rcp_table": (C.c_int, [_P, _P]),
+    "set_rsqrt_table": (C.c_int, [_P, _P]),
+    "get_rsqrt_table": (C.c_int, [_P, _P]),
     "create_vbo": (_SZ, [_P]), "create_ibo": (_SZ, [_P]), "create_vao": (_SZ, [_P]),
     "create_ubo": (_SZ, [_P]), "create_texture": (_SZ, [_P]), "create_framebuffer": (_SZ, [_P]),
     "destroy_vbo": (C.c_int, [_P, _SZ]), "destroy_ibo": (C.c_int, [_P, _SZ]), "destroy_vao": (C.c_int, [_P, _SZ]),
@@ -326,6 +328,16 @@ class Context:
     def get_rcp_table(self) -> np.ndarray:
         t = np.zeros(2048, dtype=np.uint32)
         self._chk(self.f["get_rcp_table"](self.h, _ptr(t)), "get_rcp_table")
+        return t
+
+    def set_rsqrt_table(self, table: np.ndarray):
+        table = np.ascontiguousarray(table, dtype=np.uint32)
+        assert table.size == 4096
+        return self.f["set_rsqrt_table"](self.h, _ptr(table))
+
+    def get_rsqrt_table(self) -> np.ndarray:
+        t = np.zeros(4096, dtype=np.uint32)
+        self._chk(self.f["get_rsqrt_table"](self.h, _ptr(t)), "get_rsqrt_table")
         return t
 
     # -- resources ----------------------------------------------------------

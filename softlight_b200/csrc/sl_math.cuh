@@ -193,6 +193,14 @@ SLD_FN float round(float n) { return rintf(n); }                                
 SLD_FN float fmod_1(float n) { return n - (float)sl_cvt_tr(n); }                      /* :170 */
 SLD_FN float rcp(float x) { return sl_rcp(x); }                                       /* :220 rcpss */
 SLD_FN float fmadd(float x, float m, float a) { return sl_fma(x, m, a); }             /* :599 */
+SLD_FN float inversesqrt(float x)                                                     /* :183-197: rsqrtss + one Newton step (FMA branch) */
+{
+    const float rsqr = sl_rsqrt(x);
+    const float sqrr = x * rsqr;
+    const float subr = sl_fma(-sqrr, rsqr, 3.f);
+    const float hlfr = 0.5f * rsqr;
+    return subr * hlfr;
+}
 SLD_FN int sign_mask(float x) { return sl_signbit(x) ? 1 : 0; }                       /* :250 */
 SLD_FN float sqrt(float x) { return sqrtf(x); }
 SLD_FN float abs(float x) { return __uint_as_float(__float_as_uint(x) & 0x7fffffffu); }

@@ -1623,6 +1623,16 @@ SLD_FN float sl_load_depth(const unsigned char* base, int bpt, size_t idx)
 /* depth write (src/SL_FragmentProcessor.cpp:526-529) */
 SLD_FN void sl_store_depth(unsigned char* base, int bpt, size_t idx, float z)
 {
+    if (z != z)
+    {
+        /* cvtps2ph / cvtss2sd keep a NaN's sign and the top of its payload and set the quiet bit; the GPU's conversions
+         * return one canonical NaN */
+        const uint32_t u = __float_as_uint(z);
+        if (bpt == 2) reinterpret_cast<uint16_t*>(base)[idx] = (uint16_t)(((u >> 16) & 0x8000u) | 0x7e00u | ((u >> 13) & 0x3ffu));
+        else if (bpt == 4) reinterpret_cast<float*>(base)[idx] = z;
+        else reinterpret_cast<unsigned long long*>(base)[idx] = ((unsigned long long)(u >> 31) << 63) | 0x7ff8000000000000ull | ((unsigned long long)(u & 0x3fffffu) << 29);
+        return;
+    }
     if (bpt == 2) reinterpret_cast<uint16_t*>(base)[idx] = sl_f2h_rn(z);
     else if (bpt == 4) reinterpret_cast<float*>(base)[idx] = z;
     else reinterpret_cast<double*>(base)[idx] = (double)z;

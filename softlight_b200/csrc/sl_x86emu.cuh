@@ -2,6 +2,7 @@
  * sl_x86emu.cuh -- device primitives that reproduce the x86 instructions the
  * reference's source path is written in:
  *
+ *   rsqrtss      -> sl_rsqrt(): 2 x 2048-entry table (exponent parity, top 11 mantissa bits), measured the same way.
  *   rcpss/rcpps  -> sl_rcp():   2048-entry table indexed by the top 11 mantissa
  *                   bits, exponent handled exactly; the table is measured from
  *                   the host CPU at context creation (or pinned by a test).
@@ -52,6 +53,23 @@ __device__ __forceinline__ float sl_rcp_tab(const uint32_t* __restrict__ table, 
     const int re = (int)((r >> 23) & 0xffu) - ((int)e - 127);
     if (re <= 0) return __uint_as_float(s);
     return __uint_as_float(s | ((uint32_t)re << 23) | (r & 0x7fffffu));
+}
+
+/* rsqrtss: exponent parity and the top 11 mantissa bits pick the entry, the exponent is exact (slcu.cu verifies this
+ * structure against the host instruction when it measures the table) */
+__device__ uint32_t g_rsqrt_table[4096];
+__device__ __forceinline__ float sl_rsqrt(float x)
+{
+    const uint32_t xb = __float_as_uint(x);
+    const uint32_t e = (xb >> 23) & 0xffu;
+    const uint32_t m = xb & 0x7fffffu;
+    if (e == 0xffu) return m ? __uint_as_float(xb | 0x00400000u) : ((xb >> 31) ? __uint_as_float(0xffc00000u) : 0.f);
+    if (e == 0u) return __uint_as_float((xb & 0x80000000u) | 0x7f800000u);
+    if (xb >> 31) return __uint_as_float(0xffc00000u);
+    const int p = ((int)e - 127) & 1;
+    const uint32_t r = __ldg(&g_rsqrt_table[(uint32_t)p * 2048u + (m >> 12)]);
+    const int re = (int)((r >> 23) & 0xffu) - ((int)e - (127 + p)) / 2;
+    return __uint_as_float(((uint32_t)re << 23) | (r & 0x7fffffu));
 }
 
 __device__ __forceinline__ float sl_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }

@@ -25,6 +25,7 @@
 #include "sl_resolve2.cuh"
 #include "sl_points.cuh"
 #include "sl_wire.cuh"
+#include "sl_lines.cuh"
 #include <cub/device/device_radix_sort.cuh>
 
 using namespace sld;
@@ -41,9 +42,11 @@ typedef cudaError_t (*RasterLauncher)(unsigned grid, cudaStream_t s, const SLSha
 typedef cudaError_t (*PointVertexLauncher)(unsigned grid, cudaStream_t s, const SLPointParams& p);
 typedef cudaError_t (*PointShadeLauncher)(unsigned grid, cudaStream_t s, const SLPointShadeParams& p);
 typedef cudaError_t (*WireShadeLauncher)(unsigned grid, cudaStream_t s, const SLWireShadeParams& p);
+typedef cudaError_t (*LineVertexLauncher)(unsigned grid, cudaStream_t s, const SLLineParams& p);
+typedef cudaError_t (*LineShadeLauncher)(unsigned grid, cudaStream_t s, const SLLineShadeParams& p);
 
-struct VsEntry { const char* name; VertexLauncher launch; PointVertexLauncher launchPoints; };
-struct FsEntry { const char* name; RasterLauncher launch; PointShadeLauncher launchPoints; WireShadeLauncher launchWire; };
+struct VsEntry { const char* name; VertexLauncher launch; PointVertexLauncher launchPoints; LineVertexLauncher launchLines; };
+struct FsEntry { const char* name; RasterLauncher launch; PointShadeLauncher launchPoints; WireShadeLauncher launchWire; LineShadeLauncher launchLines; };
 static std::vector<VsEntry>& vs_registry() { static std::vector<VsEntry> r; return r; }
 static std::vector<FsEntry>& fs_registry() { static std::vector<FsEntry> r; return r; }
 
@@ -86,14 +89,24 @@ template <FsFn FS> static cudaError_t launch_wire_shade(unsigned grid, cudaStrea
     k_wire_shade<FS><<<grid, 128, 0, s>>>(p);
     return cudaGetLastError();
 }
-struct VsReg { VsReg(const char* n, VertexLauncher l, PointVertexLauncher pl) { vs_registry().push_back(VsEntry{n, l, pl}); } };
-struct FsReg { FsReg(const char* n, RasterLauncher l, PointShadeLauncher pl, WireShadeLauncher wl) { fs_registry().push_back(FsEntry{n, l, pl, wl}); } };
+template <VsFn VS> static cudaError_t launch_line_vertex(unsigned grid, cudaStream_t s, const SLLineParams& p)
+{
+    k_line_vertex<VS><<<grid, SL_LINE_BLOCK, 0, s>>>(p);
+    return cudaGetLastError();
+}
+template <FsFn FS> static cudaError_t launch_line_shade(unsigned grid, cudaStream_t s, const SLLineShadeParams& p)
+{
+    k_line_shade<FS><<<grid, 128, 0, s>>>(p);
+    return cudaGetLastError();
+}
+struct VsReg { VsReg(const char* n, VertexLauncher l, PointVertexLauncher pl, LineVertexLauncher ll) { vs_registry().push_back(VsEntry{n, l, pl, ll}); } };
+struct FsReg { FsReg(const char* n, RasterLauncher l, PointShadeLauncher pl, WireShadeLauncher wl, LineShadeLauncher ll) { fs_registry().push_back(FsEntry{n, l, pl, wl, ll}); } };
 
 #define SL_SHADER_FN static __device__ __forceinline__
 #define SL_CAT2(a, b) a##b
 #define SL_CAT(a, b) SL_CAT2(a, b)
-#define SL_REGISTER_VERTEX_SHADER(name, fn) static VsReg SL_CAT(vsreg_, fn){name, launch_vertex<fn>, launch_point_vertex<fn>};
-#define SL_REGISTER_FRAGMENT_SHADER(name, fn) static FsReg SL_CAT(fsreg_, fn){name, launch_raster<fn>, launch_point_shade<fn>, launch_wire_shade<fn>};
+#define SL_REGISTER_VERTEX_SHADER(name, fn) static VsReg SL_CAT(vsreg_, fn){name, launch_vertex<fn>, launch_point_vertex<fn>, launch_line_vertex<fn>};
+#define SL_REGISTER_FRAGMENT_SHADER(name, fn) static FsReg SL_CAT(fsreg_, fn){name, launch_raster<fn>, launch_point_shade<fn>, launch_wire_shade<fn>, launch_line_shade<fn>};
 
 namespace sld
 {
@@ -158,6 +171,39 @@ static bool measure_host_rcp_table(uint32_t* t, std::string& err)
 #endif
 }
 
+/* rsqrtss, the same way: exponent parity + 11 mantissa bits in, exact exponent (line primitives: math::inversesqrt) */
+static float h_rsqrt(const uint32_t* table, float x)
+{
+    const uint32_t xb = h_f2u(x);
+    const uint32_t e = (xb >> 23) & 0xffu, m = xb & 0x7fffffu;
+    if (e == 0xffu) return m ? h_u2f(xb | 0x00400000u) : ((xb >> 31) ? h_u2f(0xffc00000u) : 0.f);
+    if (e == 0u) return h_u2f((xb & 0x80000000u) | 0x7f800000u);
+    if (xb >> 31) return h_u2f(0xffc00000u);
+    const int p = ((int)e - 127) & 1;
+    const uint32_t r = table[(uint32_t)p * 2048u + (m >> 12)];
+    const int re = (int)((r >> 23) & 0xffu) - ((int)e - (127 + p)) / 2;
+    return h_u2f(((uint32_t)re << 23) | (r & 0x7fffffu));
+}
+static bool measure_host_rsqrt_table(uint32_t* t)
+{
+#if defined(__x86_64__)
+    auto rsq = [](float x) { float out; __asm__ volatile("rsqrtss %1, %0" : "=x"(out) : "x"(x)); return out; };
+    for (uint32_t p = 0; p < 2; ++p)
+        for (uint32_t i = 0; i < 2048; ++i) t[p * 2048u + i] = h_f2u(rsq(h_u2f(((127u + p) << 23) | (i << 12))));
+    uint64_t s = 0x9E3779B97F4A7C15ull;
+    for (int i = 0; i < 1000000; ++i)
+    {
+        s ^= s >> 12; s ^= s << 25; s ^= s >> 27;
+        const float x = h_u2f((uint32_t)((s * 0x2545F4914F6CDD1Dull) >> 32));
+        if (h_f2u(rsq(x)) != h_f2u(h_rsqrt(t, x))) return false; /* lines are then refused until a table is pinned */
+    }
+    return true;
+#else
+    (void)t;
+    return false;
+#endif
+}
+
 /* ===========================================================================
  * Context
  * =========================================================================*/
@@ -185,10 +231,10 @@ struct FboView { bool texels = false; uint16_t w = 0, h = 0, d = 0; int type = 0
 struct HostFbo { unsigned numColors = 0; size_t colors[4] = {(size_t)-1, (size_t)-1, (size_t)-1, (size_t)-1}; size_t depth = (size_t)-1; FboView colorViews[4]; FboView depthView; };
 /* kernels of a shader that was registered at run time (slcu_register_shader_source): the same templates, instantiated by
  * NVRTC for the user's __device__ callable and loaded with cudaLibraryLoadData */
-struct RtVertexKernels { cudaKernel_t vertex[2] = {nullptr, nullptr}; cudaKernel_t pointVertex = nullptr; };
-struct RtFragmentKernels { cudaKernel_t shade = nullptr, pointShade = nullptr, wireShade = nullptr; };
-struct HostShader { int cullMode, depthTest, depthMask, blend, numVaryings, numOutputs; VertexLauncher vs; RasterLauncher fs; PointVertexLauncher pointVs; PointShadeLauncher pointFs; WireShadeLauncher wireFs; size_t ubo; RtVertexKernels rtV; RtFragmentKernels rtF; };
-struct RtModule { cudaLibrary_t lib = nullptr; void* rcpTable = nullptr; };
+struct RtVertexKernels { cudaKernel_t vertex[2] = {nullptr, nullptr}; cudaKernel_t pointVertex = nullptr, lineVertex = nullptr; };
+struct RtFragmentKernels { cudaKernel_t shade = nullptr, pointShade = nullptr, wireShade = nullptr, lineShade = nullptr; };
+struct HostShader { int cullMode, depthTest, depthMask, blend, numVaryings, numOutputs; VertexLauncher vs; RasterLauncher fs; PointVertexLauncher pointVs; PointShadeLauncher pointFs; WireShadeLauncher wireFs; LineVertexLauncher lineVs; LineShadeLauncher lineFs; size_t ubo; RtVertexKernels rtV; RtFragmentKernels rtF; };
+struct RtModule { cudaLibrary_t lib = nullptr; void* rcpTable = nullptr; void* rsqrtTable = nullptr; };
 struct RtVsEntry { std::string name; RtVertexKernels k; };
 struct RtFsEntry { std::string name; RtFragmentKernels k; };
 struct UboFixup { size_t ubo, offset; int kind; size_t id, byteOffset; };
@@ -252,6 +298,8 @@ struct slcu_context
     int32_t scissor[4] = {0, 0, 65535, 65535};
     uint32_t rcpTable[2048];
     bool rcpValid = false;
+    uint32_t rsqrtTable[4096];
+    bool rsqrtValid = false;
     std::string err;
     slcu_stats stats{};
     SLCounters* counters = nullptr;     /* device */
@@ -328,6 +376,8 @@ struct KernelScope
 /* what g_rcp_table holds on each device (function attributes and __device__ symbols are per device) */
 static bool g_activeRcpValid[64];
 static uint32_t g_activeRcpCopy[64][2048];
+static bool g_activeRsqrtValid[64];
+static uint32_t g_activeRsqrtCopy[64][4096];
 
 /* execute the pending draw batch before anything that reads or changes what it uses */
 #define SLCU_FLUSH()                                                                     \
@@ -370,6 +420,20 @@ static int ensure_rcp_table(slcu_context* c)
     memcpy(g_activeRcpCopy[d], c->rcpTable, sizeof(c->rcpTable));
     g_activeRcpValid[d] = true;
     for (const RtModule& m : c->rtModules) CK(cudaMemcpy(m.rcpTable, c->rcpTable, sizeof(c->rcpTable), cudaMemcpyHostToDevice)); /* every module has its own g_rcp_table */
+    return 0;
+}
+
+static int ensure_rsqrt_table(slcu_context* c)
+{
+    if (!c->rsqrtValid) { c->err = "no rsqrt table (line primitives need one: set_rsqrt_table)"; return SLCU_ERR_UNSUPPORTED; }
+    CK(cudaSetDevice(c->device));
+    const int d = c->device & 63;
+    if (g_activeRsqrtValid[d] && memcmp(g_activeRsqrtCopy[d], c->rsqrtTable, sizeof(c->rsqrtTable)) == 0) return 0;
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyToSymbol(g_rsqrt_table, c->rsqrtTable, sizeof(c->rsqrtTable)));
+    memcpy(g_activeRsqrtCopy[d], c->rsqrtTable, sizeof(c->rsqrtTable));
+    g_activeRsqrtValid[d] = true;
+    for (const RtModule& m : c->rtModules) CK(cudaMemcpy(m.rsqrtTable, c->rsqrtTable, sizeof(c->rsqrtTable), cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -467,6 +531,16 @@ static cudaError_t launch_point_vertex_stage(const HostShader& sh, unsigned grid
     if (sh.rtV.pointVertex) return launch_rt(sh.rtV.pointVertex, grid, 256, 0, s, p);
     return sh.pointVs(grid, s, p);
 }
+static cudaError_t launch_line_vertex_stage(const HostShader& sh, unsigned grid, cudaStream_t s, const SLLineParams& p)
+{
+    if (sh.rtV.lineVertex) return launch_rt(sh.rtV.lineVertex, grid, SL_LINE_BLOCK, 0, s, p);
+    return sh.lineVs(grid, s, p);
+}
+static cudaError_t launch_line_shade_stage(const HostShader& sh, unsigned grid, cudaStream_t s, const SLLineShadeParams& p)
+{
+    if (sh.rtF.lineShade) return launch_rt(sh.rtF.lineShade, grid, 128, 0, s, p);
+    return sh.lineFs(grid, s, p);
+}
 static cudaError_t launch_point_shade_stage(const HostShader& sh, unsigned grid, cudaStream_t s, const SLPointShadeParams& p)
 {
     if (sh.rtF.pointShade) return launch_rt(sh.rtF.pointShade, grid, 128, 0, s, p);
@@ -489,6 +563,7 @@ static const size_t kMaxBatchDraws = 65535;    /* recDraw is 16 bits */
 
 static int flush_draws(slcu_context* c);
 static int run_points(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, size_t numInstances, size_t shaderId, size_t fboId);
+static int run_lines(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, size_t numInstances, size_t shaderId, size_t fboId);
 
 static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, size_t numInstances, size_t shaderId, size_t fboId)
 {
@@ -500,7 +575,7 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
         case 0x10u: case 0x30u: break;                                                                /* triangles */
         case 0x50u: case 0x70u: break;                                                                /* wireframe triangles */
         case 0x01u: case 0x03u: return run_points(c, meshes, numMeshes, numInstances, shaderId, fboId); /* points */
-        case 0x04u: case 0x0cu: c->err = "RENDER_MODE_LINES / INDEXED_LINES are not implemented (no CPU fallback)"; return SLCU_ERR_UNSUPPORTED;
+        case 0x04u: case 0x0cu: return run_lines(c, meshes, numMeshes, numInstances, shaderId, fboId);                 /* lines */
         default: c->err = "unknown render mode"; return SLCU_ERR_ARG;
     }
     const HostShader& sh = c->shaders[shaderId];
@@ -701,6 +776,145 @@ static int run_points(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes
         }
         sp.counters = c->counters;
         { KernelScope ks(c, SLCU_K_SHADE); CK(launch_point_shade_stage(sh, (unsigned)((numPoints + 127ull) / 128ull), c->stream, sp)); }
+    }
+    k_commit<<<1, 1, 0, c->stream>>>(c->counters);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+
+/* SL_LineProcessor + SL_LineRasterizer (src/SL_LineProcessor.cpp, src/SL_LineRasterizer.cpp): executed at submission, after
+ * the triangle batch that precedes it; one (vertex, emit, sort, shade) pass per mesh / per instanced draw (sl_lines.cuh). */
+static int run_lines(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, size_t numInstances, size_t shaderId, size_t fboId)
+{
+    int rc = flush_draws(c);
+    if (rc) return rc;
+    const HostShader& sh = c->shaders[shaderId];
+    const HostFbo& fbo = c->fbos[fboId];
+    if (fbo.depth == (size_t)-1 || fbo.depth >= c->textures.size()) { c->err = "fbo has no depth attachment"; return SLCU_ERR_ARG; }
+    const HostTexture& depthTex = c->textures[fbo.depth];
+    if (depthTex.w > 32767 || depthTex.h > 32767) { c->err = "framebuffer too large"; return SLCU_ERR_UNSUPPORTED; }
+    if (depthTex.bpt != 2 && depthTex.bpt != 4 && depthTex.bpt != 8) { c->err = "depth attachment must be R_HALF/R_FLOAT/R_DOUBLE"; return SLCU_ERR_ARG; }
+    for (int i = 0; i < sh.numOutputs; ++i)
+    {
+        if ((unsigned)i >= fbo.numColors || fbo.colors[i] >= c->textures.size()) { c->err = "shader writes an unattached colour buffer"; return SLCU_ERR_ARG; }
+        const HostTexture& t = c->textures[fbo.colors[i]];
+        const int kind = t.type % 7;
+        if (kind == 2 || kind == 3) { c->err = "32/64-bit integer colour targets are not implemented"; return SLCU_ERR_UNSUPPORTED; }
+        if (t.w != depthTex.w || t.h != depthTex.h) { c->err = "colour and depth attachments differ in size (SL_Framebuffer::valid -7 / -8)"; return SLCU_ERR_ARG; }
+    }
+    const size_t launches = (numInstances == 1) ? numMeshes : 1;
+    for (size_t i = 0; i < launches; ++i)
+    {
+        const slcu_mesh& m = meshes[i];
+        if (m.vaoId >= c->vaos.size()) { c->err = "bad vao id"; return SLCU_ERR_ARG; }
+        const HostVao& vao = c->vaos[m.vaoId];
+        if (vao.vbo >= c->vbos.size()) { c->err = "vao has no vertex buffer"; return SLCU_ERR_ARG; }
+        if (m.mode == 0x0cu && vao.ibo >= c->ibos.size()) { c->err = "indexed draw without index buffer"; return SLCU_ERR_ARG; }
+    }
+    rc = ensure_rcp_table(c);
+    if (rc) return rc;
+    rc = ensure_rsqrt_table(c);
+    if (rc) return rc;
+    cudaSetDevice(c->device);
+    c->stats.drawCalls++;
+    CK(cudaMemsetAsync(c->counters, 0, SL_COUNTERS_BATCH_BYTES, c->stream)); /* the per-batch part; k_commit adds it to the totals */
+    const float fboW = (float)depthTex.w, fboH = (float)depthTex.h;
+    const int NV = sh.numVaryings;
+    unsigned pixBits = 1;
+    while ((1ull << pixBits) <= (unsigned long long)depthTex.w * depthTex.h) ++pixBits; /* 2^pixBits - 1 >= w*h: the invisible key sorts last */
+    for (size_t i = 0; i < launches; ++i)
+    {
+        const slcu_mesh& m = meshes[i];
+        const unsigned long long elems = m.elementEnd > m.elementBegin ? (unsigned long long)(m.elementEnd - m.elementBegin) : 0ull;
+        const unsigned long long per = (elems + 1ull) / 2ull; /* for (i = begin; i < end; i += 2) */
+        const unsigned long long numLines = per * (numInstances == 1 ? 1 : numInstances);
+        c->stats.trisSubmitted += (elems / 3) * (numInstances == 1 ? 1 : numInstances);
+        if (!numLines) continue;
+        if (numLines > 0x3ffffff0ull) { c->err = "draw too large for one pass"; return SLCU_ERR_UNSUPPORTED; }
+        const HostVao& vao = c->vaos[m.vaoId];
+        const bool usingIndices = m.mode == 0x0cu; /* per mesh (src/SL_LineProcessor.cpp:205) */
+        SLDrawDesc d;
+        memset(&d, 0, sizeof(d));
+        snapshot_uniforms(c, sh.ubo, d.uniforms);
+        d.vao = vao.vao;
+        d.vbo.mBuffer = c->vbos[vao.vbo].ptr;
+        d.usingIndices = usingIndices ? 1 : 0;
+        d.ibo = usingIndices ? c->ibos[vao.ibo].buf.ptr : nullptr;
+        d.iboType = usingIndices ? c->ibos[vao.ibo].type : 2;
+        host_scissor_matrix(c, fboW, fboH, d.scissor);
+        host_viewport_rect(c, fboW, fboH, d.viewport);
+        d.elementBegin = m.elementBegin;
+        d.primsPerInstance = per;
+        d.numPrims = numLines;
+        CK(c->drawTable.ensure(sizeof(SLDrawDesc)));
+        CK(cudaMemcpyAsync(c->drawTable.buf.ptr, &d, sizeof(SLDrawDesc), cudaMemcpyHostToDevice, c->stream)); /* pageable source: staged before the call returns */
+        const unsigned numBlocks = (unsigned)((numLines + SL_LINE_BLOCK - 1) / SL_LINE_BLOCK);
+        CK(c->records.ensure((size_t)numLines * (2 + 2 * NV) * sizeof(float4)));
+        CK(c->cnt.ensure((size_t)numLines * sizeof(uint32_t)));
+        CK(c->segSums.ensure((size_t)numBlocks * sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(&c->counters->pixelsCovered, 0, sizeof(unsigned long long), c->stream));
+
+        SLLineParams lp;
+        memset(&lp, 0, sizeof(lp));
+        lp.draw = reinterpret_cast<const SLDrawDesc*>(c->drawTable.buf.ptr);
+        lp.numLines = numLines;
+        lp.linesPerInstance = per;
+        lp.numVaryings = NV;
+        lp.width = depthTex.w;
+        lp.height = depthTex.h;
+        lp.rank = c->partRank;
+        lp.world = c->partWorld;
+        lp.stripRows = c->partStripRows;
+        lp.lines = reinterpret_cast<float4*>(c->records.buf.ptr);
+        lp.lineCount = reinterpret_cast<uint32_t*>(c->cnt.buf.ptr);
+        lp.blockSum = reinterpret_cast<unsigned long long*>(c->segSums.buf.ptr);
+        lp.counters = c->counters;
+        { KernelScope ks(c, SLCU_K_VERTEX); CK(launch_line_vertex_stage(sh, numBlocks, c->stream, lp)); }
+        { KernelScope ks(c, SLCU_K_SCAN); k_line_offsets<<<1, 1024, 0, c->stream>>>(lp.blockSum, numBlocks); }
+        CK(cudaGetLastError());
+        /* the candidates' number sizes the next buffers: one host round trip per line draw */
+        CK(cudaMemcpyAsync(c->hostCounters, c->counters, sizeof(SLCounters), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        const unsigned long long numCands = c->hostCounters->pixelsCovered;
+        if (!numCands) continue;
+        if (numCands > 0xfffffff0ull) { c->err = "too many line fragments for one pass"; return SLCU_ERR_UNSUPPORTED; }
+        CK(c->pointKeys.ensure((size_t)numCands * 2 * sizeof(unsigned long long)));
+        CK(c->pointRecs.ensure((size_t)numCands * sizeof(float4)));
+        unsigned long long* keysA = reinterpret_cast<unsigned long long*>(c->pointKeys.buf.ptr);
+        cub::DoubleBuffer<unsigned long long> keys(keysA, keysA + numCands);
+        size_t tempBytes = 0;
+        CK(cub::DeviceRadixSort::SortKeys(nullptr, tempBytes, keys, (int)numCands, 32, 32 + (int)pixBits, c->stream));
+        CK(c->pointSortTemp.ensure(tempBytes));
+        lp.keys = keysA;
+        lp.cands = reinterpret_cast<float4*>(c->pointRecs.buf.ptr);
+        { KernelScope ks(c, SLCU_K_SPAN_FILL); k_line_emit<<<numBlocks, SL_LINE_BLOCK, 0, c->stream>>>(lp); }
+        CK(cudaGetLastError());
+        /* stable LSD sort on the texel bits only: inside a texel the keys stay in submission order */
+        { KernelScope ks(c, SLCU_K_SCAN); CK(cub::DeviceRadixSort::SortKeys(c->pointSortTemp.buf.ptr, tempBytes, keys, (int)numCands, 32, 32 + (int)pixBits, c->stream)); }
+
+        SLLineShadeParams sp;
+        memset(&sp, 0, sizeof(sp));
+        sp.draw = lp.draw;
+        sp.keys = keys.Current();
+        sp.cands = lp.cands;
+        sp.lines = lp.lines;
+        sp.numCands = numCands;
+        sp.numVaryings = NV;
+        sp.numOutputs = sh.numOutputs;
+        sp.blend = sh.blend;
+        sp.depthTest = sh.depthTest;
+        sp.depthMask = sh.depthMask;
+        sp.depth = depthTex.dev;
+        sp.depthBpt = depthTex.bpt;
+        for (int k = 0; k < 4; ++k)
+        {
+            sp.color[k] = nullptr;
+            sp.colorType[k] = 0;
+            if (k < sh.numOutputs) { const HostTexture& t = c->textures[fbo.colors[k]]; sp.color[k] = t.dev; sp.colorType[k] = t.type; }
+        }
+        sp.counters = c->counters;
+        { KernelScope ks(c, SLCU_K_SHADE); CK(launch_line_shade_stage(sh, (unsigned)((numCands + 127ull) / 128ull), c->stream, sp)); }
     }
     k_commit<<<1, 1, 0, c->stream>>>(c->counters);
     CK(cudaGetLastError());
@@ -1442,6 +1656,7 @@ static int report_device_flags(slcu_context* c, unsigned flags)
     if (flags & SL_ERR_POOL) m += " [fragment pool exhausted: fragments dropped]";
     if (flags & SL_ERR_WIRE_SEGMENT) m += " [wireframe: record segment over 256]";
     if (flags & SL_ERR_WIRE_SLOTS) m += " [wireframe: candidate slots exhausted]";
+    if (flags & SL_ERR_LINE_ALIAS) m += " [line: a segment visits texel (width, y) = (0, y + 1) twice: reference behaviour not reproduced]";
     if (flags & SL_ERR_GEOM_TIMEOUT) m += " [shared vertex stage: a rank never delivered its vertex blocks]";
     c->err = m;
     cudaMemsetAsync(&c->counters->errorFlags, 0, sizeof(unsigned), c->stream);
@@ -1469,6 +1684,7 @@ int slcu_context_create(slcu_context** out, int device)
     if (cudaMallocHost(&c->hostCounters, 2 * sizeof(SLCounters)) != cudaSuccess) { cudaFree(c->counters); cudaStreamDestroy(c->stream); delete c; return SLCU_ERR_CUDA; }
     for (Scratch* x : all_scratch(c)) x->stream = c->stream;
     c->rcpValid = measure_host_rcp_table(c->rcpTable, c->err);
+    c->rsqrtValid = measure_host_rsqrt_table(c->rsqrtTable);
     c->syncDraws = getenv("SLCU_SYNC_DRAWS") != nullptr && atoi(getenv("SLCU_SYNC_DRAWS")) != 0;
     *out = c;
     return 0;
@@ -1510,6 +1726,20 @@ int slcu_set_rcp_table(slcu_context* c, const uint32_t* t)
     if (!c || !t) return SLCU_ERR_ARG;
     memcpy(c->rcpTable, t, sizeof(c->rcpTable));
     c->rcpValid = true;
+    return 0;
+}
+int slcu_set_rsqrt_table(slcu_context* c, const uint32_t* t)
+{
+    SLCU_FLUSH();
+    if (!c || !t) return SLCU_ERR_ARG;
+    memcpy(c->rsqrtTable, t, sizeof(c->rsqrtTable));
+    c->rsqrtValid = true;
+    return 0;
+}
+int slcu_get_rsqrt_table(slcu_context* c, uint32_t* t)
+{
+    if (!c || !t || !c->rsqrtValid) return SLCU_ERR_ARG;
+    memcpy(t, c->rsqrtTable, sizeof(c->rsqrtTable));
     return 0;
 }
 int slcu_get_rcp_table(slcu_context* c, uint32_t* t)
@@ -1914,8 +2144,8 @@ struct CompiledShaders
 {
     std::vector<char> cubin;
     std::vector<ParsedRegistration> regs;
-    std::vector<std::string> lowered; /* per registration: 3 kernel names (vertex: k_vertex<,false>, k_vertex<,true>, k_point_vertex; fragment: k_shade, k_point_shade, k_wire_shade) */
-    std::string rcpName;
+    std::vector<std::string> lowered; /* per registration: 4 kernel names (vertex: k_vertex<,false>, k_vertex<,true>, k_point_vertex, k_line_vertex; fragment: k_shade, k_point_shade, k_wire_shade, k_line_shade) */
+    std::string rcpName, rsqrtName;
 };
 
 static int compile_shader_source(const char* source, CompiledShaders& out, std::string& log)
@@ -1923,7 +2153,7 @@ static int compile_shader_source(const char* source, CompiledShaders& out, std::
     if (!source) { log = "no source"; return SLCU_ERR_ARG; }
     out.regs = parse_registrations(source);
     if (out.regs.empty()) { log = "the source registers no shader (SL_REGISTER_VERTEX_SHADER / SL_REGISTER_FRAGMENT_SHADER)"; return SLCU_ERR_ARG; }
-    std::string tu = "#include \"sl_pipeline.cuh\"\n#include \"sl_points.cuh\"\n#include \"sl_wire.cuh\"\n"
+    std::string tu = "#include \"sl_pipeline.cuh\"\n#include \"sl_points.cuh\"\n#include \"sl_wire.cuh\"\n#include \"sl_lines.cuh\"\n"
                      "#define SL_SHADER_FN static __device__ __forceinline__\n"
                      "#define SL_REGISTER_VERTEX_SHADER(name, fn)\n#define SL_REGISTER_FRAGMENT_SHADER(name, fn)\n"
                      "namespace sld {\n#line 1 \"user_shader\"\n";
@@ -1949,14 +2179,17 @@ static int compile_shader_source(const char* source, CompiledShaders& out, std::
             exprs.push_back("&sld::k_vertex<sld::" + r.fn + ", false>");
             exprs.push_back("&sld::k_vertex<sld::" + r.fn + ", true>");
             exprs.push_back("&sld::k_point_vertex<sld::" + r.fn + ">");
+            exprs.push_back("&sld::k_line_vertex<sld::" + r.fn + ">");
         }
         else
         {
             exprs.push_back("&sld::k_shade<sld::" + r.fn + ">");
             exprs.push_back("&sld::k_point_shade<sld::" + r.fn + ">");
             exprs.push_back("&sld::k_wire_shade<sld::" + r.fn + ">");
+            exprs.push_back("&sld::k_line_shade<sld::" + r.fn + ">");
         }
     }
+    exprs.push_back("&sld::g_rsqrt_table");
     exprs.push_back("&sld::g_rcp_table");
     for (const std::string& e : exprs) nvrtcAddNameExpression(prog, e.c_str());
     const char* cudaHome = getenv("CUDA_HOME") ? getenv("CUDA_HOME") : "/usr/local/cuda";
@@ -1973,7 +2206,9 @@ static int compile_shader_source(const char* source, CompiledShaders& out, std::
     {
         const char* low = nullptr;
         if (nvrtcGetLoweredName(prog, exprs[i].c_str(), &low) != NVRTC_SUCCESS || !low) { log = "no lowered name for " + exprs[i]; nvrtcDestroyProgram(&prog); return SLCU_ERR_CUDA; }
-        if (i + 1 == exprs.size()) out.rcpName = low; else out.lowered.push_back(low);
+        if (i + 1 == exprs.size()) out.rcpName = low;
+        else if (i + 2 == exprs.size()) out.rsqrtName = low;
+        else out.lowered.push_back(low);
     }
     size_t bytes = 0;
     nvrtcGetCUBINSize(prog, &bytes);
@@ -2009,16 +2244,20 @@ int slcu_register_shader_source(slcu_context* c, const char* source)
     CK(cudaLibraryGetGlobal(&m.rcpTable, &rcpBytes, m.lib, cs.rcpName.c_str()));
     if (rcpBytes != sizeof(c->rcpTable)) { c->err = "run-time module: unexpected rcp table size"; return SLCU_ERR_CUDA; }
     if (c->rcpValid) CK(cudaMemcpy(m.rcpTable, c->rcpTable, sizeof(c->rcpTable), cudaMemcpyHostToDevice));
+    size_t rsqrtBytes = 0;
+    CK(cudaLibraryGetGlobal(&m.rsqrtTable, &rsqrtBytes, m.lib, cs.rsqrtName.c_str()));
+    if (rsqrtBytes != sizeof(c->rsqrtTable)) { c->err = "run-time module: unexpected rsqrt table size"; return SLCU_ERR_CUDA; }
+    if (c->rsqrtValid) CK(cudaMemcpy(m.rsqrtTable, c->rsqrtTable, sizeof(c->rsqrtTable), cudaMemcpyHostToDevice));
     for (size_t i = 0; i < cs.regs.size(); ++i)
     {
-        cudaKernel_t k[3] = {nullptr, nullptr, nullptr};
-        for (int j = 0; j < 3; ++j) CK(cudaLibraryGetKernel(&k[j], m.lib, cs.lowered[3 * i + j].c_str()));
+        cudaKernel_t k[4] = {nullptr, nullptr, nullptr, nullptr};
+        for (int j = 0; j < 4; ++j) CK(cudaLibraryGetKernel(&k[j], m.lib, cs.lowered[4 * i + j].c_str()));
         if (cs.regs[i].vertex)
         {
             CK(cudaFuncSetAttribute(reinterpret_cast<const void*>(k[1]), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVertexCacheMaxBytes));
             RtVsEntry e;
             e.name = cs.regs[i].name;
-            e.k.vertex[0] = k[0]; e.k.vertex[1] = k[1]; e.k.pointVertex = k[2];
+            e.k.vertex[0] = k[0]; e.k.vertex[1] = k[1]; e.k.pointVertex = k[2]; e.k.lineVertex = k[3];
             bool replaced = false;
             for (RtVsEntry& old : c->rtVs) if (old.name == e.name) { old = e; replaced = true; }
             if (!replaced) c->rtVs.push_back(e);
@@ -2027,7 +2266,7 @@ int slcu_register_shader_source(slcu_context* c, const char* source)
         {
             RtFsEntry e;
             e.name = cs.regs[i].name;
-            e.k.shade = k[0]; e.k.pointShade = k[1]; e.k.wireShade = k[2];
+            e.k.shade = k[0]; e.k.pointShade = k[1]; e.k.wireShade = k[2]; e.k.lineShade = k[3];
             bool replaced = false;
             for (RtFsEntry& old : c->rtFs) if (old.name == e.name) { old = e; replaced = true; }
             if (!replaced) c->rtFs.push_back(e);
@@ -2047,9 +2286,11 @@ size_t slcu_create_shader(slcu_context* c, const slcu_vertex_shader* vs, const s
     RasterLauncher fl = nullptr;
     PointVertexLauncher pvl = nullptr;
     PointShadeLauncher pfl = nullptr;
+    LineVertexLauncher lvl = nullptr;
+    LineShadeLauncher lfl = nullptr;
     WireShadeLauncher wfl = nullptr;
-    for (const VsEntry& e : vs_registry()) if (!strcmp(e.name, vs->shader)) { vl = e.launch; pvl = e.launchPoints; }
-    for (const FsEntry& e : fs_registry()) if (!strcmp(e.name, fs->shader)) { fl = e.launch; pfl = e.launchPoints; wfl = e.launchWire; }
+    for (const VsEntry& e : vs_registry()) if (!strcmp(e.name, vs->shader)) { vl = e.launch; pvl = e.launchPoints; lvl = e.launchLines; }
+    for (const FsEntry& e : fs_registry()) if (!strcmp(e.name, fs->shader)) { fl = e.launch; pfl = e.launchPoints; wfl = e.launchWire; lfl = e.launchLines; }
     RtVertexKernels rtV;
     RtFragmentKernels rtF;
     for (const RtVsEntry& e : c->rtVs) if (e.name == vs->shader) rtV = e.k; /* a run-time registration shadows a built-in of the same name */
@@ -2061,7 +2302,7 @@ size_t slcu_create_shader(slcu_context* c, const slcu_vertex_shader* vs, const s
     }
     HostShader s;
     s.cullMode = vs->cullMode; s.depthTest = fs->depthTest; s.depthMask = fs->depthMask; s.blend = fs->blend;
-    s.numVaryings = fs->numVaryings; s.numOutputs = fs->numOutputs; s.vs = vl; s.fs = fl; s.pointVs = pvl; s.pointFs = pfl; s.wireFs = wfl; s.ubo = ubo; s.rtV = rtV; s.rtF = rtF;
+    s.numVaryings = fs->numVaryings; s.numOutputs = fs->numOutputs; s.vs = vl; s.fs = fl; s.pointVs = pvl; s.pointFs = pfl; s.wireFs = wfl; s.lineVs = lvl; s.lineFs = lfl; s.ubo = ubo; s.rtV = rtV; s.rtF = rtF;
     c->shaders.push_back(s);
     return c->shaders.size() - 1;
 }

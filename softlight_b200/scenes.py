@@ -403,10 +403,13 @@ def indoor_scene(width=3840, height=2160, rooms=(16, 16), quads=26, tex_size=512
 def random_tris_scene(seed=1, n=400, width=200, height=150, blend=A.SL_BLEND_OFF, depth_test=A.SL_DEPTH_TEST_LESS_THAN,
                       depth_mask=A.SL_DEPTH_MASK_ON, depth_type=A.SL_COLOR_R_FLOAT, color_type=A.SL_COLOR_RGBA_8U,
                       cull=A.SL_CULL_OFF, index_dtype=np.uint16, clip_fraction=0.3, clear_depth=1.0, viewport=None,
-                      scissor=None, split_draws=1, multiple=False, name=None, empty_draw=False, mrt_types=None, points=False, instances=1, wire=False) -> Scene:
+                      scissor=None, split_draws=1, multiple=False, name=None, empty_draw=False, mrt_types=None, points=False, instances=1, wire=False,
+                      lines=False) -> Scene:
     """points: the same vertices drawn as RENDER_MODE_POINTS / INDEXED_POINTS (one fragment per visible vertex,
     SL_PointProcessor / SL_PointRasterizer); instances > 1 issues draw_instanced (the vertex shader ignores the id, so every
     instance lands on the same pixels: a pure ordering test).
+    lines: the same vertices drawn as RENDER_MODE_LINES / INDEXED_LINES (SL_LineProcessor / SL_LineRasterizer): consecutive
+    element pairs are segments.
     mrt_types: colour types of render targets 1..3 (sl_mrt_test.cpp:150-200 attaches four); the "vcolor_mrt" fragment shader
     then writes four outputs and SceneInstance.read_colors() returns all attachments."""
     rng = np.random.default_rng(seed)
@@ -463,6 +466,8 @@ def random_tris_scene(seed=1, n=400, width=200, height=150, blend=A.SL_BLEND_OFF
             mode = A.RENDER_MODE_INDEXED_POINTS if idx is not None else A.RENDER_MODE_POINTS
         if wire:  # SL_TriRasterizer::render_wireframe: the same triangles, edges only
             mode = A.RENDER_MODE_INDEXED_TRI_WIRE if idx is not None else A.RENDER_MODE_TRI_WIRE
+        if lines:
+            mode = A.RENDER_MODE_INDEXED_LINES if idx is not None else A.RENDER_MODE_LINES
         per = (n // split_draws) * 3
         meshes = []
         for d in range(split_draws):

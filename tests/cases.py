@@ -123,6 +123,27 @@ WIRE_CASES = {
 }
 for _i, _name in enumerate(WIRE_CASES):
     CASES[_name] = (lambda i=_i, name=_name: S.random_tris_scene(seed=950 + i, name=name, wire=True, **WIRE_CASES[name]))
+# RENDER_MODE_LINES / INDEXED_LINES (SL_LineProcessor + SL_LineRasterizer): consecutive element pairs of the same random
+# vertices are segments; clip_fraction puts vertices behind the eye (segment dropped) or outside the frustum (Liang-Barsky
+# against the viewport rectangle), blending makes the per-texel submission order visible.
+LINE_CASES = {
+    "lines_basic": dict(n=300),
+    "lines_alpha_clip": dict(n=300, width=64, height=48, blend=1, clip_fraction=0.6),
+    "lines_premult_half_le": dict(n=2000, width=320, height=200, clip_fraction=0.5, blend=2, depth_type=A.SL_COLOR_R_HALF,
+                                  depth_test=A.SL_DEPTH_TEST_LESS_EQUAL),
+    "lines_noindex_split3_additive": dict(n=500, index_dtype=None, split_draws=3, blend=3, depth_mask=A.SL_DEPTH_MASK_OFF),
+    "lines_viewport_scissor": dict(n=500, viewport=(20, 10, 120, 90), scissor=(30, 20, 100, 80)),
+    "lines_instanced3_alpha": dict(n=300, instances=3, blend=1, depth_test=A.SL_DEPTH_TEST_LESS_EQUAL),
+    "lines_1080p": dict(n=200, width=1920, height=1080, clip_fraction=0.2),
+    "lines_tiny_1x1": dict(n=50, width=1, height=1),
+    "lines_nodepth_small": dict(n=700, width=37, height=21, clip_fraction=0.9, blend=1, depth_test=A.SL_DEPTH_TEST_OFF),
+    "lines_multi4_u32_double_ge": dict(n=333, width=257, height=131, multiple=True, split_draws=4, index_dtype=np.uint32,
+                                       depth_type=A.SL_COLOR_R_DOUBLE, depth_test=A.SL_DEPTH_TEST_GREATER_EQUAL, clear_depth=-1.0),
+    "lines_u8_rgbf": dict(n=80, index_dtype=np.uint8, color_type=A.SL_COLOR_RGB_FLOAT),
+    "lines_empty": dict(n=30, empty_draw=True),
+}
+for _i, _name in enumerate(LINE_CASES):
+    CASES[_name] = (lambda i=_i, name=_name: S.random_tris_scene(seed=1000 + i, name=name, lines=True, **LINE_CASES[name]))
 CASES["draw_test"] = S.SCENES["draw_test"]
 CASES["c1_small"] = S.SCENES["c1_small"]
 CASES["c2_small"] = S.SCENES["c2_small"]
@@ -144,17 +165,32 @@ BIG_CASES = {
 }
 
 # cases whose images are committed in full (the rest of CASES is pinned by sha256)
-FULL_IMAGE_CASES = ["draw_test", "c1_small", "c2_small", "c3_small", "c4_small", "c5_small", "sampler_matrix", "rand_blend1", "rand_clip_heavy", "rand_depth_half_premult", "points_dense", "wire_alpha"]
+FULL_IMAGE_CASES = ["draw_test", "c1_small", "c2_small", "c3_small", "c4_small", "c5_small", "sampler_matrix", "rand_blend1", "rand_clip_heavy", "rand_depth_half_premult", "points_dense", "wire_alpha", "lines_alpha_clip"]
 
 
 def bits(a: np.ndarray) -> np.ndarray:
     return a.view({1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[a.dtype.itemsize])
 
 
+_GOLDEN_RSQRT = None
+
+
+def golden_rsqrt_table():
+    """The rsqrtss table of the CPU the goldens were generated on (stored next to the rcp table)."""
+    global _GOLDEN_RSQRT
+    if _GOLDEN_RSQRT is None:
+        import os
+
+        f = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_frames.npz"))
+        _GOLDEN_RSQRT = f["rsqrt_table"]
+    return _GOLDEN_RSQRT
+
+
 def render(impl: str, scene, rcp_table=None, device=0, threads=1):
     ctx = A.Context(impl, device=device, threads=threads)
     if rcp_table is not None and not impl.startswith("ref"):
         ctx.set_rcp_table(rcp_table)
+        ctx.set_rsqrt_table(golden_rsqrt_table())  # pinned together: both tables belong to the CPU that made the goldens
     ctx.reset_stats()
     inst = S.SceneInstance(scene, ctx)
     inst.render()

@@ -27,7 +27,7 @@ def main():
         only = set(sys.argv[sys.argv.index("--only") + 1].split(","))
     ctx = A.Context("ref_strict")
     rcp = ctx.get_rcp_table()
-    frames = {"rcp_table": rcp}
+    frames = {"rcp_table": rcp, "rsqrt_table": ctx.get_rsqrt_table()}
     hashes = {}
     allcases = dict(cases.CASES)
     allcases.update(cases.BIG_CASES)
@@ -35,6 +35,9 @@ def main():
         old = json.load(open(os.path.join(HERE, "golden_hashes.json")))
         oldFrames = dict(np.load(os.path.join(HERE, "golden_frames.npz")))
         assert np.array_equal(oldFrames["rcp_table"], rcp), "the committed goldens were generated with another rcp table"
+        if "rsqrt_table" in oldFrames:
+            assert np.array_equal(oldFrames["rsqrt_table"], ctx.get_rsqrt_table()), "the committed goldens were generated with another rsqrt table"
+        oldFrames["rsqrt_table"] = ctx.get_rsqrt_table()
         assert only <= set(allcases), only - set(allcases)
         for name in sorted(only):
             scene = allcases[name]()

@@ -192,13 +192,38 @@ def test_empty_point_draw_is_a_noop():
     assert np.all(color == color[0, 0]) and np.all(depth == 1.0)
 
 
-@pytest.mark.parametrize("mode", [A.RENDER_MODE_LINES, A.RENDER_MODE_INDEXED_LINES, 0x1234])
+@pytest.mark.parametrize("mode", [0x1234, 0x02])
 def test_unimplemented_render_modes_are_refused_loudly(mode):
     ctx = A.Context("cuda")
     st = S.SceneInstance(S.random_tris_scene(seed=2, n=10), ctx)
     m = st.state["meshes"][0]
     with pytest.raises(A.SlError):
         ctx.draw(ctx.mesh(m.vaoId, m.elementBegin, m.elementEnd, mode), st.state["shader"], st.state["fbo"])
+
+
+def test_lines_between_triangle_draws_keep_submission_order(golden):
+    """triangles, lines, triangles on one framebuffer: the line pass executes between the two triangle batches, exactly
+    like the oracle's draw-by-draw execution."""
+    frames, _ = golden
+
+    def run(impl):
+        ctx = A.Context(impl)
+        ctx.set_rcp_table(frames["rcp_table"])
+        ctx.set_rsqrt_table(frames["rsqrt_table"])
+        tri = S.SceneInstance(S.random_tris_scene(seed=41, n=300, blend=1), ctx)
+        st = tri.state
+        ctx.clear_framebuffer(st["fbo"], 0, (0.1, 0.2, 0.3, 1.0), 1.0)
+        m = st["meshes"][0]
+        third = (m.elementEnd - m.elementBegin) // 9 * 3
+        ctx.draw(ctx.mesh(m.vaoId, 0, third, A.RENDER_MODE_INDEXED_TRIANGLES), st["shader"], st["fbo"])
+        ctx.draw(ctx.mesh(m.vaoId, 0, m.elementEnd, A.RENDER_MODE_INDEXED_LINES), st["shader"], st["fbo"])
+        ctx.draw(ctx.mesh(m.vaoId, third, 2 * third, A.RENDER_MODE_INDEXED_TRIANGLES), st["shader"], st["fbo"])
+        ctx.sync()
+        return tri.read_color(), tri.read_depth()
+
+    cg, dg = run("cuda")
+    co, do = run("port")
+    assert_same(cg, dg, co, do)
 
 
 def test_points_between_triangle_draws_keep_submission_order(golden):

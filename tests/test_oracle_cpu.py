@@ -73,6 +73,22 @@ def test_rcp_table_emulation_matches_host_instruction(golden):
     assert np.all(((table >> 23) & 0xFF) == 126)
 
 
+def test_rsqrt_table_shape_and_structure(golden):
+    """rsqrtss == table[exponent parity][top 11 mantissa bits] with exact exponent handling (line primitives:
+    math::inversesqrt).  The committed table came from the instruction on the generating host; the port measures its own
+    the same way, and on an Intel-class host the 11th mantissa bit is redundant (10 bits decide)."""
+    frames, _ = golden
+    ctx = A.Context("port")
+    table = ctx.get_rsqrt_table()
+    pinned = frames["rsqrt_table"]
+    assert table.shape == pinned.shape == (4096,)
+    for t in (table, pinned):
+        assert t[0] in (0x3F7FF000, 0x3F800000)          # rsqrt(1.0): just below or exactly 1
+        assert np.all(((t[:2048] >> 23) & 0xFF) >= 126)  # [1, 2) -> (0.70, 1.0]
+        assert np.all(((t[2048:] >> 23) & 0xFF) == 126)  # [2, 4) -> (0.5, 0.7071]
+        assert np.all(np.diff(t[:2048].astype(np.int64)) <= 0) and np.all(np.diff(t[2048:].astype(np.int64)) <= 0)  # monotone
+
+
 def test_half_conversion_restatement():
     """float->half RNE of the oracle (depth writes) against numpy's IEEE conversion, all finite halves +- neighbours."""
     import ctypes as C
