@@ -228,6 +228,18 @@ SLCU_EXPORT int SLCU_FN(blit_rect)(slcu_context* ctx, size_t outTexture, size_t 
                                    uint16_t srcX0, uint16_t srcY0, uint16_t srcX1, uint16_t srcY1,
                                    uint16_t dstX0, uint16_t dstY0, uint16_t dstX1, uint16_t dstY1);
 
+/* SL_Context::blit(SL_TextureView& buffer, size_t textureId[, rectangles]) (src/SL_Context.cpp:816-874): the blit into a
+ * host-side view -- the window back buffer SL_Swapchain / SL_WindowBuffer hand out.  `texels` points at w * h texels of
+ * colorType (page-locked memory from host_alloc crosses the link at full rate).  Synchronous like the reference's. */
+SLCU_EXPORT int SLCU_FN(blit_to_host)(slcu_context* ctx, void* texels, int colorType, uint16_t w, uint16_t h, size_t inTexture);
+SLCU_EXPORT int SLCU_FN(blit_to_host_rect)(slcu_context* ctx, void* texels, int colorType, uint16_t w, uint16_t h, size_t inTexture,
+                                           uint16_t srcX0, uint16_t srcY0, uint16_t srcX1, uint16_t srcY1,
+                                           uint16_t dstX0, uint16_t dstY0, uint16_t dstX1, uint16_t dstY1);
+/* ours: the same blit as a two-deep swap chain.  present(slot) returns when the blit is enqueued -- the next frame renders
+ * while this one crosses the link -- present_wait(slot) returns when the host view holds the frame. */
+SLCU_EXPORT int SLCU_FN(present)(slcu_context* ctx, unsigned slot, void* texels, int colorType, uint16_t w, uint16_t h, size_t inTexture);
+SLCU_EXPORT int SLCU_FN(present_wait)(slcu_context* ctx, unsigned slot);
+
 /* ---- sort-first multi-GPU: ours (the reference is one process; its analogue is the per-thread scan-line interleave of
  * SL_ScanlineBounds.hpp:31-50 / src/SL_TriRasterizer.cpp:436-438).  One process and one context per GPU.
  * set_partition: this context rasterises only rows y with (y / stripRows) % world == rank (geometry and uniforms are

@@ -188,6 +188,15 @@ struct SL_TextureView
     SL_ColorDataType type;
 };
 
+/* The reference's SL_TextureView over HOST texels (SL_Texture.hpp:29-44) as SL_WindowBuffer / SL_Swapchain hand it out for
+ * the window's back buffer: the destination of SL_Context::blit(SL_TextureView&, textureId) */
+struct SL_HostTextureView
+{
+    void* pTexels;
+    uint16_t width, height;
+    SL_ColorDataType type;
+};
+
 class SL_Texture : public SL_Resource
 {
     SL_TextureView mView{SLCU_INVALID_ID, 0, 0, 0, SL_COLOR_RGBA_8U};
@@ -398,6 +407,18 @@ class SL_Context
               uint16_t dstX1, uint16_t dstY1) noexcept
     {
         mStatus = slcu_blit_rect(mDev, outTextureId, inTextureId, srcX0, srcY0, srcX1, srcY1, dstX0, dstY0, dstX1, dstY1);
+    }
+
+    /* blit to a window (src/SL_Context.cpp:816-874): into a host-side view, synchronous like the reference's */
+    void blit(SL_HostTextureView& buffer, size_t textureId) noexcept
+    {
+        mStatus = slcu_blit_to_host(mDev, buffer.pTexels, (int)buffer.type, buffer.width, buffer.height, textureId);
+    }
+    void blit(SL_HostTextureView& buffer, size_t textureId, uint16_t srcX0, uint16_t srcY0, uint16_t srcX1, uint16_t srcY1, uint16_t dstX0,
+              uint16_t dstY0, uint16_t dstX1, uint16_t dstY1) noexcept
+    {
+        mStatus = slcu_blit_to_host_rect(mDev, buffer.pTexels, (int)buffer.type, buffer.width, buffer.height, textureId, srcX0, srcY0, srcX1, srcY1,
+                                         dstX0, dstY0, dstX1, dstY1);
     }
 
     /* run_clear_processors (src/SL_Context.cpp:881-963) */

@@ -169,6 +169,10 @@ _SIGS_PRODUCT = {
     "geometry_share_import": (C.c_int, [_P, C.c_uint, _P]),
     "geometry_share_address": (C.c_int, [_P, C.POINTER(_P)]),
     "geometry_share_attach": (C.c_int, [_P, C.c_uint, _P]),
+    "blit_to_host": (C.c_int, [_P, _P, C.c_int, _U16, _U16, _SZ]),
+    "blit_to_host_rect": (C.c_int, [_P, _P, C.c_int, _U16, _U16, _SZ] + [_U16] * 8),
+    "present": (C.c_int, [_P, C.c_uint, _P, C.c_int, _U16, _U16, _SZ]),
+    "present_wait": (C.c_int, [_P, C.c_uint]),
     "host_alloc": (C.c_int, [_P, C.POINTER(_P), _SZ]),
     "host_free": (C.c_int, [_P, _P]),
 }
@@ -543,6 +547,20 @@ class Context:
         self._host_allocs.append(p.value)
         buf = (C.c_ubyte * max(nbytes, 1)).from_address(p.value)
         return np.frombuffer(buf, dtype=np.uint8, count=nbytes).view(dtype).reshape(shape)
+
+    def blit_to_host(self, out: np.ndarray, color_type: int, tid: int, src_rect=None, dst_rect=None):
+        """SL_Context::blit(SL_TextureView&, textureId[, rects]): `out` is the host view, shape (h, w, channels)."""
+        h, w = out.shape[0], out.shape[1]
+        if src_rect is None and dst_rect is None:
+            self._chk(self.f["blit_to_host"](self.h, out.ctypes.data_as(C.c_void_p), color_type, w, h, tid), "blit_to_host")
+        else:
+            self._chk(self.f["blit_to_host_rect"](self.h, out.ctypes.data_as(C.c_void_p), color_type, w, h, tid, *src_rect, *dst_rect), "blit_to_host_rect")
+
+    def present(self, slot: int, ptr: int, color_type: int, w: int, h: int, tid: int):
+        self._chk(self.f["present"](self.h, slot, C.c_void_p(ptr), color_type, w, h, tid), "present")
+
+    def present_wait(self, slot: int):
+        self._chk(self.f["present_wait"](self.h, slot), "present_wait")
 
     def texture_read_into(self, tid: int, ptr: int, nbytes: int):
         self._chk(self.f["texture_read"](self.h, tid, C.c_void_p(ptr), nbytes), "texture_read")

@@ -343,6 +343,9 @@ struct slcu_context
             return true;
         }
     } geom;
+    /* present path (slcu_blit_to_host / slcu_present): a second stream for the copy into the host view, two staging slots */
+    cudaStream_t copyStream = nullptr;
+    struct PresentSlot { Scratch staging; cudaEvent_t blitDone = nullptr, copyDone = nullptr; bool busy = false; } present[2];
     /* optional per-kernel event timing (profile_begin / profile_end) */
     cudaEvent_t timerA = nullptr, timerB = nullptr;
     bool profiling = false;
@@ -1710,6 +1713,14 @@ void slcu_context_destroy(slcu_context* c)
     if (c->hostCounters) cudaFreeHost(c->hostCounters);
     for (auto& pm : c->peerMaps) if (pm.ptr) cudaIpcCloseMemHandle(pm.ptr);
     geom_release(c);
+    if (c->copyStream) cudaStreamSynchronize(c->copyStream);
+    for (auto& ps : c->present)
+    {
+        ps.staging.release();
+        if (ps.blitDone) cudaEventDestroy(ps.blitDone);
+        if (ps.copyDone) cudaEventDestroy(ps.copyDone);
+    }
+    if (c->copyStream) cudaStreamDestroy(c->copyStream);
     for (Scratch* x : all_scratch(c)) x->release();
     cudaStreamSynchronize(c->stream);
     cudaStreamDestroy(c->stream);
@@ -2347,6 +2358,34 @@ int slcu_draw_multiple(slcu_context* c, const slcu_mesh* m, size_t n, size_t sha
 int slcu_draw_instanced(slcu_context* c, const slcu_mesh* m, size_t inst, size_t shader, size_t fbo) { return run_draw(c, m, 1, inst, shader, fbo); }
 
 /* run_blit_processors replacement (src/SL_ProcessorPool.cpp:400-445) */
+/* SL_BlitProcessor::blit_nearest for one (source texture, destination texels) pair: the destination is a texture of this
+ * context or a device staging copy of a host view */
+static int blit_core(slcu_context* c, const HostTexture& s, unsigned char* dstTexels, int dstType, unsigned dstW, unsigned dstH,
+                     uint16_t sx0, uint16_t sy0, uint16_t sx1, uint16_t sy1, uint16_t dx0, uint16_t dy0, uint16_t dx1, uint16_t dy1)
+{
+    SLBlitParams p;
+    const int sk = s.type % 7, dk = dstType % 7;
+    const bool rgIntSame = s.type == dstType && s.type / 7 == 1 && sk <= 1; /* RG integer -> same type is p / max(T) in the reference (SL_Color.hpp:373-380) */
+    if (s.type == dstType && !rgIntSame) p.mode = 0;
+    else if (s.type == 26 && dstType == 21) p.mode = 1; /* RGBA_FLOAT -> RGBA_8U */
+    else if (s.type == 21 && dstType == 26) p.mode = 2; /* RGBA_8U -> RGBA_FLOAT */
+    else if (sk == 2 || sk == 3 || dk == 2 || dk == 3) { c->err = "blit: conversions from or to 32/64-bit integer layouts are not implemented"; return SLCU_ERR_UNSUPPORTED; }
+    else p.mode = 3; /* the general conversion between the twenty 8/16-bit unorm, half, float and double layouts */
+    p.srcType = s.type;
+    p.dstType = dstType;
+    if (sx1 < sx0 || sy1 < sy0 || dx1 <= dx0 || dy1 <= dy0) return 0;
+    p.src = s.dev; p.dst = dstTexels;
+    p.srcW = s.w; p.srcH = s.h; p.dstW = (uint16_t)dstW; p.dstH = (uint16_t)dstH;
+    p.srcX0 = sx0; p.srcY0 = sy0; p.srcX1 = sx1; p.srcY1 = sy1;
+    p.dstX0 = dx0; p.dstY0 = dy0; p.dstX1 = dx1; p.dstY1 = dy1;
+    p.bpt = (int)(chan_bytes(dstType) * (unsigned)(dstType / 7 + 1));
+    const unsigned outW = (unsigned)dx1 - dx0, outH = (unsigned)dy1 - dy0;
+    const dim3 grid((outW + 255u) / 256u, outH < 148u * 8u ? outH : 148u * 8u);
+    { KernelScope ks(c, SLCU_K_BLIT); k_blit<<<grid, 256, 0, c->stream>>>(p); }
+    CK(cudaGetLastError());
+    return 0;
+}
+
 int slcu_blit_rect(slcu_context* c, size_t outTex, size_t inTex, uint16_t sx0, uint16_t sy0, uint16_t sx1, uint16_t sy1,
                    uint16_t dx0, uint16_t dy0, uint16_t dx1, uint16_t dy1)
 {
@@ -2356,26 +2395,81 @@ int slcu_blit_rect(slcu_context* c, size_t outTex, size_t inTex, uint16_t sx0, u
     const HostTexture& s = c->textures[inTex];
     const HostTexture& d = c->textures[outTex];
     if (!s.dev || !d.dev || !d.w || !d.h) return SLCU_ERR_ARG;
-    SLBlitParams p;
-    const int sk = s.type % 7, dk = d.type % 7;
-    const bool rgIntSame = s.type == d.type && s.type / 7 == 1 && sk <= 1; /* RG integer -> same type is p / max(T) in the reference (SL_Color.hpp:373-380) */
-    if (s.type == d.type && !rgIntSame) p.mode = 0;
-    else if (s.type == 26 && d.type == 21) p.mode = 1; /* RGBA_FLOAT -> RGBA_8U */
-    else if (s.type == 21 && d.type == 26) p.mode = 2; /* RGBA_8U -> RGBA_FLOAT */
-    else if (sk == 2 || sk == 3 || dk == 2 || dk == 3) { c->err = "blit: conversions from or to 32/64-bit integer layouts are not implemented"; return SLCU_ERR_UNSUPPORTED; }
-    else p.mode = 3; /* the general conversion between the twenty 8/16-bit unorm, half, float and double layouts */
-    p.srcType = s.type;
-    p.dstType = d.type;
-    if (sx1 < sx0 || sy1 < sy0 || dx1 <= dx0 || dy1 <= dy0) return 0;
-    p.src = s.dev; p.dst = d.dev;
-    p.srcW = s.w; p.srcH = s.h; p.dstW = d.w; p.dstH = d.h;
-    p.srcX0 = sx0; p.srcY0 = sy0; p.srcX1 = sx1; p.srcY1 = sy1;
-    p.dstX0 = dx0; p.dstY0 = dy0; p.dstX1 = dx1; p.dstY1 = dy1;
-    p.bpt = d.bpt;
-    const unsigned outW = (unsigned)dx1 - dx0, outH = (unsigned)dy1 - dy0;
-    const dim3 grid((outW + 255u) / 256u, outH < 148u * 8u ? outH : 148u * 8u);
-    { KernelScope ks(c, SLCU_K_BLIT); k_blit<<<grid, 256, 0, c->stream>>>(p); }
-    CK(cudaGetLastError());
+    return blit_core(c, s, d.dev, d.type, d.w, d.h, sx0, sy0, sx1, sy1, dx0, dy0, dx1, dy1);
+}
+
+/* ---- the present path: SL_Context::blit(SL_TextureView& buffer, size_t textureId[, rectangles]) (src/SL_Context.cpp:816-874),
+ * the blit into a host-side view that SL_Swapchain / SL_WindowBuffer hand out as the window's back buffer.  The blit runs on
+ * the device into a staging copy of the view's geometry; the rectangle it wrote then crosses the link into the host view
+ * (every other texel of the view is left alone, like the reference's in-place blit). */
+static int present_enqueue(slcu_context* c, unsigned slot, void* texels, int colorType, uint16_t w, uint16_t h, size_t inTex,
+                           uint16_t sx0, uint16_t sy0, uint16_t sx1, uint16_t sy1, uint16_t dx0, uint16_t dy0, uint16_t dx1, uint16_t dy1)
+{
+    if (!c || slot > 1 || !texels || inTex >= c->textures.size() || colorType < 0 || colorType >= 28 || !w || !h) return SLCU_ERR_ARG;
+    cudaSetDevice(c->device);
+    const HostTexture& s = c->textures[inTex];
+    if (!s.dev) return SLCU_ERR_ARG;
+    if (dx1 > w) dx1 = w;
+    if (dy1 > h) dy1 = h;
+    slcu_context::PresentSlot& ps = c->present[slot];
+    if (!c->copyStream) CK(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+    if (!ps.blitDone)
+    {
+        CK(cudaEventCreateWithFlags(&ps.blitDone, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ps.copyDone, cudaEventDisableTiming));
+    }
+    const unsigned bpt = chan_bytes(colorType) * (unsigned)(colorType / 7 + 1);
+    if (ps.busy) CK(cudaStreamWaitEvent(c->stream, ps.copyDone, 0)); /* the staging copy's previous contents have left */
+    ps.staging.stream = c->stream;
+    CK(ps.staging.ensure((size_t)w * h * bpt));
+    const int rc = blit_core(c, s, ps.staging.buf.ptr, colorType, w, h, sx0, sy0, sx1, sy1, dx0, dy0, dx1, dy1);
+    if (rc) return rc;
+    CK(cudaEventRecord(ps.blitDone, c->stream));
+    CK(cudaStreamWaitEvent(c->copyStream, ps.blitDone, 0));
+    if (!(sx1 < sx0 || sy1 < sy0 || dx1 <= dx0 || dy1 <= dy0))
+    {
+        const size_t pitch = (size_t)w * bpt, off = (size_t)dy0 * pitch + (size_t)dx0 * bpt;
+        if (dx0 == 0 && dx1 == w) CK(cudaMemcpyAsync((unsigned char*)texels + off, ps.staging.buf.ptr + off, (size_t)(dy1 - dy0) * pitch, cudaMemcpyDeviceToHost, c->copyStream));
+        else CK(cudaMemcpy2DAsync((unsigned char*)texels + off, pitch, ps.staging.buf.ptr + off, pitch, (size_t)(dx1 - dx0) * bpt, (size_t)(dy1 - dy0), cudaMemcpyDeviceToHost, c->copyStream));
+    }
+    CK(cudaEventRecord(ps.copyDone, c->copyStream));
+    ps.busy = true;
+    return 0;
+}
+
+int slcu_blit_to_host_rect(slcu_context* c, void* texels, int colorType, uint16_t w, uint16_t h, size_t inTex,
+                           uint16_t sx0, uint16_t sy0, uint16_t sx1, uint16_t sy1, uint16_t dx0, uint16_t dy0, uint16_t dx1, uint16_t dy1)
+{
+    SLCU_FLUSH();
+    const int rc = present_enqueue(c, 0, texels, colorType, w, h, inTex, sx0, sy0, sx1, sy1, dx0, dy0, dx1, dy1);
+    if (rc) return rc;
+    CK(cudaEventSynchronize(c->present[0].copyDone)); /* synchronous, like the reference's blit */
+    return 0;
+}
+
+int slcu_blit_to_host(slcu_context* c, void* texels, int colorType, uint16_t w, uint16_t h, size_t inTex)
+{
+    if (!c || inTex >= c->textures.size()) return SLCU_ERR_ARG;
+    const HostTexture& s = c->textures[inTex];
+    return slcu_blit_to_host_rect(c, texels, colorType, w, h, inTex, 0, 0, s.w, s.h, 0, 0, w, h);
+}
+
+/* ours: the same blit without the join -- the call returns when the work is enqueued, the next frame renders while this
+ * one crosses the link (a two-deep swap chain: slot 0 / 1, one staging copy each).  present_wait(slot) is the join. */
+int slcu_present(slcu_context* c, unsigned slot, void* texels, int colorType, uint16_t w, uint16_t h, size_t inTex)
+{
+    SLCU_FLUSH();
+    if (!c || inTex >= c->textures.size()) return SLCU_ERR_ARG;
+    const HostTexture& s = c->textures[inTex];
+    return present_enqueue(c, slot, texels, colorType, w, h, inTex, 0, 0, s.w, s.h, 0, 0, w, h);
+}
+
+int slcu_present_wait(slcu_context* c, unsigned slot)
+{
+    if (!c || slot > 1) return SLCU_ERR_ARG;
+    if (!c->present[slot].busy) return 0;
+    cudaSetDevice(c->device);
+    CK(cudaEventSynchronize(c->present[slot].copyDone));
     return 0;
 }
 

@@ -52,3 +52,67 @@ def test_cross_layout_conversion_is_converted():
 @pytest.mark.parametrize("name", sorted(blit_cases.BLIT_CASES))
 def test_cuda_blit_matches_golden(name, golden_blits):
     assert sha(blit_cases.run_blit("cuda", name)) == golden_blits[name]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("src_type,dst_type", [(A.SL_COLOR_RGBA_8U, A.SL_COLOR_RGBA_8U), (A.SL_COLOR_RGBA_FLOAT, A.SL_COLOR_RGBA_8U),
+                                               (A.SL_COLOR_RGB_8U, A.SL_COLOR_RGBA_HALF), (A.SL_COLOR_RGBA_8U, A.SL_COLOR_RGB_16U)])
+def test_blit_to_host_view_equals_blit_into_a_texture(src_type, dst_type):
+    """SL_Context::blit(SL_TextureView& buffer, textureId[, rects]) (src/SL_Context.cpp:816-874), the present path: the host
+    view receives exactly what the same blit writes into a texture (pinned to the reference by the blit matrix), whole
+    view or rectangle, and every texel outside the destination rectangle keeps its value."""
+    rng = np.random.default_rng(5)
+    ctx = A.Context("cuda")
+    sw, sh, dw, dh = 97, 61, 64, 40
+    dt = A.texel_dtype(src_type)
+    nch = src_type // 7 + 1
+    src = (rng.random((sh, sw, nch)) * (255 if dt == np.uint8 else 1)).astype(dt)
+    tin = ctx.create_texture(src_type, sw, sh, 1, src)
+    for rects in (None, ((5, 3, 80, 50), (10, 7, 50, 33))):
+        tout = ctx.create_texture(dst_type, dw, dh, 1)
+        fill = ctx.host_array((dh, dw, dst_type // 7 + 1), A.texel_dtype(dst_type))
+        fill.view(np.uint8)[...] = 0xAB
+        before = fill.copy()
+        if rects is None:
+            ctx.blit(tout, tin)
+            ctx.blit_to_host(fill, dst_type, tin)
+            want = ctx.texture_read(tout, dst_type, dw, dh)
+            assert np.array_equal(fill.view(np.uint8), want.view(np.uint8))
+        else:
+            ctx.blit(tout, tin, rects[0] + rects[1])
+            ctx.blit_to_host(fill, dst_type, tin, rects[0], rects[1])
+            want = ctx.texture_read(tout, dst_type, dw, dh)
+            x0, y0, x1, y1 = rects[1]
+            assert np.array_equal(fill[y0:y1, x0:x1].view(np.uint8), want[y0:y1, x0:x1].view(np.uint8))
+            mask = np.ones((dh, dw), dtype=bool)
+            mask[y0:y1, x0:x1] = False
+            assert np.array_equal(fill[mask].view(np.uint8), before[mask].view(np.uint8)), "texels outside the rectangle were touched"
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_two_deep_present_delivers_each_frame_to_its_own_view():
+    """slcu_present: frame k's blit is enqueued, frame k+1 renders while it crosses the link; after present_wait every host
+    view holds its own frame."""
+    ctx = A.Context("cuda")
+    w, h = 320, 200
+    color = ctx.create_texture(A.SL_COLOR_RGBA_8U, w, h, 1)
+    depth = ctx.create_texture(A.SL_COLOR_R_FLOAT, w, h, 1)
+    fbo = ctx.create_framebuffer([color], depth)
+    views = [ctx.host_array((h, w, 4), np.uint8) for _ in range(2)]
+    got = []
+    for k in range(6):
+        slot = k & 1
+        ctx.present_wait(slot)
+        if k >= 2:
+            got.append(views[slot].copy())
+        ctx.clear_color_buffer(fbo, 0, (k / 8.0, 0.0, 1.0 - k / 8.0, 1.0))
+        ctx.present(slot, views[slot].ctypes.data, A.SL_COLOR_RGBA_8U, w, h, color)
+    for slot in ((6 & 1), (7 & 1)):
+        ctx.present_wait(slot)
+        got.append(views[slot].copy())
+    assert len(got) == 6
+    for k, frame in enumerate(got):
+        want = np.array([int(k / 8.0 * 255.0), 0, int((1.0 - k / 8.0) * 255.0), 255], dtype=np.uint8)
+        assert (frame == want).all(), (k, frame[0, 0], want)
+    ctx.close()
