@@ -491,6 +491,9 @@ __global__ void __launch_bounds__(SL_VB_THREADS, CACHE ? SL_VERTEX_CACHED_MIN_BL
     __syncthreads();
 
     unsigned clipCount = 0u;
+    SLClipPoly poly[2];  /* the clipper's two buffers (local memory); a queue of at most one candidate per thread keeps its */
+    int keptVerts = -1;  /* polygon from pass 1 to pass 3 instead of clipping twice                                       */
+    int keptWhich = 0;
     for (int pass = 0; pass < 4; ++pass)
     {
         const bool queuePass = (pass & 1) != 0;
@@ -512,7 +515,6 @@ __global__ void __launch_bounds__(SL_VB_THREADS, CACHE ? SL_VERTEX_CACHED_MIN_BL
                 active = primBase + p < primsPerInstance;
             }
             SLVert v[3];
-            SLClipPoly poly[2];
             int n = 0;             /* records this thread emits */
             int polyVerts = 0;     /* > 0: clipped path, polygon in poly[which] */
             int which = 0;
@@ -552,7 +554,7 @@ __global__ void __launch_bounds__(SL_VB_THREADS, CACHE ? SL_VERTEX_CACHED_MIN_BL
 #pragma unroll
                             for (int k = 0; k < 3; ++k) cp[k] = scissorMat * cp[k];
                             needClip = !sl_clip_rejects(cp[0], cp[1], cp[2]);
-                            if (needClip && queuePass)
+                            if (needClip && queuePass && !(pass == 3 && keptVerts >= 0))
                             {
 #pragma unroll
                                 for (int k = 0; k < 3; ++k)
@@ -604,7 +606,7 @@ __global__ void __launch_bounds__(SL_VB_THREADS, CACHE ? SL_VERTEX_CACHED_MIN_BL
                         else if (vis == 1)
                         {
                             needClip = !sl_clip_rejects(v[0].vert, v[1].vert, v[2].vert);
-                            if (needClip && queuePass)
+                            if (needClip && queuePass && !(pass == 3 && keptVerts >= 0))
                             {
 #pragma unroll
                                 for (int k = 0; k < 3; ++k)
@@ -624,7 +626,9 @@ __global__ void __launch_bounds__(SL_VB_THREADS, CACHE ? SL_VERTEX_CACHED_MIN_BL
                 /* every active lane is a candidate (it was one in pass 0: same inputs, same arithmetic) */
                 if (needClip)
                 {
-                    polyVerts = sl_clip_polygon(poly, NV, viewport, which);
+                    if (pass == 3 && keptVerts >= 0) { polyVerts = keptVerts; which = keptWhich; }
+                    else polyVerts = sl_clip_polygon(poly, NV, viewport, which);
+                    if (pass == 1 && clipCount <= (unsigned)SL_VB_THREADS) { keptVerts = polyVerts; keptWhich = which; }
                     const SLClipPoly& pg = poly[which];
                     if (pass == 1)
                     {
