@@ -1566,8 +1566,10 @@ struct SLFragLists
 {
     unsigned char* pool;      /* chunkCapacity * SL_CHUNK_BYTES                          */
     uint32_t* chunkNext;      /* [chunkCapacity]                                         */
+    uint32_t* chunkPrev;      /* [chunkCapacity] the chunk before (k_shade walks opaque lists from their end) */
     uint32_t* listHead;       /* [numRows * numSegs] first chunk of the list             */
     uint32_t* listCount;      /* [numRows * numSegs] fragments in the list (zeroed per batch) */
+    uint32_t* listTail;       /* [numRows * numSegs] last chunk of the list              */
     unsigned int chunkCapacity;
 };
 
@@ -1610,6 +1612,8 @@ struct SLShadeParams
     int blend;                /* SL_BlendMode */
     unsigned int width;
     unsigned int numLists;
+    unsigned int segWidth, numSegs, numSubLists; /* list l covers 2^SL_SHADE_SHIFT texels from width * row + seg * segWidth + (sub << SL_SHADE_SHIFT) */
+    int opaqueSkip;           /* blend off: shade only the fragment that ends up in the texel (see k_shade) */
     unsigned char* color[4];
     int colorType[4];         /* SL_ColorDataType */
     SLFragLists lists;
@@ -1894,6 +1898,7 @@ SLD_FN void sl_push_frags(const SLRasterParams& P, const SLListState& L, int lan
                 const uint32_t prev = lane == 0 ? tail : baseChunk + (uint32_t)lane - 1u;
                 if (prev == SL_NO_CHUNK) P.lists.listHead[L.firstList + sub] = baseChunk;
                 else P.lists.chunkNext[prev] = baseChunk + (uint32_t)lane;
+                P.lists.chunkPrev[baseChunk + (uint32_t)lane] = prev;
             }
         }
         uint32_t q = fill + (uint32_t)(incl - n);
@@ -2485,7 +2490,7 @@ __global__ void __launch_bounds__(SL_RASTER_WARPS * 32, SL_RASTER_MIN_BLOCKS) k_
         }
     }
     __syncwarp();
-    if (lane < L.nsub && L.total[lane]) P.lists.listCount[L.firstList + lane] = L.total[lane];
+    if (lane < L.nsub && L.total[lane]) { P.lists.listCount[L.firstList + lane] = L.total[lane]; P.lists.listTail[L.firstList + lane] = L.tail[lane]; }
     const bool dirty = __any_sync(0xffffffffu, shaded != 0u);
     if (staged && dirty && P.depthMask)
     {
@@ -2519,10 +2524,55 @@ constexpr int SL_SHADE_WARPS = 4;
 #define SL_SHADE_MIN_BLOCKS 8 /* 64 registers: measured best on every config (C3 shade 0.63 -> 0.54 ms) */
 #endif
 
+/* one fragment of a chunk: perspective correction (:438-460), varyings (interpolate_tri_varyings, AVX2 branch :163-193 --
+ * the reference interpolates all four slots; slots past numVaryings hold stale bin data there and are never read by a
+ * well-formed shader), the shader call (:501).  Returns the texel index. */
+template <FsFn FS>
+SLD_FN uint32_t sl_shade_fragment(const SLShadeParams& P, const unsigned char* c, int slot, SL_FragmentParam& fp, bool& haveOutputs)
+{
+    const float4 b4 = reinterpret_cast<const float4*>(c)[slot];
+    const float z = reinterpret_cast<const float*>(c + 512)[slot];
+    const uint32_t xy = reinterpret_cast<const uint32_t*>(c + 640)[slot];
+    const uint32_t recId = reinterpret_cast<const uint32_t*>(c + 768)[slot];
+    const int x = (int)(xy & 0xffffu), y = (int)(xy >> 16);
+    const float4* rec = P.records + (size_t)recId * P.recStride;
+    math::vec4 bc = math::vec4{b4.x, b4.y, b4.z, b4.w} * math::vec4{rec[0].w, rec[1].w, rec[2].w, 0.f};
+    const float persp = sl_rcp((bc.v[0] + bc.v[1]) + (bc.v[2] + bc.v[3]));
+    bc = bc * persp;
+    fp.pUniforms = &P.draws[P.recDraw[recId]].uniforms;
+    for (int s = 0; s < P.numVaryings; ++s)
+    {
+        const float4 a = rec[3 + 3 * s + 0], b = rec[3 + 3 * s + 1], cc = rec[3 + 3 * s + 2];
+        fp.pVaryings[s] = math::vec4{
+            sl_fma(bc.v[2], cc.x, sl_fma(bc.v[1], b.x, bc.v[0] * a.x)), sl_fma(bc.v[2], cc.y, sl_fma(bc.v[1], b.y, bc.v[0] * a.y)),
+            sl_fma(bc.v[2], cc.z, sl_fma(bc.v[1], b.z, bc.v[0] * a.z)), sl_fma(bc.v[2], cc.w, sl_fma(bc.v[1], b.w, bc.v[0] * a.w))};
+    }
+    fp.coord.x = (uint16_t)x;
+    fp.coord.y = (uint16_t)y;
+    fp.coord.depth = z;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) fp.pOutputs[i] = math::vec4{0.f};
+    haveOutputs = FS(fp);
+    /* every attachment is addressed as x + width*y with the depth attachment's width (the reference uses each colour view's
+     * own width; SL_Framebuffer::valid requires them to be equal, and run_draw refuses anything else); x, y are relative to
+     * the span's source row, so fragments that ran past the row end land at the start of the next row exactly like in the
+     * reference */
+    return (uint32_t)x + P.width * (uint32_t)y;
+}
+
+/* Without blending a texel ends up with the colour of the LAST fragment whose shader produced outputs; a fragment shader
+ * has no other effect (depth is written by the resolve stage).  So an opaque list is walked from its end: per chunk, one
+ * cheap pass over the texel indices finds the fragments that are the last ones of their texel (a bit per texel of the
+ * list's 128-texel window remembers what is already settled), they are collected, and shaded 32 at a time with every
+ * lane busy -- the fragments under them are never shaded at all (C3: 11.5 M fragments pass the depth test, 8.3 M texels
+ * show one).  A shader that returns false for one of them leaves the texel to an earlier fragment after all: rare, so the
+ * warp then simply runs the whole list again in submission order (below), which overwrites what the fast pass stored. */
 template <FsFn FS>
 __global__ void __launch_bounds__(SL_SHADE_WARPS * 32, SL_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ SLShadeParams P)
 {
-    const int lane = threadIdx.x & 31;
+    __shared__ uint32_t sSettled[SL_SHADE_WARPS][4];
+    __shared__ uint32_t sQueue[SL_SHADE_WARPS][64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (P.abortBatch && *P.abortBatch) return; /* the batch did not fit: it is run again, nothing visible may be written */
     /* persistent warps: lists are handed out through a ticket (a block would otherwise live as long as its longest list) */
     for (;;)
@@ -2531,8 +2581,71 @@ __global__ void __launch_bounds__(SL_SHADE_WARPS * 32, SL_SHADE_MIN_BLOCKS) k_sh
     if (lane == 0) list = atomicAdd(P.shadeTicket, 1u);
     list = __shfl_sync(0xffffffffu, list, 0);
     if (list >= P.numLists) break;
-    int remaining = (int)P.lists.listCount[list];
-    if (remaining <= 0) continue;
+    const int count = (int)P.lists.listCount[list];
+    if (count <= 0) continue;
+    bool inOrder = !P.opaqueSkip;
+    if (!inOrder)
+    {
+        const unsigned perRow = P.numSegs * P.numSubLists;
+        const unsigned row = list / perRow, rem = list - row * perRow;
+        const unsigned seg = rem / P.numSubLists, sub = rem - seg * P.numSubLists;
+        const uint32_t listBase = P.width * row + seg * P.segWidth + (sub << SL_SHADE_SHIFT_C);
+        if (lane < 4) sSettled[warp][lane] = 0u;
+        __syncwarp();
+        uint32_t* queue = sQueue[warp];
+        unsigned qn = 0u;
+        bool redo = false;
+        uint32_t chunk = P.lists.listTail[list];
+        for (int remaining = count; remaining > 0 || qn > 0u;)
+        {
+            if (remaining > 0)
+            {
+                const int n = ((remaining - 1) & 31) + 1; /* the last chunk is the partly filled one */
+                const unsigned char* c = P.lists.pool + (size_t)chunk * SL_CHUNK_BYTES;
+                uint32_t key = 0xffffff00u + (uint32_t)lane; /* idle lanes: a key no texel has */
+                bool alive = false;
+                if (lane < n)
+                {
+                    const uint32_t xy = reinterpret_cast<const uint32_t*>(c + 640)[lane];
+                    key = (xy & 0xffffu) + P.width * (xy >> 16);
+                    const uint32_t rel = key - listBase;
+                    if (rel >= (1u << SL_SHADE_SHIFT_C)) redo = true; /* not in this list's window: cannot happen; the in-order pass is exact regardless */
+                    else alive = !((sSettled[warp][rel >> 5] >> (rel & 31u)) & 1u);
+                }
+                const uint32_t peers = __match_any_sync(0xffffffffu, alive ? key : 0xffffff00u + (uint32_t)lane);
+                const bool last = alive && (peers >> lane) == 1u; /* no later fragment of the chunk on the same texel */
+                if (last) atomicOr(&sSettled[warp][(key - listBase) >> 5], 1u << ((key - listBase) & 31u));
+                const uint32_t m = __ballot_sync(0xffffffffu, last);
+                if (last) queue[qn + (unsigned)__popc(m & ((1u << lane) - 1u))] = (chunk << 5) | (uint32_t)lane;
+                qn += (unsigned)__popc(m);
+                remaining -= n;
+                if (remaining > 0) chunk = P.lists.chunkPrev[chunk];
+                __syncwarp();
+            }
+            if (qn >= 32u || (remaining <= 0 && qn > 0u))
+            {
+                const unsigned take = qn < 32u ? qn : 32u;
+                bool haveOutputs = true;
+                if ((unsigned)lane < take)
+                {
+                    const uint32_t e = queue[qn - take + (unsigned)lane]; /* the newest ones: the rest stays where it is */
+                    SL_FragmentParam fp;
+                    const uint32_t key = sl_shade_fragment<FS>(P, P.lists.pool + (size_t)(e >> 5) * SL_CHUNK_BYTES, (int)(e & 31u), fp, haveOutputs);
+                    if (haveOutputs)
+                    {
+                        for (int i = P.numOutputs - 1; i >= 0; --i) sl_store_color(P.color[i], P.colorType[i], (size_t)key, fp.pOutputs[i]);
+                    }
+                }
+                if (__any_sync(0xffffffffu, !haveOutputs)) redo = true;
+                qn -= take;
+                __syncwarp();
+            }
+        }
+        inOrder = __any_sync(0xffffffffu, redo);
+        if (inOrder) __syncwarp();
+    }
+    if (!inOrder) continue;
+    int remaining = count;
     uint32_t chunk = P.lists.listHead[list];
     for (; remaining > 0; remaining -= 32)
     {
@@ -2542,42 +2655,7 @@ __global__ void __launch_bounds__(SL_SHADE_WARPS * 32, SL_SHADE_MIN_BLOCKS) k_sh
         SL_FragmentParam fp;
         bool haveOutputs = false;
         uint32_t key = 0xffffff00u + (uint32_t)lane; /* idle lanes: a key no pixel has */
-        if (lane < n)
-        {
-            const float4 b4 = reinterpret_cast<const float4*>(c)[lane];
-            const float z = reinterpret_cast<const float*>(c + 512)[lane];
-            const uint32_t xy = reinterpret_cast<const uint32_t*>(c + 640)[lane];
-            const uint32_t recId = reinterpret_cast<const uint32_t*>(c + 768)[lane];
-            const int x = (int)(xy & 0xffffu), y = (int)(xy >> 16);
-            const float4* rec = P.records + (size_t)recId * P.recStride;
-            /* :438-460 perspective correction */
-            math::vec4 bc = math::vec4{b4.x, b4.y, b4.z, b4.w} * math::vec4{rec[0].w, rec[1].w, rec[2].w, 0.f};
-            const float persp = sl_rcp((bc.v[0] + bc.v[1]) + (bc.v[2] + bc.v[3]));
-            bc = bc * persp;
-
-            fp.pUniforms = &P.draws[P.recDraw[recId]].uniforms;
-            /* interpolate_tri_varyings, AVX2 branch (:163-193).  The reference interpolates all four slots; slots past
-             * numVaryings hold stale bin data there and are never read by a well-formed shader. */
-            for (int s = 0; s < P.numVaryings; ++s)
-            {
-                const float4 a = rec[3 + 3 * s + 0], b = rec[3 + 3 * s + 1], cc = rec[3 + 3 * s + 2];
-                fp.pVaryings[s] = math::vec4{
-                    sl_fma(bc.v[2], cc.x, sl_fma(bc.v[1], b.x, bc.v[0] * a.x)), sl_fma(bc.v[2], cc.y, sl_fma(bc.v[1], b.y, bc.v[0] * a.y)),
-                    sl_fma(bc.v[2], cc.z, sl_fma(bc.v[1], b.z, bc.v[0] * a.z)), sl_fma(bc.v[2], cc.w, sl_fma(bc.v[1], b.w, bc.v[0] * a.w))};
-            }
-            fp.coord.x = (uint16_t)x;
-            fp.coord.y = (uint16_t)y;
-            fp.coord.depth = z;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) fp.pOutputs[i] = math::vec4{0.f};
-
-            haveOutputs = FS(fp); /* :501 */
-            /* every attachment is addressed as x + width*y with the depth attachment's width (the reference uses each
-             * colour view's own width; SL_Framebuffer::valid requires them to be equal, and run_draw refuses anything
-             * else); x, y are relative to the span's source row, so fragments that ran past the row end land at the
-             * start of the next row exactly like in the reference */
-            key = (uint32_t)x + P.width * (uint32_t)y;
-        }
+        if (lane < n) key = sl_shade_fragment<FS>(P, c, lane, fp, haveOutputs);
         /* :507-523, in submission order per pixel */
         const uint32_t peers = __match_any_sync(0xffffffffu, key);
         if (P.blend == 0)

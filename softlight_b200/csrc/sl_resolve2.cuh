@@ -600,6 +600,7 @@ __global__ void __launch_bounds__(SL_R2_WARPS * 32, SL_R2_MIN_BLOCKS) k_resolve2
                         {
                             if (prev == SL_NO_CHUNK) P.lists.listHead[firstList + lane] = id;
                             else P.lists.chunkNext[prev] = id;
+                            P.lists.chunkPrev[id] = prev;
                             prev = id;
                         }
                     }
@@ -735,7 +736,13 @@ __global__ void __launch_bounds__(SL_R2_WARPS * 32, SL_R2_MIN_BLOCKS) k_resolve2
         /* ---- end of the ticket ---- */
         dirty = __any_sync(0xffffffffu, shaded != 0u) && P.depthMask != 0;
         __syncwarp();
-        if (lane < nsub && subCount[lane]) P.lists.listCount[firstList + lane] = subCount[lane];
+        /* the list's last chunk is the one that holds its last fragment: chunks are reserved for the pixels a round is about
+         * to resolve, and the ones the depth test leaves empty stay linked behind it */
+        if (lane < nsub && subCount[lane])
+        {
+            P.lists.listCount[firstList + lane] = subCount[lane];
+            P.lists.listTail[firstList + lane] = chunkRing[lane * SL_R2_CHUNK_RING + (((subCount[lane] - 1u) >> 5) & (SL_R2_CHUNK_RING - 1))];
+        }
         if (staged)
         {
             if (dirty)

@@ -1373,7 +1373,7 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
         CK(c->fragPool.ensure((size_t)chunkCap * SL_CHUNK_BYTES));
         chunkCap = c->fragPool.buf.bytes / SL_CHUNK_BYTES;
         if (chunkCap > 0xfffffff0ull) chunkCap = 0xfffffff0ull;
-        CK(c->chunkNext.ensure((size_t)chunkCap * sizeof(uint32_t)));
+        CK(c->chunkNext.ensure((size_t)chunkCap * 2 * sizeof(uint32_t))); /* next and previous chunk */
         if (sh.depthTest != 0)
         {
             handoffSlots = 4096;
@@ -1402,13 +1402,15 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
     }
 
     /* ---- fragment stage: k_resolve (depth, coverage, order) -> fragment lists -> k_shade<FS> ---- */
-    CK(c->listInfo.ensure((size_t)numLists * 2 * sizeof(uint32_t)));
+    CK(c->listInfo.ensure((size_t)numLists * 3 * sizeof(uint32_t))); /* head, count, tail */
     CK(cudaMemsetAsync(c->listInfo.buf.ptr, 0, (size_t)numLists * 2 * sizeof(uint32_t), c->stream));
     SLFragLists lists;
     lists.pool = c->fragPool.buf.ptr;
     lists.chunkNext = reinterpret_cast<uint32_t*>(c->chunkNext.buf.ptr);
+    lists.chunkPrev = lists.chunkNext + chunkCap;
     lists.listHead = reinterpret_cast<uint32_t*>(c->listInfo.buf.ptr);
     lists.listCount = lists.listHead + numLists;
+    lists.listTail = lists.listCount + numLists;
     lists.chunkCapacity = (unsigned)chunkCap;
 
     SLRasterParams rp;
@@ -1554,6 +1556,13 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
     shp.blend = sh.blend;
     shp.width = depthTex.w;
     shp.numLists = (unsigned)numLists;
+    shp.segWidth = segWidth;
+    shp.numSegs = rasterSegs;
+    shp.numSubLists = numSubLists;
+    {
+        static const bool allowOpaqueSkip = !(getenv("SLCU_OPAQUE_SKIP") && atoi(getenv("SLCU_OPAQUE_SKIP")) == 0);
+        shp.opaqueSkip = (allowOpaqueSkip && sh.blend == 0) ? 1 : 0;
+    }
     shp.lists = lists;
     for (int i = 0; i < 4; ++i)
     {
