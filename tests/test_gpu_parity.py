@@ -291,7 +291,7 @@ def test_sort_first_partition_is_bit_identical(name, world, strip, golden):
 @pytest.mark.parametrize("name,world,strip", [("c1_small", 2, 8), ("c2_small", 4, 8), ("rand_clip_heavy", 2, 1), ("rand_overflow_wide", 3, 2),
                                                ("rand_overflow_blend", 4, 1), ("rand_multi3", 2, 4), ("rand_split3", 3, 8),
                                                ("rand_index_u8", 2, 2), ("rand_depthfunc3", 4, 1), ("c4_small", 2, 8)])
-def test_shared_vertex_stage_is_bit_identical(name, world, strip, golden):
+def test_shared_vertex_stage_is_bit_identical(name, world, strip, golden, monkeypatch):
     """The ranks split the vertex stage (slcu_geometry_share_*): each shades every world-th vertex block and stores the
     records into the arenas of the ranks whose rows they touch; the device-side rendezvous replaces the host.  All ranks
     are contexts on this one GPU, one host thread each (a rank waits on the device for its peers' blocks), their arenas
@@ -303,6 +303,7 @@ def test_shared_vertex_stage_is_bit_identical(name, world, strip, golden):
 
     if name not in cases.CASES:
         pytest.skip("case not defined")
+    monkeypatch.setenv("SLCU_GEOM_SHARE_MIN_PRIMS", "0")  # by default only batches of millions of primitives are shared
     frames, hashes = golden
     scene = cases.CASES[name]()
     ctxs = []

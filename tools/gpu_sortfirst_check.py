@@ -18,6 +18,7 @@ def sha(a):
 
 
 def main():
+    os.environ.setdefault("SLCU_GEOM_SHARE_MIN_PRIMS", "0")  # the check shares every batch, however small
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group(backend="nccl")
