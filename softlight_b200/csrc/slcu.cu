@@ -220,6 +220,7 @@ struct HostTexture
     int type = 0;
     unsigned char* dev = nullptr;
     size_t allocBytes = 0;
+    unsigned depthWritesSinceClear = 0; /* as a depth attachment: depth-writing passes since its last clear (sort-first partition, run_batch) */
     std::vector<unsigned char> shadow; /* only for textures written with set_texels */
 };
 
@@ -782,6 +783,7 @@ static int run_points(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes
     }
     k_commit<<<1, 1, 0, c->stream>>>(c->counters);
     CK(cudaGetLastError());
+    if (sh.depthMask) c->textures[fbo.depth].depthWritesSinceClear++;
     return 0;
 }
 
@@ -921,6 +923,7 @@ static int run_lines(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes,
     }
     k_commit<<<1, 1, 0, c->stream>>>(c->counters);
     CK(cudaGetLastError());
+    if (sh.depthMask) c->textures[fbo.depth].depthWritesSinceClear++;
     return 0;
 }
 
@@ -958,13 +961,38 @@ static int run_batch(slcu_context* c, Batch& B)
         bool verify = false;
         const int rc = enqueue_batch(c, B, verify);
         if (rc) return rc;
-        if (!verify) return 0; /* executed with its own host round trips (wireframe) or empty */
+        if (!verify) /* executed with its own host round trips (wireframe) or empty */
+        {
+            if (c->shaders[B.shaderId].depthMask) c->textures[c->fbos[B.fboId].depth].depthWritesSinceClear++;
+            return 0;
+        }
         CK(cudaMemcpyAsync(c->hostCounters, c->counters, sizeof(SLCounters), cudaMemcpyDeviceToHost, c->stream));
         if (!c->batchDone) CK(cudaEventCreateWithFlags(&c->batchDone, cudaEventDisableTiming));
         CK(cudaEventRecord(c->batchDone, c->stream));
         CK(cudaEventSynchronize(c->batchDone));
-        if (!batch_was_refused(c)) return 0;
-        if (c->refusedPartition) { B.partFull = true; c->refusedPartition = false; }
+        HostTexture& depthTex = c->textures[c->fbos[B.fboId].depth];
+        const HostShader& bsh = c->shaders[B.shaderId];
+        if (!batch_was_refused(c))
+        {
+            if (bsh.depthMask) depthTex.depthWritesSinceClear++;
+            return 0;
+        }
+        if (c->refusedPartition)
+        {
+            /* Sort-first: a span runs past the row end into a row of another rank, so this rank also rasterises the rows such
+             * hand-overs come from.  Their depth texels were left alone by every earlier pass of the frame (another rank owns
+             * them), so with an earlier depth-writing pass behind this one the tests in those rows would see stale depth: the
+             * frame is refused loudly instead of diverging from the single-GPU result. */
+            if (bsh.depthTest != 0 && depthTex.depthWritesSinceClear != 0)
+            {
+                c->refusedPartition = false;
+                c->err = "sort-first partition: a span crosses into another rank's row in a pass that follows an earlier depth-writing pass on the same "
+                         "attachment; that row's depth is not current on this rank (render this frame without the partition)";
+                return SLCU_ERR_UNSUPPORTED;
+            }
+            B.partFull = true;
+            c->refusedPartition = false;
+        }
         B.geomLocal = true; /* shared vertex stage: the other ranks have moved on; this one repeats the batch by itself */
     }
     c->err = "batch does not fit its buffers after repeated growth";
@@ -2351,6 +2379,7 @@ int slcu_clear_depth_buffer(slcu_context* c, size_t fbo, double depth)
     const HostTexture& t = c->textures[c->fbos[fbo].depth];
     unsigned char texel[8];
     if (!host_depth_texel(t, depth, texel)) return 0; /* silently ignored like src/SL_Context.cpp:904-920 */
+    c->textures[c->fbos[fbo].depth].depthWritesSinceClear = 0;
     return clear_texture(c, t, texel);
 }
 int slcu_clear_framebuffer(slcu_context* c, size_t fbo, unsigned att, const double rgba[4], double depth)
@@ -2362,6 +2391,7 @@ int slcu_clear_framebuffer(slcu_context* c, size_t fbo, unsigned att, const doub
     if (!host_depth_texel(d, depth, texel)) return 0; /* src/SL_Context.cpp:944-960 returns before clearing anything */
     int rc = slcu_clear_color_buffer(c, fbo, att, rgba);
     if (rc) return rc;
+    c->textures[c->fbos[fbo].depth].depthWritesSinceClear = 0;
     return clear_texture(c, d, texel);
 }
 
