@@ -73,6 +73,7 @@ struct SLCounters
     unsigned int rasterTicket;        /* (row, segment) ticket of k_resolve (reset by k_scan_row_starts)                */
     unsigned int chunkAlloc;          /* fragment chunks handed out by k_resolve (reset by k_scan_row_starts)           */
     unsigned int shadeTicket;         /* list ticket of k_shade (reset by k_scan_row_starts)                            */
+    unsigned int shadeBandTicket[8];  /* ... of its later launches when the lists are shaded band by band (read-back overlap) */
     unsigned int totalEntries;        /* entries of the row lists (= rowStart[numRows]), for the host's sizing           */
     unsigned int spanTicket[2];       /* item tickets of k_span<0> / k_span<1>                                          */
     unsigned int spanItems;           /* work items of k_span (k_span_items)                                            */
@@ -1618,6 +1619,7 @@ struct SLShadeParams
     int colorType[4];         /* SL_ColorDataType */
     SLFragLists lists;
     unsigned int* shadeTicket; /* list ticket of k_shade (zeroed per batch) */
+    unsigned int listBegin;    /* this launch shades lists listBegin .. numLists - 1 (a band of rows when a read-back follows) */
     const unsigned int* abortBatch; /* SLCounters::abortBatch */
 };
 
@@ -2578,7 +2580,7 @@ __global__ void __launch_bounds__(SL_SHADE_WARPS * 32, SL_SHADE_MIN_BLOCKS) k_sh
     for (;;)
     {
     unsigned list = 0;
-    if (lane == 0) list = atomicAdd(P.shadeTicket, 1u);
+    if (lane == 0) list = P.listBegin + atomicAdd(P.shadeTicket, 1u);
     list = __shfl_sync(0xffffffffu, list, 0);
     if (list >= P.numLists) break;
     const int count = (int)P.lists.listCount[list];

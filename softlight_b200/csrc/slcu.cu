@@ -344,6 +344,11 @@ struct slcu_context
             return true;
         }
     } geom;
+    /* A texture_read that finds the batch rendering into that texture still pending: the batch's last stage (k_shade) then
+     * runs band by band and every band's rows cross the link while the next band is shaded (enqueue_batch). */
+    struct PendingRead { bool active = false, issued = false; size_t tex = 0; unsigned char* out = nullptr; size_t bytes = 0; } pendingRead;
+    cudaEvent_t bandEvent[8] = {};
+    cudaEvent_t readDone = nullptr;
     /* present path (slcu_blit_to_host / slcu_present): a second stream for the copy into the host view, two staging slots */
     cudaStream_t copyStream = nullptr;
     struct PresentSlot { Scratch staging; cudaEvent_t blitDone = nullptr, copyDone = nullptr; bool busy = false; } present[2];
@@ -1607,15 +1612,48 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
         }
     }
     shp.shadeTicket = &c->counters->shadeTicket;
+    shp.listBegin = 0u;
     shp.abortBatch = &c->counters->abortBatch;
     {
         int numSMs = 148;
         cudaDeviceGetAttribute(&numSMs, cudaDevAttrMultiProcessorCount, c->device);
-        unsigned long long grid = (unsigned long long)numSMs * SL_SHADE_MIN_BLOCKS; /* persistent warps */
-        const unsigned long long needBlocks = (numLists + SL_SHADE_WARPS - 1) / SL_SHADE_WARPS;
-        if (grid > needBlocks) grid = needBlocks;
-        KernelScope ks(c, SLCU_K_SHADE);
-        CK(launch_shade_stage(sh, (unsigned)grid, c->stream, shp));
+        /* a read-back of one of the colour attachments waits for this batch: shade the lists in bands of rows (a list's
+         * fragments only touch texels of its own row) and send every band's rows over the link while the next band is shaded */
+        int readAtt = -1;
+        if (c->pendingRead.active)
+        {
+            for (int i = 0; i < sh.numOutputs; ++i) if (fbo.colors[i] == c->pendingRead.tex) readAtt = i;
+        }
+        static const int bandsEnv = getenv("SLCU_READ_BANDS") ? atoi(getenv("SLCU_READ_BANDS")) : 4;
+        const unsigned bands = (readAtt >= 0 && bandsEnv > 1 && H >= 64u) ? (unsigned)(bandsEnv > 8 ? 8 : bandsEnv) : 1u;
+        const unsigned listsPerRow = rasterSegs * numSubLists;
+        for (unsigned b = 0; b < bands; ++b)
+        {
+            const unsigned row0 = (unsigned)((unsigned long long)H * b / bands), row1 = (unsigned)((unsigned long long)H * (b + 1) / bands);
+            shp.listBegin = row0 * listsPerRow;
+            shp.numLists = row1 * listsPerRow;
+            shp.shadeTicket = b == 0 ? &c->counters->shadeTicket : &c->counters->shadeBandTicket[b - 1];
+            const unsigned long long bandLists = (unsigned long long)(row1 - row0) * listsPerRow;
+            unsigned long long grid = (unsigned long long)numSMs * SL_SHADE_MIN_BLOCKS; /* persistent warps */
+            const unsigned long long needBlocks = (bandLists + SL_SHADE_WARPS - 1) / SL_SHADE_WARPS;
+            if (grid > needBlocks) grid = needBlocks;
+            if (grid) { KernelScope ks(c, SLCU_K_SHADE); CK(launch_shade_stage(sh, (unsigned)grid, c->stream, shp)); }
+            if (bands > 1)
+            {
+                const HostTexture& t = c->textures[c->pendingRead.tex];
+                const size_t rowBytes = (size_t)t.w * t.bpt;
+                size_t a = (size_t)row0 * rowBytes, e = (size_t)row1 * rowBytes;
+                if (b + 1 == bands) e = c->pendingRead.bytes; /* whatever the caller asked for beyond the last row */
+                if (e > c->pendingRead.bytes) e = c->pendingRead.bytes;
+                if (!c->copyStream) CK(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+                if (!c->bandEvent[b]) CK(cudaEventCreateWithFlags(&c->bandEvent[b], cudaEventDisableTiming));
+                if (!c->readDone) CK(cudaEventCreateWithFlags(&c->readDone, cudaEventDisableTiming));
+                CK(cudaEventRecord(c->bandEvent[b], c->stream));
+                CK(cudaStreamWaitEvent(c->copyStream, c->bandEvent[b], 0));
+                if (a < e) CK(cudaMemcpyAsync(c->pendingRead.out + a, t.dev + a, e - a, cudaMemcpyDeviceToHost, c->copyStream));
+                if (b + 1 == bands) { CK(cudaEventRecord(c->readDone, c->copyStream)); c->pendingRead.issued = true; }
+            }
+        }
     }
     k_commit<<<1, 1, 0, c->stream>>>(c->counters);
     CK(cudaGetLastError());
@@ -1754,6 +1792,8 @@ void slcu_context_destroy(slcu_context* c)
     for (auto& pm : c->peerMaps) if (pm.ptr) cudaIpcCloseMemHandle(pm.ptr);
     geom_release(c);
     if (c->copyStream) cudaStreamSynchronize(c->copyStream);
+    for (cudaEvent_t& e : c->bandEvent) if (e) cudaEventDestroy(e);
+    if (c->readDone) cudaEventDestroy(c->readDone);
     for (auto& ps : c->present)
     {
         ps.staging.release();
@@ -2062,9 +2102,28 @@ int slcu_texture_set_texels(slcu_context* c, size_t tex, int order, uint16_t x, 
 
 int slcu_texture_read(slcu_context* c, size_t tex, void* out, size_t numBytes)
 {
-    SLCU_FLUSH();
-    if (tex >= c->textures.size() || !out || numBytes > c->textures[tex].allocBytes) return SLCU_ERR_ARG;
+    if (!c || tex >= c->textures.size() || !out || numBytes > c->textures[tex].allocBytes) return SLCU_ERR_ARG;
+    /* the pending batch may be the one that renders into this texture: tell it, so that its rows start crossing the link
+     * while the rest of the frame is still being shaded (enqueue_batch) */
+    const HostTexture& t = c->textures[tex];
+    c->pendingRead = slcu_context::PendingRead{};
+    if (!c->batch.descs.empty() && !c->batch.wire && numBytes >= (size_t)t.w * t.h * t.bpt)
+    {
+        c->pendingRead.active = true;
+        c->pendingRead.tex = tex;
+        c->pendingRead.out = (unsigned char*)out;
+        c->pendingRead.bytes = numBytes;
+    }
+    const int frc = c->batch.descs.empty() ? 0 : flush_draws(c);
+    const bool issued = c->pendingRead.issued;
+    c->pendingRead = slcu_context::PendingRead{};
+    if (frc) return frc;
     cudaSetDevice(c->device);
+    if (issued)
+    {
+        CK(cudaEventSynchronize(c->readDone)); /* the last band's copy; the batch itself was joined by run_batch */
+        return 0;
+    }
     CK(cudaMemcpyAsync(out, c->textures[tex].dev, numBytes, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return 0;
