@@ -26,7 +26,7 @@
 #include "sl_points.cuh"
 #include "sl_wire.cuh"
 #include "sl_lines.cuh"
-#include <cub/device/device_radix_sort.cuh>
+#include "sl_sort.cuh"
 
 using namespace sld;
 
@@ -561,6 +561,52 @@ static cudaError_t launch_wire_shade_stage(const HostShader& sh, unsigned grid, 
     return sh.wireFs(grid, s, p);
 }
 
+/* The ordering step of the point / line / wireframe paths (sl_sort.cuh): stable LSD radix sort of `n` 64-bit keys (and
+ * values) on bits [bitBegin, bitEnd).  keys / vals are double buffers (A at [0, n), B at [n, 2n)); returns 0 or 1 = the half
+ * that holds the result, or a negative error. */
+static int sort_u64(slcu_context* c, unsigned long long* keys, unsigned long long* vals, unsigned long long n, int bitBegin, int bitEnd)
+{
+    if (n > 0xfffffff0ull) { c->err = "too many keys for one sort"; return SLCU_ERR_UNSUPPORTED; }
+    const int bitsTotal = bitEnd - bitBegin;
+    if (bitsTotal <= 0) return 0;
+    const int passes = (bitsTotal + SL_SORT_MAX_BITS - 1) / SL_SORT_MAX_BITS;
+    const int perPass = (bitsTotal + passes - 1) / passes;
+    const unsigned numTiles = (unsigned)((n + SL_SORT_TILE - 1) / SL_SORT_TILE);
+    const size_t histBytes = ((size_t)(1u << perPass) * numTiles * sizeof(uint32_t) + 255) & ~(size_t)255;
+    CK(c->pointSortTemp.ensure(histBytes + (size_t)(1u << perPass) * sizeof(uint32_t)));
+    const unsigned smem = (unsigned)((SL_SORT_WARPS + 1) * (1u << perPass) * sizeof(uint32_t));
+    static bool attrSet[64] = {};
+    if (!attrSet[c->device & 63])
+    {
+        CK(cudaFuncSetAttribute(k_sort_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((SL_SORT_WARPS + 1) * (1u << SL_SORT_MAX_BITS) * sizeof(uint32_t))));
+        attrSet[c->device & 63] = true;
+    }
+    int cur = 0;
+    for (int shift = bitBegin; shift < bitEnd; shift += perPass)
+    {
+        const int bits = bitEnd - shift < perPass ? bitEnd - shift : perPass;
+        SLSortPass sp;
+        sp.keysIn = keys + (size_t)cur * n;
+        sp.keysOut = keys + (size_t)(cur ^ 1) * n;
+        sp.valsIn = vals ? vals + (size_t)cur * n : nullptr;
+        sp.valsOut = vals ? vals + (size_t)(cur ^ 1) * n : nullptr;
+        sp.hist = reinterpret_cast<uint32_t*>(c->pointSortTemp.buf.ptr);
+        sp.totals = reinterpret_cast<uint32_t*>(c->pointSortTemp.buf.ptr + histBytes);
+        sp.n = n;
+        sp.numTiles = numTiles;
+        sp.numDigits = 1u << bits;
+        sp.shift = shift;
+        KernelScope ks(c, SLCU_K_SCAN);
+        k_sort_hist<<<numTiles, SL_SORT_THREADS, 0, c->stream>>>(sp);
+        k_sort_rows<<<sp.numDigits, SL_SORT_THREADS, 0, c->stream>>>(sp.hist, sp.totals, numTiles);
+        k_sort_scatter<<<numTiles, SL_SORT_THREADS, smem, c->stream>>>(sp);
+        CK(cudaGetLastError());
+        c->stats.kernelLaunches += 2;
+        cur ^= 1;
+    }
+    return cur;
+}
+
 /* Draws are not executed one by one.  Consecutive draws that use the same shader object and framebuffer are collected
  * into a batch (their uniforms, viewport and scissor are snapshotted at submission, like the reference's synchronous draw
  * would have read them) and the whole batch goes through the pipeline at once when anything else needs the result: a draw
@@ -743,11 +789,6 @@ static int run_points(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes
         CK(c->pointKeys.ensure((size_t)numPoints * 2 * sizeof(unsigned long long)));
         CK(c->pointRecs.ensure((size_t)numPoints * (1 + NV) * sizeof(float4)));
         unsigned long long* keysA = reinterpret_cast<unsigned long long*>(c->pointKeys.buf.ptr);
-        cub::DoubleBuffer<unsigned long long> keys(keysA, keysA + numPoints);
-        size_t tempBytes = 0;
-        CK(cub::DeviceRadixSort::SortKeys(nullptr, tempBytes, keys, (int)numPoints, 32, 32 + (int)pixBits, c->stream));
-        CK(c->pointSortTemp.ensure(tempBytes));
-
         SLPointParams vp;
         vp.draw = reinterpret_cast<const SLDrawDesc*>(c->drawTable.buf.ptr);
         vp.numPoints = numPoints;
@@ -763,11 +804,12 @@ static int run_points(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes
         vp.counters = c->counters;
         { KernelScope ks(c, SLCU_K_VERTEX); CK(launch_point_vertex_stage(sh, (unsigned)((numPoints + 255ull) / 256ull), c->stream, vp)); }
         /* stable LSD sort on the pixel bits only: inside a pixel the keys stay in submission order */
-        { KernelScope ks(c, SLCU_K_SCAN); CK(cub::DeviceRadixSort::SortKeys(c->pointSortTemp.buf.ptr, tempBytes, keys, (int)numPoints, 32, 32 + (int)pixBits, c->stream)); }
+        const int sortedHalf = sort_u64(c, keysA, nullptr, numPoints, 32, 32 + (int)pixBits);
+        if (sortedHalf < 0) return sortedHalf;
 
         SLPointShadeParams sp;
         sp.draw = vp.draw;
-        sp.keys = keys.Current();
+        sp.keys = keysA + (size_t)sortedHalf * numPoints;
         sp.points = vp.points;
         sp.numPoints = numPoints;
         sp.numVaryings = NV;
@@ -892,21 +934,18 @@ static int run_lines(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes,
         CK(c->pointKeys.ensure((size_t)numCands * 2 * sizeof(unsigned long long)));
         CK(c->pointRecs.ensure((size_t)numCands * sizeof(float4)));
         unsigned long long* keysA = reinterpret_cast<unsigned long long*>(c->pointKeys.buf.ptr);
-        cub::DoubleBuffer<unsigned long long> keys(keysA, keysA + numCands);
-        size_t tempBytes = 0;
-        CK(cub::DeviceRadixSort::SortKeys(nullptr, tempBytes, keys, (int)numCands, 32, 32 + (int)pixBits, c->stream));
-        CK(c->pointSortTemp.ensure(tempBytes));
         lp.keys = keysA;
         lp.cands = reinterpret_cast<float4*>(c->pointRecs.buf.ptr);
         { KernelScope ks(c, SLCU_K_SPAN_FILL); k_line_emit<<<numBlocks, SL_LINE_BLOCK, 0, c->stream>>>(lp); }
         CK(cudaGetLastError());
         /* stable LSD sort on the texel bits only: inside a texel the keys stay in submission order */
-        { KernelScope ks(c, SLCU_K_SCAN); CK(cub::DeviceRadixSort::SortKeys(c->pointSortTemp.buf.ptr, tempBytes, keys, (int)numCands, 32, 32 + (int)pixBits, c->stream)); }
+        const int sortedHalf = sort_u64(c, keysA, nullptr, numCands, 32, 32 + (int)pixBits);
+        if (sortedHalf < 0) return sortedHalf;
 
         SLLineShadeParams sp;
         memset(&sp, 0, sizeof(sp));
         sp.draw = lp.draw;
-        sp.keys = keys.Current();
+        sp.keys = keysA + (size_t)sortedHalf * numCands;
         sp.cands = lp.cands;
         sp.lines = lp.lines;
         sp.numCands = numCands;
@@ -1229,12 +1268,8 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
 
             unsigned pixBits = 1;
             while ((1ull << pixBits) < (unsigned long long)depthTex.w * H) ++pixBits;
-            cub::DoubleBuffer<unsigned long long> keys(keysA, keysA + numFrags);
-            cub::DoubleBuffer<unsigned long long> slots(valsA, valsA + numFrags);
-            size_t tempBytes = 0;
-            CK(cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, keys, slots, (int)numFrags, 0, wp.lowBits + (int)pixBits, c->stream));
-            CK(c->pointSortTemp.ensure(tempBytes));
-            { KernelScope ks(c, SLCU_K_SCAN); CK(cub::DeviceRadixSort::SortPairs(c->pointSortTemp.buf.ptr, tempBytes, keys, slots, (int)numFrags, 0, wp.lowBits + (int)pixBits, c->stream)); }
+            const int sortedHalf = sort_u64(c, keysA, valsA, numFrags, 0, wp.lowBits + (int)pixBits);
+            if (sortedHalf < 0) return sortedHalf;
 
             SLWireShadeParams ws;
             ws.draws = reinterpret_cast<const SLDrawDesc*>(c->drawTable.buf.ptr);
@@ -1242,8 +1277,8 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
             ws.records = wp.records;
             ws.recStride = recStride;
             ws.lowBits = wp.lowBits;
-            ws.keys = keys.Current();
-            ws.vals = slots.Current();
+            ws.keys = keysA + (size_t)sortedHalf * numFrags;
+            ws.vals = valsA + (size_t)sortedHalf * numFrags;
             ws.fragBc = wp.fragBc;
             ws.fragXY = wp.fragXY;
             ws.fragRec = wp.fragRec;

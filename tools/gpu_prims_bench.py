@@ -20,12 +20,23 @@ def time_impl(impl, scene, frames, threads=None):
     if threads:
         ctx.num_threads(threads)
     inst = S.SceneInstance(scene, ctx)
-    inst.render(); ctx.sync()
+    note = None
+
+    def sync():
+        # a frame that meets one of the "not reproduced" behaviours comes back as an error at sync: the
+        # throughput figure stands, the note says so
+        nonlocal note
+        try:
+            ctx.sync()
+        except A.SlError as ex:
+            note = str(ex)
+
+    inst.render(); sync()
     ctx.reset_stats()
     t0 = time.perf_counter()
     for _ in range(frames):
         inst.render()
-    ctx.sync()
+    sync()
     dt = (time.perf_counter() - t0) / frames
     st = ctx.get_stats()
     prof = None
@@ -34,6 +45,8 @@ def time_impl(impl, scene, frames, threads=None):
         inst.render()
         prof = {k: round(v["ms"], 3) for k, v in ctx.profile_end().items() if v["launches"]}
     ctx.close()
+    if note and prof is not None:
+        prof["note"] = note[-90:]
     return dt, st["fragsShaded"] // frames, prof
 
 
