@@ -1,4 +1,12 @@
 mkdir -p gpurun_out
-SLCU_RESOLVE=1 timeout -k 10 900 python -m pytest tests -m gpu -q --maxfail=10 2>&1 | tail -4
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 --print-limit 20 python -m pytest tests/test_gpu_parity.py tests/test_blit.py -m gpu -q -x -k "test_cuda_matches_oracle and (c1_small or c2_small or c3_small or c4_small or rand_clip_heavy or overflow_blend or overflow_half_ge or rand_blend1 or tiny_1x1 or ragged or lines_ or points_dense or wire_alpha or rand_index_u8) or shared_vertex and c2_small or present or blit_to_host" > gpurun_out/r03c_sanitize_memcheck.log 2>&1
-echo "memcheck rc=$?"; grep -E "ERROR SUMMARY|passed|failed|Invalid|out of bounds" gpurun_out/r03c_sanitize_memcheck.log | tail -8
+timeout -k 10 1200 python -m pytest tests -m gpu -q --maxfail=20 2>&1 | tail -5
+for vc in 1 0; do
+for c in c3_indoor2m c4_skinned100 c2_instancing10k c1_sphere100k; do
+  SLCU_VERTEX_CACHE=$vc timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-other-configs --config $c > gpurun_out/ab.json 2> gpurun_out/ab.err
+  python - "vcache=$vc" "$c" <<'PY' || tail -3 gpurun_out/ab.err
+import json, sys
+d = json.loads(open('gpurun_out/ab.json').read().splitlines()[-1])
+k = d['roofline']['kernel_ms_per_frame']
+print(sys.argv[1], sys.argv[2], round(d['ms_per_step'], 3), 'ms e2e', round(d['e2e']['ms_per_step'], 3), {a: round(b, 3) for a, b in k.items()}, flush=True)
+PY
+done; done 2>&1 | tee gpurun_out/ab_r03d.txt
