@@ -52,8 +52,8 @@ struct SLWireParams
     float4* fragBc;
     uint32_t* fragXY;
     uint32_t* fragRec;
-    uint32_t* recBase;                    /* EMIT out: [record] first slot of the record's candidates (visit order)     */
-    uint32_t* recCount;                   /* EMIT out: [record] candidates stored                                         */
+    uint32_t* recBase;                    /* [record] first slot of the record's candidates (k_wire_offsets: submission order) */
+    uint32_t* recCount;                   /* [record] candidates (COUNT out; EMIT zeroes what could not be stored)         */
     SLCounters* counters;                 /* pixelsCovered: candidates (COUNT) / slot allocator (EMIT); rowEndCuts: records with 600+ candidates (COUNT) */
 };
 
@@ -154,25 +154,22 @@ __global__ void __launch_bounds__(128) k_wire(const __grid_constant__ SLWirePara
     {
         if (lane == 0)
         {
+            P.recCount[recId] = n; /* k_wire_offsets turns the counts into slots in submission order */
             if (n) atomicAdd(&P.counters->pixelsCovered, (unsigned long long)n);
             if (n >= SL_WIRE_QUEUE) atomicAdd(&P.counters->rowEndCuts, 1ull);
         }
         return;
     }
     rowsHit = __reduce_add_sync(0xffffffffu, rowsHit);
-    unsigned long long base = 0;
-    if (lane == 0)
+    /* the record's slots: handed out in submission order (k_wire_offsets), so that a stable sort on the pixel bits alone
+     * leaves every pixel's candidates in (record, line, run) order */
+    const unsigned long long base = P.recBase[recId];
+    if (lane == 0 && rowsHit) atomicAdd(&P.counters->spans, (unsigned long long)rowsHit); /* the statistic: (record, line) pairs with a visit */
+    const bool fits = base + n <= P.capacity && n == P.recCount[recId];
+    if (lane == 0 && !fits)
     {
-        if (rowsHit) atomicAdd(&P.counters->spans, (unsigned long long)rowsHit); /* the statistic: (record, line) pairs with a visit */
-        if (n) base = atomicAdd(&P.counters->pixelsCovered, (unsigned long long)n);
-    }
-    base = __shfl_sync(0xffffffffu, base, 0);
-    const bool fits = base + n <= P.capacity;
-    if (lane == 0)
-    {
-        P.recCount[recId] = fits ? n : 0u;
-        P.recBase[recId] = (uint32_t)base;
-        if (!fits) atomicOr(&P.counters->errorFlags, SL_ERR_WIRE_SLOTS);
+        P.recCount[recId] = 0u;
+        atomicOr(&P.counters->errorFlags, SL_ERR_WIRE_SLOTS);
     }
     if (!n || !fits) return;
 
@@ -222,6 +219,46 @@ __global__ void __launch_bounds__(128) k_wire(const __grid_constant__ SLWirePara
             P.fragRec[slot] = recId;
             ++slot;
         });
+    }
+}
+
+/* Slots of every record's candidates in submission order: an exclusive prefix of recCount over the records taken
+ * segment by segment ((round, warp) regions of the vertex blocks, the order k_span uses too).  One CTA: every thread sums a
+ * contiguous run of segments, the run totals are scanned in shared memory, the run is walked again to hand out the bases. */
+__global__ void __launch_bounds__(1024) k_wire_offsets(const SLBlockInfo* blockInfo, unsigned numBlocks, const uint32_t* recCount, uint32_t* recBase)
+{
+    __shared__ unsigned long long sWarp[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned numSegs = numBlocks * (unsigned)SL_VB_SEGS;
+    const unsigned per = (numSegs + 1023u) / 1024u;
+    const unsigned a = min((unsigned)tid * per, numSegs), b = min(a + per, numSegs);
+    unsigned long long sum = 0ull;
+    for (unsigned sIdx = a; sIdx < b; ++sIdx)
+    {
+        const SLSegment sg = blockInfo[sIdx / SL_VB_SEGS].seg[sIdx % SL_VB_SEGS];
+        const uint32_t cnt = min(sg.count, 256u);
+        for (uint32_t i = 0; i < cnt; ++i) sum += recCount[sg.base + i];
+    }
+    unsigned long long incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) sWarp[warp] = incl;
+    __syncthreads();
+    unsigned long long run = incl - sum;
+    for (int w = 0; w < warp; ++w) run += sWarp[w];
+    for (unsigned sIdx = a; sIdx < b; ++sIdx)
+    {
+        const SLSegment sg = blockInfo[sIdx / SL_VB_SEGS].seg[sIdx % SL_VB_SEGS];
+        const uint32_t cnt = min(sg.count, 256u);
+        for (uint32_t i = 0; i < cnt; ++i)
+        {
+            recBase[sg.base + i] = (uint32_t)run;
+            run += recCount[sg.base + i];
+        }
     }
 }
 

@@ -1229,7 +1229,11 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
             wp.stripRows = c->partStripRows;
             wp.counters = c->counters;
             const unsigned wireGrid = numBlocks * SL_WIRE_BLOCKS_PER_VB; /* one warp per record slot */
+            CK(c->wireRecInfo.ensure((size_t)recCapacity * 2 * sizeof(uint32_t)));
+            wp.recBase = reinterpret_cast<uint32_t*>(c->wireRecInfo.buf.ptr);
+            wp.recCount = wp.recBase + recCapacity;
             { KernelScope ks(c, SLCU_K_SPAN_COUNT); k_wire<0><<<wireGrid, 128, 0, c->stream>>>(wp); }
+            { KernelScope ks(c, SLCU_K_SCAN); k_wire_offsets<<<1, 1024, 0, c->stream>>>(wp.blockInfo, numBlocks, wp.recCount, wp.recBase); }
             CK(cudaGetLastError());
             CK(cudaMemcpyAsync(c->hostCounters, c->counters, sizeof(SLCounters), cudaMemcpyDeviceToHost, c->stream));
             CK(cudaStreamSynchronize(c->stream));
@@ -1246,7 +1250,6 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
             CK(c->wireSlots.ensure((size_t)numFrags * 2 * sizeof(unsigned long long)));
             const unsigned long long bigRecords = c->hostCounters->rowEndCuts; /* records with 600+ candidates: their queue flushes are observable */
             CK(c->pointRecs.ensure((size_t)numFrags * (sizeof(float4) + 3 * sizeof(uint32_t) + sizeof(uint16_t) + 2)));
-            CK(c->wireRecInfo.ensure((size_t)recCapacity * 2 * sizeof(uint32_t)));
             unsigned long long* keysA = reinterpret_cast<unsigned long long*>(c->pointKeys.buf.ptr);
             unsigned long long* valsA = reinterpret_cast<unsigned long long*>(c->wireSlots.buf.ptr);
             int ordBits = 13; /* segment (5) + index (8) + the bits of the vertex block */
@@ -1260,15 +1263,14 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
             wp.fragRec = wp.fragXY + numFrags;
             uint16_t* fragEpoch = reinterpret_cast<uint16_t*>(wp.fragRec + numFrags);
             uint8_t* fragPass = reinterpret_cast<uint8_t*>(fragEpoch + numFrags);
-            wp.recBase = reinterpret_cast<uint32_t*>(c->wireRecInfo.buf.ptr);
-            wp.recCount = wp.recBase + recCapacity;
             CK(cudaMemsetAsync(&c->counters->pixelsCovered, 0, sizeof(unsigned long long), c->stream)); /* now the slot allocator */
             { KernelScope ks(c, SLCU_K_SPAN_FILL); k_wire<1><<<wireGrid, 128, 0, c->stream>>>(wp); }
             CK(cudaGetLastError());
 
             unsigned pixBits = 1;
             while ((1ull << pixBits) < (unsigned long long)depthTex.w * H) ++pixBits;
-            const int sortedHalf = sort_u64(c, keysA, valsA, numFrags, 0, wp.lowBits + (int)pixBits);
+            /* slots are in submission order already: only the pixel bits take part */
+            const int sortedHalf = sort_u64(c, keysA, valsA, numFrags, wp.lowBits, wp.lowBits + (int)pixBits);
             if (sortedHalf < 0) return sortedHalf;
 
             SLWireShadeParams ws;
