@@ -355,9 +355,9 @@ class Harness:
         self.barrier()
         step_ms = []
         for i in range(steps):
-            self.flush_l2()
             if self.dist is not None:
                 self.barrier()  # untimed: the ranks start the frame together (they meet on the device inside it when the vertex stage is shared)
+            self.flush_l2()     # enqueued, not waited for: like at N = 1 the frame is submitted while the flush still runs
             self.ctx.timer_begin()
             self.render_frame(i)
             step_ms.append(self.ctx.timer_end())
