@@ -1105,9 +1105,11 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
     bool sharded = false;
     size_t arenaRecDraw = 0, arenaBlockInfo = 0, arenaRecMask = 0;
     /* sharing pays when the vertex stage is long against the ranks' skew at the rendezvous (they start a frame ~0.1 ms
-     * apart: measured at 8 GPUs, profiles/r02y_share_ab_x8.txt: C2, 10.2 M primitives, 0.94 -> 0.68 ms; C3, 2.1 M, 0.86 -> 0.91) */
+     * apart: measured at 8 GPUs, profiles/r02y_share_ab_x8.txt: C2, 10.2 M primitives, 0.94 -> 0.68 ms; C3, 2.1 M, 0.86 -> 0.91)
+     * and there are enough ranks to spread the routed records over (from 4 on) */
     const unsigned long long geomShareMinPrims = (getenv("SLCU_GEOM_SHARE_MIN_PRIMS") && *getenv("SLCU_GEOM_SHARE_MIN_PRIMS")) ? strtoull(getenv("SLCU_GEOM_SHARE_MIN_PRIMS"), nullptr, 10) : 4000000ull;
-    if (allowGeomShare && !B.wire && c->geom.ready(world) && totalPrims >= geomShareMinPrims)
+    const unsigned geomShareMinWorld = (getenv("SLCU_GEOM_SHARE_MIN_PRIMS") && *getenv("SLCU_GEOM_SHARE_MIN_PRIMS")) ? 2u : 4u; /* two ranks route half the records over one link pair: C2 1.17 ms shared, 1.11 replicated */
+    if (allowGeomShare && !B.wire && c->geom.ready(world) && totalPrims >= geomShareMinPrims && world >= geomShareMinWorld)
     {
         const unsigned long long slice = (totalPrims / 8 + 4096) / world + 1024;
         const unsigned long long cap = recFixed + slice * world;
