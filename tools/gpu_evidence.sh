@@ -18,7 +18,7 @@ launches)
 ncu|ncu1|ncu2)
   # (a call's outputs come back only while they stay under 64 MiB: the captures are split over two calls)
   SPECS="c3_indoor2m:k_resolve2:resolve2_c3 c3_indoor2m:k_shade:shade_c3 c2_instancing10k:k_vertex:vertex_c2"
-  [ $what = ncu2 ] && SPECS="c3_indoor2m:k_span:span_c3 c2_instancing10k:k_resolve2:resolve2_c2 c3_indoor2m:k_vertex:vertex_c3"
+  [ $what = ncu2 ] && SPECS="c3_indoor2m:^k_span$:span_c3 c2_instancing10k:k_resolve2:resolve2_c2 c3_indoor2m:k_vertex:vertex_c3"
   for spec in $SPECS; do
     IFS=: read cfg kern out <<< "$spec"
     timeout -k 10 600 ncu --set full --clock-control none --import-source on -k regex:$kern -s 6 -c 1 -f -o gpurun_out/${TAG}_$out python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-other-configs --config $cfg > gpurun_out/${TAG}_ncu_$out.log 2>&1
