@@ -208,9 +208,37 @@ static void store_color(SL_Texture& t, uint16_t x, uint16_t y, const math::vec4&
             for (unsigned i = 0; i < n; ++i) { const double d = (double)c.v[i]; memcpy(p + 8 * i, &d, 8); }
             break;
         }
+        case 2: /* 32U: color_cast<uint32_t,float> = (vec4<u32>)(c * (float)UINT32_MAX); the vec4 conversion is cvtps2dq
+                 * (x86/vec4f_impl.h:333-342): signed, RNE, 0x80000000 from 0.5 upwards -- reproduced, not repaired */
+        {
+            const math::vec4 s = c * 4294967296.f;
+            for (unsigned i = 0; i < n; ++i) { const uint32_t u = (uint32_t)cvt_rn(s.v[i]); memcpy(p + 4 * i, &u, 4); }
+            break;
+        }
+        case 3: /* 64U: the generic element-wise (uint64_t)float of vec4_impl.h:184-187 as g++ compiles it: cvttss2si below
+                 * 2^63 (NaN and negatives included: unordered compares take this branch), otherwise cvttss2si(f - 2^63) ^ 2^63 */
+        {
+            const math::vec4 s = c * 18446744073709551616.f;
+            for (unsigned i = 0; i < n; ++i)
+            {
+                const float f = s.v[i];
+                auto cvtt64 = [](float x) -> int64_t { return (x >= -9223372036854775808.f && x < 9223372036854775808.f) ? (int64_t)x : INT64_MIN; };
+                const uint64_t u = !(f >= 9223372036854775808.f) ? (uint64_t)cvtt64(f) : ((uint64_t)cvtt64(f - 9223372036854775808.f) ^ 0x8000000000000000ull);
+                memcpy(p + 8 * i, &u, 8);
+            }
+            break;
+        }
         default:
-            break; /* 32U/64U colour targets: not covered by the oracle */
+            break;
     }
+}
+
+/* vec4<uint32_t> -> vec4<float> (x86/vec4f_impl.h:236-245): (float)(v >> 1) twice plus (float)(v & 1), every step rounded */
+static inline float u32_to_float(uint32_t v)
+{
+    const float v2f = (float)(int32_t)(v >> 1);
+    const float v1f = (float)(int32_t)(v & 1u);
+    return (v2f + v2f) + v1f;
 }
 
 static math::vec4 load_color_as_float(const SL_Texture& t, uint16_t x, uint16_t y)
@@ -228,6 +256,8 @@ static math::vec4 load_color_as_float(const SL_Texture& t, uint16_t x, uint16_t 
         {
             case 0: return (float)p[i];
             case 1: { uint16_t u; memcpy(&u, p + 2 * i, 2); return (float)u; }
+            case 2: { uint32_t u; memcpy(&u, p + 4 * i, 4); return u32_to_float(u); }
+            case 3: { uint64_t u; memcpy(&u, p + 8 * i, 8); return (float)u; } /* cvtsi2ss, or the halve / round-to-odd / double sequence: correctly rounded */
             case 4: { uint16_t u; memcpy(&u, p + 2 * i, 2); return half_to_float(u); }
             case 5: { float f; memcpy(&f, p + 4 * i, 4); return f; }
             case 6: { double d; memcpy(&d, p + 8 * i, 8); return (float)d; }
@@ -238,6 +268,8 @@ static math::vec4 load_color_as_float(const SL_Texture& t, uint16_t x, uint16_t 
     {
         case 0: lo = 0.f; hi = 255.f; scale = 0.00392156862745f; break;
         case 1: lo = 0.f; hi = 65535.f; scale = 1.f / 65535.f; break;
+        case 2: lo = 0.f; hi = u32_to_float(0xffffffffu); scale = 1.f / 4294967296.f; break;
+        case 3: lo = 0.f; hi = (float)0xffffffffffffffffull; scale = 1.f / 18446744073709551616.f; break;
         default: lo = 0.f; hi = 1.f; scale = 1.f; break;
     }
     switch (n)
@@ -248,7 +280,7 @@ static math::vec4 load_color_as_float(const SL_Texture& t, uint16_t x, uint16_t 
         default: ch[0] = rd(0); ch[1] = rd(1); ch[2] = rd(2); ch[3] = rd(3); break;
     }
     math::vec4 d{ch[0], ch[1], ch[2], ch[3]};
-    if (kind == 0 || kind == 1) d = d * scale;
+    if (kind <= 3) d = d * scale;
     return d;
 }
 

@@ -1684,6 +1684,25 @@ __device__ __noinline__ void sl_store_color_generic(unsigned char* base, int typ
             p[i] = (uint16_t)(v < 0 ? 0 : (v > 65535 ? 65535 : v));
         }
     }
+    else if (kind == 2)
+    {
+        /* color_cast<uint32_t,float> = (vec4<u32>)(c * (float)UINT32_MAX) with the vec4 conversion cvtps2dq (x86/vec4f_impl.h:
+         * 333-342): signed, RNE, 0x80000000 from 0.5 upwards -- reproduced, not repaired */
+        uint32_t* p = reinterpret_cast<uint32_t*>(base) + idx * n;
+        for (int i = 0; i < n; ++i) p[i] = (uint32_t)sl_cvt_rn(c.v[i] * 4294967296.f);
+    }
+    else if (kind == 3)
+    {
+        /* the generic element-wise (uint64_t)float (vec4_impl.h:184-187) as g++ compiles it: cvttss2si below 2^63 (NaN and
+         * negatives included: unordered compares take this branch), otherwise cvttss2si(f - 2^63) ^ 2^63 */
+        unsigned long long* p = reinterpret_cast<unsigned long long*>(base) + idx * n;
+        for (int i = 0; i < n; ++i)
+        {
+            const float f = c.v[i] * 18446744073709551616.f;
+            p[i] = !(f >= 9223372036854775808.f) ? (unsigned long long)sl_cvt_tr64(f)
+                                                 : ((unsigned long long)sl_cvt_tr64(f - 9223372036854775808.f) ^ 0x8000000000000000ull);
+        }
+    }
     else if (kind == 4)
     {
         uint16_t* p = reinterpret_cast<uint16_t*>(base) + idx * n;
@@ -1734,6 +1753,21 @@ __device__ __noinline__ math::vec4 sl_load_color_generic(const unsigned char* ba
         hi = 65535.f;
         scale = 1.f / 65535.f;
     }
+    else if (kind == 2)
+    {
+        /* vec4<uint32_t> -> vec4<float> (x86/vec4f_impl.h:236-245): (float)(v >> 1) twice plus (float)(v & 1), every step rounded */
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(base) + idx * n;
+        for (int i = 0; i < n; ++i) ch[i] = sl_u32_to_float(p[i]);
+        hi = sl_u32_to_float(0xffffffffu);
+        scale = 1.f / 4294967296.f;
+    }
+    else if (kind == 3)
+    {
+        const unsigned long long* p = reinterpret_cast<const unsigned long long*>(base) + idx * n;
+        for (int i = 0; i < n; ++i) ch[i] = __ull2float_rn(p[i]); /* g++'s uint64 -> float sequence is correctly rounded */
+        hi = __ull2float_rn(0xffffffffffffffffull);
+        scale = 1.f / 18446744073709551616.f;
+    }
     else if (kind == 4)
     {
         const uint16_t* p = reinterpret_cast<const uint16_t*>(base) + idx * n;
@@ -1754,7 +1788,7 @@ __device__ __noinline__ math::vec4 sl_load_color_generic(const unsigned char* ba
     else if (n == 2) d = math::vec4{ch[0], ch[1], 0.f, hi};
     else if (n == 3) d = math::vec4{ch[0], ch[0], ch[0], hi};
     else d = math::vec4{ch[0], ch[1], ch[2], ch[3]};
-    if (kind <= 1) d = d * scale;
+    if (kind <= 3) d = d * scale;
     return d;
 }
 

@@ -102,6 +102,20 @@ __device__ __forceinline__ int32_t sl_cvt_tr(float x)
     return __float2int_rz(x);
 }
 
+/* cvttss2si, 64-bit: "integer indefinite" on NaN / overflow */
+__device__ __forceinline__ long long sl_cvt_tr64(float x)
+{
+    if (!(x >= -9223372036854775808.0f && x < 9223372036854775808.0f)) return (long long)0x8000000000000000ull;
+    return __float2ll_rz(x);
+}
+/* vec4<uint32_t> -> vec4<float> of the reference: (float)(int)(v >> 1) + itself + (float)(int)(v & 1), every step rounded */
+__device__ __forceinline__ float sl_u32_to_float(uint32_t v)
+{
+    const float v2f = __int2float_rn((int)(v >> 1));
+    const float v1f = __int2float_rn((int)(v & 1u));
+    return __fadd_rn(__fadd_rn(v2f, v2f), v1f);
+}
+
 __device__ __forceinline__ uint16_t sl_f2h_rn(float f) { return __half_as_ushort(__float2half_rn(f)); }
 __device__ __forceinline__ uint16_t sl_f2h_rz(float f) { return __half_as_ushort(__float2half_rz(f)); }
 __device__ __forceinline__ float sl_h2f(uint16_t h) { return __half2float(__ushort_as_half(h)); }

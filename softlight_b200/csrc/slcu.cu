@@ -648,8 +648,6 @@ static int run_draw(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes, 
     {
         if ((unsigned)i >= fbo.numColors || fbo.colors[i] >= c->textures.size()) { c->err = "shader writes an unattached colour buffer"; return SLCU_ERR_ARG; }
         const HostTexture& t = c->textures[fbo.colors[i]];
-        const int kind = t.type % 7;
-        if (kind == 2 || kind == 3) { c->err = "32/64-bit integer colour targets are not implemented"; return SLCU_ERR_UNSUPPORTED; }
         if (t.w != depthTex.w || t.h != depthTex.h) { c->err = "colour and depth attachments differ in size (SL_Framebuffer::valid -7 / -8)"; return SLCU_ERR_ARG; }
     }
     const float fboW = (float)depthTex.w, fboH = (float)depthTex.h;
@@ -739,8 +737,6 @@ static int run_points(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes
     {
         if ((unsigned)i >= fbo.numColors || fbo.colors[i] >= c->textures.size()) { c->err = "shader writes an unattached colour buffer"; return SLCU_ERR_ARG; }
         const HostTexture& t = c->textures[fbo.colors[i]];
-        const int kind = t.type % 7;
-        if (kind == 2 || kind == 3) { c->err = "32/64-bit integer colour targets are not implemented"; return SLCU_ERR_UNSUPPORTED; }
         if (t.w != depthTex.w || t.h != depthTex.h) { c->err = "colour and depth attachments differ in size (SL_Framebuffer::valid -7 / -8)"; return SLCU_ERR_ARG; }
     }
     const size_t launches = (numInstances == 1) ? numMeshes : 1;
@@ -851,8 +847,6 @@ static int run_lines(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes,
     {
         if ((unsigned)i >= fbo.numColors || fbo.colors[i] >= c->textures.size()) { c->err = "shader writes an unattached colour buffer"; return SLCU_ERR_ARG; }
         const HostTexture& t = c->textures[fbo.colors[i]];
-        const int kind = t.type % 7;
-        if (kind == 2 || kind == 3) { c->err = "32/64-bit integer colour targets are not implemented"; return SLCU_ERR_UNSUPPORTED; }
         if (t.w != depthTex.w || t.h != depthTex.h) { c->err = "colour and depth attachments differ in size (SL_Framebuffer::valid -7 / -8)"; return SLCU_ERR_ARG; }
     }
     const size_t launches = (numInstances == 1) ? numMeshes : 1;

@@ -47,6 +47,12 @@ def _variants():
     # here: with clip-generated spans thousands of pixels long, the reference enters the behaviours DESIGN.md section 2 lists
     # as not reproduced -- its oracle restatement already differs there; widths up to 7680 (config C5) are pinned.)
     v.append(("tall_8192", dict(n=600, width=48, height=8192, clip_fraction=0.4)))
+    # 32- and 64-bit integer colour targets: the reference converts with cvtps2dq (0.5 and above become 0x80000000) and with
+    # g++'s float -> uint64 sequence (1.0 becomes 0); reproduced as they are
+    for ct in (A.SL_COLOR_R_32U, A.SL_COLOR_R_64U, A.SL_COLOR_RG_32U, A.SL_COLOR_RG_64U, A.SL_COLOR_RGB_32U, A.SL_COLOR_RGB_64U,
+               A.SL_COLOR_RGBA_32U, A.SL_COLOR_RGBA_64U):
+        v.append((f"color{ct}", dict(color_type=ct)))
+        v.append((f"color{ct}_alpha", dict(color_type=ct, blend=1)))
     return v
 
 
