@@ -529,7 +529,7 @@ def run_cuda(args, rank, world, local_rank, dist):
         "gpu_launches": d["launches"], "clocks": d["clocks"], "e2e": e2e, "roofline": roofline,
     }
     h.close()
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:  # the CPU leg is reported at N = 1 only
         line["cpu_baseline"] = cpu_baseline_leg(args.config)
     if rank == 0 and world == 1 and not args.no_other_configs and args.config == DEFAULT_CONFIG:
         others = {}
