@@ -47,8 +47,12 @@ enum SL_ColorDataType : int
     SL_COLOR_R_8U = 0, SL_COLOR_R_16U, SL_COLOR_R_32U, SL_COLOR_R_64U, SL_COLOR_R_HALF, SL_COLOR_R_FLOAT, SL_COLOR_R_DOUBLE,
     SL_COLOR_RG_8U, SL_COLOR_RG_16U, SL_COLOR_RG_32U, SL_COLOR_RG_64U, SL_COLOR_RG_HALF, SL_COLOR_RG_FLOAT, SL_COLOR_RG_DOUBLE,
     SL_COLOR_RGB_8U, SL_COLOR_RGB_16U, SL_COLOR_RGB_32U, SL_COLOR_RGB_64U, SL_COLOR_RGB_HALF, SL_COLOR_RGB_FLOAT, SL_COLOR_RGB_DOUBLE,
-    SL_COLOR_RGBA_8U, SL_COLOR_RGBA_16U, SL_COLOR_RGBA_32U, SL_COLOR_RGBA_64U, SL_COLOR_RGBA_HALF, SL_COLOR_RGBA_FLOAT, SL_COLOR_RGBA_DOUBLE
+    SL_COLOR_RGBA_8U, SL_COLOR_RGBA_16U, SL_COLOR_RGBA_32U, SL_COLOR_RGBA_64U, SL_COLOR_RGBA_HALF, SL_COLOR_RGBA_FLOAT, SL_COLOR_RGBA_DOUBLE,
+    /* the packed types of SL_ColorCompressed.hpp: one unsigned integer per texel, r in the lowest bits */
+    SL_COLOR_RGB_332, SL_COLOR_RGB_565, SL_COLOR_RGBA_5551, SL_COLOR_RGBA_4444, SL_COLOR_RGBA_1010102
 };
+/* sl_is_compressed_color (SL_Color.hpp:94-102) */
+constexpr bool sl_is_compressed_color(SL_ColorDataType p) noexcept { return (int)p >= (int)SL_COLOR_RGB_332 && (int)p <= (int)SL_COLOR_RGBA_1010102; }
 enum SL_DataType : int { VERTEX_DATA_BYTE = 0, VERTEX_DATA_SHORT, VERTEX_DATA_INT, VERTEX_DATA_LONG, VERTEX_DATA_FLOAT, VERTEX_DATA_DOUBLE };
 enum SL_Dimension : int { VERTEX_DIMENSION_1 = 0, VERTEX_DIMENSION_2, VERTEX_DIMENSION_3, VERTEX_DIMENSION_4 };
 enum SL_RenderMode : uint32_t
@@ -204,7 +208,8 @@ class SL_Texture : public SL_Resource
 
     static size_t bytes_per_texel(SL_ColorDataType t) noexcept
     {
-        static const size_t chan[7] = {1, 2, 4, 8, 2, 4, 8};
+        static const size_t chan[7] = {1, 2, 4, 8, 2, 4, 8}, packed[5] = {1, 2, 2, 2, 4};
+        if (sl_is_compressed_color(t)) return packed[(int)t - (int)SL_COLOR_RGB_332];
         return chan[(int)t % 7] * (size_t)((int)t / 7 + 1);
     }
 

@@ -170,10 +170,32 @@ namespace slo
 /* ---- colour placement: assign_pixel<T> (src/SL_Framebuffer.cpp:44-217) ---- */
 static inline unsigned chan_bytes(int type) { static const unsigned b[7] = {1, 2, 4, 8, 2, 4, 8}; return b[type % 7]; }
 
+/* the packed colour types (RGB332 ... RGBA1010102, see the conversions further down): field widths, r lowest */
+static const int kPackBits[5][4] = {{3, 3, 2, 0}, {5, 6, 5, 0}, {5, 5, 5, 1}, {4, 4, 4, 4}, {10, 10, 10, 2}};
+static const unsigned kPackBytes[5] = {1, 2, 2, 2, 4};
+static inline bool is_packed(int type) { return type >= 28; }
+static inline uint32_t pack_max(int ci, int j) { return (1u << kPackBits[ci][j]) - 1u; }
+static inline void unpack(int ci, uint32_t v, uint32_t c[4])
+{
+    for (int j = 0, sh = 0; j < 4; sh += kPackBits[ci][j], ++j) c[j] = (v >> sh) & pack_max(ci, j);
+}
+static inline uint32_t pack(int ci, const uint32_t c[4])
+{
+    uint32_t v = 0;
+    for (int j = 0, sh = 0; j < 4; sh += kPackBits[ci][j], ++j) v |= (c[j] & pack_max(ci, j)) << sh;
+    return v;
+}
+static inline uint32_t load_packed(const unsigned char* p, int ci) { uint32_t v = 0; memcpy(&v, p, kPackBytes[ci]); return v; }
+static inline void store_packed(unsigned char* p, int ci, uint32_t v) { memcpy(p, &v, kPackBytes[ci]); }
+
+static uint32_t packed_from_float(int ci, const math::vec4& c); /* rgba_cast<packed, float> */
+static math::vec4 float_from_packed(int ci, uint32_t v);        /* rgba_cast<float, packed> */
+
 static void store_color(SL_Texture& t, uint16_t x, uint16_t y, const math::vec4& c)
 {
     const size_t idx = (size_t)x + (size_t)t.mWidth * y; /* linear, never swizzled */
     unsigned char* p = t.mTexels + idx * t.mBpt;
+    if (is_packed(t.mType)) { store_packed(p, t.mType - 28, packed_from_float(t.mType - 28, c)); return; } /* src/SL_Framebuffer.cpp:85-145 */
     const int kind = t.mType % 7;
     const unsigned n = t.mChannels;
     switch (kind)
@@ -247,6 +269,7 @@ static math::vec4 load_color_as_float(const SL_Texture& t, uint16_t x, uint16_t 
      * including the 3-channel quirk that replicates channel 0 (:308). */
     const size_t idx = (size_t)x + (size_t)t.mWidth * y;
     const unsigned char* p = t.mTexels + idx * t.mBpt;
+    if (is_packed(t.mType)) return float_from_packed(t.mType - 28, load_packed(p, t.mType - 28)); /* :371-590 */
     const int kind = t.mType % 7;
     const unsigned n = t.mChannels;
     float ch[4];
@@ -1309,6 +1332,13 @@ static void clear_texture(SL_Texture& t, const void* texel)
 /* sl_match_color_for_type (src/SL_Color.cpp:135-190): vecN<double> -> typed texel */
 static void match_color(int type, const double rgba[4], unsigned char out[32])
 {
+    if (is_packed(type)) /* rgba_cast<packed, double>: (value_type)(c * (double)max(field)), truncated into the field */
+    {
+        uint32_t f[4];
+        for (int j = 0; j < 4; ++j) f[j] = (uint32_t)(type == 32 ? (uint16_t)(rgba[j] * (double)pack_max(4, j)) : (uint8_t)(rgba[j] * (double)pack_max(type - 28, j)));
+        store_packed(out, type - 28, pack(type - 28, f));
+        return;
+    }
     const int kind = type % 7;
     const unsigned n = (unsigned)(type / 7 + 1);
     for (unsigned i = 0; i < n; ++i)
@@ -1483,12 +1513,20 @@ int slor_ubo_bind_buffer(slcu_context* c, size_t ubo, size_t off, size_t vbo, si
 
 int slor_texture_init(slcu_context* c, size_t tex, int type, uint16_t w, uint16_t h, uint16_t d)
 {
-    if (tex >= c->textures.size() || type < 0 || type >= 28) return SLCU_ERR_ARG;
+    if (tex >= c->textures.size() || type < 0 || type >= 33) return SLCU_ERR_ARG;
     SL_Texture& t = *c->textures[tex];
     free(t.mTexels);
     t.mWidth = w; t.mHeight = h; t.mDepth = d;
-    t.mChannels = (uint8_t)(type / 7 + 1);
-    t.mBpt = (uint8_t)(chan_bytes(type) * t.mChannels);
+    if (type >= 28) /* the packed types (src/SL_Color.cpp:10-110) */
+    {
+        t.mChannels = (uint8_t)(type <= 29 ? 3 : 4);
+        t.mBpt = (uint8_t)slo::kPackBytes[type - 28];
+    }
+    else
+    {
+        t.mChannels = (uint8_t)(type / 7 + 1);
+        t.mBpt = (uint8_t)(chan_bytes(type) * t.mChannels);
+    }
     t.mType = type;
     /* _sl_allocate_texture (src/SL_Texture.cpp:28-54): every dimension padded up by 4-(dim%4) */
     const size_t pw = w + (4 - (w % 4)), ph = h + (4 - (h % 4)), pd = d + (4 - (d % 4));
@@ -1794,7 +1832,139 @@ static void blit_texel(const unsigned char* src, int srcType, unsigned char* dst
     {
         const int from = blit_channel_source(srcN, dstN, j);
         const TexelValue in = from >= 0 ? load_component(src + from * kBytes[ik], ik) : limit_component(ik, from == -2);
-        store_component(dst + j * kBytes[ok], ok, convert_component(in, ik, ok, width));
+        TexelValue out = convert_component(in, ik, ok, width);
+        /* the constant alpha of a double colour, 1.0 * (double)UINT64_MAX = 2^64, is converted by the compiler, which
+         * saturates; the same product at run time (a float colour's alpha) goes through the cvttss2si sequence and gives 0 */
+        if (from == -2 && ik == 6 && ok == 3) out.u = kIntMax[3];
+        store_component(dst + j * kBytes[ok], ok, out);
+    }
+}
+
+/* ---- the packed colour types ("compressed", include/softlight/SL_ColorCompressed.hpp): RGB332, RGB565, RGBA5551,
+ * RGBA4444, RGBA1010102 -- bit-fields with r in the lowest bits.  Conversions are rgb_cast / rgba_cast; which of the two a
+ * blit uses is fixed by the functor (src/SL_BlitCompressedProcessor.cpp:20-258):
+ *   packed -> R, RGB: rgb_cast (component 0 for R);   packed -> RG, RGBA: rgba_cast (leading two for RG);
+ *   R/RG/RGB/RGBA -> packed: ALWAYS rgb_cast of (r, min, min) / (r, g, min) / (r, g, b) / (r, g, b): a source alpha is
+ *   dropped, the packed alpha becomes its maximum;
+ *   packed -> another packed: through uint8 (uint16 towards 1010102), rgb_cast both ways towards the 3-component
+ *   types, rgba_cast both ways towards the 4-component ones.
+ * 1010102 has its own arithmetic (:745-775, 830-870): the integer rgb_cast multiplies by max(T) in T's own (promoted)
+ * width and divides by (T)1023 -- for uint8 that is the LOW 8 bits, for the 32/64-bit types the product wraps; the integer
+ * rgba_cast multiplies by (uint32_t)max(T) in 32 bits; and the AVX2 specialisations for float and uint8 RGBA sign-extend
+ * the fields (abs() of it for float: 1023 reads as 1/1023; the top eight bits for uint8). */
+/* rgb_cast / rgba_cast<packed, U>: integers c / (max(U) / (U)max(field)), float kinds (value_type)(c * (U)max(field)) */
+static uint32_t packed_from_plain(const TexelValue* c, int ik, int ci, bool withAlpha)
+{
+    uint32_t out[4] = {0, 0, 0, pack_max(ci, 3)};
+    const int elemKind = ci == 4 ? 1 : 0; /* the casts go to the packed colour's value_type: uint8_t, uint16_t for 1010102 */
+    for (int j = 0; j < (withAlpha ? 4 : 3); ++j)
+    {
+        const uint32_t cm = pack_max(ci, j);
+        if (!cm) continue;
+        if (ik <= 3)
+        {
+            const uint64_t uMax = kIntMax[ik];
+            out[j] = (uint32_t)((c[j].u / (uMax / ((uint64_t)cm & uMax))) & kIntMax[elemKind]);
+        }
+        else if (ik == 6) out[j] = (uint32_t)trunc_to_int(c[j].d * (double)cm, false, elemKind);
+        else if (ik == 5) out[j] = (uint32_t)trunc_to_int((double)(c[j].f * (float)cm), true, elemKind);
+        else
+        {
+            const uint16_t h = float_to_half_rn(half_to_float(c[j].h) * half_to_float(float_to_half_rn((float)cm))); /* half * half rounds to half */
+            out[j] = (uint32_t)trunc_to_int((double)half_to_float(h), true, elemKind);
+        }
+    }
+    return pack(ci, out);
+}
+/* rgba_cast<SL_ColorRGB1010102, float>, the AVX2 specialisation (:745-762): cvtps2dq, shift, mask */
+static uint32_t packed1010102_from_float(const math::vec4& c)
+{
+    static const float kMax[4] = {1023.f, 1023.f, 1023.f, 3.f};
+    static const int kShift[4] = {0, 10, 20, 30};
+    static const uint32_t kMask[4] = {0x000003ffu, 0x000ffc00u, 0x3ff00000u, 0xc0000000u};
+    uint32_t v = 0;
+    for (int j = 0; j < 4; ++j) v |= ((uint32_t)cvt_rn(c.v[j] * kMax[j]) << kShift[j]) & kMask[j];
+    return v;
+}
+/* rgb_cast (rgba == false) / rgba_cast (rgba == true) <T, packed>; out[3] is only written by rgba_cast */
+static void plain_from_packed(uint32_t v, int ci, int ok, bool rgba, TexelValue out[4])
+{
+    uint32_t c[4];
+    unpack(ci, v, c);
+    for (int j = 0; j < (rgba ? 4 : 3); ++j)
+    {
+        const uint32_t cm = pack_max(ci, j);
+        TexelValue o{};
+        if (!cm) { out[j] = limit_component(ok, true); continue; } /* 332 / 565 have no alpha: max(T) */
+        if (ok <= 3)
+        {
+            const uint64_t tMax = kIntMax[ok];
+            if (ci != 4) o.u = ((uint64_t)c[j] * (tMax / ((uint64_t)cm & tMax))) & tMax;
+            else if (!rgba)
+            {
+                uint64_t prod = (uint64_t)c[j] * tMax; /* int for uint8/uint16 (no overflow), else T's own width */
+                if (ok == 2) prod &= 0xffffffffull;
+                o.u = (prod / (1023ull & tMax)) & tMax;
+            }
+            else if (ok == 0) o.u = j < 3 ? (uint64_t)((c[j] >> 2) & 0xffu) : (uint64_t)(c[j] * 85u); /* AVX2 specialisation (:846-866) */
+            else o.u = (uint64_t)((uint32_t)(c[j] * (uint32_t)tMax) / cm) & tMax;
+        }
+        else if (ci == 4 && rgba && ok == 5) /* AVX2 specialisation (:830-843): sign-extended field, abs, * (1 / max) */
+        {
+            const int bits = kPackBits[ci][j];
+            const int32_t ext = (int32_t)(c[j] << (32 - bits)) >> (32 - bits);
+            o.f = (float)(ext < 0 ? -ext : ext) * (1.f / (float)cm);
+        }
+        else if (ok == 5) o.f = (float)c[j] / (float)cm;
+        else if (ok == 6) o.d = (double)c[j] / (double)cm;
+        else o.h = float_to_half_rn((float)c[j] / (float)cm); /* half / half: float division, rounded to half */
+        out[j] = o;
+    }
+}
+static uint32_t packed_from_packed(uint32_t v, int si, int di)
+{
+    if (si == di) return v;
+    const bool viaRgba = di >= 2;
+    const int midKind = di == 4 ? 1 : 0;
+    TexelValue mid[4];
+    plain_from_packed(v, si, midKind, viaRgba, mid);
+    return packed_from_plain(mid, midKind, di, viaRgba);
+}
+extern "C++" { /* declared next to store_color, outside the C ABI block */
+static uint32_t packed_from_float(int ci, const math::vec4& c)
+{
+    if (ci == 4) return packed1010102_from_float(c);
+    TexelValue t[4];
+    for (int j = 0; j < 4; ++j) { t[j] = TexelValue{}; t[j].f = c.v[j]; }
+    return packed_from_plain(t, 5, ci, true);
+}
+static math::vec4 float_from_packed(int ci, uint32_t v)
+{
+    TexelValue t[4];
+    plain_from_packed(v, ci, 5, true, t);
+    return math::vec4{t[0].f, t[1].f, t[2].f, t[3].f};
+}
+} // extern "C++"
+static void blit_texel_packed(const unsigned char* src, int srcType, unsigned char* dst, int dstType)
+{
+    static const int kBytes[7] = {1, 2, 4, 8, 2, 4, 8};
+    if (is_packed(srcType) && is_packed(dstType))
+    {
+        store_packed(dst, dstType - 28, packed_from_packed(load_packed(src, srcType - 28), srcType - 28, dstType - 28));
+    }
+    else if (is_packed(dstType))
+    {
+        const int ik = srcType % 7, srcN = srcType / 7 + 1;
+        TexelValue c[3];
+        for (int j = 0; j < 3; ++j) c[j] = j < srcN ? load_component(src + j * kBytes[ik], ik) : limit_component(ik, false);
+        store_packed(dst, dstType - 28, packed_from_plain(c, ik, dstType - 28, false));
+    }
+    else
+    {
+        const int ok = dstType % 7, dstN = dstType / 7 + 1;
+        TexelValue c[4];
+        plain_from_packed(load_packed(src, srcType - 28), srcType - 28, ok, dstN == 2 || dstN == 4, c);
+        for (int j = 0; j < dstN; ++j) store_component(dst + j * kBytes[ok], ok, c[j]);
     }
 }
 } // namespace slo
@@ -1821,11 +1991,23 @@ int slor_blit_rect(slcu_context* c, size_t outTex, size_t inTex, uint16_t sx0, u
             if (srcX >= s.mWidth || srcY >= s.mHeight) continue;
             const size_t si = (size_t)(srcX + (uint64_t)s.mWidth * srcY), di = (size_t)(x + totalOutW * y);
             const bool rgIntQuirk = s.mType == d.mType && s.mType / 7 == 1 && s.mType % 7 <= 3; /* RG integer -> same type: p / max(T), see convert_component */
-            if (s.mType == d.mType && !rgIntQuirk) memcpy(d.mTexels + di * d.mBpt, s.mTexels + si * s.mBpt, d.mBpt);
+            if (slo::is_packed(s.mType) || slo::is_packed(d.mType)) slo::blit_texel_packed(s.mTexels + si * s.mBpt, s.mType, d.mTexels + di * d.mBpt, d.mType);
+            else if (s.mType == d.mType && !rgIntQuirk) memcpy(d.mTexels + di * d.mBpt, s.mTexels + si * s.mBpt, d.mBpt);
             else slo::blit_texel(s.mTexels + si * s.mBpt, s.mType, d.mTexels + di * d.mBpt, d.mType);
         }
     }
     return 0;
+}
+/* test hooks: the packed render-target casts on their own (tests/test_texel_host_check.py compares the product's device
+ * header, compiled for the host, with them) */
+SLCU_EXPORT uint32_t slor_test_packed_from_float(int type, const float rgba[4])
+{
+    return slo::packed_from_float(type - 28, slo::math::vec4{rgba[0], rgba[1], rgba[2], rgba[3]});
+}
+SLCU_EXPORT void slor_test_float_from_packed(int type, uint32_t v, float out[4])
+{
+    const slo::math::vec4 c = slo::float_from_packed(type - 28, v);
+    memcpy(out, c.v, 16);
 }
 int slor_blit(slcu_context* c, size_t outTex, size_t inTex)
 {

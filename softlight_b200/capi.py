@@ -40,16 +40,32 @@ INVALID_ID = C.c_size_t(-1).value
  SL_COLOR_RG_8U, SL_COLOR_RG_16U, SL_COLOR_RG_32U, SL_COLOR_RG_64U, SL_COLOR_RG_HALF, SL_COLOR_RG_FLOAT, SL_COLOR_RG_DOUBLE,
  SL_COLOR_RGB_8U, SL_COLOR_RGB_16U, SL_COLOR_RGB_32U, SL_COLOR_RGB_64U, SL_COLOR_RGB_HALF, SL_COLOR_RGB_FLOAT, SL_COLOR_RGB_DOUBLE,
  SL_COLOR_RGBA_8U, SL_COLOR_RGBA_16U, SL_COLOR_RGBA_32U, SL_COLOR_RGBA_64U, SL_COLOR_RGBA_HALF, SL_COLOR_RGBA_FLOAT,
- SL_COLOR_RGBA_DOUBLE) = range(28)
+ SL_COLOR_RGBA_DOUBLE,
+ # the packed ("compressed") types of SL_ColorCompressed.hpp: one unsigned integer per texel, r in the lowest bits
+ SL_COLOR_RGB_332, SL_COLOR_RGB_565, SL_COLOR_RGBA_5551, SL_COLOR_RGBA_4444, SL_COLOR_RGBA_1010102) = range(33)
 
 _CHAN_BYTES = [1, 2, 4, 8, 2, 4, 8]
+_PACKED_BYTES = {SL_COLOR_RGB_332: 1, SL_COLOR_RGB_565: 2, SL_COLOR_RGBA_5551: 2, SL_COLOR_RGBA_4444: 2, SL_COLOR_RGBA_1010102: 4}
+
+
+def is_packed_color(color_type: int) -> bool:
+    return color_type in _PACKED_BYTES
+
+
+def texel_channels(color_type: int) -> int:
+    """Array elements per texel: the component count, 1 for a packed type (the whole texel is one integer)."""
+    return 1 if color_type in _PACKED_BYTES else color_type // 7 + 1
 
 
 def bytes_per_texel(color_type: int) -> int:
+    if color_type in _PACKED_BYTES:
+        return _PACKED_BYTES[color_type]
     return _CHAN_BYTES[color_type % 7] * (color_type // 7 + 1)
 
 
 def texel_dtype(color_type: int):
+    if color_type in _PACKED_BYTES:
+        return {1: np.uint8, 2: np.uint16, 4: np.uint32}[_PACKED_BYTES[color_type]]
     return [np.uint8, np.uint16, np.uint32, np.uint64, np.float16, np.float32, np.float64][color_type % 7]
 
 
@@ -413,7 +429,7 @@ class Context:
         return tid
 
     def texture_read(self, tid: int, color_type: int, w: int, h: int, d: int = 1) -> np.ndarray:
-        nch = color_type // 7 + 1
+        nch = texel_channels(color_type)
         out = np.zeros((d, h, w, nch) if d > 1 else (h, w, nch), dtype=texel_dtype(color_type))
         self._chk(self.f["texture_read"](self.h, tid, _ptr(out), out.nbytes), "texture_read")
         return out

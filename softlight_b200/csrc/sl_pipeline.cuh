@@ -33,6 +33,7 @@
 #pragma once
 
 #include "sl_shader_api.cuh"
+#include "sl_texel.cuh"
 
 namespace sld
 {
@@ -1667,6 +1668,12 @@ SLD_FN bool sl_depth_cmp(int func, float z, float d)
  * have inline fast paths below, and the rasteriser's instruction footprint matters (profiles/). */
 __device__ __noinline__ void sl_store_color_generic(unsigned char* base, int type, size_t idx, const math::vec4& c)
 {
+    if (sl_is_packed(type)) /* assign_pixel<SL_ColorRGB332 ... SL_ColorRGB1010102> (src/SL_Framebuffer.cpp:85-145) */
+    {
+        const int ci = type - 28;
+        sl_packed_store(base + idx * (size_t)sl_pack_bytes(ci), ci, sl_packed_from_float(ci, c));
+        return;
+    }
     const int kind = type % 7;
     const int n = type / 7 + 1;
     if (kind == 0)
@@ -1735,6 +1742,11 @@ SLD_FN void sl_store_color(unsigned char* base, int type, size_t idx, const math
 /* destination read of assign_alpha_pixel (src/SL_Framebuffer.cpp:284-312), 3-channel quirk (:308) included */
 __device__ __noinline__ math::vec4 sl_load_color_generic(const unsigned char* base, int type, size_t idx)
 {
+    if (sl_is_packed(type)) /* rgba_cast<float, packed>, the destination read of the packed assign_alpha_pixel (:371-590) */
+    {
+        const int ci = type - 28;
+        return sl_float_from_packed(ci, sl_packed_load(base + idx * (size_t)sl_pack_bytes(ci), ci));
+    }
     const int kind = type % 7;
     const int n = type / 7 + 1;
     float ch[4];
@@ -2759,15 +2771,7 @@ __global__ void k_clear(const __grid_constant__ SLClearParams P)
  * neighbour, 16.16 fixed point, vertically flipped, format converting.  One
  * thread per destination texel.
  *
- * Conversions (src/SL_BlitProcessor.cpp:20-426 + color_cast, SL_Color.hpp:236-700) between the twenty 8/16-bit unorm,
- * half, float and double layouts.  A blit functor builds a colour of the DESTINATION's channel count in the SOURCE's
- * component type (missing channels are the type's minimum, alpha its maximum; R lands in the LAST colour channel of
- * RGB/RGBA, RG in the middle of RGBA), converts it with color_cast and stores it; "to R" functors convert the whole source
- * colour and keep component 0.  Four-component conversions go through vec4_t's SSE cast operators where one exists
- * (x86/vec4f_impl.h:190-355: float -> u8/u16 = cvtps2dq + saturating packs, float -> half = cvtps2ph toward zero), the
- * others are element-wise C casts (cvttss2si / cvttsd2si and the low bits; scalar half conversions round to nearest).
- * The two-component integer overload scales by max(T) instead of by the ratio of the maxima (SL_Color.hpp:373-380) --
- * reproduced, including for equal types.
+ * The texel conversions (all 33 x 33 type pairs) are in sl_texel.cuh.
  * ----------------------------------------------------------------------*/
 struct SLBlitParams
 {
@@ -2779,110 +2783,6 @@ struct SLBlitParams
     int srcType, dstType;  /* SL_ColorDataType */
 };
 
-struct SLTexelValue /* one component in its own type: kind 0 u8, 1 u16, 4 half, 5 float, 6 double */
-{
-    uint32_t u;
-    float f;
-    double d;
-};
-
-SLD_FN SLTexelValue sl_blit_load(const unsigned char* p, int kind)
-{
-    SLTexelValue t{0u, 0.f, 0.0};
-    if (kind == 0) t.u = *p;
-    else if (kind == 1 || kind == 4) t.u = *reinterpret_cast<const uint16_t*>(p);
-    else if (kind == 5) t.f = *reinterpret_cast<const float*>(p);
-    else t.d = *reinterpret_cast<const double*>(p);
-    return t;
-}
-SLD_FN void sl_blit_store(unsigned char* p, int kind, const SLTexelValue& t)
-{
-    if (kind == 0) *p = (unsigned char)t.u;
-    else if (kind == 1 || kind == 4) *reinterpret_cast<uint16_t*>(p) = (uint16_t)t.u;
-    else if (kind == 5) *reinterpret_cast<float*>(p) = t.f;
-    else *reinterpret_cast<double*>(p) = t.d;
-}
-/* (uint8_t) / (uint16_t) of a float or double the way the x86 code does it: cvttss2si / cvttsd2si, then the low bits */
-SLD_FN uint32_t sl_blit_trunc_f(float x, uint32_t mask) { return (uint32_t)sl_cvt_tr(x) & mask; }
-SLD_FN uint32_t sl_blit_trunc_d(double x, uint32_t mask)
-{
-    const int32_t v = (x > -2147483649.0 && x < 2147483648.0) ? __double2int_rz(x) : (int32_t)0x80000000;
-    return (uint32_t)v & mask;
-}
-SLD_FN SLTexelValue sl_blit_convert(const SLTexelValue& in, int ik, int ok, int width)
-{
-    const bool simd4 = width == 4;
-    SLTexelValue o{0u, 0.f, 0.0};
-    const uint32_t tMax = ok == 0 ? 0xffu : 0xffffu, uMax = ik == 0 ? 0xffu : 0xffffu;
-    if (ik <= 1 && ok <= 1) /* integer -> integer */
-    {
-        if (width == 2) o.u = tMax > uMax ? ((in.u * tMax) & tMax) : ((in.u / tMax) & tMax);
-        else o.u = tMax > uMax ? ((in.u * (tMax / uMax)) & tMax) : ((in.u / (uMax / tMax)) & tMax);
-        return o;
-    }
-    if (ok <= 1) /* half / float / double -> integer: p * (U)max(T), then the cast */
-    {
-        if (ik == 6) { o.u = sl_blit_trunc_d(in.d * (double)tMax, tMax); return o; }
-        const float x = (ik == 4 ? sl_h2f((uint16_t)in.u) : in.f) * (float)tMax;
-        if (simd4)
-        {
-            const int32_t r = sl_cvt_rn(x); /* cvtps2dq */
-            if (ok == 0) { const int32_t q = r < -32768 ? -32768 : (r > 32767 ? 32767 : r); o.u = (uint32_t)(q < 0 ? 0 : (q > 255 ? 255 : q)); } /* packs_epi32, packus_epi16 */
-            else o.u = (uint32_t)(r < 0 ? 0 : (r > 65535 ? 65535 : r));                                                                          /* packus_epi32 */
-        }
-        else o.u = sl_blit_trunc_f(x, tMax);
-        return o;
-    }
-    if (ik <= 1) /* integer -> half / float / double */
-    {
-        if (ok == 6) { o.d = (double)in.u * (ik == 0 ? (1.0 / 255.0) : (1.0 / 65535.0)); return o; }
-        const float scale = ik == 0 ? (ok == 5 ? 0.00392156862745f : (1.f / 255.f)) : (1.f / 65535.f);
-        const float f = (float)in.u * scale;
-        if (ok == 5) o.f = f;
-        else o.u = simd4 ? sl_f2h_rz(f) : sl_f2h_rn(f);
-        return o;
-    }
-    /* float kinds -> float kinds: plain casts; half only talks to float */
-    if (ik == ok) return in;
-    if (ik == 4)
-    {
-        const float f = sl_h2f((uint16_t)in.u);
-        if (ok == 5) o.f = f; else o.d = (double)f;
-        return o;
-    }
-    if (ik == 5)
-    {
-        if (ok == 6) o.d = (double)in.f;
-        else o.u = simd4 ? sl_f2h_rz(in.f) : sl_f2h_rn(in.f);
-        return o;
-    }
-    if (ok == 5) o.f = __double2float_rn(in.d);
-    else o.u = sl_f2h_rn(__double2float_rn(in.d)); /* vec4_t<double> has no SSE cast: (half)(float)(double) */
-    return o;
-}
-/* which source component (or limit) feeds destination component j: 0..3 = source component, -1 = min, -2 = max */
-SLD_FN int sl_blit_channel_source(int srcN, int dstN, int j)
-{
-    if (dstN <= srcN) return j;
-    if (srcN == 1) return dstN == 2 ? (j == 0 ? 0 : -1) : (j == 2 ? 0 : (j == 3 ? -2 : -1));
-    if (srcN == 2) return dstN == 3 ? (j < 2 ? j : -1) : (j == 0 ? -1 : (j == 3 ? -2 : j - 1));
-    return j < 3 ? j : -2;
-}
-SLD_FN void sl_blit_texel(const unsigned char* src, int srcType, unsigned char* dst, int dstType)
-{
-    const int ik = srcType % 7, srcN = srcType / 7 + 1, ok = dstType % 7, dstN = dstType / 7 + 1;
-    const int ib = ik == 0 ? 1 : (ik == 5 ? 4 : (ik == 6 ? 8 : 2)), ob = ok == 0 ? 1 : (ok == 5 ? 4 : (ok == 6 ? 8 : 2));
-    const int width = dstN == 1 ? srcN : dstN; /* the channel count color_cast runs on */
-    for (int j = 0; j < dstN; ++j)
-    {
-        const int from = sl_blit_channel_source(srcN, dstN, j);
-        SLTexelValue in{0u, 0.f, 0.0};
-        if (from >= 0) in = sl_blit_load(src + from * ib, ik);
-        else if (from == -2) { if (ik <= 1) in.u = ik == 0 ? 0xffu : 0xffffu; else if (ik == 4) in.u = 0x3c00u; else if (ik == 5) in.f = 1.f; else in.d = 1.0; }
-        sl_blit_store(dst + j * ob, ok, sl_blit_convert(in, ik, ok, width));
-    }
-}
-
 __global__ void __launch_bounds__(256) k_blit(const __grid_constant__ SLBlitParams P)
 {
     const unsigned long long inW = (unsigned long long)P.srcX1 - P.srcX0, inH = (unsigned long long)P.srcY1 - P.srcY0;
@@ -2893,7 +2793,7 @@ __global__ void __launch_bounds__(256) k_blit(const __grid_constant__ SLBlitPara
     const unsigned long long foutH = ((inH << 16) / P.dstH) + 1ull;
     const unsigned long long x = x0 + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= x1) return;
-    const int srcBpt = (P.srcType / 7 + 1) * (P.srcType % 7 == 0 ? 1 : (P.srcType % 7 == 5 ? 4 : (P.srcType % 7 == 6 ? 8 : 2)));
+    const int srcBpt = sl_texel_bytes(P.srcType);
     for (unsigned long long y = (unsigned long long)P.dstY0 + blockIdx.y; y < P.dstY1 && y < P.dstH; y += gridDim.y)
     {
         const unsigned long long yf = (y * foutH) >> 16;

@@ -447,6 +447,14 @@ static int ensure_rsqrt_table(slcu_context* c)
 }
 
 static inline unsigned chan_bytes(int type) { static const unsigned b[7] = {1, 2, 4, 8, 2, 4, 8}; return b[type % 7]; }
+/* the packed types SL_COLOR_RGB_332 ... SL_COLOR_RGBA_1010102 (28..32, SL_ColorCompressed.hpp): one integer per texel */
+static inline bool type_is_packed(int type) { return type >= 28; }
+static inline unsigned type_channels(int type) { return type_is_packed(type) ? (type <= 29 ? 3u : 4u) : (unsigned)(type / 7 + 1); }
+static inline unsigned type_bpt(int type)
+{
+    static const unsigned packed[5] = {1, 2, 2, 2, 4};
+    return type_is_packed(type) ? packed[type - 28] : chan_bytes(type) * (unsigned)(type / 7 + 1);
+}
 
 static int upload_texture_descs(slcu_context* c)
 {
@@ -1700,6 +1708,21 @@ static int enqueue_batch(slcu_context* c, Batch& B, bool& verify)
 static void host_match_color(int type, const double rgba[4], unsigned char out[32])
 {
     /* sl_match_color_for_type (src/SL_Color.cpp:135-190): color_cast<T,double> = (T)(c * max) element-wise */
+    if (type_is_packed(type)) /* rgba_cast<packed, double>: (value_type)(c * (double)max(field)), truncated into the field */
+    {
+        static const int bits[5][4] = {{3, 3, 2, 0}, {5, 6, 5, 0}, {5, 5, 5, 1}, {4, 4, 4, 4}, {10, 10, 10, 2}};
+        static const unsigned bytes[5] = {1, 2, 2, 2, 4};
+        const int ci = type - 28;
+        uint32_t v = 0;
+        for (int j = 0, sh = 0; j < 4; sh += bits[ci][j], ++j)
+        {
+            const uint32_t fmax = (1u << bits[ci][j]) - 1u;
+            const uint32_t f = ci == 4 ? (uint32_t)(uint16_t)(rgba[j] * (double)fmax) : (uint32_t)(uint8_t)(rgba[j] * (double)fmax);
+            v |= (f & fmax) << sh;
+        }
+        memcpy(out, &v, bytes[ci]);
+        return;
+    }
     const int kind = type % 7;
     const unsigned n = (unsigned)(type / 7 + 1);
     for (unsigned i = 0; i < n; ++i)
@@ -2081,7 +2104,7 @@ int slcu_ubo_bind_buffer(slcu_context* c, size_t ubo, size_t offset, size_t vbo,
 int slcu_texture_init(slcu_context* c, size_t tex, int type, uint16_t w, uint16_t h, uint16_t d)
 {
     SLCU_FLUSH();
-    if (tex >= c->textures.size() || type < 0 || type >= 28) return -1;
+    if (tex >= c->textures.size() || type < 0 || type >= 33) return -1;
     cudaSetDevice(c->device);
     HostTexture& t = c->textures[tex];
     CK(cudaStreamSynchronize(c->stream));
@@ -2089,8 +2112,8 @@ int slcu_texture_init(slcu_context* c, size_t tex, int type, uint16_t w, uint16_
     t.dev = nullptr;
     t.shadow.clear();
     t.w = w; t.h = h; t.d = d; t.type = type;
-    t.channels = (uint8_t)(type / 7 + 1);
-    t.bpt = (uint8_t)(chan_bytes(type) * t.channels);
+    t.channels = (uint8_t)type_channels(type);
+    t.bpt = (uint8_t)type_bpt(type);
     /* _sl_allocate_texture (src/SL_Texture.cpp:28-54): w,h padded up by 4-(dim%4), zero-filled.  The reference also
      * pads the depth to 4+ slices even for 2-D textures; the device copy keeps only the slices that can be addressed. */
     const size_t pw = w + (4 - (w % 4)), ph = h + (4 - (h % 4)), pd = (d <= 1) ? 1 : (size_t)d + (4 - (d % 4));
@@ -2498,13 +2521,11 @@ static int blit_core(slcu_context* c, const HostTexture& s, unsigned char* dstTe
                      uint16_t sx0, uint16_t sy0, uint16_t sx1, uint16_t sy1, uint16_t dx0, uint16_t dy0, uint16_t dx1, uint16_t dy1)
 {
     SLBlitParams p;
-    const int sk = s.type % 7, dk = dstType % 7;
-    const bool rgIntSame = s.type == dstType && s.type / 7 == 1 && sk <= 1; /* RG integer -> same type is p / max(T) in the reference (SL_Color.hpp:373-380) */
+    const bool rgIntSame = s.type == dstType && !type_is_packed(s.type) && s.type / 7 == 1 && s.type % 7 <= 3; /* RG integer -> same type is p / max(T) in the reference (SL_Color.hpp:373-380) */
     if (s.type == dstType && !rgIntSame) p.mode = 0;
     else if (s.type == 26 && dstType == 21) p.mode = 1; /* RGBA_FLOAT -> RGBA_8U */
     else if (s.type == 21 && dstType == 26) p.mode = 2; /* RGBA_8U -> RGBA_FLOAT */
-    else if (sk == 2 || sk == 3 || dk == 2 || dk == 3) { c->err = "blit: conversions from or to 32/64-bit integer layouts are not implemented"; return SLCU_ERR_UNSUPPORTED; }
-    else p.mode = 3; /* the general conversion between the twenty 8/16-bit unorm, half, float and double layouts */
+    else p.mode = 3; /* the general conversion (sl_texel.cuh): any pair of the 33 colour types, SL_BlitProcessor's and SL_BlitCompressedProcessor's */
     p.srcType = s.type;
     p.dstType = dstType;
     if (sx1 < sx0 || sy1 < sy0 || dx1 <= dx0 || dy1 <= dy0) return 0;
@@ -2512,7 +2533,7 @@ static int blit_core(slcu_context* c, const HostTexture& s, unsigned char* dstTe
     p.srcW = s.w; p.srcH = s.h; p.dstW = (uint16_t)dstW; p.dstH = (uint16_t)dstH;
     p.srcX0 = sx0; p.srcY0 = sy0; p.srcX1 = sx1; p.srcY1 = sy1;
     p.dstX0 = dx0; p.dstY0 = dy0; p.dstX1 = dx1; p.dstY1 = dy1;
-    p.bpt = (int)(chan_bytes(dstType) * (unsigned)(dstType / 7 + 1));
+    p.bpt = (int)type_bpt(dstType);
     const unsigned outW = (unsigned)dx1 - dx0, outH = (unsigned)dy1 - dy0;
     const dim3 grid((outW + 255u) / 256u, outH < 148u * 8u ? outH : 148u * 8u);
     { KernelScope ks(c, SLCU_K_BLIT); k_blit<<<grid, 256, 0, c->stream>>>(p); }
@@ -2539,7 +2560,7 @@ int slcu_blit_rect(slcu_context* c, size_t outTex, size_t inTex, uint16_t sx0, u
 static int present_enqueue(slcu_context* c, unsigned slot, void* texels, int colorType, uint16_t w, uint16_t h, size_t inTex,
                            uint16_t sx0, uint16_t sy0, uint16_t sx1, uint16_t sy1, uint16_t dx0, uint16_t dy0, uint16_t dx1, uint16_t dy1)
 {
-    if (!c || slot > 1 || !texels || inTex >= c->textures.size() || colorType < 0 || colorType >= 28 || !w || !h) return SLCU_ERR_ARG;
+    if (!c || slot > 1 || !texels || inTex >= c->textures.size() || colorType < 0 || colorType >= 33 || !w || !h) return SLCU_ERR_ARG;
     cudaSetDevice(c->device);
     const HostTexture& s = c->textures[inTex];
     if (!s.dev) return SLCU_ERR_ARG;
@@ -2552,7 +2573,7 @@ static int present_enqueue(slcu_context* c, unsigned slot, void* texels, int col
         CK(cudaEventCreateWithFlags(&ps.blitDone, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ps.copyDone, cudaEventDisableTiming));
     }
-    const unsigned bpt = chan_bytes(colorType) * (unsigned)(colorType / 7 + 1);
+    const unsigned bpt = type_bpt(colorType);
     if (ps.busy) CK(cudaStreamWaitEvent(c->stream, ps.copyDone, 0)); /* the staging copy's previous contents have left */
     ps.staging.stream = c->stream;
     CK(ps.staging.ensure((size_t)w * h * bpt));

@@ -53,6 +53,12 @@ def _variants():
                A.SL_COLOR_RGBA_32U, A.SL_COLOR_RGBA_64U):
         v.append((f"color{ct}", dict(color_type=ct)))
         v.append((f"color{ct}_alpha", dict(color_type=ct, blend=1)))
+    # the packed colour types as render targets (src/SL_Framebuffer.cpp:85-145, 371-590): rgba_cast both ways, incl. the
+    # sign-extending AVX2 forms of RGBA1010102
+    for ct in (A.SL_COLOR_RGB_332, A.SL_COLOR_RGB_565, A.SL_COLOR_RGBA_5551, A.SL_COLOR_RGBA_4444, A.SL_COLOR_RGBA_1010102):
+        v.append((f"color{ct}", dict(color_type=ct)))
+        v.append((f"color{ct}_alpha", dict(color_type=ct, blend=1)))
+        v.append((f"color{ct}_premult", dict(color_type=ct, blend=2)))
     return v
 
 

@@ -1,9 +1,13 @@
-"""The blit conversion matrix (SL_BlitProcessor, softlight/src/SL_BlitProcessor.cpp:20-715 + color_cast, SL_Color.hpp:236-700)
-over the twenty 8/16-bit unorm, half, float and double layouts: every (source, destination) pair.
+"""The blit conversion matrix over all 33 colour types, every (source, destination) pair:
+* SL_BlitProcessor (softlight/src/SL_BlitProcessor.cpp:20-715 + color_cast, SL_Color.hpp:236-700): the 28 x 28 pairs of
+  the plain layouts (R/RG/RGB/RGBA x u8, u16, u32, u64, half, float, double);
+* SL_BlitCompressedProcessor (softlight/src/SL_BlitCompressedProcessor.cpp + rgb_cast / rgba_cast, SL_ColorCompressed.hpp):
+  the 305 pairs with a packed type (RGB332, RGB565, RGBA5551, RGBA4444, RGBA1010102) on either side.
 
-CPU: the oracle restatement against the compiled reference on all 400 pairs (in-range and out-of-range component values),
-and against committed hashes of the reference's output where oracle/_ref is absent.
-GPU: k_blit through the C ABI against the oracle on all 400 pairs."""
+CPU: the oracle restatement against the compiled reference on all 1089 pairs (in-range and out-of-range component values)
+plus an exhaustive run of the packed pairs (every 8- and 16-bit packed value, 65536 RGBA1010102 values, edge-laden plain
+sources), and against committed hashes of the reference's output where oracle/_ref is absent.
+GPU: k_blit through the C ABI against the oracle on the same inputs."""
 import hashlib
 import json
 import os
@@ -14,15 +18,16 @@ import pytest
 from softlight_b200 import capi as A
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-KINDS = [0, 1, 4, 5, 6]  # u8, u16, half, float, double
-NAMES = {0: "u8", 1: "u16", 4: "half", 5: "float", 6: "double"}
+KINDS = [0, 1, 2, 3, 4, 5, 6]  # u8, u16, u32, u64, half, float, double
+NAMES = {0: "u8", 1: "u16", 2: "u32", 3: "u64", 4: "half", 5: "float", 6: "double"}
+PACKED = {28: "rgb332", 29: "rgb565", 30: "rgba5551", 31: "rgba4444", 32: "rgba1010102"}
 HAVE_REF = os.path.exists(A.LIB_PATHS["ref_strict"])
 GOLDEN = os.path.join(ROOT, "tests", "golden", "blit_matrix_hashes.json")
 
 
 def source_texels(ctype, w, h, mode):
     rng = np.random.default_rng(ctype * 7 + mode)
-    n = ctype // 7 + 1
+    n = A.texel_channels(ctype)
     dt = A.texel_dtype(ctype)
     if np.dtype(dt).kind == "f":
         a = rng.uniform(0.0, 1.0, size=(h, w, n)) if mode == 0 else rng.uniform(-0.5, 1.5, size=(h, w, n))
@@ -30,15 +35,22 @@ def source_texels(ctype, w, h, mode):
         a[0, 0, :] = 0
         a[0, 1, :] = 1
         return a
-    return rng.integers(0, np.iinfo(dt).max, size=(h, w, n), endpoint=True).astype(dt)
+    a = rng.integers(0, np.iinfo(dt).max, size=(h, w, n), endpoint=True, dtype=np.uint64).astype(dt)
+    if np.dtype(dt).itemsize >= 4:  # the wide integers: values around the powers of two the x86 conversions branch on
+        top = np.iinfo(dt).max
+        edges = [0, 1, top, top - 1, top // 2, top // 2 + 1, 2 ** 24 + 1, 2 ** 31, 2 ** 31 - 1, 2 ** 31 + 129, 255, 256, 65535, 65536,
+                 (2 ** 53 + 1) & top, (2 ** 63 + 2 ** 39 + 1) & top]
+        a.reshape(-1)[: len(edges)] = np.array(edges, dtype=np.uint64).astype(dt)
+    return a
 
 
 def all_pairs():
-    for sk in KINDS:
-        for dk in KINDS:
-            for sn in range(1, 5):
-                for dn in range(1, 5):
-                    yield (sn - 1) * 7 + sk, (dn - 1) * 7 + dk
+    """Every (source, destination) pair of the 33 colour types: 28 x 28 through SL_BlitProcessor, the 305 pairs with a
+    packed type on either side through SL_BlitCompressedProcessor."""
+    types = list(range(28)) + sorted(PACKED)
+    for st in types:
+        for dt in types:
+            yield st, dt
 
 
 def run_matrix(impl, mode):
@@ -65,8 +77,12 @@ def digest(m):
     return h.hexdigest()
 
 
+def type_name(t):
+    return PACKED[t] if t in PACKED else f"{NAMES[t % 7]}x{t // 7 + 1}"
+
+
 def label(st, dt):
-    return f"{NAMES[st % 7]}x{st // 7 + 1}->{NAMES[dt % 7]}x{dt // 7 + 1}"
+    return f"{type_name(st)}->{type_name(dt)}"
 
 
 @pytest.mark.parametrize("mode", [0, 1])
@@ -98,14 +114,6 @@ def test_two_component_integer_quirk_known_answer():
     assert ctx.texture_read(d3, A.SL_COLOR_RGB_8U, 1, 1).reshape(-1).tolist() == [0, 0, 200]
 
 
-def test_wide_integer_layouts_are_refused():
-    ctx = A.Context("port")
-    s = ctx.create_texture(A.SL_COLOR_RGBA_8U, 4, 4, 1)
-    d = ctx.create_texture(A.SL_COLOR_RGBA_32U, 4, 4, 1)
-    # the oracle converts them its own way; the product refuses (see the gpu test) -- here only: no crash
-    ctx.blit(d, s)
-
-
 @pytest.mark.gpu
 @pytest.mark.parametrize("mode", [0, 1])
 def test_cuda_matrix_equals_oracle(mode):
@@ -114,10 +122,96 @@ def test_cuda_matrix_equals_oracle(mode):
     assert not bad, bad[:10]
 
 
+def packed_source(st):
+    """Sources for the exhaustive packed run: every value of the 8/16-bit packed types, 65536 RGBA1010102 values (random plus
+    a sweep that walks all four fields), and 64 x 256 plain textures with the values the x86 conversions branch on."""
+    rng = np.random.default_rng(st)
+    dt = A.texel_dtype(st)
+    n = A.texel_channels(st)
+    if A.is_packed_color(st):
+        nb = A.bytes_per_texel(st)
+        if nb == 1:
+            return np.arange(256, dtype=np.uint8).reshape(1, 256, 1)
+        if nb == 2:
+            return np.arange(65536, dtype=np.uint16).reshape(256, 256, 1)
+        sweep = np.arange(4096, dtype=np.uint32)
+        a = np.concatenate([rng.integers(0, 2 ** 32, size=65536 - 4096, dtype=np.uint64).astype(np.uint32),
+                            sweep * np.uint32(0x00100401) + ((sweep % 4) << 30).astype(np.uint32)])
+        return a.reshape(256, 256, 1)
+    h, w = 64, 256
+    if np.dtype(dt).kind == "f":
+        a = rng.uniform(-0.6, 1.6, size=(h, w, n))
+        a[:8] = rng.uniform(0, 1, size=(8, w, n))
+        with np.errstate(over="ignore"):
+            a = a.astype(dt)
+            a[8, :16, :] = np.array([0, 1, 0.5, 1e9, -1e9, np.inf, -np.inf, np.nan, 1e-8, 0.999999, 1.0000001, 2, 3, 4, 255.5, -0.0]).astype(dt)[:, None]
+        return a
+    a = rng.integers(0, np.iinfo(dt).max, size=(h, w, n), endpoint=True, dtype=np.uint64).astype(dt)
+    top = np.iinfo(dt).max
+    edges = [0, 1, top, top - 1, top // 2, top // 2 + 1, (2 ** 24 + 1) & top, (2 ** 31) & top, 255, 256 & top, 65535 & top, 65536 & top,
+             (2 ** 53 + 1) & top, (2 ** 63 + 2 ** 39 + 1) & top, top // 1023, top // 7]
+    a[0, :16, :] = np.array(edges, dtype=np.uint64).astype(dt)[:, None]
+    return a
+
+
+def run_packed(impl):
+    """All 305 pairs with a packed type on either side, on packed_source(); returns {(src, dst): bytes}."""
+    ctx = A.Context(impl)
+    srcs = {}
+    for st in range(33):
+        a = packed_source(st)
+        srcs[st] = (ctx.create_texture(st, a.shape[1], a.shape[0], 1, a), a.shape[1], a.shape[0])
+    out = {}
+    for st in range(33):
+        for dt in range(33):
+            if not (A.is_packed_color(st) or A.is_packed_color(dt)):
+                continue
+            tid, w, h = srcs[st]
+            d = ctx.create_texture(dt, w, h, 1)
+            ctx.blit(d, tid)
+            ctx.sync()
+            out[(st, dt)] = ctx.texture_read(d, dt, w, h).tobytes()
+    ctx.close()
+    return out
+
+
+def test_oracle_packed_pairs_match_committed_reference_hash():
+    assert digest(run_packed("port")) == json.load(open(GOLDEN))["packed_exhaustive"]
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built")
+def test_oracle_packed_pairs_equal_compiled_reference():
+    a, b = run_packed("port"), run_packed("ref_strict")
+    bad = [label(*k) for k in a if a[k] != b[k]]
+    assert not bad, bad[:10]
+
+
+def test_packed_known_answers():
+    """RGBA1010102's AVX2 casts sign-extend their fields (SL_ColorCompressed.hpp:830-866): 1023 reads back as 1/1023 in
+    float, as 255 (the top eight bits) in uint8 RGBA, and as the LOW eight bits through the integer rgb_cast."""
+    ctx = A.Context("port")
+    px = np.array([[[1023 | (512 << 10) | (511 << 20) | (3 << 30)]]], dtype=np.uint32)
+    s = ctx.create_texture(A.SL_COLOR_RGBA_1010102, 1, 1, 1, px)
+    f4 = ctx.create_texture(A.SL_COLOR_RGBA_FLOAT, 1, 1, 1)
+    ctx.blit(f4, s)
+    got = ctx.texture_read(f4, A.SL_COLOR_RGBA_FLOAT, 1, 1).reshape(-1)
+    want = np.array([1, 512, 511, 1], dtype=np.float32) * np.array([1 / 1023, 1 / 1023, 1 / 1023, 1 / 3], dtype=np.float32)
+    assert got.tolist() == want.tolist()
+    u4 = ctx.create_texture(A.SL_COLOR_RGBA_8U, 1, 1, 1)
+    ctx.blit(u4, s)
+    assert ctx.texture_read(u4, A.SL_COLOR_RGBA_8U, 1, 1).reshape(-1).tolist() == [255, 128, 127, 255]
+    u3 = ctx.create_texture(A.SL_COLOR_RGB_8U, 1, 1, 1)
+    ctx.blit(u3, s)
+    assert ctx.texture_read(u3, A.SL_COLOR_RGB_8U, 1, 1).reshape(-1).tolist() == [1023 & 255, 512 & 255, 511 & 255]
+    # a source alpha never reaches a packed destination: RGBA8 -> RGBA4444 stores the maximum (src/SL_BlitCompressedProcessor.cpp:213-233)
+    s8 = ctx.create_texture(A.SL_COLOR_RGBA_8U, 1, 1, 1, np.array([[[255, 128, 17, 0]]], dtype=np.uint8))
+    p4 = ctx.create_texture(A.SL_COLOR_RGBA_4444, 1, 1, 1)
+    ctx.blit(p4, s8)
+    assert int(ctx.texture_read(p4, A.SL_COLOR_RGBA_4444, 1, 1).reshape(-1)[0]) == 15 | (7 << 4) | (1 << 8) | (15 << 12)
+
+
 @pytest.mark.gpu
-def test_cuda_refuses_wide_integer_layouts():
-    ctx = A.Context("cuda")
-    s = ctx.create_texture(A.SL_COLOR_RGBA_8U, 4, 4, 1)
-    d = ctx.create_texture(A.SL_COLOR_RGBA_32U, 4, 4, 1)
-    with pytest.raises(A.SlError):
-        ctx.blit(d, s)
+def test_cuda_packed_pairs_equal_oracle():
+    a, b = run_packed("cuda"), run_packed("port")
+    bad = [label(*k) for k in a if a[k] != b[k]]
+    assert not bad, bad[:10]
