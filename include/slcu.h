@@ -175,7 +175,11 @@ SLCU_EXPORT int SLCU_FN(ubo_bind_buffer)(slcu_context* ctx, size_t ubo, size_t o
 
 /* SL_Texture::init(type,w,h,d) (src/SL_Texture.cpp:276-294), set_texels
  * <ORDERED|SWIZZLED> (SL_Texture.hpp:418-444; texelOrder 0 = ORDERED,
- * 1 = SWIZZLED), data() read-back of the w*h*d*bpt leading bytes. */
+ * 1 = SWIZZLED), data() read-back of the w*h*d*bpt leading bytes.
+ * colorType is any of the 33 SL_ColorDataType values (SL_Color.hpp:29-70):
+ * 0..27 the plain layouts, 28..32 the packed RGB332 / RGB565 / RGBA5551 /
+ * RGBA4444 / RGBA1010102 (SL_ColorCompressed.hpp), as textures, blit sources
+ * and destinations, and colour attachments. */
 SLCU_EXPORT int SLCU_FN(texture_init)(slcu_context* ctx, size_t tex, int colorType, uint16_t w, uint16_t h, uint16_t d);
 SLCU_EXPORT int SLCU_FN(texture_set_texels)(slcu_context* ctx, size_t tex, int texelOrder, uint16_t x, uint16_t y, uint16_t z, uint16_t w, uint16_t h, uint16_t d, const void* data);
 SLCU_EXPORT int SLCU_FN(texture_read)(slcu_context* ctx, size_t tex, void* out, size_t numBytes);
@@ -221,8 +225,11 @@ SLCU_EXPORT int SLCU_FN(draw)(slcu_context* ctx, const slcu_mesh* mesh, size_t s
 SLCU_EXPORT int SLCU_FN(draw_multiple)(slcu_context* ctx, const slcu_mesh* meshes, size_t numMeshes, size_t shader, size_t fbo);
 SLCU_EXPORT int SLCU_FN(draw_instanced)(slcu_context* ctx, const slcu_mesh* mesh, size_t numInstances, size_t shader, size_t fbo);
 
-/* SL_Context::blit(out, in[, rects]) -> run_blit_processors
- * (src/SL_Context.cpp:747-813, src/SL_BlitProcessor.cpp:620-715) */
+/* SL_Context::blit(out, in[, rects]) -> run_blit_processors /
+ * run_blit_compressed_processors (src/SL_Context.cpp:747-813,
+ * src/SL_BlitProcessor.cpp:620-715, src/SL_BlitCompressedProcessor.cpp):
+ * nearest neighbour, vertically flipped, converting between any two of the
+ * 33 colour types the way color_cast / rgb_cast / rgba_cast do. */
 SLCU_EXPORT int SLCU_FN(blit)(slcu_context* ctx, size_t outTexture, size_t inTexture);
 SLCU_EXPORT int SLCU_FN(blit_rect)(slcu_context* ctx, size_t outTexture, size_t inTexture,
                                    uint16_t srcX0, uint16_t srcY0, uint16_t srcX1, uint16_t srcY1,

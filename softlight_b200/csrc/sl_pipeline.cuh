@@ -1664,16 +1664,24 @@ SLD_FN bool sl_depth_cmp(int func, float z, float d)
     }
 }
 
+/* assign_pixel<SL_ColorRGB332 ... SL_ColorRGB1010102> (src/SL_Framebuffer.cpp:85-145) and rgba_cast<float, packed>, the
+ * destination read of the packed assign_alpha_pixel (:371-590).  Out of line and apart from the generic pair below, which
+ * stays as it was measured. */
+__device__ __noinline__ void sl_store_color_packed(unsigned char* base, int type, size_t idx, const math::vec4& c)
+{
+    const int ci = type - 28;
+    sl_packed_store(base + idx * (size_t)sl_pack_bytes(ci), ci, sl_packed_from_float(ci, c));
+}
+__device__ __noinline__ math::vec4 sl_load_color_packed(const unsigned char* base, int type, size_t idx)
+{
+    const int ci = type - 28;
+    return sl_float_from_packed(ci, sl_packed_load(base + idx * (size_t)sl_pack_bytes(ci), ci));
+}
+
 /* assign_pixel<T> (src/SL_Framebuffer.cpp:44-217), every format.  Kept out of line: the two formats the configs use
  * have inline fast paths below, and the rasteriser's instruction footprint matters (profiles/). */
 __device__ __noinline__ void sl_store_color_generic(unsigned char* base, int type, size_t idx, const math::vec4& c)
 {
-    if (sl_is_packed(type)) /* assign_pixel<SL_ColorRGB332 ... SL_ColorRGB1010102> (src/SL_Framebuffer.cpp:85-145) */
-    {
-        const int ci = type - 28;
-        sl_packed_store(base + idx * (size_t)sl_pack_bytes(ci), ci, sl_packed_from_float(ci, c));
-        return;
-    }
     const int kind = type % 7;
     const int n = type / 7 + 1;
     if (kind == 0)
@@ -1736,17 +1744,13 @@ SLD_FN void sl_store_color(unsigned char* base, int type, size_t idx, const math
     }
     else if (type == 26) /* SL_COLOR_RGBA_FLOAT */
         reinterpret_cast<float4*>(base)[idx] = make_float4(c.v[0], c.v[1], c.v[2], c.v[3]);
+    else if (sl_is_packed(type)) sl_store_color_packed(base, type, idx, c);
     else sl_store_color_generic(base, type, idx, c);
 }
 
 /* destination read of assign_alpha_pixel (src/SL_Framebuffer.cpp:284-312), 3-channel quirk (:308) included */
 __device__ __noinline__ math::vec4 sl_load_color_generic(const unsigned char* base, int type, size_t idx)
 {
-    if (sl_is_packed(type)) /* rgba_cast<float, packed>, the destination read of the packed assign_alpha_pixel (:371-590) */
-    {
-        const int ci = type - 28;
-        return sl_float_from_packed(ci, sl_packed_load(base + idx * (size_t)sl_pack_bytes(ci), ci));
-    }
     const int kind = type % 7;
     const int n = type / 7 + 1;
     float ch[4];
@@ -1816,6 +1820,7 @@ SLD_FN math::vec4 sl_load_color(const unsigned char* base, int type, size_t idx)
         const float4 f = reinterpret_cast<const float4*>(base)[idx];
         return math::vec4{f.x, f.y, f.z, f.w};
     }
+    if (sl_is_packed(type)) return sl_load_color_packed(base, type, idx);
     return sl_load_color_generic(base, type, idx);
 }
 
