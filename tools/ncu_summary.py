@@ -53,7 +53,8 @@ def launches(src, dst):
 
 
 def full(src, dst):
-    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # src: an .ncu-rep, or the CSV of `ncu -i <rep> --page raw --csv` written on the GPU box (the reports are too large to bring back)
+    out = open(src).read() if src.endswith(".csv") else subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     with open(dst, "w") as f:
