@@ -371,6 +371,14 @@ static inline bool depth_cmp(int func, float z, float d)
         default: return false;
     }
 }
+/* the functors' SCALAR overloads (SL_ShaderUtil.hpp:240-507, `constexpr int operator()(float a, float b)`), which the point,
+ * line and wireframe rasterisers call (src/SL_PointRasterizer.cpp:58, src/SL_LineRasterizer.cpp:64, src/SL_TriRasterizer.cpp:
+ * 177): the same as the SIMD ones except NOT_EQUAL, which is the C++ `a != b` -- TRUE when the fragment's depth is NaN (a
+ * zero-length line that is clipped interpolates with 0 * inf) */
+static inline bool depth_cmp_scalar(int func, float z, float d)
+{
+    return func == 6 ? (z != d) : depth_cmp(func, z, d);
+}
 
 /* SL_ScanlineBounds (SL_ScanlineBounds.hpp:125-347) */
 struct ScanlineBounds
@@ -633,7 +641,7 @@ static void render_wireframe(slcu_context* c, const Bin& bin)
             for (int k = 0; k < 4; ++k) bc.v[k] = sfma(bc0.v[k], k < 3 ? xf : 0.f, bcY.v[k]); /* :173 */
             const float z = math::dot(depth, bc);
             const float d = load_depth(depthBuffer, (size_t)(rowBase + x));
-            if (!depth_cmp(sh.depthTest, z, d)) continue;
+            if (!depth_cmp_scalar(sh.depthTest, z, d)) continue;
             QueuedFrag q;
             q.bc = bc;
             q.x = (uint16_t)x;
@@ -1009,7 +1017,7 @@ static void process_points(slcu_context* c, const slcu_mesh& m, size_t instanceI
         fp.coord.depth = tv.vert.v[2];
         const size_t idx = (size_t)fp.coord.x + (size_t)depthBuffer.mWidth * fp.coord.y;
         const float d = load_depth(depthBuffer, idx);
-        if (!depth_cmp(sh.depthTest, fp.coord.depth, d)) continue;
+        if (!depth_cmp_scalar(sh.depthTest, fp.coord.depth, d)) continue;
         for (int s2 = 0; s2 < sh.numVaryings; ++s2) fp.pVaryings[s2] = tv.varyings[s2];
         for (int k = 0; k < 4; ++k) fp.pOutputs[k] = math::vec4{0.f};
         if (idx < (size_t)depthBuffer.mWidth * depthBuffer.mHeight) c->stats.fragsShaded++;
@@ -1108,7 +1116,7 @@ static void render_line(slcu_context* c, const TransformedVert& a, const Transfo
                             const float z = z0 + ((z1 - z0) * interp); /* math::mix, scalar (generic/scalar_utils_impl.h:52) */
                             const size_t idx = (size_t)x + (size_t)depthBuffer.mWidth * y;
                             const float dd = load_depth(depthBuffer, idx);
-                            if (!depth_cmp(sh.depthTest, z, dd)) return;
+                            if (!depth_cmp_scalar(sh.depthTest, z, dd)) return;
                             queue.push_back(Queued{interp, x, y, z});
                             if (queue.size() == 600) flush(); /* SL_SHADER_MAX_QUEUED_FRAGS */
                         });

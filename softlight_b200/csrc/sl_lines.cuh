@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(128) k_line_shade(const __grid_constant__ SLLi
             {
                 const float4 c = P.cands[key & 0xffffffffull];
                 const float d = sl_load_depth(P.depth, P.depthBpt, (size_t)pix);
-                if (sl_depth_cmp(P.depthTest, c.y, d)) /* :62-66 */
+                if (sl_depth_cmp_scalar(P.depthTest, c.y, d)) /* :62-66 */
                 {
                     const uint32_t xy = __float_as_uint(c.z);
                     fp.coord.x = (uint16_t)(xy & 0xffffu);

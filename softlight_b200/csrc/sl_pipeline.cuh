@@ -1663,6 +1663,14 @@ SLD_FN bool sl_depth_cmp(int func, float z, float d)
         default: return (z < d) || (z > d);
     }
 }
+/* The functors' SCALAR overloads (SL_ShaderUtil.hpp:240-507), which the point, line and wireframe rasterisers call
+ * (src/SL_PointRasterizer.cpp:58, src/SL_LineRasterizer.cpp:64, src/SL_TriRasterizer.cpp:177): the same as the SIMD ones above
+ * except NOT_EQUAL, which is the C++ `a != b` -- TRUE when the fragment's depth is NaN (a clipped zero-length line
+ * interpolates with 0 * inf), where _CMP_NEQ_OQ says false. */
+SLD_FN bool sl_depth_cmp_scalar(int func, float z, float d)
+{
+    return func == 6 ? !(z == d) : sl_depth_cmp(func, z, d);
+}
 
 /* assign_pixel<SL_ColorRGB332 ... SL_ColorRGB1010102> (src/SL_Framebuffer.cpp:85-145) and rgba_cast<float, packed>, the
  * destination read of the packed assign_alpha_pixel (:371-590).  Out of line and apart from the generic pair below, which

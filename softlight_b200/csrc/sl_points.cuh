@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(128) k_point_shade(const __grid_constant__ SLP
                 const float4* rec = P.points + (key & 0xffffffffull) * (unsigned long long)(1 + P.numVaryings);
                 const float4 p = rec[0];
                 const float d = sl_load_depth(P.depth, P.depthBpt, (size_t)pix);
-                if (sl_depth_cmp(P.depthTest, p.z, d)) /* :58-62 */
+                if (sl_depth_cmp_scalar(P.depthTest, p.z, d)) /* :58-62 */
                 {
                     fp.coord.x = (uint16_t)__float_as_uint(p.x);
                     fp.coord.y = (uint16_t)__float_as_uint(p.y);

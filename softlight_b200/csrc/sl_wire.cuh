@@ -321,7 +321,7 @@ SLD_FN void sl_wire_walk_pixel(const SLWireShadeParams& P, unsigned long long t,
             {
                 for (int i = 0; i < gs; ++i) { if (eps[i] < ep) dSeen = zs[i]; }
             }
-            const bool pass = sl_depth_cmp(P.depthTest, z, dSeen);
+            const bool pass = sl_depth_cmp_scalar(P.depthTest, z, dSeen);
             if (!SHADE) P.fragPass[s] = pass ? 1 : 0;
             if (pass)
             {

@@ -888,6 +888,14 @@ static int run_lines(slcu_context* c, const slcu_mesh* meshes, size_t numMeshes,
         if (numLines > 0x3ffffff0ull) { c->err = "draw too large for one pass"; return SLCU_ERR_UNSUPPORTED; }
         const HostVao& vao = c->vaos[m.vaoId];
         const bool usingIndices = m.mode == 0x0cu; /* per mesh (src/SL_LineProcessor.cpp:205) */
+        if ((elems & 1ull) && usingIndices && m.elementEnd >= c->ibos[vao.ibo].count)
+        {
+            /* for (i = begin; i < end; i += 2) fetches element `end` for the last segment (src/SL_LineProcessor.cpp:236-251):
+             * past the index buffer the reference draws whatever its heap holds there; here the index would address
+             * arbitrary device memory */
+            c->err = "line draw with an odd element count: the last segment's second element lies past the index buffer";
+            return SLCU_ERR_ARG;
+        }
         SLDrawDesc d;
         memset(&d, 0, sizeof(d));
         snapshot_uniforms(c, sh.ubo, d.uniforms);

@@ -153,6 +153,13 @@ LINE_CASES = {
                                        depth_type=A.SL_COLOR_R_DOUBLE, depth_test=A.SL_DEPTH_TEST_GREATER_EQUAL, clear_depth=-1.0),
     "lines_u8_rgbf": dict(n=80, index_dtype=np.uint8, color_type=A.SL_COLOR_RGB_FLOAT),
     "lines_empty": dict(n=30, empty_draw=True),
+    # NOT_EQUAL through the functors' scalar overload (`a != b`, SL_ShaderUtil.hpp:471-476): TRUE for the NaN depth of a
+    # clipped zero-length line, where the SIMD overload the filled triangles use (_CMP_NEQ_OQ) says false
+    "lines_ne_nan": dict(n=1400, width=364, height=362, clip_fraction=0.55, depth_test=A.SL_DEPTH_TEST_NOT_EQUAL, clear_depth=0.0),
+    "lines_ne_nan_premult_nomask": dict(n=1200, width=228, height=155, clip_fraction=0.6, blend=2, depth_mask=A.SL_DEPTH_MASK_OFF,
+                                        depth_test=A.SL_DEPTH_TEST_NOT_EQUAL, depth_type=A.SL_COLOR_R_DOUBLE, viewport=(13, 20, 191, 120)),
+    "lines_ne_nan_half_1010102": dict(n=1000, width=110, height=56, clip_fraction=0.4, blend=4, depth_test=A.SL_DEPTH_TEST_NOT_EQUAL,
+                                      depth_type=A.SL_COLOR_R_HALF, color_type=A.SL_COLOR_RGBA_1010102, split_draws=2),
 }
 for _i, _name in enumerate(LINE_CASES):
     CASES[_name] = (lambda i=_i, name=_name: S.random_tris_scene(seed=1000 + i, name=name, lines=True, **LINE_CASES[name]))

@@ -56,7 +56,8 @@ def test_cuda_blit_matches_golden(name, golden_blits):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("src_type,dst_type", [(A.SL_COLOR_RGBA_8U, A.SL_COLOR_RGBA_8U), (A.SL_COLOR_RGBA_FLOAT, A.SL_COLOR_RGBA_8U),
-                                               (A.SL_COLOR_RGB_8U, A.SL_COLOR_RGBA_HALF), (A.SL_COLOR_RGBA_8U, A.SL_COLOR_RGB_16U)])
+                                               (A.SL_COLOR_RGB_8U, A.SL_COLOR_RGBA_HALF), (A.SL_COLOR_RGBA_8U, A.SL_COLOR_RGB_16U),
+                                               (A.SL_COLOR_RGBA_8U, A.SL_COLOR_RGB_565), (A.SL_COLOR_RGBA_FLOAT, A.SL_COLOR_RGBA_1010102)])
 def test_blit_to_host_view_equals_blit_into_a_texture(src_type, dst_type):
     """SL_Context::blit(SL_TextureView& buffer, textureId[, rects]) (src/SL_Context.cpp:816-874), the present path: the host
     view receives exactly what the same blit writes into a texture (pinned to the reference by the blit matrix), whole
@@ -70,7 +71,7 @@ def test_blit_to_host_view_equals_blit_into_a_texture(src_type, dst_type):
     tin = ctx.create_texture(src_type, sw, sh, 1, src)
     for rects in (None, ((5, 3, 80, 50), (10, 7, 50, 33))):
         tout = ctx.create_texture(dst_type, dw, dh, 1)
-        fill = ctx.host_array((dh, dw, dst_type // 7 + 1), A.texel_dtype(dst_type))
+        fill = ctx.host_array((dh, dw, A.texel_channels(dst_type)), A.texel_dtype(dst_type))
         fill.view(np.uint8)[...] = 0xAB
         before = fill.copy()
         if rects is None:

@@ -226,6 +226,21 @@ def test_lines_between_triangle_draws_keep_submission_order(golden):
     assert_same(cg, dg, co, do)
 
 
+def test_odd_line_element_count_past_the_index_buffer_is_refused():
+    """for (i = begin; i < end; i += 2) fetches element `end` for the last segment (src/SL_LineProcessor.cpp:236-251).  Inside
+    the index buffer that is the next element (reproduced: lines_multi4_u32_double_ge has odd sub-draws); past its end the
+    reference draws whatever its heap holds there -- the product refuses the draw instead of fetching through it."""
+    ctx = A.Context("cuda")
+    st = S.SceneInstance(S.random_tris_scene(seed=3, n=11), ctx).state  # 33 elements
+    m = st["meshes"][0]
+    assert (m.elementEnd - m.elementBegin) == 33
+    ctx.draw(ctx.mesh(m.vaoId, 0, 31, A.RENDER_MODE_INDEXED_LINES), st["shader"], st["fbo"])  # element 31 exists
+    ctx.sync()
+    with pytest.raises(A.SlError):
+        ctx.draw(ctx.mesh(m.vaoId, 0, 33, A.RENDER_MODE_INDEXED_LINES), st["shader"], st["fbo"])
+    ctx.close()
+
+
 def test_points_between_triangle_draws_keep_submission_order(golden):
     """triangles, points, triangles on one framebuffer: the point pass executes between the two triangle batches, exactly
     like the oracle's draw-by-draw execution."""
