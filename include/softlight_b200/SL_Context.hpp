@@ -371,6 +371,20 @@ class SL_Context
     SL_UniformBuffer& ubo(size_t i) noexcept { return *mUbos[i]; }
     SL_Texture& texture(size_t i) noexcept { return *mTextures[i]; }
     SL_Framebuffer& framebuffer(size_t i) noexcept { return *mFbos[i]; }
+    const SL_VertexBuffer& vbo(size_t i) const noexcept { return *mVbos[i]; }
+    const SL_IndexBuffer& ibo(size_t i) const noexcept { return *mIbos[i]; }
+    const SL_VertexArray& vao(size_t i) const noexcept { return *mVaos[i]; }
+    const SL_UniformBuffer& ubo(size_t i) const noexcept { return *mUbos[i]; }
+    const SL_Texture& texture(size_t i) const noexcept { return *mTextures[i]; }
+    const SL_Framebuffer& framebuffer(size_t i) const noexcept { return *mFbos[i]; }
+    /* the object lists (SL_Context.hpp:100-180; scene-level callers size their id ranges with them, e.g.
+     * SL_SceneGraph.cpp:1059 `mContext.vaos().size()`): pointers to the live mirrors here, objects by value there */
+    const std::vector<SL_VertexBuffer*>& vbos() const noexcept { return mVbos; }
+    const std::vector<SL_IndexBuffer*>& ibos() const noexcept { return mIbos; }
+    const std::vector<SL_VertexArray*>& vaos() const noexcept { return mVaos; }
+    const std::vector<SL_UniformBuffer*>& ubos() const noexcept { return mUbos; }
+    const std::vector<SL_Texture*>& textures() const noexcept { return mTextures; }
+    const std::vector<SL_Framebuffer*>& framebuffers() const noexcept { return mFbos; }
 
     /* SL_Context::create_shader(vertShader, fragShader, uniformIndex): index or (size_t)-1 (src/SL_Context.cpp:488-605);
      * an unregistered shader name is refused the same way */
