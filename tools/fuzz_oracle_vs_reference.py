@@ -51,6 +51,38 @@ def run_case(kw, rcp):
     return pickle.loads(data) if data else ("CRASH", status)
 
 
+def random_case(rng, family="all", max_clip=0.9):
+    """Keyword arguments of one random_tris_scene."""
+    kw = dict(seed=int(rng.integers(1, 1 << 30)), n=int(rng.integers(20, 1500)), width=int(rng.integers(1, 700)), height=int(rng.integers(1, 400)),
+              blend=int(rng.integers(0, 5)), depth_test=int(rng.integers(0, 7)), depth_mask=int(rng.integers(0, 2)),
+              depth_type=[A.SL_COLOR_R_HALF, A.SL_COLOR_R_FLOAT, A.SL_COLOR_R_DOUBLE][int(rng.integers(0, 3))],
+              color_type=int(rng.integers(0, 33)), cull=int(rng.integers(0, 3)), clip_fraction=float(rng.uniform(0, max_clip)),
+              clear_depth=float(rng.choice([1.0, 0.5, 0.0, -1.0])), split_draws=int(rng.integers(1, 4)))
+    mode = int(rng.integers(0, 10))
+    if family == "lines":
+        mode = 2
+    elif family == "tris" and mode in (0, 1, 2):
+        mode = 9
+    if mode == 0:
+        kw["points"] = True
+    elif mode == 1:
+        kw["wire"] = True
+    elif mode == 2:
+        kw["lines"] = True
+        kw["n"] = max(1, kw["n"] // (2 * kw["split_draws"])) * 2 * kw["split_draws"]
+    elif mode == 3:
+        kw["instances"] = int(rng.integers(2, 5))
+    for key in ("viewport", "scissor"):
+        if rng.random() < 0.3:
+            w, h = kw["width"], kw["height"]
+            kw[key] = (int(rng.integers(0, w)), int(rng.integers(0, h)), int(rng.integers(1, w + 1)), int(rng.integers(1, h + 1)))
+    return kw
+
+
+def classify(res):
+    return "crash" if res[0] == "CRASH" else "exc" if res[0] == "EXC" else "ok" if (res[0] == 0 and res[1] == 0) else "mismatch"
+
+
 def main():
     seed, seconds = int(sys.argv[1]), float(sys.argv[2])
     family = sys.argv[3] if len(sys.argv) > 3 else "all"
@@ -60,32 +92,10 @@ def main():
     rng = np.random.default_rng(seed)
     t0, n, stats = time.time(), 0, {}
     while time.time() - t0 < seconds:
-        kw = dict(seed=int(rng.integers(1, 1 << 30)), n=int(rng.integers(20, 1500)), width=int(rng.integers(1, 700)), height=int(rng.integers(1, 400)),
-                  blend=int(rng.integers(0, 5)), depth_test=int(rng.integers(0, 7)), depth_mask=int(rng.integers(0, 2)),
-                  depth_type=[A.SL_COLOR_R_HALF, A.SL_COLOR_R_FLOAT, A.SL_COLOR_R_DOUBLE][int(rng.integers(0, 3))],
-                  color_type=int(rng.integers(0, 33)), cull=int(rng.integers(0, 3)), clip_fraction=float(rng.uniform(0, 0.9)),
-                  clear_depth=float(rng.choice([1.0, 0.5, 0.0, -1.0])), split_draws=int(rng.integers(1, 4)))
-        mode = int(rng.integers(0, 10))
-        if family == "lines":
-            mode = 2
-        elif family == "tris" and mode in (0, 1, 2):
-            mode = 9
-        if mode == 0:
-            kw["points"] = True
-        elif mode == 1:
-            kw["wire"] = True
-        elif mode == 2:
-            kw["lines"] = True
-            kw["n"] = max(1, kw["n"] // (2 * kw["split_draws"])) * 2 * kw["split_draws"]
-        elif mode == 3:
-            kw["instances"] = int(rng.integers(2, 5))
-        for key in ("viewport", "scissor"):
-            if rng.random() < 0.3:
-                w, h = kw["width"], kw["height"]
-                kw[key] = (int(rng.integers(0, w)), int(rng.integers(0, h)), int(rng.integers(1, w + 1)), int(rng.integers(1, h + 1)))
+        kw = random_case(rng, family)
         res = run_case(kw, rcp)
         n += 1
-        kind = "crash" if res[0] == "CRASH" else "exc" if res[0] == "EXC" else "ok" if (res[0] == 0 and res[1] == 0) else "mismatch"
+        kind = classify(res)
         stats[kind] = stats.get(kind, 0) + 1
         if kind != "ok":
             print(kind.upper(), res, kw, flush=True)
