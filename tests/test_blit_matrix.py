@@ -215,3 +215,35 @@ def test_cuda_packed_pairs_equal_oracle():
     a, b = run_packed("cuda"), run_packed("port")
     bad = [label(*k) for k in a if a[k] != b[k]]
     assert not bad, bad[:10]
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built")
+def test_oracle_equals_reference_on_random_blits():
+    """Random type pairs, sizes and NON-EMPTY rectangles (resampling, vertical flip, partial destinations).  An empty source
+    rectangle makes the reference read row or column -1 and is left out."""
+    rng = np.random.default_rng(77)
+    bad = []
+    for _ in range(400):
+        st, dt = int(rng.integers(0, 33)), int(rng.integers(0, 33))
+        sw, sh, dw, dh = [int(rng.integers(1, 90)) for _ in range(4)]
+        pool = packed_source(st).reshape(-1, A.texel_channels(st))
+        a = np.ascontiguousarray(pool[rng.integers(0, pool.shape[0], size=sw * sh)].reshape(sh, sw, -1))
+        rect = None
+        if rng.random() < 0.6:
+            x0 = int(rng.integers(0, sw)); x1 = int(rng.integers(x0 + 1, sw + 1))
+            y0 = int(rng.integers(0, sh)); y1 = int(rng.integers(y0 + 1, sh + 1))
+            u0, u1 = sorted(int(v) for v in rng.integers(0, dw + 1, size=2))
+            v0, v1 = sorted(int(v) for v in rng.integers(0, dh + 1, size=2))
+            rect = (x0, y0, x1, y1, u0, v0, u1, v1)
+        outs = []
+        for impl in ("port", "ref_strict"):
+            ctx = A.Context(impl)
+            s = ctx.create_texture(st, sw, sh, 1, a)
+            d = ctx.create_texture(dt, dw, dh, 1)
+            ctx.blit(d, s, rect)
+            ctx.sync()
+            outs.append(ctx.texture_read(d, dt, dw, dh).tobytes())
+            ctx.close()
+        if outs[0] != outs[1]:
+            bad.append((label(st, dt), (sw, sh, dw, dh), rect))
+    assert not bad, bad[:5]
